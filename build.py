@@ -1,0 +1,145 @@
+#!/usr/bin/env python3
+"""In-tree native build for blackbird_b200.
+
+Generates build/build.ninja and runs ninja.  Produces
+  blackbird_b200/_bb<EXT_SUFFIX>   single pybind11 module: C++20 control plane + sm_100a data plane
+  bin/bb-keystone bin/bb-worker bin/bb-coord bin/bb-cli bin/bb-bench bin/bb-tests
+
+All CUDA is compiled for sm_100a only (`-gencode arch=compute_100a,code=sm_100a -lineinfo`);
+nvcc cross-compiles without a GPU.  cudart is linked statically and the driver API is
+resolved at runtime, so the module imports on a CPU-only box.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(ROOT, "build")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
+
+CXXFLAGS = "-std=c++20 -O2 -g1 -fPIC -Wall -Wextra -Wno-unused-parameter -Wno-missing-field-initializers -pthread"
+NVCCFLAGS = (
+    "-std=c++20 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a "
+    "-Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v --expt-relaxed-constexpr -Wno-deprecated-gpu-targets"
+)
+
+
+def _san_flags() -> str:
+    san = os.environ.get("BB_SANITIZE", "")
+    if san == "asan":
+        return " -fsanitize=address,undefined -fno-omit-frame-pointer"
+    if san == "tsan":
+        return " -fsanitize=thread -fno-omit-frame-pointer"
+    return ""
+
+
+def _rel(p: str) -> str:
+    return os.path.relpath(p, BUILD)
+
+
+def generate() -> str:
+    import pybind11
+
+    os.makedirs(BUILD, exist_ok=True)
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    pyinc = sysconfig.get_paths()["include"]
+    incs = f"-I{ROOT}/csrc -I{CUDA_HOME}/include"
+    pyincs = f"-I{pybind11.get_include()} -I{pyinc}"
+    san = _san_flags()
+
+    core_src = sorted(
+        f
+        for d in ("common", "alloc", "coord", "net", "rpc", "keystone", "worker", "client")
+        for f in glob.glob(os.path.join(ROOT, "csrc", d, "*.cpp"))
+    )
+    fabric_src = sorted(glob.glob(os.path.join(ROOT, "csrc", "fabric", "*.cpp")))
+    cu_src = sorted(glob.glob(os.path.join(ROOT, "csrc", "kernels", "*.cu")))
+    py_src = sorted(glob.glob(os.path.join(ROOT, "csrc", "py", "*.cpp")))
+    app_src = sorted(glob.glob(os.path.join(ROOT, "apps", "*.cpp")))
+
+    lines = [
+        "ninja_required_version = 1.5",
+        f"cxxflags = {CXXFLAGS}{san} {incs}",
+        f"nvccflags = {NVCCFLAGS} {incs}",
+        f"pyincs = {pyincs}",
+        "rule cxx",
+        "  command = g++ -MMD -MF $out.d $cxxflags $extra -c $in -o $out",
+        "  depfile = $out.d",
+        "  deps = gcc",
+        "  description = CXX $in",
+        "rule nvcc",
+        f"  command = {NVCC} $nvccflags -MD -MF $out.d -c $in -o $out 2> $out.ptxas.log || (cat $out.ptxas.log; false)",
+        "  depfile = $out.d",
+        "  deps = gcc",
+        "  description = NVCC $in",
+        "rule link_so",
+        f"  command = g++ -shared -o $out $in -L{CUDA_HOME}/lib64 -lcudart_static -ldl -lrt -pthread{san}",
+        "  description = LINK $out",
+        "rule link_exe",
+        f"  command = g++ -o $out $in -L{CUDA_HOME}/lib64 -lcudart_static -ldl -lrt -pthread{san}",
+        "  description = LINK $out",
+        "",
+    ]
+
+    def obj(src: str) -> str:
+        return os.path.join("obj", os.path.relpath(src, ROOT).replace("/", "_") + ".o")
+
+    lib_objs = []
+    for s in core_src + fabric_src:
+        o = obj(s)
+        lib_objs.append(o)
+        lines.append(f"build {o}: cxx {_rel(s)}")
+    for s in cu_src:
+        o = obj(s)
+        lib_objs.append(o)
+        lines.append(f"build {o}: nvcc {_rel(s)}")
+    py_objs = []
+    for s in py_src:
+        o = obj(s)
+        py_objs.append(o)
+        lines.append(f"build {o}: cxx {_rel(s)}")
+        lines.append("  extra = $pyincs -fvisibility=hidden")
+    mod = _rel(os.path.join(ROOT, "blackbird_b200", "_bb" + ext))
+    lines.append(f"build {mod}: link_so {' '.join(py_objs + lib_objs)}")
+    targets = [mod]
+    for s in app_src:
+        o = obj(s)
+        lines.append(f"build {o}: cxx {_rel(s)}")
+        name = os.path.splitext(os.path.basename(s))[0].replace("_", "-")
+        exe = _rel(os.path.join(ROOT, "bin", name))
+        lines.append(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
+        targets.append(exe)
+    lines.append(f"default {' '.join(targets)}")
+    path = os.path.join(BUILD, "build.ninja")
+    content = "\n".join(lines) + "\n"
+    old = open(path).read() if os.path.exists(path) else None
+    if old != content:
+        with open(path, "w") as f:
+            f.write(content)
+    return path
+
+
+def build(verbose: bool = False, targets: list[str] | None = None) -> None:
+    generate()
+    os.makedirs(os.path.join(ROOT, "bin"), exist_ok=True)
+    ninja = shutil.which("ninja")
+    if ninja is None:
+        raise RuntimeError("ninja not found")
+    cmd = [ninja, "-C", BUILD]
+    if verbose:
+        cmd.append("-v")
+    if targets:
+        cmd += targets
+    r = subprocess.run(cmd)
+    if r.returncode != 0:
+        raise RuntimeError("native build failed")
+
+
+if __name__ == "__main__":
+    build(verbose="-v" in sys.argv)

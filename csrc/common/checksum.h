@@ -1,0 +1,38 @@
+// CPU reference checksums: CRC32C (Castagnoli; SSE4.2 when available, slice-by-8 otherwise),
+// CRC32C combine/shift algebra (needed because GPU tiles finish out of order), and BBH64.
+// These are the golden models the CUDA kernels are tested against and what the host tiers
+// (DRAM / NVMe) use to verify data that left the GPU.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string_view>
+
+namespace bb {
+
+enum class ChecksumAlgo : uint32_t { NONE = 0, CRC32C = 1, BBH64 = 2 };
+std::string_view to_string(ChecksumAlgo a) noexcept;
+
+// Standard CRC32C: init 0xFFFFFFFF, reflected poly 0x82F63B78, final xor.  `crc` chains calls.
+uint32_t crc32c(const void* data, size_t len, uint32_t crc = 0) noexcept;
+uint32_t crc32c_sw(const void* data, size_t len, uint32_t crc = 0) noexcept;  // table path (always available)
+bool crc32c_hw_available() noexcept;
+
+// crc(A||B) from crc(A), crc(B), len(B).
+uint32_t crc32c_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) noexcept;
+
+// Raw remainder algebra over GF(2)[x]/P (reflected bit order, no init / final xor):
+//   crc32c_raw(data) = data(x) * x^32 mod P
+uint32_t crc32c_raw(const void* data, size_t len, uint32_t rem = 0) noexcept;
+uint32_t gf2_mulmod(uint32_t a, uint32_t b) noexcept;  // a(x)*b(x) mod P
+uint32_t gf2_xpow_bytes(uint64_t nbytes) noexcept;      // x^(8*nbytes) mod P
+// Converts a raw remainder of the whole message into the standard CRC32C value.
+uint32_t crc32c_from_raw(uint32_t raw, uint64_t len) noexcept;
+// Fills t[4][256] such that for a 32-bit remainder s:  s * x^(8*nbytes) mod P =
+//   t[0][s&255] ^ t[1][(s>>8)&255] ^ t[2][(s>>16)&255] ^ t[3][s>>24]   (tables used by the GPU kernel)
+void crc32c_shift_table(uint64_t nbytes, uint32_t t[4][256]) noexcept;
+
+uint64_t bbh64(const void* data, size_t len) noexcept;
+
+uint64_t checksum(ChecksumAlgo algo, const void* data, size_t len) noexcept;
+
+}  // namespace bb

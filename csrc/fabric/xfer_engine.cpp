@@ -1,0 +1,295 @@
+#include "fabric/xfer_engine.h"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "common/log.h"
+#include "common/result.h"
+#include "common/tchash_def.h"
+
+namespace bb::gpu {
+
+#define BB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      BB_LOG(ERROR) << "CUDA error " << cudaGetErrorString(_e) << " (" << static_cast<int>(_e) << ") at " #expr; \
+      last_cuda_error_ = static_cast<int>(_e);                                             \
+      return ErrorCode::FABRIC_ERROR;                                                      \
+    }                                                                                      \
+  } while (0)
+
+struct XferEngine::Slot {
+  // host (pinned): [descs | tile_start]
+  uint8_t* h_tab = nullptr;
+  // device
+  uint8_t* d_tab = nullptr;
+  uint64_t* d_sum = nullptr;
+  uint32_t* d_done = nullptr;
+  uint64_t* d_digest = nullptr;
+  uint32_t* d_status = nullptr;
+  // host (pinned) results: [digest | status]
+  uint8_t* h_res = nullptr;
+  uint32_t* d_debug = nullptr;
+  size_t d_debug_bytes = 0;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+  uint64_t ticket = 0;  // 0 = free
+  uint32_t nitems = 0;
+  uint32_t ndesc = 0;
+  uint32_t total_tiles = 0;
+  bool debug = false;
+  bool hashed = true;
+  std::vector<int32_t> item_to_desc;  // -1 for zero-size items
+};
+
+Result<std::unique_ptr<XferEngine>> XferEngine::create(int device, uint32_t max_items, int slots) {
+  std::unique_ptr<XferEngine> e(new XferEngine());
+  e->device_ = device;
+  e->max_items_ = max_items;
+  int prev = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess) return ErrorCode::FABRIC_ERROR;
+  if (cudaSetDevice(device) != cudaSuccess) return ErrorCode::FABRIC_ERROR;
+  const size_t tab_bytes = static_cast<size_t>(max_items) * sizeof(XferDesc) + (static_cast<size_t>(max_items) + 1) * 4;
+  const size_t res_bytes = static_cast<size_t>(max_items) * 12;
+  bool ok = true;
+  for (int i = 0; i < slots && ok; ++i) {
+    auto s = std::make_unique<Slot>();
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&s->h_tab), tab_bytes) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&s->h_res), res_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s->d_tab), tab_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s->d_sum), static_cast<size_t>(max_items) * 8) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s->d_done), static_cast<size_t>(max_items) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s->d_digest), static_cast<size_t>(max_items) * 8) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s->d_status), static_cast<size_t>(max_items) * 4) == cudaSuccess;
+    ok = ok && cudaMemset(s->d_sum, 0, static_cast<size_t>(max_items) * 8) == cudaSuccess;
+    ok = ok && cudaMemset(s->d_done, 0, static_cast<size_t>(max_items) * 4) == cudaSuccess;
+    ok = ok && cudaEventCreate(&s->ev_start) == cudaSuccess;
+    ok = ok && cudaEventCreate(&s->ev_stop) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    e->slots_.push_back(std::move(s));
+  }
+  ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+  cudaSetDevice(prev);
+  if (!ok) {
+    BB_LOG(ERROR) << "XferEngine: device allocation failed: " << cudaGetErrorString(cudaGetLastError());
+    return ErrorCode::OUT_OF_MEMORY;
+  }
+  return e;
+}
+
+XferEngine::~XferEngine() {
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device_);
+  for (auto& s : slots_) {
+    if (s->ev_done) cudaEventSynchronize(s->ev_done);
+    cudaFreeHost(s->h_tab);
+    cudaFreeHost(s->h_res);
+    cudaFree(s->d_tab);
+    cudaFree(s->d_sum);
+    cudaFree(s->d_done);
+    cudaFree(s->d_digest);
+    cudaFree(s->d_status);
+    if (s->d_debug) cudaFree(s->d_debug);
+    if (s->ev_start) cudaEventDestroy(s->ev_start);
+    if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
+  }
+  cudaSetDevice(prev);
+}
+
+Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, ChecksumAlgo algo, void* stream,
+                                    bool capture_debug) {
+  if (items.size() > max_items_) return ErrorCode::RESOURCE_EXHAUSTED;
+  if (algo == ChecksumAlgo::CRC32C) return ErrorCode::NOT_IMPLEMENTED;  // fused CRC32C path: see crc kernels
+  // pick a free slot (or recycle the oldest finished one)
+  Slot* s = nullptr;
+  for (auto& c : slots_)
+    if (c->ticket == 0) { s = c.get(); break; }
+  if (!s) return ErrorCode::RESOURCE_EXHAUSTED;  // caller must wait() on outstanding tickets
+
+  auto run = [&]() -> ErrorCode {
+    BB_CUDA(cudaSetDevice(device_));
+    auto* descs = reinterpret_cast<XferDesc*>(s->h_tab);
+    s->item_to_desc.assign(items.size(), -1);
+    uint32_t nd = 0, tiles = 0;
+    for (size_t i = 0; i < items.size(); ++i) {
+      const XferItem& it = items[i];
+      if (it.nbytes == 0) continue;
+      if (it.ndst == 0 || it.ndst > kMaxDst) return ErrorCode::INVALID_ARGUMENT;
+      uintptr_t al = reinterpret_cast<uintptr_t>(it.src);
+      for (uint32_t r = 0; r < it.ndst; ++r) al |= reinterpret_cast<uintptr_t>(it.dst[r]);
+      if (al & 15) return ErrorCode::INVALID_ADDRESS;
+      if ((it.flags & XFER_MULTIMEM) && (it.nbytes & 15)) return ErrorCode::INVALID_ARGUMENT;
+      XferDesc& d = descs[nd];
+      d.src = it.src;
+      for (uint32_t r = 0; r < kMaxDst; ++r) d.dst[r] = r < it.ndst ? it.dst[r] : nullptr;
+      d.nbytes = it.nbytes;
+      d.first_tile = tiles;
+      d.ndst = it.ndst;
+      d.expect = it.expect;
+      d.flags = it.flags;
+      d.reserved = 0;
+      s->item_to_desc[i] = static_cast<int32_t>(nd);
+      const uint64_t nt = (it.nbytes + kTileBytes - 1) / kTileBytes;
+      if (tiles + nt > 0xFFFFFFF0ull) return ErrorCode::VALUE_OUT_OF_RANGE;
+      tiles += static_cast<uint32_t>(nt);
+      ++nd;
+    }
+    auto* tile_start = reinterpret_cast<uint32_t*>(s->h_tab + static_cast<size_t>(nd) * sizeof(XferDesc));
+    for (uint32_t i = 0; i < nd; ++i) tile_start[i] = descs[i].first_tile;
+    tile_start[nd] = tiles;
+    s->nitems = static_cast<uint32_t>(items.size());
+    s->ndesc = nd;
+    s->total_tiles = tiles;
+    s->debug = capture_debug;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nd) {
+      const size_t tab = static_cast<size_t>(nd) * sizeof(XferDesc) + (static_cast<size_t>(nd) + 1) * 4;
+      BB_CUDA(cudaMemcpyAsync(s->d_tab, s->h_tab, tab, cudaMemcpyHostToDevice, st));
+      if (capture_debug) {
+        const size_t need = static_cast<size_t>(tiles) * tchash::kRows * tchash::kN * 4;
+        if (need > s->d_debug_bytes) {
+          if (s->d_debug) cudaFree(s->d_debug);
+          BB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_debug), need));
+          s->d_debug_bytes = need;
+        }
+      }
+      XferLaunch l;
+      l.descs = reinterpret_cast<const XferDesc*>(s->d_tab);
+      l.tile_start = reinterpret_cast<const uint32_t*>(s->d_tab + static_cast<size_t>(nd) * sizeof(XferDesc));
+      l.ndesc = nd;
+      l.total_tiles = tiles;
+      l.sum_ws = s->d_sum;
+      l.done_ws = s->d_done;
+      l.digest_out = s->d_digest;
+      l.status_out = s->d_status;
+      l.debug_d = capture_debug ? s->d_debug : nullptr;
+      l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : ALGO_NONE;
+      l.max_ctas = max_ctas_;
+      l.stream = stream;
+      BB_CUDA(cudaEventRecord(s->ev_start, st));
+      const int rc = launch_xfer(l);
+      if (rc != 0) {
+        last_cuda_error_ = rc;
+        BB_LOG(ERROR) << "launch_xfer failed: " << cuda_error_string(rc);
+        return ErrorCode::FABRIC_ERROR;
+      }
+      ++launches_;
+      BB_CUDA(cudaEventRecord(s->ev_stop, st));
+      if (algo == ChecksumAlgo::BBH64) {
+        BB_CUDA(cudaMemcpyAsync(s->h_res, s->d_digest, static_cast<size_t>(nd) * 8, cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaMemcpyAsync(s->h_res + static_cast<size_t>(max_items_) * 8, s->d_status, static_cast<size_t>(nd) * 4,
+                                cudaMemcpyDeviceToHost, st));
+      }
+    }
+    BB_CUDA(cudaEventRecord(s->ev_done, st));
+    return ErrorCode::OK;
+  };
+  ErrorCode ec = run();
+  if (ec != ErrorCode::OK) return ec;
+  s->ticket = next_ticket_++;
+  s->hashed = algo == ChecksumAlgo::BBH64;
+  return s->ticket;
+}
+
+ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
+  Slot* s = nullptr;
+  for (auto& c : slots_)
+    if (c->ticket == ticket) { s = c.get(); break; }
+  if (!s) return ErrorCode::NOT_FOUND;
+  BB_CUDA(cudaEventSynchronize(s->ev_done));
+  const bool no_hash = !s->hashed;
+  const uint32_t nd = s->ndesc;
+  if (out) {
+    out->digest.assign(s->nitems, no_hash ? 0 : tchash::finalize(0, 0));
+    out->status.assign(s->nitems, 0);
+    const auto* dg = reinterpret_cast<const uint64_t*>(s->h_res);
+    const auto* stt = reinterpret_cast<const uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);
+    if (!no_hash) {
+      for (uint32_t i = 0; i < s->nitems; ++i) {
+        const int32_t d = s->item_to_desc[i];
+        if (d >= 0) {
+          out->digest[i] = dg[d];
+          out->status[i] = stt[d];
+        }
+      }
+    }
+    out->device_ms = 0.f;
+    if (nd) cudaEventElapsedTime(&out->device_ms, s->ev_start, s->ev_stop);
+  }
+  if (s->debug && nd) {
+    debug_host_.resize(static_cast<size_t>(s->total_tiles) * tchash::kRows * tchash::kN);
+    BB_CUDA(cudaMemcpy(debug_host_.data(), s->d_debug, debug_host_.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  s->ticket = 0;
+  return ErrorCode::OK;
+}
+
+ErrorCode XferEngine::run(const std::vector<XferItem>& items, ChecksumAlgo algo, void* stream, XferResult* out) {
+  auto t = submit(items, algo, stream);
+  if (!t.ok()) return t.error();
+  return wait(t.value(), out);
+}
+
+// ---------------------------------------------------------------- helpers
+static int g_dummy_err = 0;
+#undef BB_CUDA
+#define BB_CUDA_S(expr)                                                                                      \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      BB_LOG(ERROR) << "CUDA error " << cudaGetErrorString(_e) << " at " #expr;                              \
+      g_dummy_err = static_cast<int>(_e);                                                                    \
+      return ErrorCode::FABRIC_ERROR;                                                                        \
+    }                                                                                                        \
+  } while (0)
+
+ErrorCode device_count(int* n) {
+  *n = 0;
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    *n = 0;
+    cudaGetLastError();
+  }
+  return ErrorCode::OK;
+}
+ErrorCode device_malloc(int device, uint64_t bytes, void** out) {
+  BB_CUDA_S(cudaSetDevice(device));
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ErrorCode::OUT_OF_MEMORY;
+  }
+  return ErrorCode::OK;
+}
+ErrorCode device_free(int device, void* p) {
+  BB_CUDA_S(cudaSetDevice(device));
+  BB_CUDA_S(cudaFree(p));
+  return ErrorCode::OK;
+}
+ErrorCode host_alloc_pinned(uint64_t bytes, void** out) {
+  cudaError_t e = cudaMallocHost(out, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ErrorCode::OUT_OF_MEMORY;
+  }
+  return ErrorCode::OK;
+}
+ErrorCode host_free_pinned(void* p) {
+  BB_CUDA_S(cudaFreeHost(p));
+  return ErrorCode::OK;
+}
+ErrorCode stream_synchronize(void* stream) {
+  BB_CUDA_S(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return ErrorCode::OK;
+}
+ErrorCode device_synchronize(int device) {
+  BB_CUDA_S(cudaSetDevice(device));
+  BB_CUDA_S(cudaDeviceSynchronize());
+  return ErrorCode::OK;
+}
+const char* cuda_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
+
+}  // namespace bb::gpu

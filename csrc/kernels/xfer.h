@@ -1,0 +1,70 @@
+// Host-visible API of the sm_100a data-plane kernels (plain C++; no CUDA types leak out).
+//
+// These kernels replace the reference's UCX call sites: `ucp_put_nbx`
+// (blackbird_client.cpp:231-237), `ucp_get_nbx` (:315-327) and the CPU byte compare
+// (ucx_client.cpp:277).  One launch moves a whole *batch* of objects described by a device
+// descriptor table, fusing the transfer with the checksum (and optional replica fan-out).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace bb::gpu {
+
+constexpr uint32_t kTileBytes = 16384;   // one TMA tile == one BBH64 tile (tchash_def.h)
+constexpr uint32_t kMaxDst = 3;          // replicas written by a single tile pass
+
+enum XferFlags : uint32_t {
+  XFER_VERIFY = 1u << 0,    // compare digest with `expect`; status[i] = 1 on mismatch
+  XFER_MULTIMEM = 1u << 1,  // dst[0] is an NVLS multicast address: store with multimem.st
+};
+
+// 64-byte transfer descriptor, one per (object shard, direction).
+struct XferDesc {
+  const void* src;          // 16-byte aligned; local or peer-mapped
+  void* dst[kMaxDst];       // 16-byte aligned; local, peer-mapped or multicast
+  uint64_t nbytes;
+  uint32_t first_tile;      // exclusive prefix sum of ceil(nbytes / kTileBytes)
+  uint32_t ndst;
+  uint64_t expect;          // expected digest when XFER_VERIFY
+  uint32_t flags;
+  uint32_t reserved;
+};
+static_assert(sizeof(XferDesc) == 64, "XferDesc must be 64 bytes");
+
+enum XferAlgo : int { ALGO_NONE = 0, ALGO_CRC32C = 1, ALGO_BBH64 = 2 };
+
+struct XferLaunch {
+  const XferDesc* descs = nullptr;       // device pointer, ndesc entries
+  const uint32_t* tile_start = nullptr;  // device pointer, ndesc+1 entries (prefix sums)
+  uint32_t ndesc = 0;
+  uint32_t total_tiles = 0;
+  uint64_t* sum_ws = nullptr;            // device, ndesc entries, must be zero on entry (self-cleaning)
+  uint32_t* done_ws = nullptr;           // device, ndesc entries, must be zero on entry (self-cleaning)
+  uint64_t* digest_out = nullptr;        // device, ndesc entries
+  uint32_t* status_out = nullptr;        // device, ndesc entries (0 ok / 1 checksum mismatch)
+  const uint32_t* crc_tables = nullptr;  // device, CRC32C shift tables (only ALGO_CRC32C)
+  uint32_t* debug_d = nullptr;           // optional: raw accumulators [tile][128][16] (tests)
+  int algo = ALGO_BBH64;
+  int max_ctas = 0;                      // 0 = one CTA per SM
+  void* stream = nullptr;                // cudaStream_t
+};
+
+// Returns 0 on success, else a cudaError_t value.
+int launch_xfer(const XferLaunch& l);
+int xfer_smem_bytes(int algo);
+
+// Number of tiles of an object (0 for empty objects).
+inline uint32_t tiles_of(uint64_t nbytes) { return static_cast<uint32_t>((nbytes + kTileBytes - 1) / kTileBytes); }
+
+// ---- comparators / utilities (baseline.cu)
+// Plain vectorised copy kernel (the "unfused copy kernel" comparator of BASELINE.md §4).
+int launch_copy_simt(void* dst, const void* src, uint64_t nbytes, void* stream);
+// Stand-alone CRC32C over device memory (comparator: "separate CRC32C kernel"); result is the
+// standard CRC32C written to *out (device).  `tables` = device copy of crc tables (see crc_tables_host()).
+int launch_crc32c_simt(const void* data, uint64_t nbytes, uint32_t* out, uint32_t* scratch, void* stream);
+// L2 flush helper: writes `nbytes` of a scratch buffer.
+int launch_fill(void* dst, uint64_t nbytes, uint32_t value, void* stream);
+// Fills a buffer with deterministic pseudo-random bytes (synthetic objects).
+int launch_random_fill(void* dst, uint64_t nbytes, uint64_t seed, void* stream);
+
+}  // namespace bb::gpu

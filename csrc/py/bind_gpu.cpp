@@ -1,0 +1,116 @@
+// Bindings for the sm_100a data plane: XferEngine (fused batched transfer), comparators and
+// device helpers.  Pointers cross the boundary as integers (tensor.data_ptr()), streams as
+// integers (torch.cuda.current_stream().cuda_stream).
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "fabric/xfer_engine.h"
+#include "kernels/xfer.h"
+
+namespace py = pybind11;
+using namespace bb;
+using namespace bb::gpu;
+
+namespace {
+void check(ErrorCode ec, const char* what) {
+  if (ec != ErrorCode::OK) throw std::runtime_error(std::string(what) + ": " + std::string(to_string(ec)));
+}
+void check_cuda(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": CUDA error " + std::to_string(rc) + " " + cuda_error_string(rc));
+}
+// item tuple: (src, dst | [dst...], nbytes, expect=0, flags=0)
+XferItem to_item(const py::handle& h) {
+  py::tuple t = py::cast<py::tuple>(h);
+  if (t.size() < 3) throw py::value_error("xfer item = (src, dst|[dst..], nbytes[, expect[, flags]])");
+  XferItem it;
+  it.src = reinterpret_cast<const void*>(t[0].cast<uintptr_t>());
+  if (py::isinstance<py::int_>(t[1])) {
+    it.dst[0] = reinterpret_cast<void*>(t[1].cast<uintptr_t>());
+    it.ndst = 1;
+  } else {
+    auto v = t[1].cast<std::vector<uintptr_t>>();
+    if (v.empty() || v.size() > kMaxDst) throw py::value_error("1..3 destinations");
+    it.ndst = static_cast<uint32_t>(v.size());
+    for (size_t i = 0; i < v.size(); ++i) it.dst[i] = reinterpret_cast<void*>(v[i]);
+  }
+  it.nbytes = t[2].cast<uint64_t>();
+  if (t.size() > 3) it.expect = t[3].cast<uint64_t>();
+  if (t.size() > 4) it.flags = t[4].cast<uint32_t>();
+  return it;
+}
+}  // namespace
+
+void bind_gpu(py::module_& m) {
+  m.attr("TILE_BYTES") = kTileBytes;
+  m.attr("XFER_VERIFY") = static_cast<uint32_t>(XFER_VERIFY);
+  m.attr("XFER_MULTIMEM") = static_cast<uint32_t>(XFER_MULTIMEM);
+  m.def("cuda_device_count", [] {
+    int n = 0;
+    device_count(&n);
+    return n;
+  });
+
+  py::class_<XferEngine>(m, "XferEngine")
+      .def(py::init([](int device, uint32_t max_items, int slots) {
+             auto r = XferEngine::create(device, max_items, slots);
+             if (!r.ok()) throw std::runtime_error("XferEngine.create: " + std::string(to_string(r.error())));
+             return std::move(r.value());
+           }),
+           py::arg("device") = 0, py::arg("max_items") = 1u << 16, py::arg("slots") = 4)
+      .def("run",
+           [](XferEngine& e, const py::list& items, ChecksumAlgo algo, uintptr_t stream, bool debug) {
+             std::vector<XferItem> v;
+             v.reserve(items.size());
+             for (auto h : items) v.push_back(to_item(h));
+             XferResult res;
+             {
+               py::gil_scoped_release rel;
+               auto t = e.submit(v, algo, reinterpret_cast<void*>(stream), debug);
+               if (!t.ok()) check(t.error(), "XferEngine.submit");
+               check(e.wait(t.value(), &res), "XferEngine.wait");
+             }
+             return py::make_tuple(res.digest, res.status, res.device_ms);
+           },
+           py::arg("items"), py::arg("algo") = ChecksumAlgo::BBH64, py::arg("stream") = 0, py::arg("debug") = false,
+           "Runs one fused batch; returns (digests, status, device_ms).")
+      .def("submit",
+           [](XferEngine& e, const py::list& items, ChecksumAlgo algo, uintptr_t stream) {
+             std::vector<XferItem> v;
+             v.reserve(items.size());
+             for (auto h : items) v.push_back(to_item(h));
+             auto t = e.submit(v, algo, reinterpret_cast<void*>(stream));
+             if (!t.ok()) check(t.error(), "XferEngine.submit");
+             return t.value();
+           },
+           py::arg("items"), py::arg("algo") = ChecksumAlgo::BBH64, py::arg("stream") = 0)
+      .def("wait",
+           [](XferEngine& e, uint64_t ticket) {
+             XferResult res;
+             {
+               py::gil_scoped_release rel;
+               check(e.wait(ticket, &res), "XferEngine.wait");
+             }
+             return py::make_tuple(res.digest, res.status, res.device_ms);
+           })
+      .def("debug_accumulators", [](XferEngine& e) { return e.debug_accumulators(); })
+      .def("set_max_ctas", &XferEngine::set_max_ctas)
+      .def_property_readonly("launches", &XferEngine::launches)
+      .def_property_readonly("device", &XferEngine::device);
+
+  m.def("copy_simt", [](uintptr_t dst, uintptr_t src, uint64_t n, uintptr_t stream) {
+    check_cuda(launch_copy_simt(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), n,
+                                reinterpret_cast<void*>(stream)), "copy_simt");
+  }, py::arg("dst"), py::arg("src"), py::arg("nbytes"), py::arg("stream") = 0);
+  m.def("crc32c_device", [](uintptr_t data, uint64_t n, uintptr_t out, uintptr_t scratch, uintptr_t stream) {
+    check_cuda(launch_crc32c_simt(reinterpret_cast<const void*>(data), n, reinterpret_cast<uint32_t*>(out),
+                                  reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<void*>(stream)), "crc32c_device");
+  }, py::arg("data"), py::arg("nbytes"), py::arg("out"), py::arg("scratch"), py::arg("stream") = 0,
+     "Stand-alone CRC32C; scratch needs 4*ceil(nbytes/512) bytes.");
+  m.def("fill", [](uintptr_t dst, uint64_t n, uint32_t v, uintptr_t stream) {
+    check_cuda(launch_fill(reinterpret_cast<void*>(dst), n, v, reinterpret_cast<void*>(stream)), "fill");
+  }, py::arg("dst"), py::arg("nbytes"), py::arg("value") = 0, py::arg("stream") = 0);
+  m.def("random_fill", [](uintptr_t dst, uint64_t n, uint64_t seed, uintptr_t stream) {
+    check_cuda(launch_random_fill(reinterpret_cast<void*>(dst), n, seed, reinterpret_cast<void*>(stream)), "random_fill");
+  }, py::arg("dst"), py::arg("nbytes"), py::arg("seed") = 1, py::arg("stream") = 0);
+  m.def("xfer_smem_bytes", [] { return xfer_smem_bytes(ALGO_BBH64); });
+}
