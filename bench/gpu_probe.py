@@ -67,6 +67,29 @@ def phase_probe():
         all_ok &= ok
         print(("OK  " if ok else "BAD ") + f"n={n} digest={dg[0]:#x} ref={ref:#x} copy_ok={copy_ok} ms={ms:.3f}")
     print("RANDOM_ALL_OK", all_ok)
+    all_ok = True
+    for n in sizes + [64 << 20]:
+        src = torch.randint(0, 256, (n + 64,), dtype=torch.uint8, device=dev, generator=g)[:n]
+        dst = torch.full((n + 64,), 0xAB, dtype=torch.uint8, device=dev)
+        dg, st, ms = eng.run([(src.data_ptr(), dst.data_ptr(), n)], _bb.ChecksumAlgo.CRC32C, stream())
+        torch.cuda.synchronize()
+        ref = _bb.crc32c(src.cpu().numpy())
+        copy_ok = bool(torch.equal(src, dst[:n])) and bool((dst[n:] == 0xAB).all())
+        dg2, st2, _ = eng.run([(src.data_ptr(), dst.data_ptr(), n, ref, _bb.XFER_VERIFY)], _bb.ChecksumAlgo.CRC32C, stream())
+        dg3, st3, _ = eng.run([(src.data_ptr(), dst.data_ptr(), n, ref ^ 4, _bb.XFER_VERIFY)], _bb.ChecksumAlgo.CRC32C, stream())
+        ok = (dg[0] == ref) and copy_ok and st2[0] == 0 and st3[0] == 1
+        all_ok &= ok
+        print(("OK  " if ok else "BAD ") + f"crc32c-fused n={n} digest={dg[0]:#x} ref={ref:#x} copy_ok={copy_ok} verify={st2[0]},{st3[0]} ms={ms:.3f}")
+    print("CRC_FUSED_ALL_OK", all_ok)
+    # an object large enough to straddle many CTAs (cross-CTA combine), both algos
+    n = (300 << 20) + 12345
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    h = src.cpu().numpy()
+    for algo, ref in ((_bb.ChecksumAlgo.BBH64, _bb.bbh64(h)), (_bb.ChecksumAlgo.CRC32C, _bb.crc32c(h))):
+        dg, st, ms = eng.run([(src.data_ptr(), dst.data_ptr(), n)], algo, stream())
+        print(("OK  " if dg[0] == ref else "BAD ") + f"straddle {algo.name} n={n} digest={dg[0]:#x} ref={ref:#x} copy_ok={bool(torch.equal(src, dst))} ms={ms:.3f} {n/ms/1e6:.0f} GB/s")
+    del src, dst
 
     # ---- verify flag + 3 destinations + batch of small objects
     n = 123456 * 16
@@ -140,7 +163,7 @@ def phase_perf():
         _bb.random_fill(src.data_ptr(), total, 7, stream())
         dst = torch.empty(total, dtype=torch.uint8, device=dev)
         items = [(src.data_ptr() + i * osz, dst.data_ptr() + i * osz, osz) for i in range(nobj)]
-        for algo in (_bb.ChecksumAlgo.BBH64, _bb.ChecksumAlgo.NONE):
+        for algo in (_bb.ChecksumAlgo.BBH64, _bb.ChecksumAlgo.CRC32C, _bb.ChecksumAlgo.NONE):
             kms = []
 
             def run():

@@ -40,6 +40,7 @@ struct XferEngine::Slot {
   uint32_t total_tiles = 0;
   bool debug = false;
   bool hashed = true;
+  uint64_t empty_digest = 0;
   std::vector<int32_t> item_to_desc;  // -1 for zero-size items
 };
 
@@ -102,7 +103,6 @@ XferEngine::~XferEngine() {
 Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, ChecksumAlgo algo, void* stream,
                                     bool capture_debug) {
   if (items.size() > max_items_) return ErrorCode::RESOURCE_EXHAUSTED;
-  if (algo == ChecksumAlgo::CRC32C) return ErrorCode::NOT_IMPLEMENTED;  // fused CRC32C path: see crc kernels
   // pick a free slot (or recycle the oldest finished one)
   Slot* s = nullptr;
   for (auto& c : slots_)
@@ -131,6 +131,10 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       d.expect = it.expect;
       d.flags = it.flags;
       d.reserved = 0;
+      if (algo == ChecksumAlgo::CRC32C) {
+        d.expect = (static_cast<uint64_t>(crc_init_term_for(it.nbytes)) << 32) | (it.expect & 0xFFFFFFFFull);
+        d.reserved = crc_unpad_for(it.nbytes);
+      }
       s->item_to_desc[i] = static_cast<int32_t>(nd);
       const uint64_t nt = (it.nbytes + kTileBytes - 1) / kTileBytes;
       if (tiles + nt > 0xFFFFFFF0ull) return ErrorCode::VALUE_OUT_OF_RANGE;
@@ -166,7 +170,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       l.digest_out = s->d_digest;
       l.status_out = s->d_status;
       l.debug_d = capture_debug ? s->d_debug : nullptr;
-      l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : ALGO_NONE;
+      l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : algo == ChecksumAlgo::CRC32C ? ALGO_CRC32C : ALGO_NONE;
       l.max_ctas = max_ctas_;
       l.stream = stream;
       BB_CUDA(cudaEventRecord(s->ev_start, st));
@@ -178,7 +182,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       }
       ++launches_;
       BB_CUDA(cudaEventRecord(s->ev_stop, st));
-      if (algo == ChecksumAlgo::BBH64) {
+      if (algo != ChecksumAlgo::NONE) {
         BB_CUDA(cudaMemcpyAsync(s->h_res, s->d_digest, static_cast<size_t>(nd) * 8, cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaMemcpyAsync(s->h_res + static_cast<size_t>(max_items_) * 8, s->d_status, static_cast<size_t>(nd) * 4,
                                 cudaMemcpyDeviceToHost, st));
@@ -190,7 +194,8 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
   ErrorCode ec = run();
   if (ec != ErrorCode::OK) return ec;
   s->ticket = next_ticket_++;
-  s->hashed = algo == ChecksumAlgo::BBH64;
+  s->hashed = algo != ChecksumAlgo::NONE;
+  s->empty_digest = algo == ChecksumAlgo::BBH64 ? tchash::finalize(0, 0) : 0;
   return s->ticket;
 }
 
@@ -203,7 +208,7 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
   const bool no_hash = !s->hashed;
   const uint32_t nd = s->ndesc;
   if (out) {
-    out->digest.assign(s->nitems, no_hash ? 0 : tchash::finalize(0, 0));
+    out->digest.assign(s->nitems, no_hash ? 0 : s->empty_digest);
     out->status.assign(s->nitems, 0);
     const auto* dg = reinterpret_cast<const uint64_t*>(s->h_res);
     const auto* stt = reinterpret_cast<const uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);

@@ -25,9 +25,9 @@ struct XferDesc {
   uint64_t nbytes;
   uint32_t first_tile;      // exclusive prefix sum of ceil(nbytes / kTileBytes)
   uint32_t ndst;
-  uint64_t expect;          // expected digest when XFER_VERIFY
+  uint64_t expect;          // BBH64: expected digest.  CRC32C: (init_term << 32) | expected crc
   uint32_t flags;
-  uint32_t reserved;
+  uint32_t reserved;        // CRC32C: x^(-8*pad) mod P (crc_unpad_for)
 };
 static_assert(sizeof(XferDesc) == 64, "XferDesc must be 64 bytes");
 
@@ -52,6 +52,10 @@ struct XferLaunch {
 // Returns 0 on success, else a cudaError_t value.
 int launch_xfer(const XferLaunch& l);
 int xfer_smem_bytes(int algo);
+
+// CRC32C per-object constants (host): un-padding multiplier and the init-register term.
+uint32_t crc_unpad_for(uint64_t nbytes);
+uint32_t crc_init_term_for(uint64_t nbytes);
 
 // Number of tiles of an object (0 for empty objects).
 inline uint32_t tiles_of(uint64_t nbytes) { return static_cast<uint32_t>((nbytes + kTileBytes - 1) / kTileBytes); }

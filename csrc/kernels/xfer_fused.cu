@@ -1,28 +1,36 @@
 // bb_xfer: the fused batched put/get kernel (sm_100a).
 //
 // Replaces the reference's per-shard UCX RMA calls (blackbird_client.cpp:231-237 put,
-// :315-327 get) with ONE persistent launch per batch.  Per 16 KiB tile:
+// :315-327 get) with ONE persistent launch per batch.  Every CTA owns
+// a contiguous run of 16 KiB tiles of the batch and pipelines them through 8 smem stages:
 //
 //   warp 0  producer : descriptor lookup (32 tiles looked up in parallel), zero-pads short
 //                      tiles, `cp.async.bulk` global -> shared (TMA, mbarrier complete_tx).
 //                      The source may be local HBM (put) or a peer GPU's slab over NVLink (get).
-//   warp 1  hash     : one elected thread issues 4x `tcgen05.mma.kind::i8` (M128 N16 K32) that
-//                      read the landed tile *in place* as the A operand against the BBH64 weight
-//                      matrix; accumulators live in TMEM (16 columns per stage).
-//   warp 2  store    : `cp.async.bulk` shared -> global to 1..3 destinations (local, peer-mapped,
-//                      i.e. replica fan-out with a single HBM read), or `multimem.st` to an NVLS
-//                      multicast address (one store, N replicas).
-//   warps 4-7 epilogue: `tcgen05.ld` the 128x16 s32 accumulators, fold them into the
-//                      position-dependent 64-bit digest, atomically reduce per object; the last
-//                      contributor finalises, compares with the expected digest (get/verify).
+//   warp 1  hash     : BBH64: one elected thread issues 4x `tcgen05.mma.kind::i8` (M128 N16 K32)
+//                      that read the landed tile *in place* as the A operand against the BBH64
+//                      weight matrix; accumulators live in TMEM (16 columns per stage).
+//   warp 2  store    : `cp.async.bulk` shared -> global to 1..3 destinations (local or
+//                      peer-mapped: replica fan-out with a single HBM read), or `multimem.st`
+//                      to an NVLS multicast address (one store, N replicas).
+//   warp 3  finalizer: folds the per-tile partials into per-object digests in registers; an
+//                      object that lives entirely inside this CTA's run is finalised with no
+//                      global atomics; only the <=2 objects straddling a CTA boundary use them.
+//                      Compares with the expected digest on get (CHECKSUM_MISMATCH source).
+//   warps 4-7 epilogue: BBH64: `tcgen05.ld` the 128x16 s32 accumulators -> position-dependent
+//                      64-bit row hashes -> warp sum.  CRC32C: read the tile from smem
+//                      (conflict-free lane-interleaved streams) through x^k shift tables and
+//                      combine lanes with GF(2) shift algebra.
 //
-// Payload bytes never pass through registers on the BBH64/unicast path: TMA in, tensor core
-// reads shared memory, TMA out.  Stages recycle through full -> (acc_full) -> empty mbarriers.
+// Payload bytes never pass through registers on the BBH64 / copy-only unicast path: TMA in,
+// tensor core reads shared memory, TMA out.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <mutex>
 
+#include "common/checksum.h"
 #include "common/tchash_def.h"
 #include "kernels/ptx.cuh"
 #include "kernels/xfer.h"
@@ -34,30 +42,51 @@ using namespace bb::ptx;
 
 constexpr int kStages = 8;
 constexpr int kThreads = 256;
-constexpr int kStoreLag = 2;  // stores may trail this many tiles before their stage is released
+constexpr int kStoreLag = 2;         // stores may trail this many tiles before their stage is released
 constexpr uint32_t kTmemCols = 128;  // kStages * 16 accumulator columns
 static_assert(kStages * tchash::kN == kTmemCols);
 static_assert(kTileBytes == tchash::kTileBytes);
 
 __constant__ uint64_t c_col_mul[tchash::kN];
+__constant__ uint32_t c_xpow_tiles[32];  // x^(8 * 16384 * 2^j) mod P  (CRC32C cross-CTA combine)
 
-struct StageMeta {
+// CRC shift tables: index -> byte distance
+enum CrcTab : int { T128 = 0, T4, T8, T16, T32, T64, T4096, T16384, kNumCrcTabs };
+constexpr uint64_t kCrcTabBytes[kNumCrcTabs] = {128, 4, 8, 16, 32, 64, 4096, 16384};
+
+struct StageMeta {  // 64 bytes
   uint64_t dst[kMaxDst];
+  uint64_t nbytes;
+  uint64_t expect;
   uint32_t desc;
   uint32_t tile_in_obj;
   uint32_t bytes;
   uint32_t ndst_flags;  // ndst | flags << 8
+  uint32_t obj_ntiles;
+  uint32_t crc_unpad;
+};
+static_assert(sizeof(StageMeta) == 64);
+
+struct LookupEntry {  // producer-private staging of 32 parallel lookups
+  StageMeta m;
+  uint64_t src;
+  uint64_t pad;
 };
 
-struct __align__(1024) Smem {
+template <int ALGO>
+struct __align__(1024) SmemT {
   uint8_t tile[kStages][kTileBytes];
   uint8_t w[2048];
   uint64_t full[kStages];
   uint64_t acc_full[kStages];
+  uint64_t epi_done[kStages];
   uint64_t empty[kStages];
   StageMeta meta[kStages];
+  uint64_t part[kStages][4];
+  LookupEntry lk[32];
   uint32_t dirty[kStages];
   uint32_t tmem_base;
+  uint32_t crc_t[ALGO == ALGO_CRC32C ? kNumCrcTabs : 1][4][256];
 };
 
 struct Params {
@@ -69,14 +98,9 @@ struct Params {
   uint32_t* done_ws;
   uint64_t* digest_out;
   uint32_t* status_out;
+  const uint32_t* crc_tables;  // [kNumCrcTabs][4][256]
   uint32_t* debug_d;
 };
-
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-  uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
-  uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
 
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 #pragma unroll
@@ -88,50 +112,60 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
   return v;
 }
 
-// Adds a warp's partial digest of `ntiles_part` tile-quadrants to object `d`; the last
-// contributor (4 quadrants x ntiles) finalises, verifies and re-zeroes the workspace.
-__device__ __forceinline__ void flush_partial(const Params& p, uint32_t d, uint64_t acc, uint32_t ntiles_part,
-                                              uint32_t lane) {
-  if (d == 0xFFFFFFFFu) return;
-  const uint64_t total = warp_sum64(acc);
-  if (lane == 0) {
-    atomicAdd(&p.sum_ws[d], static_cast<unsigned long long>(total));
-    __threadfence();
-    const uint32_t prev = atomicAdd(&p.done_ws[d], ntiles_part);
-    const uint32_t ntiles = __ldg(&p.tile_start[d + 1]) - __ldg(&p.tile_start[d]);
-    if (prev + ntiles_part == 4u * ntiles) {
-      __threadfence();
-      const uint64_t sum = atomicExch(&p.sum_ws[d], 0ull);
-      p.done_ws[d] = 0;
-      const XferDesc* desc = &p.descs[d];
-      const uint64_t digest = tchash::finalize(sum, desc->nbytes);
-      p.digest_out[d] = digest;
-      p.status_out[d] = ((desc->flags & XFER_VERIFY) && digest != desc->expect) ? 1u : 0u;
-    }
+// s * x^(8k) mod P through the 4x256 table of distance k.
+__device__ __forceinline__ uint32_t crc_shift(const uint32_t (*t)[256], uint32_t s) {
+  return t[0][s & 0xFFu] ^ t[1][(s >> 8) & 0xFFu] ^ t[2][(s >> 16) & 0xFFu] ^ t[3][s >> 24];
+}
+
+__device__ __forceinline__ uint32_t gf2_mulmod_dev(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 4
+  for (int i = 31; i >= 0; --i) {
+    p ^= ((a >> i) & 1u) ? b : 0u;
+    b = (b >> 1) ^ ((b & 1u) ? 0x82F63B78u : 0u);
   }
+  return p;
+}
+
+// x^(8*16384*k) mod P, computed cooperatively by a full warp (lane j owns bit j of k).
+__device__ __forceinline__ uint32_t warp_xpow_tiles(uint32_t k, uint32_t lane) {
+  uint32_t v = ((k >> lane) & 1u) ? c_xpow_tiles[lane] : 0x80000000u;  // 0x80000000 == 1
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = gf2_mulmod_dev(v, other);
+  }
+  return v;
 }
 
 template <int ALGO>
 __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_constant__ Params p) {
+  using Smem = SmemT<ALGO>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t G = gridDim.x;
-  const uint32_t my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + G - 1) / G : 0;
-  constexpr bool kHash = (ALGO == ALGO_BBH64);
+  constexpr bool kBbh = (ALGO == ALGO_BBH64);
+  constexpr bool kCrc = (ALGO == ALGO_CRC32C);
+  constexpr bool kHash = kBbh || kCrc;
+
+  // contiguous run of tiles for this CTA
+  const uint32_t tpc = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t0 = blockIdx.x * tpc;
+  const uint32_t my_tiles = t0 < p.total_tiles ? min(tpc, p.total_tiles - t0) : 0;
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.acc_full[i], 1);
-      mbar_init(&s.empty[i], kHash ? 5 : 1);  // store warp + 4 epilogue warps
+      mbar_init(&s.epi_done[i], 4);
+      mbar_init(&s.empty[i], kHash ? 2 : 1);  // store warp (+ finalizer)
       s.dirty[i] = kTileBytes;
     }
     fence_mbar_init();
   }
-  if constexpr (kHash) {
+  if constexpr (kBbh) {
     // BBH64 weight matrix W[k][n] as the UMMA B operand (N=16 rows, K-major, no swizzle).
     for (uint32_t o = threadIdx.x; o < 2048; o += kThreads)
       s.w[o] = static_cast<uint8_t>(tchash::weight(tchash::off_to_k(o), tchash::off_to_row(o)));
@@ -139,44 +173,51 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
     if (warp == 3) tmem_alloc<kTmemCols>(&s.tmem_base);
     tc_fence_before();
   }
+  if constexpr (kCrc) {
+    uint32_t* dstt = &s.crc_t[0][0][0];
+    for (uint32_t i = threadIdx.x; i < kNumCrcTabs * 1024; i += kThreads) dstt[i] = __ldg(&p.crc_tables[i]);
+  }
   __syncthreads();
-  if constexpr (kHash) tc_fence_after();
-  const uint32_t tmem_base = kHash ? s.tmem_base : 0;
+  if constexpr (kBbh) tc_fence_after();
+  const uint32_t tmem_base = kBbh ? s.tmem_base : 0;
 
   if (warp == 0) {
     // ================================================================ TMA producer
     uint32_t it = 0;
     for (uint32_t base = 0; base < my_tiles; base += 32) {
       const uint32_t idx = base + lane;
-      uint64_t src = 0, nbytes = 0, dst0 = 0, dst1 = 0, dst2 = 0;
-      uint32_t d = 0, ti = 0, ndst_flags = 0;
       if (idx < my_tiles) {
-        const uint32_t t = blockIdx.x + idx * G;
+        const uint32_t t = t0 + idx;
         uint32_t lo = 0, hi = p.ndesc;  // tile_start[lo] <= t < tile_start[hi]
         while (hi - lo > 1) {
           const uint32_t mid = (lo + hi) >> 1;
           if (__ldg(&p.tile_start[mid]) <= t) lo = mid; else hi = mid;
         }
-        d = lo;
-        ti = t - __ldg(&p.tile_start[d]);
-        const uint4* q = reinterpret_cast<const uint4*>(&p.descs[d]);
+        const uint32_t first = __ldg(&p.tile_start[lo]);
+        const uint4* q = reinterpret_cast<const uint4*>(&p.descs[lo]);
         const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
-        src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
-        dst0 = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
-        dst1 = (static_cast<uint64_t>(q1.y) << 32) | q1.x;
-        dst2 = (static_cast<uint64_t>(q1.w) << 32) | q1.z;
-        nbytes = (static_cast<uint64_t>(q2.y) << 32) | q2.x;
-        ndst_flags = (q2.w & 0xFFu) | (q3.z << 8);
+        LookupEntry& e = s.lk[lane];
+        e.src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
+        e.m.dst[0] = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
+        e.m.dst[1] = (static_cast<uint64_t>(q1.y) << 32) | q1.x;
+        e.m.dst[2] = (static_cast<uint64_t>(q1.w) << 32) | q1.z;
+        e.m.nbytes = (static_cast<uint64_t>(q2.y) << 32) | q2.x;
+        e.m.expect = (static_cast<uint64_t>(q3.y) << 32) | q3.x;
+        e.m.desc = lo;
+        e.m.tile_in_obj = t - first;
+        e.m.ndst_flags = (q2.w & 0xFFu) | (q3.z << 8);
+        e.m.obj_ntiles = __ldg(&p.tile_start[lo + 1]) - first;
+        e.m.crc_unpad = q3.w;
       }
+      __syncwarp();
       const uint32_t cnt = min(32u, my_tiles - base);
       for (uint32_t i = 0; i < cnt; ++i, ++it) {
         const uint32_t stage = it % kStages;
         const uint32_t par = (it / kStages) & 1u;
-        const uint64_t src_i = shfl64(src, i);
-        const uint64_t nbytes_i = shfl64(nbytes, i);
-        const uint32_t ti_i = __shfl_sync(0xffffffffu, ti, i);
-        const uint64_t off = static_cast<uint64_t>(ti_i) * kTileBytes;
-        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kTileBytes), nbytes_i - off));
+        const LookupEntry& e = s.lk[i];
+        const uint64_t src_i = e.src;
+        const uint64_t off = static_cast<uint64_t>(e.m.tile_in_obj) * kTileBytes;
+        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kTileBytes), e.m.nbytes - off));
         const uint32_t b16 = bytes & ~15u;
         const uint32_t tail = bytes & 15u;
         mbar_wait(&s.empty[stage], par ^ 1u);
@@ -193,24 +234,24 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
           wrote = true;
         }
         if (wrote) fence_proxy_async_smem();
+        if (lane < 4) {
+          uint4 v = reinterpret_cast<const uint4*>(&e.m)[lane];
+          if (lane == 3) v.x = bytes;  // StageMeta::bytes is the first word of uint4 #3
+          reinterpret_cast<uint4*>(&s.meta[stage])[lane] = v;
+        }
         __syncwarp();
-        const uint64_t d0 = shfl64(dst0, i), d1 = shfl64(dst1, i), d2 = shfl64(dst2, i);
-        const uint32_t d_i = __shfl_sync(0xffffffffu, d, i);
-        const uint32_t nf_i = __shfl_sync(0xffffffffu, ndst_flags, i);
         if (lane == 0) {
           s.dirty[stage] = (bytes + 15u) & ~15u;
-          StageMeta& m = s.meta[stage];
-          m.dst[0] = d0; m.dst[1] = d1; m.dst[2] = d2;
-          m.desc = d_i; m.tile_in_obj = ti_i; m.bytes = bytes; m.ndst_flags = nf_i;
           mbar_arrive_expect_tx(&s.full[stage], b16);
           if (b16) bulk_g2s(s.tile[stage], reinterpret_cast<const void*>(src_i + off), b16, &s.full[stage]);
         }
         __syncwarp();
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================================================ tensor-core hash issuer
-    if constexpr (kHash) {
+    if constexpr (kBbh) {
       constexpr uint32_t idesc = umma_idesc_i8(tchash::kRows, tchash::kN, false, false);
       const uint32_t w_addr = smem_u32(s.w);
       for (uint32_t it = 0; it < my_tiles; ++it) {
@@ -238,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
       const uint32_t stage = it % kStages;
       const uint32_t par = (it / kStages) & 1u;
       mbar_wait(&s.full[stage], par);
-      const StageMeta m = s.meta[stage];
+      const StageMeta& m = s.meta[stage];
       const uint64_t off = static_cast<uint64_t>(m.tile_in_obj) * kTileBytes;
       const uint32_t b16 = m.bytes & ~15u;
       const uint32_t tail = m.bytes & 15u;
@@ -269,13 +310,82 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
       for (uint32_t it = first; it < my_tiles; ++it) mbar_arrive(&s.empty[it % kStages]);
       bulk_wait<0>();  // writes performed before the kernel retires
     }
-  } else if (warp >= 4) {
-    // ================================================================ epilogue: TMEM -> digest
+  } else if (warp == 3) {
+    // ================================================================ finalizer
     if constexpr (kHash) {
+      uint32_t cur_d = 0xFFFFFFFFu, cnt = 0;
+      uint64_t acc = 0;
+      for (uint32_t it = 0; it < my_tiles; ++it) {
+        const uint32_t stage = it % kStages;
+        const uint32_t par = (it / kStages) & 1u;
+        mbar_wait(&s.epi_done[stage], par);
+        const StageMeta m = s.meta[stage];
+        const uint64_t p0 = s.part[stage][0], p1 = s.part[stage][1], p2 = s.part[stage][2], p3 = s.part[stage][3];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[stage]);
+        if (m.desc != cur_d) {
+          cur_d = m.desc;
+          acc = 0;
+          cnt = 0;
+        }
+        if constexpr (kBbh) {
+          acc += p0 + p1 + p2 + p3;
+        } else {
+          const auto* t4k = s.crc_t[T4096];
+          uint32_t t = crc_shift(t4k, static_cast<uint32_t>(p0)) ^ static_cast<uint32_t>(p1);
+          t = crc_shift(t4k, t) ^ static_cast<uint32_t>(p2);
+          t = crc_shift(t4k, t) ^ static_cast<uint32_t>(p3);
+          acc = crc_shift(s.crc_t[T16384], static_cast<uint32_t>(acc)) ^ t;
+        }
+        ++cnt;
+        const bool obj_end = (m.tile_in_obj + 1 == m.obj_ntiles);
+        if (obj_end || it + 1 == my_tiles) {
+          // ---- this CTA's contribution to object cur_d is complete
+          uint64_t digest = 0;
+          bool have = false;
+          if (cnt == m.obj_ntiles) {  // object lives entirely in this CTA: no atomics
+            if constexpr (kBbh) digest = tchash::finalize(acc, m.nbytes);
+            else digest = gf2_mulmod_dev(static_cast<uint32_t>(acc), m.crc_unpad) ^ static_cast<uint32_t>(m.expect >> 32) ^ 0xFFFFFFFFu;
+            have = true;
+          } else {
+            uint64_t contrib = acc;
+            if constexpr (kCrc) {
+              const uint32_t after = m.obj_ntiles - 1u - m.tile_in_obj;  // tiles of this object after my run
+              contrib = gf2_mulmod_dev(static_cast<uint32_t>(acc), warp_xpow_tiles(after, lane));
+            }
+            uint32_t prev = 0;
+            if (lane == 0) {
+              if constexpr (kBbh) atomicAdd(&p.sum_ws[cur_d], static_cast<unsigned long long>(contrib));
+              else atomicXor(&p.sum_ws[cur_d], static_cast<unsigned long long>(contrib));
+              __threadfence();
+              prev = atomicAdd(&p.done_ws[cur_d], cnt);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev + cnt == m.obj_ntiles) {  // last contributor finalises and re-zeroes
+              if (lane == 0) {
+                __threadfence();
+                const uint64_t sum = atomicExch(&p.sum_ws[cur_d], 0ull);
+                p.done_ws[cur_d] = 0;
+                if constexpr (kBbh) digest = tchash::finalize(sum, m.nbytes);
+                else digest = gf2_mulmod_dev(static_cast<uint32_t>(sum), m.crc_unpad) ^ static_cast<uint32_t>(m.expect >> 32) ^ 0xFFFFFFFFu;
+              }
+              have = true;
+            }
+          }
+          if (have && lane == 0) {
+            const uint64_t want = kBbh ? m.expect : (m.expect & 0xFFFFFFFFull);
+            p.digest_out[cur_d] = digest;
+            p.status_out[cur_d] = (((m.ndst_flags >> 8) & XFER_VERIFY) && digest != want) ? 1u : 0u;
+          }
+          cur_d = 0xFFFFFFFFu;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps 4..7
+    if constexpr (kBbh) {
       const uint32_t q = warp & 3u;
       const uint32_t row = q * 32 + lane;
-      uint32_t cur_d = 0xFFFFFFFFu, cur_tiles = 0;
-      uint64_t acc = 0;
       for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint32_t stage = it % kStages;
         const uint32_t par = (it / kStages) & 1u;
@@ -285,37 +395,54 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_base + ((q * 32u) << 16) + stage * tchash::kN, r);
         tmem_ld_wait();
-        const uint32_t d = s.meta[stage].desc;
-        const uint32_t ti = s.meta[stage].tile_in_obj;
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[stage]);
-        if (d != cur_d) {
-          flush_partial(p, cur_d, acc, cur_tiles, lane);
-          cur_d = d;
-          acc = 0;
-          cur_tiles = 0;
-        }
+        const uint32_t ti = s.meta[stage].tile_in_obj;
         uint64_t rr = 0;
 #pragma unroll
         for (int n = 0; n < 16; ++n) rr += static_cast<uint64_t>(r[n]) * c_col_mul[n];
-        acc += tchash::row_contrib(rr, static_cast<uint64_t>(ti) * tchash::kRows + row);
-        ++cur_tiles;
+        const uint64_t tot = warp_sum64(tchash::row_contrib(rr, static_cast<uint64_t>(ti) * tchash::kRows + row));
+        if (lane == 0) {
+          s.part[stage][q] = tot;
+          mbar_arrive(&s.epi_done[stage]);
+        }
         if (p.debug_d) {
-          const uint64_t t = blockIdx.x + static_cast<uint64_t>(it) * G;
-          uint32_t* o = p.debug_d + (t * tchash::kRows + row) * tchash::kN;
+          uint32_t* o = p.debug_d + (static_cast<uint64_t>(t0 + it) * tchash::kRows + row) * tchash::kN;
 #pragma unroll
           for (int n = 0; n < 16; ++n) o[n] = r[n];
         }
       }
-      flush_partial(p, cur_d, acc, cur_tiles, lane);
+    } else if constexpr (kCrc) {
+      const uint32_t q = warp & 3u;
+      for (uint32_t it = 0; it < my_tiles; ++it) {
+        const uint32_t stage = it % kStages;
+        const uint32_t par = (it / kStages) & 1u;
+        mbar_wait(&s.full[stage], par);
+        // lane l streams words l, l+32, ... of this warp's 4 KiB quarter (bank-conflict free);
+        // consecutive words of a lane are 128 B apart -> shift by x^(8*128) per step.
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&s.tile[stage][q * 4096]) + lane;
+        const auto* t128 = s.crc_t[T128];
+        uint32_t a = 0;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) a = crc_shift(t128, a) ^ wp[i * 32];
+        // combine lanes: value(l) covers bytes [4l, 4l+4) of each 128-byte row group
+        uint32_t o;
+        o = __shfl_down_sync(0xffffffffu, a, 1);  a = crc_shift(s.crc_t[T4], a) ^ o;
+        o = __shfl_down_sync(0xffffffffu, a, 2);  a = crc_shift(s.crc_t[T8], a) ^ o;
+        o = __shfl_down_sync(0xffffffffu, a, 4);  a = crc_shift(s.crc_t[T16], a) ^ o;
+        o = __shfl_down_sync(0xffffffffu, a, 8);  a = crc_shift(s.crc_t[T32], a) ^ o;
+        o = __shfl_down_sync(0xffffffffu, a, 16); a = crc_shift(s.crc_t[T64], a) ^ o;
+        if (lane == 0) {
+          s.part[stage][q] = crc_shift(s.crc_t[T4], a);  // the CRC's final x^32 factor
+          mbar_arrive(&s.epi_done[stage]);
+        }
+      }
     }
   }
 
   // ------------------------------------------------------------------ teardown
-  if constexpr (kHash) tc_fence_before();
+  if constexpr (kBbh) tc_fence_before();
   __syncthreads();
-  if constexpr (kHash) {
+  if constexpr (kBbh) {
     if (warp == 3) {
       tc_fence_after();
       tmem_dealloc<kTmemCols>(tmem_base);
@@ -323,49 +450,99 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
   }
 }
 
-int g_sm_count[16] = {0};
-bool g_const_init[16] = {false};
-
-int sm_count(int dev) {
-  if (dev < 0 || dev >= 16) dev = 0;
-  if (!g_sm_count[dev]) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    g_sm_count[dev] = n;
-  }
-  return g_sm_count[dev];
-}
+struct DeviceState {
+  bool consts = false;
+  uint32_t* crc_tables = nullptr;
+  int sm_count = 0;
+  bool attr[3] = {false, false, false};
+};
+DeviceState g_dev[16];
+std::mutex g_mu;
 
 template <int ALGO>
-cudaError_t launch_t(const XferLaunch& l, const Params& p, int grid, cudaStream_t st) {
-  static bool attr_set[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 16 && !attr_set[dev]) {
+cudaError_t launch_t(DeviceState& ds, const Params& p, int grid, cudaStream_t st) {
+  if (!ds.attr[ALGO]) {
     cudaError_t e = cudaFuncSetAttribute(bb_xfer_kernel<ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(Smem)));
+                                         static_cast<int>(sizeof(SmemT<ALGO>)));
     if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
+    ds.attr[ALGO] = true;
   }
-  bb_xfer_kernel<ALGO><<<grid, kThreads, sizeof(Smem), st>>>(p);
+  bb_xfer_kernel<ALGO><<<grid, kThreads, sizeof(SmemT<ALGO>), st>>>(p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-int xfer_smem_bytes(int) { return static_cast<int>(sizeof(Smem)); }
+int xfer_smem_bytes(int algo) {
+  switch (algo) {
+    case ALGO_NONE: return static_cast<int>(sizeof(SmemT<ALGO_NONE>));
+    case ALGO_CRC32C: return static_cast<int>(sizeof(SmemT<ALGO_CRC32C>));
+    default: return static_cast<int>(sizeof(SmemT<ALGO_BBH64>));
+  }
+}
+
+uint32_t crc_unpad_for(uint64_t nbytes) {
+  // x^(-8*pad) mod P where pad = zero bytes appended to reach a whole number of tiles.
+  const uint64_t pad = (kTileBytes - (nbytes % kTileBytes)) % kTileBytes;
+  // x^-1 in reflected form: reverse one bit-step of the LFSR applied to "1" (0x80000000).
+  // inv(x): find v with v * x == 1.  One forward step maps v -> (v>>1) ^ (v&1 ? P : 0).
+  // Reverse step of value 0x80000000: top bit set => came from ((b ^ P) << 1) | 1.
+  static const uint32_t xinv8 = [] {
+    uint32_t v = 0x80000000u;  // 1
+    for (int i = 0; i < 8; ++i) v = (v & 0x80000000u) ? (((v ^ 0x82F63B78u) << 1) | 1u) : (v << 1);
+    return v;  // x^-8
+  }();
+  uint32_t result = 0x80000000u, base = xinv8;
+  uint64_t e = pad;
+  while (e) {
+    if (e & 1) result = gf2_mulmod(result, base);
+    base = gf2_mulmod(base, base);
+    e >>= 1;
+  }
+  return result;
+}
+
+uint32_t crc_init_term_for(uint64_t nbytes) { return gf2_mulmod(0xFFFFFFFFu, gf2_xpow_bytes(nbytes)); }
 
 int launch_xfer(const XferLaunch& l) {
   if (l.ndesc == 0 || l.total_tiles == 0) return 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return static_cast<int>(e);
-  if (dev >= 0 && dev < 16 && !g_const_init[dev]) {
-    uint64_t h[tchash::kN];
-    for (uint32_t n = 0; n < tchash::kN; ++n) h[n] = tchash::col_mul(n);
-    e = cudaMemcpyToSymbol(c_col_mul, h, sizeof h);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    g_const_init[dev] = true;
+  if (dev < 0 || dev >= 16) return static_cast<int>(cudaErrorInvalidDevice);
+  DeviceState& ds = g_dev[dev];
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!ds.consts) {
+      uint64_t h[tchash::kN];
+      for (uint32_t n = 0; n < tchash::kN; ++n) h[n] = tchash::col_mul(n);
+      e = cudaMemcpyToSymbol(c_col_mul, h, sizeof h);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      uint32_t xp[32];
+      uint32_t b = gf2_xpow_bytes(kTileBytes);
+      for (int j = 0; j < 32; ++j) {
+        xp[j] = b;
+        b = gf2_mulmod(b, b);
+      }
+      e = cudaMemcpyToSymbol(c_xpow_tiles, xp, sizeof xp);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      int n = 0;
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+      ds.sm_count = n;
+      ds.consts = true;
+    }
+    if (l.algo == ALGO_CRC32C && !ds.crc_tables) {
+      static uint32_t host_t[kNumCrcTabs][4][256];
+      static bool host_init = false;
+      if (!host_init) {
+        for (int t = 0; t < kNumCrcTabs; ++t) crc32c_shift_table(kCrcTabBytes[t], host_t[t]);
+        host_init = true;
+      }
+      e = cudaMalloc(reinterpret_cast<void**>(&ds.crc_tables), sizeof host_t);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaMemcpy(ds.crc_tables, host_t, sizeof host_t, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
   }
   Params p;
   p.descs = l.descs;
@@ -376,13 +553,15 @@ int launch_xfer(const XferLaunch& l) {
   p.done_ws = l.done_ws;
   p.digest_out = l.digest_out;
   p.status_out = l.status_out;
+  p.crc_tables = ds.crc_tables;
   p.debug_d = l.debug_d;
-  int grid = l.max_ctas > 0 ? l.max_ctas : sm_count(dev);
+  int grid = l.max_ctas > 0 ? l.max_ctas : ds.sm_count;
   grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(grid), l.total_tiles));
   cudaStream_t st = static_cast<cudaStream_t>(l.stream);
   switch (l.algo) {
-    case ALGO_NONE: e = launch_t<ALGO_NONE>(l, p, grid, st); break;
-    case ALGO_BBH64: e = launch_t<ALGO_BBH64>(l, p, grid, st); break;
+    case ALGO_NONE: e = launch_t<ALGO_NONE>(ds, p, grid, st); break;
+    case ALGO_CRC32C: e = launch_t<ALGO_CRC32C>(ds, p, grid, st); break;
+    case ALGO_BBH64: e = launch_t<ALGO_BBH64>(ds, p, grid, st); break;
     default: return static_cast<int>(cudaErrorNotSupported);
   }
   return static_cast<int>(e);
