@@ -1,0 +1,587 @@
+#include "alloc/allocator.h"
+
+#include <algorithm>
+#include <unordered_set>
+
+#include "common/log.h"
+
+namespace bb::alloc {
+
+// ================================================================ PoolAllocator
+namespace {
+uint32_t rkey_from_hex(const std::string& hex) {
+  auto bytes = hex_to_bytes(hex);
+  if (!bytes || bytes->empty()) return 0;
+  if (bytes->size() <= 4) {
+    uint32_t v = 0;
+    for (uint8_t b : *bytes) v = (v << 8) | b;
+    return v;
+  }
+  return crc32c(bytes->data(), bytes->size());  // long fabric handles: stable 32-bit tag
+}
+}  // namespace
+
+PoolAllocator::PoolAllocator(const MemoryPool& pool, uint64_t align)
+    : pool_id_(pool.id),
+      storage_class_(pool.storage_class),
+      node_id_(pool.node_id),
+      base_addr_(pool.ucx_remote_addr ? pool.ucx_remote_addr : pool.base_addr),
+      rkey_(rkey_from_hex(pool.ucx_rkey_hex)),
+      pool_size_(pool.size),
+      align_(align ? align : 1) {
+  const uint64_t usable = pool.size / align_ * align_;
+  if (usable) insert_free(0, usable);
+}
+
+void PoolAllocator::insert_free(uint64_t off, uint64_t len) {
+  by_offset_[off] = len;
+  by_size_.insert({len, off});
+  free_bytes_ += len;
+}
+
+void PoolAllocator::erase_free(std::map<uint64_t, uint64_t>::iterator it) {
+  by_size_.erase({it->second, it->first});
+  free_bytes_ -= it->second;
+  by_offset_.erase(it);
+}
+
+std::optional<Range> PoolAllocator::allocate(uint64_t size, bool prefer_best_fit) {
+  const uint64_t need = aligned(size);
+  std::lock_guard<std::mutex> lk(mu_);
+  if (need == 0) return Range(0, 0);
+  std::map<uint64_t, uint64_t>::iterator it = by_offset_.end();
+  if (prefer_best_fit) {
+    auto s = by_size_.lower_bound({need, 0});  // tightest hole; lowest offset among equals
+    if (s == by_size_.end()) return std::nullopt;
+    it = by_offset_.find(s->second);
+  } else {
+    for (auto f = by_offset_.begin(); f != by_offset_.end(); ++f)
+      if (f->second >= need) {
+        it = f;
+        break;
+      }
+    if (it == by_offset_.end()) return std::nullopt;
+  }
+  const uint64_t off = it->first, len = it->second;
+  erase_free(it);
+  if (len > need) insert_free(off + need, len - need);
+  return Range(off, need);
+}
+
+bool PoolAllocator::allocate_at(uint64_t offset, uint64_t size) {
+  const uint64_t need = aligned(size);
+  if (need == 0) return true;
+  if (offset % align_) return false;
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = by_offset_.upper_bound(offset);
+  if (it == by_offset_.begin()) return false;
+  --it;
+  const uint64_t off = it->first, len = it->second;
+  if (offset < off || offset + need > off + len) return false;
+  erase_free(it);
+  if (offset > off) insert_free(off, offset - off);
+  if (off + len > offset + need) insert_free(offset + need, off + len - offset - need);
+  return true;
+}
+
+void PoolAllocator::free(const Range& range) {
+  if (range.length == 0) return;
+  std::lock_guard<std::mutex> lk(mu_);
+  uint64_t off = range.offset, len = range.length;
+  auto next = by_offset_.lower_bound(off);
+  if (next != by_offset_.begin()) {
+    auto prev = std::prev(next);
+    if (prev->first + prev->second == off) {
+      off = prev->first;
+      len += prev->second;
+      erase_free(prev);
+    } else if (prev->first + prev->second > off) {
+      BB_LOG(ERROR) << "PoolAllocator(" << pool_id_ << "): double free / overlap at offset " << range.offset;
+      return;
+    }
+  }
+  next = by_offset_.lower_bound(range.offset);
+  if (next != by_offset_.end()) {
+    if (range.offset + range.length == next->first) {
+      len += next->second;
+      erase_free(next);
+    } else if (range.offset + range.length > next->first) {
+      BB_LOG(ERROR) << "PoolAllocator(" << pool_id_ << "): double free / overlap at offset " << range.offset;
+      if (off != range.offset) insert_free(off, len - range.length);  // restore the merged predecessor
+      return;
+    }
+  }
+  insert_free(off, len);
+}
+
+size_t PoolAllocator::total_free() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  return free_bytes_;
+}
+size_t PoolAllocator::largest_free_block() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  return by_size_.empty() ? 0 : by_size_.rbegin()->first;
+}
+double PoolAllocator::fragmentation_ratio() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (free_bytes_ == 0) return 0.0;
+  return 1.0 - static_cast<double>(by_size_.rbegin()->first) / static_cast<double>(free_bytes_);
+}
+bool PoolAllocator::can_allocate(uint64_t size) const {
+  const uint64_t need = aligned(size);
+  std::lock_guard<std::mutex> lk(mu_);
+  return need == 0 || (!by_size_.empty() && by_size_.rbegin()->first >= need);
+}
+std::vector<Range> PoolAllocator::free_ranges() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  std::vector<Range> v;
+  v.reserve(by_offset_.size());
+  for (const auto& [o, l] : by_offset_) v.emplace_back(o, l);
+  return v;
+}
+MemoryLocation PoolAllocator::to_memory_location(const Range& r) const {
+  return MemoryLocation{base_addr_ + r.offset, rkey_, r.length};
+}
+
+// ================================================================ RangeAllocator
+PoolAllocator* RangeAllocator::find_pool(const MemoryPoolId& id) const {
+  std::shared_lock<std::shared_mutex> lk(pools_mu_);
+  auto it = pool_allocators_.find(id);
+  return it == pool_allocators_.end() ? nullptr : it->second.get();
+}
+
+PoolAllocator* RangeAllocator::ensure_pool(const MemoryPool& pool) {
+  if (PoolAllocator* p = find_pool(pool.id)) return p;
+  std::unique_lock<std::shared_mutex> lk(pools_mu_);
+  auto& slot = pool_allocators_[pool.id];
+  if (!slot) slot = std::make_unique<PoolAllocator>(pool);
+  return slot.get();
+}
+
+std::vector<RangeAllocator::Candidate> RangeAllocator::rank_candidates(const AllocationRequest& req, const PoolMap& pools,
+                                                                       bool* spill) const {
+  std::vector<Candidate> v;
+  v.reserve(pools.size());
+  auto preferred = [&](StorageClass c) {
+    return req.preferred_classes.empty() ||
+           std::find(req.preferred_classes.begin(), req.preferred_classes.end(), c) != req.preferred_classes.end();
+  };
+  std::string client_domain;
+  if (!req.client_node.empty())
+    for (const auto& [id, p] : pools)
+      if (p.node_id == req.client_node && !p.fabric_domain.empty()) client_domain = p.fabric_domain;
+  for (const auto& [id, p] : pools) {
+    if (!req.preferred_node.empty() && p.node_id != req.preferred_node) continue;
+    if (std::find(req.exclude_pools.begin(), req.exclude_pools.end(), id) != req.exclude_pools.end()) continue;
+    Candidate c;
+    c.id = id;
+    c.preferred = preferred(p.storage_class);
+    c.locality = 0;
+    if (req.enable_locality_awareness && !req.client_node.empty()) {
+      if (p.node_id == req.client_node) c.locality = 2;
+      else if (!client_domain.empty() && p.fabric_domain == client_domain) c.locality = 1;
+    }
+    c.bw = p.max_bw_gbps;
+    if (const PoolAllocator* pa = find_pool(id)) {
+      c.free_bytes = pa->total_free();
+      c.largest = pa->largest_free_block();
+    } else {
+      c.free_bytes = p.size / PoolAllocator::kDefaultAlign * PoolAllocator::kDefaultAlign;
+      c.largest = c.free_bytes;
+    }
+    c.worker = p.worker_id.empty() ? ("pool:" + id) : p.worker_id;
+    v.push_back(std::move(c));
+  }
+  std::sort(v.begin(), v.end(), [](const Candidate& a, const Candidate& b) {
+    if (a.preferred != b.preferred) return a.preferred;
+    if (a.locality != b.locality) return a.locality > b.locality;
+    if (a.bw != b.bw) return a.bw > b.bw;
+    if (a.free_bytes != b.free_bytes) return a.free_bytes > b.free_bytes;
+    return a.id < b.id;
+  });
+  if (spill) *spill = false;
+  return v;
+}
+
+Result<ShardPlacement> RangeAllocator::make_shard(const MemoryPool& pool, const Range& r, uint64_t length) const {
+  ShardPlacement s;
+  s.pool_id = pool.id;
+  s.worker_id = pool.worker_id;
+  s.storage_class = pool.storage_class;
+  s.length = length;
+  if (!pool.ucx_endpoint.empty()) {
+    auto hp = split_host_port(pool.ucx_endpoint);
+    if (!hp) return ErrorCode::INVALID_PARAMETERS;
+    s.endpoint.ip = hp->first;
+    s.endpoint.port = hp->second;
+  }
+  if (!pool.ucx_rkey_hex.empty()) {
+    auto key = hex_to_bytes(pool.ucx_rkey_hex);
+    if (!key) return ErrorCode::INVALID_PARAMETERS;
+    s.endpoint.worker_key = std::move(*key);
+  }
+  switch (pool.storage_class) {
+    case StorageClass::RAM_GPU:
+      s.location = GpuSlabLocation{static_cast<uint32_t>(pool.gpu_device_id < 0 ? 0 : pool.gpu_device_id), 0, r.offset, length};
+      break;
+    case StorageClass::NVME:
+    case StorageClass::SSD:
+    case StorageClass::HDD:
+      s.location = FileLocation{pool.mount_path.empty() ? pool.id : pool.mount_path + "/" + pool.id + ".dat", r.offset};
+      break;
+    case StorageClass::CXL_MEMORY:
+    case StorageClass::CXL_TYPE2_DEVICE:
+      s.location = CxlMemoryLocation{pool.id, r.offset / 256, r.offset, length};
+      break;
+    default: {
+      const PoolAllocator* pa = find_pool(pool.id);
+      MemoryLocation m = pa ? pa->to_memory_location(r) : MemoryLocation{pool.ucx_remote_addr + r.offset, 0, r.length};
+      m.size = length;
+      s.location = m;
+    }
+  }
+  return s;
+}
+
+void RangeAllocator::rollback(const std::vector<Extent>& extents) {
+  for (const auto& e : extents)
+    if (PoolAllocator* pa = find_pool(e.pool)) pa->free(e.range);
+}
+
+Result<AllocationResult> RangeAllocator::place(const AllocationRequest& req, const PoolMap& pools,
+                                               const std::vector<Candidate>& cands, bool spill) {
+  const size_t n = cands.size();
+  const size_t repl = std::max<size_t>(1, req.replication_factor);
+  size_t wpc = std::min(std::max<size_t>(1, req.max_workers_per_copy), n);
+  if (!req.enable_striping || req.prefer_contiguous) wpc = 1;
+  if (repl > 1 && n > wpc) {
+    const size_t ideal = n / repl;  // leave room for the other replicas on distinct pools
+    if (ideal >= 1) wpc = std::min(wpc, ideal);
+  }
+  if (wpc > 1 && req.data_size / wpc < req.min_shard_size) {
+    if (req.strict_min_shard) return ErrorCode::INSUFFICIENT_SPACE;
+    wpc = std::max<size_t>(1, std::min(wpc, req.data_size / std::max<size_t>(1, req.min_shard_size)));
+  }
+
+  AllocationResult result;
+  std::vector<Extent> all;
+  std::unordered_set<std::string> workers_used;  // failure domains taken by earlier copies
+  std::unordered_set<MemoryPoolId> pools_used;
+  size_t rot = 0;
+  for (size_t c = 0; c < repl; ++c) {
+    CopyPlacement copy;
+    copy.copy_index = static_cast<uint32_t>(c);
+    std::unordered_set<MemoryPoolId> in_copy;
+    std::unordered_set<std::string> workers_in_copy;
+    const size_t base = req.data_size / wpc, rem = req.data_size % wpc;
+    for (size_t i = 0; i < wpc; ++i) {
+      const uint64_t len = base + (i < rem ? 1 : 0);
+      bool placed = false;
+      // pass 0: a pool on a worker no other copy uses; pass 1: any pool not yet in this copy;
+      // pass 2: anything with space (tiny clusters)
+      for (int pass = 0; pass < 3 && !placed; ++pass) {
+        for (size_t k = 0; k < n && !placed; ++k) {
+          const Candidate& cd = cands[(rot + k) % n];
+          if (pass < 2 && in_copy.count(cd.id)) continue;
+          if (pass == 0 && (workers_used.count(cd.worker) || pools_used.count(cd.id))) continue;
+          if (pass == 1 && repl > 1 && pools_used.count(cd.id) && n >= repl * wpc) continue;
+          const MemoryPool& pool = pools.at(cd.id);
+          PoolAllocator* pa = ensure_pool(pool);
+          auto r = pa->allocate(len, true);
+          if (!r) continue;
+          auto shard = make_shard(pool, *r, len);
+          if (!shard.ok()) {
+            pa->free(*r);
+            rollback(all);
+            return shard.error();
+          }
+          all.push_back({cd.id, *r, len});
+          copy.shards.push_back(std::move(shard.value()));
+          in_copy.insert(cd.id);
+          workers_in_copy.insert(cd.worker);
+          if (!cd.preferred) spill = true;
+          placed = true;
+          rot = (rot + k + 1) % n;
+        }
+      }
+      if (!placed) {
+        rollback(all);
+        return ErrorCode::INSUFFICIENT_SPACE;
+      }
+    }
+    for (const auto& w : workers_in_copy) workers_used.insert(w);
+    for (const auto& p : in_copy) pools_used.insert(p);
+    result.total_shards_created += copy.shards.size();
+    result.copies.push_back(std::move(copy));
+  }
+
+  // commit to the ledger
+  {
+    std::unique_lock<std::shared_mutex> lk(alloc_mu_);
+    if (objects_.count(req.object_key)) {
+      lk.unlock();
+      rollback(all);
+      return ErrorCode::OBJECT_ALREADY_EXISTS;
+    }
+    ObjectAllocation oa;
+    oa.total_size = req.data_size;
+    for (const auto& e : all) used_by_pool_[e.pool] += e.range.length;
+    oa.extents = std::move(all);
+    objects_.emplace(req.object_key, std::move(oa));
+  }
+  result.pools_used = pools_used.size();
+  result.stats.required_spillover = spill;
+  result.stats.avg_shard_size = result.total_shards_created ? req.data_size * repl / result.total_shards_created : 0;
+  double frag = 0;
+  size_t cnt = 0;
+  for (const auto& p : pools_used)
+    if (PoolAllocator* pa = find_pool(p)) {
+      frag += pa->fragmentation_ratio();
+      ++cnt;
+    }
+  result.stats.fragmentation_score = cnt ? static_cast<size_t>(frag / static_cast<double>(cnt) * 100.0) : 0;
+  return result;
+}
+
+Result<AllocationResult> RangeAllocator::place_symmetric(const AllocationRequest& req, const PoolMap& pools,
+                                                         const std::vector<Candidate>& cands, bool spill) {
+  const size_t repl = std::max<size_t>(1, req.replication_factor);
+  // pick `repl` pools on distinct workers, best ranked first
+  std::vector<const Candidate*> chosen;
+  std::unordered_set<std::string> workers;
+  for (const auto& c : cands) {
+    if (workers.count(c.worker)) continue;
+    if (c.largest < req.data_size) continue;
+    chosen.push_back(&c);
+    workers.insert(c.worker);
+    if (chosen.size() == repl) break;
+  }
+  if (chosen.size() < repl) return ErrorCode::INSUFFICIENT_SPACE;
+  std::vector<PoolAllocator*> pas;
+  for (auto* c : chosen) pas.push_back(ensure_pool(pools.at(c->id)));
+  const uint64_t need = pas[0]->aligned(req.data_size);
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    // intersect the free lists (address ordered) and take the tightest common hole
+    std::vector<Range> common = pas[0]->free_ranges();
+    for (size_t i = 1; i < pas.size() && !common.empty(); ++i) {
+      const std::vector<Range> other = pas[i]->free_ranges();
+      std::vector<Range> out;
+      size_t a = 0, b = 0;
+      while (a < common.size() && b < other.size()) {
+        const uint64_t lo = std::max(common[a].offset, other[b].offset);
+        const uint64_t hi = std::min(common[a].end(), other[b].end());
+        if (hi > lo) out.emplace_back(lo, hi - lo);
+        if (common[a].end() < other[b].end()) ++a; else ++b;
+      }
+      common.swap(out);
+    }
+    const Range* best = nullptr;
+    for (const auto& r : common)
+      if (r.length >= need && (!best || r.length < best->length)) best = &r;
+    if (!best) return ErrorCode::INSUFFICIENT_SPACE;
+    const uint64_t off = best->offset;
+    size_t got = 0;
+    for (; got < pas.size(); ++got)
+      if (!pas[got]->allocate_at(off, req.data_size)) break;
+    if (got == pas.size()) {
+      AllocationResult result;
+      std::vector<Extent> all;
+      for (size_t i = 0; i < pas.size(); ++i) {
+        const MemoryPool& pool = pools.at(chosen[i]->id);
+        Range r(off, need);
+        auto shard = make_shard(pool, r, req.data_size);
+        if (!shard.ok()) {
+          for (auto* pa : pas) pa->free(r);
+          return shard.error();
+        }
+        CopyPlacement cp;
+        cp.copy_index = static_cast<uint32_t>(i);
+        cp.shards.push_back(std::move(shard.value()));
+        result.copies.push_back(std::move(cp));
+        all.push_back({chosen[i]->id, r, req.data_size});
+        if (!chosen[i]->preferred) spill = true;
+      }
+      std::unique_lock<std::shared_mutex> lk(alloc_mu_);
+      if (objects_.count(req.object_key)) {
+        lk.unlock();
+        rollback(all);
+        return ErrorCode::OBJECT_ALREADY_EXISTS;
+      }
+      ObjectAllocation oa;
+      oa.total_size = req.data_size;
+      for (const auto& e : all) used_by_pool_[e.pool] += e.range.length;
+      oa.extents = std::move(all);
+      objects_.emplace(req.object_key, std::move(oa));
+      result.total_shards_created = repl;
+      result.pools_used = repl;
+      result.stats.required_spillover = spill;
+      result.stats.avg_shard_size = req.data_size;
+      return result;
+    }
+    for (size_t i = 0; i < got; ++i) pas[i]->free(Range(off, need));  // raced with another writer: retry
+  }
+  return ErrorCode::ALLOCATION_FAILED;
+}
+
+Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, const PoolMap& pools) {
+  if (req.object_key.empty()) return ErrorCode::INVALID_KEY;
+  if (req.replication_factor == 0 || req.max_workers_per_copy == 0) return ErrorCode::INVALID_PARAMETERS;
+  {
+    std::shared_lock<std::shared_mutex> lk(alloc_mu_);
+    if (objects_.count(req.object_key)) return ErrorCode::OBJECT_ALREADY_EXISTS;
+  }
+  if (pools.empty()) return ErrorCode::INSUFFICIENT_SPACE;
+  // validate registration data up-front so that malformed pools are reported as such
+  for (const auto& [id, p] : pools) {
+    if (!p.ucx_endpoint.empty() && !split_host_port(p.ucx_endpoint)) return ErrorCode::INVALID_PARAMETERS;
+    if (!p.ucx_rkey_hex.empty() && !hex_to_bytes(p.ucx_rkey_hex)) return ErrorCode::INVALID_PARAMETERS;
+  }
+  bool spill = false;
+  std::vector<Candidate> cands = rank_candidates(req, pools, &spill);
+  if (cands.empty()) return ErrorCode::INSUFFICIENT_SPACE;
+  if (req.symmetric_replicas && req.replication_factor > 1) return place_symmetric(req, pools, cands, spill);
+  return place(req, pools, cands, spill);
+}
+
+ErrorCode RangeAllocator::free(const ObjectKey& key) {
+  ObjectAllocation oa;
+  {
+    std::unique_lock<std::shared_mutex> lk(alloc_mu_);
+    auto it = objects_.find(key);
+    if (it == objects_.end()) return ErrorCode::OBJECT_NOT_FOUND;
+    oa = std::move(it->second);
+    objects_.erase(it);
+    for (const auto& e : oa.extents) {
+      auto u = used_by_pool_.find(e.pool);
+      if (u != used_by_pool_.end()) u->second -= std::min(u->second, static_cast<size_t>(e.range.length));
+    }
+  }
+  rollback(oa.extents);
+  return ErrorCode::OK;
+}
+
+AllocatorStats RangeAllocator::get_stats(std::optional<StorageClass> sc) const {
+  AllocatorStats st;
+  size_t largest = 0;
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    for (const auto& [id, pa] : pool_allocators_) {
+      if (sc && pa->storage_class() != *sc) continue;
+      st.total_free_bytes += pa->total_free();
+      largest = std::max(largest, pa->largest_free_block());
+      st.bytes_per_class[pa->storage_class()] += pa->capacity() - pa->total_free();
+    }
+  }
+  {
+    std::shared_lock<std::shared_mutex> lk(alloc_mu_);
+    for (const auto& [key, oa] : objects_) {
+      bool counted = false;
+      for (const auto& e : oa.extents) {
+        const PoolAllocator* pa = find_pool(e.pool);
+        if (sc && (!pa || pa->storage_class() != *sc)) continue;
+        st.total_allocated_bytes += e.range.length;
+        ++st.total_shards;
+        counted = true;
+      }
+      if (counted || (!sc && oa.extents.empty())) ++st.total_objects;
+    }
+  }
+  st.fragmentation_ratio = st.total_free_bytes ? 1.0 - static_cast<double>(largest) / static_cast<double>(st.total_free_bytes) : 0.0;
+  return st;
+}
+
+size_t RangeAllocator::get_free_space(StorageClass sc) const {
+  size_t total = 0;
+  std::shared_lock<std::shared_mutex> lk(pools_mu_);
+  for (const auto& [id, pa] : pool_allocators_)
+    if (pa->storage_class() == sc) total += pa->total_free();
+  return total;
+}
+
+bool RangeAllocator::can_allocate(const AllocationRequest& req, const PoolMap& pools) const {
+  if (req.replication_factor == 0 || req.max_workers_per_copy == 0 || pools.empty()) return false;
+  bool spill = false;
+  auto cands = rank_candidates(req, pools, &spill);
+  if (cands.empty()) return false;
+  // only preferred classes count (reference test "can_allocate class filter")
+  uint64_t total = 0;
+  size_t usable = 0;
+  for (const auto& c : cands) {
+    if (!c.preferred) continue;
+    total += c.free_bytes;
+    ++usable;
+  }
+  if (usable == 0) return false;
+  const uint64_t need = static_cast<uint64_t>(req.data_size) * req.replication_factor;
+  return total >= need;
+}
+
+void RangeAllocator::forget_pool(const MemoryPoolId& id) {
+  std::unique_lock<std::shared_mutex> lk(pools_mu_);
+  pool_allocators_.erase(id);
+}
+
+size_t RangeAllocator::pool_used_bytes(const MemoryPoolId& id) const {
+  std::shared_lock<std::shared_mutex> lk(alloc_mu_);
+  auto it = used_by_pool_.find(id);
+  return it == used_by_pool_.end() ? 0 : it->second;
+}
+
+std::vector<ObjectKey> RangeAllocator::objects_on_pool(const MemoryPoolId& id) const {
+  std::vector<ObjectKey> v;
+  std::shared_lock<std::shared_mutex> lk(alloc_mu_);
+  for (const auto& [key, oa] : objects_)
+    for (const auto& e : oa.extents)
+      if (e.pool == id) {
+        v.push_back(key);
+        break;
+      }
+  return v;
+}
+
+// ================================================================ factory / adapter
+std::unique_ptr<IAllocator> AllocatorFactory::create(Strategy) { return std::make_unique<RangeAllocator>(); }
+std::unique_ptr<IAllocator> AllocatorFactory::create_range_based() { return std::make_unique<RangeAllocator>(); }
+
+KeystoneAllocatorAdapter::KeystoneAllocatorAdapter(std::unique_ptr<IAllocator> allocator) : allocator_(std::move(allocator)) {}
+
+AllocationRequest KeystoneAllocatorAdapter::to_request(const ObjectKey& key, size_t data_size, const WorkerConfig& c) {
+  AllocationRequest r;
+  r.object_key = key;
+  r.data_size = data_size;
+  r.replication_factor = c.replication_factor;
+  r.max_workers_per_copy = c.max_workers_per_copy;
+  r.preferred_classes = c.preferred_classes;
+  r.preferred_node = c.preferred_node;
+  r.enable_locality_awareness = c.enable_locality_awareness;
+  r.enable_striping = c.max_workers_per_copy > 1;
+  r.prefer_contiguous = c.prefer_contiguous;
+  r.min_shard_size = c.min_shard_size;
+  r.symmetric_replicas = c.symmetric_replicas;
+  return r;
+}
+
+Result<std::vector<CopyPlacement>> KeystoneAllocatorAdapter::allocate_data_copies(const ObjectKey& key, size_t data_size,
+                                                                                  const WorkerConfig& config,
+                                                                                  const IAllocator::PoolMap& pools,
+                                                                                  const std::string& client_node,
+                                                                                  const std::vector<MemoryPoolId>& exclude) {
+  AllocationRequest r = to_request(key, data_size, config);
+  r.client_node = client_node;
+  r.exclude_pools = exclude;
+  auto res = allocator_->allocate(r, pools);
+  if (!res.ok()) return res.error();
+  return std::move(res.value().copies);
+}
+
+ErrorCode KeystoneAllocatorAdapter::free_object(const ObjectKey& key) { return allocator_->free(key); }
+
+AllocatorStats KeystoneAllocatorAdapter::get_allocator_stats(std::optional<StorageClass> sc) const { return allocator_->get_stats(sc); }
+
+Result<bool> KeystoneAllocatorAdapter::can_allocate_object(size_t data_size, const WorkerConfig& config,
+                                                           const IAllocator::PoolMap& pools) const {
+  if (config.replication_factor == 0 || config.max_workers_per_copy == 0) return ErrorCode::INVALID_PARAMETERS;
+  return allocator_->can_allocate(to_request("probe", data_size, config), pools);
+}
+
+}  // namespace bb::alloc

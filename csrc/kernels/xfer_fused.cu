@@ -28,7 +28,10 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "common/checksum.h"
 #include "common/tchash_def.h"
@@ -483,26 +486,45 @@ int xfer_smem_bytes(int algo) {
 
 uint32_t crc_unpad_for(uint64_t nbytes) {
   // x^(-8*pad) mod P where pad = zero bytes appended to reach a whole number of tiles.
-  const uint64_t pad = (kTileBytes - (nbytes % kTileBytes)) % kTileBytes;
-  // x^-1 in reflected form: reverse one bit-step of the LFSR applied to "1" (0x80000000).
-  // inv(x): find v with v * x == 1.  One forward step maps v -> (v>>1) ^ (v&1 ? P : 0).
-  // Reverse step of value 0x80000000: top bit set => came from ((b ^ P) << 1) | 1.
+  // Memoised per pad value (pad < 16384): batches of equal-size objects pay one table hit.
+  const uint32_t pad = static_cast<uint32_t>((kTileBytes - (nbytes % kTileBytes)) % kTileBytes);
+  static std::mutex mu;
+  static std::vector<uint32_t> cache(kTileBytes, 0);  // 0 is never a valid power of x
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache[pad]) return cache[pad];
+  }
+  // x^-1 in reflected form: reverse one LFSR bit-step.  Forward: v -> (v>>1) ^ (v&1 ? P : 0);
+  // a set top bit means the step XORed P in, so v_prev = ((v ^ P) << 1) | 1.
   static const uint32_t xinv8 = [] {
     uint32_t v = 0x80000000u;  // 1
     for (int i = 0; i < 8; ++i) v = (v & 0x80000000u) ? (((v ^ 0x82F63B78u) << 1) | 1u) : (v << 1);
     return v;  // x^-8
   }();
   uint32_t result = 0x80000000u, base = xinv8;
-  uint64_t e = pad;
-  while (e) {
+  for (uint32_t e = pad; e; e >>= 1) {
     if (e & 1) result = gf2_mulmod(result, base);
     base = gf2_mulmod(base, base);
-    e >>= 1;
   }
+  std::lock_guard<std::mutex> lk(mu);
+  cache[pad] = result;
   return result;
 }
 
-uint32_t crc_init_term_for(uint64_t nbytes) { return gf2_mulmod(0xFFFFFFFFu, gf2_xpow_bytes(nbytes)); }
+uint32_t crc_init_term_for(uint64_t nbytes) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, uint32_t> cache;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(nbytes);
+    if (it != cache.end()) return it->second;
+  }
+  const uint32_t v = gf2_mulmod(0xFFFFFFFFu, gf2_xpow_bytes(nbytes));
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(nbytes, v);
+  return v;
+}
 
 int launch_xfer(const XferLaunch& l) {
   if (l.ndesc == 0 || l.total_tiles == 0) return 0;
@@ -555,7 +577,10 @@ int launch_xfer(const XferLaunch& l) {
   p.status_out = l.status_out;
   p.crc_tables = ds.crc_tables;
   p.debug_d = l.debug_d;
-  int grid = l.max_ctas > 0 ? l.max_ctas : ds.sm_count;
+  // Measured on B200 (profiles/xfer_single_gpu.md): 96-128 persistent CTAs saturate HBM for
+  // large batches (3.2 TB/s payload); all 148 lose ~6% to DRAM contention.  BB_XFER_CTAS overrides.
+  static const int env_ctas = [] { const char* e = std::getenv("BB_XFER_CTAS"); return e ? std::atoi(e) : 0; }();
+  int grid = l.max_ctas > 0 ? l.max_ctas : env_ctas > 0 ? env_ctas : std::min(ds.sm_count, 128);
   grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(grid), l.total_tiles));
   cudaStream_t st = static_cast<cudaStream_t>(l.stream);
   switch (l.algo) {
