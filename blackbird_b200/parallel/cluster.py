@@ -1,0 +1,183 @@
+"""Cluster bootstrap helpers.
+
+LocalCluster   : in-process Keystone (+ optional RPC/HTTP endpoints) with N workers — the
+                 plumbing configuration of BASELINE config #1, also used by tests.
+GpuRankCluster : one process per GPU (torchrun).  Rank 0 hosts the Keystone; every rank runs a
+                 GPU-tier worker whose HBM slab is exported to all peers over CUDA IPC, plus a
+                 client with the fused-kernel device transport.
+"""
+from __future__ import annotations
+
+import os
+import socket
+from typing import Optional
+
+from .. import _bb
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class LocalCluster:
+    def __init__(self, cluster_id: str = "local", n_workers: int = 2, pool_bytes: int = 64 << 20,
+                 storage_class=None, serve_rpc: bool = True, coord: Optional[str] = None,
+                 keystone_cfg: Optional["_bb.KeystoneConfig"] = None, lease_ttl_sec: int = 3,
+                 heartbeat_interval_sec: int = 1, mount_path: str = ""):
+        self.cluster_id = cluster_id
+        cfg = keystone_cfg or _bb.KeystoneConfig()
+        cfg.cluster_id = cluster_id
+        cfg.listen_address = "127.0.0.1:0"
+        cfg.http_metrics_port = "0"
+        self.cfg = cfg
+        self.coord_uri = coord if coord is not None else f"mem://{cluster_id}-{os.getpid()}-{id(self)}"
+        self.coord = _bb.CoordService(self.coord_uri)
+        assert self.coord.connect() == _bb.ErrorCode.OK
+        self.keystone = _bb.KeystoneService(cfg, self.coord)
+        assert self.keystone.initialize() == _bb.ErrorCode.OK
+        assert self.keystone.start() == _bb.ErrorCode.OK
+        self.rpc = None
+        if serve_rpc:
+            self.rpc = _bb.RpcService(self.keystone, cfg)
+            assert self.rpc.start() == _bb.ErrorCode.OK
+        self.workers = []
+        sc = storage_class if storage_class is not None else _bb.StorageClass.RAM_CPU
+        for i in range(n_workers):
+            self.add_worker(f"worker-{i}", f"node-{i}", [(f"pool-{i}", sc, pool_bytes, mount_path)],
+                            lease_ttl_sec, heartbeat_interval_sec)
+
+    def add_worker(self, worker_id, node_id, pools, lease_ttl_sec=3, heartbeat_interval_sec=1, fabric_domain=""):
+        wc = _bb.WorkerServiceConfig()
+        wc.worker_id = worker_id
+        wc.node_id = node_id
+        wc.cluster_id = self.cluster_id
+        wc.ucx_endpoint = "127.0.0.1:0"
+        wc.lease_ttl_sec = lease_ttl_sec
+        wc.heartbeat_interval_sec = heartbeat_interval_sec
+        wc.fabric_domain = fabric_domain
+        wc.storage_pools = [_bb.StoragePoolConfig(pid, sc, size, mp) for (pid, sc, size, mp) in pools]
+        w = _bb.WorkerService(wc, _bb.CoordService(self.coord_uri))
+        assert w.create_storage_pools_from_config() == _bb.ErrorCode.OK, "backend creation failed"
+        assert w.initialize() == _bb.ErrorCode.OK
+        assert w.start() == _bb.ErrorCode.OK
+        self.workers.append(w)
+        self.coord.store().flush_events()
+        return w
+
+    def client(self, node_id: str = "", io_parallelism: int = 4, in_process: bool = False):
+        if in_process or self.rpc is None:
+            c = _bb.BlackbirdClient(_bb.LocalKeystoneApi(self.keystone), _bb.BlackbirdClientOptions(node_id=node_id, io_parallelism=io_parallelism))
+        else:
+            c = _bb.BlackbirdClient(_bb.BlackbirdClientOptions("127.0.0.1", self.rpc.rpc_port, 30000, io_parallelism, node_id))
+        assert c.connect() == _bb.ErrorCode.OK
+        return c
+
+    def stop(self):
+        for w in self.workers:
+            w.stop()
+        self.workers = []
+        if self.rpc is not None:
+            self.rpc.stop()
+        self.keystone.stop()
+        if self.coord_uri.startswith("mem://"):
+            _bb.drop_shared_mem_coord(self.coord_uri[len("mem://"):])
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.stop()
+
+
+class GpuRankCluster:
+    """One process per GPU.  Requires torch + CUDA; rendezvous through torch.distributed when world>1."""
+
+    def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dist = dist if self.world > 1 else None
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        _bb.install_gpu_backend_factory()
+        self.node_id = f"gpu{self.rank}"
+        self.keystone = None
+        self.rpc = None
+        port_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if self.rank == 0:
+            cfg = _bb.KeystoneConfig()
+            cfg.cluster_id = cluster_id
+            cfg.listen_address = f"127.0.0.1:{keystone_port or 0}"
+            cfg.http_metrics_port = "0"
+            cfg.enable_gc = False
+            cfg.high_watermark = 1.0
+            cfg.rpc_threads = 4
+            self.keystone = _bb.KeystoneService(cfg, None)
+            assert self.keystone.initialize() == _bb.ErrorCode.OK
+            assert self.keystone.start() == _bb.ErrorCode.OK
+            self.rpc = _bb.RpcService(self.keystone, cfg)
+            assert self.rpc.start() == _bb.ErrorCode.OK
+            port_t[0] = self.rpc.rpc_port
+        if self.world > 1:
+            dist.broadcast(port_t, 0)
+        self.keystone_port = int(port_t.item())
+        if self.rank == 0:
+            self.api = _bb.LocalKeystoneApi(self.keystone)
+        else:
+            self.api = _bb.KeystoneRpcClient()
+            assert self.api.connect("127.0.0.1", self.keystone_port, 10000) == _bb.ErrorCode.OK
+        # worker: one GPU-tier pool on this rank's device, registered directly with the keystone
+        wc = _bb.WorkerServiceConfig()
+        wc.worker_id = f"worker-gpu{self.rank}"
+        wc.node_id = self.node_id
+        wc.cluster_id = cluster_id
+        wc.ucx_endpoint = "127.0.0.1:0"
+        wc.interconnects = ["nvlink", "tcp"]
+        wc.max_bw_gbps = 7200.0
+        wc.fabric_domain = "nvswitch-0"
+        wc.lease_ttl_sec = 30
+        wc.heartbeat_interval_sec = 5
+        wc.storage_pools = [_bb.StoragePoolConfig(f"hbm{self.rank}", _bb.StorageClass.RAM_GPU, slab_bytes, "", self.local_rank)]
+        self.worker = _bb.WorkerService(wc, None, self.api)
+        assert self.worker.create_storage_pools_from_config() == _bb.ErrorCode.OK
+        assert self.worker.initialize() == _bb.ErrorCode.OK
+        assert self.worker.start() == _bb.ErrorCode.OK
+        self.barrier()
+        opts = _bb.BlackbirdClientOptions("127.0.0.1", self.keystone_port, 60000, 4, self.node_id)
+        self.client_api = self.api if self.rank == 0 else self._new_api()
+        self.client = _bb.BlackbirdClient(self.client_api, opts)
+        assert self.client.connect() == _bb.ErrorCode.OK
+        self.fabric = _bb.GpuFabric(self.local_rank, self.client_api)
+        assert self.fabric.mapped_pools() == self.world, f"mapped {self.fabric.mapped_pools()} of {self.world} slabs"
+        _bb.attach_fabric(self.client, self.fabric)
+        self.barrier()
+
+    def _new_api(self):
+        api = _bb.KeystoneRpcClient()
+        assert api.connect("127.0.0.1", self.keystone_port, 10000) == _bb.ErrorCode.OK
+        return api
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def stop(self):
+        self.barrier()
+        self.client = None
+        self.fabric = None
+        self.worker.stop()
+        self.barrier()
+        if self.rpc is not None:
+            self.rpc.stop()
+        if self.keystone is not None:
+            self.keystone.stop()

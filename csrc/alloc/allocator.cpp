@@ -539,6 +539,39 @@ std::vector<ObjectKey> RangeAllocator::objects_on_pool(const MemoryPoolId& id) c
   return v;
 }
 
+ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools) {
+  ObjectAllocation oa;
+  for (const auto& c : copies)
+    for (const auto& s : c.shards) {
+      auto pit = pools.find(s.pool_id);
+      if (pit == pools.end()) continue;
+      PoolAllocator* pa = ensure_pool(pit->second);
+      uint64_t off = 0;
+      if (auto* g = std::get_if<GpuSlabLocation>(&s.location)) off = g->offset;
+      else if (auto* f = std::get_if<FileLocation>(&s.location)) off = f->file_offset;
+      else if (auto* x = std::get_if<CxlMemoryLocation>(&s.location)) off = x->offset;
+      else if (auto* m = std::get_if<MemoryLocation>(&s.location)) {
+        const uint64_t base = pit->second.ucx_remote_addr ? pit->second.ucx_remote_addr : pit->second.base_addr;
+        off = m->remote_addr >= base ? m->remote_addr - base : 0;
+      }
+      if (!pa->allocate_at(off, s.length)) {
+        BB_LOG(WARNING) << "adopt: extent of " << key << " on " << s.pool_id << " is no longer free";
+        continue;
+      }
+      oa.extents.push_back({s.pool_id, Range(off, pa->aligned(s.length)), s.length});
+      oa.total_size += s.length;
+    }
+  std::unique_lock<std::shared_mutex> lk(alloc_mu_);
+  if (objects_.count(key)) {
+    lk.unlock();
+    rollback(oa.extents);
+    return ErrorCode::OBJECT_ALREADY_EXISTS;
+  }
+  for (const auto& e : oa.extents) used_by_pool_[e.pool] += e.range.length;
+  objects_.emplace(key, std::move(oa));
+  return ErrorCode::OK;
+}
+
 // ================================================================ factory / adapter
 std::unique_ptr<IAllocator> AllocatorFactory::create(Strategy) { return std::make_unique<RangeAllocator>(); }
 std::unique_ptr<IAllocator> AllocatorFactory::create_range_based() { return std::make_unique<RangeAllocator>(); }

@@ -156,6 +156,9 @@ class RangeAllocator : public IAllocator {
   void forget_pool(const MemoryPoolId& id) override;
   size_t pool_used_bytes(const MemoryPoolId& id) const override;
   std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const override;
+  // Re-reserves the exact extents of already placed copies (metadata recovery after a leader
+  // change).  Extents on unknown pools are skipped.
+  ErrorCode adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools);
 
  private:
   struct Extent {

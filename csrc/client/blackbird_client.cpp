@@ -1,0 +1,557 @@
+#include "client/blackbird_client.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <future>
+#include <thread>
+
+#include "common/log.h"
+#include "rpc/wire.h"
+#include "worker/worker_service.h"
+
+namespace bb::client {
+
+using keystone::PutStartItem;
+using keystone::ShardChecksums;
+
+namespace {
+double us_since(TimePoint t0) { return std::chrono::duration<double, std::micro>(Clock::now() - t0).count(); }
+
+// Runs fn(i) for i in [0, n) on up to `par` threads; returns the first error.
+template <typename F>
+ErrorCode parallel_for(size_t n, size_t par, F&& fn) {
+  if (n == 0) return ErrorCode::OK;
+  par = std::max<size_t>(1, std::min(par, n));
+  if (par == 1) {
+    for (size_t i = 0; i < n; ++i) {
+      ErrorCode ec = fn(i);
+      if (ec != ErrorCode::OK) return ec;
+    }
+    return ErrorCode::OK;
+  }
+  std::atomic<size_t> next{0};
+  std::atomic<uint32_t> first_err{0};
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < par; ++t)
+    th.emplace_back([&] {
+      while (first_err.load() == 0) {
+        const size_t i = next.fetch_add(1);
+        if (i >= n) break;
+        ErrorCode ec = fn(i);
+        if (ec != ErrorCode::OK) {
+          uint32_t z = 0;
+          first_err.compare_exchange_strong(z, static_cast<uint32_t>(ec));
+        }
+      }
+    });
+  for (auto& t : th) t.join();
+  return static_cast<ErrorCode>(first_err.load());
+}
+}  // namespace
+
+BlackbirdClient::BlackbirdClient(BlackbirdClientOptions opts) : opts_(std::move(opts)) {}
+BlackbirdClient::BlackbirdClient(std::shared_ptr<rpc::KeystoneApi> keystone, BlackbirdClientOptions opts)
+    : opts_(std::move(opts)), keystone_(std::move(keystone)) {
+  if (keystone_) keystone_->set_identity(session_id_, opts_.node_id);
+}
+BlackbirdClient::~BlackbirdClient() = default;
+
+ErrorCode BlackbirdClient::connect() {
+  if (!keystone_) {
+    auto c = std::make_shared<rpc::KeystoneRpcClient>();
+    c->set_timeout_ms(opts_.rpc_timeout_ms);
+    ErrorCode ec = c->connect(opts_.keystone_host, opts_.keystone_port, std::min(opts_.rpc_timeout_ms, 5000));
+    if (ec != ErrorCode::OK) return ec;
+    keystone_ = c;
+  }
+  if (opts_.register_session) {
+    auto s = keystone_->client_register(opts_.node_id);
+    if (!s.ok()) return s.error();
+    session_id_ = s.value();
+  }
+  keystone_->set_identity(session_id_, opts_.node_id);
+  return ErrorCode::OK;
+}
+
+// ================================================================ worker connections
+std::shared_ptr<net::RpcClient> BlackbirdClient::acquire(const std::string& endpoint) {
+  {
+    std::lock_guard<std::mutex> lk(conn_mu_);
+    auto& v = idle_conns_[endpoint];
+    if (!v.empty()) {
+      auto c = v.back();
+      v.pop_back();
+      return c;
+    }
+  }
+  auto hp = split_host_port(endpoint);
+  if (!hp) return nullptr;
+  auto c = std::make_shared<net::RpcClient>();
+  if (c->connect(hp->first, static_cast<uint16_t>(hp->second), std::min(opts_.rpc_timeout_ms, 5000)) != ErrorCode::OK) return nullptr;
+  return c;
+}
+
+void BlackbirdClient::release(const std::string& endpoint, std::shared_ptr<net::RpcClient> c) {
+  if (!c || !c->connected()) return;
+  std::lock_guard<std::mutex> lk(conn_mu_);
+  auto& v = idle_conns_[endpoint];
+  if (v.size() < 16) v.push_back(std::move(c));
+}
+
+uint64_t BlackbirdClient::shard_offset(const ShardPlacement& s) {
+  if (auto* g = std::get_if<GpuSlabLocation>(&s.location)) return g->offset;
+  if (auto* f = std::get_if<FileLocation>(&s.location)) return f->file_offset;
+  if (auto* c = std::get_if<CxlMemoryLocation>(&s.location)) return c->offset;
+  return 0;
+}
+
+ErrorCode BlackbirdClient::write_shard(const ShardPlacement& s, const uint8_t* src, uint64_t* digest, ChecksumAlgo algo) {
+  const std::string ep = s.endpoint.ip + ":" + std::to_string(s.endpoint.port);
+  uint64_t base_off = shard_offset(s);
+  bool absolute = false;
+  if (auto* m = std::get_if<MemoryLocation>(&s.location)) {
+    base_off = m->remote_addr;  // absolute address; the worker subtracts its base
+    absolute = true;
+  }
+  uint64_t dig_crc = 0;
+  constexpr uint64_t kChunk = 8ull << 20;
+  auto conn = acquire(ep);
+  if (!conn) return ErrorCode::CONNECTION_FAILED;
+  for (uint64_t pos = 0; pos < s.length || (s.length == 0 && pos == 0); pos += kChunk) {
+    const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, s.length - pos));
+    wire::Writer w;
+    w.str(s.pool_id);
+    w.u64((base_off + pos) | (absolute ? (1ull << 63) : 0));
+    w.u32(n);
+    w.raw(src + pos, n);
+    auto r = conn->call(worker::D_WRITE, w.data(), opts_.rpc_timeout_ms);
+    if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+    wire::Reader rd(r.value());
+    const ErrorCode ec = rd.ec();
+    if (ec != ErrorCode::OK) {
+      release(ep, conn);
+      return ec;
+    }
+    if (algo == ChecksumAlgo::CRC32C) dig_crc = crc32c(src + pos, n, static_cast<uint32_t>(dig_crc));
+    if (s.length == 0) break;
+  }
+  release(ep, conn);
+  if (digest) *digest = algo == ChecksumAlgo::CRC32C ? dig_crc : algo == ChecksumAlgo::BBH64 ? bbh64(src, s.length) : 0;
+  return ErrorCode::OK;
+}
+
+ErrorCode BlackbirdClient::read_shard(const ShardPlacement& s, uint8_t* dst, ChecksumAlgo algo) {
+  const std::string ep = s.endpoint.ip + ":" + std::to_string(s.endpoint.port);
+  uint64_t base_off = shard_offset(s);
+  bool absolute = false;
+  if (auto* m = std::get_if<MemoryLocation>(&s.location)) {
+    base_off = m->remote_addr;
+    absolute = true;
+  }
+  constexpr uint64_t kChunk = 8ull << 20;
+  auto conn = acquire(ep);
+  if (!conn) return ErrorCode::CONNECTION_FAILED;
+  for (uint64_t pos = 0; pos < s.length; pos += kChunk) {
+    const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, s.length - pos));
+    wire::Writer w;
+    w.str(s.pool_id);
+    w.u64((base_off + pos) | (absolute ? (1ull << 63) : 0));
+    w.u32(n);
+    auto r = conn->call(worker::D_READ, w.data(), opts_.rpc_timeout_ms);
+    if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+    const std::string& resp = r.value();
+    if (resp.size() < 4) return ErrorCode::TRANSFER_FAILED;
+    uint32_t e;
+    std::memcpy(&e, resp.data(), 4);
+    if (e != 0) {
+      release(ep, conn);
+      return static_cast<ErrorCode>(e);
+    }
+    if (resp.size() != 4 + static_cast<size_t>(n)) return ErrorCode::TRANSFER_FAILED;
+    std::memcpy(dst + pos, resp.data() + 4, n);
+  }
+  release(ep, conn);
+  if (algo != ChecksumAlgo::NONE && s.checksum_algo == algo) {
+    const uint64_t got = checksum(algo, dst, s.length);
+    if (got != s.checksum) {
+      metrics_.inc("checksum_mismatch_total");
+      return ErrorCode::CHECKSUM_MISMATCH;
+    }
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode BlackbirdClient::transfer_put(const std::vector<CopyPlacement>& copies, const uint8_t* data, ChecksumAlgo algo,
+                                        ShardChecksums* sums) {
+  struct Job {
+    size_t c, s;
+    uint64_t off;
+  };
+  std::vector<Job> jobs;
+  sums->assign(copies.size(), {});
+  for (size_t c = 0; c < copies.size(); ++c) {
+    uint64_t off = 0;
+    (*sums)[c].assign(copies[c].shards.size(), 0);
+    for (size_t s = 0; s < copies[c].shards.size(); ++s) {
+      jobs.push_back({c, s, off});
+      off += copies[c].shards[s].length;  // the source offset is the running shard offset (bug #8)
+    }
+  }
+  return parallel_for(jobs.size(), opts_.io_parallelism, [&](size_t i) {
+    const Job& j = jobs[i];
+    return write_shard(copies[j.c].shards[j.s], data + j.off, &(*sums)[j.c][j.s], algo);
+  });
+}
+
+ErrorCode BlackbirdClient::transfer_get(const std::vector<CopyPlacement>& copies, uint8_t* dst, size_t size) {
+  ErrorCode last = ErrorCode::NO_COMPLETE_WORKER;
+  for (const auto& copy : copies) {  // replica fail-over (reference reads copy 0 only, :283-287)
+    uint64_t total = 0;
+    for (const auto& s : copy.shards) total += s.length;
+    if (total != size) {
+      last = ErrorCode::DATA_CORRUPTION;
+      continue;
+    }
+    std::vector<uint64_t> offs(copy.shards.size());
+    uint64_t off = 0;
+    for (size_t s = 0; s < copy.shards.size(); ++s) {
+      offs[s] = off;
+      off += copy.shards[s].length;
+    }
+    last = parallel_for(copy.shards.size(), opts_.io_parallelism, [&](size_t s) {
+      return read_shard(copy.shards[s], dst + offs[s], copy.shards[s].checksum_algo);
+    });
+    if (last == ErrorCode::OK) return ErrorCode::OK;
+    metrics_.inc("replica_failover_total");
+    BB_LOG(WARNING) << "get: copy " << copy.copy_index << " failed with " << to_string(last) << ", trying next replica";
+  }
+  return last;
+}
+
+// ================================================================ reference API
+Result<bool> BlackbirdClient::object_exists(const ObjectKey& key) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  return keystone_->object_exists(key);
+}
+
+Result<std::vector<CopyPlacement>> BlackbirdClient::get_workers(const ObjectKey& key) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  return keystone_->get_workers(key);
+}
+
+ErrorCode BlackbirdClient::put(const ObjectKey& key, const uint8_t* data, size_t size, const WorkerConfig& cfg) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  if (!data && size) return ErrorCode::INVALID_PARAMETERS;
+  const TimePoint t0 = Clock::now();
+  auto placed = keystone_->put_start(key, size, cfg);
+  if (!placed.ok()) return placed.error();
+  ShardChecksums sums;
+  ErrorCode ec = transfer_put(placed.value(), data, cfg.checksum, &sums);
+  if (ec != ErrorCode::OK) {
+    keystone_->put_cancel(key);
+    metrics_.inc("put_failed_total");
+    return ec;
+  }
+  ec = keystone_->put_complete(key, sums);
+  if (ec == ErrorCode::OK) {
+    metrics_.inc("put_total");
+    metrics_.inc("put_bytes_total", size);
+    metrics_.observe("put_latency_us", us_since(t0));
+  }
+  return ec;
+}
+
+Result<std::vector<uint8_t>> BlackbirdClient::get(const ObjectKey& key) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  const TimePoint t0 = Clock::now();
+  auto copies = keystone_->get_workers(key);
+  if (!copies.ok()) return copies.error();
+  if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
+  size_t size = 0;
+  for (const auto& s : copies.value().front().shards) size += s.length;
+  std::vector<uint8_t> buf(size);
+  ErrorCode ec = transfer_get(copies.value(), buf.data(), size);
+  if (ec != ErrorCode::OK) return ec;
+  metrics_.inc("get_total");
+  metrics_.inc("get_bytes_total", size);
+  metrics_.observe("get_latency_us", us_since(t0));
+  return buf;
+}
+
+ErrorCode BlackbirdClient::get_into(const ObjectKey& key, void* buf, size_t capacity, size_t* out_size) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  auto copies = keystone_->get_workers(key);
+  if (!copies.ok()) return copies.error();
+  if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
+  size_t size = 0;
+  for (const auto& s : copies.value().front().shards) size += s.length;
+  if (out_size) *out_size = size;
+  if (size > capacity) return ErrorCode::BUFFER_OVERFLOW;
+  return transfer_get(copies.value(), static_cast<uint8_t*>(buf), size);
+}
+
+ErrorCode BlackbirdClient::remove(const ObjectKey& key) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  return keystone_->remove_object(key);
+}
+
+Result<ClusterStats> BlackbirdClient::cluster_stats() {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  return keystone_->get_cluster_stats();
+}
+
+// ================================================================ batched host API
+std::vector<ErrorCode> BlackbirdClient::batch_put(const std::vector<ObjectKey>& keys, const std::vector<const uint8_t*>& data,
+                                                  const std::vector<size_t>& sizes, const WorkerConfig& cfg) {
+  std::vector<ErrorCode> out(keys.size(), ErrorCode::INVALID_PARAMETERS);
+  if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
+  if (data.size() != keys.size() || sizes.size() != keys.size()) return out;
+  std::vector<PutStartItem> items(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) items[i] = PutStartItem{keys[i], sizes[i], cfg};
+  auto placed = keystone_->batch_put_start(items);  // ONE control-plane round trip for the batch
+  std::vector<ShardChecksums> sums(keys.size());
+  std::vector<ObjectKey> done_keys, cancel_keys;
+  std::vector<ShardChecksums> done_sums;
+  std::vector<size_t> done_idx;
+  parallel_for(keys.size(), opts_.io_parallelism, [&](size_t i) {
+    if (!placed[i].ok()) {
+      out[i] = placed[i].error();
+      return ErrorCode::OK;
+    }
+    out[i] = transfer_put(placed[i].value(), data[i], cfg.checksum, &sums[i]);
+    return ErrorCode::OK;
+  });
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!placed[i].ok()) continue;
+    if (out[i] == ErrorCode::OK) {
+      done_keys.push_back(keys[i]);
+      done_sums.push_back(std::move(sums[i]));
+      done_idx.push_back(i);
+    } else {
+      cancel_keys.push_back(keys[i]);
+    }
+  }
+  if (!cancel_keys.empty()) keystone_->batch_put_cancel(cancel_keys);
+  if (!done_keys.empty()) {
+    auto ecs = keystone_->batch_put_complete(done_keys, done_sums);
+    for (size_t k = 0; k < done_idx.size(); ++k) out[done_idx[k]] = ecs[k];
+  }
+  return out;
+}
+
+std::vector<Result<std::vector<uint8_t>>> BlackbirdClient::batch_get(const std::vector<ObjectKey>& keys) {
+  std::vector<Result<std::vector<uint8_t>>> out(keys.size(), Result<std::vector<uint8_t>>(ErrorCode::CLIENT_DISCONNECTED));
+  if (!keystone_) return out;
+  auto placed = keystone_->batch_get_workers(keys);
+  parallel_for(keys.size(), opts_.io_parallelism, [&](size_t i) {
+    if (!placed[i].ok()) {
+      out[i] = placed[i].error();
+      return ErrorCode::OK;
+    }
+    if (placed[i].value().empty()) {
+      out[i] = ErrorCode::NO_COMPLETE_WORKER;
+      return ErrorCode::OK;
+    }
+    size_t size = 0;
+    for (const auto& s : placed[i].value().front().shards) size += s.length;
+    std::vector<uint8_t> buf(size);
+    ErrorCode ec = transfer_get(placed[i].value(), buf.data(), size);
+    if (ec == ErrorCode::OK) out[i] = std::move(buf);
+    else out[i] = ec;
+    return ErrorCode::OK;
+  });
+  return out;
+}
+
+std::vector<ErrorCode> BlackbirdClient::batch_remove(const std::vector<ObjectKey>& keys) {
+  if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
+  return keystone_->batch_remove_object(keys);
+}
+
+std::vector<Result<bool>> BlackbirdClient::batch_exists(const std::vector<ObjectKey>& keys) {
+  if (!keystone_) return std::vector<Result<bool>>(keys.size(), Result<bool>(ErrorCode::CLIENT_DISCONNECTED));
+  return keystone_->batch_object_exists(keys);
+}
+
+// ================================================================ batched device API
+std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<ObjectKey>& keys, const std::vector<const void*>& dev_ptrs,
+                                                         const std::vector<size_t>& sizes, const WorkerConfig& cfg, void* stream) {
+  std::vector<ErrorCode> out(keys.size(), ErrorCode::INVALID_PARAMETERS);
+  if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
+  if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
+  if (dev_ptrs.size() != keys.size() || sizes.size() != keys.size()) return out;
+  const TimePoint t0 = Clock::now();
+  std::vector<PutStartItem> items(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) items[i] = PutStartItem{keys[i], sizes[i], cfg};
+  auto placed = keystone_->batch_put_start(items);
+  // One descriptor per (object, shard): copy 0's placement plus the same shard of every other
+  // copy as extra destinations, so the kernel reads the source once and fans out.
+  std::vector<DeviceShardOp> ops;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!placed[i].ok()) {
+      out[i] = placed[i].error();
+      continue;
+    }
+    out[i] = ErrorCode::OK;
+    const auto& copies = placed[i].value();
+    if (copies.empty()) continue;
+    bool same_layout = true;
+    for (const auto& c : copies) same_layout &= c.shards.size() == copies[0].shards.size();
+    uint64_t off = 0;
+    for (size_t s = 0; s < copies[0].shards.size(); ++s) {
+      if (same_layout) {
+        DeviceShardOp op;
+        op.item = i;
+        op.copy = 0;
+        op.shard = s;
+        op.placement = &copies[0].shards[s];
+        op.obj_offset = off;
+        for (size_t c = 1; c < copies.size(); ++c) op.replicas.push_back(&copies[c].shards[s]);
+        ops.push_back(std::move(op));
+      }
+      off += copies[0].shards[s].length;
+    }
+    if (!same_layout) {
+      for (size_t c = 0; c < copies.size(); ++c) {
+        uint64_t o2 = 0;
+        for (size_t s = 0; s < copies[c].shards.size(); ++s) {
+          DeviceShardOp op;
+          op.item = i;
+          op.copy = c;
+          op.shard = s;
+          op.placement = &copies[c].shards[s];
+          op.obj_offset = o2;
+          ops.push_back(std::move(op));
+          o2 += copies[c].shards[s].length;
+        }
+      }
+    }
+  }
+  std::vector<uint64_t> digests;
+  ErrorCode ec = device_->put_shards(ops, dev_ptrs, cfg.checksum, stream, &digests);
+  std::vector<ObjectKey> done_keys, cancel_keys;
+  std::vector<ShardChecksums> done_sums;
+  std::vector<size_t> done_idx;
+  if (ec != ErrorCode::OK) {
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (placed[i].ok()) {
+        out[i] = ec;
+        cancel_keys.push_back(keys[i]);
+      }
+  } else {
+    std::vector<ShardChecksums> sums(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (placed[i].ok()) {
+        sums[i].resize(placed[i].value().size());
+        for (size_t c = 0; c < sums[i].size(); ++c) sums[i][c].assign(placed[i].value()[c].shards.size(), 0);
+      }
+    for (size_t k = 0; k < ops.size(); ++k) {
+      const auto& op = ops[k];
+      sums[op.item][op.copy][op.shard] = digests[k];
+      for (size_t r = 0; r < op.replicas.size(); ++r) sums[op.item][r + 1][op.shard] = digests[k];
+    }
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (placed[i].ok()) {
+        done_keys.push_back(keys[i]);
+        done_sums.push_back(std::move(sums[i]));
+        done_idx.push_back(i);
+      }
+  }
+  if (!cancel_keys.empty()) keystone_->batch_put_cancel(cancel_keys);
+  if (!done_keys.empty()) {
+    auto ecs = keystone_->batch_put_complete(done_keys, done_sums);
+    for (size_t k = 0; k < done_idx.size(); ++k) out[done_idx[k]] = ecs[k];
+  }
+  metrics_.inc("device_put_batches_total");
+  metrics_.observe("device_put_batch_latency_us", us_since(t0));
+  return out;
+}
+
+std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<ObjectKey>& keys, const std::vector<void*>& dev_ptrs,
+                                                         const std::vector<size_t>& capacity, void* stream,
+                                                         std::vector<size_t>* out_sizes) {
+  std::vector<ErrorCode> out(keys.size(), ErrorCode::INVALID_PARAMETERS);
+  if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
+  if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
+  if (dev_ptrs.size() != keys.size() || capacity.size() != keys.size()) return out;
+  const TimePoint t0 = Clock::now();
+  auto placed = keystone_->batch_get_workers(keys);
+  if (out_sizes) out_sizes->assign(keys.size(), 0);
+  // choose for every object the first copy the fabric can reach; later passes retry failures
+  std::vector<size_t> copy_choice(keys.size(), 0);
+  std::vector<bool> pending(keys.size(), false);
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!placed[i].ok()) {
+      out[i] = placed[i].error();
+      continue;
+    }
+    if (placed[i].value().empty()) {
+      out[i] = ErrorCode::NO_COMPLETE_WORKER;
+      continue;
+    }
+    size_t size = 0;
+    for (const auto& s : placed[i].value()[0].shards) size += s.length;
+    if (out_sizes) (*out_sizes)[i] = size;
+    if (size > capacity[i]) {
+      out[i] = ErrorCode::BUFFER_OVERFLOW;
+      continue;
+    }
+    pending[i] = true;
+    // spread readers over replicas: different clients start at different copies
+    copy_choice[i] = std::hash<std::string>{}(opts_.node_id + keys[i]) % placed[i].value().size();
+  }
+  for (size_t attempt = 0; attempt < 4; ++attempt) {
+    std::vector<DeviceShardOp> ops;
+    for (size_t i = 0; i < keys.size(); ++i) {
+      if (!pending[i]) continue;
+      const auto& copies = placed[i].value();
+      const auto& copy = copies[copy_choice[i] % copies.size()];
+      uint64_t off = 0;
+      for (size_t s = 0; s < copy.shards.size(); ++s) {
+        DeviceShardOp op;
+        op.item = i;
+        op.copy = copy_choice[i] % copies.size();
+        op.shard = s;
+        op.placement = &copy.shards[s];
+        op.obj_offset = off;
+        ops.push_back(std::move(op));
+        off += copy.shards[s].length;
+      }
+    }
+    if (ops.empty()) break;
+    std::vector<uint32_t> status;
+    ErrorCode ec = device_->get_shards(ops, dev_ptrs, ChecksumAlgo::NONE /* per-shard algo from placement */, stream, &status);
+    std::vector<bool> bad(keys.size(), false);
+    if (ec != ErrorCode::OK) {
+      for (size_t i = 0; i < keys.size(); ++i)
+        if (pending[i]) out[i] = ec;
+      break;
+    }
+    for (size_t k = 0; k < ops.size(); ++k)
+      if (status[k] != 0) bad[ops[k].item] = true;
+    bool any_retry = false;
+    for (size_t i = 0; i < keys.size(); ++i) {
+      if (!pending[i]) continue;
+      if (!bad[i]) {
+        out[i] = ErrorCode::OK;
+        pending[i] = false;
+      } else {
+        metrics_.inc("checksum_mismatch_total");
+        if (attempt + 1 < placed[i].value().size()) {
+          ++copy_choice[i];  // fail over to the next replica
+          any_retry = true;
+        } else {
+          out[i] = ErrorCode::CHECKSUM_MISMATCH;
+          pending[i] = false;
+        }
+      }
+    }
+    if (!any_retry) break;
+  }
+  metrics_.inc("device_get_batches_total");
+  metrics_.observe("device_get_batch_latency_us", us_since(t0));
+  return out;
+}
+
+}  // namespace bb::client

@@ -1,0 +1,121 @@
+// BlackbirdClient: the SDK.
+//
+// Parity: reference include/blackbird/client/blackbird_client.h:22-139 — BlackbirdClientOptions
+// (keystone_host/port, rpc_timeout, io_parallelism), connect, object_exists, get_workers,
+// get(key) -> bytes, put(key, ptr, size, cfg), put(key, vector, cfg), remove.
+// New surface required by BASELINE.json: batch_put / batch_get for host buffers and for device
+// pointers (the fused NVLink kernel path, installed by fabric/gpu_fabric.h as a DeviceTransport).
+//
+// Behavioural fixes over the reference: rpc_timeout and io_parallelism are honoured (:204-205
+// ignores them); the source pointer of a shard is `data + running offset` (not `data +
+// remote_addr`, bug #8); connections to workers are cached instead of re-created per call;
+// every shard is checksummed and verified; reads fail over to the next replica; a failed put is
+// cancelled.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common/metrics.h"
+#include "net/tcp.h"
+#include "rpc/rpc_service.h"
+
+namespace bb::client {
+
+struct BlackbirdClientOptions {
+  std::string keystone_host = "127.0.0.1";
+  uint16_t keystone_port = 9090;
+  int rpc_timeout_ms = 30000;
+  size_t io_parallelism = 4;
+  std::string node_id;        // where this client runs (locality-aware placement)
+  bool register_session = false;
+};
+
+// One device-side transfer request of a batch (a shard).
+struct DeviceShardOp {
+  size_t item = 0;            // index of the object in the batch
+  size_t copy = 0, shard = 0;
+  const ShardPlacement* placement = nullptr;
+  std::vector<const ShardPlacement*> replicas;  // same shard on the other copies (put fan-out)
+  uint64_t obj_offset = 0;    // byte offset of this shard inside the object
+};
+
+// Implemented by the GPU fabric: moves shards between client device buffers and worker slabs
+// with the fused kernels.  Returns per-op digests (put) or verifies them (get).
+class DeviceTransport {
+ public:
+  virtual ~DeviceTransport() = default;
+  // dev_ptrs[item] is the client's device buffer of object `item`.
+  virtual ErrorCode put_shards(const std::vector<DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
+                               ChecksumAlgo algo, void* stream, std::vector<uint64_t>* digests) = 0;
+  virtual ErrorCode get_shards(const std::vector<DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, ChecksumAlgo algo,
+                               void* stream, std::vector<uint32_t>* status) = 0;
+  virtual bool can_reach(const ShardPlacement& s) const = 0;
+  virtual uint64_t launches() const = 0;
+};
+
+class BlackbirdClient {
+ public:
+  explicit BlackbirdClient(BlackbirdClientOptions opts = {});
+  // In-process deployment: talk to a KeystoneApi directly (no TCP to the control plane).
+  BlackbirdClient(std::shared_ptr<rpc::KeystoneApi> keystone, BlackbirdClientOptions opts = {});
+  ~BlackbirdClient();
+
+  ErrorCode connect();
+  bool connected() const { return keystone_ != nullptr; }
+  const std::string& session_id() const { return session_id_; }
+
+  // ---- reference API
+  Result<bool> object_exists(const ObjectKey& key);
+  Result<std::vector<CopyPlacement>> get_workers(const ObjectKey& key);
+  Result<std::vector<uint8_t>> get(const ObjectKey& key);
+  ErrorCode get_into(const ObjectKey& key, void* buf, size_t capacity, size_t* out_size);
+  ErrorCode put(const ObjectKey& key, const uint8_t* data, size_t size, const WorkerConfig& cfg = {});
+  ErrorCode put(const ObjectKey& key, const std::vector<uint8_t>& data, const WorkerConfig& cfg = {}) {
+    return put(key, data.data(), data.size(), cfg);
+  }
+  ErrorCode remove(const ObjectKey& key);
+
+  // ---- batched host-memory API
+  std::vector<ErrorCode> batch_put(const std::vector<ObjectKey>& keys, const std::vector<const uint8_t*>& data,
+                                   const std::vector<size_t>& sizes, const WorkerConfig& cfg = {});
+  std::vector<Result<std::vector<uint8_t>>> batch_get(const std::vector<ObjectKey>& keys);
+  std::vector<ErrorCode> batch_remove(const std::vector<ObjectKey>& keys);
+  std::vector<Result<bool>> batch_exists(const std::vector<ObjectKey>& keys);
+
+  // ---- batched device-memory API (fused kernels; requires a DeviceTransport)
+  void set_device_transport(std::shared_ptr<DeviceTransport> t) { device_ = std::move(t); }
+  std::vector<ErrorCode> batch_put_device(const std::vector<ObjectKey>& keys, const std::vector<const void*>& dev_ptrs,
+                                          const std::vector<size_t>& sizes, const WorkerConfig& cfg, void* stream);
+  // out_sizes[i] receives the object size; buffers must be large enough (capacity[i]).
+  std::vector<ErrorCode> batch_get_device(const std::vector<ObjectKey>& keys, const std::vector<void*>& dev_ptrs,
+                                          const std::vector<size_t>& capacity, void* stream, std::vector<size_t>* out_sizes);
+
+  Result<ClusterStats> cluster_stats();
+  rpc::KeystoneApi& keystone() { return *keystone_; }
+  std::string metrics_text() const { return metrics_.render("bb_client_"); }
+
+ private:
+  struct WorkerConn;
+  std::shared_ptr<net::RpcClient> acquire(const std::string& endpoint);
+  void release(const std::string& endpoint, std::shared_ptr<net::RpcClient> c);
+  ErrorCode write_shard(const ShardPlacement& s, const uint8_t* src, uint64_t* digest, ChecksumAlgo algo);
+  ErrorCode read_shard(const ShardPlacement& s, uint8_t* dst, ChecksumAlgo algo);
+  ErrorCode transfer_put(const std::vector<CopyPlacement>& copies, const uint8_t* data, ChecksumAlgo algo,
+                         keystone::ShardChecksums* sums);
+  ErrorCode transfer_get(const std::vector<CopyPlacement>& copies, uint8_t* dst, size_t size);
+  static uint64_t shard_offset(const ShardPlacement& s);
+  static ChecksumAlgo algo_of(const std::vector<CopyPlacement>& copies, ChecksumAlgo hint);
+
+  BlackbirdClientOptions opts_;
+  std::shared_ptr<rpc::KeystoneApi> keystone_;
+  std::shared_ptr<DeviceTransport> device_;
+  std::string session_id_;
+  std::mutex conn_mu_;
+  std::map<std::string, std::vector<std::shared_ptr<net::RpcClient>>> idle_conns_;
+  mutable Metrics metrics_;
+};
+
+}  // namespace bb::client

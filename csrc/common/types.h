@@ -107,7 +107,8 @@ struct ShardPlacement {
   StorageClass storage_class = StorageClass::STORAGE_UNSPECIFIED;
   uint64_t length = 0;
   LocationDetail location;
-  uint64_t checksum = 0;  // digest of this shard's bytes (algo in the owning object)
+  uint64_t checksum = 0;  // digest of this shard's bytes, valid once the put completed
+  ChecksumAlgo checksum_algo = ChecksumAlgo::NONE;
   bool operator==(const ShardPlacement&) const = default;
 };
 

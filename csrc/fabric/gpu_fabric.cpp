@@ -1,0 +1,292 @@
+#include "fabric/gpu_fabric.h"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "common/log.h"
+
+namespace bb::gpu {
+
+namespace {
+struct LocalSlab {
+  int device;
+  void* base;
+  uint64_t size;
+};
+std::mutex g_local_mu;
+std::map<std::string, LocalSlab> g_local;
+
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  BB_LOG(ERROR) << "CUDA error in " << what << ": " << cudaGetErrorString(e);
+  cudaGetLastError();
+  return false;
+}
+}  // namespace
+
+void register_local_slab(const std::string& pool_id, int device, void* base, uint64_t size) {
+  std::lock_guard<std::mutex> lk(g_local_mu);
+  g_local[pool_id] = LocalSlab{device, base, size};
+}
+void unregister_local_slab(const std::string& pool_id) {
+  std::lock_guard<std::mutex> lk(g_local_mu);
+  g_local.erase(pool_id);
+}
+
+// ================================================================ GpuSlabBackend
+GpuSlabBackend::GpuSlabBackend(uint64_t capacity, worker::BackendOptions opts)
+    : StorageBackend(StorageClass::RAM_GPU, capacity, std::move(opts)) {}
+GpuSlabBackend::~GpuSlabBackend() { shutdown(); }
+
+ErrorCode GpuSlabBackend::initialize() {
+  if (initialized_) return ErrorCode::OK;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || opts_.gpu_device_id >= n) {
+    cudaGetLastError();
+    return ErrorCode::INITIALIZATION_FAILED;
+  }
+  if (!cuda_ok(cudaSetDevice(opts_.gpu_device_id), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
+  void* p = nullptr;
+  if (!cuda_ok(cudaMalloc(&p, capacity_), "cudaMalloc(slab)")) return ErrorCode::OUT_OF_MEMORY;
+  base_ = static_cast<uint8_t*>(p);
+  cudaIpcMemHandle_t h;
+  if (cuda_ok(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle")) {
+    std::vector<uint8_t> raw(sizeof h);
+    std::memcpy(raw.data(), &h, sizeof h);
+    handle_hex_ = bytes_to_hex(raw);
+  }
+  cudaStream_t st;
+  if (cuda_ok(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) stream_ = st;
+  rkey_ = reinterpret_cast<uint64_t>(p) >> 8;
+  init_allocator();
+  register_local_slab(pool_id_, opts_.gpu_device_id, base_, capacity_);
+  initialized_ = true;
+  return ErrorCode::OK;
+}
+
+void GpuSlabBackend::shutdown() {
+  if (!base_) return;
+  unregister_local_slab(pool_id_);
+  cudaSetDevice(opts_.gpu_device_id);
+  if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+  cudaFree(base_);
+  base_ = nullptr;
+  stream_ = nullptr;
+  initialized_ = false;
+}
+
+ErrorCode GpuSlabBackend::write(uint64_t offset, const void* data, uint64_t len) {
+  BB_TRY(check_range(offset, len));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (!cuda_ok(cudaSetDevice(opts_.gpu_device_id), "cudaSetDevice") ||
+      !cuda_ok(cudaMemcpyAsync(base_ + offset, data, len, cudaMemcpyHostToDevice, st), "H2D") ||
+      !cuda_ok(cudaStreamSynchronize(st), "sync"))
+    return ErrorCode::FABRIC_ERROR;
+  bytes_written_ += len;
+  return ErrorCode::OK;
+}
+
+ErrorCode GpuSlabBackend::read(uint64_t offset, void* data, uint64_t len) {
+  BB_TRY(check_range(offset, len));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (!cuda_ok(cudaSetDevice(opts_.gpu_device_id), "cudaSetDevice") ||
+      !cuda_ok(cudaMemcpyAsync(data, base_ + offset, len, cudaMemcpyDeviceToHost, st), "D2H") ||
+      !cuda_ok(cudaStreamSynchronize(st), "sync"))
+    return ErrorCode::FABRIC_ERROR;
+  bytes_read_ += len;
+  return ErrorCode::OK;
+}
+
+void install_gpu_backend_factory() {
+  worker::set_gpu_backend_factory([](uint64_t capacity, const worker::BackendOptions& o) -> std::unique_ptr<worker::StorageBackend> {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return std::make_unique<GpuSlabBackend>(capacity, o);
+  });
+}
+
+// ================================================================ GpuFabric
+Result<std::shared_ptr<GpuFabric>> GpuFabric::create(int device, std::shared_ptr<rpc::KeystoneApi> keystone) {
+  std::shared_ptr<GpuFabric> f(new GpuFabric());
+  f->device_ = device;
+  f->keystone_ = std::move(keystone);
+  auto e = XferEngine::create(device, 1u << 16, 4);
+  if (!e.ok()) return e.error();
+  f->engine_ = std::move(e.value());
+  if (f->keystone_) f->refresh_pools();
+  return f;
+}
+
+GpuFabric::~GpuFabric() {
+  std::lock_guard<std::mutex> lk(mu_);
+  cudaSetDevice(device_);
+  for (auto& [id, m] : pools_)
+    if (m.ipc_opened && m.base) cudaIpcCloseMemHandle(m.base);
+}
+
+size_t GpuFabric::mapped_pools() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  return pools_.size();
+}
+
+ErrorCode GpuFabric::refresh_pools() {
+  if (!keystone_) return ErrorCode::INVALID_STATE;
+  auto pools = keystone_->get_memory_pools();
+  if (!pools.ok()) return pools.error();
+  if (!cuda_ok(cudaSetDevice(device_), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
+  std::lock_guard<std::mutex> lk(mu_);
+  for (const auto& p : pools.value()) {
+    if (p.storage_class != StorageClass::RAM_GPU || pools_.count(p.id)) continue;
+    Mapping m;
+    m.size = p.size;
+    m.device = p.gpu_device_id;
+    {
+      std::lock_guard<std::mutex> l2(g_local_mu);
+      auto it = g_local.find(p.id);
+      if (it != g_local.end()) {
+        m.base = static_cast<uint8_t*>(it->second.base);
+        m.device = it->second.device;
+      }
+    }
+    if (m.base) {
+      if (m.device != device_) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, device_, m.device);
+        if (!can) {
+          BB_LOG(WARNING) << "GPU " << device_ << " cannot access peer " << m.device << "; pool " << p.id << " unreachable";
+          continue;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(m.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cuda_ok(e, "cudaDeviceEnablePeerAccess");
+          continue;
+        }
+        cudaGetLastError();
+      }
+    } else {
+      auto raw = hex_to_bytes(p.ucx_rkey_hex);
+      if (!raw || raw->size() != sizeof(cudaIpcMemHandle_t)) {
+        BB_LOG(WARNING) << "pool " << p.id << " has no usable IPC handle";
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, raw->data(), sizeof h);
+      void* ptr = nullptr;
+      if (!cuda_ok(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) continue;
+      m.base = static_cast<uint8_t*>(ptr);
+      m.ipc_opened = true;
+    }
+    pools_[p.id] = m;
+  }
+  return ErrorCode::OK;
+}
+
+bool GpuFabric::can_reach(const ShardPlacement& s) const {
+  if (s.storage_class != StorageClass::RAM_GPU) return false;
+  std::lock_guard<std::mutex> lk(mu_);
+  return pools_.count(s.pool_id) > 0;
+}
+
+Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
+  const auto* g = std::get_if<GpuSlabLocation>(&s.location);
+  if (!g) return ErrorCode::INVALID_ADDRESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = pools_.find(s.pool_id);
+      if (it != pools_.end()) {
+        if (g->offset + s.length > it->second.size) return ErrorCode::MEMORY_ACCESS_ERROR;
+        return static_cast<void*>(it->second.base + g->offset);
+      }
+    }
+    if (attempt == 0) refresh_pools();  // a worker joined after we started
+  }
+  return ErrorCode::MEMORY_POOL_NOT_FOUND;
+}
+
+ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
+                                void* stream, std::vector<uint64_t>* digests) {
+  std::vector<XferItem> items;
+  std::vector<size_t> op_of_item;
+  items.reserve(ops.size());
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const auto& op = ops[k];
+    XferItem it;
+    it.src = static_cast<const uint8_t*>(dev_ptrs[op.item]) + op.obj_offset;
+    it.nbytes = op.placement->length;
+    auto d0 = resolve(*op.placement);
+    if (!d0.ok()) return d0.error();
+    it.dst[0] = d0.value();
+    it.ndst = 1;
+    size_t r = 0;
+    for (; r < op.replicas.size() && it.ndst < kMaxDst; ++r) {
+      auto d = resolve(*op.replicas[r]);
+      if (!d.ok()) return d.error();
+      it.dst[it.ndst++] = d.value();
+    }
+    items.push_back(it);
+    op_of_item.push_back(k);
+    // more replicas than one tile pass can fan out to: extra passes
+    while (r < op.replicas.size()) {
+      XferItem more;
+      more.src = it.src;
+      more.nbytes = it.nbytes;
+      more.ndst = 0;
+      for (; r < op.replicas.size() && more.ndst < kMaxDst; ++r) {
+        auto d = resolve(*op.replicas[r]);
+        if (!d.ok()) return d.error();
+        more.dst[more.ndst++] = d.value();
+      }
+      items.push_back(more);
+      op_of_item.push_back(k);
+    }
+  }
+  XferResult res;
+  ErrorCode ec = engine_->run(items, algo, stream, &res);
+  if (ec != ErrorCode::OK) return ec;
+  last_ms_ = res.device_ms;
+  if (digests) {
+    digests->assign(ops.size(), 0);
+    for (size_t i = items.size(); i-- > 0;) (*digests)[op_of_item[i]] = res.digest[i];
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode GpuFabric::get_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, ChecksumAlgo,
+                                void* stream, std::vector<uint32_t>* status) {
+  if (status) status->assign(ops.size(), 0);
+  // one launch per checksum algorithm present in the batch (normally exactly one)
+  for (ChecksumAlgo algo : {ChecksumAlgo::BBH64, ChecksumAlgo::CRC32C, ChecksumAlgo::NONE}) {
+    std::vector<XferItem> items;
+    std::vector<size_t> idx;
+    for (size_t k = 0; k < ops.size(); ++k) {
+      const auto& op = ops[k];
+      if (op.placement->checksum_algo != algo) continue;
+      XferItem it;
+      auto s = resolve(*op.placement);
+      if (!s.ok()) return s.error();
+      it.src = s.value();
+      it.dst[0] = static_cast<uint8_t*>(dev_ptrs[op.item]) + op.obj_offset;
+      it.ndst = 1;
+      it.nbytes = op.placement->length;
+      it.expect = op.placement->checksum;
+      it.flags = algo == ChecksumAlgo::NONE ? 0u : static_cast<uint32_t>(XFER_VERIFY);
+      items.push_back(it);
+      idx.push_back(k);
+    }
+    if (items.empty()) continue;
+    XferResult res;
+    ErrorCode ec = engine_->run(items, algo, stream, &res);
+    if (ec != ErrorCode::OK) return ec;
+    last_ms_ = res.device_ms;
+    if (status)
+      for (size_t i = 0; i < idx.size(); ++i) (*status)[idx[i]] = res.status[i];
+  }
+  return ErrorCode::OK;
+}
+
+}  // namespace bb::gpu

@@ -1,0 +1,95 @@
+// GPU fabric: the B200-native replacement of the reference's UcxEngine.
+//
+//   reference (src/transport/ucx_engine.cpp)            here
+//   ucp_mem_map + ucp_rkey_pack of a malloc'd pool  ->  cudaMalloc'd HBM slab + cudaIpcGetMemHandle
+//   rkey hex advertised through etcd pool JSON      ->  IPC handle hex in the same JSON field
+//   client ucp_ep_create + ucp_ep_rkey_unpack/call  ->  one-time cudaIpcOpenMemHandle per peer slab
+//   ucp_put_nbx / ucp_get_nbx per shard + busy poll ->  one fused kernel launch per *batch* issuing
+//                                                       TMA loads/stores on the peer-mapped pointers
+//
+// GpuSlabBackend is the RAM_GPU storage tier (`malloc` + "Does not work" in the reference,
+// ram_backend.cpp:188, worker_service.cpp:196).  GpuFabric implements client::DeviceTransport.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "client/blackbird_client.h"
+#include "fabric/xfer_engine.h"
+#include "worker/storage_backend.h"
+
+namespace bb::gpu {
+
+class GpuSlabBackend : public worker::StorageBackend {
+ public:
+  GpuSlabBackend(uint64_t capacity, worker::BackendOptions opts);
+  ~GpuSlabBackend() override;
+  StorageClass get_storage_class() const override { return StorageClass::RAM_GPU; }
+  uint64_t get_total_capacity() const override { return capacity_; }
+  uint64_t get_base_address() const override { return reinterpret_cast<uint64_t>(base_); }
+  uint64_t get_rkey() const override { return rkey_; }
+  ErrorCode initialize() override;
+  void shutdown() override;
+  // Slow path (host tiers, TCP clients, tier demotion): staged cudaMemcpy.
+  ErrorCode write(uint64_t offset, const void* data, uint64_t len) override;
+  ErrorCode read(uint64_t offset, void* data, uint64_t len) override;
+  int device() const { return opts_.gpu_device_id; }
+  void* device_ptr() const { return base_; }
+  // 64-byte cudaIpcMemHandle_t as 128 hex chars: the "rkey" peers open the slab with.
+  std::string ipc_handle_hex() const { return handle_hex_; }
+  std::string registration_key_hex() const override { return handle_hex_; }
+
+ private:
+  uint8_t* base_ = nullptr;
+  uint64_t rkey_ = 0;
+  std::string handle_hex_;
+  void* stream_ = nullptr;
+};
+
+// Registers the GPU tier with worker::create_storage_backend (call once at start-up).
+void install_gpu_backend_factory();
+
+class GpuFabric : public client::DeviceTransport {
+ public:
+  // `device`: CUDA ordinal the client's kernels run on.
+  static Result<std::shared_ptr<GpuFabric>> create(int device, std::shared_ptr<rpc::KeystoneApi> keystone);
+  ~GpuFabric() override;
+
+  ErrorCode put_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
+                       void* stream, std::vector<uint64_t>* digests) override;
+  ErrorCode get_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, ChecksumAlgo algo, void* stream,
+                       std::vector<uint32_t>* status) override;
+  bool can_reach(const ShardPlacement& s) const override;
+  uint64_t launches() const override { return engine_->launches(); }
+
+  // Re-reads the pool registry from the keystone and maps any new GPU slab.
+  ErrorCode refresh_pools();
+  size_t mapped_pools() const;
+  XferEngine& engine() { return *engine_; }
+  float last_device_ms() const { return last_ms_; }
+
+ private:
+  GpuFabric() = default;
+  struct Mapping {
+    uint8_t* base = nullptr;
+    uint64_t size = 0;
+    int device = -1;
+    bool ipc_opened = false;
+  };
+  Result<void*> resolve(const ShardPlacement& s);
+  int device_ = 0;
+  std::shared_ptr<rpc::KeystoneApi> keystone_;
+  std::unique_ptr<XferEngine> engine_;
+  mutable std::mutex mu_;
+  std::map<std::string, Mapping> pools_;
+  float last_ms_ = 0.f;
+};
+
+// Process-local slab registry (in-process workers + clients share pointers directly; CUDA IPC
+// cannot open a handle inside the process that exported it).
+void register_local_slab(const std::string& pool_id, int device, void* base, uint64_t size);
+void unregister_local_slab(const std::string& pool_id);
+
+}  // namespace bb::gpu

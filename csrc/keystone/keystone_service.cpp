@@ -1,0 +1,929 @@
+#include "keystone/keystone_service.h"
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <set>
+
+#include "common/log.h"
+#include "rpc/wire.h"
+
+namespace bb::keystone {
+
+namespace {
+int64_t wall_ms() {
+  return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
+double us_since(TimePoint t0) {
+  return std::chrono::duration<double, std::micro>(Clock::now() - t0).count();
+}
+constexpr auto kPendingGrace = std::chrono::minutes(10);
+
+std::string encode_object(const ObjectInfo& o) {
+  wire::Writer w;
+  w.str(o.key);
+  w.u64(o.size);
+  const int64_t age_ms = std::chrono::duration_cast<std::chrono::milliseconds>(Clock::now() - o.created).count();
+  w.i64(wall_ms() - age_ms);  // wall-clock creation time survives a leader change
+  wire::put(w, o.config);
+  wire::put(w, o.copies);
+  w.u32(static_cast<uint32_t>(o.state));
+  return w.take();
+}
+bool decode_object(const std::string& s, ObjectInfo& o) {
+  wire::Reader r(s);
+  o.key = r.str();
+  o.size = r.u64();
+  const int64_t created_wall = r.i64();
+  wire::get(r, o.config);
+  wire::get(r, o.copies);
+  o.state = static_cast<ObjectState>(r.u32());
+  if (!r.ok()) return false;
+  const int64_t age = std::max<int64_t>(0, wall_ms() - created_wall);
+  o.created = Clock::now() - std::chrono::milliseconds(age);
+  o.last_accessed = Clock::now();
+  return true;
+}
+}  // namespace
+
+KeystoneService::KeystoneService(const KeystoneConfig& config, std::shared_ptr<coord::CoordService> coord)
+    : config_(config), coord_(std::move(coord)),
+      allocator_(std::make_unique<alloc::KeystoneAllocatorAdapter>(alloc::AllocatorFactory::create_range_based())) {
+  metrics_.describe("put_start_total", "put_start calls that allocated placements");
+  metrics_.describe("put_complete_total", "objects that reached COMPLETE");
+  metrics_.describe("get_workers_total", "successful placement lookups");
+  metrics_.describe("evictions_total", "objects dropped by watermark eviction");
+  metrics_.describe("demotions_total", "objects moved to a lower tier by watermark eviction");
+  metrics_.describe("expired_total", "objects reclaimed by TTL");
+  metrics_.describe("worker_deaths_total", "workers removed after heartbeat lease expiry");
+  metrics_.describe("put_bytes_total", "logical bytes admitted by put_start");
+}
+
+KeystoneService::~KeystoneService() { stop(); }
+
+// ================================================================ lifecycle
+ErrorCode KeystoneService::initialize() {
+  if (config_.service_id.empty()) config_.service_id = "keystone-" + uuid_to_string(generate_uuid()).substr(0, 12);
+  candidate_id_ = config_.service_id;
+  if (coord_) {
+    ErrorCode ec = setup_coordination();
+    if (ec != ErrorCode::OK) return ec;
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::setup_coordination() {
+  ErrorCode ec = coord_->connect();
+  if (ec != ErrorCode::OK) {
+    BB_LOG(ERROR) << "keystone: cannot reach coordination store";
+    return ec;
+  }
+  ec = coord_->register_service("blackbird-keystone", config_.service_id, config_.listen_address, config_.service_registration_ttl_sec);
+  if (ec != ErrorCode::OK) return ec;
+  if (config_.enable_ha) {
+    bool won = false;
+    ec = coord_->campaign_leader("keystone-" + config_.cluster_id, candidate_id_, config_.service_registration_ttl_sec, won);
+    if (ec != ErrorCode::OK) return ec;
+    leader_.store(won);
+    BB_LOG(INFO) << "keystone " << candidate_id_ << (won ? " is the leader" : " is a standby");
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::start() {
+  if (running_.exchange(true)) return ErrorCode::INVALID_STATE;
+  view_version_.store(1);
+  if (coord_ && coord_->is_connected()) {
+    load_existing_state();
+    const std::string p = cluster_prefix();
+    coord_->watch_prefix(p + "workers/", [this](const std::string& k, const std::string& v, bool d) { on_worker_event(k, v, d); });
+    coord_->watch_prefix(p + "memory_pools/", [this](const std::string& k, const std::string& v, bool d) { on_legacy_pool_event(k, v, d); });
+    coord_->watch_prefix(p + "heartbeat/", [this](const std::string& k, const std::string& v, bool d) { on_heartbeat_event(k, v, d); });
+    if (is_leader()) recover_objects_from_wal();
+  }
+  if (config_.enable_gc) gc_thread_ = std::thread([this] { gc_loop(); });
+  health_thread_ = std::thread([this] { health_loop(); });
+  if (coord_) keepalive_thread_ = std::thread([this] { keepalive_loop(); });
+  return ErrorCode::OK;
+}
+
+void KeystoneService::stop() {
+  if (!running_.exchange(false)) return;
+  {
+    std::lock_guard<std::mutex> lk(sleep_mu_);
+    sleep_cv_.notify_all();
+  }
+  if (gc_thread_.joinable()) gc_thread_.join();
+  if (health_thread_.joinable()) health_thread_.join();
+  if (keepalive_thread_.joinable()) keepalive_thread_.join();
+  if (coord_ && coord_->is_connected()) {
+    if (config_.enable_ha && leader_.load()) coord_->resign_leader("keystone-" + config_.cluster_id, candidate_id_);
+    coord_->unregister_service("blackbird-keystone", config_.service_id);
+  }
+  leader_.store(false);
+}
+
+bool KeystoneService::interruptible_sleep(std::chrono::milliseconds d) {
+  std::unique_lock<std::mutex> lk(sleep_mu_);
+  sleep_cv_.wait_for(lk, d, [this] { return !running_.load(); });
+  return running_.load();
+}
+
+void KeystoneService::gc_loop() {
+  while (interruptible_sleep(std::chrono::seconds(config_.gc_interval_sec))) {
+    if (is_leader()) run_gc_once();
+  }
+}
+
+void KeystoneService::health_loop() {
+  while (interruptible_sleep(std::chrono::seconds(config_.health_check_interval_sec))) {
+    if (!is_leader()) continue;
+    // workers registered without a coordination lease are aged out by heartbeat timestamps
+    std::vector<WorkerId> stale;
+    if (!coord_) {
+      std::shared_lock<std::shared_mutex> lk(workers_mu_);
+      for (const auto& [id, w] : workers_)
+        if (w.is_stale(std::chrono::seconds(config_.worker_heartbeat_ttl_sec))) stale.push_back(id);
+    }
+    for (const auto& id : stale) handle_worker_death(id);
+    // expire client sessions
+    {
+      std::lock_guard<std::mutex> lk(clients_mu_);
+      const auto now = Clock::now();
+      for (auto it = clients_.begin(); it != clients_.end();)
+        it = (now - it->second.last_ping > std::chrono::seconds(config_.client_ttl_sec)) ? clients_.erase(it) : std::next(it);
+    }
+    run_eviction_once();
+    run_repair_once();
+  }
+}
+
+void KeystoneService::keepalive_loop() {
+  const std::string election = "keystone-" + config_.cluster_id;
+  while (interruptible_sleep(std::chrono::seconds(config_.service_refresh_interval_sec))) {
+    if (!coord_ || !coord_->is_connected()) continue;
+    if (coord_->register_service("blackbird-keystone", config_.service_id, config_.listen_address,
+                                 config_.service_registration_ttl_sec) != ErrorCode::OK)
+      BB_LOG(WARNING) << "keystone: service registration refresh failed";
+    if (!config_.enable_ha) continue;
+    if (leader_.load()) {
+      if (coord_->refresh_leadership(election, candidate_id_) != ErrorCode::OK) {
+        BB_LOG(WARNING) << "keystone " << candidate_id_ << " lost leadership";
+        leader_.store(false);
+      }
+    } else {
+      bool won = false;
+      if (coord_->campaign_leader(election, candidate_id_, config_.service_registration_ttl_sec, won) == ErrorCode::OK && won) {
+        BB_LOG(INFO) << "keystone " << candidate_id_ << " took over leadership";
+        load_existing_state();
+        recover_objects_from_wal();
+        leader_.store(true);
+        bump_view();
+      }
+    }
+  }
+}
+
+// ================================================================ coordination events
+void KeystoneService::load_existing_state() {
+  std::vector<std::string> keys, values;
+  const std::string p = cluster_prefix();
+  if (coord_->get_with_prefix(p + "workers/", keys, values) == ErrorCode::OK)
+    for (size_t i = 0; i < keys.size(); ++i) on_worker_event(keys[i], values[i], false);
+  if (coord_->get_with_prefix(p + "memory_pools/", keys, values) == ErrorCode::OK)
+    for (size_t i = 0; i < keys.size(); ++i) on_legacy_pool_event(keys[i], values[i], false);
+}
+
+void KeystoneService::on_worker_event(const std::string& key, const std::string& value, bool is_delete) {
+  const std::string base = cluster_prefix() + "workers/";
+  if (key.compare(0, base.size(), base) != 0) return;
+  const std::string rest = key.substr(base.size());
+  const size_t mp = rest.find("/memory_pools/");
+  if (mp != std::string::npos) {
+    const std::string pid = rest.substr(mp + 14);
+    if (is_delete) {
+      std::unique_lock<std::shared_mutex> lk(pools_mu_);
+      pools_.erase(pid);
+      lk.unlock();
+      bump_view();
+      return;
+    }
+    auto j = Json::parse(value);
+    if (!j) return;
+    auto pool = memory_pool_from_json(*j);
+    if (!pool.ok()) {
+      BB_LOG(WARNING) << "keystone: malformed pool record at " << key;
+      return;
+    }
+    if (pool.value().worker_id.empty()) pool.value().worker_id = rest.substr(0, mp);
+    register_memory_pool(pool.value());
+    return;
+  }
+  if (rest.find('/') != std::string::npos) return;
+  if (is_delete) {
+    // explicit deregistration (clean shutdown): same handling as death, minus the metric
+    handle_worker_death(rest);
+    return;
+  }
+  auto j = Json::parse(value);
+  if (!j) return;
+  auto rec = worker_record_from_json(*j);
+  if (!rec.ok()) return;
+  if (rec.value().worker_id.empty()) rec.value().worker_id = rest;
+  register_worker(rec.value());
+}
+
+void KeystoneService::on_legacy_pool_event(const std::string& key, const std::string& value, bool is_delete) {
+  const std::string base = cluster_prefix() + "memory_pools/";
+  if (key.compare(0, base.size(), base) != 0) return;
+  const std::string pid = key.substr(base.size());
+  if (is_delete) {
+    std::unique_lock<std::shared_mutex> lk(pools_mu_);
+    pools_.erase(pid);
+    return;
+  }
+  auto j = Json::parse(value);
+  if (!j) return;
+  auto pool = memory_pool_from_json(*j);
+  if (pool.ok()) register_memory_pool(pool.value());
+}
+
+void KeystoneService::on_heartbeat_event(const std::string& key, const std::string&, bool is_delete) {
+  const std::string base = cluster_prefix() + "heartbeat/";
+  if (key.compare(0, base.size(), base) != 0) return;
+  const std::string wid = key.substr(base.size());
+  if (!is_delete) {
+    worker_heartbeat(wid);
+    return;
+  }
+  BB_LOG(WARNING) << "keystone: heartbeat lease of worker " << wid << " expired";
+  metrics_.inc("worker_deaths_total");
+  handle_worker_death(wid);
+  if (coord_ && is_leader()) {
+    const std::string p = cluster_prefix() + "workers/" + wid;
+    if (auto st = coord_->store()) st->del_prefix(p + "/");
+    coord_->del(p);
+  }
+}
+
+// ================================================================ registries
+ErrorCode KeystoneService::register_worker(const WorkerRecord& rec) {
+  if (rec.worker_id.empty()) return ErrorCode::INVALID_WORKER;
+  {
+    std::unique_lock<std::shared_mutex> lk(workers_mu_);
+    WorkerInfo& w = workers_[rec.worker_id];
+    w.worker_id = rec.worker_id;
+    w.node_id = rec.node_id;
+    w.endpoint = rec.rpc_endpoint;
+    w.record = rec;
+    w.last_heartbeat = Clock::now();
+  }
+  bump_view();
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::register_memory_pool(const MemoryPool& pool) {
+  if (pool.id.empty() || pool.size == 0) return ErrorCode::INVALID_MEMORY_POOL;
+  {
+    std::unique_lock<std::shared_mutex> lk(workers_mu_);
+    if (!pool.worker_id.empty()) {
+      WorkerInfo& w = workers_[pool.worker_id];
+      if (w.worker_id.empty()) {
+        w.worker_id = pool.worker_id;
+        w.node_id = pool.node_id;
+        w.last_heartbeat = Clock::now();
+      }
+      if (std::find(w.pools.begin(), w.pools.end(), pool.id) == w.pools.end()) w.pools.push_back(pool.id);
+    }
+    std::unique_lock<std::shared_mutex> pk(pools_mu_);
+    pools_[pool.id] = pool;
+  }
+  bump_view();
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::worker_heartbeat(const WorkerId& id) {
+  std::unique_lock<std::shared_mutex> lk(workers_mu_);
+  auto it = workers_.find(id);
+  if (it == workers_.end()) return ErrorCode::INVALID_WORKER;
+  it->second.last_heartbeat = Clock::now();
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::remove_worker(const WorkerId& id) {
+  {
+    std::shared_lock<std::shared_mutex> lk(workers_mu_);
+    if (!workers_.count(id)) return ErrorCode::INVALID_WORKER;
+  }
+  handle_worker_death(id);
+  if (coord_ && coord_->is_connected()) {
+    const std::string p = cluster_prefix();
+    if (auto st = coord_->store()) st->del_prefix(p + "workers/" + id + "/");
+    coord_->del(p + "workers/" + id);
+    coord_->del(p + "heartbeat/" + id);
+  }
+  return ErrorCode::OK;
+}
+
+void KeystoneService::handle_worker_death(const WorkerId& id) {
+  std::vector<MemoryPoolId> dead;
+  {
+    std::unique_lock<std::shared_mutex> lk(workers_mu_);
+    auto it = workers_.find(id);
+    if (it == workers_.end()) return;
+    dead = it->second.pools;
+    workers_.erase(it);
+    std::unique_lock<std::shared_mutex> pk(pools_mu_);
+    for (auto pit = pools_.begin(); pit != pools_.end();) {
+      if (pit->second.worker_id == id && std::find(dead.begin(), dead.end(), pit->first) == dead.end()) dead.push_back(pit->first);
+      ++pit;
+    }
+    for (const auto& p : dead) pools_.erase(p);
+  }
+  for (const auto& p : dead) allocator_->allocator().forget_pool(p);
+  // invalidate every copy that had a shard on the dead pools
+  const std::set<MemoryPoolId> dead_set(dead.begin(), dead.end());
+  size_t lost_objects = 0, degraded = 0;
+  for (auto& sh : shards_) {
+    std::vector<ObjectKey> gone;
+    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    for (auto& [key, info] : sh.objects) {
+      const size_t before = info.copies.size();
+      info.copies.erase(std::remove_if(info.copies.begin(), info.copies.end(),
+                                       [&](const CopyPlacement& c) {
+                                         for (const auto& s : c.shards)
+                                           if (dead_set.count(s.pool_id)) return true;
+                                         return false;
+                                       }),
+                        info.copies.end());
+      if (info.copies.size() == before) continue;
+      if (info.copies.empty()) gone.push_back(key);
+      else {
+        ++degraded;
+        if (info.state == ObjectState::COMPLETE) persist_object(info);
+      }
+    }
+    for (const auto& k : gone) {
+      erase_locked(sh, k, true);
+      ++lost_objects;
+    }
+  }
+  if (lost_objects || degraded)
+    BB_LOG(WARNING) << "worker " << id << " died: " << lost_objects << " objects lost, " << degraded << " degraded";
+  metrics_.inc("objects_lost_total", lost_objects);
+  bump_view();
+}
+
+bool KeystoneService::pool_alive(const MemoryPoolId& id) const {
+  std::shared_lock<std::shared_mutex> lk(pools_mu_);
+  return pools_.count(id) > 0;
+}
+
+// ================================================================ object API
+ErrorCode KeystoneService::erase_locked(Shard& sh, const ObjectKey& key, bool free_ranges) {
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
+  const bool was_complete = it->second.state == ObjectState::COMPLETE;
+  const std::vector<std::string> extra = std::move(it->second.extra_ledgers);
+  sh.objects.erase(it);
+  if (free_ranges) {
+    allocator_->free_object(key);
+    for (const auto& l : extra) allocator_->free_object(l);  // ledgers created by repair / demotion
+  }
+  if (was_complete) unpersist_object(key);
+  return ErrorCode::OK;
+}
+
+Result<bool> KeystoneService::object_exists(const ObjectKey& key) {
+  if (key.empty()) return ErrorCode::INVALID_KEY;
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end() || it->second.is_expired() || it->second.state != ObjectState::COMPLETE) return false;
+  it->second.touch();
+  return true;
+}
+
+Result<std::vector<CopyPlacement>> KeystoneService::get_workers(const ObjectKey& key) {
+  if (key.empty()) return ErrorCode::INVALID_KEY;
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end() || it->second.is_expired()) return ErrorCode::OBJECT_NOT_FOUND;
+  if (it->second.state != ObjectState::COMPLETE) return ErrorCode::OBJECT_NOT_READY;
+  if (it->second.copies.empty()) return ErrorCode::NO_COMPLETE_WORKER;
+  it->second.touch();
+  metrics_.inc("get_workers_total");
+  return it->second.copies;
+}
+
+Result<std::vector<CopyPlacement>> KeystoneService::put_start(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
+                                                              const std::string& client_id, const std::string& client_node) {
+  const TimePoint t0 = Clock::now();
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  if (key.empty() || key.find('\x01') != std::string::npos) return ErrorCode::INVALID_KEY;
+  if (config.replication_factor == 0 || config.max_workers_per_copy == 0) return ErrorCode::INVALID_PARAMETERS;
+  if (config_.max_replicas > 0 && config.replication_factor > static_cast<size_t>(config_.max_replicas)) return ErrorCode::VALUE_OUT_OF_RANGE;
+  std::shared_lock<std::shared_mutex> pk(pools_mu_);  // lock order: pools -> shard
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it != sh.objects.end()) {
+    if (!it->second.is_expired()) return ErrorCode::OBJECT_ALREADY_EXISTS;
+    erase_locked(sh, key, true);  // expired but not yet swept: reclaim inline
+    metrics_.inc("expired_total");
+  }
+  auto copies = allocator_->allocate_data_copies(key, data_size, config, pools_, client_node);
+  if (!copies.ok()) {
+    metrics_.inc("put_start_failed_total");
+    return copies.error();
+  }
+  ObjectInfo info;
+  info.key = key;
+  info.size = data_size;
+  info.created = info.last_accessed = Clock::now();
+  info.config = config;
+  for (auto& c : copies.value())
+    for (auto& s : c.shards) s.checksum_algo = config.checksum;
+  info.copies = copies.value();
+  info.state = ObjectState::PENDING;
+  info.owner_client = client_id;
+  sh.objects.emplace(key, std::move(info));
+  lk.unlock();
+  pk.unlock();
+  bump_view();
+  metrics_.inc("put_start_total");
+  metrics_.inc("put_bytes_total", data_size);
+  metrics_.observe("put_start_latency_us", us_since(t0));
+  return copies;
+}
+
+ErrorCode KeystoneService::put_complete(const ObjectKey& key) { return put_complete(key, {}); }
+
+ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksums& checksums) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end() || it->second.is_expired()) return ErrorCode::OBJECT_NOT_FOUND;
+  ObjectInfo& info = it->second;
+  if (!checksums.empty()) {
+    if (checksums.size() != info.copies.size()) return ErrorCode::INVALID_PARAMETERS;
+    for (size_t c = 0; c < checksums.size(); ++c) {
+      if (checksums[c].size() != info.copies[c].shards.size()) return ErrorCode::INVALID_PARAMETERS;
+      for (size_t s = 0; s < checksums[c].size(); ++s) info.copies[c].shards[s].checksum = checksums[c][s];
+    }
+  }
+  if (info.state != ObjectState::COMPLETE) {
+    info.state = ObjectState::COMPLETE;
+    metrics_.inc("put_complete_total");
+  }
+  info.touch();
+  persist_object(info);
+  lk.unlock();
+  bump_view();
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::put_cancel(const ObjectKey& key) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
+  if (it->second.state == ObjectState::COMPLETE) return ErrorCode::INVALID_STATE;
+  erase_locked(sh, key, true);
+  metrics_.inc("put_cancel_total");
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::remove_object(const ObjectKey& key) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  ErrorCode ec = erase_locked(sh, key, true);
+  lk.unlock();
+  if (ec == ErrorCode::OK) {
+    metrics_.inc("remove_total");
+    bump_view();
+  }
+  return ec;
+}
+
+Result<size_t> KeystoneService::remove_all_objects() {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  size_t n = 0;
+  for (auto& sh : shards_) {
+    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::vector<ObjectKey> keys;
+    keys.reserve(sh.objects.size());
+    for (const auto& [k, v] : sh.objects) keys.push_back(k);
+    for (const auto& k : keys) {
+      erase_locked(sh, k, true);  // frees allocator ranges (the reference leaks them)
+      ++n;
+    }
+  }
+  bump_view();
+  return n;
+}
+
+Result<ObjectInfo> KeystoneService::get_object_info(const ObjectKey& key) const {
+  const Shard& sh = shard_for(key);
+  std::shared_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
+  return it->second;
+}
+
+// ================================================================ batch API
+std::vector<Result<bool>> KeystoneService::batch_object_exists(const std::vector<ObjectKey>& keys) {
+  std::vector<Result<bool>> out;
+  out.reserve(keys.size());
+  for (const auto& k : keys) out.push_back(object_exists(k));
+  return out;
+}
+
+std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_get_workers(const std::vector<ObjectKey>& keys) {
+  std::vector<Result<std::vector<CopyPlacement>>> out;
+  out.reserve(keys.size());
+  for (const auto& k : keys) out.push_back(get_workers(k));
+  return out;
+}
+
+std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_put_start(const std::vector<PutStartItem>& items,
+                                                                                 const std::string& client_id,
+                                                                                 const std::string& client_node) {
+  std::vector<Result<std::vector<CopyPlacement>>> out;
+  out.reserve(items.size());
+  for (const auto& it : items) out.push_back(put_start(it.key, it.size, it.config, client_id, client_node));
+  return out;
+}
+
+std::vector<ErrorCode> KeystoneService::batch_put_complete(const std::vector<ObjectKey>& keys) {
+  std::vector<ErrorCode> out;
+  out.reserve(keys.size());
+  for (const auto& k : keys) out.push_back(put_complete(k));
+  return out;
+}
+
+std::vector<ErrorCode> KeystoneService::batch_put_complete(const std::vector<ObjectKey>& keys, const std::vector<ShardChecksums>& checksums) {
+  std::vector<ErrorCode> out;
+  out.reserve(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) out.push_back(put_complete(keys[i], i < checksums.size() ? checksums[i] : ShardChecksums{}));
+  return out;
+}
+
+std::vector<ErrorCode> KeystoneService::batch_put_cancel(const std::vector<ObjectKey>& keys) {
+  std::vector<ErrorCode> out;
+  out.reserve(keys.size());
+  for (const auto& k : keys) out.push_back(put_cancel(k));
+  return out;
+}
+
+std::vector<ErrorCode> KeystoneService::batch_remove_object(const std::vector<ObjectKey>& keys) {
+  std::vector<ErrorCode> out;
+  out.reserve(keys.size());
+  for (const auto& k : keys) out.push_back(remove_object(k));
+  return out;
+}
+
+// ================================================================ cluster
+Result<ClusterStats> KeystoneService::get_cluster_stats() const {
+  ClusterStats st;
+  {
+    std::shared_lock<std::shared_mutex> lk(workers_mu_);
+    st.total_workers = workers_.size();
+  }
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    st.total_memory_pools = pools_.size();
+    for (const auto& [id, p] : pools_) {
+      st.total_capacity += p.size;
+      st.used_capacity += allocator_->allocator().pool_used_bytes(id);
+    }
+  }
+  for (const auto& sh : shards_) {
+    std::shared_lock<std::shared_mutex> lk(sh.mu);
+    for (const auto& [k, o] : sh.objects) (o.state == ObjectState::COMPLETE ? st.total_objects : st.pending_objects) += 1;
+  }
+  {
+    std::lock_guard<std::mutex> lk(clients_mu_);
+    st.active_clients = clients_.size();
+  }
+  st.avg_utilization = st.total_capacity ? static_cast<double>(st.used_capacity) / static_cast<double>(st.total_capacity) : 0.0;
+  return st;
+}
+
+ErrorCode KeystoneService::get_workers_info(std::vector<WorkerInfo>& out) const {
+  out.clear();
+  std::shared_lock<std::shared_mutex> lk(workers_mu_);
+  for (const auto& [id, w] : workers_) out.push_back(w);
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::get_memory_pools(std::vector<MemoryPool>& out) const {
+  out.clear();
+  std::shared_lock<std::shared_mutex> lk(pools_mu_);
+  for (const auto& [id, p] : pools_) {
+    out.push_back(p);
+    out.back().used = allocator_->allocator().pool_used_bytes(id);
+  }
+  return ErrorCode::OK;
+}
+
+double KeystoneService::tier_utilization(StorageClass sc) const {
+  uint64_t cap = 0, used = 0;
+  std::shared_lock<std::shared_mutex> lk(pools_mu_);
+  for (const auto& [id, p] : pools_)
+    if (p.storage_class == sc) {
+      cap += p.size;
+      used += allocator_->allocator().pool_used_bytes(id);
+    }
+  return cap ? static_cast<double>(used) / static_cast<double>(cap) : 0.0;
+}
+
+// ================================================================ client sessions
+Result<std::string> KeystoneService::client_register(const std::string& node_id) {
+  const std::string id = "client-" + uuid_to_string(generate_uuid()).substr(0, 16);
+  std::lock_guard<std::mutex> lk(clients_mu_);
+  clients_[id] = ClientSession{node_id, Clock::now()};
+  return id;
+}
+
+Result<ViewVersionId> KeystoneService::client_ping(const std::string& client_id) {
+  std::lock_guard<std::mutex> lk(clients_mu_);
+  auto it = clients_.find(client_id);
+  if (it == clients_.end()) return ErrorCode::SESSION_EXPIRED;
+  it->second.last_ping = Clock::now();
+  return get_view_version();
+}
+
+// ================================================================ GC / eviction / repair
+void KeystoneService::set_copy_mover(CopyMover m) {
+  std::lock_guard<std::mutex> lk(mover_mu_);
+  mover_ = std::move(m);
+}
+
+size_t KeystoneService::run_gc_once() {
+  size_t n = 0;
+  const TimePoint now = Clock::now();
+  for (auto& sh : shards_) {
+    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::vector<ObjectKey> dead;
+    for (const auto& [k, o] : sh.objects) {
+      if (o.is_expired(now)) dead.push_back(k);
+      else if (o.state == ObjectState::PENDING && o.config.ttl_ms == 0 && now - o.created > kPendingGrace) dead.push_back(k);
+    }
+    for (const auto& k : dead) {
+      erase_locked(sh, k, true);
+      ++n;
+    }
+  }
+  if (n) {
+    metrics_.inc("expired_total", n);
+    bump_view();
+  }
+  return n;
+}
+
+size_t KeystoneService::run_eviction_once() {
+  // utilisation per tier from the allocator's live accounting
+  std::map<int, std::vector<StorageClass>> tiers;
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    std::set<StorageClass> seen;
+    for (const auto& [id, p] : pools_) seen.insert(p.storage_class);
+    for (auto sc : seen) tiers[tier_rank(sc)].push_back(sc);
+  }
+  CopyMover mover;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+  }
+  size_t total = 0;
+  for (const auto& [rank, classes] : tiers) {
+    for (StorageClass sc : classes) {
+      if (tier_utilization(sc) < config_.high_watermark) continue;
+      // LRU candidates that have data on this tier and are not soft-pinned
+      std::vector<std::pair<TimePoint, ObjectKey>> cands;
+      for (auto& sh : shards_) {
+        std::shared_lock<std::shared_mutex> lk(sh.mu);
+        for (const auto& [k, o] : sh.objects) {
+          if (o.state != ObjectState::COMPLETE || o.config.enable_soft_pin) continue;
+          bool here = false;
+          for (const auto& c : o.copies)
+            for (const auto& s : c.shards) here |= s.storage_class == sc;
+          if (here) cands.emplace_back(o.last_accessed, k);
+        }
+      }
+      if (cands.empty()) continue;
+      std::sort(cands.begin(), cands.end());
+      const size_t n = std::max<size_t>(1, static_cast<size_t>(static_cast<double>(cands.size()) * config_.eviction_ratio));
+      // lower tiers that exist in the cluster
+      std::vector<StorageClass> lower;
+      for (const auto& [r2, cl2] : tiers)
+        if (r2 > rank) lower.insert(lower.end(), cl2.begin(), cl2.end());
+      for (size_t i = 0; i < n && i < cands.size(); ++i) {
+        const ObjectKey& key = cands[i].second;
+        bool demoted = false;
+        if (mover && !lower.empty()) {
+          auto info = get_object_info(key);
+          if (info.ok() && !info.value().copies.empty()) {
+            WorkerConfig cfg = info.value().config;
+            cfg.preferred_classes = lower;
+            cfg.replication_factor = info.value().copies.size();
+            cfg.symmetric_replicas = false;
+            std::string ledger;
+            Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
+            for (int slot = 0; slot < 64 && !fresh.ok(); ++slot) {
+              ledger = key + "\x01" + std::to_string(slot);
+              std::shared_lock<std::shared_mutex> pk(pools_mu_);
+              // only pools of the lower tiers are eligible
+              alloc::IAllocator::PoolMap eligible;
+              for (const auto& [pid, p] : pools_)
+                if (std::find(lower.begin(), lower.end(), p.storage_class) != lower.end()) eligible.emplace(pid, p);
+              if (eligible.empty()) break;
+              fresh = allocator_->allocate_data_copies(ledger, info.value().size, cfg, eligible);
+              if (!fresh.ok() && fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+            }
+            if (fresh.ok()) {
+              bool ok = true;
+              for (size_t c = 0; c < fresh.value().size() && ok; ++c)
+                ok = mover(key, info.value().copies[std::min(c, info.value().copies.size() - 1)], fresh.value()[c],
+                           info.value().config.checksum) == ErrorCode::OK;
+              if (ok) {
+                Shard& sh = shard_for(key);
+                std::unique_lock<std::shared_mutex> lk(sh.mu);
+                auto it = sh.objects.find(key);
+                if (it != sh.objects.end() && it->second.created == info.value().created) {
+                  it->second.copies = fresh.value();
+                  const std::vector<std::string> old = std::move(it->second.extra_ledgers);
+                  it->second.extra_ledgers = {ledger};
+                  persist_object(it->second);
+                  lk.unlock();
+                  allocator_->free_object(key);  // old (upper tier) extents
+                  for (const auto& l : old) allocator_->free_object(l);
+                  demoted = true;
+                  metrics_.inc("demotions_total");
+                } else {
+                  lk.unlock();
+                  allocator_->free_object(ledger);
+                }
+              } else {
+                allocator_->free_object(ledger);
+              }
+            }
+          }
+        }
+        if (!demoted) {
+          Shard& sh = shard_for(key);
+          std::unique_lock<std::shared_mutex> lk(sh.mu);
+          if (erase_locked(sh, key, true) == ErrorCode::OK) metrics_.inc("evictions_total");
+        }
+        ++total;
+      }
+    }
+  }
+  if (total) bump_view();
+  return total;
+}
+
+size_t KeystoneService::run_repair_once() {
+  CopyMover mover;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+  }
+  if (!mover) return 0;
+  std::vector<ObjectInfo> degraded;
+  for (auto& sh : shards_) {
+    std::shared_lock<std::shared_mutex> lk(sh.mu);
+    for (const auto& [k, o] : sh.objects)
+      if (o.state == ObjectState::COMPLETE && !o.copies.empty() && o.copies.size() < o.config.replication_factor) degraded.push_back(o);
+  }
+  size_t repaired = 0;
+  for (const auto& o : degraded) {
+    WorkerConfig cfg = o.config;
+    cfg.replication_factor = 1;
+    cfg.symmetric_replicas = false;
+    std::vector<MemoryPoolId> exclude;
+    for (const auto& c : o.copies)
+      for (const auto& s : c.shards) exclude.push_back(s.pool_id);
+    std::string ledger;
+    Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
+    for (int slot = 0; slot < 64; ++slot) {
+      ledger = o.key + "\x01" + std::to_string(slot);
+      std::shared_lock<std::shared_mutex> pk(pools_mu_);
+      fresh = allocator_->allocate_data_copies(ledger, o.size, cfg, pools_, "", exclude);
+      if (fresh.ok() || fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+    }
+    if (!fresh.ok()) continue;
+    CopyPlacement dst = fresh.value()[0];
+    if (mover(o.key, o.copies[0], dst, o.config.checksum) != ErrorCode::OK) {
+      allocator_->free_object(ledger);
+      continue;
+    }
+    Shard& sh = shard_for(o.key);
+    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    auto it = sh.objects.find(o.key);
+    if (it == sh.objects.end() || it->second.created != o.created) {
+      lk.unlock();
+      allocator_->free_object(ledger);
+      continue;
+    }
+    dst.copy_index = static_cast<uint32_t>(it->second.copies.size());
+    it->second.copies.push_back(dst);
+    it->second.extra_ledgers.push_back(ledger);
+    persist_object(it->second);
+    ++repaired;
+  }
+  if (repaired) {
+    metrics_.inc("repairs_total", repaired);
+    bump_view();
+  }
+  return repaired;
+}
+
+// ================================================================ WAL
+void KeystoneService::persist_object(const ObjectInfo& info) {
+  if (!coord_ || !coord_->is_connected() || !(config_.enable_ha || !config_.wal_path.empty())) return;
+  coord_->put(cluster_prefix() + "objects/" + info.key, encode_object(info));
+}
+
+void KeystoneService::unpersist_object(const ObjectKey& key) {
+  if (!coord_ || !coord_->is_connected() || !(config_.enable_ha || !config_.wal_path.empty())) return;
+  coord_->del(cluster_prefix() + "objects/" + key);
+}
+
+void KeystoneService::recover_objects_from_wal() {
+  if (!coord_ || !coord_->is_connected()) return;
+  std::vector<std::string> keys, values;
+  if (coord_->get_with_prefix(cluster_prefix() + "objects/", keys, values) != ErrorCode::OK) return;
+  size_t n = 0;
+  std::shared_lock<std::shared_mutex> pk(pools_mu_);
+  for (size_t i = 0; i < keys.size(); ++i) {
+    ObjectInfo o;
+    if (!decode_object(values[i], o) || o.is_expired()) continue;
+    Shard& sh = shard_for(o.key);
+    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    if (sh.objects.count(o.key)) continue;
+    // re-reserve the extents so that new puts cannot overwrite recovered objects
+    static_cast<alloc::RangeAllocator&>(allocator_->allocator()).adopt(o.key, o.copies, pools_);
+    sh.objects.emplace(o.key, std::move(o));
+    ++n;
+  }
+  if (n) BB_LOG(INFO) << "keystone: recovered " << n << " objects from the metadata log";
+}
+
+// ================================================================ observability
+std::string KeystoneService::metrics_text() const {
+  auto st = get_cluster_stats();
+  if (st.ok()) {
+    metrics_.set_gauge("objects", static_cast<double>(st.value().total_objects));
+    metrics_.set_gauge("pending_objects", static_cast<double>(st.value().pending_objects));
+    metrics_.set_gauge("workers", static_cast<double>(st.value().total_workers));
+    metrics_.set_gauge("memory_pools", static_cast<double>(st.value().total_memory_pools));
+    metrics_.set_gauge("capacity_bytes", static_cast<double>(st.value().total_capacity));
+    metrics_.set_gauge("used_bytes", static_cast<double>(st.value().used_capacity));
+    metrics_.set_gauge("utilization", st.value().avg_utilization);
+    metrics_.set_gauge("active_clients", static_cast<double>(st.value().active_clients));
+  }
+  metrics_.set_gauge("view_version", static_cast<double>(get_view_version()));
+  metrics_.set_gauge("is_leader", is_leader() ? 1.0 : 0.0);
+  const auto as = allocator_->get_allocator_stats();
+  metrics_.set_gauge("allocator_fragmentation", as.fragmentation_ratio);
+  metrics_.set_gauge("allocator_shards", static_cast<double>(as.total_shards));
+  std::string out = metrics_.render("bb_");
+  // per-tier gauges with labels
+  std::map<StorageClass, std::pair<uint64_t, uint64_t>> tiers;
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    for (const auto& [id, p] : pools_) {
+      tiers[p.storage_class].first += p.size;
+      tiers[p.storage_class].second += allocator_->allocator().pool_used_bytes(id);
+    }
+  }
+  out += "# TYPE bb_tier_capacity_bytes gauge\n";
+  for (const auto& [sc, v] : tiers) out += "bb_tier_capacity_bytes{tier=\"" + std::string(to_string(sc)) + "\"} " + std::to_string(v.first) + "\n";
+  out += "# TYPE bb_tier_used_bytes gauge\n";
+  for (const auto& [sc, v] : tiers) out += "bb_tier_used_bytes{tier=\"" + std::string(to_string(sc)) + "\"} " + std::to_string(v.second) + "\n";
+  return out;
+}
+
+Json KeystoneService::stats_json() const {
+  Json j = Json::object();
+  auto st = get_cluster_stats();
+  if (st.ok()) j["cluster"] = to_json(st.value());
+  j["view_version"] = get_view_version();
+  j["is_leader"] = is_leader();
+  j["service_id"] = config_.service_id;
+  j["cluster_id"] = config_.cluster_id;
+  Json pools = Json::array();
+  std::vector<MemoryPool> mp;
+  get_memory_pools(mp);
+  for (const auto& p : mp) pools.push_back(to_json(p));
+  j["pools"] = pools;
+  return j;
+}
+
+}  // namespace bb::keystone

@@ -1,0 +1,211 @@
+// KeystoneService: the control plane.
+//
+// Parity: reference include/blackbird/keystone/keystone_service.h:84-245 — lifecycle
+// (initialize/start/stop), object API (object_exists, get_workers, put_start, put_complete,
+// put_cancel, remove_object, remove_all_objects), the five batch_* calls, get_workers_info,
+// get_memory_pools, remove_worker, get_cluster_stats, get_view_version; ObjectInfo (:21-57),
+// WorkerInfo (:62-74); coordination schema of SURVEY §2.3; TTL GC + watermark eviction
+// (keystone_service.cpp:417-451, 530-584); dead-worker cleanup (:956-1004).
+//
+// Re-designed (every item is a reference defect in SURVEY §2.7/§2.8):
+//  * explicit PENDING -> COMPLETE state machine; get_workers never serves in-flight puts (#2)
+//  * object table sharded 32 ways, no global write lock, no O(N) debug dump per put (#1, hard part 7)
+//  * expired keys are reclaimed inline by put_start (#4); eviction is LRU by last access and
+//    frees allocator ranges (#5); remove_all_objects frees ranges too
+//  * utilisation comes from the allocator's live accounting, so the watermark actually fires (#3)
+//  * tier demotion (GPU -> DRAM -> CXL -> NVMe) through a pluggable mover instead of dropping
+//  * dead workers invalidate the copies they held; surviving replicas keep serving and lost
+//    copies are re-replicated through the mover; objects with no survivor are removed
+//  * real leader election (CAS + lease) with a standby that resumes from the object WAL
+//  * client sessions (register / ping with TTL) and Prometheus metrics are real
+#pragma once
+#include <array>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "alloc/allocator.h"
+#include "common/metrics.h"
+#include "common/types.h"
+#include "coord/coord.h"
+
+namespace bb::keystone {
+
+enum class ObjectState : uint32_t { PENDING = 0, COMPLETE = 1 };
+
+struct ObjectInfo {
+  ObjectKey key;
+  size_t size = 0;
+  TimePoint created;
+  TimePoint last_accessed;
+  WorkerConfig config;
+  std::vector<CopyPlacement> copies;
+  ObjectState state = ObjectState::PENDING;
+  std::string owner_client;  // session that started the put
+  std::vector<std::string> extra_ledgers;  // allocator ledger keys besides `key` (repair / demotion)
+
+  uint64_t ttl_ms() const { return config.ttl_ms; }
+  bool is_expired(TimePoint now = Clock::now()) const {
+    return config.ttl_ms != 0 && now - created > std::chrono::milliseconds(config.ttl_ms);
+  }
+  bool has_complete_copy() const { return state == ObjectState::COMPLETE && !copies.empty(); }
+  void touch() { last_accessed = Clock::now(); }
+};
+
+struct WorkerInfo {
+  WorkerId worker_id;
+  NodeId node_id;
+  std::string endpoint;
+  TimePoint last_heartbeat;
+  std::vector<MemoryPoolId> pools;
+  WorkerRecord record;
+  bool is_stale(std::chrono::seconds ttl, TimePoint now = Clock::now()) const { return now - last_heartbeat > ttl; }
+};
+
+struct PutStartItem {
+  ObjectKey key;
+  size_t size = 0;
+  WorkerConfig config;
+};
+// Per-object shard digests reported by the writer at put_complete: [copy][shard].
+using ShardChecksums = std::vector<std::vector<uint64_t>>;
+
+// Moves the bytes of one copy to another placement (tier demotion / re-replication).  Provided
+// by the data plane (worker or client library); returns OK when dst holds a verified copy and
+// fills dst shard checksums.
+using CopyMover = std::function<ErrorCode(const ObjectKey& key, const CopyPlacement& src, CopyPlacement& dst, ChecksumAlgo algo)>;
+
+class KeystoneService {
+ public:
+  explicit KeystoneService(const KeystoneConfig& config, std::shared_ptr<coord::CoordService> coord = nullptr);
+  ~KeystoneService();
+  KeystoneService(const KeystoneService&) = delete;
+  KeystoneService& operator=(const KeystoneService&) = delete;
+
+  ErrorCode initialize();
+  ErrorCode start();
+  void stop();
+  bool is_running() const noexcept { return running_.load(); }
+  bool is_leader() const noexcept { return !config_.enable_ha || leader_.load(); }
+  const KeystoneConfig& config() const { return config_; }
+
+  // ---- object API
+  Result<bool> object_exists(const ObjectKey& key);
+  Result<std::vector<CopyPlacement>> get_workers(const ObjectKey& key);
+  Result<std::vector<CopyPlacement>> put_start(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
+                                               const std::string& client_id = "", const std::string& client_node = "");
+  ErrorCode put_complete(const ObjectKey& key);
+  ErrorCode put_complete(const ObjectKey& key, const ShardChecksums& checksums);
+  ErrorCode put_cancel(const ObjectKey& key);
+  ErrorCode remove_object(const ObjectKey& key);
+  Result<size_t> remove_all_objects();
+
+  // ---- batch API (one lock acquisition per shard group, per-item results)
+  std::vector<Result<bool>> batch_object_exists(const std::vector<ObjectKey>& keys);
+  std::vector<Result<std::vector<CopyPlacement>>> batch_get_workers(const std::vector<ObjectKey>& keys);
+  std::vector<Result<std::vector<CopyPlacement>>> batch_put_start(const std::vector<PutStartItem>& items,
+                                                                  const std::string& client_id = "",
+                                                                  const std::string& client_node = "");
+  std::vector<ErrorCode> batch_put_complete(const std::vector<ObjectKey>& keys);
+  std::vector<ErrorCode> batch_put_complete(const std::vector<ObjectKey>& keys, const std::vector<ShardChecksums>& checksums);
+  std::vector<ErrorCode> batch_put_cancel(const std::vector<ObjectKey>& keys);
+  std::vector<ErrorCode> batch_remove_object(const std::vector<ObjectKey>& keys);
+
+  // ---- cluster / admin
+  Result<ClusterStats> get_cluster_stats() const;
+  ViewVersionId get_view_version() const noexcept { return view_version_.load(); }
+  ErrorCode get_workers_info(std::vector<WorkerInfo>& out) const;
+  ErrorCode get_memory_pools(std::vector<MemoryPool>& out) const;
+  ErrorCode remove_worker(const WorkerId& id);
+  Result<ObjectInfo> get_object_info(const ObjectKey& key) const;
+
+  // Direct registration (in-process deployments and tests; the coordination watchers call
+  // the same functions).
+  ErrorCode register_worker(const WorkerRecord& rec);
+  ErrorCode register_memory_pool(const MemoryPool& pool);
+  ErrorCode worker_heartbeat(const WorkerId& id);
+  void handle_worker_death(const WorkerId& id);
+
+  // ---- client sessions (reference README "client heartbeats"; absent in its code)
+  Result<std::string> client_register(const std::string& node_id);
+  Result<ViewVersionId> client_ping(const std::string& client_id);
+
+  // ---- tiering / repair
+  void set_copy_mover(CopyMover m);
+  // Runs one TTL sweep / eviction pass / repair pass synchronously (also used by the threads).
+  size_t run_gc_once();
+  size_t run_eviction_once();
+  size_t run_repair_once();
+  double tier_utilization(StorageClass sc) const;
+
+  // ---- observability
+  std::string metrics_text() const;  // Prometheus exposition
+  Json stats_json() const;
+  alloc::AllocatorStats allocator_stats() const { return allocator_->get_allocator_stats(); }
+
+ private:
+  static constexpr size_t kShards = 32;
+  struct Shard {
+    mutable std::shared_mutex mu;
+    std::unordered_map<ObjectKey, ObjectInfo> objects;
+  };
+  Shard& shard_for(const ObjectKey& key) { return shards_[std::hash<ObjectKey>{}(key) % kShards]; }
+  const Shard& shard_for(const ObjectKey& key) const { return shards_[std::hash<ObjectKey>{}(key) % kShards]; }
+
+  ErrorCode setup_coordination();
+  void load_existing_state();
+  void on_worker_event(const std::string& key, const std::string& value, bool is_delete);
+  void on_heartbeat_event(const std::string& key, const std::string& value, bool is_delete);
+  void on_legacy_pool_event(const std::string& key, const std::string& value, bool is_delete);
+  void gc_loop();
+  void health_loop();
+  void keepalive_loop();
+  void persist_object(const ObjectInfo& info);
+  void unpersist_object(const ObjectKey& key);
+  void recover_objects_from_wal();
+  void bump_view() { view_version_.fetch_add(1); }
+  ErrorCode erase_locked(Shard& sh, const ObjectKey& key, bool free_ranges);
+  std::vector<CopyPlacement> live_copies(const ObjectInfo& info) const;
+  bool pool_alive(const MemoryPoolId& id) const;
+  std::string cluster_prefix() const { return "/blackbird/clusters/" + config_.cluster_id + "/"; }
+  bool interruptible_sleep(std::chrono::milliseconds d);
+
+  KeystoneConfig config_;
+  std::shared_ptr<coord::CoordService> coord_;
+  std::unique_ptr<alloc::KeystoneAllocatorAdapter> allocator_;
+  std::array<Shard, kShards> shards_;
+
+  mutable std::shared_mutex pools_mu_;  // lock order: workers_mu_ -> pools_mu_ -> shard.mu
+  std::unordered_map<MemoryPoolId, MemoryPool> pools_;
+  mutable std::shared_mutex workers_mu_;
+  std::unordered_map<WorkerId, WorkerInfo> workers_;
+
+  mutable std::mutex clients_mu_;
+  struct ClientSession {
+    std::string node_id;
+    TimePoint last_ping;
+  };
+  std::unordered_map<std::string, ClientSession> clients_;
+
+  std::mutex mover_mu_;
+  CopyMover mover_;
+
+  std::atomic<bool> running_{false};
+  std::atomic<bool> leader_{false};
+  std::atomic<ViewVersionId> view_version_{0};
+  std::mutex sleep_mu_;
+  std::condition_variable sleep_cv_;
+  std::thread gc_thread_, health_thread_, keepalive_thread_;
+  std::string candidate_id_;
+
+  mutable Metrics metrics_;
+};
+
+}  // namespace bb::keystone

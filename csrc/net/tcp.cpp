@@ -1,0 +1,562 @@
+#include "net/tcp.h"
+
+#include <arpa/inet.h>
+#include <fcntl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <poll.h>
+#include <sys/epoll.h>
+#include <sys/eventfd.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <chrono>
+#include <cstring>
+
+#include "common/log.h"
+
+namespace bb::net {
+
+namespace {
+void set_nodelay(int fd) {
+  int one = 1;
+  ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+}
+bool resolve(const std::string& host, uint16_t port, sockaddr_in* out) {
+  std::memset(out, 0, sizeof *out);
+  out->sin_family = AF_INET;
+  out->sin_port = htons(port);
+  std::string h = host.empty() || host == "0.0.0.0" || host == "*" ? "0.0.0.0" : host;
+  if (h == "localhost") h = "127.0.0.1";
+  if (::inet_pton(AF_INET, h.c_str(), &out->sin_addr) == 1) return true;
+  addrinfo hints{}, *res = nullptr;
+  hints.ai_family = AF_INET;
+  hints.ai_socktype = SOCK_STREAM;
+  if (::getaddrinfo(h.c_str(), nullptr, &hints, &res) != 0 || !res) return false;
+  out->sin_addr = reinterpret_cast<sockaddr_in*>(res->ai_addr)->sin_addr;
+  ::freeaddrinfo(res);
+  return true;
+}
+uint32_t rd32(const char* p) {
+  uint32_t v;
+  std::memcpy(&v, p, 4);
+  return v;
+}
+uint64_t rd64(const char* p) {
+  uint64_t v;
+  std::memcpy(&v, p, 8);
+  return v;
+}
+}  // namespace
+
+int tcp_listen(const std::string& host, uint16_t port, uint16_t* bound_port, std::string* err) {
+  sockaddr_in addr;
+  if (!resolve(host, port, &addr)) {
+    if (err) *err = "cannot resolve " + host;
+    return -1;
+  }
+  int fd = ::socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC | SOCK_NONBLOCK, 0);
+  if (fd < 0) {
+    if (err) *err = std::strerror(errno);
+    return -1;
+  }
+  int one = 1;
+  ::setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+  if (::bind(fd, reinterpret_cast<sockaddr*>(&addr), sizeof addr) != 0 || ::listen(fd, 512) != 0) {
+    if (err) *err = std::string("bind/listen: ") + std::strerror(errno);
+    ::close(fd);
+    return -1;
+  }
+  if (bound_port) {
+    socklen_t len = sizeof addr;
+    ::getsockname(fd, reinterpret_cast<sockaddr*>(&addr), &len);
+    *bound_port = ntohs(addr.sin_port);
+  }
+  return fd;
+}
+
+int tcp_connect(const std::string& host, uint16_t port, int timeout_ms, std::string* err) {
+  sockaddr_in addr;
+  if (!resolve(host == "0.0.0.0" ? "127.0.0.1" : host, port, &addr)) {
+    if (err) *err = "cannot resolve " + host;
+    return -1;
+  }
+  int fd = ::socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC | SOCK_NONBLOCK, 0);
+  if (fd < 0) {
+    if (err) *err = std::strerror(errno);
+    return -1;
+  }
+  int rc = ::connect(fd, reinterpret_cast<sockaddr*>(&addr), sizeof addr);
+  if (rc != 0 && errno == EINPROGRESS) {
+    pollfd p{fd, POLLOUT, 0};
+    rc = ::poll(&p, 1, timeout_ms);
+    int soerr = 0;
+    socklen_t len = sizeof soerr;
+    if (rc == 1) ::getsockopt(fd, SOL_SOCKET, SO_ERROR, &soerr, &len);
+    if (rc != 1 || soerr != 0) {
+      if (err) *err = rc != 1 ? "connect timeout" : std::strerror(soerr);
+      ::close(fd);
+      return -1;
+    }
+  } else if (rc != 0) {
+    if (err) *err = std::strerror(errno);
+    ::close(fd);
+    return -1;
+  }
+  int flags = ::fcntl(fd, F_GETFL, 0);
+  ::fcntl(fd, F_SETFL, flags & ~O_NONBLOCK);
+  set_nodelay(fd);
+  return fd;
+}
+
+bool send_all(int fd, const void* data, size_t len, int timeout_ms) {
+  const char* p = static_cast<const char*>(data);
+  while (len) {
+    ssize_t n = ::send(fd, p, len, MSG_NOSIGNAL);
+    if (n > 0) {
+      p += n;
+      len -= static_cast<size_t>(n);
+      continue;
+    }
+    if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) {
+      pollfd pf{fd, POLLOUT, 0};
+      if (::poll(&pf, 1, timeout_ms) <= 0) return false;
+      continue;
+    }
+    if (n < 0 && errno == EINTR) continue;
+    return false;
+  }
+  return true;
+}
+
+bool recv_all(int fd, void* data, size_t len, int timeout_ms) {
+  char* p = static_cast<char*>(data);
+  while (len) {
+    pollfd pf{fd, POLLIN, 0};
+    int rc = ::poll(&pf, 1, timeout_ms);
+    if (rc == 0) return false;
+    if (rc < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    ssize_t n = ::recv(fd, p, len, 0);
+    if (n > 0) {
+      p += n;
+      len -= static_cast<size_t>(n);
+      continue;
+    }
+    if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR)) continue;
+    return false;
+  }
+  return true;
+}
+
+// ================================================================ Connection
+Connection::~Connection() {
+  if (fd_ >= 0) ::close(fd_);
+}
+
+bool Connection::send(const void* data, size_t len) {
+  if (closed_.load()) return false;
+  std::lock_guard<std::mutex> lk(write_mu_);
+  if (!send_all(fd_, data, len, 10000)) {
+    close();
+    return false;
+  }
+  return true;
+}
+
+void Connection::close() {
+  bool exp = false;
+  if (closed_.compare_exchange_strong(exp, true)) ::shutdown(fd_, SHUT_RDWR);
+}
+
+// ================================================================ TcpServer
+TcpServer::~TcpServer() { stop(); }
+
+ErrorCode TcpServer::start(const std::string& host, uint16_t port, int worker_threads) {
+  if (running_.load()) return ErrorCode::INVALID_STATE;
+  std::string err;
+  listen_fd_ = tcp_listen(host, port, &port_, &err);
+  if (listen_fd_ < 0) {
+    BB_LOG(ERROR) << "TcpServer: cannot listen on " << host << ":" << port << ": " << err;
+    return ErrorCode::NETWORK_ERROR;
+  }
+  epoll_fd_ = ::epoll_create1(EPOLL_CLOEXEC);
+  wake_fd_ = ::eventfd(0, EFD_CLOEXEC | EFD_NONBLOCK);
+  epoll_event ev{};
+  ev.events = EPOLLIN;
+  ev.data.fd = listen_fd_;
+  ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, listen_fd_, &ev);
+  ev.data.fd = wake_fd_;
+  ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, wake_fd_, &ev);
+  running_.store(true);
+  reactor_ = std::thread([this] { reactor_loop(); });
+  for (int i = 0; i < std::max(1, worker_threads); ++i) workers_.emplace_back([this] { worker_loop(); });
+  return ErrorCode::OK;
+}
+
+void TcpServer::stop() {
+  if (!running_.exchange(false)) return;
+  uint64_t one = 1;
+  ssize_t ignored = ::write(wake_fd_, &one, sizeof one);
+  (void)ignored;
+  cv_.notify_all();
+  if (reactor_.joinable()) reactor_.join();
+  for (auto& w : workers_)
+    if (w.joinable()) w.join();
+  workers_.clear();
+  std::vector<ConnPtr> all;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& [fd, c] : conns_) all.push_back(c);
+    conns_.clear();
+    ready_.clear();
+  }
+  for (auto& c : all) {
+    c->close();
+    on_close(c);
+  }
+  if (listen_fd_ >= 0) ::close(listen_fd_);
+  if (epoll_fd_ >= 0) ::close(epoll_fd_);
+  if (wake_fd_ >= 0) ::close(wake_fd_);
+  listen_fd_ = epoll_fd_ = wake_fd_ = -1;
+}
+
+size_t TcpServer::connection_count() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  return conns_.size();
+}
+
+void TcpServer::reactor_loop() {
+  epoll_event evs[64];
+  while (running_.load()) {
+    int n = ::epoll_wait(epoll_fd_, evs, 64, 500);
+    if (n < 0) {
+      if (errno == EINTR) continue;
+      break;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int fd = evs[i].data.fd;
+      if (fd == wake_fd_) continue;
+      if (fd == listen_fd_) {
+        while (true) {
+          sockaddr_in peer{};
+          socklen_t len = sizeof peer;
+          int cfd = ::accept4(listen_fd_, reinterpret_cast<sockaddr*>(&peer), &len, SOCK_NONBLOCK | SOCK_CLOEXEC);
+          if (cfd < 0) break;
+          set_nodelay(cfd);
+          char ip[64] = {0};
+          ::inet_ntop(AF_INET, &peer.sin_addr, ip, sizeof ip);
+          ConnPtr c;
+          {
+            std::lock_guard<std::mutex> lk(mu_);
+            c = std::make_shared<Connection>(cfd, next_id_++, std::string(ip) + ":" + std::to_string(ntohs(peer.sin_port)));
+            conns_[cfd] = c;
+          }
+          on_open(c);
+          epoll_event ev{};
+          ev.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
+          ev.data.fd = cfd;
+          ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, cfd, &ev);
+        }
+        continue;
+      }
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = conns_.find(fd);
+      if (it == conns_.end()) continue;
+      ready_.push_back(it->second);
+      cv_.notify_one();
+    }
+  }
+}
+
+void TcpServer::drop(const ConnPtr& c) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = conns_.find(c->fd());
+    if (it == conns_.end() || it->second != c) return;
+    conns_.erase(it);
+  }
+  ::epoll_ctl(epoll_fd_, EPOLL_CTL_DEL, c->fd(), nullptr);
+  c->close();
+  on_close(c);
+}
+
+void TcpServer::worker_loop() {
+  char buf[65536];
+  while (true) {
+    ConnPtr c;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [this] { return !ready_.empty() || !running_.load(); });
+      if (!running_.load()) return;
+      c = ready_.front();
+      ready_.pop_front();
+    }
+    bool alive = true;
+    while (true) {
+      ssize_t n = ::recv(c->fd(), buf, sizeof buf, 0);
+      if (n > 0) {
+        c->inbuf().append(buf, static_cast<size_t>(n));
+        if (c->inbuf().size() > kMaxFrame + kFrameHeader) {
+          alive = false;
+          break;
+        }
+        continue;
+      }
+      if (n == 0) {
+        alive = false;
+        break;
+      }
+      if (errno == EINTR) continue;
+      if (errno == EAGAIN || errno == EWOULDBLOCK) break;
+      alive = false;
+      break;
+    }
+    // deliver whatever arrived, even if the peer then closed
+    if (!c->inbuf().empty() && !c->closed()) {
+      bool ok = false;
+      try {
+        ok = on_data(c);
+      } catch (const std::exception& e) {
+        BB_LOG(ERROR) << "connection handler threw: " << e.what();
+      }
+      if (!ok) alive = false;
+    }
+    if (!alive || c->closed()) {
+      drop(c);
+      continue;
+    }
+    epoll_event ev{};
+    ev.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
+    ev.data.fd = c->fd();
+    if (::epoll_ctl(epoll_fd_, EPOLL_CTL_MOD, c->fd(), &ev) != 0) drop(c);
+  }
+}
+
+// ================================================================ framed RPC
+std::string encode_frame(uint32_t method, uint64_t id, const std::string& payload) {
+  std::string f;
+  f.resize(kFrameHeader + payload.size());
+  const uint32_t len = static_cast<uint32_t>(payload.size());
+  std::memcpy(&f[0], &len, 4);
+  std::memcpy(&f[4], &method, 4);
+  std::memcpy(&f[8], &id, 8);
+  if (!payload.empty()) std::memcpy(&f[kFrameHeader], payload.data(), payload.size());
+  return f;
+}
+
+bool RpcServer::on_data(const ConnPtr& c) {
+  std::string& in = c->inbuf();
+  size_t pos = 0;
+  while (in.size() - pos >= kFrameHeader) {
+    const uint32_t len = rd32(&in[pos]);
+    if (len > kMaxFrame) return false;
+    if (in.size() - pos < kFrameHeader + len) break;
+    const uint32_t method = rd32(&in[pos + 4]);
+    const uint64_t id = rd64(&in[pos + 8]);
+    std::string payload = in.substr(pos + kFrameHeader, len);
+    pos += kFrameHeader + len;
+    auto it = handlers_.find(method);
+    std::string resp;
+    uint32_t rmethod = method;
+    if (it == handlers_.end()) {
+      rmethod = 0x7FFFFFFFu;  // unknown-method marker
+    } else {
+      try {
+        resp = it->second(c, payload);
+      } catch (const std::exception& e) {
+        BB_LOG(ERROR) << "rpc handler " << method << " threw: " << e.what();
+        rmethod = 0x7FFFFFFEu;  // handler-exception marker
+      }
+    }
+    served_.fetch_add(1, std::memory_order_relaxed);
+    if (!c->send(encode_frame(rmethod, id, resp))) return false;
+  }
+  if (pos) in.erase(0, pos);
+  return true;
+}
+
+RpcClient::~RpcClient() { close(); }
+
+ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout_ms) {
+  close();
+  std::string err;
+  int fd = tcp_connect(host, port, timeout_ms, &err);
+  if (fd < 0) {
+    BB_VLOG(1) << "RpcClient: connect " << host << ":" << port << " failed: " << err;
+    return ErrorCode::CONNECTION_FAILED;
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  fd_ = fd;
+  broken_ = false;
+  return ErrorCode::OK;
+}
+
+void RpcClient::close() {
+  reader_run_.store(false);
+  int fd;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    fd = fd_;
+    if (fd >= 0) ::shutdown(fd, SHUT_RDWR);
+  }
+  if (reader_.joinable()) reader_.join();
+  std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ >= 0) ::close(fd_);
+  fd_ = -1;
+}
+
+void RpcClient::enable_push(std::function<void(uint32_t, const std::string&)> cb) {
+  push_cb_ = std::move(cb);
+  reader_run_.store(true);
+  reader_ = std::thread([this] { reader_loop(); });
+}
+
+void RpcClient::reader_loop() {
+  while (reader_run_.load()) {
+    char hdr[kFrameHeader];
+    if (!recv_all(fd_, hdr, sizeof hdr, 500)) {
+      // distinguish timeout (keep going) from a dead socket
+      pollfd pf{fd_, POLLIN, 0};
+      int rc = ::poll(&pf, 1, 0);
+      if (rc > 0 && (pf.revents & (POLLHUP | POLLERR | POLLNVAL))) break;
+      char probe;
+      ssize_t n = ::recv(fd_, &probe, 1, MSG_PEEK | MSG_DONTWAIT);
+      if (n == 0) break;
+      if (n < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) break;
+      continue;
+    }
+    const uint32_t len = rd32(hdr);
+    const uint32_t method = rd32(hdr + 4);
+    const uint64_t id = rd64(hdr + 8);
+    std::string payload(len, '\0');
+    if (len && !recv_all(fd_, payload.data(), len, 30000)) break;
+    if (method & kPushFlag) {
+      if (push_cb_) push_cb_(method & ~kPushFlag, payload);
+    } else {
+      std::lock_guard<std::mutex> lk(resp_mu_);
+      responses_[id] = std::move(payload);
+      resp_cv_.notify_all();
+    }
+  }
+  std::lock_guard<std::mutex> lk(resp_mu_);
+  broken_ = true;
+  resp_cv_.notify_all();
+}
+
+Result<std::string> RpcClient::call(uint32_t method, const std::string& request, int timeout_ms) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
+  const uint64_t id = next_id_++;
+  const std::string f = encode_frame(method, id, request);
+  if (!send_all(fd_, f.data(), f.size(), timeout_ms)) return ErrorCode::RPC_FAILED;
+  if (reader_run_.load()) {
+    std::unique_lock<std::mutex> rl(resp_mu_);
+    if (!resp_cv_.wait_for(rl, std::chrono::milliseconds(timeout_ms), [&] { return responses_.count(id) || broken_; }))
+      return ErrorCode::OPERATION_TIMEOUT;
+    auto it = responses_.find(id);
+    if (it == responses_.end()) return ErrorCode::RPC_FAILED;
+    std::string r = std::move(it->second);
+    responses_.erase(it);
+    return r;
+  }
+  char hdr[kFrameHeader];
+  if (!recv_all(fd_, hdr, sizeof hdr, timeout_ms)) {
+    ::close(fd_);
+    fd_ = -1;
+    return ErrorCode::RPC_FAILED;
+  }
+  const uint32_t len = rd32(hdr);
+  const uint32_t rmethod = rd32(hdr + 4);
+  std::string payload(len, '\0');
+  if (len > kMaxFrame || (len && !recv_all(fd_, payload.data(), len, timeout_ms))) {
+    ::close(fd_);
+    fd_ = -1;
+    return ErrorCode::RPC_FAILED;
+  }
+  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
+  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  return payload;
+}
+
+// ================================================================ HTTP
+bool HttpServer::on_data(const ConnPtr& c) {
+  std::string& in = c->inbuf();
+  while (true) {
+    const size_t end = in.find("\r\n\r\n");
+    if (end == std::string::npos) return in.size() < 65536;
+    const std::string head = in.substr(0, end);
+    in.erase(0, end + 4);
+    const size_t sp1 = head.find(' ');
+    const size_t sp2 = sp1 == std::string::npos ? std::string::npos : head.find(' ', sp1 + 1);
+    if (sp2 == std::string::npos) return false;
+    const std::string method = head.substr(0, sp1);
+    std::string target = head.substr(sp1 + 1, sp2 - sp1 - 1);
+    std::string query;
+    const size_t qm = target.find('?');
+    if (qm != std::string::npos) {
+      query = target.substr(qm + 1);
+      target.resize(qm);
+    }
+    HttpResponse r;
+    if (method != "GET" && method != "HEAD") {
+      r.status = 405;
+      r.body = "method not allowed\n";
+    } else {
+      auto it = routes_.find(target);
+      if (it == routes_.end()) {
+        r.status = 404;
+        r.body = "not found\n";
+      } else {
+        try {
+          r = it->second(target, query);
+        } catch (const std::exception& e) {
+          r.status = 500;
+          r.body = std::string("error: ") + e.what() + "\n";
+        }
+      }
+    }
+    const char* reason = r.status == 200 ? "OK" : r.status == 404 ? "Not Found" : r.status == 405 ? "Method Not Allowed" : r.status == 503 ? "Service Unavailable" : "Error";
+    std::string out = "HTTP/1.1 " + std::to_string(r.status) + " " + reason + "\r\nContent-Type: " + r.content_type +
+                      "\r\nContent-Length: " + std::to_string(r.body.size()) + "\r\nConnection: keep-alive\r\n\r\n";
+    if (method != "HEAD") out += r.body;
+    if (!c->send(out)) return false;
+  }
+}
+
+Result<std::string> http_get(const std::string& host, uint16_t port, const std::string& path, int* status, int timeout_ms) {
+  std::string err;
+  int fd = tcp_connect(host, port, timeout_ms, &err);
+  if (fd < 0) return ErrorCode::CONNECTION_FAILED;
+  const std::string req = "GET " + path + " HTTP/1.1\r\nHost: " + host + "\r\nConnection: close\r\n\r\n";
+  std::string resp;
+  bool ok = send_all(fd, req.data(), req.size(), timeout_ms);
+  size_t body_at = std::string::npos, content_len = std::string::npos;
+  while (ok) {
+    pollfd pf{fd, POLLIN, 0};
+    if (::poll(&pf, 1, timeout_ms) <= 0) break;
+    char buf[8192];
+    ssize_t n = ::recv(fd, buf, sizeof buf, 0);
+    if (n <= 0) break;
+    resp.append(buf, static_cast<size_t>(n));
+    if (body_at == std::string::npos) {
+      const size_t e = resp.find("\r\n\r\n");
+      if (e != std::string::npos) {
+        body_at = e + 4;
+        const size_t cl = resp.find("Content-Length:");
+        if (cl != std::string::npos && cl < e) content_len = std::strtoul(resp.c_str() + cl + 15, nullptr, 10);
+      }
+    }
+    if (body_at != std::string::npos && content_len != std::string::npos && resp.size() >= body_at + content_len) break;
+  }
+  ::close(fd);
+  if (body_at == std::string::npos) return ErrorCode::NETWORK_ERROR;
+  if (status) *status = std::atoi(resp.c_str() + 9);
+  return resp.substr(body_at, content_len == std::string::npos ? std::string::npos : content_len);
+}
+
+}  // namespace bb::net

@@ -1,0 +1,188 @@
+// Network substrate: epoll reactor TCP server, framed RPC server/client, HTTP/1.1 mini server.
+//
+// Replaces yalantinglibs coro_rpc / coro_http (reference rpc_service.cpp:175-226, 360-413;
+// unavailable offline).  One reactor thread owns epoll (EPOLLONESHOT per connection) and hands
+// readable connections to a small worker pool, so slow handlers do not block accept/IO and
+// requests on one connection stay ordered.  Frames: [u32 len][u32 method][u64 id][payload].
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "common/error.h"
+#include "common/result.h"
+
+namespace bb::net {
+
+int tcp_listen(const std::string& host, uint16_t port, uint16_t* bound_port, std::string* err = nullptr);
+int tcp_connect(const std::string& host, uint16_t port, int timeout_ms, std::string* err = nullptr);
+bool send_all(int fd, const void* data, size_t len, int timeout_ms = 30000);
+bool recv_all(int fd, void* data, size_t len, int timeout_ms = 30000);
+
+class TcpServer;
+
+class Connection : public std::enable_shared_from_this<Connection> {
+ public:
+  Connection(int fd, uint64_t id, std::string peer) : fd_(fd), id_(id), peer_(std::move(peer)) {}
+  ~Connection();
+  // Thread-safe; may be called from any thread (server push).
+  bool send(const void* data, size_t len);
+  bool send(const std::string& s) { return send(s.data(), s.size()); }
+  void close();
+  bool closed() const { return closed_.load(); }
+  uint64_t id() const { return id_; }
+  const std::string& peer() const { return peer_; }
+  std::string& inbuf() { return inbuf_; }
+  int fd() const { return fd_; }
+  // arbitrary per-connection state for protocol layers (e.g. watch subscriptions)
+  std::shared_ptr<void> user;
+
+ private:
+  friend class TcpServer;
+  int fd_;
+  uint64_t id_;
+  std::string peer_;
+  std::string inbuf_;
+  std::mutex write_mu_;
+  std::atomic<bool> closed_{false};
+};
+using ConnPtr = std::shared_ptr<Connection>;
+
+class TcpServer {
+ public:
+  TcpServer() = default;
+  virtual ~TcpServer();
+  TcpServer(const TcpServer&) = delete;
+  TcpServer& operator=(const TcpServer&) = delete;
+
+  ErrorCode start(const std::string& host, uint16_t port, int worker_threads = 2);
+  void stop();
+  bool running() const { return running_.load(); }
+  uint16_t port() const { return port_; }
+  size_t connection_count() const;
+
+ protected:
+  // Called on a worker thread with newly received bytes appended to c->inbuf(); implementations
+  // consume complete messages from the buffer.  Return false to close the connection.
+  virtual bool on_data(const ConnPtr& c) = 0;
+  virtual void on_open(const ConnPtr&) {}
+  virtual void on_close(const ConnPtr&) {}
+
+ private:
+  void reactor_loop();
+  void worker_loop();
+  void drop(const ConnPtr& c);
+
+  int listen_fd_ = -1;
+  int epoll_fd_ = -1;
+  int wake_fd_ = -1;
+  uint16_t port_ = 0;
+  std::atomic<bool> running_{false};
+  std::thread reactor_;
+  std::vector<std::thread> workers_;
+  mutable std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<ConnPtr> ready_;
+  std::unordered_map<int, ConnPtr> conns_;
+  uint64_t next_id_ = 1;
+};
+
+// ---------------------------------------------------------------- framed RPC
+constexpr uint32_t kFrameHeader = 16;
+constexpr uint32_t kMaxFrame = 256u << 20;
+constexpr uint32_t kPushFlag = 0x80000000u;  // method field of unsolicited server -> client frames
+
+struct Frame {
+  uint32_t method = 0;
+  uint64_t id = 0;
+  std::string payload;
+};
+std::string encode_frame(uint32_t method, uint64_t id, const std::string& payload);
+
+class RpcServer : public TcpServer {
+ public:
+  // Handler returns the response payload.  It runs on a worker thread.
+  using Handler = std::function<std::string(const ConnPtr&, const std::string& request)>;
+  void register_method(uint32_t method, Handler h) { handlers_[method] = std::move(h); }
+  void set_close_hook(std::function<void(const ConnPtr&)> f) { close_hook_ = std::move(f); }
+  static bool push(const ConnPtr& c, uint32_t topic, const std::string& payload) {
+    return c->send(encode_frame(kPushFlag | topic, 0, payload));
+  }
+  uint64_t requests_served() const { return served_.load(); }
+
+ protected:
+  bool on_data(const ConnPtr& c) override;
+  void on_close(const ConnPtr& c) override {
+    if (close_hook_) close_hook_(c);
+  }
+
+ private:
+  std::unordered_map<uint32_t, Handler> handlers_;
+  std::function<void(const ConnPtr&)> close_hook_;
+  std::atomic<uint64_t> served_{0};
+};
+
+class RpcClient {
+ public:
+  RpcClient() = default;
+  ~RpcClient();
+  RpcClient(const RpcClient&) = delete;
+  RpcClient& operator=(const RpcClient&) = delete;
+
+  ErrorCode connect(const std::string& host, uint16_t port, int timeout_ms = 3000);
+  void close();
+  bool connected() const { return fd_ >= 0; }
+  // Blocking call; thread-safe (calls are serialised per client).
+  Result<std::string> call(uint32_t method, const std::string& request, int timeout_ms = 30000);
+  // Installs a handler for server push frames and starts a reader thread.  After this, call()
+  // responses are also routed through the reader thread.
+  void enable_push(std::function<void(uint32_t topic, const std::string& payload)> cb);
+
+ private:
+  void reader_loop();
+  int fd_ = -1;
+  std::mutex mu_;
+  uint64_t next_id_ = 1;
+  // push mode
+  std::function<void(uint32_t, const std::string&)> push_cb_;
+  std::thread reader_;
+  std::atomic<bool> reader_run_{false};
+  std::mutex resp_mu_;
+  std::condition_variable resp_cv_;
+  std::map<uint64_t, std::string> responses_;
+  bool broken_ = false;
+};
+
+// ---------------------------------------------------------------- HTTP (GET only)
+struct HttpResponse {
+  int status = 200;
+  std::string content_type = "text/plain; charset=utf-8";
+  std::string body;
+};
+
+class HttpServer : public TcpServer {
+ public:
+  using Route = std::function<HttpResponse(const std::string& path, const std::string& query)>;
+  void route(const std::string& path, Route r) { routes_[path] = std::move(r); }
+
+ protected:
+  bool on_data(const ConnPtr& c) override;
+
+ private:
+  std::map<std::string, Route> routes_;
+};
+
+// Blocking HTTP GET helper (tests, CLI).
+Result<std::string> http_get(const std::string& host, uint16_t port, const std::string& path, int* status = nullptr,
+                             int timeout_ms = 3000);
+
+}  // namespace bb::net

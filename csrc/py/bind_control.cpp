@@ -1,3 +1,825 @@
+// Python bindings of the control plane: types, allocator, coordination store, keystone, RPC,
+// worker + storage backends, client SDK.  Result<T> maps to "value or raise BlackbirdError".
+#include <pybind11/functional.h>
 #include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "alloc/allocator.h"
+#include "client/blackbird_client.h"
+#include "coord/coord.h"
+#include "keystone/keystone_service.h"
+#include "rpc/rpc_service.h"
+#include "rpc/wire.h"
+#include "worker/worker_service.h"
+
 namespace py = pybind11;
-void bind_control(py::module_& m) {}
+using namespace bb;
+
+py::object bb_json_to_py(const Json& j);
+
+namespace {
+
+struct BlackbirdError : std::runtime_error {
+  ErrorCode code;
+  explicit BlackbirdError(ErrorCode c) : std::runtime_error(std::string(to_string(c))), code(c) {}
+};
+
+template <typename T>
+T unwrap(Result<T> r) {
+  if (!r.ok()) throw BlackbirdError(r.error());
+  return std::move(r.value());
+}
+
+py::object location_to_py(const LocationDetail& l) {
+  py::dict d;
+  if (auto* m = std::get_if<MemoryLocation>(&l)) {
+    d["kind"] = "memory";
+    d["remote_addr"] = m->remote_addr;
+    d["rkey"] = m->rkey;
+    d["size"] = m->size;
+  } else if (auto* f = std::get_if<FileLocation>(&l)) {
+    d["kind"] = "file";
+    d["file_path"] = f->file_path;
+    d["file_offset"] = f->file_offset;
+  } else if (auto* c = std::get_if<CxlMemoryLocation>(&l)) {
+    d["kind"] = "cxl";
+    d["device_id"] = c->device_id;
+    d["region_id"] = c->region_id;
+    d["offset"] = c->offset;
+    d["size"] = c->size;
+  } else if (auto* g = std::get_if<GpuSlabLocation>(&l)) {
+    d["kind"] = "gpu";
+    d["device_rank"] = g->device_rank;
+    d["slab_id"] = g->slab_id;
+    d["offset"] = g->offset;
+    d["size"] = g->size;
+  }
+  return d;
+}
+
+// py results of batch calls: list of (ErrorCode, value-or-None)
+template <typename T, typename F>
+py::list results_to_py(const std::vector<Result<T>>& v, F&& conv) {
+  py::list out;
+  for (const auto& r : v) out.append(py::make_tuple(r.error(), r.ok() ? py::object(conv(r.value())) : py::object(py::none())));
+  return out;
+}
+
+}  // namespace
+
+void bind_control(py::module_& m) {
+  static py::exception<BlackbirdError> exc(m, "BlackbirdError");
+  py::register_exception_translator([](std::exception_ptr p) {
+    try {
+      if (p) std::rethrow_exception(p);
+    } catch (const BlackbirdError& e) {
+      // attach the code to the exception instance
+      PyObject* inst = PyObject_CallFunction(exc.ptr(), "s", e.what());
+      if (inst) {
+        py::object code = py::cast(e.code);
+        PyObject_SetAttrString(inst, "code", code.ptr());
+        PyErr_SetObject(exc.ptr(), inst);
+        Py_DECREF(inst);
+      }
+    }
+  });
+
+  // ---------------------------------------------------------------- types
+  py::enum_<StorageClass>(m, "StorageClass")
+      .value("STORAGE_UNSPECIFIED", StorageClass::STORAGE_UNSPECIFIED)
+      .value("RAM_CPU", StorageClass::RAM_CPU)
+      .value("RAM_GPU", StorageClass::RAM_GPU)
+      .value("NVME", StorageClass::NVME)
+      .value("SSD", StorageClass::SSD)
+      .value("HDD", StorageClass::HDD)
+      .value("CXL_MEMORY", StorageClass::CXL_MEMORY)
+      .value("CXL_TYPE2_DEVICE", StorageClass::CXL_TYPE2_DEVICE)
+      .value("CUSTOM", StorageClass::CUSTOM);
+  m.def("parse_storage_class", [](const std::string& s) -> py::object {
+    auto c = parse_storage_class(s);
+    return c ? py::cast(*c) : py::none();
+  });
+  m.def("tier_rank", &tier_rank);
+
+  py::class_<TransportEndpoint>(m, "TransportEndpoint")
+      .def(py::init<>())
+      .def_readwrite("ip", &TransportEndpoint::ip)
+      .def_readwrite("port", &TransportEndpoint::port)
+      .def_property("worker_key", [](const TransportEndpoint& e) { return py::bytes(reinterpret_cast<const char*>(e.worker_key.data()), e.worker_key.size()); },
+                    [](TransportEndpoint& e, const std::string& b) { e.worker_key.assign(b.begin(), b.end()); });
+
+  py::class_<ShardPlacement>(m, "ShardPlacement")
+      .def(py::init<>())
+      .def_readwrite("pool_id", &ShardPlacement::pool_id)
+      .def_readwrite("worker_id", &ShardPlacement::worker_id)
+      .def_readwrite("endpoint", &ShardPlacement::endpoint)
+      .def_readwrite("storage_class", &ShardPlacement::storage_class)
+      .def_readwrite("length", &ShardPlacement::length)
+      .def_readwrite("checksum", &ShardPlacement::checksum)
+      .def_readwrite("checksum_algo", &ShardPlacement::checksum_algo)
+      .def_property_readonly("location", [](const ShardPlacement& s) { return location_to_py(s.location); })
+      .def_property_readonly("offset", [](const ShardPlacement& s) -> uint64_t {
+        if (auto* g = std::get_if<GpuSlabLocation>(&s.location)) return g->offset;
+        if (auto* f = std::get_if<FileLocation>(&s.location)) return f->file_offset;
+        if (auto* c = std::get_if<CxlMemoryLocation>(&s.location)) return c->offset;
+        if (auto* mm = std::get_if<MemoryLocation>(&s.location)) return mm->remote_addr;
+        return 0;
+      });
+
+  py::class_<CopyPlacement>(m, "CopyPlacement")
+      .def(py::init<>())
+      .def_readwrite("copy_index", &CopyPlacement::copy_index)
+      .def_readwrite("shards", &CopyPlacement::shards)
+      .def("shards_size", &CopyPlacement::shards_size);
+
+  py::class_<WorkerConfig>(m, "WorkerConfig")
+      .def(py::init([](size_t replication_factor, size_t max_workers_per_copy, bool enable_soft_pin, std::string preferred_node,
+                       std::vector<StorageClass> preferred_classes, uint64_t ttl_ms, bool enable_locality_awareness,
+                       bool prefer_contiguous, size_t min_shard_size, ChecksumAlgo checksum, bool pack_fp8, bool symmetric_replicas) {
+             WorkerConfig c;
+             c.replication_factor = replication_factor;
+             c.max_workers_per_copy = max_workers_per_copy;
+             c.enable_soft_pin = enable_soft_pin;
+             c.preferred_node = std::move(preferred_node);
+             c.preferred_classes = std::move(preferred_classes);
+             c.ttl_ms = ttl_ms;
+             c.enable_locality_awareness = enable_locality_awareness;
+             c.prefer_contiguous = prefer_contiguous;
+             c.min_shard_size = min_shard_size;
+             c.checksum = checksum;
+             c.pack_fp8 = pack_fp8;
+             c.symmetric_replicas = symmetric_replicas;
+             return c;
+           }),
+           py::arg("replication_factor") = DEFAULT_REPLICATION_FACTOR, py::arg("max_workers_per_copy") = DEFAULT_MAX_WORKERS_PER_COPY,
+           py::arg("enable_soft_pin") = false, py::arg("preferred_node") = "", py::arg("preferred_classes") = std::vector<StorageClass>{},
+           py::arg("ttl_ms") = 30ull * 60 * 1000, py::arg("enable_locality_awareness") = true, py::arg("prefer_contiguous") = false,
+           py::arg("min_shard_size") = 4096, py::arg("checksum") = ChecksumAlgo::BBH64, py::arg("pack_fp8") = false,
+           py::arg("symmetric_replicas") = false)
+      .def_readwrite("replication_factor", &WorkerConfig::replication_factor)
+      .def_readwrite("max_workers_per_copy", &WorkerConfig::max_workers_per_copy)
+      .def_readwrite("enable_soft_pin", &WorkerConfig::enable_soft_pin)
+      .def_readwrite("preferred_node", &WorkerConfig::preferred_node)
+      .def_readwrite("preferred_classes", &WorkerConfig::preferred_classes)
+      .def_readwrite("ttl_ms", &WorkerConfig::ttl_ms)
+      .def_readwrite("enable_locality_awareness", &WorkerConfig::enable_locality_awareness)
+      .def_readwrite("prefer_contiguous", &WorkerConfig::prefer_contiguous)
+      .def_readwrite("min_shard_size", &WorkerConfig::min_shard_size)
+      .def_readwrite("checksum", &WorkerConfig::checksum)
+      .def_readwrite("pack_fp8", &WorkerConfig::pack_fp8)
+      .def_readwrite("symmetric_replicas", &WorkerConfig::symmetric_replicas)
+      .def("to_json", [](const WorkerConfig& c) { return to_json(c).dump(); });
+
+  py::class_<ClusterStats>(m, "ClusterStats")
+      .def_readonly("total_workers", &ClusterStats::total_workers)
+      .def_readonly("total_memory_pools", &ClusterStats::total_memory_pools)
+      .def_readonly("total_objects", &ClusterStats::total_objects)
+      .def_readonly("total_capacity", &ClusterStats::total_capacity)
+      .def_readonly("used_capacity", &ClusterStats::used_capacity)
+      .def_readonly("avg_utilization", &ClusterStats::avg_utilization)
+      .def_readonly("pending_objects", &ClusterStats::pending_objects)
+      .def_readonly("active_clients", &ClusterStats::active_clients);
+
+  py::class_<MemoryPool>(m, "MemoryPool")
+      .def(py::init([](std::string id, uint64_t size, StorageClass sc, std::string node_id, std::string worker_id, std::string endpoint,
+                       uint64_t remote_addr, std::string rkey_hex, int gpu_device_id, double max_bw_gbps, std::string fabric_domain,
+                       std::string mount_path) {
+             MemoryPool p;
+             p.id = std::move(id);
+             p.size = size;
+             p.storage_class = sc;
+             p.node_id = std::move(node_id);
+             p.worker_id = std::move(worker_id);
+             p.ucx_endpoint = std::move(endpoint);
+             p.ucx_remote_addr = remote_addr;
+             p.base_addr = remote_addr;
+             p.ucx_rkey_hex = std::move(rkey_hex);
+             p.gpu_device_id = gpu_device_id;
+             p.max_bw_gbps = max_bw_gbps;
+             p.fabric_domain = std::move(fabric_domain);
+             p.mount_path = std::move(mount_path);
+             return p;
+           }),
+           py::arg("id"), py::arg("size"), py::arg("storage_class") = StorageClass::RAM_CPU, py::arg("node_id") = "node-a",
+           py::arg("worker_id") = "", py::arg("endpoint") = "127.0.0.1:12345", py::arg("remote_addr") = 0x1000000,
+           py::arg("rkey_hex") = "deadbeef", py::arg("gpu_device_id") = -1, py::arg("max_bw_gbps") = 0.0,
+           py::arg("fabric_domain") = "", py::arg("mount_path") = "")
+      .def_readwrite("id", &MemoryPool::id)
+      .def_readwrite("node_id", &MemoryPool::node_id)
+      .def_readwrite("worker_id", &MemoryPool::worker_id)
+      .def_readwrite("size", &MemoryPool::size)
+      .def_readwrite("used", &MemoryPool::used)
+      .def_readwrite("storage_class", &MemoryPool::storage_class)
+      .def_readwrite("ucx_endpoint", &MemoryPool::ucx_endpoint)
+      .def_readwrite("ucx_remote_addr", &MemoryPool::ucx_remote_addr)
+      .def_readwrite("ucx_rkey_hex", &MemoryPool::ucx_rkey_hex)
+      .def_readwrite("gpu_device_id", &MemoryPool::gpu_device_id)
+      .def_readwrite("max_bw_gbps", &MemoryPool::max_bw_gbps)
+      .def_readwrite("fabric_domain", &MemoryPool::fabric_domain)
+      .def("available", &MemoryPool::available)
+      .def("utilization", &MemoryPool::utilization)
+      .def("to_json", [](const MemoryPool& p) { return to_json(p).dump(); })
+      .def_static("from_json", [](const std::string& s) {
+        auto j = Json::parse(s);
+        if (!j) throw py::value_error("bad json");
+        return unwrap(memory_pool_from_json(*j));
+      });
+
+  py::class_<KeystoneConfig>(m, "KeystoneConfig")
+      .def(py::init<>())
+      .def_static("from_yaml", &KeystoneConfig::from_yaml)
+      .def_readwrite("cluster_id", &KeystoneConfig::cluster_id)
+      .def_readwrite("etcd_endpoints", &KeystoneConfig::etcd_endpoints)
+      .def_readwrite("listen_address", &KeystoneConfig::listen_address)
+      .def_readwrite("http_metrics_port", &KeystoneConfig::http_metrics_port)
+      .def_readwrite("service_id", &KeystoneConfig::service_id)
+      .def_readwrite("enable_gc", &KeystoneConfig::enable_gc)
+      .def_readwrite("enable_ha", &KeystoneConfig::enable_ha)
+      .def_readwrite("eviction_ratio", &KeystoneConfig::eviction_ratio)
+      .def_readwrite("high_watermark", &KeystoneConfig::high_watermark)
+      .def_readwrite("client_ttl_sec", &KeystoneConfig::client_ttl_sec)
+      .def_readwrite("worker_heartbeat_ttl_sec", &KeystoneConfig::worker_heartbeat_ttl_sec)
+      .def_readwrite("service_registration_ttl_sec", &KeystoneConfig::service_registration_ttl_sec)
+      .def_readwrite("service_refresh_interval_sec", &KeystoneConfig::service_refresh_interval_sec)
+      .def_readwrite("gc_interval_sec", &KeystoneConfig::gc_interval_sec)
+      .def_readwrite("health_check_interval_sec", &KeystoneConfig::health_check_interval_sec)
+      .def_readwrite("max_replicas", &KeystoneConfig::max_replicas)
+      .def_readwrite("default_replicas", &KeystoneConfig::default_replicas)
+      .def_readwrite("rpc_threads", &KeystoneConfig::rpc_threads)
+      .def_readwrite("wal_path", &KeystoneConfig::wal_path)
+      .def_readwrite("log_level", &KeystoneConfig::log_level)
+      .def("validate", [](const KeystoneConfig& c) {
+        std::string err;
+        ErrorCode ec = c.validate(&err);
+        return py::make_tuple(ec, err);
+      });
+
+  m.def("bytes_to_hex", [](const std::string& b) { return bytes_to_hex(std::vector<uint8_t>(b.begin(), b.end())); });
+  m.def("hex_to_bytes", [](const std::string& h) -> py::object {
+    auto b = hex_to_bytes(h);
+    if (!b) return py::none();
+    return py::bytes(reinterpret_cast<const char*>(b->data()), b->size());
+  });
+
+  // ---------------------------------------------------------------- allocator
+  using alloc::AllocationRequest;
+  using alloc::AllocationResult;
+  using alloc::PoolAllocator;
+  using alloc::Range;
+  using alloc::RangeAllocator;
+  py::class_<Range>(m, "Range")
+      .def(py::init<uint64_t, uint64_t>())
+      .def_readwrite("offset", &Range::offset)
+      .def_readwrite("length", &Range::length)
+      .def("end", &Range::end)
+      .def("adjacent_to", &Range::adjacent_to)
+      .def("merge_with", &Range::merge_with);
+  py::class_<PoolAllocator>(m, "PoolAllocator")
+      .def(py::init<const MemoryPool&, uint64_t>(), py::arg("pool"), py::arg("align") = PoolAllocator::kDefaultAlign)
+      .def("allocate", [](PoolAllocator& a, uint64_t size, bool best) -> py::object {
+        auto r = a.allocate(size, best);
+        return r ? py::cast(*r) : py::none();
+      }, py::arg("size"), py::arg("prefer_best_fit") = true, py::call_guard<py::gil_scoped_release>())
+      .def("allocate_at", &PoolAllocator::allocate_at)
+      .def("free", &PoolAllocator::free, py::call_guard<py::gil_scoped_release>())
+      .def("total_free", &PoolAllocator::total_free)
+      .def("largest_free_block", &PoolAllocator::largest_free_block)
+      .def("fragmentation_ratio", &PoolAllocator::fragmentation_ratio)
+      .def("can_allocate", &PoolAllocator::can_allocate)
+      .def("free_ranges", &PoolAllocator::free_ranges)
+      .def("pool_id", &PoolAllocator::pool_id);
+  py::class_<AllocationRequest>(m, "AllocationRequest")
+      .def(py::init([](std::string key, size_t data_size, size_t replication_factor, size_t max_workers_per_copy,
+                       std::vector<StorageClass> preferred_classes, std::string preferred_node, bool enable_locality_awareness,
+                       bool enable_striping, bool prefer_contiguous, size_t min_shard_size, bool strict_min_shard,
+                       bool symmetric_replicas, std::string client_node) {
+             AllocationRequest r;
+             r.object_key = std::move(key);
+             r.data_size = data_size;
+             r.replication_factor = replication_factor;
+             r.max_workers_per_copy = max_workers_per_copy;
+             r.preferred_classes = std::move(preferred_classes);
+             r.preferred_node = std::move(preferred_node);
+             r.enable_locality_awareness = enable_locality_awareness;
+             r.enable_striping = enable_striping;
+             r.prefer_contiguous = prefer_contiguous;
+             r.min_shard_size = min_shard_size;
+             r.strict_min_shard = strict_min_shard;
+             r.symmetric_replicas = symmetric_replicas;
+             r.client_node = std::move(client_node);
+             return r;
+           }),
+           py::arg("object_key"), py::arg("data_size"), py::arg("replication_factor") = 1, py::arg("max_workers_per_copy") = 1,
+           py::arg("preferred_classes") = std::vector<StorageClass>{}, py::arg("preferred_node") = "",
+           py::arg("enable_locality_awareness") = true, py::arg("enable_striping") = true, py::arg("prefer_contiguous") = false,
+           py::arg("min_shard_size") = 4096, py::arg("strict_min_shard") = false, py::arg("symmetric_replicas") = false,
+           py::arg("client_node") = "");
+  py::class_<AllocationResult>(m, "AllocationResult")
+      .def_readonly("copies", &AllocationResult::copies)
+      .def_readonly("total_shards_created", &AllocationResult::total_shards_created)
+      .def_readonly("pools_used", &AllocationResult::pools_used)
+      .def_property_readonly("required_spillover", [](const AllocationResult& r) { return r.stats.required_spillover; })
+      .def_property_readonly("avg_shard_size", [](const AllocationResult& r) { return r.stats.avg_shard_size; });
+  py::class_<alloc::AllocatorStats>(m, "AllocatorStats")
+      .def_readonly("total_allocated_bytes", &alloc::AllocatorStats::total_allocated_bytes)
+      .def_readonly("total_free_bytes", &alloc::AllocatorStats::total_free_bytes)
+      .def_readonly("total_objects", &alloc::AllocatorStats::total_objects)
+      .def_readonly("total_shards", &alloc::AllocatorStats::total_shards)
+      .def_readonly("fragmentation_ratio", &alloc::AllocatorStats::fragmentation_ratio);
+  py::class_<RangeAllocator>(m, "RangeAllocator")
+      .def(py::init<>())
+      .def("allocate", [](RangeAllocator& a, const AllocationRequest& r, const std::unordered_map<MemoryPoolId, MemoryPool>& pools) {
+        return unwrap(a.allocate(r, pools));
+      })
+      .def("free", &RangeAllocator::free)
+      .def("get_stats", [](RangeAllocator& a, py::object sc) {
+        return a.get_stats(sc.is_none() ? std::nullopt : std::optional<StorageClass>(sc.cast<StorageClass>()));
+      }, py::arg("storage_class") = py::none())
+      .def("get_free_space", &RangeAllocator::get_free_space)
+      .def("can_allocate", &RangeAllocator::can_allocate)
+      .def("pool_used_bytes", &RangeAllocator::pool_used_bytes)
+      .def("forget_pool", &RangeAllocator::forget_pool);
+
+  // ---------------------------------------------------------------- coordination
+  using coord::CoordService;
+  using coord::CoordStore;
+  using coord::MemCoord;
+  py::class_<CoordStore, std::shared_ptr<CoordStore>>(m, "CoordStore")
+      .def("put", &CoordStore::put, py::arg("key"), py::arg("value"), py::arg("lease") = 0)
+      .def("get", [](CoordStore& s, const std::string& k) -> py::object {
+        auto r = s.get(k);
+        if (!r.ok()) return py::none();
+        return py::bytes(r.value());
+      })
+      .def("delete", &CoordStore::del)
+      .def("get_with_prefix", [](CoordStore& s, const std::string& p) {
+        py::list out;
+        for (auto& kv : unwrap(s.get_with_prefix(p))) out.append(py::make_tuple(kv.key, py::bytes(kv.value), kv.mod_revision, kv.lease));
+        return out;
+      })
+      .def("del_prefix", [](CoordStore& s, const std::string& p) { return unwrap(s.del_prefix(p)); })
+      .def("grant_lease", [](CoordStore& s, int64_t ttl) { return unwrap(s.grant_lease(ttl)); })
+      .def("keep_alive", &CoordStore::keep_alive)
+      .def("revoke_lease", &CoordStore::revoke_lease)
+      .def("lease_remaining_ms", [](CoordStore& s, LeaseId l) { return unwrap(s.lease_remaining_ms(l)); })
+      .def("put_if_absent", [](CoordStore& s, const std::string& k, const std::string& v, LeaseId l) { return unwrap(s.put_if_absent(k, v, l)); },
+           py::arg("key"), py::arg("value"), py::arg("lease") = 0)
+      .def("compare_and_swap", [](CoordStore& s, const std::string& k, const std::string& e, const std::string& v, LeaseId l) {
+        return unwrap(s.compare_and_swap(k, e, v, l));
+      }, py::arg("key"), py::arg("expected"), py::arg("value"), py::arg("lease") = 0)
+      .def("compare_and_delete", [](CoordStore& s, const std::string& k, const std::string& e) { return unwrap(s.compare_and_delete(k, e)); })
+      .def("watch_prefix", [](CoordStore& s, const std::string& prefix, py::function cb) {
+        auto holder = std::make_shared<py::function>(std::move(cb));
+        return unwrap(s.watch_prefix(prefix, [holder](const coord::WatchEvent& ev) {
+          py::gil_scoped_acquire g;
+          try {
+            (*holder)(ev.type == coord::EventType::DELETE ? "DELETE" : "PUT", ev.key, py::bytes(ev.value), ev.revision);
+          } catch (py::error_already_set& e) {
+            e.discard_as_unraisable("watch callback");
+          }
+        }));
+      }, py::call_guard<py::gil_scoped_release>())
+      .def("unwatch", &CoordStore::unwatch, py::call_guard<py::gil_scoped_release>())
+      .def("revision", &CoordStore::revision);
+  py::class_<MemCoord, CoordStore, std::shared_ptr<MemCoord>>(m, "MemCoord")
+      .def(py::init<>())
+      .def("advance_time_ms", &MemCoord::advance_time_ms, py::call_guard<py::gil_scoped_release>())
+      .def("flush_events", &MemCoord::flush_events, py::call_guard<py::gil_scoped_release>())
+      .def("lease_count", &MemCoord::lease_count)
+      .def("key_count", &MemCoord::key_count);
+  py::class_<coord::RemoteCoord, CoordStore, std::shared_ptr<coord::RemoteCoord>>(m, "RemoteCoord")
+      .def(py::init<>())
+      .def("connect", &coord::RemoteCoord::connect, py::arg("endpoints"), py::arg("timeout_ms") = 3000)
+      .def("close", &coord::RemoteCoord::close, py::call_guard<py::gil_scoped_release>());
+  py::class_<coord::CoordServer>(m, "CoordServer")
+      .def(py::init([](std::shared_ptr<MemCoord> st) { return std::make_unique<coord::CoordServer>(std::move(st)); }), py::arg("store") = nullptr)
+      .def("start", &coord::CoordServer::start, py::arg("host") = "127.0.0.1", py::arg("port") = 0)
+      .def("stop", &coord::CoordServer::stop, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("port", &coord::CoordServer::port)
+      .def("store", &coord::CoordServer::store);
+  m.def("shared_mem_coord", &coord::shared_mem_coord);
+  m.def("drop_shared_mem_coord", &coord::drop_shared_mem_coord);
+
+  py::class_<CoordService, std::shared_ptr<CoordService>>(m, "CoordService")
+      .def(py::init<const std::string&>(), py::arg("endpoints") = "")
+      .def(py::init<std::shared_ptr<CoordStore>>())
+      .def("connect", &CoordService::connect)
+      .def("is_connected", &CoordService::is_connected)
+      .def("store", &CoordService::store)
+      .def("put", &CoordService::put)
+      .def("get", [](CoordService& s, const std::string& k) -> py::object {
+        std::string v;
+        return s.get(k, v) == ErrorCode::OK ? py::object(py::bytes(v)) : py::object(py::none());
+      })
+      .def("delete", &CoordService::del)
+      .def("put_with_ttl", &CoordService::put_with_ttl)
+      .def("register_service", &CoordService::register_service)
+      .def("discover_service", [](CoordService& s, const std::string& name) {
+        std::vector<std::string> a;
+        s.discover_service(name, a);
+        return a;
+      })
+      .def("unregister_service", &CoordService::unregister_service)
+      .def("campaign_leader", [](CoordService& s, const std::string& e, const std::string& c, int64_t ttl) {
+        bool won = false;
+        ErrorCode ec = s.campaign_leader(e, c, ttl, won);
+        return py::make_tuple(ec, won);
+      })
+      .def("get_leader", [](CoordService& s, const std::string& e) -> py::object {
+        std::string l;
+        return s.get_leader(e, l) == ErrorCode::OK ? py::object(py::str(l)) : py::object(py::none());
+      })
+      .def("resign_leader", &CoordService::resign_leader)
+      .def("refresh_leadership", &CoordService::refresh_leadership);
+
+  // ---------------------------------------------------------------- keystone
+  using keystone::KeystoneService;
+  using keystone::PutStartItem;
+  py::enum_<keystone::ObjectState>(m, "ObjectState").value("PENDING", keystone::ObjectState::PENDING).value("COMPLETE", keystone::ObjectState::COMPLETE);
+  py::class_<KeystoneService, std::shared_ptr<KeystoneService>>(m, "KeystoneService")
+      .def(py::init<const KeystoneConfig&, std::shared_ptr<CoordService>>(), py::arg("config"), py::arg("coord") = nullptr)
+      .def("initialize", &KeystoneService::initialize, py::call_guard<py::gil_scoped_release>())
+      .def("start", &KeystoneService::start, py::call_guard<py::gil_scoped_release>())
+      .def("stop", &KeystoneService::stop, py::call_guard<py::gil_scoped_release>())
+      .def("is_running", &KeystoneService::is_running)
+      .def("is_leader", &KeystoneService::is_leader)
+      .def("object_exists", [](KeystoneService& k, const std::string& key) { return unwrap(k.object_exists(key)); })
+      .def("get_workers", [](KeystoneService& k, const std::string& key) { return unwrap(k.get_workers(key)); })
+      .def("put_start", [](KeystoneService& k, const std::string& key, size_t size, const WorkerConfig& c, const std::string& client,
+                           const std::string& node) { return unwrap(k.put_start(key, size, c, client, node)); },
+           py::arg("key"), py::arg("size"), py::arg("config") = WorkerConfig{}, py::arg("client_id") = "", py::arg("client_node") = "")
+      .def("put_complete", [](KeystoneService& k, const std::string& key, const keystone::ShardChecksums& s) { return k.put_complete(key, s); },
+           py::arg("key"), py::arg("checksums") = keystone::ShardChecksums{})
+      .def("put_cancel", &KeystoneService::put_cancel)
+      .def("remove_object", &KeystoneService::remove_object)
+      .def("remove_all_objects", [](KeystoneService& k) { return unwrap(k.remove_all_objects()); })
+      .def("batch_object_exists", [](KeystoneService& k, const std::vector<std::string>& keys) {
+        return results_to_py(k.batch_object_exists(keys), [](bool b) { return py::bool_(b); });
+      })
+      .def("batch_get_workers", [](KeystoneService& k, const std::vector<std::string>& keys) {
+        return results_to_py(k.batch_get_workers(keys), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
+      })
+      .def("batch_put_start", [](KeystoneService& k, const std::vector<std::string>& keys, const std::vector<size_t>& sizes, const WorkerConfig& c) {
+        std::vector<PutStartItem> items;
+        for (size_t i = 0; i < keys.size(); ++i) items.push_back({keys[i], i < sizes.size() ? sizes[i] : 0, c});
+        return results_to_py(k.batch_put_start(items), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
+      })
+      .def("batch_put_complete", [](KeystoneService& k, const std::vector<std::string>& keys) { return k.batch_put_complete(keys); })
+      .def("batch_put_cancel", &KeystoneService::batch_put_cancel)
+      .def("batch_remove_object", &KeystoneService::batch_remove_object)
+      .def("get_cluster_stats", [](KeystoneService& k) { return unwrap(k.get_cluster_stats()); })
+      .def("get_view_version", &KeystoneService::get_view_version)
+      .def("get_memory_pools", [](KeystoneService& k) {
+        std::vector<MemoryPool> v;
+        k.get_memory_pools(v);
+        return v;
+      })
+      .def("get_workers_info", [](KeystoneService& k) {
+        std::vector<keystone::WorkerInfo> v;
+        k.get_workers_info(v);
+        py::list out;
+        for (const auto& w : v) {
+          py::dict d;
+          d["worker_id"] = w.worker_id;
+          d["node_id"] = w.node_id;
+          d["endpoint"] = w.endpoint;
+          d["pools"] = w.pools;
+          out.append(d);
+        }
+        return out;
+      })
+      .def("remove_worker", &KeystoneService::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("register_memory_pool", &KeystoneService::register_memory_pool)
+      .def("register_worker", [](KeystoneService& k, const std::string& id, const std::string& node, const std::string& ep) {
+        WorkerRecord r;
+        r.worker_id = id;
+        r.node_id = node;
+        r.rpc_endpoint = ep;
+        return k.register_worker(r);
+      }, py::arg("worker_id"), py::arg("node_id") = "", py::arg("endpoint") = "")
+      .def("worker_heartbeat", &KeystoneService::worker_heartbeat)
+      .def("handle_worker_death", &KeystoneService::handle_worker_death, py::call_guard<py::gil_scoped_release>())
+      .def("client_register", [](KeystoneService& k, const std::string& n) { return unwrap(k.client_register(n)); })
+      .def("client_ping", [](KeystoneService& k, const std::string& id) { return unwrap(k.client_ping(id)); })
+      .def("run_gc_once", &KeystoneService::run_gc_once, py::call_guard<py::gil_scoped_release>())
+      .def("run_eviction_once", &KeystoneService::run_eviction_once, py::call_guard<py::gil_scoped_release>())
+      .def("run_repair_once", &KeystoneService::run_repair_once, py::call_guard<py::gil_scoped_release>())
+      .def("tier_utilization", &KeystoneService::tier_utilization)
+      .def("metrics_text", &KeystoneService::metrics_text)
+      .def("stats_json", [](KeystoneService& k) { return bb_json_to_py(k.stats_json()); })
+      .def("allocator_stats", &KeystoneService::allocator_stats)
+      .def("object_info", [](KeystoneService& k, const std::string& key) {
+        auto o = unwrap(k.get_object_info(key));
+        py::dict d;
+        d["size"] = o.size;
+        d["state"] = o.state;
+        d["copies"] = o.copies;
+        d["soft_pin"] = o.config.enable_soft_pin;
+        d["ttl_ms"] = o.config.ttl_ms;
+        return d;
+      })
+      // Python-implemented copy mover (tests): fn(key, src_copy, dst_copy, algo) -> (ErrorCode, [shard checksums])
+      .def("set_copy_mover", [](KeystoneService& k, py::object fn) {
+        if (fn.is_none()) {
+          k.set_copy_mover(nullptr);
+          return;
+        }
+        auto holder = std::make_shared<py::object>(std::move(fn));
+        k.set_copy_mover([holder](const ObjectKey& key, const CopyPlacement& src, CopyPlacement& dst, ChecksumAlgo algo) {
+          py::gil_scoped_acquire g;
+          try {
+            py::tuple r = (*holder)(key, src, dst, algo);
+            ErrorCode ec = r[0].cast<ErrorCode>();
+            if (ec == ErrorCode::OK && r.size() > 1) {
+              auto sums = r[1].cast<std::vector<uint64_t>>();
+              for (size_t i = 0; i < sums.size() && i < dst.shards.size(); ++i) dst.shards[i].checksum = sums[i];
+            }
+            return ec;
+          } catch (py::error_already_set& e) {
+            e.discard_as_unraisable("copy mover");
+            return ErrorCode::INTERNAL_ERROR;
+          }
+        });
+      });
+
+  py::class_<rpc::RpcService>(m, "RpcService")
+      .def(py::init<std::shared_ptr<KeystoneService>, const KeystoneConfig&>())
+      .def("start", &rpc::RpcService::start, py::call_guard<py::gil_scoped_release>())
+      .def("stop", &rpc::RpcService::stop, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("rpc_port", &rpc::RpcService::rpc_port)
+      .def_property_readonly("http_port", &rpc::RpcService::http_port)
+      .def_property_readonly("requests_served", &rpc::RpcService::requests_served);
+
+  py::class_<rpc::KeystoneApi, std::shared_ptr<rpc::KeystoneApi>>(m, "KeystoneApi")
+      .def("object_exists", [](rpc::KeystoneApi& k, const std::string& key) { return unwrap(k.object_exists(key)); }, py::call_guard<py::gil_scoped_release>())
+      .def("get_workers", [](rpc::KeystoneApi& k, const std::string& key) { return unwrap(k.get_workers(key)); }, py::call_guard<py::gil_scoped_release>())
+      .def("put_start", [](rpc::KeystoneApi& k, const std::string& key, size_t size, const WorkerConfig& c) { return unwrap(k.put_start(key, size, c)); },
+           py::arg("key"), py::arg("size"), py::arg("config") = WorkerConfig{}, py::call_guard<py::gil_scoped_release>())
+      .def("put_complete", [](rpc::KeystoneApi& k, const std::string& key, const keystone::ShardChecksums& s) { return k.put_complete(key, s); },
+           py::arg("key"), py::arg("checksums") = keystone::ShardChecksums{}, py::call_guard<py::gil_scoped_release>())
+      .def("put_cancel", &rpc::KeystoneApi::put_cancel, py::call_guard<py::gil_scoped_release>())
+      .def("remove_object", &rpc::KeystoneApi::remove_object, py::call_guard<py::gil_scoped_release>())
+      .def("remove_all_objects", [](rpc::KeystoneApi& k) { return unwrap(k.remove_all_objects()); }, py::call_guard<py::gil_scoped_release>())
+      .def("get_cluster_stats", [](rpc::KeystoneApi& k) { return unwrap(k.get_cluster_stats()); }, py::call_guard<py::gil_scoped_release>())
+      .def("get_view_version", [](rpc::KeystoneApi& k) { return unwrap(k.get_view_version()); }, py::call_guard<py::gil_scoped_release>())
+      .def("batch_object_exists", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) {
+        return results_to_py(k.batch_object_exists(keys), [](bool b) { return py::bool_(b); });
+      })
+      .def("batch_get_workers", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) {
+        return results_to_py(k.batch_get_workers(keys), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
+      })
+      .def("batch_put_start", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys, const std::vector<size_t>& sizes, const WorkerConfig& c) {
+        std::vector<PutStartItem> items;
+        for (size_t i = 0; i < keys.size(); ++i) items.push_back({keys[i], i < sizes.size() ? sizes[i] : 0, c});
+        return results_to_py(k.batch_put_start(items), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
+      })
+      .def("batch_put_complete", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) { return k.batch_put_complete(keys, {}); })
+      .def("batch_put_cancel", &rpc::KeystoneApi::batch_put_cancel)
+      .def("batch_remove_object", &rpc::KeystoneApi::batch_remove_object)
+      .def("get_memory_pools", [](rpc::KeystoneApi& k) { return unwrap(k.get_memory_pools()); })
+      .def("client_register", [](rpc::KeystoneApi& k, const std::string& n) { return unwrap(k.client_register(n)); })
+      .def("client_ping", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(k.client_ping(id)); })
+      .def("register_memory_pool", &rpc::KeystoneApi::register_memory_pool)
+      .def("worker_heartbeat", &rpc::KeystoneApi::worker_heartbeat);
+  py::class_<rpc::KeystoneRpcClient, rpc::KeystoneApi, std::shared_ptr<rpc::KeystoneRpcClient>>(m, "KeystoneRpcClient")
+      .def(py::init<>())
+      .def("connect", [](rpc::KeystoneRpcClient& c, const std::string& host, uint16_t port, int timeout_ms) { return c.connect(host, port, timeout_ms); },
+           py::arg("host"), py::arg("port"), py::arg("timeout_ms") = 3000, py::call_guard<py::gil_scoped_release>())
+      .def("connected", &rpc::KeystoneRpcClient::connected);
+  py::class_<rpc::LocalKeystoneApi, rpc::KeystoneApi, std::shared_ptr<rpc::LocalKeystoneApi>>(m, "LocalKeystoneApi")
+      .def(py::init<std::shared_ptr<KeystoneService>>());
+
+  m.def("http_get", [](const std::string& host, uint16_t port, const std::string& path) {
+    int status = 0;
+    Result<std::string> r = ErrorCode::INTERNAL_ERROR;
+    {
+      py::gil_scoped_release rel;
+      r = net::http_get(host, port, path, &status);
+    }
+    if (!r.ok()) throw BlackbirdError(r.error());
+    return py::make_tuple(status, r.value());
+  });
+
+  // ---------------------------------------------------------------- worker + backends
+  using worker::StorageBackend;
+  py::class_<worker::ReservationToken>(m, "ReservationToken")
+      .def_readonly("token_id", &worker::ReservationToken::token_id)
+      .def_readonly("pool_id", &worker::ReservationToken::pool_id)
+      .def_readonly("remote_addr", &worker::ReservationToken::remote_addr)
+      .def_readonly("rkey", &worker::ReservationToken::rkey)
+      .def_readonly("size", &worker::ReservationToken::size);
+  py::class_<worker::StorageStats>(m, "StorageStats")
+      .def_readonly("total_capacity", &worker::StorageStats::total_capacity)
+      .def_readonly("used_capacity", &worker::StorageStats::used_capacity)
+      .def_readonly("available_capacity", &worker::StorageStats::available_capacity)
+      .def_readonly("num_reservations", &worker::StorageStats::num_reservations)
+      .def_readonly("num_committed_shards", &worker::StorageStats::num_committed_shards)
+      .def_readonly("utilization", &worker::StorageStats::utilization)
+      .def_readonly("bytes_written", &worker::StorageStats::bytes_written)
+      .def_readonly("bytes_read", &worker::StorageStats::bytes_read)
+      .def_readonly("io_errors", &worker::StorageStats::io_errors);
+  py::class_<StorageBackend>(m, "StorageBackend")
+      .def("get_storage_class", &StorageBackend::get_storage_class)
+      .def("get_total_capacity", &StorageBackend::get_total_capacity)
+      .def("get_used_capacity", &StorageBackend::get_used_capacity)
+      .def("get_available_capacity", &StorageBackend::get_available_capacity)
+      .def("get_base_address", &StorageBackend::get_base_address)
+      .def("get_rkey", &StorageBackend::get_rkey)
+      .def("initialize", &StorageBackend::initialize, py::call_guard<py::gil_scoped_release>())
+      .def("shutdown", &StorageBackend::shutdown, py::call_guard<py::gil_scoped_release>())
+      .def("reserve_shard", [](StorageBackend& b, uint64_t size, const std::string& hint) { return unwrap(b.reserve_shard(size, hint)); },
+           py::arg("size"), py::arg("hint") = "", py::call_guard<py::gil_scoped_release>())
+      .def("commit_shard", &StorageBackend::commit_shard, py::call_guard<py::gil_scoped_release>())
+      .def("abort_shard", &StorageBackend::abort_shard)
+      .def("free_shard", &StorageBackend::free_shard)
+      .def("get_stats", &StorageBackend::get_stats)
+      .def("write", [](StorageBackend& b, uint64_t off, py::buffer data) {
+        py::buffer_info i = data.request();
+        py::gil_scoped_release rel;
+        return b.write(off, i.ptr, static_cast<uint64_t>(i.size * i.itemsize));
+      })
+      .def("read", [](StorageBackend& b, uint64_t off, uint64_t len) {
+        std::string out(len, '\0');
+        ErrorCode ec;
+        {
+          py::gil_scoped_release rel;
+          ec = b.read(off, out.data(), len);
+        }
+        if (ec != ErrorCode::OK) throw BlackbirdError(ec);
+        return py::bytes(out);
+      })
+      .def("flush", &StorageBackend::flush)
+      .def("set_pool_id", &StorageBackend::set_pool_id)
+      .def("set_reservation_ttl_ms", &StorageBackend::set_reservation_ttl_ms)
+      .def("has_direct_ptr", [](StorageBackend& b) { return b.direct_ptr(0) != nullptr; });
+  py::class_<worker::IoUringDiskBackend, StorageBackend>(m, "IoUringDiskBackend")
+      .def_property_readonly("sqes_submitted", &worker::IoUringDiskBackend::sqes_submitted)
+      .def_property_readonly("using_uring", &worker::IoUringDiskBackend::using_uring)
+      .def_property_readonly("using_direct_io", &worker::IoUringDiskBackend::using_direct_io)
+      .def_property_readonly("file_path", &worker::IoUringDiskBackend::file_path)
+      .def("recovered_extents", [](worker::IoUringDiskBackend& b) {
+        py::list out;
+        for (const auto& e : b.recovered_extents()) out.append(py::make_tuple(e.offset, e.size, e.crc));
+        return out;
+      });
+  py::class_<worker::CxlMemoryBackend, StorageBackend>(m, "CxlMemoryBackend")
+      .def_property_readonly("is_dax", &worker::CxlMemoryBackend::is_dax)
+      .def_property_readonly("numa_bound", &worker::CxlMemoryBackend::numa_bound)
+      .def("region_id", &worker::CxlMemoryBackend::region_id);
+  py::class_<worker::MmapDiskBackend, StorageBackend>(m, "MmapDiskBackend").def_property_readonly("file_path", &worker::MmapDiskBackend::file_path);
+  py::class_<worker::RamBackend, StorageBackend>(m, "RamBackend");
+  m.def("create_storage_backend", [](StorageClass sc, uint64_t capacity, const std::string& mount_path, uint32_t queue_depth, int numa_node,
+                                      const std::string& pool_id) -> std::unique_ptr<StorageBackend> {
+    worker::BackendOptions o;
+    o.mount_path = mount_path;
+    o.queue_depth = queue_depth;
+    o.numa_node = numa_node;
+    auto b = worker::create_storage_backend(sc, capacity, o);
+    if (b && !pool_id.empty()) b->set_pool_id(pool_id);
+    return b;
+  }, py::arg("storage_class"), py::arg("capacity"), py::arg("mount_path") = "", py::arg("queue_depth") = 64, py::arg("numa_node") = -1,
+     py::arg("pool_id") = "");
+  m.def("io_uring_supported", &worker::IoUring::supported);
+
+  py::class_<worker::StoragePoolConfig>(m, "StoragePoolConfig")
+      .def(py::init([](std::string pool_id, StorageClass sc, uint64_t size, std::string mount_path, int gpu_device_id) {
+             worker::StoragePoolConfig c;
+             c.pool_id = std::move(pool_id);
+             c.storage_class = sc;
+             c.size_bytes = size;
+             c.mount_path = std::move(mount_path);
+             c.gpu_device_id = gpu_device_id;
+             return c;
+           }),
+           py::arg("pool_id"), py::arg("storage_class"), py::arg("size_bytes"), py::arg("mount_path") = "", py::arg("gpu_device_id") = 0)
+      .def_readwrite("pool_id", &worker::StoragePoolConfig::pool_id)
+      .def_readwrite("storage_class", &worker::StoragePoolConfig::storage_class)
+      .def_readwrite("size_bytes", &worker::StoragePoolConfig::size_bytes)
+      .def_readwrite("mount_path", &worker::StoragePoolConfig::mount_path)
+      .def_readwrite("gpu_device_id", &worker::StoragePoolConfig::gpu_device_id);
+  py::class_<worker::WorkerServiceConfig>(m, "WorkerServiceConfig")
+      .def(py::init<>())
+      .def_static("from_yaml", &worker::load_worker_config_from_file)
+      .def_readwrite("worker_id", &worker::WorkerServiceConfig::worker_id)
+      .def_readwrite("node_id", &worker::WorkerServiceConfig::node_id)
+      .def_readwrite("cluster_id", &worker::WorkerServiceConfig::cluster_id)
+      .def_readwrite("etcd_endpoints", &worker::WorkerServiceConfig::etcd_endpoints)
+      .def_readwrite("keystone_address", &worker::WorkerServiceConfig::keystone_address)
+      .def_readwrite("rpc_endpoint", &worker::WorkerServiceConfig::rpc_endpoint)
+      .def_readwrite("ucx_endpoint", &worker::WorkerServiceConfig::ucx_endpoint)
+      .def_readwrite("interconnects", &worker::WorkerServiceConfig::interconnects)
+      .def_readwrite("max_bw_gbps", &worker::WorkerServiceConfig::max_bw_gbps)
+      .def_readwrite("numa_node", &worker::WorkerServiceConfig::numa_node)
+      .def_readwrite("lease_ttl_sec", &worker::WorkerServiceConfig::lease_ttl_sec)
+      .def_readwrite("heartbeat_interval_sec", &worker::WorkerServiceConfig::heartbeat_interval_sec)
+      .def_readwrite("fabric_domain", &worker::WorkerServiceConfig::fabric_domain)
+      .def_readwrite("storage_pools", &worker::WorkerServiceConfig::storage_pools);
+  py::class_<worker::WorkerService, std::shared_ptr<worker::WorkerService>>(m, "WorkerService")
+      .def(py::init<const worker::WorkerServiceConfig&, std::shared_ptr<CoordService>, std::shared_ptr<rpc::KeystoneApi>>(), py::arg("config"),
+           py::arg("coord") = nullptr, py::arg("keystone") = nullptr)
+      .def("create_storage_pools_from_config", &worker::WorkerService::create_storage_pools_from_config)
+      .def("initialize", &worker::WorkerService::initialize, py::call_guard<py::gil_scoped_release>())
+      .def("start", &worker::WorkerService::start, py::call_guard<py::gil_scoped_release>())
+      .def("stop", &worker::WorkerService::stop, py::call_guard<py::gil_scoped_release>())
+      .def("is_running", &worker::WorkerService::is_running)
+      .def("get_stats", [](worker::WorkerService& w) { return bb_json_to_py(w.get_stats()); })
+      .def("advertised_pools", &worker::WorkerService::advertised_pools)
+      .def("data_endpoint", &worker::WorkerService::data_endpoint)
+      .def("inject_fault", &worker::WorkerService::inject_fault)
+      .def("backend", [](worker::WorkerService& w, const std::string& id) { return w.backend(id); }, py::return_value_policy::reference_internal);
+
+  // ---------------------------------------------------------------- client
+  using client::BlackbirdClient;
+  using client::BlackbirdClientOptions;
+  py::class_<BlackbirdClientOptions>(m, "BlackbirdClientOptions")
+      .def(py::init([](std::string host, uint16_t port, int timeout_ms, size_t par, std::string node_id, bool session) {
+             BlackbirdClientOptions o;
+             o.keystone_host = std::move(host);
+             o.keystone_port = port;
+             o.rpc_timeout_ms = timeout_ms;
+             o.io_parallelism = par;
+             o.node_id = std::move(node_id);
+             o.register_session = session;
+             return o;
+           }),
+           py::arg("keystone_host") = "127.0.0.1", py::arg("keystone_port") = 9090, py::arg("rpc_timeout_ms") = 30000,
+           py::arg("io_parallelism") = 4, py::arg("node_id") = "", py::arg("register_session") = false)
+      .def_readwrite("keystone_host", &BlackbirdClientOptions::keystone_host)
+      .def_readwrite("keystone_port", &BlackbirdClientOptions::keystone_port)
+      .def_readwrite("rpc_timeout_ms", &BlackbirdClientOptions::rpc_timeout_ms)
+      .def_readwrite("io_parallelism", &BlackbirdClientOptions::io_parallelism)
+      .def_readwrite("node_id", &BlackbirdClientOptions::node_id);
+  py::class_<BlackbirdClient, std::shared_ptr<BlackbirdClient>>(m, "BlackbirdClient")
+      .def(py::init<BlackbirdClientOptions>(), py::arg("options") = BlackbirdClientOptions{})
+      .def(py::init<std::shared_ptr<rpc::KeystoneApi>, BlackbirdClientOptions>(), py::arg("keystone"), py::arg("options") = BlackbirdClientOptions{})
+      .def("connect", &BlackbirdClient::connect, py::call_guard<py::gil_scoped_release>())
+      .def("connected", &BlackbirdClient::connected)
+      .def_property_readonly("session_id", &BlackbirdClient::session_id)
+      .def("object_exists", [](BlackbirdClient& c, const std::string& k) { return unwrap(c.object_exists(k)); }, py::call_guard<py::gil_scoped_release>())
+      .def("get_workers", [](BlackbirdClient& c, const std::string& k) { return unwrap(c.get_workers(k)); }, py::call_guard<py::gil_scoped_release>())
+      .def("put", [](BlackbirdClient& c, const std::string& key, py::buffer data, const WorkerConfig& cfg) {
+        py::buffer_info i = data.request();
+        py::gil_scoped_release rel;
+        return c.put(key, static_cast<const uint8_t*>(i.ptr), static_cast<size_t>(i.size * i.itemsize), cfg);
+      }, py::arg("key"), py::arg("data"), py::arg("config") = WorkerConfig{})
+      .def("get", [](BlackbirdClient& c, const std::string& key) {
+        Result<std::vector<uint8_t>> r = ErrorCode::INTERNAL_ERROR;
+        {
+          py::gil_scoped_release rel;
+          r = c.get(key);
+        }
+        if (!r.ok()) throw BlackbirdError(r.error());
+        return py::bytes(reinterpret_cast<const char*>(r.value().data()), r.value().size());
+      })
+      .def("remove", &BlackbirdClient::remove, py::call_guard<py::gil_scoped_release>())
+      .def("batch_put", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<py::buffer>& data, const WorkerConfig& cfg) {
+        std::vector<const uint8_t*> ptrs;
+        std::vector<size_t> sizes;
+        std::vector<py::buffer_info> infos;
+        for (const auto& b : data) infos.push_back(b.request());
+        for (const auto& i : infos) {
+          ptrs.push_back(static_cast<const uint8_t*>(i.ptr));
+          sizes.push_back(static_cast<size_t>(i.size * i.itemsize));
+        }
+        py::gil_scoped_release rel;
+        return c.batch_put(keys, ptrs, sizes, cfg);
+      }, py::arg("keys"), py::arg("data"), py::arg("config") = WorkerConfig{})
+      .def("batch_get", [](BlackbirdClient& c, const std::vector<std::string>& keys) {
+        std::vector<Result<std::vector<uint8_t>>> r;
+        {
+          py::gil_scoped_release rel;
+          r = c.batch_get(keys);
+        }
+        py::list out;
+        for (const auto& e : r)
+          out.append(py::make_tuple(e.error(), e.ok() ? py::object(py::bytes(reinterpret_cast<const char*>(e.value().data()), e.value().size()))
+                                                      : py::object(py::none())));
+        return out;
+      })
+      .def("batch_remove", &BlackbirdClient::batch_remove, py::call_guard<py::gil_scoped_release>())
+      .def("batch_exists", [](BlackbirdClient& c, const std::vector<std::string>& keys) {
+        return results_to_py(c.batch_exists(keys), [](bool b) { return py::bool_(b); });
+      })
+      .def("batch_put_device", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<uintptr_t>& ptrs,
+                                  const std::vector<size_t>& sizes, const WorkerConfig& cfg, uintptr_t stream) {
+        std::vector<const void*> p;
+        for (auto v : ptrs) p.push_back(reinterpret_cast<const void*>(v));
+        py::gil_scoped_release rel;
+        return c.batch_put_device(keys, p, sizes, cfg, reinterpret_cast<void*>(stream));
+      }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("sizes"), py::arg("config") = WorkerConfig{}, py::arg("stream") = 0)
+      .def("batch_get_device", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<uintptr_t>& ptrs,
+                                  const std::vector<size_t>& caps, uintptr_t stream) {
+        std::vector<void*> p;
+        for (auto v : ptrs) p.push_back(reinterpret_cast<void*>(v));
+        std::vector<size_t> sizes;
+        std::vector<ErrorCode> ecs;
+        {
+          py::gil_scoped_release rel;
+          ecs = c.batch_get_device(keys, p, caps, reinterpret_cast<void*>(stream), &sizes);
+        }
+        return py::make_tuple(ecs, sizes);
+      }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("capacity"), py::arg("stream") = 0)
+      .def("cluster_stats", [](BlackbirdClient& c) { return unwrap(c.cluster_stats()); })
+      .def("metrics_text", &BlackbirdClient::metrics_text)
+      .def("keystone", [](BlackbirdClient& c) -> rpc::KeystoneApi& { return c.keystone(); }, py::return_value_policy::reference_internal);
+}

@@ -4,6 +4,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "client/blackbird_client.h"
+#include "fabric/gpu_fabric.h"
 #include "fabric/xfer_engine.h"
 #include "kernels/xfer.h"
 
@@ -113,4 +115,21 @@ void bind_gpu(py::module_& m) {
     check_cuda(launch_random_fill(reinterpret_cast<void*>(dst), n, seed, reinterpret_cast<void*>(stream)), "random_fill");
   }, py::arg("dst"), py::arg("nbytes"), py::arg("seed") = 1, py::arg("stream") = 0);
   m.def("xfer_smem_bytes", [] { return xfer_smem_bytes(ALGO_BBH64); });
+
+  // ---- fabric: GPU tier + device transport of the client SDK
+  m.def("install_gpu_backend_factory", &install_gpu_backend_factory,
+        "Registers the RAM_GPU storage tier (cudaMalloc slab + CUDA IPC export) with the worker.");
+  py::class_<GpuFabric, std::shared_ptr<GpuFabric>>(m, "GpuFabric")
+      .def(py::init([](int device, std::shared_ptr<rpc::KeystoneApi> ks) {
+             auto f = GpuFabric::create(device, std::move(ks));
+             if (!f.ok()) throw std::runtime_error("GpuFabric.create: " + std::string(to_string(f.error())));
+             return f.value();
+           }),
+           py::arg("device"), py::arg("keystone"))
+      .def("refresh_pools", &GpuFabric::refresh_pools, py::call_guard<py::gil_scoped_release>())
+      .def("mapped_pools", &GpuFabric::mapped_pools)
+      .def_property_readonly("launches", &GpuFabric::launches)
+      .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
+      .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); });
+  m.def("attach_fabric", [](client::BlackbirdClient& c, std::shared_ptr<GpuFabric> f) { c.set_device_transport(std::move(f)); });
 }

@@ -11,6 +11,6 @@ void bind_control(py::module_& m);
 PYBIND11_MODULE(_bb, m) {
   m.doc() = "blackbird_b200 native core (C++20 control plane + sm_100a data plane)";
   bind_common(m);
-  bind_gpu(m);
   bind_control(m);
+  bind_gpu(m);
 }

@@ -1,0 +1,554 @@
+#include "rpc/rpc_service.h"
+
+#include <cstdlib>
+
+#include "common/log.h"
+#include "rpc/wire.h"
+
+namespace bb::rpc {
+
+using keystone::PutStartItem;
+using keystone::ShardChecksums;
+using wire::Reader;
+using wire::Writer;
+
+namespace {
+void put_sums(Writer& w, const ShardChecksums& s) {
+  w.u32(static_cast<uint32_t>(s.size()));
+  for (const auto& c : s) {
+    w.u32(static_cast<uint32_t>(c.size()));
+    for (uint64_t v : c) w.u64(v);
+  }
+}
+void get_sums(Reader& r, ShardChecksums& s) {
+  s.resize(r.count(4));
+  for (auto& c : s) {
+    c.resize(r.count(8));
+    for (auto& v : c) v = r.u64();
+  }
+}
+void put_keys(Writer& w, const std::vector<ObjectKey>& keys) {
+  w.u32(static_cast<uint32_t>(keys.size()));
+  for (const auto& k : keys) w.str(k);
+}
+std::vector<ObjectKey> get_keys(Reader& r) {
+  std::vector<ObjectKey> v(r.count(4));
+  for (auto& k : v) k = r.str();
+  return v;
+}
+void put_copies_result(Writer& w, const Result<std::vector<CopyPlacement>>& res) {
+  w.ec(res.error());
+  if (res.ok()) wire::put(w, res.value());
+}
+Result<std::vector<CopyPlacement>> get_copies_result(Reader& r) {
+  const ErrorCode ec = r.ec();
+  if (ec != ErrorCode::OK) return ec;
+  std::vector<CopyPlacement> v;
+  wire::get(r, v);
+  if (!r.ok()) return ErrorCode::RPC_FAILED;
+  return v;
+}
+std::string ec_reply(ErrorCode ec) {
+  Writer w;
+  w.ec(ec);
+  return w.take();
+}
+std::string ecs_reply(const std::vector<ErrorCode>& v) {
+  Writer w;
+  w.ec(ErrorCode::OK);
+  w.u32(static_cast<uint32_t>(v.size()));
+  for (auto e : v) w.ec(e);
+  return w.take();
+}
+}  // namespace
+
+// ================================================================ server
+RpcService::RpcService(std::shared_ptr<keystone::KeystoneService> keystone, const KeystoneConfig& config)
+    : keystone_(std::move(keystone)), config_(config) {
+  register_handlers();
+}
+
+RpcService::~RpcService() { stop(); }
+
+void RpcService::register_handlers() {
+  auto ks = keystone_;
+  using C = const net::ConnPtr&;
+  using S = const std::string&;
+  rpc_.register_method(M_OBJECT_EXISTS, [ks](C, S q) {
+    Reader r(q);
+    auto res = ks->object_exists(r.str());
+    Writer w;
+    w.ec(res.error());
+    w.boolean(res.ok() && res.value());
+    return w.take();
+  });
+  rpc_.register_method(M_GET_WORKERS, [ks](C, S q) {
+    Reader r(q);
+    Writer w;
+    put_copies_result(w, ks->get_workers(r.str()));
+    return w.take();
+  });
+  rpc_.register_method(M_PUT_START, [ks](C, S q) {
+    Reader r(q);
+    const std::string key = r.str();
+    const uint64_t size = r.u64();
+    WorkerConfig cfg;
+    wire::get(r, cfg);
+    const std::string cid = r.str(), node = r.str();
+    Writer w;
+    if (!r.ok()) w.ec(ErrorCode::INVALID_PARAMETERS);
+    else put_copies_result(w, ks->put_start(key, size, cfg, cid, node));
+    return w.take();
+  });
+  rpc_.register_method(M_PUT_COMPLETE, [ks](C, S q) {
+    Reader r(q);
+    const std::string key = r.str();
+    ShardChecksums sums;
+    get_sums(r, sums);
+    return ec_reply(r.ok() ? ks->put_complete(key, sums) : ErrorCode::INVALID_PARAMETERS);
+  });
+  rpc_.register_method(M_PUT_CANCEL, [ks](C, S q) {
+    Reader r(q);
+    return ec_reply(ks->put_cancel(r.str()));
+  });
+  rpc_.register_method(M_REMOVE_OBJECT, [ks](C, S q) {
+    Reader r(q);
+    return ec_reply(ks->remove_object(r.str()));
+  });
+  rpc_.register_method(M_REMOVE_ALL_OBJECTS, [ks](C, S) {
+    auto res = ks->remove_all_objects();
+    Writer w;
+    w.ec(res.error());
+    w.u64(res.ok() ? res.value() : 0);
+    return w.take();
+  });
+  rpc_.register_method(M_GET_CLUSTER_STATS, [ks](C, S) {
+    auto res = ks->get_cluster_stats();
+    Writer w;
+    w.ec(res.error());
+    if (res.ok()) wire::put(w, res.value());
+    return w.take();
+  });
+  rpc_.register_method(M_GET_VIEW_VERSION, [ks](C, S) {
+    Writer w;
+    w.ec(ErrorCode::OK);
+    w.i64(ks->get_view_version());
+    return w.take();
+  });
+  rpc_.register_method(M_BATCH_OBJECT_EXISTS, [ks](C, S q) {
+    Reader r(q);
+    auto res = ks->batch_object_exists(get_keys(r));
+    Writer w;
+    w.ec(ErrorCode::OK);
+    w.u32(static_cast<uint32_t>(res.size()));
+    for (const auto& e : res) {
+      w.ec(e.error());
+      w.boolean(e.ok() && e.value());
+    }
+    return w.take();
+  });
+  rpc_.register_method(M_BATCH_GET_WORKERS, [ks](C, S q) {
+    Reader r(q);
+    auto res = ks->batch_get_workers(get_keys(r));
+    Writer w;
+    w.ec(ErrorCode::OK);
+    w.u32(static_cast<uint32_t>(res.size()));
+    for (const auto& e : res) put_copies_result(w, e);
+    return w.take();
+  });
+  rpc_.register_method(M_BATCH_PUT_START, [ks](C, S q) {
+    Reader r(q);
+    std::vector<PutStartItem> items(r.count(16));
+    for (auto& it : items) {
+      it.key = r.str();
+      it.size = r.u64();
+      wire::get(r, it.config);
+    }
+    const std::string cid = r.str(), node = r.str();
+    Writer w;
+    if (!r.ok()) {
+      w.ec(ErrorCode::INVALID_PARAMETERS);
+      return w.take();
+    }
+    auto res = ks->batch_put_start(items, cid, node);
+    w.ec(ErrorCode::OK);
+    w.u32(static_cast<uint32_t>(res.size()));
+    for (const auto& e : res) put_copies_result(w, e);
+    return w.take();
+  });
+  rpc_.register_method(M_BATCH_PUT_COMPLETE, [ks](C, S q) {
+    Reader r(q);
+    auto keys = get_keys(r);
+    std::vector<ShardChecksums> sums(r.count(4));
+    for (auto& s : sums) get_sums(r, s);
+    if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    return ecs_reply(ks->batch_put_complete(keys, sums));
+  });
+  rpc_.register_method(M_BATCH_PUT_CANCEL, [ks](C, S q) {
+    Reader r(q);
+    return ecs_reply(ks->batch_put_cancel(get_keys(r)));
+  });
+  rpc_.register_method(M_BATCH_REMOVE_OBJECT, [ks](C, S q) {
+    Reader r(q);
+    return ecs_reply(ks->batch_remove_object(get_keys(r)));
+  });
+  rpc_.register_method(M_CLIENT_REGISTER, [ks](C, S q) {
+    Reader r(q);
+    auto res = ks->client_register(r.str());
+    Writer w;
+    w.ec(res.error());
+    w.str(res.ok() ? res.value() : "");
+    return w.take();
+  });
+  rpc_.register_method(M_CLIENT_PING, [ks](C, S q) {
+    Reader r(q);
+    auto res = ks->client_ping(r.str());
+    Writer w;
+    w.ec(res.error());
+    w.i64(res.ok() ? res.value() : 0);
+    return w.take();
+  });
+  rpc_.register_method(M_GET_MEMORY_POOLS, [ks](C, S) {
+    std::vector<MemoryPool> pools;
+    ks->get_memory_pools(pools);
+    Writer w;
+    w.ec(ErrorCode::OK);
+    w.u32(static_cast<uint32_t>(pools.size()));
+    for (const auto& p : pools) wire::put(w, p);
+    return w.take();
+  });
+  rpc_.register_method(M_REGISTER_WORKER, [ks](C, S q) {
+    Reader r(q);
+    auto j = Json::parse(r.str());
+    if (!j) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    auto rec = worker_record_from_json(*j);
+    return ec_reply(rec.ok() ? ks->register_worker(rec.value()) : rec.error());
+  });
+  rpc_.register_method(M_REGISTER_MEMORY_POOL, [ks](C, S q) {
+    Reader r(q);
+    MemoryPool p;
+    wire::get(r, p);
+    return ec_reply(r.ok() ? ks->register_memory_pool(p) : ErrorCode::INVALID_PARAMETERS);
+  });
+  rpc_.register_method(M_WORKER_HEARTBEAT, [ks](C, S q) {
+    Reader r(q);
+    return ec_reply(ks->worker_heartbeat(r.str()));
+  });
+  rpc_.register_method(M_REMOVE_WORKER, [ks](C, S q) {
+    Reader r(q);
+    return ec_reply(ks->remove_worker(r.str()));
+  });
+
+  http_.route("/metrics", [ks](const std::string&, const std::string&) {
+    net::HttpResponse r;
+    r.content_type = "text/plain; version=0.0.4; charset=utf-8";
+    r.body = ks->metrics_text();
+    return r;
+  });
+  http_.route("/healthz", [ks](const std::string&, const std::string&) {
+    net::HttpResponse r;
+    r.status = ks->is_running() ? 200 : 503;
+    r.body = ks->is_running() ? (ks->is_leader() ? "ok leader\n" : "ok standby\n") : "stopped\n";
+    return r;
+  });
+  http_.route("/stats", [ks](const std::string&, const std::string&) {
+    net::HttpResponse r;
+    r.content_type = "application/json";
+    r.body = ks->stats_json().dump(2) + "\n";
+    return r;
+  });
+}
+
+ErrorCode RpcService::start() {
+  if (running_) return ErrorCode::INVALID_STATE;
+  auto hp = split_host_port(config_.listen_address);
+  if (!hp) return ErrorCode::INVALID_ADDRESS;
+  ErrorCode ec = rpc_.start(hp->first, static_cast<uint16_t>(hp->second), std::max(1, config_.rpc_threads));
+  if (ec != ErrorCode::OK) return ec;
+  if (!config_.http_metrics_port.empty() && config_.http_metrics_port != "off") {
+    const uint16_t port = static_cast<uint16_t>(std::atoi(config_.http_metrics_port.c_str()));
+    ec = http_.start(hp->first, port, 1);
+    if (ec != ErrorCode::OK) {
+      BB_LOG(WARNING) << "keystone: metrics port " << config_.http_metrics_port << " unavailable; continuing without HTTP";
+    }
+  }
+  running_ = true;
+  return ErrorCode::OK;
+}
+
+void RpcService::stop() {
+  if (!running_) return;
+  rpc_.stop();
+  http_.stop();
+  running_ = false;
+}
+
+// ================================================================ client
+ErrorCode KeystoneRpcClient::connect(const std::string& host, uint16_t port, int timeout_ms) {
+  return rpc_.connect(host, port, timeout_ms);
+}
+ErrorCode KeystoneRpcClient::connect(const std::string& host_port, int timeout_ms) {
+  auto hp = split_host_port(host_port);
+  if (!hp) return ErrorCode::INVALID_ADDRESS;
+  return connect(hp->first, static_cast<uint16_t>(hp->second), timeout_ms);
+}
+
+Result<std::string> KeystoneRpcClient::call(uint32_t method, const std::string& req) {
+  auto r = rpc_.call(method, req, timeout_ms_);
+  if (!r.ok()) return r.error() == ErrorCode::CLIENT_DISCONNECTED ? ErrorCode::CLIENT_DISCONNECTED : ErrorCode::RPC_FAILED;
+  return r;
+}
+
+#define BB_RPC(method, writer)                 \
+  auto _resp = call(method, (writer).data());  \
+  if (!_resp.ok()) return _resp.error();       \
+  Reader rd(_resp.value());
+
+Result<bool> KeystoneRpcClient::object_exists(const ObjectKey& key) {
+  Writer w;
+  w.str(key);
+  BB_RPC(M_OBJECT_EXISTS, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return rd.boolean();
+}
+Result<std::vector<CopyPlacement>> KeystoneRpcClient::get_workers(const ObjectKey& key) {
+  Writer w;
+  w.str(key);
+  BB_RPC(M_GET_WORKERS, w);
+  return get_copies_result(rd);
+}
+Result<std::vector<CopyPlacement>> KeystoneRpcClient::put_start(const ObjectKey& key, size_t size, const WorkerConfig& cfg) {
+  Writer w;
+  w.str(key);
+  w.u64(size);
+  wire::put(w, cfg);
+  w.str(client_id_);
+  w.str(node_id_);
+  BB_RPC(M_PUT_START, w);
+  return get_copies_result(rd);
+}
+ErrorCode KeystoneRpcClient::put_complete(const ObjectKey& key, const ShardChecksums& sums) {
+  Writer w;
+  w.str(key);
+  put_sums(w, sums);
+  BB_RPC(M_PUT_COMPLETE, w);
+  return rd.ec();
+}
+ErrorCode KeystoneRpcClient::put_cancel(const ObjectKey& key) {
+  Writer w;
+  w.str(key);
+  BB_RPC(M_PUT_CANCEL, w);
+  return rd.ec();
+}
+ErrorCode KeystoneRpcClient::remove_object(const ObjectKey& key) {
+  Writer w;
+  w.str(key);
+  BB_RPC(M_REMOVE_OBJECT, w);
+  return rd.ec();
+}
+Result<size_t> KeystoneRpcClient::remove_all_objects() {
+  Writer w;
+  BB_RPC(M_REMOVE_ALL_OBJECTS, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return static_cast<size_t>(rd.u64());
+}
+Result<ClusterStats> KeystoneRpcClient::get_cluster_stats() {
+  Writer w;
+  BB_RPC(M_GET_CLUSTER_STATS, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  ClusterStats s;
+  wire::get(rd, s);
+  return s;
+}
+Result<ViewVersionId> KeystoneRpcClient::get_view_version() {
+  Writer w;
+  BB_RPC(M_GET_VIEW_VERSION, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return static_cast<ViewVersionId>(rd.i64());
+}
+
+std::vector<Result<bool>> KeystoneRpcClient::batch_object_exists(const std::vector<ObjectKey>& keys) {
+  Writer w;
+  put_keys(w, keys);
+  auto resp = call(M_BATCH_OBJECT_EXISTS, w.data());
+  std::vector<Result<bool>> out;
+  if (!resp.ok()) {
+    out.assign(keys.size(), Result<bool>(resp.error()));
+    return out;
+  }
+  Reader rd(resp.value());
+  rd.ec();
+  const uint32_t n = rd.count(5);
+  for (uint32_t i = 0; i < n; ++i) {
+    const ErrorCode ec = rd.ec();
+    const bool b = rd.boolean();
+    out.push_back(ec == ErrorCode::OK ? Result<bool>(b) : Result<bool>(ec));
+  }
+  out.resize(keys.size(), Result<bool>(ErrorCode::RPC_FAILED));
+  return out;
+}
+
+std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_get_workers(const std::vector<ObjectKey>& keys) {
+  Writer w;
+  put_keys(w, keys);
+  auto resp = call(M_BATCH_GET_WORKERS, w.data());
+  std::vector<Result<std::vector<CopyPlacement>>> out;
+  if (!resp.ok()) {
+    out.assign(keys.size(), Result<std::vector<CopyPlacement>>(resp.error()));
+    return out;
+  }
+  Reader rd(resp.value());
+  rd.ec();
+  const uint32_t n = rd.count(4);
+  for (uint32_t i = 0; i < n; ++i) out.push_back(get_copies_result(rd));
+  out.resize(keys.size(), Result<std::vector<CopyPlacement>>(ErrorCode::RPC_FAILED));
+  return out;
+}
+
+std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_put_start(const std::vector<PutStartItem>& items) {
+  Writer w;
+  w.u32(static_cast<uint32_t>(items.size()));
+  for (const auto& it : items) {
+    w.str(it.key);
+    w.u64(it.size);
+    wire::put(w, it.config);
+  }
+  w.str(client_id_);
+  w.str(node_id_);
+  auto resp = call(M_BATCH_PUT_START, w.data());
+  std::vector<Result<std::vector<CopyPlacement>>> out;
+  if (!resp.ok()) {
+    out.assign(items.size(), Result<std::vector<CopyPlacement>>(resp.error()));
+    return out;
+  }
+  Reader rd(resp.value());
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) {
+    out.assign(items.size(), Result<std::vector<CopyPlacement>>(ec));
+    return out;
+  }
+  const uint32_t n = rd.count(4);
+  for (uint32_t i = 0; i < n; ++i) out.push_back(get_copies_result(rd));
+  out.resize(items.size(), Result<std::vector<CopyPlacement>>(ErrorCode::RPC_FAILED));
+  return out;
+}
+
+namespace {
+std::vector<ErrorCode> parse_ecs(const Result<std::string>& resp, size_t n_expected) {
+  std::vector<ErrorCode> out;
+  if (!resp.ok()) {
+    out.assign(n_expected, resp.error());
+    return out;
+  }
+  Reader rd(resp.value());
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) {
+    out.assign(n_expected, ec);
+    return out;
+  }
+  const uint32_t n = rd.count(4);
+  for (uint32_t i = 0; i < n; ++i) out.push_back(rd.ec());
+  out.resize(n_expected, ErrorCode::RPC_FAILED);
+  return out;
+}
+}  // namespace
+
+std::vector<ErrorCode> KeystoneRpcClient::batch_put_complete(const std::vector<ObjectKey>& keys, const std::vector<ShardChecksums>& sums) {
+  Writer w;
+  put_keys(w, keys);
+  w.u32(static_cast<uint32_t>(sums.size()));
+  for (const auto& s : sums) put_sums(w, s);
+  return parse_ecs(call(M_BATCH_PUT_COMPLETE, w.data()), keys.size());
+}
+std::vector<ErrorCode> KeystoneRpcClient::batch_put_cancel(const std::vector<ObjectKey>& keys) {
+  Writer w;
+  put_keys(w, keys);
+  return parse_ecs(call(M_BATCH_PUT_CANCEL, w.data()), keys.size());
+}
+std::vector<ErrorCode> KeystoneRpcClient::batch_remove_object(const std::vector<ObjectKey>& keys) {
+  Writer w;
+  put_keys(w, keys);
+  return parse_ecs(call(M_BATCH_REMOVE_OBJECT, w.data()), keys.size());
+}
+
+Result<std::vector<MemoryPool>> KeystoneRpcClient::get_memory_pools() {
+  Writer w;
+  BB_RPC(M_GET_MEMORY_POOLS, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  std::vector<MemoryPool> v(rd.count(16));
+  for (auto& p : v) wire::get(rd, p);
+  if (!rd.ok()) return ErrorCode::RPC_FAILED;
+  return v;
+}
+Result<std::string> KeystoneRpcClient::client_register(const std::string& node_id) {
+  Writer w;
+  w.str(node_id);
+  BB_RPC(M_CLIENT_REGISTER, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return rd.str();
+}
+Result<ViewVersionId> KeystoneRpcClient::client_ping(const std::string& client_id) {
+  Writer w;
+  w.str(client_id);
+  BB_RPC(M_CLIENT_PING, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return static_cast<ViewVersionId>(rd.i64());
+}
+ErrorCode KeystoneRpcClient::register_worker(const WorkerRecord& rec) {
+  Writer w;
+  w.str(to_json(rec).dump());
+  BB_RPC(M_REGISTER_WORKER, w);
+  return rd.ec();
+}
+ErrorCode KeystoneRpcClient::register_memory_pool(const MemoryPool& pool) {
+  Writer w;
+  wire::put(w, pool);
+  BB_RPC(M_REGISTER_MEMORY_POOL, w);
+  return rd.ec();
+}
+ErrorCode KeystoneRpcClient::worker_heartbeat(const WorkerId& id) {
+  Writer w;
+  w.str(id);
+  BB_RPC(M_WORKER_HEARTBEAT, w);
+  return rd.ec();
+}
+
+// ================================================================ bootstrap
+Result<KeystoneBundle> create_and_start_keystone(const KeystoneConfig& config) {
+  KeystoneBundle b;
+  std::string err;
+  ErrorCode ec = config.validate(&err);
+  if (ec != ErrorCode::OK) {
+    BB_LOG(ERROR) << "keystone config invalid: " << err;
+    return ec;
+  }
+  if (!config.etcd_endpoints.empty() && config.etcd_endpoints != "none") {
+    b.coord = std::make_shared<coord::CoordService>(config.etcd_endpoints);
+    ec = b.coord->connect();
+    if (ec != ErrorCode::OK) {
+      BB_LOG(ERROR) << "cannot connect to coordination endpoints " << config.etcd_endpoints;
+      return ec;
+    }
+  }
+  b.keystone = std::make_shared<keystone::KeystoneService>(config, b.coord);
+  ec = b.keystone->initialize();
+  if (ec != ErrorCode::OK) return ec;
+  ec = b.keystone->start();
+  if (ec != ErrorCode::OK) return ec;
+  b.rpc = std::make_unique<RpcService>(b.keystone, config);
+  ec = b.rpc->start();
+  if (ec != ErrorCode::OK) {
+    b.keystone->stop();
+    return ec;
+  }
+  return b;
+}
+
+}  // namespace bb::rpc

@@ -1,0 +1,379 @@
+#include "worker/worker_service.h"
+
+#include <chrono>
+#include <stdexcept>
+
+#include "common/checksum.h"
+#include "common/log.h"
+#include "common/yaml.h"
+#include "rpc/wire.h"
+
+namespace bb::worker {
+
+// ================================================================ config
+Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::string* err) {
+  auto fail = [&](ErrorCode ec, const std::string& m) -> Result<WorkerServiceConfig> {
+    if (err) *err = m;
+    return ec;
+  };
+  if (!root.is_object() || !root.at("worker").is_object()) return fail(ErrorCode::MISSING_REQUIRED_FIELD, "missing top-level 'worker' section");
+  const Json& w = root.at("worker");
+  WorkerServiceConfig c;
+  c.worker_id = w.at("worker_id").as_string();
+  c.node_id = w.at("node_id").as_string();
+  if (w.contains("cluster_id")) c.cluster_id = w.at("cluster_id").as_string();
+  const Json& ee = w.contains("coord_endpoints") ? w.at("coord_endpoints") : w.at("etcd_endpoints");
+  if (ee.is_array()) {
+    for (const auto& e : ee.as_array()) c.etcd_endpoints += (c.etcd_endpoints.empty() ? "" : ",") + e.as_string();
+  } else if (!ee.is_null()) {
+    c.etcd_endpoints = ee.as_string();
+  }
+  if (w.contains("keystone_address")) c.keystone_address = w.at("keystone_address").as_string();
+  if (w.contains("rpc_endpoint")) c.rpc_endpoint = w.at("rpc_endpoint").as_string();
+  if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
+  if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
+  if (w.contains("interconnects")) {
+    c.interconnects.clear();
+    for (const auto& e : w.at("interconnects").as_array()) c.interconnects.push_back(e.as_string());
+  }
+  c.max_bw_gbps = w.at("max_bw_gbps").as_double(0.0);
+  c.numa_node = static_cast<int>(w.at("numa_node").as_int(-1));
+  if (w.contains("version")) c.version = w.at("version").as_string();
+  c.lease_ttl_sec = w.at("lease_ttl_sec").as_int(c.lease_ttl_sec);
+  c.heartbeat_interval_sec = w.at("heartbeat_interval_sec").as_int(c.heartbeat_interval_sec);
+  if (w.contains("fabric_domain")) c.fabric_domain = w.at("fabric_domain").as_string();
+  if (c.worker_id.empty()) return fail(ErrorCode::MISSING_REQUIRED_FIELD, "worker.worker_id is required");
+  if (c.node_id.empty()) c.node_id = c.worker_id;
+  if (c.lease_ttl_sec <= 0 || c.heartbeat_interval_sec <= 0) return fail(ErrorCode::VALUE_OUT_OF_RANGE, "worker lease/heartbeat must be positive");
+  if (c.heartbeat_interval_sec >= c.lease_ttl_sec) return fail(ErrorCode::INVALID_CONFIGURATION, "heartbeat_interval_sec must be shorter than lease_ttl_sec");
+  // pools may live at top level (reference worker.yaml) or under worker: (reference cxl_worker.yaml)
+  const Json& pools = root.contains("storage_pools") ? root.at("storage_pools") : w.at("storage_pools");
+  for (const auto& p : pools.as_array()) {
+    StoragePoolConfig pc;
+    pc.pool_id = p.at("pool_id").as_string();
+    auto sc = parse_storage_class(p.at("storage_class").as_string());
+    if (pc.pool_id.empty() || !sc) return fail(ErrorCode::INVALID_CONFIGURATION, "storage pool needs pool_id and a valid storage_class");
+    pc.storage_class = *sc;
+    const Json& size = p.contains("size_bytes") ? p.at("size_bytes") : p.at("capacity");
+    if (size.is_number()) pc.size_bytes = size.as_uint();
+    else if (auto v = parse_size(size.as_string())) pc.size_bytes = *v;
+    if (pc.size_bytes == 0) return fail(ErrorCode::VALUE_OUT_OF_RANGE, "storage pool " + pc.pool_id + " has no size");
+    pc.mount_path = p.contains("mount_path") ? p.at("mount_path").as_string() : p.at("path").as_string();
+    const Json& cfg = p.at("config");  // cxl_worker.yaml style nested block
+    if (cfg.is_object()) {
+      if (cfg.contains("dax_device")) pc.mount_path = cfg.at("dax_device").as_string();
+      pc.numa_node = static_cast<int>(cfg.at("numa_node").as_int(-1));
+    }
+    pc.gpu_device_id = static_cast<int>(p.at("gpu_device_id").as_int(0));
+    if (p.contains("numa_node")) pc.numa_node = static_cast<int>(p.at("numa_node").as_int(-1));
+    pc.queue_depth = static_cast<uint32_t>(p.at("queue_depth").as_int(64));
+    c.storage_pools.push_back(std::move(pc));
+  }
+  return c;
+}
+
+WorkerServiceConfig load_worker_config_from_file(const std::string& path) {
+  std::string err;
+  auto root = load_yaml_file(path, &err);
+  if (!root) throw std::runtime_error("Failed to load worker config '" + path + "': " + err);
+  auto c = worker_config_from_json(*root, &err);
+  if (!c.ok()) throw std::runtime_error("Invalid worker config '" + path + "': " + err);
+  return c.value();
+}
+
+// ================================================================ service
+WorkerService::WorkerService(const WorkerServiceConfig& config, std::shared_ptr<coord::CoordService> coord,
+                             std::shared_ptr<rpc::KeystoneApi> keystone)
+    : config_(config), coord_(std::move(coord)), keystone_(std::move(keystone)) {
+  register_data_handlers();
+}
+
+WorkerService::~WorkerService() { stop(); }
+
+ErrorCode WorkerService::add_storage_pool(const std::string& pool_id, std::unique_ptr<StorageBackend> backend) {
+  if (!backend || pool_id.empty()) return ErrorCode::INVALID_PARAMETERS;
+  std::lock_guard<std::mutex> lk(pools_mu_);
+  if (pools_.count(pool_id)) return ErrorCode::MEMORY_POOL_ALREADY_EXISTS;
+  backend->set_pool_id(pool_id);
+  pools_[pool_id] = std::move(backend);
+  return ErrorCode::OK;
+}
+
+ErrorCode WorkerService::create_storage_pools_from_config() {
+  for (const auto& pc : config_.storage_pools) {
+    BackendOptions o;
+    o.mount_path = pc.mount_path;
+    o.gpu_device_id = pc.gpu_device_id;
+    o.numa_node = pc.numa_node >= 0 ? pc.numa_node : config_.numa_node;
+    o.queue_depth = pc.queue_depth;
+    auto b = create_storage_backend(pc.storage_class, pc.size_bytes, o);
+    if (!b) {
+      BB_LOG(ERROR) << "worker " << config_.worker_id << ": no backend for pool " << pc.pool_id << " (" << to_string(pc.storage_class) << ")";
+      return ErrorCode::ALLOCATION_FAILED;
+    }
+    {
+      std::lock_guard<std::mutex> lk(pools_mu_);
+      pool_cfg_[pc.pool_id] = pc;
+    }
+    BB_TRY(add_storage_pool(pc.pool_id, std::move(b)));
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode WorkerService::initialize() {
+  if (initialized_.load()) return ErrorCode::OK;
+  if (!coord_ && !config_.etcd_endpoints.empty() && config_.etcd_endpoints != "none") {
+    coord_ = std::make_shared<coord::CoordService>(config_.etcd_endpoints);
+  }
+  if (coord_ && coord_->connect() != ErrorCode::OK) return ErrorCode::ETCD_ERROR;
+  if (!coord_ && !keystone_ && !config_.keystone_address.empty()) {
+    auto c = std::make_shared<rpc::KeystoneRpcClient>();
+    if (c->connect(config_.keystone_address) != ErrorCode::OK) return ErrorCode::CONNECTION_FAILED;
+    keystone_ = c;
+  }
+  {
+    std::lock_guard<std::mutex> lk(pools_mu_);
+    for (auto& [id, b] : pools_) {
+      ErrorCode ec = b->initialize();
+      if (ec != ErrorCode::OK) {
+        BB_LOG(ERROR) << "worker " << config_.worker_id << ": pool " << id << " failed to initialise: " << to_string(ec);
+        return ErrorCode::INITIALIZATION_FAILED;
+      }
+    }
+  }
+  auto hp = split_host_port(config_.ucx_endpoint);
+  if (!hp) return ErrorCode::INVALID_ADDRESS;
+  ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), 4);
+  if (ec != ErrorCode::OK) return ec;
+  initialized_.store(true);
+  return ErrorCode::OK;
+}
+
+std::string WorkerService::data_endpoint() const {
+  auto hp = split_host_port(config_.ucx_endpoint);
+  std::string host = hp ? hp->first : "127.0.0.1";
+  if (host == "0.0.0.0" || host.empty()) host = "127.0.0.1";
+  return host + ":" + std::to_string(data_server_.port());
+}
+
+void WorkerService::set_pool_rkey_hex(const std::string& pool_id, const std::string& hex) {
+  std::lock_guard<std::mutex> lk(pools_mu_);
+  pool_rkey_hex_[pool_id] = hex;
+}
+
+MemoryPool WorkerService::describe_pool(const std::string& pool_id, const StorageBackend& b) const {
+  MemoryPool p;
+  p.id = pool_id;
+  p.node_id = config_.node_id;
+  p.worker_id = config_.worker_id;
+  p.base_addr = b.get_base_address();
+  p.size = b.get_total_capacity();
+  p.used = b.get_used_capacity();
+  p.storage_class = b.get_storage_class();
+  p.ucx_endpoint = data_endpoint();
+  p.ucx_remote_addr = b.get_base_address();
+  auto rk = pool_rkey_hex_.find(pool_id);
+  p.ucx_rkey_hex = rk != pool_rkey_hex_.end() ? rk->second : b.registration_key_hex();
+  auto pc = pool_cfg_.find(pool_id);
+  p.gpu_device_id = b.get_storage_class() == StorageClass::RAM_GPU ? (pc != pool_cfg_.end() ? pc->second.gpu_device_id : 0) : -1;
+  p.numa_node = pc != pool_cfg_.end() && pc->second.numa_node >= 0 ? pc->second.numa_node : config_.numa_node;
+  p.max_bw_gbps = config_.max_bw_gbps;
+  p.fabric_domain = config_.fabric_domain;
+  if (pc != pool_cfg_.end()) p.mount_path = pc->second.mount_path;
+  return p;
+}
+
+std::vector<MemoryPool> WorkerService::advertised_pools() const {
+  std::vector<MemoryPool> v;
+  std::lock_guard<std::mutex> lk(pools_mu_);
+  for (const auto& [id, b] : pools_) v.push_back(describe_pool(id, *b));
+  return v;
+}
+
+ErrorCode WorkerService::register_all() {
+  WorkerRecord rec;
+  rec.worker_id = config_.worker_id;
+  rec.node_id = config_.node_id;
+  rec.rpc_endpoint = config_.rpc_endpoint;
+  rec.ucx_endpoint = data_endpoint();
+  rec.interconnects = config_.interconnects;
+  rec.max_bw_gbps = config_.max_bw_gbps;
+  rec.numa_node = config_.numa_node;
+  rec.version = config_.version;
+  const auto pools = advertised_pools();
+  for (const auto& p : pools)
+    if (std::find(rec.storage_classes.begin(), rec.storage_classes.end(), p.storage_class) == rec.storage_classes.end())
+      rec.storage_classes.push_back(p.storage_class);
+  if (coord_) {
+    const std::string base = cluster_prefix() + "workers/" + config_.worker_id;
+    if (coord_->put(base, to_json(rec).dump()) != ErrorCode::OK) return ErrorCode::SERVICE_REGISTRATION_FAILED;
+    for (const auto& p : pools)
+      if (coord_->put(base + "/memory_pools/" + p.id, to_json(p).dump()) != ErrorCode::OK) return ErrorCode::SERVICE_REGISTRATION_FAILED;
+    if (coord_->put_with_ttl(cluster_prefix() + "heartbeat/" + config_.worker_id, std::to_string(std::time(nullptr)), config_.lease_ttl_sec) != ErrorCode::OK)
+      return ErrorCode::SERVICE_REGISTRATION_FAILED;
+  } else if (keystone_) {
+    BB_TRY(keystone_->register_worker(rec));
+    for (const auto& p : pools) BB_TRY(keystone_->register_memory_pool(p));
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode WorkerService::start() {
+  if (!initialized_.load()) return ErrorCode::INVALID_STATE;
+  if (running_.exchange(true)) return ErrorCode::INVALID_STATE;
+  ErrorCode ec = register_all();
+  if (ec != ErrorCode::OK) {
+    running_.store(false);
+    return ec;
+  }
+  heartbeat_thread_ = std::thread([this] { heartbeat_loop(); });
+  return ErrorCode::OK;
+}
+
+void WorkerService::heartbeat_loop() {
+  while (true) {
+    {
+      std::unique_lock<std::mutex> lk(sleep_mu_);
+      sleep_cv_.wait_for(lk, std::chrono::seconds(config_.heartbeat_interval_sec), [this] { return !running_.load(); });
+    }
+    if (!running_.load()) return;
+    if (drop_heartbeat_.load()) continue;
+    ErrorCode ec = ErrorCode::OK;
+    if (coord_) ec = coord_->put_with_ttl(cluster_prefix() + "heartbeat/" + config_.worker_id, std::to_string(std::time(nullptr)), config_.lease_ttl_sec);
+    else if (keystone_) ec = keystone_->worker_heartbeat(config_.worker_id);
+    if (ec == ErrorCode::INVALID_WORKER) ec = register_all();  // keystone forgot us (restart / takeover)
+    if (ec != ErrorCode::OK) BB_LOG(WARNING) << "worker " << config_.worker_id << ": heartbeat failed: " << to_string(ec);
+    else heartbeats_sent_++;
+  }
+}
+
+void WorkerService::stop() {
+  if (running_.exchange(false)) {
+    {
+      std::lock_guard<std::mutex> lk(sleep_mu_);
+      sleep_cv_.notify_all();
+    }
+    if (heartbeat_thread_.joinable()) heartbeat_thread_.join();
+    if (coord_ && coord_->is_connected()) {
+      const std::string base = cluster_prefix() + "workers/" + config_.worker_id;
+      if (auto st = coord_->store()) st->del_prefix(base + "/");
+      coord_->del(base);
+      coord_->del(cluster_prefix() + "heartbeat/" + config_.worker_id);
+    }
+  }
+  if (initialized_.exchange(false)) {
+    data_server_.stop();
+    std::lock_guard<std::mutex> lk(pools_mu_);
+    for (auto& [id, b] : pools_) b->shutdown();
+  }
+}
+
+void WorkerService::inject_fault(const std::string& fault) { drop_heartbeat_.store(fault == "drop_heartbeat"); }
+
+StorageBackend* WorkerService::backend(const std::string& pool_id) {
+  std::lock_guard<std::mutex> lk(pools_mu_);
+  auto it = pools_.find(pool_id);
+  return it == pools_.end() ? nullptr : it->second.get();
+}
+
+Json WorkerService::get_stats() const {
+  Json j = Json::object();
+  j["worker_id"] = config_.worker_id;
+  j["node_id"] = config_.node_id;
+  j["running"] = running_.load();
+  j["data_endpoint"] = data_endpoint();
+  j["heartbeats_sent"] = heartbeats_sent_.load();
+  j["requests_served"] = data_server_.requests_served();
+  Json pools = Json::array();
+  std::lock_guard<std::mutex> lk(pools_mu_);
+  for (const auto& [id, b] : pools_) {
+    const StorageStats s = b->get_stats();
+    Json p = Json::object();
+    p["pool_id"] = id;
+    p["storage_class"] = std::string(to_string(b->get_storage_class()));
+    p["total_capacity"] = s.total_capacity;
+    p["used_capacity"] = s.used_capacity;
+    p["available_capacity"] = s.available_capacity;
+    p["utilization"] = s.utilization;
+    p["fragmentation"] = s.fragmentation;
+    p["num_reservations"] = s.num_reservations;
+    p["num_committed_shards"] = s.num_committed_shards;
+    p["bytes_written"] = s.bytes_written;
+    p["bytes_read"] = s.bytes_read;
+    p["io_errors"] = s.io_errors;
+    pools.push_back(p);
+  }
+  j["pools"] = pools;
+  return j;
+}
+
+// ================================================================ data server
+namespace {
+// Bit 63 marks an absolute address (MemoryLocation::remote_addr); otherwise a pool offset.
+uint64_t resolve_offset(const StorageBackend& b, uint64_t raw) {
+  if (raw >> 63) {
+    const uint64_t addr = raw & ~(1ull << 63);
+    return addr >= b.get_base_address() ? addr - b.get_base_address() : ~0ull;
+  }
+  return raw;
+}
+}  // namespace
+
+void WorkerService::register_data_handlers() {
+  using C = const net::ConnPtr&;
+  using S = const std::string&;
+  data_server_.register_method(D_WRITE, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string pool = r.str();
+    const uint64_t off = r.u64();
+    const uint32_t len = r.u32();
+    wire::Writer w;
+    StorageBackend* b = backend(pool);
+    if (!r.ok() || q.size() < len || !b) {
+      w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
+      return w.take();
+    }
+    const char* payload = q.data() + (q.size() - len);
+    w.ec(b->write(resolve_offset(*b, off), payload, len));
+    return w.take();
+  });
+  data_server_.register_method(D_READ, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string pool = r.str();
+    const uint64_t off = r.u64();
+    const uint32_t len = r.u32();
+    StorageBackend* b = backend(pool);
+    std::string out(4 + (b && r.ok() ? len : 0), '\0');
+    ErrorCode ec = !b ? ErrorCode::MEMORY_POOL_NOT_FOUND : !r.ok() ? ErrorCode::INVALID_PARAMETERS : b->read(resolve_offset(*b, off), out.data() + 4, len);
+    const uint32_t e = static_cast<uint32_t>(ec);
+    std::memcpy(out.data(), &e, 4);
+    if (ec != ErrorCode::OK) out.resize(4);
+    return out;
+  });
+  data_server_.register_method(D_CHECKSUM, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string pool = r.str();
+    const uint64_t off = r.u64();
+    const uint64_t len = r.u64();
+    const auto algo = static_cast<ChecksumAlgo>(r.u32());
+    wire::Writer w;
+    StorageBackend* b = backend(pool);
+    if (!b || !r.ok()) {
+      w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
+      return w.take();
+    }
+    std::vector<uint8_t> buf(len);
+    ErrorCode ec = b->read(off, buf.data(), len);
+    w.ec(ec);
+    if (ec == ErrorCode::OK) w.u64(checksum(algo, buf.data(), len));
+    return w.take();
+  });
+  data_server_.register_method(D_STATS, [this](C, S) {
+    wire::Writer w;
+    w.ec(ErrorCode::OK);
+    w.str(get_stats().dump());
+    return w.take();
+  });
+}
+
+}  // namespace bb::worker

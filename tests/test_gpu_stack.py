@@ -1,0 +1,111 @@
+"""GPU tests: fused kernels against CPU models and the full client -> keystone -> GPU worker path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need CUDA (marked gpu)")
+    return torch
+
+
+def _stream(torch):
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("algo_name", ["BBH64", "CRC32C"])
+@pytest.mark.parametrize("n", [16, 255 * 16, 16384, 16385, 100000, (1 << 20) + 7, 5 << 20])
+def test_fused_digest_matches_cpu_model(bb, torch_cuda, algo_name, n):
+    torch = torch_cuda
+    algo = getattr(bb.ChecksumAlgo, algo_name)
+    eng = bb.XferEngine(0, 1024, 2)
+    src = torch.randint(0, 256, (n + 64,), dtype=torch.uint8, device="cuda")[:n]
+    dst = torch.full((n + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+    dg, st, ms = eng.run([(src.data_ptr(), dst.data_ptr(), n)], algo, _stream(torch))
+    torch.cuda.synchronize()
+    host = src.cpu().numpy()
+    ref = bb.bbh64(host) if algo_name == "BBH64" else bb.crc32c(host)
+    assert dg[0] == ref
+    assert torch.equal(src, dst[:n]) and bool((dst[n:] == 0xAB).all())
+
+
+def test_fused_verify_and_fanout(bb, torch_cuda):
+    torch = torch_cuda
+    eng = bb.XferEngine(0, 1024, 2)
+    n = 3 * bb.TILE_BYTES + 4096
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+    dsts = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    ref = bb.bbh64(src.cpu().numpy())
+    dg, st, _ = eng.run([(src.data_ptr(), [d.data_ptr() for d in dsts], n, ref, bb.XFER_VERIFY)], bb.ChecksumAlgo.BBH64, _stream(torch))
+    assert dg[0] == ref and st[0] == 0
+    assert all(torch.equal(src, d) for d in dsts)
+    dg, st, _ = eng.run([(src.data_ptr(), dsts[0].data_ptr(), n, ref ^ 0x10, bb.XFER_VERIFY)], bb.ChecksumAlgo.BBH64, _stream(torch))
+    assert st[0] == 1  # CHECKSUM_MISMATCH detected on device
+
+
+def test_fused_batch_of_small_objects(bb, torch_cuda):
+    torch = torch_cuda
+    eng = bb.XferEngine(0, 8192, 2)
+    nobj, osz = 2048, 1024
+    big = torch.randint(0, 256, (nobj * osz,), dtype=torch.uint8, device="cuda")
+    out = torch.zeros_like(big)
+    items = [(big.data_ptr() + i * osz, out.data_ptr() + i * osz, osz) for i in range(nobj)]
+    dg, st, _ = eng.run(items, bb.ChecksumAlgo.BBH64, _stream(torch))
+    h = big.cpu().numpy()
+    assert all(dg[i] == bb.bbh64(h[i * osz:(i + 1) * osz]) for i in range(0, nobj, 97))
+    assert torch.equal(big, out)
+
+
+def test_standalone_crc32c_kernel(bb, torch_cuda):
+    torch = torch_cuda
+    for n in [1, 511, 513, 100001]:
+        src = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+        out = torch.zeros(1, dtype=torch.int32, device="cuda")
+        scratch = torch.zeros(n // 512 + 2, dtype=torch.int32, device="cuda")
+        bb.crc32c_device(src.data_ptr(), n, out.data_ptr(), scratch.data_ptr(), _stream(torch))
+        torch.cuda.synchronize()
+        assert (int(out.item()) & 0xFFFFFFFF) == bb.crc32c(src.cpu().numpy())
+
+
+def test_full_stack_put_get_gpu_tier(bb, torch_cuda):
+    """client SDK -> keystone (placement, PENDING->COMPLETE, digests) -> GPU slab via fused kernels."""
+    torch = torch_cuda
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=512 << 20, cluster_id="t-gpu")
+    try:
+        n, size = 16, (1 << 20) + 48
+        stride = ((size + 255) // 256) * 256
+        src = torch.randint(0, 256, (n * stride,), dtype=torch.uint8, device="cuda")
+        out = torch.zeros_like(src)
+        keys = [f"k{i}" for i in range(n)]
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_GPU])
+        s = _stream(torch)
+        ecs = cl.client.batch_put_device(keys, [src.data_ptr() + i * stride for i in range(n)], [size] * n, cfg, s)
+        assert all(e == bb.ErrorCode.OK for e in ecs)
+        ecs, sizes = cl.client.batch_get_device(keys, [out.data_ptr() + i * stride for i in range(n)], [stride] * n, s)
+        assert all(e == bb.ErrorCode.OK for e in ecs) and sizes == [size] * n
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert torch.equal(src[i * stride:i * stride + size], out[i * stride:i * stride + size])
+        copies = cl.client.get_workers(keys[3])
+        sh = copies[0].shards[0]
+        assert sh.storage_class == bb.StorageClass.RAM_GPU and sh.location["kind"] == "gpu"
+        assert sh.checksum == bb.bbh64(src[3 * stride:3 * stride + size].cpu().numpy())
+        # the same object is reachable through the slow path (TCP data server -> cudaMemcpy D2H)
+        host_client = bb.BlackbirdClient(cl.client_api, bb.BlackbirdClientOptions(node_id="host"))
+        assert host_client.get(keys[3]) == bytes(src[3 * stride:3 * stride + size].cpu().numpy())
+        # corruption in the slab is detected by the fused get (digest mismatch -> CHECKSUM_MISMATCH)
+        be = cl.worker.backend("hbm0")
+        be.write(sh.offset + 100, b"\xff\x00\xff\x00")
+        ecs, _ = cl.client.batch_get_device([keys[3]], [out.data_ptr()], [stride], s)
+        assert ecs[0] == bb.ErrorCode.CHECKSUM_MISMATCH
+        assert cl.client.batch_remove(keys) == [bb.ErrorCode.OK] * n
+        assert cl.fabric.launches >= 3
+    finally:
+        cl.stop()
