@@ -57,6 +57,21 @@ py::object location_to_py(const LocationDetail& l) {
   return d;
 }
 
+// Python callables captured by C++ callbacks may be released on arbitrary native threads:
+// the deleter takes the GIL before dropping the reference.
+template <typename T>
+std::shared_ptr<T> gil_safe_holder(T obj) {
+  return std::shared_ptr<T>(new T(std::move(obj)), [](T* p) {
+    if (Py_IsInitialized()) {
+      py::gil_scoped_acquire g;
+      delete p;
+    } else {
+      p->release();  // interpreter is gone: leak the reference instead of touching it
+      delete p;
+    }
+  });
+}
+
 // py results of batch calls: list of (ErrorCode, value-or-None)
 template <typename T, typename F>
 py::list results_to_py(const std::vector<Result<T>>& v, F&& conv) {
@@ -277,9 +292,13 @@ void bind_control(py::module_& m) {
   py::class_<PoolAllocator>(m, "PoolAllocator")
       .def(py::init<const MemoryPool&, uint64_t>(), py::arg("pool"), py::arg("align") = PoolAllocator::kDefaultAlign)
       .def("allocate", [](PoolAllocator& a, uint64_t size, bool best) -> py::object {
-        auto r = a.allocate(size, best);
+        std::optional<Range> r;
+        {
+          py::gil_scoped_release rel;
+          r = a.allocate(size, best);
+        }
         return r ? py::cast(*r) : py::none();
-      }, py::arg("size"), py::arg("prefer_best_fit") = true, py::call_guard<py::gil_scoped_release>())
+      }, py::arg("size"), py::arg("prefer_best_fit") = true)
       .def("allocate_at", &PoolAllocator::allocate_at)
       .def("free", &PoolAllocator::free, py::call_guard<py::gil_scoped_release>())
       .def("total_free", &PoolAllocator::total_free)
@@ -369,7 +388,7 @@ void bind_control(py::module_& m) {
       }, py::arg("key"), py::arg("expected"), py::arg("value"), py::arg("lease") = 0)
       .def("compare_and_delete", [](CoordStore& s, const std::string& k, const std::string& e) { return unwrap(s.compare_and_delete(k, e)); })
       .def("watch_prefix", [](CoordStore& s, const std::string& prefix, py::function cb) {
-        auto holder = std::make_shared<py::function>(std::move(cb));
+        auto holder = gil_safe_holder(std::move(cb));
         return unwrap(s.watch_prefix(prefix, [holder](const coord::WatchEvent& ev) {
           py::gil_scoped_acquire g;
           try {
@@ -524,7 +543,7 @@ void bind_control(py::module_& m) {
           k.set_copy_mover(nullptr);
           return;
         }
-        auto holder = std::make_shared<py::object>(std::move(fn));
+        auto holder = gil_safe_holder(std::move(fn));
         k.set_copy_mover([holder](const ObjectKey& key, const CopyPlacement& src, CopyPlacement& dst, ChecksumAlgo algo) {
           py::gil_scoped_acquire g;
           try {

@@ -1,0 +1,215 @@
+"""End-to-end on CPU (BASELINE config #1): in-process Keystone + 2 workers over loopback TCP,
+put/get/exists/remove of 1 KB objects; RPC façade (all methods), HTTP /metrics, worker
+registration + heartbeats through the coordination store, failure detection, replica
+fail-over, checksum enforcement, striping, batch API, multi-tier workers, config files."""
+import os
+import threading
+import time
+
+import pytest
+
+from blackbird_b200.parallel import LocalCluster
+
+
+@pytest.fixture
+def cluster(bb):
+    with LocalCluster("e2e", n_workers=2, pool_bytes=64 << 20) as c:
+        yield c
+
+
+def test_config1_put_get_exists_remove_1kb(bb, cluster):
+    cl = cluster.client()
+    data = os.urandom(1024)
+    cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+    assert cl.object_exists("k") is False
+    assert cl.put("k", data, cfg) == bb.ErrorCode.OK
+    assert cl.object_exists("k") is True and cl.get("k") == data
+    copies = cl.get_workers("k")
+    sh = copies[0].shards[0]
+    assert sh.length == 1024 and sh.checksum == bb.bbh64(data) and sh.storage_class == bb.StorageClass.RAM_CPU
+    assert cl.put("k", data, cfg) == bb.ErrorCode.OBJECT_ALREADY_EXISTS
+    assert cl.remove("k") == bb.ErrorCode.OK and cl.object_exists("k") is False
+    with pytest.raises(bb.BlackbirdError) as e:
+        cl.get("k")
+    assert e.value.code == bb.ErrorCode.OBJECT_NOT_FOUND
+    st = cl.cluster_stats()
+    assert st.total_workers == 2 and st.total_memory_pools == 2 and st.total_objects == 0 and st.used_capacity == 0
+
+
+def test_workers_register_through_coordination_schema(bb, cluster):
+    keys = [k for k, *_ in cluster.coord.store().get_with_prefix("/blackbird/clusters/e2e/")]
+    assert "/blackbird/clusters/e2e/workers/worker-0" in keys
+    assert "/blackbird/clusters/e2e/workers/worker-0/memory_pools/pool-0" in keys
+    assert "/blackbird/clusters/e2e/heartbeat/worker-1" in keys
+    assert cluster.coord.discover_service("blackbird-keystone") == [cluster.cfg.listen_address]
+    pool = bb.MemoryPool.from_json(cluster.coord.store().get("/blackbird/clusters/e2e/workers/worker-0/memory_pools/pool-0").decode())
+    assert pool.worker_id == "worker-0" and pool.size == 64 << 20 and pool.ucx_endpoint == cluster.workers[0].data_endpoint()
+    assert len(pool.ucx_rkey_hex) == 8  # fixed-width hex (reference bug #7: unpadded, colon separated)
+    info = {w["worker_id"]: w for w in cluster.keystone.get_workers_info()}
+    assert info["worker-0"]["pools"] == ["pool-0"]
+
+
+def test_striping_replication_and_checksums_over_tcp(bb, cluster):
+    cl = cluster.client(io_parallelism=4)
+    data = os.urandom(3 * (1 << 20) + 12345)
+    for algo in (bb.ChecksumAlgo.CRC32C, bb.ChecksumAlgo.BBH64, bb.ChecksumAlgo.NONE):
+        key = f"striped-{algo.name}"
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=2, checksum=algo, min_shard_size=4096)
+        assert cl.put(key, data, cfg) == bb.ErrorCode.OK
+        copies = cl.get_workers(key)
+        assert len(copies) == 2 and sum(s.length for s in copies[0].shards) == len(data)
+        if algo == bb.ChecksumAlgo.CRC32C:
+            off = 0
+            for s in copies[0].shards:
+                assert s.checksum == bb.crc32c(data[off:off + s.length])
+                off += s.length
+        assert cl.get(key) == data
+
+
+def test_corruption_is_detected_and_reads_fail_over_to_replica(bb, cluster):
+    cl = cluster.client()
+    data = os.urandom(200000)
+    assert cl.put("r2", data, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1)) == bb.ErrorCode.OK
+    copies = cl.get_workers("r2")
+    victim = copies[0].shards[0]
+    worker = next(w for w in cluster.workers if w.data_endpoint() == f"{victim.endpoint.ip}:{victim.endpoint.port}")
+    base = worker.backend(victim.pool_id).get_base_address()
+    worker.backend(victim.pool_id).write(victim.offset - base + 1000, b"\x00" * 64)  # silent corruption of copy 0
+    assert cl.get("r2") == data  # served from the intact replica
+    assert "bb_client_replica_failover_total 1" in cl.metrics_text() and "bb_client_checksum_mismatch_total 1" in cl.metrics_text()
+    cl.put("r1", data, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1))
+    s1 = cl.get_workers("r1")[0].shards[0]
+    w1 = next(w for w in cluster.workers if w.data_endpoint() == f"{s1.endpoint.ip}:{s1.endpoint.port}")
+    w1.backend(s1.pool_id).write(s1.offset - w1.backend(s1.pool_id).get_base_address(), b"\xff" * 8)
+    with pytest.raises(bb.BlackbirdError) as e:
+        cl.get("r1")
+    assert e.value.code == bb.ErrorCode.CHECKSUM_MISMATCH  # the code exists in the reference but nothing produces it
+
+
+def test_batch_put_get_remove(bb, cluster):
+    cl = cluster.client()
+    keys = [f"b{i}" for i in range(50)]
+    blobs = [os.urandom(1024 + i) for i in range(50)]
+    cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+    assert cl.batch_put(keys, blobs, cfg) == [bb.ErrorCode.OK] * 50
+    assert cl.batch_put(keys[:2], blobs[:2], cfg) == [bb.ErrorCode.OBJECT_ALREADY_EXISTS] * 2
+    res = cl.batch_get(keys + ["missing"])
+    assert [r[1] for r in res[:50]] == blobs and res[50][0] == bb.ErrorCode.OBJECT_NOT_FOUND
+    assert [v for _, v in cl.batch_exists(keys[:3] + ["missing"])] == [True, True, True, False]
+    assert cl.batch_remove(keys) == [bb.ErrorCode.OK] * 50
+    assert cluster.keystone.get_cluster_stats().used_capacity == 0
+
+
+def test_rpc_facade_all_methods_and_http(bb, cluster):
+    api = bb.KeystoneRpcClient()
+    assert api.connect("127.0.0.1", cluster.rpc.rpc_port) == bb.ErrorCode.OK
+    cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+    v0 = api.get_view_version()
+    copies = api.put_start("rpc-k", 5000, cfg)
+    assert copies[0].shards[0].length == 5000 and copies[0].shards[0].endpoint.port > 0
+    assert api.put_complete("rpc-k", [[42]]) == bb.ErrorCode.OK
+    assert api.object_exists("rpc-k") is True and api.get_workers("rpc-k")[0].shards[0].checksum == 42
+    assert api.get_view_version() > v0
+    res = api.batch_put_start(["x1", "x2", "rpc-k"], [10, 20, 30], cfg)
+    assert [r[0] for r in res] == [bb.ErrorCode.OK, bb.ErrorCode.OK, bb.ErrorCode.OBJECT_ALREADY_EXISTS]
+    assert api.batch_put_complete(["x1"]) == [bb.ErrorCode.OK]
+    assert api.batch_put_cancel(["x2", "nope"]) == [bb.ErrorCode.OK, bb.ErrorCode.OBJECT_NOT_FOUND]
+    assert [r[1] for r in api.batch_object_exists(["x1", "x2"])] == [True, False]
+    assert api.batch_get_workers(["x1", "x2"])[1][0] == bb.ErrorCode.OBJECT_NOT_FOUND
+    st = api.get_cluster_stats()
+    assert st.total_objects == 2 and st.total_workers == 2
+    assert {p.id for p in api.get_memory_pools()} == {"pool-0", "pool-1"}
+    cid = api.client_register("node-9")
+    assert api.client_ping(cid) >= 1
+    assert api.batch_remove_object(["x1"]) == [bb.ErrorCode.OK]
+    assert api.remove_object("rpc-k") == bb.ErrorCode.OK and api.remove_all_objects() == 0
+    assert api.put_cancel("nope") == bb.ErrorCode.OBJECT_NOT_FOUND
+    status, body = bb.http_get("127.0.0.1", cluster.rpc.http_port, "/metrics")
+    assert status == 200 and "bb_put_start_total" in body and "# TYPE bb_objects gauge" in body
+    status, body = bb.http_get("127.0.0.1", cluster.rpc.http_port, "/healthz")
+    assert status == 200 and body.startswith("ok")
+    status, body = bb.http_get("127.0.0.1", cluster.rpc.http_port, "/stats")
+    assert status == 200 and bb.parse_json(body)["cluster"]["total_workers"] == 2
+    assert bb.http_get("127.0.0.1", cluster.rpc.http_port, "/nope")[0] == 404
+    assert cluster.rpc.requests_served > 15
+
+
+def test_many_concurrent_rpc_clients(bb, cluster):
+    errs = []
+
+    def run(t):
+        try:
+            cl = cluster.client()
+            cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+            for i in range(40):
+                d = os.urandom(777)
+                assert cl.put(f"c{t}/{i}", d, cfg) == bb.ErrorCode.OK
+                assert cl.get(f"c{t}/{i}") == d
+                assert cl.remove(f"c{t}/{i}") == bb.ErrorCode.OK
+        except Exception as ex:  # noqa: BLE001
+            errs.append(repr(ex))
+
+    ts = [threading.Thread(target=run, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs[:2]
+
+
+def test_failure_detection_lease_expiry_removes_worker_and_objects(bb):
+    with LocalCluster("fd", n_workers=2, pool_bytes=8 << 20, lease_ttl_sec=2, heartbeat_interval_sec=1) as c:
+        cl = c.client()
+        data = os.urandom(4096)
+        assert cl.put("both", data, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        assert cl.put("only0", data, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_node="node-0")) == bb.ErrorCode.OK
+        c.workers[0].inject_fault("drop_heartbeat")  # worker-0 hangs: stops refreshing its lease
+        store = c.coord.store()
+        deadline = time.time() + 10
+        while c.keystone.get_cluster_stats().total_workers == 2 and time.time() < deadline:
+            time.sleep(0.1)
+        store.flush_events()
+        st = c.keystone.get_cluster_stats()
+        assert st.total_workers == 1 and st.total_memory_pools == 1
+        assert store.get("/blackbird/clusters/fd/workers/worker-0") is None  # keystone cleaned the registry
+        assert cl.get("both") == data  # surviving replica
+        with pytest.raises(bb.BlackbirdError):
+            cl.get("only0")  # its only copy died with the worker
+        assert "bb_worker_deaths_total 1" in c.keystone.metrics_text()
+        # new puts avoid the dead worker
+        assert cl.put("after", data, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        assert cl.get_workers("after")[0].shards[0].worker_id == "worker-1"
+
+
+def test_multi_tier_worker_and_class_preference(bb, tmp_path):
+    with LocalCluster("tiers", n_workers=0) as c:
+        c.add_worker("w-tiers", "node-t", [("dram", bb.StorageClass.RAM_CPU, 8 << 20, ""), ("nvme", bb.StorageClass.NVME, 32 << 20, str(tmp_path)),
+                                            ("cxl", bb.StorageClass.CXL_MEMORY, 8 << 20, ""), ("hdd", bb.StorageClass.HDD, 16 << 20, str(tmp_path))])
+        cl = c.client()
+        data = os.urandom(300000)
+        for name, sc in [("dram", bb.StorageClass.RAM_CPU), ("nvme", bb.StorageClass.NVME), ("cxl", bb.StorageClass.CXL_MEMORY), ("hdd", bb.StorageClass.HDD)]:
+            cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[sc], checksum=bb.ChecksumAlgo.CRC32C)
+            assert cl.put(f"on-{name}", data, cfg) == bb.ErrorCode.OK
+            sh = cl.get_workers(f"on-{name}")[0].shards[0]
+            assert sh.pool_id == name and sh.storage_class == sc
+            assert cl.get(f"on-{name}") == data
+        stats = c.workers[0].get_stats()
+        assert {p["pool_id"] for p in stats["pools"]} == {"dram", "nvme", "cxl", "hdd"} and stats["requests_served"] >= 8
+        assert all(p["bytes_written"] >= 300000 for p in stats["pools"])
+
+
+def test_config_files_parse(bb, tmp_path):
+    ks = bb.KeystoneConfig.from_yaml("/root/reference/configs/keystone.yaml")  # reference sample parses unchanged
+    assert ks.cluster_id == "blackbird_cluster" and ks.etcd_endpoints == "localhost:2379" and ks.high_watermark == 0.8
+    assert ks.client_ttl_sec == 300 and ks.max_replicas == 3 and ks.log_level == "INFO"
+    wc = bb.WorkerServiceConfig.from_yaml("/root/reference/configs/worker.yaml")
+    assert wc.worker_id == "worker-1" and wc.interconnects == ["rdma", "tcp"] and wc.heartbeat_interval_sec == 5
+    assert wc.storage_pools[0].pool_id == "ram_pool_0" and wc.storage_pools[0].size_bytes == 2 << 30
+    for name in ("keystone.yaml", "worker.yaml", "gpu_worker.yaml", "tiered_worker.yaml"):
+        path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "configs", name)
+        (bb.KeystoneConfig.from_yaml if name.startswith("keystone") else bb.WorkerServiceConfig.from_yaml)(path)
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("keystone:\n  cluster_id: x\n  high_watermark: 1.5\n")
+    with pytest.raises(RuntimeError, match="high_watermark"):
+        bb.KeystoneConfig.from_yaml(str(bad))
+    bad.write_text("worker:\n  worker_id: w\n  lease_ttl_sec: 5\n  heartbeat_interval_sec: 9\n")
+    with pytest.raises(RuntimeError, match="heartbeat_interval_sec"):
+        bb.WorkerServiceConfig.from_yaml(str(bad))

@@ -1,0 +1,311 @@
+"""keystone/: object state machine, batch ops, TTL GC, LRU + soft-pin eviction with tier demotion,
+dead-worker handling + repair, sessions, metrics, HA fail-over with WAL recovery, and one
+regression test per reference defect listed in SURVEY §2.8."""
+import time
+
+import pytest
+
+
+def ks_cfg(bb, **kw):
+    c = bb.KeystoneConfig()
+    c.cluster_id = kw.pop("cluster_id", "t")
+    c.listen_address = "127.0.0.1:0"
+    c.http_metrics_port = "0"
+    c.gc_interval_sec = 3600
+    c.health_check_interval_sec = 3600
+    c.service_refresh_interval_sec = 3600
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def mkpool(bb, pid, size, sc=None, node="node-a", worker=None):
+    return bb.MemoryPool(pid, size, sc if sc is not None else bb.StorageClass.RAM_CPU, node, worker if worker is not None else "w-" + pid,
+                         "127.0.0.1:12345", 0x1000000, "deadbeef")
+
+
+@pytest.fixture
+def ks(bb):
+    k = bb.KeystoneService(ks_cfg(bb), None)
+    assert k.initialize() == bb.ErrorCode.OK and k.start() == bb.ErrorCode.OK
+    for i in range(4):
+        assert k.register_memory_pool(mkpool(bb, f"p{i}", 1 << 20)) == bb.ErrorCode.OK
+    yield k
+    k.stop()
+
+
+def cfg1(bb, **kw):
+    kw.setdefault("replication_factor", 1)
+    kw.setdefault("max_workers_per_copy", 1)
+    return bb.WorkerConfig(**kw)
+
+
+def test_put_state_machine_pending_complete(bb, ks):
+    v0 = ks.get_view_version()
+    copies = ks.put_start("k", 10000, cfg1(bb))
+    assert len(copies) == 1 and copies[0].shards[0].length == 10000
+    # bug #2: an in-flight put is not visible to readers
+    assert ks.object_exists("k") is False
+    with pytest.raises(bb.BlackbirdError) as e:
+        ks.get_workers("k")
+    assert e.value.code == bb.ErrorCode.OBJECT_NOT_READY
+    assert ks.get_cluster_stats().pending_objects == 1 and ks.get_cluster_stats().total_objects == 0
+    with pytest.raises(bb.BlackbirdError) as e:
+        ks.put_start("k", 10, cfg1(bb))
+    assert e.value.code == bb.ErrorCode.OBJECT_ALREADY_EXISTS
+    assert ks.put_complete("k", [[0xABCDEF]]) == bb.ErrorCode.OK
+    assert ks.put_complete("k") == bb.ErrorCode.OK  # idempotent
+    got = ks.get_workers("k")
+    assert got[0].shards[0].checksum == 0xABCDEF and got[0].shards[0].checksum_algo == bb.ChecksumAlgo.BBH64
+    assert ks.object_exists("k") is True and ks.get_view_version() > v0
+    assert ks.put_cancel("k") == bb.ErrorCode.INVALID_STATE  # cannot cancel a completed put
+    assert ks.remove_object("k") == bb.ErrorCode.OK and ks.remove_object("k") == bb.ErrorCode.OBJECT_NOT_FOUND
+    assert ks.get_cluster_stats().used_capacity == 0
+
+
+def test_argument_validation(bb, ks):
+    for key, size, cfg, code in [("", 10, cfg1(bb), bb.ErrorCode.INVALID_KEY),
+                                 ("k", 10, cfg1(bb, replication_factor=0), bb.ErrorCode.INVALID_PARAMETERS),
+                                 ("k", 10, cfg1(bb, replication_factor=9), bb.ErrorCode.VALUE_OUT_OF_RANGE),
+                                 ("k", 64 << 20, cfg1(bb), bb.ErrorCode.INSUFFICIENT_SPACE)]:
+        with pytest.raises(bb.BlackbirdError) as e:
+            ks.put_start(key, size, cfg)
+        assert e.value.code == code
+    assert ks.put_complete("nope") == bb.ErrorCode.OBJECT_NOT_FOUND
+    assert ks.put_complete("nope", [[1]]) == bb.ErrorCode.OBJECT_NOT_FOUND
+    ks.put_start("c", 100, cfg1(bb))
+    assert ks.put_complete("c", [[1], [2]]) == bb.ErrorCode.INVALID_PARAMETERS  # shape mismatch
+
+
+def test_put_cancel_frees_ranges(bb, ks):
+    ks.put_start("k", 500000, cfg1(bb))
+    assert ks.get_cluster_stats().used_capacity >= 500000
+    assert ks.put_cancel("k") == bb.ErrorCode.OK
+    assert ks.get_cluster_stats().used_capacity == 0 and ks.put_cancel("k") == bb.ErrorCode.OBJECT_NOT_FOUND
+
+
+def test_default_client_config_works_wpc1(bb, ks):
+    """Bug #6: max_workers_per_copy == 1 returned NOT_IMPLEMENTED in the reference."""
+    copies = ks.put_start("single", 4096, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1))
+    assert len(copies[0].shards) == 1
+
+
+def test_batch_ops_per_item_results(bb, ks):
+    res = ks.batch_put_start(["a", "b", "", "a"], [1000, 2000, 10, 5], cfg1(bb))
+    assert [r[0] for r in res] == [bb.ErrorCode.OK, bb.ErrorCode.OK, bb.ErrorCode.INVALID_KEY, bb.ErrorCode.OBJECT_ALREADY_EXISTS]
+    assert ks.batch_put_complete(["a", "b", "zzz"]) == [bb.ErrorCode.OK, bb.ErrorCode.OK, bb.ErrorCode.OBJECT_NOT_FOUND]
+    ex = ks.batch_object_exists(["a", "b", "zzz"])
+    assert [(e, v) for e, v in ex] == [(bb.ErrorCode.OK, True), (bb.ErrorCode.OK, True), (bb.ErrorCode.OK, False)]
+    gw = ks.batch_get_workers(["a", "zzz"])
+    assert gw[0][0] == bb.ErrorCode.OK and len(gw[0][1]) == 1 and gw[1][0] == bb.ErrorCode.OBJECT_NOT_FOUND
+    ks.batch_put_start(["c"], [10], cfg1(bb))
+    assert ks.batch_put_cancel(["c", "a"]) == [bb.ErrorCode.OK, bb.ErrorCode.INVALID_STATE]
+    assert ks.batch_remove_object(["a", "b", "q"]) == [bb.ErrorCode.OK, bb.ErrorCode.OK, bb.ErrorCode.OBJECT_NOT_FOUND]
+
+
+def test_remove_all_objects_frees_allocator_ranges(bb, ks):
+    """Bug #5: the reference cleared the map but leaked every range."""
+    for i in range(10):
+        ks.put_start(f"o{i}", 100000, cfg1(bb))
+        ks.put_complete(f"o{i}")
+    assert ks.get_cluster_stats().used_capacity > 0
+    assert ks.remove_all_objects() == 10
+    st = ks.get_cluster_stats()
+    assert st.total_objects == 0 and st.used_capacity == 0 and ks.allocator_stats().total_objects == 0
+
+
+def test_ttl_expiry_gc_and_inline_reclaim(bb, ks):
+    ks.put_start("short", 1000, cfg1(bb, ttl_ms=60))
+    ks.put_complete("short")
+    ks.put_start("forever", 1000, cfg1(bb, ttl_ms=0))
+    ks.put_complete("forever")
+    time.sleep(0.15)
+    assert ks.object_exists("short") is False
+    with pytest.raises(bb.BlackbirdError) as e:
+        ks.get_workers("short")
+    assert e.value.code == bb.ErrorCode.OBJECT_NOT_FOUND
+    # bug #4: an expired-but-unswept key could not be re-put until the GC thread ran
+    assert len(ks.put_start("short", 2000, cfg1(bb, ttl_ms=60))) == 1
+    ks.put_complete("short")
+    time.sleep(0.15)
+    assert ks.run_gc_once() == 1
+    assert ks.object_exists("forever") is True and ks.allocator_stats().total_objects == 1
+    assert "bb_expired_total 2" in ks.metrics_text()
+
+
+def test_cluster_stats_live_accounting(bb, ks):
+    """Bug #3: utilisation came from a registration snapshot that never changed; total_workers was never set."""
+    st = ks.get_cluster_stats()
+    assert st.total_workers == 4 and st.total_memory_pools == 4 and st.total_capacity == 4 << 20 and st.used_capacity == 0
+    ks.put_start("x", 1 << 19, cfg1(bb))
+    st = ks.get_cluster_stats()
+    assert st.used_capacity == 1 << 19 and abs(st.avg_utilization - 0.125) < 1e-9
+    assert sum(p.used for p in ks.get_memory_pools()) == 1 << 19
+
+
+def test_eviction_lru_soft_pin_and_frees_ranges(bb):
+    k = bb.KeystoneService(ks_cfg(bb, high_watermark=0.5, eviction_ratio=0.34), None)
+    k.initialize(), k.start()
+    k.register_memory_pool(mkpool(bb, "p", 1 << 20))
+    for name, pin in [("old", False), ("pinned", True), ("mid", False), ("new", False)]:
+        k.put_start(name, 150000, cfg1(bb, enable_soft_pin=pin))
+        k.put_complete(name)
+        time.sleep(0.01)
+    k.get_workers("old")  # touch: "old" becomes most recently used -> LRU victim is "mid"
+    assert k.tier_utilization(bb.StorageClass.RAM_CPU) > 0.5
+    used0 = k.get_cluster_stats().used_capacity
+    assert k.run_eviction_once() == 1
+    assert k.object_exists("mid") is False and k.object_exists("pinned") and k.object_exists("old") and k.object_exists("new")
+    assert k.get_cluster_stats().used_capacity < used0  # ranges really freed
+    assert "bb_evictions_total 1" in k.metrics_text()
+    k.stop()
+
+
+def test_eviction_demotes_to_lower_tier_through_mover(bb):
+    k = bb.KeystoneService(ks_cfg(bb, high_watermark=0.5, eviction_ratio=1.0), None)
+    k.initialize(), k.start()
+    k.register_memory_pool(mkpool(bb, "hbm", 1 << 20, bb.StorageClass.RAM_GPU))
+    k.register_memory_pool(mkpool(bb, "dram", 8 << 20, bb.StorageClass.RAM_CPU))
+    moved = []
+
+    def mover(key, src, dst, algo):
+        moved.append((key, src.shards[0].pool_id, dst.shards[0].pool_id))
+        return (bb.ErrorCode.OK, [0x77] * len(dst.shards))
+
+    k.set_copy_mover(mover)
+    gpu_only = dict(preferred_classes=[bb.StorageClass.RAM_GPU])
+    for n in ("a", "b"):
+        k.put_start(n, 300000, cfg1(bb, **gpu_only))
+        k.put_complete(n)
+    k.put_start("pin", 100000, cfg1(bb, enable_soft_pin=True, **gpu_only))
+    k.put_complete("pin")
+    assert k.run_eviction_once() == 2
+    assert sorted(m[0] for m in moved) == ["a", "b"] and all(m[1] == "hbm" and m[2] == "dram" for m in moved)
+    for n in ("a", "b"):
+        sh = k.get_workers(n)[0].shards[0]
+        assert sh.pool_id == "dram" and sh.storage_class == bb.StorageClass.RAM_CPU and sh.checksum == 0x77
+    assert k.get_workers("pin")[0].shards[0].pool_id == "hbm"  # soft-pinned objects stay
+    assert k.tier_utilization(bb.StorageClass.RAM_GPU) < 0.2
+    assert "bb_demotions_total 2" in k.metrics_text()
+    assert k.remove_object("a") == bb.ErrorCode.OK
+    assert k.get_cluster_stats().used_capacity == 300032 + 100096  # b (dram) + pin (hbm), 256 B aligned
+    k.set_copy_mover(None)
+    k.stop()
+
+
+def test_dead_worker_invalidates_copies_and_repairs(bb):
+    k = bb.KeystoneService(ks_cfg(bb), None)
+    k.initialize(), k.start()
+    for i in range(3):
+        k.register_memory_pool(mkpool(bb, f"p{i}", 1 << 20, worker=f"w{i}"))
+    k.put_start("r2", 5000, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1))
+    k.put_complete("r2", [[5], [5]])
+    k.put_start("r1", 5000, cfg1(bb))
+    k.put_complete("r1")
+    victim = k.get_workers("r1")[0].shards[0].worker_id
+    r2_pools = {c.shards[0].worker_id for c in k.get_workers("r2")}
+    k.handle_worker_death(victim)
+    st = k.get_cluster_stats()
+    assert st.total_workers == 2 and st.total_memory_pools == 2
+    # the single-copy object on the dead worker is gone (the reference left a dangling placement)
+    with pytest.raises(bb.BlackbirdError) as e:
+        k.get_workers("r1")
+    assert e.value.code == bb.ErrorCode.OBJECT_NOT_FOUND
+    if victim in r2_pools:
+        live = k.get_workers("r2")
+        assert len(live) == 1 and live[0].shards[0].worker_id != victim  # survivor keeps serving
+        k.set_copy_mover(lambda key, src, dst, algo: (bb.ErrorCode.OK, [5]))
+        assert k.run_repair_once() == 1
+        healed = k.get_workers("r2")
+        assert len(healed) == 2 and len({c.shards[0].worker_id for c in healed}) == 2 and victim not in {c.shards[0].worker_id for c in healed}
+        k.set_copy_mover(None)
+    else:
+        assert len(k.get_workers("r2")) == 2
+    assert k.remove_worker("ghost") == bb.ErrorCode.INVALID_WORKER
+    k.stop()
+
+
+def test_client_sessions_ttl(bb):
+    k = bb.KeystoneService(ks_cfg(bb, client_ttl_sec=1, health_check_interval_sec=1), None)
+    k.initialize(), k.start()
+    cid = k.client_register("node-x")
+    assert cid.startswith("client-") and k.client_ping(cid) == k.get_view_version()
+    assert k.get_cluster_stats().active_clients == 1
+    time.sleep(2.3)  # health thread expires the silent session
+    with pytest.raises(bb.BlackbirdError) as e:
+        k.client_ping(cid)
+    assert e.value.code == bb.ErrorCode.SESSION_EXPIRED
+    k.stop()
+
+
+def test_metrics_exposition_format(bb, ks):
+    ks.put_start("m", 1000, cfg1(bb))
+    ks.put_complete("m")
+    ks.get_workers("m")
+    text = ks.metrics_text()
+    for needle in ["# TYPE bb_put_start_total counter", "bb_put_start_total 1", "bb_put_complete_total 1", "bb_get_workers_total 1",
+                   "bb_objects 1", "bb_workers 4", "bb_capacity_bytes 4194304", "bb_is_leader 1", 'bb_tier_used_bytes{tier="RAM_CPU"} 1024',
+                   "bb_put_start_latency_us_bucket{le=\"+Inf\"} 1", "bb_put_start_latency_us_count 1"]:
+        assert needle in text, needle
+    sj = ks.stats_json()
+    assert sj["cluster"]["total_objects"] == 1 and len(sj["pools"]) == 4 and sj["is_leader"] is True
+
+
+def test_concurrent_puts_across_shards(bb, ks):
+    import threading
+
+    errs = []
+
+    def run(t):
+        for i in range(200):
+            key = f"t{t}/o{i}"
+            try:
+                ks.put_start(key, 512, cfg1(bb))
+                assert ks.put_complete(key) == bb.ErrorCode.OK
+                assert ks.object_exists(key)
+                assert ks.remove_object(key) == bb.ErrorCode.OK
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+
+    ts = [threading.Thread(target=run, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs and ks.get_cluster_stats().used_capacity == 0 and ks.allocator_stats().total_objects == 0
+
+
+def test_ha_leader_failover_recovers_objects_from_wal(bb):
+    """Real leader election + metadata log (the reference has neither: §2.7, §5.4)."""
+    store = bb.MemCoord()
+    mk = lambda sid: bb.KeystoneService(ks_cfg(bb, cluster_id="ha", enable_ha=True, service_id=sid, service_registration_ttl_sec=4,
+                                                service_refresh_interval_sec=1), bb.CoordService(store))
+    a, b = mk("ks-a"), mk("ks-b")
+    assert a.initialize() == bb.ErrorCode.OK and a.start() == bb.ErrorCode.OK
+    assert b.initialize() == bb.ErrorCode.OK and b.start() == bb.ErrorCode.OK
+    assert a.is_leader() and not b.is_leader()
+    # a worker registers through the coordination store: both keystones learn about it
+    pool = mkpool(bb, "p0", 1 << 20, worker="w0")
+    store.put("/blackbird/clusters/ha/workers/w0", '{"worker_id":"w0","node_id":"n0"}')
+    store.put("/blackbird/clusters/ha/workers/w0/memory_pools/p0", pool.to_json())
+    store.flush_events()
+    assert a.get_cluster_stats().total_memory_pools == 1 and b.get_cluster_stats().total_memory_pools == 1
+    with pytest.raises(bb.BlackbirdError) as e:
+        b.put_start("x", 10, cfg1(bb))
+    assert e.value.code == bb.ErrorCode.NOT_LEADER  # standby refuses mutations
+    placed = a.put_start("obj", 4096, cfg1(bb, ttl_ms=0))
+    assert a.put_complete("obj", [[0x1234]]) == bb.ErrorCode.OK
+    a.put_start("pending-only", 4096, cfg1(bb))  # never completed: not in the WAL
+    # leader crashes (no clean resign): its lease expires, the standby takes over on its next campaign
+    store.advance_time_ms(5000)
+    deadline = time.time() + 5
+    while not b.is_leader() and time.time() < deadline:
+        time.sleep(0.05)
+    assert b.is_leader()
+    got = b.get_workers("obj")
+    assert got[0].shards[0].checksum == 0x1234 and got[0].shards[0].offset == placed[0].shards[0].offset
+    with pytest.raises(bb.BlackbirdError):
+        b.get_workers("pending-only")
+    # recovered extents are reserved: a new object must not overlap the recovered one
+    fresh = b.put_start("fresh", 4096, cfg1(bb))
+    assert fresh[0].shards[0].offset != placed[0].shards[0].offset
+    assert store.get("/blackbird/elections/keystone-ha/leader") == b"ks-b"
+    a.stop(), b.stop()

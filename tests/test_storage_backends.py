@@ -1,0 +1,165 @@
+"""worker/storage: reserve/commit/abort/free lifecycle (semantics of the reference's 16
+IoUringDiskBackend tests, tests/storage/test_iouring_disk_backend.cpp) on every tier, plus what
+the reference lacks: a real data path, real io_uring submissions, manifest recovery."""
+import os
+import threading
+import time
+
+import pytest
+
+MiB = 1 << 20
+
+
+def make(bb, sc, cap, tmp_path, pool_id="pool0", **kw):
+    b = bb.create_storage_backend(sc, cap, str(tmp_path), pool_id=pool_id, **kw)
+    assert b is not None, f"factory returned nothing for {sc}"
+    assert b.initialize() == bb.ErrorCode.OK
+    return b
+
+
+ALL = ["RAM_CPU", "NVME", "SSD", "HDD", "CXL_MEMORY", "CXL_TYPE2_DEVICE"]
+
+
+@pytest.mark.parametrize("sc_name", ALL)
+def test_factory_builds_every_host_tier_and_accounts_capacity(bb, tmp_path, sc_name):
+    """The reference factory returns nullptr for NVME/SSD/HDD (ram_backend.cpp:299-301)."""
+    sc = getattr(bb.StorageClass, sc_name)
+    b = make(bb, sc, 8 * MiB, tmp_path)
+    assert b.get_storage_class() == sc and b.get_total_capacity() == 8 * MiB
+    assert b.get_used_capacity() == 0 and b.get_available_capacity() == 8 * MiB
+    tok = b.reserve_shard(102400)
+    assert tok.size == 102400 and tok.pool_id == "pool0" and tok.remote_addr >= b.get_base_address()
+    assert b.get_used_capacity() >= 102400 and b.get_stats().num_reservations == 1
+    assert b.commit_shard(tok) == bb.ErrorCode.OK
+    st = b.get_stats()
+    assert st.num_reservations == 0 and st.num_committed_shards == 1 and 0 < st.utilization < 1
+    assert b.free_shard(tok.remote_addr, tok.size) == bb.ErrorCode.OK
+    assert b.get_used_capacity() == 0
+    b.shutdown()
+
+
+def test_gpu_tier_needs_the_cuda_factory(bb):
+    # on a CPU-only host the RAM_GPU class cannot be built (no silent malloc stand-in)
+    if bb.cuda_device_count() == 0:
+        assert bb.create_storage_backend(bb.StorageClass.RAM_GPU, MiB) is None
+
+
+def test_out_of_space_zero_size_unknown_tokens(bb, tmp_path):
+    b = make(bb, bb.StorageClass.NVME, 4 * MiB, tmp_path)
+    with pytest.raises(bb.BlackbirdError) as e:
+        b.reserve_shard(0)
+    assert e.value.code == bb.ErrorCode.INVALID_PARAMETERS
+    with pytest.raises(bb.BlackbirdError) as e:
+        b.reserve_shard(5 * MiB)
+    assert e.value.code == bb.ErrorCode.OUT_OF_MEMORY
+    tok = b.reserve_shard(MiB)
+    assert b.abort_shard(tok) == bb.ErrorCode.OK and b.get_used_capacity() == 0  # abort restores capacity
+    assert b.abort_shard(tok) == bb.ErrorCode.INVALID_PARAMETERS
+    assert b.commit_shard(tok) == bb.ErrorCode.INVALID_PARAMETERS
+    tok = b.reserve_shard(MiB)
+    b.commit_shard(tok)
+    assert b.free_shard(tok.remote_addr, tok.size + 8192) == bb.ErrorCode.INVALID_PARAMETERS  # size mismatch
+    assert b.free_shard(tok.remote_addr + 4096, 4096) == bb.ErrorCode.OBJECT_NOT_FOUND  # unknown address
+
+
+def test_expired_token_times_out_and_is_reclaimed(bb, tmp_path):
+    b = make(bb, bb.StorageClass.RAM_CPU, 4 * MiB, tmp_path)
+    b.set_reservation_ttl_ms(30)
+    tok = b.reserve_shard(3 * MiB)
+    time.sleep(0.08)
+    assert b.commit_shard(tok) == bb.ErrorCode.OPERATION_TIMEOUT and b.get_used_capacity() == 0
+    tok2 = b.reserve_shard(3 * MiB)  # abandoned reservation...
+    time.sleep(0.08)
+    tok3 = b.reserve_shard(3 * MiB)  # ...is reclaimed by the next reserve instead of exhausting the tier
+    assert tok3.remote_addr == tok2.remote_addr
+
+
+def test_uncommitted_reservations_never_overlap(bb, tmp_path):
+    """Bug #11: RamBackend::find_free_offset ignored uncommitted reservations."""
+    b = make(bb, bb.StorageClass.RAM_CPU, 4 * MiB, tmp_path)
+    toks = [b.reserve_shard(256 * 1024) for _ in range(8)]
+    spans = sorted((t.remote_addr, t.remote_addr + t.size) for t in toks)
+    assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    assert b.get_stats().num_reservations == 8  # and get_stats does not self-deadlock (bug #10)
+
+
+def test_concurrent_reserve_commit(bb, tmp_path):
+    b = make(bb, bb.StorageClass.SSD, 64 * MiB, tmp_path)
+    toks = []
+    lock = threading.Lock()
+
+    def run():
+        for _ in range(50):
+            t = b.reserve_shard(64 * 1024)
+            assert b.commit_shard(t) == bb.ErrorCode.OK
+            with lock:
+                toks.append(t)
+
+    ts = [threading.Thread(target=run) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len({t.remote_addr for t in toks}) == 200 and b.get_stats().num_committed_shards == 200
+
+
+@pytest.mark.parametrize("sc_name", ALL)
+def test_data_path_roundtrip(bb, tmp_path, sc_name):
+    """The reference backends have no read/write API at all."""
+    b = make(bb, getattr(bb.StorageClass, sc_name), 16 * MiB, tmp_path)
+    for off, n in [(0, 1), (4096, 4096), (8192 + 256, 100001), (1 * MiB, 5 * MiB + 13)]:
+        data = os.urandom(n)
+        assert b.write(off, data) == bb.ErrorCode.OK
+        assert b.read(off, n) == data
+    assert b.write(16 * MiB - 10, b"x" * 11) == bb.ErrorCode.MEMORY_ACCESS_ERROR  # bounds are enforced
+    st = b.get_stats()
+    assert st.bytes_written > 5 * MiB and st.bytes_read > 5 * MiB and st.io_errors == 0
+
+
+def test_io_uring_backend_submits_real_sqes_and_persists(bb, tmp_path):
+    """The reference opens a ring and never submits an SQE."""
+    b = make(bb, bb.StorageClass.NVME, 32 * MiB, tmp_path, queue_depth=32)
+    assert os.path.exists(b.file_path) and os.path.getsize(b.file_path) == 32 * MiB
+    data = os.urandom(3 * MiB + 777)
+    tok = b.reserve_shard(len(data))
+    off = tok.remote_addr - b.get_base_address()
+    assert b.write(off, data) == bb.ErrorCode.OK
+    assert b.commit_shard(tok) == bb.ErrorCode.OK and b.flush() == bb.ErrorCode.OK
+    if bb.io_uring_supported():
+        assert b.using_uring and b.sqes_submitted >= 12  # 256 KiB pieces through the ring
+    with open(b.file_path, "rb") as f:  # bytes are really on disk at the advertised offset
+        f.seek(off)
+        assert f.read(len(data)) == data
+    tok2 = b.reserve_shard(4096)
+    b.commit_shard(tok2)
+    b.free_shard(tok2.remote_addr, 4096)
+    b.shutdown()
+    # a restarted worker recovers the committed extent (offset, size, crc32c) from the manifest
+    b2 = make(bb, bb.StorageClass.NVME, 32 * MiB, tmp_path, queue_depth=32)
+    rec = b2.recovered_extents()
+    assert rec == [(off, len(data), bb.crc32c(data))]
+    assert b2.read(off, len(data)) == data and b2.get_stats().num_committed_shards == 1
+    tok3 = b2.reserve_shard(MiB)
+    assert not (off < tok3.remote_addr - b2.get_base_address() + MiB and tok3.remote_addr - b2.get_base_address() < off + len(data))
+
+
+def test_mmap_backend_is_file_backed(bb, tmp_path):
+    b = make(bb, bb.StorageClass.HDD, 4 * MiB, tmp_path, pool_id="hdd0")
+    assert b.has_direct_ptr() and b.file_path.endswith("hdd0.dat")
+    b.write(12345, b"hello-mmap")
+    assert b.flush() == bb.ErrorCode.OK
+    with open(b.file_path, "rb") as f:
+        f.seek(12345)
+        assert f.read(10) == b"hello-mmap"
+
+
+def test_cxl_backend_placeholder_cacheline_and_regions(bb, tmp_path):
+    b = make(bb, bb.StorageClass.CXL_MEMORY, 4 * MiB + 17, tmp_path / "no-dax-device")
+    assert b.get_total_capacity() % 64 == 0 and not b.is_dax and b.has_direct_ptr()
+    tok = b.reserve_shard(100)  # sizes are cache-line granular
+    assert tok.size == 128 and b.region_id(0) == 0 and b.region_id(1024) == 4
+    bad = bb.create_storage_backend(bb.StorageClass.CXL_MEMORY, 0)
+    assert bad.initialize() == bb.ErrorCode.INVALID_ARGUMENT  # one of the codes the reference forgot to declare
+
+
+def test_unwritable_directory_fails_cleanly(bb):
+    b = bb.create_storage_backend(bb.StorageClass.NVME, MiB, "/proc/definitely/not/writable")
+    assert b.initialize() == bb.ErrorCode.IO_ERROR
