@@ -45,8 +45,9 @@ def reference_arm() -> int:
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--ctas", type=int, default=0, help="persistent CTAs of the fused kernel (0 = default)")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--objects", type=int, default=64, help="objects per batch per rank")
     ap.add_argument("--object-mib", type=float, default=16.0)
@@ -113,14 +114,16 @@ def main() -> int:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    if args.ctas:
+        cl.fabric.set_max_ctas(args.ctas)
     # ---------------------------------------------------------------- warm-up + correctness
+    sampler = ClockSampler(cl.local_rank, 100).start() if rank == 0 else None
     for i in range(max(3, args.warmup)):
         step("w", i)
     torch.cuda.synchronize()
     assert torch.equal(src, out), "payload mismatch after put+get"
 
     # ---------------------------------------------------------------- device-resident timed region
-    sampler = ClockSampler(cl.local_rank).start() if rank == 0 else None
     launches0 = cl.fabric.launches
     cl.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -132,7 +135,14 @@ def main() -> int:
     cl.barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = int(sum_over_ranks(cl.fabric.launches - launches0))
+    if sampler and ms < 1500:  # give nvidia-smi time to take samples under the same load
+        t_end = time.time() + 1.2
+        i = 0
+        while time.time() < t_end:
+            step("c", i)
+            i += 1
     clocks = sampler.stop() if sampler else None
+    phases = {k: round(v[1] / max(v[0], 1), 1) for k, v in cl.client.phase_summary().items() if k.startswith("phase_")}
     total_bytes = 2.0 * step_bytes * args.steps * world
     value = total_bytes / (ms * 1e-3) / 1e9
 
@@ -258,6 +268,7 @@ def main() -> int:
                     "steps": args.e2e_steps, "ms_per_step": round(e2e_ms / args.e2e_steps, 3),
                     "note": "every step: cudaMemcpyAsync of the payload from pinned host memory, batch_put_device + batch_get_device through the public client API, D2H of 4 KiB of every returned object (verified on the host) plus digests/status"},
             "gpu_launches": launches,
+            "host_phase_mean_us": phases,
             "clocks": clocks,
             "comparators": comparators,
             "baseline_note": "vs_baseline divides by the reference's only throughput figure, an unsourced '~233 MB/sec' config comment (BASELINE.md section 1)",

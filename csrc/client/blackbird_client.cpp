@@ -366,7 +366,10 @@ std::vector<Result<std::vector<uint8_t>>> BlackbirdClient::batch_get(const std::
 
 std::vector<ErrorCode> BlackbirdClient::batch_remove(const std::vector<ObjectKey>& keys) {
   if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
-  return keystone_->batch_remove_object(keys);
+  const TimePoint t0 = Clock::now();
+  auto r = keystone_->batch_remove_object(keys);
+  metrics_.observe("phase_remove_us", us_since(t0));
+  return r;
 }
 
 std::vector<Result<bool>> BlackbirdClient::batch_exists(const std::vector<ObjectKey>& keys) {
@@ -385,6 +388,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
   std::vector<PutStartItem> items(keys.size());
   for (size_t i = 0; i < keys.size(); ++i) items[i] = PutStartItem{keys[i], sizes[i], cfg};
   auto placed = keystone_->batch_put_start(items);
+  metrics_.observe("phase_put_start_us", us_since(t0));
   // One descriptor per (object, shard): copy 0's placement plus the same shard of every other
   // copy as extra destinations, so the kernel reads the source once and fans out.
   std::vector<DeviceShardOp> ops;
@@ -429,7 +433,10 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
     }
   }
   std::vector<uint64_t> digests;
+  const TimePoint t1 = Clock::now();
   ErrorCode ec = device_->put_shards(ops, dev_ptrs, cfg.checksum, stream, &digests);
+  metrics_.observe("phase_put_xfer_us", us_since(t1));
+  const TimePoint t2 = Clock::now();
   std::vector<ObjectKey> done_keys, cancel_keys;
   std::vector<ShardChecksums> done_sums;
   std::vector<size_t> done_idx;
@@ -463,6 +470,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
     auto ecs = keystone_->batch_put_complete(done_keys, done_sums);
     for (size_t k = 0; k < done_idx.size(); ++k) out[done_idx[k]] = ecs[k];
   }
+  metrics_.observe("phase_put_complete_us", us_since(t2));
   metrics_.inc("device_put_batches_total");
   metrics_.observe("device_put_batch_latency_us", us_since(t0));
   return out;
@@ -477,6 +485,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   if (dev_ptrs.size() != keys.size() || capacity.size() != keys.size()) return out;
   const TimePoint t0 = Clock::now();
   auto placed = keystone_->batch_get_workers(keys);
+  metrics_.observe("phase_get_workers_us", us_since(t0));
   if (out_sizes) out_sizes->assign(keys.size(), 0);
   // choose for every object the first copy the fabric can reach; later passes retry failures
   std::vector<size_t> copy_choice(keys.size(), 0);
@@ -521,7 +530,9 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
     }
     if (ops.empty()) break;
     std::vector<uint32_t> status;
+    const TimePoint t1 = Clock::now();
     ErrorCode ec = device_->get_shards(ops, dev_ptrs, ChecksumAlgo::NONE /* per-shard algo from placement */, stream, &status);
+    metrics_.observe("phase_get_xfer_us", us_since(t1));
     std::vector<bool> bad(keys.size(), false);
     if (ec != ErrorCode::OK) {
       for (size_t i = 0; i < keys.size(); ++i)

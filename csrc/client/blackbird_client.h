@@ -96,6 +96,7 @@ class BlackbirdClient {
   Result<ClusterStats> cluster_stats();
   rpc::KeystoneApi& keystone() { return *keystone_; }
   std::string metrics_text() const { return metrics_.render("bb_client_"); }
+  std::map<std::string, std::vector<double>> phase_summary() const { return metrics_.histogram_summary(); }
 
  private:
   struct WorkerConn;

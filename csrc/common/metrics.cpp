@@ -94,6 +94,13 @@ void Metrics::describe(const std::string& name, const std::string& help) {
   help_[name] = help;
 }
 
+std::map<std::string, std::vector<double>> Metrics::histogram_summary() const {
+  std::map<std::string, std::vector<double>> out;
+  std::lock_guard<std::mutex> lk(mu_);
+  for (const auto& [n, h] : hists_) out[n] = {static_cast<double>(h->count()), h->sum(), h->quantile(0.5), h->quantile(0.99)};
+  return out;
+}
+
 std::string Metrics::render(const std::string& prefix) const {
   std::ostringstream out;
   std::lock_guard<std::mutex> lk(mu_);

@@ -40,6 +40,8 @@ class Metrics {
   // Prometheus text format, metric names prefixed with `prefix`.
   std::string render(const std::string& prefix = "bb_") const;
   static std::vector<double> default_latency_bounds_us();
+  // name -> (count, sum, p50, p99) of every histogram
+  std::map<std::string, std::vector<double>> histogram_summary() const;
 
  private:
   mutable std::mutex mu_;

@@ -840,5 +840,6 @@ void bind_control(py::module_& m) {
       }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("capacity"), py::arg("stream") = 0)
       .def("cluster_stats", [](BlackbirdClient& c) { return unwrap(c.cluster_stats()); })
       .def("metrics_text", &BlackbirdClient::metrics_text)
+      .def("phase_summary", &BlackbirdClient::phase_summary, "histogram name -> [count, sum_us, p50_us, p99_us]")
       .def("keystone", [](BlackbirdClient& c) -> rpc::KeystoneApi& { return c.keystone(); }, py::return_value_policy::reference_internal);
 }
