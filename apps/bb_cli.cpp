@@ -1,0 +1,144 @@
+// bb-cli: command-line client (reference clients/ucx_client.cpp: put + get + compare with
+// timings; examples/simple_client_test.cpp: connectivity + /metrics smoke).
+//   bb-cli --keystone 127.0.0.1:9090 put KEY FILE [--replicas R] [--max-workers W] [--ttl-ms T] [--class RAM_CPU]
+//   bb-cli get KEY [OUTFILE] | exists KEY | remove KEY | stats | smoke [--size N] | metrics --http 127.0.0.1:9091
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+#include <random>
+
+#include "apps/cli_util.h"
+#include "client/blackbird_client.h"
+#include "common/log.h"
+
+using namespace bb;
+
+namespace {
+double ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+const char* name(ErrorCode ec) {
+  static thread_local std::string s;
+  s = std::string(to_string(ec));
+  return s.c_str();
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  auto args = bbapp::parse_args(argc, argv);
+  if (args.positional.empty() || args.has("help")) {
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | stats | smoke | metrics --http host:port>\n");
+    return args.has("help") ? 0 : 2;
+  }
+  const std::string cmd = args.positional[0];
+  if (cmd == "metrics") {
+    auto hp = split_host_port(args.get("http", "127.0.0.1:9091"));
+    if (!hp) return 2;
+    int status = 0;
+    auto r = net::http_get(hp->first, static_cast<uint16_t>(hp->second), args.get("path", "/metrics"), &status);
+    if (!r.ok()) {
+      std::fprintf(stderr, "http error: %s\n", name(r.error()));
+      return 1;
+    }
+    std::printf("%s", r.value().c_str());
+    return status == 200 ? 0 : 1;
+  }
+  auto hp = split_host_port(args.get("keystone", "127.0.0.1:9090"));
+  if (!hp) return 2;
+  client::BlackbirdClientOptions o;
+  o.keystone_host = hp->first;
+  o.keystone_port = static_cast<uint16_t>(hp->second);
+  o.node_id = args.get("node-id");
+  o.io_parallelism = static_cast<size_t>(args.num("parallelism", 4));
+  client::BlackbirdClient cl(o);
+  auto t0 = std::chrono::steady_clock::now();
+  ErrorCode ec = cl.connect();
+  if (ec != ErrorCode::OK) {
+    std::fprintf(stderr, "cannot connect to keystone %s: %s\n", args.get("keystone", "127.0.0.1:9090").c_str(), name(ec));
+    return 1;
+  }
+  const double connect_ms = ms_since(t0);
+  WorkerConfig cfg;
+  cfg.replication_factor = static_cast<size_t>(args.num("replicas", 1));
+  cfg.max_workers_per_copy = static_cast<size_t>(args.num("max-workers", 1));
+  cfg.ttl_ms = static_cast<uint64_t>(args.num("ttl-ms", 30 * 60 * 1000));
+  cfg.enable_soft_pin = args.has("soft-pin");
+  if (args.has("class"))
+    if (auto sc = parse_storage_class(args.get("class"))) cfg.preferred_classes = {*sc};
+  if (args.get("checksum") == "crc32c") cfg.checksum = ChecksumAlgo::CRC32C;
+
+  if (cmd == "put" && args.positional.size() >= 3) {
+    std::ifstream f(args.positional[2], std::ios::binary);
+    if (!f) {
+      std::fprintf(stderr, "cannot read %s\n", args.positional[2].c_str());
+      return 2;
+    }
+    std::vector<uint8_t> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    t0 = std::chrono::steady_clock::now();
+    ec = cl.put(args.positional[1], data, cfg);
+    const double ms = ms_since(t0);
+    std::printf("put %s: %s (%zu bytes, %.3f ms, %.1f MB/s)\n", args.positional[1].c_str(), name(ec), data.size(), ms, data.size() / ms / 1e3);
+    return ec == ErrorCode::OK ? 0 : 1;
+  }
+  if (cmd == "get" && args.positional.size() >= 2) {
+    t0 = std::chrono::steady_clock::now();
+    auto r = cl.get(args.positional[1]);
+    const double ms = ms_since(t0);
+    if (!r.ok()) {
+      std::fprintf(stderr, "get %s: %s\n", args.positional[1].c_str(), name(r.error()));
+      return 1;
+    }
+    if (args.positional.size() >= 3) {
+      std::ofstream o2(args.positional[2], std::ios::binary);
+      o2.write(reinterpret_cast<const char*>(r.value().data()), static_cast<std::streamsize>(r.value().size()));
+    }
+    std::printf("get %s: OK (%zu bytes, %.3f ms, %.1f MB/s, checksum verified)\n", args.positional[1].c_str(), r.value().size(), ms, r.value().size() / ms / 1e3);
+    return 0;
+  }
+  if (cmd == "exists" && args.positional.size() >= 2) {
+    auto r = cl.object_exists(args.positional[1]);
+    std::printf("%s\n", r.ok() && r.value() ? "true" : "false");
+    return r.ok() && r.value() ? 0 : 1;
+  }
+  if (cmd == "remove" && args.positional.size() >= 2) {
+    ec = cl.remove(args.positional[1]);
+    std::printf("remove %s: %s\n", args.positional[1].c_str(), name(ec));
+    return ec == ErrorCode::OK ? 0 : 1;
+  }
+  if (cmd == "stats") {
+    auto st = cl.cluster_stats();
+    if (!st.ok()) return 1;
+    std::printf("%s\n", to_json(st.value()).dump(2).c_str());
+    return 0;
+  }
+  if (cmd == "smoke") {
+    // put -> get -> compare -> placements -> remove, with timings (reference clients/ucx_client.cpp:188-334)
+    const size_t n = static_cast<size_t>(args.num("size", 64));
+    std::vector<uint8_t> data(n);
+    std::mt19937 rng(42);
+    for (auto& b : data) b = static_cast<uint8_t>(rng());
+    const std::string key = args.get("key", "smoke-" + std::to_string(std::chrono::steady_clock::now().time_since_epoch().count()));
+    t0 = std::chrono::steady_clock::now();
+    ec = cl.put(key, data, cfg);
+    const double put_ms = ms_since(t0);
+    if (ec != ErrorCode::OK) {
+      std::fprintf(stderr, "smoke put failed: %s\n", name(ec));
+      return 1;
+    }
+    t0 = std::chrono::steady_clock::now();
+    auto back = cl.get(key);
+    const double get_ms = ms_since(t0);
+    const bool same = back.ok() && back.value() == data;
+    auto placed = cl.get_workers(key);
+    size_t shards = 0;
+    if (placed.ok())
+      for (const auto& c : placed.value()) shards += c.shards.size();
+    cl.remove(key);
+    std::printf("connect %.3f ms | put %.3f ms (%.2f MB/s) | get %.3f ms (%.2f MB/s) | copies %zu shards %zu | verify %s\n", connect_ms, put_ms,
+                n / put_ms / 1e3, get_ms, n / get_ms / 1e3, placed.ok() ? placed.value().size() : 0, shards, same ? "PASS" : "FAIL");
+    return same ? 0 : 1;
+  }
+  std::fprintf(stderr, "unknown command\n");
+  return 2;
+}

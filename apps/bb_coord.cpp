@@ -1,0 +1,36 @@
+// bb-coord: the coordination daemon (the role `etcd` plays in the reference's
+// scripts/start_cluster.sh:119-147).  Serves a MemCoord over the framed RPC protocol.
+//   bb-coord --listen 127.0.0.1:2379
+#include <chrono>
+#include <cstdio>
+#include <thread>
+
+#include "apps/cli_util.h"
+#include "common/log.h"
+#include "coord/coord.h"
+
+int main(int argc, char** argv) {
+  auto args = bbapp::parse_args(argc, argv);
+  if (args.has("help")) {
+    std::printf("usage: bb-coord [--listen host:port] [--log-level info]\n");
+    return 0;
+  }
+  if (args.has("log-level")) setenv("BB_LOG_LEVEL", args.get("log-level").c_str(), 1);
+  bb::set_log_level(bb::LogLevel::INFO);
+  auto hp = bb::split_host_port(args.get("listen", "127.0.0.1:2379"));
+  if (!hp) {
+    std::fprintf(stderr, "bb-coord: bad --listen\n");
+    return 2;
+  }
+  bbapp::install_signal_handlers();
+  bb::coord::CoordServer srv;
+  if (srv.start(hp->first, static_cast<uint16_t>(hp->second)) != bb::ErrorCode::OK) {
+    std::fprintf(stderr, "bb-coord: cannot listen on %s\n", args.get("listen", "127.0.0.1:2379").c_str());
+    return 1;
+  }
+  std::printf("bb-coord listening on %s:%u\n", hp->first.c_str(), srv.port());
+  std::fflush(stdout);
+  while (!bbapp::g_stop) std::this_thread::sleep_for(std::chrono::milliseconds(200));
+  srv.stop();
+  return 0;
+}

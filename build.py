@@ -49,7 +49,7 @@ def generate() -> str:
     os.makedirs(BUILD, exist_ok=True)
     ext = sysconfig.get_config_var("EXT_SUFFIX")
     pyinc = sysconfig.get_paths()["include"]
-    incs = f"-I{ROOT}/csrc -I{CUDA_HOME}/include"
+    incs = f"-I{ROOT}/csrc -I{ROOT} -I{CUDA_HOME}/include"
     pyincs = f"-I{pybind11.get_include()} -I{pyinc}"
     san = _san_flags()
 

@@ -268,6 +268,22 @@ Result<AllocationResult> RangeAllocator::place(const AllocationRequest& req, con
   std::unordered_set<std::string> workers_used;  // failure domains taken by earlier copies
   std::unordered_set<MemoryPoolId> pools_used;
   size_t rot = 0;
+  // Failure-domain partition: with >= repl distinct workers, worker w belongs to replica group
+  // (rank of w) % repl, and copy c first tries to stay inside group c.  Losing one worker then
+  // costs at most one copy (two pools of one worker never hold shards of different copies).
+  std::unordered_map<std::string, size_t> worker_group;
+  if (repl > 1) {
+    std::vector<std::string> order;
+    for (const auto& cd : cands)
+      if (!worker_group.count(cd.worker)) {
+        worker_group[cd.worker] = 0;
+        order.push_back(cd.worker);
+      }
+    if (order.size() >= repl)
+      for (size_t i = 0; i < order.size(); ++i) worker_group[order[i]] = i % repl;
+    else
+      worker_group.clear();
+  }
   for (size_t c = 0; c < repl; ++c) {
     CopyPlacement copy;
     copy.copy_index = static_cast<uint32_t>(c);
@@ -283,7 +299,9 @@ Result<AllocationResult> RangeAllocator::place(const AllocationRequest& req, con
         for (size_t k = 0; k < n && !placed; ++k) {
           const Candidate& cd = cands[(rot + k) % n];
           if (pass < 2 && in_copy.count(cd.id)) continue;
-          if (pass == 0 && (workers_used.count(cd.worker) || pools_used.count(cd.id))) continue;
+          if (pass == 0) {
+            if (!worker_group.empty() ? worker_group[cd.worker] != c : (workers_used.count(cd.worker) || pools_used.count(cd.id))) continue;
+          }
           if (pass == 1 && repl > 1 && pools_used.count(cd.id) && n >= repl * wpc) continue;
           const MemoryPool& pool = pools.at(cd.id);
           PoolAllocator* pa = ensure_pool(pool);

@@ -1,0 +1,169 @@
+"""Process-level integration: the real bb-coord / bb-keystone / bb-worker / bb-cli / bb-bench
+executables on loopback (what scripts/start_cluster.sh automates), including keystone fail-over
+between two server processes."""
+import json
+import os
+import signal
+import socket
+import subprocess
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin")
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def wait_port(port, timeout=10.0):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        try:
+            socket.create_connection(("127.0.0.1", port), 0.2).close()
+            return True
+        except OSError:
+            time.sleep(0.05)
+    return False
+
+
+class Procs:
+    def __init__(self):
+        self.procs = []
+
+    def spawn(self, *cmd):
+        p = subprocess.Popen(list(cmd), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        self.procs.append(p)
+        return p
+
+    def stop(self):
+        for p in reversed(self.procs):
+            if p.poll() is None:
+                p.send_signal(signal.SIGTERM)
+        for p in self.procs:
+            try:
+                p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                p.kill()
+
+
+@pytest.fixture
+def procs():
+    p = Procs()
+    yield p
+    p.stop()
+
+
+def run_cli(*args, timeout=30):
+    return subprocess.run([os.path.join(BIN, "bb-cli"), *args], capture_output=True, text=True, timeout=timeout)
+
+
+def write_worker_cfg(path, wid, mount):
+    path.write_text(f"""
+worker:
+  worker_id: "{wid}"
+  node_id: "node-{wid}"
+  lease_ttl_sec: 3
+  heartbeat_interval_sec: 1
+storage_pools:
+  - pool_id: "ram-{wid}"
+    storage_class: "RAM_CPU"
+    size_bytes: 64_MB
+  - pool_id: "nvme-{wid}"
+    storage_class: "NVME"
+    size_bytes: 64_MB
+    mount_path: "{mount}"
+""")
+
+
+def test_cluster_of_real_processes(procs, tmp_path, bb):
+    cport, rport, hport = free_port(), free_port(), free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    procs.spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+                "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "proc")
+    assert wait_port(rport) and wait_port(hport)
+    workers = []
+    for i in range(2):
+        cfg = tmp_path / f"w{i}.yaml"
+        write_worker_cfg(cfg, f"w{i}", tmp_path / f"nvme{i}")
+        workers.append(procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "proc"))
+    ks = f"127.0.0.1:{rport}"
+    deadline = time.time() + 10
+    while time.time() < deadline:
+        st = run_cli("--keystone", ks, "stats")
+        if st.returncode == 0 and json.loads(st.stdout)["total_memory_pools"] == 4:
+            break
+        time.sleep(0.1)
+    assert json.loads(st.stdout)["total_workers"] == 2
+    r = run_cli("--keystone", ks, "smoke", "--size", "1024")
+    assert r.returncode == 0 and "verify PASS" in r.stdout, r.stdout + r.stderr
+    blob = tmp_path / "blob.bin"
+    blob.write_bytes(os.urandom(3 << 20))
+    r = run_cli("--keystone", ks, "put", "file-key", str(blob), "--replicas", "2", "--max-workers", "2", "--class", "NVME", "--checksum", "crc32c")
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = tmp_path / "out.bin"
+    assert run_cli("--keystone", ks, "get", "file-key", str(out)).returncode == 0
+    assert out.read_bytes() == blob.read_bytes()
+    assert run_cli("--keystone", ks, "exists", "file-key").stdout.strip() == "true"
+    m = run_cli("metrics", "--http", f"127.0.0.1:{hport}")
+    assert m.returncode == 0 and "bb_objects 1" in m.stdout and 'bb_tier_used_bytes{tier="NVME"}' in m.stdout
+    b = subprocess.run([os.path.join(BIN, "bb-bench"), "client", "--keystone", ks, "--size", "65536", "--iterations", "20", "--batch", "4"],
+                       capture_output=True, text=True, timeout=60)
+    res = json.loads(b.stdout)
+    assert b.returncode == 0 and res["failures"] == 0 and res["iterations"] == 20 and res["write_MiBps"] > 0
+    # kill -9 one worker: its heartbeat lease expires, the keystone drops it, the replica keeps serving
+    workers[0].kill()
+    deadline = time.time() + 15
+    while time.time() < deadline and json.loads(run_cli("--keystone", ks, "stats").stdout)["total_workers"] != 1:
+        time.sleep(0.2)
+    assert json.loads(run_cli("--keystone", ks, "stats").stdout)["total_workers"] == 1
+    assert run_cli("--keystone", ks, "get", "file-key", str(out)).returncode == 0 and out.read_bytes() == blob.read_bytes()
+    assert run_cli("--keystone", ks, "remove", "file-key").returncode == 0
+
+
+def test_backend_microbenchmark_binary(tmp_path):
+    b = subprocess.run([os.path.join(BIN, "bb-bench"), "backend", "--class", "NVME", "--path", str(tmp_path), "--ops", "20", "--size", "4096"],
+                       capture_output=True, text=True, timeout=60)
+    assert b.returncode == 0 and "lifecycle ops/s" in b.stdout and "20 ops" in b.stdout
+
+
+def test_keystone_process_failover(procs, tmp_path):
+    cport = free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    cfg = tmp_path / "ks.yaml"
+    cfg.write_text("keystone:\n  cluster_id: ha\n  enable_ha: true\n  service_registration_ttl_sec: 3\n  service_refresh_interval_sec: 1\n  http_metrics_port: \"0\"\n")
+    ports, servers = [], []
+    for i in range(2):
+        rp = free_port()
+        ports.append(rp)
+        servers.append(procs.spawn(os.path.join(BIN, "bb-keystone"), str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--listen-address",
+                                   f"127.0.0.1:{rp}", "--service-id", f"ks-{i}"))
+        assert wait_port(rp)
+        time.sleep(0.3)
+    wcfg = tmp_path / "w.yaml"
+    write_worker_cfg(wcfg, "w0", tmp_path / "nvme")
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(wcfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "ha")
+    time.sleep(1.0)
+    blob = tmp_path / "b.bin"
+    blob.write_bytes(os.urandom(100000))
+    r0 = run_cli("--keystone", f"127.0.0.1:{ports[0]}", "put", "ha-key", str(blob))
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1 = run_cli("--keystone", f"127.0.0.1:{ports[1]}", "put", "other", str(blob))
+    assert r1.returncode != 0 and "NOT_LEADER" in r1.stdout + r1.stderr  # the standby refuses mutations
+    servers[0].kill()  # leader crashes; the standby wins the next campaign and recovers the object log
+    out = tmp_path / "o.bin"
+    deadline = time.time() + 20
+    ok = False
+    while time.time() < deadline and not ok:
+        ok = run_cli("--keystone", f"127.0.0.1:{ports[1]}", "get", "ha-key", str(out)).returncode == 0
+        time.sleep(0.3)
+    assert ok and out.read_bytes() == blob.read_bytes()
+    assert run_cli("--keystone", f"127.0.0.1:{ports[1]}", "put", "after-failover", str(blob)).returncode == 0
