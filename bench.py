@@ -50,10 +50,11 @@ def main() -> int:
     ap.add_argument("--ctas", type=int, default=0, help="persistent CTAs of the fused kernel (0 = default)")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--objects", type=int, default=64, help="objects per batch per rank")
-    ap.add_argument("--object-mib", type=float, default=16.0)
+    ap.add_argument("--object-mib", type=float, default=64.0)
     ap.add_argument("--algo", default="bbh64", choices=["bbh64", "crc32c", "none"])
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-comparators", action="store_true")
+    ap.add_argument("--idle-odd", action="store_true", help="diagnostic: odd ranks idle (unidirectional NVLink traffic)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm()
@@ -91,8 +92,10 @@ def main() -> int:
     sizes = [osz] * nobj
     OK = _bb.ErrorCode.OK
 
-    def step(tag: str, i: int):
-        keys = [f"r{rank}/{tag}{i}/o{j}" for j in range(nobj)]
+    def step(tag: str, i: int, keys=None):
+        if args.idle_odd and rank % 2 == 1:
+            return
+        keys = keys or [f"r{rank}/{tag}{i}/o{j}" for j in range(nobj)]
         ecs = cl.client.batch_put_device(keys, src_ptrs, sizes, cfg, stream)
         assert all(e == OK for e in ecs), f"put failed: {[str(e) for e in ecs if e != OK][:3]}"
         ecs, got = cl.client.batch_get_device(keys, out_ptrs, sizes, stream)
@@ -125,11 +128,12 @@ def main() -> int:
 
     # ---------------------------------------------------------------- device-resident timed region
     launches0 = cl.fabric.launches
+    all_keys = [[f"r{rank}/t{i}/o{j}" for j in range(nobj)] for i in range(args.steps)]  # fresh keys every step
     cl.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step("t", i)
+        step("t", i, all_keys[i])
     e1.record()
     torch.cuda.synchronize()
     cl.barrier()
@@ -143,6 +147,10 @@ def main() -> int:
             i += 1
     clocks = sampler.stop() if sampler else None
     phases = {k: round(v[1] / max(v[0], 1), 1) for k, v in cl.client.phase_summary().items() if k.startswith("phase_")}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, phases)
+        phases = {f"rank{r}": g for r, g in enumerate(gathered)}
     total_bytes = 2.0 * step_bytes * args.steps * world
     value = total_bytes / (ms * 1e-3) / 1e9
 
@@ -237,7 +245,7 @@ def main() -> int:
         per_gpu = value / world
         roof = (peaks.get("hbm_gbs", 6650.0) / 2.0) if world == 1 else 770.0 * 2.0
         line = {
-            "metric": "batched put+get payload throughput (GB/s), 16 MiB random-byte objects, GPU tier, checksum fused",
+            "metric": "batched put+get payload throughput (GB/s), %g MiB random-byte objects, GPU tier, checksum fused" % args.object_mib,
             "value": round(value, 2),
             "unit": "GB/s",
             "n_gpus": world,

@@ -31,6 +31,20 @@ PoolAllocator::PoolAllocator(const MemoryPool& pool, uint64_t align)
       align_(align ? align : 1) {
   const uint64_t usable = pool.size / align_ * align_;
   if (usable) insert_free(0, usable);
+  if (!pool.ucx_endpoint.empty()) {
+    auto hp = split_host_port(pool.ucx_endpoint);
+    if (hp) {
+      endpoint_.ip = hp->first;
+      endpoint_.port = hp->second;
+    } else {
+      reg_valid_ = false;
+    }
+  }
+  if (!pool.ucx_rkey_hex.empty()) {
+    auto key = hex_to_bytes(pool.ucx_rkey_hex);
+    if (key) endpoint_.worker_key = std::move(*key);
+    else reg_valid_ = false;
+  }
 }
 
 void PoolAllocator::insert_free(uint64_t off, uint64_t len) {
@@ -209,16 +223,10 @@ Result<ShardPlacement> RangeAllocator::make_shard(const MemoryPool& pool, const 
   s.worker_id = pool.worker_id;
   s.storage_class = pool.storage_class;
   s.length = length;
-  if (!pool.ucx_endpoint.empty()) {
-    auto hp = split_host_port(pool.ucx_endpoint);
-    if (!hp) return ErrorCode::INVALID_PARAMETERS;
-    s.endpoint.ip = hp->first;
-    s.endpoint.port = hp->second;
-  }
-  if (!pool.ucx_rkey_hex.empty()) {
-    auto key = hex_to_bytes(pool.ucx_rkey_hex);
-    if (!key) return ErrorCode::INVALID_PARAMETERS;
-    s.endpoint.worker_key = std::move(*key);
+  const PoolAllocator* reg = find_pool(pool.id);
+  if (reg) {
+    if (!reg->registration_valid()) return ErrorCode::INVALID_PARAMETERS;
+    s.endpoint = reg->endpoint();
   }
   switch (pool.storage_class) {
     case StorageClass::RAM_GPU:
@@ -449,11 +457,6 @@ Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, 
     if (objects_.count(req.object_key)) return ErrorCode::OBJECT_ALREADY_EXISTS;
   }
   if (pools.empty()) return ErrorCode::INSUFFICIENT_SPACE;
-  // validate registration data up-front so that malformed pools are reported as such
-  for (const auto& [id, p] : pools) {
-    if (!p.ucx_endpoint.empty() && !split_host_port(p.ucx_endpoint)) return ErrorCode::INVALID_PARAMETERS;
-    if (!p.ucx_rkey_hex.empty() && !hex_to_bytes(p.ucx_rkey_hex)) return ErrorCode::INVALID_PARAMETERS;
-  }
   bool spill = false;
   std::vector<Candidate> cands = rank_candidates(req, pools, &spill);
   if (cands.empty()) return ErrorCode::INSUFFICIENT_SPACE;

@@ -112,6 +112,9 @@ class PoolAllocator {
   StorageClass storage_class() const { return storage_class_; }
   const std::string& node_id() const { return node_id_; }
   MemoryLocation to_memory_location(const Range& r) const;
+  // Registration data parsed once per pool (endpoint "host:port", hex key) instead of per shard.
+  bool registration_valid() const { return reg_valid_; }
+  const TransportEndpoint& endpoint() const { return endpoint_; }
 
  private:
   void insert_free(uint64_t off, uint64_t len);
@@ -124,6 +127,8 @@ class PoolAllocator {
   uint32_t rkey_;
   size_t pool_size_;
   uint64_t align_;
+  TransportEndpoint endpoint_;
+  bool reg_valid_ = true;
   mutable std::mutex mu_;
   std::map<uint64_t, uint64_t> by_offset_;              // offset -> length
   std::set<std::pair<uint64_t, uint64_t>> by_size_;     // (length, offset)

@@ -6,6 +6,7 @@
 
 #include "alloc/allocator.h"
 #include "client/blackbird_client.h"
+#include "client/copy_mover.h"
 #include "coord/coord.h"
 #include "keystone/keystone_service.h"
 #include "rpc/rpc_service.h"
@@ -537,6 +538,8 @@ void bind_control(py::module_& m) {
         d["ttl_ms"] = o.config.ttl_ms;
         return d;
       })
+      .def("install_data_server_mover", [](KeystoneService& k) { k.set_copy_mover(client::make_data_server_mover()); },
+           "Tier demotion / re-replication move bytes through the workers' data servers (the default in bb-keystone).")
       // Python-implemented copy mover (tests): fn(key, src_copy, dst_copy, algo) -> (ErrorCode, [shard checksums])
       .def("set_copy_mover", [](KeystoneService& k, py::object fn) {
         if (fn.is_none()) {

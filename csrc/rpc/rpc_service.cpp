@@ -1,5 +1,7 @@
 #include "rpc/rpc_service.h"
 
+#include "client/copy_mover.h"
+
 #include <cstdlib>
 
 #include "common/log.h"
@@ -542,6 +544,7 @@ Result<KeystoneBundle> create_and_start_keystone(const KeystoneConfig& config) {
   if (ec != ErrorCode::OK) return ec;
   ec = b.keystone->start();
   if (ec != ErrorCode::OK) return ec;
+  b.keystone->set_copy_mover(client::make_data_server_mover());  // tier demotion + re-replication move real bytes
   b.rpc = std::make_unique<RpcService>(b.keystone, config);
   ec = b.rpc->start();
   if (ec != ErrorCode::OK) {

@@ -368,6 +368,42 @@ void WorkerService::register_data_handlers() {
     if (ec == ErrorCode::OK) w.u64(checksum(algo, buf.data(), len));
     return w.take();
   });
+  // Intra-worker tier move (GPU slab -> DRAM -> NVMe ...): bytes stay inside this process.
+  data_server_.register_method(D_COPY, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string sp = r.str();
+    const uint64_t so = r.u64();
+    const std::string dp = r.str();
+    const uint64_t doff = r.u64();
+    const uint64_t len = r.u64();
+    const auto algo = static_cast<ChecksumAlgo>(r.u32());
+    wire::Writer w;
+    StorageBackend* sb = backend(sp);
+    StorageBackend* db = backend(dp);
+    if (!r.ok() || !sb || !db) {
+      w.ec(!r.ok() ? ErrorCode::INVALID_PARAMETERS : ErrorCode::MEMORY_POOL_NOT_FOUND);
+      return w.take();
+    }
+    const uint64_t s0 = resolve_offset(*sb, so), d0 = resolve_offset(*db, doff);
+    constexpr uint64_t kChunk = 8ull << 20;
+    std::vector<uint8_t> buf(std::min(len, kChunk));
+    std::vector<uint8_t> whole;  // BBH64 is tile-position dependent: hash the whole shard at the end
+    if (algo == ChecksumAlgo::BBH64) whole.reserve(len);
+    uint32_t crc = 0;
+    ErrorCode ec = ErrorCode::OK;
+    for (uint64_t pos = 0; pos < len && ec == ErrorCode::OK; pos += kChunk) {
+      const uint64_t n = std::min(kChunk, len - pos);
+      ec = sb->read(s0 + pos, buf.data(), n);
+      if (ec != ErrorCode::OK) break;
+      if (algo == ChecksumAlgo::CRC32C) crc = crc32c(buf.data(), n, crc);
+      else if (algo == ChecksumAlgo::BBH64) whole.insert(whole.end(), buf.begin(), buf.begin() + static_cast<std::ptrdiff_t>(n));
+      ec = db->write(d0 + pos, buf.data(), n);
+    }
+    if (ec == ErrorCode::OK) ec = db->flush();
+    w.ec(ec);
+    if (ec == ErrorCode::OK) w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64(whole.data(), whole.size()) : 0);
+    return w.take();
+  });
   data_server_.register_method(D_STATS, [this](C, S) {
     wire::Writer w;
     w.ec(ErrorCode::OK);

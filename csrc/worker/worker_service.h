@@ -59,7 +59,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
 // Throws std::runtime_error on unreadable / invalid files (as the reference does).
 WorkerServiceConfig load_worker_config_from_file(const std::string& path);
 
-enum DataMethod : uint32_t { D_WRITE = 1, D_READ = 2, D_CHECKSUM = 3, D_STATS = 4 };
+enum DataMethod : uint32_t { D_WRITE = 1, D_READ = 2, D_CHECKSUM = 3, D_STATS = 4, D_COPY = 5 };
 
 class WorkerService {
  public:
