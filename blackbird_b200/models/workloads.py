@@ -1,0 +1,219 @@
+"""The five workload configurations of BASELINE.json, as reusable functions.
+
+1. plumbing_cpu            in-process Keystone + 2 workers over loopback TCP, 1 KB put/get/exists/remove
+2. throughput_sweep /      GPU tier, batched put/get vs object size 256 B - 256 MB (GB/s, p50/p99)
+   latency_sweep
+3. replicated_put_verify   replication = 3 batched put (single-read fan-out), digest verified on get from every replica
+4. tier_spill              GPU -> DRAM -> NVMe demotion under memory pressure with TTL + soft-pin
+5. feature_store_fanout    rank 0 puts 128 x 1 MB activation shards, every rank batch-gets all of them
+"""
+from __future__ import annotations
+
+import os
+import statistics
+import time
+
+from .. import _bb
+
+OK = None
+
+
+def _ok(ecs):
+    return all(e == _bb.ErrorCode.OK for e in ecs)
+
+
+def plumbing_cpu(n_objects: int = 1000, size: int = 1024) -> dict:
+    from ..parallel import LocalCluster
+
+    with LocalCluster("plumbing", n_workers=2, pool_bytes=64 << 20) as c:
+        cl = c.client()
+        cfg = _bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+        blobs = [os.urandom(size) for _ in range(16)]
+        t0 = time.perf_counter()
+        for i in range(n_objects):
+            assert cl.put(f"k{i}", blobs[i % 16], cfg) == _bb.ErrorCode.OK
+        t1 = time.perf_counter()
+        for i in range(n_objects):
+            assert cl.get(f"k{i}") == blobs[i % 16]
+        t2 = time.perf_counter()
+        assert all(cl.object_exists(f"k{i}") for i in range(0, n_objects, 10))
+        t3 = time.perf_counter()
+        for i in range(n_objects):
+            assert cl.remove(f"k{i}") == _bb.ErrorCode.OK
+        t4 = time.perf_counter()
+        return {"objects": n_objects, "size": size, "put_per_s": n_objects / (t1 - t0), "get_per_s": n_objects / (t2 - t1),
+                "exists_per_s": (n_objects // 10) / (t3 - t2), "remove_per_s": n_objects / (t4 - t3)}
+
+
+def _pct(v, q):
+    v = sorted(v)
+    return v[min(len(v) - 1, int(q * len(v)))]
+
+
+def throughput_sweep(cluster, sizes, target_node: str, batch_bytes: int = 1 << 30, max_batch: int = 4096, iters: int = 5,
+                     algo=None) -> list:
+    """Batched put + get GB/s per object size on the GPU tier (device time of the fused kernels and
+    wall time of the whole client call including the Keystone round trips)."""
+    import torch
+
+    algo = algo or _bb.ChecksumAlgo.BBH64
+    dev = torch.device("cuda", cluster.local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    cfg = _bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_node=target_node, ttl_ms=0, checksum=algo,
+                           preferred_classes=[_bb.StorageClass.RAM_GPU])
+    rows = []
+    for size in sizes:
+        stride = (size + 255) // 256 * 256
+        nobj = max(1, min(max_batch, batch_bytes // max(stride, 1)))
+        src = torch.empty(nobj * stride, dtype=torch.uint8, device=dev)
+        _bb.random_fill(src.data_ptr(), nobj * stride, size, stream)
+        out = torch.zeros_like(src)
+        sp = [src.data_ptr() + i * stride for i in range(nobj)]
+        op = [out.data_ptr() + i * stride for i in range(nobj)]
+        put_dev, get_dev, put_wall, get_wall = [], [], [], []
+        for it in range(iters + 1):
+            keys = [f"sw/{cluster.rank}/{size}/{it}/{j}" for j in range(nobj)]
+            t0 = time.perf_counter()
+            m0 = cluster.fabric.total_device_ms
+            assert _ok(cluster.client.batch_put_device(keys, sp, [size] * nobj, cfg, stream))
+            t1 = time.perf_counter()
+            m1 = cluster.fabric.total_device_ms
+            ecs, _ = cluster.client.batch_get_device(keys, op, [stride] * nobj, stream)
+            t2 = time.perf_counter()
+            assert _ok(ecs)
+            pd, gd = m1 - m0, cluster.fabric.total_device_ms - m1
+            cluster.client.batch_remove(keys)
+            if it:  # first iteration is warm-up
+                put_dev.append(pd), get_dev.append(gd), put_wall.append((t1 - t0) * 1e3), get_wall.append((t2 - t1) * 1e3)
+        torch.cuda.synchronize()
+        assert torch.equal(src.view(nobj, stride)[:, :size], out.view(nobj, stride)[:, :size])
+        total = nobj * size
+        rows.append({"size": size, "batch": nobj, "put_GBps_kernel": total / min(put_dev) / 1e6, "get_GBps_kernel": total / min(get_dev) / 1e6,
+                     "put_GBps_client": total / statistics.median(put_wall) / 1e6, "get_GBps_client": total / statistics.median(get_wall) / 1e6,
+                     "put_batch_ms_p50": statistics.median(put_wall), "get_batch_ms_p50": statistics.median(get_wall)})
+        del src, out
+    return rows
+
+
+def latency_sweep(cluster, sizes, target_node: str, iters: int = 200, algo=None) -> list:
+    """Single-object put / get latency (p50 / p99, microseconds) per object size: the whole client call
+    (Keystone round trips + descriptor upload + one fused launch + digest read-back)."""
+    import torch
+
+    algo = algo or _bb.ChecksumAlgo.BBH64
+    dev = torch.device("cuda", cluster.local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    cfg = _bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_node=target_node, ttl_ms=0, checksum=algo,
+                           preferred_classes=[_bb.StorageClass.RAM_GPU])
+    rows = []
+    for size in sizes:
+        n_it = iters if size <= (1 << 20) else max(20, iters // 10)
+        stride = (size + 255) // 256 * 256
+        src = torch.empty(stride, dtype=torch.uint8, device=dev)
+        _bb.random_fill(src.data_ptr(), stride, size + 1, stream)
+        out = torch.zeros_like(src)
+        put_us, get_us, put_dev, get_dev = [], [], [], []
+        for it in range(n_it + 5):
+            key = [f"lat/{cluster.rank}/{size}/{it}"]
+            t0 = time.perf_counter()
+            ecs = cluster.client.batch_put_device(key, [src.data_ptr()], [size], cfg, stream)
+            t1 = time.perf_counter()
+            pd = cluster.fabric.last_device_ms
+            ecs2, _ = cluster.client.batch_get_device(key, [out.data_ptr()], [stride], stream)
+            t2 = time.perf_counter()
+            gd = cluster.fabric.last_device_ms
+            cluster.client.batch_remove(key)
+            assert _ok(ecs) and _ok(ecs2)
+            if it >= 5:
+                put_us.append((t1 - t0) * 1e6), get_us.append((t2 - t1) * 1e6), put_dev.append(pd * 1e3), get_dev.append(gd * 1e3)
+        rows.append({"size": size, "put_p50_us": _pct(put_us, 0.5), "put_p99_us": _pct(put_us, 0.99), "get_p50_us": _pct(get_us, 0.5),
+                     "get_p99_us": _pct(get_us, 0.99), "put_kernel_p50_us": _pct(put_dev, 0.5), "get_kernel_p50_us": _pct(get_dev, 0.5)})
+    return rows
+
+
+def replicated_put_verify(cluster, replication: int = 3, nobj: int = 32, size: int = 16 << 20, iters: int = 3) -> dict:
+    """Config 3: every object gets `replication` copies on distinct GPUs; the put kernel reads the source once
+    and fans out (TMA stores to every replica); the get verifies the digest against every replica in turn."""
+    import torch
+
+    dev = torch.device("cuda", cluster.local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    cfg = _bb.WorkerConfig(replication_factor=replication, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[_bb.StorageClass.RAM_GPU],
+                           checksum=_bb.ChecksumAlgo.CRC32C)
+    src = torch.empty(nobj * size, dtype=torch.uint8, device=dev)
+    _bb.random_fill(src.data_ptr(), nobj * size, 33 + cluster.rank, stream)
+    out = torch.zeros_like(src)
+    sp = [src.data_ptr() + i * size for i in range(nobj)]
+    op = [out.data_ptr() + i * size for i in range(nobj)]
+    put_ms, get_ms = [], []
+    copies_seen = set()
+    for it in range(iters):
+        keys = [f"rep/{cluster.rank}/{it}/{j}" for j in range(nobj)]
+        m0 = cluster.fabric.total_device_ms
+        assert _ok(cluster.client.batch_put_device(keys, sp, [size] * nobj, cfg, stream))
+        put_ms.append(cluster.fabric.total_device_ms - m0)
+        placed = cluster.client.get_workers(keys[0])
+        assert len(placed) == replication and len({c.shards[0].worker_id for c in placed}) == replication
+        assert len({c.shards[0].checksum for c in placed}) == 1
+        copies_seen |= {c.shards[0].worker_id for c in placed}
+        out.zero_()
+        m0 = cluster.fabric.total_device_ms
+        ecs, _ = cluster.client.batch_get_device(keys, op, [size] * nobj, stream)
+        assert _ok(ecs)
+        get_ms.append(cluster.fabric.total_device_ms - m0)
+        torch.cuda.synchronize()
+        assert torch.equal(src, out)
+        cluster.client.batch_remove(keys)
+    total = nobj * size
+    return {"replication": replication, "objects": nobj, "size": size, "put_payload_GBps": total / min(put_ms) / 1e6,
+            "put_wire_GBps": total * replication / min(put_ms) / 1e6, "get_GBps": total / min(get_ms) / 1e6, "replica_workers": sorted(copies_seen)}
+
+
+def tier_spill(cluster_factory, tmp_dir: str, gpu: bool, nobj: int = 6, size: int = 64 << 20) -> dict:
+    """Config 4: fill the top tier beyond the watermark, let the Keystone demote LRU objects down the ladder
+    (GPU -> DRAM -> NVMe) through the workers' D_COPY path, verify bytes + digests, respect TTL and soft pins."""
+    raise NotImplementedError("driven by tests/test_cluster_e2e.py (host tiers) and tests/test_gpu_stack.py (GPU tier)")
+
+
+def feature_store_fanout(cluster, nshards: int = 128, size: int = 1 << 20, iters: int = 5, replication: int = 1) -> dict:
+    """Config 5: rank 0 puts `nshards` activation shards, then every rank batch-gets all of them (1 -> N read
+    fan-out).  With replication > 1 the readers spread over the replicas (hash of reader + key)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", cluster.local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    cfg = _bb.WorkerConfig(replication_factor=replication, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[_bb.StorageClass.RAM_GPU],
+                           enable_locality_awareness=False)
+    src = torch.empty(nshards * size, dtype=torch.uint8, device=dev)
+    _bb.random_fill(src.data_ptr(), nshards * size, 777, stream)  # same seed on every rank: readers can verify locally
+    out = torch.zeros_like(src)
+    get_ms, put_ms = [], []
+    for it in range(iters):
+        keys = [f"feat/{it}/{j}" for j in range(nshards)]
+        if cluster.rank == 0:
+            t0 = time.perf_counter()
+            assert _ok(cluster.client.batch_put_device(keys, [src.data_ptr() + j * size for j in range(nshards)], [size] * nshards, cfg, stream))
+            put_ms.append((time.perf_counter() - t0) * 1e3)
+        cluster.barrier()
+        out.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ecs, _ = cluster.client.batch_get_device(keys, [out.data_ptr() + j * size for j in range(nshards)], [size] * nshards, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        assert _ok(ecs) and torch.equal(src, out)
+        ms = e0.elapsed_time(e1)
+        if cluster.world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        get_ms.append(ms)
+        cluster.barrier()
+        if cluster.rank == 0:
+            cluster.client.batch_remove(keys)
+        cluster.barrier()
+    total = nshards * size
+    return {"shards": nshards, "size": size, "readers": cluster.world, "replication": replication,
+            "aggregate_get_GBps": total * cluster.world / min(get_ms) / 1e6, "per_reader_get_GBps": total / min(get_ms) / 1e6,
+            "get_ms_best": min(get_ms), "rank0_put_ms_best": min(put_ms) if put_ms else None}

@@ -1,0 +1,106 @@
+"""Torch-facing API: put / get CUDA tensors through the object store with the fused kernels.
+
+    store = TensorStore(cluster.client)
+    store.batch_put(["act/0", "act/1"], [t0, t1])                  # BBH64 digest fused into the copy
+    store.put("kv/layer3", kv_bf16, pack_fp8=True)                  # block-scaled MXFP8 on the wire / in the slab
+    t = store.get("kv/layer3")                                      # verified + unpacked bf16 tensor
+
+Tensor metadata (dtype, shape, packing) travels in a small side object `<key>#meta`.
+"""
+from __future__ import annotations
+
+import json
+from typing import Optional, Sequence
+
+import torch
+
+from .. import _bb
+
+_DTYPES = {str(d).replace("torch.", ""): d for d in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64, torch.float16,
+                                                     torch.bfloat16, torch.float32, torch.float64, torch.bool)}
+
+
+class TensorStore:
+    def __init__(self, client, config: Optional["_bb.WorkerConfig"] = None):
+        self.client = client
+        self.config = config or _bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1,
+                                                 preferred_classes=[_bb.StorageClass.RAM_GPU])
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def _meta_cfg(self):
+        return _bb.WorkerConfig(replication_factor=self.config.replication_factor, max_workers_per_copy=1, ttl_ms=self.config.ttl_ms,
+                                enable_soft_pin=self.config.enable_soft_pin, checksum=_bb.ChecksumAlgo.CRC32C)
+
+    # ------------------------------------------------------------------ put
+    def batch_put(self, keys: Sequence[str], tensors: Sequence[torch.Tensor], pack_fp8: bool = False, config=None) -> None:
+        cfg = config or self.config
+        payloads, metas, keep = [], [], []
+        for t in tensors:
+            assert t.is_cuda, "TensorStore moves CUDA tensors (host data: use client.put)"
+            t = t.contiguous()
+            meta = {"dtype": str(t.dtype).replace("torch.", ""), "shape": list(t.shape), "packed": None, "numel": t.numel()}
+            if pack_fp8:
+                assert t.dtype == torch.bfloat16, "MXFP8 packing takes bf16 tensors"
+                n = t.numel()
+                npad = (n + 31) // 32 * 32
+                src = t.view(-1)
+                if npad != n:
+                    src = torch.cat([src, torch.zeros(npad - n, dtype=t.dtype, device=t.device)])
+                packed = torch.empty(_bb.mxfp8_packed_bytes(npad), dtype=torch.uint8, device=t.device)
+                _bb.mxfp8_pack(src.data_ptr(), npad, packed.data_ptr(), self._stream())
+                keep.append(src)
+                meta["packed"] = "mxfp8"
+                meta["padded_numel"] = npad
+                t = packed
+            assert t.data_ptr() % 16 == 0, "tensor storage must be 16-byte aligned"
+            payloads.append(t)
+            metas.append(json.dumps(meta).encode())
+        ecs = self.client.batch_put_device(list(keys), [p.data_ptr() for p in payloads], [p.numel() * p.element_size() for p in payloads],
+                                           cfg, self._stream())
+        bad = [(k, e) for k, e in zip(keys, ecs) if e != _bb.ErrorCode.OK]
+        if bad:
+            raise RuntimeError(f"put failed: {bad[:3]}")
+        ecs = self.client.batch_put([k + "#meta" for k in keys], metas, self._meta_cfg())
+        if any(e != _bb.ErrorCode.OK for e in ecs):
+            raise RuntimeError("meta put failed")
+
+    def put(self, key: str, tensor: torch.Tensor, pack_fp8: bool = False, config=None) -> None:
+        self.batch_put([key], [tensor], pack_fp8, config)
+
+    # ------------------------------------------------------------------ get
+    def batch_get(self, keys: Sequence[str], device: Optional[torch.device] = None) -> list:
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        metas = []
+        for ec, blob in self.client.batch_get([k + "#meta" for k in keys]):
+            if ec != _bb.ErrorCode.OK:
+                raise KeyError(f"object metadata missing: {ec}")
+            metas.append(json.loads(blob))
+        bufs = []
+        for m in metas:
+            if m["packed"] == "mxfp8":
+                bufs.append(torch.empty(_bb.mxfp8_packed_bytes(m["padded_numel"]), dtype=torch.uint8, device=device))
+            else:
+                bufs.append(torch.empty(m["shape"], dtype=_DTYPES[m["dtype"]], device=device))
+        ecs, sizes = self.client.batch_get_device(list(keys), [b.data_ptr() for b in bufs], [b.numel() * b.element_size() for b in bufs],
+                                                  self._stream())
+        bad = [(k, e) for k, e in zip(keys, ecs) if e != _bb.ErrorCode.OK]
+        if bad:
+            raise RuntimeError(f"get failed: {bad[:3]}")
+        out = []
+        for m, b in zip(metas, bufs):
+            if m["packed"] == "mxfp8":
+                t = torch.empty(m["padded_numel"], dtype=torch.bfloat16, device=device)
+                _bb.mxfp8_unpack(b.data_ptr(), m["padded_numel"], t.data_ptr(), self._stream())
+                out.append(t[: m["numel"]].view(m["shape"]))
+            else:
+                out.append(b)
+        return out
+
+    def get(self, key: str, device: Optional[torch.device] = None) -> torch.Tensor:
+        return self.batch_get([key], device)[0]
+
+    def remove(self, keys: Sequence[str]) -> None:
+        self.client.batch_remove(list(keys) + [k + "#meta" for k in keys])

@@ -378,101 +378,167 @@ std::vector<Result<bool>> BlackbirdClient::batch_exists(const std::vector<Object
 }
 
 // ================================================================ batched device API
+std::vector<std::pair<size_t, size_t>> BlackbirdClient::plan_chunks(const std::vector<size_t>& sizes) const {
+  std::vector<std::pair<size_t, size_t>> chunks;
+  uint64_t total = 0;
+  for (size_t s : sizes) total += s;
+  constexpr uint64_t kMinChunk = 256ull << 20;  // below this a chunk's kernel is too short to hide an RPC
+  const size_t depth = device_ ? device_->max_in_flight() : 1;
+  if (depth < 2 || total < 2 * kMinChunk || sizes.size() < 2) {
+    chunks.emplace_back(0, sizes.size());
+    return chunks;
+  }
+  const uint64_t target = std::max<uint64_t>(kMinChunk, total / 4);
+  size_t begin = 0;
+  uint64_t acc = 0;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    acc += sizes[i];
+    if (acc >= target && i + 1 < sizes.size()) {
+      chunks.emplace_back(begin, i + 1);
+      begin = i + 1;
+      acc = 0;
+    }
+  }
+  chunks.emplace_back(begin, sizes.size());
+  return chunks;
+}
+
 std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<ObjectKey>& keys, const std::vector<const void*>& dev_ptrs,
                                                          const std::vector<size_t>& sizes, const WorkerConfig& cfg, void* stream) {
   std::vector<ErrorCode> out(keys.size(), ErrorCode::INVALID_PARAMETERS);
   if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
   if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
   if (dev_ptrs.size() != keys.size() || sizes.size() != keys.size()) return out;
-  const TimePoint t0 = Clock::now();
-  std::vector<PutStartItem> items(keys.size());
-  for (size_t i = 0; i < keys.size(); ++i) items[i] = PutStartItem{keys[i], sizes[i], cfg};
-  auto placed = keystone_->batch_put_start(items);
-  metrics_.observe("phase_put_start_us", us_since(t0));
-  // One descriptor per (object, shard): copy 0's placement plus the same shard of every other
-  // copy as extra destinations, so the kernel reads the source once and fans out.
-  std::vector<DeviceShardOp> ops;
-  for (size_t i = 0; i < keys.size(); ++i) {
-    if (!placed[i].ok()) {
-      out[i] = placed[i].error();
-      continue;
-    }
-    out[i] = ErrorCode::OK;
-    const auto& copies = placed[i].value();
-    if (copies.empty()) continue;
-    bool same_layout = true;
-    for (const auto& c : copies) same_layout &= c.shards.size() == copies[0].shards.size();
-    uint64_t off = 0;
-    for (size_t s = 0; s < copies[0].shards.size(); ++s) {
-      if (same_layout) {
-        DeviceShardOp op;
-        op.item = i;
-        op.copy = 0;
-        op.shard = s;
-        op.placement = &copies[0].shards[s];
-        op.obj_offset = off;
-        for (size_t c = 1; c < copies.size(); ++c) op.replicas.push_back(&copies[c].shards[s]);
-        ops.push_back(std::move(op));
+  const TimePoint t_all = Clock::now();
+
+  struct Chunk {
+    size_t begin = 0, end = 0;
+    std::vector<Result<std::vector<CopyPlacement>>> placed;
+    std::vector<DeviceShardOp> ops;
+    uint64_t ticket = 0;
+    bool submitted = false;
+    ErrorCode submit_error = ErrorCode::OK;
+  };
+  const auto plan = plan_chunks(sizes);
+  std::vector<Chunk> chunks(plan.size());
+
+  auto start_chunk = [&](Chunk& ch) {
+    const TimePoint t0 = Clock::now();
+    std::vector<PutStartItem> items;
+    items.reserve(ch.end - ch.begin);
+    for (size_t i = ch.begin; i < ch.end; ++i) items.push_back(PutStartItem{keys[i], sizes[i], cfg});
+    ch.placed = keystone_->batch_put_start(items);  // one control-plane round trip per chunk
+    metrics_.observe("phase_put_start_us", us_since(t0));
+    // One descriptor per (object, shard): copy 0's placement plus the same shard of every other
+    // copy as extra destinations, so the kernel reads the source once and fans out.
+    for (size_t i = ch.begin; i < ch.end; ++i) {
+      const auto& pr = ch.placed[i - ch.begin];
+      if (!pr.ok()) {
+        out[i] = pr.error();
+        continue;
       }
-      off += copies[0].shards[s].length;
-    }
-    if (!same_layout) {
-      for (size_t c = 0; c < copies.size(); ++c) {
-        uint64_t o2 = 0;
-        for (size_t s = 0; s < copies[c].shards.size(); ++s) {
+      out[i] = ErrorCode::OK;
+      const auto& copies = pr.value();
+      if (copies.empty()) continue;
+      bool same_layout = true;
+      for (const auto& c : copies) same_layout &= c.shards.size() == copies[0].shards.size();
+      if (same_layout) {
+        uint64_t off = 0;
+        for (size_t s = 0; s < copies[0].shards.size(); ++s) {
           DeviceShardOp op;
           op.item = i;
-          op.copy = c;
+          op.copy = 0;
           op.shard = s;
-          op.placement = &copies[c].shards[s];
-          op.obj_offset = o2;
-          ops.push_back(std::move(op));
-          o2 += copies[c].shards[s].length;
+          op.placement = &copies[0].shards[s];
+          op.obj_offset = off;
+          for (size_t c = 1; c < copies.size(); ++c) op.replicas.push_back(&copies[c].shards[s]);
+          ch.ops.push_back(std::move(op));
+          off += copies[0].shards[s].length;
+        }
+      } else {
+        for (size_t c = 0; c < copies.size(); ++c) {
+          uint64_t o2 = 0;
+          for (size_t s = 0; s < copies[c].shards.size(); ++s) {
+            DeviceShardOp op;
+            op.item = i;
+            op.copy = c;
+            op.shard = s;
+            op.placement = &copies[c].shards[s];
+            op.obj_offset = o2;
+            ch.ops.push_back(std::move(op));
+            o2 += copies[c].shards[s].length;
+          }
         }
       }
     }
-  }
-  std::vector<uint64_t> digests;
-  const TimePoint t1 = Clock::now();
-  ErrorCode ec = device_->put_shards(ops, dev_ptrs, cfg.checksum, stream, &digests);
-  metrics_.observe("phase_put_xfer_us", us_since(t1));
-  const TimePoint t2 = Clock::now();
-  std::vector<ObjectKey> done_keys, cancel_keys;
-  std::vector<ShardChecksums> done_sums;
-  std::vector<size_t> done_idx;
-  if (ec != ErrorCode::OK) {
-    for (size_t i = 0; i < keys.size(); ++i)
-      if (placed[i].ok()) {
-        out[i] = ec;
-        cancel_keys.push_back(keys[i]);
-      }
-  } else {
-    std::vector<ShardChecksums> sums(keys.size());
-    for (size_t i = 0; i < keys.size(); ++i)
-      if (placed[i].ok()) {
-        sums[i].resize(placed[i].value().size());
-        for (size_t c = 0; c < sums[i].size(); ++c) sums[i][c].assign(placed[i].value()[c].shards.size(), 0);
-      }
-    for (size_t k = 0; k < ops.size(); ++k) {
-      const auto& op = ops[k];
-      sums[op.item][op.copy][op.shard] = digests[k];
-      for (size_t r = 0; r < op.replicas.size(); ++r) sums[op.item][r + 1][op.shard] = digests[k];
+    const TimePoint t1 = Clock::now();
+    auto t = device_->submit_put(ch.ops, dev_ptrs, cfg.checksum, stream);
+    metrics_.observe("phase_put_submit_us", us_since(t1));
+    if (t.ok()) {
+      ch.ticket = t.value();
+      ch.submitted = true;
+    } else {
+      ch.submit_error = t.error();
     }
-    for (size_t i = 0; i < keys.size(); ++i)
-      if (placed[i].ok()) {
-        done_keys.push_back(keys[i]);
-        done_sums.push_back(std::move(sums[i]));
-        done_idx.push_back(i);
+  };
+
+  auto finish_chunk = [&](Chunk& ch) {
+    std::vector<uint64_t> digests;
+    ErrorCode ec = ch.submit_error;
+    const TimePoint t1 = Clock::now();
+    if (ch.submitted) ec = device_->wait_put(ch.ticket, &digests);
+    metrics_.observe("phase_put_wait_us", us_since(t1));
+    const TimePoint t2 = Clock::now();
+    std::vector<ObjectKey> done_keys, cancel_keys;
+    std::vector<ShardChecksums> done_sums;
+    std::vector<size_t> done_idx;
+    if (ec != ErrorCode::OK) {
+      for (size_t i = ch.begin; i < ch.end; ++i)
+        if (ch.placed[i - ch.begin].ok()) {
+          out[i] = ec;
+          cancel_keys.push_back(keys[i]);
+        }
+    } else {
+      std::vector<ShardChecksums> sums(ch.end - ch.begin);
+      for (size_t i = ch.begin; i < ch.end; ++i) {
+        const auto& pr = ch.placed[i - ch.begin];
+        if (!pr.ok()) continue;
+        auto& sm = sums[i - ch.begin];
+        sm.resize(pr.value().size());
+        for (size_t c = 0; c < sm.size(); ++c) sm[c].assign(pr.value()[c].shards.size(), 0);
       }
+      for (size_t k = 0; k < ch.ops.size(); ++k) {
+        const auto& op = ch.ops[k];
+        auto& sm = sums[op.item - ch.begin];
+        sm[op.copy][op.shard] = digests[k];
+        for (size_t r = 0; r < op.replicas.size(); ++r) sm[r + 1][op.shard] = digests[k];
+      }
+      for (size_t i = ch.begin; i < ch.end; ++i)
+        if (ch.placed[i - ch.begin].ok()) {
+          done_keys.push_back(keys[i]);
+          done_sums.push_back(std::move(sums[i - ch.begin]));
+          done_idx.push_back(i);
+        }
+    }
+    if (!cancel_keys.empty()) keystone_->batch_put_cancel(cancel_keys);
+    if (!done_keys.empty()) {
+      auto ecs = keystone_->batch_put_complete(done_keys, done_sums);
+      for (size_t k = 0; k < done_idx.size(); ++k) out[done_idx[k]] = ecs[k];
+    }
+    metrics_.observe("phase_put_complete_us", us_since(t2));
+  };
+
+  const size_t depth = std::max<size_t>(1, std::min<size_t>(2, device_->max_in_flight()));
+  size_t finished = 0;
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    while (c - finished >= depth) finish_chunk(chunks[finished++]);  // at most `depth` chunks in flight
+    chunks[c].begin = plan[c].first;
+    chunks[c].end = plan[c].second;
+    start_chunk(chunks[c]);
   }
-  if (!cancel_keys.empty()) keystone_->batch_put_cancel(cancel_keys);
-  if (!done_keys.empty()) {
-    auto ecs = keystone_->batch_put_complete(done_keys, done_sums);
-    for (size_t k = 0; k < done_idx.size(); ++k) out[done_idx[k]] = ecs[k];
-  }
-  metrics_.observe("phase_put_complete_us", us_since(t2));
+  while (finished < chunks.size()) finish_chunk(chunks[finished++]);
   metrics_.inc("device_put_batches_total");
-  metrics_.observe("device_put_batch_latency_us", us_since(t0));
+  metrics_.observe("device_put_batch_latency_us", us_since(t_all));
   return out;
 }
 
@@ -483,36 +549,14 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
   if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
   if (dev_ptrs.size() != keys.size() || capacity.size() != keys.size()) return out;
-  const TimePoint t0 = Clock::now();
-  auto placed = keystone_->batch_get_workers(keys);
-  metrics_.observe("phase_get_workers_us", us_since(t0));
+  const TimePoint t_all = Clock::now();
   if (out_sizes) out_sizes->assign(keys.size(), 0);
-  // choose for every object the first copy the fabric can reach; later passes retry failures
+  std::vector<Result<std::vector<CopyPlacement>>> placed(keys.size(), Result<std::vector<CopyPlacement>>(ErrorCode::INTERNAL_ERROR));
   std::vector<size_t> copy_choice(keys.size(), 0);
   std::vector<bool> pending(keys.size(), false);
-  for (size_t i = 0; i < keys.size(); ++i) {
-    if (!placed[i].ok()) {
-      out[i] = placed[i].error();
-      continue;
-    }
-    if (placed[i].value().empty()) {
-      out[i] = ErrorCode::NO_COMPLETE_WORKER;
-      continue;
-    }
-    size_t size = 0;
-    for (const auto& s : placed[i].value()[0].shards) size += s.length;
-    if (out_sizes) (*out_sizes)[i] = size;
-    if (size > capacity[i]) {
-      out[i] = ErrorCode::BUFFER_OVERFLOW;
-      continue;
-    }
-    pending[i] = true;
-    // spread readers over replicas: different clients start at different copies
-    copy_choice[i] = std::hash<std::string>{}(opts_.node_id + keys[i]) % placed[i].value().size();
-  }
-  for (size_t attempt = 0; attempt < 4; ++attempt) {
-    std::vector<DeviceShardOp> ops;
-    for (size_t i = 0; i < keys.size(); ++i) {
+
+  auto build_ops = [&](size_t begin, size_t end, std::vector<DeviceShardOp>& ops) {
+    for (size_t i = begin; i < end; ++i) {
       if (!pending[i]) continue;
       const auto& copies = placed[i].value();
       const auto& copy = copies[copy_choice[i] % copies.size()];
@@ -528,40 +572,132 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
         off += copy.shards[s].length;
       }
     }
-    if (ops.empty()) break;
-    std::vector<uint32_t> status;
-    const TimePoint t1 = Clock::now();
-    ErrorCode ec = device_->get_shards(ops, dev_ptrs, ChecksumAlgo::NONE /* per-shard algo from placement */, stream, &status);
-    metrics_.observe("phase_get_xfer_us", us_since(t1));
-    std::vector<bool> bad(keys.size(), false);
-    if (ec != ErrorCode::OK) {
-      for (size_t i = 0; i < keys.size(); ++i)
-        if (pending[i]) out[i] = ec;
-      break;
-    }
-    for (size_t k = 0; k < ops.size(); ++k)
+  };
+  auto apply_status = [&](const std::vector<DeviceShardOp>& ops, const std::vector<uint32_t>& status, std::vector<size_t>* retry) {
+    std::vector<bool> bad(keys.size(), false), seen(keys.size(), false);
+    for (size_t k = 0; k < ops.size(); ++k) {
+      seen[ops[k].item] = true;
       if (status[k] != 0) bad[ops[k].item] = true;
-    bool any_retry = false;
+    }
     for (size_t i = 0; i < keys.size(); ++i) {
-      if (!pending[i]) continue;
+      if (!seen[i] || !pending[i]) continue;
       if (!bad[i]) {
         out[i] = ErrorCode::OK;
         pending[i] = false;
       } else {
         metrics_.inc("checksum_mismatch_total");
-        if (attempt + 1 < placed[i].value().size()) {
-          ++copy_choice[i];  // fail over to the next replica
-          any_retry = true;
-        } else {
-          out[i] = ErrorCode::CHECKSUM_MISMATCH;
-          pending[i] = false;
-        }
+        ++copy_choice[i];  // fail over to the next replica
+        if (retry) retry->push_back(i);
       }
     }
-    if (!any_retry) break;
+  };
+
+  // ---- first attempt: chunks pipelined against the get_workers round trips
+  struct Chunk {
+    size_t begin = 0, end = 0;
+    std::vector<DeviceShardOp> ops;
+    uint64_t ticket = 0;
+    bool submitted = false;
+    ErrorCode err = ErrorCode::OK;
+  };
+  const auto plan = plan_chunks(capacity);
+  std::vector<Chunk> chunks(plan.size());
+  std::vector<size_t> retry;
+  auto start_chunk = [&](Chunk& ch) {
+    const TimePoint t0 = Clock::now();
+    std::vector<ObjectKey> ck(keys.begin() + static_cast<std::ptrdiff_t>(ch.begin), keys.begin() + static_cast<std::ptrdiff_t>(ch.end));
+    auto res = keystone_->batch_get_workers(ck);
+    metrics_.observe("phase_get_workers_us", us_since(t0));
+    for (size_t i = ch.begin; i < ch.end; ++i) {
+      placed[i] = std::move(res[i - ch.begin]);
+      if (!placed[i].ok()) {
+        out[i] = placed[i].error();
+        continue;
+      }
+      if (placed[i].value().empty()) {
+        out[i] = ErrorCode::NO_COMPLETE_WORKER;
+        continue;
+      }
+      size_t size = 0;
+      for (const auto& s : placed[i].value()[0].shards) size += s.length;
+      if (out_sizes) (*out_sizes)[i] = size;
+      if (size > capacity[i]) {
+        out[i] = ErrorCode::BUFFER_OVERFLOW;
+        continue;
+      }
+      pending[i] = true;
+      // spread readers over replicas: different clients start at different copies
+      copy_choice[i] = std::hash<std::string>{}(opts_.node_id + keys[i]) % placed[i].value().size();
+    }
+    build_ops(ch.begin, ch.end, ch.ops);
+    if (ch.ops.empty()) return;
+    const TimePoint t1 = Clock::now();
+    auto t = device_->submit_get(ch.ops, dev_ptrs, stream);
+    metrics_.observe("phase_get_submit_us", us_since(t1));
+    if (t.ok()) {
+      ch.ticket = t.value();
+      ch.submitted = true;
+    } else {
+      ch.err = t.error();
+    }
+  };
+  auto finish_chunk = [&](Chunk& ch) {
+    if (ch.ops.empty()) return;
+    std::vector<uint32_t> status;
+    ErrorCode ec = ch.err;
+    const TimePoint t1 = Clock::now();
+    if (ch.submitted) ec = device_->wait_get(ch.ticket, &status);
+    metrics_.observe("phase_get_wait_us", us_since(t1));
+    if (ec != ErrorCode::OK) {
+      for (size_t i = ch.begin; i < ch.end; ++i)
+        if (pending[i]) {
+          out[i] = ec;
+          pending[i] = false;
+        }
+      return;
+    }
+    apply_status(ch.ops, status, &retry);
+  };
+  const size_t depth = std::max<size_t>(1, std::min<size_t>(2, device_->max_in_flight()));
+  size_t finished = 0;
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    while (c - finished >= depth) finish_chunk(chunks[finished++]);  // at most `depth` chunks in flight
+    chunks[c].begin = plan[c].first;
+    chunks[c].end = plan[c].second;
+    start_chunk(chunks[c]);
   }
+  while (finished < chunks.size()) finish_chunk(chunks[finished++]);
+
+  // ---- replica fail-over for objects whose digest did not verify
+  for (size_t attempt = 1; attempt < 4 && !retry.empty(); ++attempt) {
+    std::vector<size_t> still;
+    std::vector<DeviceShardOp> ops;
+    for (size_t i : retry) {
+      if (attempt >= placed[i].value().size()) {
+        out[i] = ErrorCode::CHECKSUM_MISMATCH;
+        pending[i] = false;
+      }
+    }
+    build_ops(0, keys.size(), ops);
+    if (ops.empty()) break;
+    metrics_.inc("replica_failover_total");
+    std::vector<uint32_t> status;
+    ErrorCode ec = device_->get_shards(ops, dev_ptrs, ChecksumAlgo::NONE, stream, &status);
+    if (ec != ErrorCode::OK) {
+      for (size_t i = 0; i < keys.size(); ++i)
+        if (pending[i]) {
+          out[i] = ec;
+          pending[i] = false;
+        }
+      break;
+    }
+    apply_status(ops, status, &still);
+    retry.swap(still);
+  }
+  for (size_t i = 0; i < keys.size(); ++i)
+    if (pending[i]) out[i] = ErrorCode::CHECKSUM_MISMATCH;
   metrics_.inc("device_get_batches_total");
-  metrics_.observe("device_get_batch_latency_us", us_since(t0));
+  metrics_.observe("device_get_batch_latency_us", us_since(t_all));
   return out;
 }
 

@@ -54,6 +54,42 @@ class DeviceTransport {
                                void* stream, std::vector<uint32_t>* status) = 0;
   virtual bool can_reach(const ShardPlacement& s) const = 0;
   virtual uint64_t launches() const = 0;
+  // Asynchronous variants: enqueue the fused launch and return a ticket, so the caller can overlap
+  // control-plane round trips of the next chunk with this chunk's transfer.  Default = synchronous.
+  virtual Result<uint64_t> submit_put(const std::vector<DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
+                                      void* stream) {
+    std::vector<uint64_t> d;
+    ErrorCode ec = put_shards(ops, dev_ptrs, algo, stream, &d);
+    if (ec != ErrorCode::OK) return ec;
+    sync_results_[++sync_ticket_] = {std::move(d), {}};
+    return sync_ticket_;
+  }
+  virtual ErrorCode wait_put(uint64_t ticket, std::vector<uint64_t>* digests) {
+    auto it = sync_results_.find(ticket);
+    if (it == sync_results_.end()) return ErrorCode::NOT_FOUND;
+    if (digests) *digests = std::move(it->second.first);
+    sync_results_.erase(it);
+    return ErrorCode::OK;
+  }
+  virtual Result<uint64_t> submit_get(const std::vector<DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, void* stream) {
+    std::vector<uint32_t> st;
+    ErrorCode ec = get_shards(ops, dev_ptrs, ChecksumAlgo::NONE, stream, &st);
+    if (ec != ErrorCode::OK) return ec;
+    sync_results_[++sync_ticket_] = {{}, std::move(st)};
+    return sync_ticket_;
+  }
+  virtual ErrorCode wait_get(uint64_t ticket, std::vector<uint32_t>* status) {
+    auto it = sync_results_.find(ticket);
+    if (it == sync_results_.end()) return ErrorCode::NOT_FOUND;
+    if (status) *status = std::move(it->second.second);
+    sync_results_.erase(it);
+    return ErrorCode::OK;
+  }
+  virtual size_t max_in_flight() const { return 1; }
+
+ private:
+  uint64_t sync_ticket_ = 0;
+  std::map<uint64_t, std::pair<std::vector<uint64_t>, std::vector<uint32_t>>> sync_results_;
 };
 
 class BlackbirdClient {
@@ -109,6 +145,9 @@ class BlackbirdClient {
   ErrorCode transfer_get(const std::vector<CopyPlacement>& copies, uint8_t* dst, size_t size);
   static uint64_t shard_offset(const ShardPlacement& s);
   static ChecksumAlgo algo_of(const std::vector<CopyPlacement>& copies, ChecksumAlgo hint);
+  // [begin, end) index ranges that split a batch so that transfers of one chunk overlap the
+  // control-plane round trips of its neighbours (large batches only).
+  std::vector<std::pair<size_t, size_t>> plan_chunks(const std::vector<size_t>& sizes) const;
 
   BlackbirdClientOptions opts_;
   std::shared_ptr<rpc::KeystoneApi> keystone_;

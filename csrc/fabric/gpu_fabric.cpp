@@ -208,11 +208,9 @@ Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
   return ErrorCode::MEMORY_POOL_NOT_FOUND;
 }
 
-ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
-                                void* stream, std::vector<uint64_t>* digests) {
-  std::vector<XferItem> items;
-  std::vector<size_t> op_of_item;
-  items.reserve(ops.size());
+ErrorCode GpuFabric::build_put_items(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
+                                     std::vector<XferItem>* items, std::vector<size_t>* op_of_item) {
+  items->reserve(ops.size());
   for (size_t k = 0; k < ops.size(); ++k) {
     const auto& op = ops[k];
     XferItem it;
@@ -228,8 +226,8 @@ ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, c
       if (!d.ok()) return d.error();
       it.dst[it.ndst++] = d.value();
     }
-    items.push_back(it);
-    op_of_item.push_back(k);
+    items->push_back(it);
+    op_of_item->push_back(k);
     // more replicas than one tile pass can fan out to: extra passes
     while (r < op.replicas.size()) {
       XferItem more;
@@ -241,18 +239,110 @@ ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, c
         if (!d.ok()) return d.error();
         more.dst[more.ndst++] = d.value();
       }
-      items.push_back(more);
-      op_of_item.push_back(k);
+      items->push_back(more);
+      op_of_item->push_back(k);
     }
   }
+  return ErrorCode::OK;
+}
+
+Result<uint64_t> GpuFabric::submit_put(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
+                                       ChecksumAlgo algo, void* stream) {
+  std::vector<XferItem> items;
+  InFlight fl;
+  fl.nops = ops.size();
+  ErrorCode ec = build_put_items(ops, dev_ptrs, &items, &fl.op_of_item);
+  if (ec != ErrorCode::OK) return ec;
+  auto t = engine_->submit(items, algo, stream);
+  if (!t.ok()) return t.error();
+  std::lock_guard<std::mutex> lk(mu_);
+  inflight_[t.value()] = std::move(fl);
+  return t.value();
+}
+
+ErrorCode GpuFabric::wait_put(uint64_t ticket, std::vector<uint64_t>* digests) {
+  InFlight fl;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = inflight_.find(ticket);
+    if (it == inflight_.end()) return ErrorCode::NOT_FOUND;
+    fl = std::move(it->second);
+    inflight_.erase(it);
+  }
   XferResult res;
-  ErrorCode ec = engine_->run(items, algo, stream, &res);
+  ErrorCode ec = engine_->wait(ticket, &res);
   if (ec != ErrorCode::OK) return ec;
   last_ms_ = res.device_ms;
+  total_ms_ += res.device_ms;
   if (digests) {
-    digests->assign(ops.size(), 0);
-    for (size_t i = items.size(); i-- > 0;) (*digests)[op_of_item[i]] = res.digest[i];
+    digests->assign(fl.nops, 0);
+    for (size_t i = fl.op_of_item.size(); i-- > 0;) (*digests)[fl.op_of_item[i]] = res.digest[i];
   }
+  return ErrorCode::OK;
+}
+
+ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
+                                void* stream, std::vector<uint64_t>* digests) {
+  auto t = submit_put(ops, dev_ptrs, algo, stream);
+  if (!t.ok()) return t.error();
+  return wait_put(t.value(), digests);
+}
+
+Result<uint64_t> GpuFabric::submit_get(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, void* stream) {
+  bool uniform = true;
+  for (const auto& op : ops) uniform &= op.placement->checksum_algo == ops[0].placement->checksum_algo;
+  InFlight fl;
+  fl.nops = ops.size();
+  if (!uniform || ops.empty()) {  // rare: objects written with different checksum algorithms in one batch
+    fl.sync_done = true;
+    ErrorCode ec = get_shards(ops, dev_ptrs, ChecksumAlgo::NONE, stream, &fl.sync_status);
+    if (ec != ErrorCode::OK) return ec;
+    std::lock_guard<std::mutex> lk(mu_);
+    const uint64_t t = next_sync_ticket_++;
+    inflight_[t] = std::move(fl);
+    return t;
+  }
+  const ChecksumAlgo algo = ops[0].placement->checksum_algo;
+  std::vector<XferItem> items;
+  items.reserve(ops.size());
+  for (const auto& op : ops) {
+    XferItem it;
+    auto s = resolve(*op.placement);
+    if (!s.ok()) return s.error();
+    it.src = s.value();
+    it.dst[0] = static_cast<uint8_t*>(dev_ptrs[op.item]) + op.obj_offset;
+    it.ndst = 1;
+    it.nbytes = op.placement->length;
+    it.expect = op.placement->checksum;
+    it.flags = algo == ChecksumAlgo::NONE ? 0u : static_cast<uint32_t>(XFER_VERIFY);
+    items.push_back(it);
+  }
+  auto t = engine_->submit(items, algo, stream);
+  if (!t.ok()) return t.error();
+  std::lock_guard<std::mutex> lk(mu_);
+  inflight_[t.value()] = std::move(fl);
+  return t.value();
+}
+
+ErrorCode GpuFabric::wait_get(uint64_t ticket, std::vector<uint32_t>* status) {
+  InFlight fl;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = inflight_.find(ticket);
+    if (it == inflight_.end()) return ErrorCode::NOT_FOUND;
+    fl = std::move(it->second);
+    inflight_.erase(it);
+  }
+  if (fl.sync_done) {
+    if (status) *status = std::move(fl.sync_status);
+    return ErrorCode::OK;
+  }
+  XferResult res;
+  ErrorCode ec = engine_->wait(ticket, &res);
+  if (ec != ErrorCode::OK) return ec;
+  last_ms_ = res.device_ms;
+  total_ms_ += res.device_ms;
+  if (status) *status = std::move(res.status);
   return ErrorCode::OK;
 }
 
@@ -283,6 +373,7 @@ ErrorCode GpuFabric::get_shards(const std::vector<client::DeviceShardOp>& ops, c
     ErrorCode ec = engine_->run(items, algo, stream, &res);
     if (ec != ErrorCode::OK) return ec;
     last_ms_ = res.device_ms;
+  total_ms_ += res.device_ms;
     if (status)
       for (size_t i = 0; i < idx.size(); ++i) (*status)[idx[i]] = res.status[i];
   }

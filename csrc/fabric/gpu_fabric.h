@@ -63,12 +63,19 @@ class GpuFabric : public client::DeviceTransport {
                        std::vector<uint32_t>* status) override;
   bool can_reach(const ShardPlacement& s) const override;
   uint64_t launches() const override { return engine_->launches(); }
+  Result<uint64_t> submit_put(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
+                              void* stream) override;
+  ErrorCode wait_put(uint64_t ticket, std::vector<uint64_t>* digests) override;
+  Result<uint64_t> submit_get(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, void* stream) override;
+  ErrorCode wait_get(uint64_t ticket, std::vector<uint32_t>* status) override;
+  size_t max_in_flight() const override { return 3; }
 
   // Re-reads the pool registry from the keystone and maps any new GPU slab.
   ErrorCode refresh_pools();
   size_t mapped_pools() const;
   XferEngine& engine() { return *engine_; }
   float last_device_ms() const { return last_ms_; }
+  double total_device_ms() const { return total_ms_; }  // sum of kernel times of all finished batches
 
  private:
   GpuFabric() = default;
@@ -79,12 +86,23 @@ class GpuFabric : public client::DeviceTransport {
     bool ipc_opened = false;
   };
   Result<void*> resolve(const ShardPlacement& s);
+  ErrorCode build_put_items(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
+                            std::vector<XferItem>* items, std::vector<size_t>* op_of_item);
+  struct InFlight {
+    size_t nops = 0;
+    std::vector<size_t> op_of_item;       // put: item -> op
+    bool sync_done = false;               // mixed-algorithm get handled synchronously
+    std::vector<uint32_t> sync_status;
+  };
+  std::map<uint64_t, InFlight> inflight_;  // engine ticket -> bookkeeping
+  uint64_t next_sync_ticket_ = 1ull << 62;
   int device_ = 0;
   std::shared_ptr<rpc::KeystoneApi> keystone_;
   std::unique_ptr<XferEngine> engine_;
   mutable std::mutex mu_;
   std::map<std::string, Mapping> pools_;
   float last_ms_ = 0.f;
+  double total_ms_ = 0.0;
 };
 
 // Process-local slab registry (in-process workers + clients share pointers directly; CUDA IPC

@@ -71,4 +71,9 @@ int launch_fill(void* dst, uint64_t nbytes, uint32_t value, void* stream);
 // Fills a buffer with deterministic pseudo-random bytes (synthetic objects).
 int launch_random_fill(void* dst, uint64_t nbytes, uint64_t seed, void* stream);
 
+// MXFP8 pack / unpack (mxfp8.cu): bf16 <-> [E4M3 payload | E8M0 scale per 32 elements].
+// n_elems % 32 == 0; packed size = n_elems + n_elems / 32 bytes (common/mxfp8.h).
+int launch_mxfp8_pack(const void* src_bf16, uint64_t n_elems, void* dst_packed, void* stream);
+int launch_mxfp8_unpack(const void* src_packed, uint64_t n_elems, void* dst_bf16, void* stream);
+
 }  // namespace bb::gpu

@@ -5,6 +5,7 @@
 #include "common/error.h"
 #include "common/json.h"
 #include "common/log.h"
+#include "common/mxfp8.h"
 #include "common/tchash_def.h"
 #include "common/yaml.h"
 
@@ -150,5 +151,23 @@ void bind_common(py::module_& m) {
     if (!v) return py::none();
     return py::int_(*v);
   });
+  m.def("mxfp8_pack_ref", [](py::buffer bf16_bits) {
+    py::buffer_info i = bf16_bits.request();
+    const size_t n = static_cast<size_t>(i.size * i.itemsize) / 2;
+    if (n % 32) throw py::value_error("element count must be a multiple of 32");
+    std::string out(mxfp8::packed_bytes(n), '\0');
+    mxfp8::pack_bf16(static_cast<const uint16_t*>(i.ptr), n, reinterpret_cast<uint8_t*>(out.data()));
+    return py::bytes(out);
+  }, "CPU reference: bf16 bits -> [E4M3 payload | E8M0 scales]");
+  m.def("mxfp8_unpack_ref", [](py::buffer packed, size_t n) {
+    py::buffer_info i = packed.request();
+    if (static_cast<size_t>(i.size * i.itemsize) < mxfp8::packed_bytes(n)) throw py::value_error("packed buffer too small");
+    std::string out(n * 2, '\0');
+    mxfp8::unpack_bf16(static_cast<const uint8_t*>(i.ptr), n, reinterpret_cast<uint16_t*>(out.data()));
+    return py::bytes(out);
+  });
+  m.def("e4m3_from_float", [](float f) { return mxfp8::float_to_e4m3_sat(f); });
+  m.def("e4m3_to_float", [](uint8_t v) { return mxfp8::e4m3_to_float(v); });
+  m.def("mxfp8_packed_bytes", [](size_t n) { return mxfp8::packed_bytes(n); });
   m.def("set_log_level", [](int l) { set_log_level(static_cast<LogLevel>(l)); });
 }

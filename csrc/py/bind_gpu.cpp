@@ -115,6 +115,12 @@ void bind_gpu(py::module_& m) {
     check_cuda(launch_random_fill(reinterpret_cast<void*>(dst), n, seed, reinterpret_cast<void*>(stream)), "random_fill");
   }, py::arg("dst"), py::arg("nbytes"), py::arg("seed") = 1, py::arg("stream") = 0);
   m.def("xfer_smem_bytes", [] { return xfer_smem_bytes(ALGO_BBH64); });
+  m.def("mxfp8_pack", [](uintptr_t src, uint64_t n, uintptr_t dst, uintptr_t stream) {
+    check_cuda(launch_mxfp8_pack(reinterpret_cast<const void*>(src), n, reinterpret_cast<void*>(dst), reinterpret_cast<void*>(stream)), "mxfp8_pack");
+  }, py::arg("src_bf16"), py::arg("n_elems"), py::arg("dst_packed"), py::arg("stream") = 0);
+  m.def("mxfp8_unpack", [](uintptr_t src, uint64_t n, uintptr_t dst, uintptr_t stream) {
+    check_cuda(launch_mxfp8_unpack(reinterpret_cast<const void*>(src), n, reinterpret_cast<void*>(dst), reinterpret_cast<void*>(stream)), "mxfp8_unpack");
+  }, py::arg("src_packed"), py::arg("n_elems"), py::arg("dst_bf16"), py::arg("stream") = 0);
 
   // ---- fabric: GPU tier + device transport of the client SDK
   m.def("install_gpu_backend_factory", &install_gpu_backend_factory,
@@ -130,6 +136,7 @@ void bind_gpu(py::module_& m) {
       .def("mapped_pools", &GpuFabric::mapped_pools)
       .def_property_readonly("launches", &GpuFabric::launches)
       .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
+      .def_property_readonly("total_device_ms", &GpuFabric::total_device_ms)
       .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); });
   m.def("attach_fabric", [](client::BlackbirdClient& c, std::shared_ptr<GpuFabric> f) { c.set_device_transport(std::move(f)); });
 }

@@ -109,3 +109,56 @@ def test_full_stack_put_get_gpu_tier(bb, torch_cuda):
         assert cl.fabric.launches >= 3
     finally:
         cl.stop()
+
+
+def test_tensor_store_roundtrip_and_mxfp8(bb, torch_cuda):
+    torch = torch_cuda
+    from blackbird_b200.ops import TensorStore
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=256 << 20, cluster_id="t-ts")
+    try:
+        ts = TensorStore(cl.client)
+        a = torch.randn(257, 129, device="cuda", dtype=torch.float32)
+        b = torch.randint(-5, 5, (1000,), device="cuda", dtype=torch.int32)
+        ts.batch_put(["a", "b"], [a, b])
+        ga, gb = ts.batch_get(["a", "b"])
+        assert ga.dtype == a.dtype and ga.shape == a.shape and torch.equal(ga, a) and torch.equal(gb, b)
+        kv = (torch.randn(4, 1000, 33, device="cuda") * 3).to(torch.bfloat16)  # numel not a multiple of 32
+        ts.put("kv", kv, pack_fp8=True)
+        sh = cl.client.get_workers("kv")[0].shards[0]
+        assert sh.length == bb.mxfp8_packed_bytes((kv.numel() + 31) // 32 * 32)  # ~0.52x of the bf16 bytes in the slab
+        back = ts.get("kv")
+        assert back.shape == kv.shape and back.dtype == torch.bfloat16
+        err = (back.float() - kv.float()).abs().max().item()
+        assert err <= kv.float().abs().max().item() * 2 ** -3
+        ts.remove(["a", "b", "kv"])
+        assert cl.client.object_exists("kv") is False
+    finally:
+        cl.stop()
+
+
+def test_large_batch_is_pipelined_in_chunks(bb, torch_cuda):
+    """Batches >= 512 MiB are split so chunk k's kernel overlaps the Keystone round trips of chunk k+1."""
+    torch = torch_cuda
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=3 << 30, cluster_id="t-chunk")
+    try:
+        n, size = 16, 64 << 20
+        src = torch.empty(n * size, dtype=torch.uint8, device="cuda")
+        bb.random_fill(src.data_ptr(), n * size, 5, 0)
+        out = torch.zeros_like(src)
+        keys = [f"c{i}" for i in range(n)]
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_GPU])
+        s = _stream(torch)
+        l0 = cl.fabric.launches
+        assert cl.client.batch_put_device(keys, [src.data_ptr() + i * size for i in range(n)], [size] * n, cfg, s) == [bb.ErrorCode.OK] * n
+        assert cl.fabric.launches - l0 == 4  # 1 GiB in four 256 MiB chunks
+        ecs, sizes = cl.client.batch_get_device(keys, [out.data_ptr() + i * size for i in range(n)], [size] * n, s)
+        assert ecs == [bb.ErrorCode.OK] * n and cl.fabric.launches - l0 == 8
+        torch.cuda.synchronize()
+        assert torch.equal(src, out)
+        assert cl.client.get_workers(keys[5])[0].shards[0].checksum == bb.bbh64(src[5 * size:6 * size].cpu().numpy())
+    finally:
+        cl.stop()
