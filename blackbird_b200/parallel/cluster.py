@@ -96,7 +96,8 @@ class LocalCluster:
 class GpuRankCluster:
     """One process per GPU.  Requires torch + CUDA; rendezvous through torch.distributed when world>1."""
 
-    def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None):
+    def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None,
+                 nvls_arena_bytes: int = 0, nvls_group_size: int = 3):
         import torch
         import torch.distributed as dist
 
@@ -160,6 +161,42 @@ class GpuRankCluster:
         assert self.fabric.mapped_pools() == self.world, f"mapped {self.fabric.mapped_pools()} of {self.world} slabs"
         _bb.attach_fabric(self.client, self.fabric)
         self.barrier()
+        self.arena = None
+        if nvls_arena_bytes:
+            self._setup_nvls(cluster_id, nvls_arena_bytes, nvls_group_size)
+
+    def _setup_nvls(self, cluster_id: str, arena_bytes: int, group_size: int):
+        """Replica arenas: ring groups {g, g+1, .., g+R-1} of R GPUs, each bound to one NVSwitch multicast object."""
+        R = min(group_size, self.world)
+        if R < 2 or not _bb.NvlsArena.supported(self.local_rank):
+            return
+        if R == self.world:
+            groups = [list(range(self.world))]
+        else:
+            groups = [[(g + k) % self.world for k in range(R)] for g in range(self.world)]
+        tag = f"{cluster_id}-{self.keystone_port}"
+        arena = _bb.NvlsArena(self.local_rank, self.rank, self.world, tag, groups, arena_bytes)
+        for phase in (arena.phase1_create, arena.phase2_join, arena.phase3_bind, arena.phase4_map_peers):
+            ec = phase()
+            ok = self.torch.tensor([1 if ec == _bb.ErrorCode.OK else 0], device="cuda")
+            if self.dist is not None:
+                self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if self.rank == 0:
+                    print(f"[blackbird_b200] NVLS arena unavailable ({phase.__name__}: {arena.last_error}); replicas use unicast fan-out")
+                return
+            self.barrier()
+        self.arena = arena
+        self.fabric.set_arena(arena)
+        # every member registers its arena of every group it belongs to as a RAM_GPU pool of that multicast domain
+        for g in range(arena.num_groups()):
+            if not arena.member_of(g):
+                continue
+            pool = _bb.MemoryPool(_bb.NvlsArena.pool_id(g, self.rank), arena.arena_bytes, _bb.StorageClass.RAM_GPU, self.node_id,
+                                  f"worker-gpu{self.rank}", self.worker.data_endpoint(), 0, "", self.local_rank, 7200.0,
+                                  _bb.NvlsArena.domain(g))
+            assert self.api.register_memory_pool(pool) == _bb.ErrorCode.OK
+        self.barrier()
 
     def _new_api(self):
         api = _bb.KeystoneRpcClient()
@@ -175,6 +212,7 @@ class GpuRankCluster:
         self.barrier()
         self.client = None
         self.fabric = None
+        self.arena = None
         self.worker.stop()
         self.barrier()
         if self.rpc is not None:

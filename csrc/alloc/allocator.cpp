@@ -187,6 +187,8 @@ std::vector<RangeAllocator::Candidate> RangeAllocator::rank_candidates(const All
   for (const auto& [id, p] : pools) {
     if (!req.preferred_node.empty() && p.node_id != req.preferred_node) continue;
     if (std::find(req.exclude_pools.begin(), req.exclude_pools.end(), id) != req.exclude_pools.end()) continue;
+    // NVLS replica arenas ("nvls-g<k>" domains) are reserved for symmetric multicast placement
+    if (!req.symmetric_replicas && p.fabric_domain.compare(0, 5, "nvls-") == 0) continue;
     Candidate c;
     c.id = id;
     c.preferred = preferred(p.storage_class);
@@ -372,15 +374,54 @@ Result<AllocationResult> RangeAllocator::place(const AllocationRequest& req, con
 Result<AllocationResult> RangeAllocator::place_symmetric(const AllocationRequest& req, const PoolMap& pools,
                                                          const std::vector<Candidate>& cands, bool spill) {
   const size_t repl = std::max<size_t>(1, req.replication_factor);
-  // pick `repl` pools on distinct workers, best ranked first
-  std::vector<const Candidate*> chosen;
-  std::unordered_set<std::string> workers;
+  // pick `repl` pools on distinct workers, best ranked first.  When the cluster advertises NVLS
+  // replica arenas, all replicas must come from ONE multicast group (same "nvls-g<k>" domain):
+  // the group with the most free space among those that can hold the object on `repl` members.
+  std::unordered_map<std::string, std::vector<const Candidate*>> by_domain;
   for (const auto& c : cands) {
-    if (workers.count(c.worker)) continue;
-    if (c.largest < req.data_size) continue;
-    chosen.push_back(&c);
-    workers.insert(c.worker);
-    if (chosen.size() == repl) break;
+    const std::string& dom = pools.at(c.id).fabric_domain;
+    if (dom.compare(0, 5, "nvls-") == 0 && c.largest >= req.data_size) by_domain[dom].push_back(&c);
+  }
+  std::vector<const Candidate*> chosen;
+  if (!by_domain.empty()) {
+    const std::vector<const Candidate*>* best = nullptr;
+    uint64_t best_free = 0;
+    std::string best_dom;
+    for (const auto& [dom, v] : by_domain) {
+      std::unordered_set<std::string> w;
+      uint64_t min_free = ~0ull;
+      for (auto* c : v) {
+        w.insert(c->worker);
+        min_free = std::min(min_free, c->free_bytes);
+      }
+      if (w.size() < repl) continue;
+      if (!best || min_free > best_free || (min_free == best_free && dom < best_dom)) {
+        best = &v;
+        best_free = min_free;
+        best_dom = dom;
+      }
+    }
+    if (best) {
+      std::unordered_set<std::string> workers;
+      for (auto* c : *best) {
+        if (workers.count(c->worker)) continue;
+        chosen.push_back(c);
+        workers.insert(c->worker);
+        if (chosen.size() == repl) break;
+      }
+    }
+  }
+  if (chosen.size() < repl) {
+    chosen.clear();
+    std::unordered_set<std::string> workers;
+    for (const auto& c : cands) {
+      if (workers.count(c.worker)) continue;
+      if (c.largest < req.data_size) continue;
+      if (pools.at(c.id).fabric_domain.compare(0, 5, "nvls-") == 0) continue;  // partial groups cannot multicast
+      chosen.push_back(&c);
+      workers.insert(c.worker);
+      if (chosen.size() == repl) break;
+    }
   }
   if (chosen.size() < repl) return ErrorCode::INSUFFICIENT_SPACE;
   std::vector<PoolAllocator*> pas;

@@ -194,6 +194,14 @@ bool GpuFabric::can_reach(const ShardPlacement& s) const {
 Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
   const auto* g = std::get_if<GpuSlabLocation>(&s.location);
   if (!g) return ErrorCode::INVALID_ADDRESS;
+  size_t grp = 0;
+  int member = 0;
+  if (arena_ && NvlsArena::parse_pool_id(s.pool_id, &grp, &member)) {
+    auto* base = static_cast<uint8_t*>(arena_->peer_ptr(grp, member));
+    if (!base) return ErrorCode::MEMORY_POOL_NOT_FOUND;
+    if (g->offset + s.length > arena_->arena_bytes()) return ErrorCode::MEMORY_ACCESS_ERROR;
+    return static_cast<void*>(base + g->offset);
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -216,6 +224,27 @@ ErrorCode GpuFabric::build_put_items(const std::vector<client::DeviceShardOp>& o
     XferItem it;
     it.src = static_cast<const uint8_t*>(dev_ptrs[op.item]) + op.obj_offset;
     it.nbytes = op.placement->length;
+    // NVLS: the replica set is one whole multicast group at one offset -> a single multimem.st stream
+    if (arena_ && !op.replicas.empty() && (it.nbytes & 15) == 0) {
+      size_t grp = 0, g2 = 0;
+      int m0 = 0, m2 = 0;
+      const auto* loc0 = std::get_if<GpuSlabLocation>(&op.placement->location);
+      bool mc_ok = loc0 && NvlsArena::parse_pool_id(op.placement->pool_id, &grp, &m0) && grp < arena_->num_groups() &&
+                   arena_->member_of(grp) && arena_->mc_ptr(grp) && op.replicas.size() + 1 == arena_->members(grp).size();
+      for (size_t r = 0; mc_ok && r < op.replicas.size(); ++r) {
+        const auto* lr = std::get_if<GpuSlabLocation>(&op.replicas[r]->location);
+        mc_ok = lr && lr->offset == loc0->offset && NvlsArena::parse_pool_id(op.replicas[r]->pool_id, &g2, &m2) && g2 == grp;
+      }
+      if (mc_ok) {
+        it.dst[0] = static_cast<uint8_t*>(arena_->mc_ptr(grp)) + loc0->offset;
+        it.ndst = 1;
+        it.flags |= XFER_MULTIMEM;
+        items->push_back(it);
+        op_of_item->push_back(k);
+        ++multicast_puts_;
+        continue;
+      }
+    }
     auto d0 = resolve(*op.placement);
     if (!d0.ok()) return d0.error();
     it.dst[0] = d0.value();

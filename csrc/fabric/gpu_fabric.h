@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "client/blackbird_client.h"
+#include "fabric/nvls.h"
 #include "fabric/xfer_engine.h"
 #include "worker/storage_backend.h"
 
@@ -73,6 +74,10 @@ class GpuFabric : public client::DeviceTransport {
   // Re-reads the pool registry from the keystone and maps any new GPU slab.
   ErrorCode refresh_pools();
   size_t mapped_pools() const;
+  // NVLS replica arenas: pools named mc<g>@gpu<r> resolve through the arena; a put whose replica set is
+  // exactly one multicast group (same offset everywhere) becomes ONE multimem.st stream.
+  void set_arena(std::shared_ptr<NvlsArena> a) { arena_ = std::move(a); }
+  uint64_t multicast_puts() const { return multicast_puts_; }
   XferEngine& engine() { return *engine_; }
   float last_device_ms() const { return last_ms_; }
   double total_device_ms() const { return total_ms_; }  // sum of kernel times of all finished batches
@@ -101,6 +106,8 @@ class GpuFabric : public client::DeviceTransport {
   std::unique_ptr<XferEngine> engine_;
   mutable std::mutex mu_;
   std::map<std::string, Mapping> pools_;
+  std::shared_ptr<NvlsArena> arena_;
+  uint64_t multicast_puts_ = 0;
   float last_ms_ = 0.f;
   double total_ms_ = 0.0;
 };

@@ -137,6 +137,25 @@ void bind_gpu(py::module_& m) {
       .def_property_readonly("launches", &GpuFabric::launches)
       .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
       .def_property_readonly("total_device_ms", &GpuFabric::total_device_ms)
-      .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); });
+      .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); })
+      .def("set_arena", &GpuFabric::set_arena)
+      .def_property_readonly("multicast_puts", &GpuFabric::multicast_puts);
+  py::class_<NvlsArena, std::shared_ptr<NvlsArena>>(m, "NvlsArena")
+      .def(py::init<int, int, int, std::string, std::vector<std::vector<int>>, uint64_t>(), py::arg("device"), py::arg("rank"), py::arg("world"),
+           py::arg("tag"), py::arg("groups"), py::arg("arena_bytes"))
+      .def_static("supported", &NvlsArena::supported)
+      .def("phase1_create", &NvlsArena::phase1_create, py::call_guard<py::gil_scoped_release>())
+      .def("phase2_join", &NvlsArena::phase2_join, py::call_guard<py::gil_scoped_release>())
+      .def("phase3_bind", &NvlsArena::phase3_bind, py::call_guard<py::gil_scoped_release>())
+      .def("phase4_map_peers", &NvlsArena::phase4_map_peers, py::call_guard<py::gil_scoped_release>())
+      .def("num_groups", &NvlsArena::num_groups)
+      .def("members", &NvlsArena::members)
+      .def("member_of", &NvlsArena::member_of)
+      .def_property_readonly("arena_bytes", &NvlsArena::arena_bytes)
+      .def("mc_ptr", [](NvlsArena& a, size_t g) { return reinterpret_cast<uintptr_t>(a.mc_ptr(g)); })
+      .def("peer_ptr", [](NvlsArena& a, size_t g, int r) { return reinterpret_cast<uintptr_t>(a.peer_ptr(g, r)); })
+      .def_static("pool_id", &NvlsArena::pool_id)
+      .def_static("domain", &NvlsArena::domain)
+      .def_property_readonly("last_error", &NvlsArena::last_error);
   m.def("attach_fabric", [](client::BlackbirdClient& c, std::shared_ptr<GpuFabric> f) { c.set_device_transport(std::move(f)); });
 }
