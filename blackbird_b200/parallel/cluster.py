@@ -97,7 +97,7 @@ class GpuRankCluster:
     """One process per GPU.  Requires torch + CUDA; rendezvous through torch.distributed when world>1."""
 
     def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None,
-                 nvls_arena_bytes: int = 0, nvls_group_size: int = 3):
+                 nvls_arena_bytes: int = 0, nvls_group_size: int = 3, rpc_busy_poll_us: int = 5000):
         import torch
         import torch.distributed as dist
 
@@ -122,6 +122,7 @@ class GpuRankCluster:
             cfg.enable_gc = False
             cfg.high_watermark = 1.0
             cfg.rpc_threads = 4
+            cfg.rpc_busy_poll_us = rpc_busy_poll_us  # clients issue RPCs between kernels a few ms apart
             self.keystone = _bb.KeystoneService(cfg, None)
             assert self.keystone.initialize() == _bb.ErrorCode.OK
             assert self.keystone.start() == _bb.ErrorCode.OK

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstring>
 #include <future>
+#include <map>
 #include <thread>
 
 #include "common/log.h"
@@ -378,22 +379,39 @@ std::vector<Result<bool>> BlackbirdClient::batch_exists(const std::vector<Object
 }
 
 // ================================================================ batched device API
-std::vector<std::pair<size_t, size_t>> BlackbirdClient::plan_chunks(const std::vector<size_t>& sizes) const {
+std::vector<std::pair<size_t, size_t>> BlackbirdClient::plan_chunks(const std::vector<size_t>& sizes, double rpc_us_per_object) const {
   std::vector<std::pair<size_t, size_t>> chunks;
   uint64_t total = 0;
   for (size_t s : sizes) total += s;
   constexpr uint64_t kMinChunk = 256ull << 20;  // below this a chunk's kernel is too short to hide an RPC
+  constexpr double kLaunchPenaltyUs = 40.0;     // measured: ramp + tail + launch gap of one more fused launch
   const size_t depth = device_ ? device_->max_in_flight() : 1;
-  if (depth < 2 || total < 2 * kMinChunk || sizes.size() < 2) {
+  size_t want = 1;
+  if (depth >= 2 && sizes.size() >= 2 && total >= 2 * kMinChunk) {
+    if (pipeline_chunks_ > 0) {
+      want = pipeline_chunks_;
+    } else {
+      // Splitting hides (1 - 1/c) of the control-plane time behind kernels and costs (c - 1) launch penalties.
+      // An in-process Keystone (tens of us per batch) is not worth a split; a remote one (100s of us) is.
+      const double rpc_us = rpc_us_per_object * static_cast<double>(sizes.size());
+      double best = 0;
+      for (size_t c : {size_t{2}, size_t{4}}) {
+        const double gain = rpc_us * (1.0 - 1.0 / static_cast<double>(c)) - static_cast<double>(c - 1) * kLaunchPenaltyUs;
+        if (gain > best) best = gain, want = c;
+      }
+    }
+    want = std::min<size_t>({want, static_cast<size_t>(total / kMinChunk), sizes.size()});
+  }
+  if (want <= 1) {
     chunks.emplace_back(0, sizes.size());
     return chunks;
   }
-  const uint64_t target = std::max<uint64_t>(kMinChunk, total / 4);
+  const uint64_t target = total / want;
   size_t begin = 0;
   uint64_t acc = 0;
   for (size_t i = 0; i < sizes.size(); ++i) {
     acc += sizes[i];
-    if (acc >= target && i + 1 < sizes.size()) {
+    if (acc >= target && i + 1 < sizes.size() && chunks.size() + 1 < want) {
       chunks.emplace_back(begin, i + 1);
       begin = i + 1;
       acc = 0;
@@ -401,6 +419,11 @@ std::vector<std::pair<size_t, size_t>> BlackbirdClient::plan_chunks(const std::v
   }
   chunks.emplace_back(begin, sizes.size());
   return chunks;
+}
+
+static void ewma_update(std::atomic<double>& v, double sample) {
+  const double old = v.load(std::memory_order_relaxed);
+  v.store(old == 0 ? sample : 0.75 * old + 0.25 * sample, std::memory_order_relaxed);
 }
 
 std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<ObjectKey>& keys, const std::vector<const void*>& dev_ptrs,
@@ -419,8 +442,11 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
     bool submitted = false;
     ErrorCode submit_error = ErrorCode::OK;
   };
-  const auto plan = plan_chunks(sizes);
+  const auto plan = plan_chunks(sizes, put_rpc_us_per_obj_.load(std::memory_order_relaxed));
+  double rpc_us_total = 0;
   std::vector<Chunk> chunks(plan.size());
+  std::vector<size_t> host_put;                      // objects whose placement is not on the GPU fabric
+  std::map<size_t, std::vector<CopyPlacement>> host_placed;
 
   auto start_chunk = [&](Chunk& ch) {
     const TimePoint t0 = Clock::now();
@@ -428,6 +454,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
     items.reserve(ch.end - ch.begin);
     for (size_t i = ch.begin; i < ch.end; ++i) items.push_back(PutStartItem{keys[i], sizes[i], cfg});
     ch.placed = keystone_->batch_put_start(items);  // one control-plane round trip per chunk
+    rpc_us_total += us_since(t0);
     metrics_.observe("phase_put_start_us", us_since(t0));
     // One descriptor per (object, shard): copy 0's placement plus the same shard of every other
     // copy as extra destinations, so the kernel reads the source once and fans out.
@@ -440,6 +467,15 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
       out[i] = ErrorCode::OK;
       const auto& copies = pr.value();
       if (copies.empty()) continue;
+      // placements on host tiers (DRAM / CXL / NVMe): stage through host memory and use the data servers
+      bool on_fabric = true;
+      for (const auto& c : copies)
+        for (const auto& sh : c.shards) on_fabric &= device_->can_reach(sh);
+      if (!on_fabric) {
+        host_put.push_back(i);
+        host_placed[i] = copies;
+        continue;
+      }
       bool same_layout = true;
       for (const auto& c : copies) same_layout &= c.shards.size() == copies[0].shards.size();
       if (same_layout) {
@@ -514,7 +550,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
         for (size_t r = 0; r < op.replicas.size(); ++r) sm[r + 1][op.shard] = digests[k];
       }
       for (size_t i = ch.begin; i < ch.end; ++i)
-        if (ch.placed[i - ch.begin].ok()) {
+        if (ch.placed[i - ch.begin].ok() && !host_placed.count(i)) {
           done_keys.push_back(keys[i]);
           done_sums.push_back(std::move(sums[i - ch.begin]));
           done_idx.push_back(i);
@@ -525,6 +561,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
       auto ecs = keystone_->batch_put_complete(done_keys, done_sums);
       for (size_t k = 0; k < done_idx.size(); ++k) out[done_idx[k]] = ecs[k];
     }
+    rpc_us_total += us_since(t2);
     metrics_.observe("phase_put_complete_us", us_since(t2));
   };
 
@@ -537,6 +574,18 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
     start_chunk(chunks[c]);
   }
   while (finished < chunks.size()) finish_chunk(chunks[finished++]);
+  // host-tier placements: D2H into a staging buffer, then the TCP data path (checksums on the CPU)
+  for (size_t i : host_put) {
+    std::vector<uint8_t> stage(sizes[i]);
+    ErrorCode ec = device_->copy_d2h(stage.data(), dev_ptrs[i], sizes[i], stream);
+    ShardChecksums sums;
+    if (ec == ErrorCode::OK) ec = transfer_put(host_placed[i], stage.data(), cfg.checksum, &sums);
+    if (ec == ErrorCode::OK) ec = keystone_->put_complete(keys[i], sums);
+    else keystone_->put_cancel(keys[i]);
+    out[i] = ec;
+    metrics_.inc("device_put_host_staged_total");
+  }
+  if (!keys.empty()) ewma_update(put_rpc_us_per_obj_, rpc_us_total / static_cast<double>(keys.size()));
   metrics_.inc("device_put_batches_total");
   metrics_.observe("device_put_batch_latency_us", us_since(t_all));
   return out;
@@ -600,13 +649,15 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
     bool submitted = false;
     ErrorCode err = ErrorCode::OK;
   };
-  const auto plan = plan_chunks(capacity);
+  const auto plan = plan_chunks(capacity, get_rpc_us_per_obj_.load(std::memory_order_relaxed));
+  double rpc_us_total = 0;
   std::vector<Chunk> chunks(plan.size());
   std::vector<size_t> retry;
   auto start_chunk = [&](Chunk& ch) {
     const TimePoint t0 = Clock::now();
     std::vector<ObjectKey> ck(keys.begin() + static_cast<std::ptrdiff_t>(ch.begin), keys.begin() + static_cast<std::ptrdiff_t>(ch.end));
     auto res = keystone_->batch_get_workers(ck);
+    rpc_us_total += us_since(t0);
     metrics_.observe("phase_get_workers_us", us_since(t0));
     for (size_t i = ch.begin; i < ch.end; ++i) {
       placed[i] = std::move(res[i - ch.begin]);
@@ -625,9 +676,28 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
         out[i] = ErrorCode::BUFFER_OVERFLOW;
         continue;
       }
+      // prefer a replica that is fully reachable over the GPU fabric; otherwise stage through the host
+      const auto& copies = placed[i].value();
+      const size_t start = std::hash<std::string>{}(opts_.node_id + keys[i]) % copies.size();  // spread readers over replicas
+      bool found = false;
+      for (size_t k = 0; k < copies.size() && !found; ++k) {
+        const auto& c = copies[(start + k) % copies.size()];
+        bool ok = true;
+        for (const auto& sh : c.shards) ok &= device_->can_reach(sh);
+        if (ok) {
+          copy_choice[i] = (start + k) % copies.size();
+          found = true;
+        }
+      }
+      if (!found) {
+        std::vector<uint8_t> stage(size);
+        ErrorCode ec = transfer_get(copies, stage.data(), size);  // data servers + CPU checksum + replica fail-over
+        if (ec == ErrorCode::OK) ec = device_->copy_h2d(dev_ptrs[i], stage.data(), size, stream);
+        out[i] = ec;
+        metrics_.inc("device_get_host_staged_total");
+        continue;
+      }
       pending[i] = true;
-      // spread readers over replicas: different clients start at different copies
-      copy_choice[i] = std::hash<std::string>{}(opts_.node_id + keys[i]) % placed[i].value().size();
     }
     build_ops(ch.begin, ch.end, ch.ops);
     if (ch.ops.empty()) return;
@@ -696,6 +766,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   }
   for (size_t i = 0; i < keys.size(); ++i)
     if (pending[i]) out[i] = ErrorCode::CHECKSUM_MISMATCH;
+  if (!keys.empty()) ewma_update(get_rpc_us_per_obj_, rpc_us_total / static_cast<double>(keys.size()));
   metrics_.inc("device_get_batches_total");
   metrics_.observe("device_get_batch_latency_us", us_since(t_all));
   return out;

@@ -12,6 +12,7 @@
 // every shard is checksummed and verified; reads fail over to the next replica; a failed put is
 // cancelled.
 #pragma once
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -86,6 +87,9 @@ class DeviceTransport {
     return ErrorCode::OK;
   }
   virtual size_t max_in_flight() const { return 1; }
+  // Staging copies for objects (or shards) that live on host tiers: device <-> host buffer, synchronous.
+  virtual ErrorCode copy_h2d(void* dev, const void* host, size_t n, void* stream) { return ErrorCode::NOT_IMPLEMENTED; }
+  virtual ErrorCode copy_d2h(void* host, const void* dev, size_t n, void* stream) { return ErrorCode::NOT_IMPLEMENTED; }
 
  private:
   uint64_t sync_ticket_ = 0;
@@ -132,6 +136,8 @@ class BlackbirdClient {
   Result<ClusterStats> cluster_stats();
   rpc::KeystoneApi& keystone() { return *keystone_; }
   std::string metrics_text() const { return metrics_.render("bb_client_"); }
+  // Device batches are split into `chunks` pipelined launches; 0 = decide from the measured RPC latency.
+  void set_device_pipeline_chunks(size_t chunks) { pipeline_chunks_ = chunks; }
   std::map<std::string, std::vector<double>> phase_summary() const { return metrics_.histogram_summary(); }
 
  private:
@@ -147,11 +153,13 @@ class BlackbirdClient {
   static ChecksumAlgo algo_of(const std::vector<CopyPlacement>& copies, ChecksumAlgo hint);
   // [begin, end) index ranges that split a batch so that transfers of one chunk overlap the
   // control-plane round trips of its neighbours (large batches only).
-  std::vector<std::pair<size_t, size_t>> plan_chunks(const std::vector<size_t>& sizes) const;
+  std::vector<std::pair<size_t, size_t>> plan_chunks(const std::vector<size_t>& sizes, double rpc_us_per_object) const;
 
   BlackbirdClientOptions opts_;
   std::shared_ptr<rpc::KeystoneApi> keystone_;
   std::shared_ptr<DeviceTransport> device_;
+  size_t pipeline_chunks_ = 0;  // 0 = adaptive (from the measured control-plane latency)
+  std::atomic<double> put_rpc_us_per_obj_{0}, get_rpc_us_per_obj_{0};
   std::string session_id_;
   std::mutex conn_mu_;
   std::map<std::string, std::vector<std::shared_ptr<net::RpcClient>>> idle_conns_;

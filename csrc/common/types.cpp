@@ -157,6 +157,7 @@ Result<KeystoneConfig> KeystoneConfig::from_json(const Json& root, std::string* 
   if (k.contains("health_check_interval_sec")) c.health_check_interval_sec = k.at("health_check_interval_sec").as_int(c.health_check_interval_sec);
   if (k.contains("max_replicas")) c.max_replicas = static_cast<int32_t>(k.at("max_replicas").as_int(c.max_replicas));
   if (k.contains("default_replicas")) c.default_replicas = static_cast<int32_t>(k.at("default_replicas").as_int(c.default_replicas));
+  if (k.contains("rpc_busy_poll_us")) c.rpc_busy_poll_us = static_cast<int32_t>(k.at("rpc_busy_poll_us").as_int(0));
   if (k.contains("rpc_threads")) c.rpc_threads = static_cast<int32_t>(k.at("rpc_threads").as_int(c.rpc_threads));
   if (k.contains("wal_path")) c.wal_path = k.at("wal_path").as_string();
   const Json& lg = root.at("logging");

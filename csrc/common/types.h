@@ -173,6 +173,7 @@ struct KeystoneConfig {
   int32_t default_replicas = 1;
   // extensions
   int32_t rpc_threads = 2;
+  int32_t rpc_busy_poll_us = 0;  // RPC threads poll without sleeping this long after a request (latency vs CPU)
   std::string log_level;  // from the `logging:` section the reference ignores
   std::string log_file;
   std::string wal_path;   // object-metadata write-ahead log ("" = coordination store only)

@@ -216,6 +216,22 @@ Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
   return ErrorCode::MEMORY_POOL_NOT_FOUND;
 }
 
+ErrorCode GpuFabric::copy_h2d(void* dev, const void* host, size_t n, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!cuda_ok(cudaSetDevice(device_), "cudaSetDevice") || !cuda_ok(cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, st), "H2D") ||
+      !cuda_ok(cudaStreamSynchronize(st), "sync"))
+    return ErrorCode::FABRIC_ERROR;
+  return ErrorCode::OK;
+}
+
+ErrorCode GpuFabric::copy_d2h(void* host, const void* dev, size_t n, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!cuda_ok(cudaSetDevice(device_), "cudaSetDevice") || !cuda_ok(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, st), "D2H") ||
+      !cuda_ok(cudaStreamSynchronize(st), "sync"))
+    return ErrorCode::FABRIC_ERROR;
+  return ErrorCode::OK;
+}
+
 ErrorCode GpuFabric::build_put_items(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
                                      std::vector<XferItem>* items, std::vector<size_t>* op_of_item) {
   items->reserve(ops.size());

@@ -70,6 +70,8 @@ class GpuFabric : public client::DeviceTransport {
   Result<uint64_t> submit_get(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, void* stream) override;
   ErrorCode wait_get(uint64_t ticket, std::vector<uint32_t>* status) override;
   size_t max_in_flight() const override { return 3; }
+  ErrorCode copy_h2d(void* dev, const void* host, size_t n, void* stream) override;
+  ErrorCode copy_d2h(void* host, const void* dev, size_t n, void* stream) override;
 
   // Re-reads the pool registry from the keystone and maps any new GPU slab.
   ErrorCode refresh_pools();

@@ -256,6 +256,10 @@ void KeystoneService::on_heartbeat_event(const std::string& key, const std::stri
     worker_heartbeat(wid);
     return;
   }
+  {
+    std::shared_lock<std::shared_mutex> lk(workers_mu_);
+    if (!workers_.count(wid)) return;  // already deregistered (clean shutdown deletes the worker key first)
+  }
   BB_LOG(WARNING) << "keystone: heartbeat lease of worker " << wid << " expired";
   metrics_.inc("worker_deaths_total");
   handle_worker_death(wid);

@@ -6,6 +6,7 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
+#include <sched.h>
 #include <sys/epoll.h>
 #include <sys/eventfd.h>
 #include <sys/socket.h>
@@ -133,6 +134,29 @@ bool send_all(int fd, const void* data, size_t len, int timeout_ms) {
 
 bool recv_all(int fd, void* data, size_t len, int timeout_ms) {
   char* p = static_cast<char*>(data);
+  // A control-plane answer usually arrives within tens of microseconds: look for it without
+  // sleeping first (a poll() sleep costs a scheduler wake-up on top of the round trip).
+  static const int spin_us = [] {
+    const char* e = std::getenv("BB_RPC_SPIN_US");
+    return e ? std::atoi(e) : 50;
+  }();
+  if (spin_us > 0 && len) {
+    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+    do {
+      ssize_t n = ::recv(fd, p, len, MSG_DONTWAIT);
+      if (n > 0) {
+        p += n;
+        len -= static_cast<size_t>(n);
+        if (!len) return true;
+        continue;
+      }
+      if (n == 0) return false;
+      if (errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) return false;
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    } while (std::chrono::steady_clock::now() < until);
+  }
   while (len) {
     pollfd pf{fd, POLLIN, 0};
     int rc = ::poll(&pf, 1, timeout_ms);
@@ -187,13 +211,13 @@ ErrorCode TcpServer::start(const std::string& host, uint16_t port, int worker_th
   epoll_fd_ = ::epoll_create1(EPOLL_CLOEXEC);
   wake_fd_ = ::eventfd(0, EFD_CLOEXEC | EFD_NONBLOCK);
   epoll_event ev{};
-  ev.events = EPOLLIN;
+  ev.events = EPOLLIN | EPOLLEXCLUSIVE;
   ev.data.fd = listen_fd_;
   ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, listen_fd_, &ev);
+  ev.events = EPOLLIN;
   ev.data.fd = wake_fd_;
   ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, wake_fd_, &ev);
   running_.store(true);
-  reactor_ = std::thread([this] { reactor_loop(); });
   for (int i = 0; i < std::max(1, worker_threads); ++i) workers_.emplace_back([this] { worker_loop(); });
   return ErrorCode::OK;
 }
@@ -203,8 +227,6 @@ void TcpServer::stop() {
   uint64_t one = 1;
   ssize_t ignored = ::write(wake_fd_, &one, sizeof one);
   (void)ignored;
-  cv_.notify_all();
-  if (reactor_.joinable()) reactor_.join();
   for (auto& w : workers_)
     if (w.joinable()) w.join();
   workers_.clear();
@@ -213,7 +235,6 @@ void TcpServer::stop() {
     std::lock_guard<std::mutex> lk(mu_);
     for (auto& [fd, c] : conns_) all.push_back(c);
     conns_.clear();
-    ready_.clear();
   }
   for (auto& c : all) {
     c->close();
@@ -230,49 +251,6 @@ size_t TcpServer::connection_count() const {
   return conns_.size();
 }
 
-void TcpServer::reactor_loop() {
-  epoll_event evs[64];
-  while (running_.load()) {
-    int n = ::epoll_wait(epoll_fd_, evs, 64, 500);
-    if (n < 0) {
-      if (errno == EINTR) continue;
-      break;
-    }
-    for (int i = 0; i < n; ++i) {
-      const int fd = evs[i].data.fd;
-      if (fd == wake_fd_) continue;
-      if (fd == listen_fd_) {
-        while (true) {
-          sockaddr_in peer{};
-          socklen_t len = sizeof peer;
-          int cfd = ::accept4(listen_fd_, reinterpret_cast<sockaddr*>(&peer), &len, SOCK_NONBLOCK | SOCK_CLOEXEC);
-          if (cfd < 0) break;
-          set_nodelay(cfd);
-          char ip[64] = {0};
-          ::inet_ntop(AF_INET, &peer.sin_addr, ip, sizeof ip);
-          ConnPtr c;
-          {
-            std::lock_guard<std::mutex> lk(mu_);
-            c = std::make_shared<Connection>(cfd, next_id_++, std::string(ip) + ":" + std::to_string(ntohs(peer.sin_port)));
-            conns_[cfd] = c;
-          }
-          on_open(c);
-          epoll_event ev{};
-          ev.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
-          ev.data.fd = cfd;
-          ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, cfd, &ev);
-        }
-        continue;
-      }
-      std::lock_guard<std::mutex> lk(mu_);
-      auto it = conns_.find(fd);
-      if (it == conns_.end()) continue;
-      ready_.push_back(it->second);
-      cv_.notify_one();
-    }
-  }
-}
-
 void TcpServer::drop(const ConnPtr& c) {
   {
     std::lock_guard<std::mutex> lk(mu_);
@@ -285,29 +263,98 @@ void TcpServer::drop(const ConnPtr& c) {
   on_close(c);
 }
 
-void TcpServer::worker_loop() {
-  char buf[65536];
+static int env_busy_poll_us() {
+  const char* e = std::getenv("BB_RPC_BUSY_POLL_US");
+  return e ? std::atoi(e) : 0;
+}
+
+void TcpServer::accept_all() {
   while (true) {
+    sockaddr_in peer{};
+    socklen_t len = sizeof peer;
+    int cfd = ::accept4(listen_fd_, reinterpret_cast<sockaddr*>(&peer), &len, SOCK_NONBLOCK | SOCK_CLOEXEC);
+    if (cfd < 0) break;
+    set_nodelay(cfd);
+    char ip[64] = {0};
+    ::inet_ntop(AF_INET, &peer.sin_addr, ip, sizeof ip);
     ConnPtr c;
     {
-      std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [this] { return !ready_.empty() || !running_.load(); });
-      if (!running_.load()) return;
-      c = ready_.front();
-      ready_.pop_front();
+      std::lock_guard<std::mutex> lk(mu_);
+      c = std::make_shared<Connection>(cfd, next_id_++, std::string(ip) + ":" + std::to_string(ntohs(peer.sin_port)));
+      conns_[cfd] = c;
+    }
+    on_open(c);
+    epoll_event ev{};
+    ev.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
+    ev.data.fd = cfd;
+    ::epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, cfd, &ev);
+  }
+}
+
+// Every pool thread waits on the shared epoll set itself (EPOLLONESHOT per connection, so one
+// thread owns a connection from readiness to re-arm): a request costs one thread wake-up, not a
+// reactor wake-up plus a hand-off.  With busy polling the thread keeps spinning on a zero-timeout
+// epoll_wait for `busy_poll_us` after its last event, which takes the scheduler out of the
+// latency of back-to-back control-plane calls.
+void TcpServer::worker_loop() {
+  char buf[65536];
+  using SteadyClock = std::chrono::steady_clock;
+  const int busy_us = busy_poll_us_ >= 0 ? busy_poll_us_ : env_busy_poll_us();
+  auto spin_until = SteadyClock::now();
+  bool i_spin = false;
+  while (running_.load()) {
+    epoll_event ev{};
+    // At most one thread polls at a time: several threads hammering epoll_wait(0) serialise on the
+    // epoll mutex and make every request slower.
+    bool spin = false;
+    if (busy_us > 0) {
+      if (SteadyClock::now() < spin_until) {
+        int expect = 0;
+        spin = i_spin || spinner_.compare_exchange_strong(expect, 1);
+        i_spin = spin;
+      }
+      if (!spin && i_spin) {
+        spinner_.store(0);
+        i_spin = false;
+      }
+    }
+    int n = ::epoll_wait(epoll_fd_, &ev, 1, spin ? 0 : 500);
+    if (n < 0) {
+      if (errno == EINTR) continue;
+      break;
+    }
+    if (n == 0) {
+      // yield, not pause: a runnable thread queued behind the poller on this CPU (the client, or a
+      // pool thread the kernel woke for the same event) must not wait out the poller's time slice
+      if (spin) ::sched_yield();
+      continue;
+    }
+    const int fd = ev.data.fd;
+    if (fd == wake_fd_) continue;  // never drained: wakes every thread; the loop condition ends them
+    if (fd == listen_fd_) {
+      accept_all();
+      continue;
+    }
+    ConnPtr c;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = conns_.find(fd);
+      if (it == conns_.end()) continue;
+      c = it->second;
     }
     bool alive = true;
     while (true) {
-      ssize_t n = ::recv(c->fd(), buf, sizeof buf, 0);
-      if (n > 0) {
-        c->inbuf().append(buf, static_cast<size_t>(n));
+      ssize_t r = ::recv(c->fd(), buf, sizeof buf, 0);
+      if (r > 0) {
+        c->inbuf().append(buf, static_cast<size_t>(r));
         if (c->inbuf().size() > kMaxFrame + kFrameHeader) {
           alive = false;
           break;
         }
+        if (static_cast<size_t>(r) < sizeof buf) break;  // drained (a later arrival re-triggers after the re-arm)
         continue;
       }
-      if (n == 0) {
+      if (r == 0) {
         alive = false;
         break;
       }
@@ -330,11 +377,13 @@ void TcpServer::worker_loop() {
       drop(c);
       continue;
     }
-    epoll_event ev{};
-    ev.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
-    ev.data.fd = c->fd();
-    if (::epoll_ctl(epoll_fd_, EPOLL_CTL_MOD, c->fd(), &ev) != 0) drop(c);
+    epoll_event rearm{};
+    rearm.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
+    rearm.data.fd = c->fd();
+    if (::epoll_ctl(epoll_fd_, EPOLL_CTL_MOD, c->fd(), &rearm) != 0) drop(c);
+    if (busy_us > 0) spin_until = SteadyClock::now() + std::chrono::microseconds(busy_us);
   }
+  if (i_spin) spinner_.store(0);
 }
 
 // ================================================================ framed RPC

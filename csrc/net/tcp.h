@@ -1,9 +1,9 @@
 // Network substrate: epoll reactor TCP server, framed RPC server/client, HTTP/1.1 mini server.
 //
 // Replaces yalantinglibs coro_rpc / coro_http (reference rpc_service.cpp:175-226, 360-413;
-// unavailable offline).  One reactor thread owns epoll (EPOLLONESHOT per connection) and hands
-// readable connections to a small worker pool, so slow handlers do not block accept/IO and
-// requests on one connection stay ordered.  Frames: [u32 len][u32 method][u64 id][payload].
+// unavailable offline).  A small thread pool shares one epoll set (EPOLLONESHOT per connection, so
+// one thread owns a connection from readiness to re-arm): slow handlers do not block accept/IO,
+// requests on one connection stay ordered, and a request costs a single thread wake-up.  Frames: [u32 len][u32 method][u64 id][payload].
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -65,6 +65,8 @@ class TcpServer {
   TcpServer& operator=(const TcpServer&) = delete;
 
   ErrorCode start(const std::string& host, uint16_t port, int worker_threads = 2);
+  // Threads keep polling (no sleep) for this long after their last event; set before start().
+  void set_busy_poll_us(int us) { busy_poll_us_ = us; }
   void stop();
   bool running() const { return running_.load(); }
   uint16_t port() const { return port_; }
@@ -78,7 +80,7 @@ class TcpServer {
   virtual void on_close(const ConnPtr&) {}
 
  private:
-  void reactor_loop();
+  void accept_all();
   void worker_loop();
   void drop(const ConnPtr& c);
 
@@ -87,11 +89,10 @@ class TcpServer {
   int wake_fd_ = -1;
   uint16_t port_ = 0;
   std::atomic<bool> running_{false};
-  std::thread reactor_;
   std::vector<std::thread> workers_;
   mutable std::mutex mu_;
-  std::condition_variable cv_;
-  std::deque<ConnPtr> ready_;
+  std::atomic<int> spinner_{0};
+  int busy_poll_us_ = -1;  // -1: BB_RPC_BUSY_POLL_US from the environment (default 0 = sleep in epoll_wait)
   std::unordered_map<int, ConnPtr> conns_;
   uint64_t next_id_ = 1;
 };

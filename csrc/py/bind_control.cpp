@@ -262,6 +262,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("max_replicas", &KeystoneConfig::max_replicas)
       .def_readwrite("default_replicas", &KeystoneConfig::default_replicas)
       .def_readwrite("rpc_threads", &KeystoneConfig::rpc_threads)
+      .def_readwrite("rpc_busy_poll_us", &KeystoneConfig::rpc_busy_poll_us)
       .def_readwrite("wal_path", &KeystoneConfig::wal_path)
       .def_readwrite("log_level", &KeystoneConfig::log_level)
       .def("validate", [](const KeystoneConfig& c) {
@@ -843,6 +844,7 @@ void bind_control(py::module_& m) {
       }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("capacity"), py::arg("stream") = 0)
       .def("cluster_stats", [](BlackbirdClient& c) { return unwrap(c.cluster_stats()); })
       .def("metrics_text", &BlackbirdClient::metrics_text)
+      .def("set_device_pipeline_chunks", &BlackbirdClient::set_device_pipeline_chunks)
       .def("phase_summary", &BlackbirdClient::phase_summary, "histogram name -> [count, sum_us, p50_us, p99_us]")
       .def("keystone", [](BlackbirdClient& c) -> rpc::KeystoneApi& { return c.keystone(); }, py::return_value_policy::reference_internal);
 }

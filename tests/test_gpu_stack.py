@@ -152,6 +152,7 @@ def test_large_batch_is_pipelined_in_chunks(bb, torch_cuda):
         keys = [f"c{i}" for i in range(n)]
         cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_GPU])
         s = _stream(torch)
+        cl.client.set_device_pipeline_chunks(4)  # default: adaptive, an in-process keystone is too fast to be worth a split
         l0 = cl.fabric.launches
         assert cl.client.batch_put_device(keys, [src.data_ptr() + i * size for i in range(n)], [size] * n, cfg, s) == [bb.ErrorCode.OK] * n
         assert cl.fabric.launches - l0 == 4  # 1 GiB in four 256 MiB chunks
