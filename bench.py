@@ -54,7 +54,7 @@ def main() -> int:
     ap.add_argument("--algo", default="bbh64", choices=["bbh64", "crc32c", "none"])
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-comparators", action="store_true")
-    ap.add_argument("--sync", choices=["none", "step", "phase"], default="phase", help="N>1: ranks rendezvous per step / per put-get phase (in the timed region)")
+    ap.add_argument("--sync", choices=["none", "step", "phase"], default="none", help="N>1: ranks rendezvous per step / per put-get phase (in the timed region)")
     ap.add_argument("--idle-odd", action="store_true", help="diagnostic: odd ranks idle (unidirectional NVLink traffic)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -152,12 +152,9 @@ def main() -> int:
     cl.barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = int(sum_over_ranks(cl.fabric.launches - launches0))
-    if sampler and ms < 1500:  # give nvidia-smi time to take samples under the same load
-        t_end = time.time() + 1.2
-        i = 0
-        while time.time() < t_end:
+    if ms < 1500:  # give nvidia-smi time to take samples under the same load (same count on every rank: steps rendezvous)
+        for i in range(int(1200.0 / max(ms / args.steps, 0.05)) + 1):
             step("c", i)
-            i += 1
     clocks = sampler.stop() if sampler else None
     phases = {k: round(v[1] / max(v[0], 1), 1) for k, v in cl.client.phase_summary().items() if k.startswith("phase_")}
     if world > 1:

@@ -169,10 +169,49 @@ def replicated_put_verify(cluster, replication: int = 3, nobj: int = 32, size: i
             "put_wire_GBps": total * replication / min(put_ms) / 1e6, "get_GBps": total / min(get_ms) / 1e6, "replica_workers": sorted(copies_seen)}
 
 
-def tier_spill(cluster_factory, tmp_dir: str, gpu: bool, nobj: int = 6, size: int = 64 << 20) -> dict:
-    """Config 4: fill the top tier beyond the watermark, let the Keystone demote LRU objects down the ladder
-    (GPU -> DRAM -> NVMe) through the workers' D_COPY path, verify bytes + digests, respect TTL and soft pins."""
-    raise NotImplementedError("driven by tests/test_cluster_e2e.py (host tiers) and tests/test_gpu_stack.py (GPU tier)")
+def tier_spill(cluster, nobj: int = 10, size: int = 6 << 20) -> dict:
+    """Config 4: fill the GPU tier beyond the watermark, let the Keystone demote LRU objects down the ladder
+    (GPU -> DRAM -> NVMe) through the workers' D_COPY path, read everything back through the device API and
+    compare bytes; a soft-pinned object must stay in HBM.  `cluster` is a single-rank GpuRankCluster created with
+    dram_bytes / nvme_bytes / high_watermark < 1 (tests/test_gpu_stack.py)."""
+    import torch
+
+    dev = torch.device("cuda", cluster.local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu = dict(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[_bb.StorageClass.RAM_GPU])
+    src = torch.empty((nobj + 1) * size, dtype=torch.uint8, device=dev)
+    _bb.random_fill(src.data_ptr(), src.numel(), 4242, stream)
+    keys = [f"spill/{i}" for i in range(nobj)]
+    ks = cluster.keystone
+    t0 = time.perf_counter()
+    assert _ok(cluster.client.batch_put_device(["spill/pinned"], [src.data_ptr() + nobj * size], [size],
+                                               _bb.WorkerConfig(enable_soft_pin=True, **gpu), stream))
+    demoted_rounds = 0
+    for i, k in enumerate(keys):  # one by one: every put may push the tier over the watermark
+        ecs = cluster.client.batch_put_device([k], [src.data_ptr() + i * size], [size], _bb.WorkerConfig(**gpu), stream)
+        assert _ok(ecs), [str(e) for e in ecs]
+        if ks.tier_utilization(_bb.StorageClass.RAM_GPU) > 0.5 or ks.tier_utilization(_bb.StorageClass.RAM_CPU) > 0.5:
+            demoted_rounds += 1 if ks.run_eviction_once() else 0
+    fill_s = time.perf_counter() - t0
+    tiers = {k: cluster.client.get_workers(k)[0].shards[0].storage_class for k in keys + ["spill/pinned"]}
+    out = torch.zeros_like(src)
+    all_keys = keys + ["spill/pinned"]
+    t0 = time.perf_counter()
+    ecs, sizes = cluster.client.batch_get_device(all_keys, [out.data_ptr() + i * size for i in range(nobj + 1)], [size] * (nobj + 1), stream)
+    torch.cuda.synchronize()
+    read_s = time.perf_counter() - t0
+    assert _ok(ecs), [str(e) for e in ecs]
+    verified = sum(int(torch.equal(src[i * size:(i + 1) * size], out[i * size:(i + 1) * size])) for i in range(nobj + 1))
+    text = ks.metrics_text()
+    return {
+        "objects": nobj + 1, "size": size, "verified": verified, "eviction_rounds": demoted_rounds,
+        "demoted_to_dram": sum(1 for t in tiers.values() if t == _bb.StorageClass.RAM_CPU),
+        "demoted_to_nvme": sum(1 for t in tiers.values() if t == _bb.StorageClass.NVME),
+        "still_in_hbm": sum(1 for t in tiers.values() if t == _bb.StorageClass.RAM_GPU),
+        "pinned_tier": str(tiers["spill/pinned"]).split(".")[-1],
+        "gpu_util_after": ks.tier_utilization(_bb.StorageClass.RAM_GPU),
+        "dropped": "bb_evictions_total" in text, "fill_s": fill_s, "read_back_s": read_s,
+    }
 
 
 def feature_store_fanout(cluster, nshards: int = 128, size: int = 1 << 20, iters: int = 5, replication: int = 1) -> dict:

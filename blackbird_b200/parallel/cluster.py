@@ -97,7 +97,11 @@ class GpuRankCluster:
     """One process per GPU.  Requires torch + CUDA; rendezvous through torch.distributed when world>1."""
 
     def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None,
-                 nvls_arena_bytes: int = 0, nvls_group_size: int = 3, rpc_busy_poll_us: int = 5000):
+                 nvls_arena_bytes: int = 0, nvls_group_size: int = 3, rpc_busy_poll_us: Optional[int] = None,
+                 dram_bytes: int = 0, nvme_bytes: int = 0, nvme_path: str = "", high_watermark: float = 1.0,
+                 eviction_ratio: float = 0.1):
+        """slab_bytes: HBM slab of this rank's GPU-tier pool.  dram_bytes / nvme_bytes add host tiers to the
+        same worker (the demotion ladder GPU -> DRAM -> NVMe); high_watermark < 1 arms tier demotion."""
         import torch
         import torch.distributed as dist
 
@@ -120,12 +124,17 @@ class GpuRankCluster:
             cfg.listen_address = f"127.0.0.1:{keystone_port or 0}"
             cfg.http_metrics_port = "0"
             cfg.enable_gc = False
-            cfg.high_watermark = 1.0
+            cfg.high_watermark = high_watermark
+            cfg.eviction_ratio = eviction_ratio
+            cfg.gc_interval_sec = 3600 if high_watermark >= 1.0 else 1
             cfg.rpc_threads = 4
+            if rpc_busy_poll_us is None:
+                rpc_busy_poll_us = int(os.environ.get("BB_RPC_BUSY_POLL_US", "2000"))
             cfg.rpc_busy_poll_us = rpc_busy_poll_us  # clients issue RPCs between kernels a few ms apart
             self.keystone = _bb.KeystoneService(cfg, None)
             assert self.keystone.initialize() == _bb.ErrorCode.OK
             assert self.keystone.start() == _bb.ErrorCode.OK
+            self.keystone.install_data_server_mover()  # demotion / repair copies run worker-to-worker (D_COPY)
             self.rpc = _bb.RpcService(self.keystone, cfg)
             assert self.rpc.start() == _bb.ErrorCode.OK
             port_t[0] = self.rpc.rpc_port
@@ -149,6 +158,10 @@ class GpuRankCluster:
         wc.lease_ttl_sec = 30
         wc.heartbeat_interval_sec = 5
         wc.storage_pools = [_bb.StoragePoolConfig(f"hbm{self.rank}", _bb.StorageClass.RAM_GPU, slab_bytes, "", self.local_rank)]
+        if dram_bytes:
+            wc.storage_pools += [_bb.StoragePoolConfig(f"dram{self.rank}", _bb.StorageClass.RAM_CPU, dram_bytes, "")]
+        if nvme_bytes:
+            wc.storage_pools += [_bb.StoragePoolConfig(f"nvme{self.rank}", _bb.StorageClass.NVME, nvme_bytes, nvme_path or "/tmp")]
         self.worker = _bb.WorkerService(wc, None, self.api)
         assert self.worker.create_storage_pools_from_config() == _bb.ErrorCode.OK
         assert self.worker.initialize() == _bb.ErrorCode.OK
@@ -159,7 +172,7 @@ class GpuRankCluster:
         self.client = _bb.BlackbirdClient(self.client_api, opts)
         assert self.client.connect() == _bb.ErrorCode.OK
         self.fabric = _bb.GpuFabric(self.local_rank, self.client_api)
-        assert self.fabric.mapped_pools() == self.world, f"mapped {self.fabric.mapped_pools()} of {self.world} slabs"
+        assert self.fabric.mapped_pools() >= self.world, f"mapped {self.fabric.mapped_pools()} of {self.world} slabs"
         _bb.attach_fabric(self.client, self.fabric)
         self.barrier()
         self.arena = None

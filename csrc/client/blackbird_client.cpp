@@ -384,7 +384,7 @@ std::vector<std::pair<size_t, size_t>> BlackbirdClient::plan_chunks(const std::v
   uint64_t total = 0;
   for (size_t s : sizes) total += s;
   constexpr uint64_t kMinChunk = 256ull << 20;  // below this a chunk's kernel is too short to hide an RPC
-  constexpr double kLaunchPenaltyUs = 40.0;     // measured: ramp + tail + launch gap of one more fused launch
+  constexpr double kLaunchPenaltyUs = 120.0;    // measured: ramp + tail + launch gap + result read-back of one more fused launch
   const size_t depth = device_ ? device_->max_in_flight() : 1;
   size_t want = 1;
   if (depth >= 2 && sizes.size() >= 2 && total >= 2 * kMinChunk) {

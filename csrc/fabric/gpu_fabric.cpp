@@ -168,6 +168,9 @@ ErrorCode GpuFabric::refresh_pools() {
         cudaGetLastError();
       }
     } else {
+      size_t grp = 0;
+      int member = 0;
+      if (NvlsArena::parse_pool_id(p.id, &grp, &member)) continue;  // VMM arena pools are mapped by NvlsArena, not by IPC
       auto raw = hex_to_bytes(p.ucx_rkey_hex);
       if (!raw || raw->size() != sizeof(cudaIpcMemHandle_t)) {
         BB_LOG(WARNING) << "pool " << p.id << " has no usable IPC handle";
@@ -187,6 +190,14 @@ ErrorCode GpuFabric::refresh_pools() {
 
 bool GpuFabric::can_reach(const ShardPlacement& s) const {
   if (s.storage_class != StorageClass::RAM_GPU) return false;
+  size_t grp = 0;
+  int member = 0;
+  if (arena_ && NvlsArena::parse_pool_id(s.pool_id, &grp, &member)) return arena_->peer_ptr(grp, member) != nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (pools_.count(s.pool_id)) return true;
+  }
+  const_cast<GpuFabric*>(this)->refresh_pools();  // a worker that joined after this fabric was created
   std::lock_guard<std::mutex> lk(mu_);
   return pools_.count(s.pool_id) > 0;
 }

@@ -734,21 +734,24 @@ size_t KeystoneService::run_eviction_once() {
           auto info = get_object_info(key);
           if (info.ok() && !info.value().copies.empty()) {
             WorkerConfig cfg = info.value().config;
-            cfg.preferred_classes = lower;
             cfg.replication_factor = info.value().copies.size();
             cfg.symmetric_replicas = false;
             std::string ledger;
             Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
-            for (int slot = 0; slot < 64 && !fresh.ok(); ++slot) {
-              ledger = key + "\x01" + std::to_string(slot);
-              std::shared_lock<std::shared_mutex> pk(pools_mu_);
-              // only pools of the lower tiers are eligible
-              alloc::IAllocator::PoolMap eligible;
-              for (const auto& [pid, p] : pools_)
-                if (std::find(lower.begin(), lower.end(), p.storage_class) != lower.end()) eligible.emplace(pid, p);
-              if (eligible.empty()) break;
-              fresh = allocator_->allocate_data_copies(ledger, info.value().size, cfg, eligible);
-              if (!fresh.ok() && fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+            // one rung at a time: the next tier down that has room (GPU -> DRAM before GPU -> NVMe)
+            for (StorageClass target : lower) {
+              cfg.preferred_classes = {target};
+              for (int slot = 0; slot < 64 && !fresh.ok(); ++slot) {
+                ledger = key + "\x01" + std::to_string(slot);
+                std::shared_lock<std::shared_mutex> pk(pools_mu_);
+                alloc::IAllocator::PoolMap eligible;
+                for (const auto& [pid, p] : pools_)
+                  if (p.storage_class == target) eligible.emplace(pid, p);
+                if (eligible.empty()) break;
+                fresh = allocator_->allocate_data_copies(ledger, info.value().size, cfg, eligible);
+                if (!fresh.ok() && fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+              }
+              if (fresh.ok()) break;
             }
             if (fresh.ok()) {
               bool ok = true;

@@ -163,3 +163,21 @@ def test_large_batch_is_pipelined_in_chunks(bb, torch_cuda):
         assert cl.client.get_workers(keys[5])[0].shards[0].checksum == bb.bbh64(src[5 * size:6 * size].cpu().numpy())
     finally:
         cl.stop()
+
+
+def test_gpu_tier_spill_gpu_to_dram_to_nvme(bb, torch_cuda, tmp_path):
+    """BASELINE config #4 on the GPU tier: HBM over the watermark -> LRU objects demoted to DRAM, DRAM over the
+    watermark -> demoted to NVMe; soft-pinned objects stay in HBM; the device API reads demoted objects back
+    bit-exact (host-staged path), and the digests recorded at put time survive both moves."""
+    torch = torch_cuda
+    from blackbird_b200.models.workloads import tier_spill
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=64 << 20, cluster_id="t-spill", dram_bytes=64 << 20, nvme_bytes=256 << 20,
+                        nvme_path=str(tmp_path), high_watermark=0.5, eviction_ratio=0.5)
+    try:
+        r = tier_spill(cl, nobj=10, size=6 << 20)
+        assert r["demoted_to_dram"] >= 3 and r["demoted_to_nvme"] >= 1, r
+        assert r["pinned_tier"] == "RAM_GPU" and r["verified"] == 11 and r["gpu_util_after"] <= 0.55, r
+    finally:
+        cl.stop()
