@@ -54,7 +54,7 @@ def main() -> int:
     ap.add_argument("--algo", default="bbh64", choices=["bbh64", "crc32c", "none"])
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-comparators", action="store_true")
-    ap.add_argument("--sync", choices=["none", "step", "phase"], default="none", help="N>1: ranks rendezvous per step / per put-get phase (in the timed region)")
+    ap.add_argument("--sync", choices=["none", "step", "phase"], default="phase", help="N>1: ranks rendezvous per step / per put-get phase (in the timed region)")
     ap.add_argument("--idle-odd", action="store_true", help="diagnostic: odd ranks idle (unidirectional NVLink traffic)")
     args = ap.parse_args()
     if args.impl == "reference":

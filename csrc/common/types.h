@@ -17,6 +17,7 @@
 #include <variant>
 #include <vector>
 
+#include "common/cxl_config.h"
 #include "common/checksum.h"
 #include "common/error.h"
 #include "common/json.h"
@@ -170,6 +171,7 @@ struct KeystoneConfig {
   int64_t gc_interval_sec = 30;
   int64_t health_check_interval_sec = 10;
   int32_t max_replicas = 3;
+  std::vector<TierRule> tier_policy;  // size-based class preference for puts that name no preferred class
   int32_t default_replicas = 1;
   // extensions
   int32_t rpc_threads = 2;

@@ -151,7 +151,8 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (nd) {
       const size_t tab = static_cast<size_t>(nd) * sizeof(XferDesc) + (static_cast<size_t>(nd) + 1) * 4;
-      BB_CUDA(cudaMemcpyAsync(s->d_tab, s->h_tab, tab, cudaMemcpyHostToDevice, st));
+      const bool inline_tab = nd <= kInlineDescs;
+      if (!inline_tab) BB_CUDA(cudaMemcpyAsync(s->d_tab, s->h_tab, tab, cudaMemcpyHostToDevice, st));
       if (capture_debug) {
         const size_t need = static_cast<size_t>(tiles) * tchash::kRows * tchash::kN * 4;
         if (need > s->d_debug_bytes) {
@@ -167,8 +168,15 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       l.total_tiles = tiles;
       l.sum_ws = s->d_sum;
       l.done_ws = s->d_done;
-      l.digest_out = s->d_digest;
-      l.status_out = s->d_status;
+      // Small batches: the finalizer warp writes digests / status straight into the pinned result
+      // block (UVA), so the launch is the only operation on the stream.
+      const bool direct = nd <= kDirectResults;
+      l.digest_out = direct ? reinterpret_cast<uint64_t*>(s->h_res) : s->d_digest;
+      l.status_out = direct ? reinterpret_cast<uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8) : s->d_status;
+      if (inline_tab) {
+        l.host_descs = descs;
+        l.host_tile_start = tile_start;
+      }
       l.debug_d = capture_debug ? s->d_debug : nullptr;
       l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : algo == ChecksumAlgo::CRC32C ? ALGO_CRC32C : ALGO_NONE;
       l.max_ctas = max_ctas_;
@@ -182,7 +190,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       }
       ++launches_;
       BB_CUDA(cudaEventRecord(s->ev_stop, st));
-      if (algo != ChecksumAlgo::NONE) {
+      if (algo != ChecksumAlgo::NONE && !direct) {
         BB_CUDA(cudaMemcpyAsync(s->h_res, s->d_digest, static_cast<size_t>(nd) * 8, cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaMemcpyAsync(s->h_res + static_cast<size_t>(max_items_) * 8, s->d_status, static_cast<size_t>(nd) * 4,
                                 cudaMemcpyDeviceToHost, st));

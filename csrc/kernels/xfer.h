@@ -31,6 +31,9 @@ struct XferDesc {
 };
 static_assert(sizeof(XferDesc) == 64, "XferDesc must be 64 bytes");
 
+constexpr uint32_t kInlineDescs = 8;       // descriptors that fit in the kernel parameter block
+constexpr uint32_t kDirectResults = 64;    // batches up to this size write digests straight to pinned host memory
+
 enum XferAlgo : int { ALGO_NONE = 0, ALGO_CRC32C = 1, ALGO_BBH64 = 2 };
 
 struct XferLaunch {
@@ -44,6 +47,10 @@ struct XferLaunch {
   uint32_t* status_out = nullptr;        // device, ndesc entries (0 ok / 1 checksum mismatch)
   const uint32_t* crc_tables = nullptr;  // device, CRC32C shift tables (only ALGO_CRC32C)
   uint32_t* debug_d = nullptr;           // optional: raw accumulators [tile][128][16] (tests)
+  // Optional host copies of the two tables: batches of <= kInlineDescs descriptors travel in the
+  // kernel parameters instead (descs / tile_start may then be null).
+  const XferDesc* host_descs = nullptr;
+  const uint32_t* host_tile_start = nullptr;
   int algo = ALGO_BBH64;
   int max_ctas = 0;                      // 0 = one CTA per SM
   void* stream = nullptr;                // cudaStream_t

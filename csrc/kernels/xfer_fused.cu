@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -103,6 +104,11 @@ struct Params {
   uint32_t* status_out;
   const uint32_t* crc_tables;  // [kNumCrcTabs][4][256]
   uint32_t* debug_d;
+  // Small batches carry their descriptor table in the kernel parameters (constant bank): no H2D
+  // copy ahead of the launch, which is most of a single-object put/get's latency.
+  uint32_t use_inline;
+  uint32_t inl_tile_start[kInlineDescs + 1];
+  XferDesc inl_descs[kInlineDescs];
 };
 
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
@@ -192,13 +198,27 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
       if (idx < my_tiles) {
         const uint32_t t = t0 + idx;
         uint32_t lo = 0, hi = p.ndesc;  // tile_start[lo] <= t < tile_start[hi]
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (__ldg(&p.tile_start[mid]) <= t) lo = mid; else hi = mid;
+        uint32_t first, next;
+        uint4 q0, q1, q2, q3;
+        if (p.use_inline) {  // table in the parameter space (plain loads: ld.global.nc is illegal there)
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.inl_tile_start[mid] <= t) lo = mid; else hi = mid;
+          }
+          first = p.inl_tile_start[lo];
+          next = p.inl_tile_start[lo + 1];
+          const uint4* q = reinterpret_cast<const uint4*>(&p.inl_descs[lo]);
+          q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+        } else {
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&p.tile_start[mid]) <= t) lo = mid; else hi = mid;
+          }
+          first = __ldg(&p.tile_start[lo]);
+          next = __ldg(&p.tile_start[lo + 1]);
+          const uint4* q = reinterpret_cast<const uint4*>(&p.descs[lo]);
+          q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
         }
-        const uint32_t first = __ldg(&p.tile_start[lo]);
-        const uint4* q = reinterpret_cast<const uint4*>(&p.descs[lo]);
-        const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
         LookupEntry& e = s.lk[lane];
         e.src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
         e.m.dst[0] = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
@@ -209,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
         e.m.desc = lo;
         e.m.tile_in_obj = t - first;
         e.m.ndst_flags = (q2.w & 0xFFu) | (q3.z << 8);
-        e.m.obj_ntiles = __ldg(&p.tile_start[lo + 1]) - first;
+        e.m.obj_ntiles = next - first;
         e.m.crc_unpad = q3.w;
       }
       __syncwarp();
@@ -569,6 +589,12 @@ int launch_xfer(const XferLaunch& l) {
   Params p;
   p.descs = l.descs;
   p.tile_start = l.tile_start;
+  p.use_inline = 0;
+  if (l.host_descs && l.ndesc <= kInlineDescs) {
+    p.use_inline = 1;
+    std::memcpy(p.inl_descs, l.host_descs, l.ndesc * sizeof(XferDesc));
+    std::memcpy(p.inl_tile_start, l.host_tile_start, (l.ndesc + 1) * sizeof(uint32_t));
+  }
   p.ndesc = l.ndesc;
   p.total_tiles = l.total_tiles;
   p.sum_ws = reinterpret_cast<unsigned long long*>(l.sum_ws);

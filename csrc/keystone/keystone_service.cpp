@@ -437,7 +437,12 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start(const ObjectKey& k
     erase_locked(sh, key, true);  // expired but not yet swept: reclaim inline
     metrics_.inc("expired_total");
   }
-  auto copies = allocator_->allocate_data_copies(key, data_size, config, pools_, client_node);
+  WorkerConfig effective = config;
+  if (effective.preferred_classes.empty() && !config_.tier_policy.empty()) {
+    for (const auto& name : tier_classes_for_size(config_.tier_policy, data_size))
+      if (auto sc = parse_storage_class(name)) effective.preferred_classes.push_back(*sc);
+  }
+  auto copies = allocator_->allocate_data_copies(key, data_size, effective, pools_, client_node);
   if (!copies.ok()) {
     metrics_.inc("put_start_failed_total");
     return copies.error();

@@ -263,6 +263,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("default_replicas", &KeystoneConfig::default_replicas)
       .def_readwrite("rpc_threads", &KeystoneConfig::rpc_threads)
       .def_readwrite("rpc_busy_poll_us", &KeystoneConfig::rpc_busy_poll_us)
+      .def_readwrite("tier_policy", &KeystoneConfig::tier_policy)
       .def_readwrite("wal_path", &KeystoneConfig::wal_path)
       .def_readwrite("log_level", &KeystoneConfig::log_level)
       .def("validate", [](const KeystoneConfig& c) {
@@ -704,6 +705,60 @@ void bind_control(py::module_& m) {
      py::arg("pool_id") = "");
   m.def("io_uring_supported", &worker::IoUring::supported);
 
+  // CXL transport / pool configuration (reference include/blackbird/transport/cxl_transport_config.h)
+  py::enum_<CxlInterconnectType>(m, "CxlInterconnectType")
+      .value("CXL_MEM", CxlInterconnectType::CXL_MEM)
+      .value("CXL_CACHE", CxlInterconnectType::CXL_CACHE)
+      .value("CXL_IO", CxlInterconnectType::CXL_IO)
+      .value("CXL_FABRIC", CxlInterconnectType::CXL_FABRIC)
+      .value("HYBRID", CxlInterconnectType::HYBRID);
+  py::enum_<CxlTransportProtocol>(m, "CxlTransportProtocol")
+      .value("DIRECT_CXL", CxlTransportProtocol::DIRECT_CXL)
+      .value("RDMA_OVER_CXL", CxlTransportProtocol::RDMA_OVER_CXL)
+      .value("NVLINK", CxlTransportProtocol::NVLINK)
+      .value("CUSTOM", CxlTransportProtocol::CUSTOM);
+  m.def("cxl_interconnect_name", [](CxlInterconnectType t) { return std::string(to_string(t)); });
+  m.def("cxl_protocol_name", [](CxlTransportProtocol t) { return std::string(to_string(t)); });
+  py::class_<CxlTransportConfig>(m, "CxlTransportConfig")
+      .def(py::init<>())
+      .def_readwrite("interconnect_type", &CxlTransportConfig::interconnect_type)
+      .def_readwrite("transport_protocol", &CxlTransportConfig::transport_protocol)
+      .def_readwrite("enable_fabric_manager", &CxlTransportConfig::enable_fabric_manager)
+      .def_readwrite("fabric_manager_endpoint", &CxlTransportConfig::fabric_manager_endpoint)
+      .def_readwrite("max_transfer_size", &CxlTransportConfig::max_transfer_size)
+      .def_readwrite("queue_depth", &CxlTransportConfig::queue_depth)
+      .def_readwrite("enable_zero_copy", &CxlTransportConfig::enable_zero_copy)
+      .def_readwrite("enable_multipath", &CxlTransportConfig::enable_multipath)
+      .def_readwrite("fallback_transports", &CxlTransportConfig::fallback_transports)
+      .def_readwrite("priority", &CxlTransportConfig::priority)
+      .def_readwrite("bandwidth_limit_gbps", &CxlTransportConfig::bandwidth_limit_gbps)
+      .def_readwrite("enable_cxl_hdm", &CxlTransportConfig::enable_cxl_hdm)
+      .def_readwrite("enable_cxl_switch", &CxlTransportConfig::enable_cxl_switch)
+      .def_readwrite("cxl_port_id", &CxlTransportConfig::cxl_port_id)
+      .def("resolve_interconnects", &CxlTransportConfig::resolve_interconnects, py::arg("cxl_present"), py::arg("have_gpu"))
+      .def("to_dict", [](const CxlTransportConfig& c) { return bb_json_to_py(c.to_json()); });
+  py::class_<CxlMemoryPoolConfig>(m, "CxlMemoryPoolConfig")
+      .def(py::init<>())
+      .def_readwrite("device_id", &CxlMemoryPoolConfig::device_id)
+      .def_readwrite("device_path", &CxlMemoryPoolConfig::device_path)
+      .def_readwrite("dax_device", &CxlMemoryPoolConfig::dax_device)
+      .def_readwrite("capacity", &CxlMemoryPoolConfig::capacity)
+      .def_readwrite("latency_ns", &CxlMemoryPoolConfig::latency_ns)
+      .def_readwrite("bandwidth_gbps", &CxlMemoryPoolConfig::bandwidth_gbps)
+      .def_readwrite("is_persistent", &CxlMemoryPoolConfig::is_persistent)
+      .def_readwrite("enable_numa_binding", &CxlMemoryPoolConfig::enable_numa_binding)
+      .def_readwrite("numa_node", &CxlMemoryPoolConfig::numa_node)
+      .def_readwrite("interleave_ways", &CxlMemoryPoolConfig::interleave_ways)
+      .def_readwrite("interleave_granularity", &CxlMemoryPoolConfig::interleave_granularity)
+      .def_readwrite("cache_line_size", &CxlMemoryPoolConfig::cache_line_size)
+      .def("to_dict", [](const CxlMemoryPoolConfig& c) { return bb_json_to_py(c.to_json()); });
+  py::class_<TierRule>(m, "TierRule")
+      .def(py::init([](std::string sc, uint64_t lo, uint64_t hi) { return TierRule{std::move(sc), lo, hi}; }), py::arg("storage_class"),
+           py::arg("min_size") = 0, py::arg("max_size") = UINT64_MAX)
+      .def_readwrite("storage_class", &TierRule::storage_class)
+      .def_readwrite("min_size", &TierRule::min_size)
+      .def_readwrite("max_size", &TierRule::max_size);
+  m.def("tier_classes_for_size", &tier_classes_for_size);
   py::class_<worker::StoragePoolConfig>(m, "StoragePoolConfig")
       .def(py::init([](std::string pool_id, StorageClass sc, uint64_t size, std::string mount_path, int gpu_device_id) {
              worker::StoragePoolConfig c;
@@ -719,7 +774,9 @@ void bind_control(py::module_& m) {
       .def_readwrite("storage_class", &worker::StoragePoolConfig::storage_class)
       .def_readwrite("size_bytes", &worker::StoragePoolConfig::size_bytes)
       .def_readwrite("mount_path", &worker::StoragePoolConfig::mount_path)
-      .def_readwrite("gpu_device_id", &worker::StoragePoolConfig::gpu_device_id);
+      .def_readwrite("gpu_device_id", &worker::StoragePoolConfig::gpu_device_id)
+      .def_readwrite("numa_node", &worker::StoragePoolConfig::numa_node)
+      .def_readwrite("cxl", &worker::StoragePoolConfig::cxl);
   py::class_<worker::WorkerServiceConfig>(m, "WorkerServiceConfig")
       .def(py::init<>())
       .def_static("from_yaml", &worker::load_worker_config_from_file)
@@ -736,6 +793,9 @@ void bind_control(py::module_& m) {
       .def_readwrite("lease_ttl_sec", &worker::WorkerServiceConfig::lease_ttl_sec)
       .def_readwrite("heartbeat_interval_sec", &worker::WorkerServiceConfig::heartbeat_interval_sec)
       .def_readwrite("fabric_domain", &worker::WorkerServiceConfig::fabric_domain)
+      .def_readwrite("transport", &worker::WorkerServiceConfig::transport)
+      .def_readwrite("has_transport", &worker::WorkerServiceConfig::has_transport)
+      .def_readwrite("preferred_tiers", &worker::WorkerServiceConfig::preferred_tiers)
       .def_readwrite("storage_pools", &worker::WorkerServiceConfig::storage_pools);
   py::class_<worker::WorkerService, std::shared_ptr<worker::WorkerService>>(m, "WorkerService")
       .def(py::init<const worker::WorkerServiceConfig&, std::shared_ptr<CoordService>, std::shared_ptr<rpc::KeystoneApi>>(), py::arg("config"),

@@ -598,6 +598,10 @@ ErrorCode CxlMemoryBackend::write(uint64_t offset, const void* data, uint64_t le
   bytes_written_ += len;
   return ErrorCode::OK;
 }
+ErrorCode CxlMemoryBackend::flush() {
+  if (!opts_.persistent || !base_ || !dax_) return ErrorCode::OK;
+  return ::msync(base_, map_len_, MS_SYNC) == 0 ? ErrorCode::OK : ErrorCode::IO_ERROR;
+}
 ErrorCode CxlMemoryBackend::read(uint64_t offset, void* data, uint64_t len) {
   BB_TRY(check_range(offset, len));
   std::memcpy(data, base_ + offset, len);

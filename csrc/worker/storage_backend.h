@@ -62,6 +62,7 @@ struct BackendOptions {
   bool pin_memory = false;         // DRAM tier: cudaHostRegister when CUDA is present
   uint64_t reservation_ttl_ms = 10 * 60 * 1000;
   uint64_t interleave_granularity = 256;  // CXL region id granularity
+  bool persistent = false;                // CXL persistent mode: msync on commit/flush
 };
 
 class StorageBackend {
@@ -257,6 +258,7 @@ class CxlMemoryBackend : public StorageBackend {
   ErrorCode write(uint64_t offset, const void* data, uint64_t len) override;
   ErrorCode read(uint64_t offset, void* data, uint64_t len) override;
   void* direct_ptr(uint64_t offset) override { return base_ ? base_ + offset : nullptr; }
+  ErrorCode flush() override;  // persistent mode: msync the DAX mapping (no-op for volatile CXL memory)
   bool is_dax() const { return dax_; }
   bool numa_bound() const { return numa_bound_; }
   uint64_t region_id(uint64_t offset) const { return offset / (opts_.interleave_granularity ? opts_.interleave_granularity : 256); }

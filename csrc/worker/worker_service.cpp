@@ -42,6 +42,13 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   c.lease_ttl_sec = w.at("lease_ttl_sec").as_int(c.lease_ttl_sec);
   c.heartbeat_interval_sec = w.at("heartbeat_interval_sec").as_int(c.heartbeat_interval_sec);
   if (w.contains("fabric_domain")) c.fabric_domain = w.at("fabric_domain").as_string();
+  if (w.contains("listen_address") && !w.contains("data_endpoint") && !w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("listen_address").as_string();
+  if (w.at("transport").is_object()) {
+    c.transport = CxlTransportConfig::from_json(w.at("transport"));
+    c.has_transport = true;
+  }
+  if (w.at("allocation").is_object()) c.preferred_tiers = tier_rules_from_json(w.at("allocation").at("preferred_tiers"));
+  if (c.worker_id.empty() && !c.node_id.empty()) c.worker_id = c.node_id;  // cxl_worker.yaml names only the node
   if (c.worker_id.empty()) return fail(ErrorCode::MISSING_REQUIRED_FIELD, "worker.worker_id is required");
   if (c.node_id.empty()) c.node_id = c.worker_id;
   if (c.lease_ttl_sec <= 0 || c.heartbeat_interval_sec <= 0) return fail(ErrorCode::VALUE_OUT_OF_RANGE, "worker lease/heartbeat must be positive");
@@ -61,8 +68,10 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
     pc.mount_path = p.contains("mount_path") ? p.at("mount_path").as_string() : p.at("path").as_string();
     const Json& cfg = p.at("config");  // cxl_worker.yaml style nested block
     if (cfg.is_object()) {
-      if (cfg.contains("dax_device")) pc.mount_path = cfg.at("dax_device").as_string();
-      pc.numa_node = static_cast<int>(cfg.at("numa_node").as_int(-1));
+      pc.cxl = CxlMemoryPoolConfig::from_json(cfg);
+      pc.cxl.capacity = pc.size_bytes;
+      if (!pc.cxl.dax_device.empty()) pc.mount_path = pc.cxl.dax_device;
+      if (pc.cxl.enable_numa_binding || !cfg.contains("enable_numa_binding")) pc.numa_node = pc.cxl.numa_node;
     }
     pc.gpu_device_id = static_cast<int>(p.at("gpu_device_id").as_int(0));
     if (p.contains("numa_node")) pc.numa_node = static_cast<int>(p.at("numa_node").as_int(-1));
@@ -106,6 +115,8 @@ ErrorCode WorkerService::create_storage_pools_from_config() {
     o.gpu_device_id = pc.gpu_device_id;
     o.numa_node = pc.numa_node >= 0 ? pc.numa_node : config_.numa_node;
     o.queue_depth = pc.queue_depth;
+    o.interleave_granularity = pc.cxl.interleave_granularity ? pc.cxl.interleave_granularity : 256;
+    o.persistent = pc.cxl.is_persistent;
     auto b = create_storage_backend(pc.storage_class, pc.size_bytes, o);
     if (!b) {
       BB_LOG(ERROR) << "worker " << config_.worker_id << ": no backend for pool " << pc.pool_id << " (" << to_string(pc.storage_class) << ")";
@@ -197,6 +208,18 @@ ErrorCode WorkerService::register_all() {
   rec.rpc_endpoint = config_.rpc_endpoint;
   rec.ucx_endpoint = data_endpoint();
   rec.interconnects = config_.interconnects;
+  if (config_.has_transport) {
+    bool cxl_present = false, have_gpu = false;
+    {
+      std::lock_guard<std::mutex> lk(pools_mu_);
+      for (const auto& [id, b] : pools_) {
+        const StorageClass sc = b->get_storage_class();
+        have_gpu |= sc == StorageClass::RAM_GPU;
+        if (auto* cx = dynamic_cast<CxlMemoryBackend*>(b.get())) cxl_present |= cx->is_dax();
+      }
+    }
+    rec.interconnects = config_.transport.resolve_interconnects(cxl_present, have_gpu);
+  }
   rec.max_bw_gbps = config_.max_bw_gbps;
   rec.numa_node = config_.numa_node;
   rec.version = config_.version;

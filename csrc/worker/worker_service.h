@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+#include "common/cxl_config.h"
 #include "coord/coord.h"
 #include "net/tcp.h"
 #include "rpc/rpc_service.h"
@@ -35,6 +36,7 @@ struct StoragePoolConfig {
   int gpu_device_id = 0;
   int numa_node = -1;
   uint32_t queue_depth = 64;
+  CxlMemoryPoolConfig cxl;  // CXL tiers: per-pool `config:` block
 };
 
 struct WorkerServiceConfig {
@@ -52,6 +54,9 @@ struct WorkerServiceConfig {
   int64_t lease_ttl_sec = 10;
   int64_t heartbeat_interval_sec = 5;
   std::string fabric_domain;        // e.g. "nvswitch-0"
+  CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects
+  bool has_transport = false;
+  std::vector<TierRule> preferred_tiers;  // `allocation.preferred_tiers` (forwarded to the keystone as a hint)
   std::vector<StoragePoolConfig> storage_pools;
 };
 

@@ -309,3 +309,23 @@ def test_ha_leader_failover_recovers_objects_from_wal(bb):
     assert fresh[0].shards[0].offset != placed[0].shards[0].offset
     assert store.get("/blackbird/elections/keystone-ha/leader") == b"ks-b"
     a.stop(), b.stop()
+
+
+def test_size_based_tier_policy_for_puts_without_a_preferred_class(bb):
+    """keystone.tier_policy (reference cxl_worker.yaml `allocation.preferred_tiers`, consumed by nothing there)."""
+    from blackbird_b200.parallel import LocalCluster
+
+    kc = bb.KeystoneConfig()
+    kc.tier_policy = [bb.TierRule("RAM_CPU", 0, 64 << 10), bb.TierRule("CXL_MEMORY", (64 << 10) + 1)]
+    with LocalCluster("tierpol", n_workers=0, keystone_cfg=kc) as c:
+        c.add_worker("w0", "n0", [("dram", bb.StorageClass.RAM_CPU, 8 << 20, ""), ("cxl", bb.StorageClass.CXL_MEMORY, 8 << 20, "")])
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+        assert cl.put("small", b"x" * 1000, cfg) == bb.ErrorCode.OK
+        assert cl.put("big", b"y" * (1 << 20), cfg) == bb.ErrorCode.OK
+        assert cl.get_workers("small")[0].shards[0].storage_class == bb.StorageClass.RAM_CPU
+        assert cl.get_workers("big")[0].shards[0].storage_class == bb.StorageClass.CXL_MEMORY
+        # an explicit preference wins over the policy
+        assert cl.put("big2", b"z" * (1 << 20), bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU])) == bb.ErrorCode.OK
+        assert cl.get_workers("big2")[0].shards[0].storage_class == bb.StorageClass.RAM_CPU
+        assert cl.get("big") == b"y" * (1 << 20)

@@ -163,3 +163,30 @@ def test_cxl_backend_placeholder_cacheline_and_regions(bb, tmp_path):
 def test_unwritable_directory_fails_cleanly(bb):
     b = bb.create_storage_backend(bb.StorageClass.NVME, MiB, "/proc/definitely/not/writable")
     assert b.initialize() == bb.ErrorCode.IO_ERROR
+
+
+def test_cxl_worker_yaml_is_fully_parsed_and_consumed(bb):
+    """configs/cxl_worker.yaml (reference schema): per-pool `config:`, `transport:` and `allocation.preferred_tiers`
+    are parsed (the reference parses none of them) and drive the backend options / advertised interconnects."""
+    import os
+
+    cfg = bb.WorkerServiceConfig.from_yaml(os.path.join(os.path.dirname(__file__), "..", "configs", "cxl_worker.yaml"))
+    assert cfg.worker_id == "worker_cxl_node_1" and len(cfg.storage_pools) == 4
+    cxl = next(p for p in cfg.storage_pools if p.pool_id == "cxl_memory_pool")
+    assert cxl.storage_class == bb.StorageClass.CXL_MEMORY and cxl.size_bytes == 512 * 10**6 or cxl.size_bytes == 512 << 20
+    assert cxl.mount_path == "/dev/dax0.0" and cxl.numa_node == 1 and cxl.cxl.interleave_granularity == 256
+    acc = next(p for p in cfg.storage_pools if p.pool_id == "cxl_accelerator_pool")
+    assert acc.storage_class == bb.StorageClass.CXL_TYPE2_DEVICE and acc.cxl.interleave_granularity == 4096 and acc.cxl.device_id == "cxl_type2_0"
+    t = cfg.transport
+    assert cfg.has_transport and t.interconnect_type == bb.CxlInterconnectType.CXL_FABRIC
+    assert t.transport_protocol == bb.CxlTransportProtocol.RDMA_OVER_CXL and t.enable_multipath and t.queue_depth == 128
+    assert t.fallback_transports == ["ucx", "nvlink", "roce"] and t.cxl_port_id == "cxl_port_0" and t.max_transfer_size >= 4 * 10**9
+    assert bb.cxl_protocol_name(t.transport_protocol) == "RDMA over CXL" and bb.cxl_interconnect_name(t.interconnect_type) == "CXL.fabric"
+    # no CXL device and no GPU on this box: only tcp survives; with both, the primary protocol then nvlink
+    assert t.resolve_interconnects(False, False) == ["tcp"]
+    assert t.resolve_interconnects(True, True) == ["rdma_over_cxl", "nvlink", "tcp"]
+    rules = cfg.preferred_tiers
+    assert [r.storage_class for r in rules] == ["RAM_CPU", "CXL_MEMORY", "CXL_TYPE2_DEVICE", "NVME"]
+    assert bb.tier_classes_for_size(rules, 4096) == ["RAM_CPU"]
+    assert bb.tier_classes_for_size(rules, 200 * 10**6) == ["CXL_MEMORY", "CXL_TYPE2_DEVICE"]
+    assert bb.tier_classes_for_size(rules, 50 * 10**9) == ["NVME"]
