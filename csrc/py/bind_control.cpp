@@ -678,6 +678,7 @@ void bind_control(py::module_& m) {
       .def("has_direct_ptr", [](StorageBackend& b) { return b.direct_ptr(0) != nullptr; });
   py::class_<worker::IoUringDiskBackend, StorageBackend>(m, "IoUringDiskBackend")
       .def_property_readonly("sqes_submitted", &worker::IoUringDiskBackend::sqes_submitted)
+      .def_property_readonly("fixed_sqes", &worker::IoUringDiskBackend::fixed_sqes)
       .def_property_readonly("using_uring", &worker::IoUringDiskBackend::using_uring)
       .def_property_readonly("using_direct_io", &worker::IoUringDiskBackend::using_direct_io)
       .def_property_readonly("file_path", &worker::IoUringDiskBackend::file_path)

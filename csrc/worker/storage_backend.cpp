@@ -3,6 +3,7 @@
 #include <fcntl.h>
 #include <linux/io_uring.h>
 #include <sys/mman.h>
+#include <sys/uio.h>
 #include <sys/stat.h>
 #include <sys/syscall.h>
 #include <sys/types.h>
@@ -314,6 +315,21 @@ void IoUring::close() {
   if (ring_fd_ >= 0) ::close(ring_fd_);
   sqes_ = cq_ptr_ = sq_ptr_ = nullptr;
   ring_fd_ = -1;
+  fixed_base_ = nullptr;
+  fixed_len_ = 0;
+}
+
+ErrorCode IoUring::register_buffer(void* base, size_t len) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (ring_fd_ < 0) return ErrorCode::INVALID_STATE;
+  struct iovec iov;
+  iov.iov_base = base;
+  iov.iov_len = len;
+  long rc = ::syscall(__NR_io_uring_register, ring_fd_, IORING_REGISTER_BUFFERS, &iov, 1);
+  if (rc < 0) return ErrorCode::NOT_IMPLEMENTED;  // e.g. RLIMIT_MEMLOCK: plain READ/WRITE still work
+  fixed_base_ = static_cast<uint8_t*>(base);
+  fixed_len_ = len;
+  return ErrorCode::OK;
 }
 
 ErrorCode IoUring::submit_and_wait(std::vector<Op>& ops) {
@@ -329,7 +345,15 @@ ErrorCode IoUring::submit_and_wait(std::vector<Op>& ops) {
       io_uring_sqe& e = sqes[idx];
       std::memset(&e, 0, sizeof e);
       Op& op = ops[done + i];
-      e.opcode = op.write ? IORING_OP_WRITE : IORING_OP_READ;
+      auto* b8 = static_cast<uint8_t*>(op.buf);
+      const bool fixed = fixed_base_ && b8 >= fixed_base_ && b8 + op.len <= fixed_base_ + fixed_len_;
+      if (fixed) {
+        e.opcode = op.write ? IORING_OP_WRITE_FIXED : IORING_OP_READ_FIXED;
+        e.buf_index = 0;
+        ++fixed_sqes_;
+      } else {
+        e.opcode = op.write ? IORING_OP_WRITE : IORING_OP_READ;
+      }
       e.fd = op.fd;
       e.addr = reinterpret_cast<uint64_t>(op.buf);
       e.len = op.len;
@@ -398,6 +422,8 @@ ErrorCode IoUringDiskBackend::initialize() {
     BB_LOG(WARNING) << "io_uring unavailable; " << pool_id_ << " falls back to pread/pwrite";
   staging_bytes_ = std::min<uint64_t>(16ull << 20, std::max<uint64_t>(1ull << 20, static_cast<uint64_t>(opts_.queue_depth) * (256ull << 10)));
   if (::posix_memalign(reinterpret_cast<void**>(&staging_), kBlock, staging_bytes_) != 0) return ErrorCode::OUT_OF_MEMORY;
+  if (ring_.ok() && ring_.register_buffer(staging_, staging_bytes_) != ErrorCode::OK)
+    BB_LOG(INFO) << pool_id_ << ": staging buffer not registered with io_uring (memlock limit?); using READ/WRITE instead of *_FIXED";
   base_tag_ = (fnv64(file_path_) >> 32) << 32;  // synthetic "address space" of this file
   rkey_ = fnv64(manifest_path_) & 0xFFFFFFFFull;
   init_allocator();

@@ -90,6 +90,19 @@ class StorageBackend {
   virtual ErrorCode read(uint64_t offset, void* data, uint64_t len) = 0;
   virtual void* direct_ptr(uint64_t /*offset*/) { return nullptr; }  // host-mapped tiers only
   virtual ErrorCode flush() { return ErrorCode::OK; }
+  // True when a CUDA kernel in this process can address direct_ptr() (device memory, or host memory
+  // registered with the driver): such tiers take part in fused-kernel tier moves.
+  virtual bool cuda_accessible() const { return false; }
+  // Tier move with the digest computed by the fused transfer kernel (SURVEY K9 "tier-spill"): copies
+  // `len` bytes between this backend (at my_off) and `peer` (at peer_off) in ONE launch and returns the
+  // digest of the bytes moved.  NOT_IMPLEMENTED unless this backend owns a device engine and the
+  // peer is cuda_accessible(); callers then fall back to read() + write() + CPU checksum.
+  virtual ErrorCode device_copy(StorageBackend& peer, bool to_peer, uint64_t my_off, uint64_t peer_off, uint64_t len, ChecksumAlgo algo,
+                                uint64_t* digest) {
+    (void)peer, (void)to_peer, (void)my_off, (void)peer_off, (void)len, (void)algo, (void)digest;
+    return ErrorCode::NOT_IMPLEMENTED;
+  }
+  uint64_t device_copies() const { return device_copies_; }
   // Registration key advertised in the pool record ("ucx_rkey_hex"): 8 hex chars of the rkey by
   // default; the GPU tier returns its CUDA IPC handle.
   virtual std::string registration_key_hex() const;
@@ -120,6 +133,7 @@ class StorageBackend {
   std::unordered_map<uint64_t, alloc::Range> committed_;  // offset -> extent
   uint64_t next_token_ = 1;
   uint64_t usable_ = 0;  // capacity rounded down to the extent alignment
+  std::atomic<uint64_t> device_copies_{0};
   std::atomic<uint64_t> bytes_written_{0}, bytes_read_{0}, io_errors_{0};
 };
 
@@ -137,6 +151,7 @@ class RamBackend : public StorageBackend {
   ErrorCode read(uint64_t offset, void* data, uint64_t len) override;
   void* direct_ptr(uint64_t offset) override { return base_ ? base_ + offset : nullptr; }
   bool pinned() const { return pinned_; }
+  bool cuda_accessible() const override { return pinned_; }
 
  private:
   uint8_t* base_ = nullptr;
@@ -185,7 +200,12 @@ class IoUring {
     int32_t result;
   };
   ErrorCode submit_and_wait(std::vector<Op>& ops);
+  // Registers one buffer (IORING_REGISTER_BUFFERS): ops whose memory lies inside it are issued as
+  // READ_FIXED / WRITE_FIXED, which skips the per-I/O page pinning.
+  ErrorCode register_buffer(void* base, size_t len);
+  bool has_fixed_buffer() const { return fixed_base_ != nullptr; }
   uint64_t sqes_submitted() const { return submitted_; }
+  uint64_t fixed_sqes() const { return fixed_sqes_; }
   static bool supported();
 
  private:
@@ -199,6 +219,9 @@ class IoUring {
   void* cqes_ = nullptr;
   uint32_t entries_ = 0;
   uint64_t submitted_ = 0;
+  uint64_t fixed_sqes_ = 0;
+  uint8_t* fixed_base_ = nullptr;
+  size_t fixed_len_ = 0;
   std::mutex mu_;
 };
 
@@ -219,6 +242,7 @@ class IoUringDiskBackend : public StorageBackend {
   ErrorCode flush() override;
   const std::string& file_path() const { return file_path_; }
   uint64_t sqes_submitted() const { return ring_.sqes_submitted(); }
+  uint64_t fixed_sqes() const { return ring_.fixed_sqes(); }  // READ_FIXED / WRITE_FIXED on the registered staging buffer
   bool using_uring() const { return ring_.ok(); }
   bool using_direct_io() const { return direct_; }
   // Extents recorded in the manifest of a previous run (offset, size, crc32c).
@@ -274,6 +298,14 @@ class CxlMemoryBackend : public StorageBackend {
 };
 
 // Hook through which the CUDA side registers the GPU tier (keeps this library CUDA-free).
+// Page-locking hooks installed by the CUDA side (cudaHostRegister / cudaHostUnregister): a DRAM pool created
+// with BackendOptions::pin_memory becomes addressable by the fused kernels of this process.
+struct HostPinHooks {
+  std::function<bool(void*, uint64_t)> pin;
+  std::function<void(void*)> unpin;
+};
+void set_host_pin_hooks(HostPinHooks h);
+
 using GpuBackendFactory = std::function<std::unique_ptr<StorageBackend>(uint64_t capacity, const BackendOptions&)>;
 void set_gpu_backend_factory(GpuBackendFactory f);
 

@@ -125,6 +125,7 @@ def test_io_uring_backend_submits_real_sqes_and_persists(bb, tmp_path):
     assert b.commit_shard(tok) == bb.ErrorCode.OK and b.flush() == bb.ErrorCode.OK
     if bb.io_uring_supported():
         assert b.using_uring and b.sqes_submitted >= 12  # 256 KiB pieces through the ring
+        assert b.fixed_sqes in (0, b.sqes_submitted)  # registered staging buffer => every SQE is READ_FIXED / WRITE_FIXED (0: memlock limit)
     with open(b.file_path, "rb") as f:  # bytes are really on disk at the advertised offset
         f.seek(off)
         assert f.read(len(data)) == data
