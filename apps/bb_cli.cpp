@@ -1,7 +1,7 @@
 // bb-cli: command-line client (reference clients/ucx_client.cpp: put + get + compare with
 // timings; examples/simple_client_test.cpp: connectivity + /metrics smoke).
 //   bb-cli --keystone 127.0.0.1:9090 put KEY FILE [--replicas R] [--max-workers W] [--ttl-ms T] [--class RAM_CPU]
-//   bb-cli get KEY [OUTFILE] | exists KEY | remove KEY | stats | smoke [--size N] | metrics --http 127.0.0.1:9091
+//   bb-cli get KEY [OUTFILE] | exists KEY | remove KEY | migrate KEY CLASS | stats | smoke [--size N] | metrics --http 127.0.0.1:9091
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -104,6 +104,16 @@ int main(int argc, char** argv) {
   if (cmd == "remove" && args.positional.size() >= 2) {
     ec = cl.remove(args.positional[1]);
     std::printf("remove %s: %s\n", args.positional[1].c_str(), name(ec));
+    return ec == ErrorCode::OK ? 0 : 1;
+  }
+  if (cmd == "migrate" && args.positional.size() >= 3) {
+    auto sc = parse_storage_class(args.positional[2]);
+    if (!sc) {
+      std::fprintf(stderr, "unknown storage class %s\n", args.positional[2].c_str());
+      return 2;
+    }
+    ec = cl.migrate(args.positional[1], *sc);
+    std::printf("migrate %s -> %s: %s\n", args.positional[1].c_str(), args.positional[2].c_str(), name(ec));
     return ec == ErrorCode::OK ? 0 : 1;
   }
   if (cmd == "stats") {

@@ -203,7 +203,20 @@ def tier_spill(cluster, nobj: int = 10, size: int = 6 << 20) -> dict:
     assert _ok(ecs), [str(e) for e in ecs]
     verified = sum(int(torch.equal(src[i * size:(i + 1) * size], out[i * size:(i + 1) * size])) for i in range(nobj + 1))
     text = ks.metrics_text()
+    # promotion: bring the coldest object back into HBM (DRAM/NVMe -> GPU) and read it through the fused get
+    promoted = False
+    cold = next((k for k in keys if tiers[k] != _bb.StorageClass.RAM_GPU), None)
+    if cold is not None and ks.tier_utilization(_bb.StorageClass.RAM_GPU) + size / max(1, cluster.worker.backend(f"hbm{cluster.rank}").get_total_capacity()) < 1.0:
+        i = keys.index(cold)
+        assert cluster.client.migrate(cold, _bb.StorageClass.RAM_GPU) == _bb.ErrorCode.OK
+        probe = torch.zeros(size, dtype=torch.uint8, device=dev)
+        ecs, _ = cluster.client.batch_get_device([cold], [probe.data_ptr()], [size], stream)
+        torch.cuda.synchronize()
+        promoted = _ok(ecs) and cluster.client.get_workers(cold)[0].shards[0].storage_class == _bb.StorageClass.RAM_GPU and \
+            torch.equal(probe, src[i * size:(i + 1) * size])
+    hbm = cluster.worker.backend(f"hbm{cluster.rank}")
     return {
+        "fused_tier_moves": hbm.device_copies, "promoted_back": promoted,
         "objects": nobj + 1, "size": size, "verified": verified, "eviction_rounds": demoted_rounds,
         "demoted_to_dram": sum(1 for t in tiers.values() if t == _bb.StorageClass.RAM_CPU),
         "demoted_to_nvme": sum(1 for t in tiers.values() if t == _bb.StorageClass.NVME),

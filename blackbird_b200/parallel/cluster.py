@@ -159,7 +159,9 @@ class GpuRankCluster:
         wc.heartbeat_interval_sec = 5
         wc.storage_pools = [_bb.StoragePoolConfig(f"hbm{self.rank}", _bb.StorageClass.RAM_GPU, slab_bytes, "", self.local_rank)]
         if dram_bytes:
-            wc.storage_pools += [_bb.StoragePoolConfig(f"dram{self.rank}", _bb.StorageClass.RAM_CPU, dram_bytes, "")]
+            dram = _bb.StoragePoolConfig(f"dram{self.rank}", _bb.StorageClass.RAM_CPU, dram_bytes, "")
+            dram.pin_memory = True  # registered with CUDA: GPU <-> DRAM tier moves are one fused-kernel launch
+            wc.storage_pools += [dram]
         if nvme_bytes:
             wc.storage_pools += [_bb.StoragePoolConfig(f"nvme{self.rank}", _bb.StorageClass.NVME, nvme_bytes, nvme_path or "/tmp")]
         self.worker = _bb.WorkerService(wc, None, self.api)

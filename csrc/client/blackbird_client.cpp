@@ -297,6 +297,11 @@ ErrorCode BlackbirdClient::remove(const ObjectKey& key) {
   return keystone_->remove_object(key);
 }
 
+ErrorCode BlackbirdClient::migrate(const ObjectKey& key, StorageClass target) {
+  if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
+  return keystone_->migrate_object(key, target);
+}
+
 Result<ClusterStats> BlackbirdClient::cluster_stats() {
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
   return keystone_->get_cluster_stats();

@@ -117,6 +117,8 @@ class BlackbirdClient {
     return put(key, data.data(), data.size(), cfg);
   }
   ErrorCode remove(const ObjectKey& key);
+  // Moves every copy of the object to `target` (promotion to the GPU tier, demotion to DRAM / NVMe ...).
+  ErrorCode migrate(const ObjectKey& key, StorageClass target);
 
   // ---- batched host-memory API
   std::vector<ErrorCode> batch_put(const std::vector<ObjectKey>& keys, const std::vector<const uint8_t*>& data,

@@ -98,7 +98,56 @@ ErrorCode GpuSlabBackend::read(uint64_t offset, void* data, uint64_t len) {
   return ErrorCode::OK;
 }
 
+ErrorCode GpuSlabBackend::device_copy(worker::StorageBackend& peer, bool to_peer, uint64_t my_off, uint64_t peer_off, uint64_t len,
+                                      ChecksumAlgo algo, uint64_t* digest) {
+  if (!base_ || !peer.cuda_accessible()) return ErrorCode::NOT_IMPLEMENTED;
+  BB_TRY(check_range(my_off, len));
+  auto* theirs = static_cast<uint8_t*>(peer.direct_ptr(peer_off));
+  if (!theirs || peer_off + len > peer.get_total_capacity()) return ErrorCode::MEMORY_ACCESS_ERROR;
+  uint8_t* mine = base_ + my_off;
+  if ((reinterpret_cast<uintptr_t>(mine) | reinterpret_cast<uintptr_t>(theirs)) & 15) return ErrorCode::NOT_IMPLEMENTED;  // staged path handles it
+  std::lock_guard<std::mutex> lk(move_mu_);
+  if (!cuda_ok(cudaSetDevice(opts_.gpu_device_id), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
+  if (!move_engine_) {
+    auto e = XferEngine::create(opts_.gpu_device_id, 64, 1);
+    if (!e.ok()) return e.error();
+    move_engine_ = std::move(e.value());
+  }
+  XferItem it;
+  it.src = to_peer ? mine : theirs;
+  it.dst[0] = to_peer ? theirs : mine;
+  it.ndst = 1;
+  it.nbytes = len;
+  XferResult res;
+  ErrorCode ec = move_engine_->run({it}, algo, stream_, &res);
+  if (ec != ErrorCode::OK) return ec;
+  if (digest) *digest = res.digest.empty() ? 0 : res.digest[0];
+  (to_peer ? bytes_read_ : bytes_written_) += len;
+  ++device_copies_;
+  return ErrorCode::OK;
+}
+
 void install_gpu_backend_factory() {
+  worker::HostPinHooks hooks;
+  hooks.pin = [](void* p, uint64_t n) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+      cudaGetLastError();
+      return false;
+    }
+    // portable: usable from every device context of this process; the kernels address it through UVA
+    cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+      BB_LOG(WARNING) << "cudaHostRegister(" << n << " B) failed: " << cudaGetErrorString(e);
+      cudaGetLastError();
+      return false;
+    }
+    return true;
+  };
+  hooks.unpin = [](void* p) {
+    if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+  };
+  worker::set_host_pin_hooks(std::move(hooks));
   worker::set_gpu_backend_factory([](uint64_t capacity, const worker::BackendOptions& o) -> std::unique_ptr<worker::StorageBackend> {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

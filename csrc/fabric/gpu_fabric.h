@@ -36,6 +36,12 @@ class GpuSlabBackend : public worker::StorageBackend {
   // Slow path (host tiers, TCP clients, tier demotion): staged cudaMemcpy.
   ErrorCode write(uint64_t offset, const void* data, uint64_t len) override;
   ErrorCode read(uint64_t offset, void* data, uint64_t len) override;
+  void* direct_ptr(uint64_t offset) override { return base_ ? base_ + offset : nullptr; }
+  bool cuda_accessible() const override { return base_ != nullptr; }
+  // Tier move through the fused kernel (GPU slab <-> another slab or a pinned DRAM pool): one launch,
+  // digest from the tensor-core hash / fused CRC.
+  ErrorCode device_copy(worker::StorageBackend& peer, bool to_peer, uint64_t my_off, uint64_t peer_off, uint64_t len, ChecksumAlgo algo,
+                        uint64_t* digest) override;
   int device() const { return opts_.gpu_device_id; }
   void* device_ptr() const { return base_; }
   // 64-byte cudaIpcMemHandle_t as 128 hex chars: the "rkey" peers open the slab with.
@@ -47,6 +53,8 @@ class GpuSlabBackend : public worker::StorageBackend {
   uint64_t rkey_ = 0;
   std::string handle_hex_;
   void* stream_ = nullptr;
+  std::mutex move_mu_;
+  std::unique_ptr<XferEngine> move_engine_;  // created on the first tier move
 };
 
 // Registers the GPU tier with worker::create_storage_backend (call once at start-up).

@@ -695,6 +695,81 @@ size_t KeystoneService::run_gc_once() {
   return n;
 }
 
+// Moves every copy of `key` to the first class of `targets` that has room (same replication factor), through the
+// installed CopyMover (worker-to-worker D_COPY; fused kernel when the GPU tier is involved), then swaps the
+// placements atomically and frees the old extents.  Used by watermark demotion and by explicit migrate_object().
+ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets) {
+  auto info = get_object_info(key);
+  if (!info.ok()) return info.error();
+  if (info.value().copies.empty() || info.value().state != ObjectState::COMPLETE) return ErrorCode::OBJECT_NOT_READY;
+  WorkerConfig cfg = info.value().config;
+  cfg.replication_factor = info.value().copies.size();
+  cfg.symmetric_replicas = false;
+  std::string ledger;
+  Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
+  // one rung at a time: the first target tier that has room (GPU -> DRAM before GPU -> NVMe)
+  for (StorageClass target : targets) {
+    cfg.preferred_classes = {target};
+    for (int slot = 0; slot < 64 && !fresh.ok(); ++slot) {
+      ledger = key + "\x01" + std::to_string(slot);
+      std::shared_lock<std::shared_mutex> pk(pools_mu_);
+      alloc::IAllocator::PoolMap eligible;
+      for (const auto& [pid, p] : pools_)
+        if (p.storage_class == target) eligible.emplace(pid, p);
+      if (eligible.empty()) break;
+      fresh = allocator_->allocate_data_copies(ledger, info.value().size, cfg, eligible);
+      if (!fresh.ok() && fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+    }
+    if (fresh.ok()) break;
+  }
+  if (!fresh.ok()) return fresh.error();
+  ErrorCode ec = ErrorCode::OK;
+  for (size_t c = 0; c < fresh.value().size() && ec == ErrorCode::OK; ++c)
+    ec = mover(key, info.value().copies[std::min(c, info.value().copies.size() - 1)], fresh.value()[c], info.value().config.checksum);
+  if (ec != ErrorCode::OK) {
+    allocator_->free_object(ledger);
+    return ec;
+  }
+  Shard& sh = shard_for(key);
+  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  auto it = sh.objects.find(key);
+  if (it == sh.objects.end() || it->second.created != info.value().created) {  // removed / replaced while we copied
+    lk.unlock();
+    allocator_->free_object(ledger);
+    return ErrorCode::OBJECT_NOT_FOUND;
+  }
+  it->second.copies = fresh.value();
+  const std::vector<std::string> old = std::move(it->second.extra_ledgers);
+  it->second.extra_ledgers = {ledger};
+  persist_object(it->second);
+  lk.unlock();
+  allocator_->free_object(key);  // old extents
+  for (const auto& l : old) allocator_->free_object(l);
+  bump_view();
+  return ErrorCode::OK;
+}
+
+ErrorCode KeystoneService::migrate_object(const ObjectKey& key, StorageClass target) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  CopyMover mover;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+  }
+  if (!mover) return ErrorCode::NOT_IMPLEMENTED;
+  {
+    auto info = get_object_info(key);
+    if (!info.ok()) return info.error();
+    bool already = !info.value().copies.empty();
+    for (const auto& c : info.value().copies)
+      for (const auto& s : c.shards) already &= s.storage_class == target;
+    if (already) return ErrorCode::OK;
+  }
+  ErrorCode ec = migrate_with(mover, key, {target});
+  if (ec == ErrorCode::OK) metrics_.inc("migrations_total");
+  return ec;
+}
+
 size_t KeystoneService::run_eviction_once() {
   // utilisation per tier from the allocator's live accounting
   std::map<int, std::vector<StorageClass>> tiers;
@@ -734,59 +809,8 @@ size_t KeystoneService::run_eviction_once() {
         if (r2 > rank) lower.insert(lower.end(), cl2.begin(), cl2.end());
       for (size_t i = 0; i < n && i < cands.size(); ++i) {
         const ObjectKey& key = cands[i].second;
-        bool demoted = false;
-        if (mover && !lower.empty()) {
-          auto info = get_object_info(key);
-          if (info.ok() && !info.value().copies.empty()) {
-            WorkerConfig cfg = info.value().config;
-            cfg.replication_factor = info.value().copies.size();
-            cfg.symmetric_replicas = false;
-            std::string ledger;
-            Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
-            // one rung at a time: the next tier down that has room (GPU -> DRAM before GPU -> NVMe)
-            for (StorageClass target : lower) {
-              cfg.preferred_classes = {target};
-              for (int slot = 0; slot < 64 && !fresh.ok(); ++slot) {
-                ledger = key + "\x01" + std::to_string(slot);
-                std::shared_lock<std::shared_mutex> pk(pools_mu_);
-                alloc::IAllocator::PoolMap eligible;
-                for (const auto& [pid, p] : pools_)
-                  if (p.storage_class == target) eligible.emplace(pid, p);
-                if (eligible.empty()) break;
-                fresh = allocator_->allocate_data_copies(ledger, info.value().size, cfg, eligible);
-                if (!fresh.ok() && fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
-              }
-              if (fresh.ok()) break;
-            }
-            if (fresh.ok()) {
-              bool ok = true;
-              for (size_t c = 0; c < fresh.value().size() && ok; ++c)
-                ok = mover(key, info.value().copies[std::min(c, info.value().copies.size() - 1)], fresh.value()[c],
-                           info.value().config.checksum) == ErrorCode::OK;
-              if (ok) {
-                Shard& sh = shard_for(key);
-                std::unique_lock<std::shared_mutex> lk(sh.mu);
-                auto it = sh.objects.find(key);
-                if (it != sh.objects.end() && it->second.created == info.value().created) {
-                  it->second.copies = fresh.value();
-                  const std::vector<std::string> old = std::move(it->second.extra_ledgers);
-                  it->second.extra_ledgers = {ledger};
-                  persist_object(it->second);
-                  lk.unlock();
-                  allocator_->free_object(key);  // old (upper tier) extents
-                  for (const auto& l : old) allocator_->free_object(l);
-                  demoted = true;
-                  metrics_.inc("demotions_total");
-                } else {
-                  lk.unlock();
-                  allocator_->free_object(ledger);
-                }
-              } else {
-                allocator_->free_object(ledger);
-              }
-            }
-          }
-        }
+        const bool demoted = mover && !lower.empty() && migrate_with(mover, key, lower) == ErrorCode::OK;
+        if (demoted) metrics_.inc("demotions_total");
         if (!demoted) {
           Shard& sh = shard_for(key);
           std::unique_lock<std::shared_mutex> lk(sh.mu);

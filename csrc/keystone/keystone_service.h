@@ -142,6 +142,8 @@ class KeystoneService {
   // Runs one TTL sweep / eviction pass / repair pass synchronously (also used by the threads).
   size_t run_gc_once();
   size_t run_eviction_once();
+  // Explicit tier move (promotion or demotion) of every copy of `key` to `target`; no-op when already there.
+  ErrorCode migrate_object(const ObjectKey& key, StorageClass target);
   size_t run_repair_once();
   double tier_utilization(StorageClass sc) const;
 
@@ -196,6 +198,7 @@ class KeystoneService {
 
   std::mutex mover_mu_;
   CopyMover mover_;
+  ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets);
 
   std::atomic<bool> running_{false};
   std::atomic<bool> leader_{false};

@@ -474,6 +474,7 @@ void bind_control(py::module_& m) {
            py::arg("key"), py::arg("checksums") = keystone::ShardChecksums{})
       .def("put_cancel", &KeystoneService::put_cancel)
       .def("remove_object", &KeystoneService::remove_object)
+      .def("migrate_object", &KeystoneService::migrate_object, py::call_guard<py::gil_scoped_release>())
       .def("remove_all_objects", [](KeystoneService& k) { return unwrap(k.remove_all_objects()); })
       .def("batch_object_exists", [](KeystoneService& k, const std::vector<std::string>& keys) {
         return results_to_py(k.batch_object_exists(keys), [](bool b) { return py::bool_(b); });
@@ -583,6 +584,7 @@ void bind_control(py::module_& m) {
            py::arg("key"), py::arg("checksums") = keystone::ShardChecksums{}, py::call_guard<py::gil_scoped_release>())
       .def("put_cancel", &rpc::KeystoneApi::put_cancel, py::call_guard<py::gil_scoped_release>())
       .def("remove_object", &rpc::KeystoneApi::remove_object, py::call_guard<py::gil_scoped_release>())
+      .def("migrate_object", &rpc::KeystoneApi::migrate_object, py::call_guard<py::gil_scoped_release>())
       .def("remove_all_objects", [](rpc::KeystoneApi& k) { return unwrap(k.remove_all_objects()); }, py::call_guard<py::gil_scoped_release>())
       .def("get_cluster_stats", [](rpc::KeystoneApi& k) { return unwrap(k.get_cluster_stats()); }, py::call_guard<py::gil_scoped_release>())
       .def("get_view_version", [](rpc::KeystoneApi& k) { return unwrap(k.get_view_version()); }, py::call_guard<py::gil_scoped_release>())
@@ -673,6 +675,8 @@ void bind_control(py::module_& m) {
         return py::bytes(out);
       })
       .def("flush", &StorageBackend::flush)
+      .def("cuda_accessible", &StorageBackend::cuda_accessible)
+      .def_property_readonly("device_copies", &StorageBackend::device_copies, "tier moves done by the fused kernel")
       .def("set_pool_id", &StorageBackend::set_pool_id)
       .def("set_reservation_ttl_ms", &StorageBackend::set_reservation_ttl_ms)
       .def("has_direct_ptr", [](StorageBackend& b) { return b.direct_ptr(0) != nullptr; });
@@ -777,6 +781,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("mount_path", &worker::StoragePoolConfig::mount_path)
       .def_readwrite("gpu_device_id", &worker::StoragePoolConfig::gpu_device_id)
       .def_readwrite("numa_node", &worker::StoragePoolConfig::numa_node)
+      .def_readwrite("pin_memory", &worker::StoragePoolConfig::pin_memory)
       .def_readwrite("cxl", &worker::StoragePoolConfig::cxl);
   py::class_<worker::WorkerServiceConfig>(m, "WorkerServiceConfig")
       .def(py::init<>())
@@ -856,6 +861,7 @@ void bind_control(py::module_& m) {
         return py::bytes(reinterpret_cast<const char*>(r.value().data()), r.value().size());
       })
       .def("remove", &BlackbirdClient::remove, py::call_guard<py::gil_scoped_release>())
+      .def("migrate", &BlackbirdClient::migrate, py::call_guard<py::gil_scoped_release>())
       .def("batch_put", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<py::buffer>& data, const WorkerConfig& cfg) {
         std::vector<const uint8_t*> ptrs;
         std::vector<size_t> sizes;

@@ -236,6 +236,13 @@ void RpcService::register_handlers() {
     Reader r(q);
     return ec_reply(ks->worker_heartbeat(r.str()));
   });
+  rpc_.register_method(M_MIGRATE_OBJECT, [ks](C, S q) {
+    Reader r(q);
+    const std::string key = r.str();
+    const auto target = static_cast<StorageClass>(r.u32());
+    if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    return ec_reply(ks->migrate_object(key, target));
+  });
   rpc_.register_method(M_REMOVE_WORKER, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->remove_worker(r.str()));
@@ -348,6 +355,13 @@ ErrorCode KeystoneRpcClient::remove_object(const ObjectKey& key) {
   Writer w;
   w.str(key);
   BB_RPC(M_REMOVE_OBJECT, w);
+  return rd.ec();
+}
+ErrorCode KeystoneRpcClient::migrate_object(const ObjectKey& key, StorageClass target) {
+  Writer w;
+  w.str(key);
+  w.u32(static_cast<uint32_t>(target));
+  BB_RPC(M_MIGRATE_OBJECT, w);
   return rd.ec();
 }
 Result<size_t> KeystoneRpcClient::remove_all_objects() {

@@ -23,6 +23,7 @@ enum Method : uint32_t {
   M_BATCH_GET_WORKERS, M_BATCH_PUT_START, M_BATCH_PUT_COMPLETE, M_BATCH_PUT_CANCEL,
   M_BATCH_REMOVE_OBJECT, M_CLIENT_REGISTER, M_CLIENT_PING, M_GET_MEMORY_POOLS,
   M_REGISTER_WORKER, M_REGISTER_MEMORY_POOL, M_WORKER_HEARTBEAT, M_REMOVE_WORKER,
+  M_MIGRATE_OBJECT,
 };
 
 // The keystone surface a client needs; implemented in-process and over TCP.
@@ -51,6 +52,8 @@ class KeystoneApi {
   virtual ErrorCode register_worker(const WorkerRecord& rec) = 0;
   virtual ErrorCode register_memory_pool(const MemoryPool& pool) = 0;
   virtual ErrorCode worker_heartbeat(const WorkerId& id) = 0;
+  // Explicit promotion / demotion of an object to another tier (all copies).
+  virtual ErrorCode migrate_object(const ObjectKey& key, StorageClass target) = 0;
   // identity used for locality-aware placement and session ownership
   void set_identity(std::string client_id, std::string node_id) {
     client_id_ = std::move(client_id);
@@ -74,6 +77,7 @@ class LocalKeystoneApi : public KeystoneApi {
   ErrorCode put_complete(const ObjectKey& key, const keystone::ShardChecksums& sums) override { return ks_->put_complete(key, sums); }
   ErrorCode put_cancel(const ObjectKey& key) override { return ks_->put_cancel(key); }
   ErrorCode remove_object(const ObjectKey& key) override { return ks_->remove_object(key); }
+  ErrorCode migrate_object(const ObjectKey& key, StorageClass target) override { return ks_->migrate_object(key, target); }
   Result<size_t> remove_all_objects() override { return ks_->remove_all_objects(); }
   Result<ClusterStats> get_cluster_stats() override { return ks_->get_cluster_stats(); }
   Result<ViewVersionId> get_view_version() override { return ks_->get_view_version(); }
@@ -139,6 +143,7 @@ class KeystoneRpcClient : public KeystoneApi {
   ErrorCode put_complete(const ObjectKey& key, const keystone::ShardChecksums& sums) override;
   ErrorCode put_cancel(const ObjectKey& key) override;
   ErrorCode remove_object(const ObjectKey& key) override;
+  ErrorCode migrate_object(const ObjectKey& key, StorageClass target) override;
   Result<size_t> remove_all_objects() override;
   Result<ClusterStats> get_cluster_stats() override;
   Result<ViewVersionId> get_view_version() override;

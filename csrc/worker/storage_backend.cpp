@@ -167,12 +167,22 @@ ErrorCode RamBackend::initialize() {
   if (p == MAP_FAILED) return ErrorCode::OUT_OF_MEMORY;
   base_ = static_cast<uint8_t*>(p);
   rkey_ = fnv64(pool_id_) & 0xFFFFFFFFull;
+  if (opts_.pin_memory) {
+    HostPinHooks h = host_pin_hooks();
+    if (h.pin && h.pin(base_, capacity_)) pinned_ = true;
+    else BB_LOG(INFO) << "RAM pool " << pool_id_ << ": pin_memory requested but no CUDA pin hook (or registration failed); tier moves use the staged path";
+  }
   init_allocator();
   initialized_ = true;
   return ErrorCode::OK;
 }
 
 void RamBackend::shutdown() {
+  if (base_ && pinned_) {
+    HostPinHooks h = host_pin_hooks();
+    if (h.unpin) h.unpin(base_);
+    pinned_ = false;
+  }
   if (base_) ::munmap(base_, capacity_);
   base_ = nullptr;
   initialized_ = false;
@@ -636,6 +646,17 @@ ErrorCode CxlMemoryBackend::read(uint64_t offset, void* data, uint64_t len) {
 }
 
 // ================================================================ factory
+static std::mutex g_pin_mu;
+static HostPinHooks g_pin_hooks;
+void set_host_pin_hooks(HostPinHooks h) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pin_hooks = std::move(h);
+}
+HostPinHooks host_pin_hooks() {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  return g_pin_hooks;
+}
+
 void set_gpu_backend_factory(GpuBackendFactory f) {
   std::lock_guard<std::mutex> lk(g_factory_mu);
   g_gpu_factory = std::move(f);

@@ -305,6 +305,7 @@ struct HostPinHooks {
   std::function<void(void*)> unpin;
 };
 void set_host_pin_hooks(HostPinHooks h);
+HostPinHooks host_pin_hooks();
 
 using GpuBackendFactory = std::function<std::unique_ptr<StorageBackend>(uint64_t capacity, const BackendOptions&)>;
 void set_gpu_backend_factory(GpuBackendFactory f);

@@ -76,6 +76,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
     pc.gpu_device_id = static_cast<int>(p.at("gpu_device_id").as_int(0));
     if (p.contains("numa_node")) pc.numa_node = static_cast<int>(p.at("numa_node").as_int(-1));
     pc.queue_depth = static_cast<uint32_t>(p.at("queue_depth").as_int(64));
+    pc.pin_memory = p.at("pin_memory").as_bool(false);
     c.storage_pools.push_back(std::move(pc));
   }
   return c;
@@ -115,6 +116,7 @@ ErrorCode WorkerService::create_storage_pools_from_config() {
     o.gpu_device_id = pc.gpu_device_id;
     o.numa_node = pc.numa_node >= 0 ? pc.numa_node : config_.numa_node;
     o.queue_depth = pc.queue_depth;
+    o.pin_memory = pc.pin_memory;
     o.interleave_granularity = pc.cxl.interleave_granularity ? pc.cxl.interleave_granularity : 256;
     o.persistent = pc.cxl.is_persistent;
     auto b = create_storage_backend(pc.storage_class, pc.size_bytes, o);
@@ -408,6 +410,19 @@ void WorkerService::register_data_handlers() {
       return w.take();
     }
     const uint64_t s0 = resolve_offset(*sb, so), d0 = resolve_offset(*db, doff);
+    // Fused-kernel tier move: when one side is the GPU slab and the other is addressable by CUDA (another
+    // slab, or a pinned DRAM pool), ONE launch copies the shard and computes its digest on the tensor cores.
+    {
+      uint64_t digest = 0;
+      ErrorCode dc = sb->device_copy(*db, true, s0, d0, len, algo, &digest);
+      if (dc == ErrorCode::NOT_IMPLEMENTED) dc = db->device_copy(*sb, false, d0, s0, len, algo, &digest);
+      if (dc != ErrorCode::NOT_IMPLEMENTED) {
+        if (dc == ErrorCode::OK) dc = db->flush();
+        w.ec(dc);
+        if (dc == ErrorCode::OK) w.u64(digest);
+        return w.take();
+      }
+    }
     constexpr uint64_t kChunk = 8ull << 20;
     std::vector<uint8_t> buf(std::min(len, kChunk));
     std::vector<uint8_t> whole;  // BBH64 is tile-position dependent: hash the whole shard at the end

@@ -36,6 +36,7 @@ struct StoragePoolConfig {
   int gpu_device_id = 0;
   int numa_node = -1;
   uint32_t queue_depth = 64;
+  bool pin_memory = false;  // DRAM tier: register with CUDA so fused kernels can move data to / from it
   CxlMemoryPoolConfig cxl;  // CXL tiers: per-pool `config:` block
 };
 

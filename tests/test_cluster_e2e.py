@@ -256,3 +256,27 @@ def test_config4_tier_spill_dram_to_nvme_with_ttl_and_soft_pin(bb, tmp_path):
         stats = c.workers[0].get_stats()
         nv = next(p for p in stats["pools"] if p["pool_id"] == "nvme")
         assert nv["bytes_written"] >= 3 << 20
+
+
+def test_explicit_migrate_promotes_and_demotes_across_tiers(bb, tmp_path):
+    """migrate_object: every copy moves to the target tier through the workers' D_COPY path, digests are
+    re-checked by the mover, old extents are freed, and the object stays readable throughout."""
+    with LocalCluster("migrate", n_workers=0) as c:
+        c.add_worker("w0", "node-0", [("dram", bb.StorageClass.RAM_CPU, 16 << 20, ""), ("nvme", bb.StorageClass.NVME, 64 << 20, str(tmp_path))])
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        blob = os.urandom(3 << 20)
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[bb.StorageClass.RAM_CPU], checksum=bb.ChecksumAlgo.CRC32C)
+        assert cl.put("m", blob, cfg) == bb.ErrorCode.OK
+        used_before = c.keystone.tier_utilization(bb.StorageClass.RAM_CPU)
+        assert cl.migrate("m", bb.StorageClass.NVME) == bb.ErrorCode.OK
+        sh = cl.get_workers("m")[0].shards[0]
+        assert sh.storage_class == bb.StorageClass.NVME and sh.checksum == bb.crc32c(blob)
+        assert c.keystone.tier_utilization(bb.StorageClass.RAM_CPU) < used_before  # DRAM extent released
+        assert cl.get("m") == blob
+        assert cl.migrate("m", bb.StorageClass.NVME) == bb.ErrorCode.OK  # already there: no-op
+        assert cl.migrate("m", bb.StorageClass.RAM_CPU) == bb.ErrorCode.OK  # promotion
+        assert cl.get_workers("m")[0].shards[0].storage_class == bb.StorageClass.RAM_CPU and cl.get("m") == blob
+        assert cl.migrate("nope", bb.StorageClass.NVME) == bb.ErrorCode.OBJECT_NOT_FOUND
+        assert cl.migrate("m", bb.StorageClass.RAM_GPU) == bb.ErrorCode.INSUFFICIENT_SPACE  # no such tier in this cluster
+        assert "bb_migrations_total 2" in c.keystone.metrics_text()

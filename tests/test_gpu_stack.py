@@ -179,5 +179,7 @@ def test_gpu_tier_spill_gpu_to_dram_to_nvme(bb, torch_cuda, tmp_path):
         r = tier_spill(cl, nobj=10, size=6 << 20)
         assert r["demoted_to_dram"] >= 3 and r["demoted_to_nvme"] >= 1, r
         assert r["pinned_tier"] == "RAM_GPU" and r["verified"] == 11 and r["gpu_util_after"] <= 0.55, r
+        # GPU <-> pinned-DRAM moves ran as fused-kernel launches (digest on the tensor cores), not staged memcpys
+        assert r["fused_tier_moves"] >= 3 and r["promoted_back"], r
     finally:
         cl.stop()
