@@ -3,6 +3,7 @@
 // commit / free ops/s on a disk backend).
 //   bb-bench client  --keystone host:port --size 1048576 --iterations 50 [--replicas 1] [--max-workers 1] [--batch 1]
 //   bb-bench backend --class NVME --path /tmp/x --ops 50 --size 4096
+//   bb-bench control [--threads 4] [--batch 4096] [--iterations 20] [--pools 8] [--rpc]   (keystone metadata ops/s)
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -11,7 +12,11 @@
 #include <random>
 
 #include "apps/cli_util.h"
+#include <thread>
+
 #include "client/blackbird_client.h"
+#include "keystone/keystone_service.h"
+#include "rpc/rpc_service.h"
 #include "worker/storage_backend.h"
 
 using namespace bb;
@@ -30,7 +35,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   const std::string mode = args.positional.empty() ? "client" : args.positional[0];
   if (args.has("help")) {
-    std::printf("usage: bb-bench client|backend [options]\n");
+    std::printf("usage: bb-bench client|backend|control [options]\n");
     return 0;
   }
   if (mode == "backend") {
@@ -68,6 +73,90 @@ int main(int argc, char** argv) {
     std::printf("%s backend, %zu ops x %llu B: reserve %.4f ms | write %.4f ms | commit %.4f ms | free %.4f ms | %.0f lifecycle ops/s\n",
                 args.get("class", "NVME").c_str(), done, static_cast<unsigned long long>(size), avg(t_res), avg(t_wr), avg(t_com), avg(t_free),
                 done ? 1000.0 / (avg(t_res) + avg(t_wr) + avg(t_com) + avg(t_free)) : 0.0);
+    return 0;
+  }
+  if (mode == "control") {
+    // Control-plane throughput: T clients drive batch_put_start -> batch_put_complete -> batch_get_workers ->
+    // batch_remove_object against an in-process keystone with synthetic pools (no data plane involved).
+    const int threads = std::max(1, static_cast<int>(args.num("threads", 4)));
+    const int batch = std::max(1, static_cast<int>(args.num("batch", 4096)));
+    const int iters = std::max(1, static_cast<int>(args.num("iterations", 20)));
+    const int npools = std::max(1, static_cast<int>(args.num("pools", 8)));
+    const bool over_rpc = args.has("rpc");
+    KeystoneConfig kc;
+    kc.cluster_id = "bench";
+    kc.listen_address = "127.0.0.1:0";
+    kc.http_metrics_port = "off";
+    kc.enable_gc = false;
+    kc.rpc_threads = std::max(2, threads);
+    auto ks = std::make_shared<keystone::KeystoneService>(kc, nullptr);
+    if (ks->initialize() != ErrorCode::OK || ks->start() != ErrorCode::OK) return 1;
+    rpc::RpcService rpc(ks, kc);
+    if (over_rpc && rpc.start() != ErrorCode::OK) return 1;
+    for (int p = 0; p < npools; ++p) {
+      WorkerRecord w;
+      w.worker_id = "w" + std::to_string(p);
+      w.node_id = "n" + std::to_string(p);
+      w.ucx_endpoint = "127.0.0.1:1";
+      ks->register_worker(w);
+      MemoryPool mp;
+      mp.id = "p" + std::to_string(p);
+      mp.node_id = w.node_id;
+      mp.worker_id = w.worker_id;
+      mp.size = 64ull << 30;
+      mp.storage_class = StorageClass::RAM_GPU;
+      mp.ucx_endpoint = w.ucx_endpoint;
+      ks->register_memory_pool(mp);
+    }
+    std::vector<double> t_start(threads), t_done(threads), t_get(threads), t_rm(threads);
+    std::vector<std::thread> ts;
+    const auto t0 = Clk::now();
+    for (int t = 0; t < threads; ++t) {
+      ts.emplace_back([&, t] {
+        std::shared_ptr<rpc::KeystoneApi> api;
+        if (over_rpc) {
+          auto c = std::make_shared<rpc::KeystoneRpcClient>();
+          if (c->connect("127.0.0.1", rpc.rpc_port(), 5000) != ErrorCode::OK) return;
+          api = c;
+        } else {
+          api = std::make_shared<rpc::LocalKeystoneApi>(ks);
+        }
+        WorkerConfig cfg;
+        cfg.replication_factor = 1;
+        cfg.max_workers_per_copy = 1;
+        cfg.ttl_ms = 0;
+        for (int it = 0; it < iters; ++it) {
+          std::vector<keystone::PutStartItem> items;
+          std::vector<ObjectKey> keys;
+          for (int i = 0; i < batch; ++i) {
+            keys.push_back("t" + std::to_string(t) + "/" + std::to_string(it) + "/" + std::to_string(i));
+            items.push_back({keys.back(), 256, cfg});
+          }
+          const std::vector<keystone::ShardChecksums> sums(keys.size());
+          auto a = Clk::now();
+          auto placed = api->batch_put_start(items);
+          auto b = Clk::now();
+          api->batch_put_complete(keys, sums);
+          auto c = Clk::now();
+          auto got = api->batch_get_workers(keys);
+          auto d = Clk::now();
+          api->batch_remove_object(keys);
+          auto e = Clk::now();
+          t_start[t] += ms(a, b), t_done[t] += ms(b, c), t_get[t] += ms(c, d), t_rm[t] += ms(d, e);
+          if (placed.empty() || !placed[0].ok() || got.empty() || !got[0].ok()) std::fprintf(stderr, "control bench: operation failed\n");
+        }
+      });
+    }
+    for (auto& th : ts) th.join();
+    const double wall = ms(t0, Clk::now());
+    const double objs = static_cast<double>(threads) * batch * iters;
+    auto per = [&](const std::vector<double>& v) { return std::accumulate(v.begin(), v.end(), 0.0) * 1000.0 / objs; };
+    std::printf("{\"mode\": \"control\", \"transport\": \"%s\", \"threads\": %d, \"batch\": %d, \"objects\": %.0f, \"wall_ms\": %.1f, "
+                "\"object_lifecycles_per_s\": %.0f, \"put_start_us_per_obj\": %.3f, \"put_complete_us_per_obj\": %.3f, "
+                "\"get_workers_us_per_obj\": %.3f, \"remove_us_per_obj\": %.3f}\n",
+                over_rpc ? "tcp" : "in-process", threads, batch, objs, wall, objs * 1000.0 / wall, per(t_start), per(t_done), per(t_get), per(t_rm));
+    rpc.stop();
+    ks->stop();
     return 0;
   }
   auto hp = split_host_port(args.get("keystone", "127.0.0.1:9090"));

@@ -23,6 +23,35 @@ def _free_port() -> int:
     return p
 
 
+def _pin_to_gpu_numa_node(device_index: int):
+    """Bind this process (and every thread it creates later: RPC pool, data server, CUDA callbacks) to the
+    CPUs NVML reports as local to the GPU, so pinned staging buffers and the H2D/D2H copies of the end-to-end
+    path stay on the GPU's own PCIe root / NUMA node.  BB_NUMA_PIN=0 disables."""
+    if os.environ.get("BB_NUMA_PIN", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            ids = [v for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].strip().isdigit():
+                idx = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:  # no NVML, restricted cgroup, ...: run unpinned
+        pass
+    return None
+
+
 class LocalCluster:
     def __init__(self, cluster_id: str = "local", n_workers: int = 2, pool_bytes: int = 64 << 20,
                  storage_class=None, serve_rpc: bool = True, coord: Optional[str] = None,
@@ -99,7 +128,7 @@ class GpuRankCluster:
     def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None,
                  nvls_arena_bytes: int = 0, nvls_group_size: int = 3, rpc_busy_poll_us: Optional[int] = None,
                  dram_bytes: int = 0, nvme_bytes: int = 0, nvme_path: str = "", high_watermark: float = 1.0,
-                 eviction_ratio: float = 0.1):
+                 eviction_ratio: float = 0.1, max_replicas: int = 3):
         """slab_bytes: HBM slab of this rank's GPU-tier pool.  dram_bytes / nvme_bytes add host tiers to the
         same worker (the demotion ladder GPU -> DRAM -> NVMe); high_watermark < 1 arms tier demotion."""
         import torch
@@ -110,6 +139,7 @@ class GpuRankCluster:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local_rank)
+        self.cpu_affinity = _pin_to_gpu_numa_node(self.local_rank)
         self.dist = dist if self.world > 1 else None
         if self.world > 1 and not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
@@ -128,6 +158,7 @@ class GpuRankCluster:
             cfg.eviction_ratio = eviction_ratio
             cfg.gc_interval_sec = 3600 if high_watermark >= 1.0 else 1
             cfg.rpc_threads = 4
+            cfg.max_replicas = max_replicas
             if rpc_busy_poll_us is None:
                 rpc_busy_poll_us = int(os.environ.get("BB_RPC_BUSY_POLL_US", "2000"))
             cfg.rpc_busy_poll_us = rpc_busy_poll_us  # clients issue RPCs between kernels a few ms apart

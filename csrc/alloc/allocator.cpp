@@ -51,17 +51,26 @@ void PoolAllocator::insert_free(uint64_t off, uint64_t len) {
   by_offset_[off] = len;
   by_size_.insert({len, off});
   free_bytes_ += len;
+  publish();
 }
 
 void PoolAllocator::erase_free(std::map<uint64_t, uint64_t>::iterator it) {
   by_size_.erase({it->second, it->first});
   free_bytes_ -= it->second;
   by_offset_.erase(it);
+  publish();
+}
+
+// Placement ranks every pool on every put: the two numbers it needs are mirrored in atomics so ranking never
+// touches a pool's mutex (8 clients ranking 8 pools used to serialise on the busiest pool's lock).
+void PoolAllocator::publish() {
+  free_pub_.store(free_bytes_, std::memory_order_relaxed);
+  largest_pub_.store(by_size_.empty() ? 0 : by_size_.rbegin()->first, std::memory_order_relaxed);
 }
 
 std::optional<Range> PoolAllocator::allocate(uint64_t size, bool prefer_best_fit) {
   const uint64_t need = aligned(size);
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<SpinMutex> lk(mu_);
   if (need == 0) return Range(0, 0);
   std::map<uint64_t, uint64_t>::iterator it = by_offset_.end();
   if (prefer_best_fit) {
@@ -86,7 +95,7 @@ bool PoolAllocator::allocate_at(uint64_t offset, uint64_t size) {
   const uint64_t need = aligned(size);
   if (need == 0) return true;
   if (offset % align_) return false;
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<SpinMutex> lk(mu_);
   auto it = by_offset_.upper_bound(offset);
   if (it == by_offset_.begin()) return false;
   --it;
@@ -100,7 +109,7 @@ bool PoolAllocator::allocate_at(uint64_t offset, uint64_t size) {
 
 void PoolAllocator::free(const Range& range) {
   if (range.length == 0) return;
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<SpinMutex> lk(mu_);
   uint64_t off = range.offset, len = range.length;
   auto next = by_offset_.lower_bound(off);
   if (next != by_offset_.begin()) {
@@ -128,26 +137,20 @@ void PoolAllocator::free(const Range& range) {
   insert_free(off, len);
 }
 
-size_t PoolAllocator::total_free() const {
-  std::lock_guard<std::mutex> lk(mu_);
-  return free_bytes_;
-}
-size_t PoolAllocator::largest_free_block() const {
-  std::lock_guard<std::mutex> lk(mu_);
-  return by_size_.empty() ? 0 : by_size_.rbegin()->first;
-}
+size_t PoolAllocator::total_free() const { return free_pub_.load(std::memory_order_relaxed); }
+size_t PoolAllocator::largest_free_block() const { return largest_pub_.load(std::memory_order_relaxed); }
 double PoolAllocator::fragmentation_ratio() const {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<SpinMutex> lk(mu_);
   if (free_bytes_ == 0) return 0.0;
   return 1.0 - static_cast<double>(by_size_.rbegin()->first) / static_cast<double>(free_bytes_);
 }
 bool PoolAllocator::can_allocate(uint64_t size) const {
   const uint64_t need = aligned(size);
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<SpinMutex> lk(mu_);
   return need == 0 || (!by_size_.empty() && by_size_.rbegin()->first >= need);
 }
 std::vector<Range> PoolAllocator::free_ranges() const {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<SpinMutex> lk(mu_);
   std::vector<Range> v;
   v.reserve(by_offset_.size());
   for (const auto& [o, l] : by_offset_) v.emplace_back(o, l);
@@ -158,17 +161,44 @@ MemoryLocation PoolAllocator::to_memory_location(const Range& r) const {
 }
 
 // ================================================================ RangeAllocator
+// Pool lookups happen ~20 times per put (ranking + shard construction).  Readers use a per-thread copy of the
+// id -> allocator table that is refreshed only when the table's generation changes, so the hot path touches no
+// shared lock word at all.  Retired allocators are parked in `graveyard_` (never freed while this object lives),
+// which keeps every cached pointer valid.
+namespace {
+std::atomic<uint64_t> g_next_allocator_instance{1};
+struct PoolTableCache {
+  uint64_t instance = 0;
+  uint64_t generation = 0;
+  std::unordered_map<MemoryPoolId, PoolAllocator*> table;
+};
+thread_local PoolTableCache t_pool_cache;
+}  // namespace
+
+RangeAllocator::RangeAllocator() : instance_id_(g_next_allocator_instance.fetch_add(1)) {}
+
 PoolAllocator* RangeAllocator::find_pool(const MemoryPoolId& id) const {
-  std::shared_lock<std::shared_mutex> lk(pools_mu_);
-  auto it = pool_allocators_.find(id);
-  return it == pool_allocators_.end() ? nullptr : it->second.get();
+  PoolTableCache& c = t_pool_cache;
+  const uint64_t gen = generation_.load(std::memory_order_acquire);
+  if (c.instance != instance_id_ || c.generation != gen) {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    c.table.clear();
+    for (const auto& [pid, pa] : pool_allocators_) c.table.emplace(pid, pa.get());
+    c.instance = instance_id_;
+    c.generation = generation_.load(std::memory_order_relaxed);
+  }
+  auto it = c.table.find(id);
+  return it == c.table.end() ? nullptr : it->second;
 }
 
 PoolAllocator* RangeAllocator::ensure_pool(const MemoryPool& pool) {
   if (PoolAllocator* p = find_pool(pool.id)) return p;
   std::unique_lock<std::shared_mutex> lk(pools_mu_);
   auto& slot = pool_allocators_[pool.id];
-  if (!slot) slot = std::make_unique<PoolAllocator>(pool);
+  if (!slot) {
+    slot = std::make_unique<PoolAllocator>(pool);
+    generation_.fetch_add(1, std::memory_order_release);
+  }
   return slot.get();
 }
 
@@ -345,17 +375,13 @@ Result<AllocationResult> RangeAllocator::place(const AllocationRequest& req, con
 
   // commit to the ledger
   {
-    std::unique_lock<std::shared_mutex> lk(alloc_mu_);
-    if (objects_.count(req.object_key)) {
-      lk.unlock();
-      rollback(all);
-      return ErrorCode::OBJECT_ALREADY_EXISTS;
-    }
     ObjectAllocation oa;
     oa.total_size = req.data_size;
-    for (const auto& e : all) used_by_pool_[e.pool] += e.range.length;
     oa.extents = std::move(all);
-    objects_.emplace(req.object_key, std::move(oa));
+    if (!ledger_insert(req.object_key, std::move(oa))) {
+      rollback(oa.extents);
+      return ErrorCode::OBJECT_ALREADY_EXISTS;
+    }
   }
   result.pools_used = pools_used.size();
   result.stats.required_spillover = spill;
@@ -468,17 +494,13 @@ Result<AllocationResult> RangeAllocator::place_symmetric(const AllocationRequest
         all.push_back({chosen[i]->id, r, req.data_size});
         if (!chosen[i]->preferred) spill = true;
       }
-      std::unique_lock<std::shared_mutex> lk(alloc_mu_);
-      if (objects_.count(req.object_key)) {
-        lk.unlock();
-        rollback(all);
-        return ErrorCode::OBJECT_ALREADY_EXISTS;
-      }
       ObjectAllocation oa;
       oa.total_size = req.data_size;
-      for (const auto& e : all) used_by_pool_[e.pool] += e.range.length;
       oa.extents = std::move(all);
-      objects_.emplace(req.object_key, std::move(oa));
+      if (!ledger_insert(req.object_key, std::move(oa))) {
+        rollback(oa.extents);
+        return ErrorCode::OBJECT_ALREADY_EXISTS;
+      }
       result.total_shards_created = repl;
       result.pools_used = repl;
       result.stats.required_spillover = spill;
@@ -494,8 +516,9 @@ Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, 
   if (req.object_key.empty()) return ErrorCode::INVALID_KEY;
   if (req.replication_factor == 0 || req.max_workers_per_copy == 0) return ErrorCode::INVALID_PARAMETERS;
   {
-    std::shared_lock<std::shared_mutex> lk(alloc_mu_);
-    if (objects_.count(req.object_key)) return ErrorCode::OBJECT_ALREADY_EXISTS;
+    LedgerShard& ls = ledger_for(req.object_key);
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    if (ls.objects.count(req.object_key)) return ErrorCode::OBJECT_ALREADY_EXISTS;
   }
   if (pools.empty()) return ErrorCode::INSUFFICIENT_SPACE;
   bool spill = false;
@@ -508,11 +531,15 @@ Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, 
 ErrorCode RangeAllocator::free(const ObjectKey& key) {
   ObjectAllocation oa;
   {
-    std::unique_lock<std::shared_mutex> lk(alloc_mu_);
-    auto it = objects_.find(key);
-    if (it == objects_.end()) return ErrorCode::OBJECT_NOT_FOUND;
+    LedgerShard& ls = ledger_for(key);
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    auto it = ls.objects.find(key);
+    if (it == ls.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
     oa = std::move(it->second);
-    objects_.erase(it);
+    ls.objects.erase(it);
+  }
+  {
+    std::lock_guard<SpinMutex> lk(used_mu_);
     for (const auto& e : oa.extents) {
       auto u = used_by_pool_.find(e.pool);
       if (u != used_by_pool_.end()) u->second -= std::min(u->second, static_cast<size_t>(e.range.length));
@@ -534,9 +561,9 @@ AllocatorStats RangeAllocator::get_stats(std::optional<StorageClass> sc) const {
       st.bytes_per_class[pa->storage_class()] += pa->capacity() - pa->total_free();
     }
   }
-  {
-    std::shared_lock<std::shared_mutex> lk(alloc_mu_);
-    for (const auto& [key, oa] : objects_) {
+  for (const LedgerShard& ls : ledger_) {
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    for (const auto& [key, oa] : ls.objects) {
       bool counted = false;
       for (const auto& e : oa.extents) {
         const PoolAllocator* pa = find_pool(e.pool);
@@ -580,24 +607,30 @@ bool RangeAllocator::can_allocate(const AllocationRequest& req, const PoolMap& p
 
 void RangeAllocator::forget_pool(const MemoryPoolId& id) {
   std::unique_lock<std::shared_mutex> lk(pools_mu_);
-  pool_allocators_.erase(id);
+  auto it = pool_allocators_.find(id);
+  if (it == pool_allocators_.end()) return;
+  graveyard_.push_back(std::move(it->second));  // other threads may still hold the pointer through their cache
+  pool_allocators_.erase(it);
+  generation_.fetch_add(1, std::memory_order_release);
 }
 
 size_t RangeAllocator::pool_used_bytes(const MemoryPoolId& id) const {
-  std::shared_lock<std::shared_mutex> lk(alloc_mu_);
+  std::lock_guard<SpinMutex> lk(used_mu_);
   auto it = used_by_pool_.find(id);
   return it == used_by_pool_.end() ? 0 : it->second;
 }
 
 std::vector<ObjectKey> RangeAllocator::objects_on_pool(const MemoryPoolId& id) const {
   std::vector<ObjectKey> v;
-  std::shared_lock<std::shared_mutex> lk(alloc_mu_);
-  for (const auto& [key, oa] : objects_)
-    for (const auto& e : oa.extents)
-      if (e.pool == id) {
-        v.push_back(key);
-        break;
-      }
+  for (const LedgerShard& ls : ledger_) {
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    for (const auto& [key, oa] : ls.objects)
+      for (const auto& e : oa.extents)
+        if (e.pool == id) {
+          v.push_back(key);
+          break;
+        }
+  }
   return v;
 }
 
@@ -623,15 +656,33 @@ ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlac
       oa.extents.push_back({s.pool_id, Range(off, pa->aligned(s.length)), s.length});
       oa.total_size += s.length;
     }
-  std::unique_lock<std::shared_mutex> lk(alloc_mu_);
-  if (objects_.count(key)) {
-    lk.unlock();
+  if (!ledger_insert(key, std::move(oa))) {
     rollback(oa.extents);
     return ErrorCode::OBJECT_ALREADY_EXISTS;
   }
-  for (const auto& e : oa.extents) used_by_pool_[e.pool] += e.range.length;
-  objects_.emplace(key, std::move(oa));
   return ErrorCode::OK;
+}
+
+bool RangeAllocator::ledger_insert(const ObjectKey& key, ObjectAllocation&& oa) {
+  {
+    std::lock_guard<SpinMutex> lk(used_mu_);
+    for (const auto& e : oa.extents) used_by_pool_[e.pool] += e.range.length;
+  }
+  LedgerShard& ls = ledger_for(key);
+  bool inserted;
+  {
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    if (ls.objects.count(key)) inserted = false;  // `oa` is left intact for the caller's rollback
+    else inserted = ls.objects.emplace(key, std::move(oa)).second;
+  }
+  if (!inserted) {
+    std::lock_guard<SpinMutex> lk(used_mu_);
+    for (const auto& e : oa.extents) {
+      auto u = used_by_pool_.find(e.pool);
+      if (u != used_by_pool_.end()) u->second -= std::min(u->second, static_cast<size_t>(e.range.length));
+    }
+  }
+  return inserted;
 }
 
 // ================================================================ factory / adapter

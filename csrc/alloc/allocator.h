@@ -20,6 +20,8 @@
 //  * Shards smaller than `min_shard_size` shrink the stripe width instead of failing, unless
 //    `strict_min_shard` asks for the reference behaviour (INSUFFICIENT_SPACE).
 #pragma once
+#include <array>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -30,6 +32,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "common/spin.h"
 #include "common/types.h"
 
 namespace bb::alloc {
@@ -129,10 +132,12 @@ class PoolAllocator {
   uint64_t align_;
   TransportEndpoint endpoint_;
   bool reg_valid_ = true;
-  mutable std::mutex mu_;
+  mutable SpinMutex mu_;
   std::map<uint64_t, uint64_t> by_offset_;              // offset -> length
   std::set<std::pair<uint64_t, uint64_t>> by_size_;     // (length, offset)
   size_t free_bytes_ = 0;
+  std::atomic<size_t> free_pub_{0}, largest_pub_{0};  // lock-free mirrors for placement ranking
+  void publish();
 };
 
 class IAllocator {
@@ -152,7 +157,7 @@ class IAllocator {
 
 class RangeAllocator : public IAllocator {
  public:
-  RangeAllocator() = default;
+  RangeAllocator();
   Result<AllocationResult> allocate(const AllocationRequest& request, const PoolMap& pools) override;
   ErrorCode free(const ObjectKey& object_key) override;
   AllocatorStats get_stats(std::optional<StorageClass> storage_class = std::nullopt) const override;
@@ -197,9 +202,21 @@ class RangeAllocator : public IAllocator {
 
   mutable std::shared_mutex pools_mu_;
   std::unordered_map<MemoryPoolId, std::unique_ptr<PoolAllocator>> pool_allocators_;
-  mutable std::shared_mutex alloc_mu_;
-  std::unordered_map<ObjectKey, ObjectAllocation> objects_;
-  std::unordered_map<MemoryPoolId, size_t> used_by_pool_;  // guarded by alloc_mu_
+  std::vector<std::unique_ptr<PoolAllocator>> graveyard_;  // forgotten pools (kept alive for cached pointers)
+  std::atomic<uint64_t> generation_{1};
+  const uint64_t instance_id_;
+  // Object ledger, sharded by key hash so concurrent clients rarely meet on the same lock.
+  static constexpr size_t kLedgerShards = 64;
+  struct LedgerShard {
+    mutable SpinMutex mu;
+    std::unordered_map<ObjectKey, ObjectAllocation> objects;
+  };
+  LedgerShard& ledger_for(const ObjectKey& key) const { return ledger_[std::hash<ObjectKey>{}(key) % kLedgerShards]; }
+  // Inserts `oa` under `key` (false + untouched when the key already has an allocation) and accounts its extents.
+  bool ledger_insert(const ObjectKey& key, ObjectAllocation&& oa);
+  mutable std::array<LedgerShard, kLedgerShards> ledger_;
+  mutable SpinMutex used_mu_;
+  std::unordered_map<MemoryPoolId, size_t> used_by_pool_;  // guarded by used_mu_
 };
 
 class AllocatorFactory {

@@ -50,11 +50,16 @@ std::vector<double> Metrics::default_latency_bounds_us() {
   return {1, 2, 5, 10, 20, 50, 100, 200, 500, 1000, 2000, 5000, 10000, 20000, 50000, 100000, 500000, 1000000};
 }
 
-void Metrics::inc(const std::string& name, uint64_t by) {
-  std::atomic<uint64_t>* c;
+void Metrics::inc(std::string_view name, uint64_t by) {
+  std::atomic<uint64_t>* c = nullptr;
   {
-    std::lock_guard<std::mutex> lk(mu_);
-    auto& slot = counters_[name];
+    std::shared_lock<std::shared_mutex> lk(mu_);
+    auto it = counters_.find(name);
+    if (it != counters_.end()) c = it->second.get();
+  }
+  if (!c) {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto& slot = counters_[std::string(name)];
     if (!slot) slot = std::make_unique<std::atomic<uint64_t>>(0);
     c = slot.get();
   }
@@ -62,48 +67,67 @@ void Metrics::inc(const std::string& name, uint64_t by) {
 }
 
 void Metrics::set_gauge(const std::string& name, double v) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
   gauges_[name] = v;
 }
 
-void Metrics::observe(const std::string& name, double v) {
-  Histogram* h;
+void Metrics::observe(std::string_view name, double v) {
+  Histogram* h = nullptr;
   {
-    std::lock_guard<std::mutex> lk(mu_);
-    auto& slot = hists_[name];
+    std::shared_lock<std::shared_mutex> lk(mu_);
+    auto it = hists_.find(name);
+    if (it != hists_.end()) h = it->second.get();
+  }
+  if (!h) {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto& slot = hists_[std::string(name)];
     if (!slot) slot = std::make_unique<Histogram>(default_latency_bounds_us());
     h = slot.get();
   }
   h->observe(v);
 }
 
+std::atomic<uint64_t>* Metrics::counter_ref(const std::string& name) {
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  auto& slot = counters_[name];
+  if (!slot) slot = std::make_unique<std::atomic<uint64_t>>(0);
+  return slot.get();
+}
+
+Histogram* Metrics::histogram_ref(const std::string& name) {
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  auto& slot = hists_[name];
+  if (!slot) slot = std::make_unique<Histogram>(default_latency_bounds_us());
+  return slot.get();
+}
+
 uint64_t Metrics::counter(const std::string& name) const {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
   auto it = counters_.find(name);
   return it == counters_.end() ? 0 : it->second->load();
 }
 
 double Metrics::gauge(const std::string& name) const {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
   auto it = gauges_.find(name);
   return it == gauges_.end() ? 0.0 : it->second;
 }
 
 void Metrics::describe(const std::string& name, const std::string& help) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
   help_[name] = help;
 }
 
 std::map<std::string, std::vector<double>> Metrics::histogram_summary() const {
   std::map<std::string, std::vector<double>> out;
-  std::lock_guard<std::mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
   for (const auto& [n, h] : hists_) out[n] = {static_cast<double>(h->count()), h->sum(), h->quantile(0.5), h->quantile(0.99)};
   return out;
 }
 
 std::string Metrics::render(const std::string& prefix) const {
   std::ostringstream out;
-  std::lock_guard<std::mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
   auto head = [&](const std::string& n, const char* type) {
     auto h = help_.find(n);
     if (h != help_.end()) out << "# HELP " << prefix << n << ' ' << h->second << '\n';

@@ -6,6 +6,8 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
+#include <string_view>
 #include <string>
 #include <vector>
 
@@ -31,9 +33,13 @@ class Histogram {
 
 class Metrics {
  public:
-  void inc(const std::string& name, uint64_t by = 1);
+  // Hot-path calls take a string_view (no allocation) and only a shared lock once the series exists.
+  void inc(std::string_view name, uint64_t by = 1);
   void set_gauge(const std::string& name, double v);
-  void observe(const std::string& name, double v);  // latency histograms in microseconds
+  void observe(std::string_view name, double v);  // latency histograms in microseconds
+  // Stable handles for series updated on a hot path (valid for the lifetime of this Metrics).
+  std::atomic<uint64_t>* counter_ref(const std::string& name);
+  Histogram* histogram_ref(const std::string& name);
   uint64_t counter(const std::string& name) const;
   double gauge(const std::string& name) const;
   void describe(const std::string& name, const std::string& help);
@@ -44,10 +50,10 @@ class Metrics {
   std::map<std::string, std::vector<double>> histogram_summary() const;
 
  private:
-  mutable std::mutex mu_;
-  std::map<std::string, std::unique_ptr<std::atomic<uint64_t>>> counters_;
+  mutable std::shared_mutex mu_;
+  std::map<std::string, std::unique_ptr<std::atomic<uint64_t>>, std::less<>> counters_;
   std::map<std::string, double> gauges_;
-  std::map<std::string, std::unique_ptr<Histogram>> hists_;
+  std::map<std::string, std::unique_ptr<Histogram>, std::less<>> hists_;
   std::map<std::string, std::string> help_;
 };
 

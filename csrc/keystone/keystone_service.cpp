@@ -57,6 +57,14 @@ KeystoneService::KeystoneService(const KeystoneConfig& config, std::shared_ptr<c
   metrics_.describe("expired_total", "objects reclaimed by TTL");
   metrics_.describe("worker_deaths_total", "workers removed after heartbeat lease expiry");
   metrics_.describe("put_bytes_total", "logical bytes admitted by put_start");
+  // series touched on every object: resolve them once (Metrics::inc looks the name up under a lock)
+  hot_.put_start_total = metrics_.counter_ref("put_start_total");
+  hot_.put_start_failed_total = metrics_.counter_ref("put_start_failed_total");
+  hot_.put_bytes_total = metrics_.counter_ref("put_bytes_total");
+  hot_.put_complete_total = metrics_.counter_ref("put_complete_total");
+  hot_.get_workers_total = metrics_.counter_ref("get_workers_total");
+  hot_.remove_total = metrics_.counter_ref("remove_total");
+  hot_.put_start_latency = metrics_.histogram_ref("put_start_latency_us");
 }
 
 KeystoneService::~KeystoneService() { stop(); }
@@ -350,7 +358,7 @@ void KeystoneService::handle_worker_death(const WorkerId& id) {
   size_t lost_objects = 0, degraded = 0;
   for (auto& sh : shards_) {
     std::vector<ObjectKey> gone;
-    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::unique_lock<SpinMutex> lk(sh.mu);
     for (auto& [key, info] : sh.objects) {
       const size_t before = info.copies.size();
       info.copies.erase(std::remove_if(info.copies.begin(), info.copies.end(),
@@ -401,7 +409,7 @@ ErrorCode KeystoneService::erase_locked(Shard& sh, const ObjectKey& key, bool fr
 Result<bool> KeystoneService::object_exists(const ObjectKey& key) {
   if (key.empty()) return ErrorCode::INVALID_KEY;
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.is_expired() || it->second.state != ObjectState::COMPLETE) return false;
   it->second.touch();
@@ -411,13 +419,13 @@ Result<bool> KeystoneService::object_exists(const ObjectKey& key) {
 Result<std::vector<CopyPlacement>> KeystoneService::get_workers(const ObjectKey& key) {
   if (key.empty()) return ErrorCode::INVALID_KEY;
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.is_expired()) return ErrorCode::OBJECT_NOT_FOUND;
   if (it->second.state != ObjectState::COMPLETE) return ErrorCode::OBJECT_NOT_READY;
   if (it->second.copies.empty()) return ErrorCode::NO_COMPLETE_WORKER;
   it->second.touch();
-  metrics_.inc("get_workers_total");
+  hot_.get_workers_total->fetch_add(1, std::memory_order_relaxed);
   return it->second.copies;
 }
 
@@ -425,12 +433,30 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start(const ObjectKey& k
                                                               const std::string& client_id, const std::string& client_node) {
   const TimePoint t0 = Clock::now();
   if (!is_leader()) return ErrorCode::NOT_LEADER;
+  Result<std::vector<CopyPlacement>> r = ErrorCode::INTERNAL_ERROR;
+  {
+    std::shared_lock<std::shared_mutex> pk(pools_mu_);  // lock order: pools -> shard
+    r = put_start_locked(key, data_size, config, client_id, client_node);
+  }
+  if (r.ok()) {
+    bump_view();
+    hot_.put_start_total->fetch_add(1, std::memory_order_relaxed);
+    hot_.put_bytes_total->fetch_add(data_size, std::memory_order_relaxed);
+  } else {
+    hot_.put_start_failed_total->fetch_add(1, std::memory_order_relaxed);
+  }
+  hot_.put_start_latency->observe(us_since(t0));
+  return r;
+}
+
+// Caller holds pools_mu_ (shared).  No view bump / metrics here: batch_put_start does those once per batch.
+Result<std::vector<CopyPlacement>> KeystoneService::put_start_locked(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
+                                                                     const std::string& client_id, const std::string& client_node) {
   if (key.empty() || key.find('\x01') != std::string::npos) return ErrorCode::INVALID_KEY;
   if (config.replication_factor == 0 || config.max_workers_per_copy == 0) return ErrorCode::INVALID_PARAMETERS;
   if (config_.max_replicas > 0 && config.replication_factor > static_cast<size_t>(config_.max_replicas)) return ErrorCode::VALUE_OUT_OF_RANGE;
-  std::shared_lock<std::shared_mutex> pk(pools_mu_);  // lock order: pools -> shard
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it != sh.objects.end()) {
     if (!it->second.is_expired()) return ErrorCode::OBJECT_ALREADY_EXISTS;
@@ -443,10 +469,7 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start(const ObjectKey& k
       if (auto sc = parse_storage_class(name)) effective.preferred_classes.push_back(*sc);
   }
   auto copies = allocator_->allocate_data_copies(key, data_size, effective, pools_, client_node);
-  if (!copies.ok()) {
-    metrics_.inc("put_start_failed_total");
-    return copies.error();
-  }
+  if (!copies.ok()) return copies.error();
   ObjectInfo info;
   info.key = key;
   info.size = data_size;
@@ -458,12 +481,6 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start(const ObjectKey& k
   info.state = ObjectState::PENDING;
   info.owner_client = client_id;
   sh.objects.emplace(key, std::move(info));
-  lk.unlock();
-  pk.unlock();
-  bump_view();
-  metrics_.inc("put_start_total");
-  metrics_.inc("put_bytes_total", data_size);
-  metrics_.observe("put_start_latency_us", us_since(t0));
   return copies;
 }
 
@@ -472,7 +489,7 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key) { return put_compl
 ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksums& checksums) {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.is_expired()) return ErrorCode::OBJECT_NOT_FOUND;
   ObjectInfo& info = it->second;
@@ -485,7 +502,7 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksu
   }
   if (info.state != ObjectState::COMPLETE) {
     info.state = ObjectState::COMPLETE;
-    metrics_.inc("put_complete_total");
+    hot_.put_complete_total->fetch_add(1, std::memory_order_relaxed);
   }
   info.touch();
   persist_object(info);
@@ -497,7 +514,7 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksu
 ErrorCode KeystoneService::put_cancel(const ObjectKey& key) {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
   if (it->second.state == ObjectState::COMPLETE) return ErrorCode::INVALID_STATE;
@@ -509,11 +526,11 @@ ErrorCode KeystoneService::put_cancel(const ObjectKey& key) {
 ErrorCode KeystoneService::remove_object(const ObjectKey& key) {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   ErrorCode ec = erase_locked(sh, key, true);
   lk.unlock();
   if (ec == ErrorCode::OK) {
-    metrics_.inc("remove_total");
+    hot_.remove_total->fetch_add(1, std::memory_order_relaxed);
     bump_view();
   }
   return ec;
@@ -523,7 +540,7 @@ Result<size_t> KeystoneService::remove_all_objects() {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   size_t n = 0;
   for (auto& sh : shards_) {
-    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::unique_lock<SpinMutex> lk(sh.mu);
     std::vector<ObjectKey> keys;
     keys.reserve(sh.objects.size());
     for (const auto& [k, v] : sh.objects) keys.push_back(k);
@@ -538,7 +555,7 @@ Result<size_t> KeystoneService::remove_all_objects() {
 
 Result<ObjectInfo> KeystoneService::get_object_info(const ObjectKey& key) const {
   const Shard& sh = shard_for(key);
-  std::shared_lock<std::shared_mutex> lk(sh.mu);
+  std::shared_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
   return it->second;
@@ -564,7 +581,26 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_put_start
                                                                                  const std::string& client_node) {
   std::vector<Result<std::vector<CopyPlacement>>> out;
   out.reserve(items.size());
-  for (const auto& it : items) out.push_back(put_start(it.key, it.size, it.config, client_id, client_node));
+  if (!is_leader()) {
+    out.assign(items.size(), ErrorCode::NOT_LEADER);
+    return out;
+  }
+  const TimePoint t0 = Clock::now();
+  uint64_t ok = 0, bytes = 0;
+  {
+    std::shared_lock<std::shared_mutex> pk(pools_mu_);  // once per batch
+    for (const auto& it : items) {
+      out.push_back(put_start_locked(it.key, it.size, it.config, client_id, client_node));
+      if (out.back().ok()) ++ok, bytes += it.size;
+    }
+  }
+  if (ok) {
+    bump_view();
+    hot_.put_start_total->fetch_add(ok, std::memory_order_relaxed);
+    hot_.put_bytes_total->fetch_add(bytes, std::memory_order_relaxed);
+  }
+  if (ok != items.size()) hot_.put_start_failed_total->fetch_add(items.size() - ok, std::memory_order_relaxed);
+  if (!items.empty()) hot_.put_start_latency->observe(us_since(t0) / static_cast<double>(items.size()));
   return out;
 }
 
@@ -612,7 +648,7 @@ Result<ClusterStats> KeystoneService::get_cluster_stats() const {
     }
   }
   for (const auto& sh : shards_) {
-    std::shared_lock<std::shared_mutex> lk(sh.mu);
+    std::shared_lock<SpinMutex> lk(sh.mu);
     for (const auto& [k, o] : sh.objects) (o.state == ObjectState::COMPLETE ? st.total_objects : st.pending_objects) += 1;
   }
   {
@@ -677,7 +713,7 @@ size_t KeystoneService::run_gc_once() {
   size_t n = 0;
   const TimePoint now = Clock::now();
   for (auto& sh : shards_) {
-    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::unique_lock<SpinMutex> lk(sh.mu);
     std::vector<ObjectKey> dead;
     for (const auto& [k, o] : sh.objects) {
       if (o.is_expired(now)) dead.push_back(k);
@@ -731,7 +767,7 @@ ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey&
     return ec;
   }
   Shard& sh = shard_for(key);
-  std::unique_lock<std::shared_mutex> lk(sh.mu);
+  std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.created != info.value().created) {  // removed / replaced while we copied
     lk.unlock();
@@ -791,7 +827,7 @@ size_t KeystoneService::run_eviction_once() {
       // LRU candidates that have data on this tier and are not soft-pinned
       std::vector<std::pair<TimePoint, ObjectKey>> cands;
       for (auto& sh : shards_) {
-        std::shared_lock<std::shared_mutex> lk(sh.mu);
+        std::shared_lock<SpinMutex> lk(sh.mu);
         for (const auto& [k, o] : sh.objects) {
           if (o.state != ObjectState::COMPLETE || o.config.enable_soft_pin) continue;
           bool here = false;
@@ -813,7 +849,7 @@ size_t KeystoneService::run_eviction_once() {
         if (demoted) metrics_.inc("demotions_total");
         if (!demoted) {
           Shard& sh = shard_for(key);
-          std::unique_lock<std::shared_mutex> lk(sh.mu);
+          std::unique_lock<SpinMutex> lk(sh.mu);
           if (erase_locked(sh, key, true) == ErrorCode::OK) metrics_.inc("evictions_total");
         }
         ++total;
@@ -833,7 +869,7 @@ size_t KeystoneService::run_repair_once() {
   if (!mover) return 0;
   std::vector<ObjectInfo> degraded;
   for (auto& sh : shards_) {
-    std::shared_lock<std::shared_mutex> lk(sh.mu);
+    std::shared_lock<SpinMutex> lk(sh.mu);
     for (const auto& [k, o] : sh.objects)
       if (o.state == ObjectState::COMPLETE && !o.copies.empty() && o.copies.size() < o.config.replication_factor) degraded.push_back(o);
   }
@@ -860,7 +896,7 @@ size_t KeystoneService::run_repair_once() {
       continue;
     }
     Shard& sh = shard_for(o.key);
-    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::unique_lock<SpinMutex> lk(sh.mu);
     auto it = sh.objects.find(o.key);
     if (it == sh.objects.end() || it->second.created != o.created) {
       lk.unlock();
@@ -901,7 +937,7 @@ void KeystoneService::recover_objects_from_wal() {
     ObjectInfo o;
     if (!decode_object(values[i], o) || o.is_expired()) continue;
     Shard& sh = shard_for(o.key);
-    std::unique_lock<std::shared_mutex> lk(sh.mu);
+    std::unique_lock<SpinMutex> lk(sh.mu);
     if (sh.objects.count(o.key)) continue;
     // re-reserve the extents so that new puts cannot overwrite recovered objects
     static_cast<alloc::RangeAllocator&>(allocator_->allocator()).adopt(o.key, o.copies, pools_);

@@ -31,6 +31,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "common/spin.h"
 #include "alloc/allocator.h"
 #include "common/metrics.h"
 #include "common/types.h"
@@ -153,9 +154,9 @@ class KeystoneService {
   alloc::AllocatorStats allocator_stats() const { return allocator_->get_allocator_stats(); }
 
  private:
-  static constexpr size_t kShards = 32;
+  static constexpr size_t kShards = 128;
   struct Shard {
-    mutable std::shared_mutex mu;
+    mutable SpinMutex mu;  // sub-microsecond sections taken by every client on every object: never sleep on it
     std::unordered_map<ObjectKey, ObjectInfo> objects;
   };
   Shard& shard_for(const ObjectKey& key) { return shards_[std::hash<ObjectKey>{}(key) % kShards]; }
@@ -198,6 +199,13 @@ class KeystoneService {
 
   std::mutex mover_mu_;
   CopyMover mover_;
+  Result<std::vector<CopyPlacement>> put_start_locked(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
+                                                      const std::string& client_id, const std::string& client_node);
+  struct HotMetrics {
+    std::atomic<uint64_t>*put_start_total = nullptr, *put_start_failed_total = nullptr, *put_bytes_total = nullptr,
+                         *put_complete_total = nullptr, *get_workers_total = nullptr, *remove_total = nullptr;
+    Histogram* put_start_latency = nullptr;
+  } hot_;
   ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets);
 
   std::atomic<bool> running_{false};
