@@ -3,6 +3,8 @@
 // commit / free ops/s on a disk backend).
 //   bb-bench client  --keystone host:port --size 1048576 --iterations 50 [--replicas 1] [--max-workers 1] [--batch 1]
 //   bb-bench backend --class NVME --path /tmp/x --ops 50 --size 4096
+//   bb-bench gpu --keystone host:port [--device 0] [--objects 64] [--size 67108864] [--iterations 20] [--node gpu1]
+//              (device-resident batched put + get through the fused kernels: no Python, no torch)
 //   bb-bench control [--threads 4] [--batch 4096] [--iterations 20] [--pools 8] [--rpc]   (keystone metadata ops/s)
 #include <algorithm>
 #include <chrono>
@@ -15,6 +17,8 @@
 #include <thread>
 
 #include "client/blackbird_client.h"
+#include "fabric/gpu_fabric.h"
+#include "fabric/xfer_engine.h"
 #include "keystone/keystone_service.h"
 #include "rpc/rpc_service.h"
 #include "worker/storage_backend.h"
@@ -35,7 +39,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   const std::string mode = args.positional.empty() ? "client" : args.positional[0];
   if (args.has("help")) {
-    std::printf("usage: bb-bench client|backend|control [options]\n");
+    std::printf("usage: bb-bench client|backend|control|gpu [options]\n");
     return 0;
   }
   if (mode == "backend") {
@@ -74,6 +78,94 @@ int main(int argc, char** argv) {
                 args.get("class", "NVME").c_str(), done, static_cast<unsigned long long>(size), avg(t_res), avg(t_wr), avg(t_com), avg(t_free),
                 done ? 1000.0 / (avg(t_res) + avg(t_wr) + avg(t_com) + avg(t_free)) : 0.0);
     return 0;
+  }
+  if (mode == "gpu") {
+    // Native device-path benchmark: this process is a client with its own GPU; objects live in device memory and
+    // move to the GPU-tier workers' slabs (bb-worker with a RAM_GPU pool, same box) through the fused kernels.
+    auto khp = split_host_port(args.get("keystone", "127.0.0.1:9090"));
+    if (!khp) return 2;
+    const int device = static_cast<int>(args.num("device", 0));
+    const size_t nobj = static_cast<size_t>(args.num("objects", 64));
+    const size_t osz = static_cast<size_t>(args.num("size", 64ll << 20)) / 256 * 256;
+    const int iters = std::max(1, static_cast<int>(args.num("iterations", 20)));
+    int ndev = 0;
+    gpu::device_count(&ndev);
+    if (ndev <= device) {
+      std::fprintf(stderr, "bb-bench gpu: CUDA device %d not present (%d devices)\n", device, ndev);
+      return 3;
+    }
+    auto api = std::make_shared<rpc::KeystoneRpcClient>();
+    if (api->connect(khp->first, static_cast<uint16_t>(khp->second), 10000) != ErrorCode::OK) {
+      std::fprintf(stderr, "bb-bench gpu: cannot reach keystone %s\n", args.get("keystone", "127.0.0.1:9090").c_str());
+      return 1;
+    }
+    client::BlackbirdClientOptions o;
+    o.keystone_host = khp->first;
+    o.keystone_port = static_cast<uint16_t>(khp->second);
+    o.node_id = args.get("client-node", "bench-gpu" + std::to_string(device));
+    client::BlackbirdClient cl(api, o);
+    if (cl.connect() != ErrorCode::OK) return 1;
+    auto fab = gpu::GpuFabric::create(device, api);
+    if (!fab.ok()) {
+      std::fprintf(stderr, "bb-bench gpu: fabric init failed: %s\n", std::string(to_string(fab.error())).c_str());
+      return 1;
+    }
+    cl.set_device_transport(fab.value());
+    void *src = nullptr, *dst = nullptr;
+    if (gpu::device_malloc(device, nobj * osz, &src) != ErrorCode::OK || gpu::device_malloc(device, nobj * osz, &dst) != ErrorCode::OK) return 1;
+    gpu::launch_random_fill(src, nobj * osz, 0xB200, nullptr);
+    gpu::device_synchronize(device);
+    WorkerConfig cfg;
+    cfg.replication_factor = static_cast<size_t>(args.num("replicas", 1));
+    cfg.max_workers_per_copy = static_cast<size_t>(args.num("max-workers", 1));
+    cfg.ttl_ms = 0;
+    cfg.preferred_classes = {StorageClass::RAM_GPU};
+    cfg.preferred_node = args.get("node", "");
+    if (args.get("checksum") == "crc32c") cfg.checksum = ChecksumAlgo::CRC32C;
+    if (args.get("checksum") == "none") cfg.checksum = ChecksumAlgo::NONE;
+    std::vector<const void*> sp;
+    std::vector<void*> dp;
+    std::vector<size_t> sizes(nobj, osz);
+    for (size_t i = 0; i < nobj; ++i) {
+      sp.push_back(static_cast<uint8_t*>(src) + i * osz);
+      dp.push_back(static_cast<uint8_t*>(dst) + i * osz);
+    }
+    std::vector<double> put_ms, get_ms;
+    int failures = 0;
+    const double dev0 = fab.value()->total_device_ms();
+    for (int it = -2; it < iters; ++it) {  // two warm-up rounds
+      std::vector<ObjectKey> keys;
+      for (size_t i = 0; i < nobj; ++i) keys.push_back("gpubench/" + std::to_string(it + 2) + "/" + std::to_string(i));
+      auto a = Clk::now();
+      auto pe = cl.batch_put_device(keys, sp, sizes, cfg, nullptr);
+      auto b = Clk::now();
+      std::vector<size_t> got;
+      auto ge = cl.batch_get_device(keys, dp, sizes, nullptr, &got);
+      auto c = Clk::now();
+      const bool ok = std::all_of(pe.begin(), pe.end(), [](ErrorCode e) { return e == ErrorCode::OK; }) &&
+                      std::all_of(ge.begin(), ge.end(), [](ErrorCode e) { return e == ErrorCode::OK; });
+      if (!ok) ++failures;
+      cl.batch_remove(keys);
+      if (it >= 0 && ok) put_ms.push_back(ms(a, b)), get_ms.push_back(ms(b, c));
+    }
+    // spot check: first and last 64 KiB of the read-back equal the source
+    std::vector<uint8_t> h1(65536), h2(65536);
+    bool same = true;
+    for (size_t off : {size_t{0}, nobj * osz - 65536}) {
+      fab.value()->copy_d2h(h1.data(), static_cast<uint8_t*>(src) + off, 65536, nullptr);
+      fab.value()->copy_d2h(h2.data(), static_cast<uint8_t*>(dst) + off, 65536, nullptr);
+      same &= h1 == h2;
+    }
+    auto avg = [](const std::vector<double>& v) { return v.empty() ? 0.0 : std::accumulate(v.begin(), v.end(), 0.0) / static_cast<double>(v.size()); };
+    const double gb = static_cast<double>(nobj * osz) / 1e9;
+    std::printf("{\"mode\": \"gpu\", \"device\": %d, \"objects\": %zu, \"size\": %zu, \"iterations\": %zu, \"failures\": %d, \"verified\": %s, "
+                "\"put_ms_p50\": %.3f, \"get_ms_p50\": %.3f, \"put_GBps\": %.1f, \"get_GBps\": %.1f, \"kernel_ms_total\": %.2f, \"launches\": %llu}\n",
+                device, nobj, osz, put_ms.size(), failures, same ? "true" : "false", pct(put_ms, 0.5), pct(get_ms, 0.5),
+                put_ms.empty() ? 0.0 : gb / (avg(put_ms) * 1e-3), get_ms.empty() ? 0.0 : gb / (avg(get_ms) * 1e-3),
+                fab.value()->total_device_ms() - dev0, static_cast<unsigned long long>(fab.value()->launches()));
+    gpu::device_free(device, src);
+    gpu::device_free(device, dst);
+    return failures || !same ? 1 : 0;
   }
   if (mode == "control") {
     // Control-plane throughput: T clients drive batch_put_start -> batch_put_complete -> batch_get_workers ->

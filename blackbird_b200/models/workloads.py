@@ -203,6 +203,7 @@ def tier_spill(cluster, nobj: int = 10, size: int = 6 << 20) -> dict:
     assert _ok(ecs), [str(e) for e in ecs]
     verified = sum(int(torch.equal(src[i * size:(i + 1) * size], out[i * size:(i + 1) * size])) for i in range(nobj + 1))
     text = ks.metrics_text()
+    gpu_util_after = ks.tier_utilization(_bb.StorageClass.RAM_GPU)
     # promotion: bring the coldest object back into HBM (DRAM/NVMe -> GPU) and read it through the fused get
     promoted = False
     cold = next((k for k in keys if tiers[k] != _bb.StorageClass.RAM_GPU), None)
@@ -222,7 +223,7 @@ def tier_spill(cluster, nobj: int = 10, size: int = 6 << 20) -> dict:
         "demoted_to_nvme": sum(1 for t in tiers.values() if t == _bb.StorageClass.NVME),
         "still_in_hbm": sum(1 for t in tiers.values() if t == _bb.StorageClass.RAM_GPU),
         "pinned_tier": str(tiers["spill/pinned"]).split(".")[-1],
-        "gpu_util_after": ks.tier_utilization(_bb.StorageClass.RAM_GPU),
+        "gpu_util_after": gpu_util_after,
         "dropped": "bb_evictions_total" in text, "fill_s": fill_s, "read_back_s": read_s,
     }
 

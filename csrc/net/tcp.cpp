@@ -342,6 +342,7 @@ void TcpServer::worker_loop() {
       if (it == conns_.end()) continue;
       c = it->second;
     }
+    c->acquire_ownership();  // pairs with release_ownership() of the thread that re-armed this connection
     bool alive = true;
     while (true) {
       ssize_t r = ::recv(c->fd(), buf, sizeof buf, 0);
@@ -377,6 +378,7 @@ void TcpServer::worker_loop() {
       drop(c);
       continue;
     }
+    c->release_ownership();
     epoll_event rearm{};
     rearm.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;
     rearm.data.fd = c->fd();

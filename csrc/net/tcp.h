@@ -42,6 +42,10 @@ class Connection : public std::enable_shared_from_this<Connection> {
   uint64_t id() const { return id_; }
   const std::string& peer() const { return peer_; }
   std::string& inbuf() { return inbuf_; }
+  // EPOLLONESHOT hands a connection from one pool thread to the next through the kernel; these make the
+  // hand-off an explicit release/acquire pair on the connection's own state as well.
+  void release_ownership() { handoff_.fetch_add(1, std::memory_order_release); }
+  void acquire_ownership() { (void)handoff_.load(std::memory_order_acquire); }
   int fd() const { return fd_; }
   // arbitrary per-connection state for protocol layers (e.g. watch subscriptions)
   std::shared_ptr<void> user;
@@ -54,6 +58,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::string inbuf_;
   std::mutex write_mu_;
   std::atomic<bool> closed_{false};
+  std::atomic<uint64_t> handoff_{0};
 };
 using ConnPtr = std::shared_ptr<Connection>;
 

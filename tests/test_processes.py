@@ -167,3 +167,56 @@ def test_keystone_process_failover(procs, tmp_path):
         time.sleep(0.3)
     assert ok and out.read_bytes() == blob.read_bytes()
     assert run_cli("--keystone", f"127.0.0.1:{ports[1]}", "put", "after-failover", str(blob)).returncode == 0
+
+
+def test_control_plane_benchmark_binary():
+    b = subprocess.run([os.path.join(BIN, "bb-bench"), "control", "--threads", "4", "--batch", "256", "--iterations", "4"],
+                       capture_output=True, text=True, timeout=120)
+    res = json.loads(b.stdout)
+    assert b.returncode == 0 and res["objects"] == 4 * 256 * 4 and res["object_lifecycles_per_s"] > 10000, b.stdout + b.stderr
+
+
+@pytest.mark.gpu
+def test_native_gpu_path_without_python(procs, tmp_path):
+    """bb-coord + bb-keystone + bb-worker with a RAM_GPU pool + `bb-bench gpu`: the whole device path (CUDA IPC slab
+    export, fused put/get kernels, digests in the keystone) with no Python or torch in any of the processes, and
+    the client in a different process than the worker (the slab is opened through its IPC handle)."""
+    cport, rport, hport = free_port(), free_port(), free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    procs.spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+                "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "gpuproc")
+    assert wait_port(rport)
+    cfg = tmp_path / "gpu_worker.yaml"
+    cfg.write_text("""
+worker:
+  worker_id: "worker-gpu0"
+  node_id: "gpu0"
+  interconnects: ["nvlink", "tcp"]
+  fabric_domain: "nvswitch-0"
+  lease_ttl_sec: 5
+  heartbeat_interval_sec: 1
+storage_pools:
+  - pool_id: "hbm0"
+    storage_class: "RAM_GPU"
+    size_bytes: 1_GB
+    gpu_device_id: 0
+""")
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "gpuproc")
+    ks = f"127.0.0.1:{rport}"
+    deadline = time.time() + 30
+    st = None
+    while time.time() < deadline:
+        st = run_cli("--keystone", ks, "stats")
+        if st.returncode == 0 and json.loads(st.stdout)["total_memory_pools"] == 1:
+            break
+        time.sleep(0.2)
+    assert st is not None and json.loads(st.stdout)["total_memory_pools"] == 1, st.stdout if st else ""
+    b = subprocess.run([os.path.join(BIN, "bb-bench"), "gpu", "--keystone", ks, "--objects", "16", "--size", str(16 << 20), "--iterations", "5"],
+                       capture_output=True, text=True, timeout=120)
+    assert b.returncode == 0, b.stdout + b.stderr
+    res = json.loads(b.stdout.strip().splitlines()[-1])
+    assert res["failures"] == 0 and res["verified"] is True and res["launches"] >= 14 and res["put_GBps"] > 50
+    # the same objects' tier is visible to a plain TCP client
+    m = run_cli("metrics", "--http", f"127.0.0.1:{hport}")
+    assert m.returncode == 0 and "bb_put_start_total" in m.stdout
