@@ -1,3 +1,4 @@
+#include "common/trace.h"
 #include "client/blackbird_client.h"
 
 #include <algorithm>
@@ -245,6 +246,7 @@ ErrorCode BlackbirdClient::put(const ObjectKey& key, const uint8_t* data, size_t
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
   if (!data && size) return ErrorCode::INVALID_PARAMETERS;
   const TimePoint t0 = Clock::now();
+  BB_TRACE_SPAN("client.put", size);
   auto placed = keystone_->put_start(key, size, cfg);
   if (!placed.ok()) return placed.error();
   ShardChecksums sums;
@@ -266,6 +268,7 @@ ErrorCode BlackbirdClient::put(const ObjectKey& key, const uint8_t* data, size_t
 Result<std::vector<uint8_t>> BlackbirdClient::get(const ObjectKey& key) {
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
   const TimePoint t0 = Clock::now();
+  BB_TRACE_SPAN("client.get");
   auto copies = keystone_->get_workers(key);
   if (!copies.ok()) return copies.error();
   if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
@@ -438,6 +441,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
   if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
   if (dev_ptrs.size() != keys.size() || sizes.size() != keys.size()) return out;
   const TimePoint t_all = Clock::now();
+  BB_TRACE_SPAN("batch_put_device", keys.size());
 
   struct Chunk {
     size_t begin = 0, end = 0;
@@ -455,6 +459,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
 
   auto start_chunk = [&](Chunk& ch) {
     const TimePoint t0 = Clock::now();
+    BB_TRACE_SPAN("put.start_chunk", ch.end - ch.begin);
     std::vector<PutStartItem> items;
     items.reserve(ch.end - ch.begin);
     for (size_t i = ch.begin; i < ch.end; ++i) items.push_back(PutStartItem{keys[i], sizes[i], cfg});
@@ -524,6 +529,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
   };
 
   auto finish_chunk = [&](Chunk& ch) {
+    BB_TRACE_SPAN("finish_chunk", ch.end - ch.begin);
     std::vector<uint64_t> digests;
     ErrorCode ec = ch.submit_error;
     const TimePoint t1 = Clock::now();
@@ -604,6 +610,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
   if (dev_ptrs.size() != keys.size() || capacity.size() != keys.size()) return out;
   const TimePoint t_all = Clock::now();
+  BB_TRACE_SPAN("batch_get_device", keys.size());
   if (out_sizes) out_sizes->assign(keys.size(), 0);
   std::vector<Result<std::vector<CopyPlacement>>> placed(keys.size(), Result<std::vector<CopyPlacement>>(ErrorCode::INTERNAL_ERROR));
   std::vector<size_t> copy_choice(keys.size(), 0);
@@ -717,6 +724,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
     }
   };
   auto finish_chunk = [&](Chunk& ch) {
+    BB_TRACE_SPAN("finish_chunk", ch.end - ch.begin);
     if (ch.ops.empty()) return;
     std::vector<uint32_t> status;
     ErrorCode ec = ch.err;

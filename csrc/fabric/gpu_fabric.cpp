@@ -1,3 +1,4 @@
+#include "common/trace.h"
 #include "fabric/gpu_fabric.h"
 
 #include <cuda_runtime.h>
@@ -353,6 +354,7 @@ ErrorCode GpuFabric::build_put_items(const std::vector<client::DeviceShardOp>& o
 
 Result<uint64_t> GpuFabric::submit_put(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
                                        ChecksumAlgo algo, void* stream) {
+  BB_TRACE_SPAN("fabric.submit_put");
   std::vector<XferItem> items;
   InFlight fl;
   fl.nops = ops.size();
@@ -366,6 +368,7 @@ Result<uint64_t> GpuFabric::submit_put(const std::vector<client::DeviceShardOp>&
 }
 
 ErrorCode GpuFabric::wait_put(uint64_t ticket, std::vector<uint64_t>* digests) {
+  BB_TRACE_SPAN("fabric.wait_put");
   InFlight fl;
   {
     std::lock_guard<std::mutex> lk(mu_);
@@ -394,6 +397,7 @@ ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, c
 }
 
 Result<uint64_t> GpuFabric::submit_get(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, void* stream) {
+  BB_TRACE_SPAN("fabric.submit_get");
   bool uniform = true;
   for (const auto& op : ops) uniform &= op.placement->checksum_algo == ops[0].placement->checksum_algo;
   InFlight fl;
@@ -430,6 +434,7 @@ Result<uint64_t> GpuFabric::submit_get(const std::vector<client::DeviceShardOp>&
 }
 
 ErrorCode GpuFabric::wait_get(uint64_t ticket, std::vector<uint32_t>* status) {
+  BB_TRACE_SPAN("fabric.wait_get");
   InFlight fl;
   {
     std::lock_guard<std::mutex> lk(mu_);

@@ -33,6 +33,9 @@ struct XferEngine::Slot {
   uint8_t* h_res = nullptr;
   uint32_t* d_debug = nullptr;
   size_t d_debug_bytes = 0;
+  uint64_t* d_trace = nullptr;
+  size_t d_trace_bytes = 0;
+  bool traced = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   uint64_t ticket = 0;  // 0 = free
   uint32_t nitems = 0;
@@ -93,6 +96,7 @@ XferEngine::~XferEngine() {
     cudaFree(s->d_digest);
     cudaFree(s->d_status);
     if (s->d_debug) cudaFree(s->d_debug);
+    if (s->d_trace) cudaFree(s->d_trace);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
     if (s->ev_done) cudaEventDestroy(s->ev_done);
@@ -178,6 +182,17 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
         l.host_tile_start = tile_start;
       }
       l.debug_d = capture_debug ? s->d_debug : nullptr;
+      s->traced = tile_trace_;
+      if (tile_trace_) {
+        const size_t need = static_cast<size_t>(tiles) * 4 * sizeof(uint64_t);
+        if (need > s->d_trace_bytes) {
+          if (s->d_trace) cudaFree(s->d_trace);
+          BB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_trace), need));
+          s->d_trace_bytes = need;
+        }
+        BB_CUDA(cudaMemsetAsync(s->d_trace, 0, need, st));
+        l.trace_d = s->d_trace;
+      }
       l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : algo == ChecksumAlgo::CRC32C ? ALGO_CRC32C : ALGO_NONE;
       l.max_ctas = max_ctas_;
       l.stream = stream;
@@ -235,6 +250,10 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
   if (s->debug && nd) {
     debug_host_.resize(static_cast<size_t>(s->total_tiles) * tchash::kRows * tchash::kN);
     BB_CUDA(cudaMemcpy(debug_host_.data(), s->d_debug, debug_host_.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  if (s->traced && nd) {
+    trace_host_.resize(static_cast<size_t>(s->total_tiles) * 4);
+    BB_CUDA(cudaMemcpy(trace_host_.data(), s->d_trace, trace_host_.size() * 8, cudaMemcpyDeviceToHost));
   }
   s->ticket = 0;
   return ErrorCode::OK;

@@ -51,6 +51,10 @@ class XferEngine {
 
   // Raw accumulators of the last capture_debug batch: [total_tiles][128][16] (tests only).
   const std::vector<uint32_t>& debug_accumulators() const { return debug_host_; }
+  // Diagnostics: when on, every batch records per-tile pipeline timestamps (globaltimer ns):
+  // [tile][4] = load issued, landed in shared memory, store issued, slot released.  Read after wait().
+  void set_tile_trace(bool on) { tile_trace_ = on; }
+  const std::vector<uint64_t>& tile_trace() const { return trace_host_; }
 
   int device() const { return device_; }
   uint64_t launches() const { return launches_; }  // kernels launched so far
@@ -68,6 +72,8 @@ class XferEngine {
   int max_ctas_ = 0;
   int last_cuda_error_ = 0;
   std::vector<uint32_t> debug_host_;
+  bool tile_trace_ = false;
+  std::vector<uint64_t> trace_host_;
 };
 
 // Device helpers used by bindings, the worker and benchmarks (all return ErrorCode).

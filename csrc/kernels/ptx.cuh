@@ -170,4 +170,10 @@ __device__ __forceinline__ uint64_t globaltimer() {
   return t;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 }  // namespace bb::ptx

@@ -47,6 +47,7 @@ struct XferLaunch {
   uint32_t* status_out = nullptr;        // device, ndesc entries (0 ok / 1 checksum mismatch)
   const uint32_t* crc_tables = nullptr;  // device, CRC32C shift tables (only ALGO_CRC32C)
   uint32_t* debug_d = nullptr;           // optional: raw accumulators [tile][128][16] (tests)
+  uint64_t* trace_d = nullptr;           // optional: per-tile pipeline timestamps [tile][4] (globaltimer ns)
   // Optional host copies of the two tables: batches of <= kInlineDescs descriptors travel in the
   // kernel parameters instead (descs / tile_start may then be null).
   const XferDesc* host_descs = nullptr;

@@ -104,6 +104,9 @@ struct Params {
   uint32_t* status_out;
   const uint32_t* crc_tables;  // [kNumCrcTabs][4][256]
   uint32_t* debug_d;
+  // Optional per-tile pipeline trace (diagnostics): [tile][4] globaltimer ns = load issued, tile landed in smem,
+  // store issued, smem slot released.
+  unsigned long long* trace_d;
   // Small batches carry their descriptor table in the kernel parameters (constant bank): no H2D
   // copy ahead of the launch, which is most of a single-object put/get's latency.
   uint32_t use_inline;
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
           s.dirty[stage] = (bytes + 15u) & ~15u;
           mbar_arrive_expect_tx(&s.full[stage], b16);
           if (b16) bulk_g2s(s.tile[stage], reinterpret_cast<const void*>(src_i + off), b16, &s.full[stage]);
+          if (p.trace_d) p.trace_d[static_cast<uint64_t>(t0 + base + i) * 4 + 0] = globaltimer_ns();
         }
         __syncwarp();
       }
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
       const uint32_t stage = it % kStages;
       const uint32_t par = (it / kStages) & 1u;
       mbar_wait(&s.full[stage], par);
+      if (p.trace_d && lane == 0) p.trace_d[static_cast<uint64_t>(t0 + it) * 4 + 1] = globaltimer_ns();
       const StageMeta& m = s.meta[stage];
       const uint64_t off = static_cast<uint64_t>(m.tile_in_obj) * kTileBytes;
       const uint32_t b16 = m.bytes & ~15u;
@@ -317,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
           if (b16) bulk_s2g(reinterpret_cast<void*>(m.dst[r] + off), s.tile[stage], b16);
       }
       if (lane == 0) bulk_commit();
+      if (p.trace_d && lane == 0) p.trace_d[static_cast<uint64_t>(t0 + it) * 4 + 2] = globaltimer_ns();
       if (lane < tail) {
         const uint8_t b = s.tile[stage][b16 + lane];
         for (uint32_t r = 0; r < ndst; ++r) *reinterpret_cast<uint8_t*>(m.dst[r] + off + b16 + lane) = b;
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
       if (it >= kStoreLag && lane == 0) {
         bulk_wait_read<kStoreLag>();
         mbar_arrive(&s.empty[(it - kStoreLag) % kStages]);
+        if (p.trace_d) p.trace_d[static_cast<uint64_t>(t0 + it - kStoreLag) * 4 + 3] = globaltimer_ns();
       }
     }
     if (lane == 0) {
@@ -603,6 +610,7 @@ int launch_xfer(const XferLaunch& l) {
   p.status_out = l.status_out;
   p.crc_tables = ds.crc_tables;
   p.debug_d = l.debug_d;
+  p.trace_d = reinterpret_cast<unsigned long long*>(l.trace_d);
   // Measured on B200 (profiles/xfer_single_gpu.md): 96-128 persistent CTAs saturate HBM for
   // large batches (3.2 TB/s payload); all 148 lose ~6% to DRAM contention.  BB_XFER_CTAS overrides.
   static const int env_ctas = [] { const char* e = std::getenv("BB_XFER_CTAS"); return e ? std::atoi(e) : 0; }();

@@ -1,3 +1,4 @@
+#include "common/fault.h"
 #include "keystone/keystone_service.h"
 
 #include <algorithm>
@@ -488,6 +489,7 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key) { return put_compl
 
 ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksums& checksums) {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
+  if (fault::fire("fail_put_complete")) return ErrorCode::INTERNAL_ERROR;
   Shard& sh = shard_for(key);
   std::unique_lock<SpinMutex> lk(sh.mu);
   auto it = sh.objects.find(key);

@@ -1,3 +1,4 @@
+#include "common/fault.h"
 #include "net/tcp.h"
 
 #include <arpa/inet.h>
@@ -14,6 +15,7 @@
 
 #include <cerrno>
 #include <chrono>
+#include <thread>
 #include <cstring>
 
 #include "common/log.h"
@@ -418,6 +420,7 @@ bool RpcServer::on_data(const ConnPtr& c) {
       rmethod = 0x7FFFFFFFu;  // unknown-method marker
     } else {
       try {
+        if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
         resp = it->second(c, payload);
       } catch (const std::exception& e) {
         BB_LOG(ERROR) << "rpc handler " << method << " threw: " << e.what();

@@ -1,6 +1,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "common/fault.h"
+#include "common/trace.h"
 #include "common/checksum.h"
 #include "common/error.h"
 #include "common/json.h"
@@ -146,6 +148,16 @@ void bind_common(py::module_& m) {
     if (!j) throw py::value_error("json: " + err);
     return j->dump();
   });
+  // tracing + fault injection (csrc/common/trace.h, fault.h)
+  m.def("trace_enable", [](bool on, size_t cap) { trace::enable(on, cap); }, py::arg("on") = true, py::arg("ring_capacity") = size_t{1} << 16);
+  m.def("trace_enabled", &trace::enabled);
+  m.def("trace_dump", &trace::dump, "writes Chrome/Perfetto traceEvents JSON; returns the number of events");
+  m.def("trace_recorded", &trace::recorded);
+  m.def("trace_clear", &trace::clear);
+  m.def("fault_arm", &fault::arm, py::arg("name"), py::arg("value") = 1, py::arg("count") = -1);
+  m.def("fault_disarm", &fault::disarm);
+  m.def("fault_clear", &fault::clear);
+  m.def("fault_arm_from_spec", &fault::arm_from_spec);
   m.def("parse_size", [](const std::string& s) -> py::object {
     auto v = parse_size(s);
     if (!v) return py::none();

@@ -96,6 +96,8 @@ void bind_gpu(py::module_& m) {
            })
       .def("debug_accumulators", [](XferEngine& e) { return e.debug_accumulators(); })
       .def("set_max_ctas", &XferEngine::set_max_ctas)
+      .def("set_tile_trace", &XferEngine::set_tile_trace)
+      .def("tile_trace", [](XferEngine& e) { return e.tile_trace(); }, "[tile][4] globaltimer ns: load issued, landed, store issued, slot released")
       .def_property_readonly("launches", &XferEngine::launches)
       .def_property_readonly("device", &XferEngine::device);
 
@@ -138,6 +140,8 @@ void bind_gpu(py::module_& m) {
       .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
       .def_property_readonly("total_device_ms", &GpuFabric::total_device_ms)
       .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); })
+      .def("set_tile_trace", [](GpuFabric& f, bool on) { f.engine().set_tile_trace(on); })
+      .def("tile_trace", [](GpuFabric& f) { return f.engine().tile_trace(); })
       .def("set_arena", &GpuFabric::set_arena)
       .def_property_readonly("multicast_puts", &GpuFabric::multicast_puts);
   py::class_<NvlsArena, std::shared_ptr<NvlsArena>>(m, "NvlsArena")

@@ -1,3 +1,4 @@
+#include "common/fault.h"
 #include "worker/worker_service.h"
 
 #include <chrono>
@@ -262,7 +263,7 @@ void WorkerService::heartbeat_loop() {
       sleep_cv_.wait_for(lk, std::chrono::seconds(config_.heartbeat_interval_sec), [this] { return !running_.load(); });
     }
     if (!running_.load()) return;
-    if (drop_heartbeat_.load()) continue;
+    if (drop_heartbeat_.load() || fault::fire("drop_heartbeat")) continue;
     ErrorCode ec = ErrorCode::OK;
     if (coord_) ec = coord_->put_with_ttl(cluster_prefix() + "heartbeat/" + config_.worker_id, std::to_string(std::time(nullptr)), config_.lease_ttl_sec);
     else if (keystone_) ec = keystone_->worker_heartbeat(config_.worker_id);
@@ -359,7 +360,16 @@ void WorkerService::register_data_handlers() {
       return w.take();
     }
     const char* payload = q.data() + (q.size() - len);
-    w.ec(b->write(resolve_offset(*b, off), payload, len));
+    if (fault::fire("fail_data_write")) {
+      w.ec(ErrorCode::IO_ERROR);
+      return w.take();
+    }
+    ErrorCode wec = b->write(resolve_offset(*b, off), payload, len);
+    if (wec == ErrorCode::OK && len && fault::fire("corrupt_write")) {  // silent corruption: the checksum must catch it
+      const char bad = static_cast<char>(payload[len / 2] ^ 0x5A);
+      b->write(resolve_offset(*b, off) + len / 2, &bad, 1);
+    }
+    w.ec(wec);
     return w.take();
   });
   data_server_.register_method(D_READ, [this](C, S q) {
@@ -369,7 +379,9 @@ void WorkerService::register_data_handlers() {
     const uint32_t len = r.u32();
     StorageBackend* b = backend(pool);
     std::string out(4 + (b && r.ok() ? len : 0), '\0');
-    ErrorCode ec = !b ? ErrorCode::MEMORY_POOL_NOT_FOUND : !r.ok() ? ErrorCode::INVALID_PARAMETERS : b->read(resolve_offset(*b, off), out.data() + 4, len);
+    ErrorCode ec = !b ? ErrorCode::MEMORY_POOL_NOT_FOUND : !r.ok() ? ErrorCode::INVALID_PARAMETERS
+                   : fault::fire("fail_data_read") ? ErrorCode::IO_ERROR
+                                                   : b->read(resolve_offset(*b, off), out.data() + 4, len);
     const uint32_t e = static_cast<uint32_t>(ec);
     std::memcpy(out.data(), &e, 4);
     if (ec != ErrorCode::OK) out.resize(4);

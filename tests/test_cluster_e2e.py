@@ -280,3 +280,55 @@ def test_explicit_migrate_promotes_and_demotes_across_tiers(bb, tmp_path):
         assert cl.migrate("nope", bb.StorageClass.NVME) == bb.ErrorCode.OBJECT_NOT_FOUND
         assert cl.migrate("m", bb.StorageClass.RAM_GPU) == bb.ErrorCode.INSUFFICIENT_SPACE  # no such tier in this cluster
         assert "bb_migrations_total 2" in c.keystone.metrics_text()
+
+
+def test_fault_injection_corruption_and_read_errors_fail_over_to_replica(bb):
+    """BB_FAULT hooks (csrc/common/fault.h): a silently corrupted replica is caught by the per-shard digest and the
+    get is served from the other copy; an I/O error on one data server does the same; a failed write cancels the put."""
+    with LocalCluster("faults", n_workers=2, pool_bytes=16 << 20) as c:
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1, ttl_ms=0, checksum=bb.ChecksumAlgo.CRC32C)
+        blob = os.urandom(300_000)
+        try:
+            bb.fault_arm("corrupt_write", 1, 1)  # exactly one shard write is corrupted after it lands
+            assert cl.put("c1", blob, cfg) == bb.ErrorCode.OK
+            bb.fault_clear()
+            for _ in range(4):  # whichever replica is tried first, the answer is the intact one
+                assert cl.get("c1") == blob
+            assert cl.phase_summary() is not None
+            bb.fault_arm("fail_data_read", 1, 1)
+            assert cl.get("c1") == blob  # first read errors out -> next replica
+            bb.fault_arm("fail_data_write", 1, 1)
+            assert cl.put("c2", blob, cfg) != bb.ErrorCode.OK
+            bb.fault_clear()
+            assert cl.object_exists("c2") is False  # cancelled, nothing half-written is visible
+            assert cl.put("c2", blob, cfg) == bb.ErrorCode.OK and cl.get("c2") == blob
+            bb.fault_arm("fail_put_complete", 1, 1)
+            assert cl.put("c3", blob, cfg) != bb.ErrorCode.OK
+            bb.fault_clear()
+            assert cl.object_exists("c3") is False
+            assert bb.fault_arm_from_spec("drop_heartbeat, delay_rpc_ms=5, corrupt_write:3") == 3
+        finally:
+            bb.fault_clear()
+
+
+def test_trace_spans_are_recorded_and_dumped_as_chrome_trace(bb, tmp_path):
+    import json
+
+    bb.trace_clear()
+    bb.trace_enable(True, 1024)
+    try:
+        with LocalCluster("trace", n_workers=1, pool_bytes=8 << 20) as c:
+            cl = c.client()
+            assert cl.put("t", b"x" * 5000, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
+            assert cl.get("t") == b"x" * 5000
+        out = tmp_path / "trace.json"
+        n = bb.trace_dump(str(out))
+        ev = json.loads(out.read_text())["traceEvents"]
+        assert n == len(ev) and n >= 2
+        names = {e["name"] for e in ev}
+        assert {"client.put", "client.get"} <= names and all(e["ph"] in ("X", "i") for e in ev)
+        assert all(e["dur"] > 0 for e in ev if e["ph"] == "X")
+    finally:
+        bb.trace_enable(False)
+        bb.trace_clear()

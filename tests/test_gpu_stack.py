@@ -183,3 +183,23 @@ def test_gpu_tier_spill_gpu_to_dram_to_nvme(bb, torch_cuda, tmp_path):
         assert r["fused_tier_moves"] >= 3 and r["promoted_back"], r
     finally:
         cl.stop()
+
+
+def test_tile_trace_records_the_pipeline(bb, torch_cuda):
+    """Diagnostics: per-tile globaltimer stamps of the fused kernel's producer and store warps."""
+    torch = torch_cuda
+    import numpy as np
+
+    eng = bb.XferEngine(0, 64, 2)
+    n = 8 << 20
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+    dst = torch.zeros_like(src)
+    eng.set_tile_trace(True)
+    dg, st, _ = eng.run([(src.data_ptr(), dst.data_ptr(), n)], bb.ChecksumAlgo.BBH64, _stream(torch))
+    torch.cuda.synchronize()
+    assert st == [0] and torch.equal(src, dst)
+    t = np.asarray(eng.tile_trace(), dtype=np.uint64).reshape(-1, 4).astype(np.int64)
+    assert t.shape[0] == n // 16384 and (t > 0).all()
+    assert (t[:, 1] >= t[:, 0]).all() and (t[:, 2] >= t[:, 1]).all() and (t[:, 3] >= t[:, 2]).all()  # issue <= landed <= stored <= released
+    eng.set_tile_trace(False)
+    eng.run([(src.data_ptr(), dst.data_ptr(), n)], bb.ChecksumAlgo.BBH64, _stream(torch))
