@@ -337,7 +337,10 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
     if (lane == 0) {
       bulk_wait_read<0>();
       const uint32_t first = my_tiles > kStoreLag ? my_tiles - kStoreLag : 0;
-      for (uint32_t it = first; it < my_tiles; ++it) mbar_arrive(&s.empty[it % kStages]);
+      for (uint32_t it = first; it < my_tiles; ++it) {
+        mbar_arrive(&s.empty[it % kStages]);
+        if (p.trace_d) p.trace_d[static_cast<uint64_t>(t0 + it) * 4 + 3] = globaltimer_ns();
+      }
       bulk_wait<0>();  // writes performed before the kernel retires
     }
   } else if (warp == 3) {
