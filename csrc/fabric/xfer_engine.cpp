@@ -121,7 +121,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
     for (size_t i = 0; i < items.size(); ++i) {
       const XferItem& it = items[i];
       if (it.nbytes == 0) continue;
-      if (it.ndst == 0 || it.ndst > kMaxDst) return ErrorCode::INVALID_ARGUMENT;
+      if (it.ndst > kMaxDst || (it.ndst == 0 && !(it.flags & XFER_RAW_SUM))) return ErrorCode::INVALID_ARGUMENT;
       uintptr_t al = reinterpret_cast<uintptr_t>(it.src);
       for (uint32_t r = 0; r < it.ndst; ++r) al |= reinterpret_cast<uintptr_t>(it.dst[r]);
       if (al & 15) return ErrorCode::INVALID_ADDRESS;
@@ -134,7 +134,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       d.ndst = it.ndst;
       d.expect = it.expect;
       d.flags = it.flags;
-      d.reserved = 0;
+      d.reserved = (it.flags & XFER_RAW_SUM) ? it.tile_base : 0;
       if (algo == ChecksumAlgo::CRC32C) {
         d.expect = (static_cast<uint64_t>(crc_init_term_for(it.nbytes)) << 32) | (it.expect & 0xFFFFFFFFull);
         d.reserved = crc_unpad_for(it.nbytes);
@@ -256,6 +256,119 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
     BB_CUDA(cudaMemcpy(trace_host_.data(), s->d_trace, trace_host_.size() * 8, cudaMemcpyDeviceToHost));
   }
   s->ticket = 0;
+  return ErrorCode::OK;
+}
+
+struct XferEngine::Fp8State {
+  uint8_t* h_tab = nullptr;
+  uint8_t* d_tab = nullptr;
+  uint64_t* d_sum = nullptr;
+  uint64_t* h_sum = nullptr;
+  uint32_t cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ~Fp8State() {
+    if (h_tab) cudaFreeHost(h_tab);
+    if (h_sum) cudaFreeHost(h_sum);
+    if (d_tab) cudaFree(d_tab);
+    if (d_sum) cudaFree(d_sum);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+};
+
+ErrorCode XferEngine::run_fp8(const std::vector<Fp8Item>& items, bool unpack, void* stream, XferResult* out) {
+  const uint32_t n = static_cast<uint32_t>(items.size());
+  if (n == 0) return ErrorCode::OK;
+  if (n > max_items_) return ErrorCode::RESOURCE_EXHAUSTED;
+  BB_CUDA(cudaSetDevice(device_));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!fp8_) fp8_ = std::make_unique<Fp8State>();
+  Fp8State& f = *fp8_;
+  if (f.cap < n) {
+    Fp8State fresh;
+    const uint32_t cap = std::max<uint32_t>(n, 256);
+    const size_t tab = static_cast<size_t>(cap) * sizeof(XferDesc) + (static_cast<size_t>(cap) + 1) * 4;
+    BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fresh.h_tab), tab));
+    BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fresh.h_sum), static_cast<size_t>(cap) * 8));
+    BB_CUDA(cudaMalloc(reinterpret_cast<void**>(&fresh.d_tab), tab));
+    BB_CUDA(cudaMalloc(reinterpret_cast<void**>(&fresh.d_sum), static_cast<size_t>(cap) * 8));
+    BB_CUDA(cudaEventCreate(&fresh.ev0));
+    BB_CUDA(cudaEventCreate(&fresh.ev1));
+    fresh.cap = cap;
+    std::swap(f.h_tab, fresh.h_tab), std::swap(f.h_sum, fresh.h_sum), std::swap(f.d_tab, fresh.d_tab), std::swap(f.d_sum, fresh.d_sum);
+    std::swap(f.ev0, fresh.ev0), std::swap(f.ev1, fresh.ev1), std::swap(f.cap, fresh.cap);
+  }
+  auto* descs = reinterpret_cast<XferDesc*>(f.h_tab);
+  auto* tile_start = reinterpret_cast<uint32_t*>(f.h_tab + static_cast<size_t>(n) * sizeof(XferDesc));
+  uint32_t tiles = 0;
+  std::vector<XferItem> scale_items(n);  // scales region of every object, hashed as a RAW_SUM slice by bb_xfer
+  for (uint32_t i = 0; i < n; ++i) {
+    const Fp8Item& it = items[i];
+    if (!fp8_eligible(it.n_elems)) return ErrorCode::INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(it.wide) | reinterpret_cast<uintptr_t>(it.packed)) & 15) return ErrorCode::INVALID_ADDRESS;
+    auto* payload = static_cast<uint8_t*>(it.packed);
+    uint8_t* scales = payload + it.n_elems;
+    XferDesc& d = descs[i];
+    d.src = unpack ? static_cast<const void*>(payload) : it.wide;
+    d.dst[0] = unpack ? it.wide : static_cast<void*>(payload);
+    d.dst[1] = scales;
+    d.dst[2] = nullptr;
+    d.nbytes = it.n_elems;
+    d.first_tile = tiles;
+    d.ndst = 1;
+    d.expect = 0;
+    d.flags = 0;
+    d.reserved = 0;
+    tile_start[i] = tiles;
+    const uint64_t nt = it.n_elems / kTileBytes;
+    if (tiles + nt > 0xFFFFFFF0ull) return ErrorCode::VALUE_OUT_OF_RANGE;
+    tiles += static_cast<uint32_t>(nt);
+    XferItem& sc = scale_items[i];
+    sc.src = scales;
+    sc.ndst = 0;
+    sc.nbytes = it.n_elems / 32;
+    sc.flags = XFER_RAW_SUM;
+    sc.tile_base = static_cast<uint32_t>(nt);
+  }
+  tile_start[n] = tiles;
+  const size_t tab = static_cast<size_t>(n) * sizeof(XferDesc) + (static_cast<size_t>(n) + 1) * 4;
+  BB_CUDA(cudaMemcpyAsync(f.d_tab, f.h_tab, tab, cudaMemcpyHostToDevice, st));
+  BB_CUDA(cudaMemsetAsync(f.d_sum, 0, static_cast<size_t>(n) * 8, st));
+  XferLaunch l;
+  l.descs = reinterpret_cast<const XferDesc*>(f.d_tab);
+  l.tile_start = reinterpret_cast<const uint32_t*>(f.d_tab + static_cast<size_t>(n) * sizeof(XferDesc));
+  l.ndesc = n;
+  l.total_tiles = tiles;
+  l.sum_ws = f.d_sum;
+  l.max_ctas = max_ctas_;
+  l.stream = stream;
+  BB_CUDA(cudaEventRecord(f.ev0, st));
+  const int rc = launch_xfer_fp8(l, unpack);
+  if (rc != 0) {
+    last_cuda_error_ = rc;
+    BB_LOG(ERROR) << "launch_xfer_fp8 failed: " << cuda_error_string(rc);
+    return ErrorCode::FABRIC_ERROR;
+  }
+  ++launches_;
+  BB_CUDA(cudaEventRecord(f.ev1, st));
+  BB_CUDA(cudaMemcpyAsync(f.h_sum, f.d_sum, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
+  // scales: for a put they were just written by the kernel above (same stream), for a get they are read twice
+  XferResult sres;
+  ErrorCode ec = run(scale_items, ChecksumAlgo::BBH64, stream, &sres);  // waits for the stream up to here
+  if (ec != ErrorCode::OK) return ec;
+  BB_CUDA(cudaStreamSynchronize(st));
+  if (out) {
+    out->digest.assign(n, 0);
+    out->status.assign(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint64_t total = items[i].n_elems + items[i].n_elems / 32;
+      out->digest[i] = tchash::finalize(f.h_sum[i] + sres.digest[i], total);
+      if (items[i].verify && out->digest[i] != items[i].expect) out->status[i] = 1;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, f.ev0, f.ev1);
+    out->device_ms = ms + sres.device_ms;
+  }
   return ErrorCode::OK;
 }
 

@@ -24,6 +24,17 @@ struct XferItem {
   uint64_t nbytes = 0;
   uint64_t expect = 0;   // expected digest when flags & XFER_VERIFY
   uint32_t flags = 0;
+  uint32_t tile_base = 0;  // XFER_RAW_SUM: index of this slice's first tile inside the hashed object
+};
+
+// One object of a fused MXFP8 transfer: `wide` is the caller's bf16 tensor, `packed` the slab location of the
+// stored object ([E4M3 payload n_elems][E8M0 scales n_elems / 32]).
+struct Fp8Item {
+  void* wide = nullptr;
+  void* packed = nullptr;
+  uint64_t n_elems = 0;   // multiple of 16384
+  uint64_t expect = 0;    // unpack + verify: digest recorded at put time
+  bool verify = false;
 };
 
 struct XferResult {
@@ -48,6 +59,11 @@ class XferEngine {
   ErrorCode wait(uint64_t ticket, XferResult* out);
   // Convenience: submit + wait.
   ErrorCode run(const std::vector<XferItem>& items, ChecksumAlgo algo, void* stream, XferResult* out);
+  // Fused MXFP8 put (pack = bf16 -> slab) or get (unpack = slab -> bf16): the bf16 side is read / written once, the
+  // E4M3 payload is hashed on the tensor cores while it sits in shared memory, and the digest returned is the
+  // BBH64 of the stored packed object (identical to hashing the output of mxfp8_pack).  Synchronous.
+  ErrorCode run_fp8(const std::vector<Fp8Item>& items, bool unpack, void* stream, XferResult* out);
+  static bool fp8_eligible(uint64_t n_elems) { return n_elems != 0 && n_elems % kTileBytes == 0; }
 
   // Raw accumulators of the last capture_debug batch: [total_tiles][128][16] (tests only).
   const std::vector<uint32_t>& debug_accumulators() const { return debug_host_; }
@@ -74,6 +90,8 @@ class XferEngine {
   std::vector<uint32_t> debug_host_;
   bool tile_trace_ = false;
   std::vector<uint64_t> trace_host_;
+  struct Fp8State;
+  std::unique_ptr<Fp8State> fp8_;
 };
 
 // Device helpers used by bindings, the worker and benchmarks (all return ErrorCode).

@@ -16,6 +16,10 @@ constexpr uint32_t kMaxDst = 3;          // replicas written by a single tile pa
 enum XferFlags : uint32_t {
   XFER_VERIFY = 1u << 0,    // compare digest with `expect`; status[i] = 1 on mismatch
   XFER_MULTIMEM = 1u << 1,  // dst[0] is an NVLS multicast address: store with multimem.st
+  // BBH64 only: digest_out receives the *unfinalised* 64-bit tile sum and `reserved` is added to every tile
+  // index, so a byte range can be hashed as a slice of a larger object (its sums add up with the slices
+  // hashed elsewhere; the host finalises).  With ndst == 0 the descriptor is hash-only (nothing is stored).
+  XFER_RAW_SUM = 1u << 2,
 };
 
 // 64-byte transfer descriptor, one per (object shard, direction).
@@ -27,7 +31,7 @@ struct XferDesc {
   uint32_t ndst;
   uint64_t expect;          // BBH64: expected digest.  CRC32C: (init_term << 32) | expected crc
   uint32_t flags;
-  uint32_t reserved;        // CRC32C: x^(-8*pad) mod P (crc_unpad_for)
+  uint32_t reserved;        // CRC32C: x^(-8*pad) mod P (crc_unpad_for); BBH64 + XFER_RAW_SUM: tile index base
 };
 static_assert(sizeof(XferDesc) == 64, "XferDesc must be 64 bytes");
 
@@ -60,6 +64,12 @@ struct XferLaunch {
 // Returns 0 on success, else a cudaError_t value.
 int launch_xfer(const XferLaunch& l);
 int xfer_smem_bytes(int algo);
+// Fused MXFP8 transfer (xfer_mxfp8.cu).  Descriptors: pack (put): src = bf16 source, dst[0] = payload destination,
+// dst[1] = scales destination, nbytes = payload bytes (= elements, a multiple of kTileBytes); unpack (get):
+// src = payload source, dst[0] = bf16 destination, dst[1] = scales source.  `sum_ws` receives the unfinalised
+// BBH64 sum of the payload tiles per descriptor (must be zero on entry); descs / tile_start are device tables.
+int launch_xfer_fp8(const XferLaunch& l, bool unpack);
+int xfer_fp8_smem_bytes();
 
 // CRC32C per-object constants (host): un-padding multiplier and the init-register term.
 uint32_t crc_unpad_for(uint64_t nbytes);

@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
           // ---- this CTA's contribution to object cur_d is complete
           uint64_t digest = 0;
           bool have = false;
+          const bool raw = kBbh && ((m.ndst_flags >> 8) & XFER_RAW_SUM);
           if (cnt == m.obj_ntiles) {  // object lives entirely in this CTA: no atomics
-            if constexpr (kBbh) digest = tchash::finalize(acc, m.nbytes);
+            if constexpr (kBbh) digest = raw ? acc : tchash::finalize(acc, m.nbytes);
             else digest = gf2_mulmod_dev(static_cast<uint32_t>(acc), m.crc_unpad) ^ static_cast<uint32_t>(m.expect >> 32) ^ 0xFFFFFFFFu;
             have = true;
           } else {
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
                 __threadfence();
                 const uint64_t sum = atomicExch(&p.sum_ws[cur_d], 0ull);
                 p.done_ws[cur_d] = 0;
-                if constexpr (kBbh) digest = tchash::finalize(sum, m.nbytes);
+                if constexpr (kBbh) digest = raw ? sum : tchash::finalize(sum, m.nbytes);
                 else digest = gf2_mulmod_dev(static_cast<uint32_t>(sum), m.crc_unpad) ^ static_cast<uint32_t>(m.expect >> 32) ^ 0xFFFFFFFFu;
               }
               have = true;
@@ -429,7 +430,8 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
         tmem_ld_32x32b_x16(tmem_base + ((q * 32u) << 16) + stage * tchash::kN, r);
         tmem_ld_wait();
         tc_fence_before();
-        const uint32_t ti = s.meta[stage].tile_in_obj;
+        // position of this tile in the hashed object (a RAW_SUM slice starts at a non-zero tile index)
+        const uint32_t ti = s.meta[stage].tile_in_obj + (((s.meta[stage].ndst_flags >> 8) & XFER_RAW_SUM) ? s.meta[stage].crc_unpad : 0u);
         uint64_t rr = 0;
 #pragma unroll
         for (int n = 0; n < 16; ++n) rr += static_cast<uint64_t>(r[n]) * c_col_mul[n];

@@ -75,6 +75,29 @@ void bind_gpu(py::module_& m) {
            },
            py::arg("items"), py::arg("algo") = ChecksumAlgo::BBH64, py::arg("stream") = 0, py::arg("debug") = false,
            "Runs one fused batch; returns (digests, status, device_ms).")
+      .def("run_fp8",
+           [](XferEngine& e, const py::list& items, bool unpack, uintptr_t stream) {
+             std::vector<gpu::Fp8Item> v;
+             for (auto h : items) {
+               auto t = h.cast<py::tuple>();
+               gpu::Fp8Item it;
+               it.wide = reinterpret_cast<void*>(t[0].cast<uintptr_t>());
+               it.packed = reinterpret_cast<void*>(t[1].cast<uintptr_t>());
+               it.n_elems = t[2].cast<uint64_t>();
+               if (t.size() > 3) it.expect = t[3].cast<uint64_t>(), it.verify = true;
+               v.push_back(it);
+             }
+             XferResult res;
+             {
+               py::gil_scoped_release rel;
+               check(e.run_fp8(v, unpack, reinterpret_cast<void*>(stream), &res), "XferEngine.run_fp8");
+             }
+             return py::make_tuple(res.digest, res.status, res.device_ms);
+           },
+           py::arg("items"), py::arg("unpack"), py::arg("stream") = 0,
+           "Fused MXFP8 put (unpack=False: bf16 -> packed slab object) or get (unpack=True); items = (bf16_ptr, packed_ptr, "
+           "n_elems[, expected_digest]); returns (digests of the packed objects, status, device_ms).")
+      .def_static("fp8_eligible", &XferEngine::fp8_eligible)
       .def("submit",
            [](XferEngine& e, const py::list& items, ChecksumAlgo algo, uintptr_t stream) {
              std::vector<XferItem> v;

@@ -71,3 +71,43 @@ def test_gpu_pack_unpack_match_cpu_reference(bb):
     # fp32 reference of the op: dequantised values stay within the E4M3 error bound
     err = (out.float() - x.float()).abs().view(-1, 32).amax(dim=1)
     assert bool((err <= x.float().abs().view(-1, 32).amax(dim=1) * 2 ** -3 + 1e-30).all())
+
+
+@pytest.mark.gpu
+def test_fused_fp8_put_get_matches_unfused_pack_and_cpu_digest(bb):
+    """bb_xfer_fp8: pack fused into the put (bf16 read once, E4M3 payload hashed on the tensor cores in shared memory)
+    and unpack fused into the get.  The stored bytes and the digest must be identical to mxfp8_pack + bbh64."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need CUDA (marked gpu)")
+    s = torch.cuda.current_stream().cuda_stream
+    eng = bb.XferEngine(0, 1024, 2)
+    torch.manual_seed(3)
+    sizes = [16384, 16384 * 5, 16384 * 64 + 16384 * 3]
+    xs = [(torch.randn(n, device="cuda") * (1 + i)).to(torch.bfloat16) for i, n in enumerate(sizes)]
+    xs[1][100:132] = 0  # an all-zero block
+    xs[2][7] = float("inf")
+    slabs = [torch.zeros(bb.mxfp8_packed_bytes(n), dtype=torch.uint8, device="cuda") for n in sizes]
+    assert all(bb.XferEngine.fp8_eligible(n) for n in sizes) and not bb.XferEngine.fp8_eligible(16384 + 32)
+    dg, st, ms = eng.run_fp8([(x.data_ptr(), sl.data_ptr(), n) for x, sl, n in zip(xs, slabs, sizes)], False, s)
+    torch.cuda.synchronize()
+    for x, sl, n, d in zip(xs, slabs, sizes, dg):
+        ref = torch.empty_like(sl)
+        bb.mxfp8_pack(x.data_ptr(), n, ref.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert torch.equal(sl, ref), n  # byte-identical to the stand-alone pack kernel
+        assert d == bb.bbh64(sl.cpu().numpy()), n  # digest of the stored packed object
+    outs = [torch.zeros_like(x) for x in xs]
+    dg2, st2, _ = eng.run_fp8([(o.data_ptr(), sl.data_ptr(), n, d) for o, sl, n, d in zip(outs, slabs, sizes, dg)], True, s)
+    torch.cuda.synchronize()
+    assert st2 == [0, 0, 0] and dg2 == dg
+    for x, sl, n, o in zip(xs, slabs, sizes, outs):
+        ref = torch.empty_like(x)
+        bb.mxfp8_unpack(sl.data_ptr(), n, ref.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert torch.equal(o.view(torch.int16), ref.view(torch.int16)), n
+    slabs[1][5000] ^= 0x40  # corrupt the payload, and the scales of another object
+    slabs[2][sizes[2] + 17] ^= 0x01
+    _, st3, _ = eng.run_fp8([(o.data_ptr(), sl.data_ptr(), n, d) for o, sl, n, d in zip(outs, slabs, sizes, dg)], True, s)
+    assert st3 == [0, 1, 1]
