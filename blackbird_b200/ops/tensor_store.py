@@ -35,12 +35,43 @@ class TensorStore:
                                 enable_soft_pin=self.config.enable_soft_pin, checksum=_bb.ChecksumAlgo.CRC32C)
 
     # ------------------------------------------------------------------ put
+    def _fused_fp8_ok(self, t: torch.Tensor, cfg) -> bool:
+        """Pack fused into the put kernel: bf16, whole 16384-element tiles, one copy in one shard."""
+        return (t.dtype == torch.bfloat16 and self.client.device_fp8_eligible(t.numel()) and cfg.replication_factor == 1
+                and cfg.max_workers_per_copy == 1 and t.data_ptr() % 16 == 0)
+
     def batch_put(self, keys: Sequence[str], tensors: Sequence[torch.Tensor], pack_fp8: bool = False, config=None) -> None:
         cfg = config or self.config
+        keys = list(keys)
+        tensors = [t.contiguous() for t in tensors]
+        if pack_fp8:
+            # objects the fused kernel can take go through batch_put_device_fp8 (bf16 read once, packed bytes on the
+            # wire, digest of the packed object from the tensor cores); the rest are packed first (unfused path below)
+            fused = [i for i, t in enumerate(tensors) if t.is_cuda and self._fused_fp8_ok(t, cfg)]
+            if fused:
+                fk = [keys[i] for i in fused]
+                ecs = self.client.batch_put_device_fp8(fk, [tensors[i].data_ptr() for i in fused], [tensors[i].numel() for i in fused],
+                                                       cfg, self._stream())
+                done = [i for i, e in zip(fused, ecs) if e == _bb.ErrorCode.OK]
+                bad = [(keys[i], e) for i, e in zip(fused, ecs) if e not in (_bb.ErrorCode.OK, _bb.ErrorCode.NOT_IMPLEMENTED)]
+                if bad:
+                    raise RuntimeError(f"fused fp8 put failed: {bad[:3]}")
+                metas = []
+                for i in done:
+                    t = tensors[i]
+                    metas.append(json.dumps({"dtype": "bfloat16", "shape": list(t.shape), "packed": "mxfp8", "numel": t.numel(),
+                                             "padded_numel": t.numel()}).encode())
+                if done:
+                    ecs = self.client.batch_put([keys[i] + "#meta" for i in done], metas, self._meta_cfg())
+                    if any(e != _bb.ErrorCode.OK for e in ecs):
+                        raise RuntimeError("meta put failed")
+                rest = [i for i in range(len(keys)) if i not in set(done)]
+                keys, tensors = [keys[i] for i in rest], [tensors[i] for i in rest]
+                if not keys:
+                    return
         payloads, metas, keep = [], [], []
         for t in tensors:
             assert t.is_cuda, "TensorStore moves CUDA tensors (host data: use client.put)"
-            t = t.contiguous()
             meta = {"dtype": str(t.dtype).replace("torch.", ""), "shape": list(t.shape), "packed": None, "numel": t.numel()}
             if pack_fp8:
                 assert t.dtype == torch.bfloat16, "MXFP8 packing takes bf16 tensors"
@@ -78,6 +109,26 @@ class TensorStore:
             if ec != _bb.ErrorCode.OK:
                 raise KeyError(f"object metadata missing: {ec}")
             metas.append(json.loads(blob))
+        keys = list(keys)
+        result = [None] * len(keys)
+        # MXFP8 objects made of whole tiles: unpack fused into the get kernel (falls through when the object is not a
+        # single GPU-fabric shard any more, e.g. after demotion to a host tier)
+        fused = [i for i, m in enumerate(metas) if m["packed"] == "mxfp8" and m["padded_numel"] == m["numel"]
+                 and self.client.device_fp8_eligible(m["numel"])]
+        if fused:
+            outs = [torch.empty(metas[i]["numel"], dtype=torch.bfloat16, device=device) for i in fused]
+            ecs = self.client.batch_get_device_fp8([keys[i] for i in fused], [o.data_ptr() for o in outs], [metas[i]["numel"] for i in fused],
+                                                   self._stream())
+            for i, o, e in zip(fused, outs, ecs):
+                if e == _bb.ErrorCode.OK:
+                    result[i] = o.view(metas[i]["shape"])
+                elif e != _bb.ErrorCode.NOT_IMPLEMENTED:
+                    raise RuntimeError(f"fused fp8 get failed: {keys[i]}: {e}")
+        rest = [i for i in range(len(keys)) if result[i] is None]
+        if not rest:
+            return result
+        all_keys, all_metas = keys, metas
+        keys, metas = [all_keys[i] for i in rest], [all_metas[i] for i in rest]
         bufs = []
         for m in metas:
             if m["packed"] == "mxfp8":
@@ -97,7 +148,9 @@ class TensorStore:
                 out.append(t[: m["numel"]].view(m["shape"]))
             else:
                 out.append(b)
-        return out
+        for i, t in zip(rest, out):
+            result[i] = t
+        return result
 
     def get(self, key: str, device: Optional[torch.device] = None) -> torch.Tensor:
         return self.batch_get([key], device)[0]

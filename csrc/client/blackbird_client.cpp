@@ -300,6 +300,100 @@ ErrorCode BlackbirdClient::remove(const ObjectKey& key) {
   return keystone_->remove_object(key);
 }
 
+// ================================================================ fused MXFP8 device API
+std::vector<ErrorCode> BlackbirdClient::batch_put_device_fp8(const std::vector<ObjectKey>& keys, const std::vector<const void*>& bf16_ptrs,
+                                                             const std::vector<uint64_t>& n_elems, const WorkerConfig& cfg, void* stream) {
+  std::vector<ErrorCode> out(keys.size(), ErrorCode::INVALID_PARAMETERS);
+  if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
+  if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
+  if (bf16_ptrs.size() != keys.size() || n_elems.size() != keys.size()) return out;
+  BB_TRACE_SPAN("batch_put_device_fp8", keys.size());
+  WorkerConfig c = cfg;
+  c.replication_factor = 1;      // the pack kernel writes one destination
+  c.max_workers_per_copy = 1;    // payload + scales of an object stay in one shard
+  c.checksum = ChecksumAlgo::BBH64;
+  c.pack_fp8 = true;
+  if (c.preferred_classes.empty()) c.preferred_classes = {StorageClass::RAM_GPU};
+  std::vector<PutStartItem> items;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!device_->fp8_eligible(n_elems[i])) return out;
+    items.push_back(PutStartItem{keys[i], static_cast<size_t>(n_elems[i] + n_elems[i] / 32), c});
+  }
+  auto placed = keystone_->batch_put_start(items);
+  std::vector<DeviceFp8Op> ops;
+  std::vector<size_t> idx;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!placed[i].ok()) {
+      out[i] = placed[i].error();
+      continue;
+    }
+    const auto& copies = placed[i].value();
+    if (copies.size() != 1 || copies[0].shards.size() != 1 || !device_->can_reach(copies[0].shards[0])) {
+      keystone_->put_cancel(keys[i]);
+      out[i] = ErrorCode::NOT_IMPLEMENTED;  // placement is not a single GPU-fabric shard: caller packs + puts instead
+      continue;
+    }
+    ops.push_back(DeviceFp8Op{&copies[0].shards[0], const_cast<void*>(bf16_ptrs[i]), n_elems[i]});
+    idx.push_back(i);
+  }
+  std::vector<uint64_t> digests;
+  ErrorCode ec = ops.empty() ? ErrorCode::OK : device_->put_fp8(ops, stream, &digests);
+  std::vector<ObjectKey> done;
+  std::vector<ShardChecksums> sums;
+  for (size_t k = 0; k < idx.size(); ++k) {
+    if (ec != ErrorCode::OK || digests.size() != idx.size()) {
+      keystone_->put_cancel(keys[idx[k]]);
+      out[idx[k]] = ec != ErrorCode::OK ? ec : ErrorCode::INTERNAL_ERROR;
+      continue;
+    }
+    done.push_back(keys[idx[k]]);
+    sums.push_back(ShardChecksums{{digests[k]}});
+  }
+  if (!done.empty()) {
+    auto r = keystone_->batch_put_complete(done, sums);
+    size_t j = 0;
+    for (size_t k = 0; k < idx.size(); ++k)
+      if (out[idx[k]] == ErrorCode::INVALID_PARAMETERS) out[idx[k]] = r[j++];
+  }
+  metrics_.inc("device_put_fp8_batches_total");
+  return out;
+}
+
+std::vector<ErrorCode> BlackbirdClient::batch_get_device_fp8(const std::vector<ObjectKey>& keys, const std::vector<void*>& bf16_ptrs,
+                                                             const std::vector<uint64_t>& n_elems, void* stream) {
+  std::vector<ErrorCode> out(keys.size(), ErrorCode::INVALID_PARAMETERS);
+  if (!keystone_) return std::vector<ErrorCode>(keys.size(), ErrorCode::CLIENT_DISCONNECTED);
+  if (!device_) return std::vector<ErrorCode>(keys.size(), ErrorCode::NOT_IMPLEMENTED);
+  if (bf16_ptrs.size() != keys.size() || n_elems.size() != keys.size()) return out;
+  BB_TRACE_SPAN("batch_get_device_fp8", keys.size());
+  auto placed = keystone_->batch_get_workers(keys);
+  std::vector<DeviceFp8Op> ops;
+  std::vector<size_t> idx;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!placed[i].ok()) {
+      out[i] = placed[i].error();
+      continue;
+    }
+    const auto& copies = placed[i].value();
+    const uint64_t packed = n_elems[i] + n_elems[i] / 32;
+    if (!device_->fp8_eligible(n_elems[i]) || copies.empty() || copies[0].shards.size() != 1 || copies[0].shards[0].length != packed ||
+        copies[0].shards[0].checksum_algo != ChecksumAlgo::BBH64 || !device_->can_reach(copies[0].shards[0])) {
+      out[i] = ErrorCode::NOT_IMPLEMENTED;  // demoted to a host tier, striped, other digest: caller gets + unpacks instead
+      continue;
+    }
+    ops.push_back(DeviceFp8Op{&copies[0].shards[0], bf16_ptrs[i], n_elems[i]});
+    idx.push_back(i);
+  }
+  std::vector<uint32_t> status;
+  ErrorCode ec = ops.empty() ? ErrorCode::OK : device_->get_fp8(ops, stream, &status);
+  for (size_t k = 0; k < idx.size(); ++k) {
+    if (ec != ErrorCode::OK || status.size() != idx.size()) out[idx[k]] = ec != ErrorCode::OK ? ec : ErrorCode::INTERNAL_ERROR;
+    else out[idx[k]] = status[k] ? ErrorCode::CHECKSUM_MISMATCH : ErrorCode::OK;
+  }
+  metrics_.inc("device_get_fp8_batches_total");
+  return out;
+}
+
 ErrorCode BlackbirdClient::migrate(const ObjectKey& key, StorageClass target) {
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
   return keystone_->migrate_object(key, target);

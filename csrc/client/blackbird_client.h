@@ -43,6 +43,13 @@ struct DeviceShardOp {
   uint64_t obj_offset = 0;    // byte offset of this shard inside the object
 };
 
+// One object of a fused MXFP8 transfer: the whole packed object ([E4M3 payload][E8M0 scales]) is a single shard.
+struct DeviceFp8Op {
+  const ShardPlacement* placement = nullptr;
+  void* wide = nullptr;     // client's bf16 tensor (source of a put, destination of a get)
+  uint64_t n_elems = 0;
+};
+
 // Implemented by the GPU fabric: moves shards between client device buffers and worker slabs
 // with the fused kernels.  Returns per-op digests (put) or verifies them (get).
 class DeviceTransport {
@@ -87,6 +94,11 @@ class DeviceTransport {
     return ErrorCode::OK;
   }
   virtual size_t max_in_flight() const { return 1; }
+  // Fused MXFP8 put / get (pack / unpack inside the transfer kernel).  digests[i] = BBH64 of the stored packed
+  // object; status[i] != 0 = digest mismatch on get.  Objects must satisfy fp8_eligible().
+  virtual bool fp8_eligible(uint64_t n_elems) const { return false; }
+  virtual ErrorCode put_fp8(const std::vector<DeviceFp8Op>& ops, void* stream, std::vector<uint64_t>* digests) { return ErrorCode::NOT_IMPLEMENTED; }
+  virtual ErrorCode get_fp8(const std::vector<DeviceFp8Op>& ops, void* stream, std::vector<uint32_t>* status) { return ErrorCode::NOT_IMPLEMENTED; }
   // Staging copies for objects (or shards) that live on host tiers: device <-> host buffer, synchronous.
   virtual ErrorCode copy_h2d(void* dev, const void* host, size_t n, void* stream) { return ErrorCode::NOT_IMPLEMENTED; }
   virtual ErrorCode copy_d2h(void* host, const void* dev, size_t n, void* stream) { return ErrorCode::NOT_IMPLEMENTED; }
@@ -117,6 +129,14 @@ class BlackbirdClient {
     return put(key, data.data(), data.size(), cfg);
   }
   ErrorCode remove(const ObjectKey& key);
+  // bf16 tensors stored as MXFP8 (common/mxfp8.h layout) with the pack fused into the put kernel and the unpack
+  // into the get kernel.  n_elems[i] must be a multiple of 16384 (use put + mxfp8_pack otherwise); one copy, one
+  // shard per object.  The stored object is identical to packing first and putting the packed bytes.
+  std::vector<ErrorCode> batch_put_device_fp8(const std::vector<ObjectKey>& keys, const std::vector<const void*>& bf16_ptrs,
+                                              const std::vector<uint64_t>& n_elems, const WorkerConfig& cfg, void* stream);
+  std::vector<ErrorCode> batch_get_device_fp8(const std::vector<ObjectKey>& keys, const std::vector<void*>& bf16_ptrs,
+                                              const std::vector<uint64_t>& n_elems, void* stream);
+  bool device_fp8_eligible(uint64_t n_elems) const { return device_ && device_->fp8_eligible(n_elems); }
   // Moves every copy of the object to `target` (promotion to the GPU tier, demotion to DRAM / NVMe ...).
   ErrorCode migrate(const ObjectKey& key, StorageClass target);
 

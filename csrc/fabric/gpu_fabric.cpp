@@ -389,6 +389,52 @@ ErrorCode GpuFabric::wait_put(uint64_t ticket, std::vector<uint64_t>* digests) {
   return ErrorCode::OK;
 }
 
+ErrorCode GpuFabric::put_fp8(const std::vector<client::DeviceFp8Op>& ops, void* stream, std::vector<uint64_t>* digests) {
+  BB_TRACE_SPAN("fabric.put_fp8", ops.size());
+  std::vector<Fp8Item> items;
+  items.reserve(ops.size());
+  for (const auto& op : ops) {
+    auto d = resolve(*op.placement);
+    if (!d.ok()) return d.error();
+    Fp8Item it;
+    it.wide = op.wide;
+    it.packed = d.value();
+    it.n_elems = op.n_elems;
+    items.push_back(it);
+  }
+  XferResult res;
+  ErrorCode ec = engine_->run_fp8(items, false, stream, &res);
+  if (ec != ErrorCode::OK) return ec;
+  last_ms_ = res.device_ms;
+  total_ms_ += res.device_ms;
+  if (digests) *digests = std::move(res.digest);
+  return ErrorCode::OK;
+}
+
+ErrorCode GpuFabric::get_fp8(const std::vector<client::DeviceFp8Op>& ops, void* stream, std::vector<uint32_t>* status) {
+  BB_TRACE_SPAN("fabric.get_fp8", ops.size());
+  std::vector<Fp8Item> items;
+  items.reserve(ops.size());
+  for (const auto& op : ops) {
+    auto d = resolve(*op.placement);
+    if (!d.ok()) return d.error();
+    Fp8Item it;
+    it.wide = op.wide;
+    it.packed = d.value();
+    it.n_elems = op.n_elems;
+    it.expect = op.placement->checksum;
+    it.verify = true;
+    items.push_back(it);
+  }
+  XferResult res;
+  ErrorCode ec = engine_->run_fp8(items, true, stream, &res);
+  if (ec != ErrorCode::OK) return ec;
+  last_ms_ = res.device_ms;
+  total_ms_ += res.device_ms;
+  if (status) *status = std::move(res.status);
+  return ErrorCode::OK;
+}
+
 ErrorCode GpuFabric::put_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
                                 void* stream, std::vector<uint64_t>* digests) {
   auto t = submit_put(ops, dev_ptrs, algo, stream);

@@ -78,6 +78,9 @@ class GpuFabric : public client::DeviceTransport {
   Result<uint64_t> submit_get(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, void* stream) override;
   ErrorCode wait_get(uint64_t ticket, std::vector<uint32_t>* status) override;
   size_t max_in_flight() const override { return 3; }
+  bool fp8_eligible(uint64_t n_elems) const override { return XferEngine::fp8_eligible(n_elems); }
+  ErrorCode put_fp8(const std::vector<client::DeviceFp8Op>& ops, void* stream, std::vector<uint64_t>* digests) override;
+  ErrorCode get_fp8(const std::vector<client::DeviceFp8Op>& ops, void* stream, std::vector<uint32_t>* status) override;
   ErrorCode copy_h2d(void* dev, const void* host, size_t n, void* stream) override;
   ErrorCode copy_d2h(void* host, const void* dev, size_t n, void* stream) override;
 

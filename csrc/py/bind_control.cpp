@@ -862,6 +862,25 @@ void bind_control(py::module_& m) {
       })
       .def("remove", &BlackbirdClient::remove, py::call_guard<py::gil_scoped_release>())
       .def("migrate", &BlackbirdClient::migrate, py::call_guard<py::gil_scoped_release>())
+      .def("batch_put_device_fp8",
+           [](BlackbirdClient& c, const std::vector<ObjectKey>& keys, const std::vector<uintptr_t>& ptrs, const std::vector<uint64_t>& n_elems,
+              const WorkerConfig& cfg, uintptr_t stream) {
+             std::vector<const void*> p;
+             for (auto v : ptrs) p.push_back(reinterpret_cast<const void*>(v));
+             py::gil_scoped_release rel;
+             return c.batch_put_device_fp8(keys, p, n_elems, cfg, reinterpret_cast<void*>(stream));
+           },
+           py::arg("keys"), py::arg("bf16_ptrs"), py::arg("n_elems"), py::arg("config"), py::arg("stream") = 0)
+      .def("batch_get_device_fp8",
+           [](BlackbirdClient& c, const std::vector<ObjectKey>& keys, const std::vector<uintptr_t>& ptrs, const std::vector<uint64_t>& n_elems,
+              uintptr_t stream) {
+             std::vector<void*> p;
+             for (auto v : ptrs) p.push_back(reinterpret_cast<void*>(v));
+             py::gil_scoped_release rel;
+             return c.batch_get_device_fp8(keys, p, n_elems, reinterpret_cast<void*>(stream));
+           },
+           py::arg("keys"), py::arg("bf16_ptrs"), py::arg("n_elems"), py::arg("stream") = 0)
+      .def("device_fp8_eligible", &BlackbirdClient::device_fp8_eligible)
       .def("batch_put", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<py::buffer>& data, const WorkerConfig& cfg) {
         std::vector<const uint8_t*> ptrs;
         std::vector<size_t> sizes;

@@ -203,3 +203,43 @@ def test_tile_trace_records_the_pipeline(bb, torch_cuda):
     assert (t[:, 1] >= t[:, 0]).all() and (t[:, 2] >= t[:, 1]).all() and (t[:, 3] >= t[:, 2]).all()  # issue <= landed <= stored <= released
     eng.set_tile_trace(False)
     eng.run([(src.data_ptr(), dst.data_ptr(), n)], bb.ChecksumAlgo.BBH64, _stream(torch))
+
+
+def test_tensor_store_fused_fp8_path(bb, torch_cuda):
+    """TensorStore.put(pack_fp8=True) on whole-tile bf16 tensors uses the fused pack-put / unpack-get kernels; the stored
+    object is the same MXFP8 object the unfused path writes (a plain device get + mxfp8_unpack reads it too)."""
+    torch = torch_cuda
+    from blackbird_b200.ops import TensorStore
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=256 << 20, cluster_id="t-fp8")
+    try:
+        ts = TensorStore(cl.client)
+        kv = (torch.randn(8, 16384, device="cuda") * 2).to(torch.bfloat16)  # 8 tiles
+        odd = (torch.randn(1000, 33, device="cuda")).to(torch.bfloat16)     # not tile aligned -> unfused path
+        l0 = cl.fabric.launches
+        ts.batch_put(["kv", "odd"], [kv, odd], pack_fp8=True)
+        sh = cl.client.get_workers("kv")[0].shards[0]
+        n = kv.numel()
+        assert sh.length == n + n // 32 and sh.checksum_algo == bb.ChecksumAlgo.BBH64
+        raw = torch.empty(sh.length, dtype=torch.uint8, device="cuda")
+        ecs, _ = cl.client.batch_get_device(["kv"], [raw.data_ptr()], [sh.length], _stream(torch))  # plain verified get of the packed bytes
+        assert ecs == [bb.ErrorCode.OK]
+        ref = torch.empty_like(raw)
+        bb.mxfp8_pack(kv.data_ptr(), n, ref.data_ptr(), _stream(torch))
+        torch.cuda.synchronize()
+        assert torch.equal(raw, ref) and sh.checksum == bb.bbh64(raw.cpu().numpy())
+        back_kv, back_odd = ts.batch_get(["kv", "odd"])
+        torch.cuda.synchronize()
+        unp = torch.empty_like(kv)
+        bb.mxfp8_unpack(ref.data_ptr(), n, unp.data_ptr(), _stream(torch))
+        torch.cuda.synchronize()
+        assert back_kv.shape == kv.shape and torch.equal(back_kv.view(torch.int16), unp.view(torch.int16))
+        assert back_odd.shape == odd.shape and (back_odd.float() - odd.float()).abs().max().item() <= odd.float().abs().max().item() * 2 ** -3
+        # corruption of the stored scales is caught by the fused get
+        cl.worker.backend("hbm0").write(sh.offset + n + 3, b"\x7f")
+        with pytest.raises(RuntimeError):
+            ts.get("kv")
+        assert cl.fabric.launches - l0 >= 6
+    finally:
+        cl.stop()
