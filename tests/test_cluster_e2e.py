@@ -296,8 +296,9 @@ def test_fault_injection_corruption_and_read_errors_fail_over_to_replica(bb):
             for _ in range(4):  # whichever replica is tried first, the answer is the intact one
                 assert cl.get("c1") == blob
             assert cl.phase_summary() is not None
+            assert cl.put("c1b", blob, cfg) == bb.ErrorCode.OK  # two intact replicas (c1 still has its corrupted one)
             bb.fault_arm("fail_data_read", 1, 1)
-            assert cl.get("c1") == blob  # first read errors out -> next replica
+            assert cl.get("c1b") == blob  # first read errors out -> next replica
             bb.fault_arm("fail_data_write", 1, 1)
             assert cl.put("c2", blob, cfg) != bb.ErrorCode.OK
             bb.fault_clear()
