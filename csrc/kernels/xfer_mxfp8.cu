@@ -13,9 +13,8 @@
 // by bb_xfer and the host adds the two sums and finalises.  Objects must hold a multiple of 16384 elements (whole
 // payload tiles); other shapes take the unfused path.
 //
-// Warp roles (12 warps): 0 producer, 1 MMA issuer, 2 store, 3 accumulator, 4-7 epilogue (TMEM -> row hashes),
-// 8-11 + the idle lanes of nothing else: convert warps (pack / unpack).  4-stage ring:
-// per stage 32 KiB wide tile + 16 KiB payload tile + 512 B scales.
+// Warp roles (16 warps): 0 producer, 1 MMA issuer, 2 store, 3 accumulator, 4-7 epilogue (TMEM -> row hashes),
+// 8-15 convert (pack / unpack).  Two shared-memory rings: 3 x 32 KiB bf16 tiles and 6 x (16 KiB payload + 512 B scales).
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
@@ -32,20 +31,21 @@ namespace {
 
 using namespace bb::ptx;
 
-constexpr int kFpStages = 4;
-constexpr int kFpThreads = 384;
-constexpr int kConvertWarps = 4;            // warps 8..11
+constexpr int kWideStages = 3;              // ring of 32 KiB bf16 tiles
+constexpr int kTileStages = 6;              // ring of 16 KiB payload tiles (+ 512 B scales)
+constexpr int kFpThreads = 512;
+constexpr int kConvertWarps = 8;            // warps 8..15
 constexpr uint32_t kWideBytes = 2 * kTileBytes;  // bf16 side of one payload tile
 constexpr uint32_t kScaleBytes = kTileBytes / 32;
-constexpr uint32_t kFpTmemCols = 64;        // kFpStages * 16 accumulator columns
+constexpr uint32_t kFpTmemCols = 128;       // >= kTileStages * 16 accumulator columns (power of two)
 constexpr int kFpStoreLag = 1;
-static_assert(kFpStages * tchash::kN == kFpTmemCols);
+static_assert(kTileStages * tchash::kN <= kFpTmemCols);
 
 __constant__ uint64_t c_fp_col_mul[tchash::kN];
 
-struct FpMeta {
-  uint64_t dst_payload;  // pack: payload destination; unpack: bf16 destination
-  uint64_t dst_scales;   // pack: scales destination
+struct FpMeta {           // 32 bytes
+  uint64_t dst;           // pack: payload destination; unpack: bf16 destination
+  uint64_t dst_scales;    // pack: scales destination
   uint32_t desc;
   uint32_t tile_in_obj;
   uint32_t obj_ntiles;
@@ -58,18 +58,23 @@ struct FpLookup {
   uint64_t src_scales;  // unpack: scales source
 };
 
+// Two rings: the wide (bf16) ring only spans load -> convert (pack) or convert -> store (unpack), the payload
+// ring spans convert/load -> tensor-core hash -> store/accumulate.  Decoupling them lets 3 + 6 slots cover a
+// pipeline that would need 6 x 48.5 KiB as one ring.
 struct __align__(1024) SmemFp {
-  uint8_t tile[kFpStages][kTileBytes];
-  uint8_t wide[kFpStages][kWideBytes];
-  uint8_t scales[kFpStages][kScaleBytes];
+  uint8_t tile[kTileStages][kTileBytes];
+  uint8_t wide[kWideStages][kWideBytes];
+  uint8_t scales[kTileStages][kScaleBytes];
   uint8_t w[2048];
-  uint64_t loaded[kFpStages];     // TMA landed (pack: wide; unpack: tile + scales)
-  uint64_t converted[kFpStages];  // convert warps done (pack: tile + scales written; unpack: wide written)
-  uint64_t acc_full[kFpStages];
-  uint64_t epi_done[kFpStages];
-  uint64_t empty[kFpStages];
-  FpMeta meta[kFpStages];
-  uint64_t part[kFpStages][4];
+  uint64_t t_full[kTileStages];   // payload tile + scales ready (pack: convert warps; unpack: TMA)
+  uint64_t t_empty[kTileStages];
+  uint64_t w_full[kWideStages];   // wide tile ready (pack: TMA; unpack: convert warps)
+  uint64_t w_empty[kWideStages];
+  uint64_t acc_full[kTileStages];
+  uint64_t epi_done[kTileStages];
+  FpMeta t_meta[kTileStages];
+  FpMeta w_meta[kWideStages];
+  uint64_t part[kTileStages][4];
   FpLookup lk[32];
   uint32_t tmem_base;
 };
@@ -92,54 +97,57 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
   return v;
 }
 
-__device__ __forceinline__ float bf16_bits_to_float(uint32_t b16) { return __uint_as_float(b16 << 16); }
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) { return *reinterpret_cast<const __nv_bfloat162*>(&v); }
 
-// One 16-byte chunk (8 bf16) per lane, 4 lanes per 32-element block: identical arithmetic to mxfp8_pack_kernel
-// (mxfp8.cu) and to the CPU reference (common/mxfp8.cpp).
+// One 16-byte chunk (8 bf16) per lane, 4 lanes per 32-element block.  Same arithmetic as mxfp8_pack_kernel
+// (mxfp8.cu) and the CPU reference (common/mxfp8.cpp) -- the stored bytes are identical -- but on packed bf16x2
+// max / paired E4M3 conversions, which halves the instruction count of the straightforward form.
 __device__ __forceinline__ void pack_chunk(const uint4 v, uint2* payload_out, uint8_t* scale_out, bool write_scale) {
-  float f[8];
-  f[0] = bf16_bits_to_float(v.x & 0xFFFFu); f[1] = bf16_bits_to_float(v.x >> 16);
-  f[2] = bf16_bits_to_float(v.y & 0xFFFFu); f[3] = bf16_bits_to_float(v.y >> 16);
-  f[4] = bf16_bits_to_float(v.z & 0xFFFFu); f[5] = bf16_bits_to_float(v.z >> 16);
-  f[6] = bf16_bits_to_float(v.w & 0xFFFFu); f[7] = bf16_bits_to_float(v.w >> 16);
-  float amax = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float a = fabsf(f[i]);
-    amax = (a > amax) ? a : amax;  // NaN compares false and is skipped
-  }
-  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+  // |x| on bf16x2 = clear the sign bits; max on the magnitudes as *integers* (monotonic for non-negative bf16).
+  // NaN magnitudes (> 0x7F80) are skipped like the scalar code's `a > amax` does; an Inf (0x7F80) wins the max and
+  // then selects the neutral scale below, again like the scalar code
+  auto mag = [](uint32_t w) { return w & 0x7FFF7FFFu; };
+  auto finite_max = [](uint32_t m, uint32_t cur) {
+    const uint32_t lo = m & 0xFFFFu, hi = m >> 16;
+    uint32_t r = cur;
+    r = (lo <= 0x7F80u && lo > r) ? lo : r;
+    r = (hi <= 0x7F80u && hi > r) ? hi : r;
+    return r;
+  };
+  uint32_t am = 0;
+  am = finite_max(mag(v.x), am);
+  am = finite_max(mag(v.y), am);
+  am = finite_max(mag(v.z), am);
+  am = finite_max(mag(v.w), am);
+  am = max(am, __shfl_xor_sync(0xffffffffu, am, 1));
+  am = max(am, __shfl_xor_sync(0xffffffffu, am, 2));
+  // am = bf16 bits of the block's largest finite magnitude; exponent field = bits 14..7
   int e = 127;
-  if (amax > 0.f && amax < __int_as_float(0x7F800000)) {
-    const int be = (__float_as_int(amax) >> 23) & 0xFF;
+  if (am != 0 && am < 0x7F80u) {
+    const int be = static_cast<int>(am >> 7);
     e = (be == 0 ? -127 : be - 127) - 8 + 127;
     e = max(0, min(254, e));
   }
   const float inv = __int_as_float((254 - e) << 23);
-  uint32_t lo = 0, hi = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    lo |= static_cast<uint32_t>(__nv_cvt_float_to_fp8(f[i] * inv, __NV_SATFINITE, __NV_E4M3)) << (8 * i);
-    hi |= static_cast<uint32_t>(__nv_cvt_float_to_fp8(f[4 + i] * inv, __NV_SATFINITE, __NV_E4M3)) << (8 * i);
-  }
+  auto cvt2 = [&](uint32_t w) -> uint32_t {
+    const float2 f = __bfloat1622float2(as_bf162(w));
+    return static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(f.x * inv, f.y * inv), __NV_SATFINITE, __NV_E4M3));
+  };
+  const uint32_t lo = cvt2(v.x) | (cvt2(v.y) << 16);
+  const uint32_t hi = cvt2(v.z) | (cvt2(v.w) << 16);
   *payload_out = make_uint2(lo, hi);
   if (write_scale) *scale_out = static_cast<uint8_t>(e);
 }
 
 __device__ __forceinline__ uint4 unpack_chunk(const uint2 p, uint8_t scale) {
   const float s = __int_as_float(static_cast<int>(scale) << 23);  // 2^(e-127); e == 0 flushes to zero
-  uint32_t out[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t w = i < 2 ? p.x : p.y;
-    const uint8_t b0 = (w >> (16 * (i & 1))) & 0xFF, b1 = (w >> (16 * (i & 1) + 8)) & 0xFF;
-    const float f0 = __half2float(__half(__nv_cvt_fp8_to_halfraw(b0, __NV_E4M3))) * s;
-    const float f1 = __half2float(__half(__nv_cvt_fp8_to_halfraw(b1, __NV_E4M3))) * s;
-    const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-    out[i] = *reinterpret_cast<const uint32_t*>(&h);
-  }
-  return make_uint4(out[0], out[1], out[2], out[3]);
+  auto cvt2 = [&](uint32_t two) -> uint32_t {  // two E4M3 bytes -> bf16x2
+    const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(two & 0xFFFFu), __NV_E4M3);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f.x * s, f.y * s);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  };
+  return make_uint4(cvt2(p.x), cvt2(p.x >> 16), cvt2(p.y), cvt2(p.y >> 16));
 }
 
 template <bool UNPACK>
@@ -154,12 +162,15 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
   const uint32_t my_tiles = t0 < p.total_tiles ? min(tpc, p.total_tiles - t0) : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kFpStages; ++i) {
-      mbar_init(&s.loaded[i], 1);
-      mbar_init(&s.converted[i], kConvertWarps);
+    for (int i = 0; i < kTileStages; ++i) {
+      mbar_init(&s.t_full[i], UNPACK ? 1 : kConvertWarps);
+      mbar_init(&s.t_empty[i], UNPACK ? kConvertWarps + 1 : 2);  // unpack: convert warps + accumulator; pack: store + accumulator
       mbar_init(&s.acc_full[i], 1);
       mbar_init(&s.epi_done[i], 4);
-      mbar_init(&s.empty[i], 2);  // store warp + accumulator
+    }
+    for (int i = 0; i < kWideStages; ++i) {
+      mbar_init(&s.w_full[i], UNPACK ? kConvertWarps : 1);
+      mbar_init(&s.w_empty[i], UNPACK ? 1 : kConvertWarps);
     }
     fence_mbar_init();
   }
@@ -196,35 +207,41 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         e.m.desc = lo;
         e.m.tile_in_obj = ti;
         e.m.obj_ntiles = next - first;
+        e.m.pad = 0;
         if constexpr (UNPACK) {
-          e.src = src + static_cast<uint64_t>(ti) * kTileBytes;          // payload tile in the slab
-          e.src_scales = d1 + static_cast<uint64_t>(ti) * kScaleBytes;   // its scales
-          e.m.dst_payload = d0 + static_cast<uint64_t>(ti) * kWideBytes;  // bf16 destination
+          e.src = src + static_cast<uint64_t>(ti) * kTileBytes;         // payload tile in the slab
+          e.src_scales = d1 + static_cast<uint64_t>(ti) * kScaleBytes;  // its scales
+          e.m.dst = d0 + static_cast<uint64_t>(ti) * kWideBytes;        // bf16 destination
           e.m.dst_scales = 0;
         } else {
-          e.src = src + static_cast<uint64_t>(ti) * kWideBytes;           // bf16 source tile
+          e.src = src + static_cast<uint64_t>(ti) * kWideBytes;  // bf16 source tile
           e.src_scales = 0;
-          e.m.dst_payload = d0 + static_cast<uint64_t>(ti) * kTileBytes;
+          e.m.dst = d0 + static_cast<uint64_t>(ti) * kTileBytes;
           e.m.dst_scales = d1 + static_cast<uint64_t>(ti) * kScaleBytes;
         }
       }
       __syncwarp();
       const uint32_t cnt = min(32u, my_tiles - base);
       for (uint32_t i = 0; i < cnt; ++i, ++it) {
-        const uint32_t stage = it % kFpStages;
-        const uint32_t par = (it / kFpStages) & 1u;
-        mbar_wait(&s.empty[stage], par ^ 1u);
         const FpLookup& e = s.lk[i];
-        if (lane < 2) reinterpret_cast<uint4*>(&s.meta[stage])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (UNPACK) {
-            mbar_arrive_expect_tx(&s.loaded[stage], kTileBytes + kScaleBytes);
-            bulk_g2s(s.tile[stage], reinterpret_cast<const void*>(e.src), kTileBytes, &s.loaded[stage]);
-            bulk_g2s(s.scales[stage], reinterpret_cast<const void*>(e.src_scales), kScaleBytes, &s.loaded[stage]);
-          } else {
-            mbar_arrive_expect_tx(&s.loaded[stage], kWideBytes);
-            bulk_g2s(s.wide[stage], reinterpret_cast<const void*>(e.src), kWideBytes, &s.loaded[stage]);
+        if constexpr (UNPACK) {
+          const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
+          mbar_wait(&s.t_empty[ts], tp ^ 1u);
+          if (lane < 2) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&s.t_full[ts], kTileBytes + kScaleBytes);
+            bulk_g2s(s.tile[ts], reinterpret_cast<const void*>(e.src), kTileBytes, &s.t_full[ts]);
+            bulk_g2s(s.scales[ts], reinterpret_cast<const void*>(e.src_scales), kScaleBytes, &s.t_full[ts]);
+          }
+        } else {
+          const uint32_t ws = it % kWideStages, wp = (it / kWideStages) & 1u;
+          mbar_wait(&s.w_empty[ws], wp ^ 1u);
+          if (lane < 2) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&s.w_full[ws], kWideBytes);
+            bulk_g2s(s.wide[ws], reinterpret_cast<const void*>(e.src), kWideBytes, &s.w_full[ws]);
           }
         }
         __syncwarp();
@@ -236,50 +253,53 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
     constexpr uint32_t idesc = umma_idesc_i8(tchash::kRows, tchash::kN, false, false);
     const uint32_t w_addr = smem_u32(s.w);
     for (uint32_t it = 0; it < my_tiles; ++it) {
-      const uint32_t stage = it % kFpStages;
-      const uint32_t par = (it / kFpStages) & 1u;
-      if constexpr (UNPACK) mbar_wait(&s.loaded[stage], par);     // payload tile landed by TMA
-      else mbar_wait(&s.converted[stage], par);                   // payload tile written by the pack warps
+      const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
+      mbar_wait(&s.t_full[ts], tp);  // pack: written by the convert warps (generic proxy, fenced); unpack: TMA
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_addr = smem_u32(s.tile[stage]);
-        const uint32_t tmem_d = tmem_base + stage * tchash::kN;
+        const uint32_t a_addr = smem_u32(s.tile[ts]);
+        const uint32_t tmem_d = tmem_base + ts * tchash::kN;
 #pragma unroll
         for (uint32_t j = 0; j < tchash::kK / 32; ++j)
           mma_i8_ss(tmem_d, umma_desc_kmajor_noswizzle(a_addr + j * 256, 128, 1024), umma_desc_kmajor_noswizzle(w_addr + j * 256, 128, 1024),
                     idesc, j > 0 ? 1u : 0u);
-        tc_commit(&s.acc_full[stage]);
+        tc_commit(&s.acc_full[ts]);
       }
       __syncwarp();
     }
   } else if (warp == 2) {
     // ================================================================ store warp
+    constexpr int kRing = UNPACK ? kWideStages : kTileStages;
     for (uint32_t it = 0; it < my_tiles; ++it) {
-      const uint32_t stage = it % kFpStages;
-      const uint32_t par = (it / kFpStages) & 1u;
-      mbar_wait(&s.converted[stage], par);
-      if constexpr (!UNPACK) mbar_wait(&s.loaded[stage], par);  // (already complete) acquires the producer's FpMeta
-      else mbar_wait(&s.loaded[stage], par);
-      const FpMeta& m = s.meta[stage];
-      if (lane == 0) {
-        if constexpr (UNPACK) {
-          bulk_s2g(reinterpret_cast<void*>(m.dst_payload), s.wide[stage], kWideBytes);
-        } else {
-          bulk_s2g(reinterpret_cast<void*>(m.dst_payload), s.tile[stage], kTileBytes);
-          bulk_s2g(reinterpret_cast<void*>(m.dst_scales), s.scales[stage], kScaleBytes);
+      const uint32_t st = it % kRing, par = (it / kRing) & 1u;
+      if constexpr (UNPACK) {
+        mbar_wait(&s.w_full[st], par);
+        if (lane == 0) {
+          bulk_s2g(reinterpret_cast<void*>(s.w_meta[st].dst), s.wide[st], kWideBytes);
+          bulk_commit();
         }
-        bulk_commit();
+      } else {
+        mbar_wait(&s.t_full[st], par);
+        if (lane == 0) {
+          bulk_s2g(reinterpret_cast<void*>(s.t_meta[st].dst), s.tile[st], kTileBytes);
+          bulk_s2g(reinterpret_cast<void*>(s.t_meta[st].dst_scales), s.scales[st], kScaleBytes);
+          bulk_commit();
+        }
       }
       __syncwarp();
       if (it >= kFpStoreLag && lane == 0) {
         bulk_wait_read<kFpStoreLag>();
-        mbar_arrive(&s.empty[(it - kFpStoreLag) % kFpStages]);
+        if constexpr (UNPACK) mbar_arrive(&s.w_empty[(it - kFpStoreLag) % kRing]);
+        else mbar_arrive(&s.t_empty[(it - kFpStoreLag) % kRing]);
       }
     }
     if (lane == 0) {
       bulk_wait_read<0>();
       const uint32_t first = my_tiles > kFpStoreLag ? my_tiles - kFpStoreLag : 0;
-      for (uint32_t it = first; it < my_tiles; ++it) mbar_arrive(&s.empty[it % kFpStages]);
+      for (uint32_t it = first; it < my_tiles; ++it) {
+        if constexpr (UNPACK) mbar_arrive(&s.w_empty[it % kRing]);
+        else mbar_arrive(&s.t_empty[it % kRing]);
+      }
       bulk_wait<0>();
     }
   } else if (warp == 3) {
@@ -287,13 +307,12 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
     uint32_t cur_d = 0xFFFFFFFFu;
     uint64_t acc = 0;
     for (uint32_t it = 0; it < my_tiles; ++it) {
-      const uint32_t stage = it % kFpStages;
-      const uint32_t par = (it / kFpStages) & 1u;
-      mbar_wait(&s.epi_done[stage], par);
-      const uint32_t d = s.meta[stage].desc;
-      const uint64_t sum = s.part[stage][0] + s.part[stage][1] + s.part[stage][2] + s.part[stage][3];
+      const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
+      mbar_wait(&s.epi_done[ts], tp);
+      const uint32_t d = s.t_meta[ts].desc;
+      const uint64_t sum = s.part[ts][0] + s.part[ts][1] + s.part[ts][2] + s.part[ts][3];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.empty[stage]);
+      if (lane == 0) mbar_arrive(&s.t_empty[ts]);
       if (d != cur_d) {
         if (cur_d != 0xFFFFFFFFu && lane == 0) atomicAdd(&p.sum_ws[cur_d], static_cast<unsigned long long>(acc));
         cur_d = d;
@@ -307,53 +326,65 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
     const uint32_t q = warp & 3u;
     const uint32_t row = q * 32 + lane;
     for (uint32_t it = 0; it < my_tiles; ++it) {
-      const uint32_t stage = it % kFpStages;
-      const uint32_t par = (it / kFpStages) & 1u;
-      mbar_wait(&s.acc_full[stage], par);
-      mbar_wait(&s.loaded[stage], par);  // acquires the producer's FpMeta writes
+      const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
+      mbar_wait(&s.acc_full[ts], tp);
+      mbar_wait(&s.t_full[ts], tp);  // (already complete) acquires the t_meta writes
       tc_fence_after();
       uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_base + ((q * 32u) << 16) + stage * tchash::kN, r);
+      tmem_ld_32x32b_x16(tmem_base + ((q * 32u) << 16) + ts * tchash::kN, r);
       tmem_ld_wait();
       tc_fence_before();
-      const uint32_t ti = s.meta[stage].tile_in_obj;
+      const uint32_t ti = s.t_meta[ts].tile_in_obj;
       uint64_t rr = 0;
 #pragma unroll
       for (int n = 0; n < 16; ++n) rr += static_cast<uint64_t>(r[n]) * c_fp_col_mul[n];
       const uint64_t tot = warp_sum64(tchash::row_contrib(rr, static_cast<uint64_t>(ti) * tchash::kRows + row));
       if (lane == 0) {
-        s.part[stage][q] = tot;
-        mbar_arrive(&s.epi_done[stage]);
+        s.part[ts][q] = tot;
+        mbar_arrive(&s.epi_done[ts]);
       }
     }
   } else {
-    // ================================================================ convert warps 8..11
-    const uint32_t cw = warp - 8;  // 0..3
+    // ================================================================ convert warps 8..15
+    const uint32_t cw = warp - 8;  // 0..7: chunks [cw*256, cw*256+256) of the tile's 2048 16-byte bf16 chunks
     for (uint32_t it = 0; it < my_tiles; ++it) {
-      const uint32_t stage = it % kFpStages;
-      const uint32_t par = (it / kFpStages) & 1u;
-      mbar_wait(&s.loaded[stage], par);
-      // 2048 16-byte bf16 chunks per tile; warp cw takes chunks [cw*512, cw*512+512) -> 16 iterations of 32 lanes
+      const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
+      const uint32_t ws = it % kWideStages, wp = (it / kWideStages) & 1u;
       if constexpr (UNPACK) {
-        const uint2* pay = reinterpret_cast<const uint2*>(s.tile[stage]);
-        uint4* out = reinterpret_cast<uint4*>(s.wide[stage]);
+        mbar_wait(&s.t_full[ts], tp);         // payload + scales landed
+        mbar_wait(&s.w_empty[ws], wp ^ 1u);   // wide slot drained by the store warp
+        const uint2* pay = reinterpret_cast<const uint2*>(s.tile[ts]);
+        uint4* out = reinterpret_cast<uint4*>(s.wide[ws]);
 #pragma unroll 4
-        for (uint32_t k = 0; k < 16; ++k) {
-          const uint32_t c = cw * 512 + k * 32 + lane;
-          out[c] = unpack_chunk(pay[c], s.scales[stage][c >> 2]);
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint32_t c = cw * 256 + k * 32 + lane;
+          out[c] = unpack_chunk(pay[c], s.scales[ts][c >> 2]);
+        }
+        if (cw == 0 && lane < 2) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&s.t_meta[ts])[lane];
+        fence_proxy_async_smem();  // generic-proxy writes -> TMA store
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s.w_full[ws]);
+          mbar_arrive(&s.t_empty[ts]);
         }
       } else {
-        const uint4* in = reinterpret_cast<const uint4*>(s.wide[stage]);
-        uint2* pay = reinterpret_cast<uint2*>(s.tile[stage]);
+        mbar_wait(&s.w_full[ws], wp);         // bf16 tile landed
+        mbar_wait(&s.t_empty[ts], tp ^ 1u);   // payload slot released by store + accumulator
+        const uint4* in = reinterpret_cast<const uint4*>(s.wide[ws]);
+        uint2* pay = reinterpret_cast<uint2*>(s.tile[ts]);
 #pragma unroll 4
-        for (uint32_t k = 0; k < 16; ++k) {
-          const uint32_t c = cw * 512 + k * 32 + lane;
-          pack_chunk(in[c], &pay[c], &s.scales[stage][c >> 2], (c & 3u) == 0);
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint32_t c = cw * 256 + k * 32 + lane;
+          pack_chunk(in[c], &pay[c], &s.scales[ts][c >> 2], (c & 3u) == 0);
+        }
+        if (cw == 0 && lane < 2) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&s.w_meta[ws])[lane];
+        fence_proxy_async_smem();  // generic-proxy writes -> tensor core / TMA store readers
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s.t_full[ts]);
+          mbar_arrive(&s.w_empty[ws]);
         }
       }
-      fence_proxy_async_smem();  // generic-proxy writes -> tensor core / TMA store readers
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.converted[stage]);
     }
   }
 
