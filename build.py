@@ -62,6 +62,7 @@ def generate() -> str:
     cu_src = sorted(glob.glob(os.path.join(ROOT, "csrc", "kernels", "*.cu")))
     py_src = sorted(glob.glob(os.path.join(ROOT, "csrc", "py", "*.cpp")))
     app_src = sorted(glob.glob(os.path.join(ROOT, "apps", "*.cpp")))
+    example_src = sorted(glob.glob(os.path.join(ROOT, "examples", "*.cpp")))  # -> bin/bb-example-<name>
 
     lines = [
         "ninja_required_version = 1.5",
@@ -112,6 +113,13 @@ def generate() -> str:
         o = obj(s)
         lines.append(f"build {o}: cxx {_rel(s)}")
         name = os.path.splitext(os.path.basename(s))[0].replace("_", "-")
+        exe = _rel(os.path.join(ROOT, "bin", name))
+        lines.append(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
+        targets.append(exe)
+    for s in example_src:
+        o = obj(s)
+        lines.append(f"build {o}: cxx {_rel(s)}")
+        name = "bb-example-" + os.path.splitext(os.path.basename(s))[0].replace("_", "-")
         exe = _rel(os.path.join(ROOT, "bin", name))
         lines.append(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
         targets.append(exe)
