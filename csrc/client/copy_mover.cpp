@@ -123,6 +123,44 @@ keystone::CopyMover make_data_server_mover(size_t io_parallelism, int rpc_timeou
       }
       return ErrorCode::OK;
     }
+    // GPU tier on both sides, different workers: the destination worker pulls the shard out of the source slab
+    // itself (CUDA IPC mapping + one fused-kernel launch over NVLink); nothing passes through this process.
+    bool gpu_pull = src.shards.size() == dst.shards.size() && !src.shards.empty();
+    for (size_t i = 0; gpu_pull && i < src.shards.size(); ++i)
+      gpu_pull = src.shards[i].length == dst.shards[i].length && src.shards[i].storage_class == StorageClass::RAM_GPU &&
+                 dst.shards[i].storage_class == StorageClass::RAM_GPU && !src.shards[i].endpoint.worker_key.empty();
+    if (gpu_pull) {
+      bool fell_back = false;
+      for (size_t i = 0; i < src.shards.size() && !fell_back; ++i) {
+        auto c = conns->get(ep_of(dst.shards[i]));
+        if (!c) return ErrorCode::CONNECTION_FAILED;
+        wire::Writer w;
+        w.str(dst.shards[i].pool_id);
+        w.u64(raw_offset(dst.shards[i]));
+        const auto& k = src.shards[i].endpoint.worker_key;
+        w.str(std::string(k.begin(), k.end()));
+        w.u64(raw_offset(src.shards[i]));
+        w.u64(src.shards[i].length);
+        w.u32(static_cast<uint32_t>(algo));
+        auto r = c->call(worker::D_PULL, w.data(), conns->timeout_ms);
+        if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+        wire::Reader rd(r.value());
+        const ErrorCode ec = rd.ec();
+        if (ec == ErrorCode::NOT_IMPLEMENTED && i == 0) {  // e.g. both slabs in one process: relay below
+          fell_back = true;
+          break;
+        }
+        if (ec != ErrorCode::OK) return ec;
+        const uint64_t digest = rd.u64();
+        if (algo != ChecksumAlgo::NONE && src.shards[i].checksum_algo == algo && src.shards[i].checksum != digest) {
+          BB_LOG(ERROR) << "mover: source shard of " << key << " is corrupt (digest mismatch)";
+          return ErrorCode::CHECKSUM_MISMATCH;
+        }
+        dst.shards[i].checksum = digest;
+        dst.shards[i].checksum_algo = algo;
+      }
+      if (!fell_back) return ErrorCode::OK;
+    }
     // general path: relay the object through this process
     uint64_t total = 0;
     for (const auto& s : src.shards) total += s.length;

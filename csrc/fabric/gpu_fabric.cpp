@@ -68,6 +68,9 @@ ErrorCode GpuSlabBackend::initialize() {
 
 void GpuSlabBackend::shutdown() {
   if (!base_) return;
+  cudaSetDevice(opts_.gpu_device_id);
+  for (auto& [k, ptr] : peer_slabs_) cudaIpcCloseMemHandle(ptr);
+  peer_slabs_.clear();
   unregister_local_slab(pool_id_);
   cudaSetDevice(opts_.gpu_device_id);
   if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
@@ -124,6 +127,48 @@ ErrorCode GpuSlabBackend::device_copy(worker::StorageBackend& peer, bool to_peer
   if (ec != ErrorCode::OK) return ec;
   if (digest) *digest = res.digest.empty() ? 0 : res.digest[0];
   (to_peer ? bytes_read_ : bytes_written_) += len;
+  ++device_copies_;
+  return ErrorCode::OK;
+}
+
+ErrorCode GpuSlabBackend::pull_from_peer(const std::vector<uint8_t>& peer_key, uint64_t peer_off, uint64_t my_off, uint64_t len,
+                                         ChecksumAlgo algo, uint64_t* digest) {
+  if (!base_ || peer_key.size() != sizeof(cudaIpcMemHandle_t)) return ErrorCode::NOT_IMPLEMENTED;
+  BB_TRY(check_range(my_off, len));
+  std::lock_guard<std::mutex> lk(move_mu_);
+  if (!cuda_ok(cudaSetDevice(opts_.gpu_device_id), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
+  const std::string k(peer_key.begin(), peer_key.end());
+  auto it = peer_slabs_.find(k);
+  if (it == peer_slabs_.end()) {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, peer_key.data(), sizeof h);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {  // same-process slab, no peer access, stale handle: the caller relays through the data servers
+      cudaGetLastError();
+      BB_VLOG(1) << "pull_from_peer: cannot map the peer slab (" << cudaGetErrorString(e) << ")";
+      return ErrorCode::NOT_IMPLEMENTED;
+    }
+    it = peer_slabs_.emplace(k, ptr).first;
+  }
+  uint8_t* theirs = static_cast<uint8_t*>(it->second) + peer_off;
+  uint8_t* mine = base_ + my_off;
+  if ((reinterpret_cast<uintptr_t>(mine) | reinterpret_cast<uintptr_t>(theirs)) & 15) return ErrorCode::NOT_IMPLEMENTED;
+  if (!move_engine_) {
+    auto e = XferEngine::create(opts_.gpu_device_id, 64, 1);
+    if (!e.ok()) return e.error();
+    move_engine_ = std::move(e.value());
+  }
+  XferItem item;
+  item.src = theirs;
+  item.dst[0] = mine;
+  item.ndst = 1;
+  item.nbytes = len;
+  XferResult res;
+  ErrorCode ec = move_engine_->run({item}, algo, stream_, &res);
+  if (ec != ErrorCode::OK) return ec;
+  if (digest) *digest = res.digest.empty() ? 0 : res.digest[0];
+  bytes_written_ += len;
   ++device_copies_;
   return ErrorCode::OK;
 }

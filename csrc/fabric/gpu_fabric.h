@@ -42,6 +42,8 @@ class GpuSlabBackend : public worker::StorageBackend {
   // digest from the tensor-core hash / fused CRC.
   ErrorCode device_copy(worker::StorageBackend& peer, bool to_peer, uint64_t my_off, uint64_t peer_off, uint64_t len, ChecksumAlgo algo,
                         uint64_t* digest) override;
+  ErrorCode pull_from_peer(const std::vector<uint8_t>& peer_key, uint64_t peer_off, uint64_t my_off, uint64_t len, ChecksumAlgo algo,
+                           uint64_t* digest) override;
   int device() const { return opts_.gpu_device_id; }
   void* device_ptr() const { return base_; }
   // 64-byte cudaIpcMemHandle_t as 128 hex chars: the "rkey" peers open the slab with.
@@ -55,6 +57,7 @@ class GpuSlabBackend : public worker::StorageBackend {
   void* stream_ = nullptr;
   std::mutex move_mu_;
   std::unique_ptr<XferEngine> move_engine_;  // created on the first tier move
+  std::map<std::string, void*> peer_slabs_;  // IPC handle bytes -> mapped base of a peer worker's slab
 };
 
 // Registers the GPU tier with worker::create_storage_backend (call once at start-up).

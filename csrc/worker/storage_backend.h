@@ -102,6 +102,13 @@ class StorageBackend {
     (void)peer, (void)to_peer, (void)my_off, (void)peer_off, (void)len, (void)algo, (void)digest;
     return ErrorCode::NOT_IMPLEMENTED;
   }
+  // Copies `len` bytes from a peer worker's device slab (identified by its registration key = CUDA IPC handle)
+  // into this backend at my_off with the fused kernel; returns the digest of the bytes moved.
+  virtual ErrorCode pull_from_peer(const std::vector<uint8_t>& peer_key, uint64_t peer_off, uint64_t my_off, uint64_t len, ChecksumAlgo algo,
+                                   uint64_t* digest) {
+    (void)peer_key, (void)peer_off, (void)my_off, (void)len, (void)algo, (void)digest;
+    return ErrorCode::NOT_IMPLEMENTED;
+  }
   uint64_t device_copies() const { return device_copies_; }
   // Registration key advertised in the pool record ("ucx_rkey_hex"): 8 hex chars of the rkey by
   // default; the GPU tier returns its CUDA IPC handle.

@@ -454,6 +454,26 @@ void WorkerService::register_data_handlers() {
     if (ec == ErrorCode::OK) w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64(whole.data(), whole.size()) : 0);
     return w.take();
   });
+  data_server_.register_method(D_PULL, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string dp = r.str();
+    const uint64_t doff = r.u64();
+    const std::string key = r.str();  // raw registration key of the source pool (CUDA IPC handle)
+    const uint64_t soff = r.u64();
+    const uint64_t len = r.u64();
+    const auto algo = static_cast<ChecksumAlgo>(r.u32());
+    wire::Writer w;
+    StorageBackend* db = backend(dp);
+    if (!r.ok() || !db) {
+      w.ec(!r.ok() ? ErrorCode::INVALID_PARAMETERS : ErrorCode::MEMORY_POOL_NOT_FOUND);
+      return w.take();
+    }
+    uint64_t digest = 0;
+    ErrorCode ec = db->pull_from_peer(std::vector<uint8_t>(key.begin(), key.end()), soff, resolve_offset(*db, doff), len, algo, &digest);
+    w.ec(ec);
+    if (ec == ErrorCode::OK) w.u64(digest);
+    return w.take();
+  });
   data_server_.register_method(D_STATS, [this](C, S) {
     wire::Writer w;
     w.ec(ErrorCode::OK);

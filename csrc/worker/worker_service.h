@@ -65,7 +65,9 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
 // Throws std::runtime_error on unreadable / invalid files (as the reference does).
 WorkerServiceConfig load_worker_config_from_file(const std::string& path);
 
-enum DataMethod : uint32_t { D_WRITE = 1, D_READ = 2, D_CHECKSUM = 3, D_STATS = 4, D_COPY = 5 };
+// D_PULL: the destination worker copies a shard out of a *peer worker's* GPU slab itself (opens the peer's CUDA IPC
+// handle, one fused-kernel launch over NVLink) -- the re-replication / repair path between GPU-tier workers.
+enum DataMethod : uint32_t { D_WRITE = 1, D_READ = 2, D_CHECKSUM = 3, D_STATS = 4, D_COPY = 5, D_PULL = 6 };
 
 class WorkerService {
  public:
