@@ -51,6 +51,12 @@ def main():
                     "all_objects_back_to_2_replicas": ok, "replica_digests_agree": digests_ok,
                     "read_back_ok": all(e == _bb.ErrorCode.OK for e in ecs) and bool(torch.equal(src, out)),
                     "repair_GBps": round(repaired * size / repair_s / 1e9, 1) if repaired else 0.0, "repair_s": round(repair_s, 4)})
+        assert cl.client.put("repair/done", b"1", _bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == _bb.ErrorCode.OK
+    else:
+        # do NOT park in an NCCL barrier while the repair runs: the pull kernels run on these ranks' GPUs and a
+        # spinning collective kernel plus a device-synchronising driver call is a deadlock recipe
+        while cl.client.object_exists("repair/done") is not True:
+            time.sleep(0.05)
     cl.barrier()
     pulls = torch.tensor([cl.worker.backend(f"hbm{cl.rank}").device_copies], device=dev)
     allp = [torch.zeros_like(pulls) for _ in range(cl.world)]

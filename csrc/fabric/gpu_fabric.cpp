@@ -62,15 +62,16 @@ ErrorCode GpuSlabBackend::initialize() {
   rkey_ = reinterpret_cast<uint64_t>(p) >> 8;
   init_allocator();
   register_local_slab(pool_id_, opts_.gpu_device_id, base_, capacity_);
+  // engine of the tier-move / repair paths: created now, because allocating it later would synchronise the device
+  // in the middle of somebody's collective
+  if (auto e = XferEngine::create(opts_.gpu_device_id, 64, 1); e.ok()) move_engine_ = std::move(e.value());
   initialized_ = true;
   return ErrorCode::OK;
 }
 
 void GpuSlabBackend::shutdown() {
   if (!base_) return;
-  cudaSetDevice(opts_.gpu_device_id);
-  for (auto& [k, ptr] : peer_slabs_) cudaIpcCloseMemHandle(ptr);
-  peer_slabs_.clear();
+
   unregister_local_slab(pool_id_);
   cudaSetDevice(opts_.gpu_device_id);
   if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
@@ -100,6 +101,27 @@ ErrorCode GpuSlabBackend::read(uint64_t offset, void* data, uint64_t len) {
     return ErrorCode::FABRIC_ERROR;
   bytes_read_ += len;
   return ErrorCode::OK;
+}
+
+// Peer slabs are mapped once per process and device: the client-side fabric and the worker-side repair path
+// (pull_from_peer) share the mapping, and nothing is unmapped before the process exits (a mapping may be in use by
+// a kernel of either side).  Opening is a device-synchronising driver call, so it must not happen lazily on a hot path.
+static std::mutex g_ipc_mu;
+static std::map<std::pair<int, std::string>, void*> g_ipc_mapped;  // (device, handle bytes) -> base
+static void* ipc_map_peer_slab(int device, const cudaIpcMemHandle_t& h, cudaError_t* err) {
+  const std::string key(reinterpret_cast<const char*>(&h), sizeof h);
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  auto it = g_ipc_mapped.find({device, key});
+  if (it != g_ipc_mapped.end()) return it->second;
+  void* ptr = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (err) *err = e;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_ipc_mapped[{device, key}] = ptr;
+  return ptr;
 }
 
 ErrorCode GpuSlabBackend::device_copy(worker::StorageBackend& peer, bool to_peer, uint64_t my_off, uint64_t peer_off, uint64_t len,
@@ -137,21 +159,15 @@ ErrorCode GpuSlabBackend::pull_from_peer(const std::vector<uint8_t>& peer_key, u
   BB_TRY(check_range(my_off, len));
   std::lock_guard<std::mutex> lk(move_mu_);
   if (!cuda_ok(cudaSetDevice(opts_.gpu_device_id), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
-  const std::string k(peer_key.begin(), peer_key.end());
-  auto it = peer_slabs_.find(k);
-  if (it == peer_slabs_.end()) {
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, peer_key.data(), sizeof h);
-    void* ptr = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {  // same-process slab, no peer access, stale handle: the caller relays through the data servers
-      cudaGetLastError();
-      BB_VLOG(1) << "pull_from_peer: cannot map the peer slab (" << cudaGetErrorString(e) << ")";
-      return ErrorCode::NOT_IMPLEMENTED;
-    }
-    it = peer_slabs_.emplace(k, ptr).first;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, peer_key.data(), sizeof h);
+  cudaError_t e = cudaSuccess;
+  void* peer_base = ipc_map_peer_slab(opts_.gpu_device_id, h, &e);
+  if (!peer_base) {  // same-process slab, no peer access, stale handle: the caller relays through the data servers
+    BB_VLOG(1) << "pull_from_peer: cannot map the peer slab (" << cudaGetErrorString(e) << ")";
+    return ErrorCode::NOT_IMPLEMENTED;
   }
-  uint8_t* theirs = static_cast<uint8_t*>(it->second) + peer_off;
+  uint8_t* theirs = static_cast<uint8_t*>(peer_base) + peer_off;
   uint8_t* mine = base_ + my_off;
   if ((reinterpret_cast<uintptr_t>(mine) | reinterpret_cast<uintptr_t>(theirs)) & 15) return ErrorCode::NOT_IMPLEMENTED;
   if (!move_engine_) {
@@ -220,7 +236,7 @@ GpuFabric::~GpuFabric() {
   std::lock_guard<std::mutex> lk(mu_);
   cudaSetDevice(device_);
   for (auto& [id, m] : pools_)
-    if (m.ipc_opened && m.base) cudaIpcCloseMemHandle(m.base);
+    (void)m;  // IPC mappings are process-wide (ipc_map_peer_slab) and stay mapped
 }
 
 size_t GpuFabric::mapped_pools() const {
@@ -273,8 +289,12 @@ ErrorCode GpuFabric::refresh_pools() {
       }
       cudaIpcMemHandle_t h;
       std::memcpy(&h, raw->data(), sizeof h);
-      void* ptr = nullptr;
-      if (!cuda_ok(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) continue;
+      cudaError_t ipc_err = cudaSuccess;
+      void* ptr = ipc_map_peer_slab(device_, h, &ipc_err);
+      if (!ptr) {
+        cuda_ok(ipc_err, "cudaIpcOpenMemHandle");
+        continue;
+      }
       m.base = static_cast<uint8_t*>(ptr);
       m.ipc_opened = true;
     }

@@ -57,7 +57,6 @@ class GpuSlabBackend : public worker::StorageBackend {
   void* stream_ = nullptr;
   std::mutex move_mu_;
   std::unique_ptr<XferEngine> move_engine_;  // created on the first tier move
-  std::map<std::string, void*> peer_slabs_;  // IPC handle bytes -> mapped base of a peer worker's slab
 };
 
 // Registers the GPU tier with worker::create_storage_backend (call once at start-up).
