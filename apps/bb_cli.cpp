@@ -1,7 +1,7 @@
 // bb-cli: command-line client (reference clients/ucx_client.cpp: put + get + compare with
 // timings; examples/simple_client_test.cpp: connectivity + /metrics smoke).
 //   bb-cli --keystone 127.0.0.1:9090 put KEY FILE [--replicas R] [--max-workers W] [--ttl-ms T] [--class RAM_CPU]
-//   bb-cli get KEY [OUTFILE] | exists KEY | remove KEY | migrate KEY CLASS | stats | smoke [--size N] | metrics --http 127.0.0.1:9091
+//   bb-cli get KEY [OUTFILE] | exists KEY | remove KEY | migrate KEY CLASS | where KEY | pools | stats | smoke [--size N] | metrics --http 127.0.0.1:9091
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -115,6 +115,29 @@ int main(int argc, char** argv) {
     ec = cl.migrate(args.positional[1], *sc);
     std::printf("migrate %s -> %s: %s\n", args.positional[1].c_str(), args.positional[2].c_str(), name(ec));
     return ec == ErrorCode::OK ? 0 : 1;
+  }
+  if (cmd == "pools") {  // admin introspection: every registered pool with live usage
+    auto pools = cl.keystone().get_memory_pools();
+    if (!pools.ok()) return 1;
+    Json arr = Json::array();
+    for (const auto& p : pools.value()) arr.push_back(to_json(p));
+    std::printf("%s\n", arr.dump(2).c_str());
+    return 0;
+  }
+  if (cmd == "where" && args.positional.size() >= 2) {  // placement of an object: copy -> shards (pool, worker, tier, digest)
+    auto copies = cl.get_workers(args.positional[1]);
+    if (!copies.ok()) {
+      std::printf("where %s: %s\n", args.positional[1].c_str(), name(copies.error()));
+      return 1;
+    }
+    for (const auto& c : copies.value())
+      for (size_t i = 0; i < c.shards.size(); ++i) {
+        const auto& s = c.shards[i];
+        std::printf("copy %u shard %zu: pool=%s worker=%s tier=%s bytes=%llu %s=%016llx\n", c.copy_index, i, s.pool_id.c_str(), s.worker_id.c_str(),
+                    std::string(to_string(s.storage_class)).c_str(), static_cast<unsigned long long>(s.length),
+                    std::string(to_string(s.checksum_algo)).c_str(), static_cast<unsigned long long>(s.checksum));
+      }
+    return 0;
   }
   if (cmd == "stats") {
     auto st = cl.cluster_stats();

@@ -112,6 +112,10 @@ def test_cluster_of_real_processes(procs, tmp_path, bb):
     assert run_cli("--keystone", ks, "get", "file-key", str(out)).returncode == 0
     assert out.read_bytes() == blob.read_bytes()
     assert run_cli("--keystone", ks, "exists", "file-key").stdout.strip() == "true"
+    w = run_cli("--keystone", ks, "where", "file-key")
+    assert w.returncode == 0 and w.stdout.count("copy ") == 4 and "tier=NVME" in w.stdout and "crc32c=" in w.stdout  # 2 copies x 2 shards
+    pools = json.loads(run_cli("--keystone", ks, "pools").stdout)
+    assert len(pools) == 4 and sum(p["used"] for p in pools) >= 2 * (3 << 20)
     m = run_cli("metrics", "--http", f"127.0.0.1:{hport}")
     assert m.returncode == 0 and "bb_objects 1" in m.stdout and 'bb_tier_used_bytes{tier="NVME"}' in m.stdout
     b = subprocess.run([os.path.join(BIN, "bb-bench"), "client", "--keystone", ks, "--size", "65536", "--iterations", "20", "--batch", "4"],
