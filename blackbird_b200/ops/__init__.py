@@ -1,1 +1,1 @@
-from .tensor_store import TensorStore  # noqa: F401
+from .tensor_store import AsyncTensorStore, TensorStore  # noqa: F401

@@ -157,3 +157,49 @@ class TensorStore:
 
     def remove(self, keys: Sequence[str]) -> None:
         self.client.batch_remove(list(keys) + [k + "#meta" for k in keys])
+
+
+class AsyncTensorStore(TensorStore):
+    """TensorStore whose puts / gets run on a side stream from a worker thread, so they overlap the caller's compute
+    (KV-cache offload, activation checkpoints).  `put_async` orders itself after the work already queued on the
+    caller's stream (event wait), returns a `concurrent.futures.Future`; `get_async`'s future yields the tensors, already
+    synchronised with the side stream.  The native calls release the GIL."""
+
+    def __init__(self, client, config=None, workers: int = 1):
+        super().__init__(client, config)
+        from concurrent.futures import ThreadPoolExecutor
+
+        self._pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="bb-async")
+        self._device = torch.cuda.current_device()
+        self._side = torch.cuda.Stream(device=self._device)
+
+    def _stream(self) -> int:  # every native call of this store is issued on the side stream
+        return self._side.cuda_stream
+
+    def put_async(self, keys: Sequence[str], tensors: Sequence[torch.Tensor], pack_fp8: bool = False, config=None):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())  # the tensors' producers
+        tensors = list(tensors)  # keep them alive until the transfer is done
+
+        def run():
+            torch.cuda.set_device(self._device)
+            self._side.wait_event(ready)
+            with torch.cuda.stream(self._side):
+                self.batch_put(keys, tensors, pack_fp8, config)
+            self._side.synchronize()
+            return len(tensors)
+
+        return self._pool.submit(run)
+
+    def get_async(self, keys: Sequence[str]):
+        def run():
+            torch.cuda.set_device(self._device)
+            with torch.cuda.stream(self._side):
+                out = self.batch_get(keys)
+            self._side.synchronize()
+            return out
+
+        return self._pool.submit(run)
+
+    def close(self):
+        self._pool.shutdown(wait=True)

@@ -782,10 +782,20 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
         out[i] = ErrorCode::BUFFER_OVERFLOW;
         continue;
       }
-      // prefer a replica that is fully reachable over the GPU fabric; otherwise stage through the host
+      // replica choice: one that lives on this client's own GPU (HBM speed, no NVLink), else a replica that is
+      // fully reachable over the GPU fabric (readers spread over the replicas), else stage through the host
       const auto& copies = placed[i].value();
-      const size_t start = std::hash<std::string>{}(opts_.node_id + keys[i]) % copies.size();  // spread readers over replicas
+      const size_t start = std::hash<std::string>{}(opts_.node_id + keys[i]) % copies.size();
       bool found = false;
+      for (size_t k = 0; k < copies.size() && !found; ++k) {
+        bool local = !copies[k].shards.empty();
+        for (const auto& sh : copies[k].shards) local &= device_->is_local(sh);
+        if (local) {
+          copy_choice[i] = k;
+          found = true;
+          metrics_.inc("device_get_local_replica_total");
+        }
+      }
       for (size_t k = 0; k < copies.size() && !found; ++k) {
         const auto& c = copies[(start + k) % copies.size()];
         bool ok = true;

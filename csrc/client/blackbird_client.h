@@ -93,6 +93,8 @@ class DeviceTransport {
     sync_results_.erase(it);
     return ErrorCode::OK;
   }
+  // True when the shard lives in this client's own device memory (a get from it never leaves the GPU).
+  virtual bool is_local(const ShardPlacement& s) const { return false; }
   virtual size_t max_in_flight() const { return 1; }
   // Fused MXFP8 put / get (pack / unpack inside the transfer kernel).  digests[i] = BBH64 of the stored packed
   // object; status[i] != 0 = digest mismatch on get.  Objects must satisfy fp8_eligible().

@@ -317,6 +317,16 @@ bool GpuFabric::can_reach(const ShardPlacement& s) const {
   return pools_.count(s.pool_id) > 0;
 }
 
+bool GpuFabric::is_local(const ShardPlacement& s) const {
+  if (s.storage_class != StorageClass::RAM_GPU) return false;
+  size_t grp = 0;
+  int member = 0;
+  if (arena_ && NvlsArena::parse_pool_id(s.pool_id, &grp, &member)) return member == arena_->rank();
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = pools_.find(s.pool_id);
+  return it != pools_.end() && it->second.device == device_ && !it->second.ipc_opened;
+}
+
 Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
   const auto* g = std::get_if<GpuSlabLocation>(&s.location);
   if (!g) return ErrorCode::INVALID_ADDRESS;

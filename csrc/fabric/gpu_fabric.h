@@ -73,6 +73,7 @@ class GpuFabric : public client::DeviceTransport {
   ErrorCode get_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, ChecksumAlgo algo, void* stream,
                        std::vector<uint32_t>* status) override;
   bool can_reach(const ShardPlacement& s) const override;
+  bool is_local(const ShardPlacement& s) const override;
   uint64_t launches() const override { return engine_->launches(); }
   Result<uint64_t> submit_put(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
                               void* stream) override;

@@ -59,6 +59,7 @@ class NvlsArena {
   ErrorCode phase4_map_peers();// import + map every member's memory (unicast reads)
 
   size_t num_groups() const { return groups_.size(); }
+  int rank() const { return rank_; }
   const std::vector<int>& members(size_t g) const { return groups_[g]; }
   bool member_of(size_t g) const { return local_index(g) >= 0; }
   uint64_t arena_bytes() const { return bytes_; }

@@ -243,3 +243,35 @@ def test_tensor_store_fused_fp8_path(bb, torch_cuda):
         assert cl.fabric.launches - l0 >= 6
     finally:
         cl.stop()
+
+
+def test_async_tensor_store_overlaps_and_local_replica_is_preferred(bb, torch_cuda):
+    """AsyncTensorStore: transfers run on a side stream from a worker thread (futures), ordered after the producer's
+    stream; a get whose replica lives on the client's own GPU is served from it (no fabric hop)."""
+    torch = torch_cuda
+    from blackbird_b200.ops import AsyncTensorStore
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=512 << 20, cluster_id="t-async")
+    try:
+        ts = AsyncTensorStore(cl.client)
+        a = torch.randn(2048, 2048, device="cuda")
+        acts = []
+        futs = []
+        for i in range(4):
+            a = torch.tanh(a @ a.t() / 2048.0)  # producer work on the main stream
+            acts.append(a)
+            futs.append(ts.put_async([f"act/{i}"], [a]))  # must observe the finished matmul (event wait)
+        assert [f.result(timeout=60) for f in futs] == [1, 1, 1, 1]
+        got = ts.get_async([f"act/{i}" for i in range(4)]).result(timeout=60)
+        torch.cuda.synchronize()
+        for g, ref in zip(got, acts):
+            assert torch.equal(g, ref)
+        kv = (torch.randn(4, 16384, device="cuda")).to(torch.bfloat16)
+        assert ts.put_async(["kv"], [kv], pack_fp8=True).result(timeout=60) == 1
+        back = ts.get_async(["kv"]).result(timeout=60)[0]
+        assert back.shape == kv.shape and (back.float() - kv.float()).abs().max().item() <= kv.float().abs().max().item() * 2 ** -3
+        ts.close()
+        assert "bb_client_device_get_local_replica_total" in cl.client.metrics_text()
+    finally:
+        cl.stop()
