@@ -164,6 +164,7 @@ void KeystoneService::health_loop() {
     }
     run_eviction_once();
     run_repair_once();
+    run_promotion_once();
   }
 }
 
@@ -213,6 +214,7 @@ void KeystoneService::on_worker_event(const std::string& key, const std::string&
     if (is_delete) {
       std::unique_lock<std::shared_mutex> lk(pools_mu_);
       pools_.erase(pid);
+      refresh_top_tier_locked();
       lk.unlock();
       bump_view();
       return;
@@ -249,6 +251,7 @@ void KeystoneService::on_legacy_pool_event(const std::string& key, const std::st
   if (is_delete) {
     std::unique_lock<std::shared_mutex> lk(pools_mu_);
     pools_.erase(pid);
+    refresh_top_tier_locked();
     return;
   }
   auto j = Json::parse(value);
@@ -310,6 +313,7 @@ ErrorCode KeystoneService::register_memory_pool(const MemoryPool& pool) {
     }
     std::unique_lock<std::shared_mutex> pk(pools_mu_);
     pools_[pool.id] = pool;
+    refresh_top_tier_locked();
   }
   bump_view();
   return ErrorCode::OK;
@@ -352,6 +356,7 @@ void KeystoneService::handle_worker_death(const WorkerId& id) {
       ++pit;
     }
     for (const auto& p : dead) pools_.erase(p);
+    refresh_top_tier_locked();
   }
   for (const auto& p : dead) allocator_->allocator().forget_pool(p);
   // invalidate every copy that had a shard on the dead pools
@@ -427,6 +432,16 @@ Result<std::vector<CopyPlacement>> KeystoneService::get_workers(const ObjectKey&
   if (it->second.copies.empty()) return ErrorCode::NO_COMPLETE_WORKER;
   it->second.touch();
   hot_.get_workers_total->fetch_add(1, std::memory_order_relaxed);
+  if (config_.promote_after_reads > 0 && top_tier_rank_.load(std::memory_order_relaxed) >= 0) {
+    int best = 1 << 20;
+    for (const auto& c : it->second.copies)
+      for (const auto& s : c.shards) best = std::min(best, tier_rank(s.storage_class));
+    if (best > top_tier_rank_.load(std::memory_order_relaxed) &&
+        ++it->second.reads_below_top == static_cast<uint32_t>(config_.promote_after_reads)) {
+      std::lock_guard<std::mutex> pl(promo_mu_);
+      promo_queue_.push_back(key);
+    }
+  }
   return it->second.copies;
 }
 
@@ -678,6 +693,23 @@ ErrorCode KeystoneService::get_memory_pools(std::vector<MemoryPool>& out) const 
   return ErrorCode::OK;
 }
 
+void KeystoneService::refresh_top_tier_locked() {
+  int best = -1;
+  for (const auto& [id, p] : pools_) {
+    const int r = tier_rank(p.storage_class);
+    if (best < 0 || r < best) best = r;
+  }
+  top_tier_rank_.store(best, std::memory_order_relaxed);
+}
+
+uint64_t KeystoneService::tier_capacity(StorageClass sc) const {
+  uint64_t cap = 0;
+  std::shared_lock<std::shared_mutex> lk(pools_mu_);
+  for (const auto& [id, p] : pools_)
+    if (p.storage_class == sc) cap += p.size;
+  return cap;
+}
+
 double KeystoneService::tier_utilization(StorageClass sc) const {
   uint64_t cap = 0, used = 0;
   std::shared_lock<std::shared_mutex> lk(pools_mu_);
@@ -806,6 +838,57 @@ ErrorCode KeystoneService::migrate_object(const ObjectKey& key, StorageClass tar
   ErrorCode ec = migrate_with(mover, key, {target});
   if (ec == ErrorCode::OK) metrics_.inc("migrations_total");
   return ec;
+}
+
+size_t KeystoneService::run_promotion_once() {
+  std::vector<ObjectKey> keys;
+  {
+    std::lock_guard<std::mutex> lk(promo_mu_);
+    keys.swap(promo_queue_);
+  }
+  if (keys.empty() || !is_leader()) return 0;
+  CopyMover mover;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+  }
+  if (!mover) return 0;
+  // tiers present in the cluster, fastest first
+  std::map<int, std::vector<StorageClass>> tiers;
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    for (const auto& [id, p] : pools_) {
+      auto& v = tiers[tier_rank(p.storage_class)];
+      if (std::find(v.begin(), v.end(), p.storage_class) == v.end()) v.push_back(p.storage_class);
+    }
+  }
+  size_t promoted = 0;
+  for (const auto& key : keys) {
+    auto info = get_object_info(key);
+    if (!info.ok() || info.value().copies.empty()) continue;
+    int cur = 1 << 20;
+    for (const auto& c : info.value().copies)
+      for (const auto& s : c.shards) cur = std::min(cur, tier_rank(s.storage_class));
+    std::vector<StorageClass> targets;  // faster tiers that would stay under the watermark with this object added
+    for (const auto& [rank, classes] : tiers) {
+      if (rank >= cur) break;
+      for (StorageClass sc : classes) {
+        const double cap = static_cast<double>(tier_capacity(sc));
+        if (cap > 0 && tier_utilization(sc) + static_cast<double>(info.value().size * info.value().copies.size()) / cap < config_.high_watermark)
+          targets.push_back(sc);
+      }
+    }
+    if (targets.empty()) continue;
+    if (migrate_with(mover, key, targets) == ErrorCode::OK) {
+      ++promoted;
+      Shard& sh = shard_for(key);
+      std::unique_lock<SpinMutex> lk(sh.mu);
+      auto it = sh.objects.find(key);
+      if (it != sh.objects.end()) it->second.reads_below_top = 0;
+    }
+  }
+  if (promoted) metrics_.inc("promotions_total", promoted);
+  return promoted;
 }
 
 size_t KeystoneService::run_eviction_once() {

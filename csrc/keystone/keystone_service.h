@@ -51,6 +51,7 @@ struct ObjectInfo {
   ObjectState state = ObjectState::PENDING;
   std::string owner_client;  // session that started the put
   std::vector<std::string> extra_ledgers;  // allocator ledger keys besides `key` (repair / demotion)
+  uint32_t reads_below_top = 0;            // reads served while the object sat on a lower tier (promotion policy)
 
   uint64_t ttl_ms() const { return config.ttl_ms; }
   bool is_expired(TimePoint now = Clock::now()) const {
@@ -143,6 +144,10 @@ class KeystoneService {
   // Runs one TTL sweep / eviction pass / repair pass synchronously (also used by the threads).
   size_t run_gc_once();
   size_t run_eviction_once();
+  // Read-driven promotion: objects read `promote_after_reads` times on a lower tier move back to the fastest tier that has
+  // room below the watermark.  Returns the number of objects promoted.
+  size_t run_promotion_once();
+  uint64_t tier_capacity(StorageClass sc) const;
   // Explicit tier move (promotion or demotion) of every copy of `key` to `target`; no-op when already there.
   ErrorCode migrate_object(const ObjectKey& key, StorageClass target);
   size_t run_repair_once();
@@ -199,6 +204,10 @@ class KeystoneService {
 
   std::mutex mover_mu_;
   CopyMover mover_;
+  void refresh_top_tier_locked();  // caller holds pools_mu_ exclusively
+  std::atomic<int> top_tier_rank_{-1};  // rank of the fastest tier present (promotion policy fast check)
+  std::mutex promo_mu_;
+  std::vector<ObjectKey> promo_queue_;
   Result<std::vector<CopyPlacement>> put_start_locked(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
                                                       const std::string& client_id, const std::string& client_node);
   struct HotMetrics {

@@ -264,6 +264,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("rpc_threads", &KeystoneConfig::rpc_threads)
       .def_readwrite("rpc_busy_poll_us", &KeystoneConfig::rpc_busy_poll_us)
       .def_readwrite("tier_policy", &KeystoneConfig::tier_policy)
+      .def_readwrite("promote_after_reads", &KeystoneConfig::promote_after_reads)
       .def_readwrite("wal_path", &KeystoneConfig::wal_path)
       .def_readwrite("log_level", &KeystoneConfig::log_level)
       .def("validate", [](const KeystoneConfig& c) {
@@ -475,6 +476,7 @@ void bind_control(py::module_& m) {
       .def("put_cancel", &KeystoneService::put_cancel)
       .def("remove_object", &KeystoneService::remove_object)
       .def("migrate_object", &KeystoneService::migrate_object, py::call_guard<py::gil_scoped_release>())
+      .def("run_promotion_once", &KeystoneService::run_promotion_once, py::call_guard<py::gil_scoped_release>())
       .def("remove_all_objects", [](KeystoneService& k) { return unwrap(k.remove_all_objects()); })
       .def("batch_object_exists", [](KeystoneService& k, const std::vector<std::string>& keys) {
         return results_to_py(k.batch_object_exists(keys), [](bool b) { return py::bool_(b); });

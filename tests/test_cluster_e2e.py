@@ -333,3 +333,31 @@ def test_trace_spans_are_recorded_and_dumped_as_chrome_trace(bb, tmp_path):
     finally:
         bb.trace_enable(False)
         bb.trace_clear()
+
+
+def test_read_driven_promotion_back_to_the_fast_tier(bb, tmp_path):
+    """keystone.promote_after_reads: an object that keeps being read while it sits on a lower tier moves back up
+    (bytes through the mover, digest re-checked), as long as the faster tier stays under its watermark."""
+    kc = bb.KeystoneConfig()
+    kc.promote_after_reads = 3
+    kc.high_watermark = 0.9
+    kc.health_check_interval_sec = 3600
+    with LocalCluster("promo", n_workers=0, keystone_cfg=kc) as c:
+        c.add_worker("w0", "node-0", [("dram", bb.StorageClass.RAM_CPU, 8 << 20, ""), ("nvme", bb.StorageClass.NVME, 64 << 20, str(tmp_path))])
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        cold = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[bb.StorageClass.NVME], checksum=bb.ChecksumAlgo.CRC32C)
+        hot_blob, big_blob = os.urandom(1 << 20), os.urandom(12 << 20)
+        assert cl.put("hot", hot_blob, cold) == bb.ErrorCode.OK
+        assert cl.put("big", big_blob, cold) == bb.ErrorCode.OK
+        assert cl.put("idle", os.urandom(1 << 20), cold) == bb.ErrorCode.OK
+        for _ in range(2):
+            assert cl.get("hot") == hot_blob
+        assert c.keystone.run_promotion_once() == 0  # two reads: below the threshold
+        assert cl.get("hot") == hot_blob
+        for _ in range(3):
+            assert cl.get("big") == big_blob  # hot too, but 12 MiB would push the 8 MiB DRAM tier over its watermark
+        assert c.keystone.run_promotion_once() == 1
+        tier = lambda k: cl.get_workers(k)[0].shards[0].storage_class  # noqa: E731
+        assert tier("hot") == bb.StorageClass.RAM_CPU and tier("big") == bb.StorageClass.NVME and tier("idle") == bb.StorageClass.NVME
+        assert cl.get("hot") == hot_blob and "bb_promotions_total 1" in c.keystone.metrics_text()
