@@ -9,3 +9,22 @@ from . import _bb  # noqa: F401  (native core; must be built in-tree: python bui
 from ._bb import ChecksumAlgo, ErrorCode  # noqa: F401
 
 __version__ = "0.1.0"
+
+_LAZY = {
+    "LocalCluster": ("blackbird_b200.parallel", "LocalCluster"),
+    "GpuRankCluster": ("blackbird_b200.parallel", "GpuRankCluster"),
+    "TensorStore": ("blackbird_b200.ops", "TensorStore"),            # imports torch
+    "AsyncTensorStore": ("blackbird_b200.ops", "AsyncTensorStore"),
+    "BlackbirdClient": ("blackbird_b200._bb", "BlackbirdClient"),
+    "WorkerConfig": ("blackbird_b200._bb", "WorkerConfig"),
+    "StorageClass": ("blackbird_b200._bb", "StorageClass"),
+}
+
+
+def __getattr__(name):  # lazy: `import blackbird_b200` must not import torch
+    if name in _LAZY:
+        import importlib
+
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(mod), attr)
+    raise AttributeError(f"module 'blackbird_b200' has no attribute {name!r}")
