@@ -55,8 +55,11 @@ __constant__ uint64_t c_col_mul[tchash::kN];
 __constant__ uint32_t c_xpow_tiles[32];  // x^(8 * 16384 * 2^j) mod P  (CRC32C cross-CTA combine)
 
 // CRC shift tables: index -> byte distance
-enum CrcTab : int { T128 = 0, T4, T8, T16, T32, T64, T4096, T16384, kNumCrcTabs };
-constexpr uint64_t kCrcTabBytes[kNumCrcTabs] = {128, 4, 8, 16, 32, 64, 4096, 16384};
+enum CrcTab : int { T128 = 0, T4, T8, T16, T32, T64, T4096, T16384, TCHAIN, TJUMP, kNumCrcTabs };
+constexpr int kCrcChains = 8;                     // independent Horner chains per lane
+constexpr int kCrcChainRows = 32 / kCrcChains;   // rows (of 128 B) of a tile quarter per chain
+constexpr uint64_t kCrcTabBytes[kNumCrcTabs] = {128, 4, 8, 16, 32, 64, 4096, 16384, kCrcChainRows * 128,
+                                                16384 - (kCrcChainRows - 1) * 128};
 
 struct StageMeta {  // 64 bytes
   uint64_t dst[kMaxDst];
@@ -91,6 +94,11 @@ struct __align__(1024) SmemT {
   uint32_t dirty[kStages];
   uint32_t tmem_base;
   uint32_t crc_t[ALGO == ALGO_CRC32C ? kNumCrcTabs : 1][4][256];
+  // x^(8*128) shift as 8 nibble tables with one private copy per lane ([nibble][value][lane]: lane l only ever
+  // touches bank l, so the 8 lookups of a step are bank-conflict free whatever the data is).
+  // 2 KiB of slack: the kernel rounds the table's shared address up to 2048 so that the value index (bits 7-10)
+  // can be OR-ed into the lane's base address with a single LOP3.
+  uint32_t crc_nib[ALGO == ALGO_CRC32C ? 8 * 16 * 32 + 512 : 1];
 };
 
 struct Params {
@@ -127,6 +135,22 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 // s * x^(8k) mod P through the 4x256 table of distance k.
 __device__ __forceinline__ uint32_t crc_shift(const uint32_t (*t)[256], uint32_t s) {
   return t[0][s & 0xFFu] ^ t[1][(s >> 8) & 0xFFu] ^ t[2][(s >> 16) & 0xFFu] ^ t[3][s >> 24];
+}
+
+// One nibble of the lane-private x^(8*128) shift: table [nibble J][value][lane], 2 KiB per nibble, base 2 KiB aligned
+// so the value index (bits 7-10) is OR-ed into the lane's base address by one LOP3.  The table is read-only after setup.
+template <int J>
+__device__ __forceinline__ uint32_t crc_nib_lookup(uint32_t v, uint32_t nib_lane) {
+  const uint32_t x = (4 * J >= 7) ? (v >> (4 * J >= 7 ? 4 * J - 7 : 0)) : (v << (4 * J >= 7 ? 0 : 7 - 4 * J));
+  uint32_t addr, t;
+  asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(addr) : "r"(x), "r"(nib_lane));  // (x & 0x780) | base
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(t) : "r"(addr), "n"(J * 2048));
+  return t;
+}
+__device__ __forceinline__ uint32_t crc_nib_shift(uint32_t v, uint32_t nib_lane) {
+  return crc_nib_lookup<0>(v, nib_lane) ^ crc_nib_lookup<1>(v, nib_lane) ^ crc_nib_lookup<2>(v, nib_lane) ^
+         crc_nib_lookup<3>(v, nib_lane) ^ crc_nib_lookup<4>(v, nib_lane) ^ crc_nib_lookup<5>(v, nib_lane) ^
+         crc_nib_lookup<6>(v, nib_lane) ^ crc_nib_lookup<7>(v, nib_lane);
 }
 
 __device__ __forceinline__ uint32_t gf2_mulmod_dev(uint32_t a, uint32_t b) {
@@ -188,6 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
   if constexpr (kCrc) {
     uint32_t* dstt = &s.crc_t[0][0][0];
     for (uint32_t i = threadIdx.x; i < kNumCrcTabs * 1024; i += kThreads) dstt[i] = __ldg(&p.crc_tables[i]);
+    __syncthreads();
+    uint32_t* nibt = s.crc_nib + ((2048u - (smem_u32(s.crc_nib) & 2047u)) & 2047u) / 4u;
+    for (uint32_t i = threadIdx.x; i < 8 * 16 * 32; i += kThreads) {  // [nibble j][value v][lane]
+      const uint32_t j = i >> 9, v = (i >> 5) & 15u;
+      nibt[i] = crc_shift(s.crc_t[T128], v << (4 * j));
+    }
   }
   __syncthreads();
   if constexpr (kBbh) tc_fence_after();
@@ -361,18 +391,19 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
           acc = 0;
           cnt = 0;
         }
-        if constexpr (kBbh) {
-          acc += p0 + p1 + p2 + p3;
-        } else {
-          const auto* t4k = s.crc_t[T4096];
-          uint32_t t = crc_shift(t4k, static_cast<uint32_t>(p0)) ^ static_cast<uint32_t>(p1);
-          t = crc_shift(t4k, t) ^ static_cast<uint32_t>(p2);
-          t = crc_shift(t4k, t) ^ static_cast<uint32_t>(p3);
-          acc = crc_shift(s.crc_t[T16384], static_cast<uint32_t>(acc)) ^ t;
-        }
+        if constexpr (kBbh) acc += p0 + p1 + p2 + p3;
         ++cnt;
         const bool obj_end = (m.tile_in_obj + 1 == m.obj_ntiles);
         if (obj_end || it + 1 == my_tiles) {
+          if constexpr (kCrc) {
+            // The epilogue warps carry their per-lane accumulators across the tiles of an object and publish the
+            // four quarter values only here: together they are the CRC polynomial of this CTA's whole run of it.
+            const auto* t4k = s.crc_t[T4096];
+            uint32_t t = crc_shift(t4k, static_cast<uint32_t>(p0)) ^ static_cast<uint32_t>(p1);
+            t = crc_shift(t4k, t) ^ static_cast<uint32_t>(p2);
+            t = crc_shift(t4k, t) ^ static_cast<uint32_t>(p3);
+            acc = t;
+          }
           // ---- this CTA's contribution to object cur_d is complete
           uint64_t digest = 0;
           bool have = false;
@@ -447,29 +478,53 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
         }
       }
     } else if constexpr (kCrc) {
+      // Quarter q of every tile, lane l: words l, l+32, ... (bank-conflict free); consecutive words of a lane are
+      // 128 B apart -> one x^(8*128) shift per step through the lane-private nibble tables.  Four independent Horner
+      // chains per lane (kCrcChains x kCrcChainRows rows) hide the latency of the dependent lookups, and the chains
+      // run on ACROSS the tiles of an object (a chain's next row in the following tile is 16384 - (kCrcChainRows-1)*128 bytes
+      // further), so the lane / chain / quarter combine is paid once per object and CTA, not once per tile.
       const uint32_t q = warp & 3u;
+      const uint32_t nib_lane = ((smem_u32(s.crc_nib) + 2047u) & ~2047u) + lane * 4u;  // bits 7-10 clear
+      const auto* tj = s.crc_t[TJUMP];
+      uint32_t a[kCrcChains];
+#pragma unroll
+      for (int c = 0; c < kCrcChains; ++c) a[c] = 0;
       for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint32_t stage = it % kStages;
         const uint32_t par = (it / kStages) & 1u;
-        mbar_wait(&s.full[stage], par);
-        // lane l streams words l, l+32, ... of this warp's 4 KiB quarter (bank-conflict free);
-        // consecutive words of a lane are 128 B apart -> shift by x^(8*128) per step.
+        mbar_wait(&s.full[stage], par);  // also acquires the producer's StageMeta writes
+        const uint32_t tio = s.meta[stage].tile_in_obj;
+        const bool fresh = (it == 0) || (tio == 0);
+        const bool flush = (tio + 1 == s.meta[stage].obj_ntiles) || (it + 1 == my_tiles);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(&s.tile[stage][q * 4096]) + lane;
-        const auto* t128 = s.crc_t[T128];
-        uint32_t a = 0;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) a = crc_shift(t128, a) ^ wp[i * 32];
-        // combine lanes: value(l) covers bytes [4l, 4l+4) of each 128-byte row group
-        uint32_t o;
-        o = __shfl_down_sync(0xffffffffu, a, 1);  a = crc_shift(s.crc_t[T4], a) ^ o;
-        o = __shfl_down_sync(0xffffffffu, a, 2);  a = crc_shift(s.crc_t[T8], a) ^ o;
-        o = __shfl_down_sync(0xffffffffu, a, 4);  a = crc_shift(s.crc_t[T16], a) ^ o;
-        o = __shfl_down_sync(0xffffffffu, a, 8);  a = crc_shift(s.crc_t[T32], a) ^ o;
-        o = __shfl_down_sync(0xffffffffu, a, 16); a = crc_shift(s.crc_t[T64], a) ^ o;
-        if (lane == 0) {
-          s.part[stage][q] = crc_shift(s.crc_t[T4], a);  // the CRC's final x^32 factor
-          mbar_arrive(&s.epi_done[stage]);
+        if (fresh) {
+#pragma unroll
+          for (int c = 0; c < kCrcChains; ++c) a[c] = wp[c * kCrcChainRows * 32];
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCrcChains; ++c) a[c] = crc_shift(tj, a[c]) ^ wp[c * kCrcChainRows * 32];
         }
+#pragma unroll
+        for (int i = 1; i < kCrcChainRows; ++i) {
+#pragma unroll
+          for (int c = 0; c < kCrcChains; ++c) a[c] = crc_nib_shift(a[c], nib_lane) ^ wp[(c * kCrcChainRows + i) * 32];
+        }
+        if (flush) {
+          const auto* tc = s.crc_t[TCHAIN];  // chains are kCrcChainRows rows of 128 B apart
+          uint32_t v = a[0];
+#pragma unroll
+          for (int c = 1; c < kCrcChains; ++c) v = crc_shift(tc, v) ^ a[c];
+          // combine lanes: value(l) covers bytes [4l, 4l+4) of each 128-byte row group
+          uint32_t o;
+          o = __shfl_down_sync(0xffffffffu, v, 1);  v = crc_shift(s.crc_t[T4], v) ^ o;
+          o = __shfl_down_sync(0xffffffffu, v, 2);  v = crc_shift(s.crc_t[T8], v) ^ o;
+          o = __shfl_down_sync(0xffffffffu, v, 4);  v = crc_shift(s.crc_t[T16], v) ^ o;
+          o = __shfl_down_sync(0xffffffffu, v, 8);  v = crc_shift(s.crc_t[T32], v) ^ o;
+          o = __shfl_down_sync(0xffffffffu, v, 16); v = crc_shift(s.crc_t[T64], v) ^ o;
+          if (lane == 0) s.part[stage][q] = crc_shift(s.crc_t[T4], v);  // the CRC's final x^32 factor
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.epi_done[stage]);
       }
     }
   }
@@ -619,7 +674,8 @@ int launch_xfer(const XferLaunch& l) {
   // Measured on B200 (profiles/xfer_single_gpu.md): 96-128 persistent CTAs saturate HBM for
   // large batches (3.2 TB/s payload); all 148 lose ~6% to DRAM contention.  BB_XFER_CTAS overrides.
   static const int env_ctas = [] { const char* e = std::getenv("BB_XFER_CTAS"); return e ? std::atoi(e) : 0; }();
-  int grid = l.max_ctas > 0 ? l.max_ctas : env_ctas > 0 ? env_ctas : std::min(ds.sm_count, 128);
+  // The fused CRC32C is bound by shared-memory lookups per SM, not by DRAM: it takes every SM.
+  int grid = l.max_ctas > 0 ? l.max_ctas : env_ctas > 0 ? env_ctas : l.algo == ALGO_CRC32C ? ds.sm_count : std::min(ds.sm_count, 128);
   grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(grid), l.total_tiles));
   cudaStream_t st = static_cast<cudaStream_t>(l.stream);
   switch (l.algo) {
