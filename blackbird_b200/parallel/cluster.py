@@ -192,6 +192,7 @@ class GpuRankCluster:
         if dram_bytes:
             dram = _bb.StoragePoolConfig(f"dram{self.rank}", _bb.StorageClass.RAM_CPU, dram_bytes, "")
             dram.pin_memory = True  # registered with CUDA: GPU <-> DRAM tier moves are one fused-kernel launch
+            dram.shared_memory = True  # memfd-backed: GPU clients of the other ranks map it and read it over PCIe
             wc.storage_pools += [dram]
         if nvme_bytes:
             wc.storage_pools += [_bb.StoragePoolConfig(f"nvme{self.rank}", _bb.StorageClass.NVME, nvme_bytes, nvme_path or "/tmp")]

@@ -796,13 +796,17 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
           metrics_.inc("device_get_local_replica_total");
         }
       }
-      for (size_t k = 0; k < copies.size() && !found; ++k) {
-        const auto& c = copies[(start + k) % copies.size()];
-        bool ok = true;
-        for (const auto& sh : c.shards) ok &= device_->can_reach(sh);
-        if (ok) {
-          copy_choice[i] = (start + k) % copies.size();
-          found = true;
+      // HBM replicas first (NVLink), then replicas in mapped DRAM pools (PCIe)
+      for (int pass = 0; pass < 2 && !found; ++pass) {
+        for (size_t k = 0; k < copies.size() && !found; ++k) {
+          const auto& c = copies[(start + k) % copies.size()];
+          bool ok = !c.shards.empty();
+          for (const auto& sh : c.shards) ok = ok && (pass == 1 || sh.storage_class == StorageClass::RAM_GPU) && device_->can_reach(sh);
+          if (ok) {
+            copy_choice[i] = (start + k) % copies.size();
+            found = true;
+            if (pass == 1) metrics_.inc("device_get_dram_direct_total");
+          }
         }
       }
       if (!found) {

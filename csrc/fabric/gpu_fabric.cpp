@@ -235,8 +235,81 @@ Result<std::shared_ptr<GpuFabric>> GpuFabric::create(int device, std::shared_ptr
 GpuFabric::~GpuFabric() {
   std::lock_guard<std::mutex> lk(mu_);
   cudaSetDevice(device_);
-  for (auto& [id, m] : pools_)
-    (void)m;  // IPC mappings are process-wide (ipc_map_peer_slab) and stay mapped
+  for (auto& [id, m] : pools_) {
+    // IPC mappings are process-wide (ipc_map_peer_slab) and stay mapped; shared DRAM pools are ours
+    if (m.host_mapped && m.base) {
+      if (cudaHostUnregister(m.base) != cudaSuccess) cudaGetLastError();
+      worker::unmap_shared_pool(m.base, m.size);
+    }
+  }
+}
+
+size_t GpuFabric::mapped_host_pools() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  size_t n = 0;
+  for (const auto& [id, m] : pools_) n += m.host ? 1 : 0;
+  return n;
+}
+
+// DRAM-tier pools: in-process pinned pools are used as they are; pools of other worker processes on this host are
+// memfd-backed ("file:/proc/<pid>/fd/<n>" registration key) and get mapped + cudaHostRegister'ed here, once, on the
+// first shard that needs them.  Everything else (other host, private mapping) stays on the data-server path.
+bool GpuFabric::ensure_host_pool(const std::string& pool_id) {
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    HostCandidate cand;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = pools_.find(pool_id);
+      if (it != pools_.end()) return it->second.host;
+      if (host_unreachable_.count(pool_id)) return false;
+      auto c = host_candidates_.find(pool_id);
+      if (c == host_candidates_.end()) {
+        if (attempt == 1) {
+          host_unreachable_.insert(pool_id);
+          return false;
+        }
+      } else {
+        cand = c->second;
+      }
+    }
+    if (cand.size == 0) {
+      refresh_pools();  // a worker that joined after this fabric was created
+      continue;
+    }
+    Mapping m;
+    m.host = true;
+    m.size = cand.size;
+    m.remote_base = cand.remote_base;
+    worker::LocalHostPool local;
+    if (worker::find_local_host_pool(pool_id, &local) && local.size >= cand.size) {
+      m.base = static_cast<uint8_t*>(local.base);  // pinned by the worker of this process
+    } else if (auto raw = hex_to_bytes(cand.key_hex); raw) {
+      void* p = worker::map_shared_pool(*raw, cand.size);
+      if (p) {
+        if (cuda_ok(cudaSetDevice(device_), "cudaSetDevice") &&
+            cuda_ok(cudaHostRegister(p, cand.size, cudaHostRegisterPortable | cudaHostRegisterMapped), "cudaHostRegister(shared DRAM pool)")) {
+          m.base = static_cast<uint8_t*>(p);
+          m.host_mapped = true;
+        } else {
+          worker::unmap_shared_pool(p, cand.size);
+        }
+      }
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!m.base) {
+      host_unreachable_.insert(pool_id);
+      return false;
+    }
+    auto [it, fresh] = pools_.emplace(pool_id, m);
+    if (!fresh && m.host_mapped) {  // lost a race with another thread: keep theirs
+      if (cudaHostUnregister(m.base) != cudaSuccess) cudaGetLastError();
+      worker::unmap_shared_pool(m.base, m.size);
+    }
+    BB_LOG(INFO) << "GPU " << device_ << ": DRAM pool " << pool_id << " (" << (cand.size >> 20) << " MiB) is reachable by the fused kernels ("
+                 << (it->second.host_mapped ? "mapped from its worker's memfd" : "in-process pinned pool") << ")";
+    return true;
+  }
+  return false;
 }
 
 size_t GpuFabric::mapped_pools() const {
@@ -251,6 +324,10 @@ ErrorCode GpuFabric::refresh_pools() {
   if (!cuda_ok(cudaSetDevice(device_), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
   std::lock_guard<std::mutex> lk(mu_);
   for (const auto& p : pools.value()) {
+    if (p.storage_class == StorageClass::RAM_CPU && !pools_.count(p.id)) {
+      host_candidates_[p.id] = HostCandidate{p.size, p.ucx_remote_addr ? p.ucx_remote_addr : p.base_addr, p.ucx_rkey_hex};
+      continue;
+    }
     if (p.storage_class != StorageClass::RAM_GPU || pools_.count(p.id)) continue;
     Mapping m;
     m.size = p.size;
@@ -304,6 +381,8 @@ ErrorCode GpuFabric::refresh_pools() {
 }
 
 bool GpuFabric::can_reach(const ShardPlacement& s) const {
+  if (s.storage_class == StorageClass::RAM_CPU && std::holds_alternative<MemoryLocation>(s.location))
+    return const_cast<GpuFabric*>(this)->ensure_host_pool(s.pool_id);
   if (s.storage_class != StorageClass::RAM_GPU) return false;
   size_t grp = 0;
   int member = 0;
@@ -328,6 +407,13 @@ bool GpuFabric::is_local(const ShardPlacement& s) const {
 }
 
 Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
+  if (const auto* h = std::get_if<MemoryLocation>(&s.location)) {  // shared / pinned DRAM pool
+    if (!ensure_host_pool(s.pool_id)) return ErrorCode::MEMORY_POOL_NOT_FOUND;
+    std::lock_guard<std::mutex> lk(mu_);
+    const Mapping& m = pools_.at(s.pool_id);
+    if (h->remote_addr < m.remote_base || h->remote_addr - m.remote_base + s.length > m.size) return ErrorCode::MEMORY_ACCESS_ERROR;
+    return static_cast<void*>(m.base + (h->remote_addr - m.remote_base));
+  }
   const auto* g = std::get_if<GpuSlabLocation>(&s.location);
   if (!g) return ErrorCode::INVALID_ADDRESS;
   size_t grp = 0;

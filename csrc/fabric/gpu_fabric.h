@@ -11,6 +11,7 @@
 // ram_backend.cpp:188, worker_service.cpp:196).  GpuFabric implements client::DeviceTransport.
 #pragma once
 #include <map>
+#include <set>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -90,6 +91,7 @@ class GpuFabric : public client::DeviceTransport {
   // Re-reads the pool registry from the keystone and maps any new GPU slab.
   ErrorCode refresh_pools();
   size_t mapped_pools() const;
+  size_t mapped_host_pools() const;  // shared / pinned DRAM pools reachable by the fused kernels
   // NVLS replica arenas: pools named mc<g>@gpu<r> resolve through the arena; a put whose replica set is
   // exactly one multicast group (same offset everywhere) becomes ONE multimem.st stream.
   void set_arena(std::shared_ptr<NvlsArena> a) { arena_ = std::move(a); }
@@ -105,7 +107,16 @@ class GpuFabric : public client::DeviceTransport {
     uint64_t size = 0;
     int device = -1;
     bool ipc_opened = false;
+    bool host = false;           // pinned host memory (a worker's shared DRAM pool): reached over PCIe
+    bool host_mapped = false;    // mapped + registered by this fabric (unmapped in the destructor)
+    uint64_t remote_base = 0;    // host pools: the address MemoryLocation::remote_addr is relative to
   };
+  struct HostCandidate {         // DRAM pool seen in the registry; mapped lazily on first use
+    uint64_t size = 0;
+    uint64_t remote_base = 0;
+    std::string key_hex;
+  };
+  bool ensure_host_pool(const std::string& pool_id);
   Result<void*> resolve(const ShardPlacement& s);
   ErrorCode build_put_items(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs,
                             std::vector<XferItem>* items, std::vector<size_t>* op_of_item);
@@ -122,6 +133,8 @@ class GpuFabric : public client::DeviceTransport {
   std::unique_ptr<XferEngine> engine_;
   mutable std::mutex mu_;
   std::map<std::string, Mapping> pools_;
+  std::map<std::string, HostCandidate> host_candidates_;
+  std::set<std::string> host_unreachable_;
   std::shared_ptr<NvlsArena> arena_;
   uint64_t multicast_puts_ = 0;
   float last_ms_ = 0.f;

@@ -653,6 +653,7 @@ void bind_control(py::module_& m) {
       .def("get_available_capacity", &StorageBackend::get_available_capacity)
       .def("get_base_address", &StorageBackend::get_base_address)
       .def("get_rkey", &StorageBackend::get_rkey)
+      .def("registration_key_hex", &StorageBackend::registration_key_hex)
       .def("initialize", &StorageBackend::initialize, py::call_guard<py::gil_scoped_release>())
       .def("shutdown", &StorageBackend::shutdown, py::call_guard<py::gil_scoped_release>())
       .def("reserve_shard", [](StorageBackend& b, uint64_t size, const std::string& hint) { return unwrap(b.reserve_shard(size, hint)); },
@@ -698,18 +699,32 @@ void bind_control(py::module_& m) {
       .def_property_readonly("numa_bound", &worker::CxlMemoryBackend::numa_bound)
       .def("region_id", &worker::CxlMemoryBackend::region_id);
   py::class_<worker::MmapDiskBackend, StorageBackend>(m, "MmapDiskBackend").def_property_readonly("file_path", &worker::MmapDiskBackend::file_path);
-  py::class_<worker::RamBackend, StorageBackend>(m, "RamBackend");
+  py::class_<worker::RamBackend, StorageBackend>(m, "RamBackend")
+      .def_property_readonly("shared_path", &worker::RamBackend::shared_path)
+      .def_property_readonly("pinned", &worker::RamBackend::pinned);
   m.def("create_storage_backend", [](StorageClass sc, uint64_t capacity, const std::string& mount_path, uint32_t queue_depth, int numa_node,
-                                      const std::string& pool_id) -> std::unique_ptr<StorageBackend> {
+                                      const std::string& pool_id, bool shared_memory) -> std::unique_ptr<StorageBackend> {
     worker::BackendOptions o;
     o.mount_path = mount_path;
     o.queue_depth = queue_depth;
     o.numa_node = numa_node;
+    o.shared_memory = shared_memory;
     auto b = worker::create_storage_backend(sc, capacity, o);
     if (b && !pool_id.empty()) b->set_pool_id(pool_id);
     return b;
   }, py::arg("storage_class"), py::arg("capacity"), py::arg("mount_path") = "", py::arg("queue_depth") = 64, py::arg("numa_node") = -1,
-     py::arg("pool_id") = "");
+     py::arg("pool_id") = "", py::arg("shared_memory") = false);
+  // Maps another worker's shared RAM pool (registration key = hex of "file:<path>") and returns its first `n` bytes
+  // starting at `offset` (test / diagnostics helper for the mapping the GPU fabric performs).
+  m.def("read_shared_pool", [](const std::string& key_hex, uint64_t pool_size, uint64_t offset, uint64_t n) -> py::object {
+    auto raw = hex_to_bytes(key_hex);
+    if (!raw || offset + n > pool_size) return py::none();
+    void* p = worker::map_shared_pool(*raw, pool_size);
+    if (!p) return py::none();
+    py::bytes out(static_cast<const char*>(p) + offset, n);
+    worker::unmap_shared_pool(p, pool_size);
+    return out;
+  });
   m.def("io_uring_supported", &worker::IoUring::supported);
 
   // CXL transport / pool configuration (reference include/blackbird/transport/cxl_transport_config.h)
@@ -784,6 +799,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("gpu_device_id", &worker::StoragePoolConfig::gpu_device_id)
       .def_readwrite("numa_node", &worker::StoragePoolConfig::numa_node)
       .def_readwrite("pin_memory", &worker::StoragePoolConfig::pin_memory)
+      .def_readwrite("shared_memory", &worker::StoragePoolConfig::shared_memory)
       .def_readwrite("cxl", &worker::StoragePoolConfig::cxl);
   py::class_<worker::WorkerServiceConfig>(m, "WorkerServiceConfig")
       .def(py::init<>())

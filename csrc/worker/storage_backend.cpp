@@ -163,14 +163,32 @@ RamBackend::~RamBackend() { shutdown(); }
 ErrorCode RamBackend::initialize() {
   if (initialized_) return ErrorCode::OK;
   if (capacity_ == 0) return ErrorCode::INVALID_PARAMETERS;
-  void* p = ::mmap(nullptr, capacity_, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  void* p = MAP_FAILED;
+  if (opts_.shared_memory) {
+    // memfd: lives as long as this process, needs no name in /dev/shm (whose mount is tiny in containers) and is
+    // reachable by same-user peers through /proc/<pid>/fd/<n>.
+    shared_fd_ = static_cast<int>(::syscall(SYS_memfd_create, "bb-ram-pool", 1u /* MFD_CLOEXEC */));
+    if (shared_fd_ >= 0 && ::ftruncate(shared_fd_, static_cast<off_t>(capacity_)) == 0)
+      p = ::mmap(nullptr, capacity_, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, shared_fd_, 0);
+    if (p == MAP_FAILED) {
+      BB_LOG(WARNING) << "RAM pool " << pool_id_ << ": shared_memory requested but memfd setup failed (" << std::strerror(errno)
+                      << "); falling back to a private mapping";
+      if (shared_fd_ >= 0) ::close(shared_fd_);
+      shared_fd_ = -1;
+    } else {
+      shared_path_ = "/proc/" + std::to_string(::getpid()) + "/fd/" + std::to_string(shared_fd_);
+    }
+  }
+  if (p == MAP_FAILED) p = ::mmap(nullptr, capacity_, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
   if (p == MAP_FAILED) return ErrorCode::OUT_OF_MEMORY;
   base_ = static_cast<uint8_t*>(p);
   rkey_ = fnv64(pool_id_) & 0xFFFFFFFFull;
   if (opts_.pin_memory) {
     HostPinHooks h = host_pin_hooks();
-    if (h.pin && h.pin(base_, capacity_)) pinned_ = true;
-    else BB_LOG(INFO) << "RAM pool " << pool_id_ << ": pin_memory requested but no CUDA pin hook (or registration failed); tier moves use the staged path";
+    if (h.pin && h.pin(base_, capacity_)) {
+      pinned_ = true;
+      register_local_host_pool(pool_id_, base_, capacity_);
+    } else BB_LOG(INFO) << "RAM pool " << pool_id_ << ": pin_memory requested but no CUDA pin hook (or registration failed); tier moves use the staged path";
   }
   init_allocator();
   initialized_ = true;
@@ -180,12 +198,67 @@ ErrorCode RamBackend::initialize() {
 void RamBackend::shutdown() {
   if (base_ && pinned_) {
     HostPinHooks h = host_pin_hooks();
+    unregister_local_host_pool(pool_id_);
     if (h.unpin) h.unpin(base_);
     pinned_ = false;
   }
   if (base_) ::munmap(base_, capacity_);
   base_ = nullptr;
+  if (shared_fd_ >= 0) ::close(shared_fd_);
+  shared_fd_ = -1;
+  shared_path_.clear();
   initialized_ = false;
+}
+
+std::string RamBackend::registration_key_hex() const {
+  if (shared_path_.empty()) return StorageBackend::registration_key_hex();
+  const std::string key = "file:" + shared_path_;
+  static const char* hexd = "0123456789abcdef";
+  std::string out;
+  out.reserve(key.size() * 2);
+  for (unsigned char c : key) {
+    out.push_back(hexd[c >> 4]);
+    out.push_back(hexd[c & 15]);
+  }
+  return out;
+}
+
+namespace {
+std::mutex g_host_pools_mu;
+std::unordered_map<std::string, LocalHostPool> g_host_pools;
+}  // namespace
+void register_local_host_pool(const std::string& pool_id, void* base, uint64_t size) {
+  std::lock_guard<std::mutex> lk(g_host_pools_mu);
+  g_host_pools[pool_id] = LocalHostPool{base, size};
+}
+void unregister_local_host_pool(const std::string& pool_id) {
+  std::lock_guard<std::mutex> lk(g_host_pools_mu);
+  g_host_pools.erase(pool_id);
+}
+bool find_local_host_pool(const std::string& pool_id, LocalHostPool* out) {
+  std::lock_guard<std::mutex> lk(g_host_pools_mu);
+  auto it = g_host_pools.find(pool_id);
+  if (it == g_host_pools.end()) return false;
+  if (out) *out = it->second;
+  return true;
+}
+
+void* map_shared_pool(const std::vector<uint8_t>& key, uint64_t size) {
+  static const char kPrefix[] = "file:";
+  if (size == 0 || key.size() <= 5 || std::memcmp(key.data(), kPrefix, 5) != 0) return nullptr;
+  const std::string path(reinterpret_cast<const char*>(key.data()) + 5, key.size() - 5);
+  if (path.find('\0') != std::string::npos) return nullptr;
+  const int fd = ::open(path.c_str(), O_RDWR | O_CLOEXEC);
+  if (fd < 0) return nullptr;  // another host / pid namespace / user: the data server path is used instead
+  struct stat st {};
+  void* p = MAP_FAILED;
+  if (::fstat(fd, &st) == 0 && static_cast<uint64_t>(st.st_size) >= size) p = ::mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  ::close(fd);
+  return p == MAP_FAILED ? nullptr : p;
+}
+
+void unmap_shared_pool(void* base, uint64_t size) {
+  if (base) ::munmap(base, size);
 }
 
 ErrorCode RamBackend::write(uint64_t offset, const void* data, uint64_t len) {

@@ -60,6 +60,10 @@ struct BackendOptions {
   int numa_node = -1;              // CXL / DRAM binding
   uint32_t queue_depth = 64;       // io_uring
   bool pin_memory = false;         // DRAM tier: cudaHostRegister when CUDA is present
+  // DRAM tier: back the pool with a memfd and advertise "file:/proc/<pid>/fd/<n>" as its registration key, so that
+  // GPU clients in OTHER processes of the same host can map it (and register it with their CUDA context): the fused
+  // kernels then read / write the DRAM tier directly over PCIe instead of going through the TCP data server.
+  bool shared_memory = false;
   uint64_t reservation_ttl_ms = 10 * 60 * 1000;
   uint64_t interleave_granularity = 256;  // CXL region id granularity
   bool persistent = false;                // CXL persistent mode: msync on commit/flush
@@ -159,12 +163,22 @@ class RamBackend : public StorageBackend {
   void* direct_ptr(uint64_t offset) override { return base_ ? base_ + offset : nullptr; }
   bool pinned() const { return pinned_; }
   bool cuda_accessible() const override { return pinned_; }
+  // "file:<path>" (hex) for shared pools, the 8-hex-digit rkey otherwise.
+  std::string registration_key_hex() const override;
+  const std::string& shared_path() const { return shared_path_; }
 
  private:
   uint8_t* base_ = nullptr;
   uint64_t rkey_ = 0;
   bool pinned_ = false;
+  int shared_fd_ = -1;
+  std::string shared_path_;  // /proc/<pid>/fd/<n> of the backing memfd (shared pools)
 };
+
+// Maps a shared RAM pool advertised by another worker ("file:<path>" registration key, raw bytes) into this process.
+// Returns nullptr when the key is not a shared-pool key or the object is not reachable from this host / namespace.
+void* map_shared_pool(const std::vector<uint8_t>& registration_key, uint64_t size);
+void unmap_shared_pool(void* base, uint64_t size);
 
 class MmapDiskBackend : public StorageBackend {
  public:
@@ -313,6 +327,16 @@ struct HostPinHooks {
 };
 void set_host_pin_hooks(HostPinHooks h);
 HostPinHooks host_pin_hooks();
+
+// Process-local registry of pinned (CUDA-registered) RAM pools: a GPU client living in the same process addresses
+// them directly instead of mapping the backing memfd a second time.
+struct LocalHostPool {
+  void* base = nullptr;
+  uint64_t size = 0;
+};
+void register_local_host_pool(const std::string& pool_id, void* base, uint64_t size);
+void unregister_local_host_pool(const std::string& pool_id);
+bool find_local_host_pool(const std::string& pool_id, LocalHostPool* out);
 
 using GpuBackendFactory = std::function<std::unique_ptr<StorageBackend>(uint64_t capacity, const BackendOptions&)>;
 void set_gpu_backend_factory(GpuBackendFactory f);

@@ -78,6 +78,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
     if (p.contains("numa_node")) pc.numa_node = static_cast<int>(p.at("numa_node").as_int(-1));
     pc.queue_depth = static_cast<uint32_t>(p.at("queue_depth").as_int(64));
     pc.pin_memory = p.at("pin_memory").as_bool(false);
+    pc.shared_memory = p.at("shared_memory").as_bool(false);
     c.storage_pools.push_back(std::move(pc));
   }
   return c;
@@ -118,6 +119,7 @@ ErrorCode WorkerService::create_storage_pools_from_config() {
     o.numa_node = pc.numa_node >= 0 ? pc.numa_node : config_.numa_node;
     o.queue_depth = pc.queue_depth;
     o.pin_memory = pc.pin_memory;
+    o.shared_memory = pc.shared_memory;
     o.interleave_granularity = pc.cxl.interleave_granularity ? pc.cxl.interleave_granularity : 256;
     o.persistent = pc.cxl.is_persistent;
     auto b = create_storage_backend(pc.storage_class, pc.size_bytes, o);

@@ -37,6 +37,7 @@ struct StoragePoolConfig {
   int numa_node = -1;
   uint32_t queue_depth = 64;
   bool pin_memory = false;  // DRAM tier: register with CUDA so fused kernels can move data to / from it
+  bool shared_memory = false;  // DRAM tier: memfd-backed, mappable by GPU clients of other processes on this host
   CxlMemoryPoolConfig cxl;  // CXL tiers: per-pool `config:` block
 };
 

@@ -275,3 +275,44 @@ def test_async_tensor_store_overlaps_and_local_replica_is_preferred(bb, torch_cu
         assert "bb_client_device_get_local_replica_total" in cl.client.metrics_text()
     finally:
         cl.stop()
+
+
+def test_dram_tier_is_reached_by_the_fused_kernels(bb, torch_cuda):
+    """Objects placed in (or demoted to) a pinned DRAM pool are moved by the SAME fused kernel over PCIe -- TMA from /
+    to registered host memory, digest on the tensor cores -- not staged through the TCP data server."""
+    torch = torch_cuda
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=64 << 20, cluster_id="t-dram", dram_bytes=128 << 20)
+    try:
+        n, size = 8, (1 << 20) + 48
+        stride = ((size + 255) // 256) * 256
+        src = torch.randint(0, 256, (n * stride,), dtype=torch.uint8, device="cuda")
+        out = torch.zeros_like(src)
+        keys = [f"d{i}" for i in range(n)]
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU])
+        s = _stream(torch)
+        l0 = cl.fabric.launches
+        ecs = cl.client.batch_put_device(keys, [src.data_ptr() + i * stride for i in range(n)], [size] * n, cfg, s)
+        assert all(e == bb.ErrorCode.OK for e in ecs), ecs
+        assert cl.fabric.mapped_host_pools() == 1 and cl.fabric.launches == l0 + 1  # one fused launch wrote the DRAM pool
+        sh = cl.client.get_workers(keys[2])[0].shards[0]
+        assert sh.storage_class == bb.StorageClass.RAM_CPU and sh.location["kind"] == "memory"
+        assert sh.checksum == bb.bbh64(src[2 * stride:2 * stride + size].cpu().numpy())
+        ecs, sizes = cl.client.batch_get_device(keys, [out.data_ptr() + i * stride for i in range(n)], [stride] * n, s)
+        assert all(e == bb.ErrorCode.OK for e in ecs) and sizes == [size] * n
+        torch.cuda.synchronize()
+        assert cl.fabric.launches == l0 + 2
+        for i in range(n):
+            assert torch.equal(src[i * stride:i * stride + size], out[i * stride:i * stride + size])
+        assert "device_get_dram_direct_total" in cl.client.metrics_text()
+        # the worker's own view of the pool (host path) holds the same bytes, and corruption there is caught by the fused get
+        be = cl.worker.backend(f"dram{cl.rank}")
+        pool = [p for p in cl.client.keystone().get_memory_pools() if p.id == sh.pool_id][0]
+        off = sh.location["remote_addr"] - pool.ucx_remote_addr
+        assert be.read(off, 64) == bytes(src[2 * stride:2 * stride + 64].cpu().numpy())
+        be.write(off + 100, b"\xff\x00\xff\x00")
+        ecs, _ = cl.client.batch_get_device([keys[2]], [out.data_ptr()], [stride], s)
+        assert ecs[0] == bb.ErrorCode.CHECKSUM_MISMATCH
+    finally:
+        cl.stop()

@@ -224,3 +224,93 @@ storage_pools:
     # the same objects' tier is visible to a plain TCP client
     m = run_cli("metrics", "--http", f"127.0.0.1:{hport}")
     assert m.returncode == 0 and "bb_put_start_total" in m.stdout
+
+
+def test_shared_dram_pool_of_a_worker_process_is_mappable_by_clients(procs, tmp_path, bb):
+    """A bb-worker started with `shared_memory: true` backs its DRAM pool with a memfd and advertises
+    file:/proc/<pid>/fd/<n>; a client process on the same host maps it (the GPU fabric additionally registers the
+    mapping with CUDA) and finds the object's bytes at the placement's offset -- no data-server round trip."""
+    cport, rport, hport = free_port(), free_port(), free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    procs.spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+                "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "shm")
+    assert wait_port(rport)
+    cfg = tmp_path / "w.yaml"
+    cfg.write_text("""
+worker:
+  worker_id: "ws"
+  node_id: "node-ws"
+storage_pools:
+  - pool_id: "dram-ws"
+    storage_class: "RAM_CPU"
+    size_bytes: 32_MB
+    shared_memory: true
+""")
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "shm")
+    c = bb.BlackbirdClient(bb.BlackbirdClientOptions("127.0.0.1", rport, 30000, 2, "node-ws"))
+    assert c.connect() == bb.ErrorCode.OK
+    deadline = time.time() + 10
+    while time.time() < deadline and c.cluster_stats().total_memory_pools < 1:
+        time.sleep(0.1)
+    data = os.urandom(300_000)
+    wc = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU], checksum=bb.ChecksumAlgo.CRC32C)
+    assert c.put("shared/obj", data, wc) == bb.ErrorCode.OK
+    shard = c.get_workers("shared/obj")[0].shards[0]
+    pool = [p for p in c.keystone().get_memory_pools() if p.id == shard.pool_id][0]
+    assert bytes.fromhex(pool.ucx_rkey_hex).startswith(b"file:/proc/")
+    off = shard.location["remote_addr"] - pool.ucx_remote_addr
+    assert bb.read_shared_pool(pool.ucx_rkey_hex, pool.size, off, len(data)) == data
+
+
+@pytest.mark.gpu
+def test_gpu_client_maps_the_dram_pool_of_a_worker_process(procs, tmp_path, bb):
+    """Cross-process DRAM tier: the worker process owns a memfd-backed DRAM pool; this process's GPU fabric maps it,
+    registers it with CUDA and moves objects to / from it with the fused kernel (PCIe), verified against the worker's
+    TCP data path."""
+    import torch
+
+    cport, rport, hport = free_port(), free_port(), free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    procs.spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+                "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "shmgpu")
+    assert wait_port(rport)
+    cfg = tmp_path / "w.yaml"
+    cfg.write_text("""
+worker:
+  worker_id: "wd"
+  node_id: "node-wd"
+storage_pools:
+  - pool_id: "dram-wd"
+    storage_class: "RAM_CPU"
+    size_bytes: 128_MB
+    shared_memory: true
+""")
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "shmgpu")
+    api = bb.KeystoneRpcClient()
+    assert api.connect("127.0.0.1", rport, 10000) == bb.ErrorCode.OK
+    c = bb.BlackbirdClient(api, bb.BlackbirdClientOptions(node_id="node-wd"))
+    assert c.connect() == bb.ErrorCode.OK
+    deadline = time.time() + 15
+    while time.time() < deadline and c.cluster_stats().total_memory_pools < 1:
+        time.sleep(0.1)
+    fabric = bb.GpuFabric(0, api)
+    bb.attach_fabric(c, fabric)
+    n, size = 6, 2 << 20
+    src = torch.randint(0, 256, (n * size,), dtype=torch.uint8, device="cuda")
+    out = torch.zeros_like(src)
+    keys = [f"x{i}" for i in range(n)]
+    wc = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU])
+    s = torch.cuda.current_stream().cuda_stream
+    ecs = c.batch_put_device(keys, [src.data_ptr() + i * size for i in range(n)], [size] * n, wc, s)
+    assert all(e == bb.ErrorCode.OK for e in ecs), ecs
+    assert fabric.mapped_host_pools() == 1 and fabric.launches == 1
+    ecs, _ = c.batch_get_device(keys, [out.data_ptr() + i * size for i in range(n)], [size] * n, s)
+    assert all(e == bb.ErrorCode.OK for e in ecs), ecs
+    torch.cuda.synchronize()
+    assert torch.equal(src, out) and fabric.launches == 2
+    # the worker process serves the same bytes over its TCP data server
+    host = bb.BlackbirdClient(bb.BlackbirdClientOptions("127.0.0.1", rport, 30000, 2, "elsewhere"))
+    assert host.connect() == bb.ErrorCode.OK
+    assert host.get(keys[1]) == bytes(src[size:2 * size].cpu().numpy())

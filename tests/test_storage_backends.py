@@ -191,3 +191,25 @@ def test_cxl_worker_yaml_is_fully_parsed_and_consumed(bb):
     assert bb.tier_classes_for_size(rules, 4096) == ["RAM_CPU"]
     assert bb.tier_classes_for_size(rules, 200 * 10**6) == ["CXL_MEMORY", "CXL_TYPE2_DEVICE"]
     assert bb.tier_classes_for_size(rules, 50 * 10**9) == ["NVME"]
+
+
+def test_shared_ram_pool_is_mappable_through_its_registration_key(bb):
+    """DRAM pools created with shared_memory are memfd-backed: the registration key names /proc/<pid>/fd/<n>, which a
+    GPU client of another process maps (and registers with CUDA) to reach the tier with the fused kernels."""
+    cap = 8 << 20
+    b = bb.create_storage_backend(bb.StorageClass.RAM_CPU, cap, pool_id="shared-pool", shared_memory=True)
+    assert b.initialize() == bb.ErrorCode.OK
+    assert b.shared_path.startswith("/proc/") and os.path.exists(b.shared_path)
+    key_hex = b.registration_key_hex()
+    assert bytes.fromhex(key_hex).decode() == "file:" + b.shared_path
+    payload = os.urandom(70000)
+    assert b.write(4096, payload) == bb.ErrorCode.OK
+    assert bb.read_shared_pool(key_hex, cap, 4096, len(payload)) == payload  # second mapping of the same pages
+    # a private pool keeps the 8-hex-digit rkey and is not mappable
+    p = bb.create_storage_backend(bb.StorageClass.RAM_CPU, cap, pool_id="private-pool")
+    assert p.initialize() == bb.ErrorCode.OK
+    assert p.shared_path == "" and len(p.registration_key_hex()) == 8
+    assert bb.read_shared_pool(p.registration_key_hex(), cap, 0, 16) is None
+    path = b.shared_path
+    b.shutdown()
+    assert not os.path.exists(path)
