@@ -19,7 +19,13 @@ import sys
 import sysconfig
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-BUILD = os.path.join(ROOT, "build")
+# Sanitizer builds (BB_SANITIZE=asan|tsan) are kept apart from the production build: objects in build-<san>/, the
+# extension and the binaries in build-<san>/out/{blackbird_b200,bin} (the package directory there is a tree of links
+# to the python sources).  Run the suite against them with
+#   BB_PKG_ROOT=build-asan/out BB_BIN_DIR=build-asan/out/bin python -m pytest tests -m "not gpu"
+SAN = os.environ.get("BB_SANITIZE", "")
+BUILD = os.path.join(ROOT, "build" + ("-" + SAN if SAN else ""))
+OUT = os.path.join(BUILD, "out") if SAN else ROOT
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
@@ -31,7 +37,7 @@ NVCCFLAGS = (
 
 
 def _san_flags() -> str:
-    san = os.environ.get("BB_SANITIZE", "")
+    san = SAN
     if san == "asan":
         return " -fsanitize=address,undefined -fno-omit-frame-pointer"
     if san == "tsan":
@@ -106,21 +112,21 @@ def generate() -> str:
         py_objs.append(o)
         lines.append(f"build {o}: cxx {_rel(s)}")
         lines.append("  extra = $pyincs -fvisibility=hidden")
-    mod = _rel(os.path.join(ROOT, "blackbird_b200", "_bb" + ext))
+    mod = _rel(os.path.join(OUT, "blackbird_b200", "_bb" + ext))
     lines.append(f"build {mod}: link_so {' '.join(py_objs + lib_objs)}")
     targets = [mod]
     for s in app_src:
         o = obj(s)
         lines.append(f"build {o}: cxx {_rel(s)}")
         name = os.path.splitext(os.path.basename(s))[0].replace("_", "-")
-        exe = _rel(os.path.join(ROOT, "bin", name))
+        exe = _rel(os.path.join(OUT, "bin", name))
         lines.append(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
         targets.append(exe)
     for s in example_src:
         o = obj(s)
         lines.append(f"build {o}: cxx {_rel(s)}")
         name = "bb-example-" + os.path.splitext(os.path.basename(s))[0].replace("_", "-")
-        exe = _rel(os.path.join(ROOT, "bin", name))
+        exe = _rel(os.path.join(OUT, "bin", name))
         lines.append(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
         targets.append(exe)
     lines.append(f"default {' '.join(targets)}")
@@ -135,7 +141,16 @@ def generate() -> str:
 
 def build(verbose: bool = False, targets: list[str] | None = None) -> None:
     generate()
-    os.makedirs(os.path.join(ROOT, "bin"), exist_ok=True)
+    os.makedirs(os.path.join(OUT, "bin"), exist_ok=True)
+    if OUT != ROOT:  # link the python sources next to the sanitized extension
+        pkg_src, pkg_dst = os.path.join(ROOT, "blackbird_b200"), os.path.join(OUT, "blackbird_b200")
+        os.makedirs(pkg_dst, exist_ok=True)
+        for name in os.listdir(pkg_src):
+            if name.startswith("_bb.") or name == "__pycache__":
+                continue
+            dst = os.path.join(pkg_dst, name)
+            if not os.path.lexists(dst):
+                os.symlink(os.path.join(pkg_src, name), dst)
     ninja = shutil.which("ninja")
     if ninja is None:
         raise RuntimeError("ninja not found")

@@ -119,13 +119,19 @@ size_t find_key_colon(const std::string& s) {
   return std::string::npos;
 }
 
-Json flow_value(const std::string& raw);
+// Flow collections nest at most this deep; anything deeper is kept as a plain string (the parser reads operator
+// configs and registry records, and must not be driven into a stack overflow by a hostile or corrupt document).
+constexpr int kMaxFlowDepth = 32;
+constexpr int kMaxBlockDepth = 128;
 
-Json flow_value(const std::string& raw) {
+Json flow_value(const std::string& raw, int depth = 0);
+
+Json flow_value(const std::string& raw, int depth) {
   std::string s = strip(raw);
+  if (depth >= kMaxFlowDepth) return Json(s);
   if (s.size() >= 2 && s.front() == '[' && s.back() == ']') {
     Json::Array a;
-    for (auto& part : split_flow(s.substr(1, s.size() - 2))) a.push_back(flow_value(part));
+    for (auto& part : split_flow(s.substr(1, s.size() - 2))) a.push_back(flow_value(part, depth + 1));
     return Json(std::move(a));
   }
   if (s.size() >= 2 && s.front() == '{' && s.back() == '}') {
@@ -136,7 +142,7 @@ Json flow_value(const std::string& raw) {
         c = part.find(':');
         if (c == std::string::npos) continue;
       }
-      o[scalar(part.substr(0, c)).as_string()] = flow_value(part.substr(c + 1));
+      o[scalar(part.substr(0, c)).as_string()] = flow_value(part.substr(c + 1), depth + 1);
     }
     return Json(std::move(o));
   }
@@ -153,14 +159,19 @@ struct YParser {
     return false;
   }
 
+  int depth = 0;
+
   bool parse_block(int indent, Json& out) {
     if (pos >= lines.size()) {
       out = Json(nullptr);
       return true;
     }
     const Line& first = lines[pos];
-    if (first.text.rfind("- ", 0) == 0 || first.text == "-") return parse_seq(first.indent, out);
-    return parse_map(first.indent, out);
+    if (depth >= kMaxBlockDepth) return fail("nesting too deep", first.lineno);
+    ++depth;
+    const bool ok = (first.text.rfind("- ", 0) == 0 || first.text == "-") ? parse_seq(first.indent, out) : parse_map(first.indent, out);
+    --depth;
+    return ok;
   }
 
   bool parse_value_after_key(const std::string& rest, int key_indent, Json& out) {

@@ -4,8 +4,14 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+# BB_PKG_ROOT points the suite at another build of the package (sanitizer builds: build-asan/out, see build.py)
+PKG_ROOT = os.path.abspath(os.environ.get("BB_PKG_ROOT", ROOT))
+for p in (ROOT, PKG_ROOT):
+    if p in sys.path:
+        sys.path.remove(p)
+sys.path.insert(0, ROOT)
+if PKG_ROOT != ROOT:
+    sys.path.insert(0, PKG_ROOT)
 
 
 def pytest_configure(config):

@@ -24,5 +24,5 @@ def test_cpp_sdk_example_against_a_live_cluster(bb):
     from blackbird_b200.parallel import LocalCluster
 
     with LocalCluster("sdk-example", n_workers=2, pool_bytes=16 << 20) as c:
-        r = _run(os.path.join(ROOT, "bin", "bb-example-sdk-put-get"), f"127.0.0.1:{c.rpc.rpc_port}")
+        r = _run(os.path.join(os.environ.get("BB_BIN_DIR", os.path.join(ROOT, "bin")), "bb-example-sdk-put-get"), f"127.0.0.1:{c.rpc.rpc_port}")
         assert r.returncode == 0 and "sdk example OK" in r.stdout and "2 copies" in r.stdout, r.stdout + r.stderr

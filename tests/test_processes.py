@@ -11,7 +11,7 @@ import time
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "bin")
+BIN = os.environ.get("BB_BIN_DIR", os.path.join(ROOT, "bin"))
 
 
 def free_port():
