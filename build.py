@@ -19,12 +19,12 @@ import sys
 import sysconfig
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# Sanitizer builds (BB_SANITIZE=asan|tsan) are kept apart from the production build: objects in build-<san>/, the
-# extension and the binaries in build-<san>/out/{blackbird_b200,bin} (the package directory there is a tree of links
+# Sanitizer builds (BB_SANITIZE=asan|tsan) are kept apart from the production build: objects in build/<san>/, the
+# extension and the binaries in build/<san>/out/{blackbird_b200,bin} (the package directory there is a tree of links
 # to the python sources).  Run the suite against them with
-#   BB_PKG_ROOT=build-asan/out BB_BIN_DIR=build-asan/out/bin python -m pytest tests -m "not gpu"
+#   BB_PKG_ROOT=build/asan/out BB_BIN_DIR=$PWD/build/asan/out/bin python -m pytest tests -m "not gpu"
 SAN = os.environ.get("BB_SANITIZE", "")
-BUILD = os.path.join(ROOT, "build" + ("-" + SAN if SAN else ""))
+BUILD = os.path.join(ROOT, "build", SAN) if SAN else os.path.join(ROOT, "build")
 OUT = os.path.join(BUILD, "out") if SAN else ROOT
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")

@@ -1,5 +1,6 @@
 #include "coord/coord.h"
 
+#include <algorithm>
 #include <chrono>
 #include <sstream>
 
@@ -121,7 +122,10 @@ void MemCoord::dispatch_loop() {
     {
       std::lock_guard<std::mutex> lk(wmu_);
       for (auto& [id, w] : watchers_)
-        if (ev.key.compare(0, w->prefix.size(), w->prefix) == 0) targets.push_back(w);
+        if (ev.key.compare(0, w->prefix.size(), w->prefix) == 0) {
+          ++w->running;
+          targets.push_back(w);
+        }
     }
     for (auto& w : targets) {
       try {
@@ -129,6 +133,9 @@ void MemCoord::dispatch_loop() {
       } catch (const std::exception& e) {
         BB_LOG(ERROR) << "watch callback threw: " << e.what();
       }
+      std::lock_guard<std::mutex> lk(wmu_);
+      --w->running;
+      wcv_.notify_all();
     }
     {
       std::lock_guard<std::mutex> lk(qmu_);
@@ -266,8 +273,14 @@ Result<int64_t> MemCoord::watch_prefix(const std::string& prefix, WatchCallback 
 }
 
 ErrorCode MemCoord::unwatch(int64_t id) {
-  std::lock_guard<std::mutex> lk(wmu_);
-  return watchers_.erase(id) ? ErrorCode::OK : ErrorCode::ETCD_WATCH_ERROR;
+  std::unique_lock<std::mutex> lk(wmu_);
+  auto it = watchers_.find(id);
+  if (it == watchers_.end()) return ErrorCode::ETCD_WATCH_ERROR;
+  std::shared_ptr<Watcher> w = it->second;
+  watchers_.erase(it);
+  // barrier: an invocation already handed to the dispatch thread finishes before we return (unless we ARE that thread)
+  if (std::this_thread::get_id() != dispatch_thread_.get_id()) wcv_.wait(lk, [&] { return w->running == 0; });
+  return ErrorCode::OK;
 }
 
 int64_t MemCoord::revision() {
@@ -586,10 +599,20 @@ Result<int64_t> RemoteCoord::watch_prefix(const std::string& prefix, WatchCallba
         {
           std::lock_guard<std::mutex> l2(wmu_);
           auto it = watches_.find(id);
-          if (it != watches_.end()) f = it->second;
-          else pending_[id].push_back(ev);  // event raced ahead of the watch response
+          if (it != watches_.end()) {
+            f = it->second;
+            ++running_[id];
+            push_thread_ = std::this_thread::get_id();
+          } else {
+            pending_[id].push_back(ev);  // event raced ahead of the watch response
+          }
         }
-        if (f) f(ev);
+        if (f) {
+          f(ev);
+          std::lock_guard<std::mutex> l2(wmu_);
+          if (--running_[id] == 0) running_.erase(id);
+          wcv_.notify_all();
+        }
       });
       watch_connected_ = true;
     }
@@ -618,8 +641,11 @@ Result<int64_t> RemoteCoord::watch_prefix(const std::string& prefix, WatchCallba
 
 ErrorCode RemoteCoord::unwatch(int64_t id) {
   {
-    std::lock_guard<std::mutex> lk(wmu_);
+    std::unique_lock<std::mutex> lk(wmu_);
     watches_.erase(id);
+    pending_.erase(id);
+    // barrier: a callback already running on the push thread finishes before we return (unless we ARE that thread)
+    if (std::this_thread::get_id() != push_thread_) wcv_.wait(lk, [&] { return running_.find(id) == running_.end(); });
     if (!watch_connected_) return ErrorCode::ETCD_WATCH_ERROR;
   }
   wire::Writer w;
@@ -747,13 +773,23 @@ ErrorCode CoordService::revoke_lease(LeaseId lease) {
   if (!connected_) return ErrorCode::ETCD_ERROR;
   return store_->revoke_lease(lease);
 }
-ErrorCode CoordService::watch_prefix(const std::string& prefix, WatchCb cb) {
+ErrorCode CoordService::watch_prefix(const std::string& prefix, WatchCb cb, int64_t* watch_id) {
   if (!connected_) return ErrorCode::ETCD_ERROR;
   auto r = store_->watch_prefix(prefix, [cb](const WatchEvent& ev) { cb(ev.key, ev.value, ev.type == EventType::DELETE); });
   if (!r.ok()) return ErrorCode::ETCD_WATCH_ERROR;
+  if (watch_id) *watch_id = r.value();
   std::lock_guard<std::mutex> lk(mu_);
   watch_ids_.push_back(r.value());
   return ErrorCode::OK;
+}
+ErrorCode CoordService::unwatch(int64_t watch_id) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = std::find(watch_ids_.begin(), watch_ids_.end(), watch_id);
+    if (it == watch_ids_.end()) return ErrorCode::ETCD_WATCH_ERROR;
+    watch_ids_.erase(it);
+  }
+  return store_->unwatch(watch_id);  // barrier (see coord.h)
 }
 ErrorCode CoordService::watch_key(const std::string& key, WatchCb cb) {
   if (!connected_) return ErrorCode::ETCD_ERROR;

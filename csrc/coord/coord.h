@@ -115,7 +115,9 @@ class MemCoord : public CoordStore {
   struct Watcher {
     std::string prefix;
     WatchCallback cb;
+    int running = 0;  // invocations in flight (guarded by wmu_); unwatch() waits for 0
   };
+  std::condition_variable wcv_;  // signalled when a watcher's invocation returns
   int64_t now_ms() const;
   ErrorCode put_locked(const std::string& key, const std::string& value, LeaseId lease);
   bool del_locked(const std::string& key);
@@ -191,6 +193,9 @@ class RemoteCoord : public CoordStore {
   net::RpcClient watch_rpc_;  // push channel
   std::mutex wmu_;
   std::map<int64_t, WatchCallback> watches_;
+  std::map<int64_t, int> running_;  // callback invocations in flight per watch (guarded by wmu_)
+  std::condition_variable wcv_;
+  std::thread::id push_thread_{};   // thread currently delivering push events (unwatch from a callback must not wait)
   std::map<int64_t, std::vector<WatchEvent>> pending_;
   bool watch_connected_ = false;
   std::string host_;
@@ -222,7 +227,10 @@ class CoordService {
   ErrorCode revoke_lease(LeaseId lease);
   ErrorCode refresh_lease(LeaseId lease) { return keep_alive(lease); }
   using WatchCb = std::function<void(const std::string& key, const std::string& value, bool is_delete)>;
-  ErrorCode watch_prefix(const std::string& prefix, WatchCb cb);
+  // `watch_id` (optional) receives the id to pass to unwatch().  unwatch() is a barrier: when it returns, the callback
+  // is not running and will not run again, so the owner of the captured state may be destroyed.
+  ErrorCode watch_prefix(const std::string& prefix, WatchCb cb, int64_t* watch_id = nullptr);
+  ErrorCode unwatch(int64_t watch_id);
   ErrorCode watch_key(const std::string& key, WatchCb cb);
   ErrorCode unwatch_key(const std::string& key);
   // service registry: /blackbird/services/<name>/<id> -> address

@@ -105,9 +105,13 @@ ErrorCode KeystoneService::start() {
   if (coord_ && coord_->is_connected()) {
     load_existing_state();
     const std::string p = cluster_prefix();
-    coord_->watch_prefix(p + "workers/", [this](const std::string& k, const std::string& v, bool d) { on_worker_event(k, v, d); });
-    coord_->watch_prefix(p + "memory_pools/", [this](const std::string& k, const std::string& v, bool d) { on_legacy_pool_event(k, v, d); });
-    coord_->watch_prefix(p + "heartbeat/", [this](const std::string& k, const std::string& v, bool d) { on_heartbeat_event(k, v, d); });
+    int64_t id = 0;
+    if (coord_->watch_prefix(p + "workers/", [this](const std::string& k, const std::string& v, bool d) { on_worker_event(k, v, d); }, &id) == ErrorCode::OK)
+      watch_ids_.push_back(id);
+    if (coord_->watch_prefix(p + "memory_pools/", [this](const std::string& k, const std::string& v, bool d) { on_legacy_pool_event(k, v, d); }, &id) == ErrorCode::OK)
+      watch_ids_.push_back(id);
+    if (coord_->watch_prefix(p + "heartbeat/", [this](const std::string& k, const std::string& v, bool d) { on_heartbeat_event(k, v, d); }, &id) == ErrorCode::OK)
+      watch_ids_.push_back(id);
     if (is_leader()) recover_objects_from_wal();
   }
   if (config_.enable_gc) gc_thread_ = std::thread([this] { gc_loop(); });
@@ -125,6 +129,11 @@ void KeystoneService::stop() {
   if (gc_thread_.joinable()) gc_thread_.join();
   if (health_thread_.joinable()) health_thread_.join();
   if (keepalive_thread_.joinable()) keepalive_thread_.join();
+  // The watch callbacks capture `this`: unwatch() returns only once no callback is running and none will start, so the
+  // coordination client's push thread can never call into a stopped (possibly destroyed) service.
+  if (coord_)
+    for (int64_t id : watch_ids_) coord_->unwatch(id);
+  watch_ids_.clear();
   if (coord_ && coord_->is_connected()) {
     if (config_.enable_ha && leader_.load()) coord_->resign_leader("keystone-" + config_.cluster_id, candidate_id_);
     coord_->unregister_service("blackbird-keystone", config_.service_id);

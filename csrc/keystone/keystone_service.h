@@ -223,6 +223,7 @@ class KeystoneService {
   std::mutex sleep_mu_;
   std::condition_variable sleep_cv_;
   std::thread gc_thread_, health_thread_, keepalive_thread_;
+  std::vector<int64_t> watch_ids_;  // coordination watches owned by this service (released in stop(), which is a barrier)
   std::string candidate_id_;
 
   mutable Metrics metrics_;

@@ -4,7 +4,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# BB_PKG_ROOT points the suite at another build of the package (sanitizer builds: build-asan/out, see build.py)
+# BB_PKG_ROOT points the suite at another build of the package (sanitizer builds: build/asan/out, see build.py)
 PKG_ROOT = os.path.abspath(os.environ.get("BB_PKG_ROOT", ROOT))
 for p in (ROOT, PKG_ROOT):
     if p in sys.path:
