@@ -36,8 +36,9 @@ class TensorStore:
 
     # ------------------------------------------------------------------ put
     def _fused_fp8_ok(self, t: torch.Tensor, cfg) -> bool:
-        """Pack fused into the put kernel: bf16, whole 16384-element tiles, one copy in one shard."""
-        return (t.dtype == torch.bfloat16 and self.client.device_fp8_eligible(t.numel()) and cfg.replication_factor == 1
+        """Pack fused into the put kernel: bf16, whole 16384-element tiles, up to 3 copies (one tile pass fans out to
+        every replica), each copy in one shard."""
+        return (t.dtype == torch.bfloat16 and self.client.device_fp8_eligible(t.numel()) and 1 <= cfg.replication_factor <= 3
                 and cfg.max_workers_per_copy == 1 and t.data_ptr() % 16 == 0)
 
     def batch_put(self, keys: Sequence[str], tensors: Sequence[torch.Tensor], pack_fp8: bool = False, config=None) -> None:

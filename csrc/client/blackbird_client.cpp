@@ -309,7 +309,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device_fp8(const std::vector<O
   if (bf16_ptrs.size() != keys.size() || n_elems.size() != keys.size()) return out;
   BB_TRACE_SPAN("batch_put_device_fp8", keys.size());
   WorkerConfig c = cfg;
-  c.replication_factor = 1;      // the pack kernel writes one destination
+  c.replication_factor = std::max<size_t>(1, std::min<size_t>(cfg.replication_factor, 3));  // one tile pass fans out to <= 3 copies
   c.max_workers_per_copy = 1;    // payload + scales of an object stay in one shard
   c.checksum = ChecksumAlgo::BBH64;
   c.pack_fp8 = true;
@@ -328,12 +328,16 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device_fp8(const std::vector<O
       continue;
     }
     const auto& copies = placed[i].value();
-    if (copies.size() != 1 || copies[0].shards.size() != 1 || !device_->can_reach(copies[0].shards[0])) {
+    bool fits = !copies.empty() && copies.size() <= 3;
+    for (const auto& cp : copies) fits = fits && cp.shards.size() == 1 && device_->can_reach(cp.shards[0]);
+    if (!fits) {
       keystone_->put_cancel(keys[i]);
-      out[i] = ErrorCode::NOT_IMPLEMENTED;  // placement is not a single GPU-fabric shard: caller packs + puts instead
+      out[i] = ErrorCode::NOT_IMPLEMENTED;  // a copy is not a single GPU-fabric shard: caller packs + puts instead
       continue;
     }
-    ops.push_back(DeviceFp8Op{&copies[0].shards[0], const_cast<void*>(bf16_ptrs[i]), n_elems[i]});
+    DeviceFp8Op op{&copies[0].shards[0], const_cast<void*>(bf16_ptrs[i]), n_elems[i], {}};
+    for (size_t cidx = 1; cidx < copies.size(); ++cidx) op.replicas.push_back(&copies[cidx].shards[0]);
+    ops.push_back(std::move(op));
     idx.push_back(i);
   }
   std::vector<uint64_t> digests;
@@ -347,7 +351,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device_fp8(const std::vector<O
       continue;
     }
     done.push_back(keys[idx[k]]);
-    sums.push_back(ShardChecksums{{digests[k]}});
+    sums.push_back(ShardChecksums(placed[idx[k]].value().size(), std::vector<uint64_t>{digests[k]}));  // same bytes in every copy
   }
   if (!done.empty()) {
     auto r = keystone_->batch_put_complete(done, sums);
@@ -367,7 +371,7 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device_fp8(const std::vector<O
   if (bf16_ptrs.size() != keys.size() || n_elems.size() != keys.size()) return out;
   BB_TRACE_SPAN("batch_get_device_fp8", keys.size());
   auto placed = keystone_->batch_get_workers(keys);
-  std::vector<DeviceFp8Op> ops;
+  std::vector<std::vector<size_t>> candidates(keys.size());
   std::vector<size_t> idx;
   for (size_t i = 0; i < keys.size(); ++i) {
     if (!placed[i].ok()) {
@@ -376,19 +380,48 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device_fp8(const std::vector<O
     }
     const auto& copies = placed[i].value();
     const uint64_t packed = n_elems[i] + n_elems[i] / 32;
-    if (!device_->fp8_eligible(n_elems[i]) || copies.empty() || copies[0].shards.size() != 1 || copies[0].shards[0].length != packed ||
-        copies[0].shards[0].checksum_algo != ChecksumAlgo::BBH64 || !device_->can_reach(copies[0].shards[0])) {
+    // usable copies: single GPU-fabric shard holding the whole packed object with a BBH64 digest; a copy in this
+    // client's own HBM first, the others in hashed order (readers spread over the replicas)
+    std::vector<size_t> order;
+    const size_t start = copies.empty() ? 0 : std::hash<std::string>{}(opts_.node_id + keys[i]) % copies.size();
+    for (int pass = 0; pass < 2; ++pass)
+      for (size_t k = 0; k < copies.size(); ++k) {
+        const size_t cidx = (start + k) % copies.size();
+        const auto& cp = copies[cidx];
+        if (cp.shards.size() != 1 || cp.shards[0].length != packed || cp.shards[0].checksum_algo != ChecksumAlgo::BBH64) continue;
+        if (!device_->can_reach(cp.shards[0]) || device_->is_local(cp.shards[0]) != (pass == 0)) continue;
+        order.push_back(cidx);
+      }
+    if (!device_->fp8_eligible(n_elems[i]) || order.empty()) {
       out[i] = ErrorCode::NOT_IMPLEMENTED;  // demoted to a host tier, striped, other digest: caller gets + unpacks instead
       continue;
     }
-    ops.push_back(DeviceFp8Op{&copies[0].shards[0], bf16_ptrs[i], n_elems[i]});
+    candidates[i] = std::move(order);
     idx.push_back(i);
   }
-  std::vector<uint32_t> status;
-  ErrorCode ec = ops.empty() ? ErrorCode::OK : device_->get_fp8(ops, stream, &status);
-  for (size_t k = 0; k < idx.size(); ++k) {
-    if (ec != ErrorCode::OK || status.size() != idx.size()) out[idx[k]] = ec != ErrorCode::OK ? ec : ErrorCode::INTERNAL_ERROR;
-    else out[idx[k]] = status[k] ? ErrorCode::CHECKSUM_MISMATCH : ErrorCode::OK;
+  // one fused launch per attempt; objects whose digest did not verify are retried on their next replica
+  std::vector<size_t> todo = idx;
+  for (size_t attempt = 0; !todo.empty(); ++attempt) {
+    std::vector<DeviceFp8Op> ops;
+    std::vector<size_t> cur;
+    for (size_t i : todo) {
+      if (attempt >= candidates[i].size()) {
+        out[i] = ErrorCode::CHECKSUM_MISMATCH;
+        continue;
+      }
+      ops.push_back(DeviceFp8Op{&placed[i].value()[candidates[i][attempt]].shards[0], bf16_ptrs[i], n_elems[i], {}});
+      cur.push_back(i);
+    }
+    if (ops.empty()) break;
+    if (attempt > 0) metrics_.inc("replica_failover_total");
+    std::vector<uint32_t> status;
+    ErrorCode ec = device_->get_fp8(ops, stream, &status);
+    todo.clear();
+    for (size_t k = 0; k < cur.size(); ++k) {
+      if (ec != ErrorCode::OK || status.size() != cur.size()) out[cur[k]] = ec != ErrorCode::OK ? ec : ErrorCode::INTERNAL_ERROR;
+      else if (status[k]) todo.push_back(cur[k]);
+      else out[cur[k]] = ErrorCode::OK;
+    }
   }
   metrics_.inc("device_get_fp8_batches_total");
   return out;

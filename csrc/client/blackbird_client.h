@@ -48,6 +48,7 @@ struct DeviceFp8Op {
   const ShardPlacement* placement = nullptr;
   void* wide = nullptr;     // client's bf16 tensor (source of a put, destination of a get)
   uint64_t n_elems = 0;
+  std::vector<const ShardPlacement*> replicas;  // put: the other copies (<= 2), written by the same tile pass
 };
 
 // Implemented by the GPU fabric: moves shards between client device buffers and worker slabs
@@ -132,7 +133,8 @@ class BlackbirdClient {
   }
   ErrorCode remove(const ObjectKey& key);
   // bf16 tensors stored as MXFP8 (common/mxfp8.h layout) with the pack fused into the put kernel and the unpack
-  // into the get kernel.  n_elems[i] must be a multiple of 16384 (use put + mxfp8_pack otherwise); one copy, one
+  // into the get kernel.  n_elems[i] must be a multiple of 16384 (use put + mxfp8_pack otherwise); up to 3 copies
+  // (written by one tile pass: converted once, stored to every replica; gets fail over between them), one
   // shard per object.  The stored object is identical to packing first and putting the packed bytes.
   std::vector<ErrorCode> batch_put_device_fp8(const std::vector<ObjectKey>& keys, const std::vector<const void*>& bf16_ptrs,
                                               const std::vector<uint64_t>& n_elems, const WorkerConfig& cfg, void* stream);

@@ -561,6 +561,13 @@ ErrorCode GpuFabric::put_fp8(const std::vector<client::DeviceFp8Op>& ops, void* 
     it.wide = op.wide;
     it.packed = d.value();
     it.n_elems = op.n_elems;
+    if (op.replicas.size() + 1 > kMaxDst) return ErrorCode::INVALID_ARGUMENT;
+    for (const ShardPlacement* rp : op.replicas) {
+      auto dr = resolve(*rp);
+      if (!dr.ok()) return dr.error();
+      it.more_packed[it.nreplicas - 1] = dr.value();
+      ++it.nreplicas;
+    }
     items.push_back(it);
   }
   XferResult res;

@@ -306,16 +306,20 @@ ErrorCode XferEngine::run_fp8(const std::vector<Fp8Item>& items, bool unpack, vo
     const Fp8Item& it = items[i];
     if (!fp8_eligible(it.n_elems)) return ErrorCode::INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(it.wide) | reinterpret_cast<uintptr_t>(it.packed)) & 15) return ErrorCode::INVALID_ADDRESS;
+    const uint32_t nrep = unpack ? 1u : it.nreplicas;
+    if (nrep < 1 || nrep > kMaxDst) return ErrorCode::INVALID_ARGUMENT;
+    for (uint32_t r = 1; r < nrep; ++r)
+      if (!it.more_packed[r - 1] || (reinterpret_cast<uintptr_t>(it.more_packed[r - 1]) & 15)) return ErrorCode::INVALID_ADDRESS;
     auto* payload = static_cast<uint8_t*>(it.packed);
     uint8_t* scales = payload + it.n_elems;
     XferDesc& d = descs[i];
     d.src = unpack ? static_cast<const void*>(payload) : it.wide;
-    d.dst[0] = unpack ? it.wide : static_cast<void*>(payload);
-    d.dst[1] = scales;
-    d.dst[2] = nullptr;
+    d.dst[0] = unpack ? it.wide : static_cast<void*>(payload);  // pack: base of the packed object in every replica
+    d.dst[1] = nrep > 1 ? it.more_packed[0] : nullptr;
+    d.dst[2] = nrep > 2 ? it.more_packed[1] : nullptr;
     d.nbytes = it.n_elems;
     d.first_tile = tiles;
-    d.ndst = 1;
+    d.ndst = nrep;
     d.expect = 0;
     d.flags = 0;
     d.reserved = 0;

@@ -31,7 +31,9 @@ struct XferItem {
 // stored object ([E4M3 payload n_elems][E8M0 scales n_elems / 32]).
 struct Fp8Item {
   void* wide = nullptr;
-  void* packed = nullptr;
+  void* packed = nullptr;            // replica 0 (the copy a get reads)
+  void* more_packed[kMaxDst - 1] = {nullptr, nullptr};  // put: further replicas written by the same tile pass
+  uint32_t nreplicas = 1;            // put: 1..kMaxDst
   uint64_t n_elems = 0;   // multiple of 16384
   uint64_t expect = 0;    // unpack + verify: digest recorded at put time
   bool verify = false;

@@ -64,9 +64,10 @@ struct XferLaunch {
 // Returns 0 on success, else a cudaError_t value.
 int launch_xfer(const XferLaunch& l);
 int xfer_smem_bytes(int algo);
-// Fused MXFP8 transfer (xfer_mxfp8.cu).  Descriptors: pack (put): src = bf16 source, dst[0] = payload destination,
-// dst[1] = scales destination, nbytes = payload bytes (= elements, a multiple of kTileBytes); unpack (get):
-// src = payload source, dst[0] = bf16 destination, dst[1] = scales source.  `sum_ws` receives the unfinalised
+// Fused MXFP8 transfer (xfer_mxfp8.cu).  The packed object is one contiguous [payload n][scales n/32] extent.
+// Descriptors: pack (put): src = bf16 source, dst[0..ndst-1] = base of the packed object in every replica (the scales
+// follow the payload), nbytes = payload bytes (= elements, a multiple of kTileBytes); unpack (get): src = base of the
+// packed object, dst[0] = bf16 destination.  `sum_ws` receives the unfinalised
 // BBH64 sum of the payload tiles per descriptor (must be zero on entry); descs / tile_start are device tables.
 int launch_xfer_fp8(const XferLaunch& l, bool unpack);
 int xfer_fp8_smem_bytes();

@@ -3,7 +3,8 @@
 //   put  (PACK)   : TMA loads a 32 KiB bf16 tile -> 8 pack warps compute the E8M0 block scales and the E4M3
 //                   payload *in shared memory* -> the 16 KiB payload tile is hashed in place by tcgen05.mma
 //                   (BBH64, same tile hash as bb_xfer) -> TMA stores payload + 512 B of scales to the
-//                   (peer) slab.  The bf16 data is read from HBM once and only the 0.52x packed bytes cross NVLink.
+//                   (peer) slab -- to up to 3 replicas of the object from the one converted tile.  The bf16 data
+//                   is read from HBM once and only the 0.52x packed bytes cross NVLink (once per replica).
 //   get  (UNPACK) : TMA loads payload tile + scales from the slab -> tensor-core hash of the payload tile ->
 //                   8 unpack warps expand to bf16 in shared memory -> TMA stores the 32 KiB tile to the caller.
 //
@@ -43,14 +44,16 @@ static_assert(kTileStages * tchash::kN <= kFpTmemCols);
 
 __constant__ uint64_t c_fp_col_mul[tchash::kN];
 
-struct FpMeta {           // 32 bytes
-  uint64_t dst;           // pack: payload destination; unpack: bf16 destination
-  uint64_t dst_scales;    // pack: scales destination
+struct FpMeta {            // 64 bytes
+  uint64_t dst[kMaxDst];   // pack: this tile's payload address in every replica; unpack: dst[0] = bf16 destination
+  int64_t scales_delta;    // pack: (tile's scales address) - (tile's payload address), the same in every replica
   uint32_t desc;
   uint32_t tile_in_obj;
   uint32_t obj_ntiles;
-  uint32_t pad;
+  uint32_t ndst;           // pack: replicas written by this pass (1..kMaxDst)
+  uint64_t pad[2];
 };
+static_assert(sizeof(FpMeta) == 64);
 
 struct FpLookup {
   FpMeta m;
@@ -198,26 +201,33 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         const uint32_t first = __ldg(&p.tile_start[lo]);
         const uint32_t next = __ldg(&p.tile_start[lo + 1]);
         const uint4* q = reinterpret_cast<const uint4*>(&p.descs[lo]);
-        const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+        const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
         const uint64_t src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
         const uint64_t d0 = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
         const uint64_t d1 = (static_cast<uint64_t>(q1.y) << 32) | q1.x;
+        const uint64_t d2 = (static_cast<uint64_t>(q1.w) << 32) | q1.z;
+        const uint64_t nbytes = (static_cast<uint64_t>(q2.y) << 32) | q2.x;  // payload bytes == elements
         const uint32_t ti = t - first;
         FpLookup& e = s.lk[lane];
         e.m.desc = lo;
         e.m.tile_in_obj = ti;
         e.m.obj_ntiles = next - first;
-        e.m.pad = 0;
+        e.m.pad[0] = e.m.pad[1] = 0;
+        // the packed object is [payload nbytes][scales nbytes/32]: a tile's scales sit (nbytes - ti*(16384-512)) past its payload
+        e.m.scales_delta = static_cast<int64_t>(nbytes) - static_cast<int64_t>(ti) * static_cast<int64_t>(kTileBytes - kScaleBytes);
         if constexpr (UNPACK) {
-          e.src = src + static_cast<uint64_t>(ti) * kTileBytes;         // payload tile in the slab
-          e.src_scales = d1 + static_cast<uint64_t>(ti) * kScaleBytes;  // its scales
-          e.m.dst = d0 + static_cast<uint64_t>(ti) * kWideBytes;        // bf16 destination
-          e.m.dst_scales = 0;
+          e.src = src + static_cast<uint64_t>(ti) * kTileBytes;  // payload tile in the slab
+          e.src_scales = e.src + e.m.scales_delta;               // its scales
+          e.m.dst[0] = d0 + static_cast<uint64_t>(ti) * kWideBytes;  // bf16 destination
+          e.m.dst[1] = e.m.dst[2] = 0;
+          e.m.ndst = 1;
         } else {
           e.src = src + static_cast<uint64_t>(ti) * kWideBytes;  // bf16 source tile
           e.src_scales = 0;
-          e.m.dst = d0 + static_cast<uint64_t>(ti) * kTileBytes;
-          e.m.dst_scales = d1 + static_cast<uint64_t>(ti) * kScaleBytes;
+          e.m.dst[0] = d0 + static_cast<uint64_t>(ti) * kTileBytes;
+          e.m.dst[1] = d1 + static_cast<uint64_t>(ti) * kTileBytes;
+          e.m.dst[2] = d2 + static_cast<uint64_t>(ti) * kTileBytes;
+          e.m.ndst = min(max(q2.w, 1u), kMaxDst);
         }
       }
       __syncwarp();
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         if constexpr (UNPACK) {
           const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
           mbar_wait(&s.t_empty[ts], tp ^ 1u);
-          if (lane < 2) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
+          if (lane < 4) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_expect_tx(&s.t_full[ts], kTileBytes + kScaleBytes);
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         } else {
           const uint32_t ws = it % kWideStages, wp = (it / kWideStages) & 1u;
           mbar_wait(&s.w_empty[ws], wp ^ 1u);
-          if (lane < 2) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
+          if (lane < 4) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_expect_tx(&s.w_full[ws], kWideBytes);
@@ -275,14 +285,17 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
       if constexpr (UNPACK) {
         mbar_wait(&s.w_full[st], par);
         if (lane == 0) {
-          bulk_s2g(reinterpret_cast<void*>(s.w_meta[st].dst), s.wide[st], kWideBytes);
+          bulk_s2g(reinterpret_cast<void*>(s.w_meta[st].dst[0]), s.wide[st], kWideBytes);
           bulk_commit();
         }
       } else {
         mbar_wait(&s.t_full[st], par);
         if (lane == 0) {
-          bulk_s2g(reinterpret_cast<void*>(s.t_meta[st].dst), s.tile[st], kTileBytes);
-          bulk_s2g(reinterpret_cast<void*>(s.t_meta[st].dst_scales), s.scales[st], kScaleBytes);
+          const FpMeta& m = s.t_meta[st];
+          for (uint32_t r = 0; r < m.ndst; ++r) {  // replica fan-out: converted once, stored to every copy
+            bulk_s2g(reinterpret_cast<void*>(m.dst[r]), s.tile[st], kTileBytes);
+            bulk_s2g(reinterpret_cast<void*>(m.dst[r] + m.scales_delta), s.scales[st], kScaleBytes);
+          }
           bulk_commit();
         }
       }
@@ -360,7 +373,7 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
           const uint32_t c = cw * 256 + k * 32 + lane;
           out[c] = unpack_chunk(pay[c], s.scales[ts][c >> 2]);
         }
-        if (cw == 0 && lane < 2) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&s.t_meta[ts])[lane];
+        if (cw == 0 && lane < 4) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&s.t_meta[ts])[lane];
         fence_proxy_async_smem();  // generic-proxy writes -> TMA store
         __syncwarp();
         if (lane == 0) {
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
           const uint32_t c = cw * 256 + k * 32 + lane;
           pack_chunk(in[c], &pay[c], &s.scales[ts][c >> 2], (c & 3u) == 0);
         }
-        if (cw == 0 && lane < 2) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&s.w_meta[ws])[lane];
+        if (cw == 0 && lane < 4) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&s.w_meta[ws])[lane];
         fence_proxy_async_smem();  // generic-proxy writes -> tensor core / TMA store readers
         __syncwarp();
         if (lane == 0) {

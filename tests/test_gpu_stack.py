@@ -316,3 +316,55 @@ def test_dram_tier_is_reached_by_the_fused_kernels(bb, torch_cuda):
         assert ecs[0] == bb.ErrorCode.CHECKSUM_MISMATCH
     finally:
         cl.stop()
+
+
+def test_fused_fp8_put_fans_out_to_replicas_and_get_fails_over(bb, torch_cuda):
+    """Fused MXFP8 put with replication: the tile is converted once and TMA-stored to every copy (payload + scales);
+    every copy holds the bytes of the stand-alone pack kernel; a fused get whose replica is corrupt verifies the digest,
+    reports the mismatch and is retried on the next replica."""
+    torch = torch_cuda
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=256 << 20, cluster_id="t-fp8r")
+    try:
+        s = _stream(torch)
+        nobj, n = 3, 5 * 16384
+        xs = [(torch.randn(n, device="cuda") * (i + 1)).to(torch.bfloat16) for i in range(nobj)]
+        keys = [f"fp8r/{i}" for i in range(nobj)]
+        cfg = bb.WorkerConfig(replication_factor=3, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[bb.StorageClass.RAM_GPU])
+        l0 = cl.fabric.launches
+        ecs = cl.client.batch_put_device_fp8(keys, [x.data_ptr() for x in xs], [n] * nobj, cfg, s)
+        assert ecs == [bb.ErrorCode.OK] * nobj, ecs
+        assert cl.fabric.launches - l0 == 2  # pack+fan-out kernel, scales hash slice: replicas cost no extra launch
+        be = cl.worker.backend("hbm0")
+        for i, k in enumerate(keys):
+            copies = cl.client.get_workers(k)
+            assert len(copies) == 3 and len({c.shards[0].offset for c in copies}) == 3
+            ref = torch.empty(n + n // 32, dtype=torch.uint8, device="cuda")
+            bb.mxfp8_pack(xs[i].data_ptr(), n, ref.data_ptr(), s)
+            torch.cuda.synchronize()
+            ref_b = bytes(ref.cpu().numpy())
+            for c in copies:
+                sh = c.shards[0]
+                assert sh.checksum == bb.bbh64(ref.cpu().numpy()) and be.read(sh.offset, sh.length) == ref_b
+        # corrupt two of the three copies of object 1: the get must end on the intact one
+        copies = cl.client.get_workers(keys[1])
+        for c in copies[:2]:
+            be.write(c.shards[0].offset + 777, b"\x01\x02\x03\x04")
+        outs = [torch.zeros_like(x) for x in xs]
+        ecs = cl.client.batch_get_device_fp8(keys, [o.data_ptr() for o in outs], [n] * nobj, s)
+        torch.cuda.synchronize()
+        assert ecs == [bb.ErrorCode.OK] * nobj, ecs
+        for x, o in zip(xs, outs):
+            unp = torch.empty_like(x)
+            ref = torch.empty(n + n // 32, dtype=torch.uint8, device="cuda")
+            bb.mxfp8_pack(x.data_ptr(), n, ref.data_ptr(), s)
+            bb.mxfp8_unpack(ref.data_ptr(), n, unp.data_ptr(), s)
+            torch.cuda.synchronize()
+            assert torch.equal(o.view(torch.int16), unp.view(torch.int16))
+        # all three corrupt -> CHECKSUM_MISMATCH
+        be.write(copies[2].shards[0].offset + 5, b"\xee")
+        ecs = cl.client.batch_get_device_fp8([keys[1]], [outs[1].data_ptr()], [n], s)
+        assert ecs == [bb.ErrorCode.CHECKSUM_MISMATCH]
+    finally:
+        cl.stop()
