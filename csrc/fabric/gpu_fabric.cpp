@@ -284,6 +284,7 @@ bool GpuFabric::ensure_host_pool(const std::string& pool_id) {
     if (worker::find_local_host_pool(pool_id, &local) && local.size >= cand.size) {
       m.base = static_cast<uint8_t*>(local.base);  // pinned by the worker of this process
     } else if (auto raw = hex_to_bytes(cand.key_hex); raw) {
+      m.key = *raw;
       void* p = worker::map_shared_pool(*raw, cand.size);
       if (p) {
         if (cuda_ok(cudaSetDevice(device_), "cudaSetDevice") &&
@@ -324,8 +325,8 @@ ErrorCode GpuFabric::refresh_pools() {
   if (!cuda_ok(cudaSetDevice(device_), "cudaSetDevice")) return ErrorCode::FABRIC_ERROR;
   std::lock_guard<std::mutex> lk(mu_);
   for (const auto& p : pools.value()) {
-    if (p.storage_class == StorageClass::RAM_CPU && !pools_.count(p.id)) {
-      host_candidates_[p.id] = HostCandidate{p.size, p.ucx_remote_addr ? p.ucx_remote_addr : p.base_addr, p.ucx_rkey_hex};
+    if (p.storage_class == StorageClass::RAM_CPU) {
+      if (!pools_.count(p.id)) host_candidates_[p.id] = HostCandidate{p.size, p.ucx_remote_addr ? p.ucx_remote_addr : p.base_addr, p.ucx_rkey_hex};
       continue;
     }
     if (p.storage_class != StorageClass::RAM_GPU || pools_.count(p.id)) continue;
@@ -338,6 +339,7 @@ ErrorCode GpuFabric::refresh_pools() {
       if (it != g_local.end()) {
         m.base = static_cast<uint8_t*>(it->second.base);
         m.device = it->second.device;
+        if (auto raw = hex_to_bytes(p.ucx_rkey_hex)) m.key = *raw;
       }
     }
     if (m.base) {
@@ -374,13 +376,31 @@ ErrorCode GpuFabric::refresh_pools() {
       }
       m.base = static_cast<uint8_t*>(ptr);
       m.ipc_opened = true;
+      m.key = *raw;
     }
     pools_[p.id] = m;
   }
   return ErrorCode::OK;
 }
 
+void GpuFabric::drop_if_stale(const ShardPlacement& s) {
+  if (s.endpoint.worker_key.empty()) return;
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = pools_.find(s.pool_id);
+  if (it == pools_.end() || it->second.key.empty() || it->second.key == s.endpoint.worker_key) return;
+  BB_LOG(WARNING) << "GPU " << device_ << ": pool " << s.pool_id << " was re-registered under a new key; dropping the stale mapping";
+  if (it->second.host_mapped && it->second.base) {
+    if (cudaHostUnregister(it->second.base) != cudaSuccess) cudaGetLastError();
+    worker::unmap_shared_pool(it->second.base, it->second.size);
+  }
+  pools_.erase(it);
+  host_candidates_.erase(s.pool_id);  // re-read the pool record (size / base / key) on the next use
+  host_unreachable_.erase(s.pool_id);
+  ++remaps_;
+}
+
 bool GpuFabric::can_reach(const ShardPlacement& s) const {
+  const_cast<GpuFabric*>(this)->drop_if_stale(s);
   if (s.storage_class == StorageClass::RAM_CPU && std::holds_alternative<MemoryLocation>(s.location))
     return const_cast<GpuFabric*>(this)->ensure_host_pool(s.pool_id);
   if (s.storage_class != StorageClass::RAM_GPU) return false;
@@ -407,6 +427,7 @@ bool GpuFabric::is_local(const ShardPlacement& s) const {
 }
 
 Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
+  drop_if_stale(s);
   if (const auto* h = std::get_if<MemoryLocation>(&s.location)) {  // shared / pinned DRAM pool
     if (!ensure_host_pool(s.pool_id)) return ErrorCode::MEMORY_POOL_NOT_FOUND;
     std::lock_guard<std::mutex> lk(mu_);

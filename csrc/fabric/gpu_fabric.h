@@ -10,6 +10,7 @@
 // GpuSlabBackend is the RAM_GPU storage tier (`malloc` + "Does not work" in the reference,
 // ram_backend.cpp:188, worker_service.cpp:196).  GpuFabric implements client::DeviceTransport.
 #pragma once
+#include <atomic>
 #include <map>
 #include <set>
 #include <memory>
@@ -96,6 +97,7 @@ class GpuFabric : public client::DeviceTransport {
   // exactly one multicast group (same offset everywhere) becomes ONE multimem.st stream.
   void set_arena(std::shared_ptr<NvlsArena> a) { arena_ = std::move(a); }
   uint64_t multicast_puts() const { return multicast_puts_; }
+  uint64_t remaps() const { return remaps_; }  // mappings dropped because their pool was re-registered under a new key
   XferEngine& engine() { return *engine_; }
   float last_device_ms() const { return last_ms_; }
   double total_device_ms() const { return total_ms_; }  // sum of kernel times of all finished batches
@@ -110,7 +112,11 @@ class GpuFabric : public client::DeviceTransport {
     bool host = false;           // pinned host memory (a worker's shared DRAM pool): reached over PCIe
     bool host_mapped = false;    // mapped + registered by this fabric (unmapped in the destructor)
     uint64_t remote_base = 0;    // host pools: the address MemoryLocation::remote_addr is relative to
+    std::vector<uint8_t> key;    // registration key the mapping was made from (IPC handle / "file:<path>")
   };
+  // A placement carries its pool's current registration key (TransportEndpoint::worker_key): a mapping made from a
+  // different key belongs to a previous incarnation of the pool (worker restarted with the same pool id) and is dropped.
+  void drop_if_stale(const ShardPlacement& s);
   struct HostCandidate {         // DRAM pool seen in the registry; mapped lazily on first use
     uint64_t size = 0;
     uint64_t remote_base = 0;
@@ -137,6 +143,7 @@ class GpuFabric : public client::DeviceTransport {
   std::set<std::string> host_unreachable_;
   std::shared_ptr<NvlsArena> arena_;
   uint64_t multicast_puts_ = 0;
+  std::atomic<uint64_t> remaps_{0};
   float last_ms_ = 0.f;
   double total_ms_ = 0.0;
 };

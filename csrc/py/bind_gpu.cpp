@@ -160,6 +160,7 @@ void bind_gpu(py::module_& m) {
       .def("refresh_pools", &GpuFabric::refresh_pools, py::call_guard<py::gil_scoped_release>())
       .def("mapped_pools", &GpuFabric::mapped_pools)
       .def("mapped_host_pools", &GpuFabric::mapped_host_pools)
+      .def_property_readonly("remaps", &GpuFabric::remaps)
       .def_property_readonly("launches", &GpuFabric::launches)
       .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
       .def_property_readonly("total_device_ms", &GpuFabric::total_device_ms)

@@ -287,7 +287,7 @@ storage_pools:
     size_bytes: 128_MB
     shared_memory: true
 """)
-    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "shmgpu")
+    worker = procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "shmgpu")
     api = bb.KeystoneRpcClient()
     assert api.connect("127.0.0.1", rport, 10000) == bb.ErrorCode.OK
     c = bb.BlackbirdClient(api, bb.BlackbirdClientOptions(node_id="node-wd"))
@@ -314,3 +314,23 @@ storage_pools:
     host = bb.BlackbirdClient(bb.BlackbirdClientOptions("127.0.0.1", rport, 30000, 2, "elsewhere"))
     assert host.connect() == bb.ErrorCode.OK
     assert host.get(keys[1]) == bytes(src[size:2 * size].cpu().numpy())
+    # worker restart with the same pool id: the new incarnation has a new memfd; the fabric notices the changed
+    # registration key on the first placement, drops the stale mapping and maps the new pool
+    worker.send_signal(signal.SIGTERM)
+    worker.wait(timeout=10)
+    deadline = time.time() + 15
+    while time.time() < deadline and c.cluster_stats().total_memory_pools > 0:
+        time.sleep(0.1)
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "shmgpu")
+    deadline = time.time() + 15
+    while time.time() < deadline and c.cluster_stats().total_memory_pools < 1:
+        time.sleep(0.1)
+    keys2 = [f"y{i}" for i in range(n)]
+    out.zero_()
+    ecs = c.batch_put_device(keys2, [src.data_ptr() + i * size for i in range(n)], [size] * n, wc, s)
+    assert all(e == bb.ErrorCode.OK for e in ecs), ecs
+    ecs, _ = c.batch_get_device(keys2, [out.data_ptr() + i * size for i in range(n)], [size] * n, s)
+    torch.cuda.synchronize()
+    assert all(e == bb.ErrorCode.OK for e in ecs) and torch.equal(src, out)
+    assert fabric.remaps == 1 and fabric.mapped_host_pools() == 1 and fabric.launches == 4
+    assert host.get(keys2[2]) == bytes(src[2 * size:3 * size].cpu().numpy())  # the NEW worker process holds the bytes
