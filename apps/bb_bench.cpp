@@ -281,6 +281,7 @@ int main(int argc, char** argv) {
   const std::string prefix = args.get("key-prefix", "bench-" + std::to_string(Clk::now().time_since_epoch().count()));
   std::vector<double> wr, rd;
   int failures = 0;
+  std::vector<uint8_t> read_buf(batch == 1 ? size : 0);
   auto t_total = Clk::now();
   for (int it = 0; it < iters; ++it) {
     std::vector<ObjectKey> keys;
@@ -296,8 +297,10 @@ int main(int argc, char** argv) {
     auto b2 = Clk::now();
     bool ok = std::all_of(ecs.begin(), ecs.end(), [](ErrorCode e) { return e == ErrorCode::OK; });
     if (ok) {
-      if (batch == 1) ok = cl.get(keys[0]).ok();
-      else {
+      if (batch == 1) {  // like the reference's benchmark_client (:230-239): read back into a reused buffer
+        size_t got = 0;
+        ok = cl.get_into(keys[0], read_buf.data(), read_buf.size(), &got) == ErrorCode::OK && got == size;
+      } else {
         auto got = cl.batch_get(keys);
         ok = std::all_of(got.begin(), got.end(), [](const auto& r) { return r.ok(); });
       }

@@ -1,5 +1,6 @@
 #include "common/trace.h"
 #include "client/blackbird_client.h"
+#include "common/tchash_def.h"
 
 #include <algorithm>
 #include <atomic>
@@ -91,6 +92,7 @@ std::shared_ptr<net::RpcClient> BlackbirdClient::acquire(const std::string& endp
   if (!hp) return nullptr;
   auto c = std::make_shared<net::RpcClient>();
   if (c->connect(hp->first, static_cast<uint16_t>(hp->second), std::min(opts_.rpc_timeout_ms, 5000)) != ErrorCode::OK) return nullptr;
+  c->set_bulk_buffers();
   return c;
 }
 
@@ -108,6 +110,88 @@ uint64_t BlackbirdClient::shard_offset(const ShardPlacement& s) {
   return 0;
 }
 
+namespace {
+constexpr uint64_t kDataChunk = 8ull << 20;     // one D_WRITE / D_READ request
+constexpr uint64_t kStreamMin = 4ull << 20;     // a shard is split over several connections from 2x this size
+
+// Splits [0, len) into up to `par` ranges whose boundaries are multiples of the BBH64 tile (so per-range digests
+// combine) and runs fn(range_begin, range_len, range_index) on one thread each.
+template <typename F>
+ErrorCode for_each_stream(uint64_t len, size_t par, F&& fn) {
+  size_t n = static_cast<size_t>(std::min<uint64_t>(std::max<size_t>(par, 1), len / kStreamMin));
+  if (n <= 1) return fn(0, len, 0);
+  const uint64_t tiles = (len + tchash::kTileBytes - 1) / tchash::kTileBytes;
+  const uint64_t per = (tiles + n - 1) / n * tchash::kTileBytes;
+  n = static_cast<size_t>((len + per - 1) / per);
+  std::vector<ErrorCode> ecs(n, ErrorCode::OK);
+  std::vector<std::thread> th;
+  for (size_t i = 1; i < n; ++i)
+    th.emplace_back([&, i] { ecs[i] = fn(i * per, std::min<uint64_t>(per, len - i * per), i); });
+  ecs[0] = fn(0, std::min<uint64_t>(per, len), 0);
+  for (auto& t : th) t.join();
+  for (ErrorCode ec : ecs)
+    if (ec != ErrorCode::OK) return ec;
+  return ErrorCode::OK;
+}
+// Hashes a byte range on its own thread while the transfer loop moves it: the loop publishes how far the bytes are
+// valid (a put has them all from the start, a get as the chunks arrive) and collects the range digest at the end.
+class RangeHasher {
+ public:
+  RangeHasher(ChecksumAlgo algo, const uint8_t* base, uint64_t shard_len, uint64_t begin, uint64_t len, bool all_valid)
+      : algo_(algo), base_(base), shard_len_(shard_len), begin_(begin), len_(len), valid_(all_valid ? len : 0) {
+    if (algo_ != ChecksumAlgo::NONE && len_ >= (1u << 20)) th_ = std::thread([this] { run(); });
+    else inline_ = true;
+  }
+  ~RangeHasher() {
+    abort_.store(true);
+    if (th_.joinable()) th_.join();
+  }
+  void advance(uint64_t valid_len) { valid_.store(valid_len, std::memory_order_release); }
+  // crc: CRC32C of the range (standard init / final xor, combinable with crc32c_combine); bbh: unfinalised tile sum
+  void finish(uint32_t* crc, uint64_t* bbh) {
+    valid_.store(len_, std::memory_order_release);
+    if (inline_) run();
+    else if (th_.joinable()) th_.join();
+    *crc = crc_;
+    *bbh = bbh_;
+  }
+
+ private:
+  void run() {
+    constexpr uint64_t kStep = 1ull << 20;  // multiple of the BBH64 tile
+    uint64_t done = 0;
+    while (done < len_) {
+      uint64_t v = valid_.load(std::memory_order_acquire);
+      if (v <= done) {
+        if (abort_.load()) return;
+        std::this_thread::yield();
+        continue;
+      }
+      v = v == len_ ? len_ : v / kStep * kStep;  // whole steps (tile aligned) until the tail
+      if (v <= done) {
+        if (abort_.load()) return;
+        std::this_thread::yield();
+        continue;
+      }
+      const uint64_t n = std::min(kStep, v - done);
+      if (algo_ == ChecksumAlgo::CRC32C) crc_ = crc32c(base_ + begin_ + done, n, crc_);
+      else if (algo_ == ChecksumAlgo::BBH64)
+        bbh_ += bbh64_partial(base_, shard_len_, (begin_ + done) / tchash::kTileBytes, (n + tchash::kTileBytes - 1) / tchash::kTileBytes);
+      done += n;
+    }
+  }
+  ChecksumAlgo algo_;
+  const uint8_t* base_;
+  uint64_t shard_len_, begin_, len_;
+  std::atomic<uint64_t> valid_;
+  std::atomic<bool> abort_{false};
+  bool inline_ = false;
+  uint32_t crc_ = 0;
+  uint64_t bbh_ = 0;
+  std::thread th_;
+};
+}  // namespace
+
 ErrorCode BlackbirdClient::write_shard(const ShardPlacement& s, const uint8_t* src, uint64_t* digest, ChecksumAlgo algo) {
   const std::string ep = s.endpoint.ip + ":" + std::to_string(s.endpoint.port);
   uint64_t base_off = shard_offset(s);
@@ -116,30 +200,60 @@ ErrorCode BlackbirdClient::write_shard(const ShardPlacement& s, const uint8_t* s
     base_off = m->remote_addr;  // absolute address; the worker subtracts its base
     absolute = true;
   }
-  uint64_t dig_crc = 0;
-  constexpr uint64_t kChunk = 8ull << 20;
-  auto conn = acquire(ep);
-  if (!conn) return ErrorCode::CONNECTION_FAILED;
-  for (uint64_t pos = 0; pos < s.length || (s.length == 0 && pos == 0); pos += kChunk) {
-    const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, s.length - pos));
-    wire::Writer w;
-    w.str(s.pool_id);
-    w.u64((base_off + pos) | (absolute ? (1ull << 63) : 0));
-    w.u32(n);
-    w.raw(src + pos, n);
-    auto r = conn->call(worker::D_WRITE, w.data(), opts_.rpc_timeout_ms);
-    if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
-    wire::Reader rd(r.value());
-    const ErrorCode ec = rd.ec();
-    if (ec != ErrorCode::OK) {
-      release(ep, conn);
-      return ec;
+  // Large shards go out as several streams (one connection + one thread each); every stream sends its range in
+  // kDataChunk requests with a gathered write (header + bytes straight from the caller's buffer) and hashes it while the
+  // worker stores the previous chunk.  Per-stream digests combine: CRC32C by shift algebra, BBH64 by addition.
+  struct Part {
+    uint32_t crc = 0;
+    uint64_t len = 0;
+    uint64_t bbh = 0;
+  };
+  std::vector<Part> parts(std::max<size_t>(1, opts_.io_parallelism));
+  ErrorCode ec = for_each_stream(s.length, opts_.io_parallelism, [&](uint64_t begin, uint64_t len, size_t idx) -> ErrorCode {
+    auto conn = acquire(ep);
+    if (!conn) return ErrorCode::CONNECTION_FAILED;
+    Part& part = parts[idx];
+    part.len = len;
+    RangeHasher hasher(algo, src, s.length, begin, len, /*all_valid=*/true);
+    for (uint64_t pos = begin; pos < begin + len || (s.length == 0 && pos == 0); pos += kDataChunk) {
+      const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kDataChunk, begin + len - pos));
+      wire::Writer w;
+      w.str(s.pool_id);
+      w.u64((base_off + pos) | (absolute ? (1ull << 63) : 0));
+      w.u32(n);
+      auto r = conn->call_gather(worker::D_WRITE, w.data(), src + pos, n, opts_.rpc_timeout_ms);
+      if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+      wire::Reader rd(r.value());
+      const ErrorCode wec = rd.ec();
+      if (wec != ErrorCode::OK) {
+        release(ep, conn);
+        return wec;
+      }
+      if (s.length == 0) break;
     }
-    if (algo == ChecksumAlgo::CRC32C) dig_crc = crc32c(src + pos, n, static_cast<uint32_t>(dig_crc));
-    if (s.length == 0) break;
+    hasher.finish(&part.crc, &part.bbh);
+    release(ep, conn);
+    return ErrorCode::OK;
+  });
+  if (ec != ErrorCode::OK) return ec;
+  if (digest) {
+    if (algo == ChecksumAlgo::CRC32C) {
+      uint32_t crc = 0;
+      bool first = true;
+      for (const Part& p : parts) {
+        if (p.len == 0 && !first) continue;
+        crc = first ? p.crc : crc32c_combine(crc, p.crc, p.len);
+        first = false;
+      }
+      *digest = crc;
+    } else if (algo == ChecksumAlgo::BBH64) {
+      uint64_t sum = 0;
+      for (const Part& p : parts) sum += p.bbh;
+      *digest = bbh64_finalize(sum, s.length);
+    } else {
+      *digest = 0;
+    }
   }
-  release(ep, conn);
-  if (digest) *digest = algo == ChecksumAlgo::CRC32C ? dig_crc : algo == ChecksumAlgo::BBH64 ? bbh64(src, s.length) : 0;
   return ErrorCode::OK;
 }
 
@@ -151,31 +265,60 @@ ErrorCode BlackbirdClient::read_shard(const ShardPlacement& s, uint8_t* dst, Che
     base_off = m->remote_addr;
     absolute = true;
   }
-  constexpr uint64_t kChunk = 8ull << 20;
-  auto conn = acquire(ep);
-  if (!conn) return ErrorCode::CONNECTION_FAILED;
-  for (uint64_t pos = 0; pos < s.length; pos += kChunk) {
-    const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kChunk, s.length - pos));
-    wire::Writer w;
-    w.str(s.pool_id);
-    w.u64((base_off + pos) | (absolute ? (1ull << 63) : 0));
-    w.u32(n);
-    auto r = conn->call(worker::D_READ, w.data(), opts_.rpc_timeout_ms);
-    if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
-    const std::string& resp = r.value();
-    if (resp.size() < 4) return ErrorCode::TRANSFER_FAILED;
-    uint32_t e;
-    std::memcpy(&e, resp.data(), 4);
-    if (e != 0) {
-      release(ep, conn);
-      return static_cast<ErrorCode>(e);
+  const bool verify = algo != ChecksumAlgo::NONE && s.checksum_algo == algo;
+  struct Part {
+    uint32_t crc = 0;
+    uint64_t len = 0;
+    uint64_t bbh = 0;
+  };
+  std::vector<Part> parts(std::max<size_t>(1, opts_.io_parallelism));
+  // Same streams as write_shard; the response payload is received straight into the caller's buffer.
+  ErrorCode ec = for_each_stream(s.length, opts_.io_parallelism, [&](uint64_t begin, uint64_t len, size_t idx) -> ErrorCode {
+    auto conn = acquire(ep);
+    if (!conn) return ErrorCode::CONNECTION_FAILED;
+    Part& part = parts[idx];
+    part.len = len;
+    RangeHasher hasher(verify ? algo : ChecksumAlgo::NONE, dst, s.length, begin, len, /*all_valid=*/false);
+    for (uint64_t pos = begin; pos < begin + len; pos += kDataChunk) {
+      const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(kDataChunk, begin + len - pos));
+      wire::Writer w;
+      w.str(s.pool_id);
+      w.u64((base_off + pos) | (absolute ? (1ull << 63) : 0));
+      w.u32(n);
+      size_t got = 0;
+      auto r = conn->call_scatter(worker::D_READ, w.data(), 4, dst + pos, n, &got, opts_.rpc_timeout_ms);
+      if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+      if (r.value().size() < 4) return ErrorCode::TRANSFER_FAILED;
+      uint32_t e;
+      std::memcpy(&e, r.value().data(), 4);
+      if (e != 0) {
+        release(ep, conn);
+        return static_cast<ErrorCode>(e);
+      }
+      if (got != n) return ErrorCode::TRANSFER_FAILED;
+      hasher.advance(pos + n - begin);
     }
-    if (resp.size() != 4 + static_cast<size_t>(n)) return ErrorCode::TRANSFER_FAILED;
-    std::memcpy(dst + pos, resp.data() + 4, n);
-  }
-  release(ep, conn);
-  if (algo != ChecksumAlgo::NONE && s.checksum_algo == algo) {
-    const uint64_t got = checksum(algo, dst, s.length);
+    hasher.finish(&part.crc, &part.bbh);
+    release(ep, conn);
+    return ErrorCode::OK;
+  });
+  if (ec != ErrorCode::OK) return ec;
+  if (verify) {
+    uint64_t got = 0;
+    if (algo == ChecksumAlgo::CRC32C) {
+      uint32_t crc = 0;
+      bool first = true;
+      for (const Part& p : parts) {
+        if (p.len == 0 && !first) continue;
+        crc = first ? p.crc : crc32c_combine(crc, p.crc, p.len);
+        first = false;
+      }
+      got = crc;
+    } else {
+      uint64_t sum = 0;
+      for (const Part& p : parts) sum += p.bbh;
+      got = bbh64_finalize(sum, s.length);
+    }
     if (got != s.checksum) {
       metrics_.inc("checksum_mismatch_total");
       return ErrorCode::CHECKSUM_MISMATCH;

@@ -1,13 +1,16 @@
 #include "common/checksum.h"
 
 #include <array>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "common/tchash_def.h"
 
 #if defined(__x86_64__)
 #include <cpuid.h>
+#include <immintrin.h>
 #include <nmmintrin.h>
 #endif
 
@@ -145,42 +148,211 @@ void crc32c_shift_table(uint64_t nbytes, uint32_t t[4][256]) noexcept {
     for (uint32_t b = 0; b < 256; ++b) t[j][b] = gf2_mulmod(b << (8 * j), xp);
 }
 
-uint64_t bbh64(const void* data, size_t len) noexcept {
-  using namespace tchash;
-  static const std::array<std::array<uint8_t, kN>, kK> W = [] {
-    std::array<std::array<uint8_t, kN>, kK> w{};
+namespace {
+using namespace tchash;
+
+struct BbhConsts {
+  std::array<std::array<uint8_t, kN>, kK> W;  // W[k][n]
+  std::array<uint64_t, kN> KN;
+  uint64_t kn_sum128 = 0;                     // 128 * sum_n KN[n]  (mod 2^64)
+  // SIMD operand layouts of W' = W - 128 (signed 8 bit) / W (16 bit):
+  alignas(64) int8_t w4[kK / 4][kN][4];       // [k group of 4][column][k in group]  -> one zmm per k group (vpdpbusd)
+  alignas(32) int16_t w2[kK / 2][kN][2];      // [k pair][column][k in pair]         -> two ymm per k pair (vpmaddwd)
+  BbhConsts() {
     for (uint32_t k = 0; k < kK; ++k)
-      for (uint32_t n = 0; n < kN; ++n) w[k][n] = static_cast<uint8_t>(weight(k, n));
-    return w;
-  }();
-  static const std::array<uint64_t, kN> KN = [] {
-    std::array<uint64_t, kN> v{};
-    for (uint32_t n = 0; n < kN; ++n) v[n] = col_mul(n);
-    return v;
-  }();
-  const auto* p = static_cast<const uint8_t*>(data);
-  const uint64_t ntiles = (len + kTileBytes - 1) / kTileBytes;
-  uint64_t sum = 0;
-  std::vector<uint32_t> D(kRows * kN);
-  for (uint64_t t = 0; t < ntiles; ++t) {
-    std::fill(D.begin(), D.end(), 0u);
-    const uint64_t base = t * kTileBytes;
-    const uint64_t n = len > base ? std::min<uint64_t>(kTileBytes, len - base) : 0;
-    for (uint32_t o = 0; o < n; ++o) {
-      const uint32_t a = p[base + o];
-      if (!a) continue;
-      const uint32_t m = off_to_row(o), k = off_to_k(o);
-      uint32_t* d = &D[m * kN];
-      const auto& w = W[k];
-      for (uint32_t c = 0; c < kN; ++c) d[c] += a * w[c];
+      for (uint32_t n = 0; n < kN; ++n) W[k][n] = static_cast<uint8_t>(weight(k, n));
+    uint64_t s = 0;
+    for (uint32_t n = 0; n < kN; ++n) {
+      KN[n] = col_mul(n);
+      s += KN[n];
     }
-    for (uint32_t m = 0; m < kRows; ++m) {
-      uint64_t r = 0;
-      for (uint32_t c = 0; c < kN; ++c) r += static_cast<uint64_t>(D[m * kN + c]) * KN[c];
-      sum += row_contrib(r, t * kRows + m);
+    kn_sum128 = s * 128ull;
+    for (uint32_t k = 0; k < kK; ++k)
+      for (uint32_t n = 0; n < kN; ++n) {
+        w4[k / 4][n][k % 4] = static_cast<int8_t>(static_cast<int>(W[k][n]) - 128);
+        w2[k / 2][n][k % 2] = static_cast<int16_t>(W[k][n]);
+      }
+  }
+};
+const BbhConsts& bbh_consts() {
+  static const BbhConsts c;
+  return c;
+}
+
+// One full (zero padded) 16 KiB tile, byte-at-a-time definition.
+uint64_t tile_sum_scalar(const uint8_t* tile, uint64_t tile_index) noexcept {
+  const BbhConsts& C = bbh_consts();
+  uint32_t D[kRows * kN] = {0};
+  for (uint32_t o = 0; o < kTileBytes; ++o) {
+    const uint32_t a = tile[o];
+    if (!a) continue;
+    uint32_t* d = &D[off_to_row(o) * kN];
+    const auto& w = C.W[off_to_k(o)];
+    for (uint32_t c = 0; c < kN; ++c) d[c] += a * w[c];
+  }
+  uint64_t sum = 0;
+  for (uint32_t m = 0; m < kRows; ++m) {
+    uint64_t r = 0;
+    for (uint32_t c = 0; c < kN; ++c) r += static_cast<uint64_t>(D[m * kN + c]) * C.KN[c];
+    sum += row_contrib(r, tile_index * kRows + m);
+  }
+  return sum;
+}
+
+#if defined(__x86_64__)
+// Row m of a tile: block b = m / 8 (1 KiB), the 128 k bytes are 8 chunks of 16 bytes at b*1024 + kc*128 + (m%8)*16.
+// vpdpbusd: every 32-bit lane n accumulates sum_j u8(A[m][4g+j]) * s8(W'[4g+j][n]); the 4 A bytes are broadcast to all
+// 16 lanes (= the 16 hash columns).  D[m][n] = acc[n] + 128 * rowsum(A[m]) restores the unsigned weights exactly.
+__attribute__((target("avx512f,avx512bw,avx512dq,avx512vl,avx512vnni"))) uint64_t tile_sum_vnni(const uint8_t* tile,
+                                                                                                 uint64_t tile_index) noexcept {
+  const BbhConsts& C = bbh_consts();
+  const __m512i kn_lo = _mm512_loadu_si512(&C.KN[0]);
+  const __m512i kn_hi = _mm512_loadu_si512(&C.KN[8]);
+  uint64_t sum = 0;
+  for (uint32_t b = 0; b < kRows / 8; ++b) {
+    const uint8_t* blk = tile + b * 1024;
+    for (uint32_t mi = 0; mi < 8; mi += 2) {  // two rows per pass share the W' loads
+      __m512i acc0 = _mm512_setzero_si512(), acc1 = _mm512_setzero_si512();
+      __m128i sad0 = _mm_setzero_si128(), sad1 = _mm_setzero_si128();
+      for (uint32_t kc = 0; kc < 8; ++kc) {
+        const uint8_t* c0 = blk + kc * 128 + mi * 16;
+        const uint8_t* c1 = c0 + 16;
+        const __m128i v0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c0));
+        const __m128i v1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c1));
+        sad0 = _mm_add_epi64(sad0, _mm_sad_epu8(v0, _mm_setzero_si128()));
+        sad1 = _mm_add_epi64(sad1, _mm_sad_epu8(v1, _mm_setzero_si128()));
+#pragma GCC unroll 4
+        for (uint32_t j = 0; j < 4; ++j) {
+          const __m512i w = _mm512_load_si512(&C.w4[kc * 4 + j][0][0]);
+          int32_t a0, a1;
+          std::memcpy(&a0, c0 + 4 * j, 4);
+          std::memcpy(&a1, c1 + 4 * j, 4);
+          acc0 = _mm512_dpbusd_epi32(acc0, _mm512_set1_epi32(a0), w);
+          acc1 = _mm512_dpbusd_epi32(acc1, _mm512_set1_epi32(a1), w);
+        }
+      }
+      const __m512i accs[2] = {acc0, acc1};
+      const __m128i sads[2] = {sad0, sad1};
+      for (uint32_t r = 0; r < 2; ++r) {
+        const uint32_t rowsum = static_cast<uint32_t>(_mm_cvtsi128_si64(sads[r]) + _mm_extract_epi64(sads[r], 1));
+        const __m512i d = _mm512_add_epi32(accs[r], _mm512_set1_epi32(static_cast<int32_t>(rowsum * 128u)));  // exact u32 D[m][n]
+        const __m512i lo = _mm512_cvtepu32_epi64(_mm512_castsi512_si256(d));
+        const __m512i hi = _mm512_cvtepu32_epi64(_mm512_extracti64x4_epi64(d, 1));
+        const __m512i pr = _mm512_add_epi64(_mm512_mullo_epi64(lo, kn_lo), _mm512_mullo_epi64(hi, kn_hi));
+        const uint64_t rr = static_cast<uint64_t>(_mm512_reduce_add_epi64(pr));
+        sum += row_contrib(rr, tile_index * kRows + b * 8 + mi + r);
+      }
     }
   }
-  return finalize(sum, len);
+  return sum;
+}
+
+// AVX2: zero-extended bytes against 16-bit weights with vpmaddwd (exact, no saturation): lane n of the two 8-lane
+// accumulators gets A[m][k]*W[k][n] + A[m][k+1]*W[k+1][n].
+__attribute__((target("avx2"))) uint64_t tile_sum_avx2(const uint8_t* tile, uint64_t tile_index) noexcept {
+  const BbhConsts& C = bbh_consts();
+  uint64_t sum = 0;
+  for (uint32_t b = 0; b < kRows / 8; ++b) {
+    const uint8_t* blk = tile + b * 1024;
+    for (uint32_t mi = 0; mi < 8; ++mi) {
+      __m256i acc_lo = _mm256_setzero_si256(), acc_hi = _mm256_setzero_si256();
+      for (uint32_t kc = 0; kc < 8; ++kc) {
+        const uint8_t* c = blk + kc * 128 + mi * 16;
+        for (uint32_t j = 0; j < 8; ++j) {  // k pair (kc*16 + 2j, +1)
+          const uint32_t pair = static_cast<uint32_t>(c[2 * j]) | (static_cast<uint32_t>(c[2 * j + 1]) << 16);
+          const __m256i a = _mm256_set1_epi32(static_cast<int32_t>(pair));
+          const int16_t* w = &C.w2[kc * 8 + j][0][0];
+          acc_lo = _mm256_add_epi32(acc_lo, _mm256_madd_epi16(a, _mm256_load_si256(reinterpret_cast<const __m256i*>(w))));
+          acc_hi = _mm256_add_epi32(acc_hi, _mm256_madd_epi16(a, _mm256_load_si256(reinterpret_cast<const __m256i*>(w + 16))));
+        }
+      }
+      alignas(32) uint32_t d[16];
+      _mm256_store_si256(reinterpret_cast<__m256i*>(d), acc_lo);
+      _mm256_store_si256(reinterpret_cast<__m256i*>(d + 8), acc_hi);
+      uint64_t rr = 0;
+      for (uint32_t n = 0; n < kN; ++n) rr += static_cast<uint64_t>(d[n]) * C.KN[n];
+      sum += row_contrib(rr, tile_index * kRows + b * 8 + mi);
+    }
+  }
+  return sum;
+}
+#endif
+
+using TileFn = uint64_t (*)(const uint8_t*, uint64_t) noexcept;
+struct BbhImpl {
+  TileFn fn = tile_sum_scalar;
+  const char* name = "scalar";
+  BbhImpl() {
+#if defined(__x86_64__)
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512dq") &&
+        __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512vnni")) {
+      fn = tile_sum_vnni;
+      name = "avx512-vnni";
+    } else if (__builtin_cpu_supports("avx2")) {
+      fn = tile_sum_avx2;
+      name = "avx2";
+    }
+    if (const char* e = std::getenv("BB_BBH64_IMPL")) {  // tests / diagnostics: force a path the CPU supports
+      const std::string want(e);
+      if (want == "scalar") fn = tile_sum_scalar, name = "scalar";
+      else if (want == "avx2" && __builtin_cpu_supports("avx2")) fn = tile_sum_avx2, name = "avx2";
+    }
+#endif
+  }
+};
+const BbhImpl& bbh_impl() {
+  static const BbhImpl i;
+  return i;
+}
+
+uint64_t tiles_sum(TileFn fn, const uint8_t* p, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept {
+  const uint64_t total = (len + kTileBytes - 1) / kTileBytes;
+  uint64_t sum = 0;
+  for (uint64_t t = first_tile; t < first_tile + ntiles && t < total; ++t) {
+    const uint64_t base = t * kTileBytes;
+    if (len - base >= kTileBytes) {
+      sum += fn(p + base, t);
+    } else {  // short last tile: zero padded
+      alignas(64) uint8_t pad[kTileBytes];
+      std::memcpy(pad, p + base, len - base);
+      std::memset(pad + (len - base), 0, kTileBytes - (len - base));
+      sum += fn(pad, t);
+    }
+  }
+  return sum;
+}
+}  // namespace
+
+const char* bbh64_impl_name() noexcept { return bbh_impl().name; }
+
+uint64_t bbh64_partial(const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept {
+  return tiles_sum(bbh_impl().fn, static_cast<const uint8_t*>(data), len, first_tile, ntiles);
+}
+
+uint64_t bbh64_finalize(uint64_t tile_sum, size_t len) noexcept { return tchash::finalize(tile_sum, len); }
+
+uint64_t bbh64(const void* data, size_t len) noexcept {
+  return tchash::finalize(bbh64_partial(data, len, 0, (len + kTileBytes - 1) / kTileBytes), len);
+}
+
+uint64_t bbh64_using(std::string_view impl, const void* data, size_t len, bool* supported) noexcept {
+  TileFn fn = nullptr;
+  if (impl == "scalar") fn = tile_sum_scalar;
+#if defined(__x86_64__)
+  __builtin_cpu_init();
+  if (impl == "avx2" && __builtin_cpu_supports("avx2")) fn = tile_sum_avx2;
+  if (impl == "avx512-vnni" && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512dq") &&
+      __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512vnni"))
+    fn = tile_sum_vnni;
+#endif
+  if (supported) *supported = fn != nullptr;
+  if (!fn) return 0;
+  return tchash::finalize(tiles_sum(fn, static_cast<const uint8_t*>(data), len, 0, (len + kTileBytes - 1) / kTileBytes), len);
+}
+
+uint64_t bbh64_reference(const void* data, size_t len) noexcept {
+  return tchash::finalize(tiles_sum(tile_sum_scalar, static_cast<const uint8_t*>(data), len, 0, (len + kTileBytes - 1) / kTileBytes), len);
 }
 
 uint64_t checksum(ChecksumAlgo algo, const void* data, size_t len) noexcept {

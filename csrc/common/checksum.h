@@ -31,7 +31,19 @@ uint32_t crc32c_from_raw(uint32_t raw, uint64_t len) noexcept;
 //   t[0][s&255] ^ t[1][(s>>8)&255] ^ t[2][(s>>16)&255] ^ t[3][s>>24]   (tables used by the GPU kernel)
 void crc32c_shift_table(uint64_t nbytes, uint32_t t[4][256]) noexcept;
 
+// BBH64 (tchash_def.h).  bbh64() dispatches to an AVX-512 VNNI or AVX2 implementation of the same integer arithmetic
+// when the CPU has one (the host tiers and TCP clients hash at memory speed instead of 0.3 GB/s); bbh64_reference() is
+// the byte-at-a-time definition the CUDA kernels and the SIMD paths are tested against.
 uint64_t bbh64(const void* data, size_t len) noexcept;
+uint64_t bbh64_reference(const void* data, size_t len) noexcept;
+// Unfinalised sum of the tiles [first_tile, first_tile + ntiles) of an object of `len` bytes starting at `data`:
+// the tile sums are commutative, so a large object can be hashed by several threads and the parts added;
+// bbh64_finalize(sum of the parts, len) is the digest.
+uint64_t bbh64_partial(const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept;
+uint64_t bbh64_finalize(uint64_t tile_sum, size_t len) noexcept;
+const char* bbh64_impl_name() noexcept;  // "avx512-vnni" | "avx2" | "scalar"
+// Digest through a named implementation (tests); *supported = false when this CPU cannot run it.
+uint64_t bbh64_using(std::string_view impl, const void* data, size_t len, bool* supported) noexcept;
 
 uint64_t checksum(ChecksumAlgo algo, const void* data, size_t len) noexcept;
 

@@ -27,6 +27,11 @@ void set_nodelay(int fd) {
   int one = 1;
   ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
 }
+void set_buffers(int fd, int bytes) {
+  if (bytes <= 0) return;
+  ::setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &bytes, sizeof bytes);
+  ::setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &bytes, sizeof bytes);
+}
 bool resolve(const std::string& host, uint16_t port, sockaddr_in* out) {
   std::memset(out, 0, sizeof *out);
   out->sin_family = AF_INET;
@@ -179,6 +184,37 @@ bool recv_all(int fd, void* data, size_t len, int timeout_ms) {
   return true;
 }
 
+// Gathered blocking send on a non-blocking or blocking socket.
+static bool send_gather(int fd, const Connection::Piece* pieces, int n, int timeout_ms) {
+  iovec iov[4];
+  int cnt = 0;
+  for (int i = 0; i < n && cnt < 4; ++i)
+    if (pieces[i].len) iov[cnt++] = iovec{const_cast<void*>(pieces[i].data), pieces[i].len};
+  int first = 0;
+  while (first < cnt) {
+    msghdr mh{};
+    mh.msg_iov = iov + first;
+    mh.msg_iovlen = static_cast<size_t>(cnt - first);
+    ssize_t w = ::sendmsg(fd, &mh, MSG_NOSIGNAL);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      if (errno == EAGAIN || errno == EWOULDBLOCK) {
+        pollfd pf{fd, POLLOUT, 0};
+        if (::poll(&pf, 1, timeout_ms) <= 0) return false;
+        continue;
+      }
+      return false;
+    }
+    size_t left = static_cast<size_t>(w);
+    while (first < cnt && left >= iov[first].iov_len) left -= iov[first++].iov_len;
+    if (first < cnt && left) {
+      iov[first].iov_base = static_cast<char*>(iov[first].iov_base) + left;
+      iov[first].iov_len -= left;
+    }
+  }
+  return true;
+}
+
 // ================================================================ Connection
 Connection::~Connection() {
   if (fd_ >= 0) ::close(fd_);
@@ -188,6 +224,16 @@ bool Connection::send(const void* data, size_t len) {
   if (closed_.load()) return false;
   std::lock_guard<std::mutex> lk(write_mu_);
   if (!send_all(fd_, data, len, 10000)) {
+    close();
+    return false;
+  }
+  return true;
+}
+
+bool Connection::sendv(const Piece* pieces, int n) {
+  if (closed_.load()) return false;
+  std::lock_guard<std::mutex> lk(write_mu_);
+  if (!send_gather(fd_, pieces, n, 30000)) {
     close();
     return false;
   }
@@ -277,6 +323,7 @@ void TcpServer::accept_all() {
     int cfd = ::accept4(listen_fd_, reinterpret_cast<sockaddr*>(&peer), &len, SOCK_NONBLOCK | SOCK_CLOEXEC);
     if (cfd < 0) break;
     set_nodelay(cfd);
+    set_buffers(cfd, sock_buf_bytes_);
     char ip[64] = {0};
     ::inet_ntop(AF_INET, &peer.sin_addr, ip, sizeof ip);
     ConnPtr c;
@@ -366,6 +413,43 @@ void TcpServer::worker_loop() {
       alive = false;
       break;
     }
+    // A large message is pending: size the buffer once and receive straight into it until it is complete.
+    if (alive) {
+      const size_t missing = bytes_missing(c);
+      if (missing >= sizeof buf) {
+        std::string& in = c->inbuf();
+        size_t have = in.size();
+        in.resize(have + missing);
+        const auto deadline = SteadyClock::now() + std::chrono::seconds(30);
+        while (have < in.size()) {
+          ssize_t r = ::recv(c->fd(), &in[have], in.size() - have, 0);
+          if (r > 0) {
+            have += static_cast<size_t>(r);
+            continue;
+          }
+          if (r == 0) {
+            alive = false;
+            break;
+          }
+          if (errno == EINTR) continue;
+          if (errno != EAGAIN && errno != EWOULDBLOCK) {
+            alive = false;
+            break;
+          }
+          pollfd pf{c->fd(), POLLIN, 0};
+          const int rc = ::poll(&pf, 1, 1000);
+          if (rc < 0 && errno != EINTR) {
+            alive = false;
+            break;
+          }
+          if (!running_.load() || SteadyClock::now() > deadline) {
+            alive = false;  // stalled sender: give the pool thread back
+            break;
+          }
+        }
+        in.resize(have);
+      }
+    }
     // deliver whatever arrived, even if the peer then closed
     if (!c->inbuf().empty() && !c->closed()) {
       bool ok = false;
@@ -402,6 +486,15 @@ std::string encode_frame(uint32_t method, uint64_t id, const std::string& payloa
   return f;
 }
 
+size_t RpcServer::bytes_missing(const ConnPtr& c) {
+  const std::string& in = c->inbuf();
+  if (in.size() < kFrameHeader) return 0;
+  const uint32_t len = rd32(in.data());
+  if (len > kMaxFrame) return 0;  // on_data closes the connection
+  const size_t total = static_cast<size_t>(kFrameHeader) + len;
+  return total > in.size() ? total - in.size() : 0;
+}
+
 bool RpcServer::on_data(const ConnPtr& c) {
   std::string& in = c->inbuf();
   size_t pos = 0;
@@ -411,30 +504,44 @@ bool RpcServer::on_data(const ConnPtr& c) {
     if (in.size() - pos < kFrameHeader + len) break;
     const uint32_t method = rd32(&in[pos + 4]);
     const uint64_t id = rd64(&in[pos + 8]);
-    std::string payload = in.substr(pos + kFrameHeader, len);
+    const size_t body = pos + kFrameHeader;
     pos += kFrameHeader + len;
-    auto it = handlers_.find(method);
     std::string resp;
+    Reply reply;
     uint32_t rmethod = method;
-    if (it == handlers_.end()) {
-      rmethod = 0x7FFFFFFFu;  // unknown-method marker
-    } else {
-      try {
-        if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
-        resp = it->second(c, payload);
-      } catch (const std::exception& e) {
-        BB_LOG(ERROR) << "rpc handler " << method << " threw: " << e.what();
-        rmethod = 0x7FFFFFFEu;  // handler-exception marker
+    try {
+      if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
+      if (auto vit = view_handlers_.find(method); vit != view_handlers_.end()) {
+        reply = vit->second(c, std::string_view(in.data() + body, len));  // no copy of the request payload
+      } else if (auto it = handlers_.find(method); it != handlers_.end()) {
+        reply.head = it->second(c, in.substr(body, len));
+      } else {
+        rmethod = 0x7FFFFFFFu;  // unknown-method marker
       }
+    } catch (const std::exception& e) {
+      BB_LOG(ERROR) << "rpc handler " << method << " threw: " << e.what();
+      rmethod = 0x7FFFFFFEu;  // handler-exception marker
+      reply = Reply{};
     }
     served_.fetch_add(1, std::memory_order_relaxed);
-    if (!c->send(encode_frame(rmethod, id, resp))) return false;
+    char hdr[kFrameHeader];
+    const uint32_t rlen = static_cast<uint32_t>(reply.head.size() + reply.ext_len);
+    std::memcpy(hdr, &rlen, 4);
+    std::memcpy(hdr + 4, &rmethod, 4);
+    std::memcpy(hdr + 8, &id, 8);
+    const Connection::Piece pieces[3] = {{hdr, sizeof hdr}, {reply.head.data(), reply.head.size()}, {reply.ext, reply.ext_len}};
+    if (reply.head.size() + reply.ext_len > kMaxFrame || !c->sendv(pieces, 3)) return false;
   }
   if (pos) in.erase(0, pos);
   return true;
 }
 
 RpcClient::~RpcClient() { close(); }
+
+void RpcClient::set_bulk_buffers(int bytes) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ >= 0) set_buffers(fd_, bytes);
+}
 
 ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout_ms) {
   close();
@@ -535,6 +642,84 @@ Result<std::string> RpcClient::call(uint32_t method, const std::string& request,
   if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
   if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
   return payload;
+}
+
+Result<std::string> RpcClient::call_gather(uint32_t method, const std::string& head, const void* ext, size_t ext_len, int timeout_ms) {
+  if (reader_run_.load()) {  // push mode routes responses through the reader thread: take the copying path
+    std::string req = head;
+    req.append(static_cast<const char*>(ext), ext_len);
+    return call(method, req, timeout_ms);
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
+  if (head.size() + ext_len > kMaxFrame) return ErrorCode::INVALID_PARAMETERS;
+  const uint64_t id = next_id_++;
+  char hdr[kFrameHeader];
+  const uint32_t len = static_cast<uint32_t>(head.size() + ext_len);
+  std::memcpy(hdr, &len, 4);
+  std::memcpy(hdr + 4, &method, 4);
+  std::memcpy(hdr + 8, &id, 8);
+  const Connection::Piece pieces[3] = {{hdr, sizeof hdr}, {head.data(), head.size()}, {ext, ext_len}};
+  if (!send_gather(fd_, pieces, 3, timeout_ms)) return ErrorCode::RPC_FAILED;
+  char rh[kFrameHeader];
+  if (!recv_all(fd_, rh, sizeof rh, timeout_ms)) {
+    ::close(fd_);
+    fd_ = -1;
+    return ErrorCode::RPC_FAILED;
+  }
+  const uint32_t rlen = rd32(rh);
+  const uint32_t rmethod = rd32(rh + 4);
+  std::string payload(rlen <= kMaxFrame ? rlen : 0, '\0');
+  if (rlen > kMaxFrame || (rlen && !recv_all(fd_, payload.data(), rlen, timeout_ms))) {
+    ::close(fd_);
+    fd_ = -1;
+    return ErrorCode::RPC_FAILED;
+  }
+  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
+  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  return payload;
+}
+
+Result<std::string> RpcClient::call_scatter(uint32_t method, const std::string& request, size_t head_len, void* dst, size_t dst_cap,
+                                            size_t* received, int timeout_ms) {
+  if (received) *received = 0;
+  if (reader_run_.load()) {
+    auto r = call(method, request, timeout_ms);
+    if (!r.ok()) return r.error();
+    std::string& all = r.value();
+    const size_t h = std::min(head_len, all.size());
+    const size_t rest = all.size() - h;
+    if (rest > dst_cap) return ErrorCode::BUFFER_OVERFLOW;
+    if (rest) std::memcpy(dst, all.data() + h, rest);
+    if (received) *received = rest;
+    all.resize(h);
+    return std::move(all);
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
+  const uint64_t id = next_id_++;
+  const std::string f = encode_frame(method, id, request);
+  if (!send_all(fd_, f.data(), f.size(), timeout_ms)) return ErrorCode::RPC_FAILED;
+  char rh[kFrameHeader];
+  auto broken = [&]() -> Result<std::string> {
+    ::close(fd_);
+    fd_ = -1;
+    return ErrorCode::RPC_FAILED;
+  };
+  if (!recv_all(fd_, rh, sizeof rh, timeout_ms)) return broken();
+  const uint32_t rlen = rd32(rh);
+  const uint32_t rmethod = rd32(rh + 4);
+  if (rlen > kMaxFrame) return broken();
+  const size_t h = std::min<size_t>(head_len, rlen);
+  const size_t rest = rlen - h;
+  std::string head(h, '\0');
+  if (h && !recv_all(fd_, head.data(), h, timeout_ms)) return broken();
+  if (rest > dst_cap) return broken();  // cannot resynchronise the stream without draining it
+  if (rest && !recv_all(fd_, dst, rest, timeout_ms)) return broken();
+  if (received) *received = rest;
+  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
+  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  return head;
 }
 
 // ================================================================ HTTP

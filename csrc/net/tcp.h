@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -37,6 +38,12 @@ class Connection : public std::enable_shared_from_this<Connection> {
   // Thread-safe; may be called from any thread (server push).
   bool send(const void* data, size_t len);
   bool send(const std::string& s) { return send(s.data(), s.size()); }
+  // Gathered send of up to 4 pieces under one write lock (frame header + reply head + payload that stays where it is).
+  struct Piece {
+    const void* data;
+    size_t len;
+  };
+  bool sendv(const Piece* pieces, int n);
   void close();
   bool closed() const { return closed_.load(); }
   uint64_t id() const { return id_; }
@@ -72,6 +79,8 @@ class TcpServer {
   ErrorCode start(const std::string& host, uint16_t port, int worker_threads = 2);
   // Threads keep polling (no sleep) for this long after their last event; set before start().
   void set_busy_poll_us(int us) { busy_poll_us_ = us; }
+  // Socket buffer size requested for accepted connections (0 = kernel default); set before start().
+  void set_socket_buffers(int bytes) { sock_buf_bytes_ = bytes; }
   void stop();
   bool running() const { return running_.load(); }
   uint16_t port() const { return port_; }
@@ -83,6 +92,10 @@ class TcpServer {
   virtual bool on_data(const ConnPtr& c) = 0;
   virtual void on_open(const ConnPtr&) {}
   virtual void on_close(const ConnPtr&) {}
+  // Bytes still missing from the message at the front of c->inbuf() (0 = unknown / none).  When a large message is
+  // pending the pool thread sizes the buffer once and receives straight into it until the message is complete
+  // (bulk transfers do not bounce through 64 KiB reads and epoll re-arms).
+  virtual size_t bytes_missing(const ConnPtr&) { return 0; }
 
  private:
   void accept_all();
@@ -97,6 +110,7 @@ class TcpServer {
   std::vector<std::thread> workers_;
   mutable std::mutex mu_;
   std::atomic<int> spinner_{0};
+  int sock_buf_bytes_ = 0;
   int busy_poll_us_ = -1;  // -1: BB_RPC_BUSY_POLL_US from the environment (default 0 = sleep in epoll_wait)
   std::unordered_map<int, ConnPtr> conns_;
   uint64_t next_id_ = 1;
@@ -119,6 +133,15 @@ class RpcServer : public TcpServer {
   // Handler returns the response payload.  It runs on a worker thread.
   using Handler = std::function<std::string(const ConnPtr&, const std::string& request)>;
   void register_method(uint32_t method, Handler h) { handlers_[method] = std::move(h); }
+  // Bulk methods: the request is a view into the connection buffer (no copy of the payload) and the reply may point
+  // at memory that stays where it is (`ext`, e.g. a shard inside a pool) -- it is sent with a gathered write.
+  struct Reply {
+    std::string head;
+    const void* ext = nullptr;
+    size_t ext_len = 0;
+  };
+  using ViewHandler = std::function<Reply(const ConnPtr&, std::string_view request)>;
+  void register_view_method(uint32_t method, ViewHandler h) { view_handlers_[method] = std::move(h); }
   void set_close_hook(std::function<void(const ConnPtr&)> f) { close_hook_ = std::move(f); }
   static bool push(const ConnPtr& c, uint32_t topic, const std::string& payload) {
     return c->send(encode_frame(kPushFlag | topic, 0, payload));
@@ -127,12 +150,14 @@ class RpcServer : public TcpServer {
 
  protected:
   bool on_data(const ConnPtr& c) override;
+  size_t bytes_missing(const ConnPtr& c) override;
   void on_close(const ConnPtr& c) override {
     if (close_hook_) close_hook_(c);
   }
 
  private:
   std::unordered_map<uint32_t, Handler> handlers_;
+  std::unordered_map<uint32_t, ViewHandler> view_handlers_;
   std::function<void(const ConnPtr&)> close_hook_;
   std::atomic<uint64_t> served_{0};
 };
@@ -145,10 +170,18 @@ class RpcClient {
   RpcClient& operator=(const RpcClient&) = delete;
 
   ErrorCode connect(const std::string& host, uint16_t port, int timeout_ms = 3000);
+  // Asks the kernel for large socket buffers (bulk data connections); best effort.
+  void set_bulk_buffers(int bytes = 4 << 20);
   void close();
   bool connected() const { return fd_ >= 0; }
   // Blocking call; thread-safe (calls are serialised per client).
   Result<std::string> call(uint32_t method, const std::string& request, int timeout_ms = 30000);
+  // Bulk variants (not available in push mode).  call_gather: the request is `head` followed by `ext_len` bytes at
+  // `ext`, sent with one gathered write (no copy of the payload).  call_scatter: the first `head_len` bytes of the
+  // response are returned, the rest is received straight into `dst` (`*received` = its length, at most dst_cap).
+  Result<std::string> call_gather(uint32_t method, const std::string& head, const void* ext, size_t ext_len, int timeout_ms = 30000);
+  Result<std::string> call_scatter(uint32_t method, const std::string& request, size_t head_len, void* dst, size_t dst_cap, size_t* received,
+                                   int timeout_ms = 30000);
   // Installs a handler for server push frames and starts a reader thread.  After this, call()
   // responses are also routed through the reader thread.
   void enable_push(std::function<void(uint32_t topic, const std::string& payload)> cb);

@@ -126,6 +126,23 @@ void bind_common(py::module_& m) {
     py::buffer_info i = b.request();
     return bbh64(i.ptr, static_cast<size_t>(i.size * i.itemsize));
   });
+  m.def("bbh64_reference", [](py::buffer b) {
+    py::buffer_info i = b.request();
+    return bbh64_reference(i.ptr, static_cast<size_t>(i.size * i.itemsize));
+  });
+  m.def("bbh64_using", [](const std::string& impl, py::buffer b) -> py::object {
+    py::buffer_info i = b.request();
+    bool ok = false;
+    const uint64_t d = bbh64_using(impl, i.ptr, static_cast<size_t>(i.size * i.itemsize), &ok);
+    if (!ok) return py::none();
+    return py::int_(d);
+  });
+  m.def("bbh64_partial", [](py::buffer b, uint64_t first_tile, uint64_t ntiles) {
+    py::buffer_info i = b.request();
+    return bbh64_partial(i.ptr, static_cast<size_t>(i.size * i.itemsize), first_tile, ntiles);
+  });
+  m.def("bbh64_finalize", &bbh64_finalize);
+  m.def("bbh64_impl_name", [] { return std::string(bbh64_impl_name()); });
   m.def("bbh64_weight", [](uint32_t k, uint32_t n) { return tchash::weight(k, n); });
   m.def("bbh64_off_to_row", [](uint32_t o) { return tchash::off_to_row(o); });
   m.def("bbh64_off_to_k", [](uint32_t o) { return tchash::off_to_k(o); });

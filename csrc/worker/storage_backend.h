@@ -114,6 +114,8 @@ class StorageBackend {
     return ErrorCode::NOT_IMPLEMENTED;
   }
   uint64_t device_copies() const { return device_copies_; }
+  // Accounting for readers that take the bytes through direct_ptr() (zero-copy data server reads).
+  void note_read(uint64_t len) { bytes_read_ += len; }
   // Registration key advertised in the pool record ("ucx_rkey_hex"): 8 hex chars of the rkey by
   // default; the GPU tier returns its CUDA IPC handle.
   virtual std::string registration_key_hex() const;

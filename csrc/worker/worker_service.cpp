@@ -1,6 +1,8 @@
 #include "common/fault.h"
 #include "worker/worker_service.h"
 
+#include <thread>
+
 #include <chrono>
 #include <stdexcept>
 
@@ -159,7 +161,9 @@ ErrorCode WorkerService::initialize() {
   }
   auto hp = split_host_port(config_.ucx_endpoint);
   if (!hp) return ErrorCode::INVALID_ADDRESS;
-  ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), 4);
+  data_server_.set_socket_buffers(4 << 20);  // bulk transfers: fewer wake-ups per megabyte
+  const unsigned hw = std::thread::hardware_concurrency();
+  ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), static_cast<int>(std::min(16u, std::max(4u, hw / 2))));
   if (ec != ErrorCode::OK) return ec;
   initialized_.store(true);
   return ErrorCode::OK;
@@ -350,8 +354,13 @@ uint64_t resolve_offset(const StorageBackend& b, uint64_t raw) {
 void WorkerService::register_data_handlers() {
   using C = const net::ConnPtr&;
   using S = const std::string&;
-  data_server_.register_method(D_WRITE, [this](C, S q) {
-    wire::Reader r(q);
+  using V = std::string_view;
+  using Reply = net::RpcServer::Reply;
+  // D_WRITE / D_READ are bulk methods: the request payload is consumed in place from the connection buffer and a
+  // read of a host-mapped tier is answered straight out of the pool (gathered send), so a shard crosses the worker
+  // with one copy on the way in and none on the way out.
+  data_server_.register_view_method(D_WRITE, [this](C, V q) {
+    wire::Reader r(q.data(), q.size());
     const std::string pool = r.str();
     const uint64_t off = r.u64();
     const uint32_t len = r.u32();
@@ -359,12 +368,12 @@ void WorkerService::register_data_handlers() {
     StorageBackend* b = backend(pool);
     if (!r.ok() || q.size() < len || !b) {
       w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
-      return w.take();
+      return Reply{w.take()};
     }
     const char* payload = q.data() + (q.size() - len);
     if (fault::fire("fail_data_write")) {
       w.ec(ErrorCode::IO_ERROR);
-      return w.take();
+      return Reply{w.take()};
     }
     ErrorCode wec = b->write(resolve_offset(*b, off), payload, len);
     if (wec == ErrorCode::OK && len && fault::fire("corrupt_write")) {  // silent corruption: the checksum must catch it
@@ -372,22 +381,39 @@ void WorkerService::register_data_handlers() {
       b->write(resolve_offset(*b, off) + len / 2, &bad, 1);
     }
     w.ec(wec);
-    return w.take();
+    return Reply{w.take()};
   });
-  data_server_.register_method(D_READ, [this](C, S q) {
-    wire::Reader r(q);
+  data_server_.register_view_method(D_READ, [this](C, V q) {
+    wire::Reader r(q.data(), q.size());
     const std::string pool = r.str();
     const uint64_t off = r.u64();
     const uint32_t len = r.u32();
     StorageBackend* b = backend(pool);
-    std::string out(4 + (b && r.ok() ? len : 0), '\0');
+    Reply rep;
     ErrorCode ec = !b ? ErrorCode::MEMORY_POOL_NOT_FOUND : !r.ok() ? ErrorCode::INVALID_PARAMETERS
-                   : fault::fire("fail_data_read") ? ErrorCode::IO_ERROR
-                                                   : b->read(resolve_offset(*b, off), out.data() + 4, len);
+                   : fault::fire("fail_data_read") ? ErrorCode::IO_ERROR : ErrorCode::OK;
+    if (ec == ErrorCode::OK) {
+      const uint64_t o = resolve_offset(*b, off);
+      const void* direct = (b->get_storage_class() != StorageClass::RAM_GPU && o != ~0ull && o + len >= o && o + len <= b->get_total_capacity())
+                               ? b->direct_ptr(o) : nullptr;
+      if (direct && len >= 4096) {  // DRAM / CXL / mmap tiers: send from the pool itself
+        b->note_read(len);
+        rep.ext = direct;
+        rep.ext_len = len;
+        rep.head.assign(4, '\0');
+      } else {
+        rep.head.assign(4 + static_cast<size_t>(len), '\0');
+        ec = b->read(o, rep.head.data() + 4, len);
+      }
+    }
+    if (ec != ErrorCode::OK) {
+      rep.head.assign(4, '\0');
+      rep.ext = nullptr;
+      rep.ext_len = 0;
+    }
     const uint32_t e = static_cast<uint32_t>(ec);
-    std::memcpy(out.data(), &e, 4);
-    if (ec != ErrorCode::OK) out.resize(4);
-    return out;
+    std::memcpy(rep.head.data(), &e, 4);
+    return rep;
   });
   data_server_.register_method(D_CHECKSUM, [this](C, S q) {
     wire::Reader r(q);
