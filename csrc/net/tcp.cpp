@@ -413,14 +413,20 @@ void TcpServer::worker_loop() {
       alive = false;
       break;
     }
-    // A large message is pending: size the buffer once and receive straight into it until it is complete.
-    if (alive) {
-      const size_t missing = bytes_missing(c);
-      if (missing >= sizeof buf) {
-        std::string& in = c->inbuf();
-        size_t have = in.size();
-        in.resize(have + missing);
-        const auto deadline = SteadyClock::now() + std::chrono::seconds(30);
+    // A large message is pending: grow the buffer in big steps and receive straight into it until the message is
+    // complete (bulk transfers do not bounce through 64 KiB reads, buffer appends and epoll re-arms).  The buffer never
+    // grows more than kBulkStep ahead of the bytes that actually arrived, whatever the frame header claims.
+    if (alive && bytes_missing(c) >= sizeof buf) {
+      constexpr size_t kBulkStep = 16u << 20;
+      std::string& in = c->inbuf();
+      size_t have = in.size();
+      const auto deadline = SteadyClock::now() + std::chrono::seconds(30);
+      bool stalled = false;
+      while (alive && !stalled) {
+        in.resize(have);
+        const size_t missing = bytes_missing(c);
+        if (missing == 0) break;
+        in.resize(have + std::min(missing, kBulkStep));
         while (have < in.size()) {
           ssize_t r = ::recv(c->fd(), &in[have], in.size() - have, 0);
           if (r > 0) {
@@ -437,18 +443,20 @@ void TcpServer::worker_loop() {
             break;
           }
           pollfd pf{c->fd(), POLLIN, 0};
-          const int rc = ::poll(&pf, 1, 1000);
+          const int rc = ::poll(&pf, 1, 200);
           if (rc < 0 && errno != EINTR) {
             alive = false;
             break;
           }
-          if (!running_.load() || SteadyClock::now() > deadline) {
-            alive = false;  // stalled sender: give the pool thread back
+          // a sender that stalls gives the pool thread back: the connection returns to the epoll set and the rest of
+          // the message is picked up when it arrives
+          if (rc == 0 || !running_.load() || SteadyClock::now() > deadline) {
+            stalled = true;
             break;
           }
         }
-        in.resize(have);
       }
+      in.resize(have);
     }
     // deliver whatever arrived, even if the peer then closed
     if (!c->inbuf().empty() && !c->closed()) {

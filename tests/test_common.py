@@ -144,3 +144,27 @@ def test_bbh64_detects_changes(bb):
     # layout bijection of the UMMA canonical tile
     seen = {(bb.bbh64_off_to_row(o), bb.bbh64_off_to_k(o)) for o in range(16384)}
     assert len(seen) == 16384 and all(0 <= m < 128 and 0 <= k < 128 for m, k in seen)
+
+
+def test_bbh64_simd_paths_match_the_byte_at_a_time_definition(bb):
+    """bbh64() dispatches to AVX-512 VNNI / AVX2 code on the host tiers and TCP clients; every path computes the same
+    integers as the reference definition (which the CUDA kernels are tested against), tile sums add up across ranges."""
+    import numpy as np
+
+    rng = np.random.default_rng(5)
+    assert bb.bbh64_impl_name() in ("avx512-vnni", "avx2", "scalar")
+    for n in (0, 1, 15, 16, 4095, 16384, 16385, 100_000, (1 << 20) + 7):
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        ref = bb.bbh64_reference(a)
+        assert bb.bbh64(a) == ref
+        for impl in ("scalar", "avx2", "avx512-vnni"):
+            got = bb.bbh64_using(impl, a)
+            assert got is None or got == ref, (impl, n)
+    for v in (255, 128, 1):  # accumulator extremes: 128 x 255 x 255 per column must not wrap or saturate
+        a = np.full(3 * 16384 + 100, v, dtype=np.uint8)
+        assert bb.bbh64(a) == bb.bbh64_reference(a)
+        assert bb.bbh64_using("avx2", a) in (None, bb.bbh64_reference(a))
+    a = rng.integers(0, 256, (5 << 20) + 123, dtype=np.uint8)
+    tiles = (a.size + 16383) // 16384
+    parts = [bb.bbh64_partial(a, 0, 100), bb.bbh64_partial(a, 100, 57), bb.bbh64_partial(a, 157, tiles - 157)]
+    assert bb.bbh64_finalize(sum(parts) & ((1 << 64) - 1), a.size) == bb.bbh64(a)
