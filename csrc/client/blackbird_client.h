@@ -133,7 +133,7 @@ class BlackbirdClient {
   }
   ErrorCode remove(const ObjectKey& key);
   // bf16 tensors stored as MXFP8 (common/mxfp8.h layout) with the pack fused into the put kernel and the unpack
-  // into the get kernel.  n_elems[i] must be a multiple of 16384 (use put + mxfp8_pack otherwise); up to 3 copies
+  // into the get kernel.  n_elems[i] must be a multiple of 32 (whole MX blocks; pad + mxfp8_pack otherwise); up to 3 copies
   // (written by one tile pass: converted once, stored to every replica; gets fail over between them), one
   // shard per object.  The stored object is identical to packing first and putting the packed bytes.
   std::vector<ErrorCode> batch_put_device_fp8(const std::vector<ObjectKey>& keys, const std::vector<const void*>& bf16_ptrs,

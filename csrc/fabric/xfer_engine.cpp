@@ -311,7 +311,6 @@ ErrorCode XferEngine::run_fp8(const std::vector<Fp8Item>& items, bool unpack, vo
     for (uint32_t r = 1; r < nrep; ++r)
       if (!it.more_packed[r - 1] || (reinterpret_cast<uintptr_t>(it.more_packed[r - 1]) & 15)) return ErrorCode::INVALID_ADDRESS;
     auto* payload = static_cast<uint8_t*>(it.packed);
-    uint8_t* scales = payload + it.n_elems;
     XferDesc& d = descs[i];
     d.src = unpack ? static_cast<const void*>(payload) : it.wide;
     d.dst[0] = unpack ? it.wide : static_cast<void*>(payload);  // pack: base of the packed object in every replica
@@ -324,15 +323,17 @@ ErrorCode XferEngine::run_fp8(const std::vector<Fp8Item>& items, bool unpack, vo
     d.flags = 0;
     d.reserved = 0;
     tile_start[i] = tiles;
-    const uint64_t nt = it.n_elems / kTileBytes;
+    const uint64_t nt = (it.n_elems + kTileBytes - 1) / kTileBytes;  // payload tiles, the last one possibly partial
+    const uint64_t nt_full = it.n_elems / kTileBytes;                // hashed by the fused kernel
     if (tiles + nt > 0xFFFFFFF0ull) return ErrorCode::VALUE_OUT_OF_RANGE;
     tiles += static_cast<uint32_t>(nt);
+    // everything past the last whole payload tile (payload tail + scales) is hashed from the stored bytes as a slice
     XferItem& sc = scale_items[i];
-    sc.src = scales;
+    sc.src = payload + nt_full * kTileBytes;
     sc.ndst = 0;
-    sc.nbytes = it.n_elems / 32;
+    sc.nbytes = (it.n_elems - nt_full * kTileBytes) + it.n_elems / 32;
     sc.flags = XFER_RAW_SUM;
-    sc.tile_base = static_cast<uint32_t>(nt);
+    sc.tile_base = static_cast<uint32_t>(nt_full);
   }
   tile_start[n] = tiles;
   const size_t tab = static_cast<size_t>(n) * sizeof(XferDesc) + (static_cast<size_t>(n) + 1) * 4;

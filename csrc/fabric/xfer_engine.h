@@ -34,7 +34,7 @@ struct Fp8Item {
   void* packed = nullptr;            // replica 0 (the copy a get reads)
   void* more_packed[kMaxDst - 1] = {nullptr, nullptr};  // put: further replicas written by the same tile pass
   uint32_t nreplicas = 1;            // put: 1..kMaxDst
-  uint64_t n_elems = 0;   // multiple of 16384
+  uint64_t n_elems = 0;   // multiple of 32 (whole MX blocks)
   uint64_t expect = 0;    // unpack + verify: digest recorded at put time
   bool verify = false;
 };
@@ -65,7 +65,7 @@ class XferEngine {
   // E4M3 payload is hashed on the tensor cores while it sits in shared memory, and the digest returned is the
   // BBH64 of the stored packed object (identical to hashing the output of mxfp8_pack).  Synchronous.
   ErrorCode run_fp8(const std::vector<Fp8Item>& items, bool unpack, void* stream, XferResult* out);
-  static bool fp8_eligible(uint64_t n_elems) { return n_elems != 0 && n_elems % kTileBytes == 0; }
+  static bool fp8_eligible(uint64_t n_elems) { return n_elems != 0 && n_elems % 32 == 0; }  // whole MX blocks
 
   // Raw accumulators of the last capture_debug batch: [total_tiles][128][16] (tests only).
   const std::vector<uint32_t>& debug_accumulators() const { return debug_host_; }

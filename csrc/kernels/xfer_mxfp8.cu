@@ -11,8 +11,10 @@
 // The stored object keeps the layout of the unfused path ([E4M3 payload n][E8M0 scales n/32], common/mxfp8.h), and so
 // does its digest: BBH64 is a sum of per-tile terms, this kernel accumulates the payload tiles (tile index 0..T-1)
 // and returns the *unfinalised* sum per object; the scales region (tiles T..) is hashed as an XFER_RAW_SUM slice
-// by bb_xfer and the host adds the two sums and finalises.  Objects must hold a multiple of 16384 elements (whole
-// payload tiles); other shapes take the unfused path.
+// by bb_xfer and the host adds the two sums and finalises.  Objects hold any multiple of 32 elements: a tail tile is
+// converted and stored like the others (its scale bytes past the last 16-byte multiple go byte-wise) but not hashed
+// here -- in the packed object its hash tile also contains the first scale bytes, so the slice the host hashes simply
+// starts at the last whole payload tile.
 //
 // Warp roles (16 warps): 0 producer, 1 MMA issuer, 2 store, 3 accumulator, 4-7 epilogue (TMEM -> row hashes),
 // 8-15 convert (pack / unpack).  Two shared-memory rings: 3 x 32 KiB bf16 tiles and 6 x (16 KiB payload + 512 B scales).
@@ -51,7 +53,9 @@ struct FpMeta {            // 64 bytes
   uint32_t tile_in_obj;
   uint32_t obj_ntiles;
   uint32_t ndst;           // pack: replicas written by this pass (1..kMaxDst)
-  uint64_t pad[2];
+  uint32_t valid;          // payload bytes (= elements) of this tile: 16384, or the multiple-of-32 tail of the object
+  uint32_t pad32;
+  uint64_t pad;
 };
 static_assert(sizeof(FpMeta) == 64);
 
@@ -212,7 +216,9 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         e.m.desc = lo;
         e.m.tile_in_obj = ti;
         e.m.obj_ntiles = next - first;
-        e.m.pad[0] = e.m.pad[1] = 0;
+        e.m.pad32 = 0;
+        e.m.pad = 0;
+        e.m.valid = static_cast<uint32_t>(min(static_cast<uint64_t>(kTileBytes), nbytes - static_cast<uint64_t>(ti) * kTileBytes));
         // the packed object is [payload nbytes][scales nbytes/32]: a tile's scales sit (nbytes - ti*(16384-512)) past its payload
         e.m.scales_delta = static_cast<int64_t>(nbytes) - static_cast<int64_t>(ti) * static_cast<int64_t>(kTileBytes - kScaleBytes);
         if constexpr (UNPACK) {
@@ -239,10 +245,14 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
           mbar_wait(&s.t_empty[ts], tp ^ 1u);
           if (lane < 4) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
           __syncwarp();
+          // a tail tile carries valid/32 scale bytes: the 16-byte multiple by TMA, the rest byte-wise
+          const uint32_t sb = e.m.valid / 32u, sb16 = sb & ~15u;
+          if (lane < (sb & 15u)) s.scales[ts][sb16 + lane] = *reinterpret_cast<const uint8_t*>(e.src_scales + sb16 + lane);
+          __syncwarp();
           if (lane == 0) {
-            mbar_arrive_expect_tx(&s.t_full[ts], kTileBytes + kScaleBytes);
-            bulk_g2s(s.tile[ts], reinterpret_cast<const void*>(e.src), kTileBytes, &s.t_full[ts]);
-            bulk_g2s(s.scales[ts], reinterpret_cast<const void*>(e.src_scales), kScaleBytes, &s.t_full[ts]);
+            mbar_arrive_expect_tx(&s.t_full[ts], e.m.valid + sb16);
+            bulk_g2s(s.tile[ts], reinterpret_cast<const void*>(e.src), e.m.valid, &s.t_full[ts]);
+            if (sb16) bulk_g2s(s.scales[ts], reinterpret_cast<const void*>(e.src_scales), sb16, &s.t_full[ts]);
           }
         } else {
           const uint32_t ws = it % kWideStages, wp = (it / kWideStages) & 1u;
@@ -250,8 +260,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
           if (lane < 4) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&e.m)[lane];
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive_expect_tx(&s.w_full[ws], kWideBytes);
-            bulk_g2s(s.wide[ws], reinterpret_cast<const void*>(e.src), kWideBytes, &s.w_full[ws]);
+            mbar_arrive_expect_tx(&s.w_full[ws], 2u * e.m.valid);
+            bulk_g2s(s.wide[ws], reinterpret_cast<const void*>(e.src), 2u * e.m.valid, &s.w_full[ws]);
           }
         }
         __syncwarp();
@@ -285,18 +295,23 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
       if constexpr (UNPACK) {
         mbar_wait(&s.w_full[st], par);
         if (lane == 0) {
-          bulk_s2g(reinterpret_cast<void*>(s.w_meta[st].dst[0]), s.wide[st], kWideBytes);
+          bulk_s2g(reinterpret_cast<void*>(s.w_meta[st].dst[0]), s.wide[st], 2u * s.w_meta[st].valid);
           bulk_commit();
         }
       } else {
         mbar_wait(&s.t_full[st], par);
+        const FpMeta& m = s.t_meta[st];
+        const uint32_t sb = m.valid / 32u, sb16 = sb & ~15u;
         if (lane == 0) {
-          const FpMeta& m = s.t_meta[st];
           for (uint32_t r = 0; r < m.ndst; ++r) {  // replica fan-out: converted once, stored to every copy
-            bulk_s2g(reinterpret_cast<void*>(m.dst[r]), s.tile[st], kTileBytes);
-            bulk_s2g(reinterpret_cast<void*>(m.dst[r] + m.scales_delta), s.scales[st], kScaleBytes);
+            bulk_s2g(reinterpret_cast<void*>(m.dst[r]), s.tile[st], m.valid);
+            if (sb16) bulk_s2g(reinterpret_cast<void*>(m.dst[r] + m.scales_delta), s.scales[st], sb16);
           }
           bulk_commit();
+        }
+        if (lane < (sb & 15u)) {  // tail tile: the scale bytes past the last 16-byte multiple
+          const uint8_t v = s.scales[st][sb16 + lane];
+          for (uint32_t r = 0; r < m.ndst; ++r) *reinterpret_cast<uint8_t*>(m.dst[r] + m.scales_delta + sb16 + lane) = v;
         }
       }
       __syncwarp();
@@ -323,7 +338,9 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
       const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
       mbar_wait(&s.epi_done[ts], tp);
       const uint32_t d = s.t_meta[ts].desc;
-      const uint64_t sum = s.part[ts][0] + s.part[ts][1] + s.part[ts][2] + s.part[ts][3];
+      // A tail tile holds payload AND the first scale bytes of the packed object's hash tile: it is hashed from the
+      // stored bytes as part of the host's RAW_SUM slice, not here.
+      const uint64_t sum = s.t_meta[ts].valid == kTileBytes ? s.part[ts][0] + s.part[ts][1] + s.part[ts][2] + s.part[ts][3] : 0;
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.t_empty[ts]);
       if (d != cur_d) {

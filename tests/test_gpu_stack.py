@@ -368,3 +368,45 @@ def test_fused_fp8_put_fans_out_to_replicas_and_get_fails_over(bb, torch_cuda):
         assert ecs == [bb.ErrorCode.CHECKSUM_MISMATCH]
     finally:
         cl.stop()
+
+
+@pytest.mark.parametrize("n", [32, 96, 16384 + 32, 3 * 16384 + 7 * 32, 2 * 16384 + 16352, 5 * 16384])
+def test_fused_fp8_handles_any_whole_number_of_mx_blocks(bb, torch_cuda, n):
+    """The fused pack-put / unpack-get kernels take any multiple of 32 elements: the tail tile is converted and stored
+    like the others (scale bytes past the last 16-byte multiple byte-wise) and the digest still equals BBH64 of the
+    stand-alone pack kernel's output."""
+    torch = torch_cuda
+    from blackbird_b200.parallel import GpuRankCluster
+
+    cl = GpuRankCluster(slab_bytes=64 << 20, cluster_id=f"t-fp8odd{n}")
+    try:
+        s = _stream(torch)
+        x = (torch.randn(n, device="cuda") * 3).to(torch.bfloat16)
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[bb.StorageClass.RAM_GPU])
+        assert cl.client.device_fp8_eligible(n)
+        assert cl.client.batch_put_device_fp8(["odd"], [x.data_ptr()], [n], cfg, s) == [bb.ErrorCode.OK]
+        ref = torch.empty(n + n // 32, dtype=torch.uint8, device="cuda")
+        bb.mxfp8_pack(x.data_ptr(), n, ref.data_ptr(), s)
+        torch.cuda.synchronize()
+        be = cl.worker.backend("hbm0")
+        copies = cl.client.get_workers("odd")
+        assert len(copies) == 2
+        for c in copies:
+            sh = c.shards[0]
+            assert sh.length == n + n // 32 and be.read(sh.offset, sh.length) == bytes(ref.cpu().numpy())
+            assert sh.checksum == bb.bbh64(ref.cpu().numpy())
+        out = torch.zeros_like(x)
+        guard = torch.full((64,), 7, dtype=torch.bfloat16, device="cuda")  # the get must not write past n elements
+        buf = torch.cat([out, guard])
+        assert cl.client.batch_get_device_fp8(["odd"], [buf.data_ptr()], [n], s) == [bb.ErrorCode.OK]
+        unp = torch.empty_like(x)
+        bb.mxfp8_unpack(ref.data_ptr(), n, unp.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert torch.equal(buf[:n].view(torch.int16), unp.view(torch.int16)) and bool((buf[n:] == 7).all())
+        # corruption in the tail region (payload tail or scales) is caught
+        for c, pos in ((copies[0], n - 1), (copies[1], n + n // 32 - 1)):
+            off = c.shards[0].offset + pos
+            be.write(off, bytes([be.read(off, 1)[0] ^ 0xFF]))
+        assert cl.client.batch_get_device_fp8(["odd"], [buf.data_ptr()], [n], s) == [bb.ErrorCode.CHECKSUM_MISMATCH]
+    finally:
+        cl.stop()
