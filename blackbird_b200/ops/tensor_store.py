@@ -36,8 +36,8 @@ class TensorStore:
 
     # ------------------------------------------------------------------ put
     def _fused_fp8_ok(self, t: torch.Tensor, cfg) -> bool:
-        """Pack fused into the put kernel: bf16, whole 16384-element tiles, up to 3 copies (one tile pass fans out to
-        every replica), each copy in one shard."""
+        """Pack fused into the put kernel: bf16, a whole number of 32-element MX blocks, up to 3 copies (one tile pass
+        fans out to every replica), each copy in one shard."""
         return (t.dtype == torch.bfloat16 and self.client.device_fp8_eligible(t.numel()) and 1 <= cfg.replication_factor <= 3
                 and cfg.max_workers_per_copy == 1 and t.data_ptr() % 16 == 0)
 

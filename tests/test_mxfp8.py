@@ -89,7 +89,7 @@ def test_fused_fp8_put_get_matches_unfused_pack_and_cpu_digest(bb):
     xs[1][100:132] = 0  # an all-zero block
     xs[2][7] = float("inf")
     slabs = [torch.zeros(bb.mxfp8_packed_bytes(n), dtype=torch.uint8, device="cuda") for n in sizes]
-    assert all(bb.XferEngine.fp8_eligible(n) for n in sizes) and not bb.XferEngine.fp8_eligible(16384 + 32)
+    assert all(bb.XferEngine.fp8_eligible(n) for n in sizes) and bb.XferEngine.fp8_eligible(16384 + 32) and not bb.XferEngine.fp8_eligible(16384 + 8)
     dg, st, ms = eng.run_fp8([(x.data_ptr(), sl.data_ptr(), n) for x, sl, n in zip(xs, slabs, sizes)], False, s)
     torch.cuda.synchronize()
     for x, sl, n, d in zip(xs, slabs, sizes, dg):
