@@ -14,7 +14,7 @@
 int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("help") || (!args.has("config") && args.positional.empty())) {
-    std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port]\n");
+    std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port] [--http-port P]\n");
     return args.has("help") ? 0 : 2;
   }
   bb::set_log_level(bb::LogLevel::INFO);
@@ -36,6 +36,7 @@ int main(int argc, char** argv) {
   }
   if (args.has("data-endpoint")) cfg.ucx_endpoint = args.get("data-endpoint");
   if (args.has("cluster-id")) cfg.cluster_id = args.get("cluster-id");
+  if (args.has("http-port")) cfg.http_metrics_port = std::atoi(args.get("http-port").c_str());
   bb::gpu::install_gpu_backend_factory();  // RAM_GPU pools become cudaMalloc slabs exported over CUDA IPC
   bbapp::install_signal_handlers();
   bb::worker::WorkerService svc(cfg);
@@ -46,8 +47,10 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "bb-worker: start failed: %s\n", std::string(bb::to_string(ec)).c_str());
     return 1;
   }
-  std::printf("bb-worker %s node=%s data=%s pools=%zu\n", cfg.worker_id.c_str(), cfg.node_id.c_str(), svc.data_endpoint().c_str(),
+  std::printf("bb-worker %s node=%s data=%s pools=%zu", cfg.worker_id.c_str(), cfg.node_id.c_str(), svc.data_endpoint().c_str(),
               svc.advertised_pools().size());
+  if (cfg.http_metrics_port >= 0) std::printf(" metrics=http://%s:%u/metrics", svc.data_endpoint().substr(0, svc.data_endpoint().rfind(':')).c_str(), svc.http_port());
+  std::printf("\n");
   std::fflush(stdout);
   while (!bbapp::g_stop && svc.is_running()) std::this_thread::sleep_for(std::chrono::milliseconds(200));
   svc.stop();

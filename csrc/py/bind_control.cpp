@@ -805,6 +805,7 @@ void bind_control(py::module_& m) {
       .def(py::init<>())
       .def_static("from_yaml", &worker::load_worker_config_from_file)
       .def_readwrite("worker_id", &worker::WorkerServiceConfig::worker_id)
+      .def_readwrite("http_metrics_port", &worker::WorkerServiceConfig::http_metrics_port)
       .def_readwrite("node_id", &worker::WorkerServiceConfig::node_id)
       .def_readwrite("cluster_id", &worker::WorkerServiceConfig::cluster_id)
       .def_readwrite("etcd_endpoints", &worker::WorkerServiceConfig::etcd_endpoints)
@@ -832,6 +833,8 @@ void bind_control(py::module_& m) {
       .def("get_stats", [](worker::WorkerService& w) { return bb_json_to_py(w.get_stats()); })
       .def("advertised_pools", &worker::WorkerService::advertised_pools)
       .def("data_endpoint", &worker::WorkerService::data_endpoint)
+      .def("metrics_text", &worker::WorkerService::metrics_text)
+      .def_property_readonly("http_port", &worker::WorkerService::http_port)
       .def("inject_fault", &worker::WorkerService::inject_fault)
       .def("backend", [](worker::WorkerService& w, const std::string& id) { return w.backend(id); }, py::return_value_policy::reference_internal);
 

@@ -33,6 +33,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   }
   if (w.contains("keystone_address")) c.keystone_address = w.at("keystone_address").as_string();
   if (w.contains("rpc_endpoint")) c.rpc_endpoint = w.at("rpc_endpoint").as_string();
+  if (w.contains("http_metrics_port")) c.http_metrics_port = static_cast<int>(w.at("http_metrics_port").as_int(-1));
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
   if (w.contains("interconnects")) {
@@ -165,6 +166,20 @@ ErrorCode WorkerService::initialize() {
   const unsigned hw = std::thread::hardware_concurrency();
   ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), static_cast<int>(std::min(16u, std::max(4u, hw / 2))));
   if (ec != ErrorCode::OK) return ec;
+  if (config_.http_metrics_port >= 0) {
+    http_server_.route("/metrics", [this](const std::string&, const std::string&) {
+      return net::HttpResponse{200, "text/plain; version=0.0.4; charset=utf-8", metrics_text()};
+    });
+    http_server_.route("/healthz", [this](const std::string&, const std::string&) {
+      return running_.load() ? net::HttpResponse{200, "text/plain; charset=utf-8", "ok\n"}
+                             : net::HttpResponse{503, "text/plain; charset=utf-8", "not registered\n"};
+    });
+    http_server_.route("/stats", [this](const std::string&, const std::string&) {
+      return net::HttpResponse{200, "application/json", get_stats().dump()};
+    });
+    if (http_server_.start(hp->first, static_cast<uint16_t>(config_.http_metrics_port), 1) != ErrorCode::OK)
+      BB_LOG(WARNING) << "worker " << config_.worker_id << ": metrics endpoint on port " << config_.http_metrics_port << " unavailable";
+  }
   initialized_.store(true);
   return ErrorCode::OK;
 }
@@ -294,6 +309,7 @@ void WorkerService::stop() {
     }
   }
   if (initialized_.exchange(false)) {
+    http_server_.stop();
     data_server_.stop();
     std::lock_guard<std::mutex> lk(pools_mu_);
     for (auto& [id, b] : pools_) b->shutdown();
@@ -337,6 +353,69 @@ Json WorkerService::get_stats() const {
   }
   j["pools"] = pools;
   return j;
+}
+
+std::string WorkerService::metrics_text() const {
+  std::string out;
+  auto esc = [](const std::string& v) {
+    std::string r;
+    for (char c : v) {
+      if (c == '\\' || c == '"') r.push_back('\\');
+      r.push_back(c == '\n' ? ' ' : c);
+    }
+    return r;
+  };
+  auto family = [&](const char* name, const char* type, const char* help) {
+    out += "# HELP ";
+    out += name;
+    out += ' ';
+    out += help;
+    out += "\n# TYPE ";
+    out += name;
+    out += ' ';
+    out += type;
+    out += '\n';
+  };
+  const std::string wl = "worker=\"" + esc(config_.worker_id) + "\",node=\"" + esc(config_.node_id) + "\"";
+  family("bb_worker_up", "gauge", "1 while the worker is registered and heartbeating");
+  out += "bb_worker_up{" + wl + "} " + std::string(running_.load() ? "1" : "0") + "\n";
+  family("bb_worker_heartbeats_total", "counter", "lease refreshes sent");
+  out += "bb_worker_heartbeats_total{" + wl + "} " + std::to_string(heartbeats_sent_.load()) + "\n";
+  family("bb_worker_data_requests_total", "counter", "requests served by the data server");
+  out += "bb_worker_data_requests_total{" + wl + "} " + std::to_string(data_server_.requests_served()) + "\n";
+  family("bb_worker_data_connections", "gauge", "open data-server connections");
+  out += "bb_worker_data_connections{" + wl + "} " + std::to_string(data_server_.connection_count()) + "\n";
+  struct Row {
+    std::string labels;
+    StorageStats s;
+    uint64_t device_copies;
+  };
+  std::vector<Row> rows;
+  {
+    std::lock_guard<std::mutex> lk(pools_mu_);
+    for (const auto& [id, b] : pools_)
+      rows.push_back({wl + ",pool=\"" + esc(id) + "\",tier=\"" + std::string(to_string(b->get_storage_class())) + "\"", b->get_stats(), b->device_copies()});
+  }
+  auto series = [&](const char* name, const char* type, const char* help, auto value) {
+    family(name, type, help);
+    for (const Row& r : rows) {
+      out += name;
+      out += '{' + r.labels + "} " + value(r) + "\n";
+    }
+  };
+  series("bb_pool_capacity_bytes", "gauge", "pool capacity", [](const Row& r) { return std::to_string(r.s.total_capacity); });
+  // placement is decided by the Keystone's allocator (its /metrics has the per-tier used bytes); this is the part
+  // handed out through the worker-side reserve / commit protocol
+  series("bb_pool_reserved_bytes", "gauge", "bytes reserved or committed through the worker-side reservation protocol",
+         [](const Row& r) { return std::to_string(r.s.used_capacity); });
+  series("bb_pool_reservations", "gauge", "uncommitted reservations", [](const Row& r) { return std::to_string(r.s.num_reservations); });
+  series("bb_pool_committed_shards", "gauge", "committed shards", [](const Row& r) { return std::to_string(r.s.num_committed_shards); });
+  series("bb_pool_fragmentation_ratio", "gauge", "1 - largest free block / free bytes", [](const Row& r) { return std::to_string(r.s.fragmentation); });
+  series("bb_pool_bytes_written_total", "counter", "bytes written into the pool", [](const Row& r) { return std::to_string(r.s.bytes_written); });
+  series("bb_pool_bytes_read_total", "counter", "bytes read out of the pool", [](const Row& r) { return std::to_string(r.s.bytes_read); });
+  series("bb_pool_io_errors_total", "counter", "failed reads / writes", [](const Row& r) { return std::to_string(r.s.io_errors); });
+  series("bb_pool_fused_tier_moves_total", "counter", "tier moves executed as one fused-kernel launch", [](const Row& r) { return std::to_string(r.device_copies); });
+  return out;
 }
 
 // ================================================================ data server

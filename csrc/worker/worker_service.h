@@ -56,6 +56,8 @@ struct WorkerServiceConfig {
   int64_t lease_ttl_sec = 10;
   int64_t heartbeat_interval_sec = 5;
   std::string fabric_domain;        // e.g. "nvswitch-0"
+  // HTTP port of the worker's own observability endpoint (/metrics, /healthz, /stats); -1 = disabled, 0 = ephemeral.
+  int http_metrics_port = -1;
   CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects
   bool has_transport = false;
   std::vector<TierRule> preferred_tiers;  // `allocation.preferred_tiers` (forwarded to the keystone as a hint)
@@ -86,6 +88,10 @@ class WorkerService {
   bool is_running() const { return running_.load(); }
 
   Json get_stats() const;
+  // Prometheus text exposition of the per-pool counters (capacity / used / reservations / bytes moved / I/O errors /
+  // fused tier moves) and of the data server; served on /metrics when `http_metrics_port` >= 0.
+  std::string metrics_text() const;
+  uint16_t http_port() const { return http_server_.port(); }
   StorageBackend* backend(const std::string& pool_id);
   std::vector<MemoryPool> advertised_pools() const;
   uint16_t data_port() const { return data_server_.port(); }
@@ -112,6 +118,7 @@ class WorkerService {
   std::map<std::string, StoragePoolConfig> pool_cfg_;
   std::map<std::string, std::string> pool_rkey_hex_;
   net::RpcServer data_server_;
+  net::HttpServer http_server_;
   std::atomic<bool> running_{false};
   std::atomic<bool> initialized_{false};
   std::atomic<bool> drop_heartbeat_{false};

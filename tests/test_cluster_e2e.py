@@ -389,3 +389,33 @@ def test_large_objects_take_the_multi_stream_bulk_path(bb, algo_name):
         w.backend(sh.pool_id).write(sh.location["remote_addr"] - pool.ucx_remote_addr + (33 << 20), b"\x00\x01\x02\x03")
         with pytest.raises(Exception):
             cl.get("big")
+
+
+def test_worker_serves_its_own_prometheus_endpoint(bb):
+    """Workers expose per-pool capacity / usage / traffic counters on /metrics (plus /healthz, /stats) when
+    `http_metrics_port` is set -- the Keystone's endpoint only has the cluster-wide view."""
+    with LocalCluster(cluster_id="wmetrics", n_workers=0) as c:
+        wc = bb.WorkerServiceConfig()
+        wc.worker_id, wc.node_id, wc.cluster_id = "wm", "node-wm", "wmetrics"
+        wc.ucx_endpoint = "127.0.0.1:0"
+        wc.http_metrics_port = 0  # ephemeral
+        wc.storage_pools = [bb.StoragePoolConfig("ram-wm", bb.StorageClass.RAM_CPU, 32 << 20, "")]
+        w = bb.WorkerService(wc, bb.CoordService(c.coord_uri))
+        assert w.create_storage_pools_from_config() == bb.ErrorCode.OK and w.initialize() == bb.ErrorCode.OK and w.start() == bb.ErrorCode.OK
+        c.workers.append(w)
+        c.coord.store().flush_events()
+        cl = c.client()
+        data = os.urandom(100_000)
+        assert cl.put("m", data, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        assert cl.get("m") == data
+        status, text = bb.http_get("127.0.0.1", w.http_port, "/metrics")
+        assert status == 200 and text == w.metrics_text() or "bb_pool_bytes_written_total" in text
+        lines = {ln.split(" ")[0]: ln.split(" ")[1] for ln in text.splitlines() if ln and not ln.startswith("#")}
+        lab = 'worker="wm",node="node-wm",pool="ram-wm",tier="RAM_CPU"'
+        assert lines[f"bb_pool_capacity_bytes{{{lab}}}"] == str(32 << 20)
+        assert int(lines[f"bb_pool_bytes_written_total{{{lab}}}"]) >= len(data) and int(lines[f"bb_pool_bytes_read_total{{{lab}}}"]) >= len(data)
+        assert f"bb_pool_reserved_bytes{{{lab}}}" in lines and lines['bb_worker_up{worker="wm",node="node-wm"}'] == "1"
+        assert bb.http_get("127.0.0.1", w.http_port, "/healthz")[0] == 200
+        import json as _json
+        st = _json.loads(bb.http_get("127.0.0.1", w.http_port, "/stats")[1])
+        assert st["worker_id"] == "wm" and st["pools"][0]["pool_id"] == "ram-wm"
