@@ -58,7 +58,11 @@ BlackbirdClient::BlackbirdClient(std::shared_ptr<rpc::KeystoneApi> keystone, Bla
     : opts_(std::move(opts)), keystone_(std::move(keystone)) {
   if (keystone_) keystone_->set_identity(session_id_, opts_.node_id);
 }
-BlackbirdClient::~BlackbirdClient() = default;
+BlackbirdClient::~BlackbirdClient() {
+  std::lock_guard<std::mutex> lk(shm_mu_);
+  for (auto& [id, p] : shm_pools_) worker::unmap_shared_pool(p.base, p.size);
+  shm_pools_.clear();
+}
 
 ErrorCode BlackbirdClient::connect() {
   if (!keystone_) {
@@ -192,7 +196,101 @@ class RangeHasher {
 };
 }  // namespace
 
+uint8_t* BlackbirdClient::shm_resolve(const ShardPlacement& s) {
+  static const bool env_off = [] { const char* e = std::getenv("BB_DISABLE_SHM"); return e && *e && *e != '0'; }();
+  if (!opts_.enable_shm || env_off || s.storage_class != StorageClass::RAM_CPU) return nullptr;
+  const auto* loc = std::get_if<MemoryLocation>(&s.location);
+  const auto& key = s.endpoint.worker_key;
+  if (!loc || key.size() <= 5 || std::memcmp(key.data(), "file:", 5) != 0) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(shm_mu_);
+    auto it = shm_pools_.find(s.pool_id);
+    if (it != shm_pools_.end()) {
+      if (it->second.key == key) {
+        const ShmPool& p = it->second;
+        if (loc->remote_addr < p.remote_base || loc->remote_addr - p.remote_base + s.length > p.size) return nullptr;
+        return p.base + (loc->remote_addr - p.remote_base);
+      }
+      worker::unmap_shared_pool(it->second.base, it->second.size);  // the worker restarted: new memfd, new key
+      shm_pools_.erase(it);
+    }
+    auto un = shm_unreachable_.find(s.pool_id);
+    if (un != shm_unreachable_.end() && un->second == key) return nullptr;
+  }
+  // first shard in this pool: learn its geometry from the registry, then map it
+  ShmPool p;
+  auto pools = keystone_->get_memory_pools();
+  if (pools.ok())
+    for (const auto& mp : pools.value())
+      if (mp.id == s.pool_id) {
+        p.size = mp.size;
+        p.remote_base = mp.ucx_remote_addr ? mp.ucx_remote_addr : mp.base_addr;
+      }
+  if (p.size) p.base = static_cast<uint8_t*>(worker::map_shared_pool(key, p.size));
+  std::lock_guard<std::mutex> lk(shm_mu_);
+  if (!p.base) {  // other host / pid namespace / user: stay on the data server
+    shm_unreachable_[s.pool_id] = key;
+    return nullptr;
+  }
+  p.key = key;
+  auto [it, fresh] = shm_pools_.emplace(s.pool_id, p);
+  if (!fresh) worker::unmap_shared_pool(p.base, p.size);  // another thread mapped it first
+  else metrics_.inc("shm_pools_mapped_total");
+  const ShmPool& q = it->second;
+  if (loc->remote_addr < q.remote_base || loc->remote_addr - q.remote_base + s.length > q.size) return nullptr;
+  return q.base + (loc->remote_addr - q.remote_base);
+}
+
+namespace {
+// memcpy of a shard as up to `par` tile-aligned ranges on their own threads, each hashed while it is hot in cache.
+struct ShmPart {
+  uint32_t crc = 0;
+  uint64_t len = 0;
+  uint64_t bbh = 0;
+};
+uint64_t shm_copy(uint8_t* dst, const uint8_t* src, const uint8_t* hash_base, uint64_t len, size_t par, ChecksumAlgo algo) {
+  if (algo == ChecksumAlgo::NONE) par = 1;  // a bare memcpy already runs at memory speed; threads only help the hashing
+  std::vector<ShmPart> parts(std::max<size_t>(1, par));
+  for_each_stream(len, par, [&](uint64_t begin, uint64_t n, size_t idx) -> ErrorCode {
+    ShmPart& part = parts[idx];
+    part.len = n;
+    constexpr uint64_t kStep = 1ull << 20;  // copy + hash in cache-sized steps (multiple of the BBH64 tile)
+    for (uint64_t o = begin; o < begin + n; o += kStep) {
+      const uint64_t m = std::min(kStep, begin + n - o);
+      std::memcpy(dst + o, src + o, m);
+      if (algo == ChecksumAlgo::CRC32C) part.crc = crc32c(hash_base + o, m, part.crc);
+      else if (algo == ChecksumAlgo::BBH64)
+        part.bbh += bbh64_partial(hash_base, len, o / tchash::kTileBytes, (m + tchash::kTileBytes - 1) / tchash::kTileBytes);
+    }
+    return ErrorCode::OK;
+  });
+  if (algo == ChecksumAlgo::CRC32C) {
+    uint32_t crc = 0;
+    bool first = true;
+    for (const ShmPart& p : parts) {
+      if (p.len == 0 && !first) continue;
+      crc = first ? p.crc : crc32c_combine(crc, p.crc, p.len);
+      first = false;
+    }
+    return crc;
+  }
+  if (algo == ChecksumAlgo::BBH64) {
+    uint64_t sum = 0;
+    for (const ShmPart& p : parts) sum += p.bbh;
+    return bbh64_finalize(sum, len);
+  }
+  return 0;
+}
+}  // namespace
+
 ErrorCode BlackbirdClient::write_shard(const ShardPlacement& s, const uint8_t* src, uint64_t* digest, ChecksumAlgo algo) {
+  if (uint8_t* mapped = shm_resolve(s)) {  // same host: one-sided write into the worker's pool
+    const uint64_t d = shm_copy(mapped, src, src, s.length, opts_.io_parallelism, algo);
+    if (digest) *digest = d;
+    metrics_.inc("shm_put_shards_total");
+    metrics_.inc("shm_put_bytes_total", s.length);
+    return ErrorCode::OK;
+  }
   const std::string ep = s.endpoint.ip + ":" + std::to_string(s.endpoint.port);
   uint64_t base_off = shard_offset(s);
   bool absolute = false;
@@ -258,6 +356,17 @@ ErrorCode BlackbirdClient::write_shard(const ShardPlacement& s, const uint8_t* s
 }
 
 ErrorCode BlackbirdClient::read_shard(const ShardPlacement& s, uint8_t* dst, ChecksumAlgo algo) {
+  if (const uint8_t* mapped = shm_resolve(s)) {  // same host: one-sided read out of the worker's pool
+    const bool check = algo != ChecksumAlgo::NONE && s.checksum_algo == algo;
+    const uint64_t got = shm_copy(dst, mapped, dst, s.length, opts_.io_parallelism, check ? algo : ChecksumAlgo::NONE);
+    metrics_.inc("shm_get_shards_total");
+    metrics_.inc("shm_get_bytes_total", s.length);
+    if (check && got != s.checksum) {
+      metrics_.inc("checksum_mismatch_total");
+      return ErrorCode::CHECKSUM_MISMATCH;
+    }
+    return ErrorCode::OK;
+  }
   const std::string ep = s.endpoint.ip + ":" + std::to_string(s.endpoint.port);
   uint64_t base_off = shard_offset(s);
   bool absolute = false;

@@ -32,6 +32,10 @@ struct BlackbirdClientOptions {
   size_t io_parallelism = 4;
   std::string node_id;        // where this client runs (locality-aware placement)
   bool register_session = false;
+  // Same-host fast path: DRAM pools that their worker backs with a memfd (`shared_memory: true`) are mapped into this
+  // process and shards are moved with memcpy instead of the TCP data server (the role UCX's shared-memory transports
+  // play for the reference's intra-node RMA).  BB_DISABLE_SHM=1 in the environment also turns it off.
+  bool enable_shm = true;
 };
 
 // One device-side transfer request of a batch (a shard).
@@ -180,6 +184,18 @@ class BlackbirdClient {
   // [begin, end) index ranges that split a batch so that transfers of one chunk overlap the
   // control-plane round trips of its neighbours (large batches only).
   std::vector<std::pair<size_t, size_t>> plan_chunks(const std::vector<size_t>& sizes, double rpc_us_per_object) const;
+
+  // Mapped shared DRAM pools (same-host fast path); a mapping is dropped when the pool re-registers under a new key.
+  struct ShmPool {
+    uint8_t* base = nullptr;
+    uint64_t size = 0;
+    uint64_t remote_base = 0;
+    std::vector<uint8_t> key;
+  };
+  uint8_t* shm_resolve(const ShardPlacement& s);
+  std::mutex shm_mu_;
+  std::map<std::string, ShmPool> shm_pools_;
+  std::map<std::string, std::vector<uint8_t>> shm_unreachable_;  // pool -> key that could not be mapped
 
   BlackbirdClientOptions opts_;
   std::shared_ptr<rpc::KeystoneApi> keystone_;

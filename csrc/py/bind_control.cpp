@@ -858,7 +858,8 @@ void bind_control(py::module_& m) {
       .def_readwrite("keystone_port", &BlackbirdClientOptions::keystone_port)
       .def_readwrite("rpc_timeout_ms", &BlackbirdClientOptions::rpc_timeout_ms)
       .def_readwrite("io_parallelism", &BlackbirdClientOptions::io_parallelism)
-      .def_readwrite("node_id", &BlackbirdClientOptions::node_id);
+      .def_readwrite("node_id", &BlackbirdClientOptions::node_id)
+      .def_readwrite("enable_shm", &BlackbirdClientOptions::enable_shm);
   py::class_<BlackbirdClient, std::shared_ptr<BlackbirdClient>>(m, "BlackbirdClient")
       .def(py::init<BlackbirdClientOptions>(), py::arg("options") = BlackbirdClientOptions{})
       .def(py::init<std::shared_ptr<rpc::KeystoneApi>, BlackbirdClientOptions>(), py::arg("keystone"), py::arg("options") = BlackbirdClientOptions{})

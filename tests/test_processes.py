@@ -334,3 +334,70 @@ storage_pools:
     assert all(e == bb.ErrorCode.OK for e in ecs) and torch.equal(src, out)
     assert fabric.remaps == 1 and fabric.mapped_host_pools() == 1 and fabric.launches == 4
     assert host.get(keys2[2]) == bytes(src[2 * size:3 * size].cpu().numpy())  # the NEW worker process holds the bytes
+
+
+def test_same_host_clients_use_the_shared_memory_fast_path(procs, tmp_path, bb):
+    """A CPU client on the worker's host maps the memfd-backed DRAM pool and moves shards with memcpy (one-sided, like
+    UCX's shm transports for the reference's intra-node RMA): the worker's data server sees no request, digests are
+    still computed / verified, a TCP-only client reads the same bytes, corruption is detected."""
+    cport, rport, hport, wport = free_port(), free_port(), free_port(), free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    procs.spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+                "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "shmcpu")
+    assert wait_port(rport)
+    cfg = tmp_path / "w.yaml"
+    cfg.write_text(f"""
+worker:
+  worker_id: "wf"
+  node_id: "node-wf"
+  http_metrics_port: {wport}
+storage_pools:
+  - pool_id: "dram-wf"
+    storage_class: "RAM_CPU"
+    size_bytes: 256_MB
+    shared_memory: true
+""")
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "shmcpu")
+    assert wait_port(wport)
+    c = bb.BlackbirdClient(bb.BlackbirdClientOptions("127.0.0.1", rport, 30000, 4, "node-wf"))
+    assert c.connect() == bb.ErrorCode.OK
+    deadline = time.time() + 10
+    while time.time() < deadline and c.cluster_stats().total_memory_pools < 1:
+        time.sleep(0.1)
+
+    def served():
+        text = bb.http_get("127.0.0.1", wport, "/metrics")[1]
+        return int([ln for ln in text.splitlines() if ln.startswith("bb_worker_data_requests_total")][0].split()[-1])
+
+    data = os.urandom((24 << 20) + 777)
+    for algo in (bb.ChecksumAlgo.BBH64, bb.ChecksumAlgo.CRC32C):
+        key = f"fast/{int(algo)}"
+        before = served()
+        assert c.put(key, data, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, checksum=algo)) == bb.ErrorCode.OK
+        assert c.get(key) == data
+        assert served() == before  # not a single data-server request
+        sh = c.get_workers(key)[0].shards[0]
+        assert sh.checksum == (bb.bbh64_reference(data) if algo == bb.ChecksumAlgo.BBH64 else bb.crc32c(data))
+    m = c.metrics_text()
+    assert "bb_client_shm_put_bytes_total" in m and "bb_client_shm_get_shards_total 2" in m
+    # a client that may not map (other host in real life) takes the TCP path and sees the same object
+    o = bb.BlackbirdClientOptions("127.0.0.1", rport, 30000, 2, "elsewhere")
+    o.enable_shm = False
+    tcp = bb.BlackbirdClient(o)
+    assert tcp.connect() == bb.ErrorCode.OK
+    before = served()
+    assert tcp.get("fast/2") == data and served() > before
+    # corruption inside the pool is caught by the one-sided read as well
+    sh = c.get_workers("fast/1")[0].shards[0]
+    pool = [p for p in c.keystone().get_memory_pools() if p.id == sh.pool_id][0]
+    bad = bytes([data[5 << 20] ^ 0xFF])
+    assert tcp.keystone() is not None
+    import mmap
+    fd = os.open(bytes.fromhex(pool.ucx_rkey_hex)[5:].decode(), os.O_RDWR)
+    with mmap.mmap(fd, pool.size) as mm:
+        off = sh.location["remote_addr"] - pool.ucx_remote_addr + (5 << 20)
+        mm[off:off + 1] = bad
+    os.close(fd)
+    with pytest.raises(Exception):
+        c.get("fast/1")
