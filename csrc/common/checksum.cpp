@@ -211,31 +211,32 @@ __attribute__((target("avx512f,avx512bw,avx512dq,avx512vl,avx512vnni"))) uint64_
   uint64_t sum = 0;
   for (uint32_t b = 0; b < kRows / 8; ++b) {
     const uint8_t* blk = tile + b * 1024;
-    for (uint32_t mi = 0; mi < 8; mi += 2) {  // two rows per pass share the W' loads
-      __m512i acc0 = _mm512_setzero_si512(), acc1 = _mm512_setzero_si512();
-      __m128i sad0 = _mm_setzero_si128(), sad1 = _mm_setzero_si128();
+    for (uint32_t mi = 0; mi < 8; mi += 4) {  // four rows per pass share the W' loads
+      // two accumulators per row (even / odd K chunk): 8 independent vpdpbusd chains hide the 5-cycle latency
+      __m512i acc[4] = {_mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512()};
+      __m512i acd[4] = {_mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512(), _mm512_setzero_si512()};
+      __m128i sad[4] = {_mm_setzero_si128(), _mm_setzero_si128(), _mm_setzero_si128(), _mm_setzero_si128()};
+#pragma GCC unroll 8
       for (uint32_t kc = 0; kc < 8; ++kc) {
         const uint8_t* c0 = blk + kc * 128 + mi * 16;
-        const uint8_t* c1 = c0 + 16;
-        const __m128i v0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c0));
-        const __m128i v1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c1));
-        sad0 = _mm_add_epi64(sad0, _mm_sad_epu8(v0, _mm_setzero_si128()));
-        sad1 = _mm_add_epi64(sad1, _mm_sad_epu8(v1, _mm_setzero_si128()));
+#pragma GCC unroll 4
+        for (uint32_t r = 0; r < 4; ++r)
+          sad[r] = _mm_add_epi64(sad[r], _mm_sad_epu8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(c0 + 16 * r)), _mm_setzero_si128()));
 #pragma GCC unroll 4
         for (uint32_t j = 0; j < 4; ++j) {
           const __m512i w = _mm512_load_si512(&C.w4[kc * 4 + j][0][0]);
-          int32_t a0, a1;
-          std::memcpy(&a0, c0 + 4 * j, 4);
-          std::memcpy(&a1, c1 + 4 * j, 4);
-          acc0 = _mm512_dpbusd_epi32(acc0, _mm512_set1_epi32(a0), w);
-          acc1 = _mm512_dpbusd_epi32(acc1, _mm512_set1_epi32(a1), w);
+#pragma GCC unroll 4
+          for (uint32_t r = 0; r < 4; ++r) {
+            int32_t a;
+            std::memcpy(&a, c0 + 16 * r + 4 * j, 4);
+            if (kc & 1) acd[r] = _mm512_dpbusd_epi32(acd[r], _mm512_set1_epi32(a), w);
+            else acc[r] = _mm512_dpbusd_epi32(acc[r], _mm512_set1_epi32(a), w);
+          }
         }
       }
-      const __m512i accs[2] = {acc0, acc1};
-      const __m128i sads[2] = {sad0, sad1};
-      for (uint32_t r = 0; r < 2; ++r) {
-        const uint32_t rowsum = static_cast<uint32_t>(_mm_cvtsi128_si64(sads[r]) + _mm_extract_epi64(sads[r], 1));
-        const __m512i d = _mm512_add_epi32(accs[r], _mm512_set1_epi32(static_cast<int32_t>(rowsum * 128u)));  // exact u32 D[m][n]
+      for (uint32_t r = 0; r < 4; ++r) {
+        const uint32_t rowsum = static_cast<uint32_t>(_mm_cvtsi128_si64(sad[r]) + _mm_extract_epi64(sad[r], 1));
+        const __m512i d = _mm512_add_epi32(_mm512_add_epi32(acc[r], acd[r]), _mm512_set1_epi32(static_cast<int32_t>(rowsum * 128u)));  // exact u32 D[m][n]
         const __m512i lo = _mm512_cvtepu32_epi64(_mm512_castsi512_si256(d));
         const __m512i hi = _mm512_cvtepu32_epi64(_mm512_extracti64x4_epi64(d, 1));
         const __m512i pr = _mm512_add_epi64(_mm512_mullo_epi64(lo, kn_lo), _mm512_mullo_epi64(hi, kn_hi));
