@@ -20,6 +20,20 @@ def _free_port():
     return p
 
 
+def _json_objects(text):
+    dec, out, i = json.JSONDecoder(), [], 0
+    while True:
+        i = text.find('{"rank"', i)
+        if i < 0:
+            return out
+        try:
+            obj, end = dec.raw_decode(text, i)
+            out.append(obj)
+            i = end
+        except ValueError:
+            i += 1
+
+
 def test_ring_replication_fanout_and_remote_dram_on_n_gpus():
     import torch
 
@@ -31,5 +45,5 @@ def test_ring_replication_fanout_and_remote_dram_on_n_gpus():
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
-    lines = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
+    lines = _json_objects(r.stdout)  # ranks print concurrently: two objects may share a line
     assert len(lines) == world and all(x["ring"] == "ok" and "remote_dram_pool" in x for x in lines), lines
