@@ -18,9 +18,10 @@
 //                      global atomics; only the <=2 objects straddling a CTA boundary use them.
 //                      Compares with the expected digest on get (CHECKSUM_MISMATCH source).
 //   warps 4-7 epilogue: BBH64: `tcgen05.ld` the 128x16 s32 accumulators -> position-dependent
-//                      64-bit row hashes -> warp sum.  CRC32C: read the tile from smem
-//                      (conflict-free lane-interleaved streams) through x^k shift tables and
-//                      combine lanes with GF(2) shift algebra.
+//                      64-bit row hashes -> warp sum.  CRC32C: each warp streams its 4 KiB quarter of
+//                      the tile as 8 Horner chains per lane through lane-private nibble shift tables
+//                      (bank-conflict free); the chains run on across the tiles of an object and are
+//                      combined (chain / lane / quarter, GF(2) shift algebra) once per object and CTA.
 //
 // Payload bytes never pass through registers on the BBH64 / copy-only unicast path: TMA in,
 // tensor core reads shared memory, TMA out.
