@@ -9,6 +9,7 @@
 #include <random>
 
 #include "apps/cli_util.h"
+#include "net/tcp.h"
 #include "client/blackbird_client.h"
 #include "common/log.h"
 
@@ -27,6 +28,7 @@ const char* name(ErrorCode ec) {
 
 int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
+  if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.positional.empty() || args.has("help")) {
     std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | stats | smoke | metrics --http host:port>\n");
     return args.has("help") ? 0 : 2;

@@ -6,11 +6,13 @@
 #include <thread>
 
 #include "apps/cli_util.h"
+#include "net/tcp.h"
 #include "common/log.h"
 #include "coord/coord.h"
 
 int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
+  if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("help")) {
     std::printf("usage: bb-coord [--listen host:port] [--log-level info]\n");
     return 0;

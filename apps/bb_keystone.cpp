@@ -7,11 +7,13 @@
 #include <thread>
 
 #include "apps/cli_util.h"
+#include "net/tcp.h"
 #include "common/log.h"
 #include "rpc/rpc_service.h"
 
 int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
+  if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("help")) {
     std::printf("usage: bb-keystone [config.yaml] [--etcd-endpoints E] [--listen-address A] [--http-port P] [--cluster-id C] [--enable-ha] [--service-id S]\n");
     return 0;
@@ -28,6 +30,7 @@ int main(int argc, char** argv) {
   if (const char* e = std::getenv("BB_COORD_ENDPOINTS")) cfg.etcd_endpoints = e;
   if (args.has("etcd-endpoints")) cfg.etcd_endpoints = args.get("etcd-endpoints");
   if (args.has("coord-endpoints")) cfg.etcd_endpoints = args.get("coord-endpoints");
+  if (!args.has("auth-token") && !cfg.auth_token.empty()) bb::net::set_cluster_token(cfg.auth_token);  // before the coordination client connects
   if (args.has("listen-address")) cfg.listen_address = args.get("listen-address");
   if (args.has("http-port")) cfg.http_metrics_port = args.get("http-port");
   if (args.has("cluster-id")) cfg.cluster_id = args.get("cluster-id");

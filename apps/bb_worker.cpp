@@ -7,12 +7,14 @@
 #include <thread>
 
 #include "apps/cli_util.h"
+#include "net/tcp.h"
 #include "common/log.h"
 #include "fabric/gpu_fabric.h"
 #include "worker/worker_service.h"
 
 int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
+  if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("help") || (!args.has("config") && args.positional.empty())) {
     std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port] [--http-port P]\n");
     return args.has("help") ? 0 : 2;
@@ -25,6 +27,8 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "bb-worker: %s\n", e.what());
     return 2;
   }
+  if (!args.has("auth-token") && !cfg.auth_token.empty()) bb::net::set_cluster_token(cfg.auth_token);  // before any connection is made
+  if (args.has("auth-token")) cfg.auth_token = args.get("auth-token");
   if (args.has("worker-id")) cfg.worker_id = args.get("worker-id");
   if (args.has("node-id")) cfg.node_id = args.get("node-id");
   if (const char* e = std::getenv("BB_COORD_ENDPOINTS")) cfg.etcd_endpoints = e;

@@ -65,6 +65,7 @@ BlackbirdClient::~BlackbirdClient() {
 }
 
 ErrorCode BlackbirdClient::connect() {
+  if (!opts_.auth_token.empty()) net::set_cluster_token(opts_.auth_token);
   if (!keystone_) {
     auto c = std::make_shared<rpc::KeystoneRpcClient>();
     c->set_timeout_ms(opts_.rpc_timeout_ms);

@@ -36,6 +36,7 @@ struct BlackbirdClientOptions {
   // process and shards are moved with memcpy instead of the TCP data server (the role UCX's shared-memory transports
   // play for the reference's intra-node RMA).  BB_DISABLE_SHM=1 in the environment also turns it off.
   bool enable_shm = true;
+  std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
 };
 
 // One device-side transfer request of a batch (a shard).

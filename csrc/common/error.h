@@ -85,6 +85,7 @@ enum class ErrorCode : uint32_t {
   CLIENT_DISCONNECTED,
   SESSION_EXPIRED,
   INVALID_CLIENT_STATE,
+  ACCESS_DENIED,  // the peer did not present the cluster token (net/tcp.h)
   // CONFIG
   CONFIG_ERROR = 7000,
   INVALID_CONFIGURATION,

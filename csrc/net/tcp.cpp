@@ -23,6 +23,31 @@
 namespace bb::net {
 
 namespace {
+std::mutex g_token_mu;
+std::string g_token;
+bool g_token_init = false;
+}  // namespace
+
+void set_cluster_token(const std::string& token) {
+  std::lock_guard<std::mutex> lk(g_token_mu);
+  g_token = token;
+  g_token_init = true;
+}
+std::string cluster_token() {
+  std::lock_guard<std::mutex> lk(g_token_mu);
+  if (!g_token_init) {
+    if (const char* e = std::getenv("BB_AUTH_TOKEN")) g_token = e;
+    g_token_init = true;
+  }
+  return g_token;
+}
+
+namespace {
+bool token_equal(std::string_view a, const std::string& b) {  // constant time in the length of `a`
+  unsigned char diff = a.size() == b.size() ? 0 : 1;
+  for (size_t i = 0; i < a.size(); ++i) diff |= static_cast<unsigned char>(a[i]) ^ static_cast<unsigned char>(b[i % std::max<size_t>(1, b.size())]);
+  return diff == 0 && !b.empty();
+}
 void set_nodelay(int fd) {
   int one = 1;
   ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
@@ -514,6 +539,25 @@ bool RpcServer::on_data(const ConnPtr& c) {
     const uint64_t id = rd64(&in[pos + 8]);
     const size_t body = pos + kFrameHeader;
     pos += kFrameHeader + len;
+    if (!c->authed()) {
+      const std::string token = cluster_token();
+      if (method == kAuthMethod) {
+        if (token.empty() || token_equal(std::string_view(in.data() + body, len), token)) {
+          c->set_authed();
+          if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;
+          continue;
+        }
+        BB_LOG(WARNING) << "rpc: wrong cluster token from " << c->peer();
+        c->send(encode_frame(kDeniedMarker, id, std::string()));
+        return false;
+      }
+      if (!token.empty()) {
+        BB_LOG(WARNING) << "rpc: request without the cluster token from " << c->peer();
+        c->send(encode_frame(kDeniedMarker, id, std::string()));
+        return false;
+      }
+      c->set_authed();  // open cluster
+    }
     std::string resp;
     Reply reply;
     uint32_t rmethod = method;
@@ -558,6 +602,22 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
   if (fd < 0) {
     BB_VLOG(1) << "RpcClient: connect " << host << ":" << port << " failed: " << err;
     return ErrorCode::CONNECTION_FAILED;
+  }
+  const std::string token = cluster_token();
+  if (!token.empty()) {  // present the cluster token before anything else
+    const std::string f = encode_frame(kAuthMethod, 0, token);
+    char rh[kFrameHeader];
+    if (!send_all(fd, f.data(), f.size(), timeout_ms) || !recv_all(fd, rh, sizeof rh, timeout_ms)) {
+      ::close(fd);
+      return ErrorCode::CONNECTION_FAILED;
+    }
+    const uint32_t rlen = rd32(rh), rmethod = rd32(rh + 4);
+    std::string drop(rlen <= 4096 ? rlen : 0, '\0');
+    if (rlen > 4096 || (rlen && !recv_all(fd, drop.data(), rlen, timeout_ms)) || rmethod == kDeniedMarker) {
+      ::close(fd);
+      return rmethod == kDeniedMarker ? ErrorCode::ACCESS_DENIED : ErrorCode::CONNECTION_FAILED;
+    }
+    // kAuthMethod = accepted; the unknown-method marker = a server without a token (open cluster): both fine
   }
   std::lock_guard<std::mutex> lk(mu_);
   fd_ = fd;
@@ -649,6 +709,7 @@ Result<std::string> RpcClient::call(uint32_t method, const std::string& request,
   }
   if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
   if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
   return payload;
 }
 
@@ -685,6 +746,7 @@ Result<std::string> RpcClient::call_gather(uint32_t method, const std::string& h
   }
   if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
   if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
   return payload;
 }
 
@@ -727,6 +789,7 @@ Result<std::string> RpcClient::call_scatter(uint32_t method, const std::string& 
   if (received) *received = rest;
   if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
   if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
   return head;
 }
 

@@ -31,6 +31,16 @@ bool recv_all(int fd, void* data, size_t len, int timeout_ms = 30000);
 
 class TcpServer;
 
+// Shared-secret gate for the framed RPC protocol (the reference lists mTLS / ACL as roadmap, README.md:146-153; its
+// servers accept every connection).  When a cluster token is set -- `auth_token:` in keystone / worker YAML,
+// BlackbirdClientOptions::auth_token, or BB_AUTH_TOKEN in the environment of every process -- an RpcServer started in
+// this process answers nothing on a connection until its first frame presents the token (kAuthMethod), and every
+// RpcClient presents it right after connecting.  HTTP endpoints (/metrics, /healthz) stay open.
+void set_cluster_token(const std::string& token);
+std::string cluster_token();
+constexpr uint32_t kAuthMethod = 0x7FFFFF00u;
+constexpr uint32_t kDeniedMarker = 0x7FFFFFFDu;
+
 class Connection : public std::enable_shared_from_this<Connection> {
  public:
   Connection(int fd, uint64_t id, std::string peer) : fd_(fd), id_(id), peer_(std::move(peer)) {}
@@ -49,6 +59,8 @@ class Connection : public std::enable_shared_from_this<Connection> {
   uint64_t id() const { return id_; }
   const std::string& peer() const { return peer_; }
   std::string& inbuf() { return inbuf_; }
+  bool authed() const { return authed_.load(std::memory_order_acquire); }
+  void set_authed() { authed_.store(true, std::memory_order_release); }
   // EPOLLONESHOT hands a connection from one pool thread to the next through the kernel; these make the
   // hand-off an explicit release/acquire pair on the connection's own state as well.
   void release_ownership() { handoff_.fetch_add(1, std::memory_order_release); }
@@ -65,6 +77,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::string inbuf_;
   std::mutex write_mu_;
   std::atomic<bool> closed_{false};
+  std::atomic<bool> authed_{false};
   std::atomic<uint64_t> handoff_{0};
 };
 using ConnPtr = std::shared_ptr<Connection>;

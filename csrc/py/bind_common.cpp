@@ -91,6 +91,7 @@ void bind_common(py::module_& m) {
       .value("CLIENT_DISCONNECTED", ErrorCode::CLIENT_DISCONNECTED)
       .value("SESSION_EXPIRED", ErrorCode::SESSION_EXPIRED)
       .value("INVALID_CLIENT_STATE", ErrorCode::INVALID_CLIENT_STATE)
+      .value("ACCESS_DENIED", ErrorCode::ACCESS_DENIED)
       .value("CONFIG_ERROR", ErrorCode::CONFIG_ERROR)
       .value("INVALID_CONFIGURATION", ErrorCode::INVALID_CONFIGURATION)
       .value("INVALID_PARAMETERS", ErrorCode::INVALID_PARAMETERS)

@@ -726,6 +726,8 @@ void bind_control(py::module_& m) {
     return out;
   });
   m.def("io_uring_supported", &worker::IoUring::supported);
+  m.def("set_cluster_token", &net::set_cluster_token, "shared-secret gate of the RPC servers / clients of this process (net/tcp.h)");
+  m.def("cluster_token", &net::cluster_token);
 
   // CXL transport / pool configuration (reference include/blackbird/transport/cxl_transport_config.h)
   py::enum_<CxlInterconnectType>(m, "CxlInterconnectType")
@@ -859,7 +861,8 @@ void bind_control(py::module_& m) {
       .def_readwrite("rpc_timeout_ms", &BlackbirdClientOptions::rpc_timeout_ms)
       .def_readwrite("io_parallelism", &BlackbirdClientOptions::io_parallelism)
       .def_readwrite("node_id", &BlackbirdClientOptions::node_id)
-      .def_readwrite("enable_shm", &BlackbirdClientOptions::enable_shm);
+      .def_readwrite("enable_shm", &BlackbirdClientOptions::enable_shm)
+      .def_readwrite("auth_token", &BlackbirdClientOptions::auth_token);
   py::class_<BlackbirdClient, std::shared_ptr<BlackbirdClient>>(m, "BlackbirdClient")
       .def(py::init<BlackbirdClientOptions>(), py::arg("options") = BlackbirdClientOptions{})
       .def(py::init<std::shared_ptr<rpc::KeystoneApi>, BlackbirdClientOptions>(), py::arg("keystone"), py::arg("options") = BlackbirdClientOptions{})

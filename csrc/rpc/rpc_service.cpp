@@ -273,6 +273,7 @@ ErrorCode RpcService::start() {
   auto hp = split_host_port(config_.listen_address);
   if (!hp) return ErrorCode::INVALID_ADDRESS;
   if (config_.rpc_busy_poll_us > 0) rpc_.set_busy_poll_us(config_.rpc_busy_poll_us);
+  if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   ErrorCode ec = rpc_.start(hp->first, static_cast<uint16_t>(hp->second), std::max(1, config_.rpc_threads));
   if (ec != ErrorCode::OK) return ec;
   if (!config_.http_metrics_port.empty() && config_.http_metrics_port != "off") {

@@ -34,6 +34,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("keystone_address")) c.keystone_address = w.at("keystone_address").as_string();
   if (w.contains("rpc_endpoint")) c.rpc_endpoint = w.at("rpc_endpoint").as_string();
   if (w.contains("http_metrics_port")) c.http_metrics_port = static_cast<int>(w.at("http_metrics_port").as_int(-1));
+  if (w.contains("auth_token")) c.auth_token = w.at("auth_token").as_string();
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
   if (w.contains("interconnects")) {
@@ -162,6 +163,7 @@ ErrorCode WorkerService::initialize() {
   }
   auto hp = split_host_port(config_.ucx_endpoint);
   if (!hp) return ErrorCode::INVALID_ADDRESS;
+  if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   data_server_.set_socket_buffers(4 << 20);  // bulk transfers: fewer wake-ups per megabyte
   const unsigned hw = std::thread::hardware_concurrency();
   ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), static_cast<int>(std::min(16u, std::max(4u, hw / 2))));

@@ -401,3 +401,69 @@ storage_pools:
     os.close(fd)
     with pytest.raises(Exception):
         c.get("fast/1")
+
+
+def test_cluster_token_gates_every_rpc_server(procs, tmp_path, bb):
+    """With a cluster token (BB_AUTH_TOKEN / --auth-token / auth_token: in the YAMLs) bb-coord, bb-keystone and the
+    worker's data server answer nothing until a connection presents it: tools with the token work end to end, tools
+    without it (or with a wrong one) are refused with ACCESS_DENIED, raw frames get the denial marker and a close."""
+    import struct
+
+    env_ok = dict(os.environ, BB_AUTH_TOKEN="s3cret-cluster-token")
+    cport, rport, hport = free_port(), free_port(), free_port()
+
+    def spawn(*cmd):
+        p = subprocess.Popen(list(cmd), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env_ok)
+        procs.procs.append(p)
+        return p
+
+    spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+          "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "authc")
+    assert wait_port(rport)
+    cfg = tmp_path / "w.yaml"
+    write_worker_cfg(cfg, "wa", tmp_path / "nvme")
+    spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "authc")
+    ks = f"127.0.0.1:{rport}"
+
+    def cli(env, *args):
+        return subprocess.run([os.path.join(BIN, "bb-cli"), *args], capture_output=True, text=True, timeout=30, env=env)
+
+    deadline = time.time() + 10
+    while time.time() < deadline:
+        st = cli(env_ok, "--keystone", ks, "stats")
+        if st.returncode == 0 and json.loads(st.stdout)["total_memory_pools"] == 2:
+            break
+        time.sleep(0.1)
+    assert st.returncode == 0 and json.loads(st.stdout)["total_workers"] == 1, st.stdout + st.stderr
+    r = cli(env_ok, "--keystone", ks, "smoke", "--size", "4096")
+    assert r.returncode == 0 and "verify PASS" in r.stdout, r.stdout + r.stderr
+    # the flag works like the environment variable
+    env_none = {k: v for k, v in os.environ.items() if k != "BB_AUTH_TOKEN"}
+    assert cli(env_none, "--keystone", ks, "--auth-token", "s3cret-cluster-token", "stats").returncode == 0
+    for env, extra in ((env_none, []), (env_none, ["--auth-token", "wrong"]), (dict(os.environ, BB_AUTH_TOKEN="nope"), [])):
+        bad = cli(env, "--keystone", ks, *extra, "stats")
+        assert bad.returncode != 0, bad.stdout
+    # raw frames: a put_start without the token is answered with the denial marker, then the server hangs up
+    for port in (rport, cport):
+        s = socket.create_connection(("127.0.0.1", port), 2.0)
+        s.settimeout(2.0)
+        s.sendall(struct.pack("<IIQ", 0, 8, 1))  # get_cluster_stats, empty payload
+        hdr = s.recv(16)
+        assert len(hdr) == 16 and struct.unpack("<IIQ", hdr)[1] == 0x7FFFFFFD
+        assert s.recv(16) == b""
+        s.close()
+    # the metrics endpoint stays open (read-only)
+    assert cli(env_none, "metrics", "--http", f"127.0.0.1:{hport}").returncode == 0
+    # a Python client with the token in its options
+    o = bb.BlackbirdClientOptions("127.0.0.1", rport, 30000, 2, "node-wa")
+    o.auth_token = "s3cret-cluster-token"
+    try:
+        c = bb.BlackbirdClient(o)
+        assert c.connect() == bb.ErrorCode.OK
+        data = os.urandom(50_000)
+        assert c.put("authed", data, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        assert c.get("authed") == data
+    finally:
+        bb.set_cluster_token("")  # process-wide: do not leak into the other tests
