@@ -16,8 +16,8 @@
 // here -- in the packed object its hash tile also contains the first scale bytes, so the slice the host hashes simply
 // starts at the last whole payload tile.
 //
-// Warp roles (16 warps): 0 producer, 1 MMA issuer, 2 store, 3 accumulator, 4-7 epilogue (TMEM -> row hashes),
-// 8-15 convert (pack / unpack).  Two shared-memory rings: 3 x 32 KiB bf16 tiles and 6 x (16 KiB payload + 512 B scales).
+// Warp roles (24 warps): 0 producer, 1 MMA issuer, 2 store, 3 accumulator, 4-7 epilogue (TMEM -> row hashes),
+// 8-23 convert (pack / unpack).  Two shared-memory rings: 3 x 32 KiB bf16 tiles and 6 x (16 KiB payload + 512 B scales).
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
@@ -36,8 +36,8 @@ using namespace bb::ptx;
 
 constexpr int kWideStages = 3;              // ring of 32 KiB bf16 tiles
 constexpr int kTileStages = 6;              // ring of 16 KiB payload tiles (+ 512 B scales)
-constexpr int kFpThreads = 512;
-constexpr int kConvertWarps = 8;            // warps 8..15
+constexpr int kConvertWarps = 16;           // warps 8..23 (the pack side is ALU bound: ncu issue-active 51 % with 8)
+constexpr int kFpThreads = (8 + kConvertWarps) * 32;
 constexpr uint32_t kWideBytes = 2 * kTileBytes;  // bf16 side of one payload tile
 constexpr uint32_t kScaleBytes = kTileBytes / 32;
 constexpr uint32_t kFpTmemCols = 128;       // >= kTileStages * 16 accumulator columns (power of two)
@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
     }
   } else {
     // ================================================================ convert warps 8..15
-    const uint32_t cw = warp - 8;  // 0..7: chunks [cw*256, cw*256+256) of the tile's 2048 16-byte bf16 chunks
+    const uint32_t cw = warp - 8;  // convert warp: chunks [cw*kPer, (cw+1)*kPer) of the tile's 2048 16-byte bf16 chunks
+    constexpr uint32_t kPer = 2048 / kConvertWarps;
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint32_t ts = it % kTileStages, tp = (it / kTileStages) & 1u;
       const uint32_t ws = it % kWideStages, wp = (it / kWideStages) & 1u;
@@ -386,8 +387,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         const uint2* pay = reinterpret_cast<const uint2*>(s.tile[ts]);
         uint4* out = reinterpret_cast<uint4*>(s.wide[ws]);
 #pragma unroll 4
-        for (uint32_t k = 0; k < 8; ++k) {
-          const uint32_t c = cw * 256 + k * 32 + lane;
+        for (uint32_t k = 0; k < kPer / 32; ++k) {
+          const uint32_t c = cw * kPer + k * 32 + lane;
           out[c] = unpack_chunk(pay[c], s.scales[ts][c >> 2]);
         }
         if (cw == 0 && lane < 4) reinterpret_cast<uint4*>(&s.w_meta[ws])[lane] = reinterpret_cast<const uint4*>(&s.t_meta[ts])[lane];
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) bb_xfer_fp8_kernel(const __grid
         const uint4* in = reinterpret_cast<const uint4*>(s.wide[ws]);
         uint2* pay = reinterpret_cast<uint2*>(s.tile[ts]);
 #pragma unroll 4
-        for (uint32_t k = 0; k < 8; ++k) {
-          const uint32_t c = cw * 256 + k * 32 + lane;
+        for (uint32_t k = 0; k < kPer / 32; ++k) {
+          const uint32_t c = cw * kPer + k * 32 + lane;
           pack_chunk(in[c], &pay[c], &s.scales[ts][c >> 2], (c & 3u) == 0);
         }
         if (cw == 0 && lane < 4) reinterpret_cast<uint4*>(&s.t_meta[ts])[lane] = reinterpret_cast<const uint4*>(&s.w_meta[ws])[lane];
