@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | stats | smoke | metrics --http host:port>\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | migrate KEY CLASS | stats | pools | workers | remove-worker ID | smoke | metrics --http host:port> [--auth-token T]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -125,6 +125,29 @@ int main(int argc, char** argv) {
     for (const auto& p : pools.value()) arr.push_back(to_json(p));
     std::printf("%s\n", arr.dump(2).c_str());
     return 0;
+  }
+  if (cmd == "workers") {  // admin introspection: registered workers, heartbeat age, their pools
+    auto ws = cl.keystone().get_workers_info();
+    if (!ws.ok()) return 1;
+    Json arr = Json::array();
+    for (const auto& w : ws.value()) {
+      Json j = Json::object();
+      j["worker_id"] = w.worker_id;
+      j["node_id"] = w.node_id;
+      j["endpoint"] = w.endpoint;
+      j["heartbeat_age_ms"] = static_cast<int64_t>(w.heartbeat_age_ms);
+      Json ps = Json::array();
+      for (const auto& p : w.pools) ps.push_back(p);
+      j["pools"] = ps;
+      arr.push_back(j);
+    }
+    std::printf("%s\n", arr.dump(2).c_str());
+    return 0;
+  }
+  if (cmd == "remove-worker" && args.positional.size() >= 2) {  // decommission: copies there are invalidated and re-replicated
+    ec = cl.keystone().remove_worker(args.positional[1]);
+    std::printf("remove-worker %s: %s\n", args.positional[1].c_str(), name(ec));
+    return ec == ErrorCode::OK ? 0 : 1;
   }
   if (cmd == "where" && args.positional.size() >= 2) {  // placement of an object: copy -> shards (pool, worker, tier, digest)
     auto copies = cl.get_workers(args.positional[1]);

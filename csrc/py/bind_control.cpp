@@ -605,6 +605,20 @@ void bind_control(py::module_& m) {
       .def("batch_put_cancel", &rpc::KeystoneApi::batch_put_cancel)
       .def("batch_remove_object", &rpc::KeystoneApi::batch_remove_object)
       .def("get_memory_pools", [](rpc::KeystoneApi& k) { return unwrap(k.get_memory_pools()); })
+      .def("get_workers_info", [](rpc::KeystoneApi& k) {
+        py::list out;
+        for (const auto& w : unwrap(k.get_workers_info())) {
+          py::dict d;
+          d["worker_id"] = w.worker_id;
+          d["node_id"] = w.node_id;
+          d["endpoint"] = w.endpoint;
+          d["heartbeat_age_ms"] = w.heartbeat_age_ms;
+          d["pools"] = w.pools;
+          out.append(d);
+        }
+        return out;
+      })
+      .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
       .def("client_register", [](rpc::KeystoneApi& k, const std::string& n) { return unwrap(k.client_register(n)); })
       .def("client_ping", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(k.client_ping(id)); })
       .def("register_memory_pool", &rpc::KeystoneApi::register_memory_pool)

@@ -243,6 +243,23 @@ void RpcService::register_handlers() {
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
     return ec_reply(ks->migrate_object(key, target));
   });
+  rpc_.register_method(M_GET_WORKERS_INFO, [ks](C, S) {
+    std::vector<keystone::WorkerInfo> v;
+    ks->get_workers_info(v);
+    Writer w;
+    w.ec(ErrorCode::OK);
+    w.u32(static_cast<uint32_t>(v.size()));
+    const auto now = Clock::now();
+    for (const auto& wi : v) {
+      w.str(wi.worker_id);
+      w.str(wi.node_id);
+      w.str(wi.endpoint);
+      w.i64(std::chrono::duration_cast<std::chrono::milliseconds>(now - wi.last_heartbeat).count());
+      w.u32(static_cast<uint32_t>(wi.pools.size()));
+      for (const auto& p : wi.pools) w.str(p);
+    }
+    return w.take();
+  });
   rpc_.register_method(M_REMOVE_WORKER, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->remove_worker(r.str()));
@@ -363,6 +380,29 @@ ErrorCode KeystoneRpcClient::migrate_object(const ObjectKey& key, StorageClass t
   w.str(key);
   w.u32(static_cast<uint32_t>(target));
   BB_RPC(M_MIGRATE_OBJECT, w);
+  return rd.ec();
+}
+Result<std::vector<KeystoneApi::WorkerSummary>> KeystoneRpcClient::get_workers_info() {
+  Writer w;
+  BB_RPC(M_GET_WORKERS_INFO, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  std::vector<WorkerSummary> v(rd.count(16));
+  for (auto& ws : v) {
+    ws.worker_id = rd.str();
+    ws.node_id = rd.str();
+    ws.endpoint = rd.str();
+    ws.heartbeat_age_ms = rd.i64();
+    const uint32_t np = rd.count(4);
+    for (uint32_t i = 0; i < np; ++i) ws.pools.push_back(rd.str());
+  }
+  if (!rd.ok()) return ErrorCode::RPC_FAILED;
+  return v;
+}
+ErrorCode KeystoneRpcClient::remove_worker(const WorkerId& id) {
+  Writer w;
+  w.str(id);
+  BB_RPC(M_REMOVE_WORKER, w);
   return rd.ec();
 }
 Result<size_t> KeystoneRpcClient::remove_all_objects() {

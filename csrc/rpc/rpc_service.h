@@ -23,7 +23,7 @@ enum Method : uint32_t {
   M_BATCH_GET_WORKERS, M_BATCH_PUT_START, M_BATCH_PUT_COMPLETE, M_BATCH_PUT_CANCEL,
   M_BATCH_REMOVE_OBJECT, M_CLIENT_REGISTER, M_CLIENT_PING, M_GET_MEMORY_POOLS,
   M_REGISTER_WORKER, M_REGISTER_MEMORY_POOL, M_WORKER_HEARTBEAT, M_REMOVE_WORKER,
-  M_MIGRATE_OBJECT,
+  M_MIGRATE_OBJECT, M_GET_WORKERS_INFO,
 };
 
 // The keystone surface a client needs; implemented in-process and over TCP.
@@ -54,6 +54,16 @@ class KeystoneApi {
   virtual ErrorCode worker_heartbeat(const WorkerId& id) = 0;
   // Explicit promotion / demotion of an object to another tier (all copies).
   virtual ErrorCode migrate_object(const ObjectKey& key, StorageClass target) = 0;
+  // Admin introspection / maintenance (reference keystone_service.h:105-165: get_workers_info, remove_worker).
+  struct WorkerSummary {
+    WorkerId worker_id;
+    NodeId node_id;
+    std::string endpoint;
+    int64_t heartbeat_age_ms = 0;
+    std::vector<MemoryPoolId> pools;
+  };
+  virtual Result<std::vector<WorkerSummary>> get_workers_info() = 0;
+  virtual ErrorCode remove_worker(const WorkerId& id) = 0;
   // identity used for locality-aware placement and session ownership
   void set_identity(std::string client_id, std::string node_id) {
     client_id_ = std::move(client_id);
@@ -78,6 +88,16 @@ class LocalKeystoneApi : public KeystoneApi {
   ErrorCode put_cancel(const ObjectKey& key) override { return ks_->put_cancel(key); }
   ErrorCode remove_object(const ObjectKey& key) override { return ks_->remove_object(key); }
   ErrorCode migrate_object(const ObjectKey& key, StorageClass target) override { return ks_->migrate_object(key, target); }
+  Result<std::vector<WorkerSummary>> get_workers_info() override {
+    std::vector<keystone::WorkerInfo> v;
+    ks_->get_workers_info(v);
+    std::vector<WorkerSummary> out;
+    const auto now = Clock::now();
+    for (const auto& w : v)
+      out.push_back({w.worker_id, w.node_id, w.endpoint, std::chrono::duration_cast<std::chrono::milliseconds>(now - w.last_heartbeat).count(), w.pools});
+    return out;
+  }
+  ErrorCode remove_worker(const WorkerId& id) override { return ks_->remove_worker(id); }
   Result<size_t> remove_all_objects() override { return ks_->remove_all_objects(); }
   Result<ClusterStats> get_cluster_stats() override { return ks_->get_cluster_stats(); }
   Result<ViewVersionId> get_view_version() override { return ks_->get_view_version(); }
@@ -144,6 +164,8 @@ class KeystoneRpcClient : public KeystoneApi {
   ErrorCode put_cancel(const ObjectKey& key) override;
   ErrorCode remove_object(const ObjectKey& key) override;
   ErrorCode migrate_object(const ObjectKey& key, StorageClass target) override;
+  Result<std::vector<WorkerSummary>> get_workers_info() override;
+  ErrorCode remove_worker(const WorkerId& id) override;
   Result<size_t> remove_all_objects() override;
   Result<ClusterStats> get_cluster_stats() override;
   Result<ViewVersionId> get_view_version() override;

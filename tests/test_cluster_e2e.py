@@ -419,3 +419,22 @@ def test_worker_serves_its_own_prometheus_endpoint(bb):
         import json as _json
         st = _json.loads(bb.http_get("127.0.0.1", w.http_port, "/stats")[1])
         assert st["worker_id"] == "wm" and st["pools"][0]["pool_id"] == "ram-wm"
+
+
+def test_admin_calls_over_rpc_workers_info_and_remove_worker(bb):
+    """Reference admin surface (keystone_service.h:105-165) through the RPC client: get_workers_info lists workers with
+    heartbeat age and pools; remove_worker decommissions one (works with a coordination store, where the reference
+    throws): its copies are invalidated, a replicated object stays readable from the other worker."""
+    with LocalCluster(cluster_id="admin", n_workers=2) as c:
+        cl = c.client()
+        data = os.urandom(20_000)
+        assert cl.put("r2", data, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        ws = cl.keystone().get_workers_info()
+        assert sorted(w["worker_id"] for w in ws) == ["worker-0", "worker-1"]
+        assert all(w["pools"] and w["heartbeat_age_ms"] >= 0 and w["node_id"].startswith("node-") for w in ws)
+        assert cl.keystone().remove_worker("worker-0") == bb.ErrorCode.OK
+        c.coord.store().flush_events()
+        assert [w["worker_id"] for w in cl.keystone().get_workers_info()] == ["worker-1"]
+        assert cl.get("r2") == data
+        assert all(cp.shards[0].worker_id == "worker-1" for cp in cl.get_workers("r2"))
+        assert cl.keystone().remove_worker("no-such-worker") != bb.ErrorCode.OK
