@@ -558,7 +558,6 @@ bool RpcServer::on_data(const ConnPtr& c) {
       }
       c->set_authed();  // open cluster
     }
-    std::string resp;
     Reply reply;
     uint32_t rmethod = method;
     try {
