@@ -104,6 +104,8 @@ class DeviceTransport {
   virtual size_t max_in_flight() const { return 1; }
   // Fused MXFP8 put / get (pack / unpack inside the transfer kernel).  digests[i] = BBH64 of the stored packed
   // object; status[i] != 0 = digest mismatch on get.  Objects must satisfy fp8_eligible().
+  // Prometheus lines of the transport's own counters (bytes per path, launches, ...); appended to the client's metrics.
+  virtual std::string metrics_text() const { return {}; }
   virtual bool fp8_eligible(uint64_t n_elems) const { return false; }
   virtual ErrorCode put_fp8(const std::vector<DeviceFp8Op>& ops, void* stream, std::vector<uint64_t>* digests) { return ErrorCode::NOT_IMPLEMENTED; }
   virtual ErrorCode get_fp8(const std::vector<DeviceFp8Op>& ops, void* stream, std::vector<uint32_t>* status) { return ErrorCode::NOT_IMPLEMENTED; }
@@ -166,7 +168,7 @@ class BlackbirdClient {
 
   Result<ClusterStats> cluster_stats();
   rpc::KeystoneApi& keystone() { return *keystone_; }
-  std::string metrics_text() const { return metrics_.render("bb_client_"); }
+  std::string metrics_text() const { return metrics_.render("bb_client_") + (device_ ? device_->metrics_text() : std::string()); }
   // Device batches are split into `chunks` pipelined launches; 0 = decide from the measured RPC latency.
   void set_device_pipeline_chunks(size_t chunks) { pipeline_chunks_ = chunks; }
   std::map<std::string, std::vector<double>> phase_summary() const { return metrics_.histogram_summary(); }

@@ -426,6 +426,28 @@ bool GpuFabric::is_local(const ShardPlacement& s) const {
   return it != pools_.end() && it->second.device == device_ && !it->second.ipc_opened;
 }
 
+GpuFabric::Path GpuFabric::classify(const ShardPlacement& s) const {
+  if (s.storage_class != StorageClass::RAM_GPU) return PATH_PCIE;
+  return is_local(s) ? PATH_HBM : PATH_NVLINK;
+}
+
+std::string GpuFabric::metrics_text() const {
+  static const char* kPath[kNumPaths] = {"hbm", "nvlink", "pcie", "nvlink_multicast"};
+  std::string out = "# HELP bb_fabric_bytes_total payload bytes moved by the fused transfer kernels\n# TYPE bb_fabric_bytes_total counter\n";
+  const std::string g = std::to_string(device_);
+  for (int d = 0; d < 2; ++d)
+    for (int p = 0; p < kNumPaths; ++p) {
+      if (d == 1 && p == PATH_MULTICAST) continue;
+      out += "bb_fabric_bytes_total{gpu=\"" + g + "\",dir=\"" + (d == 0 ? "put" : "get") + "\",path=\"" + kPath[p] + "\"} " +
+             std::to_string(bytes_[d][p].load(std::memory_order_relaxed)) + "\n";
+    }
+  out += "# TYPE bb_fabric_launches_total counter\nbb_fabric_launches_total{gpu=\"" + g + "\"} " + std::to_string(engine_->launches()) + "\n";
+  out += "# TYPE bb_fabric_mapped_pools gauge\nbb_fabric_mapped_pools{gpu=\"" + g + "\",kind=\"all\"} " + std::to_string(mapped_pools()) + "\n";
+  out += "bb_fabric_mapped_pools{gpu=\"" + g + "\",kind=\"dram\"} " + std::to_string(mapped_host_pools()) + "\n";
+  out += "# TYPE bb_fabric_remaps_total counter\nbb_fabric_remaps_total{gpu=\"" + g + "\"} " + std::to_string(remaps_.load()) + "\n";
+  return out;
+}
+
 Result<void*> GpuFabric::resolve(const ShardPlacement& s) {
   drop_if_stale(s);
   if (const auto* h = std::get_if<MemoryLocation>(&s.location)) {  // shared / pinned DRAM pool
@@ -501,6 +523,7 @@ ErrorCode GpuFabric::build_put_items(const std::vector<client::DeviceShardOp>& o
         items->push_back(it);
         op_of_item->push_back(k);
         ++multicast_puts_;
+        count(true, PATH_MULTICAST, it.nbytes);  // one egress stream, the switch replicates
         continue;
       }
     }
@@ -508,6 +531,8 @@ ErrorCode GpuFabric::build_put_items(const std::vector<client::DeviceShardOp>& o
     if (!d0.ok()) return d0.error();
     it.dst[0] = d0.value();
     it.ndst = 1;
+    count(true, classify(*op.placement), it.nbytes);
+    for (const ShardPlacement* rp : op.replicas) count(true, classify(*rp), it.nbytes);
     size_t r = 0;
     for (; r < op.replicas.size() && it.ndst < kMaxDst; ++r) {
       auto d = resolve(*op.replicas[r]);
@@ -660,6 +685,7 @@ Result<uint64_t> GpuFabric::submit_get(const std::vector<client::DeviceShardOp>&
     it.expect = op.placement->checksum;
     it.flags = algo == ChecksumAlgo::NONE ? 0u : static_cast<uint32_t>(XFER_VERIFY);
     items.push_back(it);
+    count(false, classify(*op.placement), it.nbytes);
   }
   auto t = engine_->submit(items, algo, stream);
   if (!t.ok()) return t.error();

@@ -161,6 +161,8 @@ void bind_gpu(py::module_& m) {
       .def("mapped_pools", &GpuFabric::mapped_pools)
       .def("mapped_host_pools", &GpuFabric::mapped_host_pools)
       .def_property_readonly("remaps", &GpuFabric::remaps)
+      .def("metrics_text", &GpuFabric::metrics_text)
+      .def("path_bytes", &GpuFabric::path_bytes, py::arg("put"), py::arg("path"), "path: 0 hbm, 1 nvlink, 2 pcie, 3 nvlink multicast")
       .def_property_readonly("launches", &GpuFabric::launches)
       .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
       .def_property_readonly("total_device_ms", &GpuFabric::total_device_ms)

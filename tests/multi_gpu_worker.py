@@ -47,6 +47,8 @@ def main():
             assert torch.equal(src[i * stride:i * stride + size], out[i * stride:i * stride + size])
         cl.client.batch_remove(keys)
     res["ring"] = "ok"
+    assert cl.fabric.path_bytes(True, 1) == 2 * n * size and cl.fabric.path_bytes(False, 1) == 2 * n * size  # all of it crossed NVLink
+    assert 'path="nvlink"' in cl.client.metrics_text()
     cl.barrier()
 
     # ---- replication 2: fan-out, then corrupt one replica and read through the other

@@ -107,6 +107,10 @@ def test_full_stack_put_get_gpu_tier(bb, torch_cuda):
         assert ecs[0] == bb.ErrorCode.CHECKSUM_MISMATCH
         assert cl.client.batch_remove(keys) == [bb.ErrorCode.OK] * n
         assert cl.fabric.launches >= 3
+        # per-path payload counters (Prometheus): everything here stayed in this GPU's own HBM
+        assert cl.fabric.path_bytes(True, 0) == n * size and cl.fabric.path_bytes(False, 0) >= n * size
+        assert cl.fabric.path_bytes(True, 1) == 0 and cl.fabric.path_bytes(True, 2) == 0
+        assert 'bb_fabric_bytes_total{gpu="0",dir="put",path="hbm"} %d' % (n * size) in cl.client.metrics_text()
     finally:
         cl.stop()
 
@@ -306,6 +310,7 @@ def test_dram_tier_is_reached_by_the_fused_kernels(bb, torch_cuda):
         for i in range(n):
             assert torch.equal(src[i * stride:i * stride + size], out[i * stride:i * stride + size])
         assert "device_get_dram_direct_total" in cl.client.metrics_text()
+        assert cl.fabric.path_bytes(True, 2) == n * size and cl.fabric.path_bytes(False, 2) == n * size  # over PCIe
         # the worker's own view of the pool (host path) holds the same bytes, and corruption there is caught by the fused get
         be = cl.worker.backend(f"dram{cl.rank}")
         pool = [p for p in cl.client.keystone().get_memory_pools() if p.id == sh.pool_id][0]
