@@ -47,7 +47,7 @@ def main():
             assert torch.equal(src[i * stride:i * stride + size], out[i * stride:i * stride + size])
         cl.client.batch_remove(keys)
     res["ring"] = "ok"
-    assert cl.fabric.path_bytes(True, 1) == 2 * n * size and cl.fabric.path_bytes(False, 1) == 2 * n * size  # all of it crossed NVLink
+    assert cl.fabric.path_bytes(True, 1) >= 2 * n * size and cl.fabric.path_bytes(False, 1) >= 2 * n * size  # all of it crossed NVLink
     assert 'path="nvlink"' in cl.client.metrics_text()
     cl.barrier()
 
