@@ -405,7 +405,14 @@ void bind_control(py::module_& m) {
       .def("unwatch", &CoordStore::unwatch, py::call_guard<py::gil_scoped_release>())
       .def("revision", &CoordStore::revision);
   py::class_<MemCoord, CoordStore, std::shared_ptr<MemCoord>>(m, "MemCoord")
-      .def(py::init<>())
+      // The destructor joins the dispatch thread, which may be waiting for the GIL to deliver an event to a Python
+      // watch callback: release the GIL while the store is torn down.
+      .def(py::init([] {
+        return std::shared_ptr<MemCoord>(new MemCoord(), [](MemCoord* p) {
+          py::gil_scoped_release rel;
+          delete p;
+        });
+      }))
       .def("advance_time_ms", &MemCoord::advance_time_ms, py::call_guard<py::gil_scoped_release>())
       .def("flush_events", &MemCoord::flush_events, py::call_guard<py::gil_scoped_release>())
       .def("lease_count", &MemCoord::lease_count)
