@@ -157,3 +157,36 @@ def test_json_and_yaml_parsers_never_crash_on_mutated_documents(bb):
         _parse(bb.parse_json, '{"a":' * depth + "1" + "}" * depth)
         _parse(bb.parse_yaml, "a:\n" + "".join(" " * (i + 1) + "b:\n" for i in range(min(depth, 5000))))
         _parse(bb.parse_yaml, "[" * depth + "]" * depth)
+
+
+def test_json_parser_agrees_with_python_on_generated_documents(bb):
+    """Differential test: documents generated by hypothesis and serialised by Python's json module parse to the same
+    value in the in-tree parser, and json_roundtrip (parse + dump) is a fixed point that Python reads back."""
+    import json
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    leaves = st.one_of(st.none(), st.booleans(), st.integers(-(2 ** 53), 2 ** 53), st.floats(allow_nan=False, allow_infinity=False, width=64),
+                       st.text(max_size=20))
+    docs = st.recursive(leaves, lambda ch: st.one_of(st.lists(ch, max_size=5), st.dictionaries(st.text(max_size=8), ch, max_size=5)), max_leaves=25)
+
+    def same(a, b):
+        if isinstance(a, float) or isinstance(b, float):
+            return isinstance(a, (int, float)) and isinstance(b, (int, float)) and (a == b or abs(a - b) <= 1e-9 * max(abs(a), abs(b)))
+        if isinstance(a, dict):
+            return isinstance(b, dict) and a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, list):
+            return isinstance(b, list) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b and type(a) is type(b)
+
+    @settings(max_examples=300, deadline=None)
+    @given(docs)
+    def check(doc):
+        text = json.dumps(doc, ensure_ascii=False)
+        assert same(bb.parse_json(text), doc), text
+        assert same(bb.parse_json(json.dumps(doc, ensure_ascii=True)), doc)  # \\uXXXX escapes incl. surrogate pairs
+        again = bb.json_roundtrip(text)
+        assert same(json.loads(again), doc) and bb.json_roundtrip(again) == again
+
+    check()
