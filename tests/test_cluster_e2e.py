@@ -438,3 +438,40 @@ def test_admin_calls_over_rpc_workers_info_and_remove_worker(bb):
         assert cl.get("r2") == data
         assert all(cp.shards[0].worker_id == "worker-1" for cp in cl.get_workers("r2"))
         assert cl.keystone().remove_worker("no-such-worker") != bb.ErrorCode.OK
+
+
+@pytest.mark.parametrize("shm", [False, True])
+def test_host_paths_are_exact_at_chunk_stream_and_tile_boundaries(bb, shm):
+    """Sizes around every internal boundary of the host data paths (8 MiB request chunks, 4 MiB stream split, 1 MiB hash
+    steps, 16 KiB BBH64 tiles, empty objects) survive put -> get bit-exactly on the TCP streams and on the shared-memory
+    path, with both checksums, and the digest the Keystone records is the reference digest of the bytes."""
+    MiB = 1 << 20
+    sizes = [0, 1, 4095, 16384, 16385, MiB - 1, MiB + 1, 4 * MiB, 8 * MiB - 1, 8 * MiB, 8 * MiB + 1, 12 * MiB + 16384 + 7, 3 * 8 * MiB + 5]
+    with LocalCluster(cluster_id=f"edge-{int(shm)}", n_workers=0) as c:
+        wc = bb.WorkerServiceConfig()
+        wc.worker_id, wc.node_id, wc.cluster_id, wc.ucx_endpoint = "we", "node-we", c.cluster_id, "127.0.0.1:0"
+        pool = bb.StoragePoolConfig("ram-we", bb.StorageClass.RAM_CPU, 160 * MiB, "")
+        pool.shared_memory = shm
+        wc.storage_pools = [pool]
+        w = bb.WorkerService(wc, bb.CoordService(c.coord_uri))
+        assert w.create_storage_pools_from_config() == bb.ErrorCode.OK and w.initialize() == bb.ErrorCode.OK and w.start() == bb.ErrorCode.OK
+        c.workers.append(w)
+        c.coord.store().flush_events()
+        o = bb.BlackbirdClientOptions("127.0.0.1", c.rpc.rpc_port, 30000, 3, "node-we")  # 3 streams: uneven splits
+        o.enable_shm = shm
+        cl = bb.BlackbirdClient(o)
+        assert cl.connect() == bb.ErrorCode.OK
+        blob = os.urandom(max(sizes))
+        for algo in (bb.ChecksumAlgo.BBH64, bb.ChecksumAlgo.CRC32C):
+            cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, checksum=algo, ttl_ms=0)
+            for n in sizes:
+                key = f"e/{int(algo)}/{n}"
+                data = blob[:n]
+                assert cl.put(key, data, cfg) == bb.ErrorCode.OK, n
+                assert cl.get(key) == data, n
+                if n:
+                    sh = cl.get_workers(key)[0].shards[0]
+                    assert sh.checksum == (bb.bbh64_reference(data) if algo == bb.ChecksumAlgo.BBH64 else bb.crc32c_sw(data, 0)), n
+                assert cl.remove(key) == bb.ErrorCode.OK
+        text = cl.metrics_text()
+        assert ("bb_client_shm_put_shards_total" in text) == shm
