@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | migrate KEY CLASS | stats | pools | workers | remove-worker ID | smoke | metrics --http host:port> [--auth-token T]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | migrate KEY CLASS | stats | pools | workers | remove-worker ID | smoke | metrics --http host:port> [--auth-token T]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -124,6 +124,14 @@ int main(int argc, char** argv) {
     Json arr = Json::array();
     for (const auto& p : pools.value()) arr.push_back(to_json(p));
     std::printf("%s\n", arr.dump(2).c_str());
+    return 0;
+  }
+  if (cmd == "ls") {  // bb-cli ls [PREFIX] [--limit N] [--after KEY]
+    auto v = cl.keystone().list_objects(args.positional.size() >= 2 ? args.positional[1] : "", static_cast<size_t>(args.num("limit", 1000)),
+                                        args.get("after"));
+    if (!v.ok()) return 1;
+    for (const auto& o : v.value())
+      std::printf("%12llu  x%u  %-10s %s\n", static_cast<unsigned long long>(o.size), o.copies, std::string(to_string(o.tier)).c_str(), o.key.c_str());
     return 0;
   }
   if (cmd == "workers") {  // admin introspection: registered workers, heartbeat age, their pools

@@ -587,6 +587,31 @@ Result<ObjectInfo> KeystoneService::get_object_info(const ObjectKey& key) const 
   return it->second;
 }
 
+std::vector<KeystoneService::ListedObject> KeystoneService::list_objects(const std::string& prefix, size_t limit,
+                                                                         const std::string& start_after) const {
+  if (limit == 0 || limit > 10000) limit = 10000;
+  const TimePoint now = Clock::now();
+  std::vector<ListedObject> out;
+  for (const auto& sh : shards_) {
+    std::shared_lock<SpinMutex> lk(sh.mu);
+    for (const auto& [k, o] : sh.objects) {
+      if (o.state != ObjectState::COMPLETE || o.is_expired(now)) continue;
+      if (k.compare(0, prefix.size(), prefix) != 0 || (!start_after.empty() && k <= start_after)) continue;
+      ListedObject lo;
+      lo.key = k;
+      lo.size = o.size;
+      lo.copies = static_cast<uint32_t>(o.copies.size());
+      if (!o.copies.empty() && !o.copies[0].shards.empty()) lo.tier = o.copies[0].shards[0].storage_class;
+      out.push_back(std::move(lo));
+    }
+  }
+  // the table is hash-sharded: order globally, then cut the page (partial_sort keeps big listings cheap)
+  const size_t n = std::min(limit, out.size());
+  std::partial_sort(out.begin(), out.begin() + static_cast<std::ptrdiff_t>(n), out.end(), [](const ListedObject& a, const ListedObject& b) { return a.key < b.key; });
+  out.resize(n);
+  return out;
+}
+
 // ================================================================ batch API
 std::vector<Result<bool>> KeystoneService::batch_object_exists(const std::vector<ObjectKey>& keys) {
   std::vector<Result<bool>> out;

@@ -127,6 +127,15 @@ class KeystoneService {
   ErrorCode get_memory_pools(std::vector<MemoryPool>& out) const;
   ErrorCode remove_worker(const WorkerId& id);
   Result<ObjectInfo> get_object_info(const ObjectKey& key) const;
+  // Keys of COMPLETE, unexpired objects starting with `prefix`, in lexicographic order, at most `limit` (0 = 10000)
+  // strictly after `start_after` (pagination).  An extension: the reference has no listing call.
+  struct ListedObject {
+    ObjectKey key;
+    uint64_t size = 0;
+    uint32_t copies = 0;
+    StorageClass tier = StorageClass::STORAGE_UNSPECIFIED;  // tier of the first shard of copy 0
+  };
+  std::vector<ListedObject> list_objects(const std::string& prefix, size_t limit = 0, const std::string& start_after = "") const;
 
   // Direct registration (in-process deployments and tests; the coordination watchers call
   // the same functions).

@@ -626,6 +626,11 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("list_objects", [](rpc::KeystoneApi& k, const std::string& prefix, size_t limit, const std::string& after) {
+        py::list out;
+        for (const auto& o : unwrap(k.list_objects(prefix, limit, after))) out.append(py::make_tuple(o.key, o.size, o.copies, o.tier));
+        return out;
+      }, py::arg("prefix") = "", py::arg("limit") = 0, py::arg("start_after") = "", "[(key, size, copies, tier)] in key order")
       .def("client_register", [](rpc::KeystoneApi& k, const std::string& n) { return unwrap(k.client_register(n)); })
       .def("client_ping", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(k.client_ping(id)); })
       .def("register_memory_pool", &rpc::KeystoneApi::register_memory_pool)

@@ -260,6 +260,24 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
+  rpc_.register_method(M_LIST_OBJECTS, [ks](C, S q) {
+    Reader r(q);
+    const std::string prefix = r.str();
+    const uint64_t limit = r.u64();
+    const std::string after = r.str();
+    if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    const auto v = ks->list_objects(prefix, static_cast<size_t>(limit), after);
+    Writer w;
+    w.ec(ErrorCode::OK);
+    w.u32(static_cast<uint32_t>(v.size()));
+    for (const auto& o : v) {
+      w.str(o.key);
+      w.u64(o.size);
+      w.u32(o.copies);
+      w.u32(static_cast<uint32_t>(o.tier));
+    }
+    return w.take();
+  });
   rpc_.register_method(M_REMOVE_WORKER, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->remove_worker(r.str()));
@@ -395,6 +413,25 @@ Result<std::vector<KeystoneApi::WorkerSummary>> KeystoneRpcClient::get_workers_i
     ws.heartbeat_age_ms = rd.i64();
     const uint32_t np = rd.count(4);
     for (uint32_t i = 0; i < np; ++i) ws.pools.push_back(rd.str());
+  }
+  if (!rd.ok()) return ErrorCode::RPC_FAILED;
+  return v;
+}
+Result<std::vector<keystone::KeystoneService::ListedObject>> KeystoneRpcClient::list_objects(const std::string& prefix, size_t limit,
+                                                                                           const std::string& start_after) {
+  Writer w;
+  w.str(prefix);
+  w.u64(limit);
+  w.str(start_after);
+  BB_RPC(M_LIST_OBJECTS, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  std::vector<keystone::KeystoneService::ListedObject> v(rd.count(20));
+  for (auto& o : v) {
+    o.key = rd.str();
+    o.size = rd.u64();
+    o.copies = rd.u32();
+    o.tier = static_cast<StorageClass>(rd.u32());
   }
   if (!rd.ok()) return ErrorCode::RPC_FAILED;
   return v;

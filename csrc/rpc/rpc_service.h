@@ -23,7 +23,7 @@ enum Method : uint32_t {
   M_BATCH_GET_WORKERS, M_BATCH_PUT_START, M_BATCH_PUT_COMPLETE, M_BATCH_PUT_CANCEL,
   M_BATCH_REMOVE_OBJECT, M_CLIENT_REGISTER, M_CLIENT_PING, M_GET_MEMORY_POOLS,
   M_REGISTER_WORKER, M_REGISTER_MEMORY_POOL, M_WORKER_HEARTBEAT, M_REMOVE_WORKER,
-  M_MIGRATE_OBJECT, M_GET_WORKERS_INFO,
+  M_MIGRATE_OBJECT, M_GET_WORKERS_INFO, M_LIST_OBJECTS,
 };
 
 // The keystone surface a client needs; implemented in-process and over TCP.
@@ -63,6 +63,9 @@ class KeystoneApi {
     std::vector<MemoryPoolId> pools;
   };
   virtual Result<std::vector<WorkerSummary>> get_workers_info() = 0;
+  // Listing (extension): complete objects under `prefix`, key order, paginated with `start_after`.
+  virtual Result<std::vector<keystone::KeystoneService::ListedObject>> list_objects(const std::string& prefix, size_t limit,
+                                                                                    const std::string& start_after) = 0;
   virtual ErrorCode remove_worker(const WorkerId& id) = 0;
   // identity used for locality-aware placement and session ownership
   void set_identity(std::string client_id, std::string node_id) {
@@ -98,6 +101,10 @@ class LocalKeystoneApi : public KeystoneApi {
     return out;
   }
   ErrorCode remove_worker(const WorkerId& id) override { return ks_->remove_worker(id); }
+  Result<std::vector<keystone::KeystoneService::ListedObject>> list_objects(const std::string& prefix, size_t limit,
+                                                                            const std::string& start_after) override {
+    return ks_->list_objects(prefix, limit, start_after);
+  }
   Result<size_t> remove_all_objects() override { return ks_->remove_all_objects(); }
   Result<ClusterStats> get_cluster_stats() override { return ks_->get_cluster_stats(); }
   Result<ViewVersionId> get_view_version() override { return ks_->get_view_version(); }
@@ -166,6 +173,8 @@ class KeystoneRpcClient : public KeystoneApi {
   ErrorCode migrate_object(const ObjectKey& key, StorageClass target) override;
   Result<std::vector<WorkerSummary>> get_workers_info() override;
   ErrorCode remove_worker(const WorkerId& id) override;
+  Result<std::vector<keystone::KeystoneService::ListedObject>> list_objects(const std::string& prefix, size_t limit,
+                                                                            const std::string& start_after) override;
   Result<size_t> remove_all_objects() override;
   Result<ClusterStats> get_cluster_stats() override;
   Result<ViewVersionId> get_view_version() override;

@@ -475,3 +475,25 @@ def test_host_paths_are_exact_at_chunk_stream_and_tile_boundaries(bb, shm):
                 assert cl.remove(key) == bb.ErrorCode.OK
         text = cl.metrics_text()
         assert ("bb_client_shm_put_shards_total" in text) == shm
+
+
+def test_list_objects_prefix_order_and_pagination(bb):
+    """Listing (an extension: the reference has none): complete objects under a prefix, in key order, paginated;
+    pending and removed objects do not show up."""
+    with LocalCluster(cluster_id="ls", n_workers=2) as c:
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1)
+        keys = [f"ds/train/{i:03d}" for i in range(25)] + ["ds/val/0", "other/x"]
+        for k in keys:
+            assert cl.put(k, os.urandom(100 + len(k)), cfg) == bb.ErrorCode.OK
+        c.keystone.put_start("ds/train/pending", 10, cfg)  # never completed
+        api = cl.keystone()
+        got = api.list_objects("ds/train/")
+        assert [g[0] for g in got] == sorted(k for k in keys if k.startswith("ds/train/"))
+        assert all(g[1] == 100 + len(g[0]) and g[2] == 2 and g[3] == bb.StorageClass.RAM_CPU for g in got)
+        page1 = api.list_objects("ds/", 10)
+        page2 = api.list_objects("ds/", 10, page1[-1][0])
+        page3 = api.list_objects("ds/", 10, page2[-1][0])
+        assert [g[0] for g in page1 + page2 + page3] == sorted(k for k in keys if k.startswith("ds/")) and len(page3) == 6
+        assert cl.remove("ds/val/0") == bb.ErrorCode.OK
+        assert [g[0] for g in api.list_objects("ds/val")] == [] and len(api.list_objects()) == 26
