@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | migrate KEY CLASS | stats | pools | workers | remove-worker ID | smoke | metrics --http host:port> [--auth-token T]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | smoke | metrics --http host:port> [--auth-token T]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -132,6 +132,20 @@ int main(int argc, char** argv) {
     if (!v.ok()) return 1;
     for (const auto& o : v.value())
       std::printf("%12llu  x%u  %-10s %s\n", static_cast<unsigned long long>(o.size), o.copies, std::string(to_string(o.tier)).c_str(), o.key.c_str());
+    return 0;
+  }
+  if (cmd == "rm-prefix" && args.positional.size() >= 2) {  // remove every object under a prefix, page by page
+    size_t removed = 0;
+    while (true) {
+      auto v = cl.keystone().list_objects(args.positional[1], 1000, "");
+      if (!v.ok()) return 1;
+      if (v.value().empty()) break;
+      std::vector<ObjectKey> keys;
+      for (const auto& o : v.value()) keys.push_back(o.key);
+      for (ErrorCode e : cl.batch_remove(keys)) removed += e == ErrorCode::OK ? 1 : 0;
+      if (v.value().size() < 1000) break;
+    }
+    std::printf("removed %zu objects under %s\n", removed, args.positional[1].c_str());
     return 0;
   }
   if (cmd == "workers") {  // admin introspection: registered workers, heartbeat age, their pools

@@ -159,6 +159,16 @@ class TensorStore:
     def remove(self, keys: Sequence[str]) -> None:
         self.client.batch_remove(list(keys) + [k + "#meta" for k in keys])
 
+    def keys(self, prefix: str = "", limit: int = 0) -> list:
+        """Names of the tensors stored under `prefix` (key order; the `#meta` side objects are hidden)."""
+        out, after = [], ""
+        while True:
+            page = self.client.keystone().list_objects(prefix, 1000, after)
+            out += [k for k, _, _, _ in page if not k.endswith("#meta")]
+            if len(page) < 1000 or (limit and len(out) >= limit):
+                return out[:limit] if limit else out
+            after = page[-1][0]
+
 
 class AsyncTensorStore(TensorStore):
     """TensorStore whose puts / gets run on a side stream from a worker thread, so they overlap the caller's compute

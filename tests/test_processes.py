@@ -118,6 +118,10 @@ def test_cluster_of_real_processes(procs, tmp_path, bb):
     assert len(pools) == 4 and sum(p["used"] for p in pools) >= 2 * (3 << 20)
     m = run_cli("metrics", "--http", f"127.0.0.1:{hport}")
     assert m.returncode == 0 and "bb_objects 1" in m.stdout and 'bb_tier_used_bytes{tier="NVME"}' in m.stdout
+    ls = run_cli("--keystone", ks, "ls", "file-")
+    assert ls.returncode == 0 and "file-key" in ls.stdout and "x2" in ls.stdout and "NVME" in ls.stdout
+    wk = json.loads(run_cli("--keystone", ks, "workers").stdout)
+    assert sorted(w["worker_id"] for w in wk) == ["w0", "w1"] and all(len(w["pools"]) == 2 for w in wk)
     b = subprocess.run([os.path.join(BIN, "bb-bench"), "client", "--keystone", ks, "--size", "65536", "--iterations", "20", "--batch", "4"],
                        capture_output=True, text=True, timeout=60)
     res = json.loads(b.stdout)
@@ -129,7 +133,9 @@ def test_cluster_of_real_processes(procs, tmp_path, bb):
         time.sleep(0.2)
     assert json.loads(run_cli("--keystone", ks, "stats").stdout)["total_workers"] == 1
     assert run_cli("--keystone", ks, "get", "file-key", str(out)).returncode == 0 and out.read_bytes() == blob.read_bytes()
-    assert run_cli("--keystone", ks, "remove", "file-key").returncode == 0
+    rm = run_cli("--keystone", ks, "rm-prefix", "file-")
+    assert rm.returncode == 0 and "removed 1 objects" in rm.stdout
+    assert run_cli("--keystone", ks, "exists", "file-key").stdout.strip() == "false"
 
 
 def test_backend_microbenchmark_binary(tmp_path):
