@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | smoke | metrics --http host:port> [--auth-token T]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | compact POOL | smoke | metrics --http host:port> [--auth-token T]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -146,6 +146,15 @@ int main(int argc, char** argv) {
       if (v.value().size() < 1000) break;
     }
     std::printf("removed %zu objects under %s\n", removed, args.positional[1].c_str());
+    return 0;
+  }
+  if (cmd == "compact" && args.positional.size() >= 2) {  // defragment a pool: bb-cli compact POOL [--max-moves N]
+    auto r = cl.keystone().compact_pool(args.positional[1], static_cast<size_t>(args.num("max-moves", 64)));
+    if (!r.ok()) {
+      std::printf("compact %s: %s\n", args.positional[1].c_str(), name(r.error()));
+      return 1;
+    }
+    std::printf("compact %s: moved %zu objects\n", args.positional[1].c_str(), r.value());
     return 0;
   }
   if (cmd == "workers") {  // admin introspection: registered workers, heartbeat age, their pools

@@ -518,17 +518,42 @@ ErrorCode BlackbirdClient::put(const ObjectKey& key, const uint8_t* data, size_t
   return ec;
 }
 
+// A transfer can lose a race with the Keystone moving the object (tier demotion / promotion, migrate_object, pool
+// compaction, repair): the placements it holds were swapped and their extents re-used, which shows up as a digest
+// mismatch or a failed read.  Fresh placements that differ from the ones just tried are worth one more attempt.
+ErrorCode BlackbirdClient::get_with_refresh(const ObjectKey& key, uint8_t* (*alloc)(void*, size_t), void* ctx, size_t capacity, size_t* out_size) {
+  Result<std::vector<CopyPlacement>> copies = keystone_->get_workers(key);
+  ErrorCode ec = ErrorCode::OK;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (!copies.ok()) return copies.error();
+    if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
+    size_t size = 0;
+    for (const auto& s : copies.value().front().shards) size += s.length;
+    if (out_size) *out_size = size;
+    if (size > capacity) return ErrorCode::BUFFER_OVERFLOW;
+    uint8_t* dst = alloc(ctx, size);
+    ec = transfer_get(copies.value(), dst, size);
+    if (ec == ErrorCode::OK) return ec;
+    auto again = keystone_->get_workers(key);
+    if (!again.ok()) return again.error();              // removed (or being re-written) meanwhile: that is the answer
+    if (again.value() == copies.value()) return ec;     // same placements: the failure is real
+    metrics_.inc("get_placement_refresh_total");
+    copies = std::move(again);
+  }
+  return ec;
+}
+
 Result<std::vector<uint8_t>> BlackbirdClient::get(const ObjectKey& key) {
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
   const TimePoint t0 = Clock::now();
   BB_TRACE_SPAN("client.get");
-  auto copies = keystone_->get_workers(key);
-  if (!copies.ok()) return copies.error();
-  if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
+  std::vector<uint8_t> buf;
   size_t size = 0;
-  for (const auto& s : copies.value().front().shards) size += s.length;
-  std::vector<uint8_t> buf(size);
-  ErrorCode ec = transfer_get(copies.value(), buf.data(), size);
+  ErrorCode ec = get_with_refresh(key, [](void* c, size_t n) {
+    auto* v = static_cast<std::vector<uint8_t>*>(c);
+    v->resize(n);
+    return v->data();
+  }, &buf, ~size_t{0}, &size);
   if (ec != ErrorCode::OK) return ec;
   metrics_.inc("get_total");
   metrics_.inc("get_bytes_total", size);
@@ -538,14 +563,7 @@ Result<std::vector<uint8_t>> BlackbirdClient::get(const ObjectKey& key) {
 
 ErrorCode BlackbirdClient::get_into(const ObjectKey& key, void* buf, size_t capacity, size_t* out_size) {
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
-  auto copies = keystone_->get_workers(key);
-  if (!copies.ok()) return copies.error();
-  if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
-  size_t size = 0;
-  for (const auto& s : copies.value().front().shards) size += s.length;
-  if (out_size) *out_size = size;
-  if (size > capacity) return ErrorCode::BUFFER_OVERFLOW;
-  return transfer_get(copies.value(), static_cast<uint8_t*>(buf), size);
+  return get_with_refresh(key, [](void* c, size_t) { return static_cast<uint8_t*>(c); }, buf, capacity, out_size);
 }
 
 ErrorCode BlackbirdClient::remove(const ObjectKey& key) {

@@ -182,6 +182,7 @@ class BlackbirdClient {
   ErrorCode transfer_put(const std::vector<CopyPlacement>& copies, const uint8_t* data, ChecksumAlgo algo,
                          keystone::ShardChecksums* sums);
   ErrorCode transfer_get(const std::vector<CopyPlacement>& copies, uint8_t* dst, size_t size);
+  ErrorCode get_with_refresh(const ObjectKey& key, uint8_t* (*alloc)(void*, size_t), void* ctx, size_t capacity, size_t* out_size);
   static uint64_t shard_offset(const ShardPlacement& s);
   static ChecksumAlgo algo_of(const std::vector<CopyPlacement>& copies, ChecksumAlgo hint);
   // [begin, end) index ranges that split a batch so that transfers of one chunk overlap the

@@ -1,6 +1,8 @@
 #include "common/fault.h"
 #include "keystone/keystone_service.h"
 
+#include <unordered_set>
+
 #include <algorithm>
 #include <chrono>
 #include <map>
@@ -802,7 +804,8 @@ size_t KeystoneService::run_gc_once() {
 // Moves every copy of `key` to the first class of `targets` that has room (same replication factor), through the
 // installed CopyMover (worker-to-worker D_COPY; fused kernel when the GPU tier is involved), then swaps the
 // placements atomically and frees the old extents.  Used by watermark demotion and by explicit migrate_object().
-ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets) {
+ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets,
+                                        const PlacementFilter& accept) {
   auto info = get_object_info(key);
   if (!info.ok()) return info.error();
   if (info.value().copies.empty() || info.value().state != ObjectState::COMPLETE) return ErrorCode::OBJECT_NOT_READY;
@@ -827,6 +830,10 @@ ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey&
     if (fresh.ok()) break;
   }
   if (!fresh.ok()) return fresh.error();
+  if (accept && !accept(info.value().copies, fresh.value())) {
+    allocator_->free_object(ledger);
+    return ErrorCode::INVALID_STATE;  // the caller's filter turned the new placement down; nothing moved
+  }
   ErrorCode ec = ErrorCode::OK;
   for (size_t c = 0; c < fresh.value().size() && ec == ErrorCode::OK; ++c)
     ec = mover(key, info.value().copies[std::min(c, info.value().copies.size() - 1)], fresh.value()[c], info.value().config.checksum);
@@ -851,6 +858,71 @@ ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey&
   for (const auto& l : old) allocator_->free_object(l);
   bump_view();
   return ErrorCode::OK;
+}
+
+namespace {
+// Highest end offset (pool-relative) of an object's shards inside `pool`; 0 when it has none there.
+uint64_t top_in_pool(const std::vector<CopyPlacement>& copies, const MemoryPool& pool) {
+  uint64_t top = 0;
+  const uint64_t base = pool.ucx_remote_addr ? pool.ucx_remote_addr : pool.base_addr;
+  for (const auto& c : copies)
+    for (const auto& s : c.shards) {
+      if (s.pool_id != pool.id) continue;
+      uint64_t off = 0;
+      if (auto* g = std::get_if<GpuSlabLocation>(&s.location)) off = g->offset;
+      else if (auto* f = std::get_if<FileLocation>(&s.location)) off = f->file_offset;
+      else if (auto* x = std::get_if<CxlMemoryLocation>(&s.location)) off = x->offset;
+      else if (auto* m = std::get_if<MemoryLocation>(&s.location)) off = m->remote_addr >= base ? m->remote_addr - base : 0;
+      top = std::max(top, off + s.length);
+    }
+  return top;
+}
+}  // namespace
+
+Result<size_t> KeystoneService::compact_pool(const MemoryPoolId& pool_id, size_t max_moves) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  CopyMover mover;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+  }
+  if (!mover) return ErrorCode::NOT_IMPLEMENTED;
+  MemoryPool pool;
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    auto it = pools_.find(pool_id);
+    if (it == pools_.end()) return ErrorCode::MEMORY_POOL_NOT_FOUND;
+    pool = it->second;
+  }
+  size_t moved = 0;
+  std::unordered_set<ObjectKey> tried;  // an object whose move was turned down is not retried in this run
+  while (moved < max_moves) {
+    // the not-yet-tried object that reaches highest into the pool
+    ObjectKey victim;
+    uint64_t victim_top = 0;
+    for (const auto& sh : shards_) {
+      std::shared_lock<SpinMutex> lk(sh.mu);
+      for (const auto& [k, o] : sh.objects) {
+        if (o.state != ObjectState::COMPLETE || tried.count(k)) continue;
+        const uint64_t top = top_in_pool(o.copies, pool);
+        if (top > victim_top) victim_top = top, victim = k;
+      }
+    }
+    if (victim.empty()) break;
+    tried.insert(victim);
+    // new home: same tier, and strictly lower inside this pool (or out of it) -- otherwise the move is pointless
+    const ErrorCode ec = migrate_with(mover, victim, {pool.storage_class},
+                                      [&](const std::vector<CopyPlacement>& old_copies, const std::vector<CopyPlacement>& fresh) {
+                                        return top_in_pool(fresh, pool) < top_in_pool(old_copies, pool);
+                                      });
+    if (ec == ErrorCode::OK) {
+      ++moved;
+      tried.erase(victim);  // it may move again, further down, once other holes open
+      metrics_.inc("compaction_moves_total");
+    }
+  }
+  if (moved) bump_view();
+  return moved;
 }
 
 ErrorCode KeystoneService::migrate_object(const ObjectKey& key, StorageClass target) {

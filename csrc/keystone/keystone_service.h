@@ -135,6 +135,11 @@ class KeystoneService {
     uint32_t copies = 0;
     StorageClass tier = StorageClass::STORAGE_UNSPECIFIED;  // tier of the first shard of copy 0
   };
+  // Pool compaction (a roadmap item of the reference, README.md:146-153): re-places the objects that sit highest in
+  // `pool` into lower holes of the same tier (best fit), through the installed mover (digest re-checked, placements
+  // swapped atomically, old extents freed), until `max_moves` objects moved or nothing moves any more.  Returns the
+  // number of objects moved.  NOT_IMPLEMENTED without a mover, MEMORY_POOL_NOT_FOUND for an unknown pool.
+  Result<size_t> compact_pool(const MemoryPoolId& pool, size_t max_moves = 64);
   std::vector<ListedObject> list_objects(const std::string& prefix, size_t limit = 0, const std::string& start_after = "") const;
 
   // Direct registration (in-process deployments and tests; the coordination watchers call
@@ -224,7 +229,10 @@ class KeystoneService {
                          *put_complete_total = nullptr, *get_workers_total = nullptr, *remove_total = nullptr;
     Histogram* put_start_latency = nullptr;
   } hot_;
-  ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets);
+  // `accept` (optional) sees the old and the freshly allocated placements before any byte moves; false = roll back.
+  using PlacementFilter = std::function<bool(const std::vector<CopyPlacement>& old_copies, const std::vector<CopyPlacement>& fresh)>;
+  ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets,
+                         const PlacementFilter& accept = nullptr);
 
   std::atomic<bool> running_{false};
   std::atomic<bool> leader_{false};

@@ -521,6 +521,8 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &KeystoneService::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("compact_pool", [](KeystoneService& k, const std::string& pool, size_t max_moves) { return unwrap(k.compact_pool(pool, max_moves)); },
+           py::arg("pool"), py::arg("max_moves") = 64, py::call_guard<py::gil_scoped_release>())
       .def("register_memory_pool", &KeystoneService::register_memory_pool)
       .def("register_worker", [](KeystoneService& k, const std::string& id, const std::string& node, const std::string& ep) {
         WorkerRecord r;
@@ -626,6 +628,8 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("compact_pool", [](rpc::KeystoneApi& k, const std::string& pool, size_t max_moves) { return unwrap(k.compact_pool(pool, max_moves)); },
+           py::arg("pool"), py::arg("max_moves") = 64, py::call_guard<py::gil_scoped_release>())
       .def("list_objects", [](rpc::KeystoneApi& k, const std::string& prefix, size_t limit, const std::string& after) {
         py::list out;
         for (const auto& o : unwrap(k.list_objects(prefix, limit, after))) out.append(py::make_tuple(o.key, o.size, o.copies, o.tier));

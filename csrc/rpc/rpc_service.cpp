@@ -278,6 +278,17 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
+  rpc_.register_method(M_COMPACT_POOL, [ks](C, S q) {
+    Reader r(q);
+    const std::string pool = r.str();
+    const uint64_t max_moves = r.u64();
+    if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    auto res = ks->compact_pool(pool, static_cast<size_t>(max_moves));
+    Writer w;
+    w.ec(res.ok() ? ErrorCode::OK : res.error());
+    if (res.ok()) w.u64(res.value());
+    return w.take();
+  });
   rpc_.register_method(M_REMOVE_WORKER, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->remove_worker(r.str()));
@@ -435,6 +446,15 @@ Result<std::vector<keystone::KeystoneService::ListedObject>> KeystoneRpcClient::
   }
   if (!rd.ok()) return ErrorCode::RPC_FAILED;
   return v;
+}
+Result<size_t> KeystoneRpcClient::compact_pool(const MemoryPoolId& pool, size_t max_moves) {
+  Writer w;
+  w.str(pool);
+  w.u64(max_moves);
+  BB_RPC(M_COMPACT_POOL, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return static_cast<size_t>(rd.u64());
 }
 ErrorCode KeystoneRpcClient::remove_worker(const WorkerId& id) {
   Writer w;
