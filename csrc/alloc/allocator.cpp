@@ -620,6 +620,11 @@ size_t RangeAllocator::pool_used_bytes(const MemoryPoolId& id) const {
   return it == used_by_pool_.end() ? 0 : it->second;
 }
 
+double RangeAllocator::pool_fragmentation(const MemoryPoolId& id) const {
+  const PoolAllocator* pa = find_pool(id);
+  return pa ? pa->fragmentation_ratio() : 0.0;
+}
+
 std::vector<ObjectKey> RangeAllocator::objects_on_pool(const MemoryPoolId& id) const {
   std::vector<ObjectKey> v;
   for (const LedgerShard& ls : ledger_) {

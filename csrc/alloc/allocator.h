@@ -152,6 +152,7 @@ class IAllocator {
   // extensions used by the keystone
   virtual void forget_pool(const MemoryPoolId& id) = 0;            // worker died: drop its free lists
   virtual size_t pool_used_bytes(const MemoryPoolId& id) const = 0;  // live accounting
+  virtual double pool_fragmentation(const MemoryPoolId& id) const = 0;  // 1 - largest hole / free bytes (0 = one hole)
   virtual std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const = 0;
 };
 
@@ -165,6 +166,7 @@ class RangeAllocator : public IAllocator {
   bool can_allocate(const AllocationRequest& request, const PoolMap& pools) const override;
   void forget_pool(const MemoryPoolId& id) override;
   size_t pool_used_bytes(const MemoryPoolId& id) const override;
+  double pool_fragmentation(const MemoryPoolId& id) const override;
   std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const override;
   // Re-reserves the exact extents of already placed copies (metadata recovery after a leader
   // change).  Extents on unknown pools are skipped.

@@ -156,6 +156,7 @@ Result<KeystoneConfig> KeystoneConfig::from_json(const Json& root, std::string* 
   if (k.contains("service_refresh_interval_sec")) c.service_refresh_interval_sec = k.at("service_refresh_interval_sec").as_int(c.service_refresh_interval_sec);
   if (k.contains("gc_interval_sec")) c.gc_interval_sec = k.at("gc_interval_sec").as_int(c.gc_interval_sec);
   if (k.contains("health_check_interval_sec")) c.health_check_interval_sec = k.at("health_check_interval_sec").as_int(c.health_check_interval_sec);
+  if (k.contains("compaction_fragmentation_threshold")) c.compaction_fragmentation_threshold = k.at("compaction_fragmentation_threshold").as_double(0.0);
   if (k.contains("promote_after_reads")) c.promote_after_reads = static_cast<int32_t>(k.at("promote_after_reads").as_int(0));
   if (k.contains("tier_policy")) c.tier_policy = tier_rules_from_json(k.at("tier_policy"));
   if (k.contains("max_replicas")) c.max_replicas = static_cast<int32_t>(k.at("max_replicas").as_int(c.max_replicas));

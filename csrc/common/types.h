@@ -172,6 +172,8 @@ struct KeystoneConfig {
   int64_t gc_interval_sec = 30;
   int64_t health_check_interval_sec = 10;
   int32_t max_replicas = 3;
+  // > 0: the health loop compacts a pool (a few moves per round) whose fragmentation ratio exceeds this value
+  double compaction_fragmentation_threshold = 0.0;
   int32_t promote_after_reads = 0;    // > 0: an object read this often while it sits below the top tier is promoted back
   std::vector<TierRule> tier_policy;  // size-based class preference for puts that name no preferred class
   int32_t default_replicas = 1;

@@ -176,6 +176,7 @@ void KeystoneService::health_loop() {
     run_eviction_once();
     run_repair_once();
     run_promotion_once();
+    run_compaction_once();
   }
 }
 
@@ -922,6 +923,22 @@ Result<size_t> KeystoneService::compact_pool(const MemoryPoolId& pool_id, size_t
     }
   }
   if (moved) bump_view();
+  return moved;
+}
+
+size_t KeystoneService::run_compaction_once() {
+  if (config_.compaction_fragmentation_threshold <= 0.0 || !is_leader()) return 0;
+  std::vector<MemoryPoolId> fragmented;
+  {
+    std::shared_lock<std::shared_mutex> lk(pools_mu_);
+    for (const auto& [id, p] : pools_)
+      if (allocator_->allocator().pool_fragmentation(id) > config_.compaction_fragmentation_threshold) fragmented.push_back(id);
+  }
+  size_t moved = 0;
+  for (const auto& id : fragmented) {
+    auto r = compact_pool(id, 8);
+    if (r.ok()) moved += r.value();
+  }
   return moved;
 }
 

@@ -140,6 +140,9 @@ class KeystoneService {
   // swapped atomically, old extents freed), until `max_moves` objects moved or nothing moves any more.  Returns the
   // number of objects moved.  NOT_IMPLEMENTED without a mover, MEMORY_POOL_NOT_FOUND for an unknown pool.
   Result<size_t> compact_pool(const MemoryPoolId& pool, size_t max_moves = 64);
+  // One round of the automatic trigger (health loop): every pool above `compaction_fragmentation_threshold` gets up to
+  // 8 moves.  Returns the number of objects moved.
+  size_t run_compaction_once();
   std::vector<ListedObject> list_objects(const std::string& prefix, size_t limit = 0, const std::string& start_after = "") const;
 
   // Direct registration (in-process deployments and tests; the coordination watchers call

@@ -265,6 +265,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("rpc_busy_poll_us", &KeystoneConfig::rpc_busy_poll_us)
       .def_readwrite("tier_policy", &KeystoneConfig::tier_policy)
       .def_readwrite("promote_after_reads", &KeystoneConfig::promote_after_reads)
+      .def_readwrite("compaction_fragmentation_threshold", &KeystoneConfig::compaction_fragmentation_threshold)
       .def_readwrite("wal_path", &KeystoneConfig::wal_path)
       .def_readwrite("log_level", &KeystoneConfig::log_level)
       .def("validate", [](const KeystoneConfig& c) {
@@ -521,6 +522,7 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &KeystoneService::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("run_compaction_once", &KeystoneService::run_compaction_once, py::call_guard<py::gil_scoped_release>())
       .def("compact_pool", [](KeystoneService& k, const std::string& pool, size_t max_moves) { return unwrap(k.compact_pool(pool, max_moves)); },
            py::arg("pool"), py::arg("max_moves") = 64, py::call_guard<py::gil_scoped_release>())
       .def("register_memory_pool", &KeystoneService::register_memory_pool)

@@ -531,6 +531,30 @@ def test_compact_pool_moves_high_objects_into_holes_and_frees_the_tail(bb):
             api.compact_pool("no-such-pool")
         assert e.value.code == bb.ErrorCode.MEMORY_POOL_NOT_FOUND
         assert "bb_compaction_moves_total" in c.keystone.metrics_text()
+        # automatic trigger: off by default, armed by compaction_fragmentation_threshold (run by the health loop)
+        for k in ("big", "d"):
+            assert cl.remove(k) == bb.ErrorCode.OK
+        assert c.keystone.run_compaction_once() == 0
+
+
+def test_health_loop_compacts_pools_above_the_fragmentation_threshold(bb):
+    MiB = 1 << 20
+    kc = bb.KeystoneConfig()
+    kc.compaction_fragmentation_threshold = 0.3
+    with LocalCluster(cluster_id="autocompact", n_workers=1, pool_bytes=8 * MiB, keystone_cfg=kc) as c:
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0)
+        blobs = {k: os.urandom(MiB) for k in "abcdef"}
+        for k, v in blobs.items():
+            assert cl.put(k, v, cfg) == bb.ErrorCode.OK
+        for k in "ace":
+            assert cl.remove(k) == bb.ErrorCode.OK
+        pool = lambda: [p for p in cl.keystone().get_memory_pools() if p.id == "pool-0"][0]  # noqa: E731
+        assert c.keystone.run_compaction_once() >= 2  # what the health loop does every health_check_interval_sec
+        assert all(cl.get(k) == blobs[k] for k in "bdf")
+        assert cl.put("big", os.urandom(4 * MiB), cfg) == bb.ErrorCode.OK and pool().used >= 7 * MiB
+        assert c.keystone.run_compaction_once() == 0
 
 
 def test_readers_survive_concurrent_compaction_and_migration(bb):
