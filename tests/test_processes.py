@@ -118,6 +118,9 @@ def test_cluster_of_real_processes(procs, tmp_path, bb):
     assert len(pools) == 4 and sum(p["used"] for p in pools) >= 2 * (3 << 20)
     m = run_cli("metrics", "--http", f"127.0.0.1:{hport}")
     assert m.returncode == 0 and "bb_objects 1" in m.stdout and 'bb_tier_used_bytes{tier="NVME"}' in m.stdout
+    cp = run_cli("--keystone", ks, "compact", "nvme-w0")
+    assert cp.returncode == 0 and "moved 0 objects" in cp.stdout, cp.stdout + cp.stderr  # nothing to defragment yet
+    assert run_cli("--keystone", ks, "compact", "no-such-pool").returncode != 0
     ls = run_cli("--keystone", ks, "ls", "file-")
     assert ls.returncode == 0 and "file-key" in ls.stdout and "x2" in ls.stdout and "NVME" in ls.stdout
     wk = json.loads(run_cli("--keystone", ks, "workers").stdout)
