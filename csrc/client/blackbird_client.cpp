@@ -1191,10 +1191,84 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   }
   for (size_t i = 0; i < keys.size(); ++i)
     if (pending[i]) out[i] = ErrorCode::CHECKSUM_MISMATCH;
+  // ---- a mismatch can also mean that the Keystone moved the object under us (tier move, compaction, repair): the
+  // extents we read were freed and re-used.  Objects whose placements changed since we fetched them get one more pass.
+  static thread_local int refresh_depth = 0;
+  if (refresh_depth < 2) {
+    std::vector<size_t> bad;
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (out[i] == ErrorCode::CHECKSUM_MISMATCH && placed[i].ok()) bad.push_back(i);
+    if (!bad.empty()) {
+      std::vector<ObjectKey> bkeys;
+      for (size_t i : bad) bkeys.push_back(keys[i]);
+      auto again = keystone_->batch_get_workers(bkeys);
+      std::vector<ObjectKey> rkeys;
+      std::vector<void*> rptrs;
+      std::vector<size_t> rcaps, ridx;
+      for (size_t k = 0; k < bad.size(); ++k) {
+        const size_t i = bad[k];
+        if (!again[k].ok()) {
+          out[i] = again[k].error();  // removed (or being re-written) meanwhile: that is the answer
+        } else if (!(again[k].value() == placed[i].value())) {
+          rkeys.push_back(keys[i]), rptrs.push_back(dev_ptrs[i]), rcaps.push_back(capacity[i]), ridx.push_back(i);
+        }
+      }
+      if (!rkeys.empty()) {
+        metrics_.inc("get_placement_refresh_total", rkeys.size());
+        std::vector<size_t> rsizes;
+        ++refresh_depth;
+        auto recs = batch_get_device(rkeys, rptrs, rcaps, stream, &rsizes);
+        --refresh_depth;
+        for (size_t k = 0; k < ridx.size(); ++k) {
+          out[ridx[k]] = recs[k];
+          if (out_sizes && k < rsizes.size()) (*out_sizes)[ridx[k]] = rsizes[k];
+        }
+      }
+    }
+  }
   if (!keys.empty()) ewma_update(get_rpc_us_per_obj_, rpc_us_total / static_cast<double>(keys.size()));
   metrics_.inc("device_get_batches_total");
   metrics_.observe("device_get_batch_latency_us", us_since(t_all));
   return out;
+}
+
+// ================================================================ HostLoopbackTransport (CPU stand-in for the GPU fabric)
+bool HostLoopbackTransport::can_reach(const ShardPlacement& s) const {
+  if (s.storage_class == StorageClass::RAM_GPU) return false;
+  return reach_disk_ || !is_disk_class(s.storage_class);
+}
+
+ErrorCode HostLoopbackTransport::put_shards(const std::vector<DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo,
+                                            void*, std::vector<uint64_t>* digests) {
+  ++launches_;  // one "launch" per batch, like the fused kernel
+  if (digests) digests->assign(ops.size(), 0);
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const DeviceShardOp& op = ops[k];
+    const auto* src = static_cast<const uint8_t*>(dev_ptrs[op.item]) + op.obj_offset;
+    uint64_t d = 0;
+    ErrorCode ec = io_->write_shard(*op.placement, src, &d, algo);
+    for (size_t r = 0; r < op.replicas.size() && ec == ErrorCode::OK; ++r) ec = io_->write_shard(*op.replicas[r], src, nullptr, ChecksumAlgo::NONE);
+    if (ec != ErrorCode::OK) return ec;
+    if (digests) (*digests)[k] = d;
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode HostLoopbackTransport::get_shards(const std::vector<DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, ChecksumAlgo, void*,
+                                            std::vector<uint32_t>* status) {
+  ++launches_;
+  if (status) status->assign(ops.size(), 0);
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const DeviceShardOp& op = ops[k];
+    auto* dst = static_cast<uint8_t*>(dev_ptrs[op.item]) + op.obj_offset;
+    const ErrorCode ec = io_->read_shard(*op.placement, dst, op.placement->checksum_algo);
+    if (ec == ErrorCode::CHECKSUM_MISMATCH) {
+      if (status) (*status)[k] = 1;  // reported per shard, like the kernel's verify flag
+    } else if (ec != ErrorCode::OK) {
+      return ec;
+    }
+  }
+  return ErrorCode::OK;
 }
 
 }  // namespace bb::client

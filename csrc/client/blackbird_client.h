@@ -13,6 +13,7 @@
 // cancelled.
 #pragma once
 #include <atomic>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -118,6 +119,8 @@ class DeviceTransport {
   std::map<uint64_t, std::pair<std::vector<uint64_t>, std::vector<uint32_t>>> sync_results_;
 };
 
+class HostLoopbackTransport;
+
 class BlackbirdClient {
  public:
   explicit BlackbirdClient(BlackbirdClientOptions opts = {});
@@ -174,6 +177,7 @@ class BlackbirdClient {
   std::map<std::string, std::vector<double>> phase_summary() const { return metrics_.histogram_summary(); }
 
  private:
+  friend class HostLoopbackTransport;
   struct WorkerConn;
   std::shared_ptr<net::RpcClient> acquire(const std::string& endpoint);
   void release(const std::string& endpoint, std::shared_ptr<net::RpcClient> c);
@@ -210,6 +214,37 @@ class BlackbirdClient {
   std::mutex conn_mu_;
   std::map<std::string, std::vector<std::shared_ptr<net::RpcClient>>> idle_conns_;
   mutable Metrics metrics_;
+};
+
+// A DeviceTransport without a GPU: "device pointers" are host pointers and shards move over the host data paths of a
+// second (I/O) client.  It exists so that the device-side client logic -- chunk planning and pipelining, fan-out
+// descriptors, replica choice and fail-over, host-staged fall-backs, placement refresh -- is testable on CPU-only
+// machines (the reference has no fake transport at all); the GPU fabric replaces it in production.
+class HostLoopbackTransport : public DeviceTransport {
+ public:
+  // `io` moves the bytes (its own connections / shared-memory mappings); it must outlive the transport.
+  explicit HostLoopbackTransport(std::shared_ptr<BlackbirdClient> io, bool reach_disk_tiers = false)
+      : io_(std::move(io)), reach_disk_(reach_disk_tiers) {}
+  ErrorCode put_shards(const std::vector<DeviceShardOp>& ops, const std::vector<const void*>& dev_ptrs, ChecksumAlgo algo, void* stream,
+                       std::vector<uint64_t>* digests) override;
+  ErrorCode get_shards(const std::vector<DeviceShardOp>& ops, const std::vector<void*>& dev_ptrs, ChecksumAlgo algo, void* stream,
+                       std::vector<uint32_t>* status) override;
+  bool can_reach(const ShardPlacement& s) const override;
+  uint64_t launches() const override { return launches_; }
+  ErrorCode copy_h2d(void* dev, const void* host, size_t n, void*) override {
+    std::memcpy(dev, host, n);
+    return ErrorCode::OK;
+  }
+  ErrorCode copy_d2h(void* host, const void* dev, size_t n, void*) override {
+    std::memcpy(host, dev, n);
+    return ErrorCode::OK;
+  }
+  size_t max_in_flight() const override { return 2; }
+
+ private:
+  std::shared_ptr<BlackbirdClient> io_;
+  bool reach_disk_;
+  std::atomic<uint64_t> launches_{0};
 };
 
 }  // namespace bb::client

@@ -758,6 +758,10 @@ void bind_control(py::module_& m) {
     return out;
   });
   m.def("io_uring_supported", &worker::IoUring::supported);
+  m.def("attach_loopback_transport", [](std::shared_ptr<client::BlackbirdClient> c, std::shared_ptr<client::BlackbirdClient> io, bool reach_disk_tiers) {
+    c->set_device_transport(std::make_shared<client::HostLoopbackTransport>(std::move(io), reach_disk_tiers));
+  }, py::arg("client"), py::arg("io_client"), py::arg("reach_disk_tiers") = false,
+        "CPU stand-in for the GPU fabric: the device batch API of `client` moves host buffers through `io_client`'s host data paths");
   m.def("set_cluster_token", &net::set_cluster_token, "shared-secret gate of the RPC servers / clients of this process (net/tcp.h)");
   m.def("cluster_token", &net::cluster_token);
 
