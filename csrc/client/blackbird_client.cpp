@@ -1,5 +1,6 @@
 #include "common/trace.h"
 #include "client/blackbird_client.h"
+#include "common/mxfp8.h"
 #include "common/tchash_def.h"
 
 #include <algorithm>
@@ -1267,6 +1268,39 @@ ErrorCode HostLoopbackTransport::get_shards(const std::vector<DeviceShardOp>& op
     } else if (ec != ErrorCode::OK) {
       return ec;
     }
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode HostLoopbackTransport::put_fp8(const std::vector<DeviceFp8Op>& ops, void*, std::vector<uint64_t>* digests) {
+  ++launches_;
+  if (digests) digests->assign(ops.size(), 0);
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const DeviceFp8Op& op = ops[k];
+    std::vector<uint8_t> packed(mxfp8::packed_bytes(op.n_elems));
+    mxfp8::pack_bf16(static_cast<const uint16_t*>(op.wide), op.n_elems, packed.data());
+    uint64_t d = 0;
+    ErrorCode ec = io_->write_shard(*op.placement, packed.data(), &d, ChecksumAlgo::BBH64);
+    for (size_t r = 0; r < op.replicas.size() && ec == ErrorCode::OK; ++r) ec = io_->write_shard(*op.replicas[r], packed.data(), nullptr, ChecksumAlgo::NONE);
+    if (ec != ErrorCode::OK) return ec;
+    if (digests) (*digests)[k] = d;
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode HostLoopbackTransport::get_fp8(const std::vector<DeviceFp8Op>& ops, void*, std::vector<uint32_t>* status) {
+  ++launches_;
+  if (status) status->assign(ops.size(), 0);
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const DeviceFp8Op& op = ops[k];
+    std::vector<uint8_t> packed(mxfp8::packed_bytes(op.n_elems));
+    const ErrorCode ec = io_->read_shard(*op.placement, packed.data(), ChecksumAlgo::BBH64);
+    if (ec == ErrorCode::CHECKSUM_MISMATCH) {
+      if (status) (*status)[k] = 1;
+      continue;
+    }
+    if (ec != ErrorCode::OK) return ec;
+    mxfp8::unpack_bf16(packed.data(), op.n_elems, static_cast<uint16_t*>(op.wide));
   }
   return ErrorCode::OK;
 }

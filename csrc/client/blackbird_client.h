@@ -240,6 +240,11 @@ class HostLoopbackTransport : public DeviceTransport {
     return ErrorCode::OK;
   }
   size_t max_in_flight() const override { return 2; }
+  // MXFP8 through the CPU reference codec (common/mxfp8.h): the stored object and its digest are the ones the fused
+  // kernels produce, so the fp8 client logic (replica fan-out, fail-over between replicas) is testable on CPU too.
+  bool fp8_eligible(uint64_t n_elems) const override { return n_elems != 0 && n_elems % 32 == 0; }
+  ErrorCode put_fp8(const std::vector<DeviceFp8Op>& ops, void* stream, std::vector<uint64_t>* digests) override;
+  ErrorCode get_fp8(const std::vector<DeviceFp8Op>& ops, void* stream, std::vector<uint32_t>* status) override;
 
  private:
   std::shared_ptr<BlackbirdClient> io_;

@@ -155,3 +155,40 @@ def test_device_gets_survive_concurrent_compaction_and_migration(bb):
         [t.join() for t in ts]
         assert not errors, errors[:5]
         assert reads[0] > 30 and moves > 0
+
+
+def test_fp8_device_api_replicas_and_failover_on_cpu(bb):
+    """batch_put_device_fp8 / batch_get_device_fp8 through the loopback transport (CPU reference codec): every replica
+    holds the reference-packed bytes with the BBH64 digest, a get whose replica is corrupt is retried on the next one,
+    odd block counts work, ineligible sizes answer NOT_IMPLEMENTED (the caller packs first)."""
+    with LocalCluster(cluster_id="devfp8", n_workers=3, pool_bytes=32 * MiB) as c:
+        cl = make_client(bb, c)
+        rng = np.random.default_rng(3)
+        ns = [32, 16384 + 96, 5 * 16384]
+        xs = [(rng.standard_normal(n) * 3).astype(np.float32) for n in ns]
+        bf = [(x.view(np.uint32) >> 16).astype(np.uint16) for x in xs]  # truncated bf16 bit patterns
+        keys = [f"f/{n}" for n in ns]
+        cfg = bb.WorkerConfig(replication_factor=3, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[bb.StorageClass.RAM_CPU])
+        assert cl.batch_put_device_fp8(keys, [b.ctypes.data for b in bf], ns, cfg, 0) == [bb.ErrorCode.OK] * 3
+        pools = {p.id: p for p in cl.keystone().get_memory_pools()}
+        for k, b, n in zip(keys, bf, ns):
+            ref = bb.mxfp8_pack_ref(b)
+            copies = cl.get_workers(k)
+            assert len(copies) == 3 and len({cp.shards[0].worker_id for cp in copies}) == 3
+            for cp in copies:
+                sh = cp.shards[0]
+                assert sh.length == n + n // 32 and sh.checksum == bb.bbh64_reference(ref)
+                w = [w for w in c.workers if w.backend(sh.pool_id) is not None][0]
+                assert w.backend(sh.pool_id).read(sh.location["remote_addr"] - pools[sh.pool_id].ucx_remote_addr, sh.length) == bytes(ref)
+        # corrupt two of the three replicas of the middle object
+        copies = cl.get_workers(keys[1])
+        for cp in copies[:2]:
+            sh = cp.shards[0]
+            w = [w for w in c.workers if w.backend(sh.pool_id) is not None][0]
+            off = sh.location["remote_addr"] - pools[sh.pool_id].ucx_remote_addr + 7
+            w.backend(sh.pool_id).write(off, bytes([w.backend(sh.pool_id).read(off, 1)[0] ^ 0xFF]))
+        outs = [np.zeros(n, dtype=np.uint16) for n in ns]
+        assert cl.batch_get_device_fp8(keys, [o.ctypes.data for o in outs], ns, 0) == [bb.ErrorCode.OK] * 3
+        for b, o, n in zip(bf, outs, ns):
+            assert np.array_equal(o, np.frombuffer(bb.mxfp8_unpack_ref(bb.mxfp8_pack_ref(b), n), dtype=np.uint16))
+        assert not cl.device_fp8_eligible(40) and cl.device_fp8_eligible(64)
