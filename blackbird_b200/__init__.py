@@ -13,6 +13,7 @@ __version__ = "0.1.0"
 _LAZY = {
     "LocalCluster": ("blackbird_b200.parallel", "LocalCluster"),
     "GpuRankCluster": ("blackbird_b200.parallel", "GpuRankCluster"),
+    "CpuRankCluster": ("blackbird_b200.parallel", "CpuRankCluster"),
     "TensorStore": ("blackbird_b200.ops", "TensorStore"),            # imports torch
     "AsyncTensorStore": ("blackbird_b200.ops", "AsyncTensorStore"),
     "BlackbirdClient": ("blackbird_b200._bb", "BlackbirdClient"),

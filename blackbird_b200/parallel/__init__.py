@@ -1,1 +1,1 @@
-from .cluster import GpuRankCluster, LocalCluster  # noqa: F401
+from .cluster import CpuRankCluster, GpuRankCluster, LocalCluster  # noqa: F401

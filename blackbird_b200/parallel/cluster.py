@@ -267,3 +267,84 @@ class GpuRankCluster:
             self.rpc.stop()
         if self.keystone is not None:
             self.keystone.stop()
+
+
+class CpuRankCluster:
+    """The GpuRankCluster topology without GPUs: one process per rank (torchrun, `gloo`), rank 0 hosts the Keystone,
+    every rank runs a worker with a memfd-backed DRAM pool and a client whose device batch API goes through the
+    HostLoopbackTransport ("device pointers" are host buffers).  Shards placed on another rank's pool are written by
+    one-sided memcpy into that rank's process (same host) or over its TCP data server.  It exists so that the multi-rank
+    host-side logic -- rendezvous, registration over RPC, ring placement, cross-process pool mapping, fan-out -- runs on
+    CPU-only machines (tests/test_multi_cpu.py)."""
+
+    def __init__(self, dram_bytes: int = 64 << 20, cluster_id: str = "cpu", shared_memory: bool = True):
+        import torch
+        import torch.distributed as dist
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dist = dist if self.world > 1 else None
+        self._owns_pg = False
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("gloo")
+            self._owns_pg = True
+        self.node_id = f"cpu{self.rank}"
+        self.keystone = self.rpc = None
+        port_t = torch.zeros(1, dtype=torch.int64)
+        if self.rank == 0:
+            cfg = _bb.KeystoneConfig()
+            cfg.cluster_id = cluster_id
+            cfg.listen_address = "127.0.0.1:0"
+            cfg.http_metrics_port = "0"
+            cfg.enable_gc = False
+            cfg.rpc_threads = 4
+            self.keystone = _bb.KeystoneService(cfg, None)
+            assert self.keystone.initialize() == _bb.ErrorCode.OK and self.keystone.start() == _bb.ErrorCode.OK
+            self.keystone.install_data_server_mover()
+            self.rpc = _bb.RpcService(self.keystone, cfg)
+            assert self.rpc.start() == _bb.ErrorCode.OK
+            port_t[0] = self.rpc.rpc_port
+        if self.world > 1:
+            dist.broadcast(port_t, 0)
+        self.keystone_port = int(port_t.item())
+        self.api = _bb.LocalKeystoneApi(self.keystone) if self.rank == 0 else self._new_api()
+        wc = _bb.WorkerServiceConfig()
+        wc.worker_id, wc.node_id, wc.cluster_id = f"worker-cpu{self.rank}", self.node_id, cluster_id
+        wc.ucx_endpoint = "127.0.0.1:0"
+        wc.lease_ttl_sec, wc.heartbeat_interval_sec = 30, 5
+        pool = _bb.StoragePoolConfig(f"dram{self.rank}", _bb.StorageClass.RAM_CPU, dram_bytes, "")
+        pool.shared_memory = shared_memory
+        wc.storage_pools = [pool]
+        self.worker = _bb.WorkerService(wc, None, self.api)
+        assert self.worker.create_storage_pools_from_config() == _bb.ErrorCode.OK
+        assert self.worker.initialize() == _bb.ErrorCode.OK and self.worker.start() == _bb.ErrorCode.OK
+        self.barrier()
+        opts = _bb.BlackbirdClientOptions("127.0.0.1", self.keystone_port, 60000, 4, self.node_id)
+        self.client_api = self.api if self.rank == 0 else self._new_api()
+        self.client = _bb.BlackbirdClient(self.client_api, opts)
+        self.io_client = _bb.BlackbirdClient(self.client_api, opts)
+        assert self.client.connect() == _bb.ErrorCode.OK and self.io_client.connect() == _bb.ErrorCode.OK
+        _bb.attach_loopback_transport(self.client, self.io_client)
+        self.barrier()
+
+    def _new_api(self):
+        api = _bb.KeystoneRpcClient()
+        assert api.connect("127.0.0.1", self.keystone_port, 10000) == _bb.ErrorCode.OK
+        return api
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def stop(self):
+        self.barrier()
+        self.client = self.io_client = None
+        self.worker.stop()
+        self.barrier()
+        if self.rpc is not None:
+            self.rpc.stop()
+        if self.keystone is not None:
+            self.keystone.stop()
+        if self._owns_pg:
+            self.dist.destroy_process_group()
