@@ -31,6 +31,14 @@ T unwrap(Result<T> r) {
   return std::move(r.value());
 }
 
+// Runs a native call that may block on the network with the GIL released (other Python threads -- e.g. an in-process
+// proxy or server written in Python -- keep running); results are converted after the GIL is back.
+template <typename F>
+auto nogil(F&& f) {
+  py::gil_scoped_release rel;
+  return f();
+}
+
 py::object location_to_py(const LocationDetail& l) {
   py::dict d;
   if (auto* m = std::get_if<MemoryLocation>(&l)) {
@@ -591,8 +599,8 @@ void bind_control(py::module_& m) {
   py::class_<rpc::KeystoneApi, std::shared_ptr<rpc::KeystoneApi>>(m, "KeystoneApi")
       .def("object_exists", [](rpc::KeystoneApi& k, const std::string& key) { return unwrap(k.object_exists(key)); }, py::call_guard<py::gil_scoped_release>())
       .def("get_workers", [](rpc::KeystoneApi& k, const std::string& key) { return unwrap(k.get_workers(key)); }, py::call_guard<py::gil_scoped_release>())
-      .def("put_start", [](rpc::KeystoneApi& k, const std::string& key, size_t size, const WorkerConfig& c) { return unwrap(k.put_start(key, size, c)); },
-           py::arg("key"), py::arg("size"), py::arg("config") = WorkerConfig{}, py::call_guard<py::gil_scoped_release>())
+      .def("put_start", [](rpc::KeystoneApi& k, const std::string& key, size_t size, const WorkerConfig& c) { return unwrap(nogil([&] { return k.put_start(key, size, c); })); },
+           py::arg("key"), py::arg("size"), py::arg("config") = WorkerConfig{})
       .def("put_complete", [](rpc::KeystoneApi& k, const std::string& key, const keystone::ShardChecksums& s) { return k.put_complete(key, s); },
            py::arg("key"), py::arg("checksums") = keystone::ShardChecksums{}, py::call_guard<py::gil_scoped_release>())
       .def("put_cancel", &rpc::KeystoneApi::put_cancel, py::call_guard<py::gil_scoped_release>())
@@ -602,23 +610,23 @@ void bind_control(py::module_& m) {
       .def("get_cluster_stats", [](rpc::KeystoneApi& k) { return unwrap(k.get_cluster_stats()); }, py::call_guard<py::gil_scoped_release>())
       .def("get_view_version", [](rpc::KeystoneApi& k) { return unwrap(k.get_view_version()); }, py::call_guard<py::gil_scoped_release>())
       .def("batch_object_exists", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) {
-        return results_to_py(k.batch_object_exists(keys), [](bool b) { return py::bool_(b); });
+        return results_to_py(nogil([&] { return k.batch_object_exists(keys); }), [](bool b) { return py::bool_(b); });
       })
       .def("batch_get_workers", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) {
-        return results_to_py(k.batch_get_workers(keys), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
+        return results_to_py(nogil([&] { return k.batch_get_workers(keys); }), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
       })
       .def("batch_put_start", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys, const std::vector<size_t>& sizes, const WorkerConfig& c) {
         std::vector<PutStartItem> items;
         for (size_t i = 0; i < keys.size(); ++i) items.push_back({keys[i], i < sizes.size() ? sizes[i] : 0, c});
-        return results_to_py(k.batch_put_start(items), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
+        return results_to_py(nogil([&] { return k.batch_put_start(items); }), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
       })
       .def("batch_put_complete", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) { return k.batch_put_complete(keys, {}); })
       .def("batch_put_cancel", &rpc::KeystoneApi::batch_put_cancel)
       .def("batch_remove_object", &rpc::KeystoneApi::batch_remove_object)
-      .def("get_memory_pools", [](rpc::KeystoneApi& k) { return unwrap(k.get_memory_pools()); })
+      .def("get_memory_pools", [](rpc::KeystoneApi& k) { return unwrap(nogil([&] { return k.get_memory_pools(); })); })
       .def("get_workers_info", [](rpc::KeystoneApi& k) {
         py::list out;
-        for (const auto& w : unwrap(k.get_workers_info())) {
+        for (const auto& w : unwrap(nogil([&] { return k.get_workers_info(); }))) {
           py::dict d;
           d["worker_id"] = w.worker_id;
           d["node_id"] = w.node_id;
@@ -630,15 +638,15 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
-      .def("compact_pool", [](rpc::KeystoneApi& k, const std::string& pool, size_t max_moves) { return unwrap(k.compact_pool(pool, max_moves)); },
-           py::arg("pool"), py::arg("max_moves") = 64, py::call_guard<py::gil_scoped_release>())
+      .def("compact_pool", [](rpc::KeystoneApi& k, const std::string& pool, size_t max_moves) { return unwrap(nogil([&] { return k.compact_pool(pool, max_moves); })); },
+           py::arg("pool"), py::arg("max_moves") = 64)
       .def("list_objects", [](rpc::KeystoneApi& k, const std::string& prefix, size_t limit, const std::string& after) {
         py::list out;
-        for (const auto& o : unwrap(k.list_objects(prefix, limit, after))) out.append(py::make_tuple(o.key, o.size, o.copies, o.tier));
+        for (const auto& o : unwrap(nogil([&] { return k.list_objects(prefix, limit, after); }))) out.append(py::make_tuple(o.key, o.size, o.copies, o.tier));
         return out;
       }, py::arg("prefix") = "", py::arg("limit") = 0, py::arg("start_after") = "", "[(key, size, copies, tier)] in key order")
-      .def("client_register", [](rpc::KeystoneApi& k, const std::string& n) { return unwrap(k.client_register(n)); })
-      .def("client_ping", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(k.client_ping(id)); })
+      .def("client_register", [](rpc::KeystoneApi& k, const std::string& n) { return unwrap(nogil([&] { return k.client_register(n); })); })
+      .def("client_ping", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(nogil([&] { return k.client_ping(id); })); })
       .def("register_memory_pool", &rpc::KeystoneApi::register_memory_pool)
       .def("worker_heartbeat", &rpc::KeystoneApi::worker_heartbeat);
   py::class_<rpc::KeystoneRpcClient, rpc::KeystoneApi, std::shared_ptr<rpc::KeystoneRpcClient>>(m, "KeystoneRpcClient")
@@ -968,7 +976,7 @@ void bind_control(py::module_& m) {
       })
       .def("batch_remove", &BlackbirdClient::batch_remove, py::call_guard<py::gil_scoped_release>())
       .def("batch_exists", [](BlackbirdClient& c, const std::vector<std::string>& keys) {
-        return results_to_py(c.batch_exists(keys), [](bool b) { return py::bool_(b); });
+        return results_to_py(nogil([&] { return c.batch_exists(keys); }), [](bool b) { return py::bool_(b); });
       })
       .def("batch_put_device", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<uintptr_t>& ptrs,
                                   const std::vector<size_t>& sizes, const WorkerConfig& cfg, uintptr_t stream) {
@@ -989,7 +997,7 @@ void bind_control(py::module_& m) {
         }
         return py::make_tuple(ecs, sizes);
       }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("capacity"), py::arg("stream") = 0)
-      .def("cluster_stats", [](BlackbirdClient& c) { return unwrap(c.cluster_stats()); })
+      .def("cluster_stats", [](BlackbirdClient& c) { return unwrap(nogil([&] { return c.cluster_stats(); })); })
       .def("metrics_text", &BlackbirdClient::metrics_text)
       .def("set_device_pipeline_chunks", &BlackbirdClient::set_device_pipeline_chunks)
       .def("phase_summary", &BlackbirdClient::phase_summary, "histogram name -> [count, sum_us, p50_us, p99_us]")

@@ -190,3 +190,146 @@ def test_json_parser_agrees_with_python_on_generated_documents(bb):
         assert same(json.loads(again), doc) and bb.json_roundtrip(again) == again
 
     check()
+
+
+class _RecordingProxy:
+    """TCP proxy that records every framed request a real client sends (structure-aware seeds for the mutator)."""
+
+    def __init__(self, target_port):
+        import threading
+
+        self.target = target_port
+        self.frames = []
+        self.srv = socket.socket()
+        self.srv.bind(("127.0.0.1", 0))
+        self.srv.listen(8)
+        self.port = self.srv.getsockname()[1]
+        self.run = True
+        self.t = threading.Thread(target=self._accept, daemon=True)
+        self.t.start()
+
+    def _accept(self):
+        import threading
+
+        self.srv.settimeout(0.2)
+        while self.run:
+            try:
+                c, _ = self.srv.accept()
+            except OSError:
+                continue
+            c.settimeout(None)  # the accepted socket inherits the listener's timeout
+            u = socket.create_connection(("127.0.0.1", self.target))
+            threading.Thread(target=self._pump, args=(c, u, True), daemon=True).start()
+            threading.Thread(target=self._pump, args=(u, c, False), daemon=True).start()
+
+    def _pump(self, a, b, record):
+        buf = b""
+        try:
+            while True:
+                d = a.recv(1 << 16)
+                if not d:
+                    break
+                b.sendall(d)
+                if record:
+                    buf += d
+                    while len(buf) >= 16:
+                        n = struct.unpack_from("<I", buf)[0]
+                        if len(buf) < 16 + n:
+                            break
+                        self.frames.append(buf[:16 + n])
+                        buf = buf[16 + n:]
+        except OSError:
+            pass
+        except Exception as e:  # noqa: BLE001
+            print("proxy pump died:", repr(e), flush=True)
+        finally:
+            for s in (a, b):
+                try:
+                    s.close()
+                except OSError:
+                    pass
+
+    def stop(self):
+        self.run = False
+        self.srv.close()
+
+
+def _mutate(rng, frame):
+    f = bytearray(frame)
+    for _ in range(rng.randrange(1, 6)):
+        op = rng.randrange(6)
+        if op == 0 and len(f) > 16:
+            f[rng.randrange(16, len(f))] ^= 1 << rng.randrange(8)                 # bit flip in the payload
+        elif op == 1 and len(f) > 20:
+            pos = rng.randrange(16, len(f) - 3)
+            f[pos:pos + 4] = struct.pack("<I", rng.choice([0, 1, 0xFFFFFFFF, 0x7FFFFFFF, 1 << 24]))  # clobber a length / count
+        elif op == 2 and len(f) > 17:
+            del f[rng.randrange(16, len(f)):]                                      # truncate the payload
+        elif op == 3:
+            f += rng.randbytes(rng.randrange(1, 64))                               # trailing garbage
+        elif op == 4:
+            f[4:8] = struct.pack("<I", rng.randrange(0, 40))                       # same payload, other method
+        else:
+            a = rng.randrange(16, len(f) + 1)
+            f[a:a] = f[16:16 + rng.randrange(0, 32)]                               # duplicate a slice
+    struct.pack_into("<I", f, 0, max(0, len(f) - 16) if rng.random() < 0.8 else rng.choice([0, len(f), 1 << 20]))
+    return bytes(f)
+
+
+def test_mutated_real_requests_do_not_break_keystone_or_worker(bb):
+    """Structure-aware fuzzing: the requests of a real client session (put / get / batch / admin calls, D_WRITE / D_READ)
+    are recorded through a proxy, mutated (bit flips, clobbered lengths and counts, truncation, method swaps) and fired at
+    the Keystone and at the worker data server; both keep serving.  Under the ASAN build this covers the decoders of
+    every wire struct with inputs that are almost valid."""
+    rng = random.Random(2026)
+    with LocalCluster(cluster_id="fuzz2", n_workers=2) as c:
+        kproxy = _RecordingProxy(c.rpc.rpc_port)
+        o = bb.BlackbirdClientOptions("127.0.0.1", kproxy.port, 30000, 2, "node-0")
+        o.enable_shm = False
+        cl = bb.BlackbirdClient(o)
+        assert cl.connect() == bb.ErrorCode.OK
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=2, ttl_ms=5000, preferred_classes=[bb.StorageClass.RAM_CPU])
+        data = os.urandom(30_000)
+        assert cl.put("seed/a", data, cfg) == bb.ErrorCode.OK and cl.get("seed/a") == data
+        assert cl.batch_put(["seed/b", "seed/c"], [data[:1000], data[:2000]], cfg) == [bb.ErrorCode.OK] * 2
+        cl.batch_get(["seed/b", "seed/c", "missing"])
+        cl.batch_exists(["seed/a", "nope"])
+        cl.object_exists("seed/a")
+        cl.cluster_stats()
+        api = cl.keystone()
+        api.get_memory_pools(), api.get_workers_info(), api.list_objects("seed/", 10, ""), api.get_view_version()
+        cl.batch_remove(["seed/b"])
+        kframes = list(kproxy.frames)
+        kproxy.stop()
+        assert len(kframes) >= 12
+        # data-server seeds: a D_WRITE and a D_READ built from a real placement
+        sh = cl.get_workers("seed/a")[0].shards[0]
+        pool = sh.pool_id.encode()
+        addr = sh.location["remote_addr"] | (1 << 63)
+        dframes = [_frame(1, 1, struct.pack("<I", len(pool)) + pool + struct.pack("<QI", addr, 64) + data[:64]),
+                   _frame(2, 2, struct.pack("<I", len(pool)) + pool + struct.pack("<QI", addr, 4096))]
+        dport = int(sh.endpoint.port)
+
+        def fire(port, frames, rounds):
+            for _ in range(rounds):
+                s = socket.create_connection(("127.0.0.1", port), 2.0)
+                s.settimeout(0.05)
+                try:
+                    for _ in range(rng.randrange(1, 5)):
+                        s.sendall(_mutate(rng, rng.choice(frames)))
+                    try:
+                        s.recv(1 << 16)
+                    except OSError:
+                        pass
+                except OSError:
+                    pass
+                finally:
+                    s.close()
+
+        fire(c.rpc.rpc_port, kframes, 250)
+        fire(dport, dframes, 150)
+        fresh = c.client()
+        blob = os.urandom(12345)
+        assert fresh.put("after", blob, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        assert fresh.get("after") == blob
+        assert bb.http_get("127.0.0.1", c.rpc.http_port, "/healthz")[0] == 200
