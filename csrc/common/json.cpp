@@ -82,14 +82,20 @@ struct Parser {
           case 'r': out += '\r'; break;
           case 't': out += '\t'; break;
           case 'u': {
-            uint32_t cp;
+            uint32_t cp = 0;
             if (!hex4(cp)) return false;
             if (cp >= 0xD800 && cp <= 0xDBFF && i + 1 < s.size() && s[i] == '\\' && s[i + 1] == 'u') {
+              const size_t save = i;
               i += 2;
-              uint32_t lo;
+              uint32_t lo = 0;
               if (!hex4(lo)) return false;
-              cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+              if (lo >= 0xDC00 && lo <= 0xDFFF) {
+                cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+              } else {
+                i = save;  // not a pair: the high surrogate stands alone, the next escape is parsed on its own
+              }
             }
+            if (cp >= 0xD800 && cp <= 0xDFFF) cp = 0xFFFD;  // lone surrogate -> replacement character
             put_utf8(out, cp);
             break;
           }

@@ -168,3 +168,11 @@ def test_bbh64_simd_paths_match_the_byte_at_a_time_definition(bb):
     tiles = (a.size + 16383) // 16384
     parts = [bb.bbh64_partial(a, 0, 100), bb.bbh64_partial(a, 100, 57), bb.bbh64_partial(a, 157, tiles - 157)]
     assert bb.bbh64_finalize(sum(parts) & ((1 << 64) - 1), a.size) == bb.bbh64(a)
+
+
+def test_json_surrogate_escapes(bb):
+    """\\uXXXX pairs decode to one code point; a surrogate that is not part of a pair becomes U+FFFD instead of an invalid
+    code point (found by review of a -Wmaybe-uninitialized warning; Python's own encoder never emits such input)."""
+    assert bb.parse_json('"\\ud83d\\ude00"') == "\U0001F600"
+    assert bb.parse_json('"\\ud83d\\u0041"') == "\ufffdA" and bb.parse_json('"\\ud83dA"') == "\ufffdA"
+    assert bb.parse_json('"\\ude00x"') == "\ufffdx" and bb.parse_json('"\\ud83d"') == "\ufffd"
