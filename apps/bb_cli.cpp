@@ -46,11 +46,21 @@ int main(int argc, char** argv) {
     std::printf("%s", r.value().c_str());
     return status == 200 ? 0 : 1;
   }
-  auto hp = split_host_port(args.get("keystone", "127.0.0.1:9090"));
-  if (!hp) return 2;
+  // --keystone takes one endpoint or, for an HA pair, a comma-separated list; the client follows the leader.
   client::BlackbirdClientOptions o;
-  o.keystone_host = hp->first;
-  o.keystone_port = static_cast<uint16_t>(hp->second);
+  {
+    const std::string list = args.get("keystone", "127.0.0.1:9090");
+    size_t pos = 0;
+    while (pos <= list.size()) {
+      const size_t comma = std::min(list.find(',', pos), list.size());
+      if (comma > pos) {
+        if (!split_host_port(list.substr(pos, comma - pos))) return 2;
+        o.keystone_endpoints.push_back(list.substr(pos, comma - pos));
+      }
+      pos = comma + 1;
+    }
+    if (o.keystone_endpoints.empty()) return 2;
+  }
   o.node_id = args.get("node-id");
   o.io_parallelism = static_cast<size_t>(args.num("parallelism", 4));
   client::BlackbirdClient cl(o);

@@ -70,7 +70,9 @@ ErrorCode BlackbirdClient::connect() {
   if (!keystone_) {
     auto c = std::make_shared<rpc::KeystoneRpcClient>();
     c->set_timeout_ms(opts_.rpc_timeout_ms);
-    ErrorCode ec = c->connect(opts_.keystone_host, opts_.keystone_port, std::min(opts_.rpc_timeout_ms, 5000));
+    const int connect_ms = std::min(opts_.rpc_timeout_ms, 5000);
+    ErrorCode ec = opts_.keystone_endpoints.empty() ? c->connect(opts_.keystone_host, opts_.keystone_port, connect_ms)
+                                                    : c->connect_any(opts_.keystone_endpoints, connect_ms);
     if (ec != ErrorCode::OK) return ec;
     keystone_ = c;
   }

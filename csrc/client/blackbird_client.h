@@ -29,6 +29,9 @@ namespace bb::client {
 struct BlackbirdClientOptions {
   std::string keystone_host = "127.0.0.1";
   uint16_t keystone_port = 9090;
+  // HA deployments: every keystone ("host:port"); when set it replaces keystone_host/port and the control connection
+  // follows the elected leader (KeystoneRpcClient::connect_any).
+  std::vector<std::string> keystone_endpoints;
   int rpc_timeout_ms = 30000;
   size_t io_parallelism = 4;
   std::string node_id;        // where this client runs (locality-aware placement)

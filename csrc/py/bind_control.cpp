@@ -653,6 +653,12 @@ void bind_control(py::module_& m) {
       .def(py::init<>())
       .def("connect", [](rpc::KeystoneRpcClient& c, const std::string& host, uint16_t port, int timeout_ms) { return c.connect(host, port, timeout_ms); },
            py::arg("host"), py::arg("port"), py::arg("timeout_ms") = 3000, py::call_guard<py::gil_scoped_release>())
+      .def("connect_any", [](rpc::KeystoneRpcClient& c, const std::vector<std::string>& eps, int timeout_ms) { return c.connect_any(eps, timeout_ms); },
+           py::arg("endpoints"), py::arg("timeout_ms") = 3000, py::call_guard<py::gil_scoped_release>())
+      .def("set_timeout_ms", &rpc::KeystoneRpcClient::set_timeout_ms)
+      .def("set_failover_budget_ms", &rpc::KeystoneRpcClient::set_failover_budget_ms)
+      .def("active_endpoint", &rpc::KeystoneRpcClient::active_endpoint)
+      .def("failovers", &rpc::KeystoneRpcClient::failovers)
       .def("connected", &rpc::KeystoneRpcClient::connected);
   py::class_<rpc::LocalKeystoneApi, rpc::KeystoneApi, std::shared_ptr<rpc::LocalKeystoneApi>>(m, "LocalKeystoneApi")
       .def(py::init<std::shared_ptr<KeystoneService>>());
@@ -902,6 +908,7 @@ void bind_control(py::module_& m) {
            py::arg("io_parallelism") = 4, py::arg("node_id") = "", py::arg("register_session") = false)
       .def_readwrite("keystone_host", &BlackbirdClientOptions::keystone_host)
       .def_readwrite("keystone_port", &BlackbirdClientOptions::keystone_port)
+      .def_readwrite("keystone_endpoints", &BlackbirdClientOptions::keystone_endpoints)
       .def_readwrite("rpc_timeout_ms", &BlackbirdClientOptions::rpc_timeout_ms)
       .def_readwrite("io_parallelism", &BlackbirdClientOptions::io_parallelism)
       .def_readwrite("node_id", &BlackbirdClientOptions::node_id)

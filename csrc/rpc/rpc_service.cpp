@@ -2,7 +2,10 @@
 
 #include "client/copy_mover.h"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 
 #include "common/log.h"
 #include "rpc/wire.h"
@@ -72,11 +75,19 @@ RpcService::RpcService(std::shared_ptr<keystone::KeystoneService> keystone, cons
 
 RpcService::~RpcService() { stop(); }
 
+void RpcService::leader_only(uint32_t method, net::RpcServer::Handler h) {
+  auto ks = keystone_;
+  rpc_.register_method(method, [ks, h = std::move(h)](const net::ConnPtr& c, const std::string& q) {
+    if (!ks->is_leader()) return ec_reply(ErrorCode::NOT_LEADER);
+    return h(c, q);
+  });
+}
+
 void RpcService::register_handlers() {
   auto ks = keystone_;
   using C = const net::ConnPtr&;
   using S = const std::string&;
-  rpc_.register_method(M_OBJECT_EXISTS, [ks](C, S q) {
+  leader_only(M_OBJECT_EXISTS, [ks](C, S q) {
     Reader r(q);
     auto res = ks->object_exists(r.str());
     Writer w;
@@ -84,13 +95,13 @@ void RpcService::register_handlers() {
     w.boolean(res.ok() && res.value());
     return w.take();
   });
-  rpc_.register_method(M_GET_WORKERS, [ks](C, S q) {
+  leader_only(M_GET_WORKERS, [ks](C, S q) {
     Reader r(q);
     Writer w;
     put_copies_result(w, ks->get_workers(r.str()));
     return w.take();
   });
-  rpc_.register_method(M_PUT_START, [ks](C, S q) {
+  leader_only(M_PUT_START, [ks](C, S q) {
     Reader r(q);
     const std::string key = r.str();
     const uint64_t size = r.u64();
@@ -102,22 +113,22 @@ void RpcService::register_handlers() {
     else put_copies_result(w, ks->put_start(key, size, cfg, cid, node));
     return w.take();
   });
-  rpc_.register_method(M_PUT_COMPLETE, [ks](C, S q) {
+  leader_only(M_PUT_COMPLETE, [ks](C, S q) {
     Reader r(q);
     const std::string key = r.str();
     ShardChecksums sums;
     get_sums(r, sums);
     return ec_reply(r.ok() ? ks->put_complete(key, sums) : ErrorCode::INVALID_PARAMETERS);
   });
-  rpc_.register_method(M_PUT_CANCEL, [ks](C, S q) {
+  leader_only(M_PUT_CANCEL, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->put_cancel(r.str()));
   });
-  rpc_.register_method(M_REMOVE_OBJECT, [ks](C, S q) {
+  leader_only(M_REMOVE_OBJECT, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->remove_object(r.str()));
   });
-  rpc_.register_method(M_REMOVE_ALL_OBJECTS, [ks](C, S) {
+  leader_only(M_REMOVE_ALL_OBJECTS, [ks](C, S) {
     auto res = ks->remove_all_objects();
     Writer w;
     w.ec(res.error());
@@ -137,7 +148,7 @@ void RpcService::register_handlers() {
     w.i64(ks->get_view_version());
     return w.take();
   });
-  rpc_.register_method(M_BATCH_OBJECT_EXISTS, [ks](C, S q) {
+  leader_only(M_BATCH_OBJECT_EXISTS, [ks](C, S q) {
     Reader r(q);
     auto res = ks->batch_object_exists(get_keys(r));
     Writer w;
@@ -149,7 +160,7 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
-  rpc_.register_method(M_BATCH_GET_WORKERS, [ks](C, S q) {
+  leader_only(M_BATCH_GET_WORKERS, [ks](C, S q) {
     Reader r(q);
     auto res = ks->batch_get_workers(get_keys(r));
     Writer w;
@@ -158,7 +169,7 @@ void RpcService::register_handlers() {
     for (const auto& e : res) put_copies_result(w, e);
     return w.take();
   });
-  rpc_.register_method(M_BATCH_PUT_START, [ks](C, S q) {
+  leader_only(M_BATCH_PUT_START, [ks](C, S q) {
     Reader r(q);
     std::vector<PutStartItem> items(r.count(16));
     for (auto& it : items) {
@@ -178,7 +189,7 @@ void RpcService::register_handlers() {
     for (const auto& e : res) put_copies_result(w, e);
     return w.take();
   });
-  rpc_.register_method(M_BATCH_PUT_COMPLETE, [ks](C, S q) {
+  leader_only(M_BATCH_PUT_COMPLETE, [ks](C, S q) {
     Reader r(q);
     auto keys = get_keys(r);
     std::vector<ShardChecksums> sums(r.count(4));
@@ -186,15 +197,15 @@ void RpcService::register_handlers() {
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
     return ecs_reply(ks->batch_put_complete(keys, sums));
   });
-  rpc_.register_method(M_BATCH_PUT_CANCEL, [ks](C, S q) {
+  leader_only(M_BATCH_PUT_CANCEL, [ks](C, S q) {
     Reader r(q);
     return ecs_reply(ks->batch_put_cancel(get_keys(r)));
   });
-  rpc_.register_method(M_BATCH_REMOVE_OBJECT, [ks](C, S q) {
+  leader_only(M_BATCH_REMOVE_OBJECT, [ks](C, S q) {
     Reader r(q);
     return ecs_reply(ks->batch_remove_object(get_keys(r)));
   });
-  rpc_.register_method(M_CLIENT_REGISTER, [ks](C, S q) {
+  leader_only(M_CLIENT_REGISTER, [ks](C, S q) {
     Reader r(q);
     auto res = ks->client_register(r.str());
     Writer w;
@@ -202,7 +213,7 @@ void RpcService::register_handlers() {
     w.str(res.ok() ? res.value() : "");
     return w.take();
   });
-  rpc_.register_method(M_CLIENT_PING, [ks](C, S q) {
+  leader_only(M_CLIENT_PING, [ks](C, S q) {
     Reader r(q);
     auto res = ks->client_ping(r.str());
     Writer w;
@@ -236,7 +247,7 @@ void RpcService::register_handlers() {
     Reader r(q);
     return ec_reply(ks->worker_heartbeat(r.str()));
   });
-  rpc_.register_method(M_MIGRATE_OBJECT, [ks](C, S q) {
+  leader_only(M_MIGRATE_OBJECT, [ks](C, S q) {
     Reader r(q);
     const std::string key = r.str();
     const auto target = static_cast<StorageClass>(r.u32());
@@ -260,7 +271,7 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
-  rpc_.register_method(M_LIST_OBJECTS, [ks](C, S q) {
+  leader_only(M_LIST_OBJECTS, [ks](C, S q) {
     Reader r(q);
     const std::string prefix = r.str();
     const uint64_t limit = r.u64();
@@ -278,7 +289,7 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
-  rpc_.register_method(M_COMPACT_POOL, [ks](C, S q) {
+  leader_only(M_COMPACT_POOL, [ks](C, S q) {
     Reader r(q);
     const std::string pool = r.str();
     const uint64_t max_moves = r.u64();
@@ -289,7 +300,7 @@ void RpcService::register_handlers() {
     if (res.ok()) w.u64(res.value());
     return w.take();
   });
-  rpc_.register_method(M_REMOVE_WORKER, [ks](C, S q) {
+  leader_only(M_REMOVE_WORKER, [ks](C, S q) {
     Reader r(q);
     return ec_reply(ks->remove_worker(r.str()));
   });
@@ -342,18 +353,102 @@ void RpcService::stop() {
 
 // ================================================================ client
 ErrorCode KeystoneRpcClient::connect(const std::string& host, uint16_t port, int timeout_ms) {
-  return rpc_.connect(host, port, timeout_ms);
+  return connect_any({host + ":" + std::to_string(port)}, timeout_ms);
 }
 ErrorCode KeystoneRpcClient::connect(const std::string& host_port, int timeout_ms) {
-  auto hp = split_host_port(host_port);
-  if (!hp) return ErrorCode::INVALID_ADDRESS;
-  return connect(hp->first, static_cast<uint16_t>(hp->second), timeout_ms);
+  std::vector<std::string> eps;
+  size_t pos = 0;
+  while (pos <= host_port.size()) {
+    const size_t comma = std::min(host_port.find(',', pos), host_port.size());
+    if (comma > pos) eps.push_back(host_port.substr(pos, comma - pos));
+    pos = comma + 1;
+  }
+  return connect_any(eps, timeout_ms);
+}
+ErrorCode KeystoneRpcClient::connect_any(const std::vector<std::string>& endpoints, int timeout_ms) {
+  std::vector<std::pair<std::string, uint16_t>> parsed;
+  for (const auto& e : endpoints) {
+    auto hp = split_host_port(e);
+    if (!hp) return ErrorCode::INVALID_ADDRESS;
+    parsed.emplace_back(hp->first, static_cast<uint16_t>(hp->second));
+  }
+  if (parsed.empty()) return ErrorCode::INVALID_ADDRESS;
+  std::lock_guard<std::mutex> lk(ep_mu_);
+  endpoints_ = std::move(parsed);
+  connect_timeout_ms_ = timeout_ms;
+  ErrorCode last = ErrorCode::CONNECTION_FAILED;
+  for (size_t i = 0; i < endpoints_.size(); ++i) {
+    auto c = std::make_shared<net::RpcClient>();
+    last = c->connect(endpoints_[i].first, endpoints_[i].second, timeout_ms);
+    if (last == ErrorCode::OK) {
+      rpc_ = std::move(c);
+      active_ = i;
+      ++gen_;
+      return ErrorCode::OK;
+    }
+  }
+  return last;
+}
+
+bool KeystoneRpcClient::connected() const {
+  std::lock_guard<std::mutex> lk(ep_mu_);
+  return rpc_ && rpc_->connected();
+}
+std::string KeystoneRpcClient::active_endpoint() const {
+  std::lock_guard<std::mutex> lk(ep_mu_);
+  if (endpoints_.empty()) return {};
+  return endpoints_[active_].first + ":" + std::to_string(endpoints_[active_].second);
+}
+std::shared_ptr<net::RpcClient> KeystoneRpcClient::current(uint64_t* gen) const {
+  std::lock_guard<std::mutex> lk(ep_mu_);
+  *gen = gen_;
+  return rpc_;
+}
+void KeystoneRpcClient::rotate(uint64_t seen_gen) {
+  std::lock_guard<std::mutex> lk(ep_mu_);
+  if (gen_ != seen_gen) return;
+  const size_t n = endpoints_.size();
+  for (size_t step = 1; step <= n; ++step) {
+    const size_t i = (active_ + step) % n;
+    auto c = std::make_shared<net::RpcClient>();
+    if (c->connect(endpoints_[i].first, endpoints_[i].second, connect_timeout_ms_) != ErrorCode::OK) continue;
+    rpc_ = std::move(c);  // calls still in flight on the old connection keep their shared_ptr
+    active_ = i;
+    ++gen_;
+    failovers_.fetch_add(1);
+    return;
+  }
 }
 
 Result<std::string> KeystoneRpcClient::call(uint32_t method, const std::string& req) {
-  auto r = rpc_.call(method, req, timeout_ms_);
-  if (!r.ok()) return r.error() == ErrorCode::CLIENT_DISCONNECTED ? ErrorCode::CLIENT_DISCONNECTED : ErrorCode::RPC_FAILED;
-  return r;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(failover_budget_ms_);
+  for (size_t attempt = 1;; ++attempt) {
+    uint64_t gen = 0;
+    auto c = current(&gen);
+    if (!c) return ErrorCode::CLIENT_DISCONNECTED;
+    auto r = c->call(method, req, timeout_ms_);
+    size_t n_eps = 0;
+    {
+      std::lock_guard<std::mutex> lk(ep_mu_);
+      n_eps = endpoints_.size();
+    }
+    bool not_leader = false;
+    if (r.ok() && r.value().size() >= 4) {
+      Reader rd(r.value());
+      not_leader = rd.ec() == ErrorCode::NOT_LEADER;
+    }
+    const bool retry = n_eps > 1 && (!r.ok() || not_leader) && std::chrono::steady_clock::now() < deadline;
+    if (!retry) {
+      if (!r.ok()) return r.error() == ErrorCode::CLIENT_DISCONNECTED ? ErrorCode::CLIENT_DISCONNECTED : ErrorCode::RPC_FAILED;
+      return r;
+    }
+    rotate(gen);
+    uint64_t now_gen = 0;
+    current(&now_gen);
+    // Nothing else reachable, or every keystone has been asked and nobody is leader yet (election in progress):
+    // pace the next round.
+    if (now_gen == gen || attempt % n_eps == 0) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+  }
 }
 
 #define BB_RPC(method, writer)                 \

@@ -8,7 +8,9 @@
 // Extra methods: batch_remove_object, client_register / client_ping (sessions), pool and worker
 // introspection / registration for deployments without a coordination daemon.
 #pragma once
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -153,6 +155,9 @@ class RpcService {
 
  private:
   void register_handlers();
+  // Object-scoped methods answer NOT_LEADER on a standby (its object map is only recovered when it is elected), which is
+  // what tells a multi-endpoint KeystoneRpcClient to move on to the next keystone.
+  void leader_only(uint32_t method, net::RpcServer::Handler h);
   std::shared_ptr<keystone::KeystoneService> keystone_;
   KeystoneConfig config_;
   net::RpcServer rpc_;
@@ -164,9 +169,19 @@ class KeystoneRpcClient : public KeystoneApi {
  public:
   KeystoneRpcClient() = default;
   ErrorCode connect(const std::string& host, uint16_t port, int timeout_ms = 3000);
+  // `host_port` may be a comma-separated list of keystones ("a:9090,b:9090"); see connect_any().
   ErrorCode connect(const std::string& host_port, int timeout_ms = 3000);
+  // HA: remembers every endpoint and connects to the first reachable one.  Afterwards a call that fails on the
+  // transport (keystone died) or is answered NOT_LEADER (keystone is a standby) moves to the next endpoint and is
+  // retried, for up to failover_budget_ms; with a single endpoint behaviour is unchanged (the error is returned).
+  // A retried mutation is at-least-once: a put_start whose reply was lost with the old leader can come back
+  // OBJECT_ALREADY_EXISTS from the new one.
+  ErrorCode connect_any(const std::vector<std::string>& endpoints, int timeout_ms = 3000);
   void set_timeout_ms(int ms) { timeout_ms_ = ms; }
-  bool connected() const { return rpc_.connected(); }
+  void set_failover_budget_ms(int ms) { failover_budget_ms_ = ms; }
+  bool connected() const;
+  std::string active_endpoint() const;
+  uint64_t failovers() const { return failovers_.load(); }
   Result<bool> object_exists(const ObjectKey& key) override;
   Result<std::vector<CopyPlacement>> get_workers(const ObjectKey& key) override;
   Result<std::vector<CopyPlacement>> put_start(const ObjectKey& key, size_t size, const WorkerConfig& cfg) override;
@@ -197,8 +212,18 @@ class KeystoneRpcClient : public KeystoneApi {
 
  private:
   Result<std::string> call(uint32_t method, const std::string& req);
-  net::RpcClient rpc_;
+  std::shared_ptr<net::RpcClient> current(uint64_t* gen) const;
+  // Connects to the next reachable endpoint after the active one unless another thread already did (gen moved on).
+  void rotate(uint64_t seen_gen);
+  mutable std::mutex ep_mu_;
+  std::vector<std::pair<std::string, uint16_t>> endpoints_;
+  size_t active_ = 0;
+  uint64_t gen_ = 0;
+  std::shared_ptr<net::RpcClient> rpc_;
   int timeout_ms_ = 30000;
+  int connect_timeout_ms_ = 3000;
+  int failover_budget_ms_ = 15000;
+  std::atomic<uint64_t> failovers_{0};
 };
 
 struct KeystoneBundle {

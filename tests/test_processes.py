@@ -182,6 +182,55 @@ def test_keystone_process_failover(procs, tmp_path):
     assert run_cli("--keystone", f"127.0.0.1:{ports[1]}", "put", "after-failover", str(blob)).returncode == 0
 
 
+def test_client_follows_the_keystone_leader(procs, tmp_path):
+    """A client that knows both keystones of an HA pair: it is pointed at the standby first and lands on the leader
+    (NOT_LEADER -> next endpoint), and when the leader is killed the same client object carries on against the
+    newly elected keystone without being reconfigured (reference clients re-resolve the leader through etcd,
+    etcd_service.cpp campaign/observe; ours rotate over the configured endpoints)."""
+    import blackbird_b200._bb as bb
+    cport = free_port()
+    procs.spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+    assert wait_port(cport)
+    cfg = tmp_path / "ks.yaml"
+    cfg.write_text("keystone:\n  cluster_id: ha2\n  enable_ha: true\n  service_registration_ttl_sec: 3\n  service_refresh_interval_sec: 1\n  http_metrics_port: \"0\"\n")
+    ports, servers = [], []
+    for i in range(2):
+        rp = free_port()
+        ports.append(rp)
+        servers.append(procs.spawn(os.path.join(BIN, "bb-keystone"), str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--listen-address",
+                                   f"127.0.0.1:{rp}", "--service-id", f"ks-{i}"))
+        assert wait_port(rp)
+        time.sleep(0.3)
+    wcfg = tmp_path / "w.yaml"
+    write_worker_cfg(wcfg, "w0", tmp_path / "nvme")
+    procs.spawn(os.path.join(BIN, "bb-worker"), "--config", str(wcfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "ha2")
+    time.sleep(1.0)
+    eps = [f"127.0.0.1:{ports[1]}", f"127.0.0.1:{ports[0]}"]  # standby first
+    opts = bb.BlackbirdClientOptions()
+    opts.keystone_endpoints = eps
+    cl = bb.BlackbirdClient(opts)
+    assert cl.connect() == bb.ErrorCode.OK
+    api = cl.keystone()
+    assert api.active_endpoint() == eps[0]
+    wc = bb.WorkerConfig()
+    wc.replication_factor = 1
+    wc.max_workers_per_copy = 1
+    blob = os.urandom(200000)
+    assert cl.put("k-before", blob, wc) == bb.ErrorCode.OK  # answered NOT_LEADER by the standby, retried on the leader
+    assert api.active_endpoint() == eps[1] and api.failovers() == 1
+    assert cl.get("k-before") == blob
+    servers[0].kill()
+    servers[0].wait()
+    api.set_failover_budget_ms(20000)
+    assert cl.get("k-before") == blob  # same client: transport failure -> standby -> waits out the election
+    assert api.active_endpoint() == eps[0] and api.failovers() >= 2
+    assert cl.put("k-after", blob, wc) == bb.ErrorCode.OK and cl.get("k-after") == blob
+    # the CLI takes the same list
+    out = tmp_path / "o.bin"
+    r = run_cli("--keystone", ",".join(reversed(eps)), "get", "k-after", str(out))
+    assert r.returncode == 0 and out.read_bytes() == blob, r.stdout + r.stderr
+
+
 def test_control_plane_benchmark_binary():
     b = subprocess.run([os.path.join(BIN, "bb-bench"), "control", "--threads", "4", "--batch", "256", "--iterations", "4"],
                        capture_output=True, text=True, timeout=120)
