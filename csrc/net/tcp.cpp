@@ -9,6 +9,7 @@
 #include <poll.h>
 #include <sched.h>
 #include <sys/epoll.h>
+#include <sys/random.h>
 #include <sys/eventfd.h>
 #include <sys/socket.h>
 #include <unistd.h>
@@ -17,8 +18,10 @@
 #include <chrono>
 #include <thread>
 #include <cstring>
+#include <random>
 
 #include "common/log.h"
+#include "common/sha256.h"
 
 namespace bb::net {
 
@@ -43,10 +46,26 @@ std::string cluster_token() {
 }
 
 namespace {
-bool token_equal(std::string_view a, const std::string& b) {  // constant time in the length of `a`
-  unsigned char diff = a.size() == b.size() ? 0 : 1;
-  for (size_t i = 0; i < a.size(); ++i) diff |= static_cast<unsigned char>(a[i]) ^ static_cast<unsigned char>(b[i % std::max<size_t>(1, b.size())]);
-  return diff == 0 && !b.empty();
+constexpr size_t kNonce = 16, kMac = 32;
+constexpr char kHelloMagic[] = "BBA1";
+void fresh_nonce(char* out) {
+  size_t got = 0;
+  while (got < kNonce) {
+    const ssize_t r = ::getrandom(out + got, kNonce - got, 0);
+    if (r > 0) got += static_cast<size_t>(r);
+    else if (errno != EINTR) break;
+  }
+  if (got < kNonce) {  // no getrandom (ancient kernel / seccomp): fall back to the C++ entropy source
+    std::random_device rd;
+    for (; got < kNonce; ++got) out[got] = static_cast<char>(rd());
+  }
+}
+// HMAC(token, role || cnonce || snonce); `nonces` is cnonce followed by snonce.
+std::string handshake_mac(const std::string& token, std::string_view role, std::string_view nonces) {
+  std::string msg(role);
+  msg.append(nonces);
+  const Sha256Digest d = hmac_sha256(token, msg);
+  return std::string(reinterpret_cast<const char*>(d.data()), d.size());
 }
 void set_nodelay(int fd) {
   int one = 1;
@@ -542,12 +561,30 @@ bool RpcServer::on_data(const ConnPtr& c) {
     if (!c->authed()) {
       const std::string token = cluster_token();
       if (method == kAuthMethod) {
-        if (token.empty() || token_equal(std::string_view(in.data() + body, len), token)) {
+        const std::string_view msg(in.data() + body, len);
+        if (token.empty()) {  // open cluster: nothing to prove, tell the client so
           c->set_authed();
           if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;
           continue;
         }
-        BB_LOG(WARNING) << "rpc: wrong cluster token from " << c->peer();
+        std::string& nonces = c->auth_nonces();
+        if (nonces.empty() && msg.size() == 4 + kNonce && msg.substr(0, 4) == kHelloMagic) {
+          nonces.assign(msg.substr(4));
+          char sn[kNonce];
+          fresh_nonce(sn);
+          nonces.append(sn, kNonce);
+          std::string reply(sn, kNonce);
+          reply += handshake_mac(token, "bb-srv", nonces);
+          if (!c->send(encode_frame(kAuthMethod, id, reply))) return false;
+          continue;
+        }
+        if (nonces.size() == 2 * kNonce && msg.size() == kMac && mac_equal(msg.data(), handshake_mac(token, "bb-cli", nonces).data(), kMac)) {
+          nonces.clear();
+          c->set_authed();
+          if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;
+          continue;
+        }
+        BB_LOG(WARNING) << "rpc: failed cluster-token handshake from " << c->peer();
         c->send(encode_frame(kDeniedMarker, id, std::string()));
         return false;
       }
@@ -603,20 +640,37 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
     return ErrorCode::CONNECTION_FAILED;
   }
   const std::string token = cluster_token();
-  if (!token.empty()) {  // present the cluster token before anything else
-    const std::string f = encode_frame(kAuthMethod, 0, token);
-    char rh[kFrameHeader];
-    if (!send_all(fd, f.data(), f.size(), timeout_ms) || !recv_all(fd, rh, sizeof rh, timeout_ms)) {
-      ::close(fd);
-      return ErrorCode::CONNECTION_FAILED;
+  if (!token.empty()) {  // mutual challenge-response on the cluster token before anything else (tcp.h)
+    auto exchange = [&](uint64_t id, const std::string& body, std::string* reply) -> ErrorCode {
+      const std::string f = encode_frame(kAuthMethod, id, body);
+      char rh[kFrameHeader];
+      if (!send_all(fd, f.data(), f.size(), timeout_ms) || !recv_all(fd, rh, sizeof rh, timeout_ms)) return ErrorCode::CONNECTION_FAILED;
+      const uint32_t rlen = rd32(rh), rmethod = rd32(rh + 4);
+      reply->assign(rlen <= 4096 ? rlen : 0, '\0');
+      if (rlen > 4096 || (rlen && !recv_all(fd, reply->data(), rlen, timeout_ms))) return ErrorCode::CONNECTION_FAILED;
+      return rmethod == kAuthMethod ? ErrorCode::OK : ErrorCode::ACCESS_DENIED;
+    };
+    std::string nonces(kNonce, '\0'), reply;
+    fresh_nonce(nonces.data());
+    ErrorCode ec = exchange(0, std::string(kHelloMagic, 4) + nonces, &reply);
+    if (ec == ErrorCode::OK) {
+      if (reply.size() != kNonce + kMac) {
+        BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " has no cluster token but this client does";
+        ec = ErrorCode::ACCESS_DENIED;
+      } else {
+        nonces.append(reply, 0, kNonce);
+        if (!mac_equal(reply.data() + kNonce, handshake_mac(token, "bb-srv", nonces).data(), kMac)) {
+          BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " does not hold this cluster's token";
+          ec = ErrorCode::ACCESS_DENIED;
+        } else {
+          ec = exchange(1, handshake_mac(token, "bb-cli", nonces), &reply);
+        }
+      }
     }
-    const uint32_t rlen = rd32(rh), rmethod = rd32(rh + 4);
-    std::string drop(rlen <= 4096 ? rlen : 0, '\0');
-    if (rlen > 4096 || (rlen && !recv_all(fd, drop.data(), rlen, timeout_ms)) || rmethod == kDeniedMarker) {
+    if (ec != ErrorCode::OK) {
       ::close(fd);
-      return rmethod == kDeniedMarker ? ErrorCode::ACCESS_DENIED : ErrorCode::CONNECTION_FAILED;
+      return ec;
     }
-    // kAuthMethod = accepted; the unknown-method marker = a server without a token (open cluster): both fine
   }
   std::lock_guard<std::mutex> lk(mu_);
   fd_ = fd;

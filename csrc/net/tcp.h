@@ -34,8 +34,16 @@ class TcpServer;
 // Shared-secret gate for the framed RPC protocol (the reference lists mTLS / ACL as roadmap, README.md:146-153; its
 // servers accept every connection).  When a cluster token is set -- `auth_token:` in keystone / worker YAML,
 // BlackbirdClientOptions::auth_token, or BB_AUTH_TOKEN in the environment of every process -- an RpcServer started in
-// this process answers nothing on a connection until its first frame presents the token (kAuthMethod), and every
-// RpcClient presents it right after connecting.  HTTP endpoints (/metrics, /healthz) stay open.
+// this process answers nothing on a connection until it has passed the kAuthMethod handshake, which every RpcClient
+// runs right after connecting.  The token itself never travels -- it keys an HMAC-SHA256 over fresh nonces, in both
+// directions, so a passive listener learns nothing reusable and a client with a token refuses a server that cannot
+// prove it has the same one:
+//   C -> S  kAuthMethod  "BBA1" cnonce[16]
+//   S -> C  kAuthMethod  snonce[16] HMAC(token, "bb-srv" cnonce snonce)[32]      (empty body: the server has no token)
+//   C -> S  kAuthMethod  HMAC(token, "bb-cli" cnonce snonce)[32]
+//   S -> C  kAuthMethod  (empty) = accepted   |   kDeniedMarker, then the server hangs up
+// The stream after the handshake is neither encrypted nor MAC'd (no TLS): this is an admission gate, not a secure
+// channel.  HTTP endpoints (/metrics, /healthz) stay open.
 void set_cluster_token(const std::string& token);
 std::string cluster_token();
 constexpr uint32_t kAuthMethod = 0x7FFFFF00u;
@@ -61,6 +69,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::string& inbuf() { return inbuf_; }
   bool authed() const { return authed_.load(std::memory_order_acquire); }
   void set_authed() { authed_.store(true, std::memory_order_release); }
+  std::string& auth_nonces() { return auth_nonces_; }  // handshake in progress: cnonce + snonce
   // EPOLLONESHOT hands a connection from one pool thread to the next through the kernel; these make the
   // hand-off an explicit release/acquire pair on the connection's own state as well.
   void release_ownership() { handoff_.fetch_add(1, std::memory_order_release); }
@@ -78,6 +87,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::mutex write_mu_;
   std::atomic<bool> closed_{false};
   std::atomic<bool> authed_{false};
+  std::string auth_nonces_;
   std::atomic<uint64_t> handoff_{0};
 };
 using ConnPtr = std::shared_ptr<Connection>;

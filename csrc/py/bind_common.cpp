@@ -8,6 +8,7 @@
 #include "common/json.h"
 #include "common/log.h"
 #include "common/mxfp8.h"
+#include "common/sha256.h"
 #include "common/tchash_def.h"
 #include "common/yaml.h"
 
@@ -144,6 +145,16 @@ void bind_common(py::module_& m) {
   });
   m.def("bbh64_finalize", &bbh64_finalize);
   m.def("bbh64_impl_name", [] { return std::string(bbh64_impl_name()); });
+  m.def("sha256", [](py::bytes b) {
+    const std::string s = b;
+    const Sha256Digest d = sha256(s);
+    return py::bytes(reinterpret_cast<const char*>(d.data()), d.size());
+  });
+  m.def("hmac_sha256", [](py::bytes key, py::bytes msg) {
+    const std::string k = key, v = msg;
+    const Sha256Digest d = hmac_sha256(k, v);
+    return py::bytes(reinterpret_cast<const char*>(d.data()), d.size());
+  });
   m.def("bbh64_weight", [](uint32_t k, uint32_t n) { return tchash::weight(k, n); });
   m.def("bbh64_off_to_row", [](uint32_t o) { return tchash::off_to_row(o); });
   m.def("bbh64_off_to_k", [](uint32_t o) { return tchash::off_to_k(o); });

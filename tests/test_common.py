@@ -176,3 +176,19 @@ def test_json_surrogate_escapes(bb):
     assert bb.parse_json('"\\ud83d\\ude00"') == "\U0001F600"
     assert bb.parse_json('"\\ud83d\\u0041"') == "\ufffdA" and bb.parse_json('"\\ud83dA"') == "\ufffdA"
     assert bb.parse_json('"\\ude00x"') == "\ufffdx" and bb.parse_json('"\\ud83d"') == "\ufffd"
+
+
+def test_sha256_and_hmac_match_hashlib(bb):
+    """The handshake's SHA-256 / HMAC-SHA256 against hashlib, across every padding boundary and long keys."""
+    import hashlib
+    import hmac
+    import os
+    assert bb.sha256(b"abc").hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    for n in list(range(0, 130)) + [191, 192, 255, 256, 1000, 4096, 100_003]:
+        data = os.urandom(n)
+        assert bb.sha256(data) == hashlib.sha256(data).digest(), n
+    for klen in (0, 1, 20, 63, 64, 65, 200):
+        key = os.urandom(klen)
+        for n in (0, 1, 55, 56, 64, 300):
+            msg = os.urandom(n)
+            assert bb.hmac_sha256(key, msg) == hmac.new(key, msg, hashlib.sha256).digest(), (klen, n)

@@ -463,8 +463,9 @@ storage_pools:
 
 def test_cluster_token_gates_every_rpc_server(procs, tmp_path, bb):
     """With a cluster token (BB_AUTH_TOKEN / --auth-token / auth_token: in the YAMLs) bb-coord, bb-keystone and the
-    worker's data server answer nothing until a connection presents it: tools with the token work end to end, tools
-    without it (or with a wrong one) are refused with ACCESS_DENIED, raw frames get the denial marker and a close."""
+    worker's data server answer nothing until a connection has passed the HMAC challenge-response on it: tools with
+    the token work end to end, tools without it (or with a wrong one) are refused with ACCESS_DENIED, raw frames get the
+    denial marker and a close, and the token itself never crosses the wire."""
     import struct
 
     env_ok = dict(os.environ, BB_AUTH_TOKEN="s3cret-cluster-token")
@@ -512,6 +513,81 @@ def test_cluster_token_gates_every_rpc_server(procs, tmp_path, bb):
         assert len(hdr) == 16 and struct.unpack("<IIQ", hdr)[1] == 0x7FFFFFFD
         assert s.recv(16) == b""
         s.close()
+    # the handshake, played by hand: HMAC-SHA256 over fresh nonces in both directions, the token never travels
+    import hashlib
+    import hmac as pyhmac
+    AUTH, DENIED, tok = 0x7FFFFF00, 0x7FFFFFFD, b"s3cret-cluster-token"
+
+    def frame(method, rid, body=b""):
+        return struct.pack("<IIQ", len(body), method, rid) + body
+
+    def recv_frame(s):
+        hdr = b""
+        while len(hdr) < 16:
+            part = s.recv(16 - len(hdr))
+            if not part:
+                return None
+            hdr += part
+        n, method, _ = struct.unpack("<IIQ", hdr)
+        body = b""
+        while len(body) < n:
+            body += s.recv(n - len(body))
+        return method, body
+
+    def handshake(port, key, tamper=False):
+        s = socket.create_connection(("127.0.0.1", port), 2.0)
+        s.settimeout(2.0)
+        cn = os.urandom(16)
+        s.sendall(frame(AUTH, 0, b"BBA1" + cn))
+        method, body = recv_frame(s)
+        assert method == AUTH and len(body) == 48
+        sn, srv_mac = body[:16], body[16:]
+        assert srv_mac == pyhmac.new(tok, b"bb-srv" + cn + sn, hashlib.sha256).digest()  # the server proves itself first
+        proof = pyhmac.new(key, b"bb-cli" + cn + sn, hashlib.sha256).digest()
+        s.sendall(frame(AUTH, 1, proof[::-1] if tamper else proof))
+        return s, recv_frame(s)
+
+    for port in (rport, cport):
+        s, (method, body) = handshake(port, tok)
+        assert method == AUTH and body == b""
+        s.sendall(frame(8, 2))  # get_cluster_stats / any method: now answered
+        assert recv_frame(s)[0] != DENIED
+        s.close()
+        for key, tamper in ((b"wrong", False), (tok, True)):
+            s, (method, _) = handshake(port, key, tamper)
+            assert method == DENIED and s.recv(16) == b""
+            s.close()
+        s = socket.create_connection(("127.0.0.1", port), 2.0)  # presenting the token itself is not a handshake
+        s.settimeout(2.0)
+        s.sendall(frame(AUTH, 0, tok))
+        assert recv_frame(s)[0] == DENIED
+        s.close()
+    # an impostor that does not hold the token: the client walks away and never sent anything derived from it
+    lst = socket.socket()
+    lst.bind(("127.0.0.1", 0))
+    lst.listen(1)
+    seen = []
+
+    def impostor():
+        c, _ = lst.accept()
+        c.settimeout(2.0)
+        hello = recv_frame(c)
+        seen.append(hello)
+        c.sendall(frame(AUTH, 0, os.urandom(16) + os.urandom(32)))
+        try:
+            seen.append(c.recv(64))
+        except OSError:
+            seen.append(b"")
+        c.close()
+
+    import threading
+    th = threading.Thread(target=impostor)
+    th.start()
+    bad = cli(env_ok, "--keystone", f"127.0.0.1:{lst.getsockname()[1]}", "stats")
+    th.join()
+    lst.close()
+    assert bad.returncode != 0 and "ACCESS_DENIED" in bad.stdout + bad.stderr
+    assert seen[0][0] == AUTH and len(seen[0][1]) == 20 and tok not in seen[0][1] and seen[1] == b""
     # the metrics endpoint stays open (read-only)
     assert cli(env_none, "metrics", "--http", f"127.0.0.1:{hport}").returncode == 0
     # a Python client with the token in its options
