@@ -697,6 +697,36 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device_fp8(const std::vector<O
       else out[cur[k]] = ErrorCode::OK;
     }
   }
+  // Same rule as batch_get_device: a digest mismatch on every replica can mean the object was moved under us (tier
+  // move, compaction, repair).  Keys whose placements changed since we read them get one more pass; a key that moved
+  // to a non-fusable placement comes back NOT_IMPLEMENTED from that pass, i.e. "get + unpack instead".
+  static thread_local int fp8_refresh_depth = 0;
+  if (fp8_refresh_depth < 2) {
+    std::vector<size_t> bad;
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (out[i] == ErrorCode::CHECKSUM_MISMATCH && placed[i].ok()) bad.push_back(i);
+    if (!bad.empty()) {
+      std::vector<ObjectKey> bkeys;
+      for (size_t i : bad) bkeys.push_back(keys[i]);
+      auto again = keystone_->batch_get_workers(bkeys);
+      std::vector<ObjectKey> rkeys;
+      std::vector<void*> rptrs;
+      std::vector<uint64_t> rn;
+      std::vector<size_t> ridx;
+      for (size_t k = 0; k < bad.size(); ++k) {
+        const size_t i = bad[k];
+        if (!again[k].ok()) out[i] = again[k].error();
+        else if (!(again[k].value() == placed[i].value())) rkeys.push_back(keys[i]), rptrs.push_back(bf16_ptrs[i]), rn.push_back(n_elems[i]), ridx.push_back(i);
+      }
+      if (!rkeys.empty()) {
+        metrics_.inc("get_placement_refresh_total", rkeys.size());
+        ++fp8_refresh_depth;
+        auto recs = batch_get_device_fp8(rkeys, rptrs, rn, stream);
+        --fp8_refresh_depth;
+        for (size_t k = 0; k < ridx.size(); ++k) out[ridx[k]] = recs[k];
+      }
+    }
+  }
   metrics_.inc("device_get_fp8_batches_total");
   return out;
 }

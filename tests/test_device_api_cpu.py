@@ -192,3 +192,59 @@ def test_fp8_device_api_replicas_and_failover_on_cpu(bb):
         for b, o, n in zip(bf, outs, ns):
             assert np.array_equal(o, np.frombuffer(bb.mxfp8_unpack_ref(bb.mxfp8_pack_ref(b), n), dtype=np.uint16))
         assert not cl.device_fp8_eligible(40) and cl.device_fp8_eligible(64)
+
+
+def test_fp8_device_gets_survive_concurrent_compaction_and_migration(bb):
+    """batch_get_device_fp8 applies the same placement refresh as batch_get_device: readers of packed tensors racing
+    with compaction, tier moves and re-puts get the tensor or a clean not-found, never CHECKSUM_MISMATCH."""
+    import random
+    import threading
+    import time
+
+    with LocalCluster(cluster_id="devfp8shuffle", n_workers=1, pool_bytes=24 * MiB) as c:
+        c.keystone.install_data_server_mover()
+        c.add_worker("worker-cxl", "node-0", [("cxl-0", bb.StorageClass.CXL_MEMORY, 64 * MiB, "")])
+        cl = make_client(bb, c)
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[bb.StorageClass.RAM_CPU])
+        rng = np.random.default_rng(5)
+        names = [f"t{i}" for i in range(10)]
+        ns = {k: 16384 * (8 + i) + 32 * i for i, k in enumerate(names)}
+        bf = {k: ((rng.standard_normal(ns[k]) * 2).astype(np.float32).view(np.uint32) >> 16).astype(np.uint16) for k in names}
+        want = {k: np.frombuffer(bb.mxfp8_unpack_ref(bb.mxfp8_pack_ref(bf[k]), ns[k]), dtype=np.uint16) for k in names}
+        for k in names:
+            assert cl.batch_put_device_fp8([k], [bf[k].ctypes.data], [ns[k]], cfg, 0) == [bb.ErrorCode.OK]
+        stop = threading.Event()
+        errors, reads = [], [0]
+
+        def reader(seed):
+            rc = make_client(bb, c)
+            r = random.Random(seed)
+            while not stop.is_set():
+                ks = r.sample(names, 3)
+                outs = [np.zeros(ns[k], dtype=np.uint16) for k in ks]
+                ecs = rc.batch_get_device_fp8(ks, [o.ctypes.data for o in outs], [ns[k] for k in ks], 0)
+                for k, o, ec in zip(ks, outs, ecs):
+                    if ec == bb.ErrorCode.OK:
+                        if not np.array_equal(o, want[k]):
+                            errors.append((k, "wrong values"))
+                    elif ec not in (bb.ErrorCode.OBJECT_NOT_FOUND, bb.ErrorCode.OBJECT_NOT_READY):
+                        errors.append((k, str(ec)))
+                reads[0] += 1
+
+        ts = [threading.Thread(target=reader, args=(s,)) for s in range(3)]
+        [t.start() for t in ts]
+        api = cl.keystone()
+        r = random.Random(13)
+        moves, t_end = 0, time.time() + 2.0
+        while time.time() < t_end:
+            k = r.choice(names)
+            assert cl.remove(k) == bb.ErrorCode.OK
+            moves += api.compact_pool("pool-0", 4)
+            assert cl.batch_put_device_fp8([k], [bf[k].ctypes.data], [ns[k]], cfg, 0) == [bb.ErrorCode.OK]
+            k2 = r.choice([x for x in names if x != k])
+            tier = cl.get_workers(k2)[0].shards[0].storage_class
+            assert cl.migrate(k2, bb.StorageClass.CXL_MEMORY if tier == bb.StorageClass.RAM_CPU else bb.StorageClass.RAM_CPU) == bb.ErrorCode.OK
+        stop.set()
+        [t.join() for t in ts]
+        assert not errors, errors[:5]
+        assert reads[0] > 30 and moves > 0
