@@ -591,7 +591,10 @@ std::vector<Result<bool>> KeystoneRpcClient::batch_object_exists(const std::vect
     return out;
   }
   Reader rd(resp.value());
-  rd.ec();
+  if (const ErrorCode ec = rd.ec(); ec != ErrorCode::OK) {  // e.g. NOT_LEADER for the whole batch
+    out.assign(keys.size(), Result<bool>(ec));
+    return out;
+  }
   const uint32_t n = rd.count(5);
   for (uint32_t i = 0; i < n; ++i) {
     const ErrorCode ec = rd.ec();
@@ -612,7 +615,10 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_get_wor
     return out;
   }
   Reader rd(resp.value());
-  rd.ec();
+  if (const ErrorCode ec = rd.ec(); ec != ErrorCode::OK) {
+    out.assign(keys.size(), Result<std::vector<CopyPlacement>>(ec));
+    return out;
+  }
   const uint32_t n = rd.count(4);
   for (uint32_t i = 0; i < n; ++i) out.push_back(get_copies_result(rd));
   out.resize(keys.size(), Result<std::vector<CopyPlacement>>(ErrorCode::RPC_FAILED));

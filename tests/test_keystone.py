@@ -311,6 +311,63 @@ def test_ha_leader_failover_recovers_objects_from_wal(bb):
     a.stop(), b.stop()
 
 
+def test_rpc_client_with_both_endpoints_follows_the_leader(bb):
+    """Two keystones behind their RPC services, one KeystoneRpcClient that knows both: the standby answers NOT_LEADER to
+    object-scoped calls (reads too -- it has no object map yet) but serves cluster-scoped ones; the client lands on the
+    leader, and after the leader's lease runs out it ends up on the new one with the recovered objects."""
+    store = bb.MemCoord()
+    cfgs = [ks_cfg(bb, cluster_id="ha3", enable_ha=True, service_id=sid, service_registration_ttl_sec=4, service_refresh_interval_sec=1)
+            for sid in ("ks-a", "ks-b")]
+    kss = [bb.KeystoneService(c, bb.CoordService(store)) for c in cfgs]
+    for k in kss:
+        assert k.initialize() == bb.ErrorCode.OK and k.start() == bb.ErrorCode.OK
+    a, b = kss
+    assert a.is_leader() and not b.is_leader()
+    rpcs = [bb.RpcService(k, c) for k, c in zip(kss, cfgs)]
+    for r in rpcs:
+        assert r.start() == bb.ErrorCode.OK
+    ep_a, ep_b = (f"127.0.0.1:{r.rpc_port}" for r in rpcs)
+    store.put("/blackbird/clusters/ha3/workers/w0", '{"worker_id":"w0","node_id":"n0"}')
+    store.put("/blackbird/clusters/ha3/workers/w0/memory_pools/p0", mkpool(bb, "p0", 1 << 20, worker="w0").to_json())
+    store.flush_events()
+    try:
+        only_b = bb.KeystoneRpcClient()
+        assert only_b.connect_any([ep_b]) == bb.ErrorCode.OK
+        assert only_b.get_cluster_stats().total_memory_pools == 1  # cluster-scoped: any keystone answers
+        for call in (lambda: only_b.object_exists("obj"), lambda: only_b.get_workers("obj"), lambda: only_b.put_start("obj", 10, cfg1(bb))):
+            with pytest.raises(bb.BlackbirdError) as e:
+                call()
+            assert e.value.code == bb.ErrorCode.NOT_LEADER
+        assert [e for e, _ in only_b.batch_object_exists(["x", "y"])] == [bb.ErrorCode.NOT_LEADER] * 2 and only_b.failovers() == 0
+        assert [r[0] for r in only_b.batch_get_workers(["x"])] == [bb.ErrorCode.NOT_LEADER]
+
+        both = bb.KeystoneRpcClient()
+        assert both.connect_any([ep_b, ep_a]) == bb.ErrorCode.OK and both.active_endpoint() == ep_b
+        both.put_start("obj", 4096, cfg1(bb, ttl_ms=0))
+        assert both.active_endpoint() == ep_a and both.failovers() == 1
+        assert both.put_complete("obj", [[0x77]]) == bb.ErrorCode.OK
+        # the leader dies without resigning: its RPC port goes away and its lease expires
+        rpcs[0].stop()
+        a.stop()
+        store.advance_time_ms(5000)
+        both.set_failover_budget_ms(10000)
+        got = both.get_workers("obj")  # transport error on a -> b answers NOT_LEADER until its campaign succeeds -> b serves
+        assert got[0].shards[0].checksum == 0x77 and both.active_endpoint() == ep_b and b.is_leader()
+        assert [v for _, v in both.batch_object_exists(["obj", "nope"])] == [True, False]
+        # nobody left: the budget bounds the wait and the caller gets the transport error
+        rpcs[1].stop()
+        both.set_failover_budget_ms(300)
+        t0 = time.time()
+        with pytest.raises(bb.BlackbirdError) as e:
+            both.object_exists("obj")
+        assert e.value.code in (bb.ErrorCode.RPC_FAILED, bb.ErrorCode.CLIENT_DISCONNECTED) and time.time() - t0 < 5
+    finally:
+        for r in rpcs:
+            r.stop()
+        for k in kss:
+            k.stop()
+
+
 def test_size_based_tier_policy_for_puts_without_a_preferred_class(bb):
     """keystone.tier_policy (reference cxl_worker.yaml `allocation.preferred_tiers`, consumed by nothing there)."""
     from blackbird_b200.parallel import LocalCluster
