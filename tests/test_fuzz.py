@@ -117,6 +117,65 @@ def test_coord_daemon_survives_garbage(bb):
         srv.stop()
 
 
+def test_token_handshake_survives_garbage_and_never_admits_it(bb):
+    """A token-gated server under handshake-shaped noise: hellos of every length, proofs without a hello, repeated
+    hellos, random and truncated MACs, ordinary requests in between.  Nothing but the denial marker (or a hang-up)
+    ever comes back for a request, and a client that holds the token still gets in afterwards."""
+    AUTH, DENIED = 0x7FFFFF00, 0x7FFFFFFD
+    rng = random.Random(0xA07)
+    bb.set_cluster_token("fuzz-token")
+    srv = bb.CoordServer()
+    try:
+        assert srv.start("127.0.0.1", 0) == bb.ErrorCode.OK
+        for _ in range(300):
+            s = socket.create_connection(("127.0.0.1", srv.port), 2.0)
+            s.settimeout(0.3)
+            try:
+                for _ in range(rng.randrange(1, 5)):
+                    kind = rng.randrange(6)
+                    if kind == 0:
+                        body = b"BBA1" + rng.randbytes(rng.choice([0, 1, 15, 16, 17, 64]))
+                    elif kind == 1:
+                        body = rng.randbytes(32)  # a proof out of the blue, or a wrong one after a hello
+                    elif kind == 2:
+                        body = rng.randbytes(rng.randrange(0, 100))
+                    elif kind == 3:
+                        body = b"fuzz-token"  # the secret itself is not a credential
+                    elif kind == 4:
+                        body = b"BBA1" + rng.randbytes(16)
+                    else:
+                        s.sendall(_frame(rng.randrange(0, 32), 3, _rand_payload(rng)))  # a request before being admitted
+                        continue
+                    s.sendall(_frame(AUTH, rng.getrandbits(64), body))
+                got = b""
+                try:
+                    while len(got) < 4096:
+                        part = s.recv(4096)
+                        if not part:
+                            break
+                        got += part
+                except OSError:
+                    pass
+                # every complete frame that came back is a handshake reply or the denial marker -- never an RPC response
+                pos = 0
+                while len(got) - pos >= 16:
+                    n, method, _ = struct.unpack_from("<IIQ", got, pos)
+                    assert method in (AUTH, DENIED), hex(method)
+                    assert method != AUTH or n in (0, 48)
+                    if method == AUTH and n == 0:
+                        raise AssertionError("admitted without a valid proof")
+                    pos += 16 + n
+            except OSError:
+                pass
+            finally:
+                s.close()
+        cs = bb.CoordService(f"tcp://127.0.0.1:{srv.port}")
+        assert cs.connect() == bb.ErrorCode.OK and cs.put("/fuzz/auth", "v") == bb.ErrorCode.OK and cs.get("/fuzz/auth") == b"v"
+    finally:
+        bb.set_cluster_token("")
+        srv.stop()
+
+
 def _parse(fn, text):
     try:
         return fn(text)
