@@ -501,6 +501,20 @@ Result<std::vector<CopyPlacement>> BlackbirdClient::get_workers(const ObjectKey&
 ErrorCode BlackbirdClient::put(const ObjectKey& key, const uint8_t* data, size_t size, const WorkerConfig& cfg) {
   if (!keystone_) return ErrorCode::CLIENT_DISCONNECTED;
   if (!data && size) return ErrorCode::INVALID_PARAMETERS;
+  auto* ha = dynamic_cast<rpc::KeystoneRpcClient*>(keystone_.get());
+  const uint64_t failovers = ha ? ha->failovers() : 0;
+  ErrorCode ec = put_once(key, data, size, cfg);
+  // The keystone failed over in the middle of this put: only completed objects are in the metadata log, so the new
+  // leader has never heard of our pending one and put_complete comes back OBJECT_NOT_FOUND.  The bytes are still in
+  // hand -- start over against the new leader instead of handing the caller an error that is not theirs.
+  if (ec == ErrorCode::OBJECT_NOT_FOUND && ha && ha->failovers() != failovers) {
+    metrics_.inc("put_restarted_after_failover_total");
+    ec = put_once(key, data, size, cfg);
+  }
+  return ec;
+}
+
+ErrorCode BlackbirdClient::put_once(const ObjectKey& key, const uint8_t* data, size_t size, const WorkerConfig& cfg) {
   const TimePoint t0 = Clock::now();
   BB_TRACE_SPAN("client.put", size);
   auto placed = keystone_->put_start(key, size, cfg);
@@ -527,6 +541,7 @@ ErrorCode BlackbirdClient::put(const ObjectKey& key, const uint8_t* data, size_t
 ErrorCode BlackbirdClient::get_with_refresh(const ObjectKey& key, uint8_t* (*alloc)(void*, size_t), void* ctx, size_t capacity, size_t* out_size) {
   Result<std::vector<CopyPlacement>> copies = keystone_->get_workers(key);
   ErrorCode ec = ErrorCode::OK;
+  bool reread_same = false;
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (!copies.ok()) return copies.error();
     if (copies.value().empty()) return ErrorCode::NO_COMPLETE_WORKER;
@@ -539,7 +554,12 @@ ErrorCode BlackbirdClient::get_with_refresh(const ObjectKey& key, uint8_t* (*all
     if (ec == ErrorCode::OK) return ec;
     auto again = keystone_->get_workers(key);
     if (!again.ok()) return again.error();              // removed (or being re-written) meanwhile: that is the answer
-    if (again.value() == copies.value()) return ec;     // same placements: the failure is real
+    if (again.value() == copies.value()) {
+      // Same placements.  A digest mismatch can still be a race -- the key was removed and re-put onto the very same
+      // extent (first fit) and we read it half-written -- so that gets one more read; anything else is real.
+      if (ec != ErrorCode::CHECKSUM_MISMATCH || reread_same) return ec;
+      reread_same = true;
+    }
     metrics_.inc("get_placement_refresh_total");
     copies = std::move(again);
   }
@@ -716,7 +736,8 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device_fp8(const std::vector<O
       for (size_t k = 0; k < bad.size(); ++k) {
         const size_t i = bad[k];
         if (!again[k].ok()) out[i] = again[k].error();
-        else if (!(again[k].value() == placed[i].value())) rkeys.push_back(keys[i]), rptrs.push_back(bf16_ptrs[i]), rn.push_back(n_elems[i]), ridx.push_back(i);
+        // changed placements, or (once) the same ones: a remove + re-put can land on the very same extent and be read half-written
+        else if (!(again[k].value() == placed[i].value()) || fp8_refresh_depth == 0) rkeys.push_back(keys[i]), rptrs.push_back(bf16_ptrs[i]), rn.push_back(n_elems[i]), ridx.push_back(i);
       }
       if (!rkeys.empty()) {
         metrics_.inc("get_placement_refresh_total", rkeys.size());
@@ -1242,7 +1263,9 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
         const size_t i = bad[k];
         if (!again[k].ok()) {
           out[i] = again[k].error();  // removed (or being re-written) meanwhile: that is the answer
-        } else if (!(again[k].value() == placed[i].value())) {
+        } else if (!(again[k].value() == placed[i].value()) || refresh_depth == 0) {
+          // changed placements, or (once) the same ones: a remove + re-put can land on the very same extent (first fit)
+          // and be read half-written
           rkeys.push_back(keys[i]), rptrs.push_back(dev_ptrs[i]), rcaps.push_back(capacity[i]), ridx.push_back(i);
         }
       }

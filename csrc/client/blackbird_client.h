@@ -186,6 +186,7 @@ class BlackbirdClient {
   void release(const std::string& endpoint, std::shared_ptr<net::RpcClient> c);
   ErrorCode write_shard(const ShardPlacement& s, const uint8_t* src, uint64_t* digest, ChecksumAlgo algo);
   ErrorCode read_shard(const ShardPlacement& s, uint8_t* dst, ChecksumAlgo algo);
+  ErrorCode put_once(const ObjectKey& key, const uint8_t* data, size_t size, const WorkerConfig& cfg);
   ErrorCode transfer_put(const std::vector<CopyPlacement>& copies, const uint8_t* data, ChecksumAlgo algo,
                          keystone::ShardChecksums* sums);
   ErrorCode transfer_get(const std::vector<CopyPlacement>& copies, uint8_t* dst, size_t size);

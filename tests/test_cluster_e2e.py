@@ -608,3 +608,53 @@ def test_readers_survive_concurrent_compaction_and_migration(bb):
         hard = [e for e in errors if "OBJECT_NOT_FOUND" not in e[1] and "OBJECT_NOT_READY" not in e[1]]
         assert not hard, hard[:5]
         assert reads[0] > 50 and moves > 0
+
+
+def test_put_straddling_a_keystone_failover_is_restarted(bb):
+    """The leader dies between a client's put_start and its put_complete.  The pending object was never in the metadata
+    log, so the new leader answers OBJECT_NOT_FOUND to the put_complete -- the client (which knows both keystones)
+    notices that it failed over in the middle of the put and runs it again instead of returning that error."""
+    import threading
+    import time
+
+    kc = bb.KeystoneConfig()
+    kc.enable_ha = True
+    kc.service_id = "ks-a"
+    kc.service_registration_ttl_sec = 2
+    kc.service_refresh_interval_sec = 1
+    with LocalCluster(cluster_id="ha-put", n_workers=1, keystone_cfg=kc) as c:
+        kb = bb.KeystoneConfig()
+        kb.enable_ha, kb.service_id, kb.service_registration_ttl_sec, kb.service_refresh_interval_sec = True, "ks-b", 2, 1
+        kb.cluster_id, kb.listen_address, kb.http_metrics_port = "ha-put", "127.0.0.1:0", "0"
+        b = bb.KeystoneService(kb, bb.CoordService(c.coord_uri))
+        assert b.initialize() == bb.ErrorCode.OK and b.start() == bb.ErrorCode.OK
+        rb = bb.RpcService(b, kb)
+        assert rb.start() == bb.ErrorCode.OK
+        try:
+            assert c.keystone.is_leader() and not b.is_leader()
+            c.coord.store().flush_events()
+            opts = bb.BlackbirdClientOptions()
+            opts.keystone_endpoints = [f"127.0.0.1:{c.rpc.rpc_port}", f"127.0.0.1:{rb.rpc_port}"]
+            cl = bb.BlackbirdClient(opts)
+            assert cl.connect() == bb.ErrorCode.OK
+            cl.keystone().set_failover_budget_ms(20000)
+            data = os.urandom(300_000)
+            wc = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+            assert cl.put("warm", data, wc) == bb.ErrorCode.OK
+            out = []
+            bb.fault_arm("delay_rpc_ms", 400)  # every RPC takes 0.4 s: put_start | data write | put_complete
+            t = threading.Thread(target=lambda: out.append(cl.put("straddler", data, wc)))
+            t.start()
+            time.sleep(0.6)  # put_start has been answered by ks-a, the shard is on its way to the worker
+            c.rpc.stop()
+            c.keystone.stop()
+            t.join(timeout=40)
+            bb.fault_clear()
+            assert not t.is_alive() and out == [bb.ErrorCode.OK], out
+            assert b.is_leader() and cl.keystone().failovers() >= 1
+            assert cl.get("straddler") == data and cl.get("warm") == data  # "warm" came back through the metadata log
+            assert "put_restarted_after_failover_total 1" in cl.metrics_text()
+        finally:
+            bb.fault_clear()
+            rb.stop()
+            b.stop()
