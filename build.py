@@ -69,6 +69,7 @@ def generate() -> str:
     py_src = sorted(glob.glob(os.path.join(ROOT, "csrc", "py", "*.cpp")))
     app_src = sorted(glob.glob(os.path.join(ROOT, "apps", "*.cpp")))
     example_src = sorted(glob.glob(os.path.join(ROOT, "examples", "*.cpp")))  # -> bin/bb-example-<name>
+    tool_cu_src = sorted(glob.glob(os.path.join(ROOT, "bench", "*.cu")))  # stand-alone CUDA tools -> bin/bb-<name>
 
     lines = [
         "ninja_required_version = 1.5",
@@ -87,6 +88,9 @@ def generate() -> str:
         "  description = NVCC $in",
         "rule link_so",
         f"  command = g++ -shared -o $out $in -L{CUDA_HOME}/lib64 -lcudart_static -ldl -lrt -pthread{san}",
+        "  description = LINK $out",
+        "rule link_cuda_exe",
+        f"  command = g++ -o $out $in -L{CUDA_HOME}/lib64 -lcudart_static -L{CUDA_HOME}/lib64/stubs -lcuda -ldl -lrt -pthread",
         "  description = LINK $out",
         "rule link_exe",
         f"  command = g++ -o $out $in -L{CUDA_HOME}/lib64 -lcudart_static -ldl -lrt -pthread{san}",
@@ -128,6 +132,13 @@ def generate() -> str:
         name = "bb-example-" + os.path.splitext(os.path.basename(s))[0].replace("_", "-")
         exe = _rel(os.path.join(OUT, "bin", name))
         lines.append(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
+        targets.append(exe)
+    for s in tool_cu_src:
+        o = obj(s)
+        lines.append(f"build {o}: nvcc {_rel(s)}")
+        name = "bb-" + os.path.splitext(os.path.basename(s))[0].replace("_", "-")
+        exe = _rel(os.path.join(OUT, "bin", name))
+        lines.append(f"build {exe}: link_cuda_exe {o}")
         targets.append(exe)
     lines.append(f"default {' '.join(targets)}")
     path = os.path.join(BUILD, "build.ninja")

@@ -606,12 +606,27 @@ bool RangeAllocator::can_allocate(const AllocationRequest& req, const PoolMap& p
 }
 
 void RangeAllocator::forget_pool(const MemoryPoolId& id) {
-  std::unique_lock<std::shared_mutex> lk(pools_mu_);
-  auto it = pool_allocators_.find(id);
-  if (it == pool_allocators_.end()) return;
-  graveyard_.push_back(std::move(it->second));  // other threads may still hold the pointer through their cache
-  pool_allocators_.erase(it);
-  generation_.fetch_add(1, std::memory_order_release);
+  {
+    std::unique_lock<std::shared_mutex> lk(pools_mu_);
+    auto it = pool_allocators_.find(id);
+    if (it != pool_allocators_.end()) {
+      graveyard_.push_back(std::move(it->second));  // other threads may still hold the pointer through their cache
+      pool_allocators_.erase(it);
+      generation_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  // The pool's memory is gone: drop its extents from every surviving object's ledger entry.  A worker that restarts
+  // re-registers the same pool id with a fresh, all-free PoolAllocator; a stale extent left here would later be
+  // "returned" to that new allocator by free() -> rollback() and hand a live object's range out a second time.
+  for (LedgerShard& ls : ledger_) {
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    for (auto& [key, oa] : ls.objects) {
+      auto& ex = oa.extents;
+      ex.erase(std::remove_if(ex.begin(), ex.end(), [&](const Extent& e) { return e.pool == id; }), ex.end());
+    }
+  }
+  std::lock_guard<SpinMutex> lk(used_mu_);
+  used_by_pool_.erase(id);
 }
 
 size_t RangeAllocator::pool_used_bytes(const MemoryPoolId& id) const {
@@ -639,10 +654,12 @@ std::vector<ObjectKey> RangeAllocator::objects_on_pool(const MemoryPoolId& id) c
   return v;
 }
 
-ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools) {
+ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools,
+                                const MemoryPoolId& only_pool) {
   ObjectAllocation oa;
   for (const auto& c : copies)
     for (const auto& s : c.shards) {
+      if (!only_pool.empty() && s.pool_id != only_pool) continue;
       auto pit = pools.find(s.pool_id);
       if (pit == pools.end()) continue;
       PoolAllocator* pa = ensure_pool(pit->second);
@@ -661,11 +678,39 @@ ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlac
       oa.extents.push_back({s.pool_id, Range(off, pa->aligned(s.length)), s.length});
       oa.total_size += s.length;
     }
-  if (!ledger_insert(key, std::move(oa))) {
-    rollback(oa.extents);
-    return ErrorCode::OBJECT_ALREADY_EXISTS;
+  if (only_pool.empty()) {
+    if (!ledger_insert(key, std::move(oa))) {
+      rollback(oa.extents);
+      return ErrorCode::OBJECT_ALREADY_EXISTS;
+    }
+    return ErrorCode::OK;
   }
+  // late adoption of one pool's extents: merge into the object's existing ledger entry (created by the first adopt)
+  {
+    std::lock_guard<SpinMutex> lk(used_mu_);
+    for (const auto& e : oa.extents) used_by_pool_[e.pool] += e.range.length;
+  }
+  LedgerShard& ls = ledger_for(key);
+  std::lock_guard<SpinMutex> lk(ls.mu);
+  ObjectAllocation& dst = ls.objects[key];
+  dst.total_size += oa.total_size;
+  dst.extents.insert(dst.extents.end(), oa.extents.begin(), oa.extents.end());
   return ErrorCode::OK;
+}
+
+void RangeAllocator::reset() {
+  {
+    std::unique_lock<std::shared_mutex> lk(pools_mu_);
+    for (auto& [id, pa] : pool_allocators_) graveyard_.push_back(std::move(pa));  // cached pointers stay valid
+    pool_allocators_.clear();
+    generation_.fetch_add(1, std::memory_order_release);
+  }
+  for (LedgerShard& ls : ledger_) {
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    ls.objects.clear();
+  }
+  std::lock_guard<SpinMutex> lk(used_mu_);
+  used_by_pool_.clear();
 }
 
 bool RangeAllocator::ledger_insert(const ObjectKey& key, ObjectAllocation&& oa) {

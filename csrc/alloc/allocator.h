@@ -170,7 +170,12 @@ class RangeAllocator : public IAllocator {
   std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const override;
   // Re-reserves the exact extents of already placed copies (metadata recovery after a leader
   // change).  Extents on unknown pools are skipped.
-  ErrorCode adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools);
+  // `only_pool` (optional): adopt just the shards on that pool and merge them into the key's existing ledger entry
+  // (objects recovered before one of their pools had registered).
+  ErrorCode adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools,
+                  const MemoryPoolId& only_pool = {});
+  // Forgets every pool allocator and ledger entry (a Keystone that lost leadership rebuilds from the metadata log).
+  void reset();
 
  private:
   struct Extent {

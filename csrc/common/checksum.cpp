@@ -352,18 +352,20 @@ const BbhImpl& bbh_impl() {
   return i;
 }
 
-uint64_t tiles_sum(TileFn fn, const uint8_t* p, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept {
+// Tiles [first_tile, first_tile + ntiles) of the buffer p[0, len); `index_base` is added to the tile index that is mixed
+// into the hash (a chunk of a larger object is hashed as tiles index_base.. of that object).
+uint64_t tiles_sum(TileFn fn, const uint8_t* p, size_t len, uint64_t first_tile, uint64_t ntiles, uint64_t index_base = 0) noexcept {
   const uint64_t total = (len + kTileBytes - 1) / kTileBytes;
   uint64_t sum = 0;
   for (uint64_t t = first_tile; t < first_tile + ntiles && t < total; ++t) {
     const uint64_t base = t * kTileBytes;
     if (len - base >= kTileBytes) {
-      sum += fn(p + base, t);
+      sum += fn(p + base, index_base + t);
     } else {  // short last tile: zero padded
       alignas(64) uint8_t pad[kTileBytes];
       std::memcpy(pad, p + base, len - base);
       std::memset(pad + (len - base), 0, kTileBytes - (len - base));
-      sum += fn(pad, t);
+      sum += fn(pad, index_base + t);
     }
   }
   return sum;
@@ -374,6 +376,10 @@ const char* bbh64_impl_name() noexcept { return bbh_impl().name; }
 
 uint64_t bbh64_partial(const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept {
   return tiles_sum(bbh_impl().fn, static_cast<const uint8_t*>(data), len, first_tile, ntiles);
+}
+
+uint64_t bbh64_chunk(const void* data, size_t len, uint64_t tile_base) noexcept {
+  return tiles_sum(bbh_impl().fn, static_cast<const uint8_t*>(data), len, 0, (len + kTileBytes - 1) / kTileBytes, tile_base);
 }
 
 uint64_t bbh64_finalize(uint64_t tile_sum, size_t len) noexcept { return tchash::finalize(tile_sum, len); }

@@ -40,6 +40,9 @@ uint64_t bbh64_reference(const void* data, size_t len) noexcept;
 // the tile sums are commutative, so a large object can be hashed by several threads and the parts added;
 // bbh64_finalize(sum of the parts, len) is the digest.
 uint64_t bbh64_partial(const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept;
+// Unfinalised sum of a chunk [data, data + len) that is the tiles tile_base.. of a larger object (streaming: the chunk
+// must start on a tile boundary of the object; only the object's last chunk may end inside a tile).
+uint64_t bbh64_chunk(const void* data, size_t len, uint64_t tile_base) noexcept;
 uint64_t bbh64_finalize(uint64_t tile_sum, size_t len) noexcept;
 const char* bbh64_impl_name() noexcept;  // "avx512-vnni" | "avx2" | "scalar"
 // Digest through a named implementation (tests); *supported = false when this CPU cannot run it.

@@ -182,7 +182,12 @@ struct KeystoneConfig {
   int32_t rpc_busy_poll_us = 0;  // RPC threads poll without sleeping this long after a request (latency vs CPU)
   std::string log_level;  // from the `logging:` section the reference ignores
   std::string log_file;
-  std::string wal_path;   // object-metadata write-ahead log ("" = coordination store only)
+  // Local metadata log (snapshot + append-only log, csrc/common/durable_log.h) of a single, non-HA Keystone: object
+  // records are made durable under this directory before put_complete is acknowledged, and replayed on start.  HA
+  // pairs log into the coordination store instead (fenced by the leader's term), so that the standby can resume.
+  std::string wal_path;
+  bool wal_fsync = true;        // false: page-cache only (survives a process crash, not a power cut)
+  int wal_snapshot_mb = 64;     // compact the log into a snapshot once it grows past this
 
   // Throws std::runtime_error on unreadable / invalid files (as the reference does).
   static KeystoneConfig from_yaml(const std::string& file_path);

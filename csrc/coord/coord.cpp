@@ -9,6 +9,10 @@
 
 namespace bb::coord {
 
+namespace {
+enum LogOp : uint32_t { OP_PUT = 1, OP_DEL = 2, OP_GRANT = 3, OP_REVOKE = 4 };
+}
+
 // ================================================================ MemCoord
 MemCoord::MemCoord() {
   expiry_thread_ = std::thread([this] { expiry_loop(); });
@@ -35,6 +39,7 @@ int64_t MemCoord::now_ms() const {
 }
 
 void MemCoord::emit_locked(EventType t, const std::string& key, const std::string& value) {
+  if (replaying_) return;  // recovery rebuilds state; nobody is watching yet
   std::lock_guard<std::mutex> lk(qmu_);
   queue_.push_back(WatchEvent{t, key, value, revision_});
   qcv_.notify_one();
@@ -58,6 +63,14 @@ ErrorCode MemCoord::put_locked(const std::string& key, const std::string& value,
     it->second.lease = lease;
   }
   if (lease != 0) leases_[lease].keys.insert(key);
+  if (log_ && !replaying_) {
+    wire::Writer w;
+    w.u32(OP_PUT);
+    w.str(key);
+    w.str(value);
+    w.i64(lease);
+    log_locked(w.data());
+  }
   emit_locked(EventType::PUT, key, value);
   return ErrorCode::OK;
 }
@@ -72,6 +85,12 @@ bool MemCoord::del_locked(const std::string& key) {
   const std::string last = std::move(it->second.value);
   kv_.erase(it);
   ++revision_;
+  if (log_ && !replaying_) {
+    wire::Writer w;
+    w.u32(OP_DEL);
+    w.str(key);
+    log_locked(w.data());
+  }
   emit_locked(EventType::DELETE, key, last);
   return true;
 }
@@ -85,6 +104,12 @@ void MemCoord::expire_locked() {
     auto it = leases_.find(id);
     const std::set<std::string> keys = it->second.keys;
     leases_.erase(it);
+    if (log_ && !replaying_) {  // expiry is logged like a revoke: a restart must not resurrect the lease's keys
+      wire::Writer w;
+      w.u32(OP_REVOKE);
+      w.i64(id);
+      log_locked(w.data());
+    }
     for (const auto& k : keys) {
       auto kv = kv_.find(k);
       if (kv != kv_.end() && kv->second.lease == id) {
@@ -101,7 +126,157 @@ void MemCoord::expiry_loop() {
     expiry_cv_.wait_for(lk, std::chrono::milliseconds(20));
     if (stop_.load()) break;
     expire_locked();
+    if (const uint64_t seq = take_seq_locked()) {
+      lk.unlock();
+      commit(seq, ErrorCode::OK);
+      lk.lock();
+    }
   }
+}
+
+// ---------------------------------------------------------------- durability
+void MemCoord::log_locked(const std::string& rec) {
+  const uint64_t seq = log_->append(rec);
+  if (seq) pending_seq_ = seq;
+  else BB_LOG(ERROR) << "coord: metadata log append failed";
+}
+
+ErrorCode MemCoord::commit(uint64_t seq, ErrorCode ec) {
+  if (!log_ || seq == 0) return ec;
+  const ErrorCode sc = log_->sync(seq);
+  if (log_->snapshot_due()) {
+    std::unique_lock<std::mutex> sl(snap_mu_, std::try_to_lock);
+    if (sl.owns_lock() && log_->snapshot_due()) {
+      uint64_t gen;
+      std::string blob;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        gen = log_->rotate();
+        blob = snapshot_locked();
+      }
+      if (log_->install_snapshot(gen, blob) != ErrorCode::OK) BB_LOG(ERROR) << "coord: snapshot " << gen << " failed";
+      else BB_LOG(INFO) << "coord: snapshot " << gen << " (" << blob.size() << " bytes)";
+    }
+  }
+  return sc == ErrorCode::OK ? ec : ErrorCode::ETCD_ERROR;
+}
+
+std::string MemCoord::snapshot_locked() const {
+  wire::Writer w;
+  w.i64(revision_);
+  w.i64(next_lease_);
+  w.u32(static_cast<uint32_t>(leases_.size()));
+  for (const auto& [id, l] : leases_) {
+    w.i64(id);
+    w.i64(l.ttl_ms);
+  }
+  w.u32(static_cast<uint32_t>(kv_.size()));
+  for (const auto& [k, kv] : kv_) {
+    w.str(kv.key);
+    w.str(kv.value);
+    w.i64(kv.create_revision);
+    w.i64(kv.mod_revision);
+    w.i64(kv.lease);
+  }
+  return w.take();
+}
+
+void MemCoord::load_snapshot(const std::string& blob) {
+  wire::Reader r(blob);
+  revision_ = r.i64();
+  next_lease_ = r.i64();
+  const uint32_t nl = r.u32();
+  const int64_t now = now_ms();
+  for (uint32_t i = 0; i < nl && r.ok(); ++i) {
+    const LeaseId id = r.i64();
+    const int64_t ttl = r.i64();
+    leases_[id] = Lease{ttl, now + ttl, {}};
+  }
+  const uint32_t nk = r.u32();
+  for (uint32_t i = 0; i < nk && r.ok(); ++i) {
+    KeyValue kv;
+    kv.key = r.str();
+    kv.value = r.str();
+    kv.create_revision = r.i64();
+    kv.mod_revision = r.i64();
+    kv.lease = r.i64();
+    if (kv.lease) {
+      auto l = leases_.find(kv.lease);
+      if (l == leases_.end()) continue;  // its lease did not survive: neither does the key
+      l->second.keys.insert(kv.key);
+    }
+    kv_[kv.key] = std::move(kv);
+  }
+  if (!r.ok()) BB_LOG(ERROR) << "coord: snapshot is truncated";
+}
+
+void MemCoord::apply_record(std::string_view rec) {
+  wire::Reader r(rec.data(), rec.size());
+  switch (r.u32()) {
+    case OP_PUT: {
+      const std::string k = r.str(), v = r.str();
+      const LeaseId l = r.i64();
+      if (r.ok()) put_locked(k, v, leases_.count(l) ? l : 0);
+      break;
+    }
+    case OP_DEL: {
+      const std::string k = r.str();
+      if (r.ok()) del_locked(k);
+      break;
+    }
+    case OP_GRANT: {
+      const LeaseId id = r.i64();
+      const int64_t ttl = r.i64();
+      if (r.ok()) {
+        leases_[id] = Lease{ttl, now_ms() + ttl, {}};
+        next_lease_ = std::max(next_lease_, id + 1);
+      }
+      break;
+    }
+    case OP_REVOKE: {
+      const LeaseId id = r.i64();
+      auto it = leases_.find(id);
+      if (r.ok() && it != leases_.end()) {
+        const std::set<std::string> keys = it->second.keys;
+        leases_.erase(it);
+        for (const auto& k : keys) {
+          auto kv = kv_.find(k);
+          if (kv != kv_.end() && kv->second.lease == id) {
+            kv->second.lease = 0;
+            del_locked(k);
+          }
+        }
+      }
+      break;
+    }
+    default: break;
+  }
+}
+
+ErrorCode MemCoord::open_durable(const std::string& dir, bool fsync, uint64_t snapshot_bytes) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto log = std::make_unique<DurableLog>();
+  DurableLog::Options o;
+  o.dir = dir;
+  o.name = "coord";
+  o.fsync = fsync;
+  o.snapshot_bytes = snapshot_bytes;
+  std::string snap;
+  std::vector<std::string> recs;
+  ErrorCode ec = log->open(o, &snap, [&](std::string_view r) { recs.emplace_back(r); });
+  if (ec != ErrorCode::OK) return ec;
+  replaying_ = true;
+  if (!snap.empty()) load_snapshot(snap);
+  for (const auto& r : recs) apply_record(r);
+  replaying_ = false;
+  recovered_records_ = recs.size();
+  // every lease starts a full TTL from now: its holder gets one whole period to find the restarted store
+  const int64_t now = now_ms();
+  for (auto& [id, l] : leases_) l.expires_at_ms = now + l.ttl_ms;
+  log_ = std::move(log);
+  if (!snap.empty() || !recs.empty())
+    BB_LOG(INFO) << "coord: recovered " << kv_.size() << " keys, " << leases_.size() << " leases at revision " << revision_ << " from " << dir;
+  return ErrorCode::OK;
 }
 
 void MemCoord::dispatch_loop() {
@@ -152,10 +327,13 @@ void MemCoord::flush_events() {
 
 void MemCoord::advance_time_ms(int64_t ms) {
   clock_offset_ms_.fetch_add(ms);
+  uint64_t seq;
   {
     std::lock_guard<std::mutex> lk(mu_);
     expire_locked();
+    seq = take_seq_locked();
   }
+  commit(seq, ErrorCode::OK);
   flush_events();
 }
 
@@ -169,8 +347,14 @@ size_t MemCoord::key_count() {
 }
 
 ErrorCode MemCoord::put(const std::string& key, const std::string& value, LeaseId lease) {
-  std::lock_guard<std::mutex> lk(mu_);
-  return put_locked(key, value, lease);
+  ErrorCode ec;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    ec = put_locked(key, value, lease);
+    seq = take_seq_locked();
+  }
+  return commit(seq, ec);
 }
 
 Result<KeyValue> MemCoord::get_kv(const std::string& key) {
@@ -181,9 +365,13 @@ Result<KeyValue> MemCoord::get_kv(const std::string& key) {
 }
 
 ErrorCode MemCoord::del(const std::string& key) {
-  std::lock_guard<std::mutex> lk(mu_);
-  del_locked(key);
-  return ErrorCode::OK;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    del_locked(key);
+    seq = take_seq_locked();
+  }
+  return commit(seq, ErrorCode::OK);
 }
 
 Result<std::vector<KeyValue>> MemCoord::get_with_prefix(const std::string& prefix) {
@@ -195,38 +383,65 @@ Result<std::vector<KeyValue>> MemCoord::get_with_prefix(const std::string& prefi
 }
 
 Result<size_t> MemCoord::del_prefix(const std::string& prefix) {
-  std::lock_guard<std::mutex> lk(mu_);
   std::vector<std::string> keys;
-  for (auto it = kv_.lower_bound(prefix); it != kv_.end() && it->first.compare(0, prefix.size(), prefix) == 0; ++it)
-    keys.push_back(it->first);
-  for (const auto& k : keys) del_locked(k);
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto it = kv_.lower_bound(prefix); it != kv_.end() && it->first.compare(0, prefix.size(), prefix) == 0; ++it)
+      keys.push_back(it->first);
+    for (const auto& k : keys) del_locked(k);
+    seq = take_seq_locked();
+  }
+  if (commit(seq, ErrorCode::OK) != ErrorCode::OK) return ErrorCode::ETCD_ERROR;
   return keys.size();
 }
 
 Result<LeaseId> MemCoord::grant_lease(int64_t ttl_sec) {
   if (ttl_sec <= 0) return ErrorCode::INVALID_PARAMETERS;
-  std::lock_guard<std::mutex> lk(mu_);
-  const LeaseId id = next_lease_++;
-  leases_[id] = Lease{ttl_sec * 1000, now_ms() + ttl_sec * 1000, {}};
+  LeaseId id;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    id = next_lease_++;
+    leases_[id] = Lease{ttl_sec * 1000, now_ms() + ttl_sec * 1000, {}};
+    if (log_) {
+      wire::Writer w;
+      w.u32(OP_GRANT);
+      w.i64(id);
+      w.i64(ttl_sec * 1000);
+      log_locked(w.data());
+    }
+    seq = take_seq_locked();
+  }
+  if (commit(seq, ErrorCode::OK) != ErrorCode::OK) return ErrorCode::ETCD_ERROR;
   return id;
 }
 
 ErrorCode MemCoord::keep_alive(LeaseId lease) {
-  std::lock_guard<std::mutex> lk(mu_);
-  expire_locked();
-  auto it = leases_.find(lease);
-  if (it == leases_.end()) return ErrorCode::ETCD_LEASE_ERROR;
-  it->second.expires_at_ms = now_ms() + it->second.ttl_ms;
-  return ErrorCode::OK;
+  ErrorCode ec = ErrorCode::OK;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    expire_locked();
+    auto it = leases_.find(lease);
+    if (it == leases_.end()) ec = ErrorCode::ETCD_LEASE_ERROR;
+    else it->second.expires_at_ms = now_ms() + it->second.ttl_ms;  // refreshes are not logged: recovery re-arms every lease
+    seq = take_seq_locked();
+  }
+  return commit(seq, ec);
 }
 
 ErrorCode MemCoord::revoke_lease(LeaseId lease) {
-  std::lock_guard<std::mutex> lk(mu_);
-  auto it = leases_.find(lease);
-  if (it == leases_.end()) return ErrorCode::ETCD_LEASE_ERROR;
-  it->second.expires_at_ms = 0;
-  expire_locked();
-  return ErrorCode::OK;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = leases_.find(lease);
+    if (it == leases_.end()) return ErrorCode::ETCD_LEASE_ERROR;
+    it->second.expires_at_ms = 0;
+    expire_locked();
+    seq = take_seq_locked();
+  }
+  return commit(seq, ErrorCode::OK);
 }
 
 Result<int64_t> MemCoord::lease_remaining_ms(LeaseId lease) {
@@ -237,31 +452,91 @@ Result<int64_t> MemCoord::lease_remaining_ms(LeaseId lease) {
 }
 
 Result<bool> MemCoord::put_if_absent(const std::string& key, const std::string& value, LeaseId lease) {
-  std::lock_guard<std::mutex> lk(mu_);
-  expire_locked();
-  if (kv_.count(key)) return false;
-  ErrorCode ec = put_locked(key, value, lease);
+  ErrorCode ec = ErrorCode::OK;
+  bool created = false;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    expire_locked();
+    if (!kv_.count(key)) {
+      ec = put_locked(key, value, lease);
+      created = ec == ErrorCode::OK;
+    }
+    seq = take_seq_locked();
+  }
+  ec = commit(seq, ec);
   if (ec != ErrorCode::OK) return ec;
-  return true;
+  return created;
 }
 
 Result<bool> MemCoord::compare_and_swap(const std::string& key, const std::string& expected, const std::string& value,
                                         LeaseId lease) {
-  std::lock_guard<std::mutex> lk(mu_);
-  expire_locked();
-  auto it = kv_.find(key);
-  if (it == kv_.end() || it->second.value != expected) return false;
-  ErrorCode ec = put_locked(key, value, lease);
+  ErrorCode ec = ErrorCode::OK;
+  bool swapped = false;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    expire_locked();
+    auto it = kv_.find(key);
+    if (it != kv_.end() && it->second.value == expected) {
+      ec = put_locked(key, value, lease);
+      swapped = ec == ErrorCode::OK;
+    }
+    seq = take_seq_locked();
+  }
+  ec = commit(seq, ec);
   if (ec != ErrorCode::OK) return ec;
-  return true;
+  return swapped;
 }
 
 Result<bool> MemCoord::compare_and_delete(const std::string& key, const std::string& expected) {
-  std::lock_guard<std::mutex> lk(mu_);
-  auto it = kv_.find(key);
-  if (it == kv_.end() || it->second.value != expected) return false;
-  del_locked(key);
-  return true;
+  bool deleted = false;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = kv_.find(key);
+    if (it != kv_.end() && it->second.value == expected) deleted = del_locked(key);
+    seq = take_seq_locked();
+  }
+  if (commit(seq, ErrorCode::OK) != ErrorCode::OK) return ErrorCode::ETCD_ERROR;
+  return deleted;
+}
+
+Result<bool> MemCoord::guarded_put(const std::string& guard_key, int64_t guard_create_revision, const std::string& key,
+                                   const std::string& value) {
+  ErrorCode ec = ErrorCode::OK;
+  bool done = false;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    expire_locked();
+    auto g = kv_.find(guard_key);
+    if (g != kv_.end() && g->second.create_revision == guard_create_revision) {
+      ec = put_locked(key, value, 0);
+      done = ec == ErrorCode::OK;
+    }
+    seq = take_seq_locked();
+  }
+  ec = commit(seq, ec);
+  if (ec != ErrorCode::OK) return ec;
+  return done;
+}
+
+Result<bool> MemCoord::guarded_del(const std::string& guard_key, int64_t guard_create_revision, const std::string& key) {
+  bool done = false;
+  uint64_t seq;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    expire_locked();
+    auto g = kv_.find(guard_key);
+    if (g != kv_.end() && g->second.create_revision == guard_create_revision) {
+      del_locked(key);
+      done = true;
+    }
+    seq = take_seq_locked();
+  }
+  if (commit(seq, ErrorCode::OK) != ErrorCode::OK) return ErrorCode::ETCD_ERROR;
+  return done;
 }
 
 Result<int64_t> MemCoord::watch_prefix(const std::string& prefix, WatchCallback cb) {
@@ -292,7 +567,7 @@ int64_t MemCoord::revision() {
 namespace {
 enum Method : uint32_t {
   M_PUT = 1, M_GET, M_DEL, M_PREFIX, M_DEL_PREFIX, M_GRANT, M_KEEPALIVE, M_REVOKE, M_REMAINING,
-  M_PUT_IF_ABSENT, M_CAS, M_CAD, M_WATCH, M_UNWATCH, M_REVISION,
+  M_PUT_IF_ABSENT, M_CAS, M_CAD, M_WATCH, M_UNWATCH, M_REVISION, M_GUARDED_PUT, M_GUARDED_DEL,
 };
 constexpr uint32_t kTopicWatch = 1;
 
@@ -391,6 +666,22 @@ CoordServer::CoordServer(std::shared_ptr<MemCoord> store) : store_(store ? std::
     std::string k = r.str(), e = r.str();
     return reply(st->compare_and_delete(k, e), [](wire::Writer& w, bool b) { w.boolean(b); });
   });
+  rpc_.register_method(M_GUARDED_PUT, [st](const net::ConnPtr&, const std::string& q) {
+    wire::Reader r(q);
+    std::string g = r.str();
+    const int64_t rev = r.i64();
+    std::string k = r.str(), v = r.str();
+    if (!r.ok()) return reply_ec(ErrorCode::INVALID_PARAMETERS);
+    return reply(st->guarded_put(g, rev, k, v), [](wire::Writer& w, bool b) { w.boolean(b); });
+  });
+  rpc_.register_method(M_GUARDED_DEL, [st](const net::ConnPtr&, const std::string& q) {
+    wire::Reader r(q);
+    std::string g = r.str();
+    const int64_t rev = r.i64();
+    std::string k = r.str();
+    if (!r.ok()) return reply_ec(ErrorCode::INVALID_PARAMETERS);
+    return reply(st->guarded_del(g, rev, k), [](wire::Writer& w, bool b) { w.boolean(b); });
+  });
   rpc_.register_method(M_REVISION, [st](const net::ConnPtr&, const std::string&) {
     wire::Writer w;
     w.ec(ErrorCode::OK);
@@ -440,35 +731,64 @@ ErrorCode CoordServer::start(const std::string& host, uint16_t port) { return rp
 void CoordServer::stop() { rpc_.stop(); }
 
 // ================================================================ RemoteCoord
+// Connection loss is survivable (the daemon may be restarted with --data-dir and come back with the same keys, revisions
+// and lease ids): request/response calls reconnect and retry once; the watch channel is re-established by a monitor
+// thread which re-registers every watch and then *re-lists* its prefix, delivering PUTs for what exists now and DELETEs
+// for keys that were seen before and are gone -- so a watcher converges even though events were missed while the
+// store was away.  Handlers must be idempotent (the Keystone's and the workers' are).
+namespace {
+thread_local const RemoteCoord* tl_delivering = nullptr;  // set while this thread runs a watch callback of that store
+}
+
 RemoteCoord::~RemoteCoord() { close(); }
+
+bool RemoteCoord::connect_any(net::RpcClient& c, int timeout_ms) {
+  for (const auto& [h, p] : endpoints_)
+    if (c.connect(h, p, timeout_ms) == ErrorCode::OK) {
+      host_ = h;
+      port_ = p;
+      return true;
+    }
+  return false;
+}
 
 ErrorCode RemoteCoord::connect(const std::string& endpoints, int timeout_ms) {
   std::stringstream ss(endpoints);
   std::string ep;
+  endpoints_.clear();
   while (std::getline(ss, ep, ',')) {
     while (!ep.empty() && ep.front() == ' ') ep.erase(ep.begin());
     const std::string pfx = "tcp://";
     if (ep.compare(0, pfx.size(), pfx) == 0) ep = ep.substr(pfx.size());
     auto hp = split_host_port(ep);
-    if (!hp) continue;
-    if (rpc_.connect(hp->first, static_cast<uint16_t>(hp->second), timeout_ms) == ErrorCode::OK) {
-      host_ = hp->first;
-      port_ = static_cast<uint16_t>(hp->second);
-      return ErrorCode::OK;
-    }
+    if (hp) endpoints_.emplace_back(hp->first, static_cast<uint16_t>(hp->second));
   }
-  return ErrorCode::CONNECTION_FAILED;
+  closing_.store(false);
+  std::lock_guard<std::mutex> lk(conn_mu_);
+  return connect_any(rpc_, timeout_ms) ? ErrorCode::OK : ErrorCode::CONNECTION_FAILED;
 }
 
 void RemoteCoord::close() {
+  closing_.store(true);
+  if (monitor_.joinable()) monitor_.join();
   rpc_.close();
   watch_rpc_.close();
 }
 
 Result<std::string> RemoteCoord::call(uint32_t method, const std::string& req) {
-  auto r = rpc_.call(method, req, 10000);
-  if (!r.ok()) return ErrorCode::ETCD_ERROR;
-  return r;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const uint64_t gen = conn_gen_.load();
+    auto r = rpc_.call(method, req, 10000);
+    if (r.ok()) return r;
+    if (closing_.load() || (r.error() != ErrorCode::RPC_FAILED && r.error() != ErrorCode::CLIENT_DISCONNECTED)) break;
+    // the store went away: look for it again (same endpoint list) and retry the request once
+    std::lock_guard<std::mutex> lk(conn_mu_);
+    if (conn_gen_.load() != gen) continue;  // another caller already reconnected
+    if (!connect_any(rpc_, 1000)) break;
+    conn_gen_.fetch_add(1);
+    reconnects_.fetch_add(1);
+  }
+  return ErrorCode::ETCD_ERROR;
 }
 
 #define BB_COORD_CALL(method, writer)                \
@@ -580,43 +900,80 @@ int64_t RemoteCoord::revision() {
   return rd.i64();
 }
 
-Result<int64_t> RemoteCoord::watch_prefix(const std::string& prefix, WatchCallback cb) {
+Result<bool> RemoteCoord::guarded_put(const std::string& guard_key, int64_t guard_create_revision, const std::string& key,
+                                      const std::string& value) {
+  wire::Writer w;
+  w.str(guard_key);
+  w.i64(guard_create_revision);
+  w.str(key);
+  w.str(value);
+  BB_COORD_CALL(M_GUARDED_PUT, w);
+  if (_ec != ErrorCode::OK) return _ec;
+  return rd.boolean();
+}
+Result<bool> RemoteCoord::guarded_del(const std::string& guard_key, int64_t guard_create_revision, const std::string& key) {
+  wire::Writer w;
+  w.str(guard_key);
+  w.i64(guard_create_revision);
+  w.str(key);
+  BB_COORD_CALL(M_GUARDED_DEL, w);
+  if (_ec != ErrorCode::OK) return _ec;
+  return rd.boolean();
+}
+
+// Runs `cb` for one event with the bookkeeping unwatch()'s barrier relies on.
+void RemoteCoord::deliver(int64_t local_id, const WatchEvent& ev) {
+  WatchCallback f;
   {
     std::lock_guard<std::mutex> lk(wmu_);
-    if (!watch_connected_) {
-      if (watch_rpc_.connect(host_, port_, 3000) != ErrorCode::OK) return ErrorCode::ETCD_WATCH_ERROR;
-      watch_rpc_.enable_push([this](uint32_t topic, const std::string& payload) {
-        if (topic != kTopicWatch) return;
-        wire::Reader r(payload);
-        const int64_t id = r.i64();
-        WatchEvent ev;
-        ev.type = static_cast<EventType>(r.u32());
-        ev.key = r.str();
-        ev.value = r.str();
-        ev.revision = r.i64();
-        if (!r.ok()) return;
-        WatchCallback f;
-        {
-          std::lock_guard<std::mutex> l2(wmu_);
-          auto it = watches_.find(id);
-          if (it != watches_.end()) {
-            f = it->second;
-            ++running_[id];
-            push_thread_ = std::this_thread::get_id();
-          } else {
-            pending_[id].push_back(ev);  // event raced ahead of the watch response
-          }
-        }
-        if (f) {
-          f(ev);
-          std::lock_guard<std::mutex> l2(wmu_);
-          if (--running_[id] == 0) running_.erase(id);
-          wcv_.notify_all();
-        }
-      });
-      watch_connected_ = true;
-    }
+    auto it = watches_.find(local_id);
+    if (it == watches_.end()) return;
+    f = it->second.cb;
+    if (ev.type == EventType::PUT) it->second.known.insert(ev.key);
+    else it->second.known.erase(ev.key);
+    ++running_[local_id];
   }
+  const RemoteCoord* prev = tl_delivering;
+  tl_delivering = this;
+  try {
+    f(ev);
+  } catch (const std::exception& e) {
+    BB_LOG(ERROR) << "watch callback threw: " << e.what();
+  }
+  tl_delivering = prev;
+  std::lock_guard<std::mutex> lk(wmu_);
+  if (--running_[local_id] == 0) running_.erase(local_id);
+  wcv_.notify_all();
+}
+
+bool RemoteCoord::open_watch_channel() {
+  if (!connect_any(watch_rpc_, 1000)) return false;
+  watch_rpc_.enable_push([this](uint32_t topic, const std::string& payload) {
+    if (topic != kTopicWatch) return;
+    wire::Reader r(payload);
+    const int64_t server_id = r.i64();
+    WatchEvent ev;
+    ev.type = static_cast<EventType>(r.u32());
+    ev.key = r.str();
+    ev.value = r.str();
+    ev.revision = r.i64();
+    if (!r.ok()) return;
+    int64_t local = 0;
+    {
+      std::lock_guard<std::mutex> lk(wmu_);
+      auto it = by_server_.find(server_id);
+      if (it == by_server_.end()) {
+        pending_[server_id].push_back(ev);  // event raced ahead of the watch response
+        return;
+      }
+      local = it->second;
+    }
+    deliver(local, ev);
+  });
+  return true;
+}
+
+Result<int64_t> RemoteCoord::server_watch(const std::string& prefix) {
   wire::Writer w;
   w.str(prefix);
   auto resp = watch_rpc_.call(M_WATCH, w.data(), 10000);
@@ -624,36 +981,122 @@ Result<int64_t> RemoteCoord::watch_prefix(const std::string& prefix, WatchCallba
   wire::Reader rd(resp.value());
   const ErrorCode ec = rd.ec();
   if (ec != ErrorCode::OK) return ec;
-  const int64_t id = rd.i64();
+  return rd.i64();
+}
+
+Result<int64_t> RemoteCoord::watch_prefix(const std::string& prefix, WatchCallback cb) {
+  std::lock_guard<std::mutex> cl(watch_conn_mu_);
+  if (!watch_connected_) {
+    if (!open_watch_channel()) return ErrorCode::ETCD_WATCH_ERROR;
+    watch_connected_ = true;
+    if (!monitor_.joinable()) monitor_ = std::thread([this] { monitor_loop(); });
+  }
+  auto sid = server_watch(prefix);
+  if (!sid.ok()) return sid.error();
+  int64_t local;
   std::vector<WatchEvent> early;
   {
     std::lock_guard<std::mutex> lk(wmu_);
-    watches_[id] = cb;
-    auto it = pending_.find(id);
+    local = next_local_watch_++;
+    WatchReg reg;
+    reg.prefix = prefix;
+    reg.cb = std::move(cb);
+    reg.server_id = sid.value();
+    watches_[local] = std::move(reg);
+    by_server_[sid.value()] = local;
+    auto it = pending_.find(sid.value());
     if (it != pending_.end()) {
       early = std::move(it->second);
       pending_.erase(it);
     }
   }
-  for (const auto& ev : early) cb(ev);
-  return id;
+  for (const auto& ev : early) deliver(local, ev);
+  return local;
 }
 
 ErrorCode RemoteCoord::unwatch(int64_t id) {
+  int64_t server_id = 0;
   {
     std::unique_lock<std::mutex> lk(wmu_);
-    watches_.erase(id);
-    pending_.erase(id);
-    // barrier: a callback already running on the push thread finishes before we return (unless we ARE that thread)
-    if (std::this_thread::get_id() != push_thread_) wcv_.wait(lk, [&] { return running_.find(id) == running_.end(); });
-    if (!watch_connected_) return ErrorCode::ETCD_WATCH_ERROR;
+    auto it = watches_.find(id);
+    if (it == watches_.end()) return ErrorCode::ETCD_WATCH_ERROR;
+    server_id = it->second.server_id;
+    by_server_.erase(server_id);
+    pending_.erase(server_id);
+    watches_.erase(it);
+    // barrier: a callback already running on another thread finishes before we return (unless we ARE inside one)
+    if (tl_delivering != this) wcv_.wait(lk, [&] { return running_.find(id) == running_.end(); });
   }
+  if (tl_delivering == this) return ErrorCode::OK;  // server side is dropped with the connection at the latest
+  std::lock_guard<std::mutex> cl(watch_conn_mu_);
+  if (!watch_connected_ || !watch_rpc_.healthy()) return ErrorCode::OK;
   wire::Writer w;
-  w.i64(id);
+  w.i64(server_id);
   auto resp = watch_rpc_.call(M_UNWATCH, w.data(), 10000);
   if (!resp.ok()) return ErrorCode::ETCD_WATCH_ERROR;
   wire::Reader rd(resp.value());
   return rd.ec();
+}
+
+// Re-establishes the push channel after the store went away, then replays the difference to every watcher.
+void RemoteCoord::monitor_loop() {
+  while (!closing_.load()) {
+    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    if (closing_.load()) break;
+    {
+      std::lock_guard<std::mutex> cl(watch_conn_mu_);
+      if (!watch_connected_ || watch_rpc_.healthy()) continue;
+      if (!open_watch_channel()) continue;  // still down: try again on the next tick
+      reconnects_.fetch_add(1);
+      std::vector<std::pair<int64_t, std::string>> regs;
+      {
+        std::lock_guard<std::mutex> lk(wmu_);
+        by_server_.clear();
+        pending_.clear();
+        for (const auto& [id, r] : watches_) regs.emplace_back(id, r.prefix);
+      }
+      bool ok = true;
+      for (const auto& [local, prefix] : regs) {
+        auto sid = server_watch(prefix);
+        if (!sid.ok()) {
+          ok = false;
+          break;
+        }
+        std::lock_guard<std::mutex> lk(wmu_);
+        auto it = watches_.find(local);
+        if (it == watches_.end()) continue;
+        it->second.server_id = sid.value();
+        by_server_[sid.value()] = local;
+      }
+      if (!ok) {
+        watch_rpc_.close();
+        continue;
+      }
+      BB_LOG(INFO) << "coord client: watch channel re-established (" << regs.size() << " watches), re-listing";
+    }
+    // ---- resync outside the connection lock: callbacks may call back into this store
+    std::vector<std::pair<int64_t, std::string>> regs;
+    {
+      std::lock_guard<std::mutex> lk(wmu_);
+      for (const auto& [id, r] : watches_) regs.emplace_back(id, r.prefix);
+    }
+    for (const auto& [local, prefix] : regs) {
+      auto now = get_with_prefix(prefix);
+      if (!now.ok()) continue;
+      std::set<std::string> present;
+      for (const auto& kv : now.value()) present.insert(kv.key);
+      std::vector<std::string> gone;
+      {
+        std::lock_guard<std::mutex> lk(wmu_);
+        auto it = watches_.find(local);
+        if (it == watches_.end()) continue;
+        for (const auto& k : it->second.known)
+          if (!present.count(k)) gone.push_back(k);
+      }
+      for (const auto& k : gone) deliver(local, WatchEvent{EventType::DELETE, k, "", 0});
+      for (const auto& kv : now.value()) deliver(local, WatchEvent{EventType::PUT, kv.key, kv.value, kv.mod_revision});
+    }
+  }
 }
 
 // ================================================================ shared in-proc stores
@@ -836,6 +1279,7 @@ ErrorCode CoordService::campaign_leader(const std::string& election, const std::
     if (lease && store_->keep_alive(lease) == ErrorCode::OK) {
       std::lock_guard<std::mutex> lk(mu_);
       election_leases_[election] = lease;
+      election_terms_[election] = cur.value().create_revision;
       is_leader = true;
       return ErrorCode::OK;
     }
@@ -848,13 +1292,43 @@ ErrorCode CoordService::campaign_leader(const std::string& election, const std::
     return ErrorCode::LEADER_ELECTION_FAILED;
   }
   if (won.value()) {
+    auto mine = store_->get_kv(key);  // the term = create revision of the key we just created
+    if (!mine.ok() || mine.value().value != candidate) {
+      store_->revoke_lease(g.value());
+      return ErrorCode::LEADER_ELECTION_FAILED;
+    }
     std::lock_guard<std::mutex> lk(mu_);
     election_leases_[election] = g.value();
+    election_terms_[election] = mine.value().create_revision;
     is_leader = true;
   } else {
     store_->revoke_lease(g.value());
   }
   return ErrorCode::OK;
+}
+
+int64_t CoordService::leader_term(const std::string& election) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = election_terms_.find(election);
+  return it == election_terms_.end() ? 0 : it->second;
+}
+
+ErrorCode CoordService::fenced_put(const std::string& election, const std::string& key, const std::string& value) {
+  if (!connected_) return ErrorCode::ETCD_ERROR;
+  const int64_t term = leader_term(election);
+  if (term == 0) return ErrorCode::NOT_LEADER;
+  auto r = store_->guarded_put("/blackbird/elections/" + election + "/leader", term, key, value);
+  if (!r.ok()) return r.error();
+  return r.value() ? ErrorCode::OK : ErrorCode::NOT_LEADER;
+}
+
+ErrorCode CoordService::fenced_del(const std::string& election, const std::string& key) {
+  if (!connected_) return ErrorCode::ETCD_ERROR;
+  const int64_t term = leader_term(election);
+  if (term == 0) return ErrorCode::NOT_LEADER;
+  auto r = store_->guarded_del("/blackbird/elections/" + election + "/leader", term, key);
+  if (!r.ok()) return r.error();
+  return r.value() ? ErrorCode::OK : ErrorCode::NOT_LEADER;
 }
 
 ErrorCode CoordService::get_leader(const std::string& election, std::string& leader) {
@@ -873,6 +1347,7 @@ ErrorCode CoordService::resign_leader(const std::string& election, const std::st
       lease = it->second;
       election_leases_.erase(it);
     }
+    election_terms_.erase(election);
   }
   if (lease) store_->revoke_lease(lease);
   if (!r.ok()) return r.error();
@@ -887,9 +1362,18 @@ ErrorCode CoordService::refresh_leadership(const std::string& election, const st
     auto it = election_leases_.find(election);
     if (it != election_leases_.end()) lease = it->second;
   }
-  if (!lease || store_->keep_alive(lease) != ErrorCode::OK) return ErrorCode::NOT_LEADER;
-  auto cur = store_->get("/blackbird/elections/" + election + "/leader");
-  if (!cur.ok() || cur.value() != candidate) return ErrorCode::NOT_LEADER;
+  auto lost = [&] {
+    std::lock_guard<std::mutex> lk(mu_);
+    election_terms_.erase(election);
+    return ErrorCode::NOT_LEADER;
+  };
+  if (!lease) return lost();
+  const ErrorCode ka = store_->keep_alive(lease);
+  if (ka == ErrorCode::ETCD_ERROR) return ErrorCode::ETCD_ERROR;  // store unreachable: unknown, not (yet) lost
+  if (ka != ErrorCode::OK) return lost();
+  auto cur = store_->get_kv("/blackbird/elections/" + election + "/leader");
+  if (!cur.ok() && cur.error() == ErrorCode::ETCD_ERROR) return ErrorCode::ETCD_ERROR;
+  if (!cur.ok() || cur.value().value != candidate || cur.value().create_revision != leader_term(election)) return lost();
   return ErrorCode::OK;
 }
 

@@ -26,6 +26,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "common/durable_log.h"
 #include "common/types.h"
 #include "net/tcp.h"
 
@@ -66,6 +67,12 @@ class CoordStore {
   virtual Result<bool> compare_and_swap(const std::string& key, const std::string& expected, const std::string& value,
                                         LeaseId lease = 0) = 0;
   virtual Result<bool> compare_and_delete(const std::string& key, const std::string& expected) = 0;
+  // Fenced writes (etcd: txn{compare: create_revision(guard_key) == guard_create_revision; success: put | delete}).
+  // The guard is the election key and its create revision is the leader's term: a deposed leader's writes fail
+  // (value() == false) no matter how late they arrive.
+  virtual Result<bool> guarded_put(const std::string& guard_key, int64_t guard_create_revision, const std::string& key,
+                                   const std::string& value) = 0;
+  virtual Result<bool> guarded_del(const std::string& guard_key, int64_t guard_create_revision, const std::string& key) = 0;
   virtual Result<int64_t> watch_prefix(const std::string& prefix, WatchCallback cb) = 0;
   virtual ErrorCode unwatch(int64_t watch_id) = 0;
   virtual int64_t revision() = 0;
@@ -95,9 +102,20 @@ class MemCoord : public CoordStore {
   Result<bool> compare_and_swap(const std::string& key, const std::string& expected, const std::string& value,
                                 LeaseId lease = 0) override;
   Result<bool> compare_and_delete(const std::string& key, const std::string& expected) override;
+  Result<bool> guarded_put(const std::string& guard_key, int64_t guard_create_revision, const std::string& key,
+                           const std::string& value) override;
+  Result<bool> guarded_del(const std::string& guard_key, int64_t guard_create_revision, const std::string& key) override;
   Result<int64_t> watch_prefix(const std::string& prefix, WatchCallback cb) override;
   ErrorCode unwatch(int64_t watch_id) override;
   int64_t revision() override;
+
+  // Durability (`bb-coord --data-dir`): every mutation is appended to a log in `dir` and fdatasync'ed (group commit)
+  // before the call returns; the log is compacted into snapshots.  Re-opening the directory restores keys, revisions
+  // and leases (re-armed with their full TTL, like etcd after a restart; lease ids are preserved so that clients keep
+  // refreshing the leases they hold).  Call before the store is shared.
+  ErrorCode open_durable(const std::string& dir, bool fsync = true, uint64_t snapshot_bytes = 64ull << 20);
+  bool durable() const { return log_ != nullptr; }
+  uint64_t recovered_records() const { return recovered_records_; }
 
   // Test / fault-injection hooks: moves the store's clock forward (expires leases) and blocks
   // until the resulting events have been delivered.
@@ -119,6 +137,23 @@ class MemCoord : public CoordStore {
   };
   std::condition_variable wcv_;  // signalled when a watcher's invocation returns
   int64_t now_ms() const;
+  // durable log plumbing: *_locked mutators append under mu_ and leave the record's sequence number in pending_seq_;
+  // the public entry point syncs it after dropping mu_ (commit()).
+  void log_locked(const std::string& rec);
+  uint64_t take_seq_locked() {
+    const uint64_t s = pending_seq_;
+    pending_seq_ = 0;
+    return s;
+  }
+  ErrorCode commit(uint64_t seq, ErrorCode ec);
+  std::string snapshot_locked() const;
+  void load_snapshot(const std::string& blob);
+  void apply_record(std::string_view rec);
+  std::unique_ptr<DurableLog> log_;
+  uint64_t pending_seq_ = 0;
+  bool replaying_ = false;
+  uint64_t recovered_records_ = 0;
+  std::mutex snap_mu_;  // one snapshot at a time
   ErrorCode put_locked(const std::string& key, const std::string& value, LeaseId lease);
   bool del_locked(const std::string& key);
   void emit_locked(EventType t, const std::string& key, const std::string& value);
@@ -183,23 +218,46 @@ class RemoteCoord : public CoordStore {
   Result<bool> compare_and_swap(const std::string& key, const std::string& expected, const std::string& value,
                                 LeaseId lease = 0) override;
   Result<bool> compare_and_delete(const std::string& key, const std::string& expected) override;
+  Result<bool> guarded_put(const std::string& guard_key, int64_t guard_create_revision, const std::string& key,
+                           const std::string& value) override;
+  Result<bool> guarded_del(const std::string& guard_key, int64_t guard_create_revision, const std::string& key) override;
   Result<int64_t> watch_prefix(const std::string& prefix, WatchCallback cb) override;
   ErrorCode unwatch(int64_t watch_id) override;
   int64_t revision() override;
+  uint64_t reconnects() const { return reconnects_.load(); }
 
  private:
+  struct WatchReg {
+    std::string prefix;
+    WatchCallback cb;
+    int64_t server_id = 0;         // id of the current incarnation of this watch on the server
+    std::set<std::string> known;   // keys this watcher has been told exist (to synthesise DELETEs after a reconnect)
+  };
   Result<std::string> call(uint32_t method, const std::string& req);
+  bool connect_any(net::RpcClient& c, int timeout_ms);
+  bool open_watch_channel();
+  Result<int64_t> server_watch(const std::string& prefix);
+  void deliver(int64_t local_id, const WatchEvent& ev);
+  void monitor_loop();
   net::RpcClient rpc_;        // request/response
   net::RpcClient watch_rpc_;  // push channel
+  std::mutex conn_mu_;        // reconnect of rpc_
+  std::mutex watch_conn_mu_;  // watch channel (re)establishment, M_WATCH / M_UNWATCH calls
   std::mutex wmu_;
-  std::map<int64_t, WatchCallback> watches_;
+  std::map<int64_t, WatchReg> watches_;   // local id -> registration
+  std::map<int64_t, int64_t> by_server_;  // server id -> local id
+  int64_t next_local_watch_ = 1;
   std::map<int64_t, int> running_;  // callback invocations in flight per watch (guarded by wmu_)
   std::condition_variable wcv_;
-  std::thread::id push_thread_{};   // thread currently delivering push events (unwatch from a callback must not wait)
-  std::map<int64_t, std::vector<WatchEvent>> pending_;
+  std::map<int64_t, std::vector<WatchEvent>> pending_;  // by server id
   bool watch_connected_ = false;
+  std::vector<std::pair<std::string, uint16_t>> endpoints_;
   std::string host_;
   uint16_t port_ = 0;
+  std::thread monitor_;
+  std::atomic<bool> closing_{false};
+  std::atomic<uint64_t> reconnects_{0};
+  std::atomic<uint64_t> conn_gen_{0};
 };
 
 // ---------------------------------------------------------------- service facade (EtcdService parity)
@@ -243,6 +301,12 @@ class CoordService {
   ErrorCode resign_leader(const std::string& election, const std::string& candidate);
   // Keeps this candidate's leadership lease alive; NOT_LEADER when it was lost.
   ErrorCode refresh_leadership(const std::string& election, const std::string& candidate);
+  // Fencing.  The term of a leadership is the create revision of the election key (monotonic across elections, as in
+  // etcd's election recipe); 0 = this service does not hold the election.  fenced_put / fenced_del apply only while
+  // that very incarnation of the key exists: NOT_LEADER when the guard fails (a deposed leader cannot write).
+  int64_t leader_term(const std::string& election);
+  ErrorCode fenced_put(const std::string& election, const std::string& key, const std::string& value);
+  ErrorCode fenced_del(const std::string& election, const std::string& key);
 
  private:
   std::string endpoints_;
@@ -251,6 +315,7 @@ class CoordService {
   std::mutex mu_;
   std::unordered_map<std::string, LeaseId> ttl_leases_;       // key -> lease (put_with_ttl)
   std::unordered_map<std::string, LeaseId> election_leases_;  // election -> lease
+  std::unordered_map<std::string, int64_t> election_terms_;   // election -> create revision of the key we own
   std::unordered_map<std::string, int64_t> key_watches_;
   std::vector<int64_t> watch_ids_;
 };

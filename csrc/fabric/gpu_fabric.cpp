@@ -1,6 +1,7 @@
 #include "common/trace.h"
 #include "fabric/gpu_fabric.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -8,6 +9,27 @@
 #include "common/log.h"
 
 namespace bb::gpu {
+
+namespace drv {
+// cuMemGetAddressRange resolved at runtime (the module must import on a CPU-only box: no libcuda link dependency).
+bool get_address_range(const void* p, CUdeviceptr* base, size_t* size) {
+  static auto fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr)>(f);
+  }();
+  if (!fn) return false;
+  if (fn(base, size, reinterpret_cast<CUdeviceptr>(p)) != CUDA_SUCCESS) return false;
+  // the range is that of the allocation containing p; what is left of it from p on:
+  const size_t skip = reinterpret_cast<CUdeviceptr>(p) - *base;
+  *size = *size > skip ? *size - skip : 0;
+  return true;
+}
+}  // namespace drv
 
 namespace {
 struct LocalSlab {
@@ -129,7 +151,8 @@ ErrorCode GpuSlabBackend::device_copy(worker::StorageBackend& peer, bool to_peer
   if (!base_ || !peer.cuda_accessible()) return ErrorCode::NOT_IMPLEMENTED;
   BB_TRY(check_range(my_off, len));
   auto* theirs = static_cast<uint8_t*>(peer.direct_ptr(peer_off));
-  if (!theirs || peer_off + len > peer.get_total_capacity()) return ErrorCode::MEMORY_ACCESS_ERROR;
+  const uint64_t peer_cap = peer.get_total_capacity();
+  if (!theirs || len > peer_cap || peer_off > peer_cap - len) return ErrorCode::MEMORY_ACCESS_ERROR;  // overflow safe
   uint8_t* mine = base_ + my_off;
   if ((reinterpret_cast<uintptr_t>(mine) | reinterpret_cast<uintptr_t>(theirs)) & 15) return ErrorCode::NOT_IMPLEMENTED;  // staged path handles it
   std::lock_guard<std::mutex> lk(move_mu_);
@@ -166,6 +189,15 @@ ErrorCode GpuSlabBackend::pull_from_peer(const std::vector<uint8_t>& peer_key, u
   if (!peer_base) {  // same-process slab, no peer access, stale handle: the caller relays through the data servers
     BB_VLOG(1) << "pull_from_peer: cannot map the peer slab (" << cudaGetErrorString(e) << ")";
     return ErrorCode::NOT_IMPLEMENTED;
+  }
+  // The mapping covers the peer's whole cudaMalloc allocation: bound the read by its real extent, so a bad
+  // (peer_off, len) from the wire cannot make the copy kernel read past the mapped slab.
+  {
+    CUdeviceptr range_base = 0;
+    size_t range_size = 0;
+    if (!drv::get_address_range(peer_base, &range_base, &range_size) ||
+        len > range_size || peer_off > range_size - len)
+      return ErrorCode::MEMORY_ACCESS_ERROR;
   }
   uint8_t* theirs = static_cast<uint8_t*>(peer_base) + peer_off;
   uint8_t* mine = base_ + my_off;

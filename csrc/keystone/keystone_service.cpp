@@ -93,12 +93,48 @@ ErrorCode KeystoneService::setup_coordination() {
   if (ec != ErrorCode::OK) return ec;
   if (config_.enable_ha) {
     bool won = false;
-    ec = coord_->campaign_leader("keystone-" + config_.cluster_id, candidate_id_, config_.service_registration_ttl_sec, won);
+    const TimePoint t0 = Clock::now();
+    ec = coord_->campaign_leader(election_name(), candidate_id_, config_.service_registration_ttl_sec, won);
     if (ec != ErrorCode::OK) return ec;
-    leader_.store(won);
-    BB_LOG(INFO) << "keystone " << candidate_id_ << (won ? " is the leader" : " is a standby");
+    if (won) {
+      term_.store(coord_->leader_term(election_name()));
+      arm_lease_deadline(t0);
+    }
+    leader_.store(won, std::memory_order_release);
+    BB_LOG(INFO) << "keystone " << candidate_id_ << (won ? " is the leader (term " + std::to_string(term_.load()) + ")" : " is a standby");
   }
   return ErrorCode::OK;
+}
+
+// Leadership is valid in local time until `refreshed_at` (taken BEFORE the keep-alive round trip) + TTL - margin.
+void KeystoneService::arm_lease_deadline(TimePoint refreshed_at) {
+  const auto ttl = std::chrono::seconds(std::max<int64_t>(1, config_.service_registration_ttl_sec));
+  const auto margin = std::max<std::chrono::nanoseconds>(std::chrono::milliseconds(200), ttl / 10);
+  lease_deadline_.store((refreshed_at + ttl - margin).time_since_epoch().count(), std::memory_order_release);
+}
+
+void KeystoneService::step_down(const char* why) {
+  if (!leader_.exchange(false)) return;
+  BB_LOG(WARNING) << "keystone " << candidate_id_ << " steps down: " << why;
+  term_.store(0);
+  lease_deadline_.store(0);
+  metrics_.inc("leadership_lost_total");
+}
+
+// A non-leader holds no authoritative state: whatever it remembers may be changed by the next leader, so the table and
+// the allocator are rebuilt from the metadata log when (if) leadership comes back -- never patched up.
+void KeystoneService::reset_object_state() {
+  for (auto& sh : shards_) {
+    std::lock_guard<std::mutex> wl(sh.wal_mu);
+    std::lock_guard<SpinMutex> lk(sh.mu);
+    sh.objects.clear();
+    for (auto& op : sh.wal_queue)
+      if (op.result) *op.result = ErrorCode::NOT_LEADER;
+    sh.wal_queue.clear();
+  }
+  static_cast<alloc::RangeAllocator&>(allocator_->allocator()).reset();  // in place: other threads hold the adapter
+  std::lock_guard<std::mutex> ul(unadopted_mu_);
+  unadopted_.clear();
 }
 
 ErrorCode KeystoneService::start() {
@@ -114,7 +150,17 @@ ErrorCode KeystoneService::start() {
       watch_ids_.push_back(id);
     if (coord_->watch_prefix(p + "heartbeat/", [this](const std::string& k, const std::string& v, bool d) { on_heartbeat_event(k, v, d); }, &id) == ErrorCode::OK)
       watch_ids_.push_back(id);
+  }
+  if (config_.enable_ha) {
+    wal_on_.store(coord_ && coord_->is_connected());
     if (is_leader()) recover_objects_from_wal();
+  } else if (!config_.wal_path.empty()) {
+    const ErrorCode ec = open_local_wal();  // replays the local log into the table
+    if (ec != ErrorCode::OK) {
+      running_.store(false);
+      return ec;
+    }
+    wal_on_.store(true);
   }
   if (config_.enable_gc) gc_thread_ = std::thread([this] { gc_loop(); });
   health_thread_ = std::thread([this] { health_loop(); });
@@ -141,6 +187,10 @@ void KeystoneService::stop() {
     coord_->unregister_service("blackbird-keystone", config_.service_id);
   }
   leader_.store(false);
+  if (local_wal_) {
+    maybe_snapshot_local_wal();
+    local_wal_->close();
+  }
 }
 
 bool KeystoneService::interruptible_sleep(std::chrono::milliseconds d) {
@@ -181,25 +231,39 @@ void KeystoneService::health_loop() {
 }
 
 void KeystoneService::keepalive_loop() {
-  const std::string election = "keystone-" + config_.cluster_id;
-  while (interruptible_sleep(std::chrono::seconds(config_.service_refresh_interval_sec))) {
+  const std::string election = election_name();
+  // HA: the election lease must be refreshed several times per TTL, whatever the (registry) refresh interval says
+  const int64_t ttl_ms = std::max<int64_t>(1, config_.service_registration_ttl_sec) * 1000;
+  const int64_t period_ms = config_.enable_ha ? std::min<int64_t>(config_.service_refresh_interval_sec * 1000, std::max<int64_t>(100, ttl_ms / 4))
+                                              : config_.service_refresh_interval_sec * 1000;
+  bool was_leader = leader_.load();
+  while (interruptible_sleep(std::chrono::milliseconds(period_ms))) {
     if (!coord_ || !coord_->is_connected()) continue;
     if (coord_->register_service("blackbird-keystone", config_.service_id, config_.listen_address,
                                  config_.service_registration_ttl_sec) != ErrorCode::OK)
       BB_LOG(WARNING) << "keystone: service registration refresh failed";
     if (!config_.enable_ha) continue;
     if (leader_.load()) {
-      if (coord_->refresh_leadership(election, candidate_id_) != ErrorCode::OK) {
-        BB_LOG(WARNING) << "keystone " << candidate_id_ << " lost leadership";
-        leader_.store(false);
-      }
-    } else {
+      const TimePoint t0 = Clock::now();
+      const ErrorCode ec = coord_->refresh_leadership(election, candidate_id_);
+      if (ec == ErrorCode::OK) arm_lease_deadline(t0);
+      else if (ec != ErrorCode::ETCD_ERROR) step_down("the election lease is gone");
+      // ETCD_ERROR: the store is unreachable -- leadership is unknown; is_leader() lapses by itself at the deadline
+    }
+    if (was_leader && !leader_.load()) reset_object_state();  // also reached when a fenced write stepped us down
+    was_leader = leader_.load();
+    if (!leader_.load()) {
       bool won = false;
+      const TimePoint t0 = Clock::now();
       if (coord_->campaign_leader(election, candidate_id_, config_.service_registration_ttl_sec, won) == ErrorCode::OK && won) {
-        BB_LOG(INFO) << "keystone " << candidate_id_ << " took over leadership";
+        term_.store(coord_->leader_term(election));
+        BB_LOG(INFO) << "keystone " << candidate_id_ << " took over leadership (term " << term_.load() << ")";
+        reset_object_state();
         load_existing_state();
         recover_objects_from_wal();
-        leader_.store(true);
+        arm_lease_deadline(t0);
+        leader_.store(true, std::memory_order_release);
+        was_leader = true;
         bump_view();
       }
     }
@@ -224,11 +288,7 @@ void KeystoneService::on_worker_event(const std::string& key, const std::string&
   if (mp != std::string::npos) {
     const std::string pid = rest.substr(mp + 14);
     if (is_delete) {
-      std::unique_lock<std::shared_mutex> lk(pools_mu_);
-      pools_.erase(pid);
-      refresh_top_tier_locked();
-      lk.unlock();
-      bump_view();
+      handle_pool_removed(pid);
       return;
     }
     auto j = Json::parse(value);
@@ -261,9 +321,7 @@ void KeystoneService::on_legacy_pool_event(const std::string& key, const std::st
   if (key.compare(0, base.size(), base) != 0) return;
   const std::string pid = key.substr(base.size());
   if (is_delete) {
-    std::unique_lock<std::shared_mutex> lk(pools_mu_);
-    pools_.erase(pid);
-    refresh_top_tier_locked();
+    handle_pool_removed(pid);
     return;
   }
   auto j = Json::parse(value);
@@ -327,6 +385,24 @@ ErrorCode KeystoneService::register_memory_pool(const MemoryPool& pool) {
     pools_[pool.id] = pool;
     refresh_top_tier_locked();
   }
+  // objects recovered from the metadata log before this pool was known: reserve their extents now
+  std::vector<ObjectKey> waiting;
+  {
+    std::lock_guard<std::mutex> ul(unadopted_mu_);
+    auto it = unadopted_.find(pool.id);
+    if (it != unadopted_.end()) {
+      waiting = std::move(it->second);
+      unadopted_.erase(it);
+    }
+  }
+  if (!waiting.empty()) {
+    std::shared_lock<std::shared_mutex> pk(pools_mu_);
+    auto& ra = static_cast<alloc::RangeAllocator&>(allocator_->allocator());
+    for (const auto& key : waiting) {
+      auto info = get_object_info(key);
+      if (info.ok()) ra.adopt(key, info.value().copies, pools_, pool.id);
+    }
+  }
   bump_view();
   return ErrorCode::OK;
 }
@@ -354,6 +430,23 @@ ErrorCode KeystoneService::remove_worker(const WorkerId& id) {
   return ErrorCode::OK;
 }
 
+void KeystoneService::handle_pool_removed(const MemoryPoolId& pid) {
+  {
+    std::unique_lock<std::shared_mutex> lk(workers_mu_);
+    std::unique_lock<std::shared_mutex> pk(pools_mu_);
+    auto pit = pools_.find(pid);
+    if (pit == pools_.end()) return;
+    auto wit = workers_.find(pit->second.worker_id);
+    if (wit != workers_.end()) {
+      auto& v = wit->second.pools;
+      v.erase(std::remove(v.begin(), v.end(), pid), v.end());
+    }
+    pools_.erase(pit);
+    refresh_top_tier_locked();
+  }
+  invalidate_pools({pid}, "pool " + pid + " deregistered");
+}
+
 void KeystoneService::handle_worker_death(const WorkerId& id) {
   std::vector<MemoryPoolId> dead;
   {
@@ -370,13 +463,18 @@ void KeystoneService::handle_worker_death(const WorkerId& id) {
     for (const auto& p : dead) pools_.erase(p);
     refresh_top_tier_locked();
   }
+  invalidate_pools(dead, "worker " + id + " died");
+}
+
+// The pools are gone from the registry: forget their allocators and invalidate every copy that had a shard on them.
+void KeystoneService::invalidate_pools(const std::vector<MemoryPoolId>& dead, const std::string& why) {
   for (const auto& p : dead) allocator_->allocator().forget_pool(p);
   // invalidate every copy that had a shard on the dead pools
   const std::set<MemoryPoolId> dead_set(dead.begin(), dead.end());
   size_t lost_objects = 0, degraded = 0;
   for (auto& sh : shards_) {
     std::vector<ObjectKey> gone;
-    std::unique_lock<SpinMutex> lk(sh.mu);
+    ShardGuard lk(this, sh);
     for (auto& [key, info] : sh.objects) {
       const size_t before = info.copies.size();
       info.copies.erase(std::remove_if(info.copies.begin(), info.copies.end(),
@@ -390,7 +488,7 @@ void KeystoneService::handle_worker_death(const WorkerId& id) {
       if (info.copies.empty()) gone.push_back(key);
       else {
         ++degraded;
-        if (info.state == ObjectState::COMPLETE) persist_object(info);
+        if (info.state == ObjectState::COMPLETE) persist_object(sh, info);
       }
     }
     for (const auto& k : gone) {
@@ -398,8 +496,7 @@ void KeystoneService::handle_worker_death(const WorkerId& id) {
       ++lost_objects;
     }
   }
-  if (lost_objects || degraded)
-    BB_LOG(WARNING) << "worker " << id << " died: " << lost_objects << " objects lost, " << degraded << " degraded";
+  if (lost_objects || degraded) BB_LOG(WARNING) << why << ": " << lost_objects << " objects lost, " << degraded << " degraded";
   metrics_.inc("objects_lost_total", lost_objects);
   bump_view();
 }
@@ -413,14 +510,14 @@ bool KeystoneService::pool_alive(const MemoryPoolId& id) const {
 ErrorCode KeystoneService::erase_locked(Shard& sh, const ObjectKey& key, bool free_ranges) {
   auto it = sh.objects.find(key);
   if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
-  const bool was_complete = it->second.state == ObjectState::COMPLETE;
+  const bool was_complete = it->second.state == ObjectState::COMPLETE || it->second.committing;
   const std::vector<std::string> extra = std::move(it->second.extra_ledgers);
   sh.objects.erase(it);
   if (free_ranges) {
     allocator_->free_object(key);
     for (const auto& l : extra) allocator_->free_object(l);  // ledgers created by repair / demotion
   }
-  if (was_complete) unpersist_object(key);
+  if (was_complete) unpersist_object(sh, key);
   return ErrorCode::OK;
 }
 
@@ -484,7 +581,7 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start_locked(const Objec
   if (config.replication_factor == 0 || config.max_workers_per_copy == 0) return ErrorCode::INVALID_PARAMETERS;
   if (config_.max_replicas > 0 && config.replication_factor > static_cast<size_t>(config_.max_replicas)) return ErrorCode::VALUE_OUT_OF_RANGE;
   Shard& sh = shard_for(key);
-  std::unique_lock<SpinMutex> lk(sh.mu);
+  ShardGuard lk(this, sh);
   auto it = sh.objects.find(key);
   if (it != sh.objects.end()) {
     if (!it->second.is_expired()) return ErrorCode::OBJECT_ALREADY_EXISTS;
@@ -518,7 +615,7 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksu
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   if (fault::fire("fail_put_complete")) return ErrorCode::INTERNAL_ERROR;
   Shard& sh = shard_for(key);
-  std::unique_lock<SpinMutex> lk(sh.mu);
+  ShardGuard lk(this, sh);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.is_expired()) return ErrorCode::OBJECT_NOT_FOUND;
   ObjectInfo& info = it->second;
@@ -529,13 +626,44 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksu
       for (size_t s = 0; s < checksums[c].size(); ++s) info.copies[c].shards[s].checksum = checksums[c][s];
     }
   }
-  if (info.state != ObjectState::COMPLETE) {
+  if (!wal_enabled()) {  // volatile metadata: one critical section
+    if (info.state != ObjectState::COMPLETE) {
+      info.state = ObjectState::COMPLETE;
+      hot_.put_complete_total->fetch_add(1, std::memory_order_relaxed);
+    }
+    info.touch();
+    lk.finish();
+    bump_view();
+    return ErrorCode::OK;
+  }
+  // Durable before visible: the COMPLETE record is logged first (outside the spin lock); only when that succeeded does
+  // the object become readable, and only then is the client told OK.  A failed log write leaves it PENDING.
+  ErrorCode wal_ec = ErrorCode::OK;
+  const TimePoint created = info.created;
+  {
+    const ObjectState prev = info.state;
     info.state = ObjectState::COMPLETE;
+    persist_object(sh, info, &wal_ec);
+    info.state = prev;
+    info.committing = true;
+  }
+  lk.finish();  // writes the record, or waits for the thread that drained it
+  lk.relock();
+  it = sh.objects.find(key);
+  const bool same = it != sh.objects.end() && it->second.created == created;
+  if (same) it->second.committing = false;
+  if (wal_ec != ErrorCode::OK) {
+    lk.finish();
+    metrics_.inc("wal_write_failed_total");
+    return wal_ec == ErrorCode::NOT_LEADER ? wal_ec : ErrorCode::ETCD_ERROR;
+  }
+  if (!same) return ErrorCode::OBJECT_NOT_FOUND;  // cancelled / removed meanwhile (its tombstone is queued after our record)
+  if (it->second.state != ObjectState::COMPLETE) {
+    it->second.state = ObjectState::COMPLETE;
     hot_.put_complete_total->fetch_add(1, std::memory_order_relaxed);
   }
-  info.touch();
-  persist_object(info);
-  lk.unlock();
+  it->second.touch();
+  lk.finish();
   bump_view();
   return ErrorCode::OK;
 }
@@ -543,7 +671,7 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksu
 ErrorCode KeystoneService::put_cancel(const ObjectKey& key) {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   Shard& sh = shard_for(key);
-  std::unique_lock<SpinMutex> lk(sh.mu);
+  ShardGuard lk(this, sh);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
   if (it->second.state == ObjectState::COMPLETE) return ErrorCode::INVALID_STATE;
@@ -555,9 +683,9 @@ ErrorCode KeystoneService::put_cancel(const ObjectKey& key) {
 ErrorCode KeystoneService::remove_object(const ObjectKey& key) {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   Shard& sh = shard_for(key);
-  std::unique_lock<SpinMutex> lk(sh.mu);
+  ShardGuard lk(this, sh);
   ErrorCode ec = erase_locked(sh, key, true);
-  lk.unlock();
+  lk.finish();
   if (ec == ErrorCode::OK) {
     hot_.remove_total->fetch_add(1, std::memory_order_relaxed);
     bump_view();
@@ -569,7 +697,7 @@ Result<size_t> KeystoneService::remove_all_objects() {
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   size_t n = 0;
   for (auto& sh : shards_) {
-    std::unique_lock<SpinMutex> lk(sh.mu);
+    ShardGuard lk(this, sh);
     std::vector<ObjectKey> keys;
     keys.reserve(sh.objects.size());
     for (const auto& [k, v] : sh.objects) keys.push_back(k);
@@ -784,7 +912,7 @@ size_t KeystoneService::run_gc_once() {
   size_t n = 0;
   const TimePoint now = Clock::now();
   for (auto& sh : shards_) {
-    std::unique_lock<SpinMutex> lk(sh.mu);
+    ShardGuard lk(this, sh);
     std::vector<ObjectKey> dead;
     for (const auto& [k, o] : sh.objects) {
       if (o.is_expired(now)) dead.push_back(k);
@@ -843,18 +971,18 @@ ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey&
     return ec;
   }
   Shard& sh = shard_for(key);
-  std::unique_lock<SpinMutex> lk(sh.mu);
+  ShardGuard lk(this, sh);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.created != info.value().created) {  // removed / replaced while we copied
-    lk.unlock();
+    lk.finish();
     allocator_->free_object(ledger);
     return ErrorCode::OBJECT_NOT_FOUND;
   }
   it->second.copies = fresh.value();
   const std::vector<std::string> old = std::move(it->second.extra_ledgers);
   it->second.extra_ledgers = {ledger};
-  persist_object(it->second);
-  lk.unlock();
+  persist_object(sh, it->second);
+  lk.finish();
   allocator_->free_object(key);  // old extents
   for (const auto& l : old) allocator_->free_object(l);
   bump_view();
@@ -1057,7 +1185,7 @@ size_t KeystoneService::run_eviction_once() {
         if (demoted) metrics_.inc("demotions_total");
         if (!demoted) {
           Shard& sh = shard_for(key);
-          std::unique_lock<SpinMutex> lk(sh.mu);
+          ShardGuard lk(this, sh);
           if (erase_locked(sh, key, true) == ErrorCode::OK) metrics_.inc("evictions_total");
         }
         ++total;
@@ -1104,17 +1232,17 @@ size_t KeystoneService::run_repair_once() {
       continue;
     }
     Shard& sh = shard_for(o.key);
-    std::unique_lock<SpinMutex> lk(sh.mu);
+    ShardGuard lk(this, sh);
     auto it = sh.objects.find(o.key);
     if (it == sh.objects.end() || it->second.created != o.created) {
-      lk.unlock();
+      lk.finish();
       allocator_->free_object(ledger);
       continue;
     }
     dst.copy_index = static_cast<uint32_t>(it->second.copies.size());
     it->second.copies.push_back(dst);
     it->second.extra_ledgers.push_back(ledger);
-    persist_object(it->second);
+    persist_object(sh, it->second);
     ++repaired;
   }
   if (repaired) {
@@ -1124,35 +1252,180 @@ size_t KeystoneService::run_repair_once() {
   return repaired;
 }
 
-// ================================================================ WAL
-void KeystoneService::persist_object(const ObjectInfo& info) {
-  if (!coord_ || !coord_->is_connected() || !(config_.enable_ha || !config_.wal_path.empty())) return;
-  coord_->put(cluster_prefix() + "objects/" + info.key, encode_object(info));
+// ================================================================ metadata log
+void KeystoneService::persist_object(Shard& sh, const ObjectInfo& info, ErrorCode* result) {
+  if (!wal_enabled()) return;
+  sh.wal_queue.push_back(WalOp{info.key, encode_object(info), false, result});
 }
 
-void KeystoneService::unpersist_object(const ObjectKey& key) {
-  if (!coord_ || !coord_->is_connected() || !(config_.enable_ha || !config_.wal_path.empty())) return;
-  coord_->del(cluster_prefix() + "objects/" + key);
+void KeystoneService::unpersist_object(Shard& sh, const ObjectKey& key) {
+  if (!wal_enabled()) return;
+  sh.wal_queue.push_back(WalOp{key, {}, true, nullptr});
+}
+
+// Writes the shard's queued records in queue order.  Whoever holds wal_mu writes everything queued so far, so a thread
+// that finds the queue already drained only had to wait for the writer: when flush_wal returns, every record enqueued
+// by the caller before it is on the log (and `result` slots are filled).
+void KeystoneService::flush_wal(Shard& sh) {
+  std::lock_guard<std::mutex> wl(sh.wal_mu);
+  std::vector<WalOp> ops;
+  {
+    std::lock_guard<SpinMutex> lk(sh.mu);
+    ops.swap(sh.wal_queue);
+  }
+  if (ops.empty()) return;
+  uint64_t last_seq = 0;
+  for (const auto& op : ops) {
+    ErrorCode ec;
+    if (local_wal_) {
+      wire::Writer w;
+      w.u8(op.del ? 2 : 1);
+      w.str(op.key);
+      if (!op.del) w.str(op.value);
+      const uint64_t seq = local_wal_->append(w.data());
+      ec = seq ? ErrorCode::OK : ErrorCode::IO_ERROR;
+      if (seq) last_seq = seq;
+    } else {
+      ec = wal_write(op);
+    }
+    if (op.result) *op.result = ec;
+  }
+  if (local_wal_ && last_seq) {
+    const ErrorCode sc = local_wal_->sync(last_seq);  // one fdatasync for the whole batch (group commit)
+    if (sc != ErrorCode::OK)
+      for (const auto& op : ops)
+        if (op.result && *op.result == ErrorCode::OK) *op.result = sc;
+    if (local_wal_->snapshot_due()) maybe_snapshot_local_wal();
+  }
+}
+
+// Coordination-store sink: every write is a transaction guarded by the election key's create revision (the term).
+ErrorCode KeystoneService::wal_write(const WalOp& op) {
+  if (!coord_ || !coord_->is_connected()) return ErrorCode::ETCD_ERROR;
+  const std::string k = cluster_prefix() + "objects/" + op.key;
+  const ErrorCode ec = op.del ? coord_->fenced_del(election_name(), k) : coord_->fenced_put(election_name(), k, op.value);
+  if (ec == ErrorCode::NOT_LEADER) step_down("a fenced metadata write was refused (another leader holds a newer term)");
+  return ec;
 }
 
 void KeystoneService::recover_objects_from_wal() {
   if (!coord_ || !coord_->is_connected()) return;
   std::vector<std::string> keys, values;
-  if (coord_->get_with_prefix(cluster_prefix() + "objects/", keys, values) != ErrorCode::OK) return;
-  size_t n = 0;
+  const std::string pfx = cluster_prefix() + "objects/";
+  if (coord_->get_with_prefix(pfx, keys, values) != ErrorCode::OK) return;
+  std::vector<std::pair<std::string, std::string>> recs;
+  recs.reserve(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) recs.emplace_back(keys[i].substr(std::min(pfx.size(), keys[i].size())), std::move(values[i]));
+  recover_objects(recs);
+}
+
+// Rebuilds table + allocator reservations from (key, encoded ObjectInfo) records.  The table must be empty of these keys.
+void KeystoneService::recover_objects(std::vector<std::pair<std::string, std::string>>& records) {
+  size_t n = 0, deferred = 0;
   std::shared_lock<std::shared_mutex> pk(pools_mu_);
-  for (size_t i = 0; i < keys.size(); ++i) {
+  auto& ra = static_cast<alloc::RangeAllocator&>(allocator_->allocator());
+  for (auto& [k, v] : records) {
     ObjectInfo o;
-    if (!decode_object(values[i], o) || o.is_expired()) continue;
+    if (!decode_object(v, o) || o.is_expired()) continue;
+    o.state = ObjectState::COMPLETE;
     Shard& sh = shard_for(o.key);
     std::unique_lock<SpinMutex> lk(sh.mu);
     if (sh.objects.count(o.key)) continue;
-    // re-reserve the extents so that new puts cannot overwrite recovered objects
-    static_cast<alloc::RangeAllocator&>(allocator_->allocator()).adopt(o.key, o.copies, pools_);
+    // re-reserve the extents so that new puts cannot overwrite recovered objects; shards whose pool has not
+    // registered yet are adopted when it does (register_memory_pool)
+    ra.adopt(o.key, o.copies, pools_);
+    for (const auto& c : o.copies)
+      for (const auto& s : c.shards)
+        if (!pools_.count(s.pool_id)) {
+          std::lock_guard<std::mutex> ul(unadopted_mu_);
+          auto& v2 = unadopted_[s.pool_id];
+          if (v2.empty() || v2.back() != o.key) v2.push_back(o.key), ++deferred;
+        }
     sh.objects.emplace(o.key, std::move(o));
     ++n;
   }
-  if (n) BB_LOG(INFO) << "keystone: recovered " << n << " objects from the metadata log";
+  if (n) BB_LOG(INFO) << "keystone: recovered " << n << " objects from the metadata log" << (deferred ? " (" + std::to_string(deferred) + " await their pools)" : "");
+  metrics_.inc("objects_recovered_total", n);
+}
+
+// Local sink (`wal_path`): snapshot + log in a directory of this host.
+ErrorCode KeystoneService::open_local_wal() {
+  auto log = std::make_unique<DurableLog>();
+  DurableLog::Options o;
+  o.dir = config_.wal_path;
+  o.name = "keystone-" + config_.cluster_id;
+  o.fsync = config_.wal_fsync;
+  o.snapshot_bytes = config_.wal_snapshot_mb > 0 ? static_cast<uint64_t>(config_.wal_snapshot_mb) << 20 : (64ull << 20);
+  std::string snap;
+  std::unordered_map<std::string, std::string> live;
+  std::vector<std::string> order;
+  auto put = [&](std::string k, std::string v) {
+    auto [it, fresh] = live.try_emplace(k, std::move(v));
+    if (fresh) order.push_back(std::move(k));
+    else it->second = std::move(v);
+  };
+  // records first land in `pending`: the snapshot must be applied before them
+  std::vector<std::string> pending;
+  ErrorCode ec = log->open(o, &snap, [&](std::string_view r) { pending.emplace_back(r); });
+  if (ec != ErrorCode::OK) {
+    BB_LOG(ERROR) << "keystone: cannot open the metadata log under " << config_.wal_path;
+    return ec;
+  }
+  if (!snap.empty()) {
+    wire::Reader r(snap);
+    const uint32_t n = r.u32();
+    for (uint32_t i = 0; i < n && r.ok(); ++i) {
+      std::string k = r.str(), v = r.str();
+      if (r.ok()) put(std::move(k), std::move(v));
+    }
+  }
+  for (const auto& rec : pending) {
+    wire::Reader r(rec.data(), rec.size());
+    const uint8_t op = r.u8();
+    std::string k = r.str();
+    if (op == 1) {
+      std::string v = r.str();
+      if (r.ok()) put(std::move(k), std::move(v));
+    } else if (op == 2 && r.ok()) {
+      live.erase(k);
+    }
+  }
+  std::vector<std::pair<std::string, std::string>> recs;
+  for (auto& k : order) {
+    auto it = live.find(k);
+    if (it != live.end()) recs.emplace_back(k, std::move(it->second));
+  }
+  recover_objects(recs);
+  local_wal_ = std::move(log);
+  return ErrorCode::OK;
+}
+
+void KeystoneService::maybe_snapshot_local_wal() {
+  if (!local_wal_ || !local_wal_->is_open()) return;
+  std::unique_lock<std::mutex> sl(local_snap_mu_, std::try_to_lock);
+  if (!sl.owns_lock()) return;
+  // Records are whole-object PUTs / tombstones, applied to memory before they are logged (put_complete's COMPLETE
+  // record is covered by `committing`), so a state capture taken after rotate() contains every mutation of the old
+  // generations, and replaying the new generation on top of it is idempotent: no global lock is needed.
+  const uint64_t gen = local_wal_->rotate();
+  wire::Writer w;
+  std::vector<std::pair<std::string, std::string>> objs;
+  for (auto& sh : shards_) {
+    std::lock_guard<SpinMutex> lk(sh.mu);
+    for (const auto& [k, o] : sh.objects) {
+      if (o.state != ObjectState::COMPLETE && !o.committing) continue;
+      ObjectInfo c = o;
+      c.state = ObjectState::COMPLETE;
+      objs.emplace_back(k, encode_object(c));
+    }
+  }
+  w.u32(static_cast<uint32_t>(objs.size()));
+  for (const auto& [k, v] : objs) {
+    w.str(k);
+    w.str(v);
+  }
+  if (local_wal_->install_snapshot(gen, w.data()) != ErrorCode::OK) BB_LOG(ERROR) << "keystone: metadata snapshot failed";
+  else metrics_.inc("wal_snapshots_total");
 }
 
 // ================================================================ observability

@@ -31,6 +31,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "common/durable_log.h"
 #include "common/spin.h"
 #include "alloc/allocator.h"
 #include "common/metrics.h"
@@ -52,6 +53,7 @@ struct ObjectInfo {
   std::string owner_client;  // session that started the put
   std::vector<std::string> extra_ledgers;  // allocator ledger keys besides `key` (repair / demotion)
   uint32_t reads_below_top = 0;            // reads served while the object sat on a lower tier (promotion policy)
+  bool committing = false;  // put_complete has logged COMPLETE but not yet flipped `state` (snapshots count it as COMPLETE)
 
   uint64_t ttl_ms() const { return config.ttl_ms; }
   bool is_expired(TimePoint now = Clock::now()) const {
@@ -95,7 +97,15 @@ class KeystoneService {
   ErrorCode start();
   void stop();
   bool is_running() const noexcept { return running_.load(); }
-  bool is_leader() const noexcept { return !config_.enable_ha || leader_.load(); }
+  // In HA mode leadership is also bounded in *local* time: it lapses on its own `margin` before the election lease
+  // can expire at the store, so a leader that was paused (SIGSTOP, VM freeze, long GC) comes back as a non-leader and
+  // cannot acknowledge anything until it has talked to the store again.  WAL writes are additionally fenced by term.
+  bool is_leader() const noexcept {
+    if (!config_.enable_ha) return true;
+    return leader_.load(std::memory_order_acquire) &&
+           Clock::now().time_since_epoch().count() < lease_deadline_.load(std::memory_order_acquire);
+  }
+  int64_t leader_term() const noexcept { return term_.load(); }
   const KeystoneConfig& config() const { return config_; }
 
   // ---- object API
@@ -151,6 +161,8 @@ class KeystoneService {
   ErrorCode register_memory_pool(const MemoryPool& pool);
   ErrorCode worker_heartbeat(const WorkerId& id);
   void handle_worker_death(const WorkerId& id);
+  // A single pool left the registry (deregistration event): same invalidation as a death, limited to that pool.
+  void handle_pool_removed(const MemoryPoolId& pool);
 
   // ---- client sessions (reference README "client heartbeats"; absent in its code)
   Result<std::string> client_register(const std::string& node_id);
@@ -177,10 +189,38 @@ class KeystoneService {
 
  private:
   static constexpr size_t kShards = 128;
+  // One queued metadata-log operation.  Mutations enqueue under Shard::mu (which fixes their order) and the log I/O
+  // happens after that lock is dropped (flush_wal), never under the spin lock.
+  struct WalOp {
+    ObjectKey key;
+    std::string value;          // encoded ObjectInfo; empty + del = tombstone
+    bool del = false;
+    ErrorCode* result = nullptr;  // optional: where the enqueuing thread wants the write's outcome (it outlives the flush)
+  };
   struct Shard {
     mutable SpinMutex mu;  // sub-microsecond sections taken by every client on every object: never sleep on it
     std::unordered_map<ObjectKey, ObjectInfo> objects;
+    std::vector<WalOp> wal_queue;  // guarded by mu
+    std::mutex wal_mu;             // serialises the writers of this shard's log records (order = queue order)
   };
+  // unique_lock on a shard that flushes the shard's queued log records when it goes out of scope (after unlocking).
+  class ShardGuard {
+   public:
+    ShardGuard(KeystoneService* ks, Shard& sh) : ks_(ks), sh_(sh), lk_(sh.mu) {}
+    ~ShardGuard() { finish(); }
+    void finish() {
+      if (!lk_.owns_lock()) return;
+      const bool dirty = !sh_.wal_queue.empty();
+      lk_.unlock();
+      if (dirty) ks_->flush_wal(sh_);
+    }
+    void relock() { lk_.lock(); }
+   private:
+    KeystoneService* ks_;
+    Shard& sh_;
+    std::unique_lock<SpinMutex> lk_;
+  };
+  friend class ShardGuard;
   Shard& shard_for(const ObjectKey& key) { return shards_[std::hash<ObjectKey>{}(key) % kShards]; }
   const Shard& shard_for(const ObjectKey& key) const { return shards_[std::hash<ObjectKey>{}(key) % kShards]; }
 
@@ -192,13 +232,27 @@ class KeystoneService {
   void gc_loop();
   void health_loop();
   void keepalive_loop();
-  void persist_object(const ObjectInfo& info);
-  void unpersist_object(const ObjectKey& key);
+  // Metadata log.  Sinks: the coordination store (HA: shared with the standby, every write fenced by the leader's
+  // term) or a local DurableLog under `wal_path` (single Keystone: survives its own restart).  persist / unpersist are
+  // called with the shard lock held and only enqueue.
+  bool wal_enabled() const { return wal_on_.load(std::memory_order_relaxed); }
+  void persist_object(Shard& sh, const ObjectInfo& info, ErrorCode* result = nullptr);
+  void unpersist_object(Shard& sh, const ObjectKey& key);
+  void flush_wal(Shard& sh);
+  ErrorCode wal_write(const WalOp& op);
   void recover_objects_from_wal();
+  void recover_objects(std::vector<std::pair<std::string, std::string>>& records);
+  ErrorCode open_local_wal();
+  void maybe_snapshot_local_wal();
+  void reset_object_state();  // drops the object table and the allocator (leadership lost / about to be rebuilt)
+  void step_down(const char* why);
+  void arm_lease_deadline(TimePoint refreshed_at);
+  std::string election_name() const { return "keystone-" + config_.cluster_id; }
   void bump_view() { view_version_.fetch_add(1); }
   ErrorCode erase_locked(Shard& sh, const ObjectKey& key, bool free_ranges);
   std::vector<CopyPlacement> live_copies(const ObjectInfo& info) const;
   bool pool_alive(const MemoryPoolId& id) const;
+  void invalidate_pools(const std::vector<MemoryPoolId>& dead, const std::string& why);
   std::string cluster_prefix() const { return "/blackbird/clusters/" + config_.cluster_id + "/"; }
   bool interruptible_sleep(std::chrono::milliseconds d);
 
@@ -239,6 +293,14 @@ class KeystoneService {
 
   std::atomic<bool> running_{false};
   std::atomic<bool> leader_{false};
+  std::atomic<int64_t> term_{0};                 // fencing token of the current leadership (0 = none)
+  std::atomic<int64_t> lease_deadline_{0};       // Clock ticks; is_leader() is false from here on until re-armed
+  std::atomic<bool> wal_on_{false};
+  std::unique_ptr<DurableLog> local_wal_;
+  std::mutex local_snap_mu_;
+  // recovered objects whose pools had not registered yet: pool id -> keys (their extents are adopted on registration)
+  std::mutex unadopted_mu_;
+  std::unordered_map<MemoryPoolId, std::vector<ObjectKey>> unadopted_;
   std::atomic<ViewVersionId> view_version_{0};
   std::mutex sleep_mu_;
   std::condition_variable sleep_cv_;

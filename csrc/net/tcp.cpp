@@ -721,13 +721,14 @@ void RpcClient::reader_loop() {
     const uint32_t len = rd32(hdr);
     const uint32_t method = rd32(hdr + 4);
     const uint64_t id = rd64(hdr + 8);
+    if (len > kMaxFrame) break;  // never size a buffer from an unchecked wire length
     std::string payload(len, '\0');
     if (len && !recv_all(fd_, payload.data(), len, 30000)) break;
     if (method & kPushFlag) {
       if (push_cb_) push_cb_(method & ~kPushFlag, payload);
     } else {
       std::lock_guard<std::mutex> lk(resp_mu_);
-      responses_[id] = std::move(payload);
+      if (abandoned_.erase(id) == 0) responses_[id] = std::move(payload);
       resp_cv_.notify_all();
     }
   }
@@ -744,8 +745,10 @@ Result<std::string> RpcClient::call(uint32_t method, const std::string& request,
   if (!send_all(fd_, f.data(), f.size(), timeout_ms)) return ErrorCode::RPC_FAILED;
   if (reader_run_.load()) {
     std::unique_lock<std::mutex> rl(resp_mu_);
-    if (!resp_cv_.wait_for(rl, std::chrono::milliseconds(timeout_ms), [&] { return responses_.count(id) || broken_; }))
+    if (!resp_cv_.wait_for(rl, std::chrono::milliseconds(timeout_ms), [&] { return responses_.count(id) || broken_; })) {
+      abandoned_.insert(id);  // a late response to this id is dropped by the reader instead of piling up
       return ErrorCode::OPERATION_TIMEOUT;
+    }
     auto it = responses_.find(id);
     if (it == responses_.end()) return ErrorCode::RPC_FAILED;
     std::string r = std::move(it->second);
@@ -760,7 +763,7 @@ Result<std::string> RpcClient::call(uint32_t method, const std::string& request,
   }
   const uint32_t len = rd32(hdr);
   const uint32_t rmethod = rd32(hdr + 4);
-  std::string payload(len, '\0');
+  std::string payload(len <= kMaxFrame ? len : 0, '\0');
   if (len > kMaxFrame || (len && !recv_all(fd_, payload.data(), len, timeout_ms))) {
     ::close(fd_);
     fd_ = -1;

@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -197,6 +198,12 @@ class RpcClient {
   void set_bulk_buffers(int bytes = 4 << 20);
   void close();
   bool connected() const { return fd_ >= 0; }
+  // connected and (push mode) the reader thread has not seen the peer go away
+  bool healthy() {
+    if (fd_ < 0) return false;
+    std::lock_guard<std::mutex> lk(resp_mu_);
+    return !broken_;
+  }
   // Blocking call; thread-safe (calls are serialised per client).
   Result<std::string> call(uint32_t method, const std::string& request, int timeout_ms = 30000);
   // Bulk variants (not available in push mode).  call_gather: the request is `head` followed by `ext_len` bytes at
@@ -221,6 +228,7 @@ class RpcClient {
   std::mutex resp_mu_;
   std::condition_variable resp_cv_;
   std::map<uint64_t, std::string> responses_;
+  std::set<uint64_t> abandoned_;  // ids whose caller timed out (guarded by resp_mu_)
   bool broken_ = false;
 };
 

@@ -275,6 +275,8 @@ void bind_control(py::module_& m) {
       .def_readwrite("promote_after_reads", &KeystoneConfig::promote_after_reads)
       .def_readwrite("compaction_fragmentation_threshold", &KeystoneConfig::compaction_fragmentation_threshold)
       .def_readwrite("wal_path", &KeystoneConfig::wal_path)
+      .def_readwrite("wal_fsync", &KeystoneConfig::wal_fsync)
+      .def_readwrite("wal_snapshot_mb", &KeystoneConfig::wal_snapshot_mb)
       .def_readwrite("log_level", &KeystoneConfig::log_level)
       .def("validate", [](const KeystoneConfig& c) {
         std::string err;
@@ -400,6 +402,22 @@ void bind_control(py::module_& m) {
         return unwrap(s.compare_and_swap(k, e, v, l));
       }, py::arg("key"), py::arg("expected"), py::arg("value"), py::arg("lease") = 0)
       .def("compare_and_delete", [](CoordStore& s, const std::string& k, const std::string& e) { return unwrap(s.compare_and_delete(k, e)); })
+      .def("guarded_put", [](CoordStore& s, const std::string& g, int64_t rev, const std::string& k, const std::string& v) {
+        return unwrap(s.guarded_put(g, rev, k, v));
+      }, py::arg("guard_key"), py::arg("guard_create_revision"), py::arg("key"), py::arg("value"), py::call_guard<py::gil_scoped_release>())
+      .def("guarded_del", [](CoordStore& s, const std::string& g, int64_t rev, const std::string& k) { return unwrap(s.guarded_del(g, rev, k)); },
+           py::call_guard<py::gil_scoped_release>())
+      .def("get_kv", [](CoordStore& s, const std::string& k) -> py::object {
+        auto r = s.get_kv(k);
+        if (!r.ok()) return py::none();
+        py::dict d;
+        d["key"] = r.value().key;
+        d["value"] = py::bytes(r.value().value);
+        d["create_revision"] = r.value().create_revision;
+        d["mod_revision"] = r.value().mod_revision;
+        d["lease"] = r.value().lease;
+        return d;
+      })
       .def("watch_prefix", [](CoordStore& s, const std::string& prefix, py::function cb) {
         auto holder = gil_safe_holder(std::move(cb));
         return unwrap(s.watch_prefix(prefix, [holder](const coord::WatchEvent& ev) {
@@ -425,11 +443,16 @@ void bind_control(py::module_& m) {
       .def("advance_time_ms", &MemCoord::advance_time_ms, py::call_guard<py::gil_scoped_release>())
       .def("flush_events", &MemCoord::flush_events, py::call_guard<py::gil_scoped_release>())
       .def("lease_count", &MemCoord::lease_count)
-      .def("key_count", &MemCoord::key_count);
+      .def("key_count", &MemCoord::key_count)
+      .def("open_durable", &MemCoord::open_durable, py::arg("dir"), py::arg("fsync") = true, py::arg("snapshot_bytes") = 64ull << 20,
+           py::call_guard<py::gil_scoped_release>(), "Persist every mutation under `dir` (log + snapshots); replays what is there.")
+      .def_property_readonly("durable", &MemCoord::durable)
+      .def_property_readonly("recovered_records", &MemCoord::recovered_records);
   py::class_<coord::RemoteCoord, CoordStore, std::shared_ptr<coord::RemoteCoord>>(m, "RemoteCoord")
       .def(py::init<>())
       .def("connect", &coord::RemoteCoord::connect, py::arg("endpoints"), py::arg("timeout_ms") = 3000)
-      .def("close", &coord::RemoteCoord::close, py::call_guard<py::gil_scoped_release>());
+      .def("close", &coord::RemoteCoord::close, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("reconnects", &coord::RemoteCoord::reconnects);
   py::class_<coord::CoordServer>(m, "CoordServer")
       .def(py::init([](std::shared_ptr<MemCoord> st) { return std::make_unique<coord::CoordServer>(std::move(st)); }), py::arg("store") = nullptr)
       .def("start", &coord::CoordServer::start, py::arg("host") = "127.0.0.1", py::arg("port") = 0)
@@ -469,7 +492,10 @@ void bind_control(py::module_& m) {
         return s.get_leader(e, l) == ErrorCode::OK ? py::object(py::str(l)) : py::object(py::none());
       })
       .def("resign_leader", &CoordService::resign_leader)
-      .def("refresh_leadership", &CoordService::refresh_leadership);
+      .def("refresh_leadership", &CoordService::refresh_leadership, py::call_guard<py::gil_scoped_release>())
+      .def("leader_term", &CoordService::leader_term)
+      .def("fenced_put", &CoordService::fenced_put, py::call_guard<py::gil_scoped_release>())
+      .def("fenced_del", &CoordService::fenced_del, py::call_guard<py::gil_scoped_release>());
 
   // ---------------------------------------------------------------- keystone
   using keystone::KeystoneService;
@@ -482,6 +508,7 @@ void bind_control(py::module_& m) {
       .def("stop", &KeystoneService::stop, py::call_guard<py::gil_scoped_release>())
       .def("is_running", &KeystoneService::is_running)
       .def("is_leader", &KeystoneService::is_leader)
+      .def("leader_term", &KeystoneService::leader_term)
       .def("object_exists", [](KeystoneService& k, const std::string& key) { return unwrap(k.object_exists(key)); })
       .def("get_workers", [](KeystoneService& k, const std::string& key) { return unwrap(k.get_workers(key)); })
       .def("put_start", [](KeystoneService& k, const std::string& key, size_t size, const WorkerConfig& c, const std::string& client,

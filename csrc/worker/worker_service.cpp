@@ -430,6 +430,13 @@ uint64_t resolve_offset(const StorageBackend& b, uint64_t raw) {
   }
   return raw;
 }
+// Overflow-safe "[off, off + len) lies inside the pool".
+bool range_ok(const StorageBackend& b, uint64_t off, uint64_t len) {
+  const uint64_t cap = b.get_total_capacity();
+  return off != ~0ull && len <= cap && off <= cap - len;
+}
+// Unfinalised BBH64 sum of a chunk that starts `pos` bytes into the hashed object (pos is tile aligned).
+uint64_t bbh64_chunk_sum(const uint8_t* data, uint64_t n, uint64_t pos) { return bbh64_chunk(data, n, pos / 16384); }
 }  // namespace
 
 void WorkerService::register_data_handlers() {
@@ -508,10 +515,28 @@ void WorkerService::register_data_handlers() {
       w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
       return w.take();
     }
-    std::vector<uint8_t> buf(len);
-    ErrorCode ec = b->read(off, buf.data(), len);
+    // The 64-bit length comes off the wire: validate it against the pool before anything is sized from it, and
+    // hash in bounded chunks (CRC32C streams; BBH64 tile sums are additive) instead of buffering the shard.
+    const uint64_t o = resolve_offset(*b, off);
+    if (!range_ok(*b, o, len)) {
+      w.ec(ErrorCode::MEMORY_ACCESS_ERROR);
+      return w.take();
+    }
+    constexpr uint64_t kChunk = 8ull << 20;  // a multiple of the BBH64 tile
+    std::vector<uint8_t> buf(std::min(len, kChunk));
+    uint32_t crc = 0;
+    uint64_t tile_sum = 0;
+    ErrorCode ec = ErrorCode::OK;
+    for (uint64_t pos = 0; pos < len && ec == ErrorCode::OK; pos += kChunk) {
+      const uint64_t n = std::min(kChunk, len - pos);
+      ec = b->read(o + pos, buf.data(), n);
+      if (ec != ErrorCode::OK) break;
+      if (algo == ChecksumAlgo::CRC32C) crc = crc32c(buf.data(), n, crc);
+      else if (algo == ChecksumAlgo::BBH64) tile_sum += bbh64_chunk_sum(buf.data(), n, pos);
+    }
     w.ec(ec);
-    if (ec == ErrorCode::OK) w.u64(checksum(algo, buf.data(), len));
+    if (ec == ErrorCode::OK)
+      w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64_finalize(tile_sum, len) : 0);
     return w.take();
   });
   // Intra-worker tier move (GPU slab -> DRAM -> NVMe ...): bytes stay inside this process.
@@ -531,6 +556,10 @@ void WorkerService::register_data_handlers() {
       return w.take();
     }
     const uint64_t s0 = resolve_offset(*sb, so), d0 = resolve_offset(*db, doff);
+    if (!range_ok(*sb, s0, len) || !range_ok(*db, d0, len)) {
+      w.ec(ErrorCode::MEMORY_ACCESS_ERROR);
+      return w.take();
+    }
     // Fused-kernel tier move: when one side is the GPU slab and the other is addressable by CUDA (another
     // slab, or a pinned DRAM pool), ONE launch copies the shard and computes its digest on the tensor cores.
     {
@@ -546,8 +575,7 @@ void WorkerService::register_data_handlers() {
     }
     constexpr uint64_t kChunk = 8ull << 20;
     std::vector<uint8_t> buf(std::min(len, kChunk));
-    std::vector<uint8_t> whole;  // BBH64 is tile-position dependent: hash the whole shard at the end
-    if (algo == ChecksumAlgo::BBH64) whole.reserve(len);
+    uint64_t tile_sum = 0;  // BBH64 tile sums are additive: the chunk (a whole number of tiles) is hashed in place
     uint32_t crc = 0;
     ErrorCode ec = ErrorCode::OK;
     for (uint64_t pos = 0; pos < len && ec == ErrorCode::OK; pos += kChunk) {
@@ -555,12 +583,12 @@ void WorkerService::register_data_handlers() {
       ec = sb->read(s0 + pos, buf.data(), n);
       if (ec != ErrorCode::OK) break;
       if (algo == ChecksumAlgo::CRC32C) crc = crc32c(buf.data(), n, crc);
-      else if (algo == ChecksumAlgo::BBH64) whole.insert(whole.end(), buf.begin(), buf.begin() + static_cast<std::ptrdiff_t>(n));
+      else if (algo == ChecksumAlgo::BBH64) tile_sum += bbh64_chunk_sum(buf.data(), n, pos);
       ec = db->write(d0 + pos, buf.data(), n);
     }
     if (ec == ErrorCode::OK) ec = db->flush();
     w.ec(ec);
-    if (ec == ErrorCode::OK) w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64(whole.data(), whole.size()) : 0);
+    if (ec == ErrorCode::OK) w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64_finalize(tile_sum, len) : 0);
     return w.take();
   });
   data_server_.register_method(D_PULL, [this](C, S q) {

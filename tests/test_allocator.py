@@ -325,3 +325,20 @@ def test_range_locality_prefers_writer_node_then_fabric(bb):
     assert r.copies[0].shards[0].pool_id == "self"
     r = ra.allocate(req(bb, "b", 4096, classes=[G], client_node="gpu0", enable_locality_awareness=False), pools)
     assert r.copies[0].shards[0].pool_id == "far"  # most free space wins without locality
+
+
+def test_range_forget_pool_drops_extents_so_a_reregistered_pool_is_not_double_allocated(bb):
+    """worker death -> same pool id re-registered -> remove of a degraded object must not return the
+    dead incarnation's offsets to the new allocator (B and C used to receive the same range)."""
+    ra = bb.RangeAllocator()
+    pools = {"p1": mkpool(bb, "p1", 1 << 20, worker="w1"), "p2": mkpool(bb, "p2", 1 << 20, worker="w2")}
+    a = ra.allocate(req(bb, "A", 65536, repl=2, wpc=1), pools)
+    assert {c.shards[0].pool_id for c in a.copies} == {"p1", "p2"}
+    ra.forget_pool("p1")
+    assert ra.pool_used_bytes("p1") == 0
+    b = ra.allocate(req(bb, "B", 65536, repl=1, wpc=1, node="node-a"), {"p1": pools["p1"]})
+    assert ra.free("A") == bb.ErrorCode.OK  # only the surviving p2 extent goes back
+    c = ra.allocate(req(bb, "C", 65536, repl=1, wpc=1), {"p1": pools["p1"]})
+    off = lambda r: r.copies[0].shards[0].location["remote_addr"]
+    assert off(b) != off(c), "live object's range handed out twice"
+    assert ra.pool_used_bytes("p1") == 2 * 65536 and ra.pool_used_bytes("p2") == 0
