@@ -237,6 +237,7 @@ void KeystoneService::keepalive_loop() {
   const int64_t period_ms = config_.enable_ha ? std::min<int64_t>(config_.service_refresh_interval_sec * 1000, std::max<int64_t>(100, ttl_ms / 4))
                                               : config_.service_refresh_interval_sec * 1000;
   bool was_leader = leader_.load();
+  int backoff = 0;
   while (interruptible_sleep(std::chrono::milliseconds(period_ms))) {
     if (!coord_ || !coord_->is_connected()) continue;
     if (coord_->register_service("blackbird-keystone", config_.service_id, config_.listen_address,
@@ -250,8 +251,17 @@ void KeystoneService::keepalive_loop() {
       else if (ec != ErrorCode::ETCD_ERROR) step_down("the election lease is gone");
       // ETCD_ERROR: the store is unreachable -- leadership is unknown; is_leader() lapses by itself at the deadline
     }
-    if (was_leader && !leader_.load()) reset_object_state();  // also reached when a fenced write stepped us down
+    if (was_leader && !leader_.load()) {  // also reached when a fenced write stepped us down
+      reset_object_state();
+      was_leader = false;
+      backoff = 2;  // a deposed leader sits out two rounds: whoever replaced it (or a healthy standby) goes first
+      continue;
+    }
     was_leader = leader_.load();
+    if (backoff > 0) {
+      --backoff;
+      continue;
+    }
     if (!leader_.load()) {
       bool won = false;
       const TimePoint t0 = Clock::now();
