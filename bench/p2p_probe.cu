@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -213,6 +214,18 @@ __global__ void __launch_bounds__(320, 1) k_ring(const RingParams p) {
   }
 }
 
+// ---------------------------------------------------------------- launch -> completion-flag floor
+__global__ void k_flag(volatile uint32_t* flag, uint32_t v) {
+  __threadfence_system();
+  *flag = v;
+}
+__global__ void k_flag_copy(const uint4* src, uint4* dst, uint32_t n16, volatile uint32_t* flag, uint32_t v) {
+  for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncwarp();
+  if (threadIdx.x == 0) *flag = v;
+}
+
 struct Dev {
   int id;
   cudaStream_t st;
@@ -286,6 +299,7 @@ struct Opt {
   int ndev = 0;
   bool quick = false;
   bool mc = true;
+  bool latency = false;
 };
 
 void report(const char* method, const char* pattern, const std::string& cfg, const std::vector<float>& ms, size_t bytes, int iters,
@@ -313,16 +327,73 @@ int main(int argc, char** argv) {
     else if (a == "--gpus" && i + 1 < argc) o.ndev = std::atoi(argv[++i]);
     else if (a == "--quick") o.quick = true;
     else if (a == "--no-mc") o.mc = false;
+    else if (a == "--latency") o.latency = true;
   }
   int n = 0;
   CK(cudaGetDeviceCount(&n));
   if (o.ndev <= 0 || o.ndev > n) o.ndev = n;
   n = o.ndev;
-  if (n < 2) {
+  if (n < 2 && !o.latency) {
     std::printf("{\"error\": \"need >= 2 GPUs, have %d\"}\n", n);
     return 0;
   }
   const size_t bytes = o.mib << 20;
+  if (o.latency) {
+    // how long does it take, on this box, from cudaLaunchKernel to the host seeing a flag the kernel wrote to pinned
+    // memory?  (the floor under any single-object put / get latency); vs the same with an event record + synchronize
+    CK(cudaSetDevice(0));
+    if (n > 1) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(1, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+      (void)cudaGetLastError();
+    }
+    volatile uint32_t* flag = nullptr;
+    CK(cudaHostAlloc(const_cast<uint32_t**>(&flag), 64, cudaHostAllocDefault));
+    *flag = 0;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    uint4 *a = nullptr, *b = nullptr, *peer = nullptr;
+    CK(cudaMalloc(&a, 4096));
+    CK(cudaMalloc(&b, 4096));
+    if (n > 1) {
+      CK(cudaSetDevice(1));
+      CK(cudaMalloc(&peer, 4096));
+      CK(cudaSetDevice(0));
+    }
+    auto pct = [](std::vector<double> v, double q) {
+      std::sort(v.begin(), v.end());
+      return v[std::min(v.size() - 1, static_cast<size_t>(q * v.size()))];
+    };
+    auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    for (int mode = 0; mode < 5; ++mode) {
+      if (mode == 3 && !peer) continue;
+      std::vector<double> t;
+      for (uint32_t it = 1; it <= 2200; ++it) {
+        const double t0 = now_us();
+        if (mode == 0) k_flag<<<1, 32, 0, st>>>(flag, it);
+        else if (mode == 1) k_flag_copy<<<1, 32, 0, st>>>(a, b, 256, flag, it);
+        else if (mode == 3) k_flag_copy<<<1, 32, 0, st>>>(a, peer, 256, flag, it);
+        else k_flag<<<1, 32, 0, st>>>(flag, it);
+        if (mode == 2) {
+          CK(cudaEventRecord(ev, st));
+          CK(cudaEventSynchronize(ev));
+        } else if (mode == 4) {
+          CK(cudaStreamSynchronize(st));
+        } else {
+          while (*flag != it) {
+          }
+        }
+        const double t1 = now_us();
+        if (it > 200) t.push_back(t1 - t0);
+      }
+      const char* names[] = {"launch+flag (empty kernel)", "launch+flag (4 KiB local copy, 1 warp)", "launch+event record+event sync (empty kernel)",
+                             "launch+flag (4 KiB copy to peer, 1 warp)", "launch+stream sync (empty kernel)"};
+      std::printf("{\"latency\": \"%s\", \"p50_us\": %.2f, \"p99_us\": %.2f}\n", names[mode], pct(t, 0.5), pct(t, 0.99));
+    }
+    return 0;
+  }
   std::vector<Dev> dv(n);
   for (int d = 0; d < n; ++d) {
     CK(cudaSetDevice(d));

@@ -58,11 +58,9 @@ def main():
         while cl.client.object_exists("repair/done") is not True:
             time.sleep(0.05)
     cl.barrier()
-    pulls = torch.tensor([cl.worker.backend(f"hbm{cl.rank}").device_copies], device=dev)
-    allp = [torch.zeros_like(pulls) for _ in range(cl.world)]
-    dist.all_gather(allp, pulls)
+    allp = cl.rdv.gather_int(cl.worker.backend(f"hbm{cl.rank}").device_copies)
     if cl.rank == 0:
-        res["fused_pulls_per_rank"] = [int(p.item()) for p in allp]
+        res["fused_pulls_per_rank"] = allp
         print(json.dumps(res))
     cl.barrier()
     cl.stop()

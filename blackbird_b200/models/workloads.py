@@ -131,15 +131,17 @@ def latency_sweep(cluster, sizes, target_node: str, iters: int = 200, algo=None)
     return rows
 
 
-def replicated_put_verify(cluster, replication: int = 3, nobj: int = 32, size: int = 16 << 20, iters: int = 3) -> dict:
+def replicated_put_verify(cluster, replication: int = 3, nobj: int = 32, size: int = 16 << 20, iters: int = 3, symmetric: bool = False) -> dict:
     """Config 3: every object gets `replication` copies on distinct GPUs; the put kernel reads the source once
     and fans out (TMA stores to every replica); the get verifies the digest against every replica in turn."""
     import torch
 
     dev = torch.device("cuda", cluster.local_rank)
     stream = torch.cuda.current_stream().cuda_stream
+    # symmetric = the replicas share one offset in an NVLS replica arena: the put is ONE multimem.st stream per object
+    # (the switch replicates); otherwise the kernel issues one TMA store per replica (single HBM read either way)
     cfg = _bb.WorkerConfig(replication_factor=replication, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[_bb.StorageClass.RAM_GPU],
-                           checksum=_bb.ChecksumAlgo.CRC32C)
+                           checksum=_bb.ChecksumAlgo.CRC32C, symmetric_replicas=symmetric)
     src = torch.empty(nobj * size, dtype=torch.uint8, device=dev)
     _bb.random_fill(src.data_ptr(), nobj * size, 33 + cluster.rank, stream)
     out = torch.zeros_like(src)
@@ -148,7 +150,8 @@ def replicated_put_verify(cluster, replication: int = 3, nobj: int = 32, size: i
     put_ms, get_ms = [], []
     copies_seen = set()
     for it in range(iters):
-        keys = [f"rep/{cluster.rank}/{it}/{j}" for j in range(nobj)]
+        keys = [f"rep{int(symmetric)}/{cluster.rank}/{it}/{j}" for j in range(nobj)]
+        cluster.host_barrier()  # all ranks put at once (every GPU's ingress carries R x payload)
         m0 = cluster.fabric.total_device_ms
         assert _ok(cluster.client.batch_put_device(keys, sp, [size] * nobj, cfg, stream))
         put_ms.append(cluster.fabric.total_device_ms - m0)
@@ -228,11 +231,73 @@ def tier_spill(cluster, nobj: int = 10, size: int = 6 << 20) -> dict:
     }
 
 
+def tier_spill_perf(cluster, nobj: int = 48, size: int = 64 << 20) -> dict:
+    """Config 4 with numbers: `nobj` objects of `size` bytes are put into an HBM slab that holds about a third of them; the
+    Keystone's watermark eviction demotes LRU objects GPU -> DRAM (one fused launch per shard, digest carried) and, when
+    the DRAM tier passes its watermark too, DRAM -> NVMe (io_uring).  Reported: demotion GB/s (bytes moved down / time in
+    the movers), the foreground put latency with and without a demotion round in between (the stall a writer sees), the
+    final tier census, and a byte-exact read-back of everything through the device API (NVMe / DRAM objects come back
+    through their own paths).  A soft-pinned object must still be in HBM at the end."""
+    import torch
+
+    dev = torch.device("cuda", cluster.local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu = dict(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[_bb.StorageClass.RAM_GPU], checksum=_bb.ChecksumAlgo.CRC32C)
+    ks = cluster.keystone
+    nsrc = 8  # distinct payloads (the source buffer is reused round-robin; objects are identified by key)
+    src = torch.empty(nsrc * size, dtype=torch.uint8, device=dev)
+    _bb.random_fill(src.data_ptr(), src.numel(), 4242, stream)
+    torch.cuda.synchronize()
+    assert _ok(cluster.client.batch_put_device(["spill/pinned"], [src.data_ptr()], [size], _bb.WorkerConfig(enable_soft_pin=True, **gpu), stream))
+    put_us, put_us_after_evict, evict_s, moved_bytes = [], [], 0.0, 0
+    keys = [f"spill/{i}" for i in range(nobj)]
+    classes = (_bb.StorageClass.RAM_GPU, _bb.StorageClass.RAM_CPU)
+    t_fill0 = time.perf_counter()
+    for i, k in enumerate(keys):
+        evicted = False
+        if any(ks.tier_utilization(c) > 0.55 for c in classes):
+            t0 = time.perf_counter()
+            n = ks.run_eviction_once()
+            evict_s += time.perf_counter() - t0
+            evicted = n > 0
+            moved_bytes += n * size
+        t0 = time.perf_counter()
+        ecs = cluster.client.batch_put_device([k], [src.data_ptr() + (i % nsrc) * size], [size], _bb.WorkerConfig(**gpu), stream)
+        dt = (time.perf_counter() - t0) * 1e6
+        assert _ok(ecs), [str(e) for e in ecs]
+        (put_us_after_evict if evicted else put_us).append(dt)
+    fill_s = time.perf_counter() - t_fill0
+    tiers = {k: cluster.client.get_workers(k)[0].shards[0].storage_class for k in keys + ["spill/pinned"]}
+    # read everything back, HBM or not, and compare
+    out = torch.zeros(size, dtype=torch.uint8, device=dev)
+    verified, read_s = 0, 0.0
+    for i, k in enumerate(keys):
+        t0 = time.perf_counter()
+        ecs, _ = cluster.client.batch_get_device([k], [out.data_ptr()], [size], stream)
+        torch.cuda.synchronize()
+        read_s += time.perf_counter() - t0
+        verified += int(_ok(ecs) and torch.equal(out, src[(i % nsrc) * size:(i % nsrc + 1) * size]))
+    census = {str(c).split(".")[-1]: sum(1 for t in tiers.values() if t == c) for c in set(tiers.values())}
+    text = ks.metrics_text()
+    demotions = 0
+    for ln in text.splitlines():
+        if ln.startswith("bb_demotions_total"):
+            demotions = int(float(ln.split()[-1]))
+    hbm = cluster.worker.backend(f"hbm{cluster.rank}")
+    return {"objects": nobj, "size": size, "fill_s": round(fill_s, 3), "time_in_movers_s": round(evict_s, 3), "demotions": demotions,
+            "demotion_GBps": round(demotions * size / evict_s / 1e9, 2) if evict_s > 0 else 0.0,
+            "put_p50_us_no_demotion": round(_pct(put_us, 0.5), 1) if put_us else None,
+            "put_p50_us_after_a_demotion_round": round(_pct(put_us_after_evict, 0.5), 1) if put_us_after_evict else None,
+            "foreground_stall_ms_per_demotion_round_p50": None if not put_us_after_evict else round(evict_s / max(1, len(put_us_after_evict)) * 1e3, 2),
+            "tier_census": census, "pinned_tier": str(tiers["spill/pinned"]).split(".")[-1], "verified": verified,
+            "read_back_GBps": round(nobj * size / read_s / 1e9, 2), "fused_tier_moves": hbm.device_copies,
+            "dropped_objects": sum(1 for ln in text.splitlines() if ln.startswith("bb_evictions_total") and float(ln.split()[-1]) > 0)}
+
+
 def feature_store_fanout(cluster, nshards: int = 128, size: int = 1 << 20, iters: int = 5, replication: int = 1) -> dict:
     """Config 5: rank 0 puts `nshards` activation shards, then every rank batch-gets all of them (1 -> N read
     fan-out).  With replication > 1 the readers spread over the replicas (hash of reader + key)."""
     import torch
-    import torch.distributed as dist
 
     dev = torch.device("cuda", cluster.local_rank)
     stream = torch.cuda.current_stream().cuda_stream
@@ -256,11 +321,7 @@ def feature_store_fanout(cluster, nshards: int = 128, size: int = 1 << 20, iters
         e1.record()
         torch.cuda.synchronize()
         assert _ok(ecs) and torch.equal(src, out)
-        ms = e0.elapsed_time(e1)
-        if cluster.world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = cluster.max_over_ranks(e0.elapsed_time(e1))
         get_ms.append(ms)
         cluster.barrier()
         if cluster.rank == 0:

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import os
 import socket
+import time
 from typing import Optional
 
 from .. import _bb
@@ -50,6 +51,110 @@ def _pin_to_gpu_numa_node(device_index: int):
     except Exception:  # no NVML, restricted cgroup, ...: run unpinned
         pass
     return None
+
+
+class HostRendezvous:
+    """Shared-memory rendezvous of the ranks of ONE node (torchrun workers): barrier, all-reduce of a scalar and integer
+    broadcast through a small file in /dev/shm that every rank maps -- no NCCL (or any other collective library) is
+    needed to bring a cluster up, and a barrier costs ~1-2 us instead of a kernel launch + stream sync.  One 64-byte slot
+    per rank: [epoch u64 | value f64 | aux i64]; a rank publishes (value, epoch) and spins until every slot has reached
+    the epoch.  Values are read after the barrier and before anyone can start the next epoch + 1 write (two-phase)."""
+
+    SLOT = 64
+
+    def __init__(self, rank: int, world: int, tag: str = ""):
+        import mmap
+        import struct
+
+        self.rank, self.world, self._struct = rank, world, struct
+        self.epoch = 0
+        self._mm = None
+        if world <= 1:
+            return
+        name = tag or f"{os.getppid()}-{os.environ.get('MASTER_PORT', '0')}"
+        self.path = f"/dev/shm/bb-rdv-{name}"
+        size = self.SLOT * (world + 1)
+        if rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+            fd = os.open(self.path + ".tmp", os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, size)
+            os.rename(self.path + ".tmp", self.path)  # appears fully sized and zeroed
+        else:
+            deadline = time.time() + 120
+            fd = -1
+            while fd < 0:
+                try:
+                    fd = os.open(self.path, os.O_RDWR)
+                    if os.fstat(fd).st_size < size:
+                        os.close(fd)
+                        fd = -1
+                except OSError:
+                    fd = -1
+                if fd < 0:
+                    if time.time() > deadline:
+                        raise TimeoutError(f"rendezvous file {self.path} did not appear")
+                    time.sleep(0.005)
+        self._mm = mmap.mmap(fd, size)
+        os.close(fd)
+        self.barrier()
+
+    def _put(self, value: float, aux: int):
+        off = self.rank * self.SLOT
+        self._struct.pack_into("<dq", self._mm, off + 8, value, aux)
+        self._struct.pack_into("<Q", self._mm, off, self.epoch)  # epoch last: it publishes the value
+
+    def _wait(self):
+        unpack, mm, slot, ep = self._struct.unpack_from, self._mm, self.SLOT, self.epoch
+        for r in range(self.world):
+            spins = 0
+            while unpack("<Q", mm, r * slot)[0] < ep:
+                spins += 1
+                if spins > 2000:
+                    time.sleep(0)  # yield: more ranks than cores (CPU tests)
+
+    def _round(self, value: float = 0.0, aux: int = 0):
+        """One publish + wait; returns every rank's (value, aux).  A second, value-less round fences the reads."""
+        if self._mm is None:
+            return [(value, aux)]
+        self.epoch += 1
+        self._put(value, aux)
+        self._wait()
+        vals = [self._struct.unpack_from("<dq", self._mm, r * self.SLOT + 8) for r in range(self.world)]
+        self.epoch += 1
+        self._put(value, aux)
+        self._wait()
+        return vals
+
+    def barrier(self):
+        if self._mm is None:
+            return
+        self.epoch += 1
+        self._put(0.0, 0)
+        self._wait()
+
+    def allreduce(self, value: float, op: str = "max") -> float:
+        vals = [v for v, _ in self._round(float(value))]
+        return max(vals) if op == "max" else min(vals) if op == "min" else sum(vals)
+
+    def broadcast_int(self, value: int, root: int = 0) -> int:
+        return self._round(0.0, int(value))[root][1]
+
+    def gather_int(self, value: int):
+        return [a for _, a in self._round(0.0, int(value))]
+
+    def close(self):
+        if self._mm is not None:
+            self.barrier()
+            self._mm.close()
+            self._mm = None
+            if self.rank == 0:
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
 
 
 class LocalCluster:
@@ -128,7 +233,7 @@ class GpuRankCluster:
     def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None,
                  nvls_arena_bytes: int = 0, nvls_group_size: int = 3, rpc_busy_poll_us: Optional[int] = None,
                  dram_bytes: int = 0, nvme_bytes: int = 0, nvme_path: str = "", high_watermark: float = 1.0,
-                 eviction_ratio: float = 0.1, max_replicas: int = 3):
+                 eviction_ratio: float = 0.1, max_replicas: int = 3, use_nccl: bool = False):
         """slab_bytes: HBM slab of this rank's GPU-tier pool.  dram_bytes / nvme_bytes add host tiers to the
         same worker (the demotion ladder GPU -> DRAM -> NVMe); high_watermark < 1 arms tier demotion."""
         import torch
@@ -140,14 +245,17 @@ class GpuRankCluster:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local_rank)
         self.cpu_affinity = _pin_to_gpu_numa_node(self.local_rank)
-        self.dist = dist if self.world > 1 else None
-        if self.world > 1 and not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        # Bring-up needs no collective library: the ranks of the node meet through a /dev/shm rendezvous (keystone port,
+        # barriers, scalar reductions).  NCCL is initialised only on request (ensure_dist(): the benchmark comparators).
+        self.rdv = HostRendezvous(self.rank, self.world)
+        self.dist = None
+        if self.world > 1 and (use_nccl or dist.is_initialized()):
+            self.ensure_dist()
         _bb.install_gpu_backend_factory()
         self.node_id = f"gpu{self.rank}"
         self.keystone = None
         self.rpc = None
-        port_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+        port = 0
         if self.rank == 0:
             cfg = _bb.KeystoneConfig()
             cfg.cluster_id = cluster_id
@@ -168,10 +276,8 @@ class GpuRankCluster:
             self.keystone.install_data_server_mover()  # demotion / repair copies run worker-to-worker (D_COPY)
             self.rpc = _bb.RpcService(self.keystone, cfg)
             assert self.rpc.start() == _bb.ErrorCode.OK
-            port_t[0] = self.rpc.rpc_port
-        if self.world > 1:
-            dist.broadcast(port_t, 0)
-        self.keystone_port = int(port_t.item())
+            port = self.rpc.rpc_port
+        self.keystone_port = self.rdv.broadcast_int(port, 0)
         if self.rank == 0:
             self.api = _bb.LocalKeystoneApi(self.keystone)
         else:
@@ -226,10 +332,7 @@ class GpuRankCluster:
         arena = _bb.NvlsArena(self.local_rank, self.rank, self.world, tag, groups, arena_bytes)
         for phase in (arena.phase1_create, arena.phase2_join, arena.phase3_bind, arena.phase4_map_peers):
             ec = phase()
-            ok = self.torch.tensor([1 if ec == _bb.ErrorCode.OK else 0], device="cuda")
-            if self.dist is not None:
-                self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
+            if self.rdv.allreduce(1.0 if ec == _bb.ErrorCode.OK else 0.0, "min") == 0.0:
                 if self.rank == 0:
                     print(f"[blackbird_b200] NVLS arena unavailable ({phase.__name__}: {arena.last_error}); replicas use unicast fan-out")
                 return
@@ -251,10 +354,29 @@ class GpuRankCluster:
         assert api.connect("127.0.0.1", self.keystone_port, 10000) == _bb.ErrorCode.OK
         return api
 
+    def ensure_dist(self):
+        """torch.distributed over NCCL, for callers that want collectives of their own (benchmark comparators)."""
+        import torch.distributed as dist
+
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.torch.device("cuda", self.local_rank))
+        self.dist = dist if self.world > 1 else None
+        return self.dist
+
     def barrier(self):
+        """Device work of this rank done + every rank got here (host-side, shared memory)."""
         self.torch.cuda.synchronize()
-        if self.dist is not None:
-            self.dist.barrier()
+        self.rdv.barrier()
+
+    def host_barrier(self):
+        """Ranks rendezvous without touching the device (calls of the synchronous client API have completed)."""
+        self.rdv.barrier()
+
+    def max_over_ranks(self, v: float) -> float:
+        return self.rdv.allreduce(v, "max")
+
+    def sum_over_ranks(self, v: float) -> float:
+        return self.rdv.allreduce(v, "sum")
 
     def stop(self):
         self.barrier()
@@ -267,6 +389,7 @@ class GpuRankCluster:
             self.rpc.stop()
         if self.keystone is not None:
             self.keystone.stop()
+        self.rdv.close()
 
 
 class CpuRankCluster:

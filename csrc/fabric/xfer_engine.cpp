@@ -2,6 +2,9 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "common/log.h"
@@ -36,6 +39,8 @@ struct XferEngine::Slot {
   uint64_t* d_trace = nullptr;
   size_t d_trace_bytes = 0;
   bool traced = false;
+  bool flagged = false;    // completion by status flag in pinned memory (small-object latency path), no events recorded
+  void* stream = nullptr;  // stream of a flagged batch (fallback sync)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   uint64_t ticket = 0;  // 0 = free
   uint32_t nitems = 0;
@@ -104,6 +109,22 @@ XferEngine::~XferEngine() {
   cudaSetDevice(prev);
 }
 
+bool XferEngine::flag_completion_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("BB_XFER_FLAG_COMPLETION");
+    return !(e && e[0] == '0');
+  }();
+  return on && flag_completion_;
+}
+
+bool XferEngine::small_path_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("BB_XFER_SMALL");
+    return !(e && e[0] == '0');
+  }();
+  return on && small_path_;
+}
+
 Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, ChecksumAlgo algo, void* stream,
                                     bool capture_debug) {
   if (items.size() > max_items_) return ErrorCode::RESOURCE_EXHAUSTED;
@@ -118,9 +139,11 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
     auto* descs = reinterpret_cast<XferDesc*>(s->h_tab);
     s->item_to_desc.assign(items.size(), -1);
     uint32_t nd = 0, tiles = 0;
+    bool all_small = small_path_enabled();
     for (size_t i = 0; i < items.size(); ++i) {
       const XferItem& it = items[i];
       if (it.nbytes == 0) continue;
+      all_small = all_small && it.nbytes <= kSmallBytes && !(it.flags & XFER_RAW_SUM) && it.ndst >= 1;
       if (it.ndst > kMaxDst || (it.ndst == 0 && !(it.flags & XFER_RAW_SUM))) return ErrorCode::INVALID_ARGUMENT;
       uintptr_t al = reinterpret_cast<uintptr_t>(it.src);
       for (uint32_t r = 0; r < it.ndst; ++r) al |= reinterpret_cast<uintptr_t>(it.dst[r]);
@@ -196,7 +219,19 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : algo == ChecksumAlgo::CRC32C ? ALGO_CRC32C : ALGO_NONE;
       l.max_ctas = max_ctas_;
       l.stream = stream;
-      BB_CUDA(cudaEventRecord(s->ev_start, st));
+      l.small_path = all_small;
+      if (all_small) ++small_launches_;
+      // Latency path: a small batch whose results land in pinned memory completes by flag -- the launch is the ONLY
+      // stream operation (no timing events, no completion event: each costs about as much GPU time as the kernel).
+      s->flagged = all_small && direct && !capture_debug && !tile_trace_ && flag_completion_enabled();
+      if (s->flagged) {
+        auto* stt = reinterpret_cast<volatile uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);
+        for (uint32_t i = 0; i < nd; ++i) stt[i] = kSmallPending;
+        l.flag_completion = true;
+        s->stream = stream;
+      } else {
+        BB_CUDA(cudaEventRecord(s->ev_start, st));
+      }
       const int rc = launch_xfer(l);
       if (rc != 0) {
         last_cuda_error_ = rc;
@@ -204,6 +239,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
         return ErrorCode::FABRIC_ERROR;
       }
       ++launches_;
+      if (s->flagged) return ErrorCode::OK;
       BB_CUDA(cudaEventRecord(s->ev_stop, st));
       if (algo != ChecksumAlgo::NONE && !direct) {
         BB_CUDA(cudaMemcpyAsync(s->h_res, s->d_digest, static_cast<size_t>(nd) * 8, cudaMemcpyDeviceToHost, st));
@@ -214,6 +250,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
     BB_CUDA(cudaEventRecord(s->ev_done, st));
     return ErrorCode::OK;
   };
+  s->flagged = false;
   ErrorCode ec = run();
   if (ec != ErrorCode::OK) return ec;
   s->ticket = next_ticket_++;
@@ -227,9 +264,33 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
   for (auto& c : slots_)
     if (c->ticket == ticket) { s = c.get(); break; }
   if (!s) return ErrorCode::NOT_FOUND;
-  BB_CUDA(cudaEventSynchronize(s->ev_done));
-  const bool no_hash = !s->hashed;
   const uint32_t nd = s->ndesc;
+  if (s->flagged) {
+    // spin on the status words the kernel writes last (pinned memory); fall back to a stream sync if they do not show
+    // up within a generous bound, so that a launch failure surfaces as an error instead of a hang
+    const auto* stt = reinterpret_cast<const volatile uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t done = 0, spins = 0;
+    while (done < nd) {
+      if (stt[done] != kSmallPending) {
+        ++done;
+        continue;
+      }
+      if ((++spins & 0x3FFu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) {
+        BB_CUDA(cudaSetDevice(device_));
+        BB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(s->stream)));
+        if (stt[done] == kSmallPending) {
+          BB_LOG(ERROR) << "XferEngine: small-object kernel finished without publishing its results";
+          s->ticket = 0;
+          return ErrorCode::FABRIC_ERROR;
+        }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  } else {
+    BB_CUDA(cudaEventSynchronize(s->ev_done));
+  }
+  const bool no_hash = !s->hashed;
   if (out) {
     out->digest.assign(s->nitems, no_hash ? 0 : s->empty_digest);
     out->status.assign(s->nitems, 0);
@@ -245,7 +306,7 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
       }
     }
     out->device_ms = 0.f;
-    if (nd) cudaEventElapsedTime(&out->device_ms, s->ev_start, s->ev_stop);
+    if (nd && !s->flagged) cudaEventElapsedTime(&out->device_ms, s->ev_start, s->ev_stop);
   }
   if (s->debug && nd) {
     debug_host_.resize(static_cast<size_t>(s->total_tiles) * tchash::kRows * tchash::kN);
@@ -440,6 +501,24 @@ ErrorCode device_synchronize(int device) {
   BB_CUDA_S(cudaDeviceSynchronize());
   return ErrorCode::OK;
 }
+int device_memcpy_peer_async(void* dst, int dst_device, const void* src, int src_device, uint64_t nbytes, void* stream) {
+  return static_cast<int>(cudaMemcpyPeerAsync(dst, dst_device, src, src_device, nbytes, static_cast<cudaStream_t>(stream)));
+}
+int device_enable_peer_access(int device, int peer) {
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) {
+    e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+      e = cudaSuccess;
+    }
+  }
+  cudaSetDevice(prev);
+  return static_cast<int>(e);
+}
+
 const char* cuda_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
 
 }  // namespace bb::gpu

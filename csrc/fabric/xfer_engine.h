@@ -76,6 +76,12 @@ class XferEngine {
 
   int device() const { return device_; }
   uint64_t launches() const { return launches_; }  // kernels launched so far
+  uint64_t small_launches() const { return small_launches_; }  // of which warp-per-object launches (xfer_small.cu)
+  // Batches made only of objects <= kSmallBytes take the warp-per-object kernel (default on; BB_XFER_SMALL=0 disables).
+  void set_small_path(bool on) { small_path_ = on; }
+  // Small batches (<= kDirectResults objects on the warp path) complete by a flag in pinned memory instead of CUDA
+  // events (default on; BB_XFER_FLAG_COMPLETION=0 disables).  Their XferResult::device_ms is 0 (not measured).
+  void set_flag_completion(bool on) { flag_completion_ = on; }
   void set_max_ctas(int n) { max_ctas_ = n; }
   int last_cuda_error() const { return last_cuda_error_; }
 
@@ -87,6 +93,11 @@ class XferEngine {
   std::vector<std::unique_ptr<Slot>> slots_;
   uint64_t next_ticket_ = 1;
   uint64_t launches_ = 0;
+  uint64_t small_launches_ = 0;
+  bool small_path_ = true;
+  bool flag_completion_ = true;
+  bool small_path_enabled();
+  bool flag_completion_enabled();
   int max_ctas_ = 0;
   int last_cuda_error_ = 0;
   std::vector<uint32_t> debug_host_;
@@ -105,5 +116,8 @@ ErrorCode host_free_pinned(void* p);
 ErrorCode stream_synchronize(void* stream);
 ErrorCode device_synchronize(int device);
 const char* cuda_error_string(int code);
+// Comparator helpers (return a cudaError_t value).
+int device_memcpy_peer_async(void* dst, int dst_device, const void* src, int src_device, uint64_t nbytes, void* stream);
+int device_enable_peer_access(int device, int peer);
 
 }  // namespace bb::gpu

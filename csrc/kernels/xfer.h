@@ -35,6 +35,8 @@ struct XferDesc {
 };
 static_assert(sizeof(XferDesc) == 64, "XferDesc must be 64 bytes");
 
+constexpr uint32_t kSmallBytes = 4096;     // objects up to this size may take the warp-per-object path (xfer_small.cu)
+constexpr uint32_t kSmallPending = 0xFFFFFFFFu;  // value of a status slot whose object has not completed yet (flag completion)
 constexpr uint32_t kInlineDescs = 8;       // descriptors that fit in the kernel parameter block
 constexpr uint32_t kDirectResults = 64;    // batches up to this size write digests straight to pinned host memory
 
@@ -57,12 +59,16 @@ struct XferLaunch {
   const XferDesc* host_descs = nullptr;
   const uint32_t* host_tile_start = nullptr;
   int algo = ALGO_BBH64;
+  bool small_path = false;               // every descriptor is <= kSmallBytes, none is a RAW_SUM slice: warp-per-object kernel
+  bool flag_completion = false;          // small path only: status_out (pinned, preset to kSmallPending) is the completion flag
   int max_ctas = 0;                      // 0 = one CTA per SM
   void* stream = nullptr;                // cudaStream_t
 };
 
 // Returns 0 on success, else a cudaError_t value.
 int launch_xfer(const XferLaunch& l);
+// Small-object latency tier: one warp per descriptor, digest bit-identical to launch_xfer's (needs descs; not tile_start).
+int launch_xfer_small(const XferLaunch& l);
 int xfer_smem_bytes(int algo);
 // Fused MXFP8 transfer (xfer_mxfp8.cu).  The packed object is one contiguous [payload n][scales n/32] extent.
 // Descriptors: pack (put): src = bf16 source, dst[0..ndst-1] = base of the packed object in every replica (the scales

@@ -616,6 +616,7 @@ uint32_t crc_init_term_for(uint64_t nbytes) {
 
 int launch_xfer(const XferLaunch& l) {
   if (l.ndesc == 0 || l.total_tiles == 0) return 0;
+  if (l.small_path && !l.debug_d && !l.trace_d) return launch_xfer_small(l);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return static_cast<int>(e);

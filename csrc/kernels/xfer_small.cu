@@ -1,0 +1,291 @@
+// bb_xfer_small: the small-object latency tier of the fused transfer.
+//
+// The reference's only end-to-end client moves a 64-byte object with one `ucp_put_nbx` + flush and one `ucp_get_nbx`
+// (clients/ucx_client.cpp:188-257).  For objects of <= 4 KiB the persistent TMA / tcgen05 pipeline of bb_xfer_kernel is
+// all set-up cost (mbarriers, TMEM allocation, weight matrix, tile padding: ~9.5 us for one 4 KiB object), so batches made
+// of small objects only take this path instead: ONE WARP PER OBJECT, no shared-memory staging of the payload, no TMA.
+//
+//   lane l owns bytes [128 l, 128 l + 128) of the object: 8 x LDG.128 (local HBM, peer slab over NVLink, or pinned host)
+//   -> registers -> 8 x STG.128 to 1..3 destinations (local / peer-mapped), or multimem.st to an NVLS multicast window.
+//   The digest is computed on the registers and is bit-identical to the big kernel's (the Keystone cannot tell which
+//   path wrote an object):
+//     BBH64  : the tile product D = A.W is evaluated with dp4a against the same weight matrix (packed in shared memory);
+//              lane l holds K-chunk (l & 7) of rows (l >> 3) * 8 + j, partial row hashes are combined by shuffles;
+//     CRC32C : each lane runs the word-at-a-time table CRC over its 128 bytes, lanes are combined with per-lane
+//              x^(8*distance) multipliers in GF(2)[x]/P (same "raw remainder, un-pad, init term" algebra as the big kernel).
+//   A put of 4096 objects is 512 CTAs x 8 warps in one launch; a single put/get is one warp.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common/checksum.h"
+#include "common/tchash_def.h"
+#include "kernels/ptx.cuh"
+#include "kernels/xfer.h"
+
+namespace bb::gpu {
+namespace {
+
+using namespace bb::ptx;
+
+constexpr int kWarpsPerCta = 8;
+
+__constant__ uint32_t c_lane_mul[32];  // x^(8 * (128 * (31 - l) + 12288)) mod P: lane l's segment -> position in a 16 KiB tile
+
+struct SmallParams {
+  const XferDesc* descs;
+  uint32_t ndesc;
+  uint32_t use_inline;
+  uint64_t* digest_out;
+  uint32_t* status_out;
+  const uint32_t* crc_t4;  // [4][256] shift-by-4-bytes table
+  uint64_t zero_rows;      // BBH64: sum of the contributions of the all-zero rows 32..127 of tile 0
+  // Completion by flag (latency path): status_out lives in pinned host memory, was preset to kSmallPending by the host,
+  // and is written LAST, after a system-scope fence that orders it behind the object's peer / local stores -- the host
+  // spins on it instead of recording and waiting for a CUDA event (which costs more than this whole kernel).
+  uint32_t flag_mode;
+  XferDesc inl_descs[kInlineDescs];
+};
+
+__device__ __forceinline__ uint32_t gf2_mulmod_small(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 8
+  for (int i = 31; i >= 0; --i) {
+    p ^= ((a >> i) & 1u) ? b : 0u;
+    b = (b >> 1) ^ ((b & 1u) ? 0x82F63B78u : 0u);
+  }
+  return p;
+}
+
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const __grid_constant__ SmallParams p) {
+  __shared__ uint32_t s_w[ALGO == ALGO_BBH64 ? 16 * 32 : 1];       // Wp[n][w]: W[4w + b][n] in byte b
+  __shared__ uint32_t s_t4[ALGO == ALGO_CRC32C ? 4 * 256 : 1];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if constexpr (ALGO == ALGO_BBH64) {
+    for (uint32_t i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+      const uint32_t n = i >> 5, w = i & 31u;
+      s_w[i] = tchash::weight(4 * w, n) | (tchash::weight(4 * w + 1, n) << 8) | (tchash::weight(4 * w + 2, n) << 16) |
+               (tchash::weight(4 * w + 3, n) << 24);
+    }
+    __syncthreads();
+  }
+  if constexpr (ALGO == ALGO_CRC32C) {
+    for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_t4[i] = __ldg(&p.crc_t4[i]);
+    __syncthreads();
+  }
+  const uint32_t d = blockIdx.x * kWarpsPerCta + warp;
+  if (d >= p.ndesc) return;
+  // ---- descriptor (every lane reads the same words: broadcast)
+  uint64_t src, dst[kMaxDst], nbytes, expect;
+  uint32_t ndst, flags, reserved;
+  if (p.use_inline) {
+    const XferDesc& q = p.inl_descs[d];
+    src = reinterpret_cast<uint64_t>(q.src);
+#pragma unroll
+    for (uint32_t r = 0; r < kMaxDst; ++r) dst[r] = reinterpret_cast<uint64_t>(q.dst[r]);
+    nbytes = q.nbytes, expect = q.expect, ndst = q.ndst, flags = q.flags, reserved = q.reserved;
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(&p.descs[d]);
+    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
+    dst[0] = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
+    dst[1] = (static_cast<uint64_t>(q1.y) << 32) | q1.x;
+    dst[2] = (static_cast<uint64_t>(q1.w) << 32) | q1.z;
+    nbytes = (static_cast<uint64_t>(q2.y) << 32) | q2.x;
+    ndst = q2.w;
+    expect = (static_cast<uint64_t>(q3.y) << 32) | q3.x;
+    flags = q3.z;
+    reserved = q3.w;
+  }
+  const uint32_t n = static_cast<uint32_t>(nbytes);  // <= kSmallBytes (host checked)
+
+  // ---- load: lane's 128-byte segment, zero beyond the object
+  uint4 v[8];
+  const uint32_t seg = lane * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t o = seg + 16u * j;
+    if (o + 16u <= n) {
+      v[j] = ld_nc_v4(reinterpret_cast<const void*>(src + o));
+    } else {
+      v[j] = make_uint4(0, 0, 0, 0);
+      if (o < n) {  // the one partial chunk of the object: byte loads
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (uint32_t b = 0; b < n - o; ++b)
+          w[b >> 2] |= static_cast<uint32_t>(*reinterpret_cast<const uint8_t*>(src + o + b)) << (8u * (b & 3u));
+        v[j] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  // ---- store
+  if (flags & XFER_MULTIMEM) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t o = seg + 16u * j;
+      if (o + 16u <= n) multimem_st_v4(reinterpret_cast<void*>(dst[0] + o), v[j]);
+    }
+  } else {
+    for (uint32_t r = 0; r < ndst; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t o = seg + 16u * j;
+        if (o + 16u <= n) {
+          st_na_v4(reinterpret_cast<void*>(dst[r] + o), v[j]);
+        } else if (o < n) {
+          const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          for (uint32_t b = 0; b < n - o; ++b)
+            *reinterpret_cast<uint8_t*>(dst[r] + o + b) = static_cast<uint8_t>(w[b >> 2] >> (8u * (b & 3u)));
+        }
+      }
+    }
+  }
+  if constexpr (ALGO == ALGO_NONE) {
+    if (p.flag_mode) {
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        p.digest_out[d] = 0;
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(&p.status_out[d]) = 0u;
+      }
+    }
+    return;
+  }
+
+  // ---- digest on the registers
+  uint64_t digest = 0;
+  if constexpr (ALGO == ALGO_BBH64) {
+    // tile offset o = 128 lane + 16 j  ->  row (lane >> 3) * 8 + j,  K chunk kc = lane & 7 (k = 16 kc + byte)
+    const uint32_t kc = lane & 7u;
+    uint64_t rr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rr[j] = 0;
+#pragma unroll
+    for (uint32_t nn = 0; nn < 16; ++nn) {
+      const uint32_t w0 = s_w[nn * 32 + kc * 4 + 0], w1 = s_w[nn * 32 + kc * 4 + 1], w2 = s_w[nn * 32 + kc * 4 + 2],
+                     w3 = s_w[nn * 32 + kc * 4 + 3];
+      const uint64_t kn = tchash::col_mul(nn);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t dp = __dp4a(v[j].x, w0, 0u);
+        dp = __dp4a(v[j].y, w1, dp);
+        dp = __dp4a(v[j].z, w2, dp);
+        dp = __dp4a(v[j].w, w3, dp);
+        rr[j] += static_cast<uint64_t>(dp) * kn;
+      }
+    }
+    // the 8 K chunks of a row sit in the 8 lanes of a group: add them up, then lane (group, j == lane & 7) owns row j
+    uint64_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint64_t t = rr[j];
+      t += shfl_xor64(t, 1);
+      t += shfl_xor64(t, 2);
+      t += shfl_xor64(t, 4);
+      if (static_cast<uint32_t>(j) == kc) mine = t;
+    }
+    const uint32_t row = (lane >> 3) * 8u + kc;
+    uint64_t c = tchash::row_contrib(mine, row);  // tile index 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += shfl_xor64(c, o);
+    digest = tchash::finalize(c + p.zero_rows, nbytes);
+  } else {
+    // CRC32C raw remainder of the lane's 128 bytes (x^32 factor included), word at a time through the x^32 shift table
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t t = s ^ w[q];
+        s = s_t4[t & 0xFFu] ^ s_t4[256 + ((t >> 8) & 0xFFu)] ^ s_t4[512 + ((t >> 16) & 0xFFu)] ^ s_t4[768 + (t >> 24)];
+      }
+    }
+    // place the segment inside a zero-padded 16 KiB tile and add the lanes up (XOR)
+    uint32_t acc = gf2_mulmod_small(s, c_lane_mul[lane]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+    digest = gf2_mulmod_small(acc, reserved) ^ static_cast<uint32_t>(expect >> 32) ^ 0xFFFFFFFFu;
+    expect &= 0xFFFFFFFFull;
+  }
+  if (p.flag_mode) {
+    __threadfence_system();  // every lane: its stores of the payload are performed system-wide ...
+    __syncwarp();            // ... before lane 0 publishes the result
+  }
+  if (lane == 0) {
+    p.digest_out[d] = digest;
+    if (p.flag_mode) __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&p.status_out[d]) = ((flags & XFER_VERIFY) && digest != expect) ? 1u : 0u;
+  }
+}
+
+struct SmallState {
+  bool consts = false;
+  uint32_t* t4 = nullptr;
+  uint64_t zero_rows = 0;
+};
+SmallState g_small[16];
+std::mutex g_small_mu;
+
+}  // namespace
+
+int launch_xfer_small(const XferLaunch& l) {
+  if (l.ndesc == 0) return 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (dev < 0 || dev >= 16) return static_cast<int>(cudaErrorInvalidDevice);
+  SmallState& st = g_small[dev];
+  {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    if (!st.consts) {
+      uint32_t mul[32];
+      for (uint32_t ln = 0; ln < 32; ++ln) mul[ln] = gf2_xpow_bytes(128ull * (31 - ln) + (kTileBytes - kSmallBytes));
+      e = cudaMemcpyToSymbol(c_lane_mul, mul, sizeof mul);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      uint32_t t4[4][256];
+      crc32c_shift_table(4, t4);
+      e = cudaMalloc(reinterpret_cast<void**>(&st.t4), sizeof t4);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaMemcpy(st.t4, t4, sizeof t4, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      uint64_t z = 0;
+      for (uint32_t m = kSmallBytes / 128; m < tchash::kRows; ++m) z += tchash::row_contrib(0, m);
+      st.zero_rows = z;
+      st.consts = true;
+    }
+  }
+  SmallParams p;
+  p.descs = l.descs;
+  p.ndesc = l.ndesc;
+  p.use_inline = 0;
+  if (l.host_descs && l.ndesc <= kInlineDescs) {
+    p.use_inline = 1;
+    std::memcpy(p.inl_descs, l.host_descs, l.ndesc * sizeof(XferDesc));
+  }
+  p.digest_out = l.digest_out;
+  p.status_out = l.status_out;
+  p.crc_t4 = st.t4;
+  p.zero_rows = st.zero_rows;
+  p.flag_mode = l.flag_completion ? 1u : 0u;
+  const int grid = static_cast<int>((l.ndesc + kWarpsPerCta - 1) / kWarpsPerCta);
+  const int threads = l.ndesc < static_cast<uint32_t>(kWarpsPerCta) ? static_cast<int>(l.ndesc) * 32 : kWarpsPerCta * 32;
+  cudaStream_t s = static_cast<cudaStream_t>(l.stream);
+  switch (l.algo) {
+    case ALGO_NONE: bb_xfer_small_kernel<ALGO_NONE><<<grid, threads, 0, s>>>(p); break;
+    case ALGO_CRC32C: bb_xfer_small_kernel<ALGO_CRC32C><<<grid, threads, 0, s>>>(p); break;
+    case ALGO_BBH64: bb_xfer_small_kernel<ALGO_BBH64><<<grid, threads, 0, s>>>(p); break;
+    default: return static_cast<int>(cudaErrorNotSupported);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace bb::gpu

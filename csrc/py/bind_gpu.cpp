@@ -119,6 +119,9 @@ void bind_gpu(py::module_& m) {
            })
       .def("debug_accumulators", [](XferEngine& e) { return e.debug_accumulators(); })
       .def("set_max_ctas", &XferEngine::set_max_ctas)
+      .def("set_small_path", &XferEngine::set_small_path)
+      .def("set_flag_completion", &XferEngine::set_flag_completion)
+      .def_property_readonly("small_launches", &XferEngine::small_launches)
       .def("set_tile_trace", &XferEngine::set_tile_trace)
       .def("tile_trace", [](XferEngine& e) { return e.tile_trace(); }, "[tile][4] globaltimer ns: load issued, landed, store issued, slot released")
       .def_property_readonly("launches", &XferEngine::launches)
@@ -139,6 +142,12 @@ void bind_gpu(py::module_& m) {
   m.def("random_fill", [](uintptr_t dst, uint64_t n, uint64_t seed, uintptr_t stream) {
     check_cuda(launch_random_fill(reinterpret_cast<void*>(dst), n, seed, reinterpret_cast<void*>(stream)), "random_fill");
   }, py::arg("dst"), py::arg("nbytes"), py::arg("seed") = 1, py::arg("stream") = 0);
+  m.def("memcpy_peer_async", [](uintptr_t dst, int dst_dev, uintptr_t src, int src_dev, uint64_t n, uintptr_t stream) {
+    check_cuda(device_memcpy_peer_async(reinterpret_cast<void*>(dst), dst_dev, reinterpret_cast<const void*>(src), src_dev, n,
+                                        reinterpret_cast<void*>(stream)), "memcpy_peer_async");
+  }, py::arg("dst"), py::arg("dst_device"), py::arg("src"), py::arg("src_device"), py::arg("nbytes"), py::arg("stream") = 0,
+     "cudaMemcpyPeerAsync (copy engines): the naive P2P comparator of BASELINE.md section 4.");
+  m.def("enable_peer_access", [](int device, int peer) { check_cuda(device_enable_peer_access(device, peer), "enable_peer_access"); });
   m.def("xfer_smem_bytes", [] { return xfer_smem_bytes(ALGO_BBH64); });
   m.def("mxfp8_pack", [](uintptr_t src, uint64_t n, uintptr_t dst, uintptr_t stream) {
     check_cuda(launch_mxfp8_pack(reinterpret_cast<const void*>(src), n, reinterpret_cast<void*>(dst), reinterpret_cast<void*>(stream)), "mxfp8_pack");
@@ -167,6 +176,9 @@ void bind_gpu(py::module_& m) {
       .def_property_readonly("last_device_ms", &GpuFabric::last_device_ms)
       .def_property_readonly("total_device_ms", &GpuFabric::total_device_ms)
       .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); })
+      .def("set_small_path", [](GpuFabric& f, bool on) { f.engine().set_small_path(on); })
+      .def("set_flag_completion", [](GpuFabric& f, bool on) { f.engine().set_flag_completion(on); })
+      .def_property_readonly("small_launches", [](GpuFabric& f) { return f.engine().small_launches(); })
       .def("set_tile_trace", [](GpuFabric& f, bool on) { f.engine().set_tile_trace(on); })
       .def("tile_trace", [](GpuFabric& f) { return f.engine().tile_trace(); })
       .def("set_arena", &GpuFabric::set_arena)
