@@ -63,7 +63,7 @@ def main() -> int:
     ap.add_argument("--object-mib", type=float, default=64.0)
     ap.add_argument("--algo", default="crc32c", choices=["crc32c", "bbh64", "none"],
                     help="digest fused into the transfer (crc32c = the standard Castagnoli CRC, the default)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--sync", choices=["none", "step", "phase"], default="phase",
                     help="N>1: ranks rendezvous per step / per put-get phase (inside the timed region)")

@@ -99,18 +99,27 @@ class HostRendezvous:
                     time.sleep(0.005)
         self._mm = mmap.mmap(fd, size)
         os.close(fd)
+        # 8-byte aligned numpy views: every access below is ONE load / store instruction.  (struct.pack_into with a "<"
+        # format moves bytes one at a time, and a torn read of the epoch -- low byte old, high byte new -- looks like an
+        # epoch from the future.)
+        import numpy as np
+
+        self._u64 = np.frombuffer(self._mm, dtype=np.uint64)
+        self._f64 = np.frombuffer(self._mm, dtype=np.float64)
+        self._i64 = np.frombuffer(self._mm, dtype=np.int64)
         self.barrier()
 
     def _put(self, value: float, aux: int):
-        off = self.rank * self.SLOT
-        self._struct.pack_into("<dq", self._mm, off + 8, value, aux)
-        self._struct.pack_into("<Q", self._mm, off, self.epoch)  # epoch last: it publishes the value
+        w = self.rank * (self.SLOT // 8)
+        self._f64[w + 1] = value
+        self._i64[w + 2] = aux
+        self._u64[w] = self.epoch  # epoch last: it publishes the value (x86 stores are not reordered with older stores)
 
     def _wait(self):
-        unpack, mm, slot, ep = self._struct.unpack_from, self._mm, self.SLOT, self.epoch
+        u64, step, ep = self._u64, self.SLOT // 8, self.epoch
         for r in range(self.world):
             spins = 0
-            while unpack("<Q", mm, r * slot)[0] < ep:
+            while int(u64[r * step]) < ep:
                 spins += 1
                 if spins > 2000:
                     time.sleep(0)  # yield: more ranks than cores (CPU tests)
@@ -122,9 +131,10 @@ class HostRendezvous:
         self.epoch += 1
         self._put(value, aux)
         self._wait()
-        vals = [self._struct.unpack_from("<dq", self._mm, r * self.SLOT + 8) for r in range(self.world)]
+        step = self.SLOT // 8
+        vals = [(float(self._f64[r * step + 1]), int(self._i64[r * step + 2])) for r in range(self.world)]
         self.epoch += 1
-        self._put(value, aux)
+        self._u64[self.rank * step] = self.epoch
         self._wait()
         return vals
 
@@ -132,7 +142,7 @@ class HostRendezvous:
         if self._mm is None:
             return
         self.epoch += 1
-        self._put(0.0, 0)
+        self._u64[self.rank * (self.SLOT // 8)] = self.epoch
         self._wait()
 
     def allreduce(self, value: float, op: str = "max") -> float:
@@ -148,6 +158,7 @@ class HostRendezvous:
     def close(self):
         if self._mm is not None:
             self.barrier()
+            self._u64 = self._f64 = self._i64 = None  # release the buffer exports before closing the map
             self._mm.close()
             self._mm = None
             if self.rank == 0:

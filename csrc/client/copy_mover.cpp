@@ -190,4 +190,101 @@ keystone::CopyMover make_data_server_mover(size_t io_parallelism, int rpc_timeou
   };
 }
 
+keystone::ReservationHooks make_data_server_reservation_hooks(int rpc_timeout_ms) {
+  auto conns = std::make_shared<Conns>();
+  conns->timeout_ms = rpc_timeout_ms;
+  struct Group {
+    std::string ep, pool;
+    std::vector<std::pair<size_t, size_t>> at;  // (copy, shard)
+  };
+  auto group = [](const std::vector<CopyPlacement>& copies) {
+    std::map<std::pair<std::string, std::string>, Group> g;
+    for (size_t c = 0; c < copies.size(); ++c)
+      for (size_t s = 0; s < copies[c].shards.size(); ++s) {
+        const auto& sh = copies[c].shards[s];
+        Group& x = g[{ep_of(sh), sh.pool_id}];
+        x.ep = ep_of(sh);
+        x.pool = sh.pool_id;
+        x.at.emplace_back(c, s);
+      }
+    return g;
+  };
+  auto call_ec = [conns](const std::string& ep, uint32_t method, const std::string& req, std::string* body = nullptr) {
+    auto c = conns->get(ep);
+    if (!c) return ErrorCode::CONNECTION_FAILED;
+    auto r = c->call(method, req, conns->timeout_ms);
+    if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+    wire::Reader rd(r.value());
+    const ErrorCode ec = rd.ec();
+    if (body && ec == ErrorCode::OK) body->assign(r.value(), 4, std::string::npos);
+    return ec;
+  };
+  keystone::ReservationHooks h;
+  auto by_tokens = [group, call_ec](uint32_t method) {
+    return [group, call_ec, method](const std::vector<CopyPlacement>& copies, const keystone::ShardTokens& tokens) {
+      ErrorCode worst = ErrorCode::OK;
+      for (const auto& [k, g] : group(copies)) {
+        wire::Writer w;
+        w.str(g.pool);
+        uint32_t n = 0;
+        for (const auto& [c, s] : g.at) n += (c < tokens.size() && s < tokens[c].size() && !tokens[c][s].empty()) ? 1u : 0u;
+        if (!n) continue;
+        w.u32(n);
+        for (const auto& [c, s] : g.at)
+          if (c < tokens.size() && s < tokens[c].size() && !tokens[c][s].empty()) w.str(tokens[c][s]);
+        const ErrorCode ec = call_ec(g.ep, method, w.data());
+        if (ec != ErrorCode::OK && worst == ErrorCode::OK) worst = ec;
+      }
+      return worst;
+    };
+  };
+  h.commit = by_tokens(worker::D_COMMIT);
+  h.abort = by_tokens(worker::D_ABORT);
+  h.reserve = [group, call_ec, abort = h.abort](const ObjectKey& key, const std::vector<CopyPlacement>& copies, uint64_t ttl_ms,
+                                                keystone::ShardTokens* tokens) {
+    tokens->assign(copies.size(), {});
+    for (size_t c = 0; c < copies.size(); ++c) (*tokens)[c].assign(copies[c].shards.size(), std::string());
+    ErrorCode ec = ErrorCode::OK;
+    for (const auto& [k, g] : group(copies)) {
+      wire::Writer w;
+      w.str(g.pool);
+      w.str(key);
+      w.u64(ttl_ms);
+      w.u32(static_cast<uint32_t>(g.at.size()));
+      for (const auto& [c, s] : g.at) {
+        w.u64(raw_offset(copies[c].shards[s]));
+        w.u64(copies[c].shards[s].length);
+      }
+      std::string body;
+      ec = call_ec(g.ep, worker::D_RESERVE, w.data(), &body);
+      if (ec != ErrorCode::OK) break;
+      wire::Reader rd(body);
+      const uint32_t n = rd.u32();
+      if (n != g.at.size()) {
+        ec = ErrorCode::TRANSFER_FAILED;
+        break;
+      }
+      for (const auto& [c, s] : g.at) (*tokens)[c][s] = rd.str();
+    }
+    if (ec != ErrorCode::OK) abort(copies, *tokens);  // all or nothing across workers
+    return ec;
+  };
+  h.release = [group, call_ec](const std::vector<CopyPlacement>& copies) {
+    ErrorCode worst = ErrorCode::OK;
+    for (const auto& [k, g] : group(copies)) {
+      wire::Writer w;
+      w.str(g.pool);
+      w.u32(static_cast<uint32_t>(g.at.size()));
+      for (const auto& [c, s] : g.at) {
+        w.u64(raw_offset(copies[c].shards[s]));
+        w.u64(copies[c].shards[s].length);
+      }
+      const ErrorCode ec = call_ec(g.ep, worker::D_FREE, w.data());
+      if (ec != ErrorCode::OK && worst == ErrorCode::OK) worst = ec;
+    }
+    return worst;
+  };
+  return h;
+}
+
 }  // namespace bb::client

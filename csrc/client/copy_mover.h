@@ -13,4 +13,10 @@ namespace bb::client {
 
 keystone::CopyMover make_data_server_mover(size_t io_parallelism = 4, int rpc_timeout_ms = 30000);
 
+// The Keystone's side of the reservation protocol, spoken to the workers' data servers (D_RESERVE / D_COMMIT / D_ABORT /
+// D_FREE, one request per pool): put_start reserves every shard of the placement at its worker, put_complete commits,
+// put_cancel / expiry aborts, removing a COMPLETE object frees.  Reference: the contract of
+// include/blackbird/worker/storage/storage_backend.h:46-126, which no service there ever calls.
+keystone::ReservationHooks make_data_server_reservation_hooks(int rpc_timeout_ms = 5000);
+
 }  // namespace bb::client

@@ -164,6 +164,8 @@ Result<KeystoneConfig> KeystoneConfig::from_json(const Json& root, std::string* 
   if (k.contains("rpc_busy_poll_us")) c.rpc_busy_poll_us = static_cast<int32_t>(k.at("rpc_busy_poll_us").as_int(0));
   if (k.contains("rpc_threads")) c.rpc_threads = static_cast<int32_t>(k.at("rpc_threads").as_int(c.rpc_threads));
   if (k.contains("wal_path")) c.wal_path = k.at("wal_path").as_string();
+  if (k.contains("enable_reservations")) c.enable_reservations = k.at("enable_reservations").as_bool();
+  if (k.contains("reservation_ttl_ms")) c.reservation_ttl_ms = k.at("reservation_ttl_ms").as_int(c.reservation_ttl_ms);
   if (k.contains("wal_fsync")) c.wal_fsync = k.at("wal_fsync").as_bool();
   if (k.contains("wal_snapshot_mb")) c.wal_snapshot_mb = static_cast<int>(k.at("wal_snapshot_mb").as_int());
   const Json& lg = root.at("logging");

@@ -186,6 +186,11 @@ struct KeystoneConfig {
   // records are made durable under this directory before put_complete is acknowledged, and replayed on start.  HA
   // pairs log into the coordination store instead (fenced by the leader's term), so that the standby can resume.
   std::string wal_path;
+  // Reservation protocol between Keystone and workers (keystone_service.h ReservationHooks): off by default -- the GPU
+  // fast path is one-sided and a worker cannot police stores into its slab -- on for deployments that want worker-side
+  // accounting of every shard and writer-crash cleanup by token expiry.
+  bool enable_reservations = false;
+  int64_t reservation_ttl_ms = 10 * 60 * 1000;  // reference: 10 minutes (ram_backend.cpp:69)
   bool wal_fsync = true;        // false: page-cache only (survives a process crash, not a power cut)
   int wal_snapshot_mb = 64;     // compact the log into a snapshot once it grows past this
 

@@ -150,6 +150,9 @@ ErrorCode KeystoneService::start() {
       watch_ids_.push_back(id);
     if (coord_->watch_prefix(p + "heartbeat/", [this](const std::string& k, const std::string& v, bool d) { on_heartbeat_event(k, v, d); }, &id) == ErrorCode::OK)
       watch_ids_.push_back(id);
+    if (config_.enable_reservations &&
+        coord_->watch_prefix(p + "reservations_expired/", [this](const std::string& k, const std::string& v, bool d) { on_reservation_expired(k, v, d); }, &id) == ErrorCode::OK)
+      watch_ids_.push_back(id);
   }
   if (config_.enable_ha) {
     wal_on_.store(coord_ && coord_->is_connected());
@@ -522,6 +525,13 @@ ErrorCode KeystoneService::erase_locked(Shard& sh, const ObjectKey& key, bool fr
   if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
   const bool was_complete = it->second.state == ObjectState::COMPLETE || it->second.committing;
   const std::vector<std::string> extra = std::move(it->second.extra_ledgers);
+  if (it->second.reserved && reservations_enabled()) {
+    HookOp op;
+    op.release = it->second.tokens.empty();  // committed already: free the shards; else abort the outstanding tokens
+    op.tokens = std::move(it->second.tokens);
+    op.copies = std::move(it->second.copies);
+    sh.hook_queue.push_back(std::move(op));
+  }
   sh.objects.erase(it);
   if (free_ranges) {
     allocator_->free_object(key);
@@ -573,6 +583,7 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start(const ObjectKey& k
     std::shared_lock<std::shared_mutex> pk(pools_mu_);  // lock order: pools -> shard
     r = put_start_locked(key, data_size, config, client_id, client_node);
   }
+  if (r.ok() && reservations_enabled()) reserve_after_start(key, r);
   if (r.ok()) {
     bump_view();
     hot_.put_start_total->fetch_add(1, std::memory_order_relaxed);
@@ -625,6 +636,35 @@ ErrorCode KeystoneService::put_complete(const ObjectKey& key, const ShardChecksu
   if (!is_leader()) return ErrorCode::NOT_LEADER;
   if (fault::fire("fail_put_complete")) return ErrorCode::INTERNAL_ERROR;
   Shard& sh = shard_for(key);
+  if (reservations_enabled()) {
+    // the tokens must still be valid at the workers: commit them BEFORE the object becomes readable.  A token that ran
+    // out (OPERATION_TIMEOUT) means the worker has taken the range back -- the put failed, whatever the writer believes.
+    std::vector<CopyPlacement> copies;
+    ShardTokens tokens;
+    TimePoint created;
+    {
+      std::lock_guard<SpinMutex> l0(sh.mu);
+      auto i0 = sh.objects.find(key);
+      if (i0 != sh.objects.end() && !i0->second.tokens.empty()) copies = i0->second.copies, tokens = i0->second.tokens, created = i0->second.created;
+    }
+    if (!tokens.empty()) {
+      ReservationHooks hooks;
+      {
+        std::lock_guard<std::mutex> ml(mover_mu_);
+        hooks = res_hooks_;
+      }
+      const ErrorCode cec = hooks.commit(copies, tokens);
+      ShardGuard g(this, sh);
+      auto i1 = sh.objects.find(key);
+      const bool same = i1 != sh.objects.end() && i1->second.created == created;
+      if (cec != ErrorCode::OK) {
+        metrics_.inc("reservation_commit_failed_total");
+        if (same) erase_locked(sh, key, true);  // aborts whatever is still reserved, frees the ledger
+        return cec;
+      }
+      if (same) i1->second.tokens.clear();  // committed: from now on a removal frees shards instead of aborting tokens
+    }
+  }
   ShardGuard lk(this, sh);
   auto it = sh.objects.find(key);
   if (it == sh.objects.end() || it->second.is_expired()) return ErrorCode::OBJECT_NOT_FOUND;
@@ -781,11 +821,13 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_put_start
   uint64_t ok = 0, bytes = 0;
   {
     std::shared_lock<std::shared_mutex> pk(pools_mu_);  // once per batch
-    for (const auto& it : items) {
-      out.push_back(put_start_locked(it.key, it.size, it.config, client_id, client_node));
-      if (out.back().ok()) ++ok, bytes += it.size;
-    }
+    for (const auto& it : items) out.push_back(put_start_locked(it.key, it.size, it.config, client_id, client_node));
   }
+  if (reservations_enabled())
+    for (size_t i = 0; i < items.size(); ++i)
+      if (out[i].ok()) reserve_after_start(items[i].key, out[i]);
+  for (size_t i = 0; i < items.size(); ++i)
+    if (out[i].ok()) ++ok, bytes += items[i].size;
   if (ok) {
     bump_view();
     hot_.put_start_total->fetch_add(ok, std::memory_order_relaxed);
@@ -916,6 +958,81 @@ Result<ViewVersionId> KeystoneService::client_ping(const std::string& client_id)
 void KeystoneService::set_copy_mover(CopyMover m) {
   std::lock_guard<std::mutex> lk(mover_mu_);
   mover_ = std::move(m);
+}
+
+void KeystoneService::set_reservation_hooks(ReservationHooks h) {
+  std::lock_guard<std::mutex> lk(mover_mu_);
+  reservations_on_.store(static_cast<bool>(h));
+  res_hooks_ = std::move(h);
+}
+
+void KeystoneService::run_hook_ops(const std::vector<HookOp>& ops) {
+  ReservationHooks hooks;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    hooks = res_hooks_;
+  }
+  if (!hooks) return;
+  for (const auto& op : ops) {
+    const ErrorCode ec = op.release ? hooks.release(op.copies) : hooks.abort(op.copies, op.tokens);
+    if (ec != ErrorCode::OK) BB_VLOG(1) << "reservation " << (op.release ? "release" : "abort") << " at a worker failed: " << to_string(ec);
+  }
+}
+
+// After put_start_locked created the PENDING object: reserve its shards at the workers (outside every lock).  On failure
+// the object is withdrawn and `placed` carries the error.
+ErrorCode KeystoneService::reserve_after_start(const ObjectKey& key, Result<std::vector<CopyPlacement>>& placed) {
+  ReservationHooks hooks;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    hooks = res_hooks_;
+  }
+  ShardTokens tokens;
+  const ErrorCode ec = hooks.reserve(key, placed.value(), static_cast<uint64_t>(std::max<int64_t>(1, config_.reservation_ttl_ms)), &tokens);
+  Shard& sh = shard_for(key);
+  ShardGuard lk(this, sh);
+  auto it = sh.objects.find(key);
+  if (ec != ErrorCode::OK) {
+    metrics_.inc("reservation_failed_total");
+    if (it != sh.objects.end() && it->second.state == ObjectState::PENDING) erase_locked(sh, key, true);
+    placed = ec == ErrorCode::ALLOCATION_FAILED ? ErrorCode::INSUFFICIENT_SPACE : ec;
+    return ec;
+  }
+  if (it != sh.objects.end()) {
+    it->second.tokens = std::move(tokens);
+    it->second.reserved = true;
+  }
+  metrics_.inc("reservations_total");
+  return ErrorCode::OK;
+}
+
+// A worker reclaimed an expired reservation and says so: /.../reservations_expired/<worker>/<token> = <object key>.
+void KeystoneService::on_reservation_expired(const std::string& key, const std::string& owner, bool is_delete) {
+  if (is_delete || !is_leader()) return;
+  const size_t slash = key.rfind('/');
+  if (slash == std::string::npos) return;
+  const std::string token = key.substr(slash + 1);
+  bool dropped = false;
+  {
+    Shard& sh = shard_for(owner);
+    ShardGuard lk(this, sh);
+    auto it = sh.objects.find(owner);
+    if (it != sh.objects.end() && it->second.state == ObjectState::PENDING) {
+      bool mine = false;
+      for (const auto& c : it->second.tokens)
+        for (const auto& t : c) mine |= t == token;
+      if (mine) {  // not a newer incarnation of the same key
+        erase_locked(sh, owner, true);  // ledger freed; the object's OTHER tokens are aborted at their workers
+        dropped = true;
+      }
+    }
+  }
+  if (dropped) {
+    BB_LOG(INFO) << "keystone: writer of " << owner << " vanished (reservation " << token << " expired at its worker): put withdrawn";
+    metrics_.inc("reservation_expired_total");
+    bump_view();
+  }
+  if (coord_) coord_->del(key);
 }
 
 size_t KeystoneService::run_gc_once() {

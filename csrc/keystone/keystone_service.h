@@ -41,6 +41,7 @@
 namespace bb::keystone {
 
 enum class ObjectState : uint32_t { PENDING = 0, COMPLETE = 1 };
+using ShardTokens = std::vector<std::vector<std::string>>;  // [copy][shard] reservation token ids ("" = none)
 
 struct ObjectInfo {
   ObjectKey key;
@@ -53,6 +54,8 @@ struct ObjectInfo {
   std::string owner_client;  // session that started the put
   std::vector<std::string> extra_ledgers;  // allocator ledger keys besides `key` (repair / demotion)
   uint32_t reads_below_top = 0;            // reads served while the object sat on a lower tier (promotion policy)
+  ShardTokens tokens;       // reservation tokens of a PENDING object (reservation protocol); cleared once committed
+  bool reserved = false;    // its shards are reserved / committed at the workers
   bool committing = false;  // put_complete has logged COMPLETE but not yet flipped `state` (snapshots count it as COMPLETE)
 
   uint64_t ttl_ms() const { return config.ttl_ms; }
@@ -80,6 +83,18 @@ struct PutStartItem {
 };
 // Per-object shard digests reported by the writer at put_complete: [copy][shard].
 using ShardChecksums = std::vector<std::vector<uint64_t>>;
+
+// Reservation protocol (reference storage_backend.h:46-126: reserve_shard -> commit_shard | abort_shard, free_shard; SURVEY
+// section 2.7 "must be real").  With `enable_reservations` the Keystone, which decides the placement, has every shard
+// reserved at its worker before the writer sees it (token with an expiry), commits the tokens when the writer reports
+// completion, aborts them on cancel, and frees committed shards on removal; a writer that vanishes is cleaned up by the
+// WORKER (token expiry -> coordination key -> the Keystone drops the PENDING object), not by a Keystone GC pass.
+struct ReservationHooks {
+  std::function<ErrorCode(const ObjectKey& key, const std::vector<CopyPlacement>& copies, uint64_t ttl_ms, ShardTokens* tokens)> reserve;
+  std::function<ErrorCode(const std::vector<CopyPlacement>& copies, const ShardTokens& tokens)> commit, abort;
+  std::function<ErrorCode(const std::vector<CopyPlacement>& copies)> release;
+  explicit operator bool() const { return reserve && commit && abort && release; }
+};
 
 // Moves the bytes of one copy to another placement (tier demotion / re-replication).  Provided
 // by the data plane (worker or client library); returns OK when dst holds a verified copy and
@@ -170,6 +185,10 @@ class KeystoneService {
 
   // ---- tiering / repair
   void set_copy_mover(CopyMover m);
+  // Installs the transport of the reservation protocol (client/copy_mover.h: the workers' data servers).  Takes effect
+  // when `enable_reservations` is set in the configuration.
+  void set_reservation_hooks(ReservationHooks h);
+  bool reservations_enabled() const { return config_.enable_reservations && reservations_on_.load(std::memory_order_relaxed); }
   // Runs one TTL sweep / eviction pass / repair pass synchronously (also used by the threads).
   size_t run_gc_once();
   size_t run_eviction_once();
@@ -197,10 +216,16 @@ class KeystoneService {
     bool del = false;
     ErrorCode* result = nullptr;  // optional: where the enqueuing thread wants the write's outcome (it outlives the flush)
   };
+  struct HookOp {
+    std::vector<CopyPlacement> copies;
+    ShardTokens tokens;
+    bool release = false;  // committed shards of a COMPLETE object (free) vs. tokens of a PENDING one (abort)
+  };
   struct Shard {
     mutable SpinMutex mu;  // sub-microsecond sections taken by every client on every object: never sleep on it
     std::unordered_map<ObjectKey, ObjectInfo> objects;
     std::vector<WalOp> wal_queue;  // guarded by mu
+    std::vector<HookOp> hook_queue;  // guarded by mu: reservations to abort / release once the lock is dropped
     std::mutex wal_mu;             // serialises the writers of this shard's log records (order = queue order)
   };
   // unique_lock on a shard that flushes the shard's queued log records when it goes out of scope (after unlocking).
@@ -211,8 +236,11 @@ class KeystoneService {
     void finish() {
       if (!lk_.owns_lock()) return;
       const bool dirty = !sh_.wal_queue.empty();
+      std::vector<HookOp> hooks;
+      hooks.swap(sh_.hook_queue);
       lk_.unlock();
       if (dirty) ks_->flush_wal(sh_);
+      if (!hooks.empty()) ks_->run_hook_ops(hooks);
     }
     void relock() { lk_.lock(); }
    private:
@@ -246,6 +274,9 @@ class KeystoneService {
   void maybe_snapshot_local_wal();
   void reset_object_state();  // drops the object table and the allocator (leadership lost / about to be rebuilt)
   void step_down(const char* why);
+  void run_hook_ops(const std::vector<HookOp>& ops);
+  ErrorCode reserve_after_start(const ObjectKey& key, Result<std::vector<CopyPlacement>>& placed);
+  void on_reservation_expired(const std::string& key, const std::string& owner, bool is_delete);
   void arm_lease_deadline(TimePoint refreshed_at);
   std::string election_name() const { return "keystone-" + config_.cluster_id; }
   void bump_view() { view_version_.fetch_add(1); }
@@ -275,6 +306,8 @@ class KeystoneService {
 
   std::mutex mover_mu_;
   CopyMover mover_;
+  ReservationHooks res_hooks_;  // guarded by mover_mu_ (copied out before use)
+  std::atomic<bool> reservations_on_{false};
   void refresh_top_tier_locked();  // caller holds pools_mu_ exclusively
   std::atomic<int> top_tier_rank_{-1};  // rank of the fastest tier present (promotion policy fast check)
   std::mutex promo_mu_;

@@ -276,6 +276,8 @@ void bind_control(py::module_& m) {
       .def_readwrite("compaction_fragmentation_threshold", &KeystoneConfig::compaction_fragmentation_threshold)
       .def_readwrite("wal_path", &KeystoneConfig::wal_path)
       .def_readwrite("wal_fsync", &KeystoneConfig::wal_fsync)
+      .def_readwrite("enable_reservations", &KeystoneConfig::enable_reservations)
+      .def_readwrite("reservation_ttl_ms", &KeystoneConfig::reservation_ttl_ms)
       .def_readwrite("wal_snapshot_mb", &KeystoneConfig::wal_snapshot_mb)
       .def_readwrite("log_level", &KeystoneConfig::log_level)
       .def("validate", [](const KeystoneConfig& c) {
@@ -589,6 +591,8 @@ void bind_control(py::module_& m) {
         d["ttl_ms"] = o.config.ttl_ms;
         return d;
       })
+      .def("install_reservation_hooks", [](KeystoneService& k) { k.set_reservation_hooks(client::make_data_server_reservation_hooks()); },
+           "Reservation protocol over the workers' data servers (takes effect with KeystoneConfig.enable_reservations).")
       .def("install_data_server_mover", [](KeystoneService& k) { k.set_copy_mover(client::make_data_server_mover()); },
            "Tier demotion / re-replication move bytes through the workers' data servers (the default in bb-keystone).")
       // Python-implemented copy mover (tests): fn(key, src_copy, dst_copy, algo) -> (ErrorCode, [shard checksums])
@@ -896,6 +900,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("numa_node", &worker::WorkerServiceConfig::numa_node)
       .def_readwrite("lease_ttl_sec", &worker::WorkerServiceConfig::lease_ttl_sec)
       .def_readwrite("heartbeat_interval_sec", &worker::WorkerServiceConfig::heartbeat_interval_sec)
+      .def_readwrite("allocation_poll_interval_ms", &worker::WorkerServiceConfig::allocation_poll_interval_ms)
       .def_readwrite("fabric_domain", &worker::WorkerServiceConfig::fabric_domain)
       .def_readwrite("transport", &worker::WorkerServiceConfig::transport)
       .def_readwrite("has_transport", &worker::WorkerServiceConfig::has_transport)
@@ -915,6 +920,7 @@ void bind_control(py::module_& m) {
       .def("metrics_text", &worker::WorkerService::metrics_text)
       .def_property_readonly("http_port", &worker::WorkerService::http_port)
       .def("inject_fault", &worker::WorkerService::inject_fault)
+      .def("reap_reservations", &worker::WorkerService::reap_reservations, py::call_guard<py::gil_scoped_release>())
       .def("backend", [](worker::WorkerService& w, const std::string& id) { return w.backend(id); }, py::return_value_policy::reference_internal);
 
   // ---------------------------------------------------------------- client

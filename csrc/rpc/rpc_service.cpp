@@ -759,6 +759,7 @@ Result<KeystoneBundle> create_and_start_keystone(const KeystoneConfig& config) {
   ec = b.keystone->start();
   if (ec != ErrorCode::OK) return ec;
   b.keystone->set_copy_mover(client::make_data_server_mover());  // tier demotion + re-replication move real bytes
+  b.keystone->set_reservation_hooks(client::make_data_server_reservation_hooks());  // used when enable_reservations is set
   b.rpc = std::make_unique<RpcService>(b.keystone, config);
   ec = b.rpc->start();
   if (ec != ErrorCode::OK) {

@@ -91,6 +91,53 @@ Result<ReservationToken> StorageBackend::reserve_shard(uint64_t size, const std:
   return r.token;
 }
 
+Result<ReservationToken> StorageBackend::reserve_shard_at(uint64_t offset, uint64_t size, const std::string& owner, uint64_t ttl_ms) {
+  if (!initialized_) return ErrorCode::INVALID_STATE;
+  if (size == 0) return ErrorCode::INVALID_PARAMETERS;
+  BB_TRY(check_range(offset, size));
+  if (!allocator_->allocate_at(offset, size)) return ErrorCode::ALLOCATION_FAILED;
+  Reservation r;
+  r.range = alloc::Range(offset, allocator_->aligned(size));
+  r.owner = owner;
+  r.token.pool_id = pool_id_;
+  r.token.remote_addr = get_base_address() + offset;
+  r.token.rkey = get_rkey();
+  r.token.size = size;
+  r.token.expires_at = std::chrono::system_clock::now() + std::chrono::milliseconds(ttl_ms ? ttl_ms : opts_.reservation_ttl_ms);
+  std::lock_guard<std::mutex> lk(mu_);
+  r.token.token_id = pool_id_ + "#" + std::to_string(next_token_++);
+  reservations_[r.token.token_id] = r;
+  return r.token;
+}
+
+ErrorCode StorageBackend::commit_shard_id(const std::string& token_id) {
+  ReservationToken t;
+  t.token_id = token_id;
+  return commit_shard(t);
+}
+ErrorCode StorageBackend::abort_shard_id(const std::string& token_id) {
+  ReservationToken t;
+  t.token_id = token_id;
+  return abort_shard(t);
+}
+
+std::vector<std::pair<std::string, std::string>> StorageBackend::reap_expired_reservations() {
+  std::vector<std::pair<std::string, std::string>> out;
+  if (!initialized_) return out;
+  const auto now = std::chrono::system_clock::now();
+  std::lock_guard<std::mutex> lk(mu_);
+  for (auto it = reservations_.begin(); it != reservations_.end();) {
+    if (it->second.token.expires_at <= now) {
+      allocator_->free(it->second.range);
+      out.emplace_back(it->first, it->second.owner);
+      it = reservations_.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  return out;
+}
+
 ErrorCode StorageBackend::commit_shard(const ReservationToken& token) {
   Reservation r;
   {

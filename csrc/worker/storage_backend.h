@@ -87,6 +87,16 @@ class StorageBackend {
   virtual ErrorCode commit_shard(const ReservationToken& token);
   virtual ErrorCode abort_shard(const ReservationToken& token);
   virtual ErrorCode free_shard(uint64_t remote_addr, uint64_t size);
+  // Reservation protocol as the Keystone drives it (it owns the placement decision, so the extent is given): reserves
+  // exactly [offset, offset + size) for `owner` (the object key) until `ttl_ms` from now (0 = the backend's default).
+  // ALLOCATION_FAILED when any part of the range is already reserved or committed.
+  virtual Result<ReservationToken> reserve_shard_at(uint64_t offset, uint64_t size, const std::string& owner, uint64_t ttl_ms = 0);
+  ErrorCode commit_shard_id(const std::string& token_id);
+  ErrorCode abort_shard_id(const std::string& token_id);
+  // Reclaims every reservation whose token has expired (the writer vanished between put_start and put_complete) and
+  // returns (token id, owner) of each, so that the worker can tell the Keystone.  This is what the reference's
+  // `allocation_poll_interval_ms` (include/blackbird/worker/worker_service.h:37) was meant to drive.
+  std::vector<std::pair<std::string, std::string>> reap_expired_reservations();
   virtual StorageStats get_stats() const;
 
   // ---- data plane (offsets are relative to the pool base)
@@ -139,6 +149,7 @@ class StorageBackend {
   struct Reservation {
     ReservationToken token;
     alloc::Range range;
+    std::string owner;  // object key (reserve_shard_at)
   };
   mutable std::mutex mu_;  // guards reservations_/committed_; never held while calling virtuals that lock
   std::unique_ptr<alloc::PoolAllocator> allocator_;

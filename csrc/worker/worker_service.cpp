@@ -46,6 +46,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("version")) c.version = w.at("version").as_string();
   c.lease_ttl_sec = w.at("lease_ttl_sec").as_int(c.lease_ttl_sec);
   c.heartbeat_interval_sec = w.at("heartbeat_interval_sec").as_int(c.heartbeat_interval_sec);
+  c.allocation_poll_interval_ms = w.at("allocation_poll_interval_ms").as_int(c.allocation_poll_interval_ms);
   if (w.contains("fabric_domain")) c.fabric_domain = w.at("fabric_domain").as_string();
   if (w.contains("listen_address") && !w.contains("data_endpoint") && !w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("listen_address").as_string();
   if (w.at("transport").is_object()) {
@@ -276,7 +277,45 @@ ErrorCode WorkerService::start() {
     return ec;
   }
   heartbeat_thread_ = std::thread([this] { heartbeat_loop(); });
+  reaper_thread_ = std::thread([this] { reservation_reaper_loop(); });
   return ErrorCode::OK;
+}
+
+// Reservation sweep: a writer that got placements (put_start -> D_RESERVE) and vanished never commits; its tokens run
+// out, the backend takes the ranges back, and the worker tells the Keystone through the coordination store -- the only
+// channel workers and Keystone share, as in the reference -- which drops the PENDING object and its
+// ledger entry.  No Keystone-side GC pass is involved.
+size_t WorkerService::reap_reservations_once() {
+  std::vector<std::pair<std::string, std::string>> expired;  // (token id, object key)
+  {
+    std::lock_guard<std::mutex> lk(pools_mu_);
+    for (auto& [id, b] : pools_) {
+      auto v = b->reap_expired_reservations();
+      expired.insert(expired.end(), v.begin(), v.end());
+    }
+  }
+  if (expired.empty()) return 0;
+  reservations_expired_ += expired.size();
+  if (coord_ && coord_->is_connected()) {
+    for (const auto& [token, owner] : expired) {
+      const ErrorCode ec = coord_->put_with_ttl(cluster_prefix() + "reservations_expired/" + config_.worker_id + "/" + token, owner, 120);
+      if (ec != ErrorCode::OK) BB_LOG(WARNING) << "worker " << config_.worker_id << ": cannot report expired reservation " << token;
+    }
+  }
+  BB_LOG(INFO) << "worker " << config_.worker_id << ": reclaimed " << expired.size() << " expired shard reservations";
+  return expired.size();
+}
+
+void WorkerService::reservation_reaper_loop() {
+  const auto period = std::chrono::milliseconds(std::max<int64_t>(10, config_.allocation_poll_interval_ms));
+  while (true) {
+    {
+      std::unique_lock<std::mutex> lk(sleep_mu_);
+      sleep_cv_.wait_for(lk, period, [this] { return !running_.load(); });
+    }
+    if (!running_.load()) return;
+    reap_reservations_once();
+  }
 }
 
 void WorkerService::heartbeat_loop() {
@@ -303,6 +342,7 @@ void WorkerService::stop() {
       sleep_cv_.notify_all();
     }
     if (heartbeat_thread_.joinable()) heartbeat_thread_.join();
+    if (reaper_thread_.joinable()) reaper_thread_.join();
     if (coord_ && coord_->is_connected()) {
       const std::string base = cluster_prefix() + "workers/" + config_.worker_id;
       if (auto st = coord_->store()) st->del_prefix(base + "/");
@@ -609,6 +649,91 @@ void WorkerService::register_data_handlers() {
     ErrorCode ec = db->pull_from_peer(std::vector<uint8_t>(key.begin(), key.end()), soff, resolve_offset(*db, doff), len, algo, &digest);
     w.ec(ec);
     if (ec == ErrorCode::OK) w.u64(digest);
+    return w.take();
+  });
+  // ---- reservation protocol (Keystone -> worker).  Requests carry one pool and a list of shards / tokens.
+  data_server_.register_method(D_RESERVE, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string pool = r.str(), owner = r.str();
+    const uint64_t ttl_ms = r.u64();
+    const uint32_t n = r.u32();
+    wire::Writer w;
+    StorageBackend* b = backend(pool);
+    if (!r.ok() || !b || n > 65536) {
+      w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
+      return w.take();
+    }
+    std::vector<std::string> tokens;
+    ErrorCode ec = ErrorCode::OK;
+    for (uint32_t i = 0; i < n && ec == ErrorCode::OK; ++i) {
+      const uint64_t off = resolve_offset(*b, r.u64());
+      const uint64_t len = r.u64();
+      if (!r.ok() || !range_ok(*b, off, len)) {
+        ec = ErrorCode::MEMORY_ACCESS_ERROR;
+        break;
+      }
+      auto t = b->reserve_shard_at(off, len, owner, ttl_ms);
+      if (!t.ok()) ec = t.error();
+      else tokens.push_back(t.value().token_id);
+    }
+    if (ec != ErrorCode::OK)  // all or nothing
+      for (const auto& t : tokens) b->abort_shard_id(t);
+    w.ec(ec);
+    if (ec == ErrorCode::OK) {
+      w.u32(static_cast<uint32_t>(tokens.size()));
+      for (const auto& t : tokens) w.str(t);
+    }
+    return w.take();
+  });
+  auto by_token = [this](bool commit) {
+    return [this, commit](C, S q) {
+      wire::Reader r(q);
+      const std::string pool = r.str();
+      const uint32_t n = r.u32();
+      wire::Writer w;
+      StorageBackend* b = backend(pool);
+      if (!r.ok() || !b || n > 65536) {
+        w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
+        return w.take();
+      }
+      ErrorCode worst = ErrorCode::OK;
+      for (uint32_t i = 0; i < n; ++i) {
+        const std::string tok = r.str();
+        if (!r.ok()) {
+          worst = ErrorCode::INVALID_PARAMETERS;
+          break;
+        }
+        const ErrorCode ec = commit ? b->commit_shard_id(tok) : b->abort_shard_id(tok);
+        if (ec != ErrorCode::OK && worst == ErrorCode::OK) worst = ec;
+      }
+      w.ec(worst);
+      return w.take();
+    };
+  };
+  data_server_.register_method(D_COMMIT, by_token(true));
+  data_server_.register_method(D_ABORT, by_token(false));
+  data_server_.register_method(D_FREE, [this](C, S q) {
+    wire::Reader r(q);
+    const std::string pool = r.str();
+    const uint32_t n = r.u32();
+    wire::Writer w;
+    StorageBackend* b = backend(pool);
+    if (!r.ok() || !b || n > 65536) {
+      w.ec(!b ? ErrorCode::MEMORY_POOL_NOT_FOUND : ErrorCode::INVALID_PARAMETERS);
+      return w.take();
+    }
+    ErrorCode worst = ErrorCode::OK;
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint64_t off = resolve_offset(*b, r.u64());
+      const uint64_t len = r.u64();
+      if (!r.ok() || off == ~0ull) {
+        worst = ErrorCode::INVALID_PARAMETERS;
+        break;
+      }
+      const ErrorCode ec = b->free_shard(b->get_base_address() + off, len);
+      if (ec != ErrorCode::OK && worst == ErrorCode::OK) worst = ec;
+    }
+    w.ec(worst);
     return w.take();
   });
   data_server_.register_method(D_STATS, [this](C, S) {

@@ -55,6 +55,9 @@ struct WorkerServiceConfig {
   std::string version = "1.0.0";
   int64_t lease_ttl_sec = 10;
   int64_t heartbeat_interval_sec = 5;
+  // How often expired shard reservations are reclaimed and reported to the Keystone (reference worker_service.h:37,
+  // where the knob exists but nothing reads it).
+  int64_t allocation_poll_interval_ms = 1000;
   std::string fabric_domain;        // e.g. "nvswitch-0"
   // HTTP port of the worker's own observability endpoint (/metrics, /healthz, /stats); -1 = disabled, 0 = ephemeral.
   int http_metrics_port = -1;
@@ -71,7 +74,10 @@ WorkerServiceConfig load_worker_config_from_file(const std::string& path);
 
 // D_PULL: the destination worker copies a shard out of a *peer worker's* GPU slab itself (opens the peer's CUDA IPC
 // handle, one fused-kernel launch over NVLink) -- the re-replication / repair path between GPU-tier workers.
-enum DataMethod : uint32_t { D_WRITE = 1, D_READ = 2, D_CHECKSUM = 3, D_STATS = 4, D_COPY = 5, D_PULL = 6 };
+// D_RESERVE / D_COMMIT / D_ABORT / D_FREE: the reservation protocol between the Keystone and the workers
+// (StorageBackend::reserve_shard_at -> commit | abort, later free), reference storage_backend.h:46-126.
+enum DataMethod : uint32_t { D_WRITE = 1, D_READ = 2, D_CHECKSUM = 3, D_STATS = 4, D_COPY = 5, D_PULL = 6, D_RESERVE = 7, D_COMMIT = 8,
+                             D_ABORT = 9, D_FREE = 10 };
 
 class WorkerService {
  public:
@@ -101,6 +107,8 @@ class WorkerService {
   // Extra registration attributes for a pool (e.g. the CUDA IPC handle of a GPU slab).
   void set_pool_rkey_hex(const std::string& pool_id, const std::string& hex);
 
+  // Runs one reservation sweep now (tests); returns the number of expired reservations reclaimed.
+  size_t reap_reservations() { return reap_reservations_once(); }
   // Fault injection: "drop_heartbeat" stops refreshing the lease, "" clears.
   void inject_fault(const std::string& fault);
 
@@ -108,6 +116,8 @@ class WorkerService {
   void register_data_handlers();
   ErrorCode register_all();
   void heartbeat_loop();
+  void reservation_reaper_loop();
+  size_t reap_reservations_once();
   MemoryPool describe_pool(const std::string& pool_id, const StorageBackend& b) const;
   std::string cluster_prefix() const { return "/blackbird/clusters/" + config_.cluster_id + "/"; }
 
@@ -124,6 +134,8 @@ class WorkerService {
   std::atomic<bool> initialized_{false};
   std::atomic<bool> drop_heartbeat_{false};
   std::thread heartbeat_thread_;
+  std::thread reaper_thread_;
+  std::atomic<uint64_t> reservations_expired_{0};
   std::mutex sleep_mu_;
   std::condition_variable sleep_cv_;
   std::atomic<uint64_t> heartbeats_sent_{0};
