@@ -210,7 +210,9 @@ class LocalCluster:
         assert w.initialize() == _bb.ErrorCode.OK
         assert w.start() == _bb.ErrorCode.OK
         self.workers.append(w)
-        self.coord.store().flush_events()
+        st = self.coord.store()
+        if hasattr(st, "flush_events"):  # in-process store: registration events have been delivered when this returns
+            st.flush_events()
         return w
 
     def client(self, node_id: str = "", io_parallelism: int = 4, in_process: bool = False):

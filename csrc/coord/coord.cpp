@@ -1,4 +1,5 @@
 #include "coord/coord.h"
+#include "coord/etcd_coord.h"
 
 #include <algorithm>
 #include <chrono>
@@ -1132,6 +1133,11 @@ ErrorCode CoordService::connect() {
     store_ = std::make_shared<MemCoord>();
   } else if (endpoints_.compare(0, mem.size(), mem) == 0) {
     store_ = shared_mem_coord(endpoints_.substr(mem.size()));
+  } else if (endpoints_.compare(0, 7, "etcd://") == 0) {
+    // a real etcd v3 cluster through its JSON gateway (coord/etcd_coord.h); same key schema, same CoordStore semantics
+    auto ec = std::make_shared<EtcdCoord>();
+    if (ec->connect(endpoints_) != ErrorCode::OK) return ErrorCode::ETCD_ERROR;
+    store_ = ec;
   } else {
     auto rc = std::make_shared<RemoteCoord>();
     if (rc->connect(endpoints_) != ErrorCode::OK) return ErrorCode::ETCD_ERROR;

@@ -7,6 +7,7 @@
 #include "alloc/allocator.h"
 #include "client/blackbird_client.h"
 #include "client/copy_mover.h"
+#include "coord/etcd_coord.h"
 #include "coord/coord.h"
 #include "keystone/keystone_service.h"
 #include "rpc/rpc_service.h"
@@ -380,37 +381,53 @@ void bind_control(py::module_& m) {
   using coord::CoordService;
   using coord::CoordStore;
   using coord::MemCoord;
+  // Every call may block on the network (RemoteCoord, EtcdCoord): the GIL is released around the C++ call, which also
+  // lets an in-process Python server (tests/fake_etcd.py) answer it.
   py::class_<CoordStore, std::shared_ptr<CoordStore>>(m, "CoordStore")
-      .def("put", &CoordStore::put, py::arg("key"), py::arg("value"), py::arg("lease") = 0)
+      .def("put", &CoordStore::put, py::arg("key"), py::arg("value"), py::arg("lease") = 0, py::call_guard<py::gil_scoped_release>())
       .def("get", [](CoordStore& s, const std::string& k) -> py::object {
-        auto r = s.get(k);
+        Result<std::string> r = ErrorCode::INTERNAL_ERROR;
+        {
+          py::gil_scoped_release rel;
+          r = s.get(k);
+        }
         if (!r.ok()) return py::none();
         return py::bytes(r.value());
       })
-      .def("delete", &CoordStore::del)
+      .def("delete", &CoordStore::del, py::call_guard<py::gil_scoped_release>())
       .def("get_with_prefix", [](CoordStore& s, const std::string& p) {
+        Result<std::vector<coord::KeyValue>> r = ErrorCode::INTERNAL_ERROR;
+        {
+          py::gil_scoped_release rel;
+          r = s.get_with_prefix(p);
+        }
         py::list out;
-        for (auto& kv : unwrap(s.get_with_prefix(p))) out.append(py::make_tuple(kv.key, py::bytes(kv.value), kv.mod_revision, kv.lease));
+        for (auto& kv : unwrap(std::move(r))) out.append(py::make_tuple(kv.key, py::bytes(kv.value), kv.mod_revision, kv.lease));
         return out;
       })
-      .def("del_prefix", [](CoordStore& s, const std::string& p) { return unwrap(s.del_prefix(p)); })
-      .def("grant_lease", [](CoordStore& s, int64_t ttl) { return unwrap(s.grant_lease(ttl)); })
-      .def("keep_alive", &CoordStore::keep_alive)
-      .def("revoke_lease", &CoordStore::revoke_lease)
-      .def("lease_remaining_ms", [](CoordStore& s, LeaseId l) { return unwrap(s.lease_remaining_ms(l)); })
+      .def("del_prefix", [](CoordStore& s, const std::string& p) { return unwrap(s.del_prefix(p)); }, py::call_guard<py::gil_scoped_release>())
+      .def("grant_lease", [](CoordStore& s, int64_t ttl) { return unwrap(s.grant_lease(ttl)); }, py::call_guard<py::gil_scoped_release>())
+      .def("keep_alive", &CoordStore::keep_alive, py::call_guard<py::gil_scoped_release>())
+      .def("revoke_lease", &CoordStore::revoke_lease, py::call_guard<py::gil_scoped_release>())
+      .def("lease_remaining_ms", [](CoordStore& s, LeaseId l) { return unwrap(s.lease_remaining_ms(l)); }, py::call_guard<py::gil_scoped_release>())
       .def("put_if_absent", [](CoordStore& s, const std::string& k, const std::string& v, LeaseId l) { return unwrap(s.put_if_absent(k, v, l)); },
-           py::arg("key"), py::arg("value"), py::arg("lease") = 0)
+           py::arg("key"), py::arg("value"), py::arg("lease") = 0, py::call_guard<py::gil_scoped_release>())
       .def("compare_and_swap", [](CoordStore& s, const std::string& k, const std::string& e, const std::string& v, LeaseId l) {
         return unwrap(s.compare_and_swap(k, e, v, l));
-      }, py::arg("key"), py::arg("expected"), py::arg("value"), py::arg("lease") = 0)
-      .def("compare_and_delete", [](CoordStore& s, const std::string& k, const std::string& e) { return unwrap(s.compare_and_delete(k, e)); })
+      }, py::arg("key"), py::arg("expected"), py::arg("value"), py::arg("lease") = 0, py::call_guard<py::gil_scoped_release>())
+      .def("compare_and_delete", [](CoordStore& s, const std::string& k, const std::string& e) { return unwrap(s.compare_and_delete(k, e)); },
+           py::call_guard<py::gil_scoped_release>())
       .def("guarded_put", [](CoordStore& s, const std::string& g, int64_t rev, const std::string& k, const std::string& v) {
         return unwrap(s.guarded_put(g, rev, k, v));
       }, py::arg("guard_key"), py::arg("guard_create_revision"), py::arg("key"), py::arg("value"), py::call_guard<py::gil_scoped_release>())
       .def("guarded_del", [](CoordStore& s, const std::string& g, int64_t rev, const std::string& k) { return unwrap(s.guarded_del(g, rev, k)); },
            py::call_guard<py::gil_scoped_release>())
       .def("get_kv", [](CoordStore& s, const std::string& k) -> py::object {
-        auto r = s.get_kv(k);
+        Result<coord::KeyValue> r = ErrorCode::INTERNAL_ERROR;
+        {
+          py::gil_scoped_release rel;
+          r = s.get_kv(k);
+        }
         if (!r.ok()) return py::none();
         py::dict d;
         d["key"] = r.value().key;
@@ -432,7 +449,7 @@ void bind_control(py::module_& m) {
         }));
       }, py::call_guard<py::gil_scoped_release>())
       .def("unwatch", &CoordStore::unwatch, py::call_guard<py::gil_scoped_release>())
-      .def("revision", &CoordStore::revision);
+      .def("revision", &CoordStore::revision, py::call_guard<py::gil_scoped_release>());
   py::class_<MemCoord, CoordStore, std::shared_ptr<MemCoord>>(m, "MemCoord")
       // The destructor joins the dispatch thread, which may be waiting for the GIL to deliver an event to a Python
       // watch callback: release the GIL while the store is torn down.
@@ -455,6 +472,11 @@ void bind_control(py::module_& m) {
       .def("connect", &coord::RemoteCoord::connect, py::arg("endpoints"), py::arg("timeout_ms") = 3000)
       .def("close", &coord::RemoteCoord::close, py::call_guard<py::gil_scoped_release>())
       .def_property_readonly("reconnects", &coord::RemoteCoord::reconnects);
+  py::class_<coord::EtcdCoord, CoordStore, std::shared_ptr<coord::EtcdCoord>>(m, "EtcdCoord")
+      .def(py::init<>())
+      .def("connect", &coord::EtcdCoord::connect, py::arg("endpoints"), py::arg("timeout_ms") = 3000, py::call_guard<py::gil_scoped_release>())
+      .def("close", &coord::EtcdCoord::close, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("requests", &coord::EtcdCoord::requests);
   py::class_<coord::CoordServer>(m, "CoordServer")
       .def(py::init([](std::shared_ptr<MemCoord> st) { return std::make_unique<coord::CoordServer>(std::move(st)); }), py::arg("store") = nullptr)
       .def("start", &coord::CoordServer::start, py::arg("host") = "127.0.0.1", py::arg("port") = 0)
