@@ -338,7 +338,12 @@ def run_headline(args, world: int) -> int:
             t = timed(memcpy_peer_plus_crc, 3)
             comparators["unfused_memcpyPeer_plus_crc32c_kernel_GBps_per_rank"] = round(step_bytes / t / 1e6, 1)
             del peer
-            dist = cl.ensure_dist()  # NCCL, only now
+            # NCCL, only now.  It announces its version on fd 1 when the first communicator comes up: keep stdout for the
+            # one JSON line (the announcement goes to stderr instead).
+            sys.stdout.flush()
+            saved_fd = os.dup(1)
+            os.dup2(2, 1)
+            dist = cl.ensure_dist()
             nxt, prv = (rank + 1) % world, (rank - 1) % world
 
             def nccl_objects():
@@ -357,10 +362,18 @@ def run_headline(args, world: int) -> int:
             comparators["nccl_send_recv_one_message_GBps_per_rank"] = round(step_bytes / t / 1e6, 1)
             t = timed(nccl_objects, 3)
             comparators["nccl_grouped_send_recv_per_object_GBps_per_rank"] = round(step_bytes / t / 1e6, 1)
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
             comparators["fused_put_kernel_vs_unfused_memcpyPeer_plus_crc32c"] = round(
                 variants["crc32c"]["put_GBps_per_gpu"] / comparators["unfused_memcpyPeer_plus_crc32c_kernel_GBps_per_rank"], 3)
 
     cl.stop()
+    if world > 1 and cl.dist is not None:
+        try:
+            cl.dist.destroy_process_group()
+        except Exception:
+            pass
     if rank == 0:
         peaks = {}
         try:
@@ -470,7 +483,7 @@ def run_config(args, world: int) -> int:
                     config={"model": "sweep 256 B - 256 MiB, replication 1", "checksum": args.algo, "parallelism": f"ring{world}" if world > 1 else "local1"},
                     sweep=rows)
     elif args.config == "repl3":
-        cl = GpuRankCluster(slab_bytes=4 << 30, cluster_id="repl3", nvls_arena_bytes=(1 << 30) if world >= 3 else 0, nvls_group_size=3)
+        cl = GpuRankCluster(slab_bytes=4 << 30, cluster_id="repl3", nvls_arena_bytes=(256 << 20) if world >= 3 else 0, nvls_group_size=3)
         if world < 3:
             cl.stop()
             line = dict(base, metric="replication=3 batched put (BASELINE config #3)", value=None, unit="GB/s", unavailable="needs >= 3 GPUs")

@@ -246,13 +246,14 @@ class GpuRankCluster:
     def __init__(self, slab_bytes: int, cluster_id: str = "gpu", keystone_port: Optional[int] = None,
                  nvls_arena_bytes: int = 0, nvls_group_size: int = 3, rpc_busy_poll_us: Optional[int] = None,
                  dram_bytes: int = 0, nvme_bytes: int = 0, nvme_path: str = "", high_watermark: float = 1.0,
-                 eviction_ratio: float = 0.1, max_replicas: int = 3, use_nccl: bool = False):
+                 eviction_ratio: float = 0.1, max_replicas: int = 3, use_nccl: bool = False, nvls_groups: str = "all"):
         """slab_bytes: HBM slab of this rank's GPU-tier pool.  dram_bytes / nvme_bytes add host tiers to the
         same worker (the demotion ladder GPU -> DRAM -> NVMe); high_watermark < 1 arms tier demotion."""
         import torch
         import torch.distributed as dist
 
         self.torch = torch
+        self.nvls_groups = nvls_groups  # "all": every replica set gets a multicast group; "ring": {g, g+1, .., g+R-1} only
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -337,8 +338,15 @@ class GpuRankCluster:
         R = min(group_size, self.world)
         if R < 2 or not _bb.NvlsArena.supported(self.local_rank):
             return
+        import itertools
+        import math
+
         if R == self.world:
             groups = [list(range(self.world))]
+        elif self.nvls_groups == "all" and math.comb(self.world, R) <= 64:
+            # one multicast group per possible replica set (C(8,3) = 56): whatever set of GPUs the placement engine
+            # picks for a symmetric R-way put, there is a multicast object for exactly those GPUs -- no ring constraint
+            groups = [list(c) for c in itertools.combinations(range(self.world), R)]
         else:
             groups = [[(g + k) % self.world for k in range(R)] for g in range(self.world)]
         tag = f"{cluster_id}-{self.keystone_port}"

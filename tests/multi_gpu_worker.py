@@ -19,7 +19,9 @@ OK = _bb.ErrorCode.OK
 
 
 def main():
-    cl = GpuRankCluster(slab_bytes=1 << 30, cluster_id="t-multi", dram_bytes=256 << 20)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    cl = GpuRankCluster(slab_bytes=1 << 30, cluster_id="t-multi", dram_bytes=256 << 20, nvls_arena_bytes=128 << 20,
+                        nvls_group_size=min(3, world_env))
     dev = torch.device("cuda", cl.local_rank)
     s = torch.cuda.current_stream().cuda_stream
     rank, world = cl.rank, cl.world
@@ -69,6 +71,20 @@ def main():
     torch.cuda.synchronize()
     assert ecs == [OK] and torch.equal(back, blob)
     res["failover"] = "corrupted local replica -> remote replica" if mine else "no local replica"
+    cl.barrier()
+
+    # ---- NVLS: symmetric replicas are written with ONE multimem.st stream per object (the switch replicates); every rank
+    # reads the objects back (its own replica when it holds one, a peer's otherwise) and compares
+    if cl.arena is not None:
+        R = min(3, world)
+        before = cl.fabric.multicast_puts
+        m = replicated_put_verify(cl, replication=R, nobj=6, size=(2 << 20) + 4096, iters=2, symmetric=True)
+        assert cl.fabric.multicast_puts > before, "symmetric replicas did not take the multicast path"
+        assert cl.fabric.path_bytes(True, 3) > 0
+        res["nvls_multicast_put_payload_GBps"] = round(m["put_payload_GBps"], 1)
+        res["nvls_groups"] = cl.arena.num_groups()
+    else:
+        res["nvls_multicast_put_payload_GBps"] = None
     cl.barrier()
 
     # ---- config 5: rank 0 puts, everybody gets
