@@ -124,6 +124,7 @@ int main(int argc, char** argv) {
     cfg.preferred_classes = {StorageClass::RAM_GPU};
     cfg.preferred_node = args.get("node", "");
     if (args.get("checksum") == "crc32c") cfg.checksum = ChecksumAlgo::CRC32C;
+    if (args.get("checksum") == "xxh3") cfg.checksum = ChecksumAlgo::XXH3;
     if (args.get("checksum") == "none") cfg.checksum = ChecksumAlgo::NONE;
     std::vector<const void*> sp;
     std::vector<void*> dp;
@@ -273,6 +274,7 @@ int main(int argc, char** argv) {
   cfg.replication_factor = static_cast<size_t>(args.num("replicas", 1));
   cfg.max_workers_per_copy = static_cast<size_t>(args.num("max-workers", 1));
   if (args.get("checksum") == "crc32c") cfg.checksum = ChecksumAlgo::CRC32C;
+  if (args.get("checksum") == "xxh3") cfg.checksum = ChecksumAlgo::XXH3;
   if (args.get("checksum") == "none") cfg.checksum = ChecksumAlgo::NONE;
   std::vector<uint8_t> data(size);
   std::mt19937_64 rng(1);

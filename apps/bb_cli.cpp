@@ -79,6 +79,7 @@ int main(int argc, char** argv) {
   if (args.has("class"))
     if (auto sc = parse_storage_class(args.get("class"))) cfg.preferred_classes = {*sc};
   if (args.get("checksum") == "crc32c") cfg.checksum = ChecksumAlgo::CRC32C;
+  if (args.get("checksum") == "xxh3") cfg.checksum = ChecksumAlgo::XXH3;
 
   if (cmd == "put" && args.positional.size() >= 3) {
     std::ifstream f(args.positional[2], std::ios::binary);

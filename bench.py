@@ -3,7 +3,7 @@
 
 Metric (BASELINE.json): batched put/get GB/s (and p50 / p99 us) at 1/2/4/8 GPU-tier workers, synthetic random-byte
 objects, device-timed, max over ranks.  One *step* = one `batch_put_device` of B objects of S bytes (fused kernel:
-transfer + CRC32C digest, placements from the Keystone) followed by one `batch_get_device` of the same objects (fused
+transfer + XXH3 digest, placements from the Keystone) followed by one `batch_get_device` of the same objects (fused
 kernel: transfer + digest verify), then a `batch_remove` so that the slab is recycled.  `value` = payload bytes moved
 per second by the whole job (put bytes + get bytes, all ranks).
 
@@ -61,8 +61,9 @@ def main() -> int:
     ap.add_argument("--config", default="headline", choices=["headline", "sweep", "repl3", "spill", "fanout"])
     ap.add_argument("--objects", type=int, default=64, help="objects per batch per rank")
     ap.add_argument("--object-mib", type=float, default=64.0)
-    ap.add_argument("--algo", default="crc32c", choices=["crc32c", "bbh64", "none"],
-                    help="digest fused into the transfer (crc32c = the standard Castagnoli CRC, the default)")
+    ap.add_argument("--algo", default="xxh3", choices=["xxh3", "crc32c", "bbh64", "none"],
+                    help="digest fused into the transfer: xxh3 (default) = the standard XXH3-64 of every 16 KiB tile, combined order-independently; "
+                         "crc32c = standard Castagnoli CRC of the object; bbh64 = the tensor-core hash")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--sync", choices=["none", "step", "phase"], default="phase",
@@ -94,7 +95,7 @@ def run_headline(args, world: int) -> int:
     nobj = args.objects
     osz = int(args.object_mib * (1 << 20))
     step_bytes = nobj * osz
-    ALGOS = {"bbh64": _bb.ChecksumAlgo.BBH64, "crc32c": _bb.ChecksumAlgo.CRC32C, "none": _bb.ChecksumAlgo.NONE}
+    ALGOS = {"xxh3": _bb.ChecksumAlgo.XXH3, "bbh64": _bb.ChecksumAlgo.BBH64, "crc32c": _bb.ChecksumAlgo.CRC32C, "none": _bb.ChecksumAlgo.NONE}
     algo = ALGOS[args.algo]
 
     cl = GpuRankCluster(slab_bytes=3 * step_bytes + (64 << 20))
@@ -173,7 +174,7 @@ def run_headline(args, world: int) -> int:
 
     # kernel-only view of one put and one get per digest (explains the headline; the standard digest is the headline)
     variants = {}
-    for name in ("crc32c", "bbh64", "none"):
+    for name in ("xxh3", "crc32c", "bbh64", "none"):
         keys = [f"r{rank}/k-{name}/o{j}" for j in range(nobj)]
         if args.sync != "none":
             rendezvous()
@@ -397,7 +398,7 @@ def run_headline(args, world: int) -> int:
                             "this fabric whatever the kernel (profiles/r2_nvlink/), copy engines reach ~775 GB/s with larger packets"}
         line = {
             "metric": "batched put+get payload throughput (GB/s), %g MiB random-byte objects, GPU tier, %s fused" % (
-                args.object_mib, {"crc32c": "CRC32C digest", "bbh64": "BBH64 digest", "none": "no digest"}[args.algo]),
+                args.object_mib, {"xxh3": "XXH3-64 (per 16 KiB tile) digest", "crc32c": "CRC32C digest", "bbh64": "BBH64 digest", "none": "no digest"}[args.algo]),
             "value": round(value, 2),
             "unit": "GB/s",
             "n_gpus": world,
@@ -465,7 +466,7 @@ def run_config(args, world: int) -> int:
         cl = GpuRankCluster(slab_bytes=6 << 30, cluster_id="sweep")
         target = f"gpu{(cl.rank + 1) % cl.world}"
         sizes = [256, 4096, 65536, 1 << 20, 16 << 20] if args.quick else [256, 1024, 4096, 16384, 65536, 262144, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20]
-        algo = {"bbh64": _bb.ChecksumAlgo.BBH64, "crc32c": _bb.ChecksumAlgo.CRC32C, "none": _bb.ChecksumAlgo.NONE}[args.algo]
+        algo = {"xxh3": _bb.ChecksumAlgo.XXH3, "bbh64": _bb.ChecksumAlgo.BBH64, "crc32c": _bb.ChecksumAlgo.CRC32C, "none": _bb.ChecksumAlgo.NONE}[args.algo]
         thr = throughput_sweep(cl, sizes, target, algo=algo)
         lat = latency_sweep(cl, sizes, target, iters=100 if args.quick else 300, algo=algo)
         rows = []

@@ -31,7 +31,7 @@ def main():
     eng = _bb.XferEngine(cl.local_rank, 64, 2)
     src = torch.randint(0, 256, (1 << 16,), dtype=torch.uint8, device=dev)
     dst = torch.zeros_like(src)
-    for algo_name in ("BBH64", "CRC32C"):
+    for algo_name in ("XXH3", "BBH64", "CRC32C"):
         algo = getattr(_bb.ChecksumAlgo, algo_name)
         for small, flag in ((True, True), (True, False), (False, False)):
             eng.set_small_path(small)
@@ -49,7 +49,7 @@ def main():
     target = f"gpu{(cl.rank + 1) % cl.world}"
     for small in (True, False):
         cl.fabric.set_small_path(small)
-        out["client"]["small_path_on" if small else "small_path_off"] = latency_sweep(cl, sizes, target, iters=300, algo=_bb.ChecksumAlgo.CRC32C)
+        out["client"]["small_path_on" if small else "small_path_off"] = latency_sweep(cl, sizes, target, iters=300, algo=_bb.ChecksumAlgo.XXH3)
     cl.stop()
     if cl.rank == 0:
         print(json.dumps(out))

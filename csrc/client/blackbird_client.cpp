@@ -183,8 +183,8 @@ class RangeHasher {
       }
       const uint64_t n = std::min(kStep, v - done);
       if (algo_ == ChecksumAlgo::CRC32C) crc_ = crc32c(base_ + begin_ + done, n, crc_);
-      else if (algo_ == ChecksumAlgo::BBH64)
-        bbh_ += bbh64_partial(base_, shard_len_, (begin_ + done) / tchash::kTileBytes, (n + tchash::kTileBytes - 1) / tchash::kTileBytes);
+      else if (is_tile_sum(algo_))
+        bbh_ += tile_sum_partial(algo_, base_, shard_len_, (begin_ + done) / tchash::kTileBytes, (n + tchash::kTileBytes - 1) / tchash::kTileBytes);
       done += n;
     }
   }
@@ -263,8 +263,8 @@ uint64_t shm_copy(uint8_t* dst, const uint8_t* src, const uint8_t* hash_base, ui
       const uint64_t m = std::min(kStep, begin + n - o);
       std::memcpy(dst + o, src + o, m);
       if (algo == ChecksumAlgo::CRC32C) part.crc = crc32c(hash_base + o, m, part.crc);
-      else if (algo == ChecksumAlgo::BBH64)
-        part.bbh += bbh64_partial(hash_base, len, o / tchash::kTileBytes, (m + tchash::kTileBytes - 1) / tchash::kTileBytes);
+      else if (is_tile_sum(algo))
+        part.bbh += tile_sum_partial(algo, hash_base, len, o / tchash::kTileBytes, (m + tchash::kTileBytes - 1) / tchash::kTileBytes);
     }
     return ErrorCode::OK;
   });
@@ -278,10 +278,10 @@ uint64_t shm_copy(uint8_t* dst, const uint8_t* src, const uint8_t* hash_base, ui
     }
     return crc;
   }
-  if (algo == ChecksumAlgo::BBH64) {
+  if (is_tile_sum(algo)) {
     uint64_t sum = 0;
     for (const ShmPart& p : parts) sum += p.bbh;
-    return bbh64_finalize(sum, len);
+    return tile_sum_finalize(sum, len);
   }
   return 0;
 }
@@ -348,10 +348,10 @@ ErrorCode BlackbirdClient::write_shard(const ShardPlacement& s, const uint8_t* s
         first = false;
       }
       *digest = crc;
-    } else if (algo == ChecksumAlgo::BBH64) {
+    } else if (is_tile_sum(algo)) {
       uint64_t sum = 0;
       for (const Part& p : parts) sum += p.bbh;
-      *digest = bbh64_finalize(sum, s.length);
+      *digest = tile_sum_finalize(sum, s.length);
     } else {
       *digest = 0;
     }

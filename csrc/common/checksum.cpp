@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common/tchash_def.h"
+#include "common/xxh3.h"
 
 #if defined(__x86_64__)
 #include <cpuid.h>
@@ -134,6 +135,7 @@ std::string_view to_string(ChecksumAlgo a) noexcept {
     case ChecksumAlgo::NONE: return "none";
     case ChecksumAlgo::CRC32C: return "crc32c";
     case ChecksumAlgo::BBH64: return "bbh64";
+    case ChecksumAlgo::XXH3: return "xxh3";
   }
   return "unknown";
 }
@@ -407,9 +409,51 @@ uint64_t bbh64_reference(const void* data, size_t len) noexcept {
   return tchash::finalize(tiles_sum(tile_sum_scalar, static_cast<const uint8_t*>(data), len, 0, (len + kTileBytes - 1) / kTileBytes), len);
 }
 
+// ================================================================ XXH3 (tiled)
+namespace {
+uint64_t xxh_tiles_sum(const uint8_t* p, size_t len, uint64_t first_tile, uint64_t ntiles, uint64_t index_base) noexcept {
+  const uint64_t total = (len + kTileBytes - 1) / kTileBytes;
+  uint64_t sum = 0;
+  for (uint64_t t = first_tile; t < first_tile + ntiles && t < total; ++t) {
+    const uint64_t base = t * kTileBytes;
+    uint64_t h;
+    if (len - base >= kTileBytes) {
+      h = xxh3::tile_hash(p + base);
+    } else {  // short last tile: zero padded
+      alignas(64) uint8_t pad[kTileBytes];
+      std::memcpy(pad, p + base, len - base);
+      std::memset(pad + (len - base), 0, kTileBytes - (len - base));
+      h = xxh3::tile_hash(pad);
+    }
+    sum += tchash::mix64(h + (index_base + t + 1ull) * tchash::kGold);
+  }
+  return sum;
+}
+}  // namespace
+
+uint64_t xxh3_tile(const void* tile16k) noexcept { return xxh3::tile_hash(static_cast<const uint8_t*>(tile16k)); }
+uint64_t xxh3t64_partial(const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept {
+  return xxh_tiles_sum(static_cast<const uint8_t*>(data), len, first_tile, ntiles, 0);
+}
+uint64_t xxh3t64_chunk(const void* data, size_t len, uint64_t tile_base) noexcept {
+  return xxh_tiles_sum(static_cast<const uint8_t*>(data), len, 0, (len + kTileBytes - 1) / kTileBytes, tile_base);
+}
+uint64_t xxh3t64(const void* data, size_t len) noexcept {
+  return tchash::finalize(xxh3t64_partial(data, len, 0, (len + kTileBytes - 1) / kTileBytes), len);
+}
+
+uint64_t tile_sum_partial(ChecksumAlgo a, const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept {
+  return a == ChecksumAlgo::XXH3 ? xxh3t64_partial(data, len, first_tile, ntiles) : bbh64_partial(data, len, first_tile, ntiles);
+}
+uint64_t tile_sum_chunk(ChecksumAlgo a, const void* data, size_t len, uint64_t tile_base) noexcept {
+  return a == ChecksumAlgo::XXH3 ? xxh3t64_chunk(data, len, tile_base) : bbh64_chunk(data, len, tile_base);
+}
+uint64_t tile_sum_finalize(uint64_t tile_sum, size_t len) noexcept { return tchash::finalize(tile_sum, len); }
+
 uint64_t checksum(ChecksumAlgo algo, const void* data, size_t len) noexcept {
   switch (algo) {
     case ChecksumAlgo::NONE: return 0;
+    case ChecksumAlgo::XXH3: return xxh3t64(data, len);
     case ChecksumAlgo::CRC32C: return crc32c(data, len);
     case ChecksumAlgo::BBH64: return bbh64(data, len);
   }

@@ -9,7 +9,8 @@
 
 namespace bb {
 
-enum class ChecksumAlgo : uint32_t { NONE = 0, CRC32C = 1, BBH64 = 2 };
+// XXH3 = standard XXH3-64 of every 16 KiB tile, combined order-independently (common/xxh3.h).
+enum class ChecksumAlgo : uint32_t { NONE = 0, CRC32C = 1, BBH64 = 2, XXH3 = 3 };
 std::string_view to_string(ChecksumAlgo a) noexcept;
 
 // Standard CRC32C: init 0xFFFFFFFF, reflected poly 0x82F63B78, final xor.  `crc` chains calls.
@@ -47,6 +48,19 @@ uint64_t bbh64_finalize(uint64_t tile_sum, size_t len) noexcept;
 const char* bbh64_impl_name() noexcept;  // "avx512-vnni" | "avx2" | "scalar"
 // Digest through a named implementation (tests); *supported = false when this CPU cannot run it.
 uint64_t bbh64_using(std::string_view impl, const void* data, size_t len, bool* supported) noexcept;
+
+// XXH3 (common/xxh3.h): digest of a whole buffer, and the streaming pieces (same contract as bbh64_partial / _chunk).
+uint64_t xxh3t64(const void* data, size_t len) noexcept;
+uint64_t xxh3_tile(const void* tile16k) noexcept;  // the standard XXH3_64bits() of exactly 16384 bytes
+uint64_t xxh3t64_partial(const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept;
+uint64_t xxh3t64_chunk(const void* data, size_t len, uint64_t tile_base) noexcept;
+
+// The two tile-sum digests (BBH64, XXH3) share their algebra: digest = finalize(sum of per-tile terms, len).  Code that
+// hashes in pieces (parallel streams, bounded chunks, GPU slices) goes through these.
+constexpr bool is_tile_sum(ChecksumAlgo a) noexcept { return a == ChecksumAlgo::BBH64 || a == ChecksumAlgo::XXH3; }
+uint64_t tile_sum_partial(ChecksumAlgo a, const void* data, size_t len, uint64_t first_tile, uint64_t ntiles) noexcept;
+uint64_t tile_sum_chunk(ChecksumAlgo a, const void* data, size_t len, uint64_t tile_base) noexcept;
+uint64_t tile_sum_finalize(uint64_t tile_sum, size_t len) noexcept;  // the same for both
 
 uint64_t checksum(ChecksumAlgo algo, const void* data, size_t len) noexcept;
 

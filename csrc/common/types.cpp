@@ -99,7 +99,7 @@ WorkerConfig worker_config_from_json(const Json& j) {
   if (j.contains("min_shard_size")) c.min_shard_size = j.at("min_shard_size").as_uint();
   if (j.contains("checksum")) {
     const std::string s = j.at("checksum").as_string();
-    c.checksum = s == "crc32c" ? ChecksumAlgo::CRC32C : s == "none" ? ChecksumAlgo::NONE : ChecksumAlgo::BBH64;
+    c.checksum = s == "crc32c" ? ChecksumAlgo::CRC32C : s == "none" ? ChecksumAlgo::NONE : (s == "xxh3" || s == "xxhash") ? ChecksumAlgo::XXH3 : ChecksumAlgo::BBH64;
   }
   if (j.contains("pack_fp8")) c.pack_fp8 = j.at("pack_fp8").as_bool();
   if (j.contains("symmetric_replicas")) c.symmetric_replicas = j.at("symmetric_replicas").as_bool();

@@ -753,7 +753,7 @@ ErrorCode GpuFabric::get_shards(const std::vector<client::DeviceShardOp>& ops, c
                                 void* stream, std::vector<uint32_t>* status) {
   if (status) status->assign(ops.size(), 0);
   // one launch per checksum algorithm present in the batch (normally exactly one)
-  for (ChecksumAlgo algo : {ChecksumAlgo::BBH64, ChecksumAlgo::CRC32C, ChecksumAlgo::NONE}) {
+  for (ChecksumAlgo algo : {ChecksumAlgo::XXH3, ChecksumAlgo::BBH64, ChecksumAlgo::CRC32C, ChecksumAlgo::NONE}) {
     std::vector<XferItem> items;
     std::vector<size_t> idx;
     for (size_t k = 0; k < ops.size(); ++k) {

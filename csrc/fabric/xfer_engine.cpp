@@ -216,7 +216,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
         BB_CUDA(cudaMemsetAsync(s->d_trace, 0, need, st));
         l.trace_d = s->d_trace;
       }
-      l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : algo == ChecksumAlgo::CRC32C ? ALGO_CRC32C : ALGO_NONE;
+      l.algo = algo == ChecksumAlgo::BBH64 ? ALGO_BBH64 : algo == ChecksumAlgo::CRC32C ? ALGO_CRC32C : algo == ChecksumAlgo::XXH3 ? ALGO_XXH3 : ALGO_NONE;
       l.max_ctas = max_ctas_;
       l.stream = stream;
       l.small_path = all_small;
@@ -255,7 +255,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
   if (ec != ErrorCode::OK) return ec;
   s->ticket = next_ticket_++;
   s->hashed = algo != ChecksumAlgo::NONE;
-  s->empty_digest = algo == ChecksumAlgo::BBH64 ? tchash::finalize(0, 0) : 0;
+  s->empty_digest = is_tile_sum(algo) ? tchash::finalize(0, 0) : 0;
   return s->ticket;
 }
 

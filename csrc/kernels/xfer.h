@@ -16,7 +16,7 @@ constexpr uint32_t kMaxDst = 3;          // replicas written by a single tile pa
 enum XferFlags : uint32_t {
   XFER_VERIFY = 1u << 0,    // compare digest with `expect`; status[i] = 1 on mismatch
   XFER_MULTIMEM = 1u << 1,  // dst[0] is an NVLS multicast address: store with multimem.st
-  // BBH64 only: digest_out receives the *unfinalised* 64-bit tile sum and `reserved` is added to every tile
+  // BBH64 / XXH3 (the tile-sum digests): digest_out receives the *unfinalised* 64-bit tile sum and `reserved` is added to every tile
   // index, so a byte range can be hashed as a slice of a larger object (its sums add up with the slices
   // hashed elsewhere; the host finalises).  With ndst == 0 the descriptor is hash-only (nothing is stored).
   XFER_RAW_SUM = 1u << 2,
@@ -40,7 +40,7 @@ constexpr uint32_t kSmallPending = 0xFFFFFFFFu;  // value of a status slot whose
 constexpr uint32_t kInlineDescs = 8;       // descriptors that fit in the kernel parameter block
 constexpr uint32_t kDirectResults = 64;    // batches up to this size write digests straight to pinned host memory
 
-enum XferAlgo : int { ALGO_NONE = 0, ALGO_CRC32C = 1, ALGO_BBH64 = 2 };
+enum XferAlgo : int { ALGO_NONE = 0, ALGO_CRC32C = 1, ALGO_BBH64 = 2, ALGO_XXH3 = 3 };
 
 struct XferLaunch {
   const XferDesc* descs = nullptr;       // device pointer, ndesc entries

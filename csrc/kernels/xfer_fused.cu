@@ -37,6 +37,7 @@
 
 #include "common/checksum.h"
 #include "common/tchash_def.h"
+#include "common/xxh3.h"
 #include "kernels/ptx.cuh"
 #include "kernels/xfer.h"
 
@@ -54,6 +55,7 @@ static_assert(kTileBytes == tchash::kTileBytes);
 
 __constant__ uint64_t c_col_mul[tchash::kN];
 __constant__ uint32_t c_xpow_tiles[32];  // x^(8 * 16384 * 2^j) mod P  (CRC32C cross-CTA combine)
+__constant__ uint8_t c_xxh_secret[xxh3::kSecretSize];  // XXH3 default secret
 
 // CRC shift tables: index -> byte distance
 enum CrcTab : int { T128 = 0, T4, T8, T16, T32, T64, T4096, T16384, TCHAIN, TJUMP, kNumCrcTabs };
@@ -100,6 +102,11 @@ struct __align__(1024) SmemT {
   // 2 KiB of slack: the kernel rounds the table's shared address up to 2048 so that the value index (bits 7-10)
   // can be OR-ed into the lane's base address with a single LOP3.
   uint32_t crc_nib[ALGO == ALGO_CRC32C ? 8 * 16 * 32 + 512 : 1];
+  // XXH3: per-(block, lane) stripe sums of every tile in flight, written by the epilogue warps and consumed by the
+  // finalizer's scramble chain; and the secret words in the order the epilogue indexes them
+  // ([0..22] = accumulate keys (word s + lane), [24..31] = keys of the last stripe, [32..39] = scramble keys, [40..47] = merge keys).
+  uint64_t xs[ALGO == ALGO_XXH3 ? kStages : 1][ALGO == ALGO_XXH3 ? 16 : 1][8];
+  uint64_t xkey[ALGO == ALGO_XXH3 ? 48 : 1];
 };
 
 struct Params {
@@ -122,6 +129,17 @@ struct Params {
   uint32_t inl_tile_start[kInlineDescs + 1];
   XferDesc inl_descs[kInlineDescs];
 };
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 #pragma unroll
@@ -184,7 +202,9 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
   const uint32_t lane = threadIdx.x & 31u;
   constexpr bool kBbh = (ALGO == ALGO_BBH64);
   constexpr bool kCrc = (ALGO == ALGO_CRC32C);
-  constexpr bool kHash = kBbh || kCrc;
+  constexpr bool kXxh = (ALGO == ALGO_XXH3);
+  constexpr bool kSum = kBbh || kXxh;  // digest = finalize(commutative sum of per-tile terms)
+  constexpr bool kHash = kBbh || kCrc || kXxh;
 
   // contiguous run of tiles for this CTA
   const uint32_t tpc = (p.total_tiles + gridDim.x - 1) / gridDim.x;
@@ -218,6 +238,16 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
     for (uint32_t i = threadIdx.x; i < 8 * 16 * 32; i += kThreads) {  // [nibble j][value v][lane]
       const uint32_t j = i >> 9, v = (i >> 5) & 15u;
       nibt[i] = crc_shift(s.crc_t[T128], v << (4 * j));
+    }
+  }
+  if constexpr (kXxh) {
+    if (threadIdx.x < 48) {
+      const uint32_t i = threadIdx.x;
+      uint64_t v = 0;
+      const uint32_t off = i < 24 ? 8u * min(i, 22u) : i < 32 ? xxh3::kSecretSize - xxh3::kStripe - xxh3::kLastAccStart + 8u * (i - 24)
+                           : i < 40 ? xxh3::kSecretSize - xxh3::kStripe + 8u * (i - 32) : xxh3::kMergeStart + 8u * (i - 40);
+      for (int b = 7; b >= 0; --b) v = (v << 8) | c_xxh_secret[off + b];
+      s.xkey[i] = v;
     }
   }
   __syncthreads();
@@ -379,20 +409,15 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
     if constexpr (kHash) {
       uint32_t cur_d = 0xFFFFFFFFu, cnt = 0;
       uint64_t acc = 0;
-      for (uint32_t it = 0; it < my_tiles; ++it) {
-        const uint32_t stage = it % kStages;
-        const uint32_t par = (it / kStages) & 1u;
-        mbar_wait(&s.epi_done[stage], par);
-        const StageMeta m = s.meta[stage];
-        const uint64_t p0 = s.part[stage][0], p1 = s.part[stage][1], p2 = s.part[stage][2], p3 = s.part[stage][3];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[stage]);
+      // Folds one finished tile (its StageMeta `m` and the epilogue's partials) into the running per-object state and,
+      // when this CTA's share of the object is complete, publishes / combines it.
+      auto account = [&](uint32_t it, const StageMeta& m, uint64_t p0, uint64_t p1, uint64_t p2, uint64_t p3) {
         if (m.desc != cur_d) {
           cur_d = m.desc;
           acc = 0;
           cnt = 0;
         }
-        if constexpr (kBbh) acc += p0 + p1 + p2 + p3;
+        if constexpr (kSum) acc += p0 + p1 + p2 + p3;
         ++cnt;
         const bool obj_end = (m.tile_in_obj + 1 == m.obj_ntiles);
         if (obj_end || it + 1 == my_tiles) {
@@ -408,9 +433,9 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
           // ---- this CTA's contribution to object cur_d is complete
           uint64_t digest = 0;
           bool have = false;
-          const bool raw = kBbh && ((m.ndst_flags >> 8) & XFER_RAW_SUM);
+          const bool raw = kSum && ((m.ndst_flags >> 8) & XFER_RAW_SUM);
           if (cnt == m.obj_ntiles) {  // object lives entirely in this CTA: no atomics
-            if constexpr (kBbh) digest = raw ? acc : tchash::finalize(acc, m.nbytes);
+            if constexpr (kSum) digest = raw ? acc : tchash::finalize(acc, m.nbytes);
             else digest = gf2_mulmod_dev(static_cast<uint32_t>(acc), m.crc_unpad) ^ static_cast<uint32_t>(m.expect >> 32) ^ 0xFFFFFFFFu;
             have = true;
           } else {
@@ -421,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
             }
             uint32_t prev = 0;
             if (lane == 0) {
-              if constexpr (kBbh) atomicAdd(&p.sum_ws[cur_d], static_cast<unsigned long long>(contrib));
+              if constexpr (kSum) atomicAdd(&p.sum_ws[cur_d], static_cast<unsigned long long>(contrib));
               else atomicXor(&p.sum_ws[cur_d], static_cast<unsigned long long>(contrib));
               __threadfence();
               prev = atomicAdd(&p.done_ws[cur_d], cnt);
@@ -432,18 +457,61 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
                 __threadfence();
                 const uint64_t sum = atomicExch(&p.sum_ws[cur_d], 0ull);
                 p.done_ws[cur_d] = 0;
-                if constexpr (kBbh) digest = raw ? sum : tchash::finalize(sum, m.nbytes);
+                if constexpr (kSum) digest = raw ? sum : tchash::finalize(sum, m.nbytes);
                 else digest = gf2_mulmod_dev(static_cast<uint32_t>(sum), m.crc_unpad) ^ static_cast<uint32_t>(m.expect >> 32) ^ 0xFFFFFFFFu;
               }
               have = true;
             }
           }
           if (have && lane == 0) {
-            const uint64_t want = kBbh ? m.expect : (m.expect & 0xFFFFFFFFull);
+            const uint64_t want = kSum ? m.expect : (m.expect & 0xFFFFFFFFull);
             p.digest_out[cur_d] = digest;
             p.status_out[cur_d] = (((m.ndst_flags >> 8) & XFER_VERIFY) && digest != want) ? 1u : 0u;
           }
           cur_d = 0xFFFFFFFFu;
+        }
+      };
+      if constexpr (kXxh) {
+        // XXH3: the epilogue warps left the 16 x 8 (block, lane) stripe sums of each tile in s.xs; what remains is the
+        // serial part of the algorithm -- 15 scrambles per accumulator lane, then the merge.  The chain is latency bound
+        // (~40 dependent cycles per step), so four tiles are chained at once, one per group of 8 lanes.
+        const uint32_t g = lane >> 3, l8 = lane & 7u;
+        const uint64_t skey = s.xkey[32 + l8], mkey = s.xkey[40 + l8];
+        for (uint32_t it0 = 0; it0 < my_tiles; it0 += 4) {
+          const uint32_t n = min(4u, my_tiles - it0);
+          for (uint32_t j = 0; j < n; ++j) mbar_wait(&s.epi_done[(it0 + j) % kStages], ((it0 + j) / kStages) & 1u);
+          const uint32_t st = (it0 + min(g, n - 1u)) % kStages;  // idle groups redo the last tile (their result is ignored)
+          uint64_t a = xxh3::init_acc(l8);
+#pragma unroll
+          for (int b = 0; b < 15; ++b) a = xxh3::scramble(a + s.xs[st][b][l8], skey);
+          a += s.xs[st][15][l8];
+          const uint64_t nb = shfl_u64(a, static_cast<int>((lane + 1u) & 31u));  // the odd lane's accumulator and key
+          const uint64_t nk = shfl_u64(mkey, static_cast<int>((lane + 1u) & 31u));
+          uint64_t mg = (l8 & 1u) ? 0ull : xxh3::mul128_fold64(a ^ mkey, nb ^ nk);
+          mg += shfl_xor_u64(mg, 2);
+          mg += shfl_xor_u64(mg, 4);
+          const uint64_t h = xxh3::avalanche(mg + static_cast<uint64_t>(kTileBytes) * xxh3::P64_1);  // XXH3_64bits(tile), in lanes l8 == 0
+          __syncwarp();
+          for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t stage = (it0 + j) % kStages;
+            const StageMeta m = s.meta[stage];
+            const uint64_t hj = shfl_u64(h, static_cast<int>(j * 8u));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty[stage]);
+            const uint32_t ti = m.tile_in_obj + (((m.ndst_flags >> 8) & XFER_RAW_SUM) ? m.crc_unpad : 0u);
+            account(it0 + j, m, tchash::mix64(hj + (static_cast<uint64_t>(ti) + 1ull) * tchash::kGold), 0, 0, 0);
+          }
+        }
+      } else {
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+          const uint32_t stage = it % kStages;
+          const uint32_t par = (it / kStages) & 1u;
+          mbar_wait(&s.epi_done[stage], par);
+          const StageMeta m = s.meta[stage];
+          const uint64_t p0 = s.part[stage][0], p1 = s.part[stage][1], p2 = s.part[stage][2], p3 = s.part[stage][3];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.empty[stage]);
+          account(it, m, p0, p1, p2, p3);
         }
       }
     }
@@ -477,6 +545,39 @@ __global__ void __launch_bounds__(kThreads, 1) bb_xfer_kernel(const __grid_const
 #pragma unroll
           for (int n = 0; n < 16; ++n) o[n] = r[n];
         }
+      }
+    } else if constexpr (kXxh) {
+      // XXH3 stripe sums.  A block's 16 stripe contributions do not depend on the accumulator, so all 16 x 8 (block,
+      // lane) sums of the tile are computed at once: quarter-warp = one 1 KiB block, thread = (lane pair, half of the
+      // stripes), one LDS.128 per stripe = the two 8-byte lanes of the pair (so the "swap" addend stays in the thread).
+      // The odd half visits its stripes shifted by one: the 8 threads of a quarter then cover all 32 banks every time.
+      const uint32_t e = threadIdx.x - 128u;
+      const uint32_t blk = (e >> 5) * 4u + ((e & 31u) >> 3);
+      const uint32_t pair = (e >> 1) & 3u, half = e & 1u;
+      for (uint32_t it = 0; it < my_tiles; ++it) {
+        const uint32_t stage = it % kStages;
+        const uint32_t par = (it / kStages) & 1u;
+        mbar_wait(&s.full[stage], par);
+        const uint8_t* base = &s.tile[stage][blk * 1024u + pair * 16u];
+        uint64_t s0 = 0, s1 = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint32_t stp = half * 8u + ((k + half) & 7u);
+          const uint4 d = *reinterpret_cast<const uint4*>(base + stp * 64u);
+          const uint64_t dv0 = (static_cast<uint64_t>(d.y) << 32) | d.x, dv1 = (static_cast<uint64_t>(d.w) << 32) | d.z;
+          const uint32_t ki = (blk == 15u && stp == 15u) ? 24u + 2u * pair : stp + 2u * pair;  // the tile's very last stripe has its own key
+          const uint64_t q0 = dv0 ^ s.xkey[ki], q1 = dv1 ^ s.xkey[ki + 1u];
+          s0 += static_cast<uint64_t>(static_cast<uint32_t>(q0)) * (q0 >> 32) + dv1;
+          s1 += static_cast<uint64_t>(static_cast<uint32_t>(q1)) * (q1 >> 32) + dv0;
+        }
+        s0 += shfl_xor_u64(s0, 1);
+        s1 += shfl_xor_u64(s1, 1);
+        if (half == 0u) {
+          s.xs[stage][blk][2u * pair] = s0;
+          s.xs[stage][blk][2u * pair + 1u] = s1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.epi_done[stage]);
       }
     } else if constexpr (kCrc) {
       // Quarter q of every tile, lane l: words l, l+32, ... (bank-conflict free); consecutive words of a lane are
@@ -545,7 +646,7 @@ struct DeviceState {
   bool consts = false;
   uint32_t* crc_tables = nullptr;
   int sm_count = 0;
-  bool attr[3] = {false, false, false};
+  bool attr[4] = {false, false, false, false};
 };
 DeviceState g_dev[16];
 std::mutex g_mu;
@@ -568,6 +669,7 @@ int xfer_smem_bytes(int algo) {
   switch (algo) {
     case ALGO_NONE: return static_cast<int>(sizeof(SmemT<ALGO_NONE>));
     case ALGO_CRC32C: return static_cast<int>(sizeof(SmemT<ALGO_CRC32C>));
+    case ALGO_XXH3: return static_cast<int>(sizeof(SmemT<ALGO_XXH3>));
     default: return static_cast<int>(sizeof(SmemT<ALGO_BBH64>));
   }
 }
@@ -637,6 +739,8 @@ int launch_xfer(const XferLaunch& l) {
       }
       e = cudaMemcpyToSymbol(c_xpow_tiles, xp, sizeof xp);
       if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaMemcpyToSymbol(c_xxh_secret, xxh3::kSecret, sizeof xxh3::kSecret);
+      if (e != cudaSuccess) return static_cast<int>(e);
       int n = 0;
       if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
       ds.sm_count = n;
@@ -684,6 +788,7 @@ int launch_xfer(const XferLaunch& l) {
     case ALGO_NONE: e = launch_t<ALGO_NONE>(ds, p, grid, st); break;
     case ALGO_CRC32C: e = launch_t<ALGO_CRC32C>(ds, p, grid, st); break;
     case ALGO_BBH64: e = launch_t<ALGO_BBH64>(ds, p, grid, st); break;
+    case ALGO_XXH3: e = launch_t<ALGO_XXH3>(ds, p, grid, st); break;
     default: return static_cast<int>(cudaErrorNotSupported);
   }
   return static_cast<int>(e);

@@ -21,6 +21,7 @@
 
 #include "common/checksum.h"
 #include "common/tchash_def.h"
+#include "common/xxh3.h"
 #include "kernels/ptx.cuh"
 #include "kernels/xfer.h"
 
@@ -31,6 +32,10 @@ using namespace bb::ptx;
 
 constexpr int kWarpsPerCta = 8;
 
+// XXH3: [0..23] accumulate keys (word = stripe + lane), [24..31] scramble keys, [32..39] merge keys, [40..47] the stripe sum of
+// an all-zero block per lane (blocks 4..14 of a <= 4 KiB object), [48..55] the same for the tile's last block (its last
+// stripe has its own key)
+__constant__ uint64_t c_xxh[56];
 __constant__ uint32_t c_lane_mul[32];  // x^(8 * (128 * (31 - l) + 12288)) mod P: lane l's segment -> position in a 16 KiB tile
 
 struct SmallParams {
@@ -68,6 +73,7 @@ template <int ALGO>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const __grid_constant__ SmallParams p) {
   __shared__ uint32_t s_w[ALGO == ALGO_BBH64 ? 16 * 32 : 1];       // Wp[n][w]: W[4w + b][n] in byte b
   __shared__ uint32_t s_t4[ALGO == ALGO_CRC32C ? 4 * 256 : 1];
+  __shared__ uint64_t s_xk[ALGO == ALGO_XXH3 ? 24 : 1];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   if constexpr (ALGO == ALGO_BBH64) {
     for (uint32_t i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
@@ -79,6 +85,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const 
   }
   if constexpr (ALGO == ALGO_CRC32C) {
     for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_t4[i] = __ldg(&p.crc_t4[i]);
+    __syncthreads();
+  }
+  if constexpr (ALGO == ALGO_XXH3) {
+    if (threadIdx.x < 24) s_xk[threadIdx.x] = c_xxh[threadIdx.x];
     __syncthreads();
   }
   const uint32_t d = blockIdx.x * kWarpsPerCta + warp;
@@ -197,6 +207,59 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += shfl_xor64(c, o);
     digest = tchash::finalize(c + p.zero_rows, nbytes);
+  } else if constexpr (ALGO == ALGO_XXH3) {
+    // Standard XXH3-64 of the object zero padded to one 16 KiB tile.  Lane l holds stripes 2 (l & 7) and 2 (l & 7) + 1 of
+    // block l >> 3 (64 B each = the 8 accumulator lanes): it forms the 8 per-lane products of both stripes, the 8 lanes
+    // of a block group are summed by a reduce-scatter (7 exchanges), after which lane l owns stripe-sum [block l >> 3]
+    // [acc lane l & 7] -- exactly what the scramble chain of acc lane (l & 7) wants to pull in, block after block.
+    uint64_t S[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[i] = 0;
+    const uint32_t st0 = 2u * (lane & 7u);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // v[4h + q] = acc lanes 2q, 2q + 1 of stripe st0 + h
+        const uint4 d = v[4 * h + q];
+        const uint64_t dv0 = (static_cast<uint64_t>(d.y) << 32) | d.x, dv1 = (static_cast<uint64_t>(d.w) << 32) | d.z;
+        const uint64_t q0 = dv0 ^ s_xk[st0 + h + 2 * q], q1 = dv1 ^ s_xk[st0 + h + 2 * q + 1];
+        S[2 * q] += static_cast<uint64_t>(static_cast<uint32_t>(q0)) * (q0 >> 32) + dv1;
+        S[2 * q + 1] += static_cast<uint64_t>(static_cast<uint32_t>(q1)) * (q1 >> 32) + dv0;
+      }
+    }
+    uint64_t m4[4], m2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint64_t keep = (lane & 4u) ? S[i + 4] : S[i], send = (lane & 4u) ? S[i] : S[i + 4];
+      m4[i] = keep + shfl_xor64(send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint64_t keep = (lane & 2u) ? m4[i + 2] : m4[i], send = (lane & 2u) ? m4[i] : m4[i + 2];
+      m2[i] = keep + shfl_xor64(send, 2);
+    }
+    const uint64_t tot = ((lane & 1u) ? m2[1] : m2[0]) + shfl_xor64((lane & 1u) ? m2[0] : m2[1], 1);  // [block lane >> 3][acc lane & 7]
+    const uint32_t l8 = lane & 7u;
+    uint64_t a = xxh3::init_acc(l8);
+    const uint64_t skey = c_xxh[24 + l8], zero_blk = c_xxh[40 + l8];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tot), static_cast<int>(l8 + 8u * b));
+      const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tot >> 32), static_cast<int>(l8 + 8u * b));
+      a = xxh3::scramble(a + ((static_cast<uint64_t>(hi) << 32) | lo), skey);
+    }
+#pragma unroll
+    for (int b = 4; b < 15; ++b) a = xxh3::scramble(a + zero_blk, skey);
+    a += c_xxh[48 + l8];
+    const uint64_t mkey = c_xxh[32 + l8];
+    const uint32_t nlo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(a), static_cast<int>((lane + 1u) & 31u));
+    const uint32_t nhi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(a >> 32), static_cast<int>((lane + 1u) & 31u));
+    const uint64_t nb = (static_cast<uint64_t>(nhi) << 32) | nlo;
+    uint64_t mg = (l8 & 1u) ? 0ull : xxh3::mul128_fold64(a ^ mkey, nb ^ c_xxh[32 + ((l8 + 1u) & 7u)]);
+    mg += shfl_xor64(mg, 2);
+    mg += shfl_xor64(mg, 4);
+    const uint64_t h = xxh3::avalanche(mg + static_cast<uint64_t>(kTileBytes) * xxh3::P64_1);
+    digest = tchash::finalize(tchash::mix64(h + tchash::kGold), nbytes);  // tile index 0
   } else {
     // CRC32C raw remainder of the lane's 128 bytes (x^32 factor included), word at a time through the x^32 shift table
     uint32_t s = 0;
@@ -260,6 +323,24 @@ int launch_xfer_small(const XferLaunch& l) {
       uint64_t z = 0;
       for (uint32_t m = kSmallBytes / 128; m < tchash::kRows; ++m) z += tchash::row_contrib(0, m);
       st.zero_rows = z;
+      uint64_t xk[56] = {};
+      for (uint32_t i = 0; i < 23; ++i) xk[i] = xxh3::secret64(8 * i);
+      for (uint32_t i = 0; i < 8; ++i) {
+        xk[24 + i] = xxh3::scramble_key(i);
+        xk[32 + i] = xxh3::merge_key(i);
+        uint64_t zsum = 0, zlast = 0;
+        for (uint32_t sidx = 0; sidx < 16; ++sidx) {
+          const uint64_t k = xxh3::stripe_key(sidx, i);
+          zsum += static_cast<uint64_t>(static_cast<uint32_t>(k)) * (k >> 32);
+          if (sidx < 15) zlast += static_cast<uint64_t>(static_cast<uint32_t>(k)) * (k >> 32);
+        }
+        const uint64_t lk = xxh3::last_key(i);
+        zlast += static_cast<uint64_t>(static_cast<uint32_t>(lk)) * (lk >> 32);
+        xk[40 + i] = zsum;
+        xk[48 + i] = zlast;
+      }
+      e = cudaMemcpyToSymbol(c_xxh, xk, sizeof xk);
+      if (e != cudaSuccess) return static_cast<int>(e);
       st.consts = true;
     }
   }
@@ -283,6 +364,7 @@ int launch_xfer_small(const XferLaunch& l) {
     case ALGO_NONE: bb_xfer_small_kernel<ALGO_NONE><<<grid, threads, 0, s>>>(p); break;
     case ALGO_CRC32C: bb_xfer_small_kernel<ALGO_CRC32C><<<grid, threads, 0, s>>>(p); break;
     case ALGO_BBH64: bb_xfer_small_kernel<ALGO_BBH64><<<grid, threads, 0, s>>>(p); break;
+    case ALGO_XXH3: bb_xfer_small_kernel<ALGO_XXH3><<<grid, threads, 0, s>>>(p); break;
     default: return static_cast<int>(cudaErrorNotSupported);
   }
   return static_cast<int>(cudaGetLastError());

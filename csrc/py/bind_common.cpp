@@ -105,7 +105,8 @@ void bind_common(py::module_& m) {
   py::enum_<ChecksumAlgo>(m, "ChecksumAlgo")
       .value("NONE", ChecksumAlgo::NONE)
       .value("CRC32C", ChecksumAlgo::CRC32C)
-      .value("BBH64", ChecksumAlgo::BBH64);
+      .value("BBH64", ChecksumAlgo::BBH64)
+      .value("XXH3", ChecksumAlgo::XXH3);
 
   m.def("crc32c", [](py::buffer b, uint32_t crc) {
     py::buffer_info i = b.request();
@@ -127,6 +128,19 @@ void bind_common(py::module_& m) {
   m.def("bbh64", [](py::buffer b) {
     py::buffer_info i = b.request();
     return bbh64(i.ptr, static_cast<size_t>(i.size * i.itemsize));
+  });
+  m.def("xxh3t64", [](py::buffer b) {
+    py::buffer_info i = b.request();
+    return xxh3t64(i.ptr, static_cast<size_t>(i.size * i.itemsize));
+  }, "Tiled XXH3: the standard XXH3-64 of every 16 KiB tile (last one zero padded), combined order-independently.");
+  m.def("xxh3_tile", [](py::buffer b) {
+    py::buffer_info i = b.request();
+    if (i.size * i.itemsize != 16384) throw py::value_error("xxh3_tile wants exactly 16384 bytes");
+    return xxh3_tile(i.ptr);
+  }, "XXH3_64bits() of one 16 KiB tile (default secret, seed 0) -- equals xxhash.xxh3_64_intdigest(tile).");
+  m.def("xxh3t64_partial", [](py::buffer b, uint64_t first_tile, uint64_t ntiles) {
+    py::buffer_info i = b.request();
+    return xxh3t64_partial(i.ptr, static_cast<size_t>(i.size * i.itemsize), first_tile, ntiles);
   });
   m.def("bbh64_reference", [](py::buffer b) {
     py::buffer_info i = b.request();

@@ -475,8 +475,8 @@ bool range_ok(const StorageBackend& b, uint64_t off, uint64_t len) {
   const uint64_t cap = b.get_total_capacity();
   return off != ~0ull && len <= cap && off <= cap - len;
 }
-// Unfinalised BBH64 sum of a chunk that starts `pos` bytes into the hashed object (pos is tile aligned).
-uint64_t bbh64_chunk_sum(const uint8_t* data, uint64_t n, uint64_t pos) { return bbh64_chunk(data, n, pos / 16384); }
+// Unfinalised tile sum (BBH64 / XXH3) of a chunk that starts `pos` bytes into the hashed object (pos is tile aligned).
+uint64_t chunk_tile_sum(ChecksumAlgo algo, const uint8_t* data, uint64_t n, uint64_t pos) { return tile_sum_chunk(algo, data, n, pos / 16384); }
 }  // namespace
 
 void WorkerService::register_data_handlers() {
@@ -572,11 +572,11 @@ void WorkerService::register_data_handlers() {
       ec = b->read(o + pos, buf.data(), n);
       if (ec != ErrorCode::OK) break;
       if (algo == ChecksumAlgo::CRC32C) crc = crc32c(buf.data(), n, crc);
-      else if (algo == ChecksumAlgo::BBH64) tile_sum += bbh64_chunk_sum(buf.data(), n, pos);
+      else if (is_tile_sum(algo)) tile_sum += chunk_tile_sum(algo, buf.data(), n, pos);
     }
     w.ec(ec);
     if (ec == ErrorCode::OK)
-      w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64_finalize(tile_sum, len) : 0);
+      w.u64(algo == ChecksumAlgo::CRC32C ? crc : is_tile_sum(algo) ? tile_sum_finalize(tile_sum, len) : 0);
     return w.take();
   });
   // Intra-worker tier move (GPU slab -> DRAM -> NVMe ...): bytes stay inside this process.
@@ -623,12 +623,12 @@ void WorkerService::register_data_handlers() {
       ec = sb->read(s0 + pos, buf.data(), n);
       if (ec != ErrorCode::OK) break;
       if (algo == ChecksumAlgo::CRC32C) crc = crc32c(buf.data(), n, crc);
-      else if (algo == ChecksumAlgo::BBH64) tile_sum += bbh64_chunk_sum(buf.data(), n, pos);
+      else if (is_tile_sum(algo)) tile_sum += chunk_tile_sum(algo, buf.data(), n, pos);
       ec = db->write(d0 + pos, buf.data(), n);
     }
     if (ec == ErrorCode::OK) ec = db->flush();
     w.ec(ec);
-    if (ec == ErrorCode::OK) w.u64(algo == ChecksumAlgo::CRC32C ? crc : algo == ChecksumAlgo::BBH64 ? bbh64_finalize(tile_sum, len) : 0);
+    if (ec == ErrorCode::OK) w.u64(algo == ChecksumAlgo::CRC32C ? crc : is_tile_sum(algo) ? tile_sum_finalize(tile_sum, len) : 0);
     return w.take();
   });
   data_server_.register_method(D_PULL, [this](C, S q) {

@@ -658,3 +658,24 @@ def test_put_straddling_a_keystone_failover_is_restarted(bb):
             bb.fault_clear()
             rb.stop()
             b.stop()
+
+
+def test_xxh3_digest_on_the_host_path_put_get_and_corruption(bb):
+    """ChecksumAlgo.XXH3 through the TCP data path: parallel streams hash their tile ranges and the sums add up to the
+    digest the GPU kernels produce for the same bytes (bb.xxh3t64 is the shared model)."""
+    import os
+
+    from blackbird_b200.parallel import LocalCluster
+
+    with LocalCluster("xxh3-host", n_workers=2, pool_bytes=32 << 20) as c:
+        cl = c.client(io_parallelism=4)
+        wc = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1, ttl_ms=0, checksum=bb.ChecksumAlgo.XXH3)
+        blob = os.urandom((9 << 20) + 12345)
+        assert cl.put("x", blob, wc) == bb.ErrorCode.OK
+        copies = cl.get_workers("x")
+        assert all(cp.shards[0].checksum == bb.xxh3t64(blob) and cp.shards[0].checksum_algo == bb.ChecksumAlgo.XXH3 for cp in copies)
+        assert cl.get("x") == blob
+        sh = copies[0].shards[0]
+        w = next(w for i, w in enumerate(c.workers) if f"pool-{i}" == sh.pool_id)
+        w.backend(sh.pool_id).write(sh.location["remote_addr"] - w.backend(sh.pool_id).get_base_address() + 5000, b"\x00\x01\x02\x03")
+        assert cl.get("x") == blob  # digest mismatch on replica 0 -> served from replica 1

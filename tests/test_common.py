@@ -192,3 +192,41 @@ def test_sha256_and_hmac_match_hashlib(bb):
         for n in (0, 1, 55, 56, 64, 300):
             msg = os.urandom(n)
             assert bb.hmac_sha256(key, msg) == hmac.new(key, msg, hashlib.sha256).digest(), (klen, n)
+
+
+def test_xxh3_tiles_are_the_standard_xxh3_64_and_the_combine_matches_the_model(bb):
+    """ChecksumAlgo.XXH3 (csrc/common/xxh3.h): every 16 KiB tile is hashed with the unmodified XXH3-64 (checked against the
+    python-xxhash binding of the reference implementation), tiles are combined by the position-keyed commutative sum."""
+    import os
+
+    xxhash = pytest.importorskip("xxhash")
+    for _ in range(8):
+        t = os.urandom(16384)
+        assert bb.xxh3_tile(t) == xxhash.xxh3_64_intdigest(t)
+    assert bb.xxh3_tile(bytes(16384)) == xxhash.xxh3_64_intdigest(bytes(16384))
+    M = (1 << 64) - 1
+    GOLD, LENMUL = 0x9E3779B97F4A7C15, 0xD6E8FEB86659FD93
+
+    def mix64(x):
+        x ^= x >> 33
+        x = (x * 0xff51afd7ed558ccd) & M
+        x ^= x >> 33
+        x = (x * 0xc4ceb9fe1a85ec53) & M
+        return x ^ (x >> 33)
+
+    def model(b):
+        s = 0
+        for t in range((len(b) + 16383) // 16384):
+            tile = b[t * 16384:(t + 1) * 16384].ljust(16384, b"\0")
+            s = (s + mix64((xxhash.xxh3_64_intdigest(tile) + (t + 1) * GOLD) & M)) & M
+        return mix64(s ^ ((len(b) * LENMUL) & M))
+
+    for n in [0, 1, 100, 4096, 16383, 16384, 16385, 100000, (1 << 20) + 7]:
+        b = os.urandom(n)
+        assert bb.xxh3t64(b) == model(b), n
+    # slices add up (what parallel streams / chunked hashing / GPU RAW_SUM slices rely on)
+    b = os.urandom(5 * 16384 + 100)
+    parts = (bb.xxh3t64_partial(b, 0, 2) + bb.xxh3t64_partial(b, 2, 3) + bb.xxh3t64_partial(b, 5, 1)) & M
+    assert bb.bbh64_finalize(parts, len(b)) == bb.xxh3t64(b)
+    # position dependence and length binding
+    assert bb.xxh3t64(b[16384:] + b[:16384]) != bb.xxh3t64(b) and bb.xxh3t64(b + b"\0") != bb.xxh3t64(b)

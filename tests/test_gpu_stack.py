@@ -18,7 +18,7 @@ def _stream(torch):
     return torch.cuda.current_stream().cuda_stream
 
 
-@pytest.mark.parametrize("algo_name", ["BBH64", "CRC32C"])
+@pytest.mark.parametrize("algo_name", ["BBH64", "CRC32C", "XXH3"])
 @pytest.mark.parametrize("n", [16, 255 * 16, 16384, 16385, 100000, (1 << 20) + 7, 5 << 20])
 def test_fused_digest_matches_cpu_model(bb, torch_cuda, algo_name, n):
     torch = torch_cuda
@@ -29,7 +29,7 @@ def test_fused_digest_matches_cpu_model(bb, torch_cuda, algo_name, n):
     dg, st, ms = eng.run([(src.data_ptr(), dst.data_ptr(), n)], algo, _stream(torch))
     torch.cuda.synchronize()
     host = src.cpu().numpy()
-    ref = bb.bbh64(host) if algo_name == "BBH64" else bb.crc32c(host)
+    ref = bb.bbh64(host) if algo_name == "BBH64" else bb.xxh3t64(host) if algo_name == "XXH3" else bb.crc32c(host)
     assert dg[0] == ref
     assert torch.equal(src, dst[:n]) and bool((dst[n:] == 0xAB).all())
 
@@ -61,7 +61,7 @@ def test_fused_batch_of_small_objects(bb, torch_cuda):
     assert torch.equal(big, out)
 
 
-@pytest.mark.parametrize("algo_name", ["BBH64", "CRC32C", "NONE"])
+@pytest.mark.parametrize("algo_name", ["BBH64", "CRC32C", "XXH3", "NONE"])
 def test_small_object_warp_path_matches_cpu_models_and_the_big_kernel(bb, torch_cuda, algo_name):
     """xfer_small.cu: batches made only of objects <= 4 KiB take the warp-per-object kernel; bytes and digests are
     identical to the CPU models and to what the TMA / tcgen05 kernel produces for the same objects."""
@@ -82,7 +82,7 @@ def test_small_object_warp_path_matches_cpu_models_and_the_big_kernel(bb, torch_
     for i, sz in enumerate(sizes):
         blob = h[i * stride:i * stride + sz]
         if algo_name != "NONE":
-            assert dg[i] == (bb.bbh64(blob) if algo_name == "BBH64" else bb.crc32c(blob)), (i, sz)
+            assert dg[i] == (bb.bbh64(blob) if algo_name == "BBH64" else bb.xxh3t64(blob) if algo_name == "XXH3" else bb.crc32c(blob)), (i, sz)
         for o in outs:
             assert torch.equal(o[i * stride:i * stride + sz], src[i * stride:i * stride + sz]), (i, sz)
             assert bool((o[i * stride + sz:(i + 1) * stride] == 0xCD).all()), (i, sz)  # nothing written past the object
