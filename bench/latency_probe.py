@@ -33,9 +33,10 @@ def main():
     dst = torch.zeros_like(src)
     for algo_name in ("XXH3", "BBH64", "CRC32C"):
         algo = getattr(_bb.ChecksumAlgo, algo_name)
-        for small, flag in ((True, True), (True, False), (False, False)):
+        for small, flag, mail in ((True, True, True), (True, True, False), (True, False, False), (False, False, False)):
             eng.set_small_path(small)
             eng.set_flag_completion(flag)
+            eng.set_mailbox(mail)
             for size in sizes:
                 ts, ks = [], []
                 for it in range(305):
@@ -44,18 +45,19 @@ def main():
                     t1 = time.perf_counter()
                     if it >= 5:
                         ts.append((t1 - t0) * 1e6), ks.append(ms * 1e3)
-                out["engine"].append({"algo": algo_name, "small_path": small, "flag_completion": flag, "size": size, "call_p50_us": round(pct(ts, 0.5), 2),
+                out["engine"].append({"algo": algo_name, "small_path": small, "flag_completion": flag, "mailbox": mail, "size": size, "call_p50_us": round(pct(ts, 0.5), 2),
                                       "call_p99_us": round(pct(ts, 0.99), 2), "kernel_p50_us": round(pct(ks, 0.5), 2)})
     target = f"gpu{(cl.rank + 1) % cl.world}"
     for small in (True, False):
         cl.fabric.set_small_path(small)
+        cl.fabric.set_mailbox(small)
         out["client"]["small_path_on" if small else "small_path_off"] = latency_sweep(cl, sizes, target, iters=300, algo=_bb.ChecksumAlgo.XXH3)
     cl.stop()
     if cl.rank == 0:
         print(json.dumps(out))
         for r in out["engine"]:
-            print("  engine %-6s small=%-5s flag=%-5s %6d B: call p50 %6.2f p99 %6.2f us, kernel p50 %5.2f us" % (
-                r["algo"], r["small_path"], r["flag_completion"], r["size"], r["call_p50_us"], r["call_p99_us"], r["kernel_p50_us"]), file=sys.stderr)
+            print("  engine %-6s small=%-5s flag=%-5s mailbox=%-5s %6d B: call p50 %6.2f p99 %6.2f us, kernel p50 %5.2f us" % (
+                r["algo"], r["small_path"], r["flag_completion"], r["mailbox"], r["size"], r["call_p50_us"], r["call_p99_us"], r["kernel_p50_us"]), file=sys.stderr)
         for k, rows in out["client"].items():
             for r in rows:
                 print("  client %-14s %6d B: put p50 %6.1f p99 %6.1f | get p50 %6.1f p99 %6.1f us" % (

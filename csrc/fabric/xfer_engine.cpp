@@ -39,6 +39,8 @@ struct XferEngine::Slot {
   uint64_t* d_trace = nullptr;
   size_t d_trace_bytes = 0;
   bool traced = false;
+  bool mailed = false;     // served by the resident mailbox warp: results arrive in the mailbox's result ring
+  uint32_t mail_first = 0;  // first sequence number of this batch in the mailbox
   bool flagged = false;    // completion by status flag in pinned memory (small-object latency path), no events recorded
   void* stream = nullptr;  // stream of a flagged batch (fallback sync)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
@@ -107,6 +109,121 @@ XferEngine::~XferEngine() {
     if (s->ev_done) cudaEventDestroy(s->ev_done);
   }
   cudaSetDevice(prev);
+}
+
+struct XferEngine::Mailbox {
+  MailSlot* slots = nullptr;      // pinned host
+  MailResult* results = nullptr;  // pinned host
+  MailCtl* ctl = nullptr;         // pinned host
+  cudaStream_t stream = nullptr;  // non-blocking: never synchronises with the legacy default stream
+  uint32_t next_seq = 1;          // next sequence number to hand out
+  uint32_t epoch = 0;             // incarnation counter (0 = never launched)
+  uint32_t outstanding = 0;       // posted requests whose results have not been collected
+  uint64_t linger_ns = 200000, max_ns = 50000000;
+  ~Mailbox() {
+    if (stream) {
+      cudaStreamSynchronize(stream);  // the resident warp leaves by itself after linger_ns
+      cudaStreamDestroy(stream);
+    }
+    if (slots) cudaFreeHost(slots);
+    if (results) cudaFreeHost(results);
+    if (ctl) cudaFreeHost(ctl);
+  }
+};
+
+bool XferEngine::mailbox_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("BB_XFER_MAILBOX");
+    return !(e && e[0] == '0');
+  }();
+  return on && mailbox_on_;
+}
+
+ErrorCode XferEngine::mailbox_launch_locked(uint32_t first_seq) {
+  Mailbox& m = *mb_;
+  ++m.epoch;
+  const int rc = launch_mailbox(m.slots, m.results, m.ctl, first_seq, m.epoch, m.linger_ns, m.max_ns, m.stream);
+  if (rc != 0) {
+    last_cuda_error_ = rc;
+    BB_LOG(ERROR) << "launch_mailbox failed: " << cuda_error_string(rc);
+    return ErrorCode::FABRIC_ERROR;
+  }
+  ++mailbox_launches_;
+  ++launches_;
+  return ErrorCode::OK;
+}
+
+// Hands `nd` small single-destination descriptors to the resident warp.  Slot layout and ordering: the 64-byte slot is
+// written field by field, the sequence number last (x86 stores stay in order); the warp reads the whole line in one PCIe
+// request and acts only when the sequence number is the one it expects.
+ErrorCode XferEngine::mailbox_post(Slot* s, const XferDesc* descs, uint32_t nd, int algo) {
+  if (!mb_) {
+    auto m = std::make_unique<Mailbox>();
+    BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->slots), sizeof(MailSlot) * kMailSlots));
+    BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->results), sizeof(MailResult) * kMailSlots));
+    BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->ctl), sizeof(MailCtl)));
+    std::memset(m->slots, 0, sizeof(MailSlot) * kMailSlots);
+    std::memset(m->results, 0, sizeof(MailResult) * kMailSlots);
+    std::memset(m->ctl, 0, sizeof(MailCtl));
+    BB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (const char* e = std::getenv("BB_MAILBOX_LINGER_US")) m->linger_ns = static_cast<uint64_t>(std::max(1, std::atoi(e))) * 1000ull;
+    mb_ = std::move(m);
+  }
+  Mailbox& m = *mb_;
+  s->mail_first = m.next_seq;
+  for (uint32_t i = 0; i < nd; ++i) {
+    const uint32_t seq = m.next_seq++;
+    MailSlot& q = m.slots[seq % kMailSlots];
+    q.src = reinterpret_cast<uint64_t>(descs[i].src);
+    q.dst = reinterpret_cast<uint64_t>(descs[i].dst[0]);
+    q.expect = descs[i].expect;
+    q.nbytes = static_cast<uint32_t>(descs[i].nbytes);
+    q.flags = descs[i].flags;
+    q.algo = static_cast<uint32_t>(algo);
+    q.reserved = descs[i].reserved;
+    std::atomic_thread_fence(std::memory_order_release);
+    *reinterpret_cast<volatile uint32_t*>(&q.seq) = seq;
+  }
+  m.outstanding += nd;
+  mailbox_requests_ += nd;
+  // is anybody polling?  (exit_epoch == epoch: the last incarnation has announced its exit; epoch 0: never launched)
+  if (m.epoch == 0 || *reinterpret_cast<volatile uint32_t*>(&m.ctl->exit_epoch) == m.epoch) {
+    const uint32_t first = m.epoch == 0 ? s->mail_first : *reinterpret_cast<volatile uint32_t*>(&m.ctl->next_seq);
+    return mailbox_launch_locked(first);
+  }
+  return ErrorCode::OK;
+}
+
+ErrorCode XferEngine::mailbox_wait(Slot* s) {
+  Mailbox& m = *mb_;
+  const uint32_t nd = s->ndesc;
+  auto* dg = reinterpret_cast<uint64_t*>(s->h_res);
+  auto* stt = reinterpret_cast<uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t i = 0; i < nd; ++i) {
+    const uint32_t seq = s->mail_first + i;
+    const volatile MailResult* r = &m.results[seq % kMailSlots];
+    uint32_t spins = 0;
+    while (r->seq != seq) {
+      if ((++spins & 0x3Fu) != 0) continue;
+      // the warp may have left just before our request landed (it lingers only so long): start the next incarnation
+      if (*reinterpret_cast<volatile uint32_t*>(&m.ctl->exit_epoch) == m.epoch && r->seq != seq) {
+        BB_CUDA(cudaSetDevice(device_));
+        const ErrorCode ec = mailbox_launch_locked(*reinterpret_cast<volatile uint32_t*>(&m.ctl->next_seq));
+        if (ec != ErrorCode::OK) return ec;
+      }
+      if ((spins & 0xFFFFu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
+        BB_LOG(ERROR) << "XferEngine: the mailbox warp did not answer request " << seq;
+        m.outstanding -= std::min(m.outstanding, nd - i);
+        return ErrorCode::FABRIC_ERROR;
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    dg[i] = r->digest;
+    stt[i] = r->status;
+  }
+  m.outstanding -= std::min(m.outstanding, nd);
+  return ErrorCode::OK;
 }
 
 bool XferEngine::flag_completion_enabled() {
@@ -220,9 +337,22 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
       l.max_ctas = max_ctas_;
       l.stream = stream;
       l.small_path = all_small;
-      if (all_small) ++small_launches_;
       // Latency path: a small batch whose results land in pinned memory completes by flag -- the launch is the ONLY
       // stream operation (no timing events, no completion event: each costs about as much GPU time as the kernel).
+      // (1) resident mailbox warp: no launch at all.  The request bypasses `stream`, so everything already queued there
+      // must have finished (the caller's source data is ready), and only one mailed batch is in flight at a time.
+      if (all_small && direct && nd <= kMailSlots / 2 && !capture_debug && !tile_trace_ && mailbox_enabled() &&
+          (!mb_ || mb_->outstanding == 0)) {
+        bool simple = true;
+        for (uint32_t i = 0; i < nd; ++i) simple = simple && descs[i].ndst == 1 && !(descs[i].flags & XFER_MULTIMEM);
+        if (simple && cudaStreamQuery(st) == cudaSuccess) {
+          const ErrorCode mec = mailbox_post(s, descs, nd, l.algo);
+          if (mec != ErrorCode::OK) return mec;
+          s->mailed = true;
+          return ErrorCode::OK;
+        }
+        cudaGetLastError();  // cudaErrorNotReady is not sticky, but keep the error state clean
+      }
       s->flagged = all_small && direct && !capture_debug && !tile_trace_ && flag_completion_enabled();
       if (s->flagged) {
         auto* stt = reinterpret_cast<volatile uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);
@@ -239,6 +369,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
         return ErrorCode::FABRIC_ERROR;
       }
       ++launches_;
+      if (all_small && !capture_debug && !tile_trace_) ++small_launches_;
       if (s->flagged) return ErrorCode::OK;
       BB_CUDA(cudaEventRecord(s->ev_stop, st));
       if (algo != ChecksumAlgo::NONE && !direct) {
@@ -251,6 +382,7 @@ Result<uint64_t> XferEngine::submit(const std::vector<XferItem>& items, Checksum
     return ErrorCode::OK;
   };
   s->flagged = false;
+  s->mailed = false;
   ErrorCode ec = run();
   if (ec != ErrorCode::OK) return ec;
   s->ticket = next_ticket_++;
@@ -265,7 +397,13 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
     if (c->ticket == ticket) { s = c.get(); break; }
   if (!s) return ErrorCode::NOT_FOUND;
   const uint32_t nd = s->ndesc;
-  if (s->flagged) {
+  if (s->mailed) {
+    const ErrorCode mec = mailbox_wait(s);
+    if (mec != ErrorCode::OK) {
+      s->ticket = 0;
+      return mec;
+    }
+  } else if (s->flagged) {
     // spin on the status words the kernel writes last (pinned memory); fall back to a stream sync if they do not show
     // up within a generous bound, so that a launch failure surfaces as an error instead of a hang
     const auto* stt = reinterpret_cast<const volatile uint32_t*>(s->h_res + static_cast<size_t>(max_items_) * 8);
@@ -306,7 +444,7 @@ ErrorCode XferEngine::wait(uint64_t ticket, XferResult* out) {
       }
     }
     out->device_ms = 0.f;
-    if (nd && !s->flagged) cudaEventElapsedTime(&out->device_ms, s->ev_start, s->ev_stop);
+    if (nd && !s->flagged && !s->mailed) cudaEventElapsedTime(&out->device_ms, s->ev_start, s->ev_stop);
   }
   if (s->debug && nd) {
     debug_host_.resize(static_cast<size_t>(s->total_tiles) * tchash::kRows * tchash::kN);

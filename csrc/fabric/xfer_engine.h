@@ -82,6 +82,12 @@ class XferEngine {
   // Small batches (<= kDirectResults objects on the warp path) complete by a flag in pinned memory instead of CUDA
   // events (default on; BB_XFER_FLAG_COMPLETION=0 disables).  Their XferResult::device_ms is 0 (not measured).
   void set_flag_completion(bool on) { flag_completion_ = on; }
+  // Batches of <= 8 single-destination small objects whose stream has nothing pending are handed to the resident mailbox
+  // warp (xfer_small.cu) instead of being launched: no cudaLaunchKernel in the steady state.  Default on;
+  // BB_XFER_MAILBOX=0 disables; BB_MAILBOX_LINGER_US (default 200) = how long the warp waits for the next request.
+  void set_mailbox(bool on) { mailbox_on_ = on; }
+  uint64_t mailbox_requests() const { return mailbox_requests_; }   // objects served by the resident warp
+  uint64_t mailbox_launches() const { return mailbox_launches_; }   // incarnations of the mailbox kernel
   void set_max_ctas(int n) { max_ctas_ = n; }
   int last_cuda_error() const { return last_cuda_error_; }
 
@@ -96,6 +102,14 @@ class XferEngine {
   uint64_t small_launches_ = 0;
   bool small_path_ = true;
   bool flag_completion_ = true;
+  bool mailbox_on_ = true;
+  bool mailbox_enabled();
+  struct Mailbox;
+  std::unique_ptr<Mailbox> mb_;
+  ErrorCode mailbox_post(Slot* s, const XferDesc* descs, uint32_t nd, int algo);
+  ErrorCode mailbox_wait(Slot* s);
+  ErrorCode mailbox_launch_locked(uint32_t first_seq);
+  uint64_t mailbox_requests_ = 0, mailbox_launches_ = 0;
   bool small_path_enabled();
   bool flag_completion_enabled();
   int max_ctas_ = 0;

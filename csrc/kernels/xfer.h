@@ -67,6 +67,38 @@ struct XferLaunch {
 
 // Returns 0 on success, else a cudaError_t value.
 int launch_xfer(const XferLaunch& l);
+// ---- mailbox (xfer_small.cu): a resident warp fed through pinned host memory, so that a single small put / get costs no
+// kernel launch.  All three structures live in pinned host memory (the device reads / writes them over PCIe).
+constexpr uint32_t kMailSlots = 16;
+struct MailSlot {  // 64 bytes = one cache line = one PCIe read; the host writes `seq` LAST
+  uint64_t src;
+  uint64_t dst;
+  uint64_t expect;     // as XferDesc::expect
+  uint32_t nbytes;     // <= kSmallBytes
+  uint32_t flags;      // XferFlags (no MULTIMEM, no RAW_SUM)
+  uint32_t algo;       // XferAlgo
+  uint32_t reserved;   // as XferDesc::reserved
+  uint32_t pad[5];
+  uint32_t seq;        // word 15
+};
+static_assert(sizeof(MailSlot) == 64, "MailSlot must be one cache line");
+struct MailResult {  // 64 bytes; the device writes `seq` LAST
+  uint64_t digest;
+  uint32_t status;
+  uint32_t seq;
+  uint32_t pad[12];
+};
+static_assert(sizeof(MailResult) == 64);
+struct MailCtl {
+  uint32_t exit_epoch;  // epoch of the last kernel incarnation that has exited (== the launched epoch: nobody is polling)
+  uint32_t next_seq;    // first sequence number that incarnation did NOT consume
+  uint32_t pad[14];
+};
+// Launches one incarnation of the mailbox kernel on `stream`: it serves requests from sequence number `first_seq` on and
+// exits after `linger_ns` without a request or `max_ns` in total, then writes (next_seq, exit_epoch = epoch) into *ctl.
+int launch_mailbox(const MailSlot* slots, MailResult* results, MailCtl* ctl, uint32_t first_seq, uint32_t epoch, uint64_t linger_ns,
+                   uint64_t max_ns, void* stream);
+
 // Small-object latency tier: one warp per descriptor, digest bit-identical to launch_xfer's (needs descs; not tile_start).
 int launch_xfer_small(const XferLaunch& l);
 int xfer_smem_bytes(int algo);

@@ -69,54 +69,16 @@ __device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-template <int ALGO>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const __grid_constant__ SmallParams p) {
-  __shared__ uint32_t s_w[ALGO == ALGO_BBH64 ? 16 * 32 : 1];       // Wp[n][w]: W[4w + b][n] in byte b
-  __shared__ uint32_t s_t4[ALGO == ALGO_CRC32C ? 4 * 256 : 1];
-  __shared__ uint64_t s_xk[ALGO == ALGO_XXH3 ? 24 : 1];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  if constexpr (ALGO == ALGO_BBH64) {
-    for (uint32_t i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
-      const uint32_t n = i >> 5, w = i & 31u;
-      s_w[i] = tchash::weight(4 * w, n) | (tchash::weight(4 * w + 1, n) << 8) | (tchash::weight(4 * w + 2, n) << 16) |
-               (tchash::weight(4 * w + 3, n) << 24);
-    }
-    __syncthreads();
-  }
-  if constexpr (ALGO == ALGO_CRC32C) {
-    for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_t4[i] = __ldg(&p.crc_t4[i]);
-    __syncthreads();
-  }
-  if constexpr (ALGO == ALGO_XXH3) {
-    if (threadIdx.x < 24) s_xk[threadIdx.x] = c_xxh[threadIdx.x];
-    __syncthreads();
-  }
-  const uint32_t d = blockIdx.x * kWarpsPerCta + warp;
-  if (d >= p.ndesc) return;
-  // ---- descriptor (every lane reads the same words: broadcast)
-  uint64_t src, dst[kMaxDst], nbytes, expect;
-  uint32_t ndst, flags, reserved;
-  if (p.use_inline) {
-    const XferDesc& q = p.inl_descs[d];
-    src = reinterpret_cast<uint64_t>(q.src);
-#pragma unroll
-    for (uint32_t r = 0; r < kMaxDst; ++r) dst[r] = reinterpret_cast<uint64_t>(q.dst[r]);
-    nbytes = q.nbytes, expect = q.expect, ndst = q.ndst, flags = q.flags, reserved = q.reserved;
-  } else {
-    const uint4* q = reinterpret_cast<const uint4*>(&p.descs[d]);
-    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
-    src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
-    dst[0] = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
-    dst[1] = (static_cast<uint64_t>(q1.y) << 32) | q1.x;
-    dst[2] = (static_cast<uint64_t>(q1.w) << 32) | q1.z;
-    nbytes = (static_cast<uint64_t>(q2.y) << 32) | q2.x;
-    ndst = q2.w;
-    expect = (static_cast<uint64_t>(q3.y) << 32) | q3.x;
-    flags = q3.z;
-    reserved = q3.w;
-  }
+// The per-object work of one warp: load (<= 4 KiB, lane l owns bytes [128 l, 128 l + 128)), store to the destinations, digest on
+// the registers.  Shared by the batch kernel (one warp per descriptor) and the mailbox kernel (one resident warp).
+// s_w / s_t4 / s_xk: shared-memory tables of the algorithm (BBH64 packed weights, CRC32C x^32 table, XXH3 accumulate keys).
+// VOL: the caller is a resident kernel -- source loads must bypass L1 (`ld.volatile`): a line cached by an earlier request for
+// the same address would otherwise be served stale (L1 is only invalidated at kernel boundaries).
+template <int ALGO, bool VOL>
+__device__ __forceinline__ void small_object(uint64_t src, const uint64_t (&dst)[kMaxDst], uint32_t ndst, uint64_t nbytes, uint64_t expect,
+                                             uint32_t flags, uint32_t reserved, uint32_t lane, uint64_t zero_rows, const uint32_t* s_w,
+                                             const uint32_t* s_t4, const uint64_t* s_xk, uint64_t* digest_out, uint32_t* status_out) {
   const uint32_t n = static_cast<uint32_t>(nbytes);  // <= kSmallBytes (host checked)
-
   // ---- load: lane's 128-byte segment, zero beyond the object
   uint4 v[8];
   const uint32_t seg = lane * 128u;
@@ -124,13 +86,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const 
   for (int j = 0; j < 8; ++j) {
     const uint32_t o = seg + 16u * j;
     if (o + 16u <= n) {
-      v[j] = ld_nc_v4(reinterpret_cast<const void*>(src + o));
+      if constexpr (VOL) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src + o) : "memory");
+      } else {
+        v[j] = ld_nc_v4(reinterpret_cast<const void*>(src + o));
+      }
     } else {
       v[j] = make_uint4(0, 0, 0, 0);
       if (o < n) {  // the one partial chunk of the object: byte loads
         uint32_t w[4] = {0, 0, 0, 0};
         for (uint32_t b = 0; b < n - o; ++b)
-          w[b >> 2] |= static_cast<uint32_t>(*reinterpret_cast<const uint8_t*>(src + o + b)) << (8u * (b & 3u));
+          w[b >> 2] |= static_cast<uint32_t>(*reinterpret_cast<const volatile uint8_t*>(src + o + b)) << (8u * (b & 3u));
         v[j] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
@@ -158,15 +124,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const 
     }
   }
   if constexpr (ALGO == ALGO_NONE) {
-    if (p.flag_mode) {
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {
-        p.digest_out[d] = 0;
-        __threadfence_system();
-        *reinterpret_cast<volatile uint32_t*>(&p.status_out[d]) = 0u;
-      }
-    }
+    *digest_out = 0;
+    *status_out = 0;
     return;
   }
 
@@ -206,7 +165,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const 
     uint64_t c = tchash::row_contrib(mine, row);  // tile index 0
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += shfl_xor64(c, o);
-    digest = tchash::finalize(c + p.zero_rows, nbytes);
+    digest = tchash::finalize(c + zero_rows, nbytes);
   } else if constexpr (ALGO == ALGO_XXH3) {
     // Standard XXH3-64 of the object zero padded to one 16 KiB tile.  Lane l holds stripes 2 (l & 7) and 2 (l & 7) + 1 of
     // block l >> 3 (64 B each = the 8 accumulator lanes): it forms the 8 per-lane products of both stripes, the 8 lanes
@@ -279,14 +238,145 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const 
     digest = gf2_mulmod_small(acc, reserved) ^ static_cast<uint32_t>(expect >> 32) ^ 0xFFFFFFFFu;
     expect &= 0xFFFFFFFFull;
   }
+  *digest_out = digest;
+  *status_out = ((flags & XFER_VERIFY) && digest != expect) ? 1u : 0u;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) bb_xfer_small_kernel(const __grid_constant__ SmallParams p) {
+  __shared__ uint32_t s_w[ALGO == ALGO_BBH64 ? 16 * 32 : 1];       // Wp[n][w]: W[4w + b][n] in byte b
+  __shared__ uint32_t s_t4[ALGO == ALGO_CRC32C ? 4 * 256 : 1];
+  __shared__ uint64_t s_xk[ALGO == ALGO_XXH3 ? 24 : 1];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if constexpr (ALGO == ALGO_BBH64) {
+    for (uint32_t i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+      const uint32_t n = i >> 5, w = i & 31u;
+      s_w[i] = tchash::weight(4 * w, n) | (tchash::weight(4 * w + 1, n) << 8) | (tchash::weight(4 * w + 2, n) << 16) |
+               (tchash::weight(4 * w + 3, n) << 24);
+    }
+    __syncthreads();
+  }
+  if constexpr (ALGO == ALGO_CRC32C) {
+    for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_t4[i] = __ldg(&p.crc_t4[i]);
+    __syncthreads();
+  }
+  if constexpr (ALGO == ALGO_XXH3) {
+    if (threadIdx.x < 24) s_xk[threadIdx.x] = c_xxh[threadIdx.x];
+    __syncthreads();
+  }
+  const uint32_t d = blockIdx.x * kWarpsPerCta + warp;
+  if (d >= p.ndesc) return;
+  // ---- descriptor (every lane reads the same words: broadcast)
+  uint64_t src, dst[kMaxDst], nbytes, expect;
+  uint32_t ndst, flags, reserved;
+  if (p.use_inline) {
+    const XferDesc& q = p.inl_descs[d];
+    src = reinterpret_cast<uint64_t>(q.src);
+#pragma unroll
+    for (uint32_t r = 0; r < kMaxDst; ++r) dst[r] = reinterpret_cast<uint64_t>(q.dst[r]);
+    nbytes = q.nbytes, expect = q.expect, ndst = q.ndst, flags = q.flags, reserved = q.reserved;
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(&p.descs[d]);
+    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    src = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
+    dst[0] = (static_cast<uint64_t>(q0.w) << 32) | q0.z;
+    dst[1] = (static_cast<uint64_t>(q1.y) << 32) | q1.x;
+    dst[2] = (static_cast<uint64_t>(q1.w) << 32) | q1.z;
+    nbytes = (static_cast<uint64_t>(q2.y) << 32) | q2.x;
+    ndst = q2.w;
+    expect = (static_cast<uint64_t>(q3.y) << 32) | q3.x;
+    flags = q3.z;
+    reserved = q3.w;
+  }
+  uint64_t digest = 0;
+  uint32_t status = 0;
+  small_object<ALGO, false>(src, dst, ndst, nbytes, expect, flags, reserved, lane, p.zero_rows, s_w, s_t4, s_xk, &digest, &status);
   if (p.flag_mode) {
     __threadfence_system();  // every lane: its stores of the payload are performed system-wide ...
     __syncwarp();            // ... before lane 0 publishes the result
   }
   if (lane == 0) {
-    p.digest_out[d] = digest;
+    if (ALGO != ALGO_NONE || p.flag_mode) p.digest_out[d] = digest;
     if (p.flag_mode) __threadfence_system();
-    *reinterpret_cast<volatile uint32_t*>(&p.status_out[d]) = ((flags & XFER_VERIFY) && digest != expect) ? 1u : 0u;
+    if (ALGO != ALGO_NONE || p.flag_mode) *reinterpret_cast<volatile uint32_t*>(&p.status_out[d]) = status;
+  }
+}
+
+// ================================================================ the mailbox: a resident warp instead of a launch
+// A single small put / get through the batch kernel costs a kernel launch: ~8.9 us on this box before anything else
+// (profiles/r2_nvlink/README.md).  The mailbox kernel removes the launch from the steady state: ONE warp stays resident and
+// polls a ring of 64-byte request slots in pinned host memory (one PCIe read per poll, ~1.4 us); the host posts a request by
+// filling a slot and writing its sequence number last, the warp runs small_object() on it and writes digest + status +
+// sequence number into the matching result slot (pinned), which the host spins on.  The kernel *lingers*: it exits by itself
+// after `linger_ns` without a request (and unconditionally after `max_ns`), announcing it in MailCtl, so cudaDeviceSynchronize
+// and friends never wait longer than that; the next request simply launches it again (and that launch carries the request).
+__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(32) bb_mailbox_kernel(const MailSlot* slots, MailResult* results, MailCtl* ctl, uint32_t first_seq,
+                                                        uint32_t epoch, uint64_t linger_ns, uint64_t max_ns, const uint32_t* crc_t4,
+                                                        uint64_t zero_rows) {
+  __shared__ uint32_t s_w[16 * 32];
+  __shared__ uint32_t s_t4[4 * 256];
+  __shared__ uint64_t s_xk[24];
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t i = lane; i < 16 * 32; i += 32) {
+    const uint32_t n = i >> 5, w = i & 31u;
+    s_w[i] = tchash::weight(4 * w, n) | (tchash::weight(4 * w + 1, n) << 8) | (tchash::weight(4 * w + 2, n) << 16) | (tchash::weight(4 * w + 3, n) << 24);
+  }
+  for (uint32_t i = lane; i < 4 * 256; i += 32) s_t4[i] = __ldg(&crc_t4[i]);
+  if (lane < 24) s_xk[lane] = c_xxh[lane];
+  __syncwarp();
+  uint32_t seq = first_seq;
+  const uint64_t t_start = globaltimer_ns();
+  uint64_t t_last = t_start;
+  while (true) {
+    // one 64-byte read of the slot (16 lanes x 4 B, a single PCIe request = a consistent snapshot of the cache line);
+    // word 15 is the sequence number the host writes last
+    const volatile uint32_t* sp = reinterpret_cast<const volatile uint32_t*>(&slots[seq % kMailSlots]);
+    const uint32_t word = lane < 16 ? ld_sys_u32(sp + lane) : 0u;
+    if (__shfl_sync(0xffffffffu, word, 15) != seq) {
+      const uint64_t now = globaltimer_ns();
+      if (now - t_last > linger_ns || now - t_start > max_ns) break;
+      continue;
+    }
+    auto w64 = [&](int i) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, word, i), hi = __shfl_sync(0xffffffffu, word, i + 1);
+      return (static_cast<uint64_t>(hi) << 32) | lo;
+    };
+    const uint64_t src = w64(0);
+    const uint64_t dst[kMaxDst] = {w64(2), 0, 0};
+    const uint64_t expect = w64(4);
+    const uint32_t nbytes = __shfl_sync(0xffffffffu, word, 6), flags = __shfl_sync(0xffffffffu, word, 7);
+    const uint32_t algo = __shfl_sync(0xffffffffu, word, 8), reserved = __shfl_sync(0xffffffffu, word, 9);
+    uint64_t digest = 0;
+    uint32_t status = 0;
+    switch (algo) {
+      case ALGO_XXH3: small_object<ALGO_XXH3, true>(src, dst, 1, nbytes, expect, flags, reserved, lane, zero_rows, s_w, s_t4, s_xk, &digest, &status); break;
+      case ALGO_BBH64: small_object<ALGO_BBH64, true>(src, dst, 1, nbytes, expect, flags, reserved, lane, zero_rows, s_w, s_t4, s_xk, &digest, &status); break;
+      case ALGO_CRC32C: small_object<ALGO_CRC32C, true>(src, dst, 1, nbytes, expect, flags, reserved, lane, zero_rows, s_w, s_t4, s_xk, &digest, &status); break;
+      default: small_object<ALGO_NONE, true>(src, dst, 1, nbytes, expect, flags, reserved, lane, zero_rows, s_w, s_t4, s_xk, &digest, &status); break;
+    }
+    __threadfence_system();  // the object's stores (peer slab / local / host) are performed before the result says so
+    __syncwarp();
+    if (lane == 0) {
+      MailResult* r = &results[seq % kMailSlots];
+      r->digest = digest;
+      r->status = status;
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t*>(&r->seq) = seq;
+    }
+    ++seq;
+    t_last = globaltimer_ns();
+  }
+  if (lane == 0) {  // tell the host this incarnation is gone (posted writes stay in order: results first, then this)
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&ctl->next_seq) = seq;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&ctl->exit_epoch) = epoch;
   }
 }
 
@@ -298,17 +388,14 @@ struct SmallState {
 SmallState g_small[16];
 std::mutex g_small_mu;
 
-}  // namespace
-
-int launch_xfer_small(const XferLaunch& l) {
-  if (l.ndesc == 0) return 0;
+// Per-device constants and tables of the small-object kernels (idempotent).
+int ensure_small_state(SmallState** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (dev < 0 || dev >= 16) return static_cast<int>(cudaErrorInvalidDevice);
   SmallState& st = g_small[dev];
-  {
-    std::lock_guard<std::mutex> lk(g_small_mu);
+  std::lock_guard<std::mutex> lk(g_small_mu);
     if (!st.consts) {
       uint32_t mul[32];
       for (uint32_t ln = 0; ln < 32; ++ln) mul[ln] = gf2_xpow_bytes(128ull * (31 - ln) + (kTileBytes - kSmallBytes));
@@ -343,7 +430,25 @@ int launch_xfer_small(const XferLaunch& l) {
       if (e != cudaSuccess) return static_cast<int>(e);
       st.consts = true;
     }
-  }
+  *out = &st;
+  return 0;
+}
+}  // namespace
+
+int launch_mailbox(const MailSlot* slots, MailResult* results, MailCtl* ctl, uint32_t first_seq, uint32_t epoch, uint64_t linger_ns,
+                   uint64_t max_ns, void* stream) {
+  SmallState* st = nullptr;
+  if (const int rc = ensure_small_state(&st)) return rc;
+  bb_mailbox_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(slots, results, ctl, first_seq, epoch, linger_ns, max_ns, st->t4, st->zero_rows);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_xfer_small(const XferLaunch& l) {
+  if (l.ndesc == 0) return 0;
+  SmallState* stp = nullptr;
+  if (const int rc = ensure_small_state(&stp)) return rc;
+  SmallState& st = *stp;
+  cudaError_t e = cudaSuccess;
   SmallParams p;
   p.descs = l.descs;
   p.ndesc = l.ndesc;

@@ -121,6 +121,9 @@ void bind_gpu(py::module_& m) {
       .def("set_max_ctas", &XferEngine::set_max_ctas)
       .def("set_small_path", &XferEngine::set_small_path)
       .def("set_flag_completion", &XferEngine::set_flag_completion)
+      .def("set_mailbox", &XferEngine::set_mailbox)
+      .def_property_readonly("mailbox_requests", &XferEngine::mailbox_requests)
+      .def_property_readonly("mailbox_launches", &XferEngine::mailbox_launches)
       .def_property_readonly("small_launches", &XferEngine::small_launches)
       .def("set_tile_trace", &XferEngine::set_tile_trace)
       .def("tile_trace", [](XferEngine& e) { return e.tile_trace(); }, "[tile][4] globaltimer ns: load issued, landed, store issued, slot released")
@@ -178,6 +181,9 @@ void bind_gpu(py::module_& m) {
       .def("set_max_ctas", [](GpuFabric& f, int n) { f.engine().set_max_ctas(n); })
       .def("set_small_path", [](GpuFabric& f, bool on) { f.engine().set_small_path(on); })
       .def("set_flag_completion", [](GpuFabric& f, bool on) { f.engine().set_flag_completion(on); })
+      .def("set_mailbox", [](GpuFabric& f, bool on) { f.engine().set_mailbox(on); })
+      .def_property_readonly("mailbox_requests", [](GpuFabric& f) { return f.engine().mailbox_requests(); })
+      .def_property_readonly("mailbox_launches", [](GpuFabric& f) { return f.engine().mailbox_launches(); })
       .def_property_readonly("small_launches", [](GpuFabric& f) { return f.engine().small_launches(); })
       .def("set_tile_trace", [](GpuFabric& f, bool on) { f.engine().set_tile_trace(on); })
       .def("tile_trace", [](GpuFabric& f) { return f.engine().tile_trace(); })

@@ -104,6 +104,71 @@ def test_small_object_warp_path_matches_cpu_models_and_the_big_kernel(bb, torch_
     assert dg1[0] == dg[20] and st1[0] == 0
 
 
+def test_mailbox_resident_warp_serves_single_small_objects_without_a_launch(bb, torch_cuda):
+    """xfer_small.cu bb_mailbox_kernel: a lingering resident warp fed through pinned memory.  Same bytes and digests as the
+    launched paths; stays resident across back-to-back requests (no launch), sees fresh source data every time (volatile
+    loads: L1 is not invalidated inside a resident kernel), leaves by itself after the linger time and comes back on the
+    next request; device-wide synchronisation never waits for more than the linger time."""
+    import time
+
+    torch = torch_cuda
+    eng = bb.XferEngine(0, 256, 2)
+    s = _stream(torch)
+    src = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    dst = torch.zeros(4096 + 64, dtype=torch.uint8, device="cuda")
+    algos = [("XXH3", bb.xxh3t64), ("BBH64", bb.bbh64), ("CRC32C", bb.crc32c), ("NONE", None)]
+    l0, r0 = eng.mailbox_launches, eng.mailbox_requests
+    n_req = 0
+    for rnd in range(40):
+        name, ref = algos[rnd % 4]
+        n = [1, 17, 256, 1000, 4095, 4096][rnd % 6]
+        src.copy_(torch.randint(0, 256, (4096,), dtype=torch.uint8, device="cuda"))  # same address, new contents every round
+        dst.fill_(0xEE)
+        torch.cuda.current_stream().synchronize()  # the mailbox is only used when the stream has nothing pending
+        dg, st, _ = eng.run([(src.data_ptr(), dst.data_ptr(), n)], getattr(bb.ChecksumAlgo, name), s)
+        n_req += 1
+        host = src[:n].cpu().numpy()
+        if ref is not None:
+            assert dg[0] == ref(host), (rnd, name, n)
+        assert torch.equal(dst[:n], src[:n]) and bool((dst[n:] == 0xEE).all()), (rnd, name, n)
+    assert eng.mailbox_requests == r0 + n_req
+    assert eng.mailbox_launches - l0 <= 3, "the warp should have stayed resident across back-to-back requests"
+    # verify flag travels through the mailbox too
+    good = bb.xxh3t64(src.cpu().numpy())
+    _, st, _ = eng.run([(src.data_ptr(), dst.data_ptr(), 4096, good ^ 1, bb.XFER_VERIFY)], bb.ChecksumAlgo.XXH3, s)
+    assert st[0] == 1
+    # a batch of 8 small objects is 8 mailbox requests; 9 go through the launched warp-per-object kernel
+    many = torch.randint(0, 256, (9 * 4096,), dtype=torch.uint8, device="cuda")
+    out = torch.zeros_like(many)
+    torch.cuda.synchronize()
+    r1, sl1 = eng.mailbox_requests, eng.small_launches
+    dg8, _, _ = eng.run([(many.data_ptr() + i * 4096, out.data_ptr() + i * 4096, 3000 + i) for i in range(8)], bb.ChecksumAlgo.CRC32C, s)
+    assert eng.mailbox_requests == r1 + 8 and eng.small_launches == sl1
+    dg9, _, _ = eng.run([(many.data_ptr() + i * 4096, out.data_ptr() + i * 4096, 3000 + i) for i in range(9)], bb.ChecksumAlgo.CRC32C, s)
+    assert eng.mailbox_requests == r1 + 8 and eng.small_launches == sl1 + 1 and list(dg9[:8]) == list(dg8)
+    h = many.cpu().numpy()
+    assert all(dg9[i] == bb.crc32c(h[i * 4096:i * 4096 + 3000 + i]) for i in range(9))
+    # work pending on the stream -> not the mailbox (ordering with the caller's stream would be lost)
+    big = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    r2 = eng.mailbox_requests
+    big.fill_(7)
+    big.fill_(8)
+    eng.run([(src.data_ptr(), dst.data_ptr(), 4096)], bb.ChecksumAlgo.XXH3, s)
+    torch.cuda.synchronize()
+    # (either path is correct; when the fills were still running the request must have been launched)
+    assert eng.mailbox_requests - r2 in (0, 1)
+    # linger: the warp leaves on its own; a device-wide sync is quick; the next request brings it back
+    t0 = time.perf_counter()
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 0.05
+    time.sleep(0.3)
+    l1 = eng.mailbox_launches
+    dg, _, _ = eng.run([(src.data_ptr(), dst.data_ptr(), 4096)], bb.ChecksumAlgo.XXH3, s)
+    assert dg[0] == good and eng.mailbox_launches == l1 + 1
+    # engines can be dropped while their warp still lingers
+    del eng
+
+
 def test_standalone_crc32c_kernel(bb, torch_cuda):
     torch = torch_cuda
     for n in [1, 511, 513, 100001]:
