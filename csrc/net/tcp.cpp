@@ -11,7 +11,10 @@
 #include <sys/epoll.h>
 #include <sys/random.h>
 #include <sys/eventfd.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <cerrno>
@@ -553,6 +556,176 @@ size_t RpcServer::bytes_missing(const ConnPtr& c) {
   return total > in.size() ? total - in.size() : 0;
 }
 
+// ---------------------------------------------------------------- shared-memory channels (server side)
+struct RpcServer::ShmChan {
+  ShmChanHeader* hdr = nullptr;
+  ConnPtr conn;                 // the TCP connection that offered it (handlers see this connection)
+  uint64_t served = 0;          // last request sequence number answered (poller-private)
+  std::atomic<bool> closed{false};
+  std::mutex ov_mu;
+  std::string overflow;         // a response that did not fit: collected over TCP with kShmFetchMethod
+  ~ShmChan() {
+    if (hdr) ::munmap(hdr, kShmChanBytes);
+  }
+};
+
+RpcServer::Reply RpcServer::dispatch(const ConnPtr& c, uint32_t method, std::string_view request, uint32_t* rmethod) {
+  Reply reply;
+  *rmethod = method;
+  try {
+    if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
+    if (auto vit = view_handlers_.find(method); vit != view_handlers_.end()) {
+      reply = vit->second(c, request);  // no copy of the request payload
+    } else if (auto it = handlers_.find(method); it != handlers_.end()) {
+      reply.head = it->second(c, std::string(request));
+    } else {
+      *rmethod = 0x7FFFFFFFu;  // unknown-method marker
+    }
+  } catch (const std::exception& e) {
+    BB_LOG(ERROR) << "rpc handler " << method << " threw: " << e.what();
+    *rmethod = 0x7FFFFFFEu;  // handler-exception marker
+    reply = Reply{};
+  }
+  return reply;
+}
+
+ErrorCode RpcServer::shm_attach(const ConnPtr& c, const std::string& path) {
+  // only paths of the form /proc/<pid>/fd/<n> (a memfd of a process on this host) are accepted
+  if (path.compare(0, 6, "/proc/") != 0 || path.find("/fd/") == std::string::npos || path.find("..") != std::string::npos) return ErrorCode::INVALID_PARAMETERS;
+  const int fd = ::open(path.c_str(), O_RDWR | O_CLOEXEC);
+  if (fd < 0) return ErrorCode::NOT_FOUND;  // another host / namespace / user: the client stays on TCP
+  struct stat st{};
+  if (::fstat(fd, &st) != 0 || static_cast<size_t>(st.st_size) != kShmChanBytes) {
+    ::close(fd);
+    return ErrorCode::INVALID_PARAMETERS;
+  }
+  void* m = ::mmap(nullptr, kShmChanBytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  ::close(fd);
+  if (m == MAP_FAILED) return ErrorCode::OUT_OF_MEMORY;
+  auto ch = std::make_shared<ShmChan>();
+  ch->hdr = static_cast<ShmChanHeader*>(m);
+  if (ch->hdr->magic != kShmMagic || ch->hdr->version != 1) return ErrorCode::INVALID_PARAMETERS;
+  ch->conn = c;
+  ch->served = ch->hdr->req_seq.load(std::memory_order_acquire);
+  std::lock_guard<std::mutex> lk(shm_mu_);
+  for (auto& old : shm_chans_)
+    if (old->conn == c) old->closed.store(true);  // a connection has at most one channel
+  shm_chans_.erase(std::remove_if(shm_chans_.begin(), shm_chans_.end(), [](const auto& x) { return x->closed.load(); }), shm_chans_.end());
+  shm_chans_.push_back(ch);
+  shm_gen_.fetch_add(1, std::memory_order_release);
+  if (!shm_run_.exchange(true)) {
+    const size_t n = std::max<size_t>(1, std::min<size_t>(4, std::thread::hardware_concurrency() / 4));
+    for (size_t i = 0; i < n; ++i) shm_pollers_.emplace_back([this, i] { shm_poll_loop(i); });
+  }
+  return ErrorCode::OK;
+}
+
+std::string RpcServer::shm_take_overflow(const ConnPtr& c) {
+  std::shared_ptr<ShmChan> ch;
+  {
+    std::lock_guard<std::mutex> lk(shm_mu_);
+    for (auto& x : shm_chans_)
+      if (x->conn == c) ch = x;
+  }
+  if (!ch) return {};
+  std::lock_guard<std::mutex> lk(ch->ov_mu);
+  return std::move(ch->overflow);
+}
+
+size_t RpcServer::shm_channels() const {
+  std::lock_guard<std::mutex> lk(shm_mu_);
+  return shm_chans_.size();
+}
+
+// Poller i serves the channels whose index in the list is congruent to i.  It spins while requests keep coming and
+// backs off to short sleeps after `busy` of silence (like the epoll threads' busy-poll window).
+void RpcServer::shm_poll_loop(size_t idx) {
+  std::vector<std::shared_ptr<ShmChan>> mine;
+  uint64_t gen = ~0ull;
+  const size_t stride = std::max<size_t>(1, std::min<size_t>(4, std::thread::hardware_concurrency() / 4));
+  auto last_active = std::chrono::steady_clock::now();
+  const auto busy = std::chrono::microseconds(2000);
+  while (shm_run_.load(std::memory_order_acquire)) {
+    if (shm_gen_.load(std::memory_order_acquire) != gen) {
+      std::lock_guard<std::mutex> lk(shm_mu_);
+      gen = shm_gen_.load();
+      mine.clear();
+      for (size_t i = idx; i < shm_chans_.size(); i += stride) mine.push_back(shm_chans_[i]);
+    }
+    bool any = false;
+    for (auto& ch : mine) {
+      if (ch->closed.load(std::memory_order_relaxed)) continue;
+      ShmChanHeader* h = ch->hdr;
+      const uint64_t seq = h->req_seq.load(std::memory_order_acquire);
+      if (seq == ch->served) continue;
+      any = true;
+      const uint32_t method = h->req_method;
+      const uint32_t len = std::min<uint32_t>(h->req_len, kShmReqBytes);
+      const char* req = reinterpret_cast<const char*>(h) + 4096;
+      uint32_t rmethod = method;
+      Reply r = dispatch(ch->conn, method, std::string_view(req, len), &rmethod);
+      char* resp = reinterpret_cast<char*>(h) + 4096 + kShmReqBytes;
+      const size_t rlen = r.head.size() + r.ext_len;
+      if (rlen > kShmRespBytes) {  // too big for the channel: park it, the client collects it over TCP
+        std::lock_guard<std::mutex> lk(ch->ov_mu);
+        ch->overflow = std::move(r.head);
+        if (r.ext_len) ch->overflow.append(static_cast<const char*>(r.ext), r.ext_len);
+        h->resp_method = kShmOverflowMarker;
+        h->resp_len = 0;
+      } else {
+        std::memcpy(resp, r.head.data(), r.head.size());
+        if (r.ext_len) std::memcpy(resp + r.head.size(), r.ext, r.ext_len);
+        h->resp_method = rmethod;
+        h->resp_len = static_cast<uint32_t>(rlen);
+      }
+      ch->served = seq;
+      h->resp_seq.store(seq, std::memory_order_release);
+      served_.fetch_add(1, std::memory_order_relaxed);
+      shm_served_.fetch_add(1, std::memory_order_relaxed);
+    }
+    const auto now = std::chrono::steady_clock::now();
+    if (any) last_active = now;
+    else if (now - last_active > busy)  // idle: short naps at first (a request after a pause waits <= 30 us), longer ones later
+      std::this_thread::sleep_for(std::chrono::microseconds(mine.empty() ? 2000 : now - last_active > std::chrono::milliseconds(200) ? 250 : 30));
+    else {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+}
+
+void RpcServer::on_close(const ConnPtr& c) {
+  {
+    std::lock_guard<std::mutex> lk(shm_mu_);
+    bool changed = false;
+    for (auto& ch : shm_chans_)
+      if (ch->conn == c) {
+        ch->closed.store(true);
+        changed = true;
+      }
+    if (changed) {
+      shm_chans_.erase(std::remove_if(shm_chans_.begin(), shm_chans_.end(), [](const auto& x) { return x->closed.load(); }), shm_chans_.end());
+      shm_gen_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  if (close_hook_) close_hook_(c);
+}
+
+void RpcServer::stop_shm() {
+  if (shm_run_.exchange(false))
+    for (auto& t : shm_pollers_)
+      if (t.joinable()) t.join();
+  shm_pollers_.clear();
+  std::lock_guard<std::mutex> lk(shm_mu_);
+  shm_chans_.clear();
+}
+
+RpcServer::~RpcServer() {
+  stop();
+  stop_shm();
+}
+
 bool RpcServer::on_data(const ConnPtr& c) {
   std::string& in = c->inbuf();
   size_t pos = 0;
@@ -603,19 +776,14 @@ bool RpcServer::on_data(const ConnPtr& c) {
     }
     Reply reply;
     uint32_t rmethod = method;
-    try {
-      if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
-      if (auto vit = view_handlers_.find(method); vit != view_handlers_.end()) {
-        reply = vit->second(c, std::string_view(in.data() + body, len));  // no copy of the request payload
-      } else if (auto it = handlers_.find(method); it != handlers_.end()) {
-        reply.head = it->second(c, in.substr(body, len));
-      } else {
-        rmethod = 0x7FFFFFFFu;  // unknown-method marker
-      }
-    } catch (const std::exception& e) {
-      BB_LOG(ERROR) << "rpc handler " << method << " threw: " << e.what();
-      rmethod = 0x7FFFFFFEu;  // handler-exception marker
-      reply = Reply{};
+    if (method == kShmAttachMethod) {
+      const ErrorCode ec = shm_attach(c, in.substr(body, len));
+      const uint32_t e = static_cast<uint32_t>(ec);
+      reply.head.assign(reinterpret_cast<const char*>(&e), 4);
+    } else if (method == kShmFetchMethod) {
+      reply.head = shm_take_overflow(c);
+    } else {
+      reply = dispatch(c, method, std::string_view(in.data() + body, len), &rmethod);
     }
     served_.fetch_add(1, std::memory_order_relaxed);
     char hdr[kFrameHeader];
@@ -678,9 +846,12 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
       return ec;
     }
   }
-  std::lock_guard<std::mutex> lk(mu_);
-  fd_ = fd;
-  broken_ = false;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    fd_ = fd;
+    broken_ = false;
+  }
+  if (host == "127.0.0.1" || host == "localhost" || host == "0.0.0.0" || host == "::1") offer_shm(std::min(timeout_ms, 1000));
   return ErrorCode::OK;
 }
 
@@ -696,6 +867,7 @@ void RpcClient::close() {
   std::lock_guard<std::mutex> lk(mu_);
   if (fd_ >= 0) ::close(fd_);
   fd_ = -1;
+  drop_shm();
 }
 
 void RpcClient::enable_push(std::function<void(uint32_t, const std::string&)> cb) {
@@ -737,8 +909,103 @@ void RpcClient::reader_loop() {
   resp_cv_.notify_all();
 }
 
+// ---------------------------------------------------------------- shared-memory channel (client side)
+bool RpcClient::offer_shm(int timeout_ms) {
+  if (const char* e = std::getenv("BB_RPC_SHM"); e && e[0] == '0') return false;
+  std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ < 0 || shm_ || reader_run_.load()) return false;
+  const int mfd = static_cast<int>(::syscall(SYS_memfd_create, "bb-rpc-chan", 1u /* MFD_CLOEXEC */));
+  if (mfd < 0) return false;
+  if (::ftruncate(mfd, static_cast<off_t>(kShmChanBytes)) != 0) {
+    ::close(mfd);
+    return false;
+  }
+  void* m = ::mmap(nullptr, kShmChanBytes, PROT_READ | PROT_WRITE, MAP_SHARED, mfd, 0);
+  if (m == MAP_FAILED) {
+    ::close(mfd);
+    return false;
+  }
+  auto* h = new (m) ShmChanHeader();
+  h->version = 1;
+  h->req_seq.store(0);
+  h->resp_seq.store(0);
+  h->magic = kShmMagic;
+  const std::string path = "/proc/" + std::to_string(::getpid()) + "/fd/" + std::to_string(mfd);
+  auto r = call_tcp_locked(kShmAttachMethod, path, timeout_ms);
+  uint32_t ec = 1;
+  if (r.ok() && r.value().size() == 4) std::memcpy(&ec, r.value().data(), 4);
+  if (ec != 0) {  // server elsewhere, too old (unknown method), or unwilling: TCP it is
+    ::munmap(m, kShmChanBytes);
+    ::close(mfd);
+    return false;
+  }
+  shm_ = h;
+  shm_fd_ = mfd;
+  shm_seq_ = 0;
+  return true;
+}
+
+void RpcClient::drop_shm() {
+  if (shm_) ::munmap(shm_, kShmChanBytes);
+  if (shm_fd_ >= 0) ::close(shm_fd_);
+  shm_ = nullptr;
+  shm_fd_ = -1;
+}
+
 Result<std::string> RpcClient::call(uint32_t method, const std::string& request, int timeout_ms) {
   std::lock_guard<std::mutex> lk(mu_);
+  if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
+  if (shm_ && request.size() <= kShmReqBytes) {
+    ShmChanHeader* h = shm_;
+    std::memcpy(reinterpret_cast<char*>(h) + 4096, request.data(), request.size());
+    h->req_method = method;
+    h->req_len = static_cast<uint32_t>(request.size());
+    const uint64_t seq = ++shm_seq_;
+    h->req_seq.store(seq, std::memory_order_release);
+    ++shm_calls_;
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    while (h->resp_seq.load(std::memory_order_acquire) != seq) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((++spins & 0xFFFu) == 0) {
+        const auto waited = std::chrono::steady_clock::now() - t0;
+        if (waited > std::chrono::milliseconds(timeout_ms)) {
+          drop_shm();  // the server is not polling this channel (any more): do not reuse it
+          return ErrorCode::OPERATION_TIMEOUT;
+        }
+        if (waited > std::chrono::microseconds(200)) {
+          // a long handler, or the server died: the TCP connection tells which
+          pollfd pf{fd_, POLLIN, 0};
+          if (::poll(&pf, 1, 0) > 0 && (pf.revents & (POLLHUP | POLLERR | POLLNVAL))) {
+            drop_shm();
+            ::close(fd_);
+            fd_ = -1;
+            return ErrorCode::RPC_FAILED;
+          }
+          char probe;
+          if (::recv(fd_, &probe, 1, MSG_PEEK | MSG_DONTWAIT) == 0) {
+            drop_shm();
+            ::close(fd_);
+            fd_ = -1;
+            return ErrorCode::RPC_FAILED;
+          }
+          std::this_thread::yield();
+        }
+      }
+    }
+    const uint32_t rmethod = h->resp_method;
+    if (rmethod == kShmOverflowMarker) return call_tcp_locked(kShmFetchMethod, std::string(), timeout_ms);
+    if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
+    if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+    if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
+    return std::string(reinterpret_cast<const char*>(h) + 4096 + kShmReqBytes, h->resp_len);
+  }
+  return call_tcp_locked(method, request, timeout_ms);
+}
+
+Result<std::string> RpcClient::call_tcp_locked(uint32_t method, const std::string& request, int timeout_ms) {
   if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
   const uint64_t id = next_id_++;
   const std::string f = encode_frame(method, id, request);

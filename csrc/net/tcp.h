@@ -48,6 +48,30 @@ class TcpServer;
 void set_cluster_token(const std::string& token);
 std::string cluster_token();
 constexpr uint32_t kAuthMethod = 0x7FFFFF00u;
+// Same-host fast path of the framed RPC protocol: after connecting (and authenticating) over TCP a client may offer a
+// shared-memory channel -- a memfd holding one request and one response area -- by sending its /proc/<pid>/fd/<n> path in
+// a kShmAttachMethod frame.  A server on the same host (same user / PID namespace) maps it and serves the channel from a
+// small pool of polling threads: a call is then a store into shared memory on both sides (~1-2 us round trip instead of
+// ~15 us through the loopback TCP stack + epoll wake-up).  The TCP connection stays: it carries push frames, messages
+// that do not fit the channel, and its closing detaches the channel.  BB_RPC_SHM=0 disables the offer.
+// (UCX gives the reference the same thing under the hood: its `sysv,posix,cma` transports for intra-node peers,
+// examples/benchmark_ucx_transports.cpp:146-149.)
+constexpr uint32_t kShmAttachMethod = 0x7FFFFF01u;
+constexpr uint32_t kShmFetchMethod = 0x7FFFFF02u;   // collect a response that did not fit the channel's response area
+constexpr uint32_t kShmOverflowMarker = 0x7FFFFFFCu;
+constexpr size_t kShmReqBytes = 2u << 20, kShmRespBytes = 6u << 20;
+struct ShmChanHeader {  // at offset 0 of the mapping; request bytes at 4096, response bytes at 4096 + kShmReqBytes
+  uint32_t magic;       // 'BBSH'
+  uint32_t version;
+  alignas(64) std::atomic<uint64_t> req_seq;   // client: ++ after the request is in place (release)
+  uint32_t req_method;
+  uint32_t req_len;
+  alignas(64) std::atomic<uint64_t> resp_seq;  // server: = req_seq after the response is in place (release)
+  uint32_t resp_method;                        // echo of the method, or one of the 0x7FFFFFFx markers
+  uint32_t resp_len;
+};
+constexpr uint32_t kShmMagic = 0x48534242u;
+constexpr size_t kShmChanBytes = 4096 + kShmReqBytes + kShmRespBytes;
 constexpr uint32_t kDeniedMarker = 0x7FFFFFFDu;
 
 class Connection : public std::enable_shared_from_this<Connection> {
@@ -171,15 +195,28 @@ class RpcServer : public TcpServer {
     return c->send(encode_frame(kPushFlag | topic, 0, payload));
   }
   uint64_t requests_served() const { return served_.load(); }
+  uint64_t shm_requests_served() const { return shm_served_.load(); }
+  size_t shm_channels() const;
+  ~RpcServer() override;
+  void stop_shm();  // joins the channel pollers (RpcServer owners call stop(), which ends with this)
 
  protected:
   bool on_data(const ConnPtr& c) override;
   size_t bytes_missing(const ConnPtr& c) override;
-  void on_close(const ConnPtr& c) override {
-    if (close_hook_) close_hook_(c);
-  }
+  void on_close(const ConnPtr& c) override;
 
  private:
+  struct ShmChan;
+  Reply dispatch(const ConnPtr& c, uint32_t method, std::string_view request, uint32_t* rmethod);
+  ErrorCode shm_attach(const ConnPtr& c, const std::string& path);
+  std::string shm_take_overflow(const ConnPtr& c);
+  void shm_poll_loop(size_t idx);
+  mutable std::mutex shm_mu_;
+  std::vector<std::shared_ptr<ShmChan>> shm_chans_;
+  std::atomic<uint64_t> shm_gen_{0};
+  std::vector<std::thread> shm_pollers_;
+  std::atomic<bool> shm_run_{false};
+  std::atomic<uint64_t> shm_served_{0};
   std::unordered_map<uint32_t, Handler> handlers_;
   std::unordered_map<uint32_t, ViewHandler> view_handlers_;
   std::function<void(const ConnPtr&)> close_hook_;
@@ -215,9 +252,20 @@ class RpcClient {
   // Installs a handler for server push frames and starts a reader thread.  After this, call()
   // responses are also routed through the reader thread.
   void enable_push(std::function<void(uint32_t topic, const std::string& payload)> cb);
+  // Offers the server a shared-memory channel (see kShmAttachMethod).  Called by connect() for loopback peers; returns
+  // false (and stays on TCP) when the server is not on this host, predates the feature, or BB_RPC_SHM=0.
+  bool offer_shm(int timeout_ms = 1000);
+  bool shm_active() const { return shm_ != nullptr; }
+  uint64_t shm_calls() const { return shm_calls_; }
 
  private:
   void reader_loop();
+  Result<std::string> call_tcp_locked(uint32_t method, const std::string& request, int timeout_ms);
+  void drop_shm();
+  ShmChanHeader* shm_ = nullptr;  // mapped channel (nullptr = TCP only)
+  int shm_fd_ = -1;
+  uint64_t shm_seq_ = 0;
+  uint64_t shm_calls_ = 0;
   int fd_ = -1;
   std::mutex mu_;
   uint64_t next_id_ = 1;

@@ -647,7 +647,9 @@ void bind_control(py::module_& m) {
       .def("stop", &rpc::RpcService::stop, py::call_guard<py::gil_scoped_release>())
       .def_property_readonly("rpc_port", &rpc::RpcService::rpc_port)
       .def_property_readonly("http_port", &rpc::RpcService::http_port)
-      .def_property_readonly("requests_served", &rpc::RpcService::requests_served);
+      .def_property_readonly("requests_served", &rpc::RpcService::requests_served)
+      .def_property_readonly("shm_requests_served", &rpc::RpcService::shm_requests_served)
+      .def_property_readonly("shm_channels", &rpc::RpcService::shm_channels);
 
   py::class_<rpc::KeystoneApi, std::shared_ptr<rpc::KeystoneApi>>(m, "KeystoneApi")
       .def("object_exists", [](rpc::KeystoneApi& k, const std::string& key) { return unwrap(k.object_exists(key)); }, py::call_guard<py::gil_scoped_release>())

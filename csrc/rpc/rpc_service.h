@@ -151,6 +151,8 @@ class RpcService {
   uint16_t rpc_port() const { return rpc_.port(); }
   uint16_t http_port() const { return http_.port(); }
   uint64_t requests_served() const { return rpc_.requests_served(); }
+  uint64_t shm_requests_served() const { return rpc_.shm_requests_served(); }  // of which over same-host shared-memory channels
+  size_t shm_channels() const { return rpc_.shm_channels(); }
   std::shared_ptr<keystone::KeystoneService> keystone() { return keystone_; }
 
  private:

@@ -335,12 +335,13 @@ def _mutate(rng, frame):
     return bytes(f)
 
 
-def test_mutated_real_requests_do_not_break_keystone_or_worker(bb):
+def test_mutated_real_requests_do_not_break_keystone_or_worker(bb, monkeypatch):
     """Structure-aware fuzzing: the requests of a real client session (put / get / batch / admin calls, D_WRITE / D_READ)
     are recorded through a proxy, mutated (bit flips, clobbered lengths and counts, truncation, method swaps) and fired at
     the Keystone and at the worker data server; both keep serving.  Under the ASAN build this covers the decoders of
     every wire struct with inputs that are almost valid."""
     rng = random.Random(2026)
+    monkeypatch.setenv("BB_RPC_SHM", "0")  # the recording proxy only sees TCP: keep the session off the shared-memory channel
     with LocalCluster(cluster_id="fuzz2", n_workers=2) as c:
         kproxy = _RecordingProxy(c.rpc.rpc_port)
         o = bb.BlackbirdClientOptions("127.0.0.1", kproxy.port, 30000, 2, "node-0")

@@ -1,0 +1,58 @@
+"""Shared-memory channel of the framed RPC protocol (net/tcp.h kShmAttachMethod): same-host clients talk to a server
+through a memfd instead of the loopback TCP stack; the TCP connection stays for push frames, oversized messages and
+liveness."""
+import os
+import time
+
+import pytest
+
+from blackbird_b200.parallel import LocalCluster
+
+
+def test_keystone_rpc_rides_the_shm_channel_and_falls_back(bb, monkeypatch):
+    with LocalCluster("shm-rpc", n_workers=1, pool_bytes=64 << 20) as c:
+        api = bb.KeystoneRpcClient()
+        assert api.connect("127.0.0.1", c.rpc.rpc_port, 3000) == bb.ErrorCode.OK
+        before = c.rpc.shm_requests_served
+        wc = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0)
+        for i in range(200):
+            api.put_start(f"k{i}", 1024, wc)
+            assert api.put_complete(f"k{i}") == bb.ErrorCode.OK
+        assert c.rpc.shm_requests_served - before >= 400 and c.rpc.shm_channels >= 1
+        # latency: a same-host metadata call is a couple of microseconds of shared-memory ping-pong
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            api.object_exists("k7")
+        per_call_us = (time.perf_counter() - t0) / 2000 * 1e6
+        # a big batch: request and response well over the size of a TCP frame buffer, still through the channel
+        keys = [f"b{i:05d}" for i in range(6000)]
+        res = api.batch_put_start(keys, [256] * len(keys), wc)
+        assert all(e == bb.ErrorCode.OK for e, _ in res)
+        assert api.batch_put_complete(keys) == [bb.ErrorCode.OK] * len(keys)
+        assert [e for e, _ in api.batch_get_workers(keys[:10])] == [bb.ErrorCode.OK] * 10
+        # BB_RPC_SHM=0: same calls over TCP
+        monkeypatch.setenv("BB_RPC_SHM", "0")
+        tcp = bb.KeystoneRpcClient()
+        assert tcp.connect("127.0.0.1", c.rpc.rpc_port, 3000) == bb.ErrorCode.OK
+        s0 = c.rpc.shm_requests_served
+        assert tcp.object_exists("k7") is True
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            tcp.object_exists("k7")
+        tcp_us = (time.perf_counter() - t0) / 2000 * 1e6
+        assert c.rpc.shm_requests_served == s0
+        print(f"object_exists round trip: shm {per_call_us:.1f} us, tcp {tcp_us:.1f} us")
+        assert per_call_us < tcp_us  # (typically 2-4 us vs 12-25 us; the assertion only asks for "faster")
+
+
+def test_shm_client_notices_a_dead_server(bb):
+    c = LocalCluster("shm-dead", n_workers=1, pool_bytes=8 << 20)
+    api = bb.KeystoneRpcClient()
+    assert api.connect("127.0.0.1", c.rpc.rpc_port, 3000) == bb.ErrorCode.OK
+    api.set_timeout_ms(2000)
+    assert api.get_view_version() > 0
+    c.stop()  # server gone: the channel is never answered again; the TCP connection says why
+    t0 = time.time()
+    with pytest.raises(bb.BlackbirdError):
+        api.get_view_version()
+    assert time.time() - t0 < 3.0
