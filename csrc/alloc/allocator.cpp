@@ -522,10 +522,63 @@ Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, 
   }
   if (pools.empty()) return ErrorCode::INSUFFICIENT_SPACE;
   bool spill = false;
+  // Ranking walks every pool, copies ids and sorts: ~1 us that a batch of thousands of equal requests pays per object for
+  // an answer that barely moves.  A thread keeps its last ranking and reuses it for up to kRankReuse consecutive requests
+  // with the same shape against the same pool set (only the free-space figures are refreshed, from atomics; a placement that
+  // fails on a reused ranking is retried on a fresh one).
+  struct RankCache {
+    const RangeAllocator* owner = nullptr;
+    uint64_t gen = 0;
+    size_t npools = 0;
+    int left = 0;
+    std::vector<StorageClass> classes;
+    NodeId preferred_node, client_node;
+    bool locality = false, symmetric = false;
+    std::vector<Candidate> cands;
+  };
+  constexpr int kRankReuse = 256;
+  thread_local RankCache rc;
+  const bool cacheable = req.exclude_pools.empty();
+  const uint64_t gen = generation_.load(std::memory_order_acquire);
+  const bool hit = cacheable && rc.owner == this && rc.left > 0 && rc.gen == gen && rc.npools == pools.size() && rc.classes == req.preferred_classes &&
+                   rc.preferred_node == req.preferred_node && rc.client_node == req.client_node && rc.locality == req.enable_locality_awareness &&
+                   rc.symmetric == req.symmetric_replicas;
+  if (hit) {
+    --rc.left;
+    // same pools, same shape: only the free-space figures move.  Refresh them from the allocators' live counters and
+    // restore the order (the comparator is the one rank_candidates uses, so the outcome equals a fresh ranking)
+    for (Candidate& c : rc.cands)
+      if (const PoolAllocator* pa = find_pool(c.id)) {
+        c.free_bytes = pa->total_free();
+        c.largest = pa->largest_free_block();
+      }
+    std::sort(rc.cands.begin(), rc.cands.end(), [](const Candidate& a, const Candidate& b) {
+      if (a.preferred != b.preferred) return a.preferred;
+      if (a.locality != b.locality) return a.locality > b.locality;
+      if (a.bw != b.bw) return a.bw > b.bw;
+      if (a.free_bytes != b.free_bytes) return a.free_bytes > b.free_bytes;
+      return a.id < b.id;
+    });
+    auto r = (req.symmetric_replicas && req.replication_factor > 1) ? place_symmetric(req, pools, rc.cands, spill) : place(req, pools, rc.cands, spill);
+    if (r.ok()) return r;
+    rc.left = 0;  // stale ranking (a pool filled up?): fall through to a fresh one
+  }
   std::vector<Candidate> cands = rank_candidates(req, pools, &spill);
   if (cands.empty()) return ErrorCode::INSUFFICIENT_SPACE;
-  if (req.symmetric_replicas && req.replication_factor > 1) return place_symmetric(req, pools, cands, spill);
-  return place(req, pools, cands, spill);
+  auto r = (req.symmetric_replicas && req.replication_factor > 1) ? place_symmetric(req, pools, cands, spill) : place(req, pools, cands, spill);
+  if (cacheable && r.ok()) {
+    rc.owner = this;
+    rc.gen = gen;
+    rc.npools = pools.size();
+    rc.left = kRankReuse;
+    rc.classes = req.preferred_classes;
+    rc.preferred_node = req.preferred_node;
+    rc.client_node = req.client_node;
+    rc.locality = req.enable_locality_awareness;
+    rc.symmetric = req.symmetric_replicas;
+    rc.cands = std::move(cands);
+  }
+  return r;
 }
 
 ErrorCode RangeAllocator::free(const ObjectKey& key) {

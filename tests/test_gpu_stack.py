@@ -132,7 +132,14 @@ def test_mailbox_resident_warp_serves_single_small_objects_without_a_launch(bb, 
             assert dg[0] == ref(host), (rnd, name, n)
         assert torch.equal(dst[:n], src[:n]) and bool((dst[n:] == 0xEE).all()), (rnd, name, n)
     assert eng.mailbox_requests == r0 + n_req
-    assert eng.mailbox_launches - l0 <= 3, "the warp should have stayed resident across back-to-back requests"
+    # (each round spends a few hundred microseconds in torch between requests, so the warp lingers out now and then;
+    # back-to-back requests below must all be served by one incarnation)
+    assert eng.mailbox_launches - l0 < n_req
+    l_b2b = eng.mailbox_launches
+    for _ in range(50):
+        eng.run([(src.data_ptr(), dst.data_ptr(), 4096)], bb.ChecksumAlgo.XXH3, s)
+    assert eng.mailbox_launches - l_b2b <= 1, "the warp should have stayed resident across back-to-back requests"
+    n_req += 50
     # verify flag travels through the mailbox too
     good = bb.xxh3t64(src.cpu().numpy())
     _, st, _ = eng.run([(src.data_ptr(), dst.data_ptr(), 4096, good ^ 1, bb.XFER_VERIFY)], bb.ChecksumAlgo.XXH3, s)
