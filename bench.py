@@ -367,7 +367,9 @@ def run_headline(args, world: int) -> int:
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
             comparators["fused_put_kernel_vs_unfused_memcpyPeer_plus_crc32c"] = round(
-                variants["crc32c"]["put_GBps_per_gpu"] / comparators["unfused_memcpyPeer_plus_crc32c_kernel_GBps_per_rank"], 3)
+                kernel_only["put_GBps_per_gpu"] / comparators["unfused_memcpyPeer_plus_crc32c_kernel_GBps_per_rank"], 3)
+            comparators["fused_put_kernel_vs_per_object_cudaMemcpyPeerAsync_without_digest"] = round(
+                kernel_only["put_GBps_per_gpu"] / comparators["per_object_cudaMemcpyPeerAsync_GBps_per_rank"], 3)
 
     cl.stop()
     if world > 1 and cl.dist is not None:
