@@ -581,6 +581,90 @@ Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, 
   return r;
 }
 
+bool RangeAllocator::allocate_run(const AllocationRequest& shape, const std::vector<const ObjectKey*>& keys, const PoolMap& pools,
+                                  std::vector<RunSlot>& out) {
+  if (keys.empty() || shape.replication_factor != 1 || shape.max_workers_per_copy == 0 || shape.symmetric_replicas || !shape.exclude_pools.empty())
+    return false;
+  bool spill = false;
+  std::vector<Candidate> cands = rank_candidates(shape, pools, &spill);
+  {  // stripe width exactly as place() derives it; anything wider than one shard takes the general path
+    size_t wpc = std::min(std::max<size_t>(1, shape.max_workers_per_copy), std::max<size_t>(1, cands.size()));
+    if (!shape.enable_striping || shape.prefer_contiguous) wpc = 1;
+    if (wpc > 1 && shape.data_size / wpc < shape.min_shard_size) {
+      if (shape.strict_min_shard) return false;
+      wpc = std::max<size_t>(1, std::min(wpc, shape.data_size / std::max<size_t>(1, shape.min_shard_size)));
+    }
+    if (wpc != 1) return false;
+  }
+  const size_t count = keys.size();
+  out.assign(count, RunSlot{});
+  if (cands.empty()) return true;  // every slot INSUFFICIENT_SPACE, as allocate() reports it
+  size_t tie = 1;  // pools that rank equal but for their free space: the run is dealt out among them
+  while (tie < cands.size() && cands[tie].preferred == cands[0].preferred && cands[tie].locality == cands[0].locality && cands[tie].bw == cands[0].bw) ++tie;
+  struct Piece {
+    const MemoryPool* pool;
+    Range range;
+  };
+  std::vector<Piece> pieces(count, Piece{nullptr, Range(0, 0)});
+  size_t next = 0;
+  auto take = [&](const Candidate& cd, size_t want) {
+    const MemoryPool& pool = pools.at(cd.id);
+    PoolAllocator* pa = ensure_pool(pool);
+    if (!pa->registration_valid()) return;
+    const uint64_t need = pa->aligned(shape.data_size);
+    int races = 0;
+    while (want > 0 && next < count) {
+      size_t chunk = want;
+      if (need) {
+        chunk = std::min<uint64_t>(want, pa->largest_free_block() / need);
+        if (chunk == 0) return;
+      }
+      auto r = pa->allocate(static_cast<uint64_t>(chunk) * need, true);
+      if (!r) {
+        if (++races > 4) return;  // another writer took the hole between the probe and the call
+        continue;
+      }
+      for (size_t k = 0; k < chunk; ++k) pieces[next + k] = Piece{&pool, Range(r->offset + k * need, need)};
+      next += chunk;
+      want -= chunk;
+    }
+  };
+  const size_t per = (count + tie - 1) / tie;
+  for (size_t c = 0; c < tie && next < count; ++c) take(cands[c], std::min(per, count - next));
+  for (size_t c = 0; c < cands.size() && next < count; ++c) take(cands[c], count - next);
+  // ledger + shard descriptors; pool accounting once per run
+  std::unordered_map<const MemoryPool*, size_t> used;
+  for (size_t i = 0; i < next; ++i) {
+    const Piece& pc = pieces[i];
+    const ObjectKey& key = *keys[i];
+    auto shard = make_shard(*pc.pool, pc.range, shape.data_size);
+    bool ok = shard.ok();
+    if (ok) {
+      ObjectAllocation oa;
+      oa.total_size = shape.data_size;
+      oa.extents.push_back({pc.pool->id, pc.range, shape.data_size});
+      LedgerShard& ls = ledger_for(key);
+      std::lock_guard<SpinMutex> lk(ls.mu);
+      ok = ls.objects.emplace(key, std::move(oa)).second;
+      if (!ok) out[i].status = ErrorCode::OBJECT_ALREADY_EXISTS;
+    } else {
+      out[i].status = shard.error();
+    }
+    if (!ok) {
+      if (PoolAllocator* pa = find_pool(pc.pool->id)) pa->free(pc.range);
+      continue;
+    }
+    used[pc.pool] += pc.range.length;
+    out[i].status = ErrorCode::OK;
+    out[i].shard = std::move(shard.value());
+  }
+  if (!used.empty()) {
+    std::lock_guard<SpinMutex> lk(used_mu_);
+    for (const auto& [pool, bytes] : used) used_by_pool_[pool->id] += bytes;
+  }
+  return true;
+}
+
 ErrorCode RangeAllocator::free(const ObjectKey& key) {
   ObjectAllocation oa;
   {
@@ -821,6 +905,14 @@ Result<std::vector<CopyPlacement>> KeystoneAllocatorAdapter::allocate_data_copie
   auto res = allocator_->allocate(r, pools);
   if (!res.ok()) return res.error();
   return std::move(res.value().copies);
+}
+
+bool KeystoneAllocatorAdapter::allocate_run(const std::vector<const ObjectKey*>& keys, size_t data_size, const WorkerConfig& config,
+                                            const IAllocator::PoolMap& pools, const std::string& client_node,
+                                            std::vector<IAllocator::RunSlot>& out) {
+  AllocationRequest r = to_request(ObjectKey(), data_size, config);
+  r.client_node = client_node;
+  return allocator_->allocate_run(r, keys, pools, out);
 }
 
 ErrorCode KeystoneAllocatorAdapter::free_object(const ObjectKey& key) { return allocator_->free(key); }

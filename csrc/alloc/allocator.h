@@ -154,6 +154,19 @@ class IAllocator {
   virtual size_t pool_used_bytes(const MemoryPoolId& id) const = 0;  // live accounting
   virtual double pool_fragmentation(const MemoryPoolId& id) const = 0;  // 1 - largest hole / free bytes (0 = one hole)
   virtual std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const = 0;
+  // Run placement: `keys.size()` objects of one size and one policy (`shape`; its object_key is ignored), each stored as a
+  // single shard on a single pool (replication 1, stripe width 1).  The pools are ranked once and each pool allocator is
+  // called once per chunk, not per object; the run is spread over the pools that tie at the head of the ranking, as
+  // object-by-object placement would.  Returns false -- nothing placed -- when the shape needs the general path.
+  struct RunSlot {
+    ErrorCode status = ErrorCode::INSUFFICIENT_SPACE;
+    ShardPlacement shard;
+  };
+  virtual bool allocate_run(const AllocationRequest& shape, const std::vector<const ObjectKey*>& keys, const PoolMap& pools,
+                            std::vector<RunSlot>& out) {
+    (void)shape, (void)keys, (void)pools, (void)out;
+    return false;
+  }
 };
 
 class RangeAllocator : public IAllocator {
@@ -168,6 +181,8 @@ class RangeAllocator : public IAllocator {
   size_t pool_used_bytes(const MemoryPoolId& id) const override;
   double pool_fragmentation(const MemoryPoolId& id) const override;
   std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const override;
+  bool allocate_run(const AllocationRequest& shape, const std::vector<const ObjectKey*>& keys, const PoolMap& pools,
+                    std::vector<RunSlot>& out) override;
   // Re-reserves the exact extents of already placed copies (metadata recovery after a leader
   // change).  Extents on unknown pools are skipped.
   // `only_pool` (optional): adopt just the shards on that pool and merge them into the key's existing ledger entry
@@ -243,6 +258,10 @@ class KeystoneAllocatorAdapter {
   Result<std::vector<CopyPlacement>> allocate_data_copies(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
                                                           const IAllocator::PoolMap& pools, const std::string& client_node = "",
                                                           const std::vector<MemoryPoolId>& exclude = {});
+  // One-shard-per-object placement of a run of equally sized objects under one policy (IAllocator::allocate_run); false =
+  // the policy needs allocate_data_copies per object.
+  bool allocate_run(const std::vector<const ObjectKey*>& keys, size_t data_size, const WorkerConfig& config, const IAllocator::PoolMap& pools,
+                    const std::string& client_node, std::vector<IAllocator::RunSlot>& out);
   ErrorCode free_object(const ObjectKey& key);
   AllocatorStats get_allocator_stats(std::optional<StorageClass> sc = std::nullopt) const;
   // Returns OK or INVALID_PARAMETERS (the reference throws on bad arguments, :113-169).

@@ -808,6 +808,78 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_get_worke
   return out;
 }
 
+bool KeystoneService::put_start_run(const std::vector<PutStartItem>& items, size_t first, size_t last, const std::string& client_id,
+                                    const std::string& client_node, std::vector<Result<std::vector<CopyPlacement>>>& out) {
+  const WorkerConfig& config = items[first].config;
+  const size_t data_size = items[first].size;
+  if (config.replication_factor != 1 || config.max_workers_per_copy == 0) return false;
+  if (config_.max_replicas > 0 && config.replication_factor > static_cast<size_t>(config_.max_replicas)) return false;
+  WorkerConfig tiered;
+  const WorkerConfig* effective = &config;
+  if (config.preferred_classes.empty() && !config_.tier_policy.empty()) {
+    tiered = config;
+    for (const auto& name : tier_classes_for_size(config_.tier_policy, data_size))
+      if (auto sc = parse_storage_class(name)) tiered.preferred_classes.push_back(*sc);
+    effective = &tiered;
+  }
+  std::vector<const ObjectKey*> keys;
+  std::vector<size_t> index;  // keys[k] is items[index[k]]
+  keys.reserve(last - first), index.reserve(last - first);
+  for (size_t i = first; i < last; ++i) {
+    const ObjectKey& key = items[i].key;
+    if (key.empty() || key.find('\x01') != std::string::npos) {
+      out[i] = ErrorCode::INVALID_KEY;
+      continue;
+    }
+    keys.push_back(&key), index.push_back(i);
+  }
+  std::vector<alloc::IAllocator::RunSlot> slots;
+  if (!keys.empty() && !allocator_->allocate_run(keys, data_size, *effective, pools_, client_node, slots)) return false;
+  const TimePoint now = Clock::now();
+  for (size_t k = 0; k < keys.size(); ++k) {
+    const size_t i = index[k];
+    const ObjectKey& key = *keys[k];
+    if (slots[k].status == ErrorCode::OBJECT_ALREADY_EXISTS) {
+      // live object, expired-but-unswept one, or a racing put of the same key: the per-object path sorts out which
+      out[i] = put_start_locked(key, data_size, config, client_id, client_node);
+      continue;
+    }
+    if (slots[k].status != ErrorCode::OK) {
+      out[i] = slots[k].status;
+      continue;
+    }
+    slots[k].shard.checksum_algo = config.checksum;
+    std::vector<CopyPlacement> copies(1);
+    copies[0].copy_index = 0;
+    copies[0].shards.push_back(std::move(slots[k].shard));
+    bool clash = false;
+    {
+      Shard& sh = shard_for(key);
+      ShardGuard lk(this, sh);
+      if (sh.objects.count(key)) {
+        clash = true;  // an object without a ledger entry (its pools were forgotten): give the extent back, then as above
+      } else {
+        ObjectInfo info;
+        info.key = key;
+        info.size = data_size;
+        info.created = info.last_accessed = now;
+        info.config = config;
+        info.copies = copies;
+        info.state = ObjectState::PENDING;
+        info.owner_client = client_id;
+        sh.objects.emplace(key, std::move(info));
+      }
+    }
+    if (clash) {
+      allocator_->free_object(key);
+      out[i] = put_start_locked(key, data_size, config, client_id, client_node);
+      continue;
+    }
+    out[i] = std::move(copies);
+  }
+  return true;
+}
+
 std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_put_start(const std::vector<PutStartItem>& items,
                                                                                  const std::string& client_id,
                                                                                  const std::string& client_node) {
@@ -821,7 +893,22 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneService::batch_put_start
   uint64_t ok = 0, bytes = 0;
   {
     std::shared_lock<std::shared_mutex> pk(pools_mu_);  // once per batch
-    for (const auto& it : items) out.push_back(put_start_locked(it.key, it.size, it.config, client_id, client_node));
+    // Runs of items with one size and one policy (a batch of activations, KV blocks, feature rows) are placed together
+    constexpr size_t kMinRun = 8;
+    size_t i = 0;
+    while (i < items.size()) {
+      size_t j = i + 1;
+      while (j < items.size() && items[j].size == items[i].size && items[j].config == items[i].config) ++j;
+      if (j - i >= kMinRun) {
+        out.resize(j, ErrorCode::INTERNAL_ERROR);
+        if (put_start_run(items, i, j, client_id, client_node, out)) {
+          i = j;
+          continue;
+        }
+        out.resize(i, ErrorCode::INTERNAL_ERROR);
+      }
+      for (; i < j; ++i) out.push_back(put_start_locked(items[i].key, items[i].size, items[i].config, client_id, client_node));
+    }
   }
   if (reservations_enabled())
     for (size_t i = 0; i < items.size(); ++i)

@@ -312,6 +312,10 @@ class KeystoneService {
   std::atomic<int> top_tier_rank_{-1};  // rank of the fastest tier present (promotion policy fast check)
   std::mutex promo_mu_;
   std::vector<ObjectKey> promo_queue_;
+  // items[first, last) share one size and one WorkerConfig: place them as a run (one ranking, one allocator call per chunk).
+  // False = the policy is not a one-shard-per-object one; nothing was done.  Caller holds pools_mu_ (shared).
+  bool put_start_run(const std::vector<PutStartItem>& items, size_t first, size_t last, const std::string& client_id,
+                     const std::string& client_node, std::vector<Result<std::vector<CopyPlacement>>>& out);
   Result<std::vector<CopyPlacement>> put_start_locked(const ObjectKey& key, size_t data_size, const WorkerConfig& config,
                                                       const std::string& client_id, const std::string& client_node);
   struct HotMetrics {

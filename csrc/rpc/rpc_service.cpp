@@ -166,16 +166,21 @@ void RpcService::register_handlers() {
     Writer w;
     w.ec(ErrorCode::OK);
     w.u32(static_cast<uint32_t>(res.size()));
-    for (const auto& e : res) put_copies_result(w, e);
+    wire::PlacementBatchWriter pw(w);
+    for (const auto& e : res) pw.put(e);
     return w.take();
   });
   leader_only(M_BATCH_PUT_START, [ks](C, S q) {
     Reader r(q);
-    std::vector<PutStartItem> items(r.count(16));
+    std::vector<PutStartItem> items(r.count(12));
+    const bool one_config = r.boolean();  // the usual batch: one policy for every item, sent once
+    WorkerConfig shared;
+    if (one_config) wire::get(r, shared);
     for (auto& it : items) {
       it.key = r.str();
       it.size = r.u64();
-      wire::get(r, it.config);
+      if (one_config) it.config = shared;
+      else wire::get(r, it.config);
     }
     const std::string cid = r.str(), node = r.str();
     Writer w;
@@ -186,7 +191,8 @@ void RpcService::register_handlers() {
     auto res = ks->batch_put_start(items, cid, node);
     w.ec(ErrorCode::OK);
     w.u32(static_cast<uint32_t>(res.size()));
-    for (const auto& e : res) put_copies_result(w, e);
+    wire::PlacementBatchWriter pw(w);
+    for (const auto& e : res) pw.put(e);
     return w.take();
   });
   leader_only(M_BATCH_PUT_COMPLETE, [ks](C, S q) {
@@ -620,7 +626,9 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_get_wor
     return out;
   }
   const uint32_t n = rd.count(4);
-  for (uint32_t i = 0; i < n; ++i) out.push_back(get_copies_result(rd));
+  out.reserve(keys.size());
+  wire::PlacementBatchReader pr(rd);
+  for (uint32_t i = 0; i < n; ++i) out.push_back(pr.get());
   out.resize(keys.size(), Result<std::vector<CopyPlacement>>(ErrorCode::RPC_FAILED));
   return out;
 }
@@ -628,10 +636,14 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_get_wor
 std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_put_start(const std::vector<PutStartItem>& items) {
   Writer w;
   w.u32(static_cast<uint32_t>(items.size()));
+  bool one_config = !items.empty();
+  for (size_t i = 1; i < items.size() && one_config; ++i) one_config = items[i].config == items[0].config;
+  w.boolean(one_config);
+  if (one_config) wire::put(w, items[0].config);
   for (const auto& it : items) {
     w.str(it.key);
     w.u64(it.size);
-    wire::put(w, it.config);
+    if (!one_config) wire::put(w, it.config);
   }
   w.str(client_id_);
   w.str(node_id_);
@@ -648,7 +660,9 @@ std::vector<Result<std::vector<CopyPlacement>>> KeystoneRpcClient::batch_put_sta
     return out;
   }
   const uint32_t n = rd.count(4);
-  for (uint32_t i = 0; i < n; ++i) out.push_back(get_copies_result(rd));
+  out.reserve(items.size());
+  wire::PlacementBatchReader pr(rd);
+  for (uint32_t i = 0; i < n; ++i) out.push_back(pr.get());
   out.resize(items.size(), Result<std::vector<CopyPlacement>>(ErrorCode::RPC_FAILED));
   return out;
 }

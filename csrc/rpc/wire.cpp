@@ -117,6 +117,80 @@ void get(Reader& r, std::vector<CopyPlacement>& v) {
   for (auto& c : v) get(r, c);
 }
 
+namespace {
+// Where a shard sits inside its pool -- the one location field two shards of one pool differ in.
+uint64_t position_of(const LocationDetail& l) {
+  if (auto* m = std::get_if<MemoryLocation>(&l)) return m->remote_addr;
+  if (auto* f = std::get_if<FileLocation>(&l)) return f->file_offset;
+  if (auto* c = std::get_if<CxlMemoryLocation>(&l)) return c->offset;
+  return std::get<GpuSlabLocation>(l).offset;
+}
+void set_position(LocationDetail& l, uint64_t pos) {
+  if (auto* m = std::get_if<MemoryLocation>(&l)) m->remote_addr = pos;
+  else if (auto* f = std::get_if<FileLocation>(&l)) f->file_offset = pos;
+  else if (auto* c = std::get_if<CxlMemoryLocation>(&l)) c->offset = pos, c->region_id = pos / 256;
+  else std::get<GpuSlabLocation>(l).offset = pos;
+}
+bool same_but_position(const LocationDetail& a, const LocationDetail& b) {
+  if (a.index() != b.index()) return false;
+  if (auto* m = std::get_if<MemoryLocation>(&a)) {
+    const auto& n = std::get<MemoryLocation>(b);
+    return m->rkey == n.rkey && m->size == n.size;
+  }
+  if (auto* f = std::get_if<FileLocation>(&a)) return f->file_path == std::get<FileLocation>(b).file_path;
+  if (auto* c = std::get_if<CxlMemoryLocation>(&a)) {
+    const auto& d = std::get<CxlMemoryLocation>(b);
+    return c->device_id == d.device_id && c->size == d.size && c->region_id == c->offset / 256 && d.region_id == d.offset / 256;
+  }
+  const auto& g = std::get<GpuSlabLocation>(a);
+  const auto& h = std::get<GpuSlabLocation>(b);
+  return g.device_rank == h.device_rank && g.slab_id == h.slab_id && g.size == h.size;
+}
+constexpr uint8_t kPlacementFull = 0, kPlacementDelta = 1;
+}  // namespace
+
+void PlacementBatchWriter::put(const Result<std::vector<CopyPlacement>>& res) {
+  w_.ec(res.error());
+  if (!res.ok()) return;
+  const auto& v = res.value();
+  const ShardPlacement* s = (v.size() == 1 && v[0].copy_index == 0 && v[0].shards.size() == 1) ? &v[0].shards[0] : nullptr;
+  if (s && base_ && s->length == base_->length && s->storage_class == base_->storage_class && s->checksum_algo == base_->checksum_algo &&
+      s->pool_id == base_->pool_id && s->worker_id == base_->worker_id && s->endpoint == base_->endpoint &&
+      same_but_position(s->location, base_->location)) {
+    w_.u8(kPlacementDelta);
+    w_.u64(position_of(s->location));
+    w_.u64(s->checksum);
+    return;
+  }
+  w_.u8(kPlacementFull);
+  wire::put(w_, v);
+  base_ = s;  // results live until the reply is written
+}
+
+Result<std::vector<CopyPlacement>> PlacementBatchReader::get() {
+  const ErrorCode ec = r_.ec();
+  if (ec != ErrorCode::OK) return ec;
+  const uint8_t tag = r_.u8();
+  if (tag == kPlacementDelta) {
+    const uint64_t pos = r_.u64(), sum = r_.u64();
+    if (!r_.ok() || !have_base_) {
+      r_.fail();
+      return ErrorCode::RPC_FAILED;
+    }
+    std::vector<CopyPlacement> v = base_;
+    set_position(v[0].shards[0].location, pos);
+    v[0].shards[0].checksum = sum;
+    return v;
+  }
+  std::vector<CopyPlacement> v;
+  if (tag == kPlacementFull) wire::get(r_, v);
+  else r_.fail();
+  if (!r_.ok()) return ErrorCode::RPC_FAILED;
+  have_base_ = v.size() == 1 && v[0].copy_index == 0 && v[0].shards.size() == 1;
+  if (have_base_) base_ = v;
+  return v;
+}
+
 void put(Writer& w, const WorkerConfig& c) {
   w.u64(c.replication_factor);
   w.u64(c.max_workers_per_copy);

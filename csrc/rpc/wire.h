@@ -94,6 +94,28 @@ void put(Writer& w, const std::vector<CopyPlacement>& v);
 void get(Reader& r, std::vector<CopyPlacement>& v);
 void put(Writer& w, const WorkerConfig& c);
 void get(Reader& r, WorkerConfig& c);
+// Batch replies (batch_put_start / batch_get_workers) mostly carry thousands of one-shard placements on the same few pools
+// that differ only in where the shard sits and in its digest.  A result that matches the last fully written one that way is
+// sent as (position, checksum) and rebuilt from that one by the reader.
+class PlacementBatchWriter {
+ public:
+  explicit PlacementBatchWriter(Writer& w) : w_(w) {}
+  void put(const Result<std::vector<CopyPlacement>>& res);
+
+ private:
+  Writer& w_;
+  const ShardPlacement* base_ = nullptr;  // shard of the last result written in full
+};
+class PlacementBatchReader {
+ public:
+  explicit PlacementBatchReader(Reader& r) : r_(r) {}
+  Result<std::vector<CopyPlacement>> get();
+
+ private:
+  Reader& r_;
+  std::vector<CopyPlacement> base_;
+  bool have_base_ = false;
+};
 void put(Writer& w, const ClusterStats& s);
 void get(Reader& r, ClusterStats& s);
 void put(Writer& w, const MemoryPool& p);

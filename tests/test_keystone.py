@@ -386,3 +386,55 @@ def test_size_based_tier_policy_for_puts_without_a_preferred_class(bb):
         assert cl.put("big2", b"z" * (1 << 20), bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU])) == bb.ErrorCode.OK
         assert cl.get_workers("big2")[0].shards[0].storage_class == bb.StorageClass.RAM_CPU
         assert cl.get("big") == b"y" * (1 << 20)
+
+
+def test_batch_put_start_places_uniform_runs_together(bb, ks):
+    """Runs of >= 8 items with one size and one policy take the run path (one ranking, one allocator call per chunk):
+    same per-item results as the object-by-object path, spread over the pools that tie in the ranking, no overlap,
+    and every extent comes back on remove."""
+    cfg = cfg1(bb, ttl_ms=0)
+    keys = [f"run/{i}" for i in range(64)]
+    ks.put_start("run/7", 512, cfg)  # a live duplicate inside the run
+    names = keys[:20] + [""] + keys[20:] + ["run/3"]  # an invalid key and a duplicate of an item of the same batch
+    res = ks.batch_put_start(names, [4096] * len(names), cfg)
+    codes = [r[0] for r in res]
+    assert codes[20] == bb.ErrorCode.INVALID_KEY and codes[-1] == bb.ErrorCode.OBJECT_ALREADY_EXISTS
+    assert codes[7] == bb.ErrorCode.OBJECT_ALREADY_EXISTS
+    ok = [(n, r[1]) for n, r in zip(names, res) if r[0] == bb.ErrorCode.OK]
+    assert len(ok) == 63
+    seen, per_pool = set(), {}
+    for name, copies in ok:
+        assert len(copies) == 1 and len(copies[0].shards) == 1
+        sh = copies[0].shards[0]
+        assert sh.length == 4096 and sh.checksum_algo == cfg.checksum
+        loc = (sh.pool_id, sh.location["remote_addr"])
+        assert loc not in seen
+        seen.add(loc)
+        per_pool[sh.pool_id] = per_pool.get(sh.pool_id, 0) + 1
+    assert len(per_pool) == 4 and min(per_pool.values()) >= 12 and max(per_pool.values()) <= 17  # four equal pools: dealt out evenly
+    # extents of one pool do not overlap
+    for pid in per_pool:
+        addrs = sorted(a for p, a in seen if p == pid)
+        assert all(b - a >= 4096 for a, b in zip(addrs, addrs[1:]))
+    assert ks.get_cluster_stats().pending_objects == 64
+    done = [n for n, _ in ok]
+    assert set(ks.batch_put_complete(done)) == {bb.ErrorCode.OK}
+    assert ks.get_workers("run/5")[0].shards[0].length == 4096
+    assert set(ks.batch_remove_object(done + ["run/7"])) == {bb.ErrorCode.OK}
+    assert ks.get_cluster_stats().used_capacity == 0
+    # the whole capacity is allocatable again as one extent per pool
+    big = ks.batch_put_start([f"big/{i}" for i in range(4)], [1 << 20] * 4, cfg)
+    assert [r[0] for r in big] == [bb.ErrorCode.OK] * 4
+
+
+def test_batch_put_start_run_overflows_down_the_ranking_and_reports_the_rest(bb, ks):
+    cfg = cfg1(bb, ttl_ms=0)
+    n = 40  # 4 pools x 1 MiB hold 32 objects of 128 KiB
+    res = ks.batch_put_start([f"o/{i}" for i in range(n)], [128 << 10] * n, cfg)
+    codes = [r[0] for r in res]
+    assert codes.count(bb.ErrorCode.OK) == 32 and codes.count(bb.ErrorCode.INSUFFICIENT_SPACE) == 8
+    # striped or replicated policies keep the general path (two shards per copy here)
+    assert set(ks.batch_remove_object([f"o/{i}" for i in range(n) if codes[i] == bb.ErrorCode.OK])) == {bb.ErrorCode.OK}
+    wide = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=2, ttl_ms=0)
+    res = ks.batch_put_start([f"s/{i}" for i in range(16)], [64 << 10] * 16, wide)
+    assert all(r[0] == bb.ErrorCode.OK and len(r[1][0].shards) == 2 for r in res)
