@@ -478,6 +478,7 @@ def run_config(args, world: int) -> int:
                 row[k] = round(cl.sum_over_ranks(t[k]), 2)  # whole job
             for k in ("put_p50_us", "put_p99_us", "get_p50_us", "get_p99_us"):
                 row[k] = round(cl.max_over_ranks(l[k]), 1)
+            row["rank0_client_phases"] = t.get("phases", {})  # Keystone round trips vs launch vs kernel wait, ms per batch
             rows.append(row)
         cl.stop()
         big = rows[-1]

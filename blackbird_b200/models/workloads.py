@@ -71,7 +71,10 @@ def throughput_sweep(cluster, sizes, target_node: str, batch_bytes: int = 1 << 3
         sp = [src.data_ptr() + i * stride for i in range(nobj)]
         op = [out.data_ptr() + i * stride for i in range(nobj)]
         put_dev, get_dev, put_wall, get_wall = [], [], [], []
+        ph0 = None
         for it in range(iters + 1):
+            if it == 1:
+                ph0 = cluster.client.phase_summary()
             keys = [f"sw/{cluster.rank}/{size}/{it}/{j}" for j in range(nobj)]
             t0 = time.perf_counter()
             m0 = cluster.fabric.total_device_ms
@@ -88,9 +91,16 @@ def throughput_sweep(cluster, sizes, target_node: str, batch_bytes: int = 1 << 3
         torch.cuda.synchronize()
         assert torch.equal(src.view(nobj, stride)[:, :size], out.view(nobj, stride)[:, :size])
         total = nobj * size
+        # where the client call spends its time: Keystone round trips vs descriptor build + launch vs waiting for the kernel
+        ph1 = cluster.client.phase_summary()
+        phases = {}
+        for name, v in ph1.items():
+            if name.startswith("phase_"):
+                d = v[1] - (ph0.get(name, [0, 0])[1] if ph0 else 0)
+                phases[name[len("phase_"):-len("_us")] + "_ms_per_batch"] = round(d / 1e3 / max(1, iters), 4)
         rows.append({"size": size, "batch": nobj, "put_GBps_kernel": total / min(put_dev) / 1e6, "get_GBps_kernel": total / min(get_dev) / 1e6,
                      "put_GBps_client": total / statistics.median(put_wall) / 1e6, "get_GBps_client": total / statistics.median(get_wall) / 1e6,
-                     "put_batch_ms_p50": statistics.median(put_wall), "get_batch_ms_p50": statistics.median(get_wall)})
+                     "put_batch_ms_p50": statistics.median(put_wall), "get_batch_ms_p50": statistics.median(get_wall), "phases": phases})
         del src, out
     return rows
 

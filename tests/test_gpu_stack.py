@@ -530,3 +530,84 @@ def test_fused_fp8_handles_any_whole_number_of_mx_blocks(bb, torch_cuda, n):
         assert cl.client.batch_get_device_fp8(["odd"], [buf.data_ptr()], [n], s) == [bb.ErrorCode.CHECKSUM_MISMATCH]
     finally:
         cl.stop()
+
+
+def test_pipeline_soak_random_layouts_tails_and_fanout(bb, torch_cuda):
+    """Soak of the kernel's mbarrier / stage-metadata protocol (the racecheck report reasons about it; this stresses it): ~10^6
+    tiles through the persistent pipeline as batches of randomly sized objects (whole tiles, tiles +- a few bytes, odd tails,
+    multi-MiB objects split over CTAs) with 1-3 destinations each and a different digest every round.  A tile handled with another
+    tile's metadata (stale size, destination, object index, tile index) shows up as a wrong byte, a stray write outside the
+    objects, a digest that differs from the CPU model, or a verify mismatch on the read-back."""
+    torch = torch_cuda
+    tile = bb.TILE_BYTES
+    B = 512 << 20
+    eng = bb.XferEngine(0, 1 << 16, 2)
+    stream = _stream(torch)
+    src = torch.empty(B, dtype=torch.uint8, device="cuda")
+    dsts = [torch.empty(B, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    back = torch.empty(B, dtype=torch.uint8, device="cuda")
+    rng = np.random.default_rng(0xB200)
+    algos = [("XXH3", bb.xxh3t64), ("CRC32C", bb.crc32c), ("BBH64", bb.bbh64), ("NONE", None)]
+    tiles_done, rnd = 0, -1
+    while tiles_done < 1_000_000:
+        rnd += 1
+        name, host_digest = algos[rnd % len(algos)]
+        algo = getattr(bb.ChecksumAlgo, name)
+        bb.random_fill(src.data_ptr(), B, 1000 + rnd, stream)
+        for d in dsts:
+            d.zero_()
+        back.zero_()
+        # layout: objects back to back at 256-byte aligned offsets
+        sizes, offs, ndst, off = [], [], [], 0
+        while True:
+            kind = rng.integers(0, 10)
+            if kind < 3:
+                n = int(rng.integers(1, 12)) * tile
+            elif kind < 6:
+                n = max(1, int(rng.integers(1, 12)) * tile + int(rng.integers(-255, 256)))
+            elif kind < 9:
+                n = int(rng.integers(1, 200000))
+            else:
+                n = int(rng.integers(1 << 20, 8 << 20)) + int(rng.integers(0, 16))
+            if off + n > B:
+                break
+            sizes.append(n), offs.append(off), ndst.append(int(rng.integers(1, 4)))
+            off = (off + n + 255) // 256 * 256
+        nobj = len(sizes)
+        items = [(src.data_ptr() + o, [dsts[k].data_ptr() + o for k in range(r)], n) for o, n, r in zip(offs, sizes, ndst)]
+        dg, st, _ = eng.run(items, algo, stream)
+        assert not any(st)
+        tiles_done += sum((n + tile - 1) // tile for n in sizes)
+        t_off = torch.tensor(offs, dtype=torch.int64, device="cuda")
+        t_end = t_off + torch.tensor(sizes, dtype=torch.int64, device="cuda")
+        t_nd = torch.tensor(ndst, dtype=torch.int64, device="cuda")
+        masks = []
+        for k in range(3):
+            sel = t_nd > k
+            edge = torch.zeros(B + 1, dtype=torch.int8, device="cuda")
+            edge[t_off[sel]] += 1
+            edge[t_end[sel]] -= 1
+            m = torch.cumsum(edge, 0, dtype=torch.int8)[:B] > 0
+            masks.append(m)
+            assert torch.equal(dsts[k][m], src[m]), f"round {rnd}: wrong bytes in destination {k}"
+            assert not bool(dsts[k][~m].any()), f"round {rnd}: stray write in destination {k}"
+            del edge
+        if host_digest is not None:
+            for i in rng.choice(nobj, size=24, replace=False):
+                h = src[offs[i]:offs[i] + sizes[i]].cpu().numpy()
+                assert dg[i] == host_digest(h), f"round {rnd}: digest of object {i} ({sizes[i]} B)"
+        # read everything back with on-device verification; one object of the stored copy is corrupted first
+        bad = int(rng.integers(0, nobj))
+        pos = offs[bad] + int(rng.integers(0, sizes[bad]))
+        dsts[0][pos] ^= 0x40
+        items = [(dsts[0].data_ptr() + o, back.data_ptr() + o, n, int(d), bb.XFER_VERIFY) for o, n, d in zip(offs, sizes, dg)]
+        dg2, st2, _ = eng.run(items, algo, stream)
+        tiles_done += sum((n + tile - 1) // tile for n in sizes)
+        if host_digest is not None:
+            assert [i for i, s in enumerate(st2) if s] == [bad], f"round {rnd}: verify flagged {[i for i, s in enumerate(st2) if s][:8]}, corrupted {bad}"
+            assert all(a == b for i, (a, b) in enumerate(zip(dg, dg2)) if i != bad)
+        dsts[0][pos] ^= 0x40
+        back[pos] ^= 0x40
+        assert torch.equal(back[masks[0]], src[masks[0]]) and not bool(back[~masks[0]].any())
+        del masks
+    assert rnd >= 4  # every digest took part

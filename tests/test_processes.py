@@ -601,3 +601,24 @@ def test_cluster_token_gates_every_rpc_server(procs, tmp_path, bb):
         assert c.get("authed") == data
     finally:
         bb.set_cluster_token("")  # process-wide: do not leak into the other tests
+
+
+def test_start_cluster_script_brings_up_a_keystone_pair(tmp_path):
+    """scripts/start_cluster.sh --ha: durable coordinator, two Keystones, workers, smoke test through both endpoints;
+    scripts/stop_cluster.sh stops exactly the recorded PIDs."""
+    if BIN != os.path.join(ROOT, "bin"):
+        pytest.skip("the scripts start the binaries under bin/")
+    env = dict(os.environ, BB_COORD_PORT=str(free_port()), BB_RPC_PORT=str(free_port()), BB_HTTP_PORT=str(free_port()))
+    run = tmp_path / "run"
+    try:
+        up = subprocess.run([os.path.join(ROOT, "scripts", "start_cluster.sh"), "-n", "2", "--ha", "-d", str(run)], env=env, capture_output=True,
+                            text=True, timeout=90)
+        assert up.returncode == 0, up.stdout + up.stderr
+        assert "verify PASS" in up.stdout and "bb_workers 2" in up.stdout
+        assert (run / "keystone2.pid").exists() and (run / "coord-data").is_dir()
+        rpc2 = int(env["BB_RPC_PORT"]) + 10
+        st = run_cli("--keystone", f"127.0.0.1:{env['BB_RPC_PORT']},127.0.0.1:{rpc2}", "stats")
+        assert st.returncode == 0, st.stdout + st.stderr
+    finally:
+        down = subprocess.run([os.path.join(ROOT, "scripts", "stop_cluster.sh"), "-d", str(run)], capture_output=True, text=True, timeout=60)
+    assert "stopped keystone2" in down.stdout and "stopped coord" in down.stdout
