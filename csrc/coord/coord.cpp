@@ -745,11 +745,7 @@ RemoteCoord::~RemoteCoord() { close(); }
 
 bool RemoteCoord::connect_any(net::RpcClient& c, int timeout_ms) {
   for (const auto& [h, p] : endpoints_)
-    if (c.connect(h, p, timeout_ms) == ErrorCode::OK) {
-      host_ = h;
-      port_ = p;
-      return true;
-    }
+    if (c.connect(h, p, timeout_ms) == ErrorCode::OK) return true;
   return false;
 }
 

@@ -252,8 +252,6 @@ class RemoteCoord : public CoordStore {
   std::map<int64_t, std::vector<WatchEvent>> pending_;  // by server id
   bool watch_connected_ = false;
   std::vector<std::pair<std::string, uint16_t>> endpoints_;
-  std::string host_;
-  uint16_t port_ = 0;
   std::thread monitor_;
   std::atomic<bool> closing_{false};
   std::atomic<uint64_t> reconnects_{0};

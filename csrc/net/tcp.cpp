@@ -561,6 +561,8 @@ struct RpcServer::ShmChan {
   ShmChanHeader* hdr = nullptr;
   ConnPtr conn;                 // the TCP connection that offered it (handlers see this connection)
   uint64_t served = 0;          // last request sequence number answered (poller-private)
+  size_t owner = 0;             // the one poller that serves this channel, fixed at attach time: a partition by list index
+                                // would shift when another channel closes and let two pollers answer the same request
   std::atomic<bool> closed{false};
   std::mutex ov_mu;
   std::string overflow;         // a response that did not fit: collected over TCP with kShmFetchMethod
@@ -589,6 +591,8 @@ RpcServer::Reply RpcServer::dispatch(const ConnPtr& c, uint32_t method, std::str
   return reply;
 }
 
+static size_t shm_poller_count() { return std::max<size_t>(1, std::min<size_t>(4, std::thread::hardware_concurrency() / 4)); }
+
 ErrorCode RpcServer::shm_attach(const ConnPtr& c, const std::string& path) {
   // only paths of the form /proc/<pid>/fd/<n> (a memfd of a process on this host) are accepted
   if (path.compare(0, 6, "/proc/") != 0 || path.find("/fd/") == std::string::npos || path.find("..") != std::string::npos) return ErrorCode::INVALID_PARAMETERS;
@@ -611,10 +615,11 @@ ErrorCode RpcServer::shm_attach(const ConnPtr& c, const std::string& path) {
   for (auto& old : shm_chans_)
     if (old->conn == c) old->closed.store(true);  // a connection has at most one channel
   shm_chans_.erase(std::remove_if(shm_chans_.begin(), shm_chans_.end(), [](const auto& x) { return x->closed.load(); }), shm_chans_.end());
+  ch->owner = shm_next_owner_++ % shm_poller_count();
   shm_chans_.push_back(ch);
   shm_gen_.fetch_add(1, std::memory_order_release);
   if (!shm_run_.exchange(true)) {
-    const size_t n = std::max<size_t>(1, std::min<size_t>(4, std::thread::hardware_concurrency() / 4));
+    const size_t n = shm_poller_count();
     for (size_t i = 0; i < n; ++i) shm_pollers_.emplace_back([this, i] { shm_poll_loop(i); });
   }
   return ErrorCode::OK;
@@ -637,12 +642,11 @@ size_t RpcServer::shm_channels() const {
   return shm_chans_.size();
 }
 
-// Poller i serves the channels whose index in the list is congruent to i.  It spins while requests keep coming and
-// backs off to short sleeps after `busy` of silence (like the epoll threads' busy-poll window).
+// Poller i serves the channels it owns.  It spins while requests keep coming and backs off to short sleeps after `busy`
+// of silence (like the epoll threads' busy-poll window).
 void RpcServer::shm_poll_loop(size_t idx) {
   std::vector<std::shared_ptr<ShmChan>> mine;
   uint64_t gen = ~0ull;
-  const size_t stride = std::max<size_t>(1, std::min<size_t>(4, std::thread::hardware_concurrency() / 4));
   auto last_active = std::chrono::steady_clock::now();
   const auto busy = std::chrono::microseconds(2000);
   while (shm_run_.load(std::memory_order_acquire)) {
@@ -650,7 +654,8 @@ void RpcServer::shm_poll_loop(size_t idx) {
       std::lock_guard<std::mutex> lk(shm_mu_);
       gen = shm_gen_.load();
       mine.clear();
-      for (size_t i = idx; i < shm_chans_.size(); i += stride) mine.push_back(shm_chans_[i]);
+      for (const auto& ch : shm_chans_)
+        if (ch->owner == idx) mine.push_back(ch);
     }
     bool any = false;
     for (auto& ch : mine) {
@@ -721,10 +726,12 @@ void RpcServer::stop_shm() {
   shm_chans_.clear();
 }
 
-RpcServer::~RpcServer() {
-  stop();
+void RpcServer::stop() {
   stop_shm();
+  TcpServer::stop();
 }
+
+RpcServer::~RpcServer() { stop(); }
 
 bool RpcServer::on_data(const ConnPtr& c) {
   std::string& in = c->inbuf();

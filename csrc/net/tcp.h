@@ -129,7 +129,7 @@ class TcpServer {
   void set_busy_poll_us(int us) { busy_poll_us_ = us; }
   // Socket buffer size requested for accepted connections (0 = kernel default); set before start().
   void set_socket_buffers(int bytes) { sock_buf_bytes_ = bytes; }
-  void stop();
+  virtual void stop();
   bool running() const { return running_.load(); }
   uint16_t port() const { return port_; }
   size_t connection_count() const;
@@ -198,7 +198,8 @@ class RpcServer : public TcpServer {
   uint64_t shm_requests_served() const { return shm_served_.load(); }
   size_t shm_channels() const;
   ~RpcServer() override;
-  void stop_shm();  // joins the channel pollers (RpcServer owners call stop(), which ends with this)
+  void stop() override;  // channel pollers first (no request may reach a handler once stop() returned), then the sockets
+  void stop_shm();       // joins the channel pollers
 
  protected:
   bool on_data(const ConnPtr& c) override;
@@ -214,6 +215,7 @@ class RpcServer : public TcpServer {
   mutable std::mutex shm_mu_;
   std::vector<std::shared_ptr<ShmChan>> shm_chans_;
   std::atomic<uint64_t> shm_gen_{0};
+  size_t shm_next_owner_ = 0;  // guarded by shm_mu_: round-robin assignment of channels to pollers
   std::vector<std::thread> shm_pollers_;
   std::atomic<bool> shm_run_{false};
   std::atomic<uint64_t> shm_served_{0};
