@@ -39,6 +39,7 @@ double pct(std::vector<double> v, double q) {
 int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
+  if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   const std::string mode = args.positional.empty() ? "client" : args.positional[0];
   if (args.has("help")) {
     std::printf("usage: bb-bench client|backend|control|gpu [options]\n");

@@ -41,6 +41,7 @@ struct BlackbirdClientOptions {
   // play for the reference's intra-node RMA).  BB_DISABLE_SHM=1 in the environment also turns it off.
   bool enable_shm = true;
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
+  bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h); also BB_ENCRYPT_TRANSPORT=1
 };
 
 // One device-side transfer request of a batch (a shard).

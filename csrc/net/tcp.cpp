@@ -47,10 +47,24 @@ std::string cluster_token() {
   }
   return g_token;
 }
+namespace {
+std::atomic<int> g_encrypt{-1};  // -1: not decided yet (BB_ENCRYPT_TRANSPORT)
+}
+void set_transport_encryption(bool on) { g_encrypt.store(on ? 1 : 0); }
+bool transport_encryption() {
+  int v = g_encrypt.load();
+  if (v < 0) {
+    const char* e = std::getenv("BB_ENCRYPT_TRANSPORT");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    g_encrypt.store(v);
+  }
+  return v == 1;
+}
 
 namespace {
 constexpr size_t kNonce = 16, kMac = 32;
 constexpr char kHelloMagic[] = "BBA1";
+constexpr char kHelloSecure[] = "BBA2";  // as BBA1, and every frame after the handshake is sealed (tcp.h)
 void fresh_nonce(char* out) {
   size_t got = 0;
   while (got < kNonce) {
@@ -273,24 +287,66 @@ Connection::~Connection() {
   if (fd_ >= 0) ::close(fd_);
 }
 
+bool Connection::enable_secure(const uint8_t rx_key[kAeadKey], const uint8_t tx_key[kAeadKey]) {
+  std::lock_guard<std::mutex> lk(write_mu_);
+  if (!rx_.set_key(rx_key, true) || !tx_.set_key(tx_key, false)) return false;
+  secure_.store(true, std::memory_order_release);
+  return true;
+}
+
+// One sealed frame: [len + tag][method][id] in clear (authenticated), then ciphertext and tag.  The payload is copied
+// while it is encrypted -- zero-copy replies (a pool's bytes) must not be encrypted where they live.
+bool Connection::send_sealed_locked(const char* hdr, const Aead::CSpan* payload, int n, int timeout_ms) {
+  size_t len = 0;
+  for (int i = 0; i < n; ++i) len += payload[i].len;
+  if (len > kMaxFrame) return false;
+  std::string out(kFrameHeader + len + kAeadTag, '\0');
+  const uint32_t wire_len = static_cast<uint32_t>(len + kAeadTag);
+  std::memcpy(&out[0], &wire_len, 4);
+  std::memcpy(&out[4], hdr + 4, kFrameHeader - 4);
+  if (!tx_.seal(out.data(), kFrameHeader, payload, n, &out[kFrameHeader])) return false;
+  return send_all(fd_, out.data(), out.size(), timeout_ms);
+}
+
 bool Connection::send(const void* data, size_t len) {
   if (closed_.load()) return false;
   std::lock_guard<std::mutex> lk(write_mu_);
-  if (!send_all(fd_, data, len, 10000)) {
-    close();
-    return false;
+  bool ok = true;
+  if (secure_.load(std::memory_order_relaxed)) {  // `data` is one or more whole frames (every sender builds them with encode_frame)
+    const char* p = static_cast<const char*>(data);
+    while (ok && len) {
+      uint32_t flen = 0;
+      if (len >= kFrameHeader) std::memcpy(&flen, p, 4);
+      if (len < kFrameHeader || len - kFrameHeader < flen) {
+        ok = false;
+        break;
+      }
+      const Aead::CSpan body{p + kFrameHeader, flen};
+      ok = send_sealed_locked(p, &body, 1, 10000);
+      p += kFrameHeader + flen;
+      len -= kFrameHeader + flen;
+    }
+  } else {
+    ok = send_all(fd_, data, len, 10000);
   }
-  return true;
+  if (!ok) close();
+  return ok;
 }
 
 bool Connection::sendv(const Piece* pieces, int n) {
   if (closed_.load()) return false;
   std::lock_guard<std::mutex> lk(write_mu_);
-  if (!send_gather(fd_, pieces, n, 30000)) {
-    close();
-    return false;
+  bool ok;
+  if (secure_.load(std::memory_order_relaxed)) {  // pieces[0] is the frame header, the rest its payload
+    Aead::CSpan body[3];
+    int nb = 0;
+    for (int i = 1; i < n && nb < 3; ++i) body[nb++] = Aead::CSpan{pieces[i].data, pieces[i].len};
+    ok = n >= 1 && n <= 4 && pieces[0].len == kFrameHeader && send_sealed_locked(static_cast<const char*>(pieces[0].data), body, nb, 30000);
+  } else {
+    ok = send_gather(fd_, pieces, n, 30000);
   }
-  return true;
+  if (!ok) close();
+  return ok;
 }
 
 void Connection::close() {
@@ -450,7 +506,7 @@ void TcpServer::worker_loop() {
       ssize_t r = ::recv(c->fd(), buf, sizeof buf, 0);
       if (r > 0) {
         c->inbuf().append(buf, static_cast<size_t>(r));
-        if (c->inbuf().size() > kMaxFrame + kFrameHeader) {
+        if (c->inbuf().size() > kMaxFrame + kFrameHeader + kAeadTag) {
           alive = false;
           break;
         }
@@ -551,7 +607,7 @@ size_t RpcServer::bytes_missing(const ConnPtr& c) {
   const std::string& in = c->inbuf();
   if (in.size() < kFrameHeader) return 0;
   const uint32_t len = rd32(in.data());
-  if (len > kMaxFrame) return 0;  // on_data closes the connection
+  if (len > kMaxFrame + kAeadTag) return 0;  // on_data closes the connection
   const size_t total = static_cast<size_t>(kFrameHeader) + len;
   return total > in.size() ? total - in.size() : 0;
 }
@@ -738,23 +794,50 @@ bool RpcServer::on_data(const ConnPtr& c) {
   size_t pos = 0;
   while (in.size() - pos >= kFrameHeader) {
     const uint32_t len = rd32(&in[pos]);
-    if (len > kMaxFrame) return false;
+    if (len > kMaxFrame + (c->secure() ? kAeadTag : 0)) return false;
     if (in.size() - pos < kFrameHeader + len) break;
     const uint32_t method = rd32(&in[pos + 4]);
     const uint64_t id = rd64(&in[pos + 8]);
     const size_t body = pos + kFrameHeader;
+    const size_t frame_at = pos;
     pos += kFrameHeader + len;
+    uint32_t plen = len;  // payload bytes handed to the handler
+    if (c->secure()) {    // sealed frame: open it in place, the clear header is the authenticated data
+      const Aead::Span ct{&in[body], len >= kAeadTag ? len - kAeadTag : 0};
+      if (len < kAeadTag || !c->rx().open(&in[frame_at], kFrameHeader, &ct, 1, &in[body + len - kAeadTag])) {
+        if (log_denial()) BB_LOG(WARNING) << "rpc: frame from " << c->peer() << " failed authentication (altered, replayed or out of order): closing";
+        return false;
+      }
+      plen = len - static_cast<uint32_t>(kAeadTag);
+    }
     if (!c->authed()) {
       const std::string token = cluster_token();
       if (method == kAuthMethod) {
         const std::string_view msg(in.data() + body, len);
+        if (token.empty() && transport_encryption()) {
+          if (log_denial()) BB_LOG(ERROR) << "rpc: encrypt_transport is set but there is no cluster token to derive keys from: refusing " << c->peer();
+          c->send(encode_frame(kDeniedMarker, id, std::string()));
+          return false;
+        }
         if (token.empty()) {  // open cluster: nothing to prove, tell the client so
           c->set_authed();
           if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;
           continue;
         }
         std::string& nonces = c->auth_nonces();
-        if (nonces.empty() && msg.size() == 4 + kNonce && msg.substr(0, 4) == kHelloMagic) {
+        const bool hello = nonces.empty() && msg.size() == 4 + kNonce;
+        if (hello && msg.substr(0, 4) == kHelloMagic && transport_encryption()) {
+          if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " does not encrypt but this server requires it (encrypt_transport)";
+          c->send(encode_frame(kDeniedMarker, id, std::string()));
+          return false;
+        }
+        if (hello && msg.substr(0, 4) == kHelloSecure && !Aead::available()) {
+          if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " asks for an encrypted connection but libcrypto is not available here";
+          c->send(encode_frame(kDeniedMarker, id, std::string()));
+          return false;
+        }
+        if (hello && (msg.substr(0, 4) == kHelloMagic || msg.substr(0, 4) == kHelloSecure)) {
+          c->wants_secure() = msg.substr(0, 4) == kHelloSecure;
           nonces.assign(msg.substr(4));
           char sn[kNonce];
           fresh_nonce(sn);
@@ -765,16 +848,22 @@ bool RpcServer::on_data(const ConnPtr& c) {
           continue;
         }
         if (nonces.size() == 2 * kNonce && msg.size() == kMac && mac_equal(msg.data(), handshake_mac(token, "bb-cli", nonces).data(), kMac)) {
-          nonces.clear();
           c->set_authed();
-          if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;
+          if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;  // the last clear frame
+          if (c->wants_secure()) {
+            uint8_t c2s[kAeadKey], s2c[kAeadKey];
+            derive_key(token, "bb-key-c2s", nonces, c2s);
+            derive_key(token, "bb-key-s2c", nonces, s2c);
+            if (!c->enable_secure(c2s, s2c)) return false;
+          }
+          nonces.clear();
           continue;
         }
         if (log_denial()) BB_LOG(WARNING) << "rpc: failed cluster-token handshake from " << c->peer();
         c->send(encode_frame(kDeniedMarker, id, std::string()));
         return false;
       }
-      if (!token.empty()) {
+      if (!token.empty() || transport_encryption()) {  // (encryption without a token cannot be keyed: nothing gets in)
         if (log_denial()) BB_LOG(WARNING) << "rpc: request without the cluster token from " << c->peer();
         c->send(encode_frame(kDeniedMarker, id, std::string()));
         return false;
@@ -784,13 +873,13 @@ bool RpcServer::on_data(const ConnPtr& c) {
     Reply reply;
     uint32_t rmethod = method;
     if (method == kShmAttachMethod) {
-      const ErrorCode ec = shm_attach(c, in.substr(body, len));
+      const ErrorCode ec = shm_attach(c, in.substr(body, plen));
       const uint32_t e = static_cast<uint32_t>(ec);
       reply.head.assign(reinterpret_cast<const char*>(&e), 4);
     } else if (method == kShmFetchMethod) {
       reply.head = shm_take_overflow(c);
     } else {
-      reply = dispatch(c, method, std::string_view(in.data() + body, len), &rmethod);
+      reply = dispatch(c, method, std::string_view(in.data() + body, plen), &rmethod);
     }
     served_.fetch_add(1, std::memory_order_relaxed);
     char hdr[kFrameHeader];
@@ -821,6 +910,18 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
     return ErrorCode::CONNECTION_FAILED;
   }
   const std::string token = cluster_token();
+  const bool want_secure = transport_encryption();
+  secure_ = false;
+  if (want_secure) {
+    std::string why;
+    if (token.empty()) why = "no cluster token to derive keys from";
+    else Aead::available(&why);
+    if (!why.empty()) {
+      BB_LOG(ERROR) << "RpcClient: encrypt_transport is set but cannot be honoured: " << why;
+      ::close(fd);
+      return ErrorCode::ACCESS_DENIED;
+    }
+  }
   if (!token.empty()) {  // mutual challenge-response on the cluster token before anything else (tcp.h)
     auto exchange = [&](uint64_t id, const std::string& body, std::string* reply) -> ErrorCode {
       const std::string f = encode_frame(kAuthMethod, id, body);
@@ -833,7 +934,7 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
     };
     std::string nonces(kNonce, '\0'), reply;
     fresh_nonce(nonces.data());
-    ErrorCode ec = exchange(0, std::string(kHelloMagic, 4) + nonces, &reply);
+    ErrorCode ec = exchange(0, std::string(want_secure ? kHelloSecure : kHelloMagic, 4) + nonces, &reply);
     if (ec == ErrorCode::OK) {
       if (reply.size() != kNonce + kMac) {
         BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " has no cluster token but this client does";
@@ -847,6 +948,13 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
           ec = exchange(1, handshake_mac(token, "bb-cli", nonces), &reply);
         }
       }
+    }
+    if (ec == ErrorCode::OK && want_secure) {  // everything after the server's acknowledgement is sealed, both ways
+      uint8_t c2s[kAeadKey], s2c[kAeadKey];
+      derive_key(token, "bb-key-c2s", nonces, c2s);
+      derive_key(token, "bb-key-s2c", nonces, s2c);
+      if (!tx_.set_key(c2s, false) || !rx_.set_key(s2c, true)) ec = ErrorCode::INTERNAL_ERROR;
+      else secure_ = true;
     }
     if (ec != ErrorCode::OK) {
       ::close(fd);
@@ -883,10 +991,66 @@ void RpcClient::enable_push(std::function<void(uint32_t, const std::string&)> cb
   reader_ = std::thread([this] { reader_loop(); });
 }
 
+bool RpcClient::send_request(uint32_t method, uint64_t id, const void* a, size_t a_len, const void* b, size_t b_len, int timeout_ms) {
+  if (a_len + b_len > kMaxFrame) return false;
+  char hdr[kFrameHeader];
+  const uint32_t len = static_cast<uint32_t>(a_len + b_len + (secure_ ? kAeadTag : 0));
+  std::memcpy(hdr, &len, 4);
+  std::memcpy(hdr + 4, &method, 4);
+  std::memcpy(hdr + 8, &id, 8);
+  if (!secure_) {
+    const Connection::Piece pieces[3] = {{hdr, sizeof hdr}, {a, a_len}, {b, b_len}};
+    return send_gather(fd_, pieces, 3, timeout_ms);
+  }
+  std::string out(kFrameHeader + a_len + b_len + kAeadTag, '\0');
+  std::memcpy(&out[0], hdr, kFrameHeader);
+  const Aead::CSpan parts[2] = {{a, a_len}, {b, b_len}};
+  if (!tx_.seal(hdr, kFrameHeader, parts, 2, &out[kFrameHeader])) return false;
+  return send_all(fd_, out.data(), out.size(), timeout_ms);
+}
+
+bool RpcClient::recv_frame(uint32_t* method, uint64_t* id, std::string* head, size_t head_len, void* dst, size_t dst_cap, size_t* received,
+                           int hdr_timeout_ms, int body_timeout_ms, bool* idle) {
+  if (idle) *idle = false;
+  if (received) *received = 0;
+  char hdr[kFrameHeader];
+  if (!recv_all(fd_, hdr, sizeof hdr, hdr_timeout_ms)) {
+    if (idle) *idle = true;  // nothing (complete) arrived in time; the caller decides whether the socket is dead
+    return false;
+  }
+  const uint32_t len = rd32(hdr);
+  *method = rd32(hdr + 4);
+  if (id) *id = rd64(hdr + 8);
+  const size_t overhead = secure_ ? kAeadTag : 0;
+  if (len > kMaxFrame + overhead || len < overhead) return false;  // never size a buffer from an unchecked wire length
+  const size_t plen = len - overhead;
+  const size_t h = dst ? std::min(head_len, plen) : plen;
+  const size_t rest = plen - h;
+  head->assign(h, '\0');
+  if (h && !recv_all(fd_, head->data(), h, body_timeout_ms)) return false;
+  if (rest > dst_cap) return false;  // cannot resynchronise the stream without draining it
+  if (rest && !recv_all(fd_, dst, rest, body_timeout_ms)) return false;
+  if (secure_) {
+    char tag[kAeadTag];
+    if (!recv_all(fd_, tag, sizeof tag, body_timeout_ms)) return false;
+    const Aead::Span parts[2] = {{head->data(), h}, {dst, rest}};
+    if (!rx_.open(hdr, kFrameHeader, parts, 2, tag)) {
+      BB_LOG(WARNING) << "RpcClient: response failed authentication (altered, replayed or out of order): closing the connection";
+      return false;
+    }
+  }
+  if (received) *received = rest;
+  return true;
+}
+
 void RpcClient::reader_loop() {
   while (reader_run_.load()) {
-    char hdr[kFrameHeader];
-    if (!recv_all(fd_, hdr, sizeof hdr, 500)) {
+    uint32_t method = 0;
+    uint64_t id = 0;
+    std::string payload;
+    bool idle = false;
+    if (!recv_frame(&method, &id, &payload, 0, nullptr, 0, nullptr, 500, 30000, &idle)) {
+      if (!idle) break;
       // distinguish timeout (keep going) from a dead socket
       pollfd pf{fd_, POLLIN, 0};
       int rc = ::poll(&pf, 1, 0);
@@ -897,12 +1061,6 @@ void RpcClient::reader_loop() {
       if (n < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) break;
       continue;
     }
-    const uint32_t len = rd32(hdr);
-    const uint32_t method = rd32(hdr + 4);
-    const uint64_t id = rd64(hdr + 8);
-    if (len > kMaxFrame) break;  // never size a buffer from an unchecked wire length
-    std::string payload(len, '\0');
-    if (len && !recv_all(fd_, payload.data(), len, 30000)) break;
     if (method & kPushFlag) {
       if (push_cb_) push_cb_(method & ~kPushFlag, payload);
     } else {
@@ -1012,11 +1170,19 @@ Result<std::string> RpcClient::call(uint32_t method, const std::string& request,
   return call_tcp_locked(method, request, timeout_ms);
 }
 
+namespace {
+Result<std::string> marker_or(uint32_t rmethod, std::string&& payload) {
+  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
+  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
+  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
+  return std::move(payload);
+}
+}  // namespace
+
 Result<std::string> RpcClient::call_tcp_locked(uint32_t method, const std::string& request, int timeout_ms) {
   if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
   const uint64_t id = next_id_++;
-  const std::string f = encode_frame(method, id, request);
-  if (!send_all(fd_, f.data(), f.size(), timeout_ms)) return ErrorCode::RPC_FAILED;
+  if (!send_request(method, id, request.data(), request.size(), nullptr, 0, timeout_ms)) return ErrorCode::RPC_FAILED;
   if (reader_run_.load()) {
     std::unique_lock<std::mutex> rl(resp_mu_);
     if (!resp_cv_.wait_for(rl, std::chrono::milliseconds(timeout_ms), [&] { return responses_.count(id) || broken_; })) {
@@ -1029,24 +1195,14 @@ Result<std::string> RpcClient::call_tcp_locked(uint32_t method, const std::strin
     responses_.erase(it);
     return r;
   }
-  char hdr[kFrameHeader];
-  if (!recv_all(fd_, hdr, sizeof hdr, timeout_ms)) {
+  uint32_t rmethod = 0;
+  std::string payload;
+  if (!recv_frame(&rmethod, nullptr, &payload, 0, nullptr, 0, nullptr, timeout_ms, timeout_ms)) {
     ::close(fd_);
     fd_ = -1;
     return ErrorCode::RPC_FAILED;
   }
-  const uint32_t len = rd32(hdr);
-  const uint32_t rmethod = rd32(hdr + 4);
-  std::string payload(len <= kMaxFrame ? len : 0, '\0');
-  if (len > kMaxFrame || (len && !recv_all(fd_, payload.data(), len, timeout_ms))) {
-    ::close(fd_);
-    fd_ = -1;
-    return ErrorCode::RPC_FAILED;
-  }
-  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
-  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
-  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
-  return payload;
+  return marker_or(rmethod, std::move(payload));
 }
 
 Result<std::string> RpcClient::call_gather(uint32_t method, const std::string& head, const void* ext, size_t ext_len, int timeout_ms) {
@@ -1059,37 +1215,21 @@ Result<std::string> RpcClient::call_gather(uint32_t method, const std::string& h
   if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
   if (head.size() + ext_len > kMaxFrame) return ErrorCode::INVALID_PARAMETERS;
   const uint64_t id = next_id_++;
-  char hdr[kFrameHeader];
-  const uint32_t len = static_cast<uint32_t>(head.size() + ext_len);
-  std::memcpy(hdr, &len, 4);
-  std::memcpy(hdr + 4, &method, 4);
-  std::memcpy(hdr + 8, &id, 8);
-  const Connection::Piece pieces[3] = {{hdr, sizeof hdr}, {head.data(), head.size()}, {ext, ext_len}};
-  if (!send_gather(fd_, pieces, 3, timeout_ms)) return ErrorCode::RPC_FAILED;
-  char rh[kFrameHeader];
-  if (!recv_all(fd_, rh, sizeof rh, timeout_ms)) {
+  if (!send_request(method, id, head.data(), head.size(), ext, ext_len, timeout_ms)) return ErrorCode::RPC_FAILED;
+  uint32_t rmethod = 0;
+  std::string payload;
+  if (!recv_frame(&rmethod, nullptr, &payload, 0, nullptr, 0, nullptr, timeout_ms, timeout_ms)) {
     ::close(fd_);
     fd_ = -1;
     return ErrorCode::RPC_FAILED;
   }
-  const uint32_t rlen = rd32(rh);
-  const uint32_t rmethod = rd32(rh + 4);
-  std::string payload(rlen <= kMaxFrame ? rlen : 0, '\0');
-  if (rlen > kMaxFrame || (rlen && !recv_all(fd_, payload.data(), rlen, timeout_ms))) {
-    ::close(fd_);
-    fd_ = -1;
-    return ErrorCode::RPC_FAILED;
-  }
-  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
-  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
-  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
-  return payload;
+  return marker_or(rmethod, std::move(payload));
 }
 
 Result<std::string> RpcClient::call_scatter(uint32_t method, const std::string& request, size_t head_len, void* dst, size_t dst_cap,
                                             size_t* received, int timeout_ms) {
   if (received) *received = 0;
-  if (reader_run_.load()) {
+  if (reader_run_.load() || dst == nullptr) {
     auto r = call(method, request, timeout_ms);
     if (!r.ok()) return r.error();
     std::string& all = r.value();
@@ -1104,29 +1244,15 @@ Result<std::string> RpcClient::call_scatter(uint32_t method, const std::string& 
   std::lock_guard<std::mutex> lk(mu_);
   if (fd_ < 0) return ErrorCode::CLIENT_DISCONNECTED;
   const uint64_t id = next_id_++;
-  const std::string f = encode_frame(method, id, request);
-  if (!send_all(fd_, f.data(), f.size(), timeout_ms)) return ErrorCode::RPC_FAILED;
-  char rh[kFrameHeader];
-  auto broken = [&]() -> Result<std::string> {
+  if (!send_request(method, id, request.data(), request.size(), nullptr, 0, timeout_ms)) return ErrorCode::RPC_FAILED;
+  uint32_t rmethod = 0;
+  std::string head;
+  if (!recv_frame(&rmethod, nullptr, &head, head_len, dst, dst_cap, received, timeout_ms, timeout_ms)) {
     ::close(fd_);
     fd_ = -1;
     return ErrorCode::RPC_FAILED;
-  };
-  if (!recv_all(fd_, rh, sizeof rh, timeout_ms)) return broken();
-  const uint32_t rlen = rd32(rh);
-  const uint32_t rmethod = rd32(rh + 4);
-  if (rlen > kMaxFrame) return broken();
-  const size_t h = std::min<size_t>(head_len, rlen);
-  const size_t rest = rlen - h;
-  std::string head(h, '\0');
-  if (h && !recv_all(fd_, head.data(), h, timeout_ms)) return broken();
-  if (rest > dst_cap) return broken();  // cannot resynchronise the stream without draining it
-  if (rest && !recv_all(fd_, dst, rest, timeout_ms)) return broken();
-  if (received) *received = rest;
-  if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
-  if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
-  if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
-  return head;
+  }
+  return marker_or(rmethod, std::move(head));
 }
 
 // ================================================================ HTTP

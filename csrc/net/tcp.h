@@ -22,6 +22,7 @@
 
 #include "common/error.h"
 #include "common/result.h"
+#include "net/aead.h"
 
 namespace bb::net {
 
@@ -43,10 +44,22 @@ class TcpServer;
 //   S -> C  kAuthMethod  snonce[16] HMAC(token, "bb-srv" cnonce snonce)[32]      (empty body: the server has no token)
 //   C -> S  kAuthMethod  HMAC(token, "bb-cli" cnonce snonce)[32]
 //   S -> C  kAuthMethod  (empty) = accepted   |   kDeniedMarker, then the server hangs up
-// The stream after the handshake is neither encrypted nor MAC'd (no TLS): this is an admission gate, not a secure
-// channel.  HTTP endpoints (/metrics, /healthz) stay open.
+// By default the stream after the handshake is neither encrypted nor MAC'd: the token is an admission gate.
+//
+// Secure mode (`encrypt_transport: true` in keystone / worker YAML, BlackbirdClientOptions::encrypt_transport,
+// --encrypt-transport, or BB_ENCRYPT_TRANSPORT=1; needs a token): the client opens with "BBA2" instead of "BBA1", and once
+// the handshake has passed every frame in both directions is protected with AES-256-GCM (net/aead.h):
+//   [u32 len + 16][u32 method][u64 id][ciphertext(len)][tag(16)]        header = additional authenticated data
+// Keys are per connection and per direction, HMAC(token, "bb-key-c2s" | "bb-key-s2c" || cnonce || snonce); the IV is the
+// direction's frame counter, so a replayed, dropped, reordered or altered frame fails authentication and the connection
+// is closed.  A server in secure mode refuses "BBA1" clients; a server that is not still accepts "BBA2" ones (rolling
+// change).  This is a pre-shared-key channel (confidentiality + integrity for everyone who holds the token), not mTLS:
+// there are no per-client identities.  Shared-memory channels (same host) carry plain frames; HTTP endpoints
+// (/metrics, /healthz) stay open and clear.
 void set_cluster_token(const std::string& token);
 std::string cluster_token();
+void set_transport_encryption(bool on);
+bool transport_encryption();
 constexpr uint32_t kAuthMethod = 0x7FFFFF00u;
 // Same-host fast path of the framed RPC protocol: after connecting (and authenticating) over TCP a client may offer a
 // shared-memory channel -- a memfd holding one request and one response area -- by sending its /proc/<pid>/fd/<n> path in
@@ -95,6 +108,11 @@ class Connection : public std::enable_shared_from_this<Connection> {
   bool authed() const { return authed_.load(std::memory_order_acquire); }
   void set_authed() { authed_.store(true, std::memory_order_release); }
   std::string& auth_nonces() { return auth_nonces_; }  // handshake in progress: cnonce + snonce
+  bool& wants_secure() { return wants_secure_; }       // the client opened with "BBA2"
+  // Secure mode: from now on send() / sendv() seal every frame and the owner opens incoming ones with rx().
+  bool enable_secure(const uint8_t rx_key[kAeadKey], const uint8_t tx_key[kAeadKey]);
+  bool secure() const { return secure_.load(std::memory_order_acquire); }
+  Aead& rx() { return rx_; }
   // EPOLLONESHOT hands a connection from one pool thread to the next through the kernel; these make the
   // hand-off an explicit release/acquire pair on the connection's own state as well.
   void release_ownership() { handoff_.fetch_add(1, std::memory_order_release); }
@@ -113,6 +131,10 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::atomic<bool> closed_{false};
   std::atomic<bool> authed_{false};
   std::string auth_nonces_;
+  bool wants_secure_ = false;
+  std::atomic<bool> secure_{false};
+  Aead rx_, tx_;  // rx_: the thread that owns the connection; tx_: under write_mu_
+  bool send_sealed_locked(const char* hdr, const Aead::CSpan* payload, int n, int timeout_ms);
   std::atomic<uint64_t> handoff_{0};
 };
 using ConnPtr = std::shared_ptr<Connection>;
@@ -264,6 +286,17 @@ class RpcClient {
   void reader_loop();
   Result<std::string> call_tcp_locked(uint32_t method, const std::string& request, int timeout_ms);
   void drop_shm();
+  // One request frame out of up to two payload pieces (sealed in secure mode).  Caller holds mu_.
+  bool send_request(uint32_t method, uint64_t id, const void* a, size_t a_len, const void* b, size_t b_len, int timeout_ms);
+  // One frame in: the first `head_len` payload bytes into *head, the rest into dst (nullptr: everything is head).  In
+  // secure mode the payload is opened in place before it is returned.  False = stream unusable (caller closes).
+  bool recv_frame(uint32_t* method, uint64_t* id, std::string* head, size_t head_len, void* dst, size_t dst_cap, size_t* received,
+                  int hdr_timeout_ms, int body_timeout_ms, bool* idle = nullptr);
+  bool secure_ = false;
+  Aead tx_, rx_;  // tx_: under mu_; rx_: the one thread that reads responses (the caller, or the push reader)
+ public:
+  bool secure() const { return secure_; }
+ private:
   ShmChanHeader* shm_ = nullptr;  // mapped channel (nullptr = TCP only)
   int shm_fd_ = -1;
   uint64_t shm_seq_ = 0;

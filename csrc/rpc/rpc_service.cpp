@@ -337,6 +337,7 @@ ErrorCode RpcService::start() {
   if (!hp) return ErrorCode::INVALID_ADDRESS;
   if (config_.rpc_busy_poll_us > 0) rpc_.set_busy_poll_us(config_.rpc_busy_poll_us);
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
+  if (config_.encrypt_transport) net::set_transport_encryption(true);
   ErrorCode ec = rpc_.start(hp->first, static_cast<uint16_t>(hp->second), std::max(1, config_.rpc_threads));
   if (ec != ErrorCode::OK) return ec;
   if (!config_.http_metrics_port.empty() && config_.http_metrics_port != "off") {

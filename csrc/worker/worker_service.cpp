@@ -35,6 +35,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("rpc_endpoint")) c.rpc_endpoint = w.at("rpc_endpoint").as_string();
   if (w.contains("http_metrics_port")) c.http_metrics_port = static_cast<int>(w.at("http_metrics_port").as_int(-1));
   if (w.contains("auth_token")) c.auth_token = w.at("auth_token").as_string();
+  if (w.contains("encrypt_transport")) c.encrypt_transport = w.at("encrypt_transport").as_bool();
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
   if (w.contains("interconnects")) {
@@ -165,6 +166,7 @@ ErrorCode WorkerService::initialize() {
   auto hp = split_host_port(config_.ucx_endpoint);
   if (!hp) return ErrorCode::INVALID_ADDRESS;
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
+  if (config_.encrypt_transport) net::set_transport_encryption(true);
   data_server_.set_socket_buffers(4 << 20);  // bulk transfers: fewer wake-ups per megabyte
   const unsigned hw = std::thread::hardware_concurrency();
   ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), static_cast<int>(std::min(16u, std::max(4u, hw / 2))));

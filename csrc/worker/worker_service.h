@@ -62,6 +62,7 @@ struct WorkerServiceConfig {
   // HTTP port of the worker's own observability endpoint (/metrics, /healthz, /stats); -1 = disabled, 0 = ephemeral.
   int http_metrics_port = -1;
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
+  bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h)
   CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects
   bool has_transport = false;
   std::vector<TierRule> preferred_tiers;  // `allocation.preferred_tiers` (forwarded to the keystone as a hint)
