@@ -453,6 +453,10 @@ Result<AllocationResult> RangeAllocator::place_symmetric(const AllocationRequest
   std::vector<PoolAllocator*> pas;
   for (auto* c : chosen) pas.push_back(ensure_pool(pools.at(c->id)));
   const uint64_t need = pas[0]->aligned(req.data_size);
+  // Concurrent symmetric placements all compute the same "tightest common hole" and would take it from each other attempt
+  // after attempt (8 ranks x 32 objects at once exhausted the retries on the 8-GPU box): they go one at a time.  What is left
+  // to race with is ordinary placement on the same pools, which the retry loop absorbs.
+  std::lock_guard<std::mutex> one_at_a_time(symmetric_mu_);
   for (int attempt = 0; attempt < 8; ++attempt) {
     // intersect the free lists (address ordered) and take the tightest common hole
     std::vector<Range> common = pas[0]->free_ranges();

@@ -237,6 +237,7 @@ class RangeAllocator : public IAllocator {
   // Inserts `oa` under `key` (false + untouched when the key already has an allocation) and accounts its extents.
   bool ledger_insert(const ObjectKey& key, ObjectAllocation&& oa);
   mutable std::array<LedgerShard, kLedgerShards> ledger_;
+  std::mutex symmetric_mu_;  // one symmetric (same offset on every replica) placement at a time: see place_symmetric
   mutable SpinMutex used_mu_;
   std::unordered_map<MemoryPoolId, size_t> used_by_pool_;  // guarded by used_mu_
 };

@@ -438,3 +438,37 @@ def test_batch_put_start_run_overflows_down_the_ranking_and_reports_the_rest(bb,
     wide = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=2, ttl_ms=0)
     res = ks.batch_put_start([f"s/{i}" for i in range(16)], [64 << 10] * 16, wide)
     assert all(r[0] == bb.ErrorCode.OK and len(r[1][0].shards) == 2 for r in res)
+
+
+def test_concurrent_symmetric_placements_do_not_starve_each_other(bb, monkeypatch):
+    """Symmetric replicas (same offset on every replica, for NVLS multicast) are found by intersecting free lists and then
+    claiming the offset pool by pool.  Eight writers doing that at once all aim at the same hole; they used to exhaust the
+    retry budget (ALLOCATION_FAILED on the 8-GPU box).  Symmetric placements now go one at a time."""
+    import threading
+
+    from blackbird_b200.parallel import LocalCluster
+
+    monkeypatch.setenv("BB_RPC_SHM", "0")  # one epoll pool thread per busy connection: the requests really overlap
+    with LocalCluster(cluster_id="sym", n_workers=0) as c:
+        G = bb.StorageClass.RAM_GPU
+        for i in range(8):
+            assert c.keystone.register_memory_pool(bb.MemoryPool(f"g{i}", 64 << 20, G, f"gpu{i}", f"w{i}", "127.0.0.1:1", 0, "00", i)) == bb.ErrorCode.OK
+        cfg = bb.WorkerConfig(replication_factor=3, max_workers_per_copy=1, ttl_ms=0, symmetric_replicas=True, preferred_classes=[G])
+        errors, lock = [], threading.Lock()
+
+        def writer(t):
+            api = bb.KeystoneRpcClient()
+            assert api.connect("127.0.0.1", c.rpc.rpc_port, 3000) == bb.ErrorCode.OK
+            for rnd in range(6):
+                res = api.batch_put_start([f"s/{t}/{rnd}/{j}" for j in range(32)], [64 << 10] * 32, cfg)
+                bad = [r[0] for r in res if r[0] != bb.ErrorCode.OK]
+                offs = [{cp.shards[0].location["offset"] for cp in r[1]} for r in res if r[0] == bb.ErrorCode.OK]
+                with lock:
+                    errors.extend(bad)
+                    errors.extend("offsets differ" for o in offs if len(o) != 1)
+
+        ts = [threading.Thread(target=writer, args=(t,)) for t in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert errors == []
+        assert c.keystone.get_cluster_stats().pending_objects == 8 * 6 * 32
