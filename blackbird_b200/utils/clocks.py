@@ -8,7 +8,7 @@ import threading
 _QUERY = (
     "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
     "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
 )
 
 
@@ -50,7 +50,7 @@ class ClockSampler:
                 self._proc.kill()
         if self._thread is not None:
             self._thread.join(timeout=2)
-        sm, smax, reasons = [], [], set()
+        sm, smax, busy, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self._lines:
             parts = [p.strip() for p in line.split(",")]
@@ -61,12 +61,19 @@ class ClockSampler:
                 smax.append(float(parts[2]))
             except ValueError:
                 continue
+            try:  # samples taken while kernels were resident: the idle stretches of a multi-phase run (cluster bring-up,
+                if len(parts) > 9 and float(parts[9]) > 0:  # rendezvous, host-side verification) sit at the idle clock
+                    busy.append(sm[-1])
+            except ValueError:
+                pass
             for name, val in zip(names, parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {
-            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_mhz": statistics.median(busy) if busy else (statistics.median(sm) if sm else None),
             "sm_max_mhz": max(smax) if smax else None,
             "samples": len(sm),
+            "samples_under_load": len(busy),
+            "sm_mhz_all_samples": statistics.median(sm) if sm else None,
             "reasons": sorted(reasons),
         }
