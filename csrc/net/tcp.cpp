@@ -668,6 +668,7 @@ ErrorCode RpcServer::shm_attach(const ConnPtr& c, const std::string& path) {
   ch->conn = c;
   ch->served = ch->hdr->req_seq.load(std::memory_order_acquire);
   std::lock_guard<std::mutex> lk(shm_mu_);
+  if (shm_stopped_) return ErrorCode::WORKER_NOT_READY;  // stopping: the client stays on TCP for its last requests
   for (auto& old : shm_chans_)
     if (old->conn == c) old->closed.store(true);  // a connection has at most one channel
   shm_chans_.erase(std::remove_if(shm_chans_.begin(), shm_chans_.end(), [](const auto& x) { return x->closed.load(); }), shm_chans_.end());
@@ -774,10 +775,15 @@ void RpcServer::on_close(const ConnPtr& c) {
 }
 
 void RpcServer::stop_shm() {
-  if (shm_run_.exchange(false))
-    for (auto& t : shm_pollers_)
-      if (t.joinable()) t.join();
-  shm_pollers_.clear();
+  std::vector<std::thread> pollers;
+  {
+    std::lock_guard<std::mutex> lk(shm_mu_);  // an epoll thread may be inside shm_attach, growing the poller list
+    shm_stopped_ = true;                      // ... and no channel is accepted from here on
+    shm_run_.store(false);
+    pollers.swap(shm_pollers_);
+  }
+  for (auto& t : pollers)
+    if (t.joinable()) t.join();
   std::lock_guard<std::mutex> lk(shm_mu_);
   shm_chans_.clear();
 }
@@ -785,6 +791,8 @@ void RpcServer::stop_shm() {
 void RpcServer::stop() {
   stop_shm();
   TcpServer::stop();
+  std::lock_guard<std::mutex> lk(shm_mu_);
+  shm_stopped_ = false;  // no epoll thread is left that could attach; a restarted server accepts channels again
 }
 
 RpcServer::~RpcServer() { stop(); }

@@ -238,6 +238,7 @@ class RpcServer : public TcpServer {
   std::vector<std::shared_ptr<ShmChan>> shm_chans_;
   std::atomic<uint64_t> shm_gen_{0};
   size_t shm_next_owner_ = 0;  // guarded by shm_mu_: round-robin assignment of channels to pollers
+  bool shm_stopped_ = false;   // guarded by shm_mu_: stop() is joining the pollers
   std::vector<std::thread> shm_pollers_;
   std::atomic<bool> shm_run_{false};
   std::atomic<uint64_t> shm_served_{0};
