@@ -5,6 +5,7 @@
 //   bb-bench backend --class NVME --path /tmp/x --ops 50 --size 4096
 //   bb-bench gpu --keystone host:port [--device 0] [--objects 64] [--size 67108864] [--iterations 20] [--node gpu1]
 //              (device-resident batched put + get through the fused kernels: no Python, no torch)
+//   bb-bench devclient [--batch 4096] [--size 4096] [--iterations 20]   (client-level cost of the device batch API, transfers free)
 //   bb-bench control [--threads 4] [--batch 4096] [--iterations 20] [--pools 8] [--rpc]   (keystone metadata ops/s)
 #include <algorithm>
 #include <chrono>
@@ -42,7 +43,7 @@ int main(int argc, char** argv) {
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   const std::string mode = args.positional.empty() ? "client" : args.positional[0];
   if (args.has("help")) {
-    std::printf("usage: bb-bench client|backend|control|gpu [options]\n");
+    std::printf("usage: bb-bench client|backend|control|devclient|gpu [options]\n");
     return 0;
   }
   if (mode == "backend") {
@@ -170,6 +171,92 @@ int main(int argc, char** argv) {
     gpu::device_free(device, src);
     gpu::device_free(device, dst);
     return failures || !same ? 1 : 0;
+  }
+  if (mode == "devclient") {
+    // Client-level cost of the device batch API without a GPU: an in-process keystone behind the real RPC server (the client
+    // reaches it over the same-host shared-memory channel), synthetic GPU pools, and a transport whose transfers are free.
+    // What is left is exactly what bounds batches of small objects: Keystone round trips + the client's own per-object work.
+    struct NullTransport : client::DeviceTransport {
+      ErrorCode put_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<const void*>&, ChecksumAlgo, void*,
+                           std::vector<uint64_t>* digests) override {
+        if (digests) digests->assign(ops.size(), 0x1234);
+        ++n;
+        return ErrorCode::OK;
+      }
+      ErrorCode get_shards(const std::vector<client::DeviceShardOp>& ops, const std::vector<void*>&, ChecksumAlgo, void*,
+                           std::vector<uint32_t>* status) override {
+        if (status) status->assign(ops.size(), 0);
+        ++n;
+        return ErrorCode::OK;
+      }
+      bool can_reach(const ShardPlacement&) const override { return true; }
+      uint64_t launches() const override { return n; }
+      uint64_t n = 0;
+    };
+    const int batch = std::max(1, static_cast<int>(args.num("batch", 4096)));
+    const int iters = std::max(1, static_cast<int>(args.num("iterations", 20)));
+    const size_t size = static_cast<size_t>(args.num("size", 4096));
+    KeystoneConfig kc;
+    kc.cluster_id = "bench";
+    kc.listen_address = "127.0.0.1:0";
+    kc.http_metrics_port = "off";
+    kc.enable_gc = false;
+    auto ks = std::make_shared<keystone::KeystoneService>(kc, nullptr);
+    if (ks->initialize() != ErrorCode::OK || ks->start() != ErrorCode::OK) return 1;
+    rpc::RpcService rpc(ks, kc);
+    if (rpc.start() != ErrorCode::OK) return 1;
+    for (int p = 0; p < 8; ++p) {
+      MemoryPool mp;
+      mp.id = "hbm" + std::to_string(p);
+      mp.node_id = "gpu" + std::to_string(p);
+      mp.worker_id = "w" + std::to_string(p);
+      mp.size = 64ull << 30;
+      mp.storage_class = StorageClass::RAM_GPU;
+      mp.gpu_device_id = p;
+      mp.ucx_endpoint = "127.0.0.1:1";
+      ks->register_memory_pool(mp);
+    }
+    client::BlackbirdClientOptions o;
+    o.keystone_host = "127.0.0.1";
+    o.keystone_port = rpc.rpc_port();
+    o.node_id = "gpu0";
+    o.register_session = false;
+    client::BlackbirdClient cl(o);
+    if (cl.connect() != ErrorCode::OK) return 1;
+    cl.set_device_transport(std::make_shared<NullTransport>());
+    WorkerConfig cfg;
+    cfg.replication_factor = 1;
+    cfg.max_workers_per_copy = 1;
+    cfg.ttl_ms = 0;
+    cfg.preferred_node = "gpu1";
+    cfg.preferred_classes = {StorageClass::RAM_GPU};
+    std::vector<const void*> src(static_cast<size_t>(batch), reinterpret_cast<const void*>(0x10000));
+    std::vector<void*> dst(static_cast<size_t>(batch), reinterpret_cast<void*>(0x10000));
+    const std::vector<size_t> sizes(static_cast<size_t>(batch), size);
+    double t_put = 0, t_get = 0, t_rm = 0;
+    for (int it = 0; it < iters + 1; ++it) {
+      std::vector<ObjectKey> keys;
+      for (int i = 0; i < batch; ++i) keys.push_back("dc/" + std::to_string(it) + "/" + std::to_string(i));
+      auto a = Clk::now();
+      auto e1 = cl.batch_put_device(keys, src, sizes, cfg, nullptr);
+      auto b = Clk::now();
+      auto e2 = cl.batch_get_device(keys, dst, sizes, nullptr, nullptr);
+      auto c = Clk::now();
+      cl.batch_remove(keys);
+      auto d = Clk::now();
+      if (e1[0] != ErrorCode::OK || e2[0] != ErrorCode::OK) {
+        std::fprintf(stderr, "devclient bench: %s / %s\n", std::string(to_string(e1[0])).c_str(), std::string(to_string(e2[0])).c_str());
+        return 1;
+      }
+      if (it) t_put += ms(a, b), t_get += ms(b, c), t_rm += ms(c, d);  // first round warms the channel and the caches up
+    }
+    const double n = static_cast<double>(batch) * iters;
+    std::printf("{\"mode\": \"devclient\", \"batch\": %d, \"size\": %zu, \"put_us_per_obj\": %.3f, \"get_us_per_obj\": %.3f, "
+                "\"remove_us_per_obj\": %.3f, \"put_objects_per_s\": %.0f, \"get_objects_per_s\": %.0f}\n",
+                batch, size, t_put * 1000 / n, t_get * 1000 / n, t_rm * 1000 / n, n / t_put * 1000, n / t_get * 1000);
+    rpc.stop();
+    ks->stop();
+    return 0;
   }
   if (mode == "control") {
     // Control-plane throughput: T clients drive batch_put_start -> batch_put_complete -> batch_get_workers ->

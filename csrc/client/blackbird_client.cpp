@@ -910,6 +910,8 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
   std::vector<size_t> host_put;                      // objects whose placement is not on the GPU fabric
   std::map<size_t, std::vector<CopyPlacement>> host_placed;
 
+  std::string reach_pool;
+  bool reach_answer = false;
   auto start_chunk = [&](Chunk& ch) {
     const TimePoint t0 = Clock::now();
     BB_TRACE_SPAN("put.start_chunk", ch.end - ch.begin);
@@ -933,7 +935,14 @@ std::vector<ErrorCode> BlackbirdClient::batch_put_device(const std::vector<Objec
       // placements on host tiers (DRAM / CXL / NVMe): stage through host memory and use the data servers
       bool on_fabric = true;
       for (const auto& c : copies)
-        for (const auto& sh : c.shards) on_fabric &= device_->can_reach(sh);
+        for (const auto& sh : c.shards) {
+          // a batch lands on a handful of pools: ask the transport once per run of shards on the same pool
+          if (reach_pool.empty() || reach_pool != sh.pool_id || !reach_answer) {
+            reach_answer = device_->can_reach(sh);
+            reach_pool = sh.pool_id;
+          }
+          on_fabric &= reach_answer;
+        }
       if (!on_fabric) {
         host_put.push_back(i);
         host_placed[i] = copies;
@@ -1118,9 +1127,35 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   double rpc_us_total = 0;
   std::vector<Chunk> chunks(plan.size());
   std::vector<size_t> retry;
+  // A batch mostly reads from a handful of pools: remember the transport's answer for the last pool asked about instead of
+  // taking its lock and looking the pool id up once per shard, and count per-object events locally (a named counter is a
+  // map lookup under a mutex).
+  const std::string* local_pool = nullptr;
+  bool local_answer = false;
+  auto pool_is_local = [&](const ShardPlacement& sh) {
+    if (!local_pool || *local_pool != sh.pool_id) {
+      local_answer = device_->is_local(sh);
+      local_pool = &sh.pool_id;
+    }
+    return local_answer;
+  };
+  std::string reach_pool;
+  bool reach_answer = false;
+  auto pool_reachable = [&](const ShardPlacement& sh) {
+    if (reach_pool.empty() || reach_pool != sh.pool_id || !reach_answer) {
+      reach_answer = device_->can_reach(sh);
+      reach_pool = sh.pool_id;
+    }
+    return reach_answer;
+  };
+  uint64_t n_local = 0, n_dram_direct = 0;
   auto start_chunk = [&](Chunk& ch) {
     const TimePoint t0 = Clock::now();
-    std::vector<ObjectKey> ck(keys.begin() + static_cast<std::ptrdiff_t>(ch.begin), keys.begin() + static_cast<std::ptrdiff_t>(ch.end));
+    local_pool = nullptr;  // the cached pointer refers into the previous chunk's placements
+    const bool whole = ch.begin == 0 && ch.end == keys.size();
+    std::vector<ObjectKey> part;
+    if (!whole) part.assign(keys.begin() + static_cast<std::ptrdiff_t>(ch.begin), keys.begin() + static_cast<std::ptrdiff_t>(ch.end));
+    const std::vector<ObjectKey>& ck = whole ? keys : part;
     auto res = keystone_->batch_get_workers(ck);
     rpc_us_total += us_since(t0);
     metrics_.observe("phase_get_workers_us", us_since(t0));
@@ -1144,15 +1179,16 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
       // replica choice: one that lives on this client's own GPU (HBM speed, no NVLink), else a replica that is
       // fully reachable over the GPU fabric (readers spread over the replicas), else stage through the host
       const auto& copies = placed[i].value();
-      const size_t start = std::hash<std::string>{}(opts_.node_id + keys[i]) % copies.size();
+      // (the spread over replicas only matters when there is more than one; thousands of single-copy objects skip the hash)
+      const size_t start = copies.size() > 1 ? std::hash<std::string>{}(opts_.node_id + keys[i]) % copies.size() : 0;
       bool found = false;
       for (size_t k = 0; k < copies.size() && !found; ++k) {
         bool local = !copies[k].shards.empty();
-        for (const auto& sh : copies[k].shards) local &= device_->is_local(sh);
+        for (const auto& sh : copies[k].shards) local &= pool_is_local(sh);
         if (local) {
           copy_choice[i] = k;
           found = true;
-          metrics_.inc("device_get_local_replica_total");
+          ++n_local;
         }
       }
       // HBM replicas first (NVLink), then replicas in mapped DRAM pools (PCIe)
@@ -1160,11 +1196,11 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
         for (size_t k = 0; k < copies.size() && !found; ++k) {
           const auto& c = copies[(start + k) % copies.size()];
           bool ok = !c.shards.empty();
-          for (const auto& sh : c.shards) ok = ok && (pass == 1 || sh.storage_class == StorageClass::RAM_GPU) && device_->can_reach(sh);
+          for (const auto& sh : c.shards) ok = ok && (pass == 1 || sh.storage_class == StorageClass::RAM_GPU) && pool_reachable(sh);
           if (ok) {
             copy_choice[i] = (start + k) % copies.size();
             found = true;
-            if (pass == 1) metrics_.inc("device_get_dram_direct_total");
+            if (pass == 1) ++n_dram_direct;
           }
         }
       }
@@ -1246,6 +1282,8 @@ std::vector<ErrorCode> BlackbirdClient::batch_get_device(const std::vector<Objec
   }
   for (size_t i = 0; i < keys.size(); ++i)
     if (pending[i]) out[i] = ErrorCode::CHECKSUM_MISMATCH;
+  if (n_local) metrics_.inc("device_get_local_replica_total", n_local);
+  if (n_dram_direct) metrics_.inc("device_get_dram_direct_total", n_dram_direct);
   // ---- a mismatch can also mean that the Keystone moved the object under us (tier move, compaction, repair): the
   // extents we read were freed and re-used.  Objects whose placements changed since we fetched them get one more pass.
   static thread_local int refresh_depth = 0;
