@@ -238,6 +238,14 @@ def test_control_plane_benchmark_binary():
     assert b.returncode == 0 and res["objects"] == 4 * 256 * 4 and res["object_lifecycles_per_s"] > 10000, b.stdout + b.stderr
 
 
+def test_device_client_benchmark_binary():
+    """`bb-bench devclient`: batch_put_device / batch_get_device / batch_remove of the real client against a keystone behind
+    the real RPC server, with a transport whose transfers cost nothing -- the per-object control cost of small-object batches."""
+    b = subprocess.run([os.path.join(BIN, "bb-bench"), "devclient", "--batch", "512", "--iterations", "3"], capture_output=True, text=True, timeout=120)
+    res = json.loads(b.stdout)
+    assert b.returncode == 0 and res["batch"] == 512 and 0 < res["put_us_per_obj"] < 200 and res["get_objects_per_s"] > 5000, b.stdout + b.stderr
+
+
 @pytest.mark.gpu
 def test_native_gpu_path_without_python(procs, tmp_path):
     """bb-coord + bb-keystone + bb-worker with a RAM_GPU pool + `bb-bench gpu`: the whole device path (CUDA IPC slab
