@@ -82,13 +82,13 @@ struct MailSlot {  // 64 bytes = one cache line = one PCIe read; the host writes
   uint32_t seq;        // word 15
 };
 static_assert(sizeof(MailSlot) == 64, "MailSlot must be one cache line");
-struct MailResult {  // 64 bytes; the device writes `seq` LAST
+struct alignas(64) MailResult {  // 64 bytes; the device writes the first 16 bytes (digest, status, seq) with one store
   uint64_t digest;
   uint32_t status;
   uint32_t seq;
   uint32_t pad[12];
 };
-static_assert(sizeof(MailResult) == 64);
+static_assert(sizeof(MailResult) == 64 && offsetof(MailResult, seq) == 12);
 struct MailCtl {
   uint32_t exit_epoch;  // epoch of the last kernel incarnation that has exited (== the launched epoch: nobody is polling)
   uint32_t next_seq;    // first sequence number that incarnation did NOT consume

@@ -363,11 +363,13 @@ __global__ void __launch_bounds__(32) bb_mailbox_kernel(const MailSlot* slots, M
     __threadfence_system();  // the object's stores (peer slab / local / host) are performed before the result says so
     __syncwarp();
     if (lane == 0) {
+      // digest, status and the sequence number leave as ONE 16-byte store = one PCIe write into one cache line of the pinned
+      // result ring: the host that sees the new `seq` sees the digest of the same write (no second system fence, which costs
+      // a PCIe round trip)
       MailResult* r = &results[seq % kMailSlots];
-      r->digest = digest;
-      r->status = status;
-      __threadfence_system();
-      *reinterpret_cast<volatile uint32_t*>(&r->seq) = seq;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(r), "r"(static_cast<uint32_t>(digest)),
+                   "r"(static_cast<uint32_t>(digest >> 32)), "r"(status), "r"(seq)
+                   : "memory");
     }
     ++seq;
     t_last = globaltimer_ns();
