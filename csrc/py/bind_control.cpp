@@ -40,6 +40,21 @@ auto nogil(F&& f) {
   return f();
 }
 
+// list[ErrorCode] for batch results.  pybind builds a fresh enum instance per element (~0.3 us); a batch of thousands of
+// objects gets the cached instance of each code instead (enum members are immutable).  GIL held.
+py::list ecs_to_py(const std::vector<ErrorCode>& v) {
+  static std::unordered_map<int, PyObject*>* cache = new std::unordered_map<int, PyObject*>();  // lives as long as the interpreter
+  py::list out(v.size());
+  for (size_t i = 0; i < v.size(); ++i) {
+    const int code = static_cast<int>(v[i]);
+    auto it = cache->find(code);
+    if (it == cache->end()) it = cache->emplace(code, py::cast(v[i]).release().ptr()).first;
+    Py_INCREF(it->second);
+    PyList_SET_ITEM(out.ptr(), static_cast<Py_ssize_t>(i), it->second);
+  }
+  return out;
+}
+
 py::object location_to_py(const LocationDetail& l) {
   py::dict d;
   if (auto* m = std::get_if<MemoryLocation>(&l)) {
@@ -1046,16 +1061,16 @@ void bind_control(py::module_& m) {
                                                       : py::object(py::none())));
         return out;
       })
-      .def("batch_remove", &BlackbirdClient::batch_remove, py::call_guard<py::gil_scoped_release>())
+      .def("batch_remove", [](BlackbirdClient& c, const std::vector<std::string>& keys) { return ecs_to_py(nogil([&] { return c.batch_remove(keys); })); })
       .def("batch_exists", [](BlackbirdClient& c, const std::vector<std::string>& keys) {
         return results_to_py(nogil([&] { return c.batch_exists(keys); }), [](bool b) { return py::bool_(b); });
       })
       .def("batch_put_device", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<uintptr_t>& ptrs,
                                   const std::vector<size_t>& sizes, const WorkerConfig& cfg, uintptr_t stream) {
         std::vector<const void*> p;
+        p.reserve(ptrs.size());
         for (auto v : ptrs) p.push_back(reinterpret_cast<const void*>(v));
-        py::gil_scoped_release rel;
-        return c.batch_put_device(keys, p, sizes, cfg, reinterpret_cast<void*>(stream));
+        return ecs_to_py(nogil([&] { return c.batch_put_device(keys, p, sizes, cfg, reinterpret_cast<void*>(stream)); }));
       }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("sizes"), py::arg("config") = WorkerConfig{}, py::arg("stream") = 0)
       .def("batch_get_device", [](BlackbirdClient& c, const std::vector<std::string>& keys, const std::vector<uintptr_t>& ptrs,
                                   const std::vector<size_t>& caps, uintptr_t stream) {
@@ -1067,7 +1082,7 @@ void bind_control(py::module_& m) {
           py::gil_scoped_release rel;
           ecs = c.batch_get_device(keys, p, caps, reinterpret_cast<void*>(stream), &sizes);
         }
-        return py::make_tuple(ecs, sizes);
+        return py::make_tuple(ecs_to_py(ecs), sizes);
       }, py::arg("keys"), py::arg("dev_ptrs"), py::arg("capacity"), py::arg("stream") = 0)
       .def("cluster_stats", [](BlackbirdClient& c) { return unwrap(nogil([&] { return c.cluster_stats(); })); })
       .def("metrics_text", &BlackbirdClient::metrics_text)
