@@ -299,6 +299,7 @@ struct Opt {
   int ndev = 0;
   bool quick = false;
   bool mc = true;
+  bool only_mc = false;
   bool latency = false;
 };
 
@@ -327,6 +328,7 @@ int main(int argc, char** argv) {
     else if (a == "--gpus" && i + 1 < argc) o.ndev = std::atoi(argv[++i]);
     else if (a == "--quick") o.quick = true;
     else if (a == "--no-mc") o.mc = false;
+    else if (a == "--only-mc") o.only_mc = true;  // skip the unicast sweep (ncu application replay re-runs the whole program)
     else if (a == "--latency") o.latency = true;
   }
   int n = 0;
@@ -468,6 +470,7 @@ int main(int argc, char** argv) {
     k_ring<<<ctas, 320, smem, me.st>>>(p);
   };
 
+  if (o.only_mc) pats.clear();
   for (const Pattern& pt : pats) {
     report("memcpy", pt.name, "cudaMemcpyPeerAsync",
            run(pt, [&](const Dev& me, const Dev& peer) { CK(cudaMemcpyPeerAsync(peer.dst, peer.id, me.src, me.id, bytes, me.st)); }), bytes,
