@@ -647,7 +647,9 @@ RpcServer::Reply RpcServer::dispatch(const ConnPtr& c, uint32_t method, std::str
   return reply;
 }
 
-static size_t shm_poller_count() { return std::max<size_t>(1, std::min<size_t>(4, std::thread::hardware_concurrency() / 4)); }
+// One poller per channel up to 8 (an 8-GPU box: every rank's control connection gets its own), never more than a quarter of
+// the cores: a poller spins while its channels are busy.
+static size_t shm_poller_count() { return std::max<size_t>(1, std::min<size_t>(8, std::thread::hardware_concurrency() / 4)); }
 
 ErrorCode RpcServer::shm_attach(const ConnPtr& c, const std::string& path) {
   // only paths of the form /proc/<pid>/fd/<n> (a memfd of a process on this host) are accepted
