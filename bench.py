@@ -64,7 +64,8 @@ def main() -> int:
     ap.add_argument("--algo", default="xxh3", choices=["xxh3", "crc32c", "bbh64", "none"],
                     help="digest fused into the transfer: xxh3 (default) = the standard XXH3-64 of every 16 KiB tile, combined order-independently; "
                          "crc32c = standard Castagnoli CRC of the object; bbh64 = the tensor-core hash")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=16,
+                    help="steps of each end-to-end mode (8.6 GB over PCIe per step per rank); the pipelined mode pays one un-overlapped H2D at the start and one D2H at the end")
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--sync", choices=["none", "step", "phase"], default="phase",
                     help="N>1: ranks rendezvous per step / per put-get phase (inside the timed region)")
