@@ -123,21 +123,32 @@ def latency_sweep(cluster, sizes, target_node: str, iters: int = 200, algo=None)
         _bb.random_fill(src.data_ptr(), stride, size + 1, stream)
         out = torch.zeros_like(src)
         put_us, get_us, put_dev, get_dev = [], [], [], []
+        fab = cluster.fabric
+        paths = {"put_mailbox": 0, "put_launches": 0, "get_mailbox": 0, "get_launches": 0}  # which engine path served the calls
         for it in range(n_it + 5):
             key = [f"lat/{cluster.rank}/{size}/{it}"]
+            c0 = (fab.mailbox_requests, fab.launches)
             t0 = time.perf_counter()
             ecs = cluster.client.batch_put_device(key, [src.data_ptr()], [size], cfg, stream)
             t1 = time.perf_counter()
+            c1 = (fab.mailbox_requests, fab.launches)
             pd = cluster.fabric.last_device_ms
             ecs2, _ = cluster.client.batch_get_device(key, [out.data_ptr()], [stride], stream)
             t2 = time.perf_counter()
+            c2 = (fab.mailbox_requests, fab.launches)
             gd = cluster.fabric.last_device_ms
+            if it >= 5:
+                paths["put_mailbox"] += c1[0] - c0[0]
+                paths["put_launches"] += c1[1] - c0[1]
+                paths["get_mailbox"] += c2[0] - c1[0]
+                paths["get_launches"] += c2[1] - c1[1]
             cluster.client.batch_remove(key)
             assert _ok(ecs) and _ok(ecs2)
             if it >= 5:
                 put_us.append((t1 - t0) * 1e6), get_us.append((t2 - t1) * 1e6), put_dev.append(pd * 1e3), get_dev.append(gd * 1e3)
         rows.append({"size": size, "put_p50_us": _pct(put_us, 0.5), "put_p99_us": _pct(put_us, 0.99), "get_p50_us": _pct(get_us, 0.5),
-                     "get_p99_us": _pct(get_us, 0.99), "put_kernel_p50_us": _pct(put_dev, 0.5), "get_kernel_p50_us": _pct(get_dev, 0.5)})
+                     "get_p99_us": _pct(get_us, 0.99), "put_kernel_p50_us": _pct(put_dev, 0.5), "get_kernel_p50_us": _pct(get_dev, 0.5),
+                     "engine_paths": paths})
     return rows
 
 
