@@ -690,9 +690,10 @@ void bind_control(py::module_& m) {
         for (size_t i = 0; i < keys.size(); ++i) items.push_back({keys[i], i < sizes.size() ? sizes[i] : 0, c});
         return results_to_py(nogil([&] { return k.batch_put_start(items); }), [](const std::vector<CopyPlacement>& v) { return py::cast(v); });
       })
-      .def("batch_put_complete", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) { return k.batch_put_complete(keys, {}); })
-      .def("batch_put_cancel", &rpc::KeystoneApi::batch_put_cancel)
-      .def("batch_remove_object", &rpc::KeystoneApi::batch_remove_object)
+      // (network calls: never with the GIL held -- an in-process Python peer, e.g. a test's fake server, could not answer)
+      .def("batch_put_complete", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) { return ecs_to_py(nogil([&] { return k.batch_put_complete(keys, {}); })); })
+      .def("batch_put_cancel", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) { return ecs_to_py(nogil([&] { return k.batch_put_cancel(keys); })); })
+      .def("batch_remove_object", [](rpc::KeystoneApi& k, const std::vector<std::string>& keys) { return ecs_to_py(nogil([&] { return k.batch_remove_object(keys); })); })
       .def("get_memory_pools", [](rpc::KeystoneApi& k) { return unwrap(nogil([&] { return k.get_memory_pools(); })); })
       .def("get_workers_info", [](rpc::KeystoneApi& k) {
         py::list out;
@@ -717,8 +718,8 @@ void bind_control(py::module_& m) {
       }, py::arg("prefix") = "", py::arg("limit") = 0, py::arg("start_after") = "", "[(key, size, copies, tier)] in key order")
       .def("client_register", [](rpc::KeystoneApi& k, const std::string& n) { return unwrap(nogil([&] { return k.client_register(n); })); })
       .def("client_ping", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(nogil([&] { return k.client_ping(id); })); })
-      .def("register_memory_pool", &rpc::KeystoneApi::register_memory_pool)
-      .def("worker_heartbeat", &rpc::KeystoneApi::worker_heartbeat);
+      .def("register_memory_pool", &rpc::KeystoneApi::register_memory_pool, py::call_guard<py::gil_scoped_release>())
+      .def("worker_heartbeat", &rpc::KeystoneApi::worker_heartbeat, py::call_guard<py::gil_scoped_release>());
   py::class_<rpc::KeystoneRpcClient, rpc::KeystoneApi, std::shared_ptr<rpc::KeystoneRpcClient>>(m, "KeystoneRpcClient")
       .def(py::init<>())
       .def("connect", [](rpc::KeystoneRpcClient& c, const std::string& host, uint16_t port, int timeout_ms) { return c.connect(host, port, timeout_ms); },

@@ -393,3 +393,161 @@ def test_mutated_real_requests_do_not_break_keystone_or_worker(bb, monkeypatch):
         assert fresh.put("after", blob, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
         assert fresh.get("after") == blob
         assert bb.http_get("127.0.0.1", c.rpc.http_port, "/healthz")[0] == 200
+
+
+def test_secure_mode_survives_garbage_after_a_valid_handshake(bb):
+    """Secure mode (BBA2): a peer that holds the token completes the handshake by hand and then sends noise instead of
+    sealed frames -- random bytes, frames with random tags, truncated frames, frames shorter than a tag, huge length
+    fields.  The server must drop every such connection without answering a request, stay up, and keep serving a real
+    client (which proves its keys and counters were not disturbed by the other connections)."""
+    import hashlib
+    import hmac as pyhmac
+
+    AUTH, tok = 0x7FFFFF00, b"fuzz-secure-token"
+    rng = random.Random(0x5EC)
+    bb.set_cluster_token(tok.decode())
+    bb.set_transport_encryption(True)
+    srv = bb.CoordServer()
+    try:
+        assert srv.start("127.0.0.1", 0) == bb.ErrorCode.OK
+
+        def recv_frame(s):
+            hdr = b""
+            while len(hdr) < 16:
+                part = s.recv(16 - len(hdr))
+                if not part:
+                    return None
+                hdr += part
+            n, method, rid = struct.unpack("<IIQ", hdr)
+            body = b""
+            while len(body) < n:
+                part = s.recv(n - len(body))
+                if not part:
+                    return None
+                body += part
+            return method, body
+
+        for _ in range(120):
+            s = socket.create_connection(("127.0.0.1", srv.port), 2.0)
+            s.settimeout(0.5)
+            try:
+                cn = rng.randbytes(16)
+                s.sendall(_frame(AUTH, 0, b"BBA2" + cn))
+                method, body = recv_frame(s)
+                assert method == AUTH and len(body) == 48
+                sn, mac = body[:16], body[16:]
+                assert pyhmac.compare_digest(mac, pyhmac.new(tok, b"bb-srv" + cn + sn, hashlib.sha256).digest())
+                s.sendall(_frame(AUTH, 1, pyhmac.new(tok, b"bb-cli" + cn + sn, hashlib.sha256).digest()))
+                method, body = recv_frame(s)
+                assert method == AUTH and body == b""  # admitted: from here on everything must be sealed
+                kind = rng.randrange(6)
+                if kind == 0:
+                    junk = rng.randbytes(rng.randrange(1, 400))
+                elif kind == 1:
+                    junk = _frame(rng.randrange(0, 32), 7, rng.randbytes(rng.randrange(16, 200)))  # random "ciphertext + tag"
+                elif kind == 2:
+                    junk = _frame(rng.randrange(0, 32), 7, rng.randbytes(rng.randrange(0, 16)))    # shorter than a tag
+                elif kind == 3:
+                    junk = struct.pack("<IIQ", 0x7FFFFFFF, 3, 9) + rng.randbytes(64)                # absurd length field
+                elif kind == 4:
+                    junk = _frame(3, 7, rng.randbytes(64))[:40]                                      # truncated, then silence
+                else:
+                    junk = _frame(3, 7, b"\0" * 48) * 3                                              # several frames, all forged
+                s.sendall(junk)
+                got = b""
+                try:
+                    while len(got) < 4096:
+                        part = s.recv(4096)
+                        if not part:
+                            break
+                        got += part
+                except OSError:
+                    pass
+                assert got == b"", f"the server answered {len(got)} bytes to a forged frame (kind {kind})"
+            finally:
+                s.close()
+        cs = bb.CoordService(f"tcp://127.0.0.1:{srv.port}")
+        assert cs.connect() == bb.ErrorCode.OK and cs.put("/fuzz/secure", "v") == bb.ErrorCode.OK and cs.get("/fuzz/secure") == b"v"
+    finally:
+        bb.set_transport_encryption(False)
+        bb.set_cluster_token("")
+        srv.stop()
+
+
+def test_client_decoders_survive_a_server_that_answers_garbage(bb, monkeypatch):
+    """The other direction: a broken (or hostile) server answers the client's batch calls with noise -- huge counts,
+    a delta-encoded placement without anything to be a delta of, truncated replies, random bytes.  The client returns
+    errors (per item or for the call); it does not crash, hang or allocate by an unchecked count."""
+    import threading
+
+    monkeypatch.setenv("BB_RPC_SHM", "0")
+    rng = random.Random(0xC11E)
+    OK = struct.pack("<i", 0)
+    replies = [
+        OK + struct.pack("<I", 0xFFFFFFF0),                                  # count far beyond the payload
+        OK + struct.pack("<I", 2) + OK + b"\x01" + struct.pack("<QQ", 4096, 7),  # delta placement without a base
+        OK + struct.pack("<I", 3) + OK + b"\x07",                            # unknown placement tag
+        OK + struct.pack("<I", 1) + OK + b"\x00" + struct.pack("<I", 0xFFFFFF),  # full placement claiming 16 M copies
+        OK,                                                                  # truncated right after the status
+        b"",
+    ] + [rng.randbytes(rng.randrange(1, 300)) for _ in range(40)]
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(4)
+    port = srv.getsockname()[1]
+    state = {"i": 0, "run": True}
+
+    def serve():
+        srv.settimeout(0.2)
+        while state["run"]:
+            try:
+                c, _ = srv.accept()
+            except OSError:
+                continue
+            threading.Thread(target=answer, args=(c,), daemon=True).start()  # a client that gives up on a connection opens the next
+
+    def answer(c):
+        if True:
+            c.settimeout(2.0)
+            try:
+                while True:
+                    hdr = b""
+                    while len(hdr) < 16:
+                        part = c.recv(16 - len(hdr))
+                        if not part:
+                            raise OSError
+                        hdr += part
+                    n, method, rid = struct.unpack("<IIQ", hdr)
+                    left = n
+                    while left:
+                        part = c.recv(min(left, 1 << 16))
+                        if not part:
+                            raise OSError
+                        left -= len(part)
+                    body = replies[state["i"] % len(replies)]
+                    state["i"] += 1
+                    c.sendall(struct.pack("<IIQ", len(body), method, rid) + body)
+            except OSError:
+                pass
+            finally:
+                c.close()
+
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    try:
+        keys = [f"k{i}" for i in range(5)]
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)
+        for _ in range(len(replies) * 2):
+            api = bb.KeystoneRpcClient()
+            assert api.connect("127.0.0.1", port, 2000) == bb.ErrorCode.OK
+            for call in (lambda: api.batch_get_workers(keys), lambda: api.batch_put_start(keys, [4096] * 5, cfg),
+                         lambda: api.batch_object_exists(keys), lambda: api.batch_put_complete(keys)):
+                try:
+                    res = call()
+                    assert len(res) == len(keys)  # per-item results, mostly errors
+                except bb.BlackbirdError:
+                    pass
+    finally:
+        state["run"] = False
+        t.join(timeout=2)
+        srv.close()
