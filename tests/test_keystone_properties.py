@@ -92,3 +92,76 @@ def test_keystone_state_machine_matches_a_dictionary_model(bb, seq):
         assert k.get_cluster_stats().used_capacity == 0
     finally:
         k.stop()
+
+
+run_ops = st.lists(st.one_of(
+    st.tuples(st.just("run"), st.integers(0, 5), st.integers(8, 40), st.sampled_from([1, 256, 1000, 4096, 65536, 70_000])),  # batch id, count, size
+    st.tuples(st.just("single"), st.integers(0, 30), st.integers(1, 100_000)),
+    st.tuples(st.just("remove_run"), st.integers(0, 5), st.integers(0, 3)),  # remove every (k+2)-th object of a batch: holes
+    st.tuples(st.just("remove_single"), st.integers(0, 30)),
+), min_size=1, max_size=30)
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(run_ops)
+def test_run_placement_never_overlaps_and_returns_every_byte(bb, seq):
+    """Run placement (one pool-allocator call for a whole chunk of a batch, sliced into per-object extents) interleaved with
+    single puts and removals that punch holes into the chunks: whatever the order, no two live objects overlap on a pool,
+    the pool accounting equals the sum of the live extents, and after removing everything each pool is one free extent again."""
+    k = bb.KeystoneService(ks_cfg(bb), None)
+    assert k.initialize() == bb.ErrorCode.OK and k.start() == bb.ErrorCode.OK
+    try:
+        pool_bytes = 4 << 20
+        for i in range(3):
+            assert k.register_memory_pool(mkpool(bb, f"p{i}", pool_bytes, worker=f"w{i}")) == bb.ErrorCode.OK
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0)
+        live = {}  # key -> (pool, addr, aligned length)
+        E = bb.ErrorCode
+
+        def record(key, copies):
+            sh = copies[0].shards[0]
+            live[key] = (sh.pool_id, sh.location["remote_addr"], (sh.length + ALIGN - 1) // ALIGN * ALIGN)
+
+        gen = 0
+        for op in seq:
+            if op[0] == "run":
+                _, b, count, size = op
+                gen += 1
+                keys = [f"b{b}/{gen}/{j}" for j in range(count)]
+                for key, (ec, copies) in zip(keys, k.batch_put_start(keys, [size] * count, cfg)):
+                    assert ec in (E.OK, E.INSUFFICIENT_SPACE)
+                    if ec == E.OK:
+                        assert len(copies) == 1 and len(copies[0].shards) == 1 and copies[0].shards[0].length == size
+                        record(key, copies)
+            elif op[0] == "single":
+                key = f"s{op[1]}"
+                ec, copies = code(bb, lambda: k.put_start(key, op[2], cfg))
+                if key in live:
+                    assert ec == E.OBJECT_ALREADY_EXISTS
+                elif ec == E.OK:
+                    record(key, copies)
+            elif op[0] == "remove_run":
+                victims = [key for key in sorted(live) if key.startswith(f"b{op[1]}/")][:: op[2] + 2]
+                if victims:
+                    assert set(k.batch_remove_object(victims)) == {E.OK}
+                    for key in victims:
+                        del live[key]
+            else:
+                key = f"s{op[1]}"
+                assert k.remove_object(key) == (E.OK if key in live else E.OBJECT_NOT_FOUND)
+                live.pop(key, None)
+            # invariants
+            by_pool = {}
+            for pool, addr, length in live.values():
+                by_pool.setdefault(pool, []).append((addr, length))
+            for pool, ext in by_pool.items():
+                ext.sort()
+                assert all(a + n <= b for (a, n), (b, _) in zip(ext, ext[1:])), f"overlap on {pool}"
+            assert k.get_cluster_stats().used_capacity == sum(n for _, _, n in live.values())
+        if live:
+            assert set(k.batch_remove_object(sorted(live))) == {E.OK}
+        assert k.get_cluster_stats().used_capacity == 0
+        whole = k.batch_put_start([f"whole{i}" for i in range(3)], [pool_bytes] * 3, cfg)
+        assert [r[0] for r in whole] == [E.OK] * 3  # every pool is one free extent again
+    finally:
+        k.stop()
