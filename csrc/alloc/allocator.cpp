@@ -288,6 +288,51 @@ void RangeAllocator::rollback(const std::vector<Extent>& extents) {
     if (PoolAllocator* pa = find_pool(e.pool)) pa->free(e.range);
 }
 
+bool RangeAllocator::single_shard(const AllocationRequest& req, size_t ncands) const {
+  if (req.replication_factor != 1 || req.symmetric_replicas) return false;
+  size_t wpc = std::min(std::max<size_t>(1, req.max_workers_per_copy), std::max<size_t>(1, ncands));  // as place() derives it
+  if (!req.enable_striping || req.prefer_contiguous) wpc = 1;
+  if (wpc > 1 && req.data_size / wpc < req.min_shard_size) {
+    if (req.strict_min_shard) return false;
+    wpc = std::max<size_t>(1, std::min(wpc, req.data_size / std::max<size_t>(1, req.min_shard_size)));
+  }
+  return wpc == 1;
+}
+
+Result<AllocationResult> RangeAllocator::place_single(const AllocationRequest& req, const PoolMap& pools, const std::vector<Candidate>& cands,
+                                                      bool spill) {
+  for (const Candidate& cd : cands) {
+    const MemoryPool& pool = pools.at(cd.id);
+    PoolAllocator* pa = ensure_pool(pool);
+    auto r = pa->allocate(req.data_size, true);
+    if (!r) continue;
+    auto shard = make_shard(pool, *r, req.data_size);
+    if (!shard.ok()) {
+      pa->free(*r);
+      return shard.error();
+    }
+    ObjectAllocation oa;
+    oa.total_size = req.data_size;
+    oa.extents.push_back({cd.id, *r, req.data_size});
+    if (!ledger_insert(req.object_key, std::move(oa))) {
+      pa->free(*r);
+      return ErrorCode::OBJECT_ALREADY_EXISTS;
+    }
+    AllocationResult result;
+    CopyPlacement copy;
+    copy.copy_index = 0;
+    copy.shards.push_back(std::move(shard.value()));
+    result.copies.push_back(std::move(copy));
+    result.total_shards_created = 1;
+    result.pools_used = 1;
+    result.stats.required_spillover = spill || !cd.preferred;
+    result.stats.avg_shard_size = req.data_size;
+    result.stats.fragmentation_score = static_cast<size_t>(pa->fragmentation_ratio() * 100.0);
+    return result;
+  }
+  return ErrorCode::INSUFFICIENT_SPACE;
+}
+
 Result<AllocationResult> RangeAllocator::place(const AllocationRequest& req, const PoolMap& pools,
                                                const std::vector<Candidate>& cands, bool spill) {
   const size_t n = cands.size();
@@ -563,13 +608,17 @@ Result<AllocationResult> RangeAllocator::allocate(const AllocationRequest& req, 
       if (a.free_bytes != b.free_bytes) return a.free_bytes > b.free_bytes;
       return a.id < b.id;
     });
-    auto r = (req.symmetric_replicas && req.replication_factor > 1) ? place_symmetric(req, pools, rc.cands, spill) : place(req, pools, rc.cands, spill);
+    auto r = (req.symmetric_replicas && req.replication_factor > 1) ? place_symmetric(req, pools, rc.cands, spill)
+             : single_shard(req, rc.cands.size())                       ? place_single(req, pools, rc.cands, spill)
+                                                                        : place(req, pools, rc.cands, spill);
     if (r.ok()) return r;
     rc.left = 0;  // stale ranking (a pool filled up?): fall through to a fresh one
   }
   std::vector<Candidate> cands = rank_candidates(req, pools, &spill);
   if (cands.empty()) return ErrorCode::INSUFFICIENT_SPACE;
-  auto r = (req.symmetric_replicas && req.replication_factor > 1) ? place_symmetric(req, pools, cands, spill) : place(req, pools, cands, spill);
+  auto r = (req.symmetric_replicas && req.replication_factor > 1) ? place_symmetric(req, pools, cands, spill)
+           : single_shard(req, cands.size())                       ? place_single(req, pools, cands, spill)
+                                                                   : place(req, pools, cands, spill);
   if (cacheable && r.ok()) {
     rc.owner = this;
     rc.gen = gen;

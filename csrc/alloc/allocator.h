@@ -217,6 +217,10 @@ class RangeAllocator : public IAllocator {
   std::vector<Candidate> rank_candidates(const AllocationRequest& req, const PoolMap& pools, bool* spill) const;
   Result<ShardPlacement> make_shard(const MemoryPool& pool, const Range& r, uint64_t length) const;
   void rollback(const std::vector<Extent>& extents);
+  // The common request -- one copy, one shard -- without place()'s replica / stripe bookkeeping (five hash containers).
+  // Same choice as place(): the first candidate in ranking order that has room.
+  bool single_shard(const AllocationRequest& req, size_t ncands) const;
+  Result<AllocationResult> place_single(const AllocationRequest& req, const PoolMap& pools, const std::vector<Candidate>& cands, bool spill);
   Result<AllocationResult> place(const AllocationRequest& req, const PoolMap& pools,
                                  const std::vector<Candidate>& cands, bool spill);
   Result<AllocationResult> place_symmetric(const AllocationRequest& req, const PoolMap& pools,
