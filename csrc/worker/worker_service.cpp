@@ -524,9 +524,13 @@ void WorkerService::register_data_handlers() {
                    : fault::fire("fail_data_read") ? ErrorCode::IO_ERROR : ErrorCode::OK;
     if (ec == ErrorCode::OK) {
       const uint64_t o = resolve_offset(*b, off);
-      const void* direct = (b->get_storage_class() != StorageClass::RAM_GPU && o != ~0ull && o + len >= o && o + len <= b->get_total_capacity())
-                               ? b->direct_ptr(o) : nullptr;
-      if (direct && len >= 4096) {  // DRAM / CXL / mmap tiers: send from the pool itself
+      // the length comes off the wire: check it against the pool BEFORE anything is sized from it (a 4 GiB `len` used to
+      // zero-fill a 4 GiB reply buffer first and fail the range check afterwards)
+      const bool in_range = o != ~0ull && o + len >= o && o + len <= b->get_total_capacity();
+      const void* direct = (in_range && b->get_storage_class() != StorageClass::RAM_GPU) ? b->direct_ptr(o) : nullptr;
+      if (!in_range) {
+        ec = ErrorCode::INVALID_PARAMETERS;
+      } else if (direct && len >= 4096) {  // DRAM / CXL / mmap tiers: send from the pool itself
         b->note_read(len);
         rep.ext = direct;
         rep.ext_len = len;

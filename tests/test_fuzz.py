@@ -551,3 +551,30 @@ def test_client_decoders_survive_a_server_that_answers_garbage(bb, monkeypatch):
         state["run"] = False
         t.join(timeout=2)
         srv.close()
+
+
+def test_data_server_checks_a_read_length_before_sizing_anything_from_it(bb):
+    """ADVICE r1 class of defect, found again by the mutated-frame fuzzer under TSAN: a D_READ whose 32-bit length is far
+    beyond the pool used to zero-fill a reply buffer of that size (4 GiB, 1-2 s of a data-server thread) and only then fail the
+    range check.  The length is validated first now: the answer is immediate and carries no payload."""
+    import resource
+    import time
+
+    with LocalCluster(cluster_id="fuzz3", n_workers=1) as c:
+        cl = c.client()
+        assert cl.put("seed", os.urandom(4096), bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU])) == bb.ErrorCode.OK
+        sh = cl.get_workers("seed")[0].shards[0]
+        pool = sh.pool_id.encode()
+        addr = sh.location["remote_addr"] | (1 << 63)
+        rss0 = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+        for n in (0xFFFFFFF0, 0x80000000, (64 << 20) + 1):
+            s = socket.create_connection(("127.0.0.1", int(sh.endpoint.port)), 2.0)
+            s.settimeout(5.0)
+            t0 = time.time()
+            s.sendall(_frame(2, 9, struct.pack("<I", len(pool)) + pool + struct.pack("<QI", addr, n)))
+            hdr = s.recv(16)
+            ln, method, rid = struct.unpack("<IIQ", hdr)
+            body = s.recv(64)
+            s.close()
+            assert time.time() - t0 < 0.5 and ln == 4 and struct.unpack("<i", body[:4])[0] == int(bb.ErrorCode.INVALID_PARAMETERS.value)
+        assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - rss0 < (256 << 10)  # KiB: nothing like a 4 GiB buffer was touched
