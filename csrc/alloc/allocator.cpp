@@ -685,8 +685,7 @@ bool RangeAllocator::allocate_run(const AllocationRequest& shape, const std::vec
   const size_t per = (count + tie - 1) / tie;
   for (size_t c = 0; c < tie && next < count; ++c) take(cands[c], std::min(per, count - next));
   for (size_t c = 0; c < cands.size() && next < count; ++c) take(cands[c], count - next);
-  // ledger + shard descriptors; pool accounting once per run
-  std::unordered_map<const MemoryPool*, size_t> used;
+  // ledger + shard descriptors (a pool's used bytes are read off its allocator: nothing to account here)
   for (size_t i = 0; i < next; ++i) {
     const Piece& pc = pieces[i];
     const ObjectKey& key = *keys[i];
@@ -707,13 +706,8 @@ bool RangeAllocator::allocate_run(const AllocationRequest& shape, const std::vec
       if (PoolAllocator* pa = find_pool(pc.pool->id)) pa->free(pc.range);
       continue;
     }
-    used[pc.pool] += pc.range.length;
     out[i].status = ErrorCode::OK;
     out[i].shard = std::move(shard.value());
-  }
-  if (!used.empty()) {
-    std::lock_guard<SpinMutex> lk(used_mu_);
-    for (const auto& [pool, bytes] : used) used_by_pool_[pool->id] += bytes;
   }
   return true;
 }
@@ -727,13 +721,6 @@ ErrorCode RangeAllocator::free(const ObjectKey& key) {
     if (it == ls.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
     oa = std::move(it->second);
     ls.objects.erase(it);
-  }
-  {
-    std::lock_guard<SpinMutex> lk(used_mu_);
-    for (const auto& e : oa.extents) {
-      auto u = used_by_pool_.find(e.pool);
-      if (u != used_by_pool_.end()) u->second -= std::min(u->second, static_cast<size_t>(e.range.length));
-    }
   }
   rollback(oa.extents);
   return ErrorCode::OK;
@@ -815,14 +802,13 @@ void RangeAllocator::forget_pool(const MemoryPoolId& id) {
       ex.erase(std::remove_if(ex.begin(), ex.end(), [&](const Extent& e) { return e.pool == id; }), ex.end());
     }
   }
-  std::lock_guard<SpinMutex> lk(used_mu_);
-  used_by_pool_.erase(id);
 }
 
+// What is handed out on a pool is what its allocator does not have free: no second set of books next to the free lists
+// (a global lock on every allocate and free, and one more thing to keep consistent across forget_pool / adopt / reset).
 size_t RangeAllocator::pool_used_bytes(const MemoryPoolId& id) const {
-  std::lock_guard<SpinMutex> lk(used_mu_);
-  auto it = used_by_pool_.find(id);
-  return it == used_by_pool_.end() ? 0 : it->second;
+  const PoolAllocator* pa = find_pool(id);
+  return pa ? pa->used_bytes() : 0;
 }
 
 double RangeAllocator::pool_fragmentation(const MemoryPoolId& id) const {
@@ -876,10 +862,6 @@ ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlac
     return ErrorCode::OK;
   }
   // late adoption of one pool's extents: merge into the object's existing ledger entry (created by the first adopt)
-  {
-    std::lock_guard<SpinMutex> lk(used_mu_);
-    for (const auto& e : oa.extents) used_by_pool_[e.pool] += e.range.length;
-  }
   LedgerShard& ls = ledger_for(key);
   std::lock_guard<SpinMutex> lk(ls.mu);
   ObjectAllocation& dst = ls.objects[key];
@@ -899,30 +881,13 @@ void RangeAllocator::reset() {
     std::lock_guard<SpinMutex> lk(ls.mu);
     ls.objects.clear();
   }
-  std::lock_guard<SpinMutex> lk(used_mu_);
-  used_by_pool_.clear();
 }
 
 bool RangeAllocator::ledger_insert(const ObjectKey& key, ObjectAllocation&& oa) {
-  {
-    std::lock_guard<SpinMutex> lk(used_mu_);
-    for (const auto& e : oa.extents) used_by_pool_[e.pool] += e.range.length;
-  }
   LedgerShard& ls = ledger_for(key);
-  bool inserted;
-  {
-    std::lock_guard<SpinMutex> lk(ls.mu);
-    if (ls.objects.count(key)) inserted = false;  // `oa` is left intact for the caller's rollback
-    else inserted = ls.objects.emplace(key, std::move(oa)).second;
-  }
-  if (!inserted) {
-    std::lock_guard<SpinMutex> lk(used_mu_);
-    for (const auto& e : oa.extents) {
-      auto u = used_by_pool_.find(e.pool);
-      if (u != used_by_pool_.end()) u->second -= std::min(u->second, static_cast<size_t>(e.range.length));
-    }
-  }
-  return inserted;
+  std::lock_guard<SpinMutex> lk(ls.mu);
+  if (ls.objects.count(key)) return false;  // `oa` is left intact for the caller's rollback
+  return ls.objects.emplace(key, std::move(oa)).second;
 }
 
 // ================================================================ factory / adapter

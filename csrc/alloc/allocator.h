@@ -109,6 +109,11 @@ class PoolAllocator {
   bool can_allocate(uint64_t size) const;
   std::vector<Range> free_ranges() const;  // address ordered snapshot
   size_t capacity() const { return pool_size_; }
+  // Bytes currently handed out (aligned extents): usable capacity minus the published free bytes -- a lock-free read.
+  size_t used_bytes() const {
+    const size_t usable = pool_size_ / align_ * align_, free_now = free_pub_.load(std::memory_order_relaxed);
+    return usable > free_now ? usable - free_now : 0;
+  }
   uint64_t aligned(uint64_t size) const { return size == 0 ? 0 : (size + align_ - 1) / align_ * align_; }
 
   const MemoryPoolId& pool_id() const { return pool_id_; }
@@ -238,12 +243,10 @@ class RangeAllocator : public IAllocator {
     std::unordered_map<ObjectKey, ObjectAllocation> objects;
   };
   LedgerShard& ledger_for(const ObjectKey& key) const { return ledger_[std::hash<ObjectKey>{}(key) % kLedgerShards]; }
-  // Inserts `oa` under `key` (false + untouched when the key already has an allocation) and accounts its extents.
+  // Inserts `oa` under `key` (false + untouched when the key already has an allocation).
   bool ledger_insert(const ObjectKey& key, ObjectAllocation&& oa);
   mutable std::array<LedgerShard, kLedgerShards> ledger_;
   std::mutex symmetric_mu_;  // one symmetric (same offset on every replica) placement at a time: see place_symmetric
-  mutable SpinMutex used_mu_;
-  std::unordered_map<MemoryPoolId, size_t> used_by_pool_;  // guarded by used_mu_
 };
 
 class AllocatorFactory {
