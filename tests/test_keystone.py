@@ -472,3 +472,45 @@ def test_concurrent_symmetric_placements_do_not_starve_each_other(bb, monkeypatc
         [t.join() for t in ts]
         assert errors == []
         assert c.keystone.get_cluster_stats().pending_objects == 8 * 6 * 32
+
+
+def test_ha_failover_recovers_a_run_placed_batch_extent_by_extent(bb):
+    """Objects placed as a run share one pool-allocator extent that was sliced; the metadata log records them one by one.
+    After a fail-over the new leader re-reserves every slice (adopt): the survivors keep their offsets, removed ones left
+    holes that are reusable, and new objects do not land on any recovered slice."""
+    store = bb.MemCoord()
+    mk = lambda sid: bb.KeystoneService(ks_cfg(bb, cluster_id="harun", enable_ha=True, service_id=sid, service_registration_ttl_sec=4,
+                                                service_refresh_interval_sec=1), bb.CoordService(store))
+    a, b = mk("ks-a"), mk("ks-b")
+    assert a.initialize() == bb.ErrorCode.OK and a.start() == bb.ErrorCode.OK
+    assert b.initialize() == bb.ErrorCode.OK and b.start() == bb.ErrorCode.OK
+    assert a.is_leader()
+    store.put("/blackbird/clusters/harun/workers/w0", '{"worker_id":"w0","node_id":"n0"}')
+    store.put("/blackbird/clusters/harun/workers/w0/memory_pools/p0", mkpool(bb, "p0", 1 << 20, worker="w0").to_json())
+    store.flush_events()
+    keys = [f"run/{i:02d}" for i in range(32)]
+    res = a.batch_put_start(keys, [8192] * 32, cfg1(bb, ttl_ms=0))
+    assert all(r[0] == bb.ErrorCode.OK for r in res)
+    offs = {k: r[1][0].shards[0].offset for k, r in zip(keys, res)}
+    assert len(set(offs.values())) == 32
+    assert set(a.batch_put_complete(keys)) == {bb.ErrorCode.OK}
+    gone = keys[1::4]
+    assert set(a.batch_remove_object(gone)) == {bb.ErrorCode.OK}  # holes inside the sliced extent
+    store.advance_time_ms(5000)  # the leader's lease runs out without a resign
+    deadline = time.time() + 5
+    while not b.is_leader() and time.time() < deadline:
+        time.sleep(0.05)
+    assert b.is_leader()
+    kept = [k for k in keys if k not in gone]
+    for k in kept:
+        assert b.get_workers(k)[0].shards[0].offset == offs[k]
+    for k in gone:
+        with pytest.raises(bb.BlackbirdError):
+            b.get_workers(k)
+    assert b.get_cluster_stats().used_capacity == len(kept) * 8192
+    # fill the rest of the pool: every new object avoids the recovered slices, and the holes are usable
+    more = b.batch_put_start([f"new/{i:03d}" for i in range(104)], [8192] * 104, cfg1(bb, ttl_ms=0))  # 128 slots - 24 kept
+    new_offs = [r[1][0].shards[0].offset for r in more if r[0] == bb.ErrorCode.OK]
+    assert len(new_offs) == 104 and not (set(new_offs) & {offs[k] for k in kept})
+    assert {offs[k] for k in gone} <= set(new_offs)
+    a.stop(), b.stop()
