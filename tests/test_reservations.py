@@ -106,3 +106,26 @@ def test_reservations_are_off_by_default_and_the_background_sweep_runs(bb):
         c.keystone.put_start("k", 4096, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1))
         # default allocation_poll_interval_ms = 1000: the reaper thread finds the expired token on its own
         assert wait_for(lambda: c.keystone.get_cluster_stats().pending_objects == 0, timeout=6)
+
+
+def test_run_placed_batches_go_through_the_reservation_protocol(bb, rcluster):
+    """A uniform batch is placed as a run (one allocator call per chunk); every object still gets its own reservation token at
+    the worker, commits and cancels still resolve them one by one, and the Keystone ledger and the workers' stats agree."""
+    c = rcluster
+    wc = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0)
+    keys = [f"rb/{i:02d}" for i in range(24)]
+    res = c.keystone.batch_put_start(keys, [16384] * 24, wc)
+    assert all(r[0] == bb.ErrorCode.OK for r in res)
+    per_pool = {}
+    for r in res:
+        per_pool[r[1][0].shards[0].pool_id] = per_pool.get(r[1][0].shards[0].pool_id, 0) + 1
+    st = pool_stats(c)
+    assert sum(s.num_reservations for s in st.values()) == 24 and sum(s.num_committed_shards for s in st.values()) == 0
+    assert sorted(per_pool.values()) == [12, 12]  # the run was dealt out over the two equal pools
+    assert set(c.keystone.batch_put_complete(keys[:16])) == {bb.ErrorCode.OK}
+    assert set(c.keystone.batch_put_cancel(keys[16:])) == {bb.ErrorCode.OK}
+    st = pool_stats(c)
+    assert sum(s.num_reservations for s in st.values()) == 0 and sum(s.num_committed_shards for s in st.values()) == 16
+    assert sum(s.used_capacity for s in st.values()) == 16 * 16384 == c.keystone.get_cluster_stats().used_capacity
+    assert set(c.keystone.batch_remove_object(keys[:16])) == {bb.ErrorCode.OK}
+    assert sum(s.used_capacity for s in pool_stats(c).values()) == 0 and c.keystone.get_cluster_stats().used_capacity == 0
