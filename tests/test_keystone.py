@@ -386,6 +386,12 @@ def test_size_based_tier_policy_for_puts_without_a_preferred_class(bb):
         assert cl.put("big2", b"z" * (1 << 20), bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, preferred_classes=[bb.StorageClass.RAM_CPU])) == bb.ErrorCode.OK
         assert cl.get_workers("big2")[0].shards[0].storage_class == bb.StorageClass.RAM_CPU
         assert cl.get("big") == b"y" * (1 << 20)
+        # a batch with two sizes = two runs: each follows the policy for its size
+        names = [f"s{i}" for i in range(12)] + [f"b{i}" for i in range(12)]
+        res = c.keystone.batch_put_start(names, [2000] * 12 + [128 << 10] * 12, cfg)
+        assert all(r[0] == bb.ErrorCode.OK for r in res)
+        assert {r[1][0].shards[0].storage_class for r in res[:12]} == {bb.StorageClass.RAM_CPU}
+        assert {r[1][0].shards[0].storage_class for r in res[12:]} == {bb.StorageClass.CXL_MEMORY}
 
 
 def test_batch_put_start_places_uniform_runs_together(bb, ks):
