@@ -42,7 +42,8 @@ def reference_arm() -> int:
            "configure needs the network (yalantinglibs / GoogleTest FetchContent) and UCX, etcd-cpp-apiv3, glog, yaml-cpp, liburing "
            "which are absent here and on the GPU box (profiles/r2_nvlink/ucx_probe.txt: no ucx_info, no /opt/hpcx, no libucp); "
            "src/worker/storage/cxl_memory_backend.cpp does not compile at this commit; its GPU pools are std::malloc")
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:  # one line for the job, also when launched under torchrun
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 
