@@ -1175,7 +1175,12 @@ Result<std::string> RpcClient::call(uint32_t method, const std::string& request,
     if (rmethod == 0x7FFFFFFFu) return ErrorCode::NOT_IMPLEMENTED;
     if (rmethod == 0x7FFFFFFEu) return ErrorCode::INTERNAL_ERROR;
     if (rmethod == kDeniedMarker) return ErrorCode::ACCESS_DENIED;
-    return std::string(reinterpret_cast<const char*>(h) + 4096 + kShmReqBytes, h->resp_len);
+    const uint32_t rlen = h->resp_len;
+    if (rlen > kShmRespBytes) {  // the length lives in memory the peer writes: never read past the mapping on its say-so
+      drop_shm();
+      return ErrorCode::RPC_FAILED;
+    }
+    return std::string(reinterpret_cast<const char*>(h) + 4096 + kShmReqBytes, rlen);
   }
   return call_tcp_locked(method, request, timeout_ms);
 }
