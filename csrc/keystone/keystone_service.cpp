@@ -836,6 +836,7 @@ bool KeystoneService::put_start_run(const std::vector<PutStartItem>& items, size
   std::vector<alloc::IAllocator::RunSlot> slots;
   if (!keys.empty() && !allocator_->allocate_run(keys, data_size, *effective, pools_, client_node, slots)) return false;
   const TimePoint now = Clock::now();
+  uint64_t placed_as_run = 0;
   for (size_t k = 0; k < keys.size(); ++k) {
     const size_t i = index[k];
     const ObjectKey& key = *keys[k];
@@ -876,7 +877,9 @@ bool KeystoneService::put_start_run(const std::vector<PutStartItem>& items, size
       continue;
     }
     out[i] = std::move(copies);
+    ++placed_as_run;
   }
+  if (placed_as_run) metrics_.inc("put_start_run_objects_total", placed_as_run);
   return true;
 }
 

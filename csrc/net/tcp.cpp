@@ -816,6 +816,7 @@ bool RpcServer::on_data(const ConnPtr& c) {
       const Aead::Span ct{&in[body], len >= kAeadTag ? len - kAeadTag : 0};
       if (len < kAeadTag || !c->rx().open(&in[frame_at], kFrameHeader, &ct, 1, &in[body + len - kAeadTag])) {
         if (log_denial()) BB_LOG(WARNING) << "rpc: frame from " << c->peer() << " failed authentication (altered, replayed or out of order): closing";
+        auth_failures_.fetch_add(1, std::memory_order_relaxed);
         return false;
       }
       plen = len - static_cast<uint32_t>(kAeadTag);
@@ -826,6 +827,7 @@ bool RpcServer::on_data(const ConnPtr& c) {
         const std::string_view msg(in.data() + body, len);
         if (token.empty() && transport_encryption()) {
           if (log_denial()) BB_LOG(ERROR) << "rpc: encrypt_transport is set but there is no cluster token to derive keys from: refusing " << c->peer();
+          auth_failures_.fetch_add(1, std::memory_order_relaxed);
           c->send(encode_frame(kDeniedMarker, id, std::string()));
           return false;
         }
@@ -838,11 +840,13 @@ bool RpcServer::on_data(const ConnPtr& c) {
         const bool hello = nonces.empty() && msg.size() == 4 + kNonce;
         if (hello && msg.substr(0, 4) == kHelloMagic && transport_encryption()) {
           if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " does not encrypt but this server requires it (encrypt_transport)";
+          auth_failures_.fetch_add(1, std::memory_order_relaxed);
           c->send(encode_frame(kDeniedMarker, id, std::string()));
           return false;
         }
         if (hello && msg.substr(0, 4) == kHelloSecure && !Aead::available()) {
           if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " asks for an encrypted connection but libcrypto is not available here";
+          auth_failures_.fetch_add(1, std::memory_order_relaxed);
           c->send(encode_frame(kDeniedMarker, id, std::string()));
           return false;
         }
@@ -865,16 +869,19 @@ bool RpcServer::on_data(const ConnPtr& c) {
             derive_key(token, "bb-key-c2s", nonces, c2s);
             derive_key(token, "bb-key-s2c", nonces, s2c);
             if (!c->enable_secure(c2s, s2c)) return false;
+            secure_handshakes_.fetch_add(1, std::memory_order_relaxed);
           }
           nonces.clear();
           continue;
         }
         if (log_denial()) BB_LOG(WARNING) << "rpc: failed cluster-token handshake from " << c->peer();
+        auth_failures_.fetch_add(1, std::memory_order_relaxed);
         c->send(encode_frame(kDeniedMarker, id, std::string()));
         return false;
       }
       if (!token.empty() || transport_encryption()) {  // (encryption without a token cannot be keyed: nothing gets in)
         if (log_denial()) BB_LOG(WARNING) << "rpc: request without the cluster token from " << c->peer();
+        auth_failures_.fetch_add(1, std::memory_order_relaxed);
         c->send(encode_frame(kDeniedMarker, id, std::string()));
         return false;
       }

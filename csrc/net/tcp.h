@@ -218,6 +218,8 @@ class RpcServer : public TcpServer {
   }
   uint64_t requests_served() const { return served_.load(); }
   uint64_t shm_requests_served() const { return shm_served_.load(); }
+  uint64_t secure_handshakes() const { return secure_handshakes_.load(); }  // connections that switched to sealed frames
+  uint64_t auth_failures() const { return auth_failures_.load(); }          // denied handshakes + frames that failed authentication
   size_t shm_channels() const;
   ~RpcServer() override;
   void stop() override;  // channel pollers first (no request may reach a handler once stop() returned), then the sockets
@@ -242,6 +244,7 @@ class RpcServer : public TcpServer {
   std::vector<std::thread> shm_pollers_;
   std::atomic<bool> shm_run_{false};
   std::atomic<uint64_t> shm_served_{0};
+  std::atomic<uint64_t> secure_handshakes_{0}, auth_failures_{0};
   std::unordered_map<uint32_t, Handler> handlers_;
   std::unordered_map<uint32_t, ViewHandler> view_handlers_;
   std::function<void(const ConnPtr&)> close_hook_;

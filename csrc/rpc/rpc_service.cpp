@@ -311,10 +311,19 @@ void RpcService::register_handlers() {
     return ec_reply(ks->remove_worker(r.str()));
   });
 
-  http_.route("/metrics", [ks](const std::string&, const std::string&) {
+  http_.route("/metrics", [ks, this](const std::string&, const std::string&) {
     net::HttpResponse r;
     r.content_type = "text/plain; version=0.0.4; charset=utf-8";
     r.body = ks->metrics_text();
+    // transport counters of this RPC server
+    auto counter = [&](const char* name, const char* help, uint64_t v) {
+      r.body += std::string("# HELP ") + name + " " + help + "\n# TYPE " + name + " counter\n" + name + " " + std::to_string(v) + "\n";
+    };
+    counter("bb_rpc_requests_total", "RPC requests served (TCP frames + shared-memory channel)", rpc_.requests_served());
+    counter("bb_rpc_shm_requests_total", "RPC requests served over same-host shared-memory channels", rpc_.shm_requests_served());
+    counter("bb_rpc_secure_handshakes_total", "connections that switched to AES-256-GCM sealed frames (encrypt_transport)", rpc_.secure_handshakes());
+    counter("bb_rpc_auth_failures_total", "denied token handshakes, requests without the token, frames that failed authentication", rpc_.auth_failures());
+    r.body += "# TYPE bb_rpc_shm_channels gauge\nbb_rpc_shm_channels " + std::to_string(rpc_.shm_channels()) + "\n";
     return r;
   });
   http_.route("/healthz", [ks](const std::string&, const std::string&) {

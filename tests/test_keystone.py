@@ -423,6 +423,7 @@ def test_batch_put_start_places_uniform_runs_together(bb, ks):
         addrs = sorted(a for p, a in seen if p == pid)
         assert all(b - a >= 4096 for a, b in zip(addrs, addrs[1:]))
     assert ks.get_cluster_stats().pending_objects == 64
+    assert "bb_put_start_run_objects_total 63" in ks.metrics_text()  # the duplicates went through the per-object path
     done = [n for n, _ in ok]
     assert set(ks.batch_put_complete(done)) == {bb.ErrorCode.OK}
     assert ks.get_workers("run/5")[0].shards[0].length == 4096

@@ -192,6 +192,11 @@ def test_encrypted_cluster_end_to_end_and_what_a_listener_sees(secure_cluster, t
     plain = {k: v for k, v in env.items() if k != "BB_ENCRYPT_TRANSPORT"}
     assert cli(plain, "--keystone", ks_direct, "stats").returncode != 0
     assert cli(env, "--keystone", ks_direct, "stats").returncode == 0
+    # the Keystone's /metrics (clear text, read-only) counts both
+    m = cli(env, "metrics", "--http", f"127.0.0.1:{secure_cluster['http']}")
+    assert m.returncode == 0, m.stdout + m.stderr
+    vals = {ln.split()[0]: float(ln.split()[1]) for ln in m.stdout.splitlines() if ln.startswith("bb_rpc_")}
+    assert vals["bb_rpc_secure_handshakes_total"] >= 3 and vals["bb_rpc_auth_failures_total"] >= 1 and vals["bb_rpc_requests_total"] > 0
 
 
 def test_altered_and_replayed_frames_close_the_connection(secure_cluster, bb):
