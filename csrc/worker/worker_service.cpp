@@ -427,6 +427,12 @@ std::string WorkerService::metrics_text() const {
   out += "bb_worker_heartbeats_total{" + wl + "} " + std::to_string(heartbeats_sent_.load()) + "\n";
   family("bb_worker_data_requests_total", "counter", "requests served by the data server");
   out += "bb_worker_data_requests_total{" + wl + "} " + std::to_string(data_server_.requests_served()) + "\n";
+  family("bb_worker_data_shm_requests_total", "counter", "data-server requests served over same-host shared-memory channels");
+  out += "bb_worker_data_shm_requests_total{" + wl + "} " + std::to_string(data_server_.shm_requests_served()) + "\n";
+  family("bb_worker_data_secure_handshakes_total", "counter", "data-server connections that switched to sealed frames (encrypt_transport)");
+  out += "bb_worker_data_secure_handshakes_total{" + wl + "} " + std::to_string(data_server_.secure_handshakes()) + "\n";
+  family("bb_worker_data_auth_failures_total", "counter", "denied handshakes and frames that failed authentication at the data server");
+  out += "bb_worker_data_auth_failures_total{" + wl + "} " + std::to_string(data_server_.auth_failures()) + "\n";
   family("bb_worker_data_connections", "gauge", "open data-server connections");
   out += "bb_worker_data_connections{" + wl + "} " + std::to_string(data_server_.connection_count()) + "\n";
   struct Row {
