@@ -521,3 +521,55 @@ def test_ha_failover_recovers_a_run_placed_batch_extent_by_extent(bb):
     assert len(new_offs) == 104 and not (set(new_offs) & {offs[k] for k in kept})
     assert {offs[k] for k in gone} <= set(new_offs)
     a.stop(), b.stop()
+
+
+def test_concurrent_run_placements_and_removals_never_overlap(bb, monkeypatch):
+    """Several clients place uniform batches (run path: sliced pool extents) and remove parts of them at the same time, over
+    the RPC server's thread pool.  Afterwards no two live objects share a byte and the books balance."""
+    import threading
+
+    from blackbird_b200.parallel import LocalCluster
+
+    monkeypatch.setenv("BB_RPC_SHM", "0")
+    with LocalCluster(cluster_id="runrace", n_workers=0) as c:
+        for i in range(3):
+            assert c.keystone.register_memory_pool(mkpool(bb, f"p{i}", 8 << 20, worker=f"w{i}")) == bb.ErrorCode.OK
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0)
+        live, lock, errors = {}, threading.Lock(), []
+
+        def client(t):
+            api = bb.KeystoneRpcClient()
+            assert api.connect("127.0.0.1", c.rpc.rpc_port, 3000) == bb.ErrorCode.OK
+            mine = {}
+            for rnd in range(12):
+                size = (1024, 4096, 12288)[(t + rnd) % 3]
+                keys = [f"t{t}/{rnd}/{j}" for j in range(48)]
+                for key, (ec, copies) in zip(keys, api.batch_put_start(keys, [size] * 48, cfg)):
+                    if ec == bb.ErrorCode.OK:
+                        sh = copies[0].shards[0]
+                        mine[key] = (sh.pool_id, sh.location["remote_addr"], (size + 255) // 256 * 256)
+                    elif ec != bb.ErrorCode.INSUFFICIENT_SPACE:
+                        errors.append((key, ec))
+                done = [k for k in keys if k in mine]
+                if done and set(api.batch_put_complete(done)) != {bb.ErrorCode.OK}:
+                    errors.append(("complete", t, rnd))
+                victims = done[rnd % 2::2]
+                if victims and set(api.batch_remove_object(victims)) != {bb.ErrorCode.OK}:
+                    errors.append(("remove", t, rnd))
+                for k in victims:
+                    del mine[k]
+            with lock:
+                live.update(mine)
+
+        ts = [threading.Thread(target=client, args=(t,)) for t in range(6)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert errors == []
+        by_pool = {}
+        for pool, addr, n in live.values():
+            by_pool.setdefault(pool, []).append((addr, n))
+        for pool, ext in by_pool.items():
+            ext.sort()
+            assert all(a + n <= b for (a, n), (b, _) in zip(ext, ext[1:])), f"overlap on {pool}"
+        assert c.keystone.get_cluster_stats().used_capacity == sum(n for _, _, n in live.values())
+        assert c.keystone.get_cluster_stats().total_objects == len(live)
