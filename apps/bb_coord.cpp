@@ -15,6 +15,7 @@ int main(int argc, char** argv) {
   auto args = bbapp::parse_args(argc, argv);
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
+  if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.has("help")) {
     std::printf("usage: bb-coord [--listen host:port] [--data-dir DIR [--no-fsync] [--snapshot-mb N]] [--log-level info]\n"
                 "  --data-dir   persist keys, revisions and leases (append-only log + snapshots, fdatasync group commit);\n"

@@ -68,6 +68,7 @@ BlackbirdClient::~BlackbirdClient() {
 ErrorCode BlackbirdClient::connect() {
   if (!opts_.auth_token.empty()) net::set_cluster_token(opts_.auth_token);
   if (opts_.encrypt_transport) net::set_transport_encryption(true);
+  if (!opts_.auth_token_ro.empty()) net::set_cluster_token_ro(opts_.auth_token_ro);
   if (!keystone_) {
     auto c = std::make_shared<rpc::KeystoneRpcClient>();
     c->set_timeout_ms(opts_.rpc_timeout_ms);

@@ -42,6 +42,7 @@ struct BlackbirdClientOptions {
   bool enable_shm = true;
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
   bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h); also BB_ENCRYPT_TRANSPORT=1
+  std::string auth_token_ro;       // read-only membership: set this INSTEAD of auth_token (net/tcp.h); also BB_AUTH_TOKEN_RO
 };
 
 // One device-side transfer request of a batch (a shard).

@@ -609,6 +609,8 @@ struct CoordServer::ConnState {
 
 CoordServer::CoordServer(std::shared_ptr<MemCoord> store) : store_(store ? std::move(store) : std::make_shared<MemCoord>()) {
   auto st = store_;
+  // read-only members may look and listen, nothing else (no writes, no leases, no elections)
+  rpc_.allow_read_only({M_GET, M_PREFIX, M_REMAINING, M_REVISION, M_WATCH, M_UNWATCH});
   rpc_.register_method(M_PUT, [st](const net::ConnPtr&, const std::string& q) {
     wire::Reader r(q);
     std::string k = r.str(), v = r.str();

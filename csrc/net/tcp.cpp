@@ -48,6 +48,23 @@ std::string cluster_token() {
   return g_token;
 }
 namespace {
+std::string g_token_ro;
+bool g_token_ro_init = false;
+}  // namespace
+void set_cluster_token_ro(const std::string& token) {
+  std::lock_guard<std::mutex> lk(g_token_mu);
+  g_token_ro = token;
+  g_token_ro_init = true;
+}
+std::string cluster_token_ro() {
+  std::lock_guard<std::mutex> lk(g_token_mu);
+  if (!g_token_ro_init) {
+    if (const char* e = std::getenv("BB_AUTH_TOKEN_RO")) g_token_ro = e;
+    g_token_ro_init = true;
+  }
+  return g_token_ro;
+}
+namespace {
 std::atomic<int> g_encrypt{-1};  // -1: not decided yet (BB_ENCRYPT_TRANSPORT)
 }
 void set_transport_encryption(bool on) { g_encrypt.store(on ? 1 : 0); }
@@ -65,6 +82,7 @@ namespace {
 constexpr size_t kNonce = 16, kMac = 32;
 constexpr char kHelloMagic[] = "BBA1";
 constexpr char kHelloSecure[] = "BBA2";  // as BBA1, and every frame after the handshake is sealed (tcp.h)
+constexpr char kHelloRo[] = "BBR1", kHelloRoSecure[] = "BBR2";  // the same two, proving the read-only token instead
 void fresh_nonce(char* out) {
   size_t got = 0;
   while (got < kNonce) {
@@ -630,6 +648,11 @@ struct RpcServer::ShmChan {
 RpcServer::Reply RpcServer::dispatch(const ConnPtr& c, uint32_t method, std::string_view request, uint32_t* rmethod) {
   Reply reply;
   *rmethod = method;
+  if (c && c->read_only() && !ro_methods_.count(method)) {  // a read-only member asking for more than it may: refused, not hung up on
+    ro_denials_.fetch_add(1, std::memory_order_relaxed);
+    *rmethod = kDeniedMarker;
+    return reply;
+  }
   try {
     if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
     if (auto vit = view_handlers_.find(method); vit != view_handlers_.end()) {
@@ -838,36 +861,50 @@ bool RpcServer::on_data(const ConnPtr& c) {
         }
         std::string& nonces = c->auth_nonces();
         const bool hello = nonces.empty() && msg.size() == 4 + kNonce;
-        if (hello && msg.substr(0, 4) == kHelloMagic && transport_encryption()) {
+        const std::string_view magic = msg.substr(0, std::min<size_t>(4, msg.size()));
+        const bool ro_hello = hello && (magic == kHelloRo || magic == kHelloRoSecure);
+        if (ro_hello && cluster_token_ro().empty()) {
+          if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " presents a read-only token but this server has none (auth_token_ro)";
+          auth_failures_.fetch_add(1, std::memory_order_relaxed);
+          c->send(encode_frame(kDeniedMarker, id, std::string()));
+          return false;
+        }
+        if (hello && (magic == kHelloMagic || magic == kHelloRo) && transport_encryption()) {
           if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " does not encrypt but this server requires it (encrypt_transport)";
           auth_failures_.fetch_add(1, std::memory_order_relaxed);
           c->send(encode_frame(kDeniedMarker, id, std::string()));
           return false;
         }
-        if (hello && msg.substr(0, 4) == kHelloSecure && !Aead::available()) {
+        if (hello && (magic == kHelloSecure || magic == kHelloRoSecure) && !Aead::available()) {
           if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " asks for an encrypted connection but libcrypto is not available here";
           auth_failures_.fetch_add(1, std::memory_order_relaxed);
           c->send(encode_frame(kDeniedMarker, id, std::string()));
           return false;
         }
-        if (hello && (msg.substr(0, 4) == kHelloMagic || msg.substr(0, 4) == kHelloSecure)) {
-          c->wants_secure() = msg.substr(0, 4) == kHelloSecure;
+        if (hello && (magic == kHelloMagic || magic == kHelloSecure || ro_hello)) {
+          c->wants_secure() = magic == kHelloSecure || magic == kHelloRoSecure;
+          c->hello_read_only() = ro_hello;
           nonces.assign(msg.substr(4));
           char sn[kNonce];
           fresh_nonce(sn);
           nonces.append(sn, kNonce);
           std::string reply(sn, kNonce);
-          reply += handshake_mac(token, "bb-srv", nonces);
+          reply += ro_hello ? handshake_mac(cluster_token_ro(), "bb-srv-ro", nonces) : handshake_mac(token, "bb-srv", nonces);
           if (!c->send(encode_frame(kAuthMethod, id, reply))) return false;
           continue;
         }
-        if (nonces.size() == 2 * kNonce && msg.size() == kMac && mac_equal(msg.data(), handshake_mac(token, "bb-cli", nonces).data(), kMac)) {
+        // the proof is checked against the secret of the role the hello named, under that role's label
+        const bool ro = c->hello_read_only();
+        const std::string proven = ro ? cluster_token_ro() : token;
+        if (nonces.size() == 2 * kNonce && msg.size() == kMac && !proven.empty() &&
+            mac_equal(msg.data(), handshake_mac(proven, ro ? "bb-cli-ro" : "bb-cli", nonces).data(), kMac)) {
+          if (ro) c->set_read_only();
           c->set_authed();
           if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;  // the last clear frame
           if (c->wants_secure()) {
             uint8_t c2s[kAeadKey], s2c[kAeadKey];
-            derive_key(token, "bb-key-c2s", nonces, c2s);
-            derive_key(token, "bb-key-s2c", nonces, s2c);
+            derive_key(proven, "bb-key-c2s", nonces, c2s);
+            derive_key(proven, "bb-key-s2c", nonces, s2c);
             if (!c->enable_secure(c2s, s2c)) return false;
             secure_handshakes_.fetch_add(1, std::memory_order_relaxed);
           }
@@ -926,7 +963,10 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
     BB_VLOG(1) << "RpcClient: connect " << host << ":" << port << " failed: " << err;
     return ErrorCode::CONNECTION_FAILED;
   }
-  const std::string token = cluster_token();
+  std::string token = cluster_token();
+  // a process that holds only the read-only token joins as a read-only member
+  const bool ro = token.empty() && !cluster_token_ro().empty();
+  if (ro) token = cluster_token_ro();
   const bool want_secure = transport_encryption();
   secure_ = false;
   if (want_secure) {
@@ -951,18 +991,19 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
     };
     std::string nonces(kNonce, '\0'), reply;
     fresh_nonce(nonces.data());
-    ErrorCode ec = exchange(0, std::string(want_secure ? kHelloSecure : kHelloMagic, 4) + nonces, &reply);
+    const char* hello = ro ? (want_secure ? kHelloRoSecure : kHelloRo) : (want_secure ? kHelloSecure : kHelloMagic);
+    ErrorCode ec = exchange(0, std::string(hello, 4) + nonces, &reply);
     if (ec == ErrorCode::OK) {
       if (reply.size() != kNonce + kMac) {
         BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " has no cluster token but this client does";
         ec = ErrorCode::ACCESS_DENIED;
       } else {
         nonces.append(reply, 0, kNonce);
-        if (!mac_equal(reply.data() + kNonce, handshake_mac(token, "bb-srv", nonces).data(), kMac)) {
+        if (!mac_equal(reply.data() + kNonce, handshake_mac(token, ro ? "bb-srv-ro" : "bb-srv", nonces).data(), kMac)) {
           BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " does not hold this cluster's token";
           ec = ErrorCode::ACCESS_DENIED;
         } else {
-          ec = exchange(1, handshake_mac(token, "bb-cli", nonces), &reply);
+          ec = exchange(1, handshake_mac(token, ro ? "bb-cli-ro" : "bb-cli", nonces), &reply);
         }
       }
     }

@@ -56,8 +56,18 @@ class TcpServer;
 // change).  This is a pre-shared-key channel (confidentiality + integrity for everyone who holds the token), not mTLS:
 // there are no per-client identities.  Shared-memory channels (same host) carry plain frames; HTTP endpoints
 // (/metrics, /healthz) stay open and clear.
+//
+// Read-only members (`auth_token_ro:` / BB_AUTH_TOKEN_RO on the servers; a client that holds ONLY that token -- `--auth-token-ro`,
+// BlackbirdClientOptions::auth_token_ro, BB_AUTH_TOKEN_RO -- uses it): the same handshake with "BBR1" / "BBR2" and the
+// role-bound labels "bb-srv-ro" / "bb-cli-ro", keyed by the second secret.  The connection is then marked read-only and the
+// server dispatches only the methods its owner put on the read-only list (RpcServer::allow_read_only: object_exists /
+// get_workers / stats / listings on the Keystone, D_READ / D_CHECKSUM on a data server, get / list / watch on the
+// coordination store); everything else is answered with the denial marker (ACCESS_DENIED at the caller) and the
+// connection stays open.  Holders of the read-only token cannot put, remove, migrate, register workers or touch leases.
 void set_cluster_token(const std::string& token);
 std::string cluster_token();
+void set_cluster_token_ro(const std::string& token);
+std::string cluster_token_ro();
 void set_transport_encryption(bool on);
 bool transport_encryption();
 constexpr uint32_t kAuthMethod = 0x7FFFFF00u;
@@ -108,7 +118,10 @@ class Connection : public std::enable_shared_from_this<Connection> {
   bool authed() const { return authed_.load(std::memory_order_acquire); }
   void set_authed() { authed_.store(true, std::memory_order_release); }
   std::string& auth_nonces() { return auth_nonces_; }  // handshake in progress: cnonce + snonce
-  bool& wants_secure() { return wants_secure_; }       // the client opened with "BBA2"
+  bool& wants_secure() { return wants_secure_; }       // the client opened with "BBA2" / "BBR2"
+  bool& hello_read_only() { return hello_ro_; }        // the client opened with "BBR1" / "BBR2" (handshake in progress)
+  bool read_only() const { return read_only_.load(std::memory_order_acquire); }
+  void set_read_only() { read_only_.store(true, std::memory_order_release); }
   // Secure mode: from now on send() / sendv() seal every frame and the owner opens incoming ones with rx().
   bool enable_secure(const uint8_t rx_key[kAeadKey], const uint8_t tx_key[kAeadKey]);
   bool secure() const { return secure_.load(std::memory_order_acquire); }
@@ -132,6 +145,8 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::atomic<bool> authed_{false};
   std::string auth_nonces_;
   bool wants_secure_ = false;
+  bool hello_ro_ = false;
+  std::atomic<bool> read_only_{false};
   std::atomic<bool> secure_{false};
   Aead rx_, tx_;  // rx_: the thread that owns the connection; tx_: under write_mu_
   bool send_sealed_locked(const char* hdr, const Aead::CSpan* payload, int n, int timeout_ms);
@@ -212,6 +227,9 @@ class RpcServer : public TcpServer {
   };
   using ViewHandler = std::function<Reply(const ConnPtr&, std::string_view request)>;
   void register_view_method(uint32_t method, ViewHandler h) { view_handlers_[method] = std::move(h); }
+  // Methods a read-only member (a connection admitted with the read-only token) may call; set before start().
+  void allow_read_only(std::initializer_list<uint32_t> methods) { ro_methods_.insert(methods.begin(), methods.end()); }
+  uint64_t read_only_denials() const { return ro_denials_.load(); }
   void set_close_hook(std::function<void(const ConnPtr&)> f) { close_hook_ = std::move(f); }
   static bool push(const ConnPtr& c, uint32_t topic, const std::string& payload) {
     return c->send(encode_frame(kPushFlag | topic, 0, payload));
@@ -244,7 +262,8 @@ class RpcServer : public TcpServer {
   std::vector<std::thread> shm_pollers_;
   std::atomic<bool> shm_run_{false};
   std::atomic<uint64_t> shm_served_{0};
-  std::atomic<uint64_t> secure_handshakes_{0}, auth_failures_{0};
+  std::atomic<uint64_t> secure_handshakes_{0}, auth_failures_{0}, ro_denials_{0};
+  std::set<uint32_t> ro_methods_;
   std::unordered_map<uint32_t, Handler> handlers_;
   std::unordered_map<uint32_t, ViewHandler> view_handlers_;
   std::function<void(const ConnPtr&)> close_hook_;

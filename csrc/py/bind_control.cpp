@@ -848,6 +848,7 @@ void bind_control(py::module_& m) {
   }, py::arg("client"), py::arg("io_client"), py::arg("reach_disk_tiers") = false,
         "CPU stand-in for the GPU fabric: the device batch API of `client` moves host buffers through `io_client`'s host data paths");
   m.def("set_cluster_token", &net::set_cluster_token, "shared-secret gate of the RPC servers / clients of this process (net/tcp.h)");
+  m.def("set_cluster_token_ro", &net::set_cluster_token_ro, "second secret: members that prove only this one are read-only (net/tcp.h)");
   m.def("set_transport_encryption", &net::set_transport_encryption, "secure mode of the RPC protocol: AES-256-GCM on every frame, keyed from the cluster token");
   m.def("transport_encryption", &net::transport_encryption);
   m.def("aead_available", [] {
@@ -994,7 +995,8 @@ void bind_control(py::module_& m) {
       .def_readwrite("node_id", &BlackbirdClientOptions::node_id)
       .def_readwrite("enable_shm", &BlackbirdClientOptions::enable_shm)
       .def_readwrite("auth_token", &BlackbirdClientOptions::auth_token)
-      .def_readwrite("encrypt_transport", &BlackbirdClientOptions::encrypt_transport);
+      .def_readwrite("encrypt_transport", &BlackbirdClientOptions::encrypt_transport)
+      .def_readwrite("auth_token_ro", &BlackbirdClientOptions::auth_token_ro);
   py::class_<BlackbirdClient, std::shared_ptr<BlackbirdClient>>(m, "BlackbirdClient")
       .def(py::init<BlackbirdClientOptions>(), py::arg("options") = BlackbirdClientOptions{})
       .def(py::init<std::shared_ptr<rpc::KeystoneApi>, BlackbirdClientOptions>(), py::arg("keystone"), py::arg("options") = BlackbirdClientOptions{})

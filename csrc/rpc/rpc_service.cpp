@@ -84,6 +84,9 @@ void RpcService::leader_only(uint32_t method, net::RpcServer::Handler h) {
 }
 
 void RpcService::register_handlers() {
+  // what a holder of the read-only token may ask the Keystone: existence, placements (to read the data), statistics, listings
+  rpc_.allow_read_only({M_OBJECT_EXISTS, M_GET_WORKERS, M_GET_CLUSTER_STATS, M_GET_VIEW_VERSION, M_BATCH_OBJECT_EXISTS, M_BATCH_GET_WORKERS,
+                        M_GET_MEMORY_POOLS, M_GET_WORKERS_INFO, M_LIST_OBJECTS, M_CLIENT_REGISTER, M_CLIENT_PING});
   auto ks = keystone_;
   using C = const net::ConnPtr&;
   using S = const std::string&;
@@ -323,6 +326,7 @@ void RpcService::register_handlers() {
     counter("bb_rpc_shm_requests_total", "RPC requests served over same-host shared-memory channels", rpc_.shm_requests_served());
     counter("bb_rpc_secure_handshakes_total", "connections that switched to AES-256-GCM sealed frames (encrypt_transport)", rpc_.secure_handshakes());
     counter("bb_rpc_auth_failures_total", "denied token handshakes, requests without the token, frames that failed authentication", rpc_.auth_failures());
+    counter("bb_rpc_read_only_denials_total", "requests of read-only members for methods outside the read-only list", rpc_.read_only_denials());
     r.body += "# TYPE bb_rpc_shm_channels gauge\nbb_rpc_shm_channels " + std::to_string(rpc_.shm_channels()) + "\n";
     return r;
   });
@@ -347,6 +351,7 @@ ErrorCode RpcService::start() {
   if (config_.rpc_busy_poll_us > 0) rpc_.set_busy_poll_us(config_.rpc_busy_poll_us);
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   if (config_.encrypt_transport) net::set_transport_encryption(true);
+  if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
   ErrorCode ec = rpc_.start(hp->first, static_cast<uint16_t>(hp->second), std::max(1, config_.rpc_threads));
   if (ec != ErrorCode::OK) return ec;
   if (!config_.http_metrics_port.empty() && config_.http_metrics_port != "off") {

@@ -36,6 +36,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("http_metrics_port")) c.http_metrics_port = static_cast<int>(w.at("http_metrics_port").as_int(-1));
   if (w.contains("auth_token")) c.auth_token = w.at("auth_token").as_string();
   if (w.contains("encrypt_transport")) c.encrypt_transport = w.at("encrypt_transport").as_bool();
+  if (w.contains("auth_token_ro")) c.auth_token_ro = w.at("auth_token_ro").as_string();
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
   if (w.contains("interconnects")) {
@@ -167,6 +168,7 @@ ErrorCode WorkerService::initialize() {
   if (!hp) return ErrorCode::INVALID_ADDRESS;
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   if (config_.encrypt_transport) net::set_transport_encryption(true);
+  if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
   data_server_.set_socket_buffers(4 << 20);  // bulk transfers: fewer wake-ups per megabyte
   const unsigned hw = std::thread::hardware_concurrency();
   ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), static_cast<int>(std::min(16u, std::max(4u, hw / 2))));
@@ -488,6 +490,7 @@ uint64_t chunk_tile_sum(ChecksumAlgo algo, const uint8_t* data, uint64_t n, uint
 }  // namespace
 
 void WorkerService::register_data_handlers() {
+  data_server_.allow_read_only({D_READ, D_CHECKSUM, D_STATS});  // read-only members read shards; they never write, copy, pull or reserve
   using C = const net::ConnPtr&;
   using S = const std::string&;
   using V = std::string_view;

@@ -63,6 +63,7 @@ struct WorkerServiceConfig {
   int http_metrics_port = -1;
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
   bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h)
+  std::string auth_token_ro;       // read-only members' token (net/tcp.h)
   CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects
   bool has_transport = false;
   std::vector<TierRule> preferred_tiers;  // `allocation.preferred_tiers` (forwarded to the keystone as a hint)

@@ -291,3 +291,87 @@ def test_full_client_with_watches_over_sealed_frames(secure_cluster, bb):
     finally:
         bb.set_transport_encryption(False)
         bb.set_cluster_token("")
+
+
+def test_read_only_token_reads_but_cannot_write(tmp_path):
+    """A second secret (`auth_token_ro` / BB_AUTH_TOKEN_RO on the servers) admits read-only members: a client that holds only
+    that token gets, lists and inspects, but every mutating call -- put, remove, migrate, a write to a data server, a write
+    to the coordination store -- is refused with ACCESS_DENIED while the connection stays usable.  Works sealed as well."""
+    import json
+
+    RO = "read-only-secret"
+    srv_env = dict(os.environ, BB_AUTH_TOKEN=TOKEN, BB_AUTH_TOKEN_RO=RO, BB_ENCRYPT_TRANSPORT="1")
+    cport, rport, hport = free_port(), free_port(), free_port()
+    procs = []
+
+    def spawn(*cmd):
+        procs.append(subprocess.Popen(list(cmd), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=srv_env))
+
+    try:
+        spawn(os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}")
+        assert wait_port(cport)
+        spawn(os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+              "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "roc")
+        assert wait_port(rport)
+        cfg = tmp_path / "w.yaml"
+        cfg.write_text('worker: {worker_id: "wr", node_id: "node-wr", lease_ttl_sec: 3, heartbeat_interval_sec: 1}\n'
+                       'storage_pools:\n  - {pool_id: "ram-wr", storage_class: "RAM_CPU", size_bytes: 64_MB}\n')
+        spawn(os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "roc")
+        ks = f"127.0.0.1:{rport}"
+        full = dict(os.environ, BB_AUTH_TOKEN=TOKEN, BB_ENCRYPT_TRANSPORT="1")
+        ro = {k: v for k, v in os.environ.items() if k != "BB_AUTH_TOKEN"}
+        ro.update(BB_AUTH_TOKEN_RO=RO, BB_ENCRYPT_TRANSPORT="1")
+        wait_pools(full, ks, 1)
+        blob = tmp_path / "blob"
+        blob.write_bytes(os.urandom(200_000))
+        assert cli(full, "--keystone", ks, "put", "ro/obj", str(blob)).returncode == 0
+        # the read-only member reads everything ...
+        out = tmp_path / "copy"
+        r = cli(ro, "--keystone", ks, "get", "ro/obj", str(out))
+        assert r.returncode == 0 and out.read_bytes() == blob.read_bytes(), r.stdout + r.stderr
+        assert cli(ro, "--keystone", ks, "exists", "ro/obj").returncode == 0
+        st = cli(ro, "--keystone", ks, "stats")
+        assert st.returncode == 0 and json.loads(st.stdout)["total_objects"] == 1
+        assert "ro/obj" in cli(ro, "--keystone", ks, "ls", "ro/").stdout
+        # ... and changes nothing
+        for args in (("put", "ro/new", str(blob)), ("remove", "ro/obj"), ("migrate", "ro/obj", "NVME"), ("remove-worker", "wr")):
+            bad = cli(ro, "--keystone", ks, *args)
+            assert bad.returncode != 0, (args, bad.stdout)
+        assert cli(full, "--keystone", ks, "exists", "ro/obj").returncode == 0 and cli(full, "--keystone", ks, "exists", "ro/new").returncode != 0
+        # the flag works like the environment variable; a wrong read-only token is no token
+        none = {k: v for k, v in os.environ.items() if k not in ("BB_AUTH_TOKEN", "BB_AUTH_TOKEN_RO")}
+        none["BB_ENCRYPT_TRANSPORT"] = "1"
+        assert cli(none, "--keystone", ks, "--auth-token-ro", RO, "exists", "ro/obj").returncode == 0
+        assert cli(none, "--keystone", ks, "--auth-token-ro", "guess", "exists", "ro/obj").returncode != 0
+        m = cli(full, "metrics", "--http", f"127.0.0.1:{hport}")
+        vals = {ln.split()[0]: float(ln.split()[1]) for ln in m.stdout.splitlines() if ln.startswith("bb_rpc_")}
+        assert vals["bb_rpc_read_only_denials_total"] >= 4
+        # the coordination store: a read-only member may look and listen, not write, delete or take leases
+        from blackbird_b200 import _bb as bb
+
+        bb.set_cluster_token("")
+        bb.set_cluster_token_ro(RO)
+        bb.set_transport_encryption(True)
+        try:
+            st = bb.RemoteCoord()
+            assert st.connect(f"127.0.0.1:{cport}", 3000) == bb.ErrorCode.OK
+            listed = lambda: [kv[0] for kv in st.get_with_prefix("/blackbird/clusters/roc/workers/")]
+            assert any(k.endswith("/workers/wr") for k in listed())
+            assert st.put("/blackbird/clusters/roc/evil", "x") != bb.ErrorCode.OK
+            assert st.delete("/blackbird/clusters/roc/workers/wr") != bb.ErrorCode.OK
+            with pytest.raises(bb.BlackbirdError):
+                st.grant_lease(5)  # no lease for a read-only member
+            assert any(k.endswith("/workers/wr") for k in listed()) and st.get("/blackbird/clusters/roc/evil") is None
+            st.close()
+        finally:
+            bb.set_transport_encryption(False)
+            bb.set_cluster_token_ro("")
+            bb.set_cluster_token("")
+    finally:
+        for p in reversed(procs):
+            p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                p.kill()
