@@ -142,7 +142,7 @@ def test_token_handshake_survives_garbage_and_never_admits_it(bb):
                     elif kind == 3:
                         body = b"fuzz-token"  # the secret itself is not a credential
                     elif kind == 4:
-                        body = b"BBA1" + rng.randbytes(16)
+                        body = rng.choice([b"BBA1", b"BBR1", b"BBR2", b"BBA2"]) + rng.randbytes(16)  # (no read-only token here: BBRx is refused)
                     else:
                         s.sendall(_frame(rng.randrange(0, 32), 3, _rand_payload(rng)))  # a request before being admitted
                         continue
