@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | compact POOL | smoke | metrics --http host:port> [--auth-token T]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | compact POOL | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T] [--encrypt-transport]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];

@@ -435,6 +435,8 @@ std::string WorkerService::metrics_text() const {
   out += "bb_worker_data_secure_handshakes_total{" + wl + "} " + std::to_string(data_server_.secure_handshakes()) + "\n";
   family("bb_worker_data_auth_failures_total", "counter", "denied handshakes and frames that failed authentication at the data server");
   out += "bb_worker_data_auth_failures_total{" + wl + "} " + std::to_string(data_server_.auth_failures()) + "\n";
+  family("bb_worker_data_read_only_denials_total", "counter", "data-server requests of read-only members outside the read-only list");
+  out += "bb_worker_data_read_only_denials_total{" + wl + "} " + std::to_string(data_server_.read_only_denials()) + "\n";
   family("bb_worker_data_connections", "gauge", "open data-server connections");
   out += "bb_worker_data_connections{" + wl + "} " + std::to_string(data_server_.connection_count()) + "\n";
   struct Row {
