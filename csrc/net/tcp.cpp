@@ -25,6 +25,7 @@
 
 #include "common/log.h"
 #include "common/sha256.h"
+#include "common/trace.h"
 
 namespace bb::net {
 
@@ -653,6 +654,7 @@ RpcServer::Reply RpcServer::dispatch(const ConnPtr& c, uint32_t method, std::str
     *rmethod = kDeniedMarker;
     return reply;
   }
+  BB_TRACE_SPAN("rpc.serve", method);  // server side of every RPC (TCP and shared-memory path) on the same timeline as the client's phases
   try {
     if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
     if (auto vit = view_handlers_.find(method); vit != view_handlers_.end()) {

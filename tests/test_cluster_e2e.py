@@ -328,7 +328,7 @@ def test_trace_spans_are_recorded_and_dumped_as_chrome_trace(bb, tmp_path):
         ev = json.loads(out.read_text())["traceEvents"]
         assert n == len(ev) and n >= 2
         names = {e["name"] for e in ev}
-        assert {"client.put", "client.get"} <= names and all(e["ph"] in ("X", "i") for e in ev)
+        assert {"client.put", "client.get", "rpc.serve"} <= names and all(e["ph"] in ("X", "i") for e in ev)  # client phases and the servers' side of each RPC
         assert all(e["dur"] > 0 for e in ev if e["ph"] == "X")
     finally:
         bb.trace_enable(False)
