@@ -9,6 +9,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("BB_PKG_ROOT"):  # sanitizer builds of the package (tests/conftest.py): the worker processes must load the same one
+    sys.path.insert(0, os.path.abspath(os.environ["BB_PKG_ROOT"]))
 from blackbird_b200 import _bb  # noqa: E402
 from blackbird_b200.parallel import CpuRankCluster  # noqa: E402
 
