@@ -573,3 +573,64 @@ def test_concurrent_run_placements_and_removals_never_overlap(bb, monkeypatch):
             assert all(a + n <= b for (a, n), (b, _) in zip(ext, ext[1:])), f"overlap on {pool}"
         assert c.keystone.get_cluster_stats().used_capacity == sum(n for _, _, n in live.values())
         assert c.keystone.get_cluster_stats().total_objects == len(live)
+
+
+def test_batch_replies_over_the_rpc_equal_the_in_process_ones_for_every_placement_shape(bb, tmp_path, monkeypatch):
+    """Batch replies delta-encode placements (one-shard results that differ from the last fully written one only in position
+    and digest travel as 17 bytes).  Whatever the mix -- memory / file / CXL locations, striped and replicated objects in
+    between, errors, runs on alternating pools -- the client must rebuild exactly what the Keystone returned."""
+    from blackbird_b200.parallel import LocalCluster
+
+    monkeypatch.setenv("BB_RPC_SHM", "0")
+    with LocalCluster("delta", n_workers=0) as c:
+        c.add_worker("w0", "n0", [("dram0", bb.StorageClass.RAM_CPU, 8 << 20, ""), ("nvme0", bb.StorageClass.NVME, 8 << 20, str(tmp_path / "n0")),
+                                  ("cxl0", bb.StorageClass.CXL_MEMORY, 8 << 20, "")])
+        c.add_worker("w1", "n1", [("dram1", bb.StorageClass.RAM_CPU, 8 << 20, ""), ("nvme1", bb.StorageClass.NVME, 8 << 20, str(tmp_path / "n1"))])
+        ks = c.keystone
+        api = bb.KeystoneRpcClient()
+        assert api.connect("127.0.0.1", c.rpc.rpc_port, 3000) == bb.ErrorCode.OK
+        keys, n = [], 0
+
+        def put(tier, size, repl=1, wpc=1, count=1):
+            nonlocal n
+            cfg = bb.WorkerConfig(replication_factor=repl, max_workers_per_copy=wpc, ttl_ms=0, preferred_classes=[tier], min_shard_size=256)
+            names = [f"o/{n + i:03d}" for i in range(count)]
+            n += count
+            res = ks.batch_put_start(names, [size] * count, cfg)
+            assert all(r[0] == bb.ErrorCode.OK for r in res), [r[0] for r in res]
+            assert set(ks.batch_put_complete(names)) == {bb.ErrorCode.OK}
+            keys.extend(names)
+
+        R, N, X = bb.StorageClass.RAM_CPU, bb.StorageClass.NVME, bb.StorageClass.CXL_MEMORY
+        put(R, 4096, count=12)            # a run: deltas
+        put(N, 8192, count=9)             # file locations: deltas on another variant
+        put(R, 6000, repl=2)              # replicated: written in full, resets nothing it should not
+        put(R, 4096, count=3)
+        put(X, 4096, count=8)             # CXL: region id derived from the offset
+        put(R, 20000, wpc=2)              # striped
+        put(N, 8192, count=2)
+        put(R, 100)                       # different length: full again
+        asked = keys[:5] + ["missing/1"] + keys[5:] + ["missing/2"]
+        direct = ks.batch_get_workers(asked)
+        remote = api.batch_get_workers(asked)
+        assert len(direct) == len(remote) == len(asked)
+
+        def flat(res):
+            out = []
+            for ec, copies in res:
+                if ec != bb.ErrorCode.OK:
+                    out.append((ec,))
+                    continue
+                out.append((ec, [(cp.copy_index, [(s.pool_id, s.worker_id, s.storage_class, s.length, s.checksum, s.checksum_algo, repr(s.location),
+                                                    s.endpoint.ip, s.endpoint.port) for s in cp.shards]) for cp in copies]))
+            return out
+
+        assert flat(direct) == flat(remote)
+        assert [r[0] for r in remote].count(bb.ErrorCode.OBJECT_NOT_FOUND) == 2
+        # and the reply of a put_start batch (run placement on two pools in turn) comes back identical too
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_classes=[R])
+        names = [f"p/{i:03d}" for i in range(40)]
+        placed = api.batch_put_start(names, [2048] * 40, cfg)
+        assert all(r[0] == bb.ErrorCode.OK for r in placed)
+        assert set(ks.batch_put_complete(names)) == {bb.ErrorCode.OK}
+        assert flat(placed) == flat([(ec, [type("C", (), {"copy_index": cp.copy_index, "shards": cp.shards})() for cp in copies]) for ec, copies in ks.batch_get_workers(names)])
