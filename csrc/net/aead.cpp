@@ -22,6 +22,7 @@ struct Crypto {
   int (*dec_update)(void*, unsigned char*, int*, const unsigned char*, int) = nullptr;
   int (*dec_final)(void*, unsigned char*, int*) = nullptr;
   int (*ctx_ctrl)(void*, int, int, void*) = nullptr;
+  const void* (*aes_256_ctr)() = nullptr;
   std::string error;
   bool ok = false;
 };
@@ -51,6 +52,7 @@ const Crypto& crypto() {
     c.dec_update = reinterpret_cast<decltype(c.dec_update)>(sym("EVP_DecryptUpdate"));
     c.dec_final = reinterpret_cast<decltype(c.dec_final)>(sym("EVP_DecryptFinal_ex"));
     c.ctx_ctrl = reinterpret_cast<decltype(c.ctx_ctrl)>(sym("EVP_CIPHER_CTX_ctrl"));
+    c.aes_256_ctr = reinterpret_cast<decltype(c.aes_256_ctr)>(sym("EVP_aes_256_ctr"));
     c.ok = c.ctx_new && c.ctx_free && c.aes_256_gcm && c.enc_init && c.enc_update && c.enc_final && c.dec_init && c.dec_update && c.dec_final && c.ctx_ctrl;
     if (!c.ok) c.error = "libcrypto lacks the EVP AES-GCM interface";
   });
@@ -136,6 +138,42 @@ bool Aead::open(const void* aad, size_t aad_len, const Span* pieces, int n, cons
   if (c.ctx_ctrl(ctx_, kCtrlSetTag, static_cast<int>(kAeadTag), t) != 1) return false;
   unsigned char dummy[16];
   return c.dec_final(ctx_, dummy, &outl) == 1;  // the tag comparison
+}
+
+bool OffsetCipher::set_key(const uint8_t key[kAeadKey], const uint8_t nonce[8]) {
+  const Crypto& c = crypto();
+  if (!c.ok || !c.aes_256_ctr) return false;
+  std::memcpy(key_, key, kAeadKey);
+  std::memcpy(nonce_, nonce, 8);
+  ready_ = true;
+  return true;
+}
+
+bool OffsetCipher::crypt(uint64_t offset, const void* in, void* out, size_t n) const {
+  if (!ready_) return false;
+  const Crypto& c = crypto();
+  void* ctx = c.ctx_new();
+  if (!ctx) return false;
+  // counter block = nonce(8) || big-endian index of the 16-byte block the range starts in
+  unsigned char iv[16];
+  std::memcpy(iv, nonce_, 8);
+  const uint64_t block = offset / 16;
+  for (int i = 0; i < 8; ++i) iv[8 + i] = static_cast<unsigned char>(block >> (56 - 8 * i));
+  bool ok = c.enc_init(ctx, c.aes_256_ctr(), nullptr, key_, iv) == 1;
+  int outl = 0;
+  if (ok && (offset % 16)) {  // start inside a block: burn the key stream bytes before the range
+    unsigned char skip[16] = {0}, sink[16];
+    ok = c.enc_update(ctx, sink, &outl, skip, static_cast<int>(offset % 16)) == 1;
+  }
+  const auto* p = static_cast<const unsigned char*>(in);
+  auto* o = static_cast<unsigned char*>(out);
+  while (ok && n) {
+    const size_t take = n < kSlice ? n : kSlice;
+    ok = c.enc_update(ctx, o, &outl, p, static_cast<int>(take)) == 1;
+    p += take, o += take, n -= take;
+  }
+  c.ctx_free(ctx);
+  return ok;
 }
 
 void derive_key(const std::string& token, const char* label, const std::string& nonces, uint8_t out[kAeadKey]) {

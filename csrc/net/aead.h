@@ -48,6 +48,23 @@ class Aead {
   uint64_t counter_ = 0;    // messages protected so far in this direction
 };
 
+// AES-256-CTR addressed by byte offset, for data at rest (file-backed tiers): byte i of the pool is XORed with byte i of a key
+// stream that depends only on (key, pool nonce, i), so any range can be written and read independently and in place.  No
+// authentication here -- the object digests (computed on the plain bytes) already detect any change.  Same libcrypto, same
+// dlopen.
+class OffsetCipher {
+ public:
+  bool set_key(const uint8_t key[kAeadKey], const uint8_t nonce[8]);
+  bool ready() const { return ready_; }
+  // out[0..n) = in[0..n) XOR keystream[offset .. offset + n); in == out is fine.  Thread-safe (a context per call).
+  bool crypt(uint64_t offset, const void* in, void* out, size_t n) const;
+
+ private:
+  uint8_t key_[kAeadKey] = {};
+  uint8_t nonce_[8] = {};
+  bool ready_ = false;
+};
+
 // key = HMAC-SHA256(token, label || nonces): one key per direction ("bb-key-c2s" / "bb-key-s2c").
 void derive_key(const std::string& token, const char* label, const std::string& nonces, uint8_t out[kAeadKey]);
 

@@ -820,17 +820,19 @@ void bind_control(py::module_& m) {
       .def_property_readonly("shared_path", &worker::RamBackend::shared_path)
       .def_property_readonly("pinned", &worker::RamBackend::pinned);
   m.def("create_storage_backend", [](StorageClass sc, uint64_t capacity, const std::string& mount_path, uint32_t queue_depth, int numa_node,
-                                      const std::string& pool_id, bool shared_memory) -> std::unique_ptr<StorageBackend> {
+                                      const std::string& pool_id, bool shared_memory, const std::string& at_rest_key) -> std::unique_ptr<StorageBackend> {
     worker::BackendOptions o;
     o.mount_path = mount_path;
     o.queue_depth = queue_depth;
     o.numa_node = numa_node;
     o.shared_memory = shared_memory;
+    o.at_rest_key = at_rest_key;
+    o.at_rest_scope = pool_id;
     auto b = worker::create_storage_backend(sc, capacity, o);
     if (b && !pool_id.empty()) b->set_pool_id(pool_id);
     return b;
   }, py::arg("storage_class"), py::arg("capacity"), py::arg("mount_path") = "", py::arg("queue_depth") = 64, py::arg("numa_node") = -1,
-     py::arg("pool_id") = "", py::arg("shared_memory") = false);
+     py::arg("pool_id") = "", py::arg("shared_memory") = false, py::arg("at_rest_key") = "");
   // Maps another worker's shared RAM pool (registration key = hex of "file:<path>") and returns its first `n` bytes
   // starting at `offset` (test / diagnostics helper for the mapping the GPU fabric performs).
   m.def("read_shared_pool", [](const std::string& key_hex, uint64_t pool_size, uint64_t offset, uint64_t n) -> py::object {
@@ -931,6 +933,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("numa_node", &worker::StoragePoolConfig::numa_node)
       .def_readwrite("pin_memory", &worker::StoragePoolConfig::pin_memory)
       .def_readwrite("shared_memory", &worker::StoragePoolConfig::shared_memory)
+      .def_readwrite("encrypt_at_rest", &worker::StoragePoolConfig::encrypt_at_rest)
       .def_readwrite("cxl", &worker::StoragePoolConfig::cxl);
   py::class_<worker::WorkerServiceConfig>(m, "WorkerServiceConfig")
       .def(py::init<>())
@@ -949,6 +952,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("lease_ttl_sec", &worker::WorkerServiceConfig::lease_ttl_sec)
       .def_readwrite("heartbeat_interval_sec", &worker::WorkerServiceConfig::heartbeat_interval_sec)
       .def_readwrite("allocation_poll_interval_ms", &worker::WorkerServiceConfig::allocation_poll_interval_ms)
+      .def_readwrite("at_rest_key", &worker::WorkerServiceConfig::at_rest_key)
       .def_readwrite("fabric_domain", &worker::WorkerServiceConfig::fabric_domain)
       .def_readwrite("transport", &worker::WorkerServiceConfig::transport)
       .def_readwrite("has_transport", &worker::WorkerServiceConfig::has_transport)

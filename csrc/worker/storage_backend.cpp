@@ -16,6 +16,7 @@
 
 #include "common/checksum.h"
 #include "common/log.h"
+#include "common/sha256.h"
 
 namespace bb::worker {
 
@@ -42,6 +43,29 @@ void StorageBackend::init_allocator() {
   const uint64_t align = is_disk_class(class_) ? kBlock : (class_ == StorageClass::CXL_MEMORY || class_ == StorageClass::CXL_TYPE2_DEVICE) ? 64 : 256;
   allocator_ = std::make_unique<alloc::PoolAllocator>(p, align);
   usable_ = allocator_->total_free();
+}
+
+const net::OffsetCipher* StorageBackend::at_rest() {
+  if (opts_.at_rest_key.empty()) return nullptr;
+  std::call_once(at_rest_once_, [this] {
+    // one key and one counter-block prefix per (passphrase, pool): the same passphrase on two pools never reuses a key stream
+    const std::string& scope = opts_.at_rest_scope.empty() ? pool_id_ : opts_.at_rest_scope;
+    const Sha256Digest k = hmac_sha256(opts_.at_rest_key, "bb-at-rest-key:" + scope);
+    const Sha256Digest n = hmac_sha256(opts_.at_rest_key, "bb-at-rest-nonce:" + scope);
+    if (!at_rest_cipher_.set_key(k.data(), n.data()))
+      BB_LOG(ERROR) << "pool " << pool_id_ << ": at_rest_key is set but libcrypto's AES-CTR is not available; refusing I/O";
+  });
+  return &at_rest_cipher_;  // not ready() -> crypt() fails -> I/O fails: never falls back to plain text
+}
+
+ErrorCode StorageBackend::at_rest_check() const {
+  if (opts_.at_rest_key.empty()) return ErrorCode::OK;
+  std::string why;
+  if (!net::Aead::available(&why)) {
+    BB_LOG(ERROR) << "encryption at rest requested but unavailable: " << why;
+    return ErrorCode::CONFIG_ERROR;
+  }
+  return ErrorCode::OK;
 }
 
 ErrorCode StorageBackend::check_range(uint64_t offset, uint64_t len) const {
@@ -328,6 +352,7 @@ MmapDiskBackend::~MmapDiskBackend() { shutdown(); }
 ErrorCode MmapDiskBackend::initialize() {
   if (initialized_) return ErrorCode::OK;
   if (!is_disk_class(class_)) return ErrorCode::INVALID_PARAMETERS;
+  BB_TRY(at_rest_check());
   std::error_code fe;
   const std::string dir = (opts_.mount_path.empty() ? std::string("/tmp") : opts_.mount_path) + "/blackbird_mmap_storage";
   std::filesystem::create_directories(dir, fe);
@@ -367,13 +392,21 @@ void MmapDiskBackend::shutdown() {
 
 ErrorCode MmapDiskBackend::write(uint64_t offset, const void* data, uint64_t len) {
   BB_TRY(check_range(offset, len));
-  std::memcpy(map_ + offset, data, len);
+  if (const net::OffsetCipher* c = at_rest()) {
+    if (!c->crypt(offset, data, map_ + offset, len)) return ErrorCode::IO_ERROR;  // encrypts straight into the mapping
+  } else {
+    std::memcpy(map_ + offset, data, len);
+  }
   bytes_written_ += len;
   return ErrorCode::OK;
 }
 ErrorCode MmapDiskBackend::read(uint64_t offset, void* data, uint64_t len) {
   BB_TRY(check_range(offset, len));
-  std::memcpy(data, map_ + offset, len);
+  if (const net::OffsetCipher* c = at_rest()) {
+    if (!c->crypt(offset, map_ + offset, data, len)) return ErrorCode::IO_ERROR;
+  } else {
+    std::memcpy(data, map_ + offset, len);
+  }
   bytes_read_ += len;
   return ErrorCode::OK;
 }
@@ -527,6 +560,7 @@ IoUringDiskBackend::~IoUringDiskBackend() { shutdown(); }
 ErrorCode IoUringDiskBackend::initialize() {
   if (initialized_) return ErrorCode::OK;
   if (!is_disk_class(class_)) return ErrorCode::INVALID_PARAMETERS;
+  BB_TRY(at_rest_check());
   std::error_code fe;
   dir_ = (opts_.mount_path.empty() ? std::string("/tmp") : opts_.mount_path) + "/blackbird_storage";
   std::filesystem::create_directories(dir_, fe);
@@ -670,9 +704,25 @@ ErrorCode IoUringDiskBackend::io(bool is_write, uint64_t offset, void* data, uin
 }
 
 ErrorCode IoUringDiskBackend::write(uint64_t offset, const void* data, uint64_t len) {
+  if (const net::OffsetCipher* c = at_rest()) {  // what reaches the ring (and the file) is cipher text
+    BB_TRY(check_range(offset, len));
+    constexpr uint64_t kPiece = 8ull << 20;
+    std::vector<uint8_t> enc(std::min<uint64_t>(len, kPiece));
+    for (uint64_t pos = 0; pos < len; pos += kPiece) {
+      const uint64_t n = std::min<uint64_t>(kPiece, len - pos);
+      if (!c->crypt(offset + pos, static_cast<const uint8_t*>(data) + pos, enc.data(), n)) return ErrorCode::IO_ERROR;
+      BB_TRY(io(true, offset + pos, enc.data(), n));
+    }
+    return ErrorCode::OK;
+  }
   return io(true, offset, const_cast<void*>(data), len);
 }
-ErrorCode IoUringDiskBackend::read(uint64_t offset, void* data, uint64_t len) { return io(false, offset, data, len); }
+ErrorCode IoUringDiskBackend::read(uint64_t offset, void* data, uint64_t len) {
+  BB_TRY(io(false, offset, data, len));
+  if (const net::OffsetCipher* c = at_rest())
+    if (!c->crypt(offset, data, data, len)) return ErrorCode::IO_ERROR;  // in place
+  return ErrorCode::OK;
+}
 ErrorCode IoUringDiskBackend::flush() { return fd_ >= 0 && ::fsync(fd_) == 0 ? ErrorCode::OK : ErrorCode::IO_ERROR; }
 
 ErrorCode IoUringDiskBackend::commit_shard(const ReservationToken& token) {

@@ -29,6 +29,7 @@
 
 #include "alloc/allocator.h"
 #include "common/types.h"
+#include "net/aead.h"
 
 namespace bb::worker {
 
@@ -67,6 +68,11 @@ struct BackendOptions {
   uint64_t reservation_ttl_ms = 10 * 60 * 1000;
   uint64_t interleave_granularity = 256;  // CXL region id granularity
   bool persistent = false;                // CXL persistent mode: msync on commit/flush
+  // File-backed tiers (NVMe / SSD / HDD): what reaches the file is AES-256-CTR of the pool bytes, keyed from this
+  // passphrase (worker `at_rest_key:` / BB_AT_REST_KEY) and the pool id.  Empty = plain.  (net/aead.h OffsetCipher)
+  std::string at_rest_key;
+  std::string at_rest_scope;  // what the key and counter prefix are bound to besides the passphrase: the pool id, known to the
+                              // worker before the backend exists (initialize() may already read extents back)
 };
 
 class StorageBackend {
@@ -139,6 +145,13 @@ class StorageBackend {
   StorageBackend(StorageClass sc, uint64_t capacity, BackendOptions opts);
   void init_allocator();  // call from initialize() once capacity is final
   ErrorCode check_range(uint64_t offset, uint64_t len) const;
+  // Encryption at rest (BackendOptions::at_rest_key): the cipher of this pool, keyed on first use (the pool id is part of
+  // the derivation and is assigned after construction); nullptr = the pool stores plain bytes.  at_rest_check() is for
+  // initialize(): a key without a usable libcrypto must fail loudly, not store plain text.
+  const net::OffsetCipher* at_rest();
+  ErrorCode at_rest_check() const;
+  std::once_flag at_rest_once_;
+  net::OffsetCipher at_rest_cipher_;
 
   StorageClass class_;
   uint64_t capacity_;
@@ -205,7 +218,8 @@ class MmapDiskBackend : public StorageBackend {
   void shutdown() override;
   ErrorCode write(uint64_t offset, const void* data, uint64_t len) override;
   ErrorCode read(uint64_t offset, void* data, uint64_t len) override;
-  void* direct_ptr(uint64_t offset) override { return map_ ? map_ + offset : nullptr; }
+  // (an encrypted pool has no plain bytes anybody could point at)
+  void* direct_ptr(uint64_t offset) override { return map_ && opts_.at_rest_key.empty() ? map_ + offset : nullptr; }
   ErrorCode flush() override;
   const std::string& file_path() const { return file_path_; }
 

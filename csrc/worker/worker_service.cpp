@@ -37,6 +37,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("auth_token")) c.auth_token = w.at("auth_token").as_string();
   if (w.contains("encrypt_transport")) c.encrypt_transport = w.at("encrypt_transport").as_bool();
   if (w.contains("auth_token_ro")) c.auth_token_ro = w.at("auth_token_ro").as_string();
+  if (w.contains("at_rest_key")) c.at_rest_key = w.at("at_rest_key").as_string();
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
   if (w.contains("interconnects")) {
@@ -86,6 +87,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
     pc.queue_depth = static_cast<uint32_t>(p.at("queue_depth").as_int(64));
     pc.pin_memory = p.at("pin_memory").as_bool(false);
     pc.shared_memory = p.at("shared_memory").as_bool(false);
+    pc.encrypt_at_rest = p.at("encrypt_at_rest").as_bool(false);
     c.storage_pools.push_back(std::move(pc));
   }
   return c;
@@ -127,6 +129,16 @@ ErrorCode WorkerService::create_storage_pools_from_config() {
     o.queue_depth = pc.queue_depth;
     o.pin_memory = pc.pin_memory;
     o.shared_memory = pc.shared_memory;
+    if (pc.encrypt_at_rest) {
+      o.at_rest_scope = pc.pool_id;
+      o.at_rest_key = config_.at_rest_key;
+      if (o.at_rest_key.empty())
+        if (const char* e = std::getenv("BB_AT_REST_KEY")) o.at_rest_key = e;
+      if (o.at_rest_key.empty()) {
+        BB_LOG(ERROR) << "pool " << pc.pool_id << ": encrypt_at_rest needs a key (worker at_rest_key: or BB_AT_REST_KEY)";
+        return ErrorCode::CONFIG_ERROR;
+      }
+    }
     o.interleave_granularity = pc.cxl.interleave_granularity ? pc.cxl.interleave_granularity : 256;
     o.persistent = pc.cxl.is_persistent;
     auto b = create_storage_backend(pc.storage_class, pc.size_bytes, o);

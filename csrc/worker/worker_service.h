@@ -38,6 +38,7 @@ struct StoragePoolConfig {
   uint32_t queue_depth = 64;
   bool pin_memory = false;  // DRAM tier: register with CUDA so fused kernels can move data to / from it
   bool shared_memory = false;  // DRAM tier: memfd-backed, mappable by GPU clients of other processes on this host
+  bool encrypt_at_rest = false;  // file-backed tiers: AES-256-CTR of the pool bytes, keyed from WorkerServiceConfig::at_rest_key
   CxlMemoryPoolConfig cxl;  // CXL tiers: per-pool `config:` block
 };
 
@@ -64,6 +65,7 @@ struct WorkerServiceConfig {
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
   bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h)
   std::string auth_token_ro;       // read-only members' token (net/tcp.h)
+  std::string at_rest_key;         // passphrase of pools with encrypt_at_rest (BB_AT_REST_KEY is the default)
   CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects
   bool has_transport = false;
   std::vector<TierRule> preferred_tiers;  // `allocation.preferred_tiers` (forwarded to the keystone as a hint)
