@@ -853,6 +853,16 @@ void bind_control(py::module_& m) {
   m.def("set_cluster_token_ro", &net::set_cluster_token_ro, "second secret: members that prove only this one are read-only (net/tcp.h)");
   m.def("set_transport_encryption", &net::set_transport_encryption, "secure mode of the RPC protocol: AES-256-GCM on every frame, keyed from the cluster token");
   m.def("transport_encryption", &net::transport_encryption);
+  // test hook: AES-256-CTR by byte offset (net::OffsetCipher) over a buffer
+  m.def("offset_cipher_crypt", [](const py::bytes& key32, const py::bytes& nonce8, uint64_t offset, const py::bytes& data) -> py::object {
+    const std::string k = key32, n = nonce8, d = data;
+    if (k.size() != net::kAeadKey || n.size() != 8) throw py::value_error("key = 32 bytes, nonce = 8 bytes");
+    net::OffsetCipher c;
+    if (!c.set_key(reinterpret_cast<const uint8_t*>(k.data()), reinterpret_cast<const uint8_t*>(n.data()))) return py::none();
+    std::string out(d.size(), '\0');
+    if (!c.crypt(offset, d.data(), out.data(), d.size())) return py::none();
+    return py::bytes(out);
+  });
   m.def("aead_available", [] {
     std::string why;
     const bool ok = net::Aead::available(&why);
