@@ -1,16 +1,22 @@
 #!/bin/bash
 # Starts a local blackbird_b200 cluster: bb-coord -> bb-keystone -> N bb-workers -> smoke test.
 # (Role of the reference's scripts/start_cluster.sh: etcd -> keystone -> worker -> smoke.)
-#   scripts/start_cluster.sh [-n WORKERS] [-d RUN_DIR] [--gpu] [--ha]     env: BB_COORD_PORT BB_RPC_PORT BB_HTTP_PORT
+#   scripts/start_cluster.sh [-n WORKERS] [-d RUN_DIR] [--gpu] [--ha] [--secure]     env: BB_COORD_PORT BB_RPC_PORT BB_HTTP_PORT
+#   --secure: a fresh cluster token (RUN_DIR/token, mode 600) gates every RPC server and keys AES-256-GCM on every frame;
+#             clients need  BB_AUTH_TOKEN="$(cat RUN_DIR/token)" BB_ENCRYPT_TRANSPORT=1
 #   --ha: durable bb-coord (log + snapshots under RUN_DIR/coord-data) and a Keystone pair (second one on RPC_PORT+10 /
 #         HTTP_PORT+10); the elected leader serves, the standby takes over from the metadata log; clients get both endpoints.
 set -euo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 BIN="$ROOT/bin"
-N=1; RUN_DIR="${TMPDIR:-/tmp}/blackbird_b200_cluster"; GPU=0; HA=0
-while [ $# -gt 0 ]; do case "$1" in -n) N="$2"; shift 2;; -d) RUN_DIR="$2"; shift 2;; --gpu) GPU=1; shift;; --ha) HA=1; shift;; *) echo "unknown arg $1"; exit 2;; esac; done
+N=1; RUN_DIR="${TMPDIR:-/tmp}/blackbird_b200_cluster"; GPU=0; HA=0; SECURE=0
+while [ $# -gt 0 ]; do case "$1" in -n) N="$2"; shift 2;; -d) RUN_DIR="$2"; shift 2;; --gpu) GPU=1; shift;; --ha) HA=1; shift;; --secure) SECURE=1; shift;; *) echo "unknown arg $1"; exit 2;; esac; done
 COORD_PORT="${BB_COORD_PORT:-2379}"; RPC_PORT="${BB_RPC_PORT:-9090}"; HTTP_PORT="${BB_HTTP_PORT:-9091}"
 mkdir -p "$RUN_DIR"
+if [ "$SECURE" = 1 ]; then
+  ( umask 077; head -c 24 /dev/urandom | base64 | tr -d '\n' > "$RUN_DIR/token" )
+  export BB_AUTH_TOKEN="$(cat "$RUN_DIR/token")" BB_ENCRYPT_TRANSPORT=1
+fi
 for b in bb-coord bb-keystone bb-worker bb-cli; do [ -x "$BIN/$b" ] || { echo "missing $BIN/$b (run: python build.py)"; exit 1; }; done
 port_free() { ! (exec 3<>"/dev/tcp/127.0.0.1/$1") 2>/dev/null; }
 for p in "$COORD_PORT" "$RPC_PORT" "$HTTP_PORT"; do port_free "$p" || { echo "port $p is in use"; exit 1; }; done
@@ -54,4 +60,5 @@ sleep 0.5
 "$BIN/bb-cli" --keystone "$KEYSTONES" smoke --size 1024
 "$BIN/bb-cli" metrics --http "127.0.0.1:$HTTP_PORT" | grep -E "^bb_(workers|memory_pools|objects) "
 echo "cluster is up: coord=$COORD_PORT keystone=$KEYSTONES metrics=http://127.0.0.1:$HTTP_PORT/metrics run_dir=$RUN_DIR"
+[ "$SECURE" = 1 ] && echo "secure cluster: clients need BB_AUTH_TOKEN=\"\$(cat $RUN_DIR/token)\" BB_ENCRYPT_TRANSPORT=1"
 echo "stop with: scripts/stop_cluster.sh -d $RUN_DIR"
