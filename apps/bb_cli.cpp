@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | compact POOL | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T] [--encrypt-transport]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | drain-worker ID | compact POOL | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T] [--encrypt-transport]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -192,6 +192,15 @@ int main(int argc, char** argv) {
     ec = cl.keystone().remove_worker(args.positional[1]);
     std::printf("remove-worker %s: %s\n", args.positional[1].c_str(), name(ec));
     return ec == ErrorCode::OK ? 0 : 1;
+  }
+  if (cmd == "drain-worker" && args.positional.size() >= 2) {  // graceful decommission: move everything off first, then remove
+    auto r = cl.keystone().drain_worker(args.positional[1]);
+    if (!r.ok()) {
+      std::printf("drain-worker %s: %s\n", args.positional[1].c_str(), name(r.error()));
+      return 1;
+    }
+    std::printf("drain-worker %s: OK, %zu objects moved\n", args.positional[1].c_str(), r.value());
+    return 0;
   }
   if (cmd == "where" && args.positional.size() >= 2) {  // placement of an object: copy -> shards (pool, worker, tier, digest)
     auto copies = cl.get_workers(args.positional[1]);

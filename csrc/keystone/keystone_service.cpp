@@ -443,6 +443,78 @@ ErrorCode KeystoneService::remove_worker(const WorkerId& id) {
   return ErrorCode::OK;
 }
 
+Result<size_t> KeystoneService::drain_worker(const WorkerId& id) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  CopyMover mover;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+  }
+  if (!mover) return ErrorCode::NOT_IMPLEMENTED;
+  std::vector<MemoryPoolId> mine;
+  {
+    std::shared_lock<std::shared_mutex> wl(workers_mu_);
+    auto it = workers_.find(id);
+    if (it == workers_.end()) return ErrorCode::INVALID_WORKER;
+    mine = it->second.pools;
+  }
+  {
+    std::unique_lock<std::shared_mutex> pk(pools_mu_);
+    for (const auto& p : mine)
+      if (std::find(draining_.begin(), draining_.end(), p) == draining_.end()) draining_.push_back(p);
+  }
+  bump_view();
+  size_t moved = 0, stuck = 0;
+  std::unordered_set<ObjectKey> handled;
+  for (const auto& pid : mine) {
+    StorageClass tier = StorageClass::STORAGE_UNSPECIFIED;
+    {
+      std::shared_lock<std::shared_mutex> pk(pools_mu_);
+      auto it = pools_.find(pid);
+      if (it == pools_.end()) continue;
+      tier = it->second.storage_class;
+    }
+    // same tier first, then down the ladder the tier policy / eviction uses
+    std::vector<StorageClass> targets = {tier};
+    {
+      std::map<int, std::vector<StorageClass>> lower;  // the tiers below, nearest first, that exist on the other workers
+      std::shared_lock<std::shared_mutex> pk(pools_mu_);
+      for (const auto& [opid, op] : pools_)
+        if (tier_rank(op.storage_class) > tier_rank(tier) && std::find(mine.begin(), mine.end(), opid) == mine.end()) {
+          auto& v = lower[tier_rank(op.storage_class)];
+          if (std::find(v.begin(), v.end(), op.storage_class) == v.end()) v.push_back(op.storage_class);
+        }
+      for (const auto& [r, v] : lower) targets.insert(targets.end(), v.begin(), v.end());
+    }
+    for (const ObjectKey& raw : allocator_->allocator().objects_on_pool(pid)) {
+      const ObjectKey key = raw.substr(0, raw.find('\x01'));  // ledgers of moved objects are "<key>\x01<slot>"
+      if (!handled.insert(key).second) continue;  // several shards / ledgers of one object: it moves as a whole, once
+      const ErrorCode ec = migrate_with(mover, key, targets, [&](const std::vector<CopyPlacement>&, const std::vector<CopyPlacement>& fresh) {
+        for (const auto& c : fresh)
+          for (const auto& s : c.shards)
+            if (std::find(mine.begin(), mine.end(), s.pool_id) != mine.end()) return false;
+        return true;
+      });
+      if (ec == ErrorCode::OK) {
+        ++moved;
+        metrics_.inc("drain_moves_total");
+      } else if (ec != ErrorCode::OBJECT_NOT_FOUND && ec != ErrorCode::OBJECT_NOT_READY) {
+        ++stuck;
+        BB_LOG(WARNING) << "drain " << id << ": " << key << " stays on " << pid << " (" << to_string(ec) << ")";
+      }
+    }
+  }
+  if (stuck) return ErrorCode::INSUFFICIENT_SPACE;  // still draining: free space elsewhere and call again
+  const ErrorCode rc = remove_worker(id);
+  {
+    std::unique_lock<std::shared_mutex> pk(pools_mu_);
+    draining_.erase(std::remove_if(draining_.begin(), draining_.end(), [&](const MemoryPoolId& p) { return std::find(mine.begin(), mine.end(), p) != mine.end(); }),
+                    draining_.end());
+  }
+  if (rc != ErrorCode::OK) return rc;
+  return moved;
+}
+
 void KeystoneService::handle_pool_removed(const MemoryPoolId& pid) {
   {
     std::unique_lock<std::shared_mutex> lk(workers_mu_);
@@ -614,7 +686,7 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start_locked(const Objec
     for (const auto& name : tier_classes_for_size(config_.tier_policy, data_size))
       if (auto sc = parse_storage_class(name)) effective.preferred_classes.push_back(*sc);
   }
-  auto copies = allocator_->allocate_data_copies(key, data_size, effective, pools_, client_node);
+  auto copies = allocator_->allocate_data_copies(key, data_size, effective, pools_, client_node, draining_);  // (usually empty)
   if (!copies.ok()) return copies.error();
   ObjectInfo info;
   info.key = key;
@@ -813,6 +885,7 @@ bool KeystoneService::put_start_run(const std::vector<PutStartItem>& items, size
   const WorkerConfig& config = items[first].config;
   const size_t data_size = items[first].size;
   if (config.replication_factor != 1 || config.max_workers_per_copy == 0) return false;
+  if (!draining_.empty()) return false;  // a worker is being drained: the per-object path knows which pools to leave alone
   if (config_.max_replicas > 0 && config.replication_factor > static_cast<size_t>(config_.max_replicas)) return false;
   WorkerConfig tiered;
   const WorkerConfig* effective = &config;
@@ -1168,7 +1241,7 @@ ErrorCode KeystoneService::migrate_with(const CopyMover& mover, const ObjectKey&
       std::shared_lock<std::shared_mutex> pk(pools_mu_);
       alloc::IAllocator::PoolMap eligible;
       for (const auto& [pid, p] : pools_)
-        if (p.storage_class == target) eligible.emplace(pid, p);
+        if (p.storage_class == target && std::find(draining_.begin(), draining_.end(), pid) == draining_.end()) eligible.emplace(pid, p);
       if (eligible.empty()) break;
       fresh = allocator_->allocate_data_copies(ledger, info.value().size, cfg, eligible);
       if (!fresh.ok() && fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;

@@ -165,6 +165,11 @@ class KeystoneService {
   // swapped atomically, old extents freed), until `max_moves` objects moved or nothing moves any more.  Returns the
   // number of objects moved.  NOT_IMPLEMENTED without a mover, MEMORY_POOL_NOT_FOUND for an unknown pool.
   Result<size_t> compact_pool(const MemoryPoolId& pool, size_t max_moves = 64);
+  // Decommission without losing redundancy: the worker's pools stop receiving placements, every object with a shard there
+  // is re-placed on the other workers (same tier first, bytes through the mover, digests re-checked) while its old copies
+  // keep serving, and only then is the worker removed.  Returns the number of objects moved; objects that found no room
+  // elsewhere stay where they are, the worker stays registered (still draining) and the call reports INSUFFICIENT_SPACE.
+  Result<size_t> drain_worker(const WorkerId& id);
   // One round of the automatic trigger (health loop): every pool above `compaction_fragmentation_threshold` gets up to
   // 8 moves.  Returns the number of objects moved.
   size_t run_compaction_once();
@@ -306,6 +311,7 @@ class KeystoneService {
 
   std::mutex mover_mu_;
   CopyMover mover_;
+  std::vector<MemoryPoolId> draining_;  // guarded by pools_mu_: pools of workers being drained (no new placements)
   ReservationHooks res_hooks_;  // guarded by mover_mu_ (copied out before use)
   std::atomic<bool> reservations_on_{false};
   void refresh_top_tier_locked();  // caller holds pools_mu_ exclusively

@@ -596,6 +596,8 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &KeystoneService::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("drain_worker", [](KeystoneService& k, const std::string& id) { return unwrap(nogil([&] { return k.drain_worker(id); })); },
+           "move every object off the worker (old copies keep serving), then remove it; returns the number of objects moved")
       .def("run_compaction_once", &KeystoneService::run_compaction_once, py::call_guard<py::gil_scoped_release>())
       .def("compact_pool", [](KeystoneService& k, const std::string& pool, size_t max_moves) { return unwrap(k.compact_pool(pool, max_moves)); },
            py::arg("pool"), py::arg("max_moves") = 64, py::call_guard<py::gil_scoped_release>())
@@ -709,6 +711,7 @@ void bind_control(py::module_& m) {
         return out;
       })
       .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
+      .def("drain_worker", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(nogil([&] { return k.drain_worker(id); })); })
       .def("compact_pool", [](rpc::KeystoneApi& k, const std::string& pool, size_t max_moves) { return unwrap(nogil([&] { return k.compact_pool(pool, max_moves); })); },
            py::arg("pool"), py::arg("max_moves") = 64)
       .def("list_objects", [](rpc::KeystoneApi& k, const std::string& prefix, size_t limit, const std::string& after) {

@@ -298,6 +298,16 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
+  leader_only(M_DRAIN_WORKER, [ks](C, S q) {
+    Reader r(q);
+    const std::string id = r.str();
+    if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    auto res = ks->drain_worker(id);
+    Writer w;
+    w.ec(res.ok() ? ErrorCode::OK : res.error());
+    w.u64(res.ok() ? res.value() : 0);
+    return w.take();
+  });
   leader_only(M_COMPACT_POOL, [ks](C, S q) {
     Reader r(q);
     const std::string pool = r.str();
@@ -568,6 +578,14 @@ Result<size_t> KeystoneRpcClient::compact_pool(const MemoryPoolId& pool, size_t 
   w.str(pool);
   w.u64(max_moves);
   BB_RPC(M_COMPACT_POOL, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  return static_cast<size_t>(rd.u64());
+}
+Result<size_t> KeystoneRpcClient::drain_worker(const WorkerId& id) {
+  Writer w;
+  w.str(id);
+  BB_RPC(M_DRAIN_WORKER, w);
   const ErrorCode ec = rd.ec();
   if (ec != ErrorCode::OK) return ec;
   return static_cast<size_t>(rd.u64());

@@ -679,3 +679,62 @@ def test_xxh3_digest_on_the_host_path_put_get_and_corruption(bb):
         w = next(w for i, w in enumerate(c.workers) if f"pool-{i}" == sh.pool_id)
         w.backend(sh.pool_id).write(sh.location["remote_addr"] - w.backend(sh.pool_id).get_base_address() + 5000, b"\x00\x01\x02\x03")
         assert cl.get("x") == blob  # digest mismatch on replica 0 -> served from replica 1
+
+
+def test_drain_worker_moves_everything_off_before_the_worker_leaves(bb, tmp_path):
+    """`drain_worker` (bb-cli drain-worker ID): the graceful form of remove-worker.  The worker's pools stop taking placements,
+    every object with a shard there is re-placed on the others while the old copies keep serving, nothing is ever degraded or
+    lost, and the worker is removed at the end."""
+    with LocalCluster("drain", n_workers=0) as c:
+        for i in range(3):
+            c.add_worker(f"w{i}", f"n{i}", [(f"dram{i}", bb.StorageClass.RAM_CPU, 16 << 20, ""), (f"nvme{i}", bb.StorageClass.NVME, 16 << 20, str(tmp_path / f"d{i}"))])
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        blobs = {}
+        for i in range(12):
+            cfg = bb.WorkerConfig(replication_factor=2 if i % 2 else 1, max_workers_per_copy=1, ttl_ms=0,
+                                  preferred_classes=[bb.StorageClass.RAM_CPU if i % 3 else bb.StorageClass.NVME])
+            blobs[f"d/{i}"] = os.urandom(200_000 + i)
+            assert cl.put(f"d/{i}", blobs[f"d/{i}"], cfg) == bb.ErrorCode.OK
+        on_w0 = [k for k in blobs if any(s.worker_id == "w0" for cp in cl.get_workers(k) for s in cp.shards)]
+        assert on_w0, "the test needs objects on the worker it drains"
+        copies_before = {k: len(cl.get_workers(k)) for k in blobs}
+        moved = c.keystone.drain_worker("w0")
+        assert moved == len(on_w0)
+        assert all(w["worker_id"] != "w0" for w in cl.keystone().get_workers_info())
+        for k, v in blobs.items():
+            placed = cl.get_workers(k)
+            assert len(placed) == copies_before[k]  # same redundancy as before: nothing was degraded on the way
+            assert all(s.worker_id != "w0" for cp in placed for s in cp.shards)
+            assert cl.get(k) == v
+        text = c.keystone.metrics_text()
+        assert f"bb_drain_moves_total {len(on_w0)}" in text and ("bb_objects_lost_total 0" in text or "bb_objects_lost_total" not in text)
+        # new objects avoid nothing now; a second drain of a worker that is gone is an error, not a crash
+        assert cl.put("after", b"x" * 1000, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        with pytest.raises(bb.BlackbirdError) as e:
+            c.keystone.drain_worker("w0")
+        assert e.value.code == bb.ErrorCode.INVALID_WORKER
+
+
+def test_drain_worker_without_room_elsewhere_keeps_the_worker_and_its_objects(bb):
+    """No space on the other workers: nothing is lost, the objects stay where they are, the call says INSUFFICIENT_SPACE and
+    the worker stays registered (draining: it takes no new placements until the drain is repeated or it is removed)."""
+    with LocalCluster("drain2", n_workers=0) as c:
+        c.add_worker("big", "n0", [("dram-big", bb.StorageClass.RAM_CPU, 8 << 20, "")])
+        c.add_worker("tiny", "n1", [("dram-tiny", bb.StorageClass.RAM_CPU, 1 << 20, "")])
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1, ttl_ms=0, preferred_node="n0")
+        blobs = {f"k{i}": os.urandom(900_000) for i in range(4)}
+        for k, v in blobs.items():
+            assert cl.put(k, v, cfg) == bb.ErrorCode.OK
+        with pytest.raises(bb.BlackbirdError) as e:
+            c.keystone.drain_worker("big")
+        assert e.value.code == bb.ErrorCode.INSUFFICIENT_SPACE
+        assert any(w["worker_id"] == "big" for w in cl.keystone().get_workers_info())
+        for k, v in blobs.items():
+            assert cl.get(k) == v
+        # draining: new objects go elsewhere (or nowhere), never onto the worker that is leaving
+        r = cl.put("new-small", b"y" * 1000, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1))
+        if r == bb.ErrorCode.OK:
+            assert all(s.worker_id != "big" for cp in cl.get_workers("new-small") for s in cp.shards)
