@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | drain-worker ID | compact POOL | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T] [--encrypt-transport]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | drain-worker ID | scrub [PREFIX] [MAX] | compact POOL | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T] [--encrypt-transport]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -201,6 +201,20 @@ int main(int argc, char** argv) {
     }
     std::printf("drain-worker %s: OK, %zu objects moved\n", args.positional[1].c_str(), r.value());
     return 0;
+  }
+  if (cmd == "scrub") {  // re-hash stored copies where they lie; replace the ones that no longer match their digest
+    const std::string prefix = args.positional.size() >= 2 ? args.positional[1] : "";
+    const size_t max_objects = args.positional.size() >= 3 ? std::strtoull(args.positional[2].c_str(), nullptr, 10) : 0;
+    auto r = cl.keystone().scrub(prefix, max_objects);
+    if (!r.ok()) {
+      std::printf("scrub: %s\n", name(r.error()));
+      return 1;
+    }
+    const auto& v = r.value();
+    std::printf("scrub: %llu objects, %llu copies hashed, %llu corrupt, %llu healed, %llu unrecoverable, %llu unreachable\n",
+                (unsigned long long)v.objects, (unsigned long long)v.copies, (unsigned long long)v.corrupt, (unsigned long long)v.healed,
+                (unsigned long long)v.unrecoverable, (unsigned long long)v.unreachable);
+    return v.unrecoverable ? 2 : 0;
   }
   if (cmd == "where" && args.positional.size() >= 2) {  // placement of an object: copy -> shards (pool, worker, tier, digest)
     auto copies = cl.get_workers(args.positional[1]);

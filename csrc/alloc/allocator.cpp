@@ -196,7 +196,9 @@ PoolAllocator* RangeAllocator::ensure_pool(const MemoryPool& pool) {
   std::unique_lock<std::shared_mutex> lk(pools_mu_);
   auto& slot = pool_allocators_[pool.id];
   if (!slot) {
-    slot = std::make_unique<PoolAllocator>(pool);
+    // flash / disk pools are carved in 4 KiB blocks so a shard starts where O_DIRECT can reach it (the worker's own
+    // allocator uses the same block for reserved extents); memory tiers keep the 256 B TMA granule
+    slot = std::make_unique<PoolAllocator>(pool, is_disk_class(pool.storage_class) ? 4096 : PoolAllocator::kDefaultAlign);
     generation_.fetch_add(1, std::memory_order_release);
   }
   return slot.get();
@@ -830,6 +832,41 @@ std::vector<ObjectKey> RangeAllocator::objects_on_pool(const MemoryPoolId& id) c
   return v;
 }
 
+uint64_t pool_offset_of(const ShardPlacement& s, const MemoryPool& pool) {
+  if (auto* g = std::get_if<GpuSlabLocation>(&s.location)) return g->offset;
+  if (auto* f = std::get_if<FileLocation>(&s.location)) return f->file_offset;
+  if (auto* x = std::get_if<CxlMemoryLocation>(&s.location)) return x->offset;
+  if (auto* m = std::get_if<MemoryLocation>(&s.location)) {
+    const uint64_t base = pool.ucx_remote_addr ? pool.ucx_remote_addr : pool.base_addr;
+    return m->remote_addr >= base ? m->remote_addr - base : 0;
+  }
+  return 0;
+}
+
+size_t RangeAllocator::free_extents(const ObjectKey& key, const std::vector<ShardPlacement>& shards, const PoolMap& pools) {
+  std::vector<Extent> gone;
+  {
+    LedgerShard& ls = ledger_for(key);
+    std::lock_guard<SpinMutex> lk(ls.mu);
+    auto it = ls.objects.find(key);
+    if (it == ls.objects.end()) return 0;
+    for (const auto& s : shards) {
+      auto pit = pools.find(s.pool_id);
+      if (pit == pools.end()) continue;
+      const uint64_t off = pool_offset_of(s, pit->second);
+      auto& ex = it->second.extents;
+      auto e = std::find_if(ex.begin(), ex.end(), [&](const Extent& x) { return x.pool == s.pool_id && x.range.offset == off; });
+      if (e == ex.end()) continue;
+      it->second.total_size -= std::min<size_t>(it->second.total_size, e->length);
+      gone.push_back(*e);
+      ex.erase(e);
+    }
+    if (it->second.extents.empty()) ls.objects.erase(it);
+  }
+  rollback(gone);
+  return gone.size();
+}
+
 ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlacement>& copies, const PoolMap& pools,
                                 const MemoryPoolId& only_pool) {
   ObjectAllocation oa;
@@ -839,14 +876,7 @@ ErrorCode RangeAllocator::adopt(const ObjectKey& key, const std::vector<CopyPlac
       auto pit = pools.find(s.pool_id);
       if (pit == pools.end()) continue;
       PoolAllocator* pa = ensure_pool(pit->second);
-      uint64_t off = 0;
-      if (auto* g = std::get_if<GpuSlabLocation>(&s.location)) off = g->offset;
-      else if (auto* f = std::get_if<FileLocation>(&s.location)) off = f->file_offset;
-      else if (auto* x = std::get_if<CxlMemoryLocation>(&s.location)) off = x->offset;
-      else if (auto* m = std::get_if<MemoryLocation>(&s.location)) {
-        const uint64_t base = pit->second.ucx_remote_addr ? pit->second.ucx_remote_addr : pit->second.base_addr;
-        off = m->remote_addr >= base ? m->remote_addr - base : 0;
-      }
+      const uint64_t off = pool_offset_of(s, pit->second);
       if (!pa->allocate_at(off, s.length)) {
         BB_LOG(WARNING) << "adopt: extent of " << key << " on " << s.pool_id << " is no longer free";
         continue;

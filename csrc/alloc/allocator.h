@@ -145,6 +145,9 @@ class PoolAllocator {
   void publish();
 };
 
+// Where a placed shard starts inside its pool (the inverse of the allocator's Range -> location mapping).
+uint64_t pool_offset_of(const ShardPlacement& s, const MemoryPool& pool);
+
 class IAllocator {
  public:
   using PoolMap = std::unordered_map<MemoryPoolId, MemoryPool>;
@@ -159,6 +162,12 @@ class IAllocator {
   virtual size_t pool_used_bytes(const MemoryPoolId& id) const = 0;  // live accounting
   virtual double pool_fragmentation(const MemoryPoolId& id) const = 0;  // 1 - largest hole / free bytes (0 = one hole)
   virtual std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const = 0;
+  // Releases the extents of ledger entry `key` that back `shards` (matched by pool + offset inside the pool); the rest of the
+  // entry stays.  Returns how many extents were released (scrub swaps one bad replica out of an object that keeps the others).
+  virtual size_t free_extents(const ObjectKey& key, const std::vector<ShardPlacement>& shards, const PoolMap& pools) {
+    (void)key, (void)shards, (void)pools;
+    return 0;
+  }
   // Run placement: `keys.size()` objects of one size and one policy (`shape`; its object_key is ignored), each stored as a
   // single shard on a single pool (replication 1, stripe width 1).  The pools are ranked once and each pool allocator is
   // called once per chunk, not per object; the run is spread over the pools that tie at the head of the ranking, as
@@ -186,6 +195,7 @@ class RangeAllocator : public IAllocator {
   size_t pool_used_bytes(const MemoryPoolId& id) const override;
   double pool_fragmentation(const MemoryPoolId& id) const override;
   std::vector<ObjectKey> objects_on_pool(const MemoryPoolId& id) const override;
+  size_t free_extents(const ObjectKey& key, const std::vector<ShardPlacement>& shards, const PoolMap& pools) override;
   bool allocate_run(const AllocationRequest& shape, const std::vector<const ObjectKey*>& keys, const PoolMap& pools,
                     std::vector<RunSlot>& out) override;
   // Re-reserves the exact extents of already placed copies (metadata recovery after a leader

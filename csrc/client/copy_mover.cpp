@@ -190,6 +190,35 @@ keystone::CopyMover make_data_server_mover(size_t io_parallelism, int rpc_timeou
   };
 }
 
+keystone::CopyVerifier make_data_server_verifier(int rpc_timeout_ms) {
+  auto conns = std::make_shared<Conns>();
+  conns->timeout_ms = rpc_timeout_ms;
+  return [conns](const ObjectKey& key, const CopyPlacement& copy, ChecksumAlgo algo) -> ErrorCode {
+    for (const auto& s : copy.shards) {
+      if (algo == ChecksumAlgo::NONE || s.checksum_algo != algo || s.length == 0) continue;  // nothing recorded to compare with
+      auto c = conns->get(ep_of(s));
+      if (!c) return ErrorCode::CONNECTION_FAILED;
+      wire::Writer w;
+      w.str(s.pool_id);
+      w.u64(raw_offset(s));
+      w.u64(s.length);
+      w.u32(static_cast<uint32_t>(algo));
+      auto r = c->call(worker::D_CHECKSUM, w.data(), conns->timeout_ms);
+      if (!r.ok()) return ErrorCode::TRANSFER_FAILED;
+      wire::Reader rd(r.value());
+      const ErrorCode ec = rd.ec();
+      if (ec != ErrorCode::OK) return ec;
+      const uint64_t digest = rd.u64();
+      if (!rd.ok()) return ErrorCode::TRANSFER_FAILED;
+      if (digest != s.checksum) {
+        BB_LOG(ERROR) << "scrub: shard of " << key << " on " << s.pool_id << " does not match its digest";
+        return ErrorCode::CHECKSUM_MISMATCH;
+      }
+    }
+    return ErrorCode::OK;
+  };
+}
+
 keystone::ReservationHooks make_data_server_reservation_hooks(int rpc_timeout_ms) {
   auto conns = std::make_shared<Conns>();
   conns->timeout_ms = rpc_timeout_ms;

@@ -13,6 +13,11 @@ namespace bb::client {
 
 keystone::CopyMover make_data_server_mover(size_t io_parallelism = 4, int rpc_timeout_ms = 30000);
 
+// Scrub: asks the worker that holds each shard of `copy` to hash it where it lies (D_CHECKSUM: the bytes never cross the
+// network) and compares with the digest recorded at put_complete.  OK = every shard matches, CHECKSUM_MISMATCH = bit rot,
+// anything else = the worker could not be asked.
+keystone::CopyVerifier make_data_server_verifier(int rpc_timeout_ms = 30000);
+
 // The Keystone's side of the reservation protocol, spoken to the workers' data servers (D_RESERVE / D_COMMIT / D_ABORT /
 // D_FREE, one request per pool): put_start reserves every shard of the placement at its worker, put_complete commits,
 // put_cancel / expiry aborts, removing a COMPLETE object frees.  Reference: the contract of

@@ -156,6 +156,7 @@ Result<KeystoneConfig> KeystoneConfig::from_json(const Json& root, std::string* 
   if (k.contains("worker_heartbeat_ttl_sec")) c.worker_heartbeat_ttl_sec = k.at("worker_heartbeat_ttl_sec").as_int(c.worker_heartbeat_ttl_sec);
   if (k.contains("service_registration_ttl_sec")) c.service_registration_ttl_sec = k.at("service_registration_ttl_sec").as_int(c.service_registration_ttl_sec);
   if (k.contains("service_refresh_interval_sec")) c.service_refresh_interval_sec = k.at("service_refresh_interval_sec").as_int(c.service_refresh_interval_sec);
+  if (k.contains("scrub_objects_per_round")) c.scrub_objects_per_round = static_cast<int32_t>(k.at("scrub_objects_per_round").as_int(c.scrub_objects_per_round));
   if (k.contains("gc_interval_sec")) c.gc_interval_sec = k.at("gc_interval_sec").as_int(c.gc_interval_sec);
   if (k.contains("health_check_interval_sec")) c.health_check_interval_sec = k.at("health_check_interval_sec").as_int(c.health_check_interval_sec);
   if (k.contains("compaction_fragmentation_threshold")) c.compaction_fragmentation_threshold = k.at("compaction_fragmentation_threshold").as_double(0.0);
@@ -223,6 +224,7 @@ Json to_json(const KeystoneConfig& c) {
   j["service_registration_ttl_sec"] = c.service_registration_ttl_sec;
   j["service_refresh_interval_sec"] = c.service_refresh_interval_sec;
   j["gc_interval_sec"] = c.gc_interval_sec;
+  j["scrub_objects_per_round"] = c.scrub_objects_per_round;
   j["health_check_interval_sec"] = c.health_check_interval_sec;
   j["max_replicas"] = c.max_replicas;
   j["default_replicas"] = c.default_replicas;

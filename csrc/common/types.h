@@ -176,6 +176,9 @@ struct KeystoneConfig {
   int32_t max_replicas = 3;
   // > 0: the health loop compacts a pool (a few moves per round) whose fragmentation ratio exceeds this value
   double compaction_fragmentation_threshold = 0.0;
+  // > 0: every health round re-hashes about this many objects at their workers and replaces copies that rotted (scrub);
+  // the walk resumes where the last round stopped, so a full pass takes objects / scrub_objects_per_round rounds
+  int32_t scrub_objects_per_round = 0;
   int32_t promote_after_reads = 0;    // > 0: an object read this often while it sits below the top tier is promoted back
   std::vector<TierRule> tier_policy;  // size-based class preference for puts that name no preferred class
   int32_t default_replicas = 1;

@@ -230,6 +230,7 @@ void KeystoneService::health_loop() {
     run_repair_once();
     run_promotion_once();
     run_compaction_once();
+    if (config_.scrub_objects_per_round > 0) scrub_from("", static_cast<size_t>(config_.scrub_objects_per_round), scrub_cursor_);
   }
 }
 
@@ -1123,6 +1124,11 @@ void KeystoneService::set_copy_mover(CopyMover m) {
   mover_ = std::move(m);
 }
 
+void KeystoneService::set_copy_verifier(CopyVerifier v) {
+  std::lock_guard<std::mutex> lk(mover_mu_);
+  verifier_ = std::move(v);
+}
+
 void KeystoneService::set_reservation_hooks(ReservationHooks h) {
   std::lock_guard<std::mutex> lk(mover_mu_);
   reservations_on_.store(static_cast<bool>(h));
@@ -1517,7 +1523,10 @@ size_t KeystoneService::run_repair_once() {
     }
     if (!fresh.ok()) continue;
     CopyPlacement dst = fresh.value()[0];
-    if (mover(o.key, o.copies[0], dst, o.config.checksum) != ErrorCode::OK) {
+    // any surviving copy can be the source: one that fails its digest on the way (bit rot) must not block the repair
+    ErrorCode mec = ErrorCode::OBJECT_NOT_FOUND;
+    for (size_t c = 0; c < o.copies.size() && mec != ErrorCode::OK; ++c) mec = mover(o.key, o.copies[c], dst, o.config.checksum);
+    if (mec != ErrorCode::OK) {
       allocator_->free_object(ledger);
       continue;
     }
@@ -1540,6 +1549,127 @@ size_t KeystoneService::run_repair_once() {
     bump_view();
   }
   return repaired;
+}
+
+Result<ScrubReport> KeystoneService::scrub(const std::string& prefix, size_t max_objects) {
+  if (!is_leader()) return ErrorCode::NOT_LEADER;
+  size_t cursor = 0;
+  return scrub_from(prefix, max_objects, cursor);
+}
+
+Result<ScrubReport> KeystoneService::scrub_from(const std::string& prefix, size_t max_objects, size_t& cursor) {
+  CopyMover mover;
+  CopyVerifier verify;
+  {
+    std::lock_guard<std::mutex> lk(mover_mu_);
+    mover = mover_;
+    verify = verifier_;
+  }
+  if (!verify) return ErrorCode::NOT_IMPLEMENTED;
+  ScrubReport rep;
+  // whole metadata shards at a time, starting where the last background round stopped
+  for (size_t n = 0; n < shards_.size() && (max_objects == 0 || rep.objects < max_objects); ++n, cursor = (cursor + 1) % shards_.size()) {
+    std::vector<ObjectInfo> batch;
+    {
+      Shard& sh = shards_[cursor % shards_.size()];
+      std::shared_lock<SpinMutex> lk(sh.mu);
+      for (const auto& [k, o] : sh.objects)
+        if (o.state == ObjectState::COMPLETE && !o.copies.empty() && k.compare(0, prefix.size(), prefix) == 0) batch.push_back(o);
+    }
+    for (const auto& o : batch) {
+      ++rep.objects;
+      const ChecksumAlgo algo = o.config.checksum;
+      std::vector<size_t> good, bad;
+      for (size_t c = 0; c < o.copies.size(); ++c) {
+        ++rep.copies;
+        const ErrorCode ec = verify(o.key, o.copies[c], algo);
+        if (ec == ErrorCode::OK) good.push_back(c);
+        else if (ec == ErrorCode::CHECKSUM_MISMATCH) bad.push_back(c);
+        else ++rep.unreachable;
+      }
+      if (bad.empty()) continue;
+      rep.corrupt += bad.size();
+      metrics_.inc("scrub_corrupt_copies_total", bad.size());
+      if (good.empty()) {
+        if (bad.size() == o.copies.size()) {
+          ++rep.unrecoverable;
+          metrics_.inc("scrub_unrecoverable_total");
+          BB_LOG(ERROR) << "scrub: " << o.key << " has no copy left that matches its digest";
+        }
+        continue;  // (a copy that could not be asked may still be fine: try again next round)
+      }
+      if (!mover) continue;
+      for (size_t c : bad)
+        if (replace_copy(mover, o, c, o.copies[good[0]]) == ErrorCode::OK) {
+          ++rep.healed;
+          metrics_.inc("scrub_healed_total");
+        }
+    }
+  }
+  metrics_.inc("scrub_objects_total", rep.objects);
+  if (rep.healed) bump_view();
+  return rep;
+}
+
+// Swaps copy `idx` of `o` for a fresh one made from `source` (a copy of the same object that verified): new extents under
+// their own ledger entry, bytes moved and digested by the mover, metadata switched under the shard lock if the object is
+// still the same incarnation, and only then the bad extents handed back to the allocator.
+ErrorCode KeystoneService::replace_copy(const CopyMover& mover, const ObjectInfo& o, size_t idx, const CopyPlacement& source) {
+  WorkerConfig cfg = o.config;
+  cfg.replication_factor = 1;
+  cfg.symmetric_replicas = false;
+  std::vector<MemoryPoolId> exclude;  // the pools of the copies that stay: one pool, one replica
+  for (size_t c = 0; c < o.copies.size(); ++c)
+    if (c != idx)
+      for (const auto& s : o.copies[c].shards) exclude.push_back(s.pool_id);
+  std::string ledger;
+  Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
+  for (int slot = 0; slot < 64; ++slot) {
+    ledger = o.key + "\x01" + std::to_string(slot);
+    std::shared_lock<std::shared_mutex> pk(pools_mu_);
+    alloc::IAllocator::PoolMap eligible;
+    for (const auto& [pid, p] : pools_)
+      if (std::find(draining_.begin(), draining_.end(), pid) == draining_.end()) eligible.emplace(pid, p);
+    fresh = allocator_->allocate_data_copies(ledger, o.size, cfg, eligible, "", exclude);
+    if (fresh.ok() || fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+  }
+  if (!fresh.ok()) return fresh.error();
+  CopyPlacement dst = fresh.value()[0];
+  const ErrorCode mec = mover(o.key, source, dst, o.config.checksum);
+  if (mec != ErrorCode::OK) {
+    allocator_->free_object(ledger);
+    return mec;
+  }
+  std::vector<std::string> ledgers;
+  {
+    Shard& sh = shard_for(o.key);
+    ShardGuard lk(this, sh);
+    auto it = sh.objects.find(o.key);
+    // the copy list may have changed under us (migration, repair, a pool that left): only swap what we looked at
+    if (it == sh.objects.end() || it->second.created != o.created || idx >= it->second.copies.size() || !(it->second.copies[idx] == o.copies[idx])) {
+      lk.finish();
+      allocator_->free_object(ledger);
+      return ErrorCode::OBJECT_NOT_FOUND;
+    }
+    dst.copy_index = it->second.copies[idx].copy_index;
+    it->second.copies[idx] = dst;
+    it->second.extra_ledgers.push_back(ledger);
+    ledgers = it->second.extra_ledgers;
+    persist_object(sh, it->second);
+  }
+  // hand the bad extents back: they sit in the object's own ledger entry or in one a repair / migration made
+  alloc::IAllocator::PoolMap pools;
+  {
+    std::shared_lock<std::shared_mutex> pk(pools_mu_);
+    for (const auto& s : o.copies[idx].shards) {
+      auto pit = pools_.find(s.pool_id);
+      if (pit != pools_.end()) pools.emplace(pit->first, pit->second);
+    }
+  }
+  size_t freed = allocator_->allocator().free_extents(o.key, o.copies[idx].shards, pools);
+  for (const auto& l : ledgers)
+    if (freed < o.copies[idx].shards.size() && l != ledger) freed += allocator_->allocator().free_extents(l, o.copies[idx].shards, pools);
+  return ErrorCode::OK;
 }
 
 // ================================================================ metadata log

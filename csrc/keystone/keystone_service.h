@@ -101,6 +101,18 @@ struct ReservationHooks {
 // fills dst shard checksums.
 using CopyMover = std::function<ErrorCode(const ObjectKey& key, const CopyPlacement& src, CopyPlacement& dst, ChecksumAlgo algo)>;
 
+// Scrub: re-hashes one stored copy where it lies and compares with the recorded digests (client/copy_mover.h).
+using CopyVerifier = std::function<ErrorCode(const ObjectKey& key, const CopyPlacement& copy, ChecksumAlgo algo)>;
+
+struct ScrubReport {
+  uint64_t objects = 0;        // COMPLETE objects looked at
+  uint64_t copies = 0;         // copies hashed
+  uint64_t corrupt = 0;        // copies whose bytes no longer match their digest
+  uint64_t healed = 0;         // ... replaced by a fresh copy made from a healthy replica
+  uint64_t unrecoverable = 0;  // objects with no healthy copy left (still listed; reads fail their digest check)
+  uint64_t unreachable = 0;    // copies whose worker could not be asked (left to failure detection)
+};
+
 class KeystoneService {
  public:
   explicit KeystoneService(const KeystoneConfig& config, std::shared_ptr<coord::CoordService> coord = nullptr);
@@ -204,6 +216,11 @@ class KeystoneService {
   // Explicit tier move (promotion or demotion) of every copy of `key` to `target`; no-op when already there.
   ErrorCode migrate_object(const ObjectKey& key, StorageClass target);
   size_t run_repair_once();
+  // Scrub (the reference never re-reads what it stored): every COMPLETE object under `prefix` (at most `max_objects`, 0 = all)
+  // has each copy hashed by the worker that holds it.  A copy that no longer matches is replaced from a healthy replica --
+  // new extents, verified bytes, the bad extents released -- so the object is never served from, or repaired out of, bit rot.
+  void set_copy_verifier(CopyVerifier v);
+  Result<ScrubReport> scrub(const std::string& prefix = "", size_t max_objects = 0);
   double tier_utilization(StorageClass sc) const;
 
   // ---- observability
@@ -311,6 +328,7 @@ class KeystoneService {
 
   std::mutex mover_mu_;
   CopyMover mover_;
+  CopyVerifier verifier_;
   std::vector<MemoryPoolId> draining_;  // guarded by pools_mu_: pools of workers being drained (no new placements)
   ReservationHooks res_hooks_;  // guarded by mover_mu_ (copied out before use)
   std::atomic<bool> reservations_on_{false};
@@ -331,6 +349,9 @@ class KeystoneService {
   } hot_;
   // `accept` (optional) sees the old and the freshly allocated placements before any byte moves; false = roll back.
   using PlacementFilter = std::function<bool(const std::vector<CopyPlacement>& old_copies, const std::vector<CopyPlacement>& fresh)>;
+  Result<ScrubReport> scrub_from(const std::string& prefix, size_t max_objects, size_t& cursor);
+  ErrorCode replace_copy(const CopyMover& mover, const ObjectInfo& o, size_t idx, const CopyPlacement& source);
+  size_t scrub_cursor_ = 0;  // health loop only
   ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets,
                          const PlacementFilter& accept = nullptr);
 

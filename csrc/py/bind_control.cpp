@@ -55,6 +55,17 @@ py::list ecs_to_py(const std::vector<ErrorCode>& v) {
   return out;
 }
 
+py::dict scrub_to_py(const keystone::ScrubReport& r) {
+  py::dict d;
+  d["objects"] = r.objects;
+  d["copies"] = r.copies;
+  d["corrupt"] = r.corrupt;
+  d["healed"] = r.healed;
+  d["unrecoverable"] = r.unrecoverable;
+  d["unreachable"] = r.unreachable;
+  return d;
+}
+
 py::object location_to_py(const LocationDetail& l) {
   py::dict d;
   if (auto* m = std::get_if<MemoryLocation>(&l)) {
@@ -282,6 +293,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("service_registration_ttl_sec", &KeystoneConfig::service_registration_ttl_sec)
       .def_readwrite("service_refresh_interval_sec", &KeystoneConfig::service_refresh_interval_sec)
       .def_readwrite("gc_interval_sec", &KeystoneConfig::gc_interval_sec)
+      .def_readwrite("scrub_objects_per_round", &KeystoneConfig::scrub_objects_per_round)
       .def_readwrite("health_check_interval_sec", &KeystoneConfig::health_check_interval_sec)
       .def_readwrite("max_replicas", &KeystoneConfig::max_replicas)
       .def_readwrite("default_replicas", &KeystoneConfig::default_replicas)
@@ -632,7 +644,10 @@ void bind_control(py::module_& m) {
       })
       .def("install_reservation_hooks", [](KeystoneService& k) { k.set_reservation_hooks(client::make_data_server_reservation_hooks()); },
            "Reservation protocol over the workers' data servers (takes effect with KeystoneConfig.enable_reservations).")
-      .def("install_data_server_mover", [](KeystoneService& k) { k.set_copy_mover(client::make_data_server_mover()); },
+      .def("scrub", [](KeystoneService& k, const std::string& prefix, size_t max_objects) { return scrub_to_py(unwrap(nogil([&] { return k.scrub(prefix, max_objects); }))); },
+           py::arg("prefix") = "", py::arg("max_objects") = 0)
+      .def("install_data_server_verifier", [](KeystoneService& k) { k.set_copy_verifier(client::make_data_server_verifier()); })
+      .def("install_data_server_mover", [](KeystoneService& k) { k.set_copy_verifier(client::make_data_server_verifier()); k.set_copy_mover(client::make_data_server_mover()); },
            "Tier demotion / re-replication move bytes through the workers' data servers (the default in bb-keystone).")
       // Python-implemented copy mover (tests): fn(key, src_copy, dst_copy, algo) -> (ErrorCode, [shard checksums])
       .def("set_copy_mover", [](KeystoneService& k, py::object fn) {
@@ -712,6 +727,8 @@ void bind_control(py::module_& m) {
       })
       .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
       .def("drain_worker", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(nogil([&] { return k.drain_worker(id); })); })
+      .def("scrub", [](rpc::KeystoneApi& k, const std::string& prefix, size_t max_objects) { return scrub_to_py(unwrap(nogil([&] { return k.scrub(prefix, max_objects); }))); },
+           py::arg("prefix") = "", py::arg("max_objects") = 0)
       .def("compact_pool", [](rpc::KeystoneApi& k, const std::string& pool, size_t max_moves) { return unwrap(nogil([&] { return k.compact_pool(pool, max_moves); })); },
            py::arg("pool"), py::arg("max_moves") = 64)
       .def("list_objects", [](rpc::KeystoneApi& k, const std::string& prefix, size_t limit, const std::string& after) {

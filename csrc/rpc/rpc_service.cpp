@@ -308,6 +308,18 @@ void RpcService::register_handlers() {
     w.u64(res.ok() ? res.value() : 0);
     return w.take();
   });
+  leader_only(M_SCRUB, [ks](C, S q) {
+    Reader r(q);
+    const std::string prefix = r.str();
+    const uint64_t max_objects = r.u64();
+    if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    auto res = ks->scrub(prefix, static_cast<size_t>(max_objects));
+    Writer w;
+    w.ec(res.ok() ? ErrorCode::OK : res.error());
+    if (res.ok())
+      for (uint64_t v : {res.value().objects, res.value().copies, res.value().corrupt, res.value().healed, res.value().unrecoverable, res.value().unreachable}) w.u64(v);
+    return w.take();
+  });
   leader_only(M_COMPACT_POOL, [ks](C, S q) {
     Reader r(q);
     const std::string pool = r.str();
@@ -590,6 +602,18 @@ Result<size_t> KeystoneRpcClient::drain_worker(const WorkerId& id) {
   if (ec != ErrorCode::OK) return ec;
   return static_cast<size_t>(rd.u64());
 }
+Result<keystone::ScrubReport> KeystoneRpcClient::scrub(const std::string& prefix, size_t max_objects) {
+  Writer w;
+  w.str(prefix);
+  w.u64(max_objects);
+  BB_RPC(M_SCRUB, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  keystone::ScrubReport rep;
+  for (uint64_t* v : {&rep.objects, &rep.copies, &rep.corrupt, &rep.healed, &rep.unrecoverable, &rep.unreachable}) *v = rd.u64();
+  if (!rd.ok()) return ErrorCode::RPC_FAILED;
+  return rep;
+}
 ErrorCode KeystoneRpcClient::remove_worker(const WorkerId& id) {
   Writer w;
   w.str(id);
@@ -805,6 +829,7 @@ Result<KeystoneBundle> create_and_start_keystone(const KeystoneConfig& config) {
   if (ec != ErrorCode::OK) return ec;
   ec = b.keystone->start();
   if (ec != ErrorCode::OK) return ec;
+  b.keystone->set_copy_verifier(client::make_data_server_verifier());  // scrub hashes copies at their workers
   b.keystone->set_copy_mover(client::make_data_server_mover());  // tier demotion + re-replication move real bytes
   b.keystone->set_reservation_hooks(client::make_data_server_reservation_hooks());  // used when enable_reservations is set
   b.rpc = std::make_unique<RpcService>(b.keystone, config);

@@ -572,6 +572,7 @@ ErrorCode IoUringDiskBackend::initialize() {
   if (class_ == StorageClass::NVME || class_ == StorageClass::SSD) {
     fd_ = ::open(file_path_.c_str(), O_RDWR | O_CREAT | O_CLOEXEC | O_DIRECT, 0644);
     direct_ = fd_ >= 0;
+    if (direct_) buffered_fd_ = ::open(file_path_.c_str(), O_RDWR | O_CLOEXEC);
   }
   if (fd_ < 0) fd_ = ::open(file_path_.c_str(), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
   if (fd_ < 0) return ErrorCode::IO_ERROR;
@@ -604,6 +605,8 @@ void IoUringDiskBackend::shutdown() {
     ::close(fd_);
   }
   if (manifest_fd_ >= 0) ::close(manifest_fd_);
+  if (buffered_fd_ >= 0) ::close(buffered_fd_);
+  buffered_fd_ = -1;
   ring_.close();
   std::free(staging_);
   staging_ = nullptr;
@@ -639,27 +642,46 @@ ErrorCode IoUringDiskBackend::io(bool is_write, uint64_t offset, void* data, uin
   if (len == 0) return ErrorCode::OK;
   std::lock_guard<std::mutex> lk(io_mu_);
   const bool aligned = (offset % kBlock) == 0;
-  const bool bounce = direct_ || !ring_.ok() ? true : false;
-  (void)bounce;
   auto* user = static_cast<uint8_t*>(data);
+  // buffered side door for what O_DIRECT cannot express (odd offsets, sub-block tails); the kernel keeps it coherent with
+  // the direct fd (direct I/O writes back / invalidates the page-cache range it touches)
+  auto buffered = [&](uint64_t at, uint8_t* p, uint64_t n) {
+    const int bfd = buffered_fd_ >= 0 ? buffered_fd_ : fd_;
+    for (uint64_t done = 0; done < n;) {
+      const ssize_t rc = is_write ? ::pwrite(bfd, p + done, n - done, static_cast<off_t>(at + done))
+                                  : ::pread(bfd, p + done, n - done, static_cast<off_t>(at + done));
+      if (rc <= 0) return false;
+      done += static_cast<uint64_t>(rc);
+    }
+    return true;
+  };
   uint64_t pos = 0;
   while (pos < len) {
-    const uint64_t chunk = std::min<uint64_t>(len - pos, staging_bytes_);
-    const uint64_t padded = direct_ ? (chunk + kBlock - 1) / kBlock * kBlock : chunk;
-    if (direct_ && (!aligned || offset + pos + padded > capacity_)) {
-      // O_DIRECT needs block alignment: fall back to buffered syscalls for odd extents
-      int bfd = ::open(file_path_.c_str(), O_RDWR | O_CLOEXEC);
-      if (bfd < 0) return ErrorCode::IO_ERROR;
-      ssize_t rc = is_write ? ::pwrite(bfd, user + pos, chunk, static_cast<off_t>(offset + pos))
-                            : ::pread(bfd, user + pos, chunk, static_cast<off_t>(offset + pos));
-      ::close(bfd);
-      if (rc != static_cast<ssize_t>(chunk)) {
+    uint64_t chunk = std::min<uint64_t>(len - pos, staging_bytes_);
+    if (direct_ && (!aligned || offset + pos + (chunk + kBlock - 1) / kBlock * kBlock > capacity_)) {
+      if (!buffered(offset + pos, user + pos, chunk)) {
         io_errors_++;
         return ErrorCode::IO_ERROR;
       }
       pos += chunk;
       continue;
     }
+    // A direct READ may run past the request into the bounce buffer; a direct WRITE must not: Keystone packs extents at
+    // 256 B granularity, so the bytes after `len` can be a neighbour's.  (A zero-padded tail block used to wipe up to 4 KiB
+    // of the object placed behind this one.)  Write whole blocks directly and the sub-block tail through the page cache.
+    if (direct_ && is_write && chunk % kBlock) {
+      const uint64_t body = chunk / kBlock * kBlock;
+      if (body == 0) {
+        if (!buffered(offset + pos, user + pos, chunk)) {
+          io_errors_++;
+          return ErrorCode::IO_ERROR;
+        }
+        pos += chunk;
+        continue;
+      }
+      chunk = body;  // the tail is picked up by the next turn of the loop
+    }
+    const uint64_t padded = direct_ ? (chunk + kBlock - 1) / kBlock * kBlock : chunk;
     if (is_write) {
       std::memcpy(staging_, user + pos, chunk);
       if (padded > chunk) std::memset(staging_ + chunk, 0, padded - chunk);

@@ -307,6 +307,7 @@ class IoUringDiskBackend : public StorageBackend {
   std::string dir_, file_path_, manifest_path_;
   int fd_ = -1;
   int manifest_fd_ = -1;
+  int buffered_fd_ = -1;  // same file without O_DIRECT: odd offsets and sub-block tails
   bool direct_ = false;
   IoUring ring_;
   uint8_t* staging_ = nullptr;  // aligned bounce buffer for O_DIRECT

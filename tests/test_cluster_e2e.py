@@ -707,6 +707,10 @@ def test_drain_worker_moves_everything_off_before_the_worker_leaves(bb, tmp_path
             assert len(placed) == copies_before[k]  # same redundancy as before: nothing was degraded on the way
             assert all(s.worker_id != "w0" for cp in placed for s in cp.shards)
             assert cl.get(k) == v
+        # every copy, not just the one a read happens to pick (a padded O_DIRECT write used to wipe the head of the object
+        # stored behind the one being moved; the read path hid it by failing over to the other replica)
+        rep = c.keystone.scrub()
+        assert rep["objects"] == len(blobs) and rep["corrupt"] == 0 and rep["unreachable"] == 0
         text = c.keystone.metrics_text()
         assert f"bb_drain_moves_total {len(on_w0)}" in text and ("bb_objects_lost_total 0" in text or "bb_objects_lost_total" not in text)
         # new objects avoid nothing now; a second drain of a worker that is gone is an error, not a crash
@@ -738,3 +742,88 @@ def test_drain_worker_without_room_elsewhere_keeps_the_worker_and_its_objects(bb
         r = cl.put("new-small", b"y" * 1000, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1))
         if r == bb.ErrorCode.OK:
             assert all(s.worker_id != "big" for cp in cl.get_workers("new-small") for s in cp.shards)
+
+
+def _rot(cluster, shard, at=1000, n=64):
+    """Silent corruption of a stored shard: bytes change inside the pool, nobody is told."""
+    w = next(w for w in cluster.workers if w.data_endpoint() == f"{shard.endpoint.ip}:{shard.endpoint.port}")
+    b = w.backend(shard.pool_id)
+    off = shard.offset - (b.get_base_address() if shard.location["kind"] == "memory" else 0)
+    old = b.read(off + at, n)
+    assert int(b.write(off + at, bytes(x ^ 0x5A for x in old))) == 0
+
+
+@pytest.mark.parametrize("tier", ["RAM_CPU", "NVME"])
+def test_scrub_finds_a_rotted_copy_and_replaces_it_from_a_healthy_one(bb, tmp_path, tier):
+    """Scrub (the reference never re-reads what it stored): the workers hash every copy where it lies; the copy that no longer
+    matches its digest is replaced by a fresh one made from a replica that does, its extents go back to the allocator, and the
+    next scrub finds nothing.  Without it the rot waits for a read -- or for the day the healthy replica's worker dies."""
+    sc = getattr(bb.StorageClass, tier)
+    with LocalCluster("scrub", n_workers=0) as c:
+        for i in range(3):
+            c.add_worker(f"w{i}", f"n{i}", [(f"p{i}", sc, 16 << 20, str(tmp_path / f"d{i}") if tier == "NVME" else "")])
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1, ttl_ms=0)
+        blobs = {f"s/{i}": os.urandom(300_000 + 17 * i) for i in range(6)}
+        for k, v in blobs.items():
+            assert cl.put(k, v, cfg) == bb.ErrorCode.OK
+        clean = c.keystone.scrub()
+        assert clean == {"objects": 6, "copies": 12, "corrupt": 0, "healed": 0, "unrecoverable": 0, "unreachable": 0}
+        victim = cl.get_workers("s/2")[1]
+        survivor_pool = cl.get_workers("s/2")[0].shards[0].pool_id
+        _rot(c, victim.shards[0])
+        rep = cl.keystone().scrub("s/")  # the same call over RPC-shaped API (bb-cli scrub)
+        assert rep["corrupt"] == 1 and rep["healed"] == 1 and rep["unrecoverable"] == 0 and rep["objects"] == 6
+        after = cl.get_workers("s/2")
+        assert len(after) == 2 and after[0].shards[0].pool_id == survivor_pool
+        fresh = after[1].shards[0]
+        assert fresh.pool_id != survivor_pool  # still one replica per pool
+        assert (fresh.pool_id, fresh.offset) != (victim.shards[0].pool_id, victim.shards[0].offset)  # new extents, not a patch in place
+        assert c.keystone.scrub() == clean  # every copy of every object matches again
+        for k, v in blobs.items():
+            assert cl.get(k) == v
+        text = c.keystone.metrics_text()
+        assert "bb_scrub_corrupt_copies_total 1" in text and "bb_scrub_healed_total 1" in text
+        # the bad extents went back: removing everything leaves the pools empty
+        for k in blobs:
+            assert cl.remove(k) == bb.ErrorCode.OK
+        assert cl.cluster_stats().used_capacity == 0
+
+
+def test_scrub_reports_an_object_with_no_healthy_copy_left(bb):
+    """One replica, rotted: there is nothing to heal from.  The object stays listed, scrub says so (bb-cli exits 2), the metric
+    counts it, and a read fails its digest check instead of returning the wrong bytes."""
+    with LocalCluster("scrub1", n_workers=2) as c:
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        blob = os.urandom(100_000)
+        assert cl.put("only", blob, bb.WorkerConfig(replication_factor=1, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        assert cl.put("fine", blob, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1)) == bb.ErrorCode.OK
+        _rot(c, cl.get_workers("only")[0].shards[0], at=0, n=8)
+        rep = c.keystone.scrub()
+        assert rep["objects"] == 2 and rep["corrupt"] == 1 and rep["healed"] == 0 and rep["unrecoverable"] == 1
+        assert cl.object_exists("only") and "bb_scrub_unrecoverable_total 1" in c.keystone.metrics_text()
+        with pytest.raises(bb.BlackbirdError) as e:
+            cl.get("only")
+        assert e.value.code == bb.ErrorCode.CHECKSUM_MISMATCH
+        assert c.keystone.scrub("fine", 1)["objects"] == 1  # prefix + object budget
+
+
+def test_repair_uses_a_copy_that_verifies_when_the_first_one_rotted(bb):
+    """Re-replication after a worker death reads a surviving copy; if that copy fails its digest on the way the next one is
+    used (the first was the only candidate before: a rotted copy 0 blocked the repair for good)."""
+    with LocalCluster("rep", n_workers=4) as c:
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        blob = os.urandom(200_000)
+        assert cl.put("r3", blob, bb.WorkerConfig(replication_factor=3, max_workers_per_copy=1, ttl_ms=0)) == bb.ErrorCode.OK
+        copies = cl.get_workers("r3")
+        _rot(c, copies[0].shards[0])
+        assert c.keystone.remove_worker(copies[2].shards[0].worker_id) == bb.ErrorCode.OK  # degraded: 2 of 3 copies left
+        assert len(cl.get_workers("r3")) == 2
+        assert c.keystone.run_repair_once() == 1
+        assert len(cl.get_workers("r3")) == 3
+        rep = c.keystone.scrub()  # ... and scrub then replaces the rotted one as well
+        assert rep["corrupt"] == 1 and rep["healed"] == 1
+        assert c.keystone.scrub()["corrupt"] == 0 and cl.get("r3") == blob

@@ -123,6 +123,8 @@ def test_cluster_of_real_processes(procs, tmp_path, bb):
     assert run_cli("--keystone", ks, "compact", "no-such-pool").returncode != 0
     ls = run_cli("--keystone", ks, "ls", "file-")
     assert ls.returncode == 0 and "file-key" in ls.stdout and "x2" in ls.stdout and "NVME" in ls.stdout
+    sc = run_cli("--keystone", ks, "scrub", "file-")  # the workers re-hash what they hold: 1 object, 2 copies, nothing rotted
+    assert sc.returncode == 0 and "1 objects, 2 copies hashed, 0 corrupt" in sc.stdout, sc.stdout + sc.stderr
     wk = json.loads(run_cli("--keystone", ks, "workers").stdout)
     assert sorted(w["worker_id"] for w in wk) == ["w0", "w1"] and all(len(w["pools"]) == 2 for w in wk)
     b = subprocess.run([os.path.join(BIN, "bb-bench"), "client", "--keystone", ks, "--size", "65536", "--iterations", "20", "--batch", "4"],
