@@ -1588,6 +1588,14 @@ Result<ScrubReport> KeystoneService::scrub_from(const std::string& prefix, size_
         else ++rep.unreachable;
       }
       if (bad.empty()) continue;
+      {
+        // hashed from a snapshot: an object that was removed, replaced or moved meanwhile had its extents reused under the
+        // hash -- that is a lost race, not rot, and the new incarnation is looked at on the next pass
+        Shard& sh = shard_for(o.key);
+        std::shared_lock<SpinMutex> lk(sh.mu);
+        auto it = sh.objects.find(o.key);
+        if (it == sh.objects.end() || it->second.created != o.created || !(it->second.copies == o.copies)) continue;
+      }
       rep.corrupt += bad.size();
       metrics_.inc("scrub_corrupt_copies_total", bad.size());
       if (good.empty()) {

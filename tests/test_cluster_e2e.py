@@ -827,3 +827,75 @@ def test_repair_uses_a_copy_that_verifies_when_the_first_one_rotted(bb):
         rep = c.keystone.scrub()  # ... and scrub then replaces the rotted one as well
         assert rep["corrupt"] == 1 and rep["healed"] == 1
         assert c.keystone.scrub()["corrupt"] == 0 and cl.get("r3") == blob
+
+
+def test_scrub_runs_next_to_writers_removers_and_rot(bb):
+    """Scrub while objects are being replaced and removed and copies keep rotting: it never swaps a copy of an object that was
+    replaced in the meantime, readers never see wrong bytes, and when everything is removed the pools are empty again (no extent
+    of a swapped-out copy is leaked or freed twice)."""
+    import random
+    import threading
+    import time
+
+    with LocalCluster("scrubrace", n_workers=3, pool_bytes=32 << 20) as c:
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        cfg = bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1, ttl_ms=0)
+        blobs = {f"k{i}": os.urandom(150_000 + 333 * i) for i in range(10)}
+        for k, v in blobs.items():
+            assert cl.put(k, v, cfg) == bb.ErrorCode.OK
+        stop = threading.Event()
+        errors, totals = [], {"corrupt": 0, "healed": 0, "rounds": 0}
+        lock = threading.Lock()
+
+        def scrubber():
+            while not stop.is_set():
+                rep = c.keystone.scrub()
+                totals["corrupt"] += rep["corrupt"]
+                totals["healed"] += rep["healed"]
+                totals["rounds"] += 1
+
+        def churn(seed):
+            rc, rng = c.client(), random.Random(seed)
+            while not stop.is_set():
+                k = rng.choice(list(blobs))
+                with lock:  # one writer per key at a time; scrub is the one running unsynchronised
+                    if rng.random() < 0.5:
+                        new = os.urandom(len(blobs[k]))
+                        rc.remove(k)
+                        if rc.put(k, new, cfg) != bb.ErrorCode.OK:
+                            errors.append((k, "put failed"))
+                        blobs[k] = new
+                    else:
+                        try:
+                            if rc.get(k) != blobs[k]:
+                                errors.append((k, "wrong bytes"))
+                        except Exception as e:  # noqa: BLE001
+                            errors.append((k, repr(e)))
+
+        def rotter():
+            rng = random.Random(3)
+            while not stop.is_set():
+                k = rng.choice(list(blobs))
+                with lock:
+                    try:
+                        copies = cl.get_workers(k)
+                        _rot(c, copies[-1].shards[0], at=rng.randrange(0, 1000), n=16)  # copy 0 stays clean: always one to heal from
+                    except bb.BlackbirdError:
+                        pass
+                time.sleep(0.02)
+
+        ts = [threading.Thread(target=scrubber), threading.Thread(target=rotter)] + [threading.Thread(target=churn, args=(s,)) for s in range(2)]
+        [t.start() for t in ts]
+        time.sleep(2.5)
+        stop.set()
+        [t.join() for t in ts]
+        assert not errors, errors[:5]
+        assert totals["rounds"] >= 2 and totals["healed"] >= 1, totals
+        last = c.keystone.scrub()  # settles what the rotter did after the scrubber's last round
+        assert last["unrecoverable"] == 0 and c.keystone.scrub()["corrupt"] == 0
+        for k, v in blobs.items():
+            assert cl.get(k) == v
+        for k in blobs:
+            assert cl.remove(k) == bb.ErrorCode.OK
+        assert cl.cluster_stats().used_capacity == 0
