@@ -468,43 +468,51 @@ Result<size_t> KeystoneService::drain_worker(const WorkerId& id) {
   size_t moved = 0, stuck = 0;
   std::unordered_set<ObjectKey> handled;
   for (const auto& pid : mine) {
-    StorageClass tier = StorageClass::STORAGE_UNSPECIFIED;
     {
       std::shared_lock<std::shared_mutex> pk(pools_mu_);
-      auto it = pools_.find(pid);
-      if (it == pools_.end()) continue;
-      tier = it->second.storage_class;
-    }
-    // same tier first, then down the ladder the tier policy / eviction uses
-    std::vector<StorageClass> targets = {tier};
-    {
-      std::map<int, std::vector<StorageClass>> lower;  // the tiers below, nearest first, that exist on the other workers
-      std::shared_lock<std::shared_mutex> pk(pools_mu_);
-      for (const auto& [opid, op] : pools_)
-        if (tier_rank(op.storage_class) > tier_rank(tier) && std::find(mine.begin(), mine.end(), opid) == mine.end()) {
-          auto& v = lower[tier_rank(op.storage_class)];
-          if (std::find(v.begin(), v.end(), op.storage_class) == v.end()) v.push_back(op.storage_class);
-        }
-      for (const auto& [r, v] : lower) targets.insert(targets.end(), v.begin(), v.end());
+      if (!pools_.count(pid)) continue;
     }
     for (const ObjectKey& raw : allocator_->allocator().objects_on_pool(pid)) {
-      const ObjectKey key = raw.substr(0, raw.find('\x01'));  // ledgers of moved objects are "<key>\x01<slot>"
-      if (!handled.insert(key).second) continue;  // several shards / ledgers of one object: it moves as a whole, once
-      const ErrorCode ec = migrate_with(mover, key, targets, [&](const std::vector<CopyPlacement>&, const std::vector<CopyPlacement>& fresh) {
-        for (const auto& c : fresh)
-          for (const auto& s : c.shards)
-            if (std::find(mine.begin(), mine.end(), s.pool_id) != mine.end()) return false;
-        return true;
-      });
-      if (ec == ErrorCode::OK) {
-        ++moved;
-        metrics_.inc("drain_moves_total");
-      } else if (ec != ErrorCode::OBJECT_NOT_FOUND && ec != ErrorCode::OBJECT_NOT_READY) {
+      const ObjectKey key = raw.substr(0, raw.find('\x01'));  // ledgers of moved copies are "<key>\x01<slot>"
+      if (!handled.insert(key).second) continue;  // several shards / ledgers of one object: handled once, as a whole
+      // Only the copies that touch this worker move (a replica elsewhere stays where it is, and keeps serving); one copy per
+      // turn, metadata re-read after every swap.  The copy that leaves is its own best source -- same bytes, and on a GPU
+      // worker the pull kernel -- and one that fails its digest on the way is rebuilt from a sibling instead.
+      bool any = false;
+      ErrorCode last = ErrorCode::OK;
+      for (int turn = 0; turn < 64; ++turn) {
+        auto info = get_object_info(key);
+        if (!info.ok() || info.value().state != ObjectState::COMPLETE) {
+          last = info.ok() ? ErrorCode::OBJECT_NOT_READY : info.error();
+          break;
+        }
+        const auto& copies = info.value().copies;
+        size_t idx = copies.size();
+        for (size_t c = 0; c < copies.size() && idx == copies.size(); ++c)
+          for (const auto& sp : copies[c].shards)
+            if (std::find(mine.begin(), mine.end(), sp.pool_id) != mine.end()) {
+              idx = c;
+              break;
+            }
+        if (idx == copies.size()) break;  // nothing of it is left here
+        last = replace_copy(mover, info.value(), idx, copies[idx]);
+        for (size_t c = 0; last == ErrorCode::CHECKSUM_MISMATCH && c < copies.size(); ++c)
+          if (c != idx) last = replace_copy(mover, info.value(), idx, copies[c]);
+        if (last != ErrorCode::OK) break;
+        any = true;
+      }
+      if (last == ErrorCode::OK) {
+        if (any) {
+          ++moved;
+          metrics_.inc("drain_moves_total");
+        }
+      } else if (last != ErrorCode::OBJECT_NOT_FOUND && last != ErrorCode::OBJECT_NOT_READY) {
         ++stuck;
-        BB_LOG(WARNING) << "drain " << id << ": " << key << " stays on " << pid << " (" << to_string(ec) << ")";
+        BB_LOG(WARNING) << "drain " << id << ": " << key << " stays on " << pid << " (" << to_string(last) << ")";
       }
     }
   }
+  if (moved) bump_view();
   if (stuck) return ErrorCode::INSUFFICIENT_SPACE;  // still draining: free space elsewhere and call again
   const ErrorCode rc = remove_worker(id);
   {
@@ -1507,22 +1515,10 @@ size_t KeystoneService::run_repair_once() {
   }
   size_t repaired = 0;
   for (const auto& o : degraded) {
-    WorkerConfig cfg = o.config;
-    cfg.replication_factor = 1;
-    cfg.symmetric_replicas = false;
-    std::vector<MemoryPoolId> exclude;
-    for (const auto& c : o.copies)
-      for (const auto& s : c.shards) exclude.push_back(s.pool_id);
     std::string ledger;
-    Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
-    for (int slot = 0; slot < 64; ++slot) {
-      ledger = o.key + "\x01" + std::to_string(slot);
-      std::shared_lock<std::shared_mutex> pk(pools_mu_);
-      fresh = allocator_->allocate_data_copies(ledger, o.size, cfg, pools_, "", exclude);
-      if (fresh.ok() || fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
-    }
-    if (!fresh.ok()) continue;
-    CopyPlacement dst = fresh.value()[0];
+    auto placed = place_extra_copy(o, o.copies.size(), ledger);
+    if (!placed.ok()) continue;
+    CopyPlacement dst = placed.value();
     // any surviving copy can be the source: one that fails its digest on the way (bit rot) must not block the repair
     ErrorCode mec = ErrorCode::OBJECT_NOT_FOUND;
     for (size_t c = 0; c < o.copies.size() && mec != ErrorCode::OK; ++c) mec = mover(o.key, o.copies[c], dst, o.config.checksum);
@@ -1622,27 +1618,53 @@ Result<ScrubReport> KeystoneService::scrub_from(const std::string& prefix, size_
 // Swaps copy `idx` of `o` for a fresh one made from `source` (a copy of the same object that verified): new extents under
 // their own ledger entry, bytes moved and digested by the mover, metadata switched under the shard lock if the object is
 // still the same incarnation, and only then the bad extents handed back to the allocator.
-ErrorCode KeystoneService::replace_copy(const CopyMover& mover, const ObjectInfo& o, size_t idx, const CopyPlacement& source) {
+// Extents for one more copy of `o` (repair) or for the successor of copy `skip` (scrub, drain): never a pool that holds
+// another replica, and -- unless the cluster is too small -- no pool of a worker that does (a worker death must not take two
+// copies).  `ledger` receives the allocator entry the extents are booked under.
+Result<CopyPlacement> KeystoneService::place_extra_copy(const ObjectInfo& o, size_t skip, std::string& ledger) {
   WorkerConfig cfg = o.config;
   cfg.replication_factor = 1;
   cfg.symmetric_replicas = false;
-  std::vector<MemoryPoolId> exclude;  // the pools of the copies that stay: one pool, one replica
-  for (size_t c = 0; c < o.copies.size(); ++c)
-    if (c != idx)
-      for (const auto& s : o.copies[c].shards) exclude.push_back(s.pool_id);
-  std::string ledger;
+  // a successor belongs on the tier the copy is on now (an object that was demoted stays demoted); the put-time
+  // preferences follow as fall-backs
+  if (skip < o.copies.size() && !o.copies[skip].shards.empty()) {
+    const StorageClass here = o.copies[skip].shards[0].storage_class;
+    cfg.preferred_classes.erase(std::remove(cfg.preferred_classes.begin(), cfg.preferred_classes.end(), here), cfg.preferred_classes.end());
+    cfg.preferred_classes.insert(cfg.preferred_classes.begin(), here);
+  }
   Result<std::vector<CopyPlacement>> fresh = ErrorCode::INSUFFICIENT_SPACE;
-  for (int slot = 0; slot < 64; ++slot) {
-    ledger = o.key + "\x01" + std::to_string(slot);
+  for (int pass = 0; pass < 2 && !fresh.ok(); ++pass) {
     std::shared_lock<std::shared_mutex> pk(pools_mu_);
+    std::vector<MemoryPoolId> exclude;
+    std::unordered_set<WorkerId> busy;
+    for (size_t c = 0; c < o.copies.size(); ++c)
+      if (c != skip)
+        for (const auto& s : o.copies[c].shards) {
+          exclude.push_back(s.pool_id);
+          busy.insert(s.worker_id);
+        }
     alloc::IAllocator::PoolMap eligible;
-    for (const auto& [pid, p] : pools_)
-      if (std::find(draining_.begin(), draining_.end(), pid) == draining_.end()) eligible.emplace(pid, p);
-    fresh = allocator_->allocate_data_copies(ledger, o.size, cfg, eligible, "", exclude);
-    if (fresh.ok() || fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+    for (const auto& [pid, p] : pools_) {
+      if (std::find(draining_.begin(), draining_.end(), pid) != draining_.end()) continue;
+      if (pass == 0 && busy.count(p.worker_id)) continue;
+      eligible.emplace(pid, p);
+    }
+    if (eligible.empty()) continue;
+    for (int slot = 0; slot < 64; ++slot) {
+      ledger = o.key + "\x01" + std::to_string(slot);
+      fresh = allocator_->allocate_data_copies(ledger, o.size, cfg, eligible, "", exclude);
+      if (fresh.ok() || fresh.error() != ErrorCode::OBJECT_ALREADY_EXISTS) break;
+    }
   }
   if (!fresh.ok()) return fresh.error();
-  CopyPlacement dst = fresh.value()[0];
+  return fresh.value()[0];
+}
+
+ErrorCode KeystoneService::replace_copy(const CopyMover& mover, const ObjectInfo& o, size_t idx, const CopyPlacement& source) {
+  std::string ledger;
+  auto placed = place_extra_copy(o, idx, ledger);
+  if (!placed.ok()) return placed.error();
+  CopyPlacement dst = placed.value();
   const ErrorCode mec = mover(o.key, source, dst, o.config.checksum);
   if (mec != ErrorCode::OK) {
     allocator_->free_object(ledger);

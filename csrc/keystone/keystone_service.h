@@ -350,6 +350,7 @@ class KeystoneService {
   // `accept` (optional) sees the old and the freshly allocated placements before any byte moves; false = roll back.
   using PlacementFilter = std::function<bool(const std::vector<CopyPlacement>& old_copies, const std::vector<CopyPlacement>& fresh)>;
   Result<ScrubReport> scrub_from(const std::string& prefix, size_t max_objects, size_t& cursor);
+  Result<CopyPlacement> place_extra_copy(const ObjectInfo& o, size_t skip, std::string& ledger);
   ErrorCode replace_copy(const CopyMover& mover, const ObjectInfo& o, size_t idx, const CopyPlacement& source);
   size_t scrub_cursor_ = 0;  // health loop only
   ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets,

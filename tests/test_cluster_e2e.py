@@ -699,8 +699,13 @@ def test_drain_worker_moves_everything_off_before_the_worker_leaves(bb, tmp_path
         on_w0 = [k for k in blobs if any(s.worker_id == "w0" for cp in cl.get_workers(k) for s in cp.shards)]
         assert on_w0, "the test needs objects on the worker it drains"
         copies_before = {k: len(cl.get_workers(k)) for k in blobs}
+        elsewhere = {k: [(s.pool_id, s.offset) for cp in cl.get_workers(k) for s in cp.shards if s.worker_id != "w0"] for k in blobs}
         moved = c.keystone.drain_worker("w0")
         assert moved == len(on_w0)
+        for k in blobs:  # only what touched w0 moved: a replica on another worker is exactly where it was
+            now = [(s.pool_id, s.offset) for cp in cl.get_workers(k) for s in cp.shards]
+            assert all(x in now for x in elsewhere[k]), (k, elsewhere[k], now)
+            assert len({s.worker_id for cp in cl.get_workers(k) for s in cp.shards}) == copies_before[k]  # one replica per worker still
         assert all(w["worker_id"] != "w0" for w in cl.keystone().get_workers_info())
         for k, v in blobs.items():
             placed = cl.get_workers(k)
