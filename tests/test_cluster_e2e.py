@@ -904,3 +904,28 @@ def test_scrub_runs_next_to_writers_removers_and_rot(bb):
         for k in blobs:
             assert cl.remove(k) == bb.ErrorCode.OK
         assert cl.cluster_stats().used_capacity == 0
+
+
+def test_background_scrub_heals_without_being_asked(bb):
+    """`keystone.scrub_objects_per_round`: the health loop walks the objects a slice at a time and replaces what rotted."""
+    import time
+
+    cfg = bb.KeystoneConfig()
+    cfg.health_check_interval_sec = 1
+    cfg.scrub_objects_per_round = 4  # 10 objects: a full pass takes a few rounds, resuming where the last one stopped
+    with LocalCluster("bgscrub", n_workers=3, keystone_cfg=cfg) as c:
+        c.keystone.install_data_server_mover()
+        cl = c.client()
+        blobs = {f"b{i}": os.urandom(50_000 + i) for i in range(10)}
+        for k, v in blobs.items():
+            assert cl.put(k, v, bb.WorkerConfig(replication_factor=2, max_workers_per_copy=1, ttl_ms=0)) == bb.ErrorCode.OK
+        for k in ("b3", "b8"):
+            _rot(c, cl.get_workers(k)[1].shards[0])
+        deadline = time.time() + 20
+        while time.time() < deadline and "bb_scrub_healed_total 2" not in c.keystone.metrics_text():
+            time.sleep(0.2)
+        text = c.keystone.metrics_text()
+        assert "bb_scrub_healed_total 2" in text and "bb_scrub_corrupt_copies_total 2" in text, [l for l in text.splitlines() if "scrub" in l]
+        assert c.keystone.scrub()["corrupt"] == 0
+        for k, v in blobs.items():
+            assert cl.get(k) == v
