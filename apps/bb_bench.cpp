@@ -16,6 +16,7 @@
 
 #include "apps/cli_util.h"
 #include "net/tcp.h"
+#include "common/tenant.h"
 #include <thread>
 
 #include "client/blackbird_client.h"
@@ -42,6 +43,7 @@ int main(int argc, char** argv) {
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
+  if (args.has("tenant")) bb::set_client_tenant(args.get("tenant"), args.get("tenant-secret"));  // else BB_TENANT / BB_TENANT_SECRET (common/tenant.h)
   const std::string mode = args.positional.empty() ? "client" : args.positional[0];
   if (args.has("help")) {
     std::printf("usage: bb-bench client|backend|control|devclient|gpu [options]\n");

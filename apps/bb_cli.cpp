@@ -10,6 +10,7 @@
 
 #include "apps/cli_util.h"
 #include "net/tcp.h"
+#include "common/tenant.h"
 #include "client/blackbird_client.h"
 #include "common/log.h"
 
@@ -31,8 +32,9 @@ int main(int argc, char** argv) {
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
+  if (args.has("tenant")) bb::set_client_tenant(args.get("tenant"), args.get("tenant-secret"));  // else BB_TENANT / BB_TENANT_SECRET (common/tenant.h)
   if (args.positional.empty() || args.has("help")) {
-    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | drain-worker ID | scrub [PREFIX] [MAX] | compact POOL | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T] [--encrypt-transport]\n");
+    std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | drain-worker ID | scrub [PREFIX] [MAX] | compact POOL | tenants | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T | --tenant NAME --tenant-secret S] [--encrypt-transport]\n");
     return args.has("help") ? 0 : 2;
   }
   const std::string cmd = args.positional[0];
@@ -200,6 +202,18 @@ int main(int argc, char** argv) {
       return 1;
     }
     std::printf("drain-worker %s: OK, %zu objects moved\n", args.positional[1].c_str(), r.value());
+    return 0;
+  }
+  if (cmd == "tenants") {  // what each tenant holds against its budget (a tenant sees its own line)
+    auto r = cl.keystone().tenant_usage();
+    if (!r.ok()) {
+      std::printf("tenants: %s\n", name(r.error()));
+      return 1;
+    }
+    std::printf("%-24s %16s %10s %16s %12s\n", "tenant", "used_bytes", "objects", "quota_bytes", "max_objects");
+    for (const auto& u : r.value())
+      std::printf("%-24s %16llu %10llu %16llu %12llu\n", u.name.c_str(), static_cast<unsigned long long>(u.used_bytes), static_cast<unsigned long long>(u.objects),
+                  static_cast<unsigned long long>(u.quota_bytes), static_cast<unsigned long long>(u.max_objects));
     return 0;
   }
   if (cmd == "scrub") {  // re-hash stored copies where they lie; replace the ones that no longer match their digest

@@ -8,6 +8,7 @@
 
 #include "apps/cli_util.h"
 #include "net/tcp.h"
+#include "common/tenant.h"
 #include "common/log.h"
 #include "rpc/rpc_service.h"
 
@@ -17,7 +18,7 @@ int main(int argc, char** argv) {
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.has("help")) {
-    std::printf("usage: bb-keystone [config.yaml] [--etcd-endpoints E] [--listen-address A] [--http-port P] [--cluster-id C] [--enable-ha] [--service-id S]\n");
+    std::printf("usage: bb-keystone [config.yaml] [--etcd-endpoints E] [--listen-address A] [--http-port P] [--cluster-id C] [--enable-ha] [--service-id S] [--tenants-file F]\n");
     return 0;
   }
   bb::set_log_level(bb::LogLevel::INFO);
@@ -33,6 +34,7 @@ int main(int argc, char** argv) {
   if (args.has("etcd-endpoints")) cfg.etcd_endpoints = args.get("etcd-endpoints");
   if (args.has("coord-endpoints")) cfg.etcd_endpoints = args.get("coord-endpoints");
   if (!args.has("auth-token") && !cfg.auth_token.empty()) bb::net::set_cluster_token(cfg.auth_token);  // before the coordination client connects
+  if (args.has("tenants-file")) cfg.tenants_file = args.get("tenants-file");  // else `tenants_file:` / BB_TENANTS_FILE (common/tenant.h)
   if (args.has("listen-address")) cfg.listen_address = args.get("listen-address");
   if (args.has("http-port")) cfg.http_metrics_port = args.get("http-port");
   if (args.has("cluster-id")) cfg.cluster_id = args.get("cluster-id");

@@ -8,6 +8,7 @@
 
 #include "apps/cli_util.h"
 #include "net/tcp.h"
+#include "common/tenant.h"
 #include "common/log.h"
 #include "fabric/gpu_fabric.h"
 #include "worker/worker_service.h"
@@ -18,7 +19,7 @@ int main(int argc, char** argv) {
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.has("help") || (!args.has("config") && args.positional.empty())) {
-    std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port] [--http-port P]\n");
+    std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port] [--http-port P] [--tenants-file F]\n");
     return args.has("help") ? 0 : 2;
   }
   bb::set_log_level(bb::LogLevel::INFO);
@@ -31,6 +32,7 @@ int main(int argc, char** argv) {
   }
   if (!args.has("auth-token") && !cfg.auth_token.empty()) bb::net::set_cluster_token(cfg.auth_token);  // before any connection is made
   if (args.has("auth-token")) cfg.auth_token = args.get("auth-token");
+  if (args.has("tenants-file")) cfg.tenants_file = args.get("tenants-file");  // else `tenants_file:` / BB_TENANTS_FILE (common/tenant.h)
   if (args.has("worker-id")) cfg.worker_id = args.get("worker-id");
   if (args.has("node-id")) cfg.node_id = args.get("node-id");
   if (const char* e = std::getenv("BB_COORD_ENDPOINTS")) cfg.etcd_endpoints = e;

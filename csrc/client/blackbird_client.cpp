@@ -1,5 +1,7 @@
 #include "common/trace.h"
 #include "client/blackbird_client.h"
+
+#include "common/tenant.h"
 #include "common/mxfp8.h"
 #include "common/tchash_def.h"
 
@@ -69,6 +71,7 @@ ErrorCode BlackbirdClient::connect() {
   if (!opts_.auth_token.empty()) net::set_cluster_token(opts_.auth_token);
   if (opts_.encrypt_transport) net::set_transport_encryption(true);
   if (!opts_.auth_token_ro.empty()) net::set_cluster_token_ro(opts_.auth_token_ro);
+  if (!opts_.tenant.empty()) set_client_tenant(opts_.tenant, opts_.tenant_secret);
   if (!keystone_) {
     auto c = std::make_shared<rpc::KeystoneRpcClient>();
     c->set_timeout_ms(opts_.rpc_timeout_ms);

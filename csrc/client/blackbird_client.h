@@ -43,6 +43,9 @@ struct BlackbirdClientOptions {
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
   bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h); also BB_ENCRYPT_TRANSPORT=1
   std::string auth_token_ro;       // read-only membership: set this INSTEAD of auth_token (net/tcp.h); also BB_AUTH_TOKEN_RO
+  // Tenant identity (common/tenant.h): set these INSTEAD of a member token.  The servers then know who is calling: keys
+  // outside the tenant's grants are ACCESS_DENIED, puts beyond its budget QUOTA_EXCEEDED.  Also BB_TENANT / BB_TENANT_SECRET.
+  std::string tenant, tenant_secret;
 };
 
 // One device-side transfer request of a batch (a shard).

@@ -62,7 +62,8 @@ constexpr Entry kTable[] = {
     {ErrorCode::CLIENT_DISCONNECTED, "CLIENT_DISCONNECTED", "Client is disconnected"},
     {ErrorCode::SESSION_EXPIRED, "SESSION_EXPIRED", "Client session TTL expired"},
     {ErrorCode::INVALID_CLIENT_STATE, "INVALID_CLIENT_STATE", "Client is in the wrong state"},
-    {ErrorCode::ACCESS_DENIED, "ACCESS_DENIED", "Cluster token missing or wrong"},
+    {ErrorCode::ACCESS_DENIED, "ACCESS_DENIED", "Cluster token missing or wrong, or key outside the tenant's grants"},
+    {ErrorCode::QUOTA_EXCEEDED, "QUOTA_EXCEEDED", "Tenant budget (bytes or objects) exceeded"},
     {ErrorCode::CONFIG_ERROR, "CONFIG_ERROR", "Generic configuration failure"},
     {ErrorCode::INVALID_CONFIGURATION, "INVALID_CONFIGURATION", "Configuration is inconsistent"},
     {ErrorCode::INVALID_PARAMETERS, "INVALID_PARAMETERS", "Parameters are invalid"},

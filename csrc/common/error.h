@@ -85,7 +85,8 @@ enum class ErrorCode : uint32_t {
   CLIENT_DISCONNECTED,
   SESSION_EXPIRED,
   INVALID_CLIENT_STATE,
-  ACCESS_DENIED,  // the peer did not present the cluster token (net/tcp.h)
+  ACCESS_DENIED,  // the peer did not present the cluster token (net/tcp.h), or a tenant asked for a key outside its grants
+  QUOTA_EXCEEDED,  // a tenant's put would exceed its budget (common/tenant.h)
   // CONFIG
   CONFIG_ERROR = 7000,
   INVALID_CONFIGURATION,

@@ -31,6 +31,7 @@ std::string encode_object(const ObjectInfo& o) {
   wire::put(w, o.config);
   wire::put(w, o.copies);
   w.u32(static_cast<uint32_t>(o.state));
+  w.str(o.tenant);  // (records written before tenants existed end here)
   return w.take();
 }
 bool decode_object(const std::string& s, ObjectInfo& o) {
@@ -41,6 +42,8 @@ bool decode_object(const std::string& s, ObjectInfo& o) {
   wire::get(r, o.config);
   wire::get(r, o.copies);
   o.state = static_cast<ObjectState>(r.u32());
+  if (!r.ok()) return false;
+  if (!r.at_end()) o.tenant = r.str();
   if (!r.ok()) return false;
   const int64_t age = std::max<int64_t>(0, wall_ms() - created_wall);
   o.created = Clock::now() - std::chrono::milliseconds(age);
@@ -133,6 +136,10 @@ void KeystoneService::reset_object_state() {
     sh.wal_queue.clear();
   }
   static_cast<alloc::RangeAllocator&>(allocator_->allocator()).reset();  // in place: other threads hold the adapter
+  {
+    std::lock_guard<std::mutex> tl(tenant_mu_);
+    tenant_usage_.clear();
+  }
   std::lock_guard<std::mutex> ul(unadopted_mu_);
   unadopted_.clear();
 }
@@ -226,6 +233,7 @@ void KeystoneService::health_loop() {
       for (auto it = clients_.begin(); it != clients_.end();)
         it = (now - it->second.last_ping > std::chrono::seconds(config_.client_ttl_sec)) ? clients_.erase(it) : std::next(it);
     }
+    reload_tenants_if_changed();  // an edited tenant table (grants, budgets, revocations) takes effect without a restart
     run_eviction_once();
     run_repair_once();
     run_promotion_once();
@@ -606,6 +614,7 @@ ErrorCode KeystoneService::erase_locked(Shard& sh, const ObjectKey& key, bool fr
   if (it == sh.objects.end()) return ErrorCode::OBJECT_NOT_FOUND;
   const bool was_complete = it->second.state == ObjectState::COMPLETE || it->second.committing;
   const std::vector<std::string> extra = std::move(it->second.extra_ledgers);
+  if (!it->second.tenant.empty()) tenant_release(it->second.tenant, tenant_charge_of(it->second));
   if (it->second.reserved && reservations_enabled()) {
     HookOp op;
     op.release = it->second.tokens.empty();  // committed already: free the shards; else abort the outstanding tokens
@@ -695,8 +704,24 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start_locked(const Objec
     for (const auto& name : tier_classes_for_size(config_.tier_policy, data_size))
       if (auto sc = parse_storage_class(name)) effective.preferred_classes.push_back(*sc);
   }
+  // admission: a tenant's put is checked against its grants and charged against its budget before anything is allocated
+  const Tenant* ten = current_tenant();
+  const uint64_t charge = static_cast<uint64_t>(data_size) * config.replication_factor;
+  if (ten) {
+    if (!ten->may_write(key)) {
+      metrics_.inc("tenant_acl_denials_total");
+      return ErrorCode::ACCESS_DENIED;
+    }
+    if (!tenant_admit(*ten, charge)) {
+      metrics_.inc("tenant_quota_denials_total");
+      return ErrorCode::QUOTA_EXCEEDED;
+    }
+  }
   auto copies = allocator_->allocate_data_copies(key, data_size, effective, pools_, client_node, draining_);  // (usually empty)
-  if (!copies.ok()) return copies.error();
+  if (!copies.ok()) {
+    if (ten) tenant_release(ten->name, charge);
+    return copies.error();
+  }
   ObjectInfo info;
   info.key = key;
   info.size = data_size;
@@ -707,6 +732,7 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start_locked(const Objec
   info.copies = copies.value();
   info.state = ObjectState::PENDING;
   info.owner_client = client_id;
+  if (ten) info.tenant = ten->name;
   sh.objects.emplace(key, std::move(info));
   return copies;
 }
@@ -895,6 +921,7 @@ bool KeystoneService::put_start_run(const std::vector<PutStartItem>& items, size
   const size_t data_size = items[first].size;
   if (config.replication_factor != 1 || config.max_workers_per_copy == 0) return false;
   if (!draining_.empty()) return false;  // a worker is being drained: the per-object path knows which pools to leave alone
+  if (current_tenant()) return false;    // a tenant's puts are admitted one by one against its grants and budget
   if (config_.max_replicas > 0 && config.replication_factor > static_cast<size_t>(config_.max_replicas)) return false;
   WorkerConfig tiered;
   const WorkerConfig* effective = &config;
@@ -1702,6 +1729,53 @@ ErrorCode KeystoneService::replace_copy(const CopyMover& mover, const ObjectInfo
   return ErrorCode::OK;
 }
 
+// ================================================================ tenants (admission control)
+bool KeystoneService::tenant_admit(const Tenant& t, uint64_t bytes) {
+  std::lock_guard<std::mutex> lk(tenant_mu_);
+  TenantCount& c = tenant_usage_[t.name];
+  if (t.quota_bytes && (bytes > t.quota_bytes || c.bytes > t.quota_bytes - bytes)) return false;
+  if (t.max_objects && c.objects >= t.max_objects) return false;
+  c.bytes += bytes;
+  c.objects += 1;
+  return true;
+}
+
+void KeystoneService::tenant_charge(const std::string& name, uint64_t bytes) {
+  std::lock_guard<std::mutex> lk(tenant_mu_);
+  TenantCount& c = tenant_usage_[name];
+  c.bytes += bytes;
+  c.objects += 1;
+}
+
+void KeystoneService::tenant_release(const std::string& name, uint64_t bytes) {
+  std::lock_guard<std::mutex> lk(tenant_mu_);
+  auto it = tenant_usage_.find(name);
+  if (it == tenant_usage_.end()) return;
+  it->second.bytes -= std::min(it->second.bytes, bytes);
+  if (it->second.objects) --it->second.objects;
+}
+
+std::vector<TenantUsage> KeystoneService::tenant_usage() const {
+  std::map<std::string, TenantUsage> by_name;
+  for (const auto& n : tenant_names()) by_name[n].name = n;
+  {
+    std::lock_guard<std::mutex> lk(tenant_mu_);
+    for (const auto& [n, c] : tenant_usage_) {
+      if (!c.objects && !c.bytes && !by_name.count(n)) continue;
+      TenantUsage& u = by_name[n];
+      u.name = n;
+      u.used_bytes = c.bytes;
+      u.objects = c.objects;
+    }
+  }
+  std::vector<TenantUsage> out;
+  for (auto& [n, u] : by_name) {
+    if (auto t = find_tenant(n)) u.quota_bytes = t->quota_bytes, u.max_objects = t->max_objects;
+    out.push_back(std::move(u));
+  }
+  return out;
+}
+
 // ================================================================ metadata log
 void KeystoneService::persist_object(Shard& sh, const ObjectInfo& info, ErrorCode* result) {
   if (!wal_enabled()) return;
@@ -1791,6 +1865,7 @@ void KeystoneService::recover_objects(std::vector<std::pair<std::string, std::st
           auto& v2 = unadopted_[s.pool_id];
           if (v2.empty() || v2.back() != o.key) v2.push_back(o.key), ++deferred;
         }
+    if (!o.tenant.empty()) tenant_charge(o.tenant, tenant_charge_of(o));
     sh.objects.emplace(o.key, std::move(o));
     ++n;
   }

@@ -35,6 +35,7 @@
 #include "common/spin.h"
 #include "alloc/allocator.h"
 #include "common/metrics.h"
+#include "common/tenant.h"
 #include "common/types.h"
 #include "coord/coord.h"
 
@@ -52,6 +53,7 @@ struct ObjectInfo {
   std::vector<CopyPlacement> copies;
   ObjectState state = ObjectState::PENDING;
   std::string owner_client;  // session that started the put
+  std::string tenant;        // the tenant it is charged to (common/tenant.h); "" = put by a member
   std::vector<std::string> extra_ledgers;  // allocator ledger keys besides `key` (repair / demotion)
   uint32_t reads_below_top = 0;            // reads served while the object sat on a lower tier (promotion policy)
   ShardTokens tokens;       // reservation tokens of a PENDING object (reservation protocol); cleared once committed
@@ -103,6 +105,15 @@ using CopyMover = std::function<ErrorCode(const ObjectKey& key, const CopyPlacem
 
 // Scrub: re-hashes one stored copy where it lies and compares with the recorded digests (client/copy_mover.h).
 using CopyVerifier = std::function<ErrorCode(const ObjectKey& key, const CopyPlacement& copy, ChecksumAlgo algo)>;
+
+// What a tenant (common/tenant.h) holds right now and what it may hold.
+struct TenantUsage {
+  std::string name;
+  uint64_t used_bytes = 0;  // size x replication_factor of every object it put and that still exists
+  uint64_t objects = 0;
+  uint64_t quota_bytes = 0;  // 0 = unlimited (from the tenant table; 0 as well for a tenant that left the table)
+  uint64_t max_objects = 0;
+};
 
 struct ScrubReport {
   uint64_t objects = 0;        // COMPLETE objects looked at
@@ -221,6 +232,9 @@ class KeystoneService {
   // new extents, verified bytes, the bad extents released -- so the object is never served from, or repaired out of, bit rot.
   void set_copy_verifier(CopyVerifier v);
   Result<ScrubReport> scrub(const std::string& prefix = "", size_t max_objects = 0);
+  // Per-tenant holdings against their budgets (every tenant in the table, plus any that still owns objects).
+  std::vector<TenantUsage> tenant_usage() const;
+  void count_acl_denial() { metrics_.inc("tenant_acl_denials_total"); }  // the RPC layer refused a key outside a tenant's grants
   double tier_utilization(StorageClass sc) const;
 
   // ---- observability
@@ -353,6 +367,16 @@ class KeystoneService {
   Result<CopyPlacement> place_extra_copy(const ObjectInfo& o, size_t skip, std::string& ledger);
   ErrorCode replace_copy(const CopyMover& mover, const ObjectInfo& o, size_t idx, const CopyPlacement& source);
   size_t scrub_cursor_ = 0;  // health loop only
+  // Admission control per tenant: charged in put_start, released wherever an object leaves the table (erase_locked).
+  struct TenantCount {
+    uint64_t bytes = 0, objects = 0;
+  };
+  mutable std::mutex tenant_mu_;
+  std::unordered_map<std::string, TenantCount> tenant_usage_;
+  bool tenant_admit(const Tenant& t, uint64_t bytes);  // false = over its budget (nothing charged)
+  void tenant_charge(const std::string& name, uint64_t bytes);  // recovery: no check
+  void tenant_release(const std::string& name, uint64_t bytes);
+  static uint64_t tenant_charge_of(const ObjectInfo& o) { return static_cast<uint64_t>(o.size) * std::max<size_t>(1, o.config.replication_factor); }
   ErrorCode migrate_with(const CopyMover& mover, const ObjectKey& key, const std::vector<StorageClass>& targets,
                          const PlacementFilter& accept = nullptr);
 

@@ -1,6 +1,8 @@
 #include "common/fault.h"
 #include "net/tcp.h"
 
+#include "common/tenant.h"
+
 #include <arpa/inet.h>
 #include <fcntl.h>
 #include <netdb.h>
@@ -84,6 +86,7 @@ constexpr size_t kNonce = 16, kMac = 32;
 constexpr char kHelloMagic[] = "BBA1";
 constexpr char kHelloSecure[] = "BBA2";  // as BBA1, and every frame after the handshake is sealed (tcp.h)
 constexpr char kHelloRo[] = "BBR1", kHelloRoSecure[] = "BBR2";  // the same two, proving the read-only token instead
+constexpr char kHelloTenant[] = "BBT1", kHelloTenantSecure[] = "BBT2";  // a tenant: the hello carries its name, the proof is keyed by its secret
 void fresh_nonce(char* out) {
   size_t got = 0;
   while (got < kNonce) {
@@ -654,6 +657,16 @@ RpcServer::Reply RpcServer::dispatch(const ConnPtr& c, uint32_t method, std::str
     *rmethod = kDeniedMarker;
     return reply;
   }
+  std::shared_ptr<const Tenant> tenant;
+  if (c && !c->tenant().empty()) {  // a tenant: looked up per request, so a grant that was edited or revoked takes effect on open connections
+    tenant = find_tenant(c->tenant());
+    if (!tenant || (!tenant->admin && !tenant_methods_.count(method))) {
+      tenant_denials_.fetch_add(1, std::memory_order_relaxed);
+      *rmethod = kDeniedMarker;
+      return reply;
+    }
+  }
+  TenantScope on_behalf_of(std::move(tenant));  // handlers (and the Keystone under them) see current_tenant()
   BB_TRACE_SPAN("rpc.serve", method);  // server side of every RPC (TCP and shared-memory path) on the same timeline as the client's phases
   try {
     if (const int64_t d = fault::value("delay_rpc_ms", 0); d > 0) std::this_thread::sleep_for(std::chrono::milliseconds(d));
@@ -856,14 +869,50 @@ bool RpcServer::on_data(const ConnPtr& c) {
           c->send(encode_frame(kDeniedMarker, id, std::string()));
           return false;
         }
-        if (token.empty()) {  // open cluster: nothing to prove, tell the client so
+        std::string& nonces = c->auth_nonces();
+        const std::string_view magic = msg.substr(0, std::min<size_t>(4, msg.size()));
+        if (nonces.empty() && msg.size() > 4 + kNonce && msg.size() <= 4 + kNonce + kMaxTenantName &&
+            (magic == kHelloTenant || magic == kHelloTenantSecure)) {
+          // A tenant names itself; its secret comes from this process's tenant table.  A name we do not know (or a server
+          // that serves no tenants) is answered like a wrong secret -- a reply under a throw-away key, denial at the proof.
+          const std::string name(msg.substr(4 + kNonce));
+          std::shared_ptr<const Tenant> t = tenant_methods_.empty() ? nullptr : find_tenant(name);
+          if (magic == kHelloTenant && transport_encryption()) {
+            if (log_denial()) BB_LOG(WARNING) << "rpc: tenant connection from " << c->peer() << " does not encrypt but this server requires it (encrypt_transport)";
+            auth_failures_.fetch_add(1, std::memory_order_relaxed);
+            c->send(encode_frame(kDeniedMarker, id, std::string()));
+            return false;
+          }
+          if (magic == kHelloTenantSecure && !Aead::available()) {
+            if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " asks for an encrypted connection but libcrypto is not available here";
+            auth_failures_.fetch_add(1, std::memory_order_relaxed);
+            c->send(encode_frame(kDeniedMarker, id, std::string()));
+            return false;
+          }
+          c->wants_secure() = magic == kHelloTenantSecure;
+          c->hello_read_only() = false;
+          c->hello_tenant() = name;
+          nonces.assign(msg.substr(4, kNonce));
+          char sn[kNonce];
+          fresh_nonce(sn);
+          nonces.append(sn, kNonce);
+          std::string key;
+          if (t) key = t->secret;
+          else {
+            key.assign(kNonce, '\0');
+            fresh_nonce(key.data());
+          }
+          std::string reply(sn, kNonce);
+          reply += handshake_mac(key, "bb-srv-t:" + name, nonces);
+          if (!c->send(encode_frame(kAuthMethod, id, reply))) return false;
+          continue;
+        }
+        if (token.empty() && c->hello_tenant().empty()) {  // open cluster: nothing to prove, tell the client so
           c->set_authed();
           if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;
           continue;
         }
-        std::string& nonces = c->auth_nonces();
         const bool hello = nonces.empty() && msg.size() == 4 + kNonce;
-        const std::string_view magic = msg.substr(0, std::min<size_t>(4, msg.size()));
         const bool ro_hello = hello && (magic == kHelloRo || magic == kHelloRoSecure);
         if (ro_hello && cluster_token_ro().empty()) {
           if (log_denial()) BB_LOG(WARNING) << "rpc: " << c->peer() << " presents a read-only token but this server has none (auth_token_ro)";
@@ -897,10 +946,17 @@ bool RpcServer::on_data(const ConnPtr& c) {
         }
         // the proof is checked against the secret of the role the hello named, under that role's label
         const bool ro = c->hello_read_only();
-        const std::string proven = ro ? cluster_token_ro() : token;
+        const std::string& tname = c->hello_tenant();
+        std::shared_ptr<const Tenant> ten = tname.empty() || tenant_methods_.empty() ? nullptr : find_tenant(tname);
+        const std::string proven = !tname.empty() ? (ten ? ten->secret : std::string()) : ro ? cluster_token_ro() : token;
+        const std::string label = !tname.empty() ? "bb-cli-t:" + tname : ro ? "bb-cli-ro" : "bb-cli";
         if (nonces.size() == 2 * kNonce && msg.size() == kMac && !proven.empty() &&
-            mac_equal(msg.data(), handshake_mac(proven, ro ? "bb-cli-ro" : "bb-cli", nonces).data(), kMac)) {
+            mac_equal(msg.data(), handshake_mac(proven, label, nonces).data(), kMac)) {
           if (ro) c->set_read_only();
+          if (ten) {
+            c->set_tenant(tname, ten->admin);
+            tenant_handshakes_.fetch_add(1, std::memory_order_relaxed);
+          }
           c->set_authed();
           if (!c->send(encode_frame(kAuthMethod, id, std::string()))) return false;  // the last clear frame
           if (c->wants_secure()) {
@@ -969,6 +1025,18 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
   // a process that holds only the read-only token joins as a read-only member
   const bool ro = token.empty() && !cluster_token_ro().empty();
   if (ro) token = cluster_token_ro();
+  // ... and one that holds no member token at all but a tenant identity presents that (common/tenant.h)
+  std::string tname;
+  if (token.empty()) {
+    auto [n, sec] = client_tenant();
+    if (!n.empty() && !sec.empty() && n.size() <= kMaxTenantName) {
+      tname = n;
+      token = sec;
+    }
+  }
+  const bool as_tenant = !tname.empty();
+  const std::string srv_label = as_tenant ? "bb-srv-t:" + tname : ro ? "bb-srv-ro" : "bb-srv";
+  const std::string cli_label = as_tenant ? "bb-cli-t:" + tname : ro ? "bb-cli-ro" : "bb-cli";
   const bool want_secure = transport_encryption();
   secure_ = false;
   if (want_secure) {
@@ -993,19 +1061,22 @@ ErrorCode RpcClient::connect(const std::string& host, uint16_t port, int timeout
     };
     std::string nonces(kNonce, '\0'), reply;
     fresh_nonce(nonces.data());
-    const char* hello = ro ? (want_secure ? kHelloRoSecure : kHelloRo) : (want_secure ? kHelloSecure : kHelloMagic);
-    ErrorCode ec = exchange(0, std::string(hello, 4) + nonces, &reply);
+    const char* hello = as_tenant ? (want_secure ? kHelloTenantSecure : kHelloTenant)
+                        : ro      ? (want_secure ? kHelloRoSecure : kHelloRo)
+                                  : (want_secure ? kHelloSecure : kHelloMagic);
+    ErrorCode ec = exchange(0, std::string(hello, 4) + nonces + tname, &reply);
     if (ec == ErrorCode::OK) {
       if (reply.size() != kNonce + kMac) {
         BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " has no cluster token but this client does";
         ec = ErrorCode::ACCESS_DENIED;
       } else {
         nonces.append(reply, 0, kNonce);
-        if (!mac_equal(reply.data() + kNonce, handshake_mac(token, ro ? "bb-srv-ro" : "bb-srv", nonces).data(), kMac)) {
-          BB_LOG(WARNING) << "RpcClient: " << host << ":" << port << " does not hold this cluster's token";
+        if (!mac_equal(reply.data() + kNonce, handshake_mac(token, srv_label, nonces).data(), kMac)) {
+          BB_LOG(WARNING) << "RpcClient: " << host << ":" << port
+                          << (as_tenant ? " does not know tenant " + tname + " (or its secret differs)" : std::string(" does not hold this cluster's token"));
           ec = ErrorCode::ACCESS_DENIED;
         } else {
-          ec = exchange(1, handshake_mac(token, ro ? "bb-cli-ro" : "bb-cli", nonces), &reply);
+          ec = exchange(1, handshake_mac(token, cli_label, nonces), &reply);
         }
       }
     }

@@ -64,6 +64,13 @@ class TcpServer;
 // get_workers / stats / listings on the Keystone, D_READ / D_CHECKSUM on a data server, get / list / watch on the
 // coordination store); everything else is answered with the denial marker (ACCESS_DENIED at the caller) and the
 // connection stays open.  Holders of the read-only token cannot put, remove, migrate, register workers or touch leases.
+//
+// Tenants (common/tenant.h; a client that holds NO member token but a tenant name + secret): "BBT1" / "BBT2" cnonce[16]
+// name[1..64], labels "bb-srv-t:<name>" / "bb-cli-t:<name>", keyed by that tenant's secret from the server's tenant table.
+// The connection then carries the tenant's name: the server dispatches only the methods on its tenant list
+// (RpcServer::allow_tenants; everything for `admin` tenants) and the handlers check keys against the tenant's grants.
+// An unknown name gets the same answer as a wrong secret (a reply MAC'd with a throw-away key, then the denial), so names
+// cannot be probed.
 void set_cluster_token(const std::string& token);
 std::string cluster_token();
 void set_cluster_token_ro(const std::string& token);
@@ -122,6 +129,15 @@ class Connection : public std::enable_shared_from_this<Connection> {
   bool& hello_read_only() { return hello_ro_; }        // the client opened with "BBR1" / "BBR2" (handshake in progress)
   bool read_only() const { return read_only_.load(std::memory_order_acquire); }
   void set_read_only() { read_only_.store(true, std::memory_order_release); }
+  // Tenant connections (common/tenant.h): the name the peer proved in the handshake ("" = a member or an open cluster).
+  // Written by the owning thread before set_authed(), read by handlers afterwards.
+  const std::string& tenant() const { return tenant_; }
+  bool tenant_admin() const { return tenant_admin_; }
+  void set_tenant(std::string name, bool admin) {
+    tenant_ = std::move(name);
+    tenant_admin_ = admin;
+  }
+  std::string& hello_tenant() { return hello_tenant_; }  // the name a "BBT1" / "BBT2" hello claimed (handshake in progress)
   // Secure mode: from now on send() / sendv() seal every frame and the owner opens incoming ones with rx().
   bool enable_secure(const uint8_t rx_key[kAeadKey], const uint8_t tx_key[kAeadKey]);
   bool secure() const { return secure_.load(std::memory_order_acquire); }
@@ -146,6 +162,8 @@ class Connection : public std::enable_shared_from_this<Connection> {
   std::string auth_nonces_;
   bool wants_secure_ = false;
   bool hello_ro_ = false;
+  std::string hello_tenant_, tenant_;
+  bool tenant_admin_ = false;
   std::atomic<bool> read_only_{false};
   std::atomic<bool> secure_{false};
   Aead rx_, tx_;  // rx_: the thread that owns the connection; tx_: under write_mu_
@@ -230,6 +248,11 @@ class RpcServer : public TcpServer {
   // Methods a read-only member (a connection admitted with the read-only token) may call; set before start().
   void allow_read_only(std::initializer_list<uint32_t> methods) { ro_methods_.insert(methods.begin(), methods.end()); }
   uint64_t read_only_denials() const { return ro_denials_.load(); }
+  // Methods a tenant connection may call (tenants marked `admin` may call everything); set before start().  A server that
+  // allows none admits no tenants at all (their hello is refused).
+  void allow_tenants(std::initializer_list<uint32_t> methods) { tenant_methods_.insert(methods.begin(), methods.end()); }
+  uint64_t tenant_denials() const { return tenant_denials_.load(); }
+  uint64_t tenant_handshakes() const { return tenant_handshakes_.load(); }
   void set_close_hook(std::function<void(const ConnPtr&)> f) { close_hook_ = std::move(f); }
   static bool push(const ConnPtr& c, uint32_t topic, const std::string& payload) {
     return c->send(encode_frame(kPushFlag | topic, 0, payload));
@@ -262,8 +285,8 @@ class RpcServer : public TcpServer {
   std::vector<std::thread> shm_pollers_;
   std::atomic<bool> shm_run_{false};
   std::atomic<uint64_t> shm_served_{0};
-  std::atomic<uint64_t> secure_handshakes_{0}, auth_failures_{0}, ro_denials_{0};
-  std::set<uint32_t> ro_methods_;
+  std::atomic<uint64_t> secure_handshakes_{0}, auth_failures_{0}, ro_denials_{0}, tenant_denials_{0}, tenant_handshakes_{0};
+  std::set<uint32_t> ro_methods_, tenant_methods_;
   std::unordered_map<uint32_t, Handler> handlers_;
   std::unordered_map<uint32_t, ViewHandler> view_handlers_;
   std::function<void(const ConnPtr&)> close_hook_;

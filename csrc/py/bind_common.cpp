@@ -93,6 +93,7 @@ void bind_common(py::module_& m) {
       .value("SESSION_EXPIRED", ErrorCode::SESSION_EXPIRED)
       .value("INVALID_CLIENT_STATE", ErrorCode::INVALID_CLIENT_STATE)
       .value("ACCESS_DENIED", ErrorCode::ACCESS_DENIED)
+      .value("QUOTA_EXCEEDED", ErrorCode::QUOTA_EXCEEDED)
       .value("CONFIG_ERROR", ErrorCode::CONFIG_ERROR)
       .value("INVALID_CONFIGURATION", ErrorCode::INVALID_CONFIGURATION)
       .value("INVALID_PARAMETERS", ErrorCode::INVALID_PARAMETERS)

@@ -4,6 +4,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "common/tenant.h"
 #include "alloc/allocator.h"
 #include "client/blackbird_client.h"
 #include "client/copy_mover.h"
@@ -65,6 +66,26 @@ py::dict scrub_to_py(const keystone::ScrubReport& r) {
   d["unreachable"] = r.unreachable;
   return d;
 }
+
+py::list tenant_usage_to_py(const std::vector<keystone::TenantUsage>& v) {
+  py::list out;
+  for (const auto& u : v) {
+    py::dict d;
+    d["name"] = u.name;
+    d["used_bytes"] = u.used_bytes;
+    d["objects"] = u.objects;
+    d["quota_bytes"] = u.quota_bytes;
+    d["max_objects"] = u.max_objects;
+    out.append(d);
+  }
+  return out;
+}
+
+// RAII TenantScope as a Python context manager: in-process callers act on behalf of a tenant (ACL + budget apply).
+struct PyTenantScope {
+  std::string name;
+  std::unique_ptr<TenantScope> scope;
+};
 
 py::object location_to_py(const LocationDetail& l) {
   py::dict d;
@@ -294,6 +315,7 @@ void bind_control(py::module_& m) {
       .def_readwrite("service_refresh_interval_sec", &KeystoneConfig::service_refresh_interval_sec)
       .def_readwrite("gc_interval_sec", &KeystoneConfig::gc_interval_sec)
       .def_readwrite("scrub_objects_per_round", &KeystoneConfig::scrub_objects_per_round)
+      .def_readwrite("tenants_file", &KeystoneConfig::tenants_file)
       .def_readwrite("health_check_interval_sec", &KeystoneConfig::health_check_interval_sec)
       .def_readwrite("max_replicas", &KeystoneConfig::max_replicas)
       .def_readwrite("default_replicas", &KeystoneConfig::default_replicas)
@@ -644,6 +666,8 @@ void bind_control(py::module_& m) {
       })
       .def("install_reservation_hooks", [](KeystoneService& k) { k.set_reservation_hooks(client::make_data_server_reservation_hooks()); },
            "Reservation protocol over the workers' data servers (takes effect with KeystoneConfig.enable_reservations).")
+      .def("tenant_usage", [](KeystoneService& k) { return tenant_usage_to_py(k.tenant_usage()); },
+           "per tenant: used_bytes (size x replicas of its live objects), objects, quota_bytes, max_objects")
       .def("scrub", [](KeystoneService& k, const std::string& prefix, size_t max_objects) { return scrub_to_py(unwrap(nogil([&] { return k.scrub(prefix, max_objects); }))); },
            py::arg("prefix") = "", py::arg("max_objects") = 0)
       .def("install_data_server_verifier", [](KeystoneService& k) { k.set_copy_verifier(client::make_data_server_verifier()); })
@@ -727,6 +751,8 @@ void bind_control(py::module_& m) {
       })
       .def("remove_worker", &rpc::KeystoneApi::remove_worker, py::call_guard<py::gil_scoped_release>())
       .def("drain_worker", [](rpc::KeystoneApi& k, const std::string& id) { return unwrap(nogil([&] { return k.drain_worker(id); })); })
+      .def("tenant_usage", [](rpc::KeystoneApi& k) { return tenant_usage_to_py(unwrap(nogil([&] { return k.tenant_usage(); }))); },
+           "what each tenant holds against its budget (a tenant connection sees only its own line)")
       .def("scrub", [](rpc::KeystoneApi& k, const std::string& prefix, size_t max_objects) { return scrub_to_py(unwrap(nogil([&] { return k.scrub(prefix, max_objects); }))); },
            py::arg("prefix") = "", py::arg("max_objects") = 0)
       .def("compact_pool", [](rpc::KeystoneApi& k, const std::string& pool, size_t max_moves) { return unwrap(nogil([&] { return k.compact_pool(pool, max_moves); })); },
@@ -871,6 +897,49 @@ void bind_control(py::module_& m) {
         "CPU stand-in for the GPU fabric: the device batch API of `client` moves host buffers through `io_client`'s host data paths");
   m.def("set_cluster_token", &net::set_cluster_token, "shared-secret gate of the RPC servers / clients of this process (net/tcp.h)");
   m.def("set_cluster_token_ro", &net::set_cluster_token_ro, "second secret: members that prove only this one are read-only (net/tcp.h)");
+  // tenants (common/tenant.h): named principals with their own secret, key-prefix grants and a budget
+  m.def("set_tenants", [](const std::vector<py::dict>& rows) {
+    std::vector<Tenant> v;
+    for (const auto& d : rows) {
+      Tenant t;
+      t.name = py::cast<std::string>(d["name"]);
+      t.secret = py::cast<std::string>(d["secret"]);
+      if (d.contains("read")) t.read_prefixes = py::cast<std::vector<std::string>>(d["read"]);
+      if (d.contains("write")) t.write_prefixes = py::cast<std::vector<std::string>>(d["write"]);
+      if (d.contains("quota_bytes")) t.quota_bytes = py::cast<uint64_t>(d["quota_bytes"]);
+      if (d.contains("max_objects")) t.max_objects = py::cast<uint64_t>(d["max_objects"]);
+      if (d.contains("admin")) t.admin = py::cast<bool>(d["admin"]);
+      if (t.name.empty() || t.name.size() > kMaxTenantName || t.secret.empty()) throw py::value_error("tenant needs a name (1..64 bytes) and a secret");
+      v.push_back(std::move(t));
+    }
+    set_tenants(std::move(v));
+  }, "install the process-wide tenant table: [{name, secret, read: [...], write: [...], quota_bytes, max_objects, admin}]");
+  m.def("load_tenants_file", [](const std::string& path) {
+    std::string err;
+    if (load_tenants_file(path, &err) != ErrorCode::OK) throw py::value_error(err);
+  });
+  m.def("load_tenants_text", [](const std::string& yaml) {
+    std::string err;
+    if (load_tenants_text(yaml, &err) != ErrorCode::OK) throw py::value_error(err);
+  });
+  m.def("reload_tenants_if_changed", &reload_tenants_if_changed);
+  m.def("tenant_names", &tenant_names);
+  m.def("set_client_tenant", &set_client_tenant, py::arg("name"), py::arg("secret"),
+        "the identity RPC clients of this process present when they hold no member token (\"\", \"\" = none)");
+  m.def("tenant_may", [](const std::string& name, const std::string& key, bool write) {
+    auto t = find_tenant(name);
+    return t && (write ? t->may_write(key) : t->may_read(key));
+  }, py::arg("tenant"), py::arg("key"), py::arg("write") = false);
+  py::class_<PyTenantScope>(m, "TenantScope", "with TenantScope(name): in-process Keystone calls of this thread run on behalf of that tenant")
+      .def(py::init([](const std::string& name) {
+        if (!find_tenant(name)) throw py::value_error("unknown tenant " + name);
+        return PyTenantScope{name, nullptr};
+      }))
+      .def("__enter__", [](PyTenantScope& s) -> PyTenantScope& {
+        s.scope = std::make_unique<TenantScope>(find_tenant(s.name));
+        return s;
+      }, py::return_value_policy::reference)
+      .def("__exit__", [](PyTenantScope& s, py::object, py::object, py::object) { s.scope.reset(); });
   m.def("set_transport_encryption", &net::set_transport_encryption, "secure mode of the RPC protocol: AES-256-GCM on every frame, keyed from the cluster token");
   m.def("transport_encryption", &net::transport_encryption);
   // test hook: AES-256-CTR by byte offset (net::OffsetCipher) over a buffer
@@ -1030,7 +1099,9 @@ void bind_control(py::module_& m) {
       .def_readwrite("enable_shm", &BlackbirdClientOptions::enable_shm)
       .def_readwrite("auth_token", &BlackbirdClientOptions::auth_token)
       .def_readwrite("encrypt_transport", &BlackbirdClientOptions::encrypt_transport)
-      .def_readwrite("auth_token_ro", &BlackbirdClientOptions::auth_token_ro);
+      .def_readwrite("auth_token_ro", &BlackbirdClientOptions::auth_token_ro)
+      .def_readwrite("tenant", &BlackbirdClientOptions::tenant)
+      .def_readwrite("tenant_secret", &BlackbirdClientOptions::tenant_secret);
   py::class_<BlackbirdClient, std::shared_ptr<BlackbirdClient>>(m, "BlackbirdClient")
       .def(py::init<BlackbirdClientOptions>(), py::arg("options") = BlackbirdClientOptions{})
       .def(py::init<std::shared_ptr<rpc::KeystoneApi>, BlackbirdClientOptions>(), py::arg("keystone"), py::arg("options") = BlackbirdClientOptions{})

@@ -58,6 +58,29 @@ std::string ec_reply(ErrorCode ec) {
   w.ec(ec);
   return w.take();
 }
+// Key-level ACL of the tenant on whose behalf this thread runs (net::RpcServer::dispatch sets the scope); members pass.
+bool may_read(const std::string& key) {
+  const Tenant* t = current_tenant();
+  return !t || t->may_read(key);
+}
+bool may_write(const std::string& key) {
+  const Tenant* t = current_tenant();
+  return !t || t->may_write(key);
+}
+bool may_read_all(const std::vector<ObjectKey>& keys) {
+  const Tenant* t = current_tenant();
+  if (!t) return true;
+  for (const auto& k : keys)
+    if (!t->may_read(k)) return false;
+  return true;
+}
+bool may_write_all(const std::vector<ObjectKey>& keys) {
+  const Tenant* t = current_tenant();
+  if (!t) return true;
+  for (const auto& k : keys)
+    if (!t->may_write(k)) return false;
+  return true;
+}
 std::string ecs_reply(const std::vector<ErrorCode>& v) {
   Writer w;
   w.ec(ErrorCode::OK);
@@ -86,22 +109,34 @@ void RpcService::leader_only(uint32_t method, net::RpcServer::Handler h) {
 void RpcService::register_handlers() {
   // what a holder of the read-only token may ask the Keystone: existence, placements (to read the data), statistics, listings
   rpc_.allow_read_only({M_OBJECT_EXISTS, M_GET_WORKERS, M_GET_CLUSTER_STATS, M_GET_VIEW_VERSION, M_BATCH_OBJECT_EXISTS, M_BATCH_GET_WORKERS,
-                        M_GET_MEMORY_POOLS, M_GET_WORKERS_INFO, M_LIST_OBJECTS, M_CLIENT_REGISTER, M_CLIENT_PING});
+                        M_GET_MEMORY_POOLS, M_GET_WORKERS_INFO, M_LIST_OBJECTS, M_CLIENT_REGISTER, M_CLIENT_PING, M_TENANT_USAGE});
+  // what a tenant may ask (common/tenant.h): the object-level calls, each checked against its key grants below; the
+  // cluster-management methods (workers, pools, migrate, drain, scrub, compact, remove_all) need an `admin` tenant or a member
+  rpc_.allow_tenants({M_OBJECT_EXISTS, M_GET_WORKERS, M_PUT_START, M_PUT_COMPLETE, M_PUT_CANCEL, M_REMOVE_OBJECT, M_GET_CLUSTER_STATS,
+                      M_GET_VIEW_VERSION, M_BATCH_OBJECT_EXISTS, M_BATCH_GET_WORKERS, M_BATCH_PUT_START, M_BATCH_PUT_COMPLETE, M_BATCH_PUT_CANCEL,
+                      M_BATCH_REMOVE_OBJECT, M_CLIENT_REGISTER, M_CLIENT_PING, M_GET_MEMORY_POOLS, M_LIST_OBJECTS, M_TENANT_USAGE});
+  auto denied = [ksm = keystone_] {
+    ksm->count_acl_denial();
+    return ErrorCode::ACCESS_DENIED;
+  };
   auto ks = keystone_;
   using C = const net::ConnPtr&;
   using S = const std::string&;
-  leader_only(M_OBJECT_EXISTS, [ks](C, S q) {
+  leader_only(M_OBJECT_EXISTS, [ks, denied](C, S q) {
     Reader r(q);
-    auto res = ks->object_exists(r.str());
+    const std::string key = r.str();
+    auto res = may_read(key) ? ks->object_exists(key) : Result<bool>(denied());
     Writer w;
     w.ec(res.error());
     w.boolean(res.ok() && res.value());
     return w.take();
   });
-  leader_only(M_GET_WORKERS, [ks](C, S q) {
+  leader_only(M_GET_WORKERS, [ks, denied](C, S q) {
     Reader r(q);
+    const std::string key = r.str();
     Writer w;
-    put_copies_result(w, ks->get_workers(r.str()));
+    if (!may_read(key)) put_copies_result(w, denied());
+    else put_copies_result(w, ks->get_workers(key));
     return w.take();
   });
   leader_only(M_PUT_START, [ks](C, S q) {
@@ -116,20 +151,23 @@ void RpcService::register_handlers() {
     else put_copies_result(w, ks->put_start(key, size, cfg, cid, node));
     return w.take();
   });
-  leader_only(M_PUT_COMPLETE, [ks](C, S q) {
+  leader_only(M_PUT_COMPLETE, [ks, denied](C, S q) {
     Reader r(q);
     const std::string key = r.str();
     ShardChecksums sums;
     get_sums(r, sums);
+    if (!may_write(key)) return ec_reply(denied());
     return ec_reply(r.ok() ? ks->put_complete(key, sums) : ErrorCode::INVALID_PARAMETERS);
   });
-  leader_only(M_PUT_CANCEL, [ks](C, S q) {
+  leader_only(M_PUT_CANCEL, [ks, denied](C, S q) {
     Reader r(q);
-    return ec_reply(ks->put_cancel(r.str()));
+    const std::string key = r.str();
+    return ec_reply(may_write(key) ? ks->put_cancel(key) : denied());
   });
-  leader_only(M_REMOVE_OBJECT, [ks](C, S q) {
+  leader_only(M_REMOVE_OBJECT, [ks, denied](C, S q) {
     Reader r(q);
-    return ec_reply(ks->remove_object(r.str()));
+    const std::string key = r.str();
+    return ec_reply(may_write(key) ? ks->remove_object(key) : denied());
   });
   leader_only(M_REMOVE_ALL_OBJECTS, [ks](C, S) {
     auto res = ks->remove_all_objects();
@@ -151,9 +189,11 @@ void RpcService::register_handlers() {
     w.i64(ks->get_view_version());
     return w.take();
   });
-  leader_only(M_BATCH_OBJECT_EXISTS, [ks](C, S q) {
+  leader_only(M_BATCH_OBJECT_EXISTS, [ks, denied](C, S q) {
     Reader r(q);
-    auto res = ks->batch_object_exists(get_keys(r));
+    const auto keys = get_keys(r);
+    if (!may_read_all(keys)) return ec_reply(denied());  // one key outside the grants refuses the batch (a whole-batch error code)
+    auto res = ks->batch_object_exists(keys);
     Writer w;
     w.ec(ErrorCode::OK);
     w.u32(static_cast<uint32_t>(res.size()));
@@ -163,9 +203,11 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
-  leader_only(M_BATCH_GET_WORKERS, [ks](C, S q) {
+  leader_only(M_BATCH_GET_WORKERS, [ks, denied](C, S q) {
     Reader r(q);
-    auto res = ks->batch_get_workers(get_keys(r));
+    const auto keys = get_keys(r);
+    if (!may_read_all(keys)) return ec_reply(denied());
+    auto res = ks->batch_get_workers(keys);
     Writer w;
     w.ec(ErrorCode::OK);
     w.u32(static_cast<uint32_t>(res.size()));
@@ -198,21 +240,26 @@ void RpcService::register_handlers() {
     for (const auto& e : res) pw.put(e);
     return w.take();
   });
-  leader_only(M_BATCH_PUT_COMPLETE, [ks](C, S q) {
+  leader_only(M_BATCH_PUT_COMPLETE, [ks, denied](C, S q) {
     Reader r(q);
     auto keys = get_keys(r);
     std::vector<ShardChecksums> sums(r.count(4));
     for (auto& s : sums) get_sums(r, s);
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    if (!may_write_all(keys)) return ec_reply(denied());
     return ecs_reply(ks->batch_put_complete(keys, sums));
   });
-  leader_only(M_BATCH_PUT_CANCEL, [ks](C, S q) {
+  leader_only(M_BATCH_PUT_CANCEL, [ks, denied](C, S q) {
     Reader r(q);
-    return ecs_reply(ks->batch_put_cancel(get_keys(r)));
+    const auto keys = get_keys(r);
+    if (!may_write_all(keys)) return ec_reply(denied());
+    return ecs_reply(ks->batch_put_cancel(keys));
   });
-  leader_only(M_BATCH_REMOVE_OBJECT, [ks](C, S q) {
+  leader_only(M_BATCH_REMOVE_OBJECT, [ks, denied](C, S q) {
     Reader r(q);
-    return ecs_reply(ks->batch_remove_object(get_keys(r)));
+    const auto keys = get_keys(r);
+    if (!may_write_all(keys)) return ec_reply(denied());
+    return ecs_reply(ks->batch_remove_object(keys));
   });
   leader_only(M_CLIENT_REGISTER, [ks](C, S q) {
     Reader r(q);
@@ -286,6 +333,7 @@ void RpcService::register_handlers() {
     const uint64_t limit = r.u64();
     const std::string after = r.str();
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
+    if (const Tenant* t = current_tenant(); t && !t->may_list(prefix)) return ec_reply(ErrorCode::ACCESS_DENIED);  // list inside a grant
     const auto v = ks->list_objects(prefix, static_cast<size_t>(limit), after);
     Writer w;
     w.ec(ErrorCode::OK);
@@ -335,6 +383,20 @@ void RpcService::register_handlers() {
     Reader r(q);
     return ec_reply(ks->remove_worker(r.str()));
   });
+  leader_only(M_TENANT_USAGE, [ks](C, S) {
+    const Tenant* me = current_tenant();  // a tenant sees its own line; members and admins see every tenant
+    Writer w;
+    w.ec(ErrorCode::OK);
+    std::vector<keystone::TenantUsage> v;
+    for (auto& u : ks->tenant_usage())
+      if (!me || me->admin || u.name == me->name) v.push_back(std::move(u));
+    w.u32(static_cast<uint32_t>(v.size()));
+    for (const auto& u : v) {
+      w.str(u.name);
+      for (uint64_t x : {u.used_bytes, u.objects, u.quota_bytes, u.max_objects}) w.u64(x);
+    }
+    return w.take();
+  });
 
   http_.route("/metrics", [ks, this](const std::string&, const std::string&) {
     net::HttpResponse r;
@@ -349,6 +411,16 @@ void RpcService::register_handlers() {
     counter("bb_rpc_secure_handshakes_total", "connections that switched to AES-256-GCM sealed frames (encrypt_transport)", rpc_.secure_handshakes());
     counter("bb_rpc_auth_failures_total", "denied token handshakes, requests without the token, frames that failed authentication", rpc_.auth_failures());
     counter("bb_rpc_read_only_denials_total", "requests of read-only members for methods outside the read-only list", rpc_.read_only_denials());
+    counter("bb_rpc_tenant_handshakes_total", "connections admitted as a tenant (common/tenant.h)", rpc_.tenant_handshakes());
+    counter("bb_rpc_tenant_denials_total", "tenant requests for methods outside the tenant list, or of tenants that left the table", rpc_.tenant_denials());
+    if (const auto tu = ks->tenant_usage(); !tu.empty()) {
+      r.body += "# HELP bb_tenant_used_bytes bytes a tenant holds (size x replicas of its live objects)\n# TYPE bb_tenant_used_bytes gauge\n";
+      for (const auto& u : tu) r.body += "bb_tenant_used_bytes{tenant=\"" + u.name + "\"} " + std::to_string(u.used_bytes) + "\n";
+      r.body += "# HELP bb_tenant_objects live objects put by a tenant\n# TYPE bb_tenant_objects gauge\n";
+      for (const auto& u : tu) r.body += "bb_tenant_objects{tenant=\"" + u.name + "\"} " + std::to_string(u.objects) + "\n";
+      r.body += "# HELP bb_tenant_quota_bytes a tenant's byte budget (0 = unlimited)\n# TYPE bb_tenant_quota_bytes gauge\n";
+      for (const auto& u : tu) r.body += "bb_tenant_quota_bytes{tenant=\"" + u.name + "\"} " + std::to_string(u.quota_bytes) + "\n";
+    }
     r.body += "# TYPE bb_rpc_shm_channels gauge\nbb_rpc_shm_channels " + std::to_string(rpc_.shm_channels()) + "\n";
     return r;
   });
@@ -374,6 +446,17 @@ ErrorCode RpcService::start() {
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   if (config_.encrypt_transport) net::set_transport_encryption(true);
   if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
+  if (!config_.tenants_file.empty()) {
+    std::string err;
+    if (load_tenants_file(config_.tenants_file, &err) != ErrorCode::OK) {
+      BB_LOG(ERROR) << "keystone: " << err;
+      return ErrorCode::INVALID_CONFIGURATION;
+    }
+  } else {
+    reload_tenants_if_changed();  // BB_TENANTS_FILE
+  }
+  if (!tenant_names().empty() && net::cluster_token().empty())
+    BB_LOG(WARNING) << "keystone: tenants are configured but there is no cluster token -- connections that present nothing are still members";
   ErrorCode ec = rpc_.start(hp->first, static_cast<uint16_t>(hp->second), std::max(1, config_.rpc_threads));
   if (ec != ErrorCode::OK) return ec;
   if (!config_.http_metrics_port.empty() && config_.http_metrics_port != "off") {
@@ -613,6 +696,19 @@ Result<keystone::ScrubReport> KeystoneRpcClient::scrub(const std::string& prefix
   for (uint64_t* v : {&rep.objects, &rep.copies, &rep.corrupt, &rep.healed, &rep.unrecoverable, &rep.unreachable}) *v = rd.u64();
   if (!rd.ok()) return ErrorCode::RPC_FAILED;
   return rep;
+}
+Result<std::vector<keystone::TenantUsage>> KeystoneRpcClient::tenant_usage() {
+  Writer w;
+  BB_RPC(M_TENANT_USAGE, w);
+  const ErrorCode ec = rd.ec();
+  if (ec != ErrorCode::OK) return ec;
+  std::vector<keystone::TenantUsage> v(rd.count(36));
+  for (auto& u : v) {
+    u.name = rd.str();
+    for (uint64_t* x : {&u.used_bytes, &u.objects, &u.quota_bytes, &u.max_objects}) *x = rd.u64();
+  }
+  if (!rd.ok()) return ErrorCode::RPC_FAILED;
+  return v;
 }
 ErrorCode KeystoneRpcClient::remove_worker(const WorkerId& id) {
   Writer w;

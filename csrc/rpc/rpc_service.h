@@ -25,7 +25,7 @@ enum Method : uint32_t {
   M_BATCH_GET_WORKERS, M_BATCH_PUT_START, M_BATCH_PUT_COMPLETE, M_BATCH_PUT_CANCEL,
   M_BATCH_REMOVE_OBJECT, M_CLIENT_REGISTER, M_CLIENT_PING, M_GET_MEMORY_POOLS,
   M_REGISTER_WORKER, M_REGISTER_MEMORY_POOL, M_WORKER_HEARTBEAT, M_REMOVE_WORKER,
-  M_MIGRATE_OBJECT, M_GET_WORKERS_INFO, M_LIST_OBJECTS, M_COMPACT_POOL, M_DRAIN_WORKER, M_SCRUB,
+  M_MIGRATE_OBJECT, M_GET_WORKERS_INFO, M_LIST_OBJECTS, M_COMPACT_POOL, M_DRAIN_WORKER, M_SCRUB, M_TENANT_USAGE,
 };
 
 // The keystone surface a client needs; implemented in-process and over TCP.
@@ -74,6 +74,8 @@ class KeystoneApi {
   virtual Result<size_t> drain_worker(const WorkerId& id) = 0;  // move everything off a worker, then remove it
   // re-hash stored copies at their workers and replace the ones that rotted (KeystoneService::scrub)
   virtual Result<keystone::ScrubReport> scrub(const std::string& prefix, size_t max_objects) = 0;
+  // what each tenant holds against its budget (a tenant sees only itself; common/tenant.h)
+  virtual Result<std::vector<keystone::TenantUsage>> tenant_usage() = 0;
   // identity used for locality-aware placement and session ownership
   void set_identity(std::string client_id, std::string node_id) {
     client_id_ = std::move(client_id);
@@ -111,6 +113,7 @@ class LocalKeystoneApi : public KeystoneApi {
   Result<size_t> compact_pool(const MemoryPoolId& pool, size_t max_moves) override { return ks_->compact_pool(pool, max_moves); }
   Result<size_t> drain_worker(const WorkerId& id) override { return ks_->drain_worker(id); }
   Result<keystone::ScrubReport> scrub(const std::string& prefix, size_t max_objects) override { return ks_->scrub(prefix, max_objects); }
+  Result<std::vector<keystone::TenantUsage>> tenant_usage() override { return ks_->tenant_usage(); }
   Result<std::vector<keystone::KeystoneService::ListedObject>> list_objects(const std::string& prefix, size_t limit,
                                                                             const std::string& start_after) override {
     return ks_->list_objects(prefix, limit, start_after);
@@ -201,6 +204,7 @@ class KeystoneRpcClient : public KeystoneApi {
   Result<size_t> compact_pool(const MemoryPoolId& pool, size_t max_moves) override;
   Result<size_t> drain_worker(const WorkerId& id) override;
   Result<keystone::ScrubReport> scrub(const std::string& prefix, size_t max_objects) override;
+  Result<std::vector<keystone::TenantUsage>> tenant_usage() override;
   Result<std::vector<keystone::KeystoneService::ListedObject>> list_objects(const std::string& prefix, size_t limit,
                                                                             const std::string& start_after) override;
   Result<size_t> remove_all_objects() override;

@@ -1,6 +1,8 @@
 #include "common/fault.h"
 #include "worker/worker_service.h"
 
+#include "common/tenant.h"
+
 #include <thread>
 
 #include <chrono>
@@ -37,6 +39,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("auth_token")) c.auth_token = w.at("auth_token").as_string();
   if (w.contains("encrypt_transport")) c.encrypt_transport = w.at("encrypt_transport").as_bool();
   if (w.contains("auth_token_ro")) c.auth_token_ro = w.at("auth_token_ro").as_string();
+  if (w.contains("tenants_file")) c.tenants_file = w.at("tenants_file").as_string();
   if (w.contains("at_rest_key")) c.at_rest_key = w.at("at_rest_key").as_string();
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
@@ -181,6 +184,15 @@ ErrorCode WorkerService::initialize() {
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   if (config_.encrypt_transport) net::set_transport_encryption(true);
   if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
+  if (!config_.tenants_file.empty()) {
+    std::string err;
+    if (load_tenants_file(config_.tenants_file, &err) != ErrorCode::OK) {
+      BB_LOG(ERROR) << "worker " << config_.worker_id << ": " << err;
+      return ErrorCode::INVALID_CONFIGURATION;
+    }
+  } else {
+    reload_tenants_if_changed();  // BB_TENANTS_FILE
+  }
   data_server_.set_socket_buffers(4 << 20);  // bulk transfers: fewer wake-ups per megabyte
   const unsigned hw = std::thread::hardware_concurrency();
   ErrorCode ec = data_server_.start(hp->first, static_cast<uint16_t>(hp->second), static_cast<int>(std::min(16u, std::max(4u, hw / 2))));
@@ -341,6 +353,7 @@ void WorkerService::heartbeat_loop() {
       sleep_cv_.wait_for(lk, std::chrono::seconds(config_.heartbeat_interval_sec), [this] { return !running_.load(); });
     }
     if (!running_.load()) return;
+    reload_tenants_if_changed();  // an edited tenant table takes effect without a restart
     if (drop_heartbeat_.load() || fault::fire("drop_heartbeat")) continue;
     ErrorCode ec = ErrorCode::OK;
     if (coord_) ec = coord_->put_with_ttl(cluster_prefix() + "heartbeat/" + config_.worker_id, std::to_string(std::time(nullptr)), config_.lease_ttl_sec);
@@ -504,6 +517,10 @@ uint64_t chunk_tile_sum(ChecksumAlgo algo, const uint8_t* data, uint64_t n, uint
 }  // namespace
 
 void WorkerService::register_data_handlers() {
+  // Tenants (common/tenant.h) move the bytes of the placements the Keystone gave them -- and nothing else: copies between
+  // pools, pulls, reservations and frees are the Keystone's and the members' business.  (Which shard a tenant may touch is
+  // decided where the placement is handed out: like an rkey in the reference, a placement is the capability.)
+  data_server_.allow_tenants({D_WRITE, D_READ, D_CHECKSUM, D_STATS});
   data_server_.allow_read_only({D_READ, D_CHECKSUM, D_STATS});  // read-only members read shards; they never write, copy, pull or reserve
   using C = const net::ConnPtr&;
   using S = const std::string&;
