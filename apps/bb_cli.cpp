@@ -32,6 +32,7 @@ int main(int argc, char** argv) {
   if (args.has("auth-token")) bb::net::set_cluster_token(args.get("auth-token"));  // else BB_AUTH_TOKEN / config
   if (args.has("encrypt-transport")) bb::net::set_transport_encryption(true);  // else BB_ENCRYPT_TRANSPORT / config
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
+  if (args.has("http-token")) bb::net::set_http_token(args.get("http-token"));  // else BB_HTTP_TOKEN / config: bearer token of /metrics and /stats
   if (args.has("tenant")) bb::set_client_tenant(args.get("tenant"), args.get("tenant-secret"));  // else BB_TENANT / BB_TENANT_SECRET (common/tenant.h)
   if (args.positional.empty() || args.has("help")) {
     std::printf("usage: bb-cli [--keystone host:port] <put KEY FILE | get KEY [OUT] | exists KEY | remove KEY | where KEY | ls [PREFIX] | rm-prefix PREFIX | migrate KEY CLASS | stats | pools | workers | remove-worker ID | drain-worker ID | scrub [PREFIX] [MAX] | compact POOL | tenants | smoke | metrics --http host:port> [--auth-token T | --auth-token-ro T | --tenant NAME --tenant-secret S] [--encrypt-transport]\n");

@@ -19,6 +19,8 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <cctype>
 #include <cerrno>
 #include <chrono>
 #include <thread>
@@ -1392,6 +1394,49 @@ Result<std::string> RpcClient::call_scatter(uint32_t method, const std::string& 
 }
 
 // ================================================================ HTTP
+namespace {
+std::mutex g_http_mu;
+std::string g_http_token;
+bool g_http_token_init = false;
+// "authorization: bearer <token>" among the header lines of `head` (names and the scheme are case-insensitive)
+bool bearer_matches(const std::string& head, const std::string& token) {
+  size_t pos = head.find("\r\n");
+  while (pos != std::string::npos) {
+    const size_t line = pos + 2;
+    const size_t eol = head.find("\r\n", line);
+    const std::string_view l(head.data() + line, (eol == std::string::npos ? head.size() : eol) - line);
+    static constexpr std::string_view kName = "authorization:";
+    if (l.size() > kName.size() && std::equal(kName.begin(), kName.end(), l.begin(), [](char a, char b) { return a == std::tolower(static_cast<unsigned char>(b)); })) {
+      std::string_view v = l.substr(kName.size());
+      while (!v.empty() && v.front() == ' ') v.remove_prefix(1);
+      static constexpr std::string_view kScheme = "bearer ";
+      if (v.size() > kScheme.size() && std::equal(kScheme.begin(), kScheme.end(), v.begin(), [](char a, char b) { return a == std::tolower(static_cast<unsigned char>(b)); })) {
+        v.remove_prefix(kScheme.size());
+        while (!v.empty() && (v.back() == ' ' || v.back() == '\t')) v.remove_suffix(1);
+        // compare digests, not strings: constant time whatever the lengths
+        const Sha256Digest a = hmac_sha256("bb-http", std::string(v)), b = hmac_sha256("bb-http", token);
+        return mac_equal(reinterpret_cast<const char*>(a.data()), reinterpret_cast<const char*>(b.data()), a.size());
+      }
+    }
+    pos = eol;
+  }
+  return false;
+}
+}  // namespace
+void set_http_token(const std::string& token) {
+  std::lock_guard<std::mutex> lk(g_http_mu);
+  g_http_token = token;
+  g_http_token_init = true;
+}
+std::string http_token() {
+  std::lock_guard<std::mutex> lk(g_http_mu);
+  if (!g_http_token_init) {
+    if (const char* e = std::getenv("BB_HTTP_TOKEN")) g_http_token = e;
+    g_http_token_init = true;
+  }
+  return g_http_token;
+}
+
 bool HttpServer::on_data(const ConnPtr& c) {
   std::string& in = c->inbuf();
   while (true) {
@@ -1411,9 +1456,13 @@ bool HttpServer::on_data(const ConnPtr& c) {
       target.resize(qm);
     }
     HttpResponse r;
+    const std::string need = http_token();
     if (method != "GET" && method != "HEAD") {
       r.status = 405;
       r.body = "method not allowed\n";
+    } else if (!need.empty() && target != "/healthz" && !bearer_matches(head, need)) {
+      r.status = 401;
+      r.body = "unauthorized\n";
     } else {
       auto it = routes_.find(target);
       if (it == routes_.end()) {
@@ -1428,8 +1477,8 @@ bool HttpServer::on_data(const ConnPtr& c) {
         }
       }
     }
-    const char* reason = r.status == 200 ? "OK" : r.status == 404 ? "Not Found" : r.status == 405 ? "Method Not Allowed" : r.status == 503 ? "Service Unavailable" : "Error";
-    std::string out = "HTTP/1.1 " + std::to_string(r.status) + " " + reason + "\r\nContent-Type: " + r.content_type +
+    const char* reason = r.status == 200 ? "OK" : r.status == 404 ? "Not Found" : r.status == 405 ? "Method Not Allowed" : r.status == 503 ? "Service Unavailable" : r.status == 401 ? "Unauthorized" : "Error";
+    std::string out = "HTTP/1.1 " + std::to_string(r.status) + " " + reason + (r.status == 401 ? "\r\nWWW-Authenticate: Bearer" : "") + "\r\nContent-Type: " + r.content_type +
                       "\r\nContent-Length: " + std::to_string(r.body.size()) + "\r\nConnection: keep-alive\r\n\r\n";
     if (method != "HEAD") out += r.body;
     if (!c->send(out)) return false;
@@ -1440,7 +1489,8 @@ Result<std::string> http_get(const std::string& host, uint16_t port, const std::
   std::string err;
   int fd = tcp_connect(host, port, timeout_ms, &err);
   if (fd < 0) return ErrorCode::CONNECTION_FAILED;
-  const std::string req = "GET " + path + " HTTP/1.1\r\nHost: " + host + "\r\nConnection: close\r\n\r\n";
+  const std::string bearer = http_token();
+  const std::string req = "GET " + path + " HTTP/1.1\r\nHost: " + host + (bearer.empty() ? "" : "\r\nAuthorization: Bearer " + bearer) + "\r\nConnection: close\r\n\r\n";
   std::string resp;
   bool ok = send_all(fd, req.data(), req.size(), timeout_ms);
   size_t body_at = std::string::npos, content_len = std::string::npos;

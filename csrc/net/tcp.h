@@ -368,6 +368,13 @@ struct HttpResponse {
   std::string body;
 };
 
+// The observability endpoints (/metrics, /stats) name workers, pools, tenants and their holdings.  With a token set --
+// `http_auth_token:` in keystone / worker YAML, --http-token, BB_HTTP_TOKEN -- every route except /healthz (liveness probes
+// carry no credentials) answers 401 unless the request has `Authorization: Bearer <token>` (what a Prometheus scrape
+// config's `bearer_token` sends); http_get() of a process that holds the token sends it.
+void set_http_token(const std::string& token);
+std::string http_token();
+
 class HttpServer : public TcpServer {
  public:
   using Route = std::function<HttpResponse(const std::string& path, const std::string& query)>;

@@ -940,6 +940,7 @@ void bind_control(py::module_& m) {
         return s;
       }, py::return_value_policy::reference)
       .def("__exit__", [](PyTenantScope& s, py::object, py::object, py::object) { s.scope.reset(); });
+  m.def("set_http_token", &net::set_http_token, "bearer token of the HTTP endpoints (/metrics, /stats) served and fetched by this process; \"\" = open");
   m.def("set_transport_encryption", &net::set_transport_encryption, "secure mode of the RPC protocol: AES-256-GCM on every frame, keyed from the cluster token");
   m.def("transport_encryption", &net::transport_encryption);
   // test hook: AES-256-CTR by byte offset (net::OffsetCipher) over a buffer

@@ -446,6 +446,7 @@ ErrorCode RpcService::start() {
   if (!config_.auth_token.empty()) net::set_cluster_token(config_.auth_token);
   if (config_.encrypt_transport) net::set_transport_encryption(true);
   if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
+  if (!config_.http_auth_token.empty()) net::set_http_token(config_.http_auth_token);
   if (!config_.tenants_file.empty()) {
     std::string err;
     if (load_tenants_file(config_.tenants_file, &err) != ErrorCode::OK) {

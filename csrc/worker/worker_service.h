@@ -65,6 +65,7 @@ struct WorkerServiceConfig {
   std::string auth_token;  // shared cluster token (net/tcp.h); empty = BB_AUTH_TOKEN / open cluster
   bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h)
   std::string auth_token_ro;       // read-only members' token (net/tcp.h)
+  std::string http_auth_token;     // bearer token of the worker's /metrics and /stats (net/tcp.h); BB_HTTP_TOKEN
   std::string tenants_file;        // tenant table (common/tenant.h): the data server admits tenants for reads and writes; BB_TENANTS_FILE
   std::string at_rest_key;         // passphrase of pools with encrypt_at_rest (BB_AT_REST_KEY is the default)
   CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects

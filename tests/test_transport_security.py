@@ -375,3 +375,69 @@ def test_read_only_token_reads_but_cannot_write(tmp_path):
                 p.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 p.kill()
+
+
+def test_http_endpoints_need_the_bearer_token_when_one_is_set(bb, tmp_path):
+    """`http_auth_token` / BB_HTTP_TOKEN / --http-token: /metrics and /stats of the Keystone and of a worker answer 401
+    without `Authorization: Bearer <token>`, /healthz stays open for liveness probes, the tools send the token."""
+    import urllib.error
+    import urllib.request
+
+    HTTP = "scrape-secret"
+    base = {k: v for k, v in os.environ.items() if not k.startswith("BB_")}
+    cport, rport, hport, wport = free_port(), free_port(), free_port(), free_port()
+    procs = []
+    try:
+        procs.append(subprocess.Popen([os.path.join(BIN, "bb-coord"), "--listen", f"127.0.0.1:{cport}"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=base))
+        assert wait_port(cport)
+        procs.append(subprocess.Popen([os.path.join(BIN, "bb-keystone"), os.path.join(ROOT, "configs", "keystone.yaml"), "--coord-endpoints", f"127.0.0.1:{cport}",
+                                       "--listen-address", f"127.0.0.1:{rport}", "--http-port", str(hport), "--cluster-id", "http", "--http-token", HTTP],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=base))
+        assert wait_port(rport) and wait_port(hport)
+        cfg = tmp_path / "w.yaml"
+        cfg.write_text(f'worker: {{worker_id: "wh", node_id: "node-wh", http_metrics_port: {wport}, http_auth_token: "{HTTP}"}}\n'
+                       'storage_pools:\n  - {pool_id: "ram-wh", storage_class: "RAM_CPU", size_bytes: 16_MB}\n')
+        procs.append(subprocess.Popen([os.path.join(BIN, "bb-worker"), "--config", str(cfg), "--coord-endpoints", f"127.0.0.1:{cport}", "--cluster-id", "http"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=base))
+        assert wait_port(wport)
+
+        def get(port, path, token=None, scheme="Bearer"):
+            req = urllib.request.Request(f"http://127.0.0.1:{port}{path}")
+            if token is not None:
+                req.add_header("Authorization", f"{scheme} {token}")
+            try:
+                with urllib.request.urlopen(req, timeout=5) as r:
+                    return r.status, r.read().decode(), dict(r.headers)
+            except urllib.error.HTTPError as e:
+                return e.code, e.read().decode(), dict(e.headers)
+
+        for port in (hport, wport):
+            st, body, hdr = get(port, "/metrics")
+            assert st == 401 and "bb_" not in body and hdr.get("WWW-Authenticate") == "Bearer"
+            assert get(port, "/stats")[0] == 401
+            assert get(port, "/metrics", "guess")[0] == 401 and get(port, "/metrics", HTTP + "x")[0] == 401 and get(port, "/metrics", "")[0] == 401
+            assert get(port, "/metrics", HTTP, scheme="Basic")[0] == 401
+            st, body, _ = get(port, "/metrics", HTTP)
+            assert st == 200 and "bb_" in body
+            assert get(port, "/metrics", HTTP, scheme="bearer")[0] == 200  # the scheme is case-insensitive
+            assert get(port, "/healthz")[0] == 200  # liveness probes carry no credentials
+            assert get(port, "/nope", HTTP)[0] == 404 and get(port, "/nope")[0] == 401  # unknown paths tell a stranger nothing either
+        # the tools: flag, environment, and the in-process helper
+        assert cli(base, "metrics", "--http", f"127.0.0.1:{hport}").returncode != 0
+        r = cli(base, "metrics", "--http", f"127.0.0.1:{hport}", "--http-token", HTTP)
+        assert r.returncode == 0 and "bb_put_start_total" in r.stdout
+        assert "bb_put_start_total" in cli(dict(base, BB_HTTP_TOKEN=HTTP), "metrics", "--http", f"127.0.0.1:{hport}").stdout
+        assert bb.http_get("127.0.0.1", hport, "/metrics")[0] == 401
+        bb.set_http_token(HTTP)
+        try:
+            assert bb.http_get("127.0.0.1", hport, "/metrics")[0] == 200
+        finally:
+            bb.set_http_token("")
+    finally:
+        for p in reversed(procs):
+            p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                p.kill()
