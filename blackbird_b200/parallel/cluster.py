@@ -215,10 +215,14 @@ class LocalCluster:
             st.flush_events()
         return w
 
-    def client(self, node_id: str = "", io_parallelism: int = 4, in_process: bool = False):
+    def client(self, node_id: str = "", io_parallelism: int = 4, in_process: bool = False, tenant: str = "", tenant_secret: str = ""):
+        """A connected client.  `tenant` / `tenant_secret`: connect as that tenant (csrc/common/tenant.h) instead of as a
+        member -- the identity is process-wide (like the cluster token), so it also covers this client's later data-server
+        connections; pass tenant="" (the default) to go back to being a member."""
         if in_process or self.rpc is None:
             c = _bb.BlackbirdClient(_bb.LocalKeystoneApi(self.keystone), _bb.BlackbirdClientOptions(node_id=node_id, io_parallelism=io_parallelism))
         else:
+            _bb.set_client_tenant(tenant, tenant_secret)
             c = _bb.BlackbirdClient(_bb.BlackbirdClientOptions("127.0.0.1", self.rpc.rpc_port, 30000, io_parallelism, node_id))
         assert c.connect() == _bb.ErrorCode.OK
         return c

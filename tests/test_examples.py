@@ -26,3 +26,8 @@ def test_cpp_sdk_example_against_a_live_cluster(bb):
     with LocalCluster("sdk-example", n_workers=2, pool_bytes=16 << 20) as c:
         r = _run(os.path.join(os.environ.get("BB_BIN_DIR", os.path.join(ROOT, "bin")), "bb-example-sdk-put-get"), f"127.0.0.1:{c.rpc.rpc_port}")
         assert r.returncode == 0 and "sdk example OK" in r.stdout and "2 copies" in r.stdout, r.stdout + r.stderr
+
+
+def test_tenants_demo_example():
+    r = _run(sys.executable, "examples/tenants_demo.py")
+    assert r.returncode == 0 and "tenants demo OK" in r.stdout and "QUOTA_EXCEEDED" in r.stdout and r.stdout.count("ACCESS_DENIED") == 3, r.stdout + r.stderr
