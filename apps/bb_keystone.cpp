@@ -19,7 +19,7 @@ int main(int argc, char** argv) {
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.has("http-token")) bb::net::set_http_token(args.get("http-token"));  // else BB_HTTP_TOKEN / config: bearer token of /metrics and /stats
   if (args.has("help")) {
-    std::printf("usage: bb-keystone [config.yaml] [--etcd-endpoints E] [--listen-address A] [--http-port P] [--cluster-id C] [--enable-ha] [--service-id S] [--tenants-file F]\n");
+    std::printf("usage: bb-keystone [config.yaml] [--etcd-endpoints E] [--listen-address A] [--http-port P] [--cluster-id C] [--enable-ha] [--service-id S] [--tenants-file F] [--audit-log F]\n");
     return 0;
   }
   bb::set_log_level(bb::LogLevel::INFO);
@@ -35,6 +35,7 @@ int main(int argc, char** argv) {
   if (args.has("etcd-endpoints")) cfg.etcd_endpoints = args.get("etcd-endpoints");
   if (args.has("coord-endpoints")) cfg.etcd_endpoints = args.get("coord-endpoints");
   if (!args.has("auth-token") && !cfg.auth_token.empty()) bb::net::set_cluster_token(cfg.auth_token);  // before the coordination client connects
+  if (args.has("audit-log")) cfg.audit_log = args.get("audit-log");  // else `audit_log:` / BB_AUDIT_LOG (common/audit.h)
   if (args.has("tenants-file")) cfg.tenants_file = args.get("tenants-file");  // else `tenants_file:` / BB_TENANTS_FILE (common/tenant.h)
   if (args.has("listen-address")) cfg.listen_address = args.get("listen-address");
   if (args.has("http-port")) cfg.http_metrics_port = args.get("http-port");

@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
   if (args.has("auth-token-ro")) bb::net::set_cluster_token_ro(args.get("auth-token-ro"));  // else BB_AUTH_TOKEN_RO / config
   if (args.has("http-token")) bb::net::set_http_token(args.get("http-token"));  // else BB_HTTP_TOKEN / config: bearer token of /metrics and /stats
   if (args.has("help") || (!args.has("config") && args.positional.empty())) {
-    std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port] [--http-port P] [--tenants-file F]\n");
+    std::printf("usage: bb-worker --config worker.yaml [--worker-id W] [--node-id N] [--coord-endpoints E] [--keystone host:port] [--data-endpoint host:port] [--http-port P] [--tenants-file F] [--audit-log F]\n");
     return args.has("help") ? 0 : 2;
   }
   bb::set_log_level(bb::LogLevel::INFO);
@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
   }
   if (!args.has("auth-token") && !cfg.auth_token.empty()) bb::net::set_cluster_token(cfg.auth_token);  // before any connection is made
   if (args.has("auth-token")) cfg.auth_token = args.get("auth-token");
+  if (args.has("audit-log")) cfg.audit_log = args.get("audit-log");  // else `audit_log:` / BB_AUDIT_LOG (common/audit.h)
   if (args.has("tenants-file")) cfg.tenants_file = args.get("tenants-file");  // else `tenants_file:` / BB_TENANTS_FILE (common/tenant.h)
   if (args.has("worker-id")) cfg.worker_id = args.get("worker-id");
   if (args.has("node-id")) cfg.node_id = args.get("node-id");

@@ -155,6 +155,7 @@ Result<KeystoneConfig> KeystoneConfig::from_json(const Json& root, std::string* 
   if (k.contains("auth_token_ro")) c.auth_token_ro = k.at("auth_token_ro").as_string();
   if (k.contains("tenants_file")) c.tenants_file = k.at("tenants_file").as_string();
   if (k.contains("http_auth_token")) c.http_auth_token = k.at("http_auth_token").as_string();
+  if (k.contains("audit_log")) c.audit_log = k.at("audit_log").as_string();
   if (k.contains("worker_heartbeat_ttl_sec")) c.worker_heartbeat_ttl_sec = k.at("worker_heartbeat_ttl_sec").as_int(c.worker_heartbeat_ttl_sec);
   if (k.contains("service_registration_ttl_sec")) c.service_registration_ttl_sec = k.at("service_registration_ttl_sec").as_int(c.service_registration_ttl_sec);
   if (k.contains("service_refresh_interval_sec")) c.service_refresh_interval_sec = k.at("service_refresh_interval_sec").as_int(c.service_refresh_interval_sec);

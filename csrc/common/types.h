@@ -169,6 +169,7 @@ struct KeystoneConfig {
   std::string auth_token_ro;       // second secret: members that prove only this one are read-only (net/tcp.h); BB_AUTH_TOKEN_RO
   bool encrypt_transport = false;  // AES-256-GCM on every RPC frame, keyed from the token (net/tcp.h secure mode); BB_ENCRYPT_TRANSPORT=1
   std::string http_auth_token;     // /metrics and /stats need `Authorization: Bearer <this>` (net/tcp.h); BB_HTTP_TOKEN
+  std::string audit_log;           // append-only JSON-lines trail of security events and management calls (common/audit.h); BB_AUDIT_LOG
   std::string tenants_file;        // YAML table of tenants: own secret, key-prefix ACL, byte / object budget (common/tenant.h); BB_TENANTS_FILE
   int64_t worker_heartbeat_ttl_sec = 30;
   int64_t service_registration_ttl_sec = 60;

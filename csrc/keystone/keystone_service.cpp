@@ -1,6 +1,8 @@
 #include "common/fault.h"
 #include "keystone/keystone_service.h"
 
+#include "common/audit.h"
+
 #include <unordered_set>
 
 #include <algorithm>
@@ -233,7 +235,8 @@ void KeystoneService::health_loop() {
       for (auto it = clients_.begin(); it != clients_.end();)
         it = (now - it->second.last_ping > std::chrono::seconds(config_.client_ttl_sec)) ? clients_.erase(it) : std::next(it);
     }
-    reload_tenants_if_changed();  // an edited tenant table (grants, budgets, revocations) takes effect without a restart
+    if (reload_tenants_if_changed())  // an edited tenant table (grants, budgets, revocations) takes effect without a restart
+      audit::event("tenants_reloaded", {{"who", "keystone"}, {"count", std::to_string(tenant_names().size())}});
     run_eviction_once();
     run_repair_once();
     run_promotion_once();
@@ -710,10 +713,12 @@ Result<std::vector<CopyPlacement>> KeystoneService::put_start_locked(const Objec
   if (ten) {
     if (!ten->may_write(key)) {
       metrics_.inc("tenant_acl_denials_total");
+      if (audit::enabled()) audit::event("acl_denied", {{"who", ten->name}, {"op", "write"}, {"key", key}});
       return ErrorCode::ACCESS_DENIED;
     }
     if (!tenant_admit(*ten, charge)) {
       metrics_.inc("tenant_quota_denials_total");
+      if (audit::enabled()) audit::event("quota_denied", {{"who", ten->name}, {"key", key}, {"bytes", std::to_string(charge)}});
       return ErrorCode::QUOTA_EXCEEDED;
     }
   }

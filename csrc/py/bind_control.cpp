@@ -4,6 +4,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "common/audit.h"
 #include "common/tenant.h"
 #include "alloc/allocator.h"
 #include "client/blackbird_client.h"
@@ -940,6 +941,8 @@ void bind_control(py::module_& m) {
         return s;
       }, py::return_value_policy::reference)
       .def("__exit__", [](PyTenantScope& s, py::object, py::object, py::object) { s.scope.reset(); });
+  m.def("audit_open", &audit::open, "append-only JSON-lines audit trail of this process's servers (common/audit.h); \"\" closes it");
+  m.def("audit_events_written", &audit::events_written);
   m.def("set_http_token", &net::set_http_token, "bearer token of the HTTP endpoints (/metrics, /stats) served and fetched by this process; \"\" = open");
   m.def("set_transport_encryption", &net::set_transport_encryption, "secure mode of the RPC protocol: AES-256-GCM on every frame, keyed from the cluster token");
   m.def("transport_encryption", &net::transport_encryption);

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <thread>
 
+#include "common/audit.h"
 #include "common/log.h"
 #include "rpc/wire.h"
 
@@ -59,26 +60,30 @@ std::string ec_reply(ErrorCode ec) {
   return w.take();
 }
 // Key-level ACL of the tenant on whose behalf this thread runs (net::RpcServer::dispatch sets the scope); members pass.
+bool acl_refused(const char* op, const std::string& key) {
+  if (audit::enabled()) audit::event("acl_denied", {{"op", op}, {"key", key}});
+  return false;
+}
 bool may_read(const std::string& key) {
   const Tenant* t = current_tenant();
-  return !t || t->may_read(key);
+  return !t || t->may_read(key) || acl_refused("read", key);
 }
 bool may_write(const std::string& key) {
   const Tenant* t = current_tenant();
-  return !t || t->may_write(key);
+  return !t || t->may_write(key) || acl_refused("write", key);
 }
 bool may_read_all(const std::vector<ObjectKey>& keys) {
   const Tenant* t = current_tenant();
   if (!t) return true;
   for (const auto& k : keys)
-    if (!t->may_read(k)) return false;
+    if (!t->may_read(k)) return acl_refused("read", k);
   return true;
 }
 bool may_write_all(const std::vector<ObjectKey>& keys) {
   const Tenant* t = current_tenant();
   if (!t) return true;
   for (const auto& k : keys)
-    if (!t->may_write(k)) return false;
+    if (!t->may_write(k)) return acl_refused("write", k);
   return true;
 }
 std::string ecs_reply(const std::vector<ErrorCode>& v) {
@@ -118,6 +123,11 @@ void RpcService::register_handlers() {
   auto denied = [ksm = keystone_] {
     ksm->count_acl_denial();
     return ErrorCode::ACCESS_DENIED;
+  };
+  // audit trail of the cluster-management calls (common/audit.h): who asked for what, and how it ended
+  auto admin = [](const char* op, const std::string& arg, ErrorCode ec) {
+    if (audit::enabled()) audit::event("admin", {{"op", op}, {"arg", arg}, {"result", to_string(ec)}});
+    return ec;
   };
   auto ks = keystone_;
   using C = const net::ConnPtr&;
@@ -169,8 +179,9 @@ void RpcService::register_handlers() {
     const std::string key = r.str();
     return ec_reply(may_write(key) ? ks->remove_object(key) : denied());
   });
-  leader_only(M_REMOVE_ALL_OBJECTS, [ks](C, S) {
+  leader_only(M_REMOVE_ALL_OBJECTS, [ks, admin](C, S) {
     auto res = ks->remove_all_objects();
+    admin("remove_all_objects", res.ok() ? std::to_string(res.value()) : "", res.ok() ? ErrorCode::OK : res.error());
     Writer w;
     w.ec(res.error());
     w.u64(res.ok() ? res.value() : 0);
@@ -303,12 +314,12 @@ void RpcService::register_handlers() {
     Reader r(q);
     return ec_reply(ks->worker_heartbeat(r.str()));
   });
-  leader_only(M_MIGRATE_OBJECT, [ks](C, S q) {
+  leader_only(M_MIGRATE_OBJECT, [ks, admin](C, S q) {
     Reader r(q);
     const std::string key = r.str();
     const auto target = static_cast<StorageClass>(r.u32());
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
-    return ec_reply(ks->migrate_object(key, target));
+    return ec_reply(admin("migrate_object", key, ks->migrate_object(key, target)));
   });
   rpc_.register_method(M_GET_WORKERS_INFO, [ks](C, S) {
     std::vector<keystone::WorkerInfo> v;
@@ -333,7 +344,10 @@ void RpcService::register_handlers() {
     const uint64_t limit = r.u64();
     const std::string after = r.str();
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
-    if (const Tenant* t = current_tenant(); t && !t->may_list(prefix)) return ec_reply(ErrorCode::ACCESS_DENIED);  // list inside a grant
+    if (const Tenant* t = current_tenant(); t && !t->may_list(prefix)) {  // list inside a grant
+      acl_refused("list", prefix);
+      return ec_reply(ErrorCode::ACCESS_DENIED);
+    }
     const auto v = ks->list_objects(prefix, static_cast<size_t>(limit), after);
     Writer w;
     w.ec(ErrorCode::OK);
@@ -346,42 +360,46 @@ void RpcService::register_handlers() {
     }
     return w.take();
   });
-  leader_only(M_DRAIN_WORKER, [ks](C, S q) {
+  leader_only(M_DRAIN_WORKER, [ks, admin](C, S q) {
     Reader r(q);
     const std::string id = r.str();
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
     auto res = ks->drain_worker(id);
+    admin("drain_worker", id, res.ok() ? ErrorCode::OK : res.error());
     Writer w;
     w.ec(res.ok() ? ErrorCode::OK : res.error());
     w.u64(res.ok() ? res.value() : 0);
     return w.take();
   });
-  leader_only(M_SCRUB, [ks](C, S q) {
+  leader_only(M_SCRUB, [ks, admin](C, S q) {
     Reader r(q);
     const std::string prefix = r.str();
     const uint64_t max_objects = r.u64();
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
     auto res = ks->scrub(prefix, static_cast<size_t>(max_objects));
+    admin("scrub", prefix, res.ok() ? ErrorCode::OK : res.error());
     Writer w;
     w.ec(res.ok() ? ErrorCode::OK : res.error());
     if (res.ok())
       for (uint64_t v : {res.value().objects, res.value().copies, res.value().corrupt, res.value().healed, res.value().unrecoverable, res.value().unreachable}) w.u64(v);
     return w.take();
   });
-  leader_only(M_COMPACT_POOL, [ks](C, S q) {
+  leader_only(M_COMPACT_POOL, [ks, admin](C, S q) {
     Reader r(q);
     const std::string pool = r.str();
     const uint64_t max_moves = r.u64();
     if (!r.ok()) return ec_reply(ErrorCode::INVALID_PARAMETERS);
     auto res = ks->compact_pool(pool, static_cast<size_t>(max_moves));
+    admin("compact_pool", pool, res.ok() ? ErrorCode::OK : res.error());
     Writer w;
     w.ec(res.ok() ? ErrorCode::OK : res.error());
     if (res.ok()) w.u64(res.value());
     return w.take();
   });
-  leader_only(M_REMOVE_WORKER, [ks](C, S q) {
+  leader_only(M_REMOVE_WORKER, [ks, admin](C, S q) {
     Reader r(q);
-    return ec_reply(ks->remove_worker(r.str()));
+    const std::string id = r.str();
+    return ec_reply(admin("remove_worker", id, ks->remove_worker(id)));
   });
   leader_only(M_TENANT_USAGE, [ks](C, S) {
     const Tenant* me = current_tenant();  // a tenant sees its own line; members and admins see every tenant
@@ -411,6 +429,7 @@ void RpcService::register_handlers() {
     counter("bb_rpc_secure_handshakes_total", "connections that switched to AES-256-GCM sealed frames (encrypt_transport)", rpc_.secure_handshakes());
     counter("bb_rpc_auth_failures_total", "denied token handshakes, requests without the token, frames that failed authentication", rpc_.auth_failures());
     counter("bb_rpc_read_only_denials_total", "requests of read-only members for methods outside the read-only list", rpc_.read_only_denials());
+    if (audit::enabled()) counter("bb_audit_events_total", "lines appended to the audit log (common/audit.h)", audit::events_written());
     counter("bb_rpc_tenant_handshakes_total", "connections admitted as a tenant (common/tenant.h)", rpc_.tenant_handshakes());
     counter("bb_rpc_tenant_denials_total", "tenant requests for methods outside the tenant list, or of tenants that left the table", rpc_.tenant_denials());
     if (const auto tu = ks->tenant_usage(); !tu.empty()) {
@@ -447,6 +466,10 @@ ErrorCode RpcService::start() {
   if (config_.encrypt_transport) net::set_transport_encryption(true);
   if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
   if (!config_.http_auth_token.empty()) net::set_http_token(config_.http_auth_token);
+  if (!config_.audit_log.empty() && !audit::open(config_.audit_log)) {
+    BB_LOG(ERROR) << "keystone: cannot open the audit log " << config_.audit_log;
+    return ErrorCode::INVALID_CONFIGURATION;
+  }
   if (!config_.tenants_file.empty()) {
     std::string err;
     if (load_tenants_file(config_.tenants_file, &err) != ErrorCode::OK) {

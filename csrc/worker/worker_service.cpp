@@ -1,6 +1,7 @@
 #include "common/fault.h"
 #include "worker/worker_service.h"
 
+#include "common/audit.h"
 #include "common/tenant.h"
 
 #include <thread>
@@ -41,6 +42,7 @@ Result<WorkerServiceConfig> worker_config_from_json(const Json& root, std::strin
   if (w.contains("auth_token_ro")) c.auth_token_ro = w.at("auth_token_ro").as_string();
   if (w.contains("tenants_file")) c.tenants_file = w.at("tenants_file").as_string();
   if (w.contains("http_auth_token")) c.http_auth_token = w.at("http_auth_token").as_string();
+  if (w.contains("audit_log")) c.audit_log = w.at("audit_log").as_string();
   if (w.contains("at_rest_key")) c.at_rest_key = w.at("at_rest_key").as_string();
   if (w.contains("ucx_endpoint")) c.ucx_endpoint = w.at("ucx_endpoint").as_string();
   if (w.contains("data_endpoint")) c.ucx_endpoint = w.at("data_endpoint").as_string();
@@ -186,6 +188,10 @@ ErrorCode WorkerService::initialize() {
   if (config_.encrypt_transport) net::set_transport_encryption(true);
   if (!config_.auth_token_ro.empty()) net::set_cluster_token_ro(config_.auth_token_ro);
   if (!config_.http_auth_token.empty()) net::set_http_token(config_.http_auth_token);
+  if (!config_.audit_log.empty() && !audit::open(config_.audit_log)) {
+    BB_LOG(ERROR) << "worker " << config_.worker_id << ": cannot open the audit log " << config_.audit_log;
+    return ErrorCode::INVALID_CONFIGURATION;
+  }
   if (!config_.tenants_file.empty()) {
     std::string err;
     if (load_tenants_file(config_.tenants_file, &err) != ErrorCode::OK) {

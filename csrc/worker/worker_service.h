@@ -66,6 +66,7 @@ struct WorkerServiceConfig {
   bool encrypt_transport = false;  // secure mode of the RPC protocol (net/tcp.h)
   std::string auth_token_ro;       // read-only members' token (net/tcp.h)
   std::string http_auth_token;     // bearer token of the worker's /metrics and /stats (net/tcp.h); BB_HTTP_TOKEN
+  std::string audit_log;           // audit trail of this worker's data server (refused handshakes, denied methods); BB_AUDIT_LOG
   std::string tenants_file;        // tenant table (common/tenant.h): the data server admits tenants for reads and writes; BB_TENANTS_FILE
   std::string at_rest_key;         // passphrase of pools with encrypt_at_rest (BB_AT_REST_KEY is the default)
   CxlTransportConfig transport;     // `transport:` block (cxl_worker.yaml); drives the advertised interconnects

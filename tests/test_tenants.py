@@ -225,7 +225,8 @@ def test_tenants_end_to_end_over_rpc(bb, tmp_path, sealed):
     tfile = tmp_path / "tenants.yaml"
     tfile.write_text(TABLE)
     base = {k: v for k, v in os.environ.items() if not k.startswith("BB_")}
-    srv_env = dict(base, BB_AUTH_TOKEN=TOKEN, BB_TENANTS_FILE=str(tfile))
+    audit = tmp_path / "audit.jsonl"  # keystone, worker and coordinator append to one file (O_APPEND, a line per write)
+    srv_env = dict(base, BB_AUTH_TOKEN=TOKEN, BB_TENANTS_FILE=str(tfile), BB_AUDIT_LOG=str(audit))
     if sealed:
         srv_env["BB_ENCRYPT_TRANSPORT"] = "1"
         base["BB_ENCRYPT_TRANSPORT"] = "1"
@@ -329,6 +330,29 @@ def test_tenants_end_to_end_over_rpc(bb, tmp_path, sealed):
             time.sleep(0.2)
         assert cli(bob, "--keystone", ks, "exists", "alice/ckpt").returncode != 0
         assert cli(alice, "--keystone", ks, "exists", "alice/ckpt").returncode == 0
+        # the audit trail (common/audit.h) names what the counters only count
+        ev = [json.loads(ln) for ln in audit.read_text().splitlines()]
+        assert all({"ts", "event", "who"} <= set(e) for e in ev)
+        kinds = lambda k: [e for e in ev if e["event"] == k]
+        assert {e["who"] for e in kinds("tenant_admitted")} >= {"alice", "bob", "ops"} and all(e["sealed"] == ("yes" if sealed else "no") for e in kinds("tenant_admitted"))
+        assert any(e["who"] == "alice" and e["op"] == "write" and e["key"] == "bob/steal" for e in kinds("acl_denied"))
+        assert any(e["who"] == "bob" and e["key"] == "alice/ckpt" and e["op"] == "write" for e in kinds("acl_denied"))
+        assert any(e["who"] == "alice" and e["op"] == "list" and e["key"] == "" for e in kinds("acl_denied"))
+        assert any(e["who"] == "alice" and e["key"] == "alice/4" and e["bytes"] == "300000" for e in kinds("quota_denied"))
+        assert any(e["who"] == "alice" and "peer" in e for e in kinds("method_denied"))  # remove-worker, migrate, scrub, workers
+        # wrong secret, unknown name, no identity at all, and bob after he left the table
+        # (a client told to encrypt that has nothing to key from gives up before it connects: no "unknown" line when sealed)
+        assert {e["who"] for e in kinds("auth_failed")} >= {"tenant:alice", "tenant:mallory", "tenant:bob"} | (set() if sealed else {"unknown"})
+        assert any(e["who"] == "keystone" and e["count"] == "2" for e in kinds("tenants_reloaded"))
+        m = cli(member, "metrics", "--http", f"127.0.0.1:{hport}").stdout
+        assert "bb_audit_events_total" in m
+        # a management call by an admin tenant and one by a member are both on record, with their outcome
+        assert cli(ops, "--keystone", ks, "migrate", "alice/ckpt", "NVME").returncode != 0  # (no such tier here)
+        assert cli(member, "--keystone", ks, "remove-worker", "no-such-worker").returncode != 0
+        ev = [json.loads(ln) for ln in audit.read_text().splitlines()]
+        adm = [e for e in ev if e["event"] == "admin"]
+        assert any(e["who"] == "ops" and e["op"] == "migrate_object" and e["arg"] == "alice/ckpt" and e["result"] != "OK" for e in adm)
+        assert any(e["who"] == "member" and e["op"] == "remove_worker" and e["arg"] == "no-such-worker" for e in adm)
     finally:
         for p in reversed(procs):
             p.terminate()
